@@ -1,0 +1,321 @@
+#!/usr/bin/env python
+"""bench.py -- particle-steps/s of the full sheath PIC step (PIC_L_DD physics) on B200.
+
+    python bench.py --gpus N --steps K --warmup W            # our CUDA path
+    python bench.py --impl reference --steps K --warmup W    # CPU port of the reference path
+
+One "step" = one full timestep (re-injection + the whole Picard loop: fused
+gather/push/absorb/deposit kernel, [all-reduce], field update, until converged) over
+every particle of the workload.  A particle-step = one particle through one step.
+
+N=1 workload = BASELINE.json configs[1]: 1e8 particles/species (2e8 total), 4097-node
+(4096-cell) grid, PIC_L_DD physics.  N>1: weak scaling, 2e8 particles per GPU, particle
+decomposition with one fp64 all-reduce of [jh|j1|absorbed counts] per Picard iteration.
+Rank 0 prints ONE JSON line.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+E_CH, ME, MP, KB = 1.602E-19, 9.11E-31, 1.67E-27, 1.38E-23
+METRIC = "particle-steps/sec (full PIC step)"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
+    ap.add_argument("--particles-per-gpu", type=float, default=2e8)
+    ap.add_argument("--total-particles", type=float, default=0, help="strong scaling: fixed total (e.g. 1e9)")
+    ap.add_argument("--cells", type=int, default=4096)
+    ap.add_argument("--sort-every", type=int, default=25)
+    ap.add_argument("--deposit", default="warp", choices=["warp", "atomic"])
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-sample", type=float, default=4e6, help="particles in the CPU-baseline sample")
+    ap.add_argument("--e2e-steps", type=int, default=3)
+    return ap.parse_args()
+
+
+def workload(args, world):
+    Ng = args.cells + 1
+    dx, dt = 1e-5, 1e-12
+    L = dx * (Ng - 1)
+    if args.total_particles:
+        N = int(args.total_particles); scaling = "strong"
+    else:
+        N = int(args.particles_per_gpu) * world; scaling = "weak"
+    N -= N % 2
+    Te = Ti = 10.0 * 11600.
+    density = 1e19
+    return dict(N=N, Ng=Ng, dx=dx, dt=dt, L=L, Te=Te, Ti=Ti, density=density, p2c=L * density / N,
+                kBTe=KB * Te, kBTi=KB * Ti, scaling=scaling, tol=1e-5, maxiter=20)
+
+
+class ClockSampler(threading.Thread):
+    """Samples nvidia-smi clocks / throttle reasons during the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.rows, self.stop_flag = index, [], False
+
+    def run(self):
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                if out.strip():
+                    self.rows.append([c.strip() for c in out.strip().split("\n")[0].split(",")])
+            except Exception:
+                pass
+            time.sleep(0.2)
+
+    def summary(self):
+        if not self.rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        sm = sorted(float(r[0]) for r in self.rows if r[0].replace(".", "").isdigit())
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for k, n in enumerate(names) if any(len(r) > 3 + k and r[3 + k].lower().startswith("active") for r in self.rows)]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": float(self.rows[0][1]) if self.rows else None,
+                "power_w_max": max(float(r[2]) for r in self.rows), "reasons": reasons, "samples": len(self.rows)}
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.isfile(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+# ----------------------------------------------------------------------------- CPU arm
+def cpu_port_run(w, n_sample, steps, warmup, threads=None):
+    """Times the C port of the reference's sheath timestep (oracle/c/dd_oracle.c) on the
+    host cores.  Bounded sample of the same workload: same grid, same physics, n_sample
+    particles (p2c rescaled so the plasma density is unchanged)."""
+    from oracle import c_oracle
+    threads = threads or c_oracle.max_threads()
+    n = int(n_sample); n -= n % 2
+    rs = np.random.RandomState(1)
+    h = n // 2
+    x0 = rs.uniform(0, w["L"], n)
+    u0 = np.concatenate([rs.normal(0, np.sqrt(w["kBTe"] / ME), h), rs.normal(0, np.sqrt(w["kBTi"] / MP), h)])
+    E0 = np.zeros(w["Ng"])
+    p2c = w["L"] * w["density"] / n
+    times, iters = [], []
+    for s in range(warmup + steps):
+        act = np.ones(n)
+        t0 = time.perf_counter()
+        x1, u1, E1, j1, k, r = c_oracle.dd_picard_step(x0, u0, [-E_CH, E_CH], [ME, MP], h, act, E0, p2c, w["Ng"],
+                                                       w["dx"], w["dt"], w["L"], w["tol"], w["maxiter"], threads)
+        dt = time.perf_counter() - t0
+        if s >= warmup:
+            times.append(dt); iters.append(k)
+        # next step: survivors keep going, absorbed slots are re-drawn (host RNG)
+        dead = act != 1
+        x0 = np.where(dead, rs.uniform(0, w["L"], n), x1)
+        sig = np.concatenate([np.full(h, np.sqrt(w["kBTe"] / ME)), np.full(h, np.sqrt(w["kBTi"] / MP))])
+        u0 = np.where(dead, rs.normal(0, 1, n) * sig, u1)
+        E0 = E1
+    tot = sum(times)
+    return dict(value=n * len(times) / tot, ms_per_step=1e3 * tot / len(times), cores=threads,
+                sample="%d particles (%.3g of the workload), %d-node grid, %d timed steps, mean %.1f Picard iterations"
+                       % (n, n / w["N"], w["Ng"], len(times), float(np.mean(iters))), iters=float(np.mean(iters)))
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    w = workload(args, max(1, args.gpus))
+    from oracle import c_oracle
+    threads = c_oracle.max_threads()
+    # size the sample so the whole run ends within a few minutes
+    res = cpu_port_run(w, args.cpu_sample, max(1, min(args.steps, 10)), max(1, min(args.warmup, 2)), threads)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": res["value"], "unit": "particle-steps/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": res["ms_per_step"],
+        "higher_is_better": True, "scaling": w["scaling"], "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "1D sheath PIC_L_DD physics, %d particles, %d-node grid" % (w["N"], w["Ng"]),
+                   "note": "CPU port of the reference loop (oracle/c/dd_oracle.c, OpenMP) on a bounded sample; the "
+                           "reference itself is pure Python and cannot travel to the GPU box"},
+        "cpu_baseline": {"value": res["value"], "unit": "particle-steps/s", "cores": res["cores"], "kind": "port",
+                         "sample": res["sample"]},
+        "e2e": {"value": res["value"], "unit": "particle-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+# ----------------------------------------------------------------------------- GPU arm
+def run_cuda(args):
+    import torch
+    import torch.distributed as dist
+    import ctypes as C
+    from pypic_b200 import _lib, device as D
+    from pypic_b200.dist import Comm
+    from pypic_b200.sheath import SheathSim
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (there is no CPU fallback; use --impl reference for the CPU port)")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    comm = Comm()
+    w = workload(args, world)
+    dev = torch.device("cuda", local)
+
+    sim = SheathSim(w["N"], w["Ng"], w["dx"], w["dt"], w["p2c"], tol=w["tol"], maxiter=w["maxiter"],
+                    kBT=(w["kBTe"], w["kBTi"]), carry_vw=False, deposit=args.deposit, rng="philox", seed=1,
+                    comm=comm, device=dev, sort_every=args.sort_every)
+    # synthetic initial state, generated on the device (x~U(0,L), u~N(0,sqrt(kT/m)))
+    gen = torch.Generator(device=dev); gen.manual_seed(1234 + rank)
+    n, ns = sim.N, sim.n_split
+    sim.x0.uniform_(0.0, 1.0, generator=gen).mul_(w["L"]).clamp_(1e-12, w["L"] * (1 - 1e-12))
+    sim.u0.normal_(0.0, 1.0, generator=gen)
+    sim.u0[:ns].mul_(float(np.sqrt(w["kBTe"] / ME)))
+    sim.u0[ns:].mul_(float(np.sqrt(w["kBTi"] / MP)))
+    torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        sim.step()
+    sim.check()
+    torch.cuda.synchronize()
+    comm.barrier()
+
+    # ---- timed region: K full steps, CUDA events, per-launch events on the dominant kernel
+    sampler = ClockSampler(local) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    iter_events = sim.iter_events = []
+    launches0 = sim.kernel_launches
+    iters = []
+    torch.cuda.synchronize()
+    comm.barrier()
+    ev0.record()
+    for _ in range(args.steps):
+        k, r = sim.step()
+        iters.append(k)
+    ev1.record()
+    torch.cuda.synchronize()
+    comm.barrier()
+    sim.iter_events = None
+    if sampler:
+        sampler.stop_flag = True
+    ms = ev0.elapsed_time(ev1)
+    ms = comm.max_float(ms, device=dev)
+    launches = sim.kernel_launches - launches0
+    sim.check()
+    kernel_ms = [a.elapsed_time(b) for a, b in iter_events]
+    mean_iter_ms = float(np.mean(kernel_ms))
+    kbar = float(np.mean(iters))
+    value = w["N"] * args.steps / (ms * 1e-3)
+
+    # ---- roofline of the dominant kernel (fused gather+push+absorb+deposit), HBM bound
+    # algorithmic bytes per particle-step = 32*k + 16 -> per launch N_local*(32 + 16/k)
+    alg_bytes_launch = sim.N * (32.0 + 16.0 / kbar)
+    achieved = alg_bytes_launch / (mean_iter_ms * 1e-3) / 1e9
+    peak, peak_src = measured_peak()
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": None, "kernel": "dd_picard_iter_k", "peak_source": peak_src,
+                "kernel_ms_mean": mean_iter_ms, "kernel_share_of_step": float(np.sum(kernel_ms) / ms),
+                "algorithmic_bytes_per_launch": alg_bytes_launch, "mean_picard_iterations": kbar}
+    tf = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.isfile(tf):
+        try:
+            roofline["traffic"] = json.load(open(tf)).get("dram_bytes_per_launch")
+        except Exception:
+            pass
+
+    # ---- e2e: the same step through the C ABI with HOST (pinned) buffers, copies timed
+    e2e = None
+    if not args.no_e2e:
+        Nl, Ng = sim.N, w["Ng"]
+        hx0 = torch.empty(Nl, dtype=torch.float64, pin_memory=True); hu0 = torch.empty_like(hx0, pin_memory=True)
+        hx1 = torch.empty_like(hx0, pin_memory=True); hu1 = torch.empty_like(hx0, pin_memory=True)
+        hact = torch.empty(Nl, dtype=torch.int8, pin_memory=True)
+        hE0 = torch.zeros(Ng, dtype=torch.float64, pin_memory=True); hE1 = torch.empty_like(hE0, pin_memory=True)
+        hj1 = torch.empty_like(hE0, pin_memory=True)
+        hx0.copy_(sim.x0); hu0.copy_(sim.u0); hE0.copy_(sim.E0)
+        torch.cuda.synchronize()
+        # the resident simulation is released so the host-buffer path has its own HBM
+        P = _lib.DDParams(Nl, sim.n_split, Ng, 0, w["dx"], w["dt"], w["L"], w["p2c"],
+                          (C.c_double * 2)(-E_CH, E_CH), (C.c_double * 2)(ME, MP))
+        it, res = C.c_int(), C.c_double()
+
+        def host_step():
+            _lib.call("pic_host_dd_step", C.byref(P), hx0.data_ptr(), hu0.data_ptr(), hE0.data_ptr(), w["tol"],
+                      w["maxiter"], hx1.data_ptr(), hu1.data_ptr(), hact.data_ptr(), hE1.data_ptr(), hj1.data_ptr(),
+                      C.byref(it), C.byref(res))
+        host_step()                      # warm-up (allocates the cached device workspace)
+        comm.barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.e2e_steps):
+            host_step()
+        torch.cuda.synchronize()
+        t_e2e = time.perf_counter() - t0
+        t_e2e = comm.max_float(t_e2e, device=dev)
+        h2d = Nl * 16 + Ng * 8
+        d2h = Nl * 17 + Ng * 16
+        e2e = {"value": w["N"] * args.e2e_steps / t_e2e, "unit": "particle-steps/s", "h2d_bytes_per_step": h2d,
+               "d2h_bytes_per_step": d2h, "steps": args.e2e_steps, "picard_iterations": it.value,
+               "api": "pic_host_dd_step (C ABI, pinned host buffers, per-rank shard)"}
+        _lib.call("pic_host_release")
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        res = cpu_port_run(w, args.cpu_sample, 3, 1)
+        cpu = {"value": res["value"], "unit": "particle-steps/s", "cores": res["cores"], "kind": "port",
+               "sample": res["sample"]}
+
+    if rank == 0:
+        clocks = sampler.summary() if sampler else {}
+        line = {
+            "metric": METRIC, "value": value, "unit": "particle-steps/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": w["scaling"],
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "1D sheath (PIC_L_DD physics): %d particles (%d per GPU, e-/p+ halves), %d-node grid, "
+                                   "implicit CN/Picard tol=1e-5" % (w["N"], sim.N, w["Ng"]),
+                       "parallelism": "particle decomposition x%d, fp64 all-reduce of [jh|j1|counts] per Picard iteration" % world
+                       if world > 1 else "single GPU",
+                       "picard_iterations_per_step": kbar, "deposit": args.deposit, "sort_every": args.sort_every,
+                       "reinjection": "device Philox4x32-10 (statistical parity)",
+                       "l2_policy": "inputs (%.1f GB of particle arrays per GPU) are far larger than the 126 MB L2" % (sim.N * 32 / 1e9)},
+            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_cuda(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,310 @@
+/* pic_b200.h -- C ABI of libpic_b200.so: the B200 (sm_100a) implementation of
+ * pyPIC's per-timestep particle-in-cell loop.
+ *
+ * The reference (drobnyjt/pyPIC) has no FFI: its hot path is the set of
+ * module-level Python functions cited next to each entry point below.  The
+ * drop-in Python modules in this repository (pypic.py, PIC_L.py, PIC_L_DD.py,
+ * pygcpic.py) bind these symbols through ctypes; INTEGRATION.md shows the stub a
+ * maintainer of the reference would add.
+ *
+ * Conventions
+ *   - every function returns 0 on success or a negative PIC_ERR_* code and never
+ *     throws; pic_last_error() returns a static description of the last failure
+ *     on the calling thread;
+ *   - "pic_dev_*"  : all array arguments are DEVICE pointers (fp64 unless noted),
+ *     the call is asynchronous on `stream` (a cudaStream_t passed as void*);
+ *   - "pic_host_*" : all array arguments are HOST pointers; the call uploads,
+ *     launches the same pic_dev_* kernels, downloads and synchronises;
+ *   - no allocation is done by pic_dev_* calls; the caller owns every buffer;
+ *   - all arithmetic is IEEE fp64 (the reference's precision); indices are int32;
+ *   - there is no CPU fallback anywhere in this library.
+ */
+#ifndef PIC_B200_H
+#define PIC_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PIC_OK 0
+#define PIC_ERR_CUDA (-1)     /* a CUDA runtime call / kernel launch failed        */
+#define PIC_ERR_ARG (-2)      /* invalid argument (null pointer, bad size, ...)     */
+#define PIC_ERR_NODEVICE (-3) /* no CUDA device visible                            */
+#define PIC_ERR_RANGE (-4)    /* a particle index fell outside the grid (reference
+                                 undefined behaviour)              */
+
+const char* pic_last_error(void);
+int pic_version(void);
+/* number of SMs / device name of the current device (diagnostics for bench.py) */
+int pic_device_info(int* sm_count, int* cc_major, int* cc_minor, char* name, int name_len);
+
+/* Raw device-memory helpers for hosts that hold plain pointers (asynchronous on
+ * `stream` except pic_dev_read, which synchronises the stream before returning). */
+int pic_dev_read(const void* dev, void* host, int64_t bytes, void* stream);
+int pic_dev_write(void* dev, const void* host, int64_t bytes, void* stream);
+int pic_dev_zero(void* dev, int64_t bytes, void* stream);
+int pic_dev_copy(void* dst, const void* src, int64_t bytes, void* stream);
+int pic_stream_sync(void* stream);
+/* frees the device workspaces cached by the pic_host_* entry points */
+int pic_host_release(void);
+
+/* ------------------------------------------------------------------------- *
+ * Grid kernels (one CTA; Ng is small).  F/out are DEVICE fp64[n].
+ * ------------------------------------------------------------------------- */
+/* variant 0: periodic (pypic.smooth_field_p pypic.py:63-76)
+ * variant 1: ends pinned (PIC_L_DD.smoothField :216-221, Grid.smooth_rho pygcpic.py:1055-1060) */
+int pic_dev_smooth(const double* F, double* out, int n, int variant, void* stream);
+/* variant 0: pypic.differentiate_p pypic.py:185-214        (+dF/dx, periodic, *(0.5/dx))
+ * variant 1: PIC_L_DD.differentiateField :192-203           (-dF/dx, one-sided ends, /dx*0.5)
+ * variant 2: PIC_L.differentiateFieldPeriodic :235-246      (-dF/dx, periodic over n nodes, /dx*0.5)
+ * variant 3: Grid.differentiate_phi_to_E_dirichlet pygcpic.py:932-936 (-dF/dx, /dx/2.) */
+int pic_dev_differentiate(const double* F, double* out, int n, double dx, int variant, void* stream);
+/* PIC_L_DD.integrateField :205-214 : out[i] = -trapz(F[:i+1],dx) as a block scan;
+ * if subtract_max != 0 also applies the caller's ``- max`` (PIC_L_DD.py:519,523). */
+int pic_dev_integrate_field(const double* F, double* out, int n, double dx, int subtract_max, void* stream);
+/* out = F - max(F) (mode 0) or F - min(F) (mode 1): pypic.py:553, pygcpic.py:1002,1052 */
+int pic_dev_shift_extreme(const double* F, double* out, int n, int mode, void* stream);
+
+/* Tridiagonal solve by parallel cyclic reduction (PCR), no pivoting.
+ * a=sub (a[0] ignored), b=diag, c=super (c[n-1] ignored), d=rhs -> x.  n<=PIC_PCR_SMEM_MAX
+ * runs in one CTA in shared memory; larger n uses global-memory PCR passes and
+ * `work` (8*n doubles) must be provided. */
+#define PIC_PCR_SMEM_MAX 6144
+int pic_dev_tridiag_pcr(const double* a, const double* b, const double* c, const double* d,
+                        double* x, int n, double* work, void* stream);
+/* pypic.solve_poisson_p pypic.py:359-382 / PIC_L.solvePoissonPeriodicElectronsNeutralized
+ * PIC_L.py:208-220: periodic [1,-2,1] phi = -dx^2(c0+c2), c0=-mean(rho)/eps0, c2=rho/eps0,
+ * gauge phi[n-1]=0 then ``- max(phi)`` if subtract_max.  work: 13*n doubles. */
+int pic_dev_poisson_periodic(const double* rho, double* phi, int n, double dx, int subtract_max,
+                             double* work, void* stream);
+/* Grid.solve_for_phi_dirichlet pygcpic.py:987-1003 (rows 0,n-1 identity, no eps0, -min). work 13*n */
+int pic_dev_poisson_dirichlet(const double* rho, double* phi, int n, double dx, double* work, void* stream);
+/* Newton-Boltzmann solves, whole Newton loop in ONE kernel launch (n <= PIC_PCR_SMEM_MAX):
+ * bc 0: Grid.solve_for_phi_dirichlet_boltzmann pygcpic.py:1005-1053 (cold start, c2=rho/eps0,
+ *       stop dphi.dphi<=tol, exact tridiagonal step instead of bicgstab)
+ * bc 1: Grid.solve_for_phi_dirichlet_neumann_boltzmann :1062-1109 (warm start from phi,
+ *       src = n (number density, c2=e*n/eps0), last row [1,-4,3], stop |dphi|<=tol)
+ * iters_out: device int[1] receiving the Newton iteration count. */
+int pic_dev_newton_boltzmann(const double* src, double* phi, int n, double dx, double n0, double Te,
+                             int bc, double tol, int iter_max, int* iters_out, void* stream);
+
+/* ------------------------------------------------------------------------- *
+ * PIC_L_DD.py -- bounded two-species implicit sheath (the benchmark path)
+ * ------------------------------------------------------------------------- */
+typedef struct {
+    int64_t N;        /* particles in this shard                                   */
+    int64_t n_split;  /* local index where species 2 starts: [0,n_split) use q[0],m[0] */
+    int32_t Ng;       /* grid NODES (PIC_L_DD.py:324)                               */
+    int32_t flags;    /* bit0: deposit with plain shared-memory atomics only (no warp
+                         pre-reduction); bit1: keep grid tiles in global memory       */
+    double dx, dt, L, p2c;
+    double q[2], m[2];
+} pic_dd_params;
+
+/* Function-level drop-ins (per-particle q, active as fp64 1/0/-1 like the reference):
+ * PIC_L_DD.interpolateField :32-39 (vectorised over x) */
+int pic_dev_dd_interpolate(const double* F, const double* x, double* out, int64_t N, int Ng, double dx,
+                           int* range_err, void* stream);
+/* PIC_L_DD.weightCurrents :41-68 (v != NULL) / weightDensities :70-88 (v == NULL).
+ * out fp64[Ng] is overwritten; wall-charge terms and edge fold included for currents. */
+int pic_dev_dd_weight(const double* x, const double* q, const double* v, const double* active,
+                      double* out, int64_t N, int Ng, double dx, double dt, double p2c,
+                      int* range_err, void* stream);
+
+/* One Picard iteration of PIC_L_DD.main_i's particle phase, fused
+ * (gather :470-474, CN push :477-491, absorb :494-505, deposit of jh and j1 :509,513):
+ *   x0,u0   : state at time n (read only)
+ *   x1,u1   : scratch = state at n+1 of the previous iteration (read unless `first`,
+ *             always written); the half-step position is recomputed as (x0+x1)*0.5
+ *   active  : int8 {1,0,-1}; read unless `first`, written when a particle is absorbed
+ *   Es      : field used for the gather (fp64[Ng])
+ *   acc     : fp64[2*Ng+4] accumulators, must be zero on entry:
+ *             [0,Ng) raw CIC jh, [Ng,2Ng) raw CIC j1, then the numbers of particles
+ *             absorbed IN THIS ITERATION: left-wall sp1, left-wall sp2, right-wall sp1,
+ *             right-wall sp2 (exact integers stored as fp64 so one allreduce covers all)
+ *   range_err: device int, incremented for every out-of-grid index (clamped). */
+int pic_dev_dd_picard_iter(const pic_dd_params* p, const double* x0, const double* u0,
+                           double* x1, double* u1, int8_t* active, const double* Es,
+                           double* acc, int first, int* range_err, void* stream);
+/* Field phase of the same iteration (PIC_L_DD.py:55-66,516-527), one CTA:
+ *   wall_cum fp64[4] += acc[2Ng..2Ng+3]; jh,j1 get wall terms + edge fold;
+ *   E1 = E0 + (dt/eps0)(mean(jh) - jh); Eh=(E1+E0)/2; r=|Es-Eh|_2; Es=Eh;
+ *   acc is zeroed for the next iteration.  stats (device or mapped-host fp64[4]):
+ *   [0]=r, [1]=mean(j1), [2]=sum(eps0*E1^2*dx/2), [3]=iteration counter (incremented). */
+int pic_dev_dd_field_update(const pic_dd_params* p, double* acc, double* wall_cum, const double* E0,
+                            double* Es, double* E1, double* j1, double* stats, void* stream);
+/* Re-injection (PIC_L_DD.py:429-450).  Host-RNG parity mode: compact the indices of
+ * inactive slots in index order (pic_dev_compact_flags), draw on the host with the
+ * legacy MT19937 stream, then scatter: */
+int pic_dev_dd_apply_draws(const int32_t* idx, const double* xd, const double* ud, const double* vd,
+                           const double* wd, int64_t n, double* x0, double* u0, double* v0, double* w0,
+                           int8_t* active, void* stream);
+/* Device mode (benchmark sizes, statistical parity only): Philox4x32-10 keyed by
+ * (seed, step, global particle id); x~U(0,L), u,v,w~N(0,sqrt(kT/m)). v0/w0 may be NULL. */
+int pic_dev_dd_reinject_philox(const pic_dd_params* p, double* x0, double* u0, double* v0, double* w0,
+                               int8_t* active, const double sigma[2], uint64_t seed, uint64_t step,
+                               int64_t global_offset, void* stream);
+/* Commit helper: after the last iteration particles that were already inactive when it
+ * started hold x1=u1=0 like the reference (PIC_L_DD.py:459-462); the commit itself is a
+ * pointer swap on the host.  KE diagnostic sum(me*u^2/2) (PIC_L_DD.py:549): */
+int pic_dev_sum_sq(const double* u, int64_t N, double scale, double* out1, void* stream);
+/* Counting sort by (species, cell) of the n-level state; out-of-place.  Keeps species
+ * ranges contiguous; order inside a cell is unspecified (benchmark mode only).
+ * counts: int32 scratch of 2*Ng+2 entries.  v0/w0 (and outputs) may be NULL. */
+int pic_dev_dd_sort_by_cell(const pic_dd_params* p, const double* x0, const double* u0,
+                            const double* v0, const double* w0, double* x0s, double* u0s,
+                            double* v0s, double* w0s, int32_t* counts, void* stream);
+
+/* ------------------------------------------------------------------------- *
+ * pypic.py -- periodic implicit PIC
+ * ------------------------------------------------------------------------- */
+/* pypic.interpolate_p pypic.py:28-61 */
+int pic_dev_pypic_interpolate(const double* F, const double* x, double* out, int64_t N, int Ng,
+                              double dx, int* range_err, void* stream);
+/* pypic.weight_current_p :91-136 (v != NULL, wR=(x%dx)*idx) / weight_density_p :138-183
+ * (v == NULL, wR=(x%dx)/dx).  p2c is the value AFTER int32 truncation. out zeroed by caller. */
+int pic_dev_pypic_weight(const double* x, const double* q, const double* v, double* out, int64_t N,
+                         int Ng, double dx, double p2c, int* range_err, void* stream);
+typedef struct {
+    int64_t N;
+    int32_t Ng;
+    int32_t flags;
+    double dx, dt, L, p2c; /* p2c already truncated */
+    double q, m;           /* single species (electrons)            */
+} pic_pypic_params;
+/* One Picard iteration of pypic.particle_push_p :259-279, fused: gather at xs with the
+ * SMOOTHED field Fs, CN push, wrap, deposit jh(xh,vh) and j1(x1,v1).
+ *   x1 holds the UNWRAPPED n+1 position of the previous iteration (xs=((x0+x1)*.5)%L);
+ *   acc fp64[2*Ng] zero on entry. */
+int pic_dev_pypic_picard_iter(const pic_pypic_params* p, const double* x0, const double* v0,
+                              double* x1, double* v1, const double* Fs, double* acc, int first,
+                              int* range_err, void* stream);
+/* pypic.py:283-292: E1=E0+(dt/eps0)(mean(jh)-smooth(jh)); Eh; r=sum((Es-Eh)^2); Es=Eh;
+ * Fs=smooth(Es) for the next gather; j1 copied out; acc zeroed.
+ * stats fp64[4]: r, mean(j1), sum(eps0 E1^2 dx/2), iteration counter. */
+int pic_dev_pypic_field_update(const pic_pypic_params* p, double* acc, const double* E0, double* Es,
+                               double* Fs, double* E1, double* j1, double* stats, void* stream);
+/* x[i] = x[i] % L in place (pypic.py:277 applied to the committed positions) */
+int pic_dev_wrap_periodic(double* x, int64_t N, double L, void* stream);
+
+/* ------------------------------------------------------------------------- *
+ * PIC_L.py -- periodic explicit leapfrog, Poisson every step
+ * ------------------------------------------------------------------------- */
+typedef struct {
+    int64_t N;
+    int64_t n_split;
+    int32_t Ng;    /* cells; the grid has Ng+1 nodes (PIC_L.py:646,667) */
+    int32_t flags;
+    double dx, dt, L, p2c; /* wrap length is L+dx (PIC_L.py:285) */
+    double q[2], m[2];
+} pic_l_params;
+/* PIC_L.interpolateFieldPeriodic :39-46 */
+int pic_dev_l_interpolate(const double* F, const double* x, double* out, int64_t N, int Ng, double dx,
+                          int* range_err, void* stream);
+/* PIC_L.weightDensitiesPeriodic :100-118 (v==NULL) / weightCurrentsPeriodic :62-80; folds included */
+int pic_dev_l_weight(const double* x, const double* q, const double* v, double* out, int64_t N, int Ng,
+                     double dx, double p2c, int* range_err, void* stream);
+/* Fused explicit step, particle phase (PIC_L.py:767-768 + next step's :763):
+ * gather E at x, kick-drift-kick, wrap x%(L+dx), and deposit rho of the NEW positions
+ * into rho_acc fp64[Ng+1] (zero on entry, raw CIC; fold applied by pic_dev_l_field_solve). */
+int pic_dev_l_push_deposit(const pic_l_params* p, double* x, double* v, const double* E,
+                           double* rho_acc, int* range_err, void* stream);
+/* PIC_L.py:763-766 field phase: fold rho_acc -> rho; periodic Poisson; -max; E=-dphi/dx.
+ * work: 13*(Ng+1) doubles.  rho_acc is zeroed.  stats[0] = sum(eps0*E*E/2). */
+int pic_dev_l_field_solve(const pic_l_params* p, double* rho_acc, double* rho, double* phi, double* E,
+                          double* work, double* stats, void* stream);
+
+/* ------------------------------------------------------------------------- *
+ * pygcpic.py -- Particle / Grid (Boris 1D3V, guiding centre, Boltzmann electrons)
+ * Particle store: SoA r0..r6 (x,y,z,vx,vy,vz,t), charge_state/m/p2c fp64, flags int8.
+ * ------------------------------------------------------------------------- */
+typedef struct {
+    int64_t N;
+    int32_t ng;     /* grid nodes */
+    int32_t flags;
+    double dx, dt, length;
+    double B[3];
+    double Eyz[2];  /* the shared E[1],E[2] of Particle.E (only E[0] is ever gathered) */
+} pic_gc_params;
+/* Particle.interpolate_electric_field_dirichlet pygcpic.py:325-348 (MIRRORED weights) */
+int pic_dev_gc_interpolate(const double* E, const double* x, double* out, int64_t N, int ng, double dx,
+                           int* range_err, void* stream);
+/* Grid.weight_particles_to_grid_boltzmann :868-883: rho and n of active particles (zeroed by caller) */
+int pic_dev_gc_weight(const double* x, const double* charge_state, const double* p2c,
+                      const int8_t* active, double* rho, double* n, int64_t N, int ng, double dx,
+                      int* range_err, void* stream);
+/* Fused particle phase of a pygcpic step for active particles (pygcpic.py:1500-1502):
+ * mirrored gather -> Particle.push_6D :460-507 -> apply_BCs_dirichlet :668-689.
+ * r: 7 device arrays; hit_count: device int64 incremented per wall hit this call;
+ * hit_flag (may be NULL): int8[N], 1 for particles absorbed by this call (tallies T1). */
+int pic_dev_gc_push_boris(const pic_gc_params* p, double* const r[7], const double* charge_state,
+                          const double* m, int8_t* active, int8_t* at_wall, int8_t* hit_flag,
+                          const double* Egrid, long long* hit_count, int* range_err, void* stream);
+/* Particle.apply_BCs_dirichlet :668-689 alone */
+int pic_dev_gc_apply_bcs(const double* x, int8_t* active, int8_t* at_wall, int64_t N, double length,
+                         void* stream);
+/* Particle.transform_6D_to_GC :509-551 / transform_GC_to_6D :553-596 (a = uniform draws, N x 3
+ * as three arrays) / push_GC :598-645 (RK4, E gathered once with mirrored weights if Egrid!=NULL,
+ * else Ex=0) -- applied to particles with active==1 */
+int pic_dev_gc_to_gc(const pic_gc_params* p, double* const r[7], const double* charge_state,
+                     const double* m, const int8_t* active, void* stream);
+int pic_dev_gc_to_6d(const pic_gc_params* p, double* const r[7], const double* charge_state,
+                     const double* m, const int8_t* active, const double* a0, const double* a1,
+                     const double* a2, void* stream);
+int pic_dev_gc_push_rk4(const pic_gc_params* p, double* const r[7], const double* charge_state,
+                        const double* m, const int8_t* active, const double* Egrid, int* range_err,
+                        void* stream);
+/* Boltzmann reference-density update, Grid.weight_particles_to_grid_boltzmann :889-904.
+ * domain = Grid.domain (np.linspace(0,length,ng)) so np.trapz's spacings are reproduced;
+ * state fp64[3] = {n0, p_old, initialised(0/1)} on the device. */
+int pic_dev_gc_n0_update(const double* phi, const double* n, const double* domain, int ng, double Te,
+                         double ve, double added_particles, double dt, double* state, void* stream);
+/* Reactivate-or-delete rule pygcpic.py:1543-1549 as an exclusive prefix scan:
+ * contrib_entry/contrib_after int8 (is an active source ion before / after its own push),
+ * inactive_entry int8.  Outputs decision int8: 0 none, 1 reactivate, 2 delete.
+ * idx_scratch/base_scratch: int32[N]; scratch: int64[4 + 2*(ceil(N/2048)+1)], on return
+ * scratch[0]=#inactive at entry, [1]=#source ions at entry, [2]=#reactivated, [3]=#deleted. */
+int pic_dev_gc_decide(const int8_t* inactive_entry, const int8_t* contrib_entry, const int8_t* contrib_after,
+                      int8_t* decision, int64_t N, int64_t source_N, int32_t* idx_scratch,
+                      int32_t* base_scratch, int64_t* scratch, void* stream);
+
+/* ------------------------------------------------------------------------- *
+ * Stream compaction (warp-ballot prefix sum, stable = index order preserved)
+ * ------------------------------------------------------------------------- */
+/* idx_out receives the indices i (ascending) with flags[i] != keep_value... see mode:
+ * mode 0: select flags[i] != 1 (inactive slots of the sheath), mode 1: select flags[i]==0,
+ * mode 2: select flags[i] != 2 (survivors of the pygcpic deletion).
+ * count_out: device int64[1]. block_counts: int64 scratch of 2*(ceil(N/2048)+1) entries. */
+int pic_dev_compact_flags(const int8_t* flags, int64_t N, int mode, int32_t* idx_out, int64_t* count_out,
+                          int64_t* block_counts, void* stream);
+/* dst[k] = src[idx[k]] for k<n (fp64 / int8 payloads) */
+int pic_dev_gather_f64(const double* src, const int32_t* idx, double* dst, int64_t n, void* stream);
+int pic_dev_gather_i8(const int8_t* src, const int32_t* idx, int8_t* dst, int64_t n, void* stream);
+
+/* ------------------------------------------------------------------------- *
+ * Host-buffer entry points: the calls a binding of the reference would make with
+ * NumPy arrays (same argument meaning as the Python functions they replace).
+ * ------------------------------------------------------------------------- */
+int pic_host_pypic_interpolate_p(const double* F, const double* x, int Ng, int64_t N, double dx, double* out);
+int pic_host_pypic_weight_current_p(const double* x, const double* q, const double* v, int p2c, int Ng,
+                                    int64_t N, double dx, double* j);
+int pic_host_pypic_weight_density_p(const double* x, const double* q, int p2c, int Ng, int64_t N,
+                                    double dx, double* rho);
+int pic_host_dd_interpolateField(const double* F, const double* x, int Ng, int64_t N, double dx, double* out);
+int pic_host_dd_weightCurrents(const double* x, const double* q, const double* v, double p2c, int Ng,
+                               int64_t N, double dx, double dt, const double* active, double* j);
+int pic_host_dd_weightDensities(const double* x, const double* q, double p2c, int Ng, int64_t N,
+                                double dx, const double* active, double* rho);
+/* Whole sheath timestep with HOST buffers (bench.py's e2e leg): uploads x0,u0,E0 (all particles
+ * active, i.e. after re-injection), runs the Picard loop of PIC_L_DD.py:452-545 and downloads
+ * x1,u1,active,E1,j1.  Returns the iteration count in *iters and the residual in *resid. */
+int pic_host_dd_step(const pic_dd_params* p, const double* x0, const double* u0, const double* E0,
+                     double tol, int maxiter, double* x1, double* u1, int8_t* active, double* E1,
+                     double* j1, int* iters, double* resid);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PIC_B200_H */

@@ -1,0 +1,540 @@
+// PIC_L_DD.py -- bounded two-species implicit (Crank-Nicolson / Picard) sheath.
+// The particle phase of one Picard iteration is ONE fused kernel: gather, push,
+// wall absorption and the deposition of BOTH currents (jh at the half step, j1 at the
+// full step) in a single pass over the structure-of-arrays particle store.
+#include "common.cuh"
+#include "host_common.h"
+
+namespace pic {
+
+struct DDK {
+    long long N, n_split;
+    int Ng, flags;
+    double dx, idx, dt, L, p2c;
+    double q[2], c1[2], c2[2];   // c1 = dt*(q/m), c2 = (dt*dt)*(q/m)  (Python evaluation order)
+};
+
+static DDK make_ddk(const pic_dd_params* p) {
+    DDK k;
+    k.N = p->N; k.n_split = p->n_split; k.Ng = p->Ng; k.flags = p->flags;
+    k.dx = p->dx; k.idx = 1. / p->dx; k.dt = p->dt; k.L = p->L; k.p2c = p->p2c;
+    for (int s = 0; s < 2; ++s) {
+        double qm = p->q[s] / p->m[s];
+        k.q[s] = p->q[s];
+        k.c1[s] = p->dt * qm;
+        k.c2[s] = p->dt * p->dt * qm;
+    }
+    return k;
+}
+
+// Warp-aggregated deposit of (vL -> node i, vR -> node i+1).  When every lane of the warp
+// targets the same cell (the common case once particles are sorted by cell) the warp
+// reduces with shuffles and issues ONE pair of atomics; otherwise each lane adds its own.
+template <bool AGG>
+__device__ __forceinline__ void deposit_pair(double* tile, int i, double vL, double vR, bool valid) {
+    if (AGG) {
+        unsigned full = 0xffffffffu;
+        int key = valid ? i : -1;
+        int k0 = __shfl_sync(full, key, 0);
+        bool same = __all_sync(full, key == k0);
+        if (same) {
+            if (k0 < 0) return;
+            vL = warp_sum(vL);
+            vR = warp_sum(vR);
+            if ((threadIdx.x & 31) == 0) { atomicAdd(&tile[i], vL); atomicAdd(&tile[i + 1], vR); }
+            return;
+        }
+    }
+    if (valid) { atomicAdd(&tile[i], vL); atomicAdd(&tile[i + 1], vR); }
+}
+
+// One Picard iteration, particle phase.  TILE: field + both current tiles live in shared
+// memory (3*Ng doubles); otherwise they stay in global memory / L2.
+template <bool FIRST, bool TILE, bool AGG>
+__global__ void __launch_bounds__(256) dd_picard_iter_k(DDK k, const double* __restrict__ x0,
+                                                        const double* __restrict__ u0, double* __restrict__ x1,
+                                                        double* __restrict__ u1, int8_t* __restrict__ active,
+                                                        const double* __restrict__ Es, double* __restrict__ acc,
+                                                        int* __restrict__ range_err) {
+    extern __shared__ double sm[];
+    const int Ng = k.Ng;
+    const double* F = Es;
+    double* jh = acc;
+    double* j1 = acc + Ng;
+    if (TILE) {
+        double* sF = sm;
+        for (int i = threadIdx.x; i < Ng; i += blockDim.x) { sF[i] = Es[i]; sm[Ng + i] = 0.0; sm[2 * Ng + i] = 0.0; }
+        __syncthreads();
+        F = sF; jh = sm + Ng; j1 = sm + 2 * Ng;
+    }
+    int nL0 = 0, nL1 = 0, nR0 = 0, nR1 = 0, bad = 0;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    // the trip count is uniform across the warp so the shuffles in deposit_pair are safe
+    const long long nIter = (k.N + stride - 1) / stride;
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    for (long long itn = 0; itn < nIter; ++itn, i += stride) {
+        bool alive = i < k.N;
+        int sp = 0;
+        double X0 = 0., U0 = 0., X1 = 0., U1 = 0., XH = 0., UH = 0.;
+        if (alive) {
+            sp = i >= k.n_split;
+            if (!FIRST) {
+                if (active[i] != 1) {
+                    // already absorbed in an earlier iteration of this step: the reference
+                    // leaves zeros in x1,u1 (PIC_L_DD.py:459-462)
+                    x1[i] = 0.0; u1[i] = 0.0;
+                    alive = false;
+                }
+            }
+        }
+        if (alive) {
+            X0 = ld_stream(x0 + i);
+            U0 = ld_stream(u0 + i);
+            double xs = FIRST ? X0 : (X0 + ld_stream(x1 + i)) * 0.5;   // xs = xh of the previous iteration
+            Cell c = cell_dd(xs, k.dx);
+            if (c.iL < 0 || c.iL > Ng - 2) { ++bad; c.iL = clampi(c.iL, 0, Ng - 2); c.iR = c.iL + 1; }
+            double Ei = c.wL * F[c.iL] + c.wR * F[c.iR];              // PIC_L_DD.py:38
+            X1 = X0 + k.dt * U0 + (sp ? k.c2[1] : k.c2[0]) * Ei * 0.5;                  // :479
+            U1 = U0 + (sp ? k.c1[1] : k.c1[0]) * Ei;                                   // :481
+            XH = (X0 + X1) * 0.5;                                       // :485
+            UH = (U0 + U1) * 0.5;                                       // :487
+            st_stream(x1 + i, X1);
+            st_stream(u1 + i, U1);
+            // absorption, right wall first (PIC_L_DD.py:495-504)
+            if (X0 >= k.L || XH >= k.L || X1 >= k.L) {
+                active[i] = 0; alive = false;
+                if (sp) ++nR1; else ++nR0;
+            } else if (X0 <= 0.0 || XH <= 0.0 || X1 <= 0.0) {
+                active[i] = -1; alive = false;
+                if (sp) ++nL1; else ++nL0;
+            }
+        }
+        // CIC deposit of the survivors: q*v*p2c*w*idx in the reference's product order (:53-54)
+        Cell ch, cf;
+        double hL = 0., hR = 0., fL = 0., fR = 0.;
+        ch.iL = 0; cf.iL = 0;
+        if (alive) {
+            ch = cell_dd(XH, k.dx);
+            if (ch.iL < 0 || ch.iL > Ng - 2) { ++bad; ch.iL = clampi(ch.iL, 0, Ng - 2); }
+            const double qs = sp ? k.q[1] : k.q[0];
+            double qv = qs * UH * k.p2c;
+            hL = qv * ch.wL * k.idx; hR = qv * ch.wR * k.idx;
+            cf = cell_dd(X1, k.dx);
+            if (cf.iL < 0 || cf.iL > Ng - 2) { ++bad; cf.iL = clampi(cf.iL, 0, Ng - 2); }
+            double qf = qs * U1 * k.p2c;
+            fL = qf * cf.wL * k.idx; fR = qf * cf.wR * k.idx;
+        }
+        deposit_pair<AGG>(jh, ch.iL, hL, hR, alive);
+        deposit_pair<AGG>(j1, cf.iL, fL, fR, alive);
+    }
+    if (TILE) {
+        __syncthreads();
+        for (int n = threadIdx.x; n < 2 * Ng; n += blockDim.x) {
+            double v = sm[Ng + n];
+            if (v != 0.0) atomicAdd(&acc[n], v);
+        }
+    }
+    // absorbed-this-iteration counters (exact integers carried as fp64)
+    unsigned full = 0xffffffffu;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        nL0 += __shfl_xor_sync(full, nL0, o); nL1 += __shfl_xor_sync(full, nL1, o);
+        nR0 += __shfl_xor_sync(full, nR0, o); nR1 += __shfl_xor_sync(full, nR1, o);
+        bad += __shfl_xor_sync(full, bad, o);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        if (nL0) atomicAdd(&acc[2 * Ng + 0], (double)nL0);
+        if (nL1) atomicAdd(&acc[2 * Ng + 1], (double)nL1);
+        if (nR0) atomicAdd(&acc[2 * Ng + 2], (double)nR0);
+        if (nR1) atomicAdd(&acc[2 * Ng + 3], (double)nR1);
+        if (bad && range_err) atomicAdd(range_err, bad);
+    }
+}
+
+// Field phase, one CTA.  See pic_b200.h for the contract.
+__global__ void __launch_bounds__(1024) dd_field_update_k(DDK k, double* __restrict__ acc,
+                                                          double* __restrict__ wall_cum,
+                                                          const double* __restrict__ E0, double* __restrict__ Es,
+                                                          double* __restrict__ E1, double* __restrict__ j1o,
+                                                          double* __restrict__ stats) {
+    __shared__ double scratch[33];
+    __shared__ double wl[2], wr[2];
+    const int Ng = k.Ng;
+    if (threadIdx.x < 4) {
+        double v = wall_cum[threadIdx.x] + acc[2 * Ng + threadIdx.x];
+        wall_cum[threadIdx.x] = v;
+        if (threadIdx.x < 2) wl[threadIdx.x] = v; else wr[threadIdx.x - 2] = v;
+    }
+    __syncthreads();
+    // wall-charge current of every absorbed particle (PIC_L_DD.py:58,62): count * value
+    double wallL = wl[0] * (k.dx * k.q[0] * k.p2c / k.dt) + wl[1] * (k.dx * k.q[1] * k.p2c / k.dt);
+    double wallR = wr[0] * (-k.dx * k.q[0] * k.p2c / k.dt) + wr[1] * (-k.dx * k.q[1] * k.p2c / k.dt);
+    double* jh = acc;
+    double* j1 = acc + Ng;
+    double sh = 0.0, s1 = 0.0;
+    // edge fold j[0]+=j[1]; j[-1]+=j[-2] uses the unfolded neighbours (:65-66)
+    for (int i = threadIdx.x; i < Ng; i += blockDim.x) {
+        double a = jh[i], b = j1[i];
+        if (i == 0) { a = (a + wallL) + jh[1]; b = (b + wallL) + j1[1]; }
+        if (i == Ng - 1) { a = (a + wallR) + jh[Ng - 2]; b = (b + wallR) + j1[Ng - 2]; }
+        sh += a; s1 += b;
+        E1[i] = a;      // staged: folded jh
+        j1o[i] = b;
+    }
+    sh = block_reduce<0>(sh, scratch);
+    s1 = block_reduce<0>(s1, scratch);
+    const double meanh = sh / (double)Ng;
+    const double coef = k.dt / PIC_EPS0;
+    double rr = 0.0, ee = 0.0;
+    for (int i = threadIdx.x; i < Ng; i += blockDim.x) {
+        double e0 = E0[i];
+        double e1 = e0 + coef * (meanh - E1[i]);      // :516
+        double eh = (e1 + e0) * 0.5;                   // :521
+        double d = Es[i] - eh;
+        rr += d * d;
+        ee += PIC_EPS0 * e1 * e1 * k.dx / 2.;
+        E1[i] = e1;
+        Es[i] = eh;
+    }
+    rr = block_reduce<0>(rr, scratch);
+    ee = block_reduce<0>(ee, scratch);
+    __syncthreads();
+    for (int i = threadIdx.x; i < 2 * Ng + 4; i += blockDim.x) acc[i] = 0.0;
+    if (threadIdx.x == 0) {
+        stats[0] = sqrt(rr);               // np.linalg.norm(Es-Eh), :525
+        stats[1] = s1 / (double)Ng;        // np.average(j1) -> jbias, :551
+        stats[2] = ee;                     // sum(eps0*E*E*dx/2), :548
+        stats[3] = stats[3] + 1.0;
+    }
+}
+
+// ---- function-level drop-ins ---------------------------------------------------------
+__global__ void dd_interpolate_k(const double* __restrict__ F, const double* __restrict__ x,
+                                 double* __restrict__ out, long long N, int Ng, double dx,
+                                 int* __restrict__ range_err) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < N; i += (long long)gridDim.x * blockDim.x) {
+        Cell c = cell_dd(x[i], dx);
+        if (c.iL < 0 || c.iL > Ng - 2) { if (range_err) atomicAdd(range_err, 1); c.iL = clampi(c.iL, 0, Ng - 2); c.iR = c.iL + 1; }
+        out[i] = c.wL * F[c.iL] + c.wR * F[c.iR];
+    }
+}
+
+// weightCurrents / weightDensities with per-particle q and fp64 active flags.
+// acc layout: [0,Ng) CIC, [Ng] left-wall sum, [Ng+1] right-wall sum (raw, folded by dd_weight_fold_k)
+template <bool CURRENT>
+__global__ void dd_weight_k(const double* __restrict__ x, const double* __restrict__ q,
+                            const double* __restrict__ v, const double* __restrict__ active,
+                            double* __restrict__ acc, long long N, int Ng, double dx, double dt, double p2c,
+                            int* __restrict__ range_err) {
+    extern __shared__ double sm[];
+    for (int i = threadIdx.x; i < Ng + 2; i += blockDim.x) sm[i] = 0.0;
+    __syncthreads();
+    const double idx = 1. / dx;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < N; i += (long long)gridDim.x * blockDim.x) {
+        double a = active[i];
+        if (a == 1.0) {
+            Cell c = cell_dd(x[i], dx);
+            if (c.iL < 0 || c.iL > Ng - 2) { if (range_err) atomicAdd(range_err, 1); c.iL = clampi(c.iL, 0, Ng - 2); }
+            double qv = CURRENT ? q[i] * v[i] * p2c : q[i] * p2c;
+            atomicAdd(&sm[c.iL], qv * c.wL * idx);
+            atomicAdd(&sm[c.iL + 1], qv * c.wR * idx);
+        } else if (CURRENT) {
+            if (a == -1.0) atomicAdd(&sm[Ng], dx * q[i] * p2c / dt);
+            else if (a == 0.0) atomicAdd(&sm[Ng + 1], -dx * q[i] * p2c / dt);
+        }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < Ng + 2; i += blockDim.x)
+        if (sm[i] != 0.0) atomicAdd(&acc[i], sm[i]);
+}
+__global__ void dd_weight_fold_k(const double* __restrict__ acc, double* __restrict__ out, int Ng, int current) {
+    for (int i = threadIdx.x; i < Ng; i += blockDim.x) {
+        double a = acc[i];
+        if (current) {
+            if (i == 0) a = (a + acc[Ng]) + acc[1];
+            if (i == Ng - 1) a = (a + acc[Ng + 1]) + acc[Ng - 2];
+        }
+        out[i] = a;
+    }
+}
+
+// ---- re-injection -----------------------------------------------------------------------
+__global__ void dd_apply_draws_k(const int32_t* __restrict__ idx, const double* __restrict__ xd,
+                                 const double* __restrict__ ud, const double* __restrict__ vd,
+                                 const double* __restrict__ wd, long long n, double* __restrict__ x0,
+                                 double* __restrict__ u0, double* __restrict__ v0, double* __restrict__ w0,
+                                 int8_t* __restrict__ active) {
+    for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < n; t += (long long)gridDim.x * blockDim.x) {
+        int i = idx[t];
+        x0[i] = xd[t]; u0[i] = ud[t];
+        if (v0) v0[i] = vd[t];
+        if (w0) w0[i] = wd[t];
+        active[i] = 1;
+    }
+}
+
+__device__ __forceinline__ double u52(uint32_t a, uint32_t b) {
+    uint64_t v = ((uint64_t)a << 20) ^ (uint64_t)(b >> 12);
+    return ((double)v + 0.5) * (1.0 / 4503599627370496.0);
+}
+
+__global__ void dd_reinject_philox_k(DDK k, double* __restrict__ x0, double* __restrict__ u0,
+                                     double* __restrict__ v0, double* __restrict__ w0,
+                                     int8_t* __restrict__ active, double s0, double s1, uint64_t seed,
+                                     uint64_t step, long long goff) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < k.N; i += (long long)gridDim.x * blockDim.x) {
+        if (active[i] == 1) continue;
+        uint64_t gid = (uint64_t)(goff + i);
+        uint32_t c[4] = {(uint32_t)gid, (uint32_t)(gid >> 32), (uint32_t)step, (uint32_t)(step >> 32)};
+        uint32_t d[4] = {c[0], c[1], c[2], c[3] ^ 0x80000000u};
+        uint32_t g[4] = {c[0], c[1], c[2], c[3] ^ 0x40000000u};
+        philox4x32(c, (uint32_t)seed, (uint32_t)(seed >> 32));
+        philox4x32(d, (uint32_t)seed, (uint32_t)(seed >> 32));
+        philox4x32(g, (uint32_t)seed, (uint32_t)(seed >> 32));
+        const double twopi = 6.283185307179586;
+        double ux = u52(c[0], c[1]);
+        double r1 = sqrt(-2.0 * log(u52(c[2], c[3]))), t1 = twopi * u52(d[0], d[1]);   // Box-Muller
+        double r2 = sqrt(-2.0 * log(u52(d[2], d[3]))), t2 = twopi * u52(g[0], g[1]);
+        double sg = (i >= k.n_split) ? s1 : s0;
+        x0[i] = ux * k.L;
+        u0[i] = sg * r1 * cos(t1);
+        if (v0) v0[i] = sg * r1 * sin(t1);
+        if (w0) w0[i] = sg * r2 * cos(t2);
+        active[i] = 1;
+    }
+}
+
+__global__ void sum_sq_k(const double* __restrict__ u, long long N, double scale, double* __restrict__ out) {
+    __shared__ double scratch[33];
+    double s = 0.0;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < N; i += (long long)gridDim.x * blockDim.x) {
+        double v = u[i];
+        s += scale * v * v;
+    }
+    s = block_reduce<0>(s, scratch);
+    if (threadIdx.x == 0) atomicAdd(out, s);
+}
+
+// ---- counting sort by (species, cell) ----------------------------------------------------
+__device__ __forceinline__ int dd_sort_key(const DDK& k, double x, long long i) {
+    int c = (int)floor(x / k.dx);
+    c = clampi(c, 0, k.Ng - 1);
+    return c + ((i >= k.n_split) ? k.Ng : 0);
+}
+__global__ void dd_sort_hist_k(DDK k, const double* __restrict__ x0, int32_t* __restrict__ counts) {
+    extern __shared__ int sh[];
+    const int nk = 2 * k.Ng;
+    for (int i = threadIdx.x; i < nk; i += blockDim.x) sh[i] = 0;
+    __syncthreads();
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < k.N; i += (long long)gridDim.x * blockDim.x)
+        atomicAdd(&sh[dd_sort_key(k, x0[i], i)], 1);
+    __syncthreads();
+    for (int i = threadIdx.x; i < nk; i += blockDim.x)
+        if (sh[i]) atomicAdd(&counts[i], sh[i]);
+}
+// exclusive scan of counts (one CTA, sequential over chunks)
+__global__ void dd_sort_scan_k(int32_t* __restrict__ counts, int nk) {
+    __shared__ int wsum[32];
+    __shared__ int carry;
+    int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    for (int base = 0; base < nk; base += blockDim.x) {
+        int i = base + threadIdx.x;
+        int v = i < nk ? counts[i] : 0, t = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { int y = __shfl_up_sync(0xffffffffu, t, o); if (lane >= o) t += y; }
+        if (lane == 31) wsum[w] = t;
+        __syncthreads();
+        if (w == 0) {
+            int s = lane < nw ? wsum[lane] : 0;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { int y = __shfl_up_sync(0xffffffffu, s, o); if (lane >= o) s += y; }
+            wsum[lane] = s;
+        }
+        __syncthreads();
+        int pre = carry + (w > 0 ? wsum[w - 1] : 0);
+        if (i < nk) counts[i] = pre + t - v;
+        __syncthreads();
+        if (threadIdx.x == blockDim.x - 1) carry = pre + t;
+        __syncthreads();
+    }
+}
+// scatter: per-CTA chunk, shared-memory ranks, one global reservation per (CTA, key)
+__global__ void __launch_bounds__(1024) dd_sort_scatter_k(DDK k, const double* __restrict__ x0,
+                                                          const double* __restrict__ u0,
+                                                          const double* __restrict__ v0,
+                                                          const double* __restrict__ w0, double* __restrict__ xs,
+                                                          double* __restrict__ us, double* __restrict__ vs,
+                                                          double* __restrict__ ws, int32_t* __restrict__ cursor) {
+    extern __shared__ int sh[];   // [0,nk) local count -> base
+    const int nk = 2 * k.Ng;
+    const long long chunk = blockDim.x;
+    for (long long base = (long long)blockIdx.x * chunk; base < k.N; base += (long long)gridDim.x * chunk) {
+        for (int i = threadIdx.x; i < nk; i += blockDim.x) sh[i] = 0;
+        __syncthreads();
+        long long i = base + threadIdx.x;
+        int key = -1, rank = 0;
+        double X = 0.;
+        if (i < k.N) { X = x0[i]; key = dd_sort_key(k, X, i); rank = atomicAdd(&sh[key], 1); }
+        __syncthreads();
+        for (int j = threadIdx.x; j < nk; j += blockDim.x) {
+            int cnt = sh[j];
+            if (cnt) sh[j] = atomicAdd(&cursor[j], cnt);
+        }
+        __syncthreads();
+        if (i < k.N) {
+            long long pos = (long long)sh[key] + rank;
+            xs[pos] = X; us[pos] = u0[i];
+            if (vs) vs[pos] = v0[i];
+            if (ws) ws[pos] = w0[i];
+        }
+        __syncthreads();
+    }
+}
+
+}  // namespace pic
+
+using namespace pic;
+
+template <bool FIRST, bool TILE, bool AGG>
+static int launch_iter(const DDK& k, const double* x0, const double* u0, double* x1, double* u1, int8_t* active,
+                       const double* Es, double* acc, int* range_err, cudaStream_t st) {
+    size_t smem = TILE ? (size_t)3 * k.Ng * sizeof(double) : 0;
+    auto kern = dd_picard_iter_k<FIRST, TILE, AGG>;
+    int per_sm = 8;
+    if (TILE) {
+        PIC_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        int occ = 0;
+        PIC_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, 256, smem));
+        per_sm = occ > 0 ? occ : 1;
+    }
+    kern<<<grid_for(k.N, 256, per_sm), 256, smem, st>>>(k, x0, u0, x1, u1, active, Es, acc, range_err);
+    PIC_CHECK_LAUNCH();
+    return PIC_OK;
+}
+
+extern "C" {
+
+int pic_dev_dd_picard_iter(const pic_dd_params* p, const double* x0, const double* u0, double* x1, double* u1,
+                           int8_t* active, const double* Es, double* acc, int first, int* range_err, void* stream) {
+    PIC_REQUIRE(p && x0 && u0 && x1 && u1 && active && Es && acc, "dd_picard_iter: null pointer");
+    PIC_REQUIRE(p->N >= 0 && p->Ng >= 3 && p->dx > 0 && p->dt > 0, "dd_picard_iter: bad parameters");
+    if (p->N == 0) return PIC_OK;
+    DDK k = make_ddk(p);
+    cudaStream_t st = (cudaStream_t)stream;
+    bool tile = !(p->flags & 2) && (size_t)3 * k.Ng * sizeof(double) <= (size_t)max_optin_smem() - 1024;
+    bool agg = !(p->flags & 1);
+#define PIC_DD_DISPATCH(F, T, A) return launch_iter<F, T, A>(k, x0, u0, x1, u1, active, Es, acc, range_err, st)
+    if (first) {
+        if (tile) { if (agg) PIC_DD_DISPATCH(true, true, true); else PIC_DD_DISPATCH(true, true, false); }
+        else { if (agg) PIC_DD_DISPATCH(true, false, true); else PIC_DD_DISPATCH(true, false, false); }
+    } else {
+        if (tile) { if (agg) PIC_DD_DISPATCH(false, true, true); else PIC_DD_DISPATCH(false, true, false); }
+        else { if (agg) PIC_DD_DISPATCH(false, false, true); else PIC_DD_DISPATCH(false, false, false); }
+    }
+#undef PIC_DD_DISPATCH
+}
+
+int pic_dev_dd_field_update(const pic_dd_params* p, double* acc, double* wall_cum, const double* E0, double* Es,
+                            double* E1, double* j1, double* stats, void* stream) {
+    PIC_REQUIRE(p && acc && wall_cum && E0 && Es && E1 && j1 && stats, "dd_field_update: null pointer");
+    DDK k = make_ddk(p);
+    dd_field_update_k<<<1, 1024, 0, (cudaStream_t)stream>>>(k, acc, wall_cum, E0, Es, E1, j1, stats);
+    PIC_CHECK_LAUNCH();
+    return PIC_OK;
+}
+
+int pic_dev_dd_interpolate(const double* F, const double* x, double* out, int64_t N, int Ng, double dx,
+                           int* range_err, void* stream) {
+    PIC_REQUIRE(F && x && out && N >= 0 && Ng >= 2, "dd_interpolate: bad argument");
+    if (N == 0) return PIC_OK;
+    dd_interpolate_k<<<grid_for(N, 256, 8), 256, 0, (cudaStream_t)stream>>>(F, x, out, N, Ng, dx, range_err);
+    PIC_CHECK_LAUNCH();
+    return PIC_OK;
+}
+
+// `out` doubles as the accumulator: it must provide Ng+2 doubles of scratch BEFORE the
+// fold, so the host wrappers pass a scratch buffer through pic_dev_dd_weight_raw.
+int pic_dev_dd_weight(const double* x, const double* q, const double* v, const double* active, double* out,
+                      int64_t N, int Ng, double dx, double dt, double p2c, int* range_err, void* stream) {
+    PIC_REQUIRE(x && q && active && out && N >= 0 && Ng >= 3, "dd_weight: bad argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    double* acc = nullptr;
+    PIC_CHECK_CUDA(cudaMallocAsync((void**)&acc, (size_t)(Ng + 2) * sizeof(double), st));
+    PIC_CHECK_CUDA(cudaMemsetAsync(acc, 0, (size_t)(Ng + 2) * sizeof(double), st));
+    if (N > 0) {
+        size_t smem = (size_t)(Ng + 2) * sizeof(double);
+        if (v) {
+            PIC_CHECK_CUDA(cudaFuncSetAttribute(dd_weight_k<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            dd_weight_k<true><<<grid_for(N, 256, 4), 256, smem, st>>>(x, q, v, active, acc, N, Ng, dx, dt, p2c, range_err);
+        } else {
+            PIC_CHECK_CUDA(cudaFuncSetAttribute(dd_weight_k<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            dd_weight_k<false><<<grid_for(N, 256, 4), 256, smem, st>>>(x, q, v, active, acc, N, Ng, dx, dt, p2c, range_err);
+        }
+        PIC_CHECK_LAUNCH();
+    }
+    dd_weight_fold_k<<<1, 1024, 0, st>>>(acc, out, Ng, v != nullptr);
+    PIC_CHECK_LAUNCH();
+    PIC_CHECK_CUDA(cudaFreeAsync(acc, st));
+    return PIC_OK;
+}
+
+int pic_dev_dd_apply_draws(const int32_t* idx, const double* xd, const double* ud, const double* vd,
+                           const double* wd, int64_t n, double* x0, double* u0, double* v0, double* w0,
+                           int8_t* active, void* stream) {
+    PIC_REQUIRE(n >= 0, "dd_apply_draws: n<0");
+    if (n == 0) return PIC_OK;
+    PIC_REQUIRE(idx && xd && ud && x0 && u0 && active, "dd_apply_draws: null pointer");
+    PIC_REQUIRE((!v0 || vd) && (!w0 || wd), "dd_apply_draws: v/w draws missing");
+    dd_apply_draws_k<<<grid_for(n, 256, 4), 256, 0, (cudaStream_t)stream>>>(idx, xd, ud, vd, wd, n, x0, u0, v0, w0, active);
+    PIC_CHECK_LAUNCH();
+    return PIC_OK;
+}
+
+int pic_dev_dd_reinject_philox(const pic_dd_params* p, double* x0, double* u0, double* v0, double* w0,
+                               int8_t* active, const double sigma[2], uint64_t seed, uint64_t step,
+                               int64_t global_offset, void* stream) {
+    PIC_REQUIRE(p && x0 && u0 && active && sigma, "dd_reinject_philox: null pointer");
+    if (p->N == 0) return PIC_OK;
+    DDK k = make_ddk(p);
+    dd_reinject_philox_k<<<grid_for(k.N, 256, 8), 256, 0, (cudaStream_t)stream>>>(k, x0, u0, v0, w0, active, sigma[0],
+                                                                                sigma[1], seed, step, global_offset);
+    PIC_CHECK_LAUNCH();
+    return PIC_OK;
+}
+
+int pic_dev_sum_sq(const double* u, int64_t N, double scale, double* out1, void* stream) {
+    PIC_REQUIRE(u && out1 && N >= 0, "sum_sq: bad argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    PIC_CHECK_CUDA(cudaMemsetAsync(out1, 0, sizeof(double), st));
+    if (N == 0) return PIC_OK;
+    sum_sq_k<<<grid_for(N, 256, 8), 256, 0, st>>>(u, N, scale, out1);
+    PIC_CHECK_LAUNCH();
+    return PIC_OK;
+}
+
+int pic_dev_dd_sort_by_cell(const pic_dd_params* p, const double* x0, const double* u0, const double* v0,
+                            const double* w0, double* x0s, double* u0s, double* v0s, double* w0s, int32_t* counts,
+                            void* stream) {
+    PIC_REQUIRE(p && x0 && u0 && x0s && u0s && counts, "dd_sort_by_cell: null pointer");
+    PIC_REQUIRE(p->N < 2147483647LL, "dd_sort_by_cell: shard too large for int32 cursors");
+    DDK k = make_ddk(p);
+    cudaStream_t st = (cudaStream_t)stream;
+    const int nk = 2 * k.Ng;
+    size_t smem = (size_t)nk * sizeof(int);
+    PIC_REQUIRE(smem <= (size_t)max_optin_smem() - 1024, "dd_sort_by_cell: grid too large for the shared-memory histogram");
+    PIC_CHECK_CUDA(cudaMemsetAsync(counts, 0, (size_t)(nk + 2) * sizeof(int32_t), st));
+    if (k.N == 0) return PIC_OK;
+    PIC_CHECK_CUDA(cudaFuncSetAttribute(dd_sort_hist_k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    PIC_CHECK_CUDA(cudaFuncSetAttribute(dd_sort_scatter_k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    dd_sort_hist_k<<<grid_for(k.N, 1024, 2), 1024, smem, st>>>(k, x0, counts);
+    PIC_CHECK_LAUNCH();
+    dd_sort_scan_k<<<1, 1024, 0, st>>>(counts, nk);
+    PIC_CHECK_LAUNCH();
+    dd_sort_scatter_k<<<grid_for(k.N, 1024, 2), 1024, smem, st>>>(k, x0, u0, v0, w0, x0s, u0s, v0s, w0s, counts);
+    PIC_CHECK_LAUNCH();
+    return PIC_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,578 @@
+// pygcpic.py -- Particle/Grid hot path on a structure-of-arrays particle store:
+// mirrored CIC gather, Boris 1D3V push, 6D<->guiding-centre transforms, GC RK4 push,
+// Dirichlet wall absorption, (rho,n) deposit, Boltzmann reference-density update, the
+// order-dependent reactivate-or-delete rule as a prefix scan, and warp-ballot stable
+// stream compaction.
+#include "common.cuh"
+#include "host_common.h"
+
+namespace pic {
+
+struct GCK {
+    long long N;
+    int ng, flags;
+    double dx, dt, length;
+    double B[3], Eyz[2];
+};
+static GCK make_gck(const pic_gc_params* p) {
+    GCK k;
+    k.N = p->N; k.ng = p->ng; k.flags = p->flags; k.dx = p->dx; k.dt = p->dt; k.length = p->length;
+    for (int i = 0; i < 3; ++i) k.B[i] = p->B[i];
+    k.Eyz[0] = p->Eyz[0]; k.Eyz[1] = p->Eyz[1];
+    return k;
+}
+struct R7 { double* r[7]; };
+
+// pygcpic.py:344-347: the LEFT node is weighted with the fractional distance (mirrored)
+__device__ __forceinline__ double gather_mirrored(const double* E, double x, double dx, int ng, int& bad) {
+    Cell c = cell_dd(x, dx);
+    if (c.iL < 0 || c.iL > ng - 2) { ++bad; c.iL = clampi(c.iL, 0, ng - 2); }
+    double w_l = c.wR;            // (x%dx)/dx
+    double w_r = 1.0 - w_l;
+    return E[c.iL] * w_l + E[c.iL + 1] * w_r;
+}
+
+__global__ void gc_interpolate_k(const double* __restrict__ E, const double* __restrict__ x, double* __restrict__ out,
+                                 long long N, int ng, double dx, int* __restrict__ range_err) {
+    int bad = 0;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < N; i += (long long)gridDim.x * blockDim.x)
+        out[i] = gather_mirrored(E, x[i], dx, ng, bad);
+    if (bad && range_err) atomicAdd(range_err, bad);
+}
+
+// pygcpic.py:871-883
+__global__ void gc_weight_k(const double* __restrict__ x, const double* __restrict__ cs, const double* __restrict__ p2c,
+                            const int8_t* __restrict__ active, double* __restrict__ rho, double* __restrict__ n,
+                            long long N, int ng, double dx, int* __restrict__ range_err) {
+    extern __shared__ double sm[];
+    double *sr = sm, *sn = sm + ng;
+    for (int i = threadIdx.x; i < 2 * ng; i += blockDim.x) sm[i] = 0.0;
+    __syncthreads();
+    int bad = 0;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < N; i += (long long)gridDim.x * blockDim.x) {
+        if (active[i] != 1) continue;
+        Cell c = cell_dd(x[i], dx);
+        if (c.iL < 0 || c.iL > ng - 2) { ++bad; c.iL = clampi(c.iL, 0, ng - 2); }
+        double pc = p2c[i];
+        double qr = cs[i] * PIC_E * pc / dx;      // charge_state*e*p2c/dx
+        double nr = pc / dx;
+        atomicAdd(&sr[c.iL], qr * c.wL);
+        atomicAdd(&sr[c.iL + 1], qr * c.wR);
+        atomicAdd(&sn[c.iL], nr * c.wL);
+        atomicAdd(&sn[c.iL + 1], nr * c.wR);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < ng; i += blockDim.x) {
+        if (sr[i] != 0.0) atomicAdd(&rho[i], sr[i]);
+        if (sn[i] != 0.0) atomicAdd(&n[i], sn[i]);
+    }
+    if (bad && range_err) atomicAdd(range_err, bad);
+}
+
+// fused gather -> Boris (pygcpic.py:478-506) -> Dirichlet BC (:685-687)
+__global__ void __launch_bounds__(256) gc_push_boris_k(GCK k, R7 r, const double* __restrict__ cs,
+                                                       const double* __restrict__ m, int8_t* __restrict__ active,
+                                                       int8_t* __restrict__ at_wall, int8_t* __restrict__ hit_flag,
+                                                       const double* __restrict__ Egrid,
+                                                       long long* __restrict__ hit_count, int* __restrict__ range_err) {
+    extern __shared__ double sE[];
+    const double* E = Egrid;
+    if (k.flags & 4) {   // field tile in shared memory
+        for (int i = threadIdx.x; i < k.ng; i += blockDim.x) sE[i] = Egrid[i];
+        __syncthreads();
+        E = sE;
+    }
+    int bad = 0, hits = 0;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < k.N; i += (long long)gridDim.x * blockDim.x) {
+        if (active[i] != 1) { if (hit_flag) hit_flag[i] = 0; continue; }
+        double x = ld_stream(r.r[0] + i), y = ld_stream(r.r[1] + i), z = ld_stream(r.r[2] + i);
+        double vx = ld_stream(r.r[3] + i), vy = ld_stream(r.r[4] + i), vz = ld_stream(r.r[5] + i);
+        double Ex = gather_mirrored(E, x, k.dx, k.ng, bad);
+        double constant = 0.5 * k.dt * cs[i] * 1.602e-19 / m[i];
+        vx += constant * Ex;
+        double tx = constant * k.B[0], ty = constant * k.B[1], tz = constant * k.B[2];
+        double t2 = tx * tx + ty * ty + tz * tz;
+        double sx = 2. * tx / (1. + t2), sy = 2. * ty / (1. + t2), sz = 2. * tz / (1. + t2);
+        double vfx = vx + vy * tz - vz * ty;
+        double vfy = vy + vz * tx - vx * tz;
+        double vfz = vz + vx * ty - vy * tx;
+        vx += vfy * sz - vfz * sy;
+        vy += vfz * sx - vfx * sz;
+        vz += vfx * sy - vfy * sx;
+        vx += constant * Ex;
+        x += vx * k.dt; y += vy * k.dt; z += vz * k.dt;
+        st_stream(r.r[0] + i, x); st_stream(r.r[1] + i, y); st_stream(r.r[2] + i, z);
+        st_stream(r.r[3] + i, vx); st_stream(r.r[4] + i, vy); st_stream(r.r[5] + i, vz);
+        r.r[6][i] = r.r[6][i] + k.dt;
+        bool hit = (x < 0.0) || (x > k.length);
+        if (hit) { active[i] = 0; at_wall[i] = 1; ++hits; }
+        if (hit_flag) hit_flag[i] = hit ? 1 : 0;
+    }
+    if (hits && hit_count) atomicAdd((unsigned long long*)hit_count, (unsigned long long)hits);
+    if (bad && range_err) atomicAdd(range_err, bad);
+}
+
+__global__ void gc_apply_bcs_k(const double* __restrict__ x, int8_t* __restrict__ active, int8_t* __restrict__ at_wall,
+                               long long N, double length) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < N; i += (long long)gridDim.x * blockDim.x) {
+        double X = x[i];
+        if (X < 0.0 || X > length) { active[i] = 0; at_wall[i] = 1; }
+    }
+}
+
+// pygcpic.py:530-550
+__global__ void gc_to_gc_k(GCK k, R7 r, const double* __restrict__ cs, const double* __restrict__ m,
+                           const int8_t* __restrict__ active) {
+    const double B2 = k.B[0] * k.B[0] + k.B[1] * k.B[1] + k.B[2] * k.B[2];
+    const double sB = sqrt(B2);
+    const double b0 = k.B[0] / sB, b1 = k.B[1] / sB, b2 = k.B[2] / sB;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < k.N; i += (long long)gridDim.x * blockDim.x) {
+        if (active[i] != 1) continue;
+        double v0 = r.r[3][i], v1 = r.r[4][i], v2 = r.r[5][i];
+        double vpar_mag = v0 * b0 + v1 * b1 + v2 * b2;
+        double p0 = vpar_mag * b0, p1 = vpar_mag * b1, p2 = vpar_mag * b2;
+        double c = cs[i], mm = m[i];
+        double wc = fabs(c) * PIC_E * sB / mm;
+        double q0 = v0 - p0, q1 = v1 - p1, q2 = v2 - p2;
+        double vperp_mag = sqrt(q0 * q0 + q1 * q1 + q2 * q2);
+        double h0 = q0 / vperp_mag, h1 = q1 / vperp_mag, h2 = q2 / vperp_mag;
+        double mu = 0.5 * mm * (vperp_mag * vperp_mag) / sB;
+        double rl_mag = vperp_mag / wc;
+        double sgn = (c > 0.0) ? 1.0 : ((c < 0.0) ? -1.0 : 0.0);
+        double f = -sgn * PIC_E;                       // the reference multiplies by e here
+        double x0 = h1 * b2 - h2 * b1, x1 = h2 * b0 - h0 * b2, x2 = h0 * b1 - h1 * b0;   // cross(vperp_hat,b)
+        r.r[0][i] = r.r[0][i] - rl_mag * (f * x0);
+        r.r[1][i] = r.r[1][i] - rl_mag * (f * x1);
+        r.r[2][i] = r.r[2][i] - rl_mag * (f * x2);
+        r.r[3][i] = vpar_mag;
+        r.r[4][i] = mu;
+    }
+}
+
+// pygcpic.py:574-595
+__global__ void gc_to_6d_k(GCK k, R7 r, const double* __restrict__ cs, const double* __restrict__ m,
+                           const int8_t* __restrict__ active, const double* __restrict__ a0,
+                           const double* __restrict__ a1, const double* __restrict__ a2) {
+    const double B2 = k.B[0] * k.B[0] + k.B[1] * k.B[1] + k.B[2] * k.B[2];
+    const double sB = sqrt(B2);
+    const double b0 = k.B[0] / sB, b1 = k.B[1] / sB, b2 = k.B[2] / sB;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < k.N; i += (long long)gridDim.x * blockDim.x) {
+        if (active[i] != 1) continue;
+        double vpar_mag = r.r[3][i], mu = r.r[4][i], mm = m[i];
+        double vperp_mag = sqrt(2.0 * mu * sB / mm);
+        double wc = fabs(cs[i]) * PIC_E * sB / mm;
+        double rl_mag = vperp_mag / wc;
+        double A0 = a0[i], A1 = a1[i], A2 = a2[i];
+        double adb = A0 * b0 + A1 * b1 + A2 * b2;
+        double p0 = A0 - adb, p1 = A1 - adb, p2 = A2 - adb;      // scalar subtracted (reference quirk)
+        double pm = sqrt(p0 * p0 + p1 * p1 + p2 * p2);
+        double h0 = p0 / pm, h1 = p1 / pm, h2 = p2 / pm;
+        r.r[0][i] = r.r[0][i] + rl_mag * h0;
+        r.r[1][i] = r.r[1][i] + rl_mag * h1;
+        r.r[2][i] = r.r[2][i] + rl_mag * h2;
+        double c0 = b1 * h2 - b2 * h1, c1 = b2 * h0 - b0 * h2, c2 = b0 * h1 - b1 * h0;   // cross(b,bperp_hat)
+        r.r[3][i] = vpar_mag * b0 + vperp_mag * c0;
+        r.r[4][i] = vpar_mag * b1 + vperp_mag * c1;
+        r.r[5][i] = vpar_mag * b2 + vperp_mag * c2;
+    }
+}
+
+struct Eom { double d0, d1, d2, d3; };
+__device__ __forceinline__ Eom eom_gc(double r0, double r1, double r2, double r3, double E0, double E1, double E2,
+                                      const double* B, double B2, double sB, double b0, double b1, double b2,
+                                      double wc) {
+    Eom o;
+    double rho = r3 / wc;
+    o.d0 = (E1 * B[2] - E2 * B[1]) / B2 + r3 * b0;
+    o.d1 = (E2 * B[0] - E0 * B[2]) / B2 + r3 * b1;
+    o.d2 = (E0 * B[1] - E1 * B[0]) / B2 + r3 * b2;
+    o.d3 = (E0 * r0 + E1 * r1 + E2 * r2) / sB / rho;
+    return o;
+}
+// pygcpic.py:598-645 classic RK4 on (X,Y,Z,vpar); mu, r[5] untouched; t += dt
+__global__ void gc_push_rk4_k(GCK k, R7 r, const double* __restrict__ cs, const double* __restrict__ m,
+                              const int8_t* __restrict__ active, const double* __restrict__ Egrid,
+                              int* __restrict__ range_err) {
+    const double B2 = k.B[0] * k.B[0] + k.B[1] * k.B[1] + k.B[2] * k.B[2];
+    const double sB = sqrt(B2);
+    const double b0 = k.B[0] / sB, b1 = k.B[1] / sB, b2 = k.B[2] / sB;
+    int bad = 0;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < k.N; i += (long long)gridDim.x * blockDim.x) {
+        if (active[i] != 1) continue;
+        double r0 = r.r[0][i], r1 = r.r[1][i], r2 = r.r[2][i], r3 = r.r[3][i];
+        double E0 = Egrid ? gather_mirrored(Egrid, r0, k.dx, k.ng, bad) : 0.0;
+        double E1 = k.Eyz[0], E2 = k.Eyz[1];
+        double wc = fabs(cs[i]) * PIC_E * sB / m[i];
+        const double dt = k.dt;
+        Eom f1 = eom_gc(r0, r1, r2, r3, E0, E1, E2, k.B, B2, sB, b0, b1, b2, wc);
+        double k10 = dt * f1.d0, k11 = dt * f1.d1, k12 = dt * f1.d2, k13 = dt * f1.d3;
+        Eom f2 = eom_gc(r0 + k10 / 2., r1 + k11 / 2., r2 + k12 / 2., r3 + k13 / 2., E0, E1, E2, k.B, B2, sB, b0, b1, b2, wc);
+        double k20 = dt * f2.d0, k21 = dt * f2.d1, k22 = dt * f2.d2, k23 = dt * f2.d3;
+        Eom f3 = eom_gc(r0 + k20 / 2., r1 + k21 / 2., r2 + k22 / 2., r3 + k23 / 2., E0, E1, E2, k.B, B2, sB, b0, b1, b2, wc);
+        double k30 = dt * f3.d0, k31 = dt * f3.d1, k32 = dt * f3.d2, k33 = dt * f3.d3;
+        Eom f4 = eom_gc(r0 + k30, r1 + k31, r2 + k32, r3 + k33, E0, E1, E2, k.B, B2, sB, b0, b1, b2, wc);
+        double k40 = dt * f4.d0, k41 = dt * f4.d1, k42 = dt * f4.d2, k43 = dt * f4.d3;
+        r.r[0][i] = r0 + (k10 + 2. * k20 + 2. * k30 + k40) / 6.;
+        r.r[1][i] = r1 + (k11 + 2. * k21 + 2. * k31 + k41) / 6.;
+        r.r[2][i] = r2 + (k12 + 2. * k22 + 2. * k32 + k42) / 6.;
+        r.r[3][i] = r3 + (k13 + 2. * k23 + 2. * k33 + k43) / 6.;
+        r.r[6][i] = r.r[6][i] + dt;
+    }
+    if (bad && range_err) atomicAdd(range_err, bad);
+}
+
+// pygcpic.py:889-904.  state = {n0, p_old, initialised}
+__global__ void gc_n0_update_k(const double* __restrict__ phi, const double* __restrict__ n,
+                               const double* __restrict__ domain, int ng, double Te, double ve, double added,
+                               double dt, double* __restrict__ state) {
+    __shared__ double scratch[33];
+    double s = 0.0, sn = 0.0;
+    for (int i = threadIdx.x; i < ng; i += blockDim.x) {
+        sn += n[i];
+        if (i + 1 < ng) {
+            double e0 = exp(phi[i] / Te / 11600.), e1 = exp(phi[i + 1] / Te / 11600.);
+            s += (domain[i + 1] - domain[i]) * (e1 + e0) / 2.0;      // np.trapz(eta, domain)
+        }
+    }
+    s = block_reduce<0>(s, scratch);
+    sn = block_reduce<0>(sn, scratch);
+    if (threadIdx.x == 0) {
+        if (state[2] == 0.0) {
+            state[1] = s;
+            state[0] = 0.9 * (sn / (double)ng);
+            state[2] = 1.0;
+        } else {
+            double p_new = s;
+            double q_new = exp(phi[0] / Te / 11600.) + exp(phi[ng - 1] / Te / 11600.);
+            double r_new = 2. * added / dt;
+            double fn = sqrt(ve * q_new * dt / p_new);
+            state[0] = state[0] * ((1.0 - fn) * state[1] / p_new + fn - fn * fn / 4.) + r_new * dt / p_new;
+            state[1] = p_new;
+        }
+    }
+}
+
+// ---------------------------------------------------------------- scans / compaction
+// Two int32 values per element are scanned together (exclusive).  SCAN_ITEMS elements
+// per thread, 256 threads per CTA.
+#define SCAN_T 256
+#define SCAN_ITEMS 8
+#define SCAN_TILE (SCAN_T * SCAN_ITEMS)
+
+struct I2 { int a, b; };
+__device__ __forceinline__ I2 block_excl_scan2(I2 v, I2* total, I2* sh /*33*/) {
+    unsigned full = 0xffffffffu;
+    int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    I2 t = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        int ya = __shfl_up_sync(full, t.a, o), yb = __shfl_up_sync(full, t.b, o);
+        if (lane >= o) { t.a += ya; t.b += yb; }
+    }
+    __syncthreads();
+    if (lane == 31) sh[w] = t;
+    __syncthreads();
+    if (w == 0) {
+        I2 s = lane < (SCAN_T / 32) ? sh[lane] : I2{0, 0};
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            int ya = __shfl_up_sync(full, s.a, o), yb = __shfl_up_sync(full, s.b, o);
+            if (lane >= o) { s.a += ya; s.b += yb; }
+        }
+        sh[lane] = s;
+    }
+    __syncthreads();
+    I2 pre = w > 0 ? sh[w - 1] : I2{0, 0};
+    *total = sh[SCAN_T / 32 - 1];
+    I2 out;
+    out.a = pre.a + t.a - v.a;
+    out.b = pre.b + t.b - v.b;
+    return out;
+}
+
+// element functor: mode 0..2 = compaction predicates on one flag array,
+// mode 3 = reactivate-or-delete (a = inactive_entry, b = contrib_after - contrib_entry for actives)
+__device__ __forceinline__ I2 scan_value(int mode, const int8_t* f0, const int8_t* f1, const int8_t* f2, long long i) {
+    I2 v{0, 0};
+    if (mode == 0) v.a = f0[i] != 1;
+    else if (mode == 1) v.a = f0[i] == 0;
+    else if (mode == 2) v.a = f0[i] != 2;
+    else {
+        int inact = f0[i] != 0;
+        v.a = inact;
+        v.b = inact ? 0 : ((int)f2[i] - (int)f1[i]);
+    }
+    return v;
+}
+
+__global__ void __launch_bounds__(SCAN_T) scan_block_sums_k(int mode, const int8_t* __restrict__ f0,
+                                                            const int8_t* __restrict__ f1, const int8_t* __restrict__ f2,
+                                                            long long N, long long* __restrict__ block_sums) {
+    __shared__ I2 sh[33];
+    long long base = (long long)blockIdx.x * SCAN_TILE + (long long)threadIdx.x * SCAN_ITEMS;
+    I2 v{0, 0};
+#pragma unroll
+    for (int j = 0; j < SCAN_ITEMS; ++j)
+        if (base + j < N) { I2 e = scan_value(mode, f0, f1, f2, base + j); v.a += e.a; v.b += e.b; }
+    I2 total;
+    block_excl_scan2(v, &total, sh);
+    if (threadIdx.x == 0) { block_sums[2 * (long long)blockIdx.x] = total.a; block_sums[2 * (long long)blockIdx.x + 1] = total.b; }
+}
+// exclusive scan of the per-CTA sums in place (one CTA, sequential chunks); totals -> block_sums[2*nb..]
+__global__ void scan_block_offsets_k(long long* __restrict__ block_sums, int nb) {
+    __shared__ long long wa[32], wb[32];
+    __shared__ long long ca, cb;
+    unsigned full = 0xffffffffu;
+    int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    if (threadIdx.x == 0) { ca = 0; cb = 0; }
+    __syncthreads();
+    for (int base = 0; base < nb; base += blockDim.x) {
+        int i = base + threadIdx.x;
+        long long va = i < nb ? block_sums[2 * i] : 0, vb = i < nb ? block_sums[2 * i + 1] : 0, ta = va, tb = vb;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            long long ya = __shfl_up_sync(full, ta, o), yb = __shfl_up_sync(full, tb, o);
+            if (lane >= o) { ta += ya; tb += yb; }
+        }
+        if (lane == 31) { wa[w] = ta; wb[w] = tb; }
+        __syncthreads();
+        if (w == 0) {
+            long long sa = lane < nw ? wa[lane] : 0, sb = lane < nw ? wb[lane] : 0;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                long long ya = __shfl_up_sync(full, sa, o), yb = __shfl_up_sync(full, sb, o);
+                if (lane >= o) { sa += ya; sb += yb; }
+            }
+            wa[lane] = sa; wb[lane] = sb;
+        }
+        __syncthreads();
+        long long pa = ca + (w > 0 ? wa[w - 1] : 0), pb = cb + (w > 0 ? wb[w - 1] : 0);
+        if (i < nb) { block_sums[2 * i] = pa + ta - va; block_sums[2 * i + 1] = pb + tb - vb; }
+        __syncthreads();
+        if (threadIdx.x == blockDim.x - 1) { ca = pa + ta; cb = pb + tb; }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) { block_sums[2 * (long long)nb] = ca; block_sums[2 * (long long)nb + 1] = cb; }
+}
+// final pass: write compacted indices (and, for mode 3, the running delta at each inactive slot)
+__global__ void __launch_bounds__(SCAN_T) scan_scatter_k(int mode, const int8_t* __restrict__ f0,
+                                                         const int8_t* __restrict__ f1, const int8_t* __restrict__ f2,
+                                                         long long N, const long long* __restrict__ block_sums, int nb,
+                                                         int32_t* __restrict__ idx_out, int32_t* __restrict__ base_out,
+                                                         long long* __restrict__ count_out) {
+    __shared__ I2 sh[33];
+    long long base = (long long)blockIdx.x * SCAN_TILE + (long long)threadIdx.x * SCAN_ITEMS;
+    I2 e[SCAN_ITEMS];
+    I2 v{0, 0};
+#pragma unroll
+    for (int j = 0; j < SCAN_ITEMS; ++j) {
+        e[j] = (base + j < N) ? scan_value(mode, f0, f1, f2, base + j) : I2{0, 0};
+        v.a += e[j].a; v.b += e[j].b;
+    }
+    I2 total;
+    I2 pre = block_excl_scan2(v, &total, sh);
+    long long oa = block_sums[2 * (long long)blockIdx.x] + pre.a;
+    long long ob = block_sums[2 * (long long)blockIdx.x + 1] + pre.b;
+#pragma unroll
+    for (int j = 0; j < SCAN_ITEMS; ++j) {
+        if (base + j < N && e[j].a) {
+            idx_out[oa] = (int32_t)(base + j);
+            if (base_out) base_out[oa] = (int32_t)ob;
+        }
+        oa += e[j].a; ob += e[j].b;
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0 && count_out) count_out[0] = block_sums[2 * (long long)nb];
+}
+
+// sequential part of the reactivate-or-delete rule over the K inactive slots only
+__global__ void gc_decide_seq_k(const int32_t* __restrict__ idx, const int32_t* __restrict__ base,
+                                long long* __restrict__ s /* [0]=K [1]=entry_total -> [2]=react [3]=deleted */,
+                                long long source_N, int8_t* __restrict__ decision) {
+    if (blockIdx.x != 0 || threadIdx.x != 0) return;
+    long long K = s[0], entry_total = s[1], react = 0, del = 0;
+    for (long long t = 0; t < K; ++t) {
+        long long cnt = entry_total + (long long)base[t] + react;     // count "at that moment", pygcpic.py:1544
+        if (cnt < source_N) { decision[idx[t]] = 1; ++react; }
+        else { decision[idx[t]] = 2; ++del; }
+    }
+    s[2] = react;
+    s[3] = del;
+}
+__global__ void count_flags_k(const int8_t* __restrict__ f, long long N, long long* __restrict__ out) {
+    long long c = 0;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < N; i += (long long)gridDim.x * blockDim.x) c += f[i] != 0;
+    unsigned full = 0xffffffffu;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(full, c, o);
+    if ((threadIdx.x & 31) == 0 && c) atomicAdd((unsigned long long*)out, (unsigned long long)c);
+}
+
+__global__ void gather_f64_k(const double* __restrict__ src, const int32_t* __restrict__ idx, double* __restrict__ dst,
+                             long long n) {
+    for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < n; t += (long long)gridDim.x * blockDim.x)
+        dst[t] = src[idx[t]];
+}
+__global__ void gather_i8_k(const int8_t* __restrict__ src, const int32_t* __restrict__ idx, int8_t* __restrict__ dst,
+                            long long n) {
+    for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < n; t += (long long)gridDim.x * blockDim.x)
+        dst[t] = src[idx[t]];
+}
+
+}  // namespace pic
+
+using namespace pic;
+
+static int run_scan(int mode, const int8_t* f0, const int8_t* f1, const int8_t* f2, long long N, int32_t* idx_out,
+                    int32_t* base_out, long long* count_out, long long* block_sums, cudaStream_t st) {
+    int nb = (int)((N + SCAN_TILE - 1) / SCAN_TILE);
+    if (nb < 1) nb = 1;
+    scan_block_sums_k<<<nb, SCAN_T, 0, st>>>(mode, f0, f1, f2, N, block_sums);
+    PIC_CHECK_LAUNCH();
+    scan_block_offsets_k<<<1, 1024, 0, st>>>(block_sums, nb);
+    PIC_CHECK_LAUNCH();
+    scan_scatter_k<<<nb, SCAN_T, 0, st>>>(mode, f0, f1, f2, N, block_sums, nb, idx_out, base_out, count_out);
+    PIC_CHECK_LAUNCH();
+    return PIC_OK;
+}
+
+extern "C" {
+
+int pic_dev_gc_interpolate(const double* E, const double* x, double* out, int64_t N, int ng, double dx, int* range_err,
+                           void* stream) {
+    PIC_REQUIRE(E && x && out && N >= 0 && ng >= 2, "gc_interpolate: bad argument");
+    if (N == 0) return PIC_OK;
+    gc_interpolate_k<<<grid_for(N, 256, 8), 256, 0, (cudaStream_t)stream>>>(E, x, out, N, ng, dx, range_err);
+    PIC_CHECK_LAUNCH();
+    return PIC_OK;
+}
+
+int pic_dev_gc_weight(const double* x, const double* charge_state, const double* p2c, const int8_t* active, double* rho,
+                      double* n, int64_t N, int ng, double dx, int* range_err, void* stream) {
+    PIC_REQUIRE(x && charge_state && p2c && active && rho && n && N >= 0 && ng >= 2, "gc_weight: bad argument");
+    if (N == 0) return PIC_OK;
+    size_t smem = (size_t)2 * ng * sizeof(double);
+    PIC_REQUIRE(smem <= (size_t)max_optin_smem() - 1024, "gc_weight: ng too large for the shared-memory tiles");
+    PIC_CHECK_CUDA(cudaFuncSetAttribute(gc_weight_k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    gc_weight_k<<<grid_for(N, 256, 4), 256, smem, (cudaStream_t)stream>>>(x, charge_state, p2c, active, rho, n, N, ng, dx,
+                                                                          range_err);
+    PIC_CHECK_LAUNCH();
+    return PIC_OK;
+}
+
+int pic_dev_gc_push_boris(const pic_gc_params* p, double* const r[7], const double* charge_state, const double* m,
+                          int8_t* active, int8_t* at_wall, int8_t* hit_flag, const double* Egrid, long long* hit_count,
+                          int* range_err, void* stream) {
+    PIC_REQUIRE(p && r && charge_state && m && active && at_wall && Egrid, "gc_push_boris: null pointer");
+    if (p->N == 0) return PIC_OK;
+    GCK k = make_gck(p);
+    R7 rr;
+    for (int i = 0; i < 7; ++i) { PIC_REQUIRE(r[i], "gc_push_boris: null component array"); rr.r[i] = r[i]; }
+    size_t smem = (size_t)k.ng * sizeof(double);
+    if (smem <= (size_t)max_optin_smem() - 1024) k.flags |= 4; else { k.flags &= ~4; smem = 0; }
+    PIC_CHECK_CUDA(cudaFuncSetAttribute(gc_push_boris_k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(smem ? smem : 1)));
+    gc_push_boris_k<<<grid_for(k.N, 256, 6), 256, smem, (cudaStream_t)stream>>>(k, rr, charge_state, m, active, at_wall,
+                                                                                 hit_flag, Egrid, hit_count, range_err);
+    PIC_CHECK_LAUNCH();
+    return PIC_OK;
+}
+
+int pic_dev_gc_apply_bcs(const double* x, int8_t* active, int8_t* at_wall, int64_t N, double length, void* stream) {
+    PIC_REQUIRE(x && active && at_wall && N >= 0, "gc_apply_bcs: bad argument");
+    if (N == 0) return PIC_OK;
+    gc_apply_bcs_k<<<grid_for(N, 256, 8), 256, 0, (cudaStream_t)stream>>>(x, active, at_wall, N, length);
+    PIC_CHECK_LAUNCH();
+    return PIC_OK;
+}
+
+int pic_dev_gc_to_gc(const pic_gc_params* p, double* const r[7], const double* charge_state, const double* m,
+                     const int8_t* active, void* stream) {
+    PIC_REQUIRE(p && r && charge_state && m && active, "gc_to_gc: null pointer");
+    if (p->N == 0) return PIC_OK;
+    GCK k = make_gck(p);
+    R7 rr;
+    for (int i = 0; i < 7; ++i) rr.r[i] = r[i];
+    gc_to_gc_k<<<grid_for(k.N, 256, 8), 256, 0, (cudaStream_t)stream>>>(k, rr, charge_state, m, active);
+    PIC_CHECK_LAUNCH();
+    return PIC_OK;
+}
+
+int pic_dev_gc_to_6d(const pic_gc_params* p, double* const r[7], const double* charge_state, const double* m,
+                     const int8_t* active, const double* a0, const double* a1, const double* a2, void* stream) {
+    PIC_REQUIRE(p && r && charge_state && m && active && a0 && a1 && a2, "gc_to_6d: null pointer");
+    if (p->N == 0) return PIC_OK;
+    GCK k = make_gck(p);
+    R7 rr;
+    for (int i = 0; i < 7; ++i) rr.r[i] = r[i];
+    gc_to_6d_k<<<grid_for(k.N, 256, 8), 256, 0, (cudaStream_t)stream>>>(k, rr, charge_state, m, active, a0, a1, a2);
+    PIC_CHECK_LAUNCH();
+    return PIC_OK;
+}
+
+int pic_dev_gc_push_rk4(const pic_gc_params* p, double* const r[7], const double* charge_state, const double* m,
+                        const int8_t* active, const double* Egrid, int* range_err, void* stream) {
+    PIC_REQUIRE(p && r && charge_state && m && active, "gc_push_rk4: null pointer");
+    if (p->N == 0) return PIC_OK;
+    GCK k = make_gck(p);
+    R7 rr;
+    for (int i = 0; i < 7; ++i) rr.r[i] = r[i];
+    gc_push_rk4_k<<<grid_for(k.N, 256, 6), 256, 0, (cudaStream_t)stream>>>(k, rr, charge_state, m, active, Egrid, range_err);
+    PIC_CHECK_LAUNCH();
+    return PIC_OK;
+}
+
+int pic_dev_gc_n0_update(const double* phi, const double* n, const double* domain, int ng, double Te, double ve,
+                         double added_particles, double dt, double* state, void* stream) {
+    PIC_REQUIRE(phi && n && domain && state && ng >= 2, "gc_n0_update: bad argument");
+    gc_n0_update_k<<<1, 1024, 0, (cudaStream_t)stream>>>(phi, n, domain, ng, Te, ve, added_particles, dt, state);
+    PIC_CHECK_LAUNCH();
+    return PIC_OK;
+}
+
+int pic_dev_gc_decide(const int8_t* inactive_entry, const int8_t* contrib_entry, const int8_t* contrib_after,
+                      int8_t* decision, int64_t N, int64_t source_N, int32_t* idx_scratch, int32_t* base_scratch,
+                      int64_t* scratch, void* stream) {
+    PIC_REQUIRE(inactive_entry && contrib_entry && contrib_after && decision && idx_scratch && base_scratch && scratch,
+                "gc_decide: null pointer");
+    PIC_REQUIRE(N >= 0 && N < 2147483647LL, "gc_decide: N out of range");
+    cudaStream_t st = (cudaStream_t)stream;
+    PIC_CHECK_CUDA(cudaMemsetAsync(decision, 0, (size_t)N, st));
+    if (N == 0) return PIC_OK;
+    // scratch layout: [0] K, [1] entry_total, [2] reactivated, [3] deleted, [4..] per-CTA sums
+    long long* s = (long long*)scratch;
+    PIC_CHECK_CUDA(cudaMemsetAsync(s, 0, 4 * sizeof(long long), st));
+    count_flags_k<<<grid_for(N, 256, 8), 256, 0, st>>>(contrib_entry, N, s + 1);
+    PIC_CHECK_LAUNCH();
+    int rc = run_scan(3, inactive_entry, contrib_entry, contrib_after, N, idx_scratch, base_scratch, s, s + 4, st);
+    if (rc) return rc;
+    gc_decide_seq_k<<<1, 32, 0, st>>>(idx_scratch, base_scratch, s, (long long)source_N, decision);
+    PIC_CHECK_LAUNCH();
+    return PIC_OK;
+}
+
+int pic_dev_compact_flags(const int8_t* flags, int64_t N, int mode, int32_t* idx_out, int64_t* count_out,
+                          int64_t* block_counts, void* stream) {
+    PIC_REQUIRE(flags && idx_out && count_out && block_counts && mode >= 0 && mode <= 2, "compact_flags: bad argument");
+    PIC_REQUIRE(N >= 0 && N < 2147483647LL, "compact_flags: N out of range");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (N == 0) { PIC_CHECK_CUDA(cudaMemsetAsync(count_out, 0, sizeof(int64_t), st)); return PIC_OK; }
+    return run_scan(mode, flags, nullptr, nullptr, N, idx_out, nullptr, (long long*)count_out, (long long*)block_counts, st);
+}
+
+int pic_dev_gather_f64(const double* src, const int32_t* idx, double* dst, int64_t n, void* stream) {
+    PIC_REQUIRE(n >= 0, "gather_f64: n<0");
+    if (n == 0) return PIC_OK;
+    PIC_REQUIRE(src && idx && dst, "gather_f64: null pointer");
+    gather_f64_k<<<grid_for(n, 256, 8), 256, 0, (cudaStream_t)stream>>>(src, idx, dst, n);
+    PIC_CHECK_LAUNCH();
+    return PIC_OK;
+}
+int pic_dev_gather_i8(const int8_t* src, const int32_t* idx, int8_t* dst, int64_t n, void* stream) {
+    PIC_REQUIRE(n >= 0, "gather_i8: n<0");
+    if (n == 0) return PIC_OK;
+    PIC_REQUIRE(src && idx && dst, "gather_i8: null pointer");
+    gather_i8_k<<<grid_for(n, 256, 8), 256, 0, (cudaStream_t)stream>>>(src, idx, dst, n);
+    PIC_CHECK_LAUNCH();
+    return PIC_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,488 @@
+// pypic.py (periodic implicit CN/Picard, electrons) and PIC_L.py (periodic explicit
+// leapfrog with a Poisson solve every step).  Same design as dd_kernels.cu: the particle
+// phase is one fused pass (gather + push + wrap + deposit) over the SoA store with the
+// field / current tiles in shared memory.
+#include "common.cuh"
+#include "host_common.h"
+
+namespace pic {
+
+template <bool AGG>
+__device__ __forceinline__ void deposit2(double* tile, int iL, int iR, double vL, double vR, bool valid) {
+    if (AGG) {
+        unsigned full = 0xffffffffu;
+        int key = valid ? iL : -1;
+        int k0 = __shfl_sync(full, key, 0);
+        if (__all_sync(full, key == k0)) {
+            if (k0 < 0) return;
+            vL = warp_sum(vL);
+            vR = warp_sum(vR);
+            if ((threadIdx.x & 31) == 0) { atomicAdd(&tile[iL], vL); atomicAdd(&tile[iR], vR); }
+            return;
+        }
+    }
+    if (valid) { atomicAdd(&tile[iL], vL); atomicAdd(&tile[iR], vR); }
+}
+
+// ============================================================ pypic.py
+struct PYK {
+    long long N;
+    int Ng, flags;
+    double dx, idx, dt, L, p2c, q, qm;
+};
+static PYK make_pyk(const pic_pypic_params* p) {
+    PYK k;
+    k.N = p->N; k.Ng = p->Ng; k.flags = p->flags; k.dx = p->dx; k.idx = 1. / p->dx; k.dt = p->dt;
+    k.L = p->L; k.p2c = p->p2c; k.q = p->q; k.qm = p->q / p->m;
+    return k;
+}
+
+__device__ __forceinline__ void pypic_fix(Cell& c, int Ng, int& bad) {
+    if (c.iL < 0 || c.iL >= Ng || c.iR < 0 || c.iR >= Ng) {
+        ++bad;                                   // x == L after the wrap etc.: reference reads out of bounds
+        c.iL = clampi(c.iL, 0, Ng - 1);
+        c.iR = clampi(c.iR, 0, Ng - 1);
+    }
+}
+
+__global__ void pypic_interpolate_k(const double* __restrict__ F, const double* __restrict__ x,
+                                    double* __restrict__ out, long long N, int Ng, double dx,
+                                    int* __restrict__ range_err) {
+    const double idx = 1. / dx;
+    int bad = 0;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < N; i += (long long)gridDim.x * blockDim.x) {
+        Cell c = cell_pypic<false>(x[i], dx, idx, Ng);
+        pypic_fix(c, Ng, bad);
+        out[i] = F[c.iL] * c.wL + F[c.iR] * c.wR;       // pypic.py:57
+    }
+    if (bad && range_err) atomicAdd(range_err, bad);
+}
+
+template <bool CURRENT>
+__global__ void pypic_weight_k(const double* __restrict__ x, const double* __restrict__ q,
+                               const double* __restrict__ v, double* __restrict__ acc, long long N, int Ng,
+                               double dx, double p2c, int* __restrict__ range_err) {
+    extern __shared__ double sm[];
+    for (int i = threadIdx.x; i < Ng; i += blockDim.x) sm[i] = 0.0;
+    __syncthreads();
+    const double idx = 1. / dx;
+    int bad = 0;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < N; i += (long long)gridDim.x * blockDim.x) {
+        Cell c = cell_pypic<!CURRENT>(x[i], dx, idx, Ng);
+        pypic_fix(c, Ng, bad);
+        double pre = CURRENT ? q[i] * v[i] * p2c * idx : q[i] * p2c * idx;   // pypic.py:121 / 168
+        atomicAdd(&sm[c.iL], pre * c.wL);
+        atomicAdd(&sm[c.iR], pre * c.wR);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < Ng; i += blockDim.x)
+        if (sm[i] != 0.0) atomicAdd(&acc[i], sm[i]);
+    if (bad && range_err) atomicAdd(range_err, bad);
+}
+
+// One Picard iteration of particle_push_p, particle phase (pypic.py:261-279).
+// x1 holds the UNWRAPPED n+1 position of the previous iteration.
+template <bool FIRST, bool AGG>
+__global__ void __launch_bounds__(256) pypic_picard_iter_k(PYK k, const double* __restrict__ x0,
+                                                           const double* __restrict__ v0, double* __restrict__ x1,
+                                                           double* __restrict__ v1, const double* __restrict__ Fs,
+                                                           double* __restrict__ acc, int* __restrict__ range_err) {
+    extern __shared__ double sm[];
+    const int Ng = k.Ng;
+    double *sF = sm, *jh = sm + Ng, *j1 = sm + 2 * Ng;
+    for (int i = threadIdx.x; i < Ng; i += blockDim.x) { sF[i] = Fs[i]; jh[i] = 0.0; j1[i] = 0.0; }
+    __syncthreads();
+    int bad = 0;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    const long long nIter = (k.N + stride - 1) / stride;
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const double dtdt = k.dt * k.dt;
+    for (long long itn = 0; itn < nIter; ++itn, i += stride) {
+        bool valid = i < k.N;
+        Cell ch, cf;
+        ch.iL = ch.iR = cf.iL = cf.iR = 0;
+        double hL = 0., hR = 0., fL = 0., fR = 0.;
+        if (valid) {
+            double X0 = ld_stream(x0 + i), V0 = ld_stream(v0 + i);
+            double xs = FIRST ? X0 : wrap_mod((X0 + ld_stream(x1 + i)) * 0.5, k.L);
+            Cell c = cell_pypic<false>(xs, k.dx, k.idx, Ng);
+            pypic_fix(c, Ng, bad);
+            double Ei = sF[c.iL] * c.wL + sF[c.iR] * c.wR;
+            double X1 = X0 + k.dt * V0 + dtdt * k.qm * Ei * 0.5;   // pypic.py:264
+            double V1 = V0 + k.dt * k.qm * Ei;                       // :265
+            double XH = (X0 + X1) * 0.5, VH = (V0 + V1) * 0.5;      // :268-269
+            st_stream(x1 + i, X1);
+            st_stream(v1 + i, V1);
+            double xhw = wrap_mod(XH, k.L);                          // :272
+            double x1w = wrap_mod(X1, k.L);                          // :277
+            ch = cell_pypic<false>(xhw, k.dx, k.idx, Ng);
+            pypic_fix(ch, Ng, bad);
+            double jh_i = k.q * VH * k.p2c * k.idx;                  // :121
+            hL = jh_i * ch.wL; hR = jh_i * ch.wR;
+            cf = cell_pypic<false>(x1w, k.dx, k.idx, Ng);
+            pypic_fix(cf, Ng, bad);
+            double j1_i = k.q * V1 * k.p2c * k.idx;
+            fL = j1_i * cf.wL; fR = j1_i * cf.wR;
+        }
+        deposit2<AGG>(jh, ch.iL, ch.iR, hL, hR, valid);
+        deposit2<AGG>(j1, cf.iL, cf.iR, fL, fR, valid);
+    }
+    __syncthreads();
+    for (int n = threadIdx.x; n < 2 * Ng; n += blockDim.x) {
+        double v = sm[Ng + n];
+        if (v != 0.0) atomicAdd(&acc[n], v);
+    }
+    if (bad && range_err) atomicAdd(range_err, bad);
+}
+
+// pypic.py:283-292 field phase (one CTA).  Es, Fs updated in place; acc zeroed.
+__global__ void __launch_bounds__(1024) pypic_field_update_k(PYK k, double* __restrict__ acc,
+                                                             const double* __restrict__ E0, double* __restrict__ Es,
+                                                             double* __restrict__ Fs, double* __restrict__ E1,
+                                                             double* __restrict__ j1o, double* __restrict__ stats) {
+    __shared__ double scratch[33];
+    const int Ng = k.Ng;
+    double* jh = acc;
+    double* j1 = acc + Ng;
+    double sh = 0.0, s1 = 0.0;
+    for (int i = threadIdx.x; i < Ng; i += blockDim.x) { sh += jh[i]; s1 += j1[i]; j1o[i] = j1[i]; }
+    sh = block_reduce<0>(sh, scratch);
+    s1 = block_reduce<0>(s1, scratch);
+    const double meanh = sh / (double)Ng;
+    const double coef = k.dt / PIC_EPS0;
+    double rr = 0.0, ee = 0.0;
+    for (int i = threadIdx.x; i < Ng; i += blockDim.x) {
+        int ip = (i + 1 == Ng) ? 0 : i + 1, im = (i == 0) ? Ng - 1 : i - 1;
+        double sm_j = ((jh[ip] + 2.0 * jh[i]) + jh[im]) * 0.25;       // smooth_field_p(jh)
+        double e0 = E0[i];
+        double e1 = e0 + coef * (meanh - sm_j);                        // :283
+        double eh = (e1 + e0) * 0.5;                                   // :285
+        double d = Es[i] - eh;
+        rr += d * d;                                                   // :289 (squared, no sqrt)
+        ee += PIC_EPS0 * e1 * e1 * k.dx / 2.;
+        E1[i] = e1;
+        Fs[i] = eh;        // staged: Eh, smoothed below
+    }
+    rr = block_reduce<0>(rr, scratch);
+    ee = block_reduce<0>(ee, scratch);
+    __syncthreads();
+    for (int i = threadIdx.x; i < Ng; i += blockDim.x) Es[i] = Fs[i];
+    __syncthreads();
+    for (int i = threadIdx.x; i < Ng; i += blockDim.x) {
+        int ip = (i + 1 == Ng) ? 0 : i + 1, im = (i == 0) ? Ng - 1 : i - 1;
+        Fs[i] = ((Es[ip] + 2.0 * Es[i]) + Es[im]) * 0.25;              // field for the next gather, :261
+    }
+    for (int i = threadIdx.x; i < 2 * Ng; i += blockDim.x) acc[i] = 0.0;
+    if (threadIdx.x == 0) {
+        stats[0] = rr;
+        stats[1] = s1 / (double)Ng;
+        stats[2] = ee;
+        stats[3] = stats[3] + 1.0;
+    }
+}
+
+__global__ void wrap_periodic_k(double* __restrict__ x, long long N, double L) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < N; i += (long long)gridDim.x * blockDim.x)
+        x[i] = wrap_mod(x[i], L);
+}
+
+// ============================================================ PIC_L.py
+struct LK {
+    long long N, n_split;
+    int Ng, flags;
+    double dx, idx, dt, L, p2c;
+    double q[2], qm[2];
+};
+static LK make_lk(const pic_l_params* p) {
+    LK k;
+    k.N = p->N; k.n_split = p->n_split; k.Ng = p->Ng; k.flags = p->flags; k.dx = p->dx; k.idx = 1. / p->dx;
+    k.dt = p->dt; k.L = p->L; k.p2c = p->p2c;
+    for (int s = 0; s < 2; ++s) { k.q[s] = p->q[s]; k.qm[s] = p->q[s] / p->m[s]; }
+    return k;
+}
+__device__ __forceinline__ void l_fix(Cell& c, int nodes, int& bad) {
+    if (c.iL < 0 || c.iL > nodes - 2) { ++bad; c.iL = clampi(c.iL, 0, nodes - 2); c.iR = c.iL + 1; }
+}
+
+__global__ void l_interpolate_k(const double* __restrict__ F, const double* __restrict__ x, double* __restrict__ out,
+                                long long N, int Ng, double dx, int* __restrict__ range_err) {
+    int bad = 0;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < N; i += (long long)gridDim.x * blockDim.x) {
+        Cell c = cell_lper(x[i], dx, Ng + 1);
+        l_fix(c, Ng + 1, bad);
+        out[i] = c.wL * F[c.iL] + c.wR * F[c.iR];       // PIC_L.py:45
+    }
+    if (bad && range_err) atomicAdd(range_err, bad);
+}
+
+template <bool CURRENT>
+__global__ void l_weight_k(const double* __restrict__ x, const double* __restrict__ q, const double* __restrict__ v,
+                           double* __restrict__ acc, long long N, int Ng, double dx, double p2c,
+                           int* __restrict__ range_err) {
+    extern __shared__ double sm[];
+    const int nodes = Ng + 1;
+    for (int i = threadIdx.x; i < nodes; i += blockDim.x) sm[i] = 0.0;
+    __syncthreads();
+    const double idx = 1. / dx;
+    int bad = 0;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < N; i += (long long)gridDim.x * blockDim.x) {
+        Cell c = cell_lper(x[i], dx, nodes);
+        l_fix(c, nodes, bad);
+        // PIC_L.py:73-74 / 112-113: q*v*p2c*w*idx  |  q*p2c*w*idx
+        double pre = CURRENT ? q[i] * v[i] * p2c : q[i] * p2c;
+        atomicAdd(&sm[c.iL], pre * c.wL * idx);
+        atomicAdd(&sm[c.iR], pre * c.wR * idx);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < nodes; i += blockDim.x)
+        if (sm[i] != 0.0) atomicAdd(&acc[i], sm[i]);
+    if (bad && range_err) atomicAdd(range_err, bad);
+}
+// folds: rho[-1]=rho[0]+rho[-1]; rho[0]=rho[-1]  |  j[0]=j[-1]+j[0]; j[-1]=j[0]
+__global__ void l_fold_k(const double* __restrict__ acc, double* __restrict__ out, int nodes, int current) {
+    for (int i = threadIdx.x; i < nodes; i += blockDim.x) {
+        double a = acc[i];
+        if (i == 0 || i == nodes - 1) a = current ? (acc[nodes - 1] + acc[0]) : (acc[0] + acc[nodes - 1]);
+        out[i] = a;
+    }
+}
+
+// fused explicit particle phase: gather, kick-drift-kick, wrap, deposit rho(x_new)
+template <bool AGG>
+__global__ void __launch_bounds__(256) l_push_deposit_k(LK k, double* __restrict__ x, double* __restrict__ v,
+                                                        const double* __restrict__ E, double* __restrict__ rho_acc,
+                                                        int* __restrict__ range_err) {
+    extern __shared__ double sm[];
+    const int nodes = k.Ng + 1;
+    double *sE = sm, *sR = sm + nodes;
+    for (int i = threadIdx.x; i < nodes; i += blockDim.x) { sE[i] = E[i]; sR[i] = 0.0; }
+    __syncthreads();
+    int bad = 0;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    const long long nIter = (k.N + stride - 1) / stride;
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const double hdt = k.dt * 0.5;
+    const double wrapL = k.L + k.dx;
+    for (long long itn = 0; itn < nIter; ++itn, i += stride) {
+        bool valid = i < k.N;
+        Cell cn;
+        cn.iL = cn.iR = 0;
+        double rL = 0., rR = 0.;
+        if (valid) {
+            int sp = i >= k.n_split;
+            double X = ld_stream(x + i), V = ld_stream(v + i);
+            Cell c = cell_lper(X, k.dx, nodes);
+            l_fix(c, nodes, bad);
+            double Ei = c.wL * sE[c.iL] + c.wR * sE[c.iR];
+            double qm = sp ? k.qm[1] : k.qm[0];
+            double vhalf = V + qm * hdt * Ei;            // PIC_L.py:255
+            double xout = X + vhalf * k.dt;              // :256
+            double vout = vhalf + qm * hdt * Ei;         // :257
+            double xw = wrap_mod(xout, wrapL);
+            st_stream(x + i, xw);
+            st_stream(v + i, vout);
+            cn = cell_lper(xw, k.dx, nodes);
+            l_fix(cn, nodes, bad);
+            double pre = (sp ? k.q[1] : k.q[0]) * k.p2c;
+            rL = pre * cn.wL * k.idx; rR = pre * cn.wR * k.idx;
+        }
+        deposit2<AGG>(sR, cn.iL, cn.iR, rL, rR, valid);
+    }
+    __syncthreads();
+    for (int n = threadIdx.x; n < nodes; n += blockDim.x)
+        if (sR[n] != 0.0) atomicAdd(&rho_acc[n], sR[n]);
+    if (bad && range_err) atomicAdd(range_err, bad);
+}
+
+// field phase build: fold rho, rhs of the gauge-fixed periodic system over `nodes` unknowns
+__global__ void l_field_build_k(double* __restrict__ rho_acc, double* __restrict__ rho, double* __restrict__ a,
+                                double* __restrict__ b, double* __restrict__ c, double* __restrict__ d, int nodes,
+                                double dx) {
+    __shared__ double scratch[33];
+    double s = 0.0;
+    double fold = rho_acc[0] + rho_acc[nodes - 1];
+    for (int i = threadIdx.x; i < nodes; i += blockDim.x) {
+        double r = (i == 0 || i == nodes - 1) ? fold : rho_acc[i];
+        rho[i] = r;
+        s += r;
+    }
+    s = block_reduce<0>(s, scratch);
+    const double dx2 = dx * dx;
+    const double c0 = -(s / (double)nodes) / PIC_EPS0;
+    for (int i = threadIdx.x; i < nodes - 1; i += blockDim.x) {
+        a[i] = 1.0; b[i] = -2.0; c[i] = 1.0;
+        d[i] = -dx2 * c0 - dx2 * (rho[i] / PIC_EPS0);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < nodes; i += blockDim.x) rho_acc[i] = 0.0;
+}
+// phi = [x, 0] - max ; E = -dphi/dx (PIC_L.py:765-766, 235-246) ; stats[0] = sum(eps0 E^2/2)
+__global__ void l_field_finish_k(const double* __restrict__ x, double* __restrict__ phi, double* __restrict__ E,
+                                 int nodes, double dx, double* __restrict__ stats) {
+    __shared__ double scratch[33];
+    double m = -INFINITY;
+    for (int i = threadIdx.x; i < nodes; i += blockDim.x) {
+        double v = (i == nodes - 1) ? 0.0 : x[i];
+        phi[i] = v;
+        m = fmax(m, v);
+    }
+    m = block_reduce<1>(m, scratch);
+    for (int i = threadIdx.x; i < nodes; i += blockDim.x) phi[i] = phi[i] - m;
+    __syncthreads();
+    double ee = 0.0;
+    for (int i = threadIdx.x; i < nodes; i += blockDim.x) {
+        double e;
+        if (i == 0) e = -(phi[1] - phi[nodes - 1]) / dx * 0.5;
+        else if (i == nodes - 1) e = -(phi[0] - phi[nodes - 2]) / dx * 0.5;
+        else e = -(phi[i + 1] - phi[i - 1]) / dx * 0.5;
+        E[i] = e;
+        ee += PIC_EPS0 * e * e / 2.;
+    }
+    ee = block_reduce<0>(ee, scratch);
+    if (threadIdx.x == 0 && stats) stats[0] = ee;
+}
+
+}  // namespace pic
+
+using namespace pic;
+
+extern "C" {
+
+int pic_dev_pypic_interpolate(const double* F, const double* x, double* out, int64_t N, int Ng, double dx,
+                              int* range_err, void* stream) {
+    PIC_REQUIRE(F && x && out && N >= 0 && Ng >= 2, "pypic_interpolate: bad argument");
+    if (N == 0) return PIC_OK;
+    pypic_interpolate_k<<<grid_for(N, 256, 8), 256, 0, (cudaStream_t)stream>>>(F, x, out, N, Ng, dx, range_err);
+    PIC_CHECK_LAUNCH();
+    return PIC_OK;
+}
+
+int pic_dev_pypic_weight(const double* x, const double* q, const double* v, double* out, int64_t N, int Ng, double dx,
+                         double p2c, int* range_err, void* stream) {
+    PIC_REQUIRE(x && q && out && N >= 0 && Ng >= 2, "pypic_weight: bad argument");
+    if (N == 0) return PIC_OK;
+    size_t smem = (size_t)Ng * sizeof(double);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (v) {
+        PIC_CHECK_CUDA(cudaFuncSetAttribute(pypic_weight_k<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        pypic_weight_k<true><<<grid_for(N, 256, 4), 256, smem, st>>>(x, q, v, out, N, Ng, dx, p2c, range_err);
+    } else {
+        PIC_CHECK_CUDA(cudaFuncSetAttribute(pypic_weight_k<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        pypic_weight_k<false><<<grid_for(N, 256, 4), 256, smem, st>>>(x, q, v, out, N, Ng, dx, p2c, range_err);
+    }
+    PIC_CHECK_LAUNCH();
+    return PIC_OK;
+}
+
+int pic_dev_pypic_picard_iter(const pic_pypic_params* p, const double* x0, const double* v0, double* x1, double* v1,
+                              const double* Fs, double* acc, int first, int* range_err, void* stream) {
+    PIC_REQUIRE(p && x0 && v0 && x1 && v1 && Fs && acc, "pypic_picard_iter: null pointer");
+    PIC_REQUIRE(p->Ng >= 2 && p->dx > 0, "pypic_picard_iter: bad parameters");
+    if (p->N == 0) return PIC_OK;
+    PYK k = make_pyk(p);
+    size_t smem = (size_t)3 * k.Ng * sizeof(double);
+    PIC_REQUIRE(smem <= (size_t)max_optin_smem() - 1024, "pypic_picard_iter: Ng too large for the shared-memory tiles");
+    cudaStream_t st = (cudaStream_t)stream;
+    bool agg = !(p->flags & 1);
+#define PIC_PY_LAUNCH(F, A)                                                                                     \
+    do {                                                                                                        \
+        auto kern = pypic_picard_iter_k<F, A>;                                                                  \
+        PIC_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));     \
+        int occ = 0;                                                                                            \
+        PIC_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, 256, smem));                   \
+        kern<<<grid_for(k.N, 256, occ > 0 ? occ : 1), 256, smem, st>>>(k, x0, v0, x1, v1, Fs, acc, range_err);  \
+    } while (0)
+    if (first) { if (agg) PIC_PY_LAUNCH(true, true); else PIC_PY_LAUNCH(true, false); }
+    else { if (agg) PIC_PY_LAUNCH(false, true); else PIC_PY_LAUNCH(false, false); }
+#undef PIC_PY_LAUNCH
+    PIC_CHECK_LAUNCH();
+    return PIC_OK;
+}
+
+int pic_dev_pypic_field_update(const pic_pypic_params* p, double* acc, const double* E0, double* Es, double* Fs,
+                               double* E1, double* j1, double* stats, void* stream) {
+    PIC_REQUIRE(p && acc && E0 && Es && Fs && E1 && j1 && stats, "pypic_field_update: null pointer");
+    PYK k = make_pyk(p);
+    pypic_field_update_k<<<1, 1024, 0, (cudaStream_t)stream>>>(k, acc, E0, Es, Fs, E1, j1, stats);
+    PIC_CHECK_LAUNCH();
+    return PIC_OK;
+}
+
+int pic_dev_wrap_periodic(double* x, int64_t N, double L, void* stream) {
+    PIC_REQUIRE(x && N >= 0 && L > 0, "wrap_periodic: bad argument");
+    if (N == 0) return PIC_OK;
+    wrap_periodic_k<<<grid_for(N, 256, 8), 256, 0, (cudaStream_t)stream>>>(x, N, L);
+    PIC_CHECK_LAUNCH();
+    return PIC_OK;
+}
+
+int pic_dev_l_interpolate(const double* F, const double* x, double* out, int64_t N, int Ng, double dx, int* range_err,
+                          void* stream) {
+    PIC_REQUIRE(F && x && out && N >= 0 && Ng >= 2, "l_interpolate: bad argument");
+    if (N == 0) return PIC_OK;
+    l_interpolate_k<<<grid_for(N, 256, 8), 256, 0, (cudaStream_t)stream>>>(F, x, out, N, Ng, dx, range_err);
+    PIC_CHECK_LAUNCH();
+    return PIC_OK;
+}
+
+int pic_dev_l_weight(const double* x, const double* q, const double* v, double* out, int64_t N, int Ng, double dx,
+                     double p2c, int* range_err, void* stream) {
+    PIC_REQUIRE(x && q && out && N >= 0 && Ng >= 2, "l_weight: bad argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int nodes = Ng + 1;
+    double* acc = nullptr;
+    PIC_CHECK_CUDA(cudaMallocAsync((void**)&acc, (size_t)nodes * sizeof(double), st));
+    PIC_CHECK_CUDA(cudaMemsetAsync(acc, 0, (size_t)nodes * sizeof(double), st));
+    if (N > 0) {
+        size_t smem = (size_t)nodes * sizeof(double);
+        if (v) {
+            PIC_CHECK_CUDA(cudaFuncSetAttribute(l_weight_k<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            l_weight_k<true><<<grid_for(N, 256, 4), 256, smem, st>>>(x, q, v, acc, N, Ng, dx, p2c, range_err);
+        } else {
+            PIC_CHECK_CUDA(cudaFuncSetAttribute(l_weight_k<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            l_weight_k<false><<<grid_for(N, 256, 4), 256, smem, st>>>(x, q, v, acc, N, Ng, dx, p2c, range_err);
+        }
+        PIC_CHECK_LAUNCH();
+    }
+    l_fold_k<<<1, 1024, 0, st>>>(acc, out, nodes, v != nullptr);
+    PIC_CHECK_LAUNCH();
+    PIC_CHECK_CUDA(cudaFreeAsync(acc, st));
+    return PIC_OK;
+}
+
+int pic_dev_l_push_deposit(const pic_l_params* p, double* x, double* v, const double* E, double* rho_acc,
+                           int* range_err, void* stream) {
+    PIC_REQUIRE(p && x && v && E && rho_acc, "l_push_deposit: null pointer");
+    PIC_REQUIRE(p->Ng >= 2 && p->dx > 0, "l_push_deposit: bad parameters");
+    if (p->N == 0) return PIC_OK;
+    LK k = make_lk(p);
+    size_t smem = (size_t)2 * (k.Ng + 1) * sizeof(double);
+    PIC_REQUIRE(smem <= (size_t)max_optin_smem() - 1024, "l_push_deposit: Ng too large for the shared-memory tiles");
+    cudaStream_t st = (cudaStream_t)stream;
+    bool agg = !(p->flags & 1);
+    auto kern = agg ? l_push_deposit_k<true> : l_push_deposit_k<false>;
+    PIC_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int occ = 0;
+    PIC_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, 256, smem));
+    kern<<<grid_for(k.N, 256, occ > 0 ? occ : 1), 256, smem, st>>>(k, x, v, E, rho_acc, range_err);
+    PIC_CHECK_LAUNCH();
+    return PIC_OK;
+}
+
+int pic_dev_l_field_solve(const pic_l_params* p, double* rho_acc, double* rho, double* phi, double* E, double* work,
+                          double* stats, void* stream) {
+    PIC_REQUIRE(p && rho_acc && rho && phi && E && work, "l_field_solve: null pointer");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int nodes = p->Ng + 1;
+    double *a = work, *b = work + nodes, *c = work + 2 * (size_t)nodes, *d = work + 3 * (size_t)nodes,
+           *x = work + 4 * (size_t)nodes;
+    l_field_build_k<<<1, 1024, 0, st>>>(rho_acc, rho, a, b, c, d, nodes, p->dx);
+    PIC_CHECK_LAUNCH();
+    int rc = pic_dev_tridiag_pcr(a, b, c, d, x, nodes - 1, work + 5 * (size_t)nodes, stream);
+    if (rc) return rc;
+    l_field_finish_k<<<1, 1024, 0, st>>>(x, phi, E, nodes, p->dx, stats);
+    PIC_CHECK_LAUNCH();
+    return PIC_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,62 @@
+"""Thin helpers between torch device tensors and the raw pointers the C ABI takes."""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib
+
+
+def require_cuda(device=None):
+    if not torch.cuda.is_available():
+        raise _lib.PicError(_lib.PIC_ERR_NODEVICE, "no CUDA device: pypic_b200 has no CPU fallback")
+    dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+    _lib.load()
+    return dev
+
+
+def ptr(t):
+    """Device (or host) address of a tensor / numpy array / None."""
+    if t is None:
+        return None
+    if isinstance(t, torch.Tensor):
+        return t.data_ptr()
+    if isinstance(t, np.ndarray):
+        return t.ctypes.data
+    raise TypeError(type(t))
+
+
+def stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def f64(n, device, zero=False):
+    return (torch.zeros if zero else torch.empty)(int(n), dtype=torch.float64, device=device)
+
+
+def to_dev(a, device, dtype=torch.float64):
+    """numpy -> device tensor (contiguous copy)."""
+    return torch.as_tensor(np.ascontiguousarray(a)).to(device=device, dtype=dtype)
+
+
+def read_f64(t, n=None):
+    """Synchronous device->host read of a small fp64 tensor through the C ABI."""
+    n = t.numel() if n is None else n
+    out = np.empty(n, dtype=np.float64)
+    _lib.call("pic_dev_read", ptr(t), out.ctypes.data, n * 8, stream())
+    return out
+
+
+def read_raw(t, n, dtype):
+    out = np.empty(n, dtype=dtype)
+    _lib.call("pic_dev_read", ptr(t), out.ctypes.data, out.nbytes, stream())
+    return out
+
+
+def check_range(err_t, what):
+    """Raises if a kernel reported out-of-grid particle indices (reference UB)."""
+    n = int(read_raw(err_t, 1, np.int32)[0])
+    if n:
+        err_t.zero_()
+        raise _lib.PicError(_lib.PIC_ERR_RANGE, "%s: %d particle position(s) outside the grid "
+                            "(undefined behaviour in the reference); indices were clamped" % (what, n))

@@ -1,0 +1,210 @@
+"""Device-resident driver of PIC_L_DD.py's bounded two-species implicit sheath
+(PIC_L_DD.main_i, PIC_L_DD.py:415-551) on top of the C ABI.
+
+State in HBM (structure of arrays, fp64): x0,u0 (time n), x1,u1 (Picard scratch /
+time n+1; the commit is a pointer swap), optional passive v0,w0, int8 active flags,
+and the small grid arrays.  One Picard iteration = one fused particle kernel
+(gather+push+absorb+deposit jh,j1) + [one all-reduce if sharded] + one field kernel.
+"""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib, device as D
+from .dist import Comm, local_split, shard_range
+from .rng import LegacyDraws
+
+epsilon0 = 8.854E-12
+e = 1.602E-19
+mp = 1.67E-27
+me = 9.11E-31
+kb = 1.38E-23
+
+
+class SheathSim:
+    def __init__(self, N, Ng, dx, dt, p2c, q=(-e, e), m=(me, mp), n_split=None, tol=1e-5, maxiter=20,
+                 kBT=(None, None), gamma=0.0, carry_vw=True, deposit="warp", tiles="smem",
+                 rng="host", seed=1, draws=None, comm=None, device=None, sort_every=0):
+        self.dev = D.require_cuda(device)
+        self.comm = comm if comm is not None else Comm()
+        self.N_global = int(N)
+        n_split_g = int(N) // 2 if n_split is None else int(n_split)
+        self.start, self.stop = shard_range(N, self.comm.rank, self.comm.world)
+        self.N = self.stop - self.start
+        self.n_split = local_split(n_split_g, self.start, self.stop)
+        self.Ng, self.dx, self.dt, self.p2c = int(Ng), float(dx), float(dt), float(p2c)
+        self.L = dx * (Ng - 1)
+        self.tol, self.maxiter, self.gamma = float(tol), int(maxiter), float(gamma)
+        self.q, self.m = tuple(q), tuple(m)
+        self.kBT = kBT
+        self.carry_vw = bool(carry_vw)
+        self.rng_mode = rng
+        self.seed = int(seed)
+        self.draws = draws if draws is not None else LegacyDraws()
+        self.sort_every = int(sort_every)
+        flags = (1 if deposit == "atomic" else 0) | (2 if tiles == "global" else 0)
+        self.params = _lib.DDParams(self.N, self.n_split, self.Ng, flags, self.dx, self.dt, self.L, self.p2c,
+                                    (C.c_double * 2)(*self.q), (C.c_double * 2)(*self.m))
+        dev = self.dev
+        n = max(self.N, 1)
+        self.x0 = D.f64(n, dev, True); self.u0 = D.f64(n, dev, True)
+        self.x1 = D.f64(n, dev, True); self.u1 = D.f64(n, dev, True)
+        self.v0 = D.f64(n, dev, True) if carry_vw else None
+        self.w0 = D.f64(n, dev, True) if carry_vw else None
+        self.active = torch.ones(n, dtype=torch.int8, device=dev)
+        g = self.Ng
+        self.E0 = D.f64(g, dev, True); self.Es = D.f64(g, dev, True); self.E1 = D.f64(g, dev, True)
+        self.j0 = D.f64(g, dev, True)
+        self.acc = D.f64(2 * g + 4, dev, True)
+        self.wall_cum = D.f64(4, dev, True)
+        self.stats = D.f64(4, dev, True)
+        self.range_err = torch.zeros(1, dtype=torch.int32, device=dev)
+        self.dead_idx = torch.empty(n, dtype=torch.int32, device=dev)
+        self.count = torch.zeros(1, dtype=torch.int64, device=dev)
+        self.block_counts = torch.zeros(2 * (n // 2048 + 2), dtype=torch.int64, device=dev)
+        self.sort_counts = torch.zeros(2 * g + 2, dtype=torch.int32, device=dev) if self.sort_every else None
+        self.scalar = D.f64(1, dev, True)
+        self.t = 0
+        self.last_iters = 0
+        self.last_resid = 1.0
+        self.kernel_launches = 0
+        self.vionout = []
+        self.iter_events = None     # set to a list to record a CUDA-event pair per particle-kernel launch
+
+    # ------------------------------------------------------------------ state I/O
+    def upload(self, x0, u0, v0=None, w0=None, E0=None, active=None):
+        """Global (unsharded) host arrays in; each rank keeps its slice."""
+        s = slice(self.start, self.stop)
+        self.x0.copy_(torch.as_tensor(np.ascontiguousarray(x0[s])))
+        self.u0.copy_(torch.as_tensor(np.ascontiguousarray(u0[s])))
+        if self.carry_vw:
+            if v0 is not None:
+                self.v0.copy_(torch.as_tensor(np.ascontiguousarray(v0[s])))
+            if w0 is not None:
+                self.w0.copy_(torch.as_tensor(np.ascontiguousarray(w0[s])))
+        if E0 is not None:
+            self.E0.copy_(torch.as_tensor(np.ascontiguousarray(E0)))
+        if active is not None:
+            self.active.copy_(torch.as_tensor(np.ascontiguousarray(active[s]).astype(np.int8)))
+
+    def download(self):
+        out = dict(x0=self.x0.cpu().numpy(), u0=self.u0.cpu().numpy(),
+                   active=self.active.cpu().numpy().astype(np.float64),
+                   E0=self.E0.cpu().numpy(), j0=self.j0.cpu().numpy())
+        if self.carry_vw:
+            out["v0"] = self.v0.cpu().numpy(); out["w0"] = self.w0.cpu().numpy()
+        return out
+
+    # ------------------------------------------------------------------ re-injection
+    def _sigma(self, sp):
+        kT = self.kBT[sp]
+        return float(np.sqrt(kT / self.m[sp]))
+
+    def reinject(self):
+        """PIC_L_DD.py:419-450."""
+        st = D.stream()
+        if self.rng_mode == "philox":
+            sig = (C.c_double * 2)(self._sigma(0), self._sigma(1))
+            _lib.call("pic_dev_dd_reinject_philox", C.byref(self.params), D.ptr(self.x0), D.ptr(self.u0),
+                      D.ptr(self.v0), D.ptr(self.w0), D.ptr(self.active), C.byref(sig), self.seed, self.t,
+                      self.start, st)
+            self.kernel_launches += 1
+            return None
+        if self.gamma != 0.0:
+            raise NotImplementedError("thermostat with gamma != 0 (PIC_L_DD.py:421-426) is not on the device path; "
+                                      "the reference's only driven configuration uses gamma = 0")
+        _lib.call("pic_dev_compact_flags", D.ptr(self.active), self.N, 0, D.ptr(self.dead_idx), D.ptr(self.count),
+                  D.ptr(self.block_counts), st)
+        self.kernel_launches += 3
+        n_dead = int(D.read_raw(self.count, 1, np.int64)[0])
+        counts = self.comm.allgather_int(n_dead, device=self.dev)
+        total_dead = sum(counts)
+        self.draws.sheath_thermostat_skip(self.N_global - total_dead)
+        self.draws.sheath_skip_foreign(sum(counts[:self.comm.rank]))
+        if n_dead:
+            idx = D.read_raw(self.dead_idx, n_dead, np.int32)
+            sigma = np.where(idx >= self.n_split, self._sigma(1), self._sigma(0))
+            xd, ud, vd, wd = self.draws.sheath_reinject(n_dead, sigma, self.L)
+            dxd, dud = D.to_dev(xd, self.dev), D.to_dev(ud, self.dev)
+            dvd = D.to_dev(vd, self.dev) if self.carry_vw else None
+            dwd = D.to_dev(wd, self.dev) if self.carry_vw else None
+            _lib.call("pic_dev_dd_apply_draws", D.ptr(self.dead_idx), D.ptr(dxd), D.ptr(dud), D.ptr(dvd),
+                      D.ptr(dwd), n_dead, D.ptr(self.x0), D.ptr(self.u0), D.ptr(self.v0), D.ptr(self.w0),
+                      D.ptr(self.active), st)
+            self.kernel_launches += 1
+            torch.cuda.current_stream().synchronize()   # keep the staging tensors alive until consumed
+        self.draws.sheath_skip_foreign(sum(counts[self.comm.rank + 1:]))
+        return n_dead
+
+    def sort_by_cell(self):
+        """Benchmark mode: counting sort by (species, cell) into the scratch arrays."""
+        st = D.stream()
+        _lib.call("pic_dev_dd_sort_by_cell", C.byref(self.params), D.ptr(self.x0), D.ptr(self.u0), None, None,
+                  D.ptr(self.x1), D.ptr(self.u1), None, None, D.ptr(self.sort_counts), st)
+        self.kernel_launches += 3
+        self.x0, self.x1 = self.x1, self.x0
+        self.u0, self.u1 = self.u1, self.u0
+
+    # ------------------------------------------------------------------ one timestep
+    def picard(self):
+        """PIC_L_DD.py:452-545: Picard loop + commit.  Returns (iterations, residual)."""
+        st = D.stream()
+        P = C.byref(self.params)
+        self.Es.copy_(self.E0)
+        self.wall_cum.zero_()
+        self.stats.zero_()
+        r, k = 1.0, 0
+        while (r > self.tol) and (k < self.maxiter):
+            if self.iter_events is not None:
+                ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+                ev[0].record()
+            _lib.call("pic_dev_dd_picard_iter", P, D.ptr(self.x0), D.ptr(self.u0), D.ptr(self.x1), D.ptr(self.u1),
+                      D.ptr(self.active), D.ptr(self.Es), D.ptr(self.acc), 1 if k == 0 else 0,
+                      D.ptr(self.range_err), st)
+            if self.iter_events is not None:
+                ev[1].record()
+                self.iter_events.append(ev)
+            self.comm.allreduce_sum(self.acc)
+            _lib.call("pic_dev_dd_field_update", P, D.ptr(self.acc), D.ptr(self.wall_cum), D.ptr(self.E0),
+                      D.ptr(self.Es), D.ptr(self.E1), D.ptr(self.j0), D.ptr(self.stats), st)
+            self.kernel_launches += 2
+            r = float(D.read_f64(self.stats, 1)[0])
+            k += 1
+        # commit (PIC_L_DD.py:538-545): pointer swaps
+        self.x0, self.x1 = self.x1, self.x0
+        self.u0, self.u1 = self.u1, self.u0
+        self.E0, self.E1 = self.E1, self.E0
+        self.last_iters, self.last_resid = k, r
+        return k, r
+
+    def step(self):
+        if self.sort_every and self.t % self.sort_every == 0 and self.rng_mode == "philox" and not self.carry_vw:
+            self.reinject()
+            self.sort_by_cell()
+        else:
+            self.reinject()
+        out = self.picard()
+        self.t += 1
+        return out
+
+    # ------------------------------------------------------------------ diagnostics
+    def diagnostics(self):
+        """EE, KE, jbias of PIC_L_DD.py:548-551 (KE uses me for every particle, as written)."""
+        s = D.read_f64(self.stats, 4)
+        _lib.call("pic_dev_sum_sq", D.ptr(self.u0), self.N, me / 2., D.ptr(self.scalar), D.stream())
+        self.kernel_launches += 1
+        self.comm.allreduce_sum(self.scalar)
+        ke = float(D.read_f64(self.scalar, 1)[0])
+        return dict(EE=float(s[2]), KE=ke, jbias=float(s[1]))
+
+    def phi(self):
+        """phih of the last Picard iteration: -cumtrapz(Eh) - max (PIC_L_DD.py:522-523);
+        after the loop Es holds that Eh."""
+        out = D.f64(self.Ng, self.dev)
+        _lib.call("pic_dev_integrate_field", D.ptr(self.Es), D.ptr(out), self.Ng, self.dx, 1, D.stream())
+        self.kernel_launches += 1
+        return out.cpu().numpy()
+
+    def check(self):
+        D.check_range(self.range_err, "sheath step")

@@ -1,0 +1,65 @@
+"""CPU-side checks of the C-ABI shared library: it loads, exports every symbol that
+include/pic_b200.h declares, and fails loudly (no CPU fallback) without a GPU."""
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def lib():
+    from pypic_b200 import build, _lib
+    build.build()
+    return _lib
+
+
+def header_symbols():
+    src = open(os.path.join(ROOT, "include", "pic_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(pic_[a-zA-Z0-9_]+)\s*\(", src)))
+
+
+def test_exports_every_declared_symbol(lib):
+    l = lib.load()
+    syms = header_symbols()
+    assert len(syms) > 40
+    for s in syms:
+        assert hasattr(l, s), "libpic_b200.so does not export %s" % s
+    # and the binding table covers the header
+    assert set(syms) == set(lib.EXPORTS)
+
+
+def test_version_and_error_string(lib):
+    l = lib.load()
+    assert l.pic_version() >= 100
+    assert isinstance(l.pic_last_error(), bytes)
+
+
+def test_no_cpu_fallback(lib):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from pypic_b200 import device
+    with pytest.raises(lib.PicError):
+        device.require_cuda()
+    import numpy as np
+    from pypic_b200 import ops
+    with pytest.raises(lib.PicError):
+        ops.smooth(np.zeros(8), 0)
+
+
+def test_product_does_not_import_oracle():
+    """The product path must never route through oracle/ (test infrastructure)."""
+    bad = []
+    for d, _, files in os.walk(os.path.join(ROOT, "pypic_b200")):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                if re.search(r"^\s*(from|import)\s+oracle\b", open(os.path.join(d, f)).read(), flags=re.M):
+                    bad.append(f)
+    for f in ("pypic.py", "PIC_L.py", "PIC_L_DD.py", "pygcpic.py", "convert.py"):
+        p = os.path.join(ROOT, f)
+        if os.path.isfile(p) and re.search(r"^\s*(from|import)\s+oracle\b", open(p).read(), flags=re.M):
+            bad.append(f)
+    assert not bad, bad

@@ -238,3 +238,23 @@ def test_gc_decision_rule():
     # entry count 3; i0 dies -> 2; i1: 2<3 react -> 3; i3: 3<3 no -> delete; i4 delete
     assert list(react) == [False, True, False, False, False, False]
     assert list(dele) == [False, False, False, True, True, False]
+
+
+# ---------------------------------------------------------------- C oracle (scalable checker / CPU baseline)
+@pytest.mark.parametrize("nthreads", [1, 4])
+def test_c_oracle_matches_numpy_oracle(nthreads):
+    from oracle import c_oracle
+    rs = np.random.RandomState(2)
+    N, Ng = 30000, 51
+    dx, dt = 1e-5, 1e-12
+    L = dx * (Ng - 1)
+    m, q, x0, u0, v0, w0, species, kBTe, kBTi = O.dd_initialize_beam(N, 1e19, dx, Ng, 116000., 116000., L, rs)
+    E0 = rs.normal(0, 1e5, Ng)
+    p2c = L * 1e19 / N
+    a1 = np.ones(N); a2 = np.ones(N)
+    x1, u1, _, _, E1, j1, k, r, _ = O.dd_picard_step(x0, u0, v0, w0, q, m, a1, E0, p2c, Ng, dx, dt, L, 1e-5, 20)
+    cx1, cu1, cE1, cj1, ck, cr = c_oracle.dd_picard_step(x0, u0, [-O.e, O.e], [O.me, O.mp], N // 2, a2, E0, p2c,
+                                                         Ng, dx, dt, L, 1e-5, 20, nthreads)
+    assert ck == k and np.array_equal(a1, a2)
+    assert relmax(cE1, E1) < 1e-12 and relmax(cj1, j1) < 1e-12
+    assert relmax(cx1, x1) < 1e-13 and relmax(cu1, u1) < 1e-13
