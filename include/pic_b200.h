@@ -97,8 +97,11 @@ typedef struct {
     int64_t N;        /* particles in this shard                                   */
     int64_t n_split;  /* local index where species 2 starts: [0,n_split) use q[0],m[0] */
     int32_t Ng;       /* grid NODES (PIC_L_DD.py:324)                               */
-    int32_t flags;    /* bit0: deposit with plain shared-memory atomics only (no warp
-                         pre-reduction); bit1: keep grid tiles in global memory       */
+    int32_t flags;    /* 0 (default): register-window deposit over contiguous chunks, tiles in
+                         shared memory; bit0: plain shared-memory atomics per particle (the
+                         "fast atomicAdd" variant benchmarked alongside); bit2: grid-stride
+                         kernel with warp-uniform pre-reduction; bit1: keep the grid tiles in
+                         global memory (grids too large for shared memory)               */
     double dx, dt, L, p2c;
     double q[2], m[2];
 } pic_dd_params;
@@ -128,6 +131,10 @@ int pic_dev_dd_weight(const double* x, const double* q, const double* v, const d
 int pic_dev_dd_picard_iter(const pic_dd_params* p, const double* x0, const double* u0,
                            double* x1, double* u1, int8_t* active, const double* Es,
                            double* acc, int first, int* range_err, void* stream);
+/* Device self test: compares the constant-divisor division and the fast cell lookup used
+ * on the hot path against the IEEE operations for n pseudo-random / adversarial operands;
+ * *mismatches_dev (device uint64, zeroed by the caller) must stay 0. */
+int pic_dev_selftest_div(double b, uint64_t n, uint64_t seed, uint64_t* mismatches_dev, void* stream);
 /* Field phase of the same iteration (PIC_L_DD.py:55-66,516-527), one CTA:
  *   wall_cum fp64[4] += acc[2Ng..2Ng+3]; jh,j1 get wall terms + edge fold;
  *   E1 = E0 + (dt/eps0)(mean(jh) - jh); Eh=(E1+E0)/2; r=|Es-Eh|_2; Es=Eh;

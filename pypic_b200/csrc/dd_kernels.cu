@@ -151,6 +151,162 @@ __global__ void __launch_bounds__(256) dd_picard_iter_k(DDK k, const double* __r
     }
 }
 
+// ---------------------------------------------------------------------------------------
+// Windowed variant (default): every CTA walks CONTIGUOUS chunks of the particle store.
+// Once the store is sorted by cell (pic_dev_dd_sort_by_cell, every S steps) the particles
+// of a chunk deposit into a handful of adjacent nodes, so each thread accumulates its
+// contributions in a small REGISTER window (DD_WIN nodes from a per-warp base cell) with
+// predicated adds -- no atomics, no shuffles per particle.  The window is reduced with
+// warp shuffles once per chunk and added to the shared-memory tile by DD_WIN lanes.
+// Particles outside the window (unsorted input, fast electrons long after a sort) take
+// the shared-memory atomic path, so the kernel is correct for any particle order.
+#define DD_THREADS 512
+#define DD_ROWS 8
+#define DD_WIN 6
+
+template <bool FIRST>
+__global__ void __launch_bounds__(DD_THREADS, 2) dd_picard_iter_win_k(
+    DDK k, const double* __restrict__ x0, const double* __restrict__ u0, double* __restrict__ x1,
+    double* __restrict__ u1, int8_t* __restrict__ active, const double* __restrict__ Es, double* __restrict__ acc,
+    int* __restrict__ range_err) {
+    extern __shared__ double sm[];
+    const int Ng = k.Ng;
+    double *sF = sm, *jh = sm + Ng, *j1 = sm + 2 * Ng;
+    for (int i = threadIdx.x; i < Ng; i += blockDim.x) { sF[i] = Es[i]; jh[i] = 0.0; j1[i] = 0.0; }
+    __syncthreads();
+    const unsigned full = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    int nL0 = 0, nL1 = 0, nR0 = 0, nR1 = 0, bad = 0;
+    const long long chunk = (long long)DD_THREADS * DD_ROWS;
+    const long long nchunks = (k.N + chunk - 1) / chunk;
+    const int NOWIN = -0x40000000;
+    for (long long ch = blockIdx.x; ch < nchunks; ch += gridDim.x) {
+        double aH[DD_WIN], aF[DD_WIN];
+#pragma unroll
+        for (int n = 0; n < DD_WIN; ++n) { aH[n] = 0.0; aF[n] = 0.0; }
+        int wb = NOWIN;                              // warp-uniform window base cell
+        long long i = ch * chunk + threadIdx.x;
+#pragma unroll 2
+        for (int row = 0; row < DD_ROWS; ++row, i += DD_THREADS) {
+            bool alive = i < k.N;
+            int sp = 0;
+            double X0 = 0., U0 = 0., X1 = 0., U1 = 0., XH = 0., UH = 0.;
+            if (alive) {
+                sp = i >= k.n_split;
+                if (!FIRST) {
+                    if (active[i] != 1) { x1[i] = 0.0; u1[i] = 0.0; alive = false; }
+                }
+            }
+            if (alive) {
+                X0 = ld_stream(x0 + i);
+                U0 = ld_stream(u0 + i);
+                double xs = FIRST ? X0 : (X0 + ld_stream(x1 + i)) * 0.5;
+                Cell c = cell_dd_fast(xs, k.dx, k.idx);
+                if (c.iL < 0 || c.iL > Ng - 2) { ++bad; c.iL = clampi(c.iL, 0, Ng - 2); c.iR = c.iL + 1; }
+                double Ei = c.wL * sF[c.iL] + c.wR * sF[c.iR];
+                X1 = X0 + k.dt * U0 + (sp ? k.c2[1] : k.c2[0]) * Ei * 0.5;
+                U1 = U0 + (sp ? k.c1[1] : k.c1[0]) * Ei;
+                XH = (X0 + X1) * 0.5;
+                UH = (U0 + U1) * 0.5;
+                st_stream(x1 + i, X1);
+                st_stream(u1 + i, U1);
+                if (X0 >= k.L || XH >= k.L || X1 >= k.L) {
+                    active[i] = 0; alive = false;
+                    if (sp) ++nR1; else ++nR0;
+                } else if (X0 <= 0.0 || XH <= 0.0 || X1 <= 0.0) {
+                    active[i] = -1; alive = false;
+                    if (sp) ++nL1; else ++nL0;
+                }
+            }
+            int cH = 0, cF = 0;
+            double hL = 0., hR = 0., fL = 0., fR = 0.;
+            if (alive) {
+                Cell a = cell_dd_fast(XH, k.dx, k.idx);
+                if (a.iL < 0 || a.iL > Ng - 2) { ++bad; a.iL = clampi(a.iL, 0, Ng - 2); }
+                const double qs = sp ? k.q[1] : k.q[0];
+                double qv = qs * UH * k.p2c;
+                hL = qv * a.wL * k.idx; hR = qv * a.wR * k.idx;
+                cH = a.iL;
+                Cell b = cell_dd_fast(X1, k.dx, k.idx);
+                if (b.iL < 0 || b.iL > Ng - 2) { ++bad; b.iL = clampi(b.iL, 0, Ng - 2); }
+                double qf = qs * U1 * k.p2c;
+                fL = qf * b.wL * k.idx; fR = qf * b.wR * k.idx;
+                cF = b.iL;
+            }
+            if (wb == NOWIN) {
+                int m = __reduce_min_sync(full, alive ? min(cH, cF) : 0x7fffffff);
+                if (m != 0x7fffffff) wb = m - 1;
+            }
+            int dH = alive ? cH - wb : -100, dF = alive ? cF - wb : -100;
+            bool outH = alive && (dH < 0 || dH > DD_WIN - 2);
+            bool outF = alive && (dF < 0 || dF > DD_WIN - 2);
+            if (outH) dH = -100;      // out-of-window particles use the atomic path ONLY
+            if (outF) dF = -100;
+#pragma unroll
+            for (int n = 0; n < DD_WIN; ++n) {
+                aH[n] += (dH == n) ? hL : ((dH == n - 1) ? hR : 0.0);
+                aF[n] += (dF == n) ? fL : ((dF == n - 1) ? fR : 0.0);
+            }
+            if (outH) { atomicAdd(&jh[cH], hL); atomicAdd(&jh[cH + 1], hR); }
+            if (outF) { atomicAdd(&j1[cF], fL); atomicAdd(&j1[cF + 1], fR); }
+        }
+        if (wb != NOWIN) {
+            double v = 0.0;
+#pragma unroll
+            for (int n = 0; n < DD_WIN; ++n) {
+                double s = warp_sum(aH[n]);
+                double t = warp_sum(aF[n]);
+                if (lane == n) v = s;
+                if (lane == n + DD_WIN) v = t;
+            }
+            if (lane < 2 * DD_WIN) {
+                int node = wb + (lane < DD_WIN ? lane : lane - DD_WIN);
+                if (node >= 0 && node < Ng && v != 0.0) atomicAdd((lane < DD_WIN ? jh : j1) + node, v);
+            }
+        }
+    }
+    __syncthreads();
+    for (int n = threadIdx.x; n < 2 * Ng; n += blockDim.x) {
+        double v = sm[Ng + n];
+        if (v != 0.0) atomicAdd(&acc[n], v);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        nL0 += __shfl_xor_sync(full, nL0, o); nL1 += __shfl_xor_sync(full, nL1, o);
+        nR0 += __shfl_xor_sync(full, nR0, o); nR1 += __shfl_xor_sync(full, nR1, o);
+        bad += __shfl_xor_sync(full, bad, o);
+    }
+    if (lane == 0) {
+        if (nL0) atomicAdd(&acc[2 * Ng + 0], (double)nL0);
+        if (nL1) atomicAdd(&acc[2 * Ng + 1], (double)nL1);
+        if (nR0) atomicAdd(&acc[2 * Ng + 2], (double)nR0);
+        if (nR1) atomicAdd(&acc[2 * Ng + 3], (double)nR1);
+        if (bad && range_err) atomicAdd(range_err, bad);
+    }
+}
+
+// exhaustive-style self test of div_const / cell_dd_fast against the IEEE operations
+__global__ void selftest_div_k(double b, unsigned long long n, unsigned long long seed,
+                               unsigned long long* __restrict__ mism) {
+    const double y = 1.0 / b;
+    unsigned long long bad = 0;
+    for (unsigned long long t = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; t < n;
+         t += (unsigned long long)gridDim.x * blockDim.x) {
+        uint32_t c[4] = {(uint32_t)t, (uint32_t)(t >> 32), (uint32_t)seed, (uint32_t)(seed >> 32)};
+        philox4x32(c, 0x1234567u, 0x89abcdefu);
+        // a in [0,b): the remainder range; plus a few values scaled across many cells
+        double a = b * (((double)(((uint64_t)c[0] << 20) ^ (c[1] >> 12))) * (1.0 / 4503599627370496.0));
+        if (a >= b) a = nextafter(b, 0.0);
+        if (div_const(a, b, y) != a / b) ++bad;
+        double x = a * (double)(1 + (c[2] & 0xfffff));          // up to ~1e6 cells
+        if ((c[3] & 7) == 0) x = b * (double)(c[2] & 0xfffff);    // node-aligned
+        if ((c[3] & 7) == 1) x = nextafter(b * (double)(c[2] & 0xfffff), (c[3] & 8) ? 0.0 : INFINITY);
+        Cell p = cell_dd(x, b), f = cell_dd_fast(x, b, y);
+        if (p.iL != f.iL || p.wR != f.wR || p.wL != f.wL) ++bad;
+    }
+    if (bad) atomicAdd(mism, bad);
+}
+
 // Field phase, one CTA.  See pic_b200.h for the contract.
 __global__ void __launch_bounds__(1024) dd_field_update_k(DDK k, double* __restrict__ acc,
                                                           double* __restrict__ wall_cum,
@@ -213,7 +369,7 @@ __global__ void dd_interpolate_k(const double* __restrict__ F, const double* __r
                                  double* __restrict__ out, long long N, int Ng, double dx,
                                  int* __restrict__ range_err) {
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < N; i += (long long)gridDim.x * blockDim.x) {
-        Cell c = cell_dd(x[i], dx);
+        Cell c = cell_dd_fast(x[i], dx, 1. / dx);
         if (c.iL < 0 || c.iL > Ng - 2) { if (range_err) atomicAdd(range_err, 1); c.iL = clampi(c.iL, 0, Ng - 2); c.iR = c.iL + 1; }
         out[i] = c.wL * F[c.iL] + c.wR * F[c.iR];
     }
@@ -425,6 +581,20 @@ int pic_dev_dd_picard_iter(const pic_dd_params* p, const double* x0, const doubl
     cudaStream_t st = (cudaStream_t)stream;
     bool tile = !(p->flags & 2) && (size_t)3 * k.Ng * sizeof(double) <= (size_t)max_optin_smem() - 1024;
     bool agg = !(p->flags & 1);
+    if (tile && !(p->flags & (1 | 4))) {
+        // default: register-window deposit over contiguous chunks
+        size_t smem = (size_t)3 * k.Ng * sizeof(double);
+        auto kern = first ? dd_picard_iter_win_k<true> : dd_picard_iter_win_k<false>;
+        PIC_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        int occ = 0;
+        PIC_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, DD_THREADS, smem));
+        long long nchunks = (k.N + (long long)DD_THREADS * DD_ROWS - 1) / ((long long)DD_THREADS * DD_ROWS);
+        long long cap = (long long)device_sm_count() * (occ > 0 ? occ : 1);
+        int grid = (int)(nchunks < cap ? nchunks : cap);
+        kern<<<grid, DD_THREADS, smem, st>>>(k, x0, u0, x1, u1, active, Es, acc, range_err);
+        PIC_CHECK_LAUNCH();
+        return PIC_OK;
+    }
 #define PIC_DD_DISPATCH(F, T, A) return launch_iter<F, T, A>(k, x0, u0, x1, u1, active, Es, acc, range_err, st)
     if (first) {
         if (tile) { if (agg) PIC_DD_DISPATCH(true, true, true); else PIC_DD_DISPATCH(true, true, false); }
@@ -434,6 +604,14 @@ int pic_dev_dd_picard_iter(const pic_dd_params* p, const double* x0, const doubl
         else { if (agg) PIC_DD_DISPATCH(false, false, true); else PIC_DD_DISPATCH(false, false, false); }
     }
 #undef PIC_DD_DISPATCH
+}
+
+int pic_dev_selftest_div(double b, uint64_t n, uint64_t seed, uint64_t* mismatches_dev, void* stream) {
+    PIC_REQUIRE(b > 0 && mismatches_dev, "selftest_div: bad argument");
+    selftest_div_k<<<device_sm_count() * 8, 256, 0, (cudaStream_t)stream>>>(b, n, seed,
+                                                                           (unsigned long long*)mismatches_dev);
+    PIC_CHECK_LAUNCH();
+    return PIC_OK;
 }
 
 int pic_dev_dd_field_update(const pic_dd_params* p, double* acc, double* wall_cum, const double* E0, double* Es,

@@ -70,7 +70,8 @@ def test_picard_step_bit_exact_particles(deposit, tiles):
     sim.check()
     out = sim.download()
     assert kk == k
-    assert abs(rr - r) <= 1e-9 * abs(r)
+    # r = |Es-Eh| is a difference of nearly equal fields: compare on the scale of |E|
+    assert abs(rr - r) <= 1e-13 * np.linalg.norm(E1)
     assert np.array_equal(out["active"], act)                  # absorb flags bit-exact
     assert int((act == 0).sum()) > 10 and int((act == -1).sum()) > 10
     # E differs from the oracle in the last bits after iteration 1 (sum order), so x1,u1
