@@ -98,6 +98,22 @@ __device__ __forceinline__ Cell cell_dd_fast(double x, double dx, double idx) {
     return c;
 }
 
+// Deposit flavour of the lookup: EXACT cell index (same rule as cell_dd_fast) but the weight
+// is r*idx (one multiply).  Deposited sums are re-associated by the parallel reduction
+// anyway, so a last-bit difference in a single contribution is below the stated tolerance;
+// per-particle state (gather -> x1,u1) always uses the exact weights of cell_dd_fast.
+__device__ __forceinline__ int cell_dd_deposit(double x, double dx, double idx, double& wR) {
+    if (!(x >= 0.0)) { Cell c = cell_dd(x, dx); wR = c.wR; return c.iL; }
+    double t = x * idx;
+    double fl = floor(t);
+    double fr = t - fl;
+    double g = 1e-9 + t * 1e-15;
+    if (fr < g || fr > 1.0 - g) fl = floor(x / dx);
+    double r = rem_exact(x, dx, fl);
+    wR = r * idx;
+    return (int)fl;
+}
+
 // PIC_L.py:40-43,103-106: index = floor(x/dx) % (Ng+1) ; right node = index+1
 __device__ __forceinline__ Cell cell_lper(double x, double dx, int nodes /*Ng+1*/) {
     Cell c = cell_dd(x, dx);

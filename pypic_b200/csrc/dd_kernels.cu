@@ -152,122 +152,138 @@ __global__ void __launch_bounds__(256) dd_picard_iter_k(DDK k, const double* __r
 }
 
 // ---------------------------------------------------------------------------------------
-// Windowed variant (default): every CTA walks CONTIGUOUS chunks of the particle store.
-// Once the store is sorted by cell (pic_dev_dd_sort_by_cell, every S steps) the particles
-// of a chunk deposit into a handful of adjacent nodes, so each thread accumulates its
-// contributions in a small REGISTER window (DD_WIN nodes from a per-warp base cell) with
-// predicated adds -- no atomics, no shuffles per particle.  The window is reduced with
-// warp shuffles once per chunk and added to the shared-memory tile by DD_WIN lanes.
-// Particles outside the window (unsorted input, fast electrons long after a sort) take
-// the shared-memory atomic path, so the kernel is correct for any particle order.
-#define DD_THREADS 512
-#define DD_ROWS 8
-#define DD_WIN 6
+// Default variant: every CTA walks CONTIGUOUS chunks of the particle store.  Once the
+// store is sorted by cell (pic_dev_dd_sort_by_cell, every S steps) the particles of a
+// chunk deposit into a handful of adjacent nodes, so each thread keeps a PRIVATE window of
+// V3_W nodes per current (layout [node][thread] in shared memory: conflict-free, plain
+// load-add-store, no atomics and no shuffles per particle).  Once per chunk each warp sums
+// its 32 private windows column-wise and adds the V3_W node totals to the global
+// accumulators with fire-and-forget RED.ADD.F64.  Particles outside the window (unsorted
+// input, fast electrons long after a sort) take the shared-memory atomic path into a
+// per-CTA tile, so the kernel is correct for any particle order.
+// Loads of row r+1 are issued before row r is processed (software pipelining).
+#define V3_T 1024
+#define V3_W 6
+#define V3_ROWS 16
 
 template <bool FIRST>
-__global__ void __launch_bounds__(DD_THREADS, 2) dd_picard_iter_win_k(
+__global__ void __launch_bounds__(V3_T, 1) dd_picard_iter_v3_k(
     DDK k, const double* __restrict__ x0, const double* __restrict__ u0, double* __restrict__ x1,
     double* __restrict__ u1, int8_t* __restrict__ active, const double* __restrict__ Es, double* __restrict__ acc,
     int* __restrict__ range_err) {
     extern __shared__ double sm[];
     const int Ng = k.Ng;
-    double *sF = sm, *jh = sm + Ng, *j1 = sm + 2 * Ng;
-    for (int i = threadIdx.x; i < Ng; i += blockDim.x) { sF[i] = Es[i]; jh[i] = 0.0; j1[i] = 0.0; }
+    double* sF = sm;                 // field tile
+    double* tj = sm + Ng;            // fallback tiles jh | j1
+    double* win = sm + 3 * Ng;       // private windows [2*V3_W][V3_T]
+    for (int i = threadIdx.x; i < Ng; i += V3_T) { sF[i] = Es[i]; tj[i] = 0.0; tj[Ng + i] = 0.0; }
+    double* myw = win + threadIdx.x;
+#pragma unroll
+    for (int n = 0; n < 2 * V3_W; ++n) myw[n * V3_T] = 0.0;
     __syncthreads();
     const unsigned full = 0xffffffffu;
     const int lane = threadIdx.x & 31;
+    const int wbase = threadIdx.x & ~31;
     int nL0 = 0, nL1 = 0, nR0 = 0, nR1 = 0, bad = 0;
-    const long long chunk = (long long)DD_THREADS * DD_ROWS;
+    const long long chunk = (long long)V3_T * V3_ROWS;
     const long long nchunks = (k.N + chunk - 1) / chunk;
     const int NOWIN = -0x40000000;
+    const double qpi0 = k.q[0] * k.p2c * k.idx, qpi1 = k.q[1] * k.p2c * k.idx;
     for (long long ch = blockIdx.x; ch < nchunks; ch += gridDim.x) {
-        double aH[DD_WIN], aF[DD_WIN];
-#pragma unroll
-        for (int n = 0; n < DD_WIN; ++n) { aH[n] = 0.0; aF[n] = 0.0; }
-        int wb = NOWIN;                              // warp-uniform window base cell
         long long i = ch * chunk + threadIdx.x;
-#pragma unroll 2
-        for (int row = 0; row < DD_ROWS; ++row, i += DD_THREADS) {
-            bool alive = i < k.N;
-            int sp = 0;
-            double X0 = 0., U0 = 0., X1 = 0., U1 = 0., XH = 0., UH = 0.;
-            if (alive) {
-                sp = i >= k.n_split;
-                if (!FIRST) {
-                    if (active[i] != 1) { x1[i] = 0.0; u1[i] = 0.0; alive = false; }
-                }
-            }
-            if (alive) {
-                X0 = ld_stream(x0 + i);
-                U0 = ld_stream(u0 + i);
-                double xs = FIRST ? X0 : (X0 + ld_stream(x1 + i)) * 0.5;
-                Cell c = cell_dd_fast(xs, k.dx, k.idx);
-                if (c.iL < 0 || c.iL > Ng - 2) { ++bad; c.iL = clampi(c.iL, 0, Ng - 2); c.iR = c.iL + 1; }
-                double Ei = c.wL * sF[c.iL] + c.wR * sF[c.iR];
-                X1 = X0 + k.dt * U0 + (sp ? k.c2[1] : k.c2[0]) * Ei * 0.5;
-                U1 = U0 + (sp ? k.c1[1] : k.c1[0]) * Ei;
-                XH = (X0 + X1) * 0.5;
-                UH = (U0 + U1) * 0.5;
-                st_stream(x1 + i, X1);
-                st_stream(u1 + i, U1);
-                if (X0 >= k.L || XH >= k.L || X1 >= k.L) {
-                    active[i] = 0; alive = false;
-                    if (sp) ++nR1; else ++nR0;
-                } else if (X0 <= 0.0 || XH <= 0.0 || X1 <= 0.0) {
-                    active[i] = -1; alive = false;
-                    if (sp) ++nL1; else ++nL0;
-                }
-            }
-            int cH = 0, cF = 0;
-            double hL = 0., hR = 0., fL = 0., fR = 0.;
-            if (alive) {
-                Cell a = cell_dd_fast(XH, k.dx, k.idx);
-                if (a.iL < 0 || a.iL > Ng - 2) { ++bad; a.iL = clampi(a.iL, 0, Ng - 2); }
-                const double qs = sp ? k.q[1] : k.q[0];
-                double qv = qs * UH * k.p2c;
-                hL = qv * a.wL * k.idx; hR = qv * a.wR * k.idx;
-                cH = a.iL;
-                Cell b = cell_dd_fast(X1, k.dx, k.idx);
-                if (b.iL < 0 || b.iL > Ng - 2) { ++bad; b.iL = clampi(b.iL, 0, Ng - 2); }
-                double qf = qs * U1 * k.p2c;
-                fL = qf * b.wL * k.idx; fR = qf * b.wR * k.idx;
-                cF = b.iL;
-            }
-            if (wb == NOWIN) {
-                int m = __reduce_min_sync(full, alive ? min(cH, cF) : 0x7fffffff);
-                if (m != 0x7fffffff) wb = m - 1;
-            }
-            int dH = alive ? cH - wb : -100, dF = alive ? cF - wb : -100;
-            bool outH = alive && (dH < 0 || dH > DD_WIN - 2);
-            bool outF = alive && (dF < 0 || dF > DD_WIN - 2);
-            if (outH) dH = -100;      // out-of-window particles use the atomic path ONLY
-            if (outF) dF = -100;
-#pragma unroll
-            for (int n = 0; n < DD_WIN; ++n) {
-                aH[n] += (dH == n) ? hL : ((dH == n - 1) ? hR : 0.0);
-                aF[n] += (dF == n) ? fL : ((dF == n - 1) ? fR : 0.0);
-            }
-            if (outH) { atomicAdd(&jh[cH], hL); atomicAdd(&jh[cH + 1], hR); }
-            if (outF) { atomicAdd(&j1[cF], fL); atomicAdd(&j1[cF + 1], fR); }
+        int wb = NOWIN;
+        // prefetch row 0
+        bool n_in = i < k.N;
+        double nX0 = 0., nU0 = 0., nX1 = 0.;
+        int nAct = 1;
+        if (n_in) {
+            nX0 = ld_stream(x0 + i); nU0 = ld_stream(u0 + i);
+            if (!FIRST) { nX1 = ld_stream(x1 + i); nAct = active[i]; }
         }
+#pragma unroll 1
+        for (int row = 0; row < V3_ROWS; ++row) {
+            const long long ci = i;
+            const bool in = n_in;
+            const double X0 = nX0, U0 = nU0, pX1 = nX1;
+            const int act = nAct;
+            i += V3_T;
+            n_in = (row + 1 < V3_ROWS) && (i < k.N);
+            if (n_in) {
+                nX0 = ld_stream(x0 + i); nU0 = ld_stream(u0 + i);
+                if (!FIRST) { nX1 = ld_stream(x1 + i); nAct = active[i]; }
+            }
+            if (row == 0) {
+                int c0 = (in && act == 1) ? (int)(X0 * k.idx) : 0x7fffffff;
+                int m = __reduce_min_sync(full, c0);
+                if (m != 0x7fffffff) wb = m - 2;
+            }
+            if (!in) continue;
+            if (!FIRST && act != 1) { x1[ci] = 0.0; u1[ci] = 0.0; continue; }   // reference leaves zeros
+            const bool sp = ci >= k.n_split;
+            double xs = FIRST ? X0 : (X0 + pX1) * 0.5;
+            Cell c = cell_dd_fast(xs, k.dx, k.idx);
+            if (c.iL < 0 || c.iL > Ng - 2) { ++bad; c.iL = clampi(c.iL, 0, Ng - 2); }
+            double Ei = c.wL * sF[c.iL] + c.wR * sF[c.iL + 1];
+            double X1 = X0 + k.dt * U0 + (sp ? k.c2[1] : k.c2[0]) * Ei * 0.5;
+            double U1 = U0 + (sp ? k.c1[1] : k.c1[0]) * Ei;
+            double XH = (X0 + X1) * 0.5;
+            double UH = (U0 + U1) * 0.5;
+            st_stream(x1 + ci, X1);
+            st_stream(u1 + ci, U1);
+            // XH lies between X0 and X1 (rounding is monotone), so testing X0 and X1 suffices
+            if (X0 >= k.L || X1 >= k.L) {
+                active[ci] = 0;
+                if (sp) ++nR1; else ++nR0;
+                continue;
+            }
+            if (X0 <= 0.0 || X1 <= 0.0) {
+                active[ci] = -1;
+                if (sp) ++nL1; else ++nL0;
+                continue;
+            }
+            double wRh, wRf;
+            int cH = cell_dd_deposit(XH, k.dx, k.idx, wRh);
+            int cF = cell_dd_deposit(X1, k.dx, k.idx, wRf);
+            if (cH < 0 || cH > Ng - 2) { ++bad; cH = clampi(cH, 0, Ng - 2); }
+            if (cF < 0 || cF > Ng - 2) { ++bad; cF = clampi(cF, 0, Ng - 2); }
+            const double qpi = sp ? qpi1 : qpi0;
+            double ah = qpi * UH, af = qpi * U1;
+            double hR = ah * wRh, hL = ah - hR;
+            double fR = af * wRf, fL = af - fR;
+            unsigned dH = (unsigned)(cH - wb), dF = (unsigned)(cF - wb);
+            if (dH <= (unsigned)(V3_W - 2)) {
+                double* p = myw + dH * V3_T;
+                p[0] += hL; p[V3_T] += hR;
+            } else { atomicAdd(&tj[cH], hL); atomicAdd(&tj[cH + 1], hR); }
+            if (dF <= (unsigned)(V3_W - 2)) {
+                double* p = myw + (V3_W + dF) * V3_T;
+                p[0] += fL; p[V3_T] += fR;
+            } else { atomicAdd(&tj[Ng + cF], fL); atomicAdd(&tj[Ng + cF + 1], fR); }
+        }
+        // column sums of the warp's 32 private windows -> global accumulators
+        __syncwarp();
         if (wb != NOWIN) {
-            double v = 0.0;
+            double s = 0.0;
+            const int n = lane >> 1, half = lane & 1;
+            if (lane < 4 * V3_W) {
+                const double* col = win + n * V3_T + wbase + half * 16;
 #pragma unroll
-            for (int n = 0; n < DD_WIN; ++n) {
-                double s = warp_sum(aH[n]);
-                double t = warp_sum(aF[n]);
-                if (lane == n) v = s;
-                if (lane == n + DD_WIN) v = t;
+                for (int j = 0; j < 16; ++j) s += col[(j + n) & 15];
             }
-            if (lane < 2 * DD_WIN) {
-                int node = wb + (lane < DD_WIN ? lane : lane - DD_WIN);
-                if (node >= 0 && node < Ng && v != 0.0) atomicAdd((lane < DD_WIN ? jh : j1) + node, v);
+            s += __shfl_xor_sync(full, s, 1);
+            if (lane < 4 * V3_W && half == 0) {
+                int node = wb + (n < V3_W ? n : n - V3_W);
+                if (node >= 0 && node < Ng && s != 0.0) atomicAdd(&acc[(n < V3_W ? 0 : Ng) + node], s);
             }
+            __syncwarp();
+#pragma unroll
+            for (int n2 = 0; n2 < 2 * V3_W; ++n2) myw[n2 * V3_T] = 0.0;
+            __syncwarp();
         }
     }
     __syncthreads();
-    for (int n = threadIdx.x; n < 2 * Ng; n += blockDim.x) {
-        double v = sm[Ng + n];
+    for (int n = threadIdx.x; n < 2 * Ng; n += V3_T) {
+        double v = tj[n];
         if (v != 0.0) atomicAdd(&acc[n], v);
     }
 #pragma unroll
@@ -581,17 +597,15 @@ int pic_dev_dd_picard_iter(const pic_dd_params* p, const double* x0, const doubl
     cudaStream_t st = (cudaStream_t)stream;
     bool tile = !(p->flags & 2) && (size_t)3 * k.Ng * sizeof(double) <= (size_t)max_optin_smem() - 1024;
     bool agg = !(p->flags & 1);
-    if (tile && !(p->flags & (1 | 4))) {
-        // default: register-window deposit over contiguous chunks
-        size_t smem = (size_t)3 * k.Ng * sizeof(double);
-        auto kern = first ? dd_picard_iter_win_k<true> : dd_picard_iter_win_k<false>;
-        PIC_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        int occ = 0;
-        PIC_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, DD_THREADS, smem));
-        long long nchunks = (k.N + (long long)DD_THREADS * DD_ROWS - 1) / ((long long)DD_THREADS * DD_ROWS);
-        long long cap = (long long)device_sm_count() * (occ > 0 ? occ : 1);
+    size_t smem3 = ((size_t)3 * k.Ng + (size_t)2 * V3_W * V3_T) * sizeof(double);
+    if (!(p->flags & (1 | 2 | 4)) && smem3 <= (size_t)max_optin_smem() - 1024) {
+        // default: private-window deposit over contiguous chunks, one persistent CTA per SM
+        auto kern = first ? dd_picard_iter_v3_k<true> : dd_picard_iter_v3_k<false>;
+        PIC_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem3));
+        long long nchunks = (k.N + (long long)V3_T * V3_ROWS - 1) / ((long long)V3_T * V3_ROWS);
+        long long cap = device_sm_count();
         int grid = (int)(nchunks < cap ? nchunks : cap);
-        kern<<<grid, DD_THREADS, smem, st>>>(k, x0, u0, x1, u1, active, Es, acc, range_err);
+        kern<<<grid, V3_T, smem3, st>>>(k, x0, u0, x1, u1, active, Es, acc, range_err);
         PIC_CHECK_LAUNCH();
         return PIC_OK;
     }

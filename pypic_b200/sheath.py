@@ -24,7 +24,7 @@ kb = 1.38E-23
 
 class SheathSim:
     def __init__(self, N, Ng, dx, dt, p2c, q=(-e, e), m=(me, mp), n_split=None, tol=1e-5, maxiter=20,
-                 kBT=(None, None), gamma=0.0, carry_vw=True, deposit="warp", tiles="smem",
+                 kBT=(None, None), gamma=0.0, carry_vw=True, deposit="window", tiles="smem",
                  rng="host", seed=1, draws=None, comm=None, device=None, sort_every=0):
         self.dev = D.require_cuda(device)
         self.comm = comm if comm is not None else Comm()
@@ -43,7 +43,10 @@ class SheathSim:
         self.seed = int(seed)
         self.draws = draws if draws is not None else LegacyDraws()
         self.sort_every = int(sort_every)
-        flags = (1 if deposit == "atomic" else 0) | (2 if tiles == "global" else 0)
+        # deposit: "window" = private-window kernel over contiguous chunks (default),
+        # "atomic" = one shared-memory atomicAdd per contribution, "warp" = grid-stride kernel
+        # with warp-uniform pre-reduction; tiles: "smem" or "global" (grid too large for smem)
+        flags = {"window": 0, "atomic": 1, "warp": 4}[deposit] | (2 if tiles == "global" else 0)
         self.params = _lib.DDParams(self.N, self.n_split, self.Ng, flags, self.dx, self.dt, self.L, self.p2c,
                                     (C.c_double * 2)(*self.q), (C.c_double * 2)(*self.m))
         dev = self.dev

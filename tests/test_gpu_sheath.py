@@ -50,7 +50,7 @@ def _one_iter_inputs(N, Ng, seed):
     return dx, L, dt, x0, u0, q, m, E0
 
 
-@pytest.mark.parametrize("deposit", ["warp", "atomic"])
+@pytest.mark.parametrize("deposit", ["window", "warp", "atomic"])
 @pytest.mark.parametrize("tiles", ["smem", "global"])
 def test_picard_step_bit_exact_particles(deposit, tiles):
     """Same inputs -> identical x1,u1 (bits), identical absorb flags and counts, identical
