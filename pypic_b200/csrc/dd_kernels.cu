@@ -152,153 +152,229 @@ __global__ void __launch_bounds__(256) dd_picard_iter_k(DDK k, const double* __r
 }
 
 // ---------------------------------------------------------------------------------------
-// Default variant: every CTA walks CONTIGUOUS chunks of the particle store.  Once the
-// store is sorted by cell (pic_dev_dd_sort_by_cell, every S steps) the particles of a
-// chunk deposit into a handful of adjacent nodes, so each thread keeps a PRIVATE window of
-// V3_W nodes per current (layout [node][thread] in shared memory: conflict-free, plain
-// load-add-store, no atomics and no shuffles per particle).  Once per chunk each warp sums
-// its 32 private windows column-wise and adds the V3_W node totals to the global
-// accumulators with fire-and-forget RED.ADD.F64.  Particles outside the window (unsorted
-// input, fast electrons long after a sort) take the shared-memory atomic path into a
-// per-CTA tile, so the kernel is correct for any particle order.
-// Loads of row r+1 are issued before row r is processed (software pipelining).
-#define V3_T 1024
-#define V3_W 6
-#define V3_ROWS 16
+// Default variant ("window"): every CTA walks CONTIGUOUS chunks of the particle store and
+// every warp a contiguous 32*V4_ROWS-particle slice of the chunk.  Once the store is sorted
+// by cell (pic_dev_dd_sort_by_cell, every S steps) the particles of a slice deposit into a
+// handful of adjacent nodes, so each thread keeps a PRIVATE window of V4_W nodes per current
+// (layout [node][thread] in shared memory: conflict-free plain load-add-store, no atomics and
+// no shuffles per particle).  Once per slice the warp sums its 32 private windows column-wise
+// and adds the node totals to the global accumulators with fire-and-forget RED.ADD.F64.
+//
+// The loop body is a branch-free FAST PATH: every rare condition (cell lookup inside the
+// rounding guard band, out-of-range remainder/index, wall absorption, particle already
+// absorbed, chunk straddling the species boundary) only sets one predicate, and such a
+// particle is redone by dd_particle_slow() with the exact IEEE operations.  Range tests on
+// doubles are done on the integer pipe by comparing bit patterns (positive doubles order
+// like unsigned integers) to keep the half-rate FP64 pipe for arithmetic.  Loads of row
+// r+1 are issued before row r is processed (software pipelining).
+#define V4_T 1024
+#define V4_W 7
+#define V4_ROWS 16
+
+struct SlowOut { int code; int bad; };   // code: 0 deposited, 1..4 absorbed (L sp0, L sp1, R sp0, R sp1), 5 skipped
+
+// Full update of ONE particle with the exact (slow) operations; deposits with shared-memory
+// atomics into the CTA's fallback tiles tj = [jh | j1].
+__device__ __noinline__ SlowOut dd_particle_slow(const DDK& k, long long i, double X0, double U0, double pX1, int act,
+                                                 bool first, const double* sF, double* tj, double* __restrict__ x1,
+                                                 double* __restrict__ u1, int8_t* __restrict__ active) {
+    SlowOut o{0, 0};
+    const int Ng = k.Ng;
+    if (!first && act != 1) { x1[i] = 0.0; u1[i] = 0.0; o.code = 5; return o; }   // reference leaves zeros
+    const bool sp = i >= k.n_split;
+    double xs = first ? X0 : (X0 + pX1) * 0.5;
+    Cell c = cell_dd(xs, k.dx);
+    if (c.iL < 0 || c.iL > Ng - 2) { ++o.bad; c.iL = clampi(c.iL, 0, Ng - 2); }
+    double Ei = c.wL * sF[c.iL] + c.wR * sF[c.iL + 1];
+    double X1 = X0 + k.dt * U0 + (sp ? k.c2[1] : k.c2[0]) * Ei * 0.5;
+    double U1 = U0 + (sp ? k.c1[1] : k.c1[0]) * Ei;
+    double XH = (X0 + X1) * 0.5;
+    double UH = (U0 + U1) * 0.5;
+    x1[i] = X1; u1[i] = U1;
+    if (X0 >= k.L || XH >= k.L || X1 >= k.L) { active[i] = 0; o.code = sp ? 4 : 3; return o; }
+    if (X0 <= 0.0 || XH <= 0.0 || X1 <= 0.0) { active[i] = -1; o.code = sp ? 2 : 1; return o; }
+    Cell a = cell_dd(XH, k.dx), b = cell_dd(X1, k.dx);
+    if (a.iL < 0 || a.iL > Ng - 2) { ++o.bad; a.iL = clampi(a.iL, 0, Ng - 2); }
+    if (b.iL < 0 || b.iL > Ng - 2) { ++o.bad; b.iL = clampi(b.iL, 0, Ng - 2); }
+    const double qs = sp ? k.q[1] : k.q[0];
+    double qv = qs * UH * k.p2c, qf = qs * U1 * k.p2c;
+    atomicAdd(&tj[a.iL], qv * a.wL * k.idx); atomicAdd(&tj[a.iL + 1], qv * a.wR * k.idx);
+    atomicAdd(&tj[Ng + b.iL], qf * b.wL * k.idx); atomicAdd(&tj[Ng + b.iL + 1], qf * b.wR * k.idx);
+    return o;
+}
+
+// per-particle fast path: everything except memory traffic and the window update.
+// Returns true when the particle must be redone by dd_particle_slow().  All range tests
+// look only at the HIGH 32-bit word of the doubles (integer pipe, immediates): they are
+// conservative -- a value within 2^-20 (relative) of a limit is sent to the slow path,
+// which decides exactly.
+struct FastC {
+    double dx, idx, dt, c1, c2, qpi;
+    unsigned hi_dx, hi_Lm1, ngm2;
+};
+struct FastO { double X1, U1, hL, hR, fL, fR; int cH, cF; };
+
+#define PIC_HI_G 0x3EB00000u                      /* hi word of 2^-20       */
+#define PIC_HI_SPAN (0x3FEFFFFEu - 0x3EB00000u)    /* hi(1-2^-19) - hi(2^-20) */
 
 template <bool FIRST>
-__global__ void __launch_bounds__(V3_T, 1) dd_picard_iter_v3_k(
-    DDK k, const double* __restrict__ x0, const double* __restrict__ u0, double* __restrict__ x1,
-    double* __restrict__ u1, int8_t* __restrict__ active, const double* __restrict__ Es, double* __restrict__ acc,
-    int* __restrict__ range_err) {
+__device__ __forceinline__ bool dd_fast(const FastC& c, const double* __restrict__ sF, int Ng, double X0, double U0,
+                                        double pX1, FastO& o) {
+    const double xs = FIRST ? X0 : (X0 + pX1) * 0.5;
+    const double ts = xs * c.idx, fs = floor(ts);
+    bool rare = ((unsigned)__double2hiint(ts - fs) - PIC_HI_G) > PIC_HI_SPAN;
+    const double rs = fma(-fs, c.dx, xs);
+    rare |= (unsigned)__double2hiint(rs) >= c.hi_dx;
+    const int is = (int)fs;
+    rare |= (unsigned)is > c.ngm2;
+    const double wRs = div_const(rs, c.dx, c.idx), wLs = 1.0 - wRs;
+    const int isc = min(max(is, 0), Ng - 2);
+    const double Ei = wLs * sF[isc] + wRs * sF[isc + 1];
+    o.X1 = X0 + c.dt * U0 + c.c2 * Ei * 0.5;            // PIC_L_DD.py:479
+    o.U1 = U0 + c.c1 * Ei;                               // :481
+    const double XH = (X0 + o.X1) * 0.5, UH = (U0 + o.U1) * 0.5;
+    // absorbed iff X0 or X1 leaves (0,L): XH lies between them (rounding is monotone)
+    rare |= ((unsigned)__double2hiint(X0) - 1u) >= c.hi_Lm1;
+    rare |= ((unsigned)__double2hiint(o.X1) - 1u) >= c.hi_Lm1;
+    const double th = XH * c.idx, fh = floor(th);
+    rare |= ((unsigned)__double2hiint(th - fh) - PIC_HI_G) > PIC_HI_SPAN;
+    const double rh = fma(-fh, c.dx, XH);
+    rare |= (unsigned)__double2hiint(rh) >= c.hi_dx;
+    o.cH = (int)fh;
+    rare |= (unsigned)o.cH > c.ngm2;
+    const double tf = o.X1 * c.idx, ff = floor(tf);
+    rare |= ((unsigned)__double2hiint(tf - ff) - PIC_HI_G) > PIC_HI_SPAN;
+    const double rf = fma(-ff, c.dx, o.X1);
+    rare |= (unsigned)__double2hiint(rf) >= c.hi_dx;
+    o.cF = (int)ff;
+    rare |= (unsigned)o.cF > c.ngm2;
+    const double ah = c.qpi * UH, af = c.qpi * o.U1;
+    o.hR = ah * (rh * c.idx); o.hL = ah - o.hR;
+    o.fR = af * (rf * c.idx); o.fL = af - o.fR;
+    return rare;
+}
+
+#define V5_T 512
+#define V5_W 7
+#define V5_ROWS 16
+#define V5_CHUNK (V5_T * 2 * V5_ROWS)
+
+__device__ __forceinline__ void win_add(double* myw, double* tj, int wb, int tile, int Ng, int c, double vL, double vR) {
+    const unsigned d = (unsigned)(c - wb);
+    if (d <= (unsigned)(V5_W - 2)) {
+        double* p = myw + (tile * V5_W + d) * V5_T;
+        p[0] += vL; p[V5_T] += vR;
+    } else { atomicAdd(&tj[tile * Ng + c], vL); atomicAdd(&tj[tile * Ng + c + 1], vR); }
+}
+
+template <bool FIRST>
+__global__ void __launch_bounds__(V5_T, 1) dd_picard_iter_v5_k(
+    const __grid_constant__ DDK k, long long nchunks, const double* __restrict__ x0, const double* __restrict__ u0,
+    double* __restrict__ x1, double* __restrict__ u1, int8_t* __restrict__ active, const double* __restrict__ Es,
+    double* __restrict__ acc, int* __restrict__ range_err) {
     extern __shared__ double sm[];
+    __shared__ int s_cnt[8];
     const int Ng = k.Ng;
     double* sF = sm;                 // field tile
     double* tj = sm + Ng;            // fallback tiles jh | j1
-    double* win = sm + 3 * Ng;       // private windows [2*V3_W][V3_T]
-    for (int i = threadIdx.x; i < Ng; i += V3_T) { sF[i] = Es[i]; tj[i] = 0.0; tj[Ng + i] = 0.0; }
+    double* win = sm + 3 * Ng;       // private windows [2*V5_W][V5_T]
+    for (int i = threadIdx.x; i < Ng; i += V5_T) { sF[i] = Es[i]; tj[i] = 0.0; tj[Ng + i] = 0.0; }
     double* myw = win + threadIdx.x;
 #pragma unroll
-    for (int n = 0; n < 2 * V3_W; ++n) myw[n * V3_T] = 0.0;
+    for (int n = 0; n < 2 * V5_W; ++n) myw[n * V5_T] = 0.0;
+    if (threadIdx.x < 8) s_cnt[threadIdx.x] = 0;
     __syncthreads();
     const unsigned full = 0xffffffffu;
     const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
     const int wbase = threadIdx.x & ~31;
-    int nL0 = 0, nL1 = 0, nR0 = 0, nR1 = 0, bad = 0;
-    const long long chunk = (long long)V3_T * V3_ROWS;
-    const long long nchunks = (k.N + chunk - 1) / chunk;
     const int NOWIN = -0x40000000;
-    const double qpi0 = k.q[0] * k.p2c * k.idx, qpi1 = k.q[1] * k.p2c * k.idx;
+    FastC fc;
+    fc.dx = k.dx; fc.idx = k.idx; fc.dt = k.dt;
+    fc.hi_dx = (unsigned)__double2hiint(k.dx);
+    fc.hi_Lm1 = (unsigned)__double2hiint(k.L) - 1u;
+    fc.ngm2 = (unsigned)(Ng - 2);
     for (long long ch = blockIdx.x; ch < nchunks; ch += gridDim.x) {
-        long long i = ch * chunk + threadIdx.x;
+        const long long cstart = ch * V5_CHUNK;
+        // one species per chunk on the fast path; the chunk holding the boundary goes slow
+        const bool straddle = cstart < k.n_split && cstart + V5_CHUNK > k.n_split;
+        const bool sp = cstart >= k.n_split;
+        fc.c1 = sp ? k.c1[1] : k.c1[0]; fc.c2 = sp ? k.c2[1] : k.c2[0];
+        fc.qpi = (sp ? k.q[1] : k.q[0]) * k.p2c * k.idx;
+        // warp-contiguous slice of 64*V5_ROWS particles; lane owns the pair (2*lane, 2*lane+1) of each row
+        long long i = cstart + (long long)warp * (64 * V5_ROWS) + 2 * lane;
         int wb = NOWIN;
-        // prefetch row 0
-        bool n_in = i < k.N;
-        double nX0 = 0., nU0 = 0., nX1 = 0.;
-        int nAct = 1;
-        if (n_in) {
-            nX0 = ld_stream(x0 + i); nU0 = ld_stream(u0 + i);
-            if (!FIRST) { nX1 = ld_stream(x1 + i); nAct = active[i]; }
-        }
+        double2 nX0 = __ldcs((const double2*)(x0 + i)), nU0 = __ldcs((const double2*)(u0 + i));
+        double2 nX1 = make_double2(0., 0.);
+        short nAct = 0x0101;
+        if (!FIRST) { nX1 = __ldcs((const double2*)(x1 + i)); nAct = *(const short*)(active + i); }
 #pragma unroll 1
-        for (int row = 0; row < V3_ROWS; ++row) {
+        for (int row = 0; row < V5_ROWS; ++row) {
             const long long ci = i;
-            const bool in = n_in;
-            const double X0 = nX0, U0 = nU0, pX1 = nX1;
-            const int act = nAct;
-            i += V3_T;
-            n_in = (row + 1 < V3_ROWS) && (i < k.N);
-            if (n_in) {
-                nX0 = ld_stream(x0 + i); nU0 = ld_stream(u0 + i);
-                if (!FIRST) { nX1 = ld_stream(x1 + i); nAct = active[i]; }
+            const double2 X0 = nX0, U0 = nU0, pX1 = nX1;
+            const short act = nAct;
+            i += 64;
+            if (row + 1 < V5_ROWS) {
+                nX0 = __ldcs((const double2*)(x0 + i)); nU0 = __ldcs((const double2*)(u0 + i));
+                if (!FIRST) { nX1 = __ldcs((const double2*)(x1 + i)); nAct = *(const short*)(active + i); }
             }
+            FastO a, b;
+            bool ra = dd_fast<FIRST>(fc, sF, Ng, X0.x, U0.x, pX1.x, a);
+            bool rb = dd_fast<FIRST>(fc, sF, Ng, X0.y, U0.y, pX1.y, b);
+            if (straddle || (!FIRST && act != 0x0101)) { ra = true; rb = true; }
             if (row == 0) {
-                int c0 = (in && act == 1) ? (int)(X0 * k.idx) : 0x7fffffff;
-                int m = __reduce_min_sync(full, c0);
-                if (m != 0x7fffffff) wb = m - 2;
+                // window base: centre on the mean deposit cell of the warp's first row
+                int nok = __reduce_add_sync(full, (ra ? 0 : 1) + (rb ? 0 : 1));
+                int sum = __reduce_add_sync(full, (ra ? 0 : a.cH) + (rb ? 0 : b.cH));
+                if (nok) wb = sum / nok - (V5_W - 2) / 2;
             }
-            if (!in) continue;
-            if (!FIRST && act != 1) { x1[ci] = 0.0; u1[ci] = 0.0; continue; }   // reference leaves zeros
-            const bool sp = ci >= k.n_split;
-            double xs = FIRST ? X0 : (X0 + pX1) * 0.5;
-            Cell c = cell_dd_fast(xs, k.dx, k.idx);
-            if (c.iL < 0 || c.iL > Ng - 2) { ++bad; c.iL = clampi(c.iL, 0, Ng - 2); }
-            double Ei = c.wL * sF[c.iL] + c.wR * sF[c.iL + 1];
-            double X1 = X0 + k.dt * U0 + (sp ? k.c2[1] : k.c2[0]) * Ei * 0.5;
-            double U1 = U0 + (sp ? k.c1[1] : k.c1[0]) * Ei;
-            double XH = (X0 + X1) * 0.5;
-            double UH = (U0 + U1) * 0.5;
-            st_stream(x1 + ci, X1);
-            st_stream(u1 + ci, U1);
-            // XH lies between X0 and X1 (rounding is monotone), so testing X0 and X1 suffices
-            if (X0 >= k.L || X1 >= k.L) {
-                active[ci] = 0;
-                if (sp) ++nR1; else ++nR0;
-                continue;
+            if (!(ra | rb)) {
+                __stcs((double2*)(x1 + ci), make_double2(a.X1, b.X1));
+                __stcs((double2*)(u1 + ci), make_double2(a.U1, b.U1));
+            } else {
+                if (ra) {
+                    SlowOut o = dd_particle_slow(k, ci, X0.x, U0.x, pX1.x, (int)(signed char)(act & 0xff), FIRST, sF, tj, x1, u1, active);
+                    if (o.code >= 1 && o.code <= 4) atomicAdd(&s_cnt[o.code], 1);
+                    if (o.bad) atomicAdd(&s_cnt[0], o.bad);
+                } else { x1[ci] = a.X1; u1[ci] = a.U1; }
+                if (rb) {
+                    SlowOut o = dd_particle_slow(k, ci + 1, X0.y, U0.y, pX1.y, (int)(signed char)(act >> 8), FIRST, sF, tj, x1, u1, active);
+                    if (o.code >= 1 && o.code <= 4) atomicAdd(&s_cnt[o.code], 1);
+                    if (o.bad) atomicAdd(&s_cnt[0], o.bad);
+                } else { x1[ci + 1] = b.X1; u1[ci + 1] = b.U1; }
             }
-            if (X0 <= 0.0 || X1 <= 0.0) {
-                active[ci] = -1;
-                if (sp) ++nL1; else ++nL0;
-                continue;
-            }
-            double wRh, wRf;
-            int cH = cell_dd_deposit(XH, k.dx, k.idx, wRh);
-            int cF = cell_dd_deposit(X1, k.dx, k.idx, wRf);
-            if (cH < 0 || cH > Ng - 2) { ++bad; cH = clampi(cH, 0, Ng - 2); }
-            if (cF < 0 || cF > Ng - 2) { ++bad; cF = clampi(cF, 0, Ng - 2); }
-            const double qpi = sp ? qpi1 : qpi0;
-            double ah = qpi * UH, af = qpi * U1;
-            double hR = ah * wRh, hL = ah - hR;
-            double fR = af * wRf, fL = af - fR;
-            unsigned dH = (unsigned)(cH - wb), dF = (unsigned)(cF - wb);
-            if (dH <= (unsigned)(V3_W - 2)) {
-                double* p = myw + dH * V3_T;
-                p[0] += hL; p[V3_T] += hR;
-            } else { atomicAdd(&tj[cH], hL); atomicAdd(&tj[cH + 1], hR); }
-            if (dF <= (unsigned)(V3_W - 2)) {
-                double* p = myw + (V3_W + dF) * V3_T;
-                p[0] += fL; p[V3_T] += fR;
-            } else { atomicAdd(&tj[Ng + cF], fL); atomicAdd(&tj[Ng + cF + 1], fR); }
+            if (!ra) { win_add(myw, tj, wb, 0, Ng, a.cH, a.hL, a.hR); win_add(myw, tj, wb, 1, Ng, a.cF, a.fL, a.fR); }
+            if (!rb) { win_add(myw, tj, wb, 0, Ng, b.cH, b.hL, b.hR); win_add(myw, tj, wb, 1, Ng, b.cF, b.fL, b.fR); }
         }
         // column sums of the warp's 32 private windows -> global accumulators
         __syncwarp();
         if (wb != NOWIN) {
             double s = 0.0;
             const int n = lane >> 1, half = lane & 1;
-            if (lane < 4 * V3_W) {
-                const double* col = win + n * V3_T + wbase + half * 16;
+            if (lane < 4 * V5_W) {
+                const double* col = win + n * V5_T + wbase + half * 16;
 #pragma unroll
                 for (int j = 0; j < 16; ++j) s += col[(j + n) & 15];
             }
             s += __shfl_xor_sync(full, s, 1);
-            if (lane < 4 * V3_W && half == 0) {
-                int node = wb + (n < V3_W ? n : n - V3_W);
-                if (node >= 0 && node < Ng && s != 0.0) atomicAdd(&acc[(n < V3_W ? 0 : Ng) + node], s);
+            if (lane < 4 * V5_W && half == 0) {
+                int node = wb + (n < V5_W ? n : n - V5_W);
+                if (node >= 0 && node < Ng && s != 0.0) atomicAdd(&acc[(n < V5_W ? 0 : Ng) + node], s);
             }
             __syncwarp();
 #pragma unroll
-            for (int n2 = 0; n2 < 2 * V3_W; ++n2) myw[n2 * V3_T] = 0.0;
+            for (int n2 = 0; n2 < 2 * V5_W; ++n2) myw[n2 * V5_T] = 0.0;
             __syncwarp();
         }
     }
     __syncthreads();
-    for (int n = threadIdx.x; n < 2 * Ng; n += V3_T) {
+    for (int n = threadIdx.x; n < 2 * Ng; n += V5_T) {
         double v = tj[n];
         if (v != 0.0) atomicAdd(&acc[n], v);
     }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        nL0 += __shfl_xor_sync(full, nL0, o); nL1 += __shfl_xor_sync(full, nL1, o);
-        nR0 += __shfl_xor_sync(full, nR0, o); nR1 += __shfl_xor_sync(full, nR1, o);
-        bad += __shfl_xor_sync(full, bad, o);
-    }
-    if (lane == 0) {
-        if (nL0) atomicAdd(&acc[2 * Ng + 0], (double)nL0);
-        if (nL1) atomicAdd(&acc[2 * Ng + 1], (double)nL1);
-        if (nR0) atomicAdd(&acc[2 * Ng + 2], (double)nR0);
-        if (nR1) atomicAdd(&acc[2 * Ng + 3], (double)nR1);
-        if (bad && range_err) atomicAdd(range_err, bad);
-    }
+    if (threadIdx.x >= 1 && threadIdx.x <= 4 && s_cnt[threadIdx.x])
+        atomicAdd(&acc[2 * Ng + threadIdx.x - 1], (double)s_cnt[threadIdx.x]);
+    if (threadIdx.x == 0 && s_cnt[0] && range_err) atomicAdd(range_err, s_cnt[0]);
 }
 
 // exhaustive-style self test of div_const / cell_dd_fast against the IEEE operations
@@ -597,16 +673,28 @@ int pic_dev_dd_picard_iter(const pic_dd_params* p, const double* x0, const doubl
     cudaStream_t st = (cudaStream_t)stream;
     bool tile = !(p->flags & 2) && (size_t)3 * k.Ng * sizeof(double) <= (size_t)max_optin_smem() - 1024;
     bool agg = !(p->flags & 1);
-    size_t smem3 = ((size_t)3 * k.Ng + (size_t)2 * V3_W * V3_T) * sizeof(double);
-    if (!(p->flags & (1 | 2 | 4)) && smem3 <= (size_t)max_optin_smem() - 1024) {
-        // default: private-window deposit over contiguous chunks, one persistent CTA per SM
-        auto kern = first ? dd_picard_iter_v3_k<true> : dd_picard_iter_v3_k<false>;
-        PIC_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem3));
-        long long nchunks = (k.N + (long long)V3_T * V3_ROWS - 1) / ((long long)V3_T * V3_ROWS);
-        long long cap = device_sm_count();
-        int grid = (int)(nchunks < cap ? nchunks : cap);
-        kern<<<grid, V3_T, smem3, st>>>(k, x0, u0, x1, u1, active, Es, acc, range_err);
-        PIC_CHECK_LAUNCH();
+    size_t smem5 = ((size_t)3 * k.Ng + (size_t)2 * V5_W * V5_T) * sizeof(double);
+    if (!(p->flags & (1 | 2 | 4)) && smem5 <= (size_t)max_optin_smem() - 512) {
+        // default: private-window deposit over contiguous chunks, one persistent CTA per SM;
+        // the remainder that does not fill a chunk is done by the generic grid-stride kernel
+        const long long nchunks = k.N / V5_CHUNK;
+        if (nchunks > 0) {
+            auto kern = first ? dd_picard_iter_v5_k<true> : dd_picard_iter_v5_k<false>;
+            PIC_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem5));
+            long long cap = device_sm_count();
+            int grid = (int)(nchunks < cap ? nchunks : cap);
+            kern<<<grid, V5_T, smem5, st>>>(k, nchunks, x0, u0, x1, u1, active, Es, acc, range_err);
+            PIC_CHECK_LAUNCH();
+        }
+        const long long done = nchunks * V5_CHUNK;
+        if (done < k.N) {
+            DDK t = k;
+            t.N = k.N - done;
+            t.n_split = k.n_split - done < 0 ? 0 : (k.n_split - done > t.N ? t.N : k.n_split - done);
+            int rc = first ? launch_iter<true, true, true>(t, x0 + done, u0 + done, x1 + done, u1 + done, active + done, Es, acc, range_err, st)
+                           : launch_iter<false, true, true>(t, x0 + done, u0 + done, x1 + done, u1 + done, active + done, Es, acc, range_err, st);
+            if (rc) return rc;
+        }
         return PIC_OK;
     }
 #define PIC_DD_DISPATCH(F, T, A) return launch_iter<F, T, A>(k, x0, u0, x1, u1, active, Es, acc, range_err, st)
