@@ -254,7 +254,9 @@ __device__ __forceinline__ bool dd_fast(const FastC& c, const double* __restrict
     return rare;
 }
 
+#ifndef V5_T
 #define V5_T 512
+#endif
 #define V5_W 7
 #define V5_ROWS 16
 #define V5_CHUNK (V5_T * 2 * V5_ROWS)
