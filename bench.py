@@ -238,13 +238,13 @@ def run_cuda(args):
     achieved = alg_bytes_launch / (mean_iter_ms * 1e-3) / 1e9
     peak, peak_src = measured_peak()
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": None, "kernel": "dd_picard_iter_k", "peak_source": peak_src,
+                "traffic": None, "kernel": "dd_picard_iter_v5_k", "peak_source": peak_src,
                 "kernel_ms_mean": mean_iter_ms, "kernel_share_of_step": float(np.sum(kernel_ms) / ms),
                 "algorithmic_bytes_per_launch": alg_bytes_launch, "mean_picard_iterations": kbar}
     tf = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.isfile(tf):
         try:
-            roofline["traffic"] = json.load(open(tf)).get("dram_bytes_per_launch")
+            roofline["traffic"] = json.load(open(tf))["dram_bytes_per_particle"] * sim.N   # ncu, per launch
         except Exception:
             pass
 

@@ -1,0 +1,175 @@
+"""Device-resident drivers of the two periodic codes:
+
+* PeriodicImplicitSim -- pypic.py's implicit Crank-Nicolson / Picard loop
+  (pypic.particle_push_p, pypic.py:216-300) for one species;
+* ExplicitSim -- PIC_L.py's explicit leapfrog loop with a Poisson solve every step
+  (PIC_L.main, PIC_L.py:762-768).
+"""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib, device as D
+from .dist import Comm, local_split, shard_range
+
+epsilon0 = 8.854E-12
+e = 1.602E-19
+mp = 1.67E-27
+me = 9.11E-31
+kb = 1.38E-23
+
+
+class PeriodicImplicitSim:
+    def __init__(self, N, Ng, dx, dt, L, p2c, q=-e, m=me, tol=1e-3, maxiter=20, deposit="warp", comm=None,
+                 device=None):
+        self.dev = D.require_cuda(device)
+        self.comm = comm if comm is not None else Comm()
+        self.N_global = int(N)
+        self.start, self.stop = shard_range(N, self.comm.rank, self.comm.world)
+        self.N = self.stop - self.start
+        self.Ng, self.dx, self.dt, self.L = int(Ng), float(dx), float(dt), float(L)
+        self.p2c = float(int(p2c))           # numba's int32 signature truncates p2c
+        self.p2c_raw = float(p2c)            # the Python-level diagnostics use the untruncated value
+        self.tol, self.maxiter = float(tol), int(maxiter)
+        flags = 1 if deposit == "atomic" else 0
+        self.params = _lib.PypicParams(self.N, self.Ng, flags, self.dx, self.dt, self.L, self.p2c, float(q), float(m))
+        dev, n, g = self.dev, max(self.N, 1), self.Ng
+        self.x0 = D.f64(n, dev, True); self.v0 = D.f64(n, dev, True)
+        self.x1 = D.f64(n, dev, True); self.v1 = D.f64(n, dev, True)
+        self.E0 = D.f64(g, dev, True); self.Es = D.f64(g, dev, True); self.Fs = D.f64(g, dev, True)
+        self.E1 = D.f64(g, dev, True); self.j0 = D.f64(g, dev, True)
+        self.acc = D.f64(2 * g, dev, True)
+        self.stats = D.f64(4, dev, True)
+        self.range_err = torch.zeros(1, dtype=torch.int32, device=dev)
+        self.last_iters, self.last_resid = 0, 1.0
+        self.kernel_launches = 0
+
+    def upload(self, x0, v0, E0=None):
+        s = slice(self.start, self.stop)
+        self.x0.copy_(torch.as_tensor(np.ascontiguousarray(x0[s])))
+        self.v0.copy_(torch.as_tensor(np.ascontiguousarray(v0[s])))
+        if E0 is not None:
+            self.E0.copy_(torch.as_tensor(np.ascontiguousarray(E0)))
+
+    def push(self):
+        """particle_push_p: Picard loop + commit (x wrapped into [0,L)).  Returns (k, r)."""
+        st = D.stream()
+        P = C.byref(self.params)
+        self.Es.copy_(self.E0)
+        _lib.call("pic_dev_smooth", D.ptr(self.Es), D.ptr(self.Fs), self.Ng, 0, st)
+        self.stats.zero_()
+        r, k = 1.0, 0
+        while (r > self.tol) and (k < self.maxiter):
+            _lib.call("pic_dev_pypic_picard_iter", P, D.ptr(self.x0), D.ptr(self.v0), D.ptr(self.x1), D.ptr(self.v1),
+                      D.ptr(self.Fs), D.ptr(self.acc), 1 if k == 0 else 0, D.ptr(self.range_err), st)
+            self.comm.allreduce_sum(self.acc)
+            _lib.call("pic_dev_pypic_field_update", P, D.ptr(self.acc), D.ptr(self.E0), D.ptr(self.Es), D.ptr(self.Fs),
+                      D.ptr(self.E1), D.ptr(self.j0), D.ptr(self.stats), st)
+            self.kernel_launches += 2
+            r = float(D.read_f64(self.stats, 1)[0])
+            k += 1
+        if k > 0:
+            self.x0, self.x1 = self.x1, self.x0
+            self.v0, self.v1 = self.v1, self.v0
+            self.E0, self.E1 = self.E1, self.E0
+            _lib.call("pic_dev_wrap_periodic", D.ptr(self.x0), self.N, self.L, st)   # x1 = x1 % L (pypic.py:277)
+            self.kernel_launches += 2
+        self.last_iters, self.last_resid = k, r
+        return k, r
+
+    def diagnostics(self, m=me):
+        s = D.read_f64(self.stats, 4)
+        sc = D.f64(1, self.dev, True)
+        _lib.call("pic_dev_sum_sq", D.ptr(self.v0), self.N, m / 2., D.ptr(sc), D.stream())
+        self.comm.allreduce_sum(sc)
+        # pypic.py:571-574: EE = sum(eps0 E^2 dx/2), KE = p2c*sum(me v^2/2), j_bias = mean(j0)
+        return dict(EE=float(s[2]), KE=self.p2c_raw * float(sc.item()), jbias=float(s[1]))
+
+    def download(self):
+        return dict(x0=self.x0.cpu().numpy(), v0=self.v0.cpu().numpy(), E0=self.E0.cpu().numpy(),
+                    j0=self.j0.cpu().numpy())
+
+    def check(self):
+        D.check_range(self.range_err, "pypic push")
+
+
+class ExplicitSim:
+    """PIC_L.main's loop: rho -> Poisson -> E -> kick-drift-kick -> wrap, with the deposit of
+    the NEXT step fused into the push kernel."""
+
+    def __init__(self, N, Ng, dx, dt, p2c, q=(-e, -e), m=(me, me), n_split=None, deposit="warp", comm=None,
+                 device=None):
+        self.dev = D.require_cuda(device)
+        self.comm = comm if comm is not None else Comm()
+        self.N_global = int(N)
+        self.start, self.stop = shard_range(N, self.comm.rank, self.comm.world)
+        self.N = self.stop - self.start
+        ns = int(N) if n_split is None else int(n_split)
+        self.n_split = local_split(ns, self.start, self.stop)
+        self.Ng, self.dx, self.dt, self.p2c = int(Ng), float(dx), float(dt), float(p2c)
+        self.L = dx * (Ng - 1)              # PIC_L.py:645; the wrap length is L+dx
+        flags = 1 if deposit == "atomic" else 0
+        self.params = _lib.LParams(self.N, self.n_split, self.Ng, flags, self.dx, self.dt, self.L, self.p2c,
+                                   (C.c_double * 2)(*q), (C.c_double * 2)(*m))
+        dev, n, g = self.dev, max(self.N, 1), self.Ng + 1
+        self.x = D.f64(n, dev, True); self.v = D.f64(n, dev, True)
+        self.q_arr = None
+        self.rho_acc = D.f64(g, dev, True)
+        self.rho = D.f64(g, dev, True); self.phi = D.f64(g, dev, True); self.E = D.f64(g, dev, True)
+        self.work = D.f64(13 * g, dev, True)
+        self.stats = D.f64(4, dev, True)
+        self.range_err = torch.zeros(1, dtype=torch.int32, device=dev)
+        self.kernel_launches = 0
+        self._have_rho = False
+        self.q, self.m = tuple(q), tuple(m)
+
+    def upload(self, x, v):
+        s = slice(self.start, self.stop)
+        self.x.copy_(torch.as_tensor(np.ascontiguousarray(x[s])))
+        self.v.copy_(torch.as_tensor(np.ascontiguousarray(v[s])))
+        self._have_rho = False
+
+    def _deposit_initial(self):
+        """rho of the current positions (PIC_L.py:763) -- only needed before the first step."""
+        qarr = torch.empty(max(self.N, 1), dtype=torch.float64, device=self.dev)
+        qarr[:self.n_split] = self.q[0]
+        qarr[self.n_split:] = self.q[1]
+        tmp = D.f64(self.Ng + 1, self.dev, True)
+        _lib.call("pic_dev_l_weight", D.ptr(self.x), D.ptr(qarr), None, D.ptr(tmp), self.N, self.Ng, self.dx, self.p2c,
+                  D.ptr(self.range_err), D.stream())
+        # l_weight already folded the ends; un-fold so that field_solve's fold is a no-op:
+        # field_solve folds rho_acc[0]+rho_acc[-1]; give it the folded value split as (v, 0)
+        self.rho_acc.copy_(tmp)
+        self.rho_acc[-1] = 0.0
+        self.kernel_launches += 2
+
+    def field_solve(self):
+        """PIC_L.py:763-766: (folded) rho -> phi (periodic Poisson, -max) -> E."""
+        if not self._have_rho:
+            self._deposit_initial()
+        self.comm.allreduce_sum(self.rho_acc)
+        _lib.call("pic_dev_l_field_solve", C.byref(self.params), D.ptr(self.rho_acc), D.ptr(self.rho), D.ptr(self.phi),
+                  D.ptr(self.E), D.ptr(self.work), D.ptr(self.stats), D.stream())
+        self.kernel_launches += 3
+
+    def push(self):
+        """PIC_L.py:767-768 + the deposit of the next step's rho."""
+        _lib.call("pic_dev_l_push_deposit", C.byref(self.params), D.ptr(self.x), D.ptr(self.v), D.ptr(self.E),
+                  D.ptr(self.rho_acc), D.ptr(self.range_err), D.stream())
+        self.kernel_launches += 1
+        self._have_rho = True
+
+    def step(self):
+        self.field_solve()
+        self.push()
+
+    def field_energy(self):
+        return float(D.read_f64(self.stats, 1)[0])
+
+    def download(self):
+        return dict(x=self.x.cpu().numpy(), v=self.v.cpu().numpy(), rho=self.rho.cpu().numpy(),
+                    phi=self.phi.cpu().numpy(), E=self.E.cpu().numpy())
+
+    def check(self):
+        D.check_range(self.range_err, "PIC_L step")

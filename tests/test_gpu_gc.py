@@ -1,0 +1,196 @@
+"""GPU parity of the pygcpic.py path (Particle/Grid on the SoA store) against golden vectors
+produced by executing the reference's classes, and against the oracle."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+from oracle import np_oracle as O
+
+
+def relmax(a, b):
+    a = np.asarray(a, float); b = np.asarray(b, float)
+    return np.max(np.abs(a - b)) / max(np.max(np.abs(b)), 1e-300)
+
+
+def test_particle_kernels_vs_reference_golden(golden):
+    from pypic_b200.gcstore import GridDev, ParticleStore
+    import torch
+    g = golden("gc")
+    B = g["B"]; r0 = g["r0"]; cs = g["cs"].astype(float); ms = g["ms"]
+    grid = GridDev(int(g["ng"]), float(g["Lg"]), 60. * 11600.)
+    assert grid.dx == float(g["dx"])
+    grid.E.copy_(torch.as_tensor(g["grid_E"]))
+    st = ParticleStore.from_arrays(r0, cs, ms, 1.0, B=B, Eyz=g["Eshared"][1:])
+    # mirrored gather (node-aligned positions included): bit-exact
+    assert np.array_equal(st.gather(grid), g["gather"])
+    # Boris push: bit-exact (same operation order, no FMA contraction)
+    hits = st.push_6D(1e-10, grid)
+    assert np.array_equal(st.r_host(), g["r_boris"])
+    exp_hit = (g["r_boris"][:, 0] < 0) | (g["r_boris"][:, 0] > float(g["Lg"]))
+    assert hits == int(exp_hit.sum())
+    assert np.array_equal(st.flags_host()["active"], np.where(exp_hit, 0, 1))
+    # GC transforms / RK4 on the charged particles only (neutrals divide by wc = 0)
+    ch = cs != 0
+    st2 = ParticleStore.from_arrays(g["r_boris"][ch], cs[ch], ms[ch], 1.0, B=B, Eyz=g["Eshared"][1:])
+    st2.transform_6D_to_GC()
+    assert relmax(st2.r_host(), g["r_gc"][ch]) < 1e-15
+    st3 = ParticleStore.from_arrays(g["r_gc"][ch], cs[ch], ms[ch], 1.0, B=B, Eyz=g["Eshared"][1:])
+    # the reference's E[0] is the value gathered BEFORE the Boris push (shared Particle.E);
+    # reproduce by giving the kernel a grid whose gather at the GC position returns it: use
+    # the oracle path for E_x instead -- push with a uniform field per particle is not
+    # expressible, so compare against the oracle evaluated with the kernel's own gather.
+    Ex = st3.gather(grid)
+    Evec = np.stack([Ex, np.full(ch.sum(), g["Eshared"][1]), np.full(ch.sum(), g["Eshared"][2])], 1)
+    ref = O.gc_push_GC(g["r_gc"][ch], Evec, B, cs[ch], ms[ch], 1e-10)
+    st3.push_GC(1e-10, grid)
+    assert relmax(st3.r_host(), ref) < 1e-14
+    st4 = ParticleStore.from_arrays(g["r_gc2"][ch], cs[ch], ms[ch], 1.0, B=B)
+    st4.transform_GC_to_6D(g["a_draws"][ch])
+    assert relmax(st4.r_host(), g["r_back"][ch]) < 1e-13
+    st.check()
+
+
+def test_gc_rk4_reference_vector(golden):
+    """SURVEY.md P5/P6 golden vectors (executed reference): 6D->GC then one RK4 step."""
+    from pypic_b200.gcstore import GridDev, ParticleStore
+    import torch
+    B = np.array([2 * np.cos(86 * np.pi / 180), 2 * np.sin(86 * np.pi / 180), 0.0])
+    r = np.array([[1e-4, 0, 0, 1e4, 2e4, -3e4, 0]])
+    st = ParticleStore.from_arrays(r, 1.0, O.mp, 1.0, B=B)
+    st.transform_6D_to_GC()
+    exp_gc = [1e-4, -1.7473996672903433e-24, 7.16472670814264e-24, 20648.845742637743, 4.0648850826489377e-19, -30000.0, 0]
+    assert relmax(st.r_host()[0], exp_gc) < 1e-15
+    grid = GridDev(11, 1e-3, 1.0)
+    grid.E.fill_(1000.0)                      # uniform E_x = 1000 as in the survey probe
+    st.push_GC(1e-10, grid)
+    exp = [1.0014403906658945e-4, 2.0598546192239223e-6, 4.987820251299122e-8, 20648.845742684232,
+           4.0648850826489377e-19, -30000.0, 1e-10]
+    assert relmax(st.r_host()[0], exp) < 1e-13
+
+
+def test_grid_kernels_vs_reference_golden(golden):
+    from pypic_b200.gcstore import GridDev, ParticleStore
+    from pypic_b200 import ops
+    import torch
+    g = golden("gc")
+    ng = int(g["dep_ng"]); L = float(g["dep_L"]); Te = float(g["dep_Te"]); dt = float(g["dep_dt"])
+    grid = GridDev(ng, L, Te)
+    N = len(g["dep_x"])
+    r = np.zeros((N, 7)); r[:, 0] = g["dep_x"]
+    st = ParticleStore.from_arrays(r, g["dep_cs"].astype(float), O.mp, g["dep_p2c"], active=g["dep_active"])
+    for it in range(3):
+        grid.weight_particles_to_grid_boltzmann(st, dt)
+        assert relmax(grid.rho.cpu().numpy(), g["dep_rho"][it]) < 1e-13
+        assert relmax(grid.n.cpu().numpy(), g["dep_n"][it]) < 1e-13
+        assert abs(grid.n0 - g["dep_n0"][it]) <= 1e-11 * abs(grid.n0)
+        grid.smooth_rho()
+        grid.reset_added_particles()
+        grid.add_particles(float(g["dep_p2c"][0]) * (it + 1))
+        grid.solve_for_phi_dirichlet_boltzmann()
+        phi = grid.phi.cpu().numpy()
+        # the reference's Newton step is bicgstab at default rtol: documented phi tolerance
+        assert np.max(np.abs(phi - g["dep_phi"][it])) < 2e-5 * max(1.0, np.max(np.abs(phi)))
+        # and the exact Newton fixed point agrees with the oracle's exact-step restatement
+        pr, _ = O.gc_solve_for_phi_dirichlet_boltzmann(grid.rho.cpu().numpy(), grid.n0, Te, grid.dx)
+        assert np.max(np.abs(phi - pr)) < 1e-9 * max(1.0, np.max(np.abs(pr)))
+        grid.phi.copy_(torch.as_tensor(g["dep_phi"][it]))       # continue from the reference's phi
+        grid.differentiate_phi_to_E_dirichlet()
+        assert np.array_equal(grid.E.cpu().numpy(), g["dep_E"][it])
+    assert relmax(grid.rho.cpu().numpy(), g["dep_rho_smooth"]) < 1e-13
+    grid.check()
+    # doctest KAT: Grid(5,4.0): rho=1 -> phi=[0,1.5,2,1.5,0]
+    assert np.allclose(ops.poisson_dirichlet(np.ones(5), 1.0), [0, 1.5, 2, 1.5, 0], rtol=0, atol=1e-14)
+    assert relmax(ops.poisson_dirichlet(g["lin_rho"], float(g["lin_dx"])), g["lin_phi"]) < 1e-11
+    # neutral plasma -> phi == 0 (doctests pygcpic.py:1013-1019, 1070-1076)
+    phi, _ = ops.newton_boltzmann(np.ones(5), None, 1.0, 1.0 / O.e, 1.0, 0, 1e-9, 1000)
+    assert np.all(np.abs(phi) < 1e-12)
+    phi, _ = ops.newton_boltzmann(np.ones(5) / O.e * O.epsilon0, np.zeros(5), 1.0, 1.0 / O.e * O.epsilon0, 1.0, 1, 1e-3, 100)
+    assert np.all(np.abs(phi) < 1e-12)
+    # Dirichlet-Neumann Newton on the golden density
+    phi, it = ops.newton_boltzmann(g["dn_n"], np.zeros(ng), float(g["dn_dx"]), float(g["dn_n0"]), Te, 1, 1e-3, 100)
+    assert np.max(np.abs(phi - g["dn_phi"])) < 1e-6 * max(1.0, np.max(np.abs(phi)))
+
+
+def test_decide_rule_and_compaction():
+    from pypic_b200.gcstore import ParticleStore
+    import torch
+    rs = np.random.RandomState(8)
+    N = 100000
+    active_entry = rs.uniform(size=N) > 0.03
+    active_after = active_entry & (rs.uniform(size=N) > 0.02)
+    src_entry = rs.uniform(size=N) > 0.1
+    src_after = src_entry | (rs.uniform(size=N) > 0.95)
+    ce = (active_entry & src_entry); ca = (active_after & src_after)
+    source_N = int(ce.sum()) - 500
+    react, dele = O.gc_particle_loop_decisions(active_entry, active_after, src_entry, src_after, source_N)
+    st = ParticleStore(N)
+    dev = st.dev
+    t8 = lambda a: torch.as_tensor(a.astype(np.int8), device=dev)
+    dec, nr, nd = st.decide(t8(~active_entry), t8(ce), t8(ca), source_N)
+    d = dec.cpu().numpy()
+    assert np.array_equal(d == 1, react) and np.array_equal(d == 2, dele)        # bit-exact decisions
+    assert nr == react.sum() and nd == dele.sum() and nr > 0 and nd > 0
+    # stable compaction: survivors keep their order
+    r = np.zeros((N, 7)); r[:, 0] = np.arange(N)
+    st = ParticleStore.from_arrays(r, 1.0, 1.0, 1.0)
+    removed = st.compact(dec)
+    assert removed == nd and st.N == N - nd
+    assert np.array_equal(st.r_host()[:, 0], np.arange(N)[~dele])
+
+
+def test_mini_driver_vs_reference_golden(golden):
+    """The particle loop of pygcpic.pic_bca_aps (pygcpic.py:1486-1563, without BCA and
+    ionisation) run by the reference's objects vs the SoA store on the GPU: same seed, same
+    legacy-MT19937 draw order, identical integer outcomes per step."""
+    from pypic_b200.gcstore import GridDev, ParticleStore
+    import torch
+    g = golden("gc")
+    Ld = float(g["drv_L"]); ngd = int(g["drv_ng"]); Nd = int(g["drv_N"]); dt = float(g["drv_dt"])
+    p2c = float(g["drv_p2c"]); Ti = float(g["drv_Ti"]); Te = float(g["drv_Te"]); source_N = int(g["drv_source_N"])
+    B = g["B"]
+    np.random.seed(int(g["drv_seed"]))
+    vth = np.sqrt(O.kb * Ti / O.mp)
+    r = np.zeros((Nd, 7))
+    for i in range(Nd):                      # Particle._initialize_6D draw order, pygcpic.py:299-301
+        r[i, 0] = np.random.uniform(0.0, Ld)
+        r[i, 3:6] = np.random.normal(0.0, vth, 3) + 0.
+    assert np.array_equal(r, g["drv_r_init"])
+    grid = GridDev(ngd, Ld, Te)
+    st = ParticleStore.from_arrays(r, 1.0, O.mp, p2c, Z=1, B=B)
+    time = 0.
+    lens, hits, ndel, nreact, n0h, phimax, ek, ang = [], [], [], [], [], [], [], []
+    for step in range(25):
+        time += dt
+        st.apply_BCs_dirichlet(grid)
+        grid.weight_particles_to_grid_boltzmann(st, dt)
+        grid.smooth_rho()
+        grid.reset_added_particles()
+        grid.solve_for_phi_dirichlet_boltzmann()
+        grid.differentiate_phi_to_E_dirichlet()
+        inactive_entry = (st.active[:st.N] != 1).to(torch.int8)
+        ce = st.source_ion_flags(1)[:st.N].contiguous()
+        h = st.push_6D(dt, grid)
+        ke, an, _ = st.wall_hit_tallies()
+        ca = st.source_ion_flags(1)[:st.N].contiguous()
+        dec, nr, nd = st.decide(inactive_entry, ce, ca, source_N)
+        ridx = torch.nonzero(dec[:st.N] == 1).flatten().cpu().numpy()
+        rn = np.zeros((len(ridx), 7))
+        for j in range(len(ridx)):           # source_distribution_6D draw order, pygcpic.py:749-752
+            x = np.random.normal(Ld / 2, Ld / 12.0)
+            x %= Ld
+            rn[j, 0] = x
+            rn[j, 3:6] = np.random.normal(0.0, vth, 3) + 0.
+        st.reactivate(ridx, rn, p2c, O.mp, 1, 1, time, grid)
+        st.compact(dec)
+        lens.append(st.N); hits.append(h); ndel.append(nd); nreact.append(nr)
+        n0h.append(grid.n0); phimax.append(float(grid.phi.max().item())); ek.append(ke); ang.append(an)
+    st.check(); grid.check()
+    assert np.array_equal(lens, g["drv_len"]) and np.array_equal(hits, g["drv_hits"])        # exact integers
+    assert np.array_equal(ndel, g["drv_ndel"]) and np.array_equal(nreact, g["drv_nreact"])
+    assert relmax(n0h, g["drv_n0"]) < 1e-9
+    assert relmax(phimax, g["drv_phimax"]) < 1e-4          # bicgstab tolerance of the reference
+    assert np.array_equal(st.flags_host()["active"], g["drv_active_final"])
+    assert relmax(st.r_host(), g["drv_r_final"]) < 1e-6
+    assert relmax(np.concatenate(ek), g["drv_ekin"]) < 1e-5
+    assert relmax(np.concatenate(ang), g["drv_ang"]) < 1e-5
