@@ -236,6 +236,10 @@ __device__ __forceinline__ bool dd_fast(const FastC& c, const double* __restrict
     // absorbed iff X0 or X1 leaves (0,L): XH lies between them (rounding is monotone)
     rare |= ((unsigned)__double2hiint(X0) - 1u) >= c.hi_Lm1;
     rare |= ((unsigned)__double2hiint(o.X1) - 1u) >= c.hi_Lm1;
+    // a particle absorbed in an EARLIER iteration of this step left either its out-of-domain
+    // position (the iteration it died in) or the reference's 0.0 (later ones) in x1, so the
+    // same range test on the previous x1 finds it without streaming the flag array
+    if (!FIRST) rare |= ((unsigned)__double2hiint(pX1) - 1u) >= c.hi_Lm1;
     const double th = XH * c.idx, fh = floor(th);
     rare |= ((unsigned)__double2hiint(th - fh) - PIC_HI_G) > PIC_HI_SPAN;
     const double rh = fma(-fh, c.dx, XH);
@@ -298,32 +302,32 @@ __global__ void __launch_bounds__(V5_T, 1) dd_picard_iter_v5_k(
     fc.ngm2 = (unsigned)(Ng - 2);
     for (long long ch = blockIdx.x; ch < nchunks; ch += gridDim.x) {
         const long long cstart = ch * V5_CHUNK;
-        // one species per chunk on the fast path; the chunk holding the boundary goes slow
-        const bool straddle = cstart < k.n_split && cstart + V5_CHUNK > k.n_split;
-        const bool sp = cstart >= k.n_split;
-        fc.c1 = sp ? k.c1[1] : k.c1[0]; fc.c2 = sp ? k.c2[1] : k.c2[0];
-        fc.qpi = (sp ? k.q[1] : k.q[0]) * k.p2c * k.idx;
         // warp-contiguous slice of 64*V5_ROWS particles; lane owns the pair (2*lane, 2*lane+1) of each row
         long long i = cstart + (long long)warp * (64 * V5_ROWS) + 2 * lane;
         int wb = NOWIN;
         double2 nX0 = __ldcs((const double2*)(x0 + i)), nU0 = __ldcs((const double2*)(u0 + i));
         double2 nX1 = make_double2(0., 0.);
-        short nAct = 0x0101;
-        if (!FIRST) { nX1 = __ldcs((const double2*)(x1 + i)); nAct = *(const short*)(active + i); }
+        if (!FIRST) nX1 = __ldcs((const double2*)(x1 + i));
 #pragma unroll 1
         for (int row = 0; row < V5_ROWS; ++row) {
             const long long ci = i;
             const double2 X0 = nX0, U0 = nU0, pX1 = nX1;
-            const short act = nAct;
             i += 64;
             if (row + 1 < V5_ROWS) {
                 nX0 = __ldcs((const double2*)(x0 + i)); nU0 = __ldcs((const double2*)(u0 + i));
-                if (!FIRST) { nX1 = __ldcs((const double2*)(x1 + i)); nAct = *(const short*)(active + i); }
+                if (!FIRST) nX1 = __ldcs((const double2*)(x1 + i));
             }
+            // one species per 64-particle row on the fast path (warp-uniform constants); only the
+            // single row that holds the species boundary is redone particle by particle
+            const long long rstart = ci - 2 * lane;
+            const bool sp = rstart >= k.n_split;
+            const bool straddle = !sp && rstart + 64 > k.n_split;
+            fc.c1 = sp ? k.c1[1] : k.c1[0]; fc.c2 = sp ? k.c2[1] : k.c2[0];
+            fc.qpi = (sp ? k.q[1] : k.q[0]) * k.p2c * k.idx;
             FastO a, b;
             bool ra = dd_fast<FIRST>(fc, sF, Ng, X0.x, U0.x, pX1.x, a);
             bool rb = dd_fast<FIRST>(fc, sF, Ng, X0.y, U0.y, pX1.y, b);
-            if (straddle || (!FIRST && act != 0x0101)) { ra = true; rb = true; }
+            if (straddle) { ra = true; rb = true; }
             if (row == 0) {
                 // window base: centre on the mean deposit cell of the warp's first row
                 int nok = __reduce_add_sync(full, (ra ? 0 : 1) + (rb ? 0 : 1));
@@ -335,12 +339,12 @@ __global__ void __launch_bounds__(V5_T, 1) dd_picard_iter_v5_k(
                 __stcs((double2*)(u1 + ci), make_double2(a.U1, b.U1));
             } else {
                 if (ra) {
-                    SlowOut o = dd_particle_slow(k, ci, X0.x, U0.x, pX1.x, (int)(signed char)(act & 0xff), FIRST, sF, tj, x1, u1, active);
+                    SlowOut o = dd_particle_slow(k, ci, X0.x, U0.x, pX1.x, FIRST ? 1 : (int)active[ci], FIRST, sF, tj, x1, u1, active);
                     if (o.code >= 1 && o.code <= 4) atomicAdd(&s_cnt[o.code], 1);
                     if (o.bad) atomicAdd(&s_cnt[0], o.bad);
                 } else { x1[ci] = a.X1; u1[ci] = a.U1; }
                 if (rb) {
-                    SlowOut o = dd_particle_slow(k, ci + 1, X0.y, U0.y, pX1.y, (int)(signed char)(act >> 8), FIRST, sF, tj, x1, u1, active);
+                    SlowOut o = dd_particle_slow(k, ci + 1, X0.y, U0.y, pX1.y, FIRST ? 1 : (int)active[ci + 1], FIRST, sF, tj, x1, u1, active);
                     if (o.code >= 1 && o.code <= 4) atomicAdd(&s_cnt[o.code], 1);
                     if (o.bad) atomicAdd(&s_cnt[0], o.bad);
                 } else { x1[ci + 1] = b.X1; u1[ci + 1] = b.U1; }
