@@ -41,7 +41,7 @@ def parse():
     ap.add_argument("--total-particles", type=float, default=0, help="strong scaling: fixed total (e.g. 1e9)")
     ap.add_argument("--cells", type=int, default=4096)
     ap.add_argument("--sort-every", type=int, default=8)
-    ap.add_argument("--deposit", default="window", choices=["window", "warp", "atomic"])
+    ap.add_argument("--deposit", default="window", choices=["window", "window-ldg", "warp", "atomic"])
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-sample", type=float, default=4e6, help="particles in the CPU-baseline sample")

@@ -100,7 +100,8 @@ typedef struct {
     int32_t flags;    /* 0 (default): register-window deposit over contiguous chunks, tiles in
                          shared memory; bit0: plain shared-memory atomics per particle (the
                          "fast atomicAdd" variant benchmarked alongside); bit2: grid-stride
-                         kernel with warp-uniform pre-reduction; bit1: keep the grid tiles in
+                         kernel with warp-uniform pre-reduction; bit3: the register-prefetch
+                         (non-TMA) build of the window kernel; bit1: keep the grid tiles in
                          global memory (grids too large for shared memory)               */
     double dx, dt, L, p2c;
     double q[2], m[2];
@@ -135,6 +136,9 @@ int pic_dev_dd_picard_iter(const pic_dd_params* p, const double* x0, const doubl
  * on the hot path against the IEEE operations for n pseudo-random / adversarial operands;
  * *mismatches_dev (device uint64, zeroed by the caller) must stay 0. */
 int pic_dev_selftest_div(double b, uint64_t n, uint64_t seed, uint64_t* mismatches_dev, void* stream);
+/* Debug aid: when buf != NULL (device uint64[2*gridDim]) the fused Picard kernels record per-CTA
+ * (start,end) %globaltimer values; pass NULL to switch it off. */
+int pic_dev_debug_cta_timer(uint64_t* buf);
 /* Field phase of the same iteration (PIC_L_DD.py:55-66,516-527), one CTA:
  *   wall_cum fp64[4] += acc[2Ng..2Ng+3]; jh,j1 get wall terms + edge fold;
  *   E1 = E0 + (dt/eps0)(mean(jh) - jh); Eh=(E1+E0)/2; r=|Es-Eh|_2; Es=Eh;

@@ -7,6 +7,10 @@
 
 namespace pic {
 
+// optional per-CTA (start,end) %globaltimer pairs for load-balance studies (tools/kbench.py)
+__device__ unsigned long long* g_cta_timer = nullptr;
+__device__ __forceinline__ unsigned long long gtimer() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
+
 struct DDK {
     long long N, n_split;
     int Ng, flags;
@@ -280,6 +284,8 @@ __global__ void __launch_bounds__(V5_T, 1) dd_picard_iter_v5_k(
     double* __restrict__ acc, int* __restrict__ range_err) {
     extern __shared__ double sm[];
     __shared__ int s_cnt[8];
+    unsigned long long* const tbuf = g_cta_timer;
+    if (tbuf && threadIdx.x == 0) tbuf[2 * blockIdx.x] = gtimer();
     const int Ng = k.Ng;
     double* sF = sm;                 // field tile
     double* tj = sm + Ng;            // fallback tiles jh | j1
@@ -381,6 +387,292 @@ __global__ void __launch_bounds__(V5_T, 1) dd_picard_iter_v5_k(
     if (threadIdx.x >= 1 && threadIdx.x <= 4 && s_cnt[threadIdx.x])
         atomicAdd(&acc[2 * Ng + threadIdx.x - 1], (double)s_cnt[threadIdx.x]);
     if (threadIdx.x == 0 && s_cnt[0] && range_err) atomicAdd(range_err, s_cnt[0]);
+    if (tbuf && threadIdx.x == 0) tbuf[2 * blockIdx.x + 1] = gtimer();
+}
+
+// ---------------------------------------------------------------------------------------
+// v6: the same fast path and private windows as v5, but the particle rows are staged through
+// shared memory by the TMA unit: one elected lane per warp issues 1-D bulk copies
+// (cp.async.bulk global -> shared, completion counted on an mbarrier) into a per-warp ring of
+// V6_NST stages, so V6_NST rows (x0,u0,x1 of 64 particles each) are in flight per warp without
+// holding a single register -- 16 warps x V6_NST x 1.5 KB outstanding per SM, enough to cover
+// the HBM latency at full bandwidth with one 512-thread CTA per SM.  The ring runs continuously
+// across the CTA's chunks (no bubble at chunk boundaries).  The rare-path / out-of-window
+// deposits go straight to the global accumulators (fire-and-forget RED), which frees the
+// shared memory the fallback tiles of v5 used for the ring.
+#define V6_T 512
+#define V6_W 7
+#define V6_ROWS 16
+#ifndef V6_NST
+#define V6_NST 4
+#endif
+#define V6_CHUNK (V6_T * 2 * V6_ROWS)
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+                 "l"(src), "r"(bytes), "r"(bar)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred P1;\n"
+        "LAB_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+        "@P1 bra DONE;\n"
+        "bra LAB_WAIT;\n"
+        "DONE:\n"
+        "}" ::"r"(bar),
+        "r"(parity)
+        : "memory");
+}
+
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n.reg .pred P;\nelect.sync _|P, 0xffffffff;\nselp.u32 %0, 1, 0, P;\n}" : "=r"(pred));
+    return pred != 0;
+}
+
+__device__ __forceinline__ void win_add6(double* myw, double* acc, int wb, int tile, int Ng, int c, double vL, double vR) {
+    const unsigned d = (unsigned)(c - wb);
+    if (d <= (unsigned)(V6_W - 2)) {
+        double* p = myw + (tile * V6_W + d) * V6_T;
+        p[0] += vL; p[V6_T] += vR;
+    } else { atomicAdd(&acc[tile * Ng + c], vL); atomicAdd(&acc[tile * Ng + c + 1], vR); }
+}
+
+// Fast path of one particle, v6 flavour.  Instead of a predicate per rare condition it returns
+// two unsigned "distances" that the caller reduces with 3-input max instructions:
+//   fr : max over the three cell lookups of hi32(frac) - hi32(2^-20); the lookup is exact iff
+//        fr <= PIC_HI_SPAN (then floor(x*idx) is the true floor quotient and the remainder
+//        x - floor*dx is exact and inside [0,dx), so no separate remainder/index test is needed)
+//   ps : max over X0, X1 (and the previous X1) of hi32(X) - 1; all are strictly inside (0,L)
+//        -- hence not absorbed, and every cell index inside the grid -- iff ps < hi32(L) - 1.
+__device__ __forceinline__ double floor_frac_hi(double xs, double idx) { const double t = xs * idx; return t - floor(t); }
+
+struct FastO6 { double X1, U1, hL, hR, fL, fR; int cH, cF; unsigned fr, ps; };
+
+template <bool FIRST>
+__device__ __forceinline__ void dd_fast6(const FastC& c, const double* __restrict__ sF, int Ng, double X0, double U0,
+                                         double pX1, FastO6& o) {
+    const double xs = FIRST ? X0 : (X0 + pX1) * 0.5;
+    const double ts = xs * c.idx, fs = floor(ts);
+    const unsigned f0 = (unsigned)__double2hiint(ts - fs) - PIC_HI_G;
+    const double rs = fma(-fs, c.dx, xs);
+    const int isc = min(max((int)fs, 0), Ng - 2);              // keeps the tile read in bounds for rare particles
+    const double wRs = div_const(rs, c.dx, c.idx), wLs = 1.0 - wRs;
+    const double Ei = wLs * sF[isc] + wRs * sF[isc + 1];
+    o.X1 = X0 + c.dt * U0 + c.c2 * Ei * 0.5;            // PIC_L_DD.py:479
+    o.U1 = U0 + c.c1 * Ei;                               // :481
+    const double XH = (X0 + o.X1) * 0.5, UH = (U0 + o.U1) * 0.5;
+    const unsigned p0 = (unsigned)__double2hiint(X0) - 1u, p1 = (unsigned)__double2hiint(o.X1) - 1u;
+    o.ps = FIRST ? max(p0, p1) : __vimax3_u32(p0, p1, (unsigned)__double2hiint(pX1) - 1u);
+    const double th = XH * c.idx, fh = floor(th);
+    const unsigned f1 = (unsigned)__double2hiint(th - fh) - PIC_HI_G;
+    const double rh = fma(-fh, c.dx, XH);
+    o.cH = (int)fh;
+    const double tf = o.X1 * c.idx, ff = floor(tf);
+    const unsigned f2 = (unsigned)__double2hiint(tf - ff) - PIC_HI_G;
+    const double rf = fma(-ff, c.dx, o.X1);
+    o.cF = (int)ff;
+    o.fr = __vimax3_u32(f0, f1, f2);
+    const double ah = c.qpi * UH, af = c.qpi * o.U1;
+    o.hR = ah * (rh * c.idx); o.hL = ah - o.hR;
+    o.fR = af * (rf * c.idx); o.fL = af - o.fR;
+}
+
+// Non-common cases of one particle, cheapest first: (1) absorbed in an earlier iteration of this
+// step -> the reference's zeros; (2) the gather lookup was exact and the particle sits strictly
+// inside the domain at entry -> the fast-path X1,U1 are the exact values, the walls are tested
+// with the reference's comparisons and a survivor deposits into the window (or the global
+// accumulators); (3) everything else -> dd_particle_slow (IEEE divisions).
+template <bool FIRST>
+__device__ __forceinline__ void dd_medium(const DDK& k, const FastC& fc, long long i, double X0, double U0, double pX1,
+                                          const FastO6& o, int act, bool straddle, bool sp, const double* sF, double* myw,
+                                          int wb, double* __restrict__ acc, int* s_cnt, double* __restrict__ x1,
+                                          double* __restrict__ u1, int8_t* __restrict__ active) {
+    if (!FIRST && act != 1) { x1[i] = 0.0; u1[i] = 0.0; return; }
+    const unsigned f0 = (unsigned)__double2hiint(floor_frac_hi(FIRST ? X0 : (X0 + pX1) * 0.5, fc.idx)) - PIC_HI_G;
+    const unsigned p0 = (unsigned)__double2hiint(X0) - 1u;
+    const unsigned pp = FIRST ? 0u : (unsigned)__double2hiint(pX1) - 1u;
+    if (!straddle && f0 <= PIC_HI_SPAN && p0 < fc.hi_Lm1 && pp < fc.hi_Lm1) {
+        const double XH = (X0 + o.X1) * 0.5;
+        if (X0 >= k.L || XH >= k.L || o.X1 >= k.L) {                    // PIC_L_DD.py:495-499
+            x1[i] = o.X1; u1[i] = o.U1; active[i] = 0; atomicAdd(&s_cnt[sp ? 4 : 3], 1); return;
+        }
+        if (X0 <= 0.0 || XH <= 0.0 || o.X1 <= 0.0) {                     // :500-504
+            x1[i] = o.X1; u1[i] = o.U1; active[i] = -1; atomicAdd(&s_cnt[sp ? 2 : 1], 1); return;
+        }
+        if (o.fr <= PIC_HI_SPAN && o.ps < fc.hi_Lm1) {
+            x1[i] = o.X1; u1[i] = o.U1;
+            win_add6(myw, acc, wb, 0, k.Ng, o.cH, o.hL, o.hR); win_add6(myw, acc, wb, 1, k.Ng, o.cF, o.fL, o.fR);
+            return;
+        }
+    }
+    SlowOut so = dd_particle_slow(k, i, X0, U0, pX1, act, FIRST, sF, acc, x1, u1, active);
+    if (so.code >= 1 && so.code <= 4) atomicAdd(&s_cnt[so.code], 1);
+    if (so.bad) atomicAdd(&s_cnt[0], so.bad);
+}
+
+template <bool FIRST>
+__global__ void __launch_bounds__(V6_T, 1) dd_picard_iter_v6_k(
+    const __grid_constant__ DDK k, int nchunks, const double* __restrict__ x0, const double* __restrict__ u0,
+    double* __restrict__ x1, double* __restrict__ u1, int8_t* __restrict__ active, const double* __restrict__ Es,
+    double* __restrict__ acc, int* __restrict__ range_err) {
+    extern __shared__ __align__(128) double sm[];
+    __shared__ int s_cnt[8];
+    unsigned long long* const tbuf = g_cta_timer;
+    if (tbuf && threadIdx.x == 0) tbuf[2 * blockIdx.x] = gtimer();
+    const int Ng = k.Ng;
+    const int NgP = (Ng + 15) & ~15;                 // keep everything behind the field tile 128-byte aligned
+    double* sF = sm;                                 // field tile
+    double* win = sm + NgP;                          // private windows [2*V6_W][V6_T]
+    double* ring = win + 2 * V6_W * V6_T;            // [warp][stage][x0|u0|x1][64]
+    unsigned long long* bars = (unsigned long long*)(ring + (V6_T / 32) * V6_NST * 192);   // [warp][stage]
+    for (int i = threadIdx.x; i < Ng; i += V6_T) sF[i] = Es[i];
+    double* myw = win + threadIdx.x;
+#pragma unroll
+    for (int n = 0; n < 2 * V6_W; ++n) myw[n * V6_T] = 0.0;
+    if (threadIdx.x < 8) s_cnt[threadIdx.x] = 0;
+    const unsigned full = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    const int wbase = threadIdx.x & ~31;
+    const int NOWIN = -0x40000000;
+    const double* wring = ring + warp * (V6_NST * 192);
+    const uint32_t ring_s = smem_u32(wring);
+    const uint32_t bar_s = smem_u32(bars + warp * V6_NST);
+    if (lane == 0) {
+#pragma unroll
+        for (int s = 0; s < V6_NST; ++s) mbar_init(bar_s + 8 * s, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    FastC fc;
+    fc.dx = k.dx; fc.idx = k.idx; fc.dt = k.dt;
+    fc.hi_dx = 0; fc.ngm2 = 0;
+    fc.hi_Lm1 = (unsigned)__double2hiint(k.L) - 1u;
+    const int my_chunks = (nchunks - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+    const long long woff = (long long)warp * (64 * V6_ROWS);
+    const long long chunk_step = (long long)gridDim.x * V6_CHUNK;
+    const uint32_t row_bytes = FIRST ? 1024u : 1536u;
+    // ---- producer: stateless -- the row requested is always the one V6_NST rows ahead of the row
+    // being consumed and goes into the stage that row just drained, so every quantity is derived
+    // from the consumer's own loop variables (nothing accumulates across iterations) ----
+    auto issue = [&](long long base, int st) {
+        if (elect_one()) {
+            const uint32_t dst = ring_s + st * 1536, bar = bar_s + 8 * st;
+            mbar_expect_tx(bar, row_bytes);
+            bulk_g2s(dst, x0 + base, 512, bar);
+            bulk_g2s(dst + 512, u0 + base, 512, bar);
+            if (!FIRST) bulk_g2s(dst + 1024, x1 + base, 512, bar);
+        }
+    };
+    long long cbase = (long long)blockIdx.x * V6_CHUNK + woff;     // first particle of this warp's slice
+    if (my_chunks > 0) {
+#pragma unroll
+        for (int s = 0; s < V6_NST; ++s) issue(cbase + 64 * s, s);
+    }
+    int stage = 0;
+    uint32_t phase = 0;
+#pragma unroll 1
+    for (int c = 0; c < my_chunks; ++c, cbase += chunk_step) {
+        // species of the slice; a slice holding the species boundary re-selects per row
+        const bool mixed = cbase < k.n_split && cbase + 64 * V6_ROWS > k.n_split;
+        const bool sp_slice = cbase >= k.n_split;
+        fc.c1 = sp_slice ? k.c1[1] : k.c1[0]; fc.c2 = sp_slice ? k.c2[1] : k.c2[0];
+        fc.qpi = (sp_slice ? k.q[1] : k.q[0]) * k.p2c * k.idx;
+        const bool more = c + 1 < my_chunks;
+        int wb = NOWIN;
+        long long ci = cbase + 2 * lane;
+#pragma unroll 1
+        for (int row = 0; row < V6_ROWS; ++row, ci += 64) {
+            mbar_wait(bar_s + 8 * stage, phase);
+            const double* sb = wring + stage * 192 + 2 * lane;
+            const double2 X0 = *(const double2*)sb, U0 = *(const double2*)(sb + 64);
+            double2 pX1 = make_double2(0., 0.);
+            if (!FIRST) pX1 = *(const double2*)(sb + 128);
+            __syncwarp();
+            // refill the stage just drained with the row V6_NST ahead (possibly in the next chunk)
+            if (row < V6_ROWS - V6_NST) issue(cbase + 64 * (row + V6_NST), stage);
+            else if (more) issue(cbase + chunk_step + 64 * (row + V6_NST - V6_ROWS), stage);
+            if (++stage == V6_NST) { stage = 0; phase ^= 1u; }
+            bool straddle = false, sp = sp_slice;
+            if (mixed) {
+                const long long rstart = cbase + 64 * row;
+                sp = rstart >= k.n_split;
+                straddle = !sp && rstart + 64 > k.n_split;
+                fc.c1 = sp ? k.c1[1] : k.c1[0]; fc.c2 = sp ? k.c2[1] : k.c2[0];
+                fc.qpi = (sp ? k.q[1] : k.q[0]) * k.p2c * k.idx;
+            }
+            FastO6 a, b;
+            dd_fast6<FIRST>(fc, sF, Ng, X0.x, U0.x, pX1.x, a);
+            dd_fast6<FIRST>(fc, sF, Ng, X0.y, U0.y, pX1.y, b);
+            const bool ra = (a.fr > PIC_HI_SPAN) | (a.ps >= fc.hi_Lm1) | straddle;
+            const bool rb = (b.fr > PIC_HI_SPAN) | (b.ps >= fc.hi_Lm1) | straddle;
+            if (row == 0) {
+                // window base: centre on the mean deposit cell of the warp's first row
+                int nok = __reduce_add_sync(full, (ra ? 0 : 1) + (rb ? 0 : 1));
+                int sum = __reduce_add_sync(full, (ra ? 0 : a.cH) + (rb ? 0 : b.cH));
+                wb = nok ? sum / nok - (V6_W - 2) / 2 : NOWIN;
+            }
+            const unsigned dah = (unsigned)(a.cH - wb), daf = (unsigned)(a.cF - wb);
+            const unsigned dbh = (unsigned)(b.cH - wb), dbf = (unsigned)(b.cF - wb);
+            const bool inwin = max(__vimax3_u32(dah, daf, dbh), dbf) <= (unsigned)(V6_W - 2);
+            if (!(ra | rb) && inwin) {
+                // the common case: two 128-bit streaming stores and eight conflict-free private RMWs
+                __stcs((double2*)(x1 + ci), make_double2(a.X1, b.X1));
+                __stcs((double2*)(u1 + ci), make_double2(a.U1, b.U1));
+                double* p = myw + dah * V6_T; p[0] += a.hL; p[V6_T] += a.hR;
+                p = myw + (V6_W + daf) * V6_T; p[0] += a.fL; p[V6_T] += a.fR;
+                p = myw + dbh * V6_T; p[0] += b.hL; p[V6_T] += b.hR;
+                p = myw + (V6_W + dbf) * V6_T; p[0] += b.fL; p[V6_T] += b.fR;
+            } else {
+                // one flag load for the pair (ci is even); dead and freshly absorbed particles are
+                // settled here without the IEEE-division path
+                int acta = 1, actb = 1;
+                if (!FIRST) {
+                    const short fl = *(const short*)(active + ci);
+                    acta = (int)(signed char)(fl & 0xff); actb = (int)(signed char)(fl >> 8);
+                }
+                dd_medium<FIRST>(k, fc, ci, X0.x, U0.x, pX1.x, a, acta, straddle, sp, sF, myw, wb, acc, s_cnt, x1, u1, active);
+                dd_medium<FIRST>(k, fc, ci + 1, X0.y, U0.y, pX1.y, b, actb, straddle, sp, sF, myw, wb, acc, s_cnt, x1, u1, active);
+            }
+            __syncwarp();                                         // reconverge before the next row's barrier wait
+        }
+        // column sums of the warp's 32 private windows -> global accumulators
+        __syncwarp();
+        if (wb != NOWIN) {
+            double s = 0.0;
+            const int n = lane >> 1, half = lane & 1;
+            if (lane < 4 * V6_W) {
+                const double* col = win + n * V6_T + wbase + half * 16;
+#pragma unroll
+                for (int j = 0; j < 16; ++j) s += col[(j + n) & 15];
+            }
+            s += __shfl_xor_sync(full, s, 1);
+            if (lane < 4 * V6_W && half == 0) {
+                int node = wb + (n < V6_W ? n : n - V6_W);
+                if (node >= 0 && node < Ng && s != 0.0) atomicAdd(&acc[(n < V6_W ? 0 : Ng) + node], s);
+            }
+            __syncwarp();
+#pragma unroll
+            for (int n2 = 0; n2 < 2 * V6_W; ++n2) myw[n2 * V6_T] = 0.0;
+            __syncwarp();
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x >= 1 && threadIdx.x <= 4 && s_cnt[threadIdx.x])
+        atomicAdd(&acc[2 * Ng + threadIdx.x - 1], (double)s_cnt[threadIdx.x]);
+    if (threadIdx.x == 0 && s_cnt[0] && range_err) atomicAdd(range_err, s_cnt[0]);
+    if (tbuf && threadIdx.x == 0) tbuf[2 * blockIdx.x + 1] = gtimer();
 }
 
 // exhaustive-style self test of div_const / cell_dd_fast against the IEEE operations
@@ -680,6 +972,31 @@ int pic_dev_dd_picard_iter(const pic_dd_params* p, const double* x0, const doubl
     bool tile = !(p->flags & 2) && (size_t)3 * k.Ng * sizeof(double) <= (size_t)max_optin_smem() - 1024;
     bool agg = !(p->flags & 1);
     size_t smem5 = ((size_t)3 * k.Ng + (size_t)2 * V5_W * V5_T) * sizeof(double);
+    const size_t smem6 = ((size_t)((k.Ng + 15) & ~15) + (size_t)2 * V6_W * V6_T + (size_t)(V6_T / 32) * V6_NST * 192 +
+                          (size_t)(V6_T / 32) * V6_NST) * sizeof(double);
+    const bool aligned16 = (((uintptr_t)x0 | (uintptr_t)u0 | (uintptr_t)x1 | (uintptr_t)u1) & 15) == 0;
+    if (!(p->flags & (1 | 2 | 4 | 8)) && aligned16 && smem6 <= (size_t)max_optin_smem() - 512) {
+        // default: TMA-staged private-window kernel, one persistent CTA per SM
+        const long long nchunks = k.N / V6_CHUNK;
+        if (nchunks > 0) {
+            auto kern = first ? dd_picard_iter_v6_k<true> : dd_picard_iter_v6_k<false>;
+            PIC_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem6));
+            long long cap = device_sm_count();
+            int grid = (int)(nchunks < cap ? nchunks : cap);
+            kern<<<grid, V6_T, smem6, st>>>(k, (int)nchunks, x0, u0, x1, u1, active, Es, acc, range_err);
+            PIC_CHECK_LAUNCH();
+        }
+        const long long done = nchunks * V6_CHUNK;
+        if (done < k.N) {
+            DDK t = k;
+            t.N = k.N - done;
+            t.n_split = k.n_split - done < 0 ? 0 : (k.n_split - done > t.N ? t.N : k.n_split - done);
+            int rc = first ? launch_iter<true, true, true>(t, x0 + done, u0 + done, x1 + done, u1 + done, active + done, Es, acc, range_err, st)
+                           : launch_iter<false, true, true>(t, x0 + done, u0 + done, x1 + done, u1 + done, active + done, Es, acc, range_err, st);
+            if (rc) return rc;
+        }
+        return PIC_OK;
+    }
     if (!(p->flags & (1 | 2 | 4)) && smem5 <= (size_t)max_optin_smem() - 512) {
         // default: private-window deposit over contiguous chunks, one persistent CTA per SM;
         // the remainder that does not fill a chunk is done by the generic grid-stride kernel
@@ -712,6 +1029,12 @@ int pic_dev_dd_picard_iter(const pic_dd_params* p, const double* x0, const doubl
         else { if (agg) PIC_DD_DISPATCH(false, false, true); else PIC_DD_DISPATCH(false, false, false); }
     }
 #undef PIC_DD_DISPATCH
+}
+
+int pic_dev_debug_cta_timer(uint64_t* buf) {
+    unsigned long long* b = (unsigned long long*)buf;
+    PIC_CHECK_CUDA(cudaMemcpyToSymbol(g_cta_timer, &b, sizeof(b)));
+    return PIC_OK;
 }
 
 int pic_dev_selftest_div(double b, uint64_t n, uint64_t seed, uint64_t* mismatches_dev, void* stream) {

@@ -43,10 +43,11 @@ class SheathSim:
         self.seed = int(seed)
         self.draws = draws if draws is not None else LegacyDraws()
         self.sort_every = int(sort_every)
-        # deposit: "window" = private-window kernel over contiguous chunks (default),
+        # deposit: "window" = TMA-staged private-window kernel over contiguous chunks (default),
+        # "window-ldg" = the same with register-prefetched loads instead of the TMA ring,
         # "atomic" = one shared-memory atomicAdd per contribution, "warp" = grid-stride kernel
         # with warp-uniform pre-reduction; tiles: "smem" or "global" (grid too large for smem)
-        flags = {"window": 0, "atomic": 1, "warp": 4}[deposit] | (2 if tiles == "global" else 0)
+        flags = {"window": 0, "window-ldg": 8, "atomic": 1, "warp": 4}[deposit] | (2 if tiles == "global" else 0)
         self.params = _lib.DDParams(self.N, self.n_split, self.Ng, flags, self.dx, self.dt, self.L, self.p2c,
                                     (C.c_double * 2)(*self.q), (C.c_double * 2)(*self.m))
         dev = self.dev

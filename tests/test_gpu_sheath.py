@@ -50,7 +50,7 @@ def _one_iter_inputs(N, Ng, seed):
     return dx, L, dt, x0, u0, q, m, E0
 
 
-@pytest.mark.parametrize("deposit", ["window", "warp", "atomic"])
+@pytest.mark.parametrize("deposit", ["window", "window-ldg", "warp", "atomic"])
 @pytest.mark.parametrize("tiles", ["smem", "global"])
 def test_picard_step_bit_exact_particles(deposit, tiles):
     """Same inputs -> identical x1,u1 (bits), identical absorb flags and counts, identical
@@ -99,10 +99,11 @@ def test_single_iteration_kernel_bit_exact():
     tEs = D.to_dev(E0, dev)
     acc = D.f64(2 * Ng + 4, dev, True)
     err = torch.zeros(1, dtype=torch.int32, device=dev)
-    # oracle: two iterations done by hand so that iteration 2 (FIRST=false) is covered too
+    # oracle: three iterations done by hand so that FIRST=false is covered, including particles
+    # absorbed one and two iterations earlier (out-of-domain / zeroed previous x1)
     act = np.ones(N)
     qm = q / m
-    for it in range(2):
+    for it in range(3):
         _lib.call("pic_dev_dd_picard_iter", C.byref(P), D.ptr(tx0), D.ptr(tu0), D.ptr(tx1), D.ptr(tu1), D.ptr(tact),
                   D.ptr(tEs), D.ptr(acc), 1 if it == 0 else 0, D.ptr(err), D.stream())
         a = act == 1
@@ -135,6 +136,38 @@ def test_single_iteration_kernel_bit_exact():
         acc.zero_()
         xh_prev = xh
     assert int(err.item()) == 0
+
+
+@pytest.mark.parametrize("sort", [False, True])
+def test_tma_ring_stress_bit_exact(sort):
+    """Many back-to-back launches of the TMA-staged kernel over 12 chunks, unsorted (every row
+    takes the divergent generic deposit path) and sorted (window fast path): x1,u1 must be
+    bit-identical to the oracle for every particle in every launch (regression test for a
+    stage/row mix-up in the per-warp bulk-copy ring)."""
+    import torch
+    from pypic_b200 import _lib, device as D
+    from pypic_b200.sheath import SheathSim
+    N, Ng = 200000, 257
+    dx, L, dt, x0, u0, q, m, E0 = _one_iter_inputs(N, Ng, 5)
+    p2c = 1e9
+    for trial in range(4):
+        b = SheathSim(N, Ng, dx, dt, p2c, kBT=(1.6e-18, 1.6e-18), carry_vw=False, rng="philox", sort_every=1 if sort else 0)
+        b.upload(x0, u0, E0=E0)
+        if sort:
+            b.sort_by_cell()
+        X0 = b.x0.cpu().numpy(); U0 = b.u0.cpu().numpy()
+        h = N // 2
+        qm = np.concatenate([np.full(h, -O.e / O.me), np.full(N - h, O.e / O.mp)])
+        Ei = O.dd_interpolateField(E0, X0, Ng, dx)
+        x1 = X0 + dt * U0 + dt * dt * qm * Ei * 0.5
+        u1 = U0 + dt * qm * Ei
+        b.Es.copy_(b.E0)
+        for rep in range(5):
+            b.acc.zero_(); b.x1.fill_(-7.0); b.u1.fill_(-7.0)
+            _lib.call("pic_dev_dd_picard_iter", C.byref(b.params), D.ptr(b.x0), D.ptr(b.u0), D.ptr(b.x1), D.ptr(b.u1),
+                      D.ptr(b.active), D.ptr(b.Es), D.ptr(b.acc), 1, D.ptr(b.range_err), D.stream())
+            assert np.array_equal(b.x1.cpu().numpy(), x1), (trial, rep)
+            assert np.array_equal(b.u1.cpu().numpy(), u1), (trial, rep)
 
 
 @pytest.mark.parametrize("tag", ["small", "default"])
