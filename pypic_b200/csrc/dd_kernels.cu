@@ -824,30 +824,47 @@ __device__ __forceinline__ double u52(uint32_t a, uint32_t b) {
     return ((double)v + 0.5) * (1.0 / 4503599627370496.0);
 }
 
+__device__ __forceinline__ void dd_reinject_one(const DDK& k, long long i, double* __restrict__ x0,
+                                                double* __restrict__ u0, double* __restrict__ v0,
+                                                double* __restrict__ w0, int8_t* __restrict__ active, double s0,
+                                                double s1, uint64_t seed, uint64_t step, long long goff) {
+    uint64_t gid = (uint64_t)(goff + i);
+    uint32_t c[4] = {(uint32_t)gid, (uint32_t)(gid >> 32), (uint32_t)step, (uint32_t)(step >> 32)};
+    uint32_t d[4] = {c[0], c[1], c[2], c[3] ^ 0x80000000u};
+    uint32_t g[4] = {c[0], c[1], c[2], c[3] ^ 0x40000000u};
+    philox4x32(c, (uint32_t)seed, (uint32_t)(seed >> 32));
+    philox4x32(d, (uint32_t)seed, (uint32_t)(seed >> 32));
+    philox4x32(g, (uint32_t)seed, (uint32_t)(seed >> 32));
+    const double twopi = 6.283185307179586;
+    double ux = u52(c[0], c[1]);
+    double r1 = sqrt(-2.0 * log(u52(c[2], c[3]))), t1 = twopi * u52(d[0], d[1]);   // Box-Muller
+    double r2 = sqrt(-2.0 * log(u52(d[2], d[3]))), t2 = twopi * u52(g[0], g[1]);
+    double sg = (i >= k.n_split) ? s1 : s0;
+    x0[i] = ux * k.L;
+    u0[i] = sg * r1 * cos(t1);
+    if (v0) v0[i] = sg * r1 * sin(t1);
+    if (w0) w0[i] = sg * r2 * cos(t2);
+    active[i] = 1;
+}
+
+// The flag array is scanned 16 flags per 128-bit load; only the (few) dead slots draw.
 __global__ void dd_reinject_philox_k(DDK k, double* __restrict__ x0, double* __restrict__ u0,
                                      double* __restrict__ v0, double* __restrict__ w0,
                                      int8_t* __restrict__ active, double s0, double s1, uint64_t seed,
                                      uint64_t step, long long goff) {
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < k.N; i += (long long)gridDim.x * blockDim.x) {
-        if (active[i] == 1) continue;
-        uint64_t gid = (uint64_t)(goff + i);
-        uint32_t c[4] = {(uint32_t)gid, (uint32_t)(gid >> 32), (uint32_t)step, (uint32_t)(step >> 32)};
-        uint32_t d[4] = {c[0], c[1], c[2], c[3] ^ 0x80000000u};
-        uint32_t g[4] = {c[0], c[1], c[2], c[3] ^ 0x40000000u};
-        philox4x32(c, (uint32_t)seed, (uint32_t)(seed >> 32));
-        philox4x32(d, (uint32_t)seed, (uint32_t)(seed >> 32));
-        philox4x32(g, (uint32_t)seed, (uint32_t)(seed >> 32));
-        const double twopi = 6.283185307179586;
-        double ux = u52(c[0], c[1]);
-        double r1 = sqrt(-2.0 * log(u52(c[2], c[3]))), t1 = twopi * u52(d[0], d[1]);   // Box-Muller
-        double r2 = sqrt(-2.0 * log(u52(d[2], d[3]))), t2 = twopi * u52(g[0], g[1]);
-        double sg = (i >= k.n_split) ? s1 : s0;
-        x0[i] = ux * k.L;
-        u0[i] = sg * r1 * cos(t1);
-        if (v0) v0[i] = sg * r1 * sin(t1);
-        if (w0) w0[i] = sg * r2 * cos(t2);
-        active[i] = 1;
+    const long long nvec = ((uintptr_t)active & 15) == 0 ? k.N / 16 : 0;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long v = (long long)blockIdx.x * blockDim.x + threadIdx.x; v < nvec; v += stride) {
+        const int4 f = __ldg((const int4*)active + v);
+        if (f.x == 0x01010101 && f.y == 0x01010101 && f.z == 0x01010101 && f.w == 0x01010101) continue;
+        const int w[4] = {f.x, f.y, f.z, f.w};
+#pragma unroll
+        for (int j = 0; j < 16; ++j)
+            if ((signed char)(w[j >> 2] >> (8 * (j & 3))) != 1)
+                dd_reinject_one(k, v * 16 + j, x0, u0, v0, w0, active, s0, s1, seed, step, goff);
     }
+    for (long long i = nvec * 16 + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < k.N; i += stride)
+        if (active[i] != 1) dd_reinject_one(k, i, x0, u0, v0, w0, active, s0, s1, seed, step, goff);
 }
 
 __global__ void sum_sq_k(const double* __restrict__ u, long long N, double scale, double* __restrict__ out) {
@@ -906,35 +923,53 @@ __global__ void dd_sort_scan_k(int32_t* __restrict__ counts, int nk) {
         __syncthreads();
     }
 }
-// scatter: per-CTA chunk, shared-memory ranks, one global reservation per (CTA, key)
-__global__ void __launch_bounds__(1024) dd_sort_scatter_k(DDK k, const double* __restrict__ x0,
-                                                          const double* __restrict__ u0,
-                                                          const double* __restrict__ v0,
-                                                          const double* __restrict__ w0, double* __restrict__ xs,
-                                                          double* __restrict__ us, double* __restrict__ vs,
-                                                          double* __restrict__ ws, int32_t* __restrict__ cursor) {
-    extern __shared__ int sh[];   // [0,nk) local count -> base
+// scatter: each CTA walks chunks of SORT_CHUNK particles; ranks inside a chunk come from
+// shared-memory counters, ONE global reservation per (chunk, key present in the chunk) by the
+// thread that drew rank 0, and the counters touched are reset by the same threads -- the cost
+// per chunk is O(particles), not O(keys) (a nearly sorted store touches a handful of keys).
+#define SORT_T 1024
+#define SORT_PER 4
+__global__ void __launch_bounds__(SORT_T) dd_sort_scatter_k(DDK k, const double* __restrict__ x0,
+                                                            const double* __restrict__ u0,
+                                                            const double* __restrict__ v0,
+                                                            const double* __restrict__ w0, double* __restrict__ xs,
+                                                            double* __restrict__ us, double* __restrict__ vs,
+                                                            double* __restrict__ ws, int32_t* __restrict__ cursor) {
+    extern __shared__ int sh[];   // [0,nk) count of the chunk, [nk,2nk) global base of the chunk's run
     const int nk = 2 * k.Ng;
-    const long long chunk = blockDim.x;
+    int* cnt = sh;
+    int* gbase = sh + nk;
+    for (int i = threadIdx.x; i < nk; i += SORT_T) cnt[i] = 0;
+    __syncthreads();
+    const long long chunk = (long long)SORT_T * SORT_PER;
     for (long long base = (long long)blockIdx.x * chunk; base < k.N; base += (long long)gridDim.x * chunk) {
-        for (int i = threadIdx.x; i < nk; i += blockDim.x) sh[i] = 0;
-        __syncthreads();
-        long long i = base + threadIdx.x;
-        int key = -1, rank = 0;
-        double X = 0.;
-        if (i < k.N) { X = x0[i]; key = dd_sort_key(k, X, i); rank = atomicAdd(&sh[key], 1); }
-        __syncthreads();
-        for (int j = threadIdx.x; j < nk; j += blockDim.x) {
-            int cnt = sh[j];
-            if (cnt) sh[j] = atomicAdd(&cursor[j], cnt);
+        int key[SORT_PER], rank[SORT_PER];
+        double X[SORT_PER];
+#pragma unroll
+        for (int j = 0; j < SORT_PER; ++j) {
+            const long long i = base + (long long)j * SORT_T + threadIdx.x;
+            key[j] = -1; rank[j] = 0; X[j] = 0.;
+            if (i < k.N) { X[j] = x0[i]; key[j] = dd_sort_key(k, X[j], i); rank[j] = atomicAdd(&cnt[key[j]], 1); }
         }
         __syncthreads();
-        if (i < k.N) {
-            long long pos = (long long)sh[key] + rank;
-            xs[pos] = X; us[pos] = u0[i];
-            if (vs) vs[pos] = v0[i];
-            if (ws) ws[pos] = w0[i];
+#pragma unroll
+        for (int j = 0; j < SORT_PER; ++j)
+            if (key[j] >= 0 && rank[j] == 0) gbase[key[j]] = atomicAdd(&cursor[key[j]], cnt[key[j]]);
+        __syncthreads();
+#pragma unroll
+        for (int j = 0; j < SORT_PER; ++j) {
+            const long long i = base + (long long)j * SORT_T + threadIdx.x;
+            if (key[j] >= 0) {
+                const long long pos = (long long)gbase[key[j]] + rank[j];
+                xs[pos] = X[j]; us[pos] = u0[i];
+                if (vs) vs[pos] = v0[i];
+                if (ws) ws[pos] = w0[i];
+            }
         }
+        __syncthreads();
+#pragma unroll
+        for (int j = 0; j < SORT_PER; ++j)
+            if (key[j] >= 0 && rank[j] == 0) cnt[key[j]] = 0;
         __syncthreads();
     }
 }
@@ -946,6 +981,8 @@ using namespace pic;
 template <bool FIRST, bool TILE, bool AGG>
 static int launch_iter(const DDK& k, const double* x0, const double* u0, double* x1, double* u1, int8_t* active,
                        const double* Es, double* acc, int* range_err, cudaStream_t st) {
+    // a short tail is cheaper with the grids left in L2 than with 3*Ng doubles staged per CTA
+    if (TILE && k.N < 16 * (long long)k.Ng) return launch_iter<FIRST, false, AGG>(k, x0, u0, x1, u1, active, Es, acc, range_err, st);
     size_t smem = TILE ? (size_t)3 * k.Ng * sizeof(double) : 0;
     auto kern = dd_picard_iter_k<FIRST, TILE, AGG>;
     int per_sm = 8;
@@ -1107,7 +1144,7 @@ int pic_dev_dd_reinject_philox(const pic_dd_params* p, double* x0, double* u0, d
     PIC_REQUIRE(p && x0 && u0 && active && sigma, "dd_reinject_philox: null pointer");
     if (p->N == 0) return PIC_OK;
     DDK k = make_ddk(p);
-    dd_reinject_philox_k<<<grid_for(k.N, 256, 8), 256, 0, (cudaStream_t)stream>>>(k, x0, u0, v0, w0, active, sigma[0],
+    dd_reinject_philox_k<<<grid_for((k.N + 15) / 16, 256, 8), 256, 0, (cudaStream_t)stream>>>(k, x0, u0, v0, w0, active, sigma[0],
                                                                                 sigma[1], seed, step, global_offset);
     PIC_CHECK_LAUNCH();
     return PIC_OK;
@@ -1132,16 +1169,17 @@ int pic_dev_dd_sort_by_cell(const pic_dd_params* p, const double* x0, const doub
     cudaStream_t st = (cudaStream_t)stream;
     const int nk = 2 * k.Ng;
     size_t smem = (size_t)nk * sizeof(int);
-    PIC_REQUIRE(smem <= (size_t)max_optin_smem() - 1024, "dd_sort_by_cell: grid too large for the shared-memory histogram");
+    const size_t smem_sc = 2 * smem;
+    PIC_REQUIRE(smem_sc <= (size_t)max_optin_smem() - 1024, "dd_sort_by_cell: grid too large for the shared-memory histogram");
     PIC_CHECK_CUDA(cudaMemsetAsync(counts, 0, (size_t)(nk + 2) * sizeof(int32_t), st));
     if (k.N == 0) return PIC_OK;
     PIC_CHECK_CUDA(cudaFuncSetAttribute(dd_sort_hist_k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    PIC_CHECK_CUDA(cudaFuncSetAttribute(dd_sort_scatter_k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    PIC_CHECK_CUDA(cudaFuncSetAttribute(dd_sort_scatter_k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_sc));
     dd_sort_hist_k<<<grid_for(k.N, 1024, 2), 1024, smem, st>>>(k, x0, counts);
     PIC_CHECK_LAUNCH();
     dd_sort_scan_k<<<1, 1024, 0, st>>>(counts, nk);
     PIC_CHECK_LAUNCH();
-    dd_sort_scatter_k<<<grid_for(k.N, 1024, 2), 1024, smem, st>>>(k, x0, u0, v0, w0, x0s, u0s, v0s, w0s, counts);
+    dd_sort_scatter_k<<<grid_for((k.N + SORT_PER - 1) / SORT_PER, SORT_T, 2), SORT_T, smem_sc, st>>>(k, x0, u0, v0, w0, x0s, u0s, v0s, w0s, counts);
     PIC_CHECK_LAUNCH();
     return PIC_OK;
 }
