@@ -219,7 +219,9 @@ int pic_dev_l_weight(const double* x, const double* q, const double* v, double* 
                      double dx, double p2c, int* range_err, void* stream);
 /* Fused explicit step, particle phase (PIC_L.py:767-768 + next step's :763):
  * gather E at x, kick-drift-kick, wrap x%(L+dx), and deposit rho of the NEW positions
- * into rho_acc fp64[Ng+1] (zero on entry, raw CIC; fold applied by pic_dev_l_field_solve). */
+ * into rho_acc fp64[Ng+1] (zero on entry, raw CIC; fold applied by pic_dev_l_field_solve).
+ * flags bit0: plain shared-memory atomics; bit1: function-level PIC_L.pushParticlesExplicit
+ * :248-259 -- x,v receive the UNWRAPPED xout,vout and nothing is deposited. */
 int pic_dev_l_push_deposit(const pic_l_params* p, double* x, double* v, const double* E,
                            double* rho_acc, int* range_err, void* stream);
 /* PIC_L.py:763-766 field phase: fold rho_acc -> rho; periodic Poisson; -max; E=-dphi/dx.
@@ -234,7 +236,9 @@ int pic_dev_l_field_solve(const pic_l_params* p, double* rho_acc, double* rho, d
 typedef struct {
     int64_t N;
     int32_t ng;     /* grid nodes */
-    int32_t flags;
+    int32_t flags;  /* bit0: the Egrid argument of push_boris / push_rk4 holds one already-gathered
+                       E_x per particle (function-level Particle.push_6D / push_GC); bit1: push_boris
+                       applies no boundary test */
     double dx, dt, length;
     double B[3];
     double Eyz[2];  /* the shared E[1],E[2] of Particle.E (only E[0] is ever gathered) */

@@ -1,0 +1,406 @@
+"""Drop-in replacement for the hot path of the reference's pygcpic.py: the ``Particle`` and
+``Grid`` classes (same constructor arguments, attributes and method names), the particle
+source generators, and a device-resident time loop.  Every numerical method -- gather, Boris
+push, 6D<->guiding-centre transforms, GC RK4, boundary tests, CIC deposit with the
+Boltzmann-electron reference density, smoothing, the linear and Newton-Boltzmann Poisson
+solves, E = -grad(phi) -- executes as a hand-written sm_100a CUDA kernel of libpic_b200.so
+(through pypic_b200).  There is no CPU fallback.
+
+Two ways to use it:
+
+* ``Particle`` / ``Grid`` objects exactly like the reference (one object per particle, NumPy
+  attributes).  Each numerical method call stages its operands to the GPU and back, so the
+  reference's doctests and object-level drivers run unchanged.  ``Grid`` methods that take a
+  list of particles stage the whole list as structure-of-arrays in ONE upload.
+* ``ParticleStore`` / ``GridDev`` (re-exported from pypic_b200.gcstore) keep the particles
+  resident in HBM as structure-of-arrays; ``run_sheath`` is the per-timestep loop of
+  pic_bca_aps (pygcpic.py:1486-1563) on that store.
+
+Out of scope: the F-TRIDYN (BCA) coupling, IEAD histograms,
+Monte-Carlo ionisation and the plotting drivers ``pic_iead`` / ``pic_bca_aps`` / ``pic_bca``.
+"""
+import numpy as np
+import torch
+
+from pypic_b200 import ops, device as _D
+from pypic_b200.gcstore import GridDev, ParticleStore  # noqa: F401  (device-resident API)
+
+# physical constants (pygcpic.py:13-17)
+epsilon0 = 8.854e-12
+e = 1.602e-19
+mp = 1.67e-27
+me = 9.11e-31
+kb = 1.38e-23
+
+
+def gaussian_distribution(x, mu, sigma):
+    """pygcpic.py:31-32."""
+    return 1. / np.sqrt(2. * np.pi * sigma * sigma) * np.exp(-(x - mu)**2 / (2. * sigma**2))
+
+
+def weighted_gaussian(x, mu, sigma):
+    """pygcpic.py:757-758."""
+    return gaussian_distribution(x, mu, sigma) * np.abs(x)
+
+
+def _store_of(particles, B=None):
+    """Stages a list of Particle objects as a structure-of-arrays ParticleStore (one upload)."""
+    n = len(particles)
+    r = np.empty((n, 7))
+    cs = np.empty(n); m = np.empty(n); p2c = np.empty(n); act = np.empty(n, dtype=np.int8)
+    for i, p in enumerate(particles):
+        r[i] = p.r; cs[i] = p.charge_state; m[i] = p.m; p2c[i] = p.p2c; act[i] = p.active
+    if B is None:
+        B = particles[0].B if n else np.zeros(3)
+    return ParticleStore.from_arrays(r, cs, m, p2c, active=act, B=tuple(float(b) for b in B))
+
+
+class Particle:
+    """pygcpic.Particle (pygcpic.py:70-720): host-side object, device-side arithmetic."""
+
+    def __init__(self, m, charge_state, p2c, T, Z, B0=np.zeros(3), E0=np.zeros(3), grid=None, vx=0.):
+        self.r = np.zeros(7)
+        self.charge_state = charge_state
+        self.Z = Z
+        self.m = m
+        self.T = T
+        self.p2c = p2c
+        self.vth = np.sqrt(kb * self.T / self.m)
+        self.mode = 0          # 0: 6D, 1: guiding centre
+        self.E = E0            # NOTE: like the reference, the default array is shared by all instances
+        self.B = B0
+        self.active = 1
+        self.at_wall = 0
+        self.from_wall = 0
+        if grid is not None:
+            self._initialize_6D(grid, vx=vx)
+
+    def __repr__(self):
+        return f'Particle({self.m}, {self.charge_state}, {self.p2c}, {self.T}, {self.Z})'
+
+    def is_active(self):
+        return self.active == 1
+
+    # -- trivial accessors (host) --------------------------------------------------------
+    @property
+    def speed(self):
+        return np.sqrt(self.r[3]**2 + self.r[4]**2 + self.r[5]**2)
+
+    @speed.setter
+    def speed(self, speed):
+        u = self.v / np.linalg.norm(self.v)
+        self.v = u * speed
+
+    @property
+    def x(self):
+        return self.r[0]
+
+    @x.setter
+    def x(self, x0):
+        self.r[0] = x0
+
+    @property
+    def y(self):
+        return self.r[1]
+
+    @property
+    def z(self):
+        return self.r[2]
+
+    @property
+    def v_x(self):
+        return self.r[3]
+
+    @v_x.setter
+    def v_x(self, v_x):
+        self.r[3] = v_x
+
+    @property
+    def v(self):
+        return self.r[3:6]
+
+    @v.setter
+    def v(self, v0):
+        self.r[3:6] = v0
+
+    def get_angle_wrt_wall(self, use_degrees=True):
+        """pygcpic.py:228-259."""
+        v = self.r[3:6]
+        alpha = np.arctan2(np.sqrt(v[1]**2 + v[2]**2), np.abs(v[0]))
+        return alpha * 180. / np.pi if use_degrees else alpha
+
+    @property
+    def kinetic_energy(self):
+        return 0.5 * self.m * self.speed**2
+
+    def _initialize_6D(self, grid, vx=0.):
+        """pygcpic.py:277-304: draw order uniform(x) then normal x3 from the global legacy stream."""
+        self.r[0] = np.random.uniform(0.0, grid.length)
+        self.r[1:3] = 0.0
+        self.r[3:6] = np.random.normal(0.0, self.vth, 3) + vx
+        self.r[6] = 0.0
+
+    def set_x_direction(self, direction):
+        """pygcpic.py:306-323."""
+        if not isinstance(direction, str):
+            raise TypeError('particle.set_x_direction(direction) received a non-string type for direction')
+        if direction.lower() == 'left':
+            self.r[3] = -abs(self.r[3])
+        elif direction.lower() == 'right':
+            self.r[3] = abs(self.r[3])
+        else:
+            raise ValueError('particle.set_x_direction() received neither right nor left')
+
+    # -- device arithmetic -----------------------------------------------------------------
+    def _dev(self):
+        return ParticleStore.from_arrays(self.r[None, :], self.charge_state, self.m, self.p2c, active=[1],
+                                         B=tuple(float(b) for b in self.B), Eyz=(float(self.E[1]), float(self.E[2])))
+
+    def interpolate_electric_field_dirichlet(self, grid):
+        """pygcpic.py:325-348 (mirrored weights; writes E[0] of the -- possibly shared -- E array)."""
+        self.E[0] = ops.gc_interpolate(grid.E, self.r[0], grid.ng, grid.dx)[0]
+
+    def push_6D(self, dt):
+        """pygcpic.py:460-507: Boris push in the particle's E, B."""
+        s = self._dev()
+        s.push_6D_given_E(dt, _D.to_dev(np.array([float(self.E[0])]), s.dev))
+        self.r[:] = s.r_host()[0]
+
+    def transform_6D_to_GC(self):
+        """pygcpic.py:509-551."""
+        s = self._dev()
+        s.transform_6D_to_GC()
+        self.r[:] = s.r_host()[0]
+        self.mode = 1
+
+    def transform_GC_to_6D(self):
+        """pygcpic.py:553-596: the gyro-phase vector a = uniform(0,1,3) comes from the global
+        legacy stream, like the reference."""
+        a = np.random.uniform(0.0, 1.0, 3)
+        s = self._dev()
+        s.transform_GC_to_6D(a[None, :])
+        self.r[:] = s.r_host()[0]
+        self.mode = 0
+
+    def push_GC(self, dt):
+        """pygcpic.py:598-645: RK4 of the guiding-centre equations, E and B frozen over the step."""
+        s = self._dev()
+        s.push_GC_given_E(dt, _D.to_dev(np.array([float(self.E[0])]), s.dev))
+        self.r[:] = s.r_host()[0]
+
+    def apply_BCs_periodic(self, grid):
+        """pygcpic.py:647-666."""
+        from pypic_b200 import _lib
+        t = _D.to_dev(np.array([float(self.r[0])]), _D.require_cuda())
+        _lib.call("pic_dev_wrap_periodic", _D.ptr(t), 1, float(grid.length), _D.stream())
+        self.r[0] = t.cpu().numpy()[0]
+
+    def apply_BCs_dirichlet(self, grid):
+        """pygcpic.py:668-689."""
+        from pypic_b200 import _lib
+        dev = _D.require_cuda()
+        x = _D.to_dev(np.array([float(self.r[0])]), dev)
+        a = torch.tensor([int(self.active)], dtype=torch.int8, device=dev)
+        w = torch.tensor([int(self.at_wall)], dtype=torch.int8, device=dev)
+        _lib.call("pic_dev_gc_apply_bcs", _D.ptr(x), _D.ptr(a), _D.ptr(w), 1, float(grid.length), _D.stream())
+        self.active = int(a.item()); self.at_wall = int(w.item())
+
+    def reactivate(self, distribution, grid, time, p2c, m, charge_state, Z):
+        """pygcpic.py:691-720."""
+        self.r = next(distribution)
+        self.p2c = p2c
+        self.m = m
+        self.charge_state = charge_state
+        self.Z = Z
+        self.r[6] = time
+        self.active = 1
+        self.at_wall = 0
+        self.from_wall = 0
+        grid.add_particles(p2c)
+
+    def attempt_first_ionization(self, *a, **k):
+        raise NotImplementedError("Monte-Carlo ionisation (pygcpic.py:350-458) is a 'next' row (SURVEY.md 8f N3), not built yet")
+
+    attempt_nth_ionization = attempt_first_ionization
+
+
+def source_distribution_6D(grid, Ti, mass, vx=0.):
+    """pygcpic.py:723-755 (host generator on the global legacy stream)."""
+    while True:
+        vth = np.sqrt(kb * Ti / mass)
+        r = np.empty(7)
+        r[0] = np.random.normal(grid.length / 2, grid.length / 12.0)
+        r[0] %= grid.length
+        r[1:3] = 0.
+        r[3:6] = np.random.normal(0.0, vth, 3) + vx
+        yield r
+
+
+def flux_distribution_6D(grid, Ti, mass, vx=0., gamma=0., vx_pert=0.):
+    """pygcpic.py:760-778."""
+    while True:
+        vth = np.sqrt(kb * Ti / mass)
+        r = np.empty(7)
+        r[0] = grid.length - grid.dx * np.random.uniform(0., 1.)
+        r[1:3] = 0.
+        r[3:6] = np.random.normal(0.0, vth, 3)
+        vels = np.linspace(-6 * vth, 6 * vth, 100)
+        dist = np.array([weighted_gaussian(vel, vx, vth) for vel in vels])
+        dist /= np.sum(dist)
+        r[3] = -np.abs(np.random.choice(vels, p=dist)) + np.random.uniform(-1, 1) * (vels[1] - vels[0]) / 2.
+        r[3] += vx
+        if np.random.uniform(0, 1) < gamma:
+            r[3] = vx_pert * vth
+        yield r
+
+
+class Grid:
+    """pygcpic.Grid (pygcpic.py:780-1117) with NumPy attributes; every method runs on the GPU."""
+
+    def __init__(self, ng, length, Te, bc='dirichlet-dirichlet'):
+        self.ng = ng
+        assert self.ng > 1, 'Number of grid points must be greater than 1'
+        self.length = length
+        assert self.length > 0.0, 'Length must be greater than 0'
+        self.domain = np.linspace(0.0, length, ng)
+        self.dx = self.domain[1] - self.domain[0]
+        self.rho = np.zeros(ng)
+        self.phi = np.zeros(ng)
+        self.E = np.zeros(ng)
+        self.n = np.zeros(ng)
+        self.n0 = None
+        self.rho0 = None
+        self.Te = Te
+        self.ve = np.sqrt(8. / np.pi * kb * self.Te / me)
+        self.added_particles = 0
+        self.bc = bc
+        if bc == 'dirichlet-dirichlet':
+            self._fill_laplacian_dirichlet()
+        elif bc == 'dirichlet-neumann':
+            self._fill_laplacian_dirichlet_neumann()
+            print(self.A)
+        elif not isinstance(bc, str):
+            raise TypeError('bc must be a string')
+        else:
+            raise ValueError('Unimplemented boundary condition. Choose dirichlet_dirichlet or dirichlet_neumann')
+
+    def __repr__(self):
+        return f'Grid({self.ng}, {self.length}, {self.Te})'
+
+    def __len__(self):
+        return int(self.ng)
+
+    def copy(self):
+        return Grid(self.ng, self.length, self.Te)
+
+    # the matrices are kept for API compatibility (attribute A); the solves use the PCR kernel
+    def _fill_laplacian_dirichlet(self):
+        """pygcpic.py:939-956."""
+        ng = self.ng
+        self.A = np.zeros((ng, ng))
+        for i in range(1, ng - 1):
+            self.A[i, i - 1] = 1.0
+            self.A[i, i] = -2.0
+            self.A[i, i + 1] = 1.0
+        self.A[0, 0] = 1.
+        self.A[-1, -1] = 1.
+
+    def _fill_laplacian_dirichlet_neumann(self):
+        """pygcpic.py:958-978."""
+        self._fill_laplacian_dirichlet()
+        self.A[-1, -1] = 3.
+        self.A[-1, -2] = -4.
+        self.A[-1, -3] = 1.
+
+    def weight_particles_to_grid_boltzmann(self, particles, dt):
+        """pygcpic.py:841-905.  `particles` is a list of Particle objects (staged as
+        structure-of-arrays in one upload) or a ParticleStore already on the device."""
+        from pypic_b200 import _lib
+        dev = _D.require_cuda()
+        if isinstance(particles, ParticleStore):
+            st = particles
+            x, cs, p2c, act = st.r[0], st.charge_state, st.p2c, st.active
+            N = st.N
+        else:
+            N = len(particles)
+            x = _D.to_dev(np.array([p.r[0] for p in particles], dtype=np.float64), dev)
+            cs = _D.to_dev(np.array([p.charge_state for p in particles], dtype=np.float64), dev)
+            p2c = _D.to_dev(np.array([p.p2c for p in particles], dtype=np.float64), dev)
+            act = _D.to_dev(np.array([p.active for p in particles], dtype=np.int8), dev, torch.int8)
+        rho = _D.f64(self.ng, dev, True); n = _D.f64(self.ng, dev, True)
+        err = torch.zeros(1, dtype=torch.int32, device=dev)
+        s = _D.stream()
+        _lib.call("pic_dev_gc_weight", _D.ptr(x), _D.ptr(cs), _D.ptr(p2c), _D.ptr(act), _D.ptr(rho), _D.ptr(n), N,
+                  int(self.ng), float(self.dx), _D.ptr(err), s)
+        _D.check_range(err, "Grid.weight_particles_to_grid_boltzmann")
+        state = _D.to_dev(np.array([0. if self.n0 is None else self.n0, getattr(self, "p_old", 0.0),
+                                    0. if self.n0 is None else 1.]), dev)
+        _lib.call("pic_dev_gc_n0_update", _D.ptr(_D.to_dev(self.phi, dev)), _D.ptr(n), _D.ptr(_D.to_dev(self.domain, dev)),
+                  int(self.ng), float(self.Te), float(self.ve), float(self.added_particles), float(dt), _D.ptr(state), s)
+        self.rho = rho.cpu().numpy(); self.n = n.cpu().numpy()
+        st3 = state.cpu().numpy()
+        self.n0 = float(st3[0]); self.p_old = float(st3[1]); self.rho0 = self.n0 * e
+
+    def differentiate_phi_to_E_dirichlet(self):
+        """pygcpic.py:907-937."""
+        self.E = ops.differentiate(self.phi, self.dx, 3)
+
+    def solve_for_phi_dirichlet(self):
+        """pygcpic.py:987-1003."""
+        self.phi = ops.poisson_dirichlet(self.rho, self.dx)
+
+    def solve_for_phi_dirichlet_boltzmann(self):
+        """pygcpic.py:1005-1053 (exact tridiagonal Newton step instead of bicgstab: same fixed point)."""
+        self.phi, self.newton_iterations = ops.newton_boltzmann(self.rho, None, self.dx, self.n0, self.Te, 0, 1e-9, 1000)
+
+    def smooth_rho(self):
+        """pygcpic.py:1055-1060."""
+        self.rho = ops.smooth(self.rho, 1)
+
+    def solve_for_phi_dirichlet_neumann_boltzmann(self):
+        """pygcpic.py:1062-1109."""
+        self.phi, self.newton_iterations = ops.newton_boltzmann(self.n, self.phi, self.dx, self.n0, self.Te, 1, 1e-3, 100)
+
+    def reset_added_particles(self):
+        self.added_particles = 0
+
+    def add_particles(self, particles):
+        """pygcpic.py:1115-1117."""
+        self.added_particles += 2 * particles
+
+
+def run_sheath(grid, store, dt, steps, source_N, source, p2c, m, charge_state=1, Z=1, time=0.0, on_step=None):
+    """Device-resident time loop with the structure of pic_bca_aps' particle phase
+    (pygcpic.py:1486-1563, without the BCA coupling and ionisation):
+
+        apply_BCs -> deposit (+Boltzmann n0) -> smooth -> Newton-Boltzmann solve -> E ->
+        [gather + Boris + BC fused] -> reactivate-or-delete decision (prefix scan) ->
+        re-activation from `source` (host generator, legacy RNG order) -> stable compaction.
+
+    grid: GridDev, store: ParticleStore.  Returns a dict of per-step tallies."""
+    out = dict(length=[], hits=[], deleted=[], reactivated=[], n0=[], ekin=[], angle=[])
+    for _ in range(int(steps)):
+        time += dt
+        store.apply_BCs_dirichlet(grid)
+        grid.weight_particles_to_grid_boltzmann(store, dt)
+        grid.smooth_rho()
+        grid.reset_added_particles()
+        grid.solve_for_phi_dirichlet_boltzmann()
+        grid.differentiate_phi_to_E_dirichlet()
+        inactive_entry = (store.active != 1).to(torch.int8)
+        contrib_entry = store.source_ion_flags(Z)
+        hits = store.push_6D(dt, grid)
+        ke, ang, _ = store.wall_hit_tallies()
+        contrib_after = store.source_ion_flags(Z)
+        dec, n_react, n_del = store.decide(inactive_entry, contrib_entry, contrib_after, source_N)
+        if n_react:
+            idx = torch.nonzero(dec[:store.N] == 1).flatten().cpu().numpy()
+            r_new = np.array([next(source) for _ in idx])
+            store.reactivate(idx, r_new, p2c, m, charge_state, Z, time, grid)
+        store.compact(dec)
+        out["length"].append(store.N); out["hits"].append(hits); out["deleted"].append(n_del)
+        out["reactivated"].append(n_react); out["n0"].append(grid.n0); out["ekin"].append(ke); out["angle"].append(ang)
+        if on_step is not None:
+            on_step(grid, store)
+    store.check(); grid.check()
+    return out

@@ -77,7 +77,9 @@ __global__ void __launch_bounds__(256) gc_push_boris_k(GCK k, R7 r, const double
                                                        long long* __restrict__ hit_count, int* __restrict__ range_err) {
     extern __shared__ double sE[];
     const double* E = Egrid;
-    if (k.flags & 4) {   // field tile in shared memory
+    const bool pre = k.flags & 1;       // Egrid holds one already-gathered E_x per particle (Particle.push_6D alone)
+    const bool nobc = k.flags & 2;      // no boundary test (Particle.push_6D alone)
+    if ((k.flags & 4) && !pre) {   // field tile in shared memory
         for (int i = threadIdx.x; i < k.ng; i += blockDim.x) sE[i] = Egrid[i];
         __syncthreads();
         E = sE;
@@ -87,7 +89,7 @@ __global__ void __launch_bounds__(256) gc_push_boris_k(GCK k, R7 r, const double
         if (active[i] != 1) { if (hit_flag) hit_flag[i] = 0; continue; }
         double x = ld_stream(r.r[0] + i), y = ld_stream(r.r[1] + i), z = ld_stream(r.r[2] + i);
         double vx = ld_stream(r.r[3] + i), vy = ld_stream(r.r[4] + i), vz = ld_stream(r.r[5] + i);
-        double Ex = gather_mirrored(E, x, k.dx, k.ng, bad);
+        double Ex = pre ? Egrid[i] : gather_mirrored(E, x, k.dx, k.ng, bad);
         double constant = 0.5 * k.dt * cs[i] * 1.602e-19 / m[i];
         vx += constant * Ex;
         double tx = constant * k.B[0], ty = constant * k.B[1], tz = constant * k.B[2];
@@ -104,7 +106,7 @@ __global__ void __launch_bounds__(256) gc_push_boris_k(GCK k, R7 r, const double
         st_stream(r.r[0] + i, x); st_stream(r.r[1] + i, y); st_stream(r.r[2] + i, z);
         st_stream(r.r[3] + i, vx); st_stream(r.r[4] + i, vy); st_stream(r.r[5] + i, vz);
         r.r[6][i] = r.r[6][i] + k.dt;
-        bool hit = (x < 0.0) || (x > k.length);
+        bool hit = !nobc && ((x < 0.0) || (x > k.length));
         if (hit) { active[i] = 0; at_wall[i] = 1; ++hits; }
         if (hit_flag) hit_flag[i] = hit ? 1 : 0;
     }
@@ -200,7 +202,7 @@ __global__ void gc_push_rk4_k(GCK k, R7 r, const double* __restrict__ cs, const 
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < k.N; i += (long long)gridDim.x * blockDim.x) {
         if (active[i] != 1) continue;
         double r0 = r.r[0][i], r1 = r.r[1][i], r2 = r.r[2][i], r3 = r.r[3][i];
-        double E0 = Egrid ? gather_mirrored(Egrid, r0, k.dx, k.ng, bad) : 0.0;
+        double E0 = Egrid ? ((k.flags & 1) ? Egrid[i] : gather_mirrored(Egrid, r0, k.dx, k.ng, bad)) : 0.0;
         double E1 = k.Eyz[0], E2 = k.Eyz[1];
         double wc = fabs(cs[i]) * PIC_E * sB / m[i];
         const double dt = k.dt;
@@ -468,7 +470,7 @@ int pic_dev_gc_push_boris(const pic_gc_params* p, double* const r[7], const doub
     R7 rr;
     for (int i = 0; i < 7; ++i) { PIC_REQUIRE(r[i], "gc_push_boris: null component array"); rr.r[i] = r[i]; }
     size_t smem = (size_t)k.ng * sizeof(double);
-    if (smem <= (size_t)max_optin_smem() - 1024) k.flags |= 4; else { k.flags &= ~4; smem = 0; }
+    if (!(k.flags & 1) && smem <= (size_t)max_optin_smem() - 1024) k.flags |= 4; else { k.flags &= ~4; smem = 0; }
     PIC_CHECK_CUDA(cudaFuncSetAttribute(gc_push_boris_k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(smem ? smem : 1)));
     gc_push_boris_k<<<grid_for(k.N, 256, 6), 256, smem, (cudaStream_t)stream>>>(k, rr, charge_state, m, active, at_wall,
                                                                                  hit_flag, Egrid, hit_count, range_err);

@@ -278,13 +278,19 @@ __global__ void __launch_bounds__(256) l_push_deposit_k(LK k, double* __restrict
             double vhalf = V + qm * hdt * Ei;            // PIC_L.py:255
             double xout = X + vhalf * k.dt;              // :256
             double vout = vhalf + qm * hdt * Ei;         // :257
-            double xw = wrap_mod(xout, wrapL);
-            st_stream(x + i, xw);
-            st_stream(v + i, vout);
-            cn = cell_lper(xw, k.dx, nodes);
-            l_fix(cn, nodes, bad);
-            double pre = (sp ? k.q[1] : k.q[0]) * k.p2c;
-            rL = pre * cn.wL * k.idx; rR = pre * cn.wR * k.idx;
+            if (k.flags & 2) {                            // function-level pushParticlesExplicit: no wrap, no deposit
+                st_stream(x + i, xout);
+                st_stream(v + i, vout);
+                valid = false;
+            } else {
+                double xw = wrap_mod(xout, wrapL);
+                st_stream(x + i, xw);
+                st_stream(v + i, vout);
+                cn = cell_lper(xw, k.dx, nodes);
+                l_fix(cn, nodes, bad);
+                double pre = (sp ? k.q[1] : k.q[0]) * k.p2c;
+                rL = pre * cn.wL * k.idx; rR = pre * cn.wR * k.idx;
+            }
         }
         deposit2<AGG>(sR, cn.iL, cn.iR, rL, rR, valid);
     }

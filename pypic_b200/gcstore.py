@@ -160,8 +160,8 @@ class ParticleStore:
     def flags_host(self):
         return {k: getattr(self, k)[:self.N].cpu().numpy() for k in self.FLAGS}
 
-    def _params(self, grid, dt=0.0):
-        return _lib.GCParams(self.N, grid.ng if grid is not None else 2, 0, grid.dx if grid is not None else 1.0,
+    def _params(self, grid, dt=0.0, flags=0):
+        return _lib.GCParams(self.N, grid.ng if grid is not None else 2, int(flags), grid.dx if grid is not None else 1.0,
                              float(dt), grid.length if grid is not None else 1.0, (C.c_double * 3)(*self.B),
                              (C.c_double * 2)(*self.Eyz))
 
@@ -191,6 +191,21 @@ class ParticleStore:
                   D.ptr(self.active), D.ptr(self.at_wall), D.ptr(self.hit_flag), D.ptr(grid.E), D.ptr(self.hit_count),
                   D.ptr(self.range_err), D.stream())
         return int(D.read_raw(self.hit_count, 1, np.int64)[0])
+
+    def push_6D_given_E(self, dt, Ex):
+        """Particle.push_6D alone (pygcpic.py:460-507): E_x per particle already gathered (device
+        tensor), no boundary test."""
+        P = self._params(None, dt, flags=3)
+        r7 = self._r7()
+        _lib.call("pic_dev_gc_push_boris", C.byref(P), C.byref(r7), D.ptr(self.charge_state), D.ptr(self.m),
+                  D.ptr(self.active), D.ptr(self.at_wall), None, D.ptr(Ex), None, D.ptr(self.range_err), D.stream())
+
+    def push_GC_given_E(self, dt, Ex):
+        """Particle.push_GC (pygcpic.py:598-645) with E_x per particle already gathered."""
+        P = self._params(None, dt, flags=1)
+        r7 = self._r7()
+        _lib.call("pic_dev_gc_push_rk4", C.byref(P), C.byref(r7), D.ptr(self.charge_state), D.ptr(self.m),
+                  D.ptr(self.active), D.ptr(Ex), D.ptr(self.range_err), D.stream())
 
     def transform_6D_to_GC(self):
         P = self._params(None)

@@ -167,6 +167,14 @@ class ExplicitSim:
     def field_energy(self):
         return float(D.read_f64(self.stats, 1)[0])
 
+    def kinetic_energy(self, m=me):
+        """sum(m v^2 / 2) over all particles (PIC_L.py:698 uses me for every particle)."""
+        sc = D.f64(1, self.dev, True)
+        _lib.call("pic_dev_sum_sq", D.ptr(self.v), self.N, m / 2., D.ptr(sc), D.stream())
+        self.kernel_launches += 1
+        self.comm.allreduce_sum(sc)
+        return float(D.read_f64(sc, 1)[0])
+
     def download(self):
         return dict(x=self.x.cpu().numpy(), v=self.v.cpu().numpy(), rho=self.rho.cpu().numpy(),
                     phi=self.phi.cpu().numpy(), E=self.E.cpu().numpy())
