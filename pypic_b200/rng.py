@@ -40,3 +40,18 @@ class LegacyDraws:
         for _ in range(int(n_dead)):
             rng.uniform(0.0, 1.0)
             rng.normal(0.0, 1.0); rng.normal(0.0, 1.0); rng.normal(0.0, 1.0)
+
+
+def sheath_step_draws(draws, counts, rank, N_global, sigma_local, L):
+    """Sharded re-injection with stream parity: advances `draws` exactly as the reference's
+    single process would for the GLOBAL particle list (PIC_L_DD.py:419-450: one thermostat
+    uniform per active particle, then x,u,v,w per dead slot in index order) and returns only the
+    draws of this rank's dead slots.  counts[r] = number of dead slots on rank r (rank order =
+    index order because shards are contiguous index ranges); sigma_local = thermal speed of each
+    of this rank's dead slots."""
+    counts = [int(c) for c in counts]
+    draws.sheath_thermostat_skip(int(N_global) - sum(counts))
+    draws.sheath_skip_foreign(sum(counts[:rank]))
+    out = draws.sheath_reinject(counts[rank], sigma_local, L)
+    draws.sheath_skip_foreign(sum(counts[rank + 1:]))
+    return out

@@ -13,7 +13,7 @@ import torch
 
 from . import _lib, device as D
 from .dist import Comm, local_split, shard_range
-from .rng import LegacyDraws
+from .rng import LegacyDraws, sheath_step_draws
 
 epsilon0 = 8.854E-12
 e = 1.602E-19
@@ -123,13 +123,10 @@ class SheathSim:
         self.kernel_launches += 3
         n_dead = int(D.read_raw(self.count, 1, np.int64)[0])
         counts = self.comm.allgather_int(n_dead, device=self.dev)
-        total_dead = sum(counts)
-        self.draws.sheath_thermostat_skip(self.N_global - total_dead)
-        self.draws.sheath_skip_foreign(sum(counts[:self.comm.rank]))
+        idx = D.read_raw(self.dead_idx, n_dead, np.int32) if n_dead else np.zeros(0, dtype=np.int32)
+        sigma = np.where(idx >= self.n_split, self._sigma(1), self._sigma(0))
+        xd, ud, vd, wd = sheath_step_draws(self.draws, counts, self.comm.rank, self.N_global, sigma, self.L)
         if n_dead:
-            idx = D.read_raw(self.dead_idx, n_dead, np.int32)
-            sigma = np.where(idx >= self.n_split, self._sigma(1), self._sigma(0))
-            xd, ud, vd, wd = self.draws.sheath_reinject(n_dead, sigma, self.L)
             dxd, dud = D.to_dev(xd, self.dev), D.to_dev(ud, self.dev)
             dvd = D.to_dev(vd, self.dev) if self.carry_vw else None
             dwd = D.to_dev(wd, self.dev) if self.carry_vw else None
@@ -138,7 +135,6 @@ class SheathSim:
                       D.ptr(self.active), st)
             self.kernel_launches += 1
             torch.cuda.current_stream().synchronize()   # keep the staging tensors alive until consumed
-        self.draws.sheath_skip_foreign(sum(counts[self.comm.rank + 1:]))
         return n_dead
 
     def sort_by_cell(self):
