@@ -599,10 +599,7 @@ __global__ void __launch_bounds__(V6_T, 1) dd_picard_iter_v6_k(
             const double2 X0 = *(const double2*)sb, U0 = *(const double2*)(sb + 64);
             double2 pX1 = make_double2(0., 0.);
             if (!FIRST) pX1 = *(const double2*)(sb + 128);
-            __syncwarp();
-            // refill the stage just drained with the row V6_NST ahead (possibly in the next chunk)
-            if (row < V6_ROWS - V6_NST) issue(cbase + 64 * (row + V6_NST), stage);
-            else if (more) issue(cbase + chunk_step + 64 * (row + V6_NST - V6_ROWS), stage);
+            const int st_cur = stage;
             if (++stage == V6_NST) { stage = 0; phase ^= 1u; }
             bool straddle = false, sp = sp_slice;
             if (mixed) {
@@ -645,7 +642,15 @@ __global__ void __launch_bounds__(V6_T, 1) dd_picard_iter_v6_k(
                 dd_medium<FIRST>(k, fc, ci, X0.x, U0.x, pX1.x, a, acta, straddle, sp, sF, myw, wb, acc, s_cnt, x1, u1, active);
                 dd_medium<FIRST>(k, fc, ci + 1, X0.y, U0.y, pX1.y, b, actb, straddle, sp, sF, myw, wb, acc, s_cnt, x1, u1, active);
             }
-            __syncwarp();                                         // reconverge before the next row's barrier wait
+            // Refill the stage this row drained with the row V6_NST ahead (possibly in the next chunk).
+            // This must not happen before every lane's LDS of the stage has EXECUTED: an LDS can sit
+            // in the load/store queue behind a burst of global atomics for longer than a bulk copy
+            // takes, and the copy (async proxy) would then overwrite the slot under it.  Every lane
+            // has consumed all three loaded vectors by now (the branch above depends on them), and
+            // the barrier orders those uses before the elected lane's copy.
+            __syncwarp();
+            if (row < V6_ROWS - V6_NST) issue(cbase + 64 * (row + V6_NST), st_cur);
+            else if (more) issue(cbase + chunk_step + 64 * (row + V6_NST - V6_ROWS), st_cur);
         }
         // column sums of the warp's 32 private windows -> global accumulators
         __syncwarp();

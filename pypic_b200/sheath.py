@@ -74,6 +74,7 @@ class SheathSim:
         self.last_resid = 1.0
         self.kernel_launches = 0
         self.vionout = []
+        self.resid_trace = None     # set to a list to record the residual of every Picard iteration
         self.iter_events = None     # set to a list to record a CUDA-event pair per particle-kernel launch
 
     # ------------------------------------------------------------------ state I/O
@@ -171,6 +172,8 @@ class SheathSim:
             self.kernel_launches += 2
             r = float(D.read_f64(self.stats, 1)[0])
             k += 1
+            if self.resid_trace is not None:
+                self.resid_trace.append(r)
         # commit (PIC_L_DD.py:538-545): pointer swaps
         self.x0, self.x1 = self.x1, self.x0
         self.u0, self.u1 = self.u1, self.u0
