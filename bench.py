@@ -227,7 +227,10 @@ def run_cuda(args):
     ms = comm.max_float(ms, device=dev)
     launches = sim.kernel_launches - launches0
     sim.check()
-    kernel_ms = [a.elapsed_time(b) for a, b in iter_events]
+    kernel_ms = [e[0].elapsed_time(e[1]) for e in iter_events]
+    ms_with_u = [e[0].elapsed_time(e[1]) for e in iter_events if e[2] and not e[3]]
+    ms_without_u = [e[0].elapsed_time(e[1]) for e in iter_events if not e[2] and not e[3]]
+    ms_first = [e[0].elapsed_time(e[1]) for e in iter_events if e[3]]
     mean_iter_ms = float(np.mean(kernel_ms))
     kbar = float(np.mean(iters))
     value = w["N"] * args.steps / (ms * 1e-3)
@@ -238,9 +241,13 @@ def run_cuda(args):
     achieved = alg_bytes_launch / (mean_iter_ms * 1e-3) / 1e9
     peak, peak_src = measured_peak()
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": None, "kernel": "dd_picard_iter_v5_k", "peak_source": peak_src,
+                "traffic": None, "kernel": "dd_picard_iter_v6_k", "peak_source": peak_src,
                 "kernel_ms_mean": mean_iter_ms, "kernel_share_of_step": float(np.sum(kernel_ms) / ms),
-                "algorithmic_bytes_per_launch": alg_bytes_launch, "mean_picard_iterations": kbar}
+                "algorithmic_bytes_per_launch": alg_bytes_launch, "mean_picard_iterations": kbar,
+                "kernel_ms_by_kind": {"first_iteration": float(np.mean(ms_first)) if ms_first else None,
+                                      "later_without_u1_store": float(np.mean(ms_without_u)) if ms_without_u else None,
+                                      "later_with_u1_store": float(np.mean(ms_with_u)) if ms_with_u else None},
+                "u1_repair_passes": int(sim.u_repairs)}
     tf = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.isfile(tf):
         try:

@@ -132,6 +132,20 @@ int pic_dev_dd_weight(const double* x, const double* q, const double* v, const d
 int pic_dev_dd_picard_iter(const pic_dd_params* p, const double* x0, const double* u0,
                            double* x1, double* u1, int8_t* active, const double* Es,
                            double* acc, int first, int* range_err, void* stream);
+/* The same iteration with the n+1 positions PING-PONGED between two buffers (x1_in is read,
+ * x1_out written; they may be equal) and the velocity store OPTIONAL: with u1 == NULL the
+ * iteration streams 32 instead of 40 bytes per particle.  u1 is only needed by the commit, so
+ * the host asks for it in the iteration it expects to be the last one (the contraction of the
+ * residual is very regular) and otherwise repairs it with pic_dev_dd_commit_u. */
+int pic_dev_dd_picard_iter2(const pic_dd_params* p, const double* x0, const double* u0, const double* x1_in,
+                            double* x1_out, double* u1, int8_t* active, const double* Es, double* acc, int first,
+                            int* range_err, void* stream);
+/* u1 of the last iteration after the fact: x1_prev/x1_last are that iteration's input and output
+ * positions, Es the field it gathered with, `first` whether it was the first iteration of the
+ * step.  Particles absorbed before it get the reference's 0.0 (PIC_L_DD.py:459-462). */
+int pic_dev_dd_commit_u(const pic_dd_params* p, const double* x0, const double* u0, const double* x1_prev,
+                        const double* x1_last, const int8_t* active, const double* Es, double* u1, int first,
+                        int* range_err, void* stream);
 /* Device self test: compares the constant-divisor division and the fast cell lookup used
  * on the hot path against the IEEE operations for n pseudo-random / adversarial operands;
  * *mismatches_dev (device uint64, zeroed by the caller) must stay 0. */

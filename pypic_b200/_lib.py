@@ -67,6 +67,8 @@ _SIGS = {
     "pic_dev_dd_interpolate": [P, P, P, I64, I32, F64, P, P],
     "pic_dev_dd_weight": [P, P, P, P, P, I64, I32, F64, F64, F64, P, P],
     "pic_dev_dd_picard_iter": [C.POINTER(DDParams), P, P, P, P, P, P, P, I32, P, P],
+    "pic_dev_dd_picard_iter2": [C.POINTER(DDParams), P, P, P, P, P, P, P, P, I32, P, P],
+    "pic_dev_dd_commit_u": [C.POINTER(DDParams), P, P, P, P, P, P, P, I32, P, P],
     "pic_dev_debug_cta_timer": [P],
     "pic_dev_selftest_div": [F64, C.c_uint64, C.c_uint64, P, P],
     "pic_dev_dd_field_update": [C.POINTER(DDParams), P, P, P, P, P, P, P, P],

@@ -56,8 +56,8 @@ __device__ __forceinline__ void deposit_pair(double* tile, int i, double vL, dou
 // memory (3*Ng doubles); otherwise they stay in global memory / L2.
 template <bool FIRST, bool TILE, bool AGG>
 __global__ void __launch_bounds__(256) dd_picard_iter_k(DDK k, const double* __restrict__ x0,
-                                                        const double* __restrict__ u0, double* __restrict__ x1,
-                                                        double* __restrict__ u1, int8_t* __restrict__ active,
+                                                        const double* __restrict__ u0, const double* x1i, double* x1,
+                                                        double* u1, int8_t* __restrict__ active,
                                                         const double* __restrict__ Es, double* __restrict__ acc,
                                                         int* __restrict__ range_err) {
     extern __shared__ double sm[];
@@ -86,7 +86,7 @@ __global__ void __launch_bounds__(256) dd_picard_iter_k(DDK k, const double* __r
                 if (active[i] != 1) {
                     // already absorbed in an earlier iteration of this step: the reference
                     // leaves zeros in x1,u1 (PIC_L_DD.py:459-462)
-                    x1[i] = 0.0; u1[i] = 0.0;
+                    x1[i] = 0.0; if (u1) u1[i] = 0.0;
                     alive = false;
                 }
             }
@@ -94,7 +94,7 @@ __global__ void __launch_bounds__(256) dd_picard_iter_k(DDK k, const double* __r
         if (alive) {
             X0 = ld_stream(x0 + i);
             U0 = ld_stream(u0 + i);
-            double xs = FIRST ? X0 : (X0 + ld_stream(x1 + i)) * 0.5;   // xs = xh of the previous iteration
+            double xs = FIRST ? X0 : (X0 + ld_stream(x1i + i)) * 0.5;   // xs = xh of the previous iteration
             Cell c = cell_dd(xs, k.dx);
             if (c.iL < 0 || c.iL > Ng - 2) { ++bad; c.iL = clampi(c.iL, 0, Ng - 2); c.iR = c.iL + 1; }
             double Ei = c.wL * F[c.iL] + c.wR * F[c.iR];              // PIC_L_DD.py:38
@@ -103,7 +103,7 @@ __global__ void __launch_bounds__(256) dd_picard_iter_k(DDK k, const double* __r
             XH = (X0 + X1) * 0.5;                                       // :485
             UH = (U0 + U1) * 0.5;                                       // :487
             st_stream(x1 + i, X1);
-            st_stream(u1 + i, U1);
+            if (u1) st_stream(u1 + i, U1);
             // absorption, right wall first (PIC_L_DD.py:495-504)
             if (X0 >= k.L || XH >= k.L || X1 >= k.L) {
                 active[i] = 0; alive = false;
@@ -180,11 +180,11 @@ struct SlowOut { int code; int bad; };   // code: 0 deposited, 1..4 absorbed (L 
 // Full update of ONE particle with the exact (slow) operations; deposits with shared-memory
 // atomics into the CTA's fallback tiles tj = [jh | j1].
 __device__ __noinline__ SlowOut dd_particle_slow(const DDK& k, long long i, double X0, double U0, double pX1, int act,
-                                                 bool first, const double* sF, double* tj, double* __restrict__ x1,
-                                                 double* __restrict__ u1, int8_t* __restrict__ active) {
+                                                 bool first, const double* sF, double* tj, double* x1,
+                                                 double* u1, int8_t* __restrict__ active) {
     SlowOut o{0, 0};
     const int Ng = k.Ng;
-    if (!first && act != 1) { x1[i] = 0.0; u1[i] = 0.0; o.code = 5; return o; }   // reference leaves zeros
+    if (!first && act != 1) { x1[i] = 0.0; if (u1) u1[i] = 0.0; o.code = 5; return o; }   // reference leaves zeros
     const bool sp = i >= k.n_split;
     double xs = first ? X0 : (X0 + pX1) * 0.5;
     Cell c = cell_dd(xs, k.dx);
@@ -194,7 +194,7 @@ __device__ __noinline__ SlowOut dd_particle_slow(const DDK& k, long long i, doub
     double U1 = U0 + (sp ? k.c1[1] : k.c1[0]) * Ei;
     double XH = (X0 + X1) * 0.5;
     double UH = (U0 + U1) * 0.5;
-    x1[i] = X1; u1[i] = U1;
+    x1[i] = X1; if (u1) u1[i] = U1;
     if (X0 >= k.L || XH >= k.L || X1 >= k.L) { active[i] = 0; o.code = sp ? 4 : 3; return o; }
     if (X0 <= 0.0 || XH <= 0.0 || X1 <= 0.0) { active[i] = -1; o.code = sp ? 2 : 1; return o; }
     Cell a = cell_dd(XH, k.dx), b = cell_dd(X1, k.dx);
@@ -280,7 +280,7 @@ __device__ __forceinline__ void win_add(double* myw, double* tj, int wb, int til
 template <bool FIRST>
 __global__ void __launch_bounds__(V5_T, 1) dd_picard_iter_v5_k(
     const __grid_constant__ DDK k, long long nchunks, const double* __restrict__ x0, const double* __restrict__ u0,
-    double* __restrict__ x1, double* __restrict__ u1, int8_t* __restrict__ active, const double* __restrict__ Es,
+    const double* x1i, double* x1, double* u1, int8_t* __restrict__ active, const double* __restrict__ Es,
     double* __restrict__ acc, int* __restrict__ range_err) {
     extern __shared__ double sm[];
     __shared__ int s_cnt[8];
@@ -313,7 +313,7 @@ __global__ void __launch_bounds__(V5_T, 1) dd_picard_iter_v5_k(
         int wb = NOWIN;
         double2 nX0 = __ldcs((const double2*)(x0 + i)), nU0 = __ldcs((const double2*)(u0 + i));
         double2 nX1 = make_double2(0., 0.);
-        if (!FIRST) nX1 = __ldcs((const double2*)(x1 + i));
+        if (!FIRST) nX1 = __ldcs((const double2*)(x1i + i));
 #pragma unroll 1
         for (int row = 0; row < V5_ROWS; ++row) {
             const long long ci = i;
@@ -321,7 +321,7 @@ __global__ void __launch_bounds__(V5_T, 1) dd_picard_iter_v5_k(
             i += 64;
             if (row + 1 < V5_ROWS) {
                 nX0 = __ldcs((const double2*)(x0 + i)); nU0 = __ldcs((const double2*)(u0 + i));
-                if (!FIRST) nX1 = __ldcs((const double2*)(x1 + i));
+                if (!FIRST) nX1 = __ldcs((const double2*)(x1i + i));
             }
             // one species per 64-particle row on the fast path (warp-uniform constants); only the
             // single row that holds the species boundary is redone particle by particle
@@ -342,18 +342,18 @@ __global__ void __launch_bounds__(V5_T, 1) dd_picard_iter_v5_k(
             }
             if (!(ra | rb)) {
                 __stcs((double2*)(x1 + ci), make_double2(a.X1, b.X1));
-                __stcs((double2*)(u1 + ci), make_double2(a.U1, b.U1));
+                if (u1) __stcs((double2*)(u1 + ci), make_double2(a.U1, b.U1));
             } else {
                 if (ra) {
                     SlowOut o = dd_particle_slow(k, ci, X0.x, U0.x, pX1.x, FIRST ? 1 : (int)active[ci], FIRST, sF, tj, x1, u1, active);
                     if (o.code >= 1 && o.code <= 4) atomicAdd(&s_cnt[o.code], 1);
                     if (o.bad) atomicAdd(&s_cnt[0], o.bad);
-                } else { x1[ci] = a.X1; u1[ci] = a.U1; }
+                } else { x1[ci] = a.X1; if (u1) u1[ci] = a.U1; }
                 if (rb) {
                     SlowOut o = dd_particle_slow(k, ci + 1, X0.y, U0.y, pX1.y, FIRST ? 1 : (int)active[ci + 1], FIRST, sF, tj, x1, u1, active);
                     if (o.code >= 1 && o.code <= 4) atomicAdd(&s_cnt[o.code], 1);
                     if (o.bad) atomicAdd(&s_cnt[0], o.bad);
-                } else { x1[ci + 1] = b.X1; u1[ci + 1] = b.U1; }
+                } else { x1[ci + 1] = b.X1; if (u1) u1[ci + 1] = b.U1; }
             }
             if (!ra) { win_add(myw, tj, wb, 0, Ng, a.cH, a.hL, a.hR); win_add(myw, tj, wb, 1, Ng, a.cF, a.fL, a.fR); }
             if (!rb) { win_add(myw, tj, wb, 0, Ng, b.cH, b.hL, b.hR); win_add(myw, tj, wb, 1, Ng, b.cF, b.fL, b.fR); }
@@ -496,22 +496,22 @@ __device__ __forceinline__ void dd_fast6(const FastC& c, const double* __restric
 template <bool FIRST>
 __device__ __forceinline__ void dd_medium(const DDK& k, const FastC& fc, long long i, double X0, double U0, double pX1,
                                           const FastO6& o, int act, bool straddle, bool sp, const double* sF, double* myw,
-                                          int wb, double* __restrict__ acc, int* s_cnt, double* __restrict__ x1,
-                                          double* __restrict__ u1, int8_t* __restrict__ active) {
-    if (!FIRST && act != 1) { x1[i] = 0.0; u1[i] = 0.0; return; }
+                                          int wb, double* __restrict__ acc, int* s_cnt, double* x1,
+                                          double* u1, int8_t* __restrict__ active) {
+    if (!FIRST && act != 1) { x1[i] = 0.0; if (u1) u1[i] = 0.0; return; }
     const unsigned f0 = (unsigned)__double2hiint(floor_frac_hi(FIRST ? X0 : (X0 + pX1) * 0.5, fc.idx)) - PIC_HI_G;
     const unsigned p0 = (unsigned)__double2hiint(X0) - 1u;
     const unsigned pp = FIRST ? 0u : (unsigned)__double2hiint(pX1) - 1u;
     if (!straddle && f0 <= PIC_HI_SPAN && p0 < fc.hi_Lm1 && pp < fc.hi_Lm1) {
         const double XH = (X0 + o.X1) * 0.5;
         if (X0 >= k.L || XH >= k.L || o.X1 >= k.L) {                    // PIC_L_DD.py:495-499
-            x1[i] = o.X1; u1[i] = o.U1; active[i] = 0; atomicAdd(&s_cnt[sp ? 4 : 3], 1); return;
+            x1[i] = o.X1; if (u1) u1[i] = o.U1; active[i] = 0; atomicAdd(&s_cnt[sp ? 4 : 3], 1); return;
         }
         if (X0 <= 0.0 || XH <= 0.0 || o.X1 <= 0.0) {                     // :500-504
-            x1[i] = o.X1; u1[i] = o.U1; active[i] = -1; atomicAdd(&s_cnt[sp ? 2 : 1], 1); return;
+            x1[i] = o.X1; if (u1) u1[i] = o.U1; active[i] = -1; atomicAdd(&s_cnt[sp ? 2 : 1], 1); return;
         }
         if (o.fr <= PIC_HI_SPAN && o.ps < fc.hi_Lm1) {
-            x1[i] = o.X1; u1[i] = o.U1;
+            x1[i] = o.X1; if (u1) u1[i] = o.U1;
             win_add6(myw, acc, wb, 0, k.Ng, o.cH, o.hL, o.hR); win_add6(myw, acc, wb, 1, k.Ng, o.cF, o.fL, o.fR);
             return;
         }
@@ -521,10 +521,10 @@ __device__ __forceinline__ void dd_medium(const DDK& k, const FastC& fc, long lo
     if (so.bad) atomicAdd(&s_cnt[0], so.bad);
 }
 
-template <bool FIRST>
+template <bool FIRST, bool WU>
 __global__ void __launch_bounds__(V6_T, 1) dd_picard_iter_v6_k(
     const __grid_constant__ DDK k, int nchunks, const double* __restrict__ x0, const double* __restrict__ u0,
-    double* __restrict__ x1, double* __restrict__ u1, int8_t* __restrict__ active, const double* __restrict__ Es,
+    const double* x1i, double* x1, double* u1, int8_t* __restrict__ active, const double* __restrict__ Es,
     double* __restrict__ acc, int* __restrict__ range_err) {
     extern __shared__ __align__(128) double sm[];
     __shared__ int s_cnt[8];
@@ -572,7 +572,7 @@ __global__ void __launch_bounds__(V6_T, 1) dd_picard_iter_v6_k(
             mbar_expect_tx(bar, row_bytes);
             bulk_g2s(dst, x0 + base, 512, bar);
             bulk_g2s(dst + 512, u0 + base, 512, bar);
-            if (!FIRST) bulk_g2s(dst + 1024, x1 + base, 512, bar);
+            if (!FIRST) bulk_g2s(dst + 1024, x1i + base, 512, bar);
         }
     };
     long long cbase = (long long)blockIdx.x * V6_CHUNK + woff;     // first particle of this warp's slice
@@ -623,14 +623,21 @@ __global__ void __launch_bounds__(V6_T, 1) dd_picard_iter_v6_k(
             const unsigned dah = (unsigned)(a.cH - wb), daf = (unsigned)(a.cF - wb);
             const unsigned dbh = (unsigned)(b.cH - wb), dbf = (unsigned)(b.cF - wb);
             const bool inwin = max(__vimax3_u32(dah, daf, dbh), dbf) <= (unsigned)(V6_W - 2);
-            if (!(ra | rb) && inwin) {
-                // the common case: two 128-bit streaming stores and eight conflict-free private RMWs
+            if (!(ra | rb)) {
+                // the common case: two 128-bit streaming stores and eight conflict-free private RMWs;
+                // a lane whose particles drifted out of the warp's window since the last sort falls
+                // back to global REDs for those contributions only
                 __stcs((double2*)(x1 + ci), make_double2(a.X1, b.X1));
-                __stcs((double2*)(u1 + ci), make_double2(a.U1, b.U1));
-                double* p = myw + dah * V6_T; p[0] += a.hL; p[V6_T] += a.hR;
-                p = myw + (V6_W + daf) * V6_T; p[0] += a.fL; p[V6_T] += a.fR;
-                p = myw + dbh * V6_T; p[0] += b.hL; p[V6_T] += b.hR;
-                p = myw + (V6_W + dbf) * V6_T; p[0] += b.fL; p[V6_T] += b.fR;
+                if (WU) __stcs((double2*)(u1 + ci), make_double2(a.U1, b.U1));
+                if (inwin) {
+                    double* p = myw + dah * V6_T; p[0] += a.hL; p[V6_T] += a.hR;
+                    p = myw + (V6_W + daf) * V6_T; p[0] += a.fL; p[V6_T] += a.fR;
+                    p = myw + dbh * V6_T; p[0] += b.hL; p[V6_T] += b.hR;
+                    p = myw + (V6_W + dbf) * V6_T; p[0] += b.fL; p[V6_T] += b.fR;
+                } else {
+                    win_add6(myw, acc, wb, 0, Ng, a.cH, a.hL, a.hR); win_add6(myw, acc, wb, 1, Ng, a.cF, a.fL, a.fR);
+                    win_add6(myw, acc, wb, 0, Ng, b.cH, b.hL, b.hR); win_add6(myw, acc, wb, 1, Ng, b.cF, b.fL, b.fR);
+                }
             } else {
                 // one flag load for the pair (ci is even); dead and freshly absorbed particles are
                 // settled here without the IEEE-division path
@@ -639,8 +646,8 @@ __global__ void __launch_bounds__(V6_T, 1) dd_picard_iter_v6_k(
                     const short fl = *(const short*)(active + ci);
                     acta = (int)(signed char)(fl & 0xff); actb = (int)(signed char)(fl >> 8);
                 }
-                dd_medium<FIRST>(k, fc, ci, X0.x, U0.x, pX1.x, a, acta, straddle, sp, sF, myw, wb, acc, s_cnt, x1, u1, active);
-                dd_medium<FIRST>(k, fc, ci + 1, X0.y, U0.y, pX1.y, b, actb, straddle, sp, sF, myw, wb, acc, s_cnt, x1, u1, active);
+                dd_medium<FIRST>(k, fc, ci, X0.x, U0.x, pX1.x, a, acta, straddle, sp, sF, myw, wb, acc, s_cnt, x1, WU ? u1 : nullptr, active);
+                dd_medium<FIRST>(k, fc, ci + 1, X0.y, U0.y, pX1.y, b, actb, straddle, sp, sF, myw, wb, acc, s_cnt, x1, WU ? u1 : nullptr, active);
             }
             // Refill the stage this row drained with the row V6_NST ahead (possibly in the next chunk).
             // This must not happen before every lane's LDS of the stage has EXECUTED: an LDS can sit
@@ -984,10 +991,11 @@ __global__ void __launch_bounds__(SORT_T) dd_sort_scatter_k(DDK k, const double*
 using namespace pic;
 
 template <bool FIRST, bool TILE, bool AGG>
-static int launch_iter(const DDK& k, const double* x0, const double* u0, double* x1, double* u1, int8_t* active,
-                       const double* Es, double* acc, int* range_err, cudaStream_t st) {
+static int launch_iter(const DDK& k, const double* x0, const double* u0, const double* x1i, double* x1, double* u1,
+                       int8_t* active, const double* Es, double* acc, int* range_err, cudaStream_t st) {
     // a short tail is cheaper with the grids left in L2 than with 3*Ng doubles staged per CTA
-    if (TILE && k.N < 16 * (long long)k.Ng) return launch_iter<FIRST, false, AGG>(k, x0, u0, x1, u1, active, Es, acc, range_err, st);
+    if (TILE && k.N < 16 * (long long)k.Ng)
+        return launch_iter<FIRST, false, AGG>(k, x0, u0, x1i, x1, u1, active, Es, acc, range_err, st);
     size_t smem = TILE ? (size_t)3 * k.Ng * sizeof(double) : 0;
     auto kern = dd_picard_iter_k<FIRST, TILE, AGG>;
     int per_sm = 8;
@@ -997,72 +1005,101 @@ static int launch_iter(const DDK& k, const double* x0, const double* u0, double*
         PIC_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, 256, smem));
         per_sm = occ > 0 ? occ : 1;
     }
-    kern<<<grid_for(k.N, 256, per_sm), 256, smem, st>>>(k, x0, u0, x1, u1, active, Es, acc, range_err);
+    kern<<<grid_for(k.N, 256, per_sm), 256, smem, st>>>(k, x0, u0, x1i, x1, u1, active, Es, acc, range_err);
     PIC_CHECK_LAUNCH();
     return PIC_OK;
 }
 
+template <bool FIRST>
+static int launch_tail(const DDK& k, long long done, const double* x0, const double* u0, const double* x1i, double* x1,
+                       double* u1, int8_t* active, const double* Es, double* acc, int* range_err, cudaStream_t st) {
+    if (done >= k.N) return PIC_OK;
+    DDK t = k;
+    t.N = k.N - done;
+    t.n_split = k.n_split - done < 0 ? 0 : (k.n_split - done > t.N ? t.N : k.n_split - done);
+    return launch_iter<FIRST, true, true>(t, x0 + done, u0 + done, x1i + done, x1 + done, u1 ? u1 + done : nullptr,
+                                          active + done, Es, acc, range_err, st);
+}
+
+// u1 = u0 + dt*(q/m)*E(xs) for every particle alive at the entry of the LAST Picard iteration,
+// 0 for the ones absorbed before it -- the velocity half of the commit when that iteration ran
+// without streaming u1 (pic_dev_dd_picard_iter2 with u1 == NULL).
+__global__ void __launch_bounds__(256) dd_commit_u_k(DDK k, const double* __restrict__ x0, const double* __restrict__ u0,
+                                                     const double* __restrict__ x1_prev, const double* __restrict__ x1_last,
+                                                     const int8_t* __restrict__ active, const double* __restrict__ Es,
+                                                     double* __restrict__ u1, int first, int* __restrict__ range_err) {
+    extern __shared__ double sF[];
+    const int Ng = k.Ng;
+    for (int i = threadIdx.x; i < Ng; i += blockDim.x) sF[i] = Es[i];
+    __syncthreads();
+    int bad = 0;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < k.N; i += (long long)gridDim.x * blockDim.x) {
+        const double X0 = ld_stream(x0 + i), U0 = ld_stream(u0 + i);
+        double xs = X0;
+        if (!first) {
+            // absorbed before the last iteration <=> flagged and the last iteration wrote the
+            // reference's zero instead of a position (PIC_L_DD.py:459-462)
+            if (active[i] != 1 && x1_last[i] == 0.0) { st_stream(u1 + i, 0.0); continue; }
+            xs = (X0 + ld_stream(x1_prev + i)) * 0.5;
+        }
+        Cell c = cell_dd_fast(xs, k.dx, k.idx);
+        if (c.iL < 0 || c.iL > Ng - 2) { ++bad; c.iL = clampi(c.iL, 0, Ng - 2); }
+        const double Ei = c.wL * sF[c.iL] + c.wR * sF[c.iL + 1];
+        st_stream(u1 + i, U0 + ((i >= k.n_split) ? k.c1[1] : k.c1[0]) * Ei);
+    }
+    if (bad && range_err) atomicAdd(range_err, bad);
+}
+
 extern "C" {
 
-int pic_dev_dd_picard_iter(const pic_dd_params* p, const double* x0, const double* u0, double* x1, double* u1,
-                           int8_t* active, const double* Es, double* acc, int first, int* range_err, void* stream) {
-    PIC_REQUIRE(p && x0 && u0 && x1 && u1 && active && Es && acc, "dd_picard_iter: null pointer");
+int pic_dev_dd_picard_iter2(const pic_dd_params* p, const double* x0, const double* u0, const double* x1_in,
+                            double* x1_out, double* u1, int8_t* active, const double* Es, double* acc, int first,
+                            int* range_err, void* stream) {
+    PIC_REQUIRE(p && x0 && u0 && x1_in && x1_out && active && Es && acc, "dd_picard_iter: null pointer");
     PIC_REQUIRE(p->N >= 0 && p->Ng >= 3 && p->dx > 0 && p->dt > 0, "dd_picard_iter: bad parameters");
     if (p->N == 0) return PIC_OK;
     DDK k = make_ddk(p);
     cudaStream_t st = (cudaStream_t)stream;
+    const double* x1i = x1_in;
+    double* x1 = x1_out;
     bool tile = !(p->flags & 2) && (size_t)3 * k.Ng * sizeof(double) <= (size_t)max_optin_smem() - 1024;
     bool agg = !(p->flags & 1);
     size_t smem5 = ((size_t)3 * k.Ng + (size_t)2 * V5_W * V5_T) * sizeof(double);
     const size_t smem6 = ((size_t)((k.Ng + 15) & ~15) + (size_t)2 * V6_W * V6_T + (size_t)(V6_T / 32) * V6_NST * 192 +
                           (size_t)(V6_T / 32) * V6_NST) * sizeof(double);
-    const bool aligned16 = (((uintptr_t)x0 | (uintptr_t)u0 | (uintptr_t)x1 | (uintptr_t)u1) & 15) == 0;
+    const bool aligned16 = (((uintptr_t)x0 | (uintptr_t)u0 | (uintptr_t)x1i | (uintptr_t)x1 | (uintptr_t)u1) & 15) == 0;
     if (!(p->flags & (1 | 2 | 4 | 8)) && aligned16 && smem6 <= (size_t)max_optin_smem() - 512) {
         // default: TMA-staged private-window kernel, one persistent CTA per SM
         const long long nchunks = k.N / V6_CHUNK;
         if (nchunks > 0) {
-            auto kern = first ? dd_picard_iter_v6_k<true> : dd_picard_iter_v6_k<false>;
+            auto kern = first ? (u1 ? dd_picard_iter_v6_k<true, true> : dd_picard_iter_v6_k<true, false>)
+                              : (u1 ? dd_picard_iter_v6_k<false, true> : dd_picard_iter_v6_k<false, false>);
             PIC_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem6));
             long long cap = device_sm_count();
             int grid = (int)(nchunks < cap ? nchunks : cap);
-            kern<<<grid, V6_T, smem6, st>>>(k, (int)nchunks, x0, u0, x1, u1, active, Es, acc, range_err);
+            kern<<<grid, V6_T, smem6, st>>>(k, (int)nchunks, x0, u0, x1i, x1, u1, active, Es, acc, range_err);
             PIC_CHECK_LAUNCH();
         }
         const long long done = nchunks * V6_CHUNK;
-        if (done < k.N) {
-            DDK t = k;
-            t.N = k.N - done;
-            t.n_split = k.n_split - done < 0 ? 0 : (k.n_split - done > t.N ? t.N : k.n_split - done);
-            int rc = first ? launch_iter<true, true, true>(t, x0 + done, u0 + done, x1 + done, u1 + done, active + done, Es, acc, range_err, st)
-                           : launch_iter<false, true, true>(t, x0 + done, u0 + done, x1 + done, u1 + done, active + done, Es, acc, range_err, st);
-            if (rc) return rc;
-        }
-        return PIC_OK;
+        return first ? launch_tail<true>(k, done, x0, u0, x1i, x1, u1, active, Es, acc, range_err, st)
+                     : launch_tail<false>(k, done, x0, u0, x1i, x1, u1, active, Es, acc, range_err, st);
     }
     if (!(p->flags & (1 | 2 | 4)) && smem5 <= (size_t)max_optin_smem() - 512) {
-        // default: private-window deposit over contiguous chunks, one persistent CTA per SM;
-        // the remainder that does not fill a chunk is done by the generic grid-stride kernel
+        // register-prefetch build of the window kernel (kept for comparison)
         const long long nchunks = k.N / V5_CHUNK;
         if (nchunks > 0) {
             auto kern = first ? dd_picard_iter_v5_k<true> : dd_picard_iter_v5_k<false>;
             PIC_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem5));
             long long cap = device_sm_count();
             int grid = (int)(nchunks < cap ? nchunks : cap);
-            kern<<<grid, V5_T, smem5, st>>>(k, nchunks, x0, u0, x1, u1, active, Es, acc, range_err);
+            kern<<<grid, V5_T, smem5, st>>>(k, nchunks, x0, u0, x1i, x1, u1, active, Es, acc, range_err);
             PIC_CHECK_LAUNCH();
         }
         const long long done = nchunks * V5_CHUNK;
-        if (done < k.N) {
-            DDK t = k;
-            t.N = k.N - done;
-            t.n_split = k.n_split - done < 0 ? 0 : (k.n_split - done > t.N ? t.N : k.n_split - done);
-            int rc = first ? launch_iter<true, true, true>(t, x0 + done, u0 + done, x1 + done, u1 + done, active + done, Es, acc, range_err, st)
-                           : launch_iter<false, true, true>(t, x0 + done, u0 + done, x1 + done, u1 + done, active + done, Es, acc, range_err, st);
-            if (rc) return rc;
-        }
-        return PIC_OK;
+        return first ? launch_tail<true>(k, done, x0, u0, x1i, x1, u1, active, Es, acc, range_err, st)
+                     : launch_tail<false>(k, done, x0, u0, x1i, x1, u1, active, Es, acc, range_err, st);
     }
-#define PIC_DD_DISPATCH(F, T, A) return launch_iter<F, T, A>(k, x0, u0, x1, u1, active, Es, acc, range_err, st)
+#define PIC_DD_DISPATCH(F, T, A) return launch_iter<F, T, A>(k, x0, u0, x1i, x1, u1, active, Es, acc, range_err, st)
     if (first) {
         if (tile) { if (agg) PIC_DD_DISPATCH(true, true, true); else PIC_DD_DISPATCH(true, true, false); }
         else { if (agg) PIC_DD_DISPATCH(true, false, true); else PIC_DD_DISPATCH(true, false, false); }
@@ -1071,6 +1108,29 @@ int pic_dev_dd_picard_iter(const pic_dd_params* p, const double* x0, const doubl
         else { if (agg) PIC_DD_DISPATCH(false, false, true); else PIC_DD_DISPATCH(false, false, false); }
     }
 #undef PIC_DD_DISPATCH
+}
+
+int pic_dev_dd_picard_iter(const pic_dd_params* p, const double* x0, const double* u0, double* x1, double* u1,
+                           int8_t* active, const double* Es, double* acc, int first, int* range_err, void* stream) {
+    PIC_REQUIRE(u1, "dd_picard_iter: null pointer");
+    return pic_dev_dd_picard_iter2(p, x0, u0, x1, x1, u1, active, Es, acc, first, range_err, stream);
+}
+
+int pic_dev_dd_commit_u(const pic_dd_params* p, const double* x0, const double* u0, const double* x1_prev,
+                        const double* x1_last, const int8_t* active, const double* Es, double* u1, int first,
+                        int* range_err, void* stream) {
+    PIC_REQUIRE(p && x0 && u0 && x1_prev && x1_last && active && Es && u1, "dd_commit_u: null pointer");
+    if (p->N == 0) return PIC_OK;
+    DDK k = make_ddk(p);
+    size_t smem = (size_t)k.Ng * sizeof(double);
+    PIC_REQUIRE(smem <= (size_t)max_optin_smem() - 1024, "dd_commit_u: grid too large for the shared-memory tile");
+    PIC_CHECK_CUDA(cudaFuncSetAttribute(dd_commit_u_k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int occ = 0;
+    PIC_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, dd_commit_u_k, 256, smem));
+    dd_commit_u_k<<<grid_for(k.N, 256, occ > 0 ? occ : 1), 256, smem, (cudaStream_t)stream>>>(
+        k, x0, u0, x1_prev, x1_last, active, Es, u1, first, range_err);
+    PIC_CHECK_LAUNCH();
+    return PIC_OK;
 }
 
 int pic_dev_debug_cta_timer(uint64_t* buf) {

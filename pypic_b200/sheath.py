@@ -25,7 +25,7 @@ kb = 1.38E-23
 class SheathSim:
     def __init__(self, N, Ng, dx, dt, p2c, q=(-e, e), m=(me, mp), n_split=None, tol=1e-5, maxiter=20,
                  kBT=(None, None), gamma=0.0, carry_vw=True, deposit="window", tiles="smem",
-                 rng="host", seed=1, draws=None, comm=None, device=None, sort_every=0):
+                 rng="host", seed=1, draws=None, comm=None, device=None, sort_every=0, elide_u=True):
         self.dev = D.require_cuda(device)
         self.comm = comm if comm is not None else Comm()
         self.N_global = int(N)
@@ -54,11 +54,18 @@ class SheathSim:
         n = max(self.N, 1)
         self.x0 = D.f64(n, dev, True); self.u0 = D.f64(n, dev, True)
         self.x1 = D.f64(n, dev, True); self.u1 = D.f64(n, dev, True)
+        # second n+1 position buffer: the Picard iterations ping-pong between x1 and x1b so that the
+        # input of the last iteration survives it (needed if its velocities must be repaired)
+        self.elide_u = bool(elide_u)
+        self.x1b = D.f64(n, dev, True) if self.elide_u else None
+        self._ratio, self._r1 = None, None      # residual contraction observed so far
+        self.u_repairs = 0
         self.v0 = D.f64(n, dev, True) if carry_vw else None
         self.w0 = D.f64(n, dev, True) if carry_vw else None
         self.active = torch.ones(n, dtype=torch.int8, device=dev)
         g = self.Ng
         self.E0 = D.f64(g, dev, True); self.Es = D.f64(g, dev, True); self.E1 = D.f64(g, dev, True)
+        self.Es_prev = D.f64(g, dev, True)
         self.j0 = D.f64(g, dev, True)
         self.acc = D.f64(2 * g + 4, dev, True)
         self.wall_cum = D.f64(4, dev, True)
@@ -148,36 +155,78 @@ class SheathSim:
         self.u0, self.u1 = self.u1, self.u0
 
     # ------------------------------------------------------------------ one timestep
+    def _expect_last(self, k, hist):
+        """Will iteration k (1-based) be the last one?  The residual contracts by a very regular
+        factor per iteration, so the next residual is predicted from the ratio observed so far; a
+        wrong guess only costs the repair pass, never correctness."""
+        if k >= self.maxiter or self._ratio is None:
+            return True
+        pred = self._r1 if k == 1 else hist[-1] * self._ratio
+        return pred is None or pred <= 100.0 * self.tol
+
     def picard(self):
-        """PIC_L_DD.py:452-545: Picard loop + commit.  Returns (iterations, residual)."""
+        """PIC_L_DD.py:452-545: Picard loop + commit.  Returns (iterations, residual).
+
+        The velocities u1 are only needed by the commit, so an iteration streams them (8 of its
+        40 bytes per particle) only when it is expected to be the last one; if the loop ends on an
+        iteration that skipped them, pic_dev_dd_commit_u recomputes them from that iteration's
+        inputs (kept intact by ping-ponging the position buffers)."""
         st = D.stream()
         P = C.byref(self.params)
         self.Es.copy_(self.E0)
         self.wall_cum.zero_()
         self.stats.zero_()
         r, k = 1.0, 0
+        hist = []
+        xin, xout = (self.x1, self.x1b) if self.elide_u else (self.x1, self.x1)
+        last_in = last_out = xout
+        wrote_u = True
         while (r > self.tol) and (k < self.maxiter):
+            want_u = (not self.elide_u) or self._expect_last(k + 1, hist)
+            if self.elide_u:
+                self.Es_prev.copy_(self.Es)
             if self.iter_events is not None:
                 ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
                 ev[0].record()
-            _lib.call("pic_dev_dd_picard_iter", P, D.ptr(self.x0), D.ptr(self.u0), D.ptr(self.x1), D.ptr(self.u1),
-                      D.ptr(self.active), D.ptr(self.Es), D.ptr(self.acc), 1 if k == 0 else 0,
-                      D.ptr(self.range_err), st)
+            _lib.call("pic_dev_dd_picard_iter2", P, D.ptr(self.x0), D.ptr(self.u0), D.ptr(xin), D.ptr(xout),
+                      D.ptr(self.u1) if want_u else None, D.ptr(self.active), D.ptr(self.Es), D.ptr(self.acc),
+                      1 if k == 0 else 0, D.ptr(self.range_err), st)
             if self.iter_events is not None:
                 ev[1].record()
-                self.iter_events.append(ev)
+                self.iter_events.append(ev + (want_u, k == 0))
             self.comm.allreduce_sum(self.acc)
             _lib.call("pic_dev_dd_field_update", P, D.ptr(self.acc), D.ptr(self.wall_cum), D.ptr(self.E0),
                       D.ptr(self.Es), D.ptr(self.E1), D.ptr(self.j0), D.ptr(self.stats), st)
             self.kernel_launches += 2
             r = float(D.read_f64(self.stats, 1)[0])
             k += 1
+            hist.append(r)
             if self.resid_trace is not None:
                 self.resid_trace.append(r)
+            wrote_u, last_in, last_out = want_u, xin, xout
+            if self.elide_u:
+                xin, xout = xout, xin
+        if k > 0 and not wrote_u:
+            _lib.call("pic_dev_dd_commit_u", P, D.ptr(self.x0), D.ptr(self.u0), D.ptr(last_in), D.ptr(last_out),
+                      D.ptr(self.active), D.ptr(self.Es_prev), D.ptr(self.u1), 1 if k == 1 else 0,
+                      D.ptr(self.range_err), st)
+            self.kernel_launches += 1
+            self.u_repairs += 1
+        if hist:
+            ratios = [b / a for a, b in zip(hist, hist[1:]) if a > 0.0]
+            self._r1 = hist[0]
+            if ratios:
+                self._ratio = max(ratios)
         # commit (PIC_L_DD.py:538-545): pointer swaps
-        self.x0, self.x1 = self.x1, self.x0
-        self.u0, self.u1 = self.u1, self.u0
-        self.E0, self.E1 = self.E1, self.E0
+        if k > 0:
+            if self.elide_u:
+                spare = self.x0
+                self.x0 = last_out
+                self.x1, self.x1b = (last_in, spare) if last_in is not last_out else (spare, self.x1b)
+            else:
+                self.x0, self.x1 = self.x1, self.x0
+            self.u0, self.u1 = self.u1, self.u0
+            self.E0, self.E1 = self.E1, self.E0
         self.last_iters, self.last_resid = k, r
         return k, r
 

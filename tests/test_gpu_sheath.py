@@ -218,6 +218,86 @@ def test_tma_kernel_at_scale_matches_grid_stride_kernel(sort):
     a.check(); b.check()
 
 
+@pytest.mark.parametrize("deposit", ["window", "warp"])
+def test_velocity_store_elision_and_repair_bit_exact(deposit):
+    """An iteration run WITHOUT the velocity store followed by pic_dev_dd_commit_u gives
+    bit-identical u1 (and identical x1, flags) to the iteration run with the store -- for the
+    first iteration, for later ones, for particles absorbed in that iteration (real values) and
+    for particles absorbed earlier (the reference's zeros)."""
+    import torch
+    from pypic_b200 import _lib, device as D
+    N, Ng = 70000, 130
+    dx, L, dt, x0, u0, q, m, E0 = _one_iter_inputs(N, Ng, 13)
+    p2c = 3.0e9
+    dev = D.require_cuda()
+    flags = {"window": 0, "warp": 4}[deposit]
+    P = _lib.DDParams(N, N // 2, Ng, flags, dx, dt, L, p2c, (C.c_double * 2)(-O.e, O.e), (C.c_double * 2)(O.me, O.mp))
+    tx0, tu0 = D.to_dev(x0, dev), D.to_dev(u0, dev)
+    err = torch.zeros(1, dtype=torch.int32, device=dev)
+    acc = D.f64(2 * Ng + 4, dev, True)
+    # reference chain: in-place x1, u1 always stored
+    rx1, ru1 = D.f64(N, dev, True), D.f64(N, dev, True)
+    ract = torch.ones(N, dtype=torch.int8, device=dev)
+    # elided chain: ping-pong buffers, u1 never stored by the iteration
+    xa, xb, eu1 = D.f64(N, dev, True), D.f64(N, dev, True), torch.full((N,), 7.0, dtype=torch.float64, device=dev)
+    eact = torch.ones(N, dtype=torch.int8, device=dev)
+    tEs = D.to_dev(E0, dev)
+    xin, xout = xa, xb
+    for it in range(4):
+        first = 1 if it == 0 else 0
+        acc.zero_()
+        _lib.call("pic_dev_dd_picard_iter", C.byref(P), D.ptr(tx0), D.ptr(tu0), D.ptr(rx1), D.ptr(ru1), D.ptr(ract),
+                  D.ptr(tEs), D.ptr(acc), first, D.ptr(err), D.stream())
+        acc_ref = acc.clone(); acc.zero_()
+        _lib.call("pic_dev_dd_picard_iter2", C.byref(P), D.ptr(tx0), D.ptr(tu0), D.ptr(xin), D.ptr(xout), None, D.ptr(eact),
+                  D.ptr(tEs), D.ptr(acc), first, D.ptr(err), D.stream())
+        assert torch.equal(xout, rx1) and torch.equal(eact, ract), it
+        assert torch.equal(acc[2 * Ng:], acc_ref[2 * Ng:])
+        assert relmax(acc.cpu().numpy()[:2 * Ng], acc_ref.cpu().numpy()[:2 * Ng]) < 1e-13
+        assert float(eu1.min()) == 7.0 and float(eu1.max()) == 7.0            # the iteration did not touch u1
+        rep = torch.full((N,), -3.0, dtype=torch.float64, device=dev)
+        _lib.call("pic_dev_dd_commit_u", C.byref(P), D.ptr(tx0), D.ptr(tu0), D.ptr(xin), D.ptr(xout), D.ptr(eact), D.ptr(tEs),
+                  D.ptr(rep), first, D.ptr(err), D.stream())
+        assert torch.equal(rep, ru1), it
+        dead = int((ract != 1).sum())
+        assert dead > 20
+        if it >= 2:
+            assert int(((ract != 1) & (ru1 == 0.0)).sum()) > 20               # zeros of the earlier-absorbed ones
+        xin, xout = xout, xin
+        tEs.mul_(0.9)
+    assert int(err.item()) == 0
+
+
+def test_sheath_sim_elision_modes_agree():
+    """SheathSim with the velocity-store elision (default), with every prediction forced wrong
+    (repair pass after every step) and without elision: same iteration counts, same fields and
+    particles to round-off over several steps."""
+    from pypic_b200.sheath import SheathSim
+    N, Ng = 200000, 257
+    dx, L, dt, x0, u0, q, m, E0 = _one_iter_inputs(N, Ng, 5)
+    sims = []
+    for mode in ("plain", "elide", "always-repair"):
+        s = SheathSim(N, Ng, dx, dt, 1e9, kBT=(1.6e-18, 1.6e-18), carry_vw=False, rng="philox", sort_every=0,
+                      elide_u=(mode != "plain"))
+        if mode == "always-repair":
+            s._expect_last = lambda k, hist: False
+        s.upload(x0, u0, E0=E0)
+        sims.append(s)
+    for step in range(5):
+        ks = [s.step()[0] for s in sims]
+        assert ks[0] == ks[1] == ks[2], ks
+        ref = sims[0].download()
+        for s in sims[1:]:
+            o = s.download()
+            assert np.array_equal(o["active"], ref["active"])
+            assert relmax(o["E0"], ref["E0"]) < 1e-12
+            assert relmax(o["x0"], ref["x0"]) < 1e-13 and relmax(o["u0"], ref["u0"]) < 1e-12
+    assert sims[0].u_repairs == 0 and sims[2].u_repairs == 5
+    assert sims[1].u_repairs <= 1            # only the very first step has no contraction history
+    for s in sims:
+        s.check()
+
+
 @pytest.mark.parametrize("tag", ["small", "default"])
 def test_whole_loop_vs_reference_golden(golden, tag):
     """PIC_L_DD.main_i itself (golden from the reference run): same seed, the host draw
