@@ -34,7 +34,7 @@ METRIC = "particle-steps/sec (full PIC step)"
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
     ap.add_argument("--particles-per-gpu", type=float, default=2e8)
@@ -65,34 +65,60 @@ def workload(args, world):
 
 
 class ClockSampler(threading.Thread):
-    """Samples nvidia-smi clocks / throttle reasons during the timed region."""
+    """Samples SM clocks / throttle reasons DURING the timed region: NVML in-process (a sample
+    costs ~0.1 ms, so even a 100 ms region sees dozens), nvidia-smi subprocess as fallback."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
+    NAMES = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
 
     def __init__(self, index):
         super().__init__(daemon=True)
-        self.index, self.rows, self.stop_flag = index, [], False
+        self.index, self.rows, self.stop_flag, self.src = index, [], False, "nvidia-smi"
+        self.h = None
+        try:
+            import pynvml as nv
+            nv.nvmlInit()
+            # NVML enumerates physical devices; honour CUDA_VISIBLE_DEVICES when it is a plain index list
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES", "")
+            phys = index
+            if vis and all(t.strip().isdigit() for t in vis.split(",")):
+                phys = int(vis.split(",")[index])
+            self.h, self.nv, self.src = nv.nvmlDeviceGetHandleByIndex(phys), nv, "nvml"
+            self.smax = float(nv.nvmlDeviceGetMaxClockInfo(self.h, nv.NVML_CLOCK_SM))
+        except Exception:
+            self.h = None
+
+    def sample(self):
+        if self.h is not None:
+            nv = self.nv
+            sm = float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+            pw = nv.nvmlDeviceGetPowerUsage(self.h) / 1e3
+            rs = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+            bits = [nv.nvmlClocksEventReasonHwSlowdown, nv.nvmlClocksEventReasonHwThermalSlowdown,
+                    nv.nvmlClocksEventReasonSwThermalSlowdown, nv.nvmlClocksEventReasonSwPowerCap]
+            return [sm, self.smax, pw] + [bool(rs & b) for b in bits]
+        out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                              "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+        c = [t.strip() for t in out.strip().split("\n")[0].split(",")]
+        return [float(c[0]), float(c[1]), float(c[2])] + [t.lower().startswith("active") for t in c[3:7]]
 
     def run(self):
         while not self.stop_flag:
             try:
-                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
-                if out.strip():
-                    self.rows.append([c.strip() for c in out.strip().split("\n")[0].split(",")])
+                self.rows.append(self.sample())
             except Exception:
                 pass
-            time.sleep(0.2)
+            time.sleep(0.005 if self.h is not None else 0.2)
 
     def summary(self):
         if not self.rows:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
-        sm = sorted(float(r[0]) for r in self.rows if r[0].replace(".", "").isdigit())
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = [n for k, n in enumerate(names) if any(len(r) > 3 + k and r[3 + k].lower().startswith("active") for r in self.rows)]
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": float(self.rows[0][1]) if self.rows else None,
-                "power_w_max": max(float(r[2]) for r in self.rows), "reasons": reasons, "samples": len(self.rows)}
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0, "source": self.src}
+        sm = sorted(r[0] for r in self.rows)
+        reasons = [n for k, n in enumerate(self.NAMES) if any(r[3 + k] for r in self.rows)]
+        return {"sm_mhz": sm[len(sm) // 2], "sm_min_mhz": sm[0], "sm_max_mhz": self.rows[0][1],
+                "power_w_max": max(r[2] for r in self.rows), "reasons": reasons, "samples": len(self.rows),
+                "source": self.src}
 
 
 def measured_peak():
