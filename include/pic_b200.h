@@ -195,7 +195,11 @@ int pic_dev_pypic_weight(const double* x, const double* q, const double* v, doub
 typedef struct {
     int64_t N;
     int32_t Ng;
-    int32_t flags;
+    int32_t flags;         /* 0 (default): TMA-staged private-window kernel over whole 16384-particle
+                              chunks (fast on a store sorted by cell), grid-stride kernel on the tail;
+                              bit0: plain shared-memory atomics per contribution; bit2: grid-stride kernel
+                              with warp-uniform pre-reduction for every particle (any particle order);
+                              bit1: x0 holds UNWRAPPED positions, ``x % L`` (pypic.py:277) is applied on load */
     double dx, dt, L, p2c; /* p2c already truncated */
     double q, m;           /* single species (electrons)            */
 } pic_pypic_params;
@@ -234,8 +238,11 @@ int pic_dev_l_weight(const double* x, const double* q, const double* v, double* 
 /* Fused explicit step, particle phase (PIC_L.py:767-768 + next step's :763):
  * gather E at x, kick-drift-kick, wrap x%(L+dx), and deposit rho of the NEW positions
  * into rho_acc fp64[Ng+1] (zero on entry, raw CIC; fold applied by pic_dev_l_field_solve).
- * flags bit0: plain shared-memory atomics; bit1: function-level PIC_L.pushParticlesExplicit
- * :248-259 -- x,v receive the UNWRAPPED xout,vout and nothing is deposited. */
+ * flags 0 (default): TMA-staged private-window kernel over whole 16384-particle chunks (fast on
+ * a store sorted by (species, cell)), grid-stride kernel on the tail; bit0: plain shared-memory
+ * atomics; bit2: grid-stride kernel with warp-uniform pre-reduction for every particle (any
+ * order); bit1: function-level PIC_L.pushParticlesExplicit :248-259 -- x,v receive the UNWRAPPED
+ * xout,vout and nothing is deposited. */
 int pic_dev_l_push_deposit(const pic_l_params* p, double* x, double* v, const double* E,
                            double* rho_acc, int* range_err, void* stream);
 /* PIC_L.py:763-766 field phase: fold rho_acc -> rho; periodic Poisson; -max; E=-dphi/dx.
@@ -332,6 +339,14 @@ int pic_host_dd_weightDensities(const double* x, const double* q, double p2c, in
 int pic_host_dd_step(const pic_dd_params* p, const double* x0, const double* u0, const double* E0,
                      double tol, int maxiter, double* x1, double* u1, int8_t* active, double* E1,
                      double* j1, int* iters, double* resid);
+/* The same for `nbatch` INDEPENDENT states (arrays of nbatch host pointers; pinned memory makes
+ * the copies asynchronous): batches are pipelined through two device slots so that the upload
+ * of batch b+1 and the download of batch b-1 overlap the Picard loop of batch b.  iters/resid
+ * receive nbatch entries. */
+int pic_host_dd_step_batches(const pic_dd_params* p, int nbatch, const double* const* x0,
+                             const double* const* u0, const double* const* E0, double tol, int maxiter,
+                             double* const* x1, double* const* u1, int8_t* const* active,
+                             double* const* E1, double* const* j1, int* iters, double* resid);
 
 #ifdef __cplusplus
 }

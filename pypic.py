@@ -180,7 +180,7 @@ def implicit_pic(T, nplot, system, density, perturbation, Kp, N, Ng, Nv, Vmax, d
         print("Total Energy: ", d["EE"] + d["KE"])
         j_bias.append(d["jbias"])
         if tracer < N:
-            trajectory_x.append(float(sim.x0[tracer].item()))
+            trajectory_x.append(float(sim.x0[tracer].item()) % L)      # the store wraps lazily
             trajectory_v.append(float(sim.v0[tracer].item()) / np.sqrt(kBTe / me))
         if plt is not None and (t % nplot == 0):
             st = sim.download()

@@ -106,6 +106,7 @@ _SIGS = {
     "pic_host_dd_weightDensities": [P, P, F64, I32, I64, F64, P, P],
     "pic_host_dd_step": [C.POINTER(DDParams), P, P, P, F64, I32, P, P, P, P, P, C.POINTER(C.c_int),
                          C.POINTER(C.c_double)],
+    "pic_host_dd_step_batches": [C.POINTER(DDParams), I32, P, P, P, F64, I32, P, P, P, P, P, P, P],
 }
 EXPORTS = sorted(list(_SIGS) + ["pic_last_error", "pic_version"])
 

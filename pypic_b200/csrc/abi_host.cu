@@ -190,54 +190,131 @@ int pic_host_dd_weightDensities(const double* x, const double* q, double p2c, in
     return host_dd_weight(x, q, nullptr, p2c, Ng, N, dx, 1.0, active, rho);
 }
 
-// ---- whole sheath timestep with host buffers ---------------------------------------
+// ---- whole sheath timesteps with host buffers ------------------------------------------
+// Pipeline of independent batches: while batch b runs its Picard loop on the compute stream,
+// the inputs of batch b+1 travel host->device and the results of batch b-1 travel device->host
+// on two more streams (two device slots).  The residual of every Picard iteration reaches the
+// host through MAPPED pinned memory written by a one-thread kernel, not through a copy-engine
+// transfer that would queue behind the bulk copies.
+namespace {
+__global__ void publish_resid_k(const double* __restrict__ stats, volatile double* host_out) { host_out[0] = stats[0]; }
+
+struct Pipe {
+    cudaStream_t h2d = nullptr, cmp = nullptr, d2h = nullptr;
+    cudaEvent_t ev_in[2] = {nullptr, nullptr}, ev_cmp[2] = {nullptr, nullptr}, ev_out[2] = {nullptr, nullptr};
+    double* resid_host = nullptr;   // mapped pinned
+    int* err_host = nullptr;        // pinned int[2]
+    int init() {
+        if (h2d) return PIC_OK;
+        PIC_CHECK_CUDA(cudaStreamCreateWithFlags(&h2d, cudaStreamNonBlocking));
+        PIC_CHECK_CUDA(cudaStreamCreateWithFlags(&cmp, cudaStreamNonBlocking));
+        PIC_CHECK_CUDA(cudaStreamCreateWithFlags(&d2h, cudaStreamNonBlocking));
+        for (int i = 0; i < 2; ++i) {
+            PIC_CHECK_CUDA(cudaEventCreateWithFlags(&ev_in[i], cudaEventDisableTiming));
+            PIC_CHECK_CUDA(cudaEventCreateWithFlags(&ev_cmp[i], cudaEventDisableTiming));
+            PIC_CHECK_CUDA(cudaEventCreateWithFlags(&ev_out[i], cudaEventDisableTiming));
+        }
+        PIC_CHECK_CUDA(cudaHostAlloc((void**)&resid_host, 8 * sizeof(double), cudaHostAllocMapped));
+        PIC_CHECK_CUDA(cudaHostAlloc((void**)&err_host, 2 * sizeof(int), cudaHostAllocDefault));
+        return PIC_OK;
+    }
+};
+Pipe g_pipe;
+}  // namespace
+
+int pic_host_dd_step_batches(const pic_dd_params* p, int nbatch, const double* const* x0, const double* const* u0,
+                             const double* const* E0, double tol, int maxiter, double* const* x1, double* const* u1,
+                             int8_t* const* active, double* const* E1, double* const* j1, int* iters, double* resid) {
+    PIC_REQUIRE(p && x0 && u0 && E0 && x1 && u1 && active && E1 && j1 && iters && resid, "dd_step_batches: null pointer");
+    PIC_REQUIRE(nbatch >= 1 && p->N >= 1 && p->Ng >= 3, "dd_step_batches: bad sizes");
+    for (int b = 0; b < nbatch; ++b)
+        PIC_REQUIRE(x0[b] && u0[b] && E0[b] && x1[b] && u1[b] && active[b] && E1[b] && j1[b], "dd_step_batches: null batch pointer");
+    std::lock_guard<std::mutex> lk(g_ws.mu);
+    int rc = g_pipe.init();
+    if (rc) return rc;
+    Pipe& q = g_pipe;
+    const int64_t N = p->N;
+    const int Ng = p->Ng;
+    const int nslot = nbatch > 1 ? 2 : 1;
+    double *dx0[2], *du0[2], *dx1[2], *du1[2], *grid[2];
+    int8_t* dact[2];
+    int* derr[2];
+    for (int s = 0; s < nslot; ++s) {
+        const size_t base = 10 + 8 * (size_t)s;
+        if ((rc = g_ws.get(base + 0, (size_t)N * 8, (void**)&dx0[s]))) return rc;
+        if ((rc = g_ws.get(base + 1, (size_t)N * 8, (void**)&du0[s]))) return rc;
+        if ((rc = g_ws.get(base + 2, (size_t)N * 8, (void**)&dx1[s]))) return rc;
+        if ((rc = g_ws.get(base + 3, (size_t)N * 8, (void**)&du1[s]))) return rc;
+        if ((rc = g_ws.get(base + 4, (size_t)N, (void**)&dact[s]))) return rc;
+        if ((rc = g_ws.get(base + 5, (8 * (size_t)Ng + 16) * 8, (void**)&grid[s]))) return rc;
+        if ((rc = g_ws.get(base + 6, sizeof(int), (void**)&derr[s]))) return rc;
+    }
+    double* resid_dev = nullptr;
+    PIC_CHECK_CUDA(cudaHostGetDevicePointer((void**)&resid_dev, q.resid_host, 0));
+    auto upload = [&](int b) -> int {
+        const int s = b & (nslot - 1);
+        // the slot's inputs were last read by the compute of batch b-2, which the host has waited for
+        PIC_CHECK_CUDA(cudaMemcpyAsync(dx0[s], x0[b], (size_t)N * 8, cudaMemcpyHostToDevice, q.h2d));
+        PIC_CHECK_CUDA(cudaMemcpyAsync(du0[s], u0[b], (size_t)N * 8, cudaMemcpyHostToDevice, q.h2d));
+        PIC_CHECK_CUDA(cudaMemcpyAsync(grid[s], E0[b], (size_t)Ng * 8, cudaMemcpyHostToDevice, q.h2d));
+        PIC_CHECK_CUDA(cudaEventRecord(q.ev_in[s], q.h2d));
+        return PIC_OK;
+    };
+    q.err_host[0] = q.err_host[1] = 0;
+    if ((rc = upload(0))) return rc;
+    for (int b = 0; b < nbatch; ++b) {
+        const int s = b & (nslot - 1);
+        if (b + 1 < nbatch && (rc = upload(b + 1))) return rc;
+        double *dE0 = grid[s], *dEs = grid[s] + Ng, *dE1 = grid[s] + 2 * Ng, *dj1 = grid[s] + 3 * Ng,
+               *dacc = grid[s] + 4 * Ng, *dwall = grid[s] + 6 * Ng + 4, *dstats = grid[s] + 6 * Ng + 8;
+        PIC_CHECK_CUDA(cudaStreamWaitEvent(q.cmp, q.ev_in[s], 0));
+        if (b >= 2) PIC_CHECK_CUDA(cudaStreamWaitEvent(q.cmp, q.ev_out[s], 0));   // results of b-2 have left the slot
+        PIC_CHECK_CUDA(cudaMemsetAsync(derr[s], 0, sizeof(int), q.cmp));
+        PIC_CHECK_CUDA(cudaMemsetAsync(dacc, 0, (size_t)(2 * Ng + 4 + 4 + 4) * 8, q.cmp));   // acc, wall_cum, stats
+        PIC_CHECK_CUDA(cudaMemsetAsync(dact[s], 1, (size_t)N, q.cmp));
+        PIC_CHECK_CUDA(cudaMemcpyAsync(dEs, dE0, (size_t)Ng * 8, cudaMemcpyDeviceToDevice, q.cmp));
+        double r = 1.0;
+        int k = 0;
+        while (r > tol && k < maxiter) {      // PIC_L_DD.py:458
+            rc = pic_dev_dd_picard_iter(p, dx0[s], du0[s], dx1[s], du1[s], dact[s], dEs, dacc, k == 0, derr[s], q.cmp);
+            if (rc) return rc;
+            rc = pic_dev_dd_field_update(p, dacc, dwall, dE0, dEs, dE1, dj1, dstats, q.cmp);
+            if (rc) return rc;
+            publish_resid_k<<<1, 1, 0, q.cmp>>>(dstats, resid_dev);
+            PIC_CHECK_LAUNCH();
+            PIC_CHECK_CUDA(cudaStreamSynchronize(q.cmp));
+            r = *(volatile double*)q.resid_host;
+            ++k;
+        }
+        iters[b] = k;
+        resid[b] = r;
+        PIC_CHECK_CUDA(cudaEventRecord(q.ev_cmp[s], q.cmp));
+        PIC_CHECK_CUDA(cudaStreamWaitEvent(q.d2h, q.ev_cmp[s], 0));
+        PIC_CHECK_CUDA(cudaMemcpyAsync(x1[b], dx1[s], (size_t)N * 8, cudaMemcpyDeviceToHost, q.d2h));
+        PIC_CHECK_CUDA(cudaMemcpyAsync(u1[b], du1[s], (size_t)N * 8, cudaMemcpyDeviceToHost, q.d2h));
+        PIC_CHECK_CUDA(cudaMemcpyAsync(active[b], dact[s], (size_t)N, cudaMemcpyDeviceToHost, q.d2h));
+        PIC_CHECK_CUDA(cudaMemcpyAsync(E1[b], dE1, (size_t)Ng * 8, cudaMemcpyDeviceToHost, q.d2h));
+        PIC_CHECK_CUDA(cudaMemcpyAsync(j1[b], dj1, (size_t)Ng * 8, cudaMemcpyDeviceToHost, q.d2h));
+        PIC_CHECK_CUDA(cudaMemcpyAsync(&q.err_host[s], derr[s], sizeof(int), cudaMemcpyDeviceToHost, q.d2h));
+        PIC_CHECK_CUDA(cudaEventRecord(q.ev_out[s], q.d2h));
+        if (b >= 1) {   // the previous batch's results (other slot) must be complete before its error word is read
+            PIC_CHECK_CUDA(cudaEventSynchronize(q.ev_out[(b - 1) & (nslot - 1)]));
+        }
+    }
+    PIC_CHECK_CUDA(cudaStreamSynchronize(q.d2h));
+    const int bad = q.err_host[0] + q.err_host[1];
+    if (bad) {
+        pic::set_error("dd_step: %d particle position(s) outside the grid (reference behaviour undefined); indices were clamped", bad);
+        return PIC_ERR_RANGE;
+    }
+    return PIC_OK;
+}
+
 int pic_host_dd_step(const pic_dd_params* p, const double* x0, const double* u0, const double* E0, double tol,
                      int maxiter, double* x1, double* u1, int8_t* active, double* E1, double* j1, int* iters,
                      double* resid) {
-    PIC_REQUIRE(p && x0 && u0 && E0 && x1 && u1 && active && E1 && j1 && iters && resid, "dd_step: null pointer");
-    PIC_REQUIRE(p->N >= 1 && p->Ng >= 3, "dd_step: bad sizes");
-    std::lock_guard<std::mutex> lk(g_ws.mu);
-    int rc = g_ws.ensure_stream();
-    if (rc) return rc;
-    cudaStream_t st = g_ws.stream;
-    const int64_t N = p->N;
-    const int Ng = p->Ng;
-    WS_GET(10, double, N, dx0);
-    WS_GET(11, double, N, du0);
-    WS_GET(12, double, N, dx1);
-    WS_GET(13, double, N, du1);
-    WS_GET(14, int8_t, N, dact);
-    WS_GET(15, double, 8 * (size_t)Ng + 16, grid);
-    WS_GET(3, int, 1, derr);
-    double *dE0 = grid, *dEs = grid + Ng, *dE1 = grid + 2 * Ng, *dj1 = grid + 3 * Ng, *dacc = grid + 4 * Ng,
-           *dwall = grid + 6 * Ng + 4, *dstats = grid + 6 * Ng + 8;
-    PIC_CHECK_CUDA(cudaMemsetAsync(derr, 0, sizeof(int), st));
-    PIC_CHECK_CUDA(cudaMemsetAsync(dacc, 0, (size_t)(2 * Ng + 4 + 4 + 4) * 8, st));   // acc, wall_cum, stats
-    PIC_CHECK_CUDA(cudaMemsetAsync(dact, 1, (size_t)N, st));
-    PIC_CHECK_CUDA(cudaMemcpyAsync(dx0, x0, (size_t)N * 8, cudaMemcpyHostToDevice, st));
-    PIC_CHECK_CUDA(cudaMemcpyAsync(du0, u0, (size_t)N * 8, cudaMemcpyHostToDevice, st));
-    PIC_CHECK_CUDA(cudaMemcpyAsync(dE0, E0, (size_t)Ng * 8, cudaMemcpyHostToDevice, st));
-    PIC_CHECK_CUDA(cudaMemcpyAsync(dEs, dE0, (size_t)Ng * 8, cudaMemcpyDeviceToDevice, st));
-    double r = 1.0;
-    int k = 0;
-    while (r > tol && k < maxiter) {      // PIC_L_DD.py:458
-        rc = pic_dev_dd_picard_iter(p, dx0, du0, dx1, du1, dact, dEs, dacc, k == 0, derr, st);
-        if (rc) return rc;
-        rc = pic_dev_dd_field_update(p, dacc, dwall, dE0, dEs, dE1, dj1, dstats, st);
-        if (rc) return rc;
-        PIC_CHECK_CUDA(cudaMemcpyAsync(g_ws.pinned, dstats, sizeof(double), cudaMemcpyDeviceToHost, st));
-        PIC_CHECK_CUDA(cudaStreamSynchronize(st));
-        r = g_ws.pinned[0];
-        ++k;
-    }
-    PIC_CHECK_CUDA(cudaMemcpyAsync(x1, dx1, (size_t)N * 8, cudaMemcpyDeviceToHost, st));
-    PIC_CHECK_CUDA(cudaMemcpyAsync(u1, du1, (size_t)N * 8, cudaMemcpyDeviceToHost, st));
-    PIC_CHECK_CUDA(cudaMemcpyAsync(active, dact, (size_t)N, cudaMemcpyDeviceToHost, st));
-    PIC_CHECK_CUDA(cudaMemcpyAsync(E1, dE1, (size_t)Ng * 8, cudaMemcpyDeviceToHost, st));
-    PIC_CHECK_CUDA(cudaMemcpyAsync(j1, dj1, (size_t)Ng * 8, cudaMemcpyDeviceToHost, st));
-    *iters = k;
-    *resid = r;
-    return check_range(derr, st, "dd_step");
+    PIC_REQUIRE(x0 && u0 && E0 && x1 && u1 && active && E1 && j1, "dd_step: null pointer");
+    return pic_host_dd_step_batches(p, 1, &x0, &u0, &E0, tol, maxiter, &x1, &u1, &active, &E1, &j1, iters, resid);
 }
 
 int pic_host_release(void) {

@@ -3,6 +3,7 @@
 // wall absorption and the deposition of BOTH currents (jh at the half step, j1 at the
 // full step) in a single pass over the structure-of-arrays particle store.
 #include "common.cuh"
+#include "ring.cuh"
 #include "host_common.h"
 
 namespace pic {
@@ -218,8 +219,6 @@ struct FastC {
 };
 struct FastO { double X1, U1, hL, hR, fL, fR; int cH, cF; };
 
-#define PIC_HI_G 0x3EB00000u                      /* hi word of 2^-20       */
-#define PIC_HI_SPAN (0x3FEFFFFEu - 0x3EB00000u)    /* hi(1-2^-19) - hi(2^-20) */
 
 template <bool FIRST>
 __device__ __forceinline__ bool dd_fast(const FastC& c, const double* __restrict__ sF, int Ng, double X0, double U0,
@@ -407,38 +406,6 @@ __global__ void __launch_bounds__(V5_T, 1) dd_picard_iter_v5_k(
 #define V6_NST 4
 #endif
 #define V6_CHUNK (V6_T * 2 * V6_ROWS)
-
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
-                 "l"(src), "r"(bytes), "r"(bar)
-                 : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-    asm volatile(
-        "{\n"
-        ".reg .pred P1;\n"
-        "LAB_WAIT:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
-        "@P1 bra DONE;\n"
-        "bra LAB_WAIT;\n"
-        "DONE:\n"
-        "}" ::"r"(bar),
-        "r"(parity)
-        : "memory");
-}
-
-__device__ __forceinline__ bool elect_one() {
-    uint32_t pred;
-    asm volatile("{\n.reg .pred P;\nelect.sync _|P, 0xffffffff;\nselp.u32 %0, 1, 0, P;\n}" : "=r"(pred));
-    return pred != 0;
-}
 
 __device__ __forceinline__ void win_add6(double* myw, double* acc, int wb, int tile, int Ng, int c, double vL, double vR) {
     const unsigned d = (unsigned)(c - wb);

@@ -3,6 +3,7 @@
 // phase is one fused pass (gather + push + wrap + deposit) over the SoA store with the
 // field / current tiles in shared memory.
 #include "common.cuh"
+#include "ring.cuh"
 #include "host_common.h"
 
 namespace pic {
@@ -104,6 +105,7 @@ __global__ void __launch_bounds__(256) pypic_picard_iter_k(PYK k, const double* 
         double hL = 0., hR = 0., fL = 0., fR = 0.;
         if (valid) {
             double X0 = ld_stream(x0 + i), V0 = ld_stream(v0 + i);
+            if (k.flags & 2) X0 = wrap_mod(X0, k.L);                 // store keeps the unwrapped x1 of the last step
             double xs = FIRST ? X0 : wrap_mod((X0 + ld_stream(x1 + i)) * 0.5, k.L);
             Cell c = cell_pypic<false>(xs, k.dx, k.idx, Ng);
             pypic_fix(c, Ng, bad);
@@ -300,6 +302,383 @@ __global__ void __launch_bounds__(256) l_push_deposit_k(LK k, double* __restrict
     if (bad && range_err) atomicAdd(range_err, bad);
 }
 
+
+// =====================================================================================
+// v2 streaming kernels: the design of dd_picard_iter_v6_k (dd_kernels.cu) applied to the two
+// periodic codes.  One persistent 512-thread CTA per SM; every warp owns contiguous slices of
+// 1024 particles whose rows (64 particles of each input array) are staged through shared
+// memory by 1-D TMA bulk copies into a per-warp ring (mbarrier completion), a lane handles two
+// consecutive particles per row, and deposits go to the lane's PRIVATE window of S_W grid
+// nodes in shared memory (conflict-free [node][thread] layout, plain LDS/DADD/STS).  The
+// window is flushed with one column sum + S_W global REDs per slice.  The fast path assumes
+// what holds for all but ~1e-5 of the particles of a store sorted by cell: position strictly
+// inside the domain before and after the push (no periodic wrap), cell lookups not within
+// 2^-20 of a cell edge (then floor(x*idx) is the true floor quotient and the remainder by one
+// fma is exact), cell inside the warp's window.  Everything else is settled per particle by
+// the exact routine of the v1 kernels with global REDs.
+#define S_T 512
+#define S_W 7
+#define S_ROWS 16
+#define S_CHUNK (S_T * 2 * S_ROWS)
+
+__device__ __forceinline__ void swin_add(double* myw, double* __restrict__ acc, int wb, int c, double vL, double vR) {
+    const unsigned d = (unsigned)(c - wb);
+    if (d <= (unsigned)(S_W - 2)) { double* p = myw + d * S_T; p[0] += vL; p[S_T] += vR; }
+    else { atomicAdd(&acc[c], vL); atomicAdd(&acc[c + 1], vR); }
+}
+
+// column sums of the warp's 32 private windows (NC = tiles * S_W columns <= 16) -> global REDs
+template <int TILES>
+__device__ __forceinline__ void swin_flush(double* win, double* myw, int wbase, int lane, int wb, double* __restrict__ acc,
+                                           int tile_stride, int nodes) {
+    constexpr int NC = TILES * S_W;
+    double s = 0.0;
+    const int n = lane >> 1, half = lane & 1;
+    if (n < NC) {
+        const double* col = win + n * S_T + wbase + half * 16;
+#pragma unroll
+        for (int j = 0; j < 16; ++j) s += col[(j + n) & 15];
+    }
+    s += __shfl_xor_sync(0xffffffffu, s, 1);
+    if (n < NC && half == 0) {
+        const int t = n / S_W;
+        const int node = wb + (n - t * S_W);
+        if (node >= 0 && node < nodes && s != 0.0) atomicAdd(&acc[t * tile_stride + node], s);
+    }
+    __syncwarp();
+#pragma unroll
+    for (int n2 = 0; n2 < NC; ++n2) myw[n2 * S_T] = 0.0;
+    __syncwarp();
+}
+
+// ---------------------------------------------------------------- PIC_L explicit step
+struct LFastC { double dx, idx, dt, qmh, qpi; unsigned hi_lim; };
+struct LFastO { double X, V, fL, fR; int cF; unsigned fr, ps; };
+
+__device__ __forceinline__ void l_fast(const LFastC& c, const double* __restrict__ sE, int nodes, double X, double V,
+                                       LFastO& o) {
+    const double ts = X * c.idx, fs = floor(ts);
+    const unsigned f0 = (unsigned)__double2hiint(ts - fs) - PIC_HI_G;
+    const double rs = fma(-fs, c.dx, X);
+    const int is = min(max((int)fs, 0), nodes - 2);
+    const double wR = div_const(rs, c.dx, c.idx), wL = 1.0 - wR;
+    const double Ei = wL * sE[is] + wR * sE[is + 1];                 // PIC_L.py:45
+    const double vh = V + c.qmh * Ei;                                 // :255
+    o.X = X + vh * c.dt;                                              // :256
+    o.V = vh + c.qmh * Ei;                                            // :257
+    o.ps = max((unsigned)__double2hiint(X) - 1u, (unsigned)__double2hiint(o.X) - 1u);
+    const double tf = o.X * c.idx, ff = floor(tf);
+    const unsigned f1 = (unsigned)__double2hiint(tf - ff) - PIC_HI_G;
+    const double rf = fma(-ff, c.dx, o.X);
+    o.cF = (int)ff;
+    o.fr = max(f0, f1);
+    o.fR = c.qpi * (rf * c.idx); o.fL = c.qpi - o.fR;                 // :112-113 up to re-association
+}
+
+// exact per-particle routine (the body of l_push_deposit_k); deposits with global REDs
+__device__ __noinline__ int l_particle_exact(const LK& k, long long i, double X, double V, const double* sE,
+                                             double* __restrict__ rho_acc, double* x, double* v) {
+    const int nodes = k.Ng + 1;
+    int bad = 0;
+    const int sp = i >= k.n_split;
+    Cell c = cell_lper(X, k.dx, nodes);
+    l_fix(c, nodes, bad);
+    const double Ei = c.wL * sE[c.iL] + c.wR * sE[c.iR];
+    const double qm = sp ? k.qm[1] : k.qm[0];
+    const double hdt = k.dt * 0.5;
+    const double vhalf = V + qm * hdt * Ei;
+    const double xout = X + vhalf * k.dt;
+    const double vout = vhalf + qm * hdt * Ei;
+    const double xw = wrap_mod(xout, k.L + k.dx);
+    x[i] = xw; v[i] = vout;
+    Cell cn = cell_lper(xw, k.dx, nodes);
+    l_fix(cn, nodes, bad);
+    const double pre = (sp ? k.q[1] : k.q[0]) * k.p2c;
+    atomicAdd(&rho_acc[cn.iL], pre * cn.wL * k.idx);
+    atomicAdd(&rho_acc[cn.iR], pre * cn.wR * k.idx);
+    return bad;
+}
+
+template <int NST>
+__global__ void __launch_bounds__(S_T, 1) l_push_deposit_v2_k(const __grid_constant__ LK k, int nchunks, double* x,
+                                                               double* v, const double* __restrict__ E,
+                                                               double* __restrict__ rho_acc, int* __restrict__ range_err) {
+    extern __shared__ __align__(128) double sm[];
+    __shared__ int s_bad;
+    const int nodes = k.Ng + 1;
+    const int NP = (nodes + 15) & ~15;
+    double* sE = sm;
+    double* win = sm + NP;                                   // [S_W][S_T]
+    double* ring = win + S_W * S_T;                          // [warp][stage][x|v][64]
+    unsigned long long* bars = (unsigned long long*)(ring + (S_T / 32) * NST * 128);
+    for (int i = threadIdx.x; i < nodes; i += S_T) sE[i] = E[i];
+    double* myw = win + threadIdx.x;
+#pragma unroll
+    for (int n = 0; n < S_W; ++n) myw[n * S_T] = 0.0;
+    if (threadIdx.x == 0) s_bad = 0;
+    const unsigned full = 0xffffffffu;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wbase = threadIdx.x & ~31;
+    const int NOWIN = -0x40000000;
+    const double* wring = ring + warp * (NST * 128);
+    const uint32_t ring_s = smem_u32(wring);
+    const uint32_t bar_s = smem_u32(bars + warp * NST);
+    if (lane == 0) {
+#pragma unroll
+        for (int s = 0; s < NST; ++s) mbar_init(bar_s + 8 * s, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    LFastC fc;
+    fc.dx = k.dx; fc.idx = k.idx; fc.dt = k.dt;
+    fc.hi_lim = (unsigned)__double2hiint(k.L + k.dx) - 1u;
+    const double hdt = k.dt * 0.5;
+    const int my_chunks = (nchunks - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+    const long long woff = (long long)warp * (64 * S_ROWS);
+    const long long chunk_step = (long long)gridDim.x * S_CHUNK;
+    auto issue = [&](long long base, int st) {
+        if (elect_one()) {
+            const uint32_t dst = ring_s + st * 1024, bar = bar_s + 8 * st;
+            mbar_expect_tx(bar, 1024u);
+            bulk_g2s(dst, x + base, 512, bar);
+            bulk_g2s(dst + 512, v + base, 512, bar);
+        }
+    };
+    long long cbase = (long long)blockIdx.x * S_CHUNK + woff;
+    if (my_chunks > 0) {
+#pragma unroll
+        for (int s = 0; s < NST; ++s) issue(cbase + 64 * s, s);
+    }
+    int stage = 0, bad = 0;
+    uint32_t phase = 0;
+#pragma unroll 1
+    for (int c = 0; c < my_chunks; ++c, cbase += chunk_step) {
+        const bool mixed = cbase < k.n_split && cbase + 64 * S_ROWS > k.n_split;
+        const bool sp_slice = cbase >= k.n_split;
+        fc.qmh = (sp_slice ? k.qm[1] : k.qm[0]) * hdt;
+        fc.qpi = (sp_slice ? k.q[1] : k.q[0]) * k.p2c * k.idx;
+        const bool more = c + 1 < my_chunks;
+        int wb = NOWIN;
+        long long ci = cbase + 2 * lane;
+#pragma unroll 1
+        for (int row = 0; row < S_ROWS; ++row, ci += 64) {
+            mbar_wait(bar_s + 8 * stage, phase);
+            const double* sb = wring + stage * 128 + 2 * lane;
+            const double2 X = *(const double2*)sb, V = *(const double2*)(sb + 64);
+            const int st_cur = stage;
+            if (++stage == NST) { stage = 0; phase ^= 1u; }
+            bool straddle = false;
+            if (mixed) {
+                const long long rstart = cbase + 64 * row;
+                const bool sp = rstart >= k.n_split;
+                straddle = !sp && rstart + 64 > k.n_split;
+                fc.qmh = (sp ? k.qm[1] : k.qm[0]) * hdt;
+                fc.qpi = (sp ? k.q[1] : k.q[0]) * k.p2c * k.idx;
+            }
+            LFastO a, b;
+            l_fast(fc, sE, nodes, X.x, V.x, a);
+            l_fast(fc, sE, nodes, X.y, V.y, b);
+            const bool ra = (a.fr > PIC_HI_SPAN) | (a.ps >= fc.hi_lim) | straddle;
+            const bool rb = (b.fr > PIC_HI_SPAN) | (b.ps >= fc.hi_lim) | straddle;
+            if (row == 0) {
+                int nok = __reduce_add_sync(full, (ra ? 0 : 1) + (rb ? 0 : 1));
+                int sum = __reduce_add_sync(full, (ra ? 0 : a.cF) + (rb ? 0 : b.cF));
+                wb = nok ? sum / nok - (S_W - 2) / 2 : NOWIN;
+            }
+            if (!(ra | rb)) {
+                __stcs((double2*)(x + ci), make_double2(a.X, b.X));
+                __stcs((double2*)(v + ci), make_double2(a.V, b.V));
+                swin_add(myw, rho_acc, wb, a.cF, a.fL, a.fR);
+                swin_add(myw, rho_acc, wb, b.cF, b.fL, b.fR);
+            } else {
+                if (ra) bad += l_particle_exact(k, ci, X.x, V.x, sE, rho_acc, x, v);
+                else { x[ci] = a.X; v[ci] = a.V; swin_add(myw, rho_acc, wb, a.cF, a.fL, a.fR); }
+                if (rb) bad += l_particle_exact(k, ci + 1, X.y, V.y, sE, rho_acc, x, v);
+                else { x[ci + 1] = b.X; v[ci + 1] = b.V; swin_add(myw, rho_acc, wb, b.cF, b.fL, b.fR); }
+            }
+            // refill the drained stage only after every lane's LDS of it has executed (see v6)
+            __syncwarp();
+            if (row < S_ROWS - NST) issue(cbase + 64 * (row + NST), st_cur);
+            else if (more) issue(cbase + chunk_step + 64 * (row + NST - S_ROWS), st_cur);
+        }
+        __syncwarp();
+        if (wb != NOWIN) swin_flush<1>(win, myw, wbase, lane, wb, rho_acc, 0, nodes);
+    }
+    if (bad) atomicAdd(&s_bad, bad);
+    __syncthreads();
+    if (threadIdx.x == 0 && s_bad && range_err) atomicAdd(range_err, s_bad);
+}
+
+// ---------------------------------------------------------------- pypic Picard iteration
+struct PFastC { double dx, idx, dt, c1, c2, qpi, L; unsigned hi_lim; };
+struct PFastO { double X1, V1, hL, hR, fL, fR; int cH, cF; unsigned fr, ps; };
+
+template <bool FIRST>
+__device__ __forceinline__ void py_fast(const PFastC& c, const double* __restrict__ sF, int Ng, double X0, double V0,
+                                        double pX1, PFastO& o) {
+    const double xs = FIRST ? X0 : (X0 + pX1) * 0.5;                  // wrapped xh of the previous iteration
+    const double ts = xs * c.idx, fs = floor(ts);
+    const unsigned f0 = (unsigned)__double2hiint(ts - fs) - PIC_HI_G;
+    const double rs = fma(-fs, c.dx, xs);
+    const int is = min(max((int)fs, 0), Ng - 2);
+    const double wR = rs * c.idx, wL = 1.0 - wR;                      // pypic.py:52-53
+    const double Ei = sF[is] * wL + sF[is + 1] * wR;                  // :57
+    o.X1 = X0 + c.dt * V0 + c.c2 * Ei * 0.5;                          // :264
+    o.V1 = V0 + c.c1 * Ei;                                            // :265
+    const double XH = (X0 + o.X1) * 0.5, VH = (V0 + o.V1) * 0.5;      // :268-269
+    const unsigned p0 = (unsigned)__double2hiint(X0) - 1u, p1 = (unsigned)__double2hiint(o.X1) - 1u;
+    o.ps = FIRST ? max(p0, p1) : __vimax3_u32(p0, p1, (unsigned)__double2hiint(pX1) - 1u);
+    const double th = XH * c.idx, fh = floor(th);
+    const unsigned f1 = (unsigned)__double2hiint(th - fh) - PIC_HI_G;
+    const double rh = fma(-fh, c.dx, XH);
+    o.cH = (int)fh;
+    const double tf = o.X1 * c.idx, ff = floor(tf);
+    const unsigned f2 = (unsigned)__double2hiint(tf - ff) - PIC_HI_G;
+    const double rf = fma(-ff, c.dx, o.X1);
+    o.cF = (int)ff;
+    o.fr = __vimax3_u32(f0, f1, f2);
+    const double ah = c.qpi * VH, af = c.qpi * o.V1;                  // :121 up to re-association
+    o.hR = ah * (rh * c.idx); o.hL = ah - o.hR;
+    o.fR = af * (rf * c.idx); o.fL = af - o.fR;
+}
+
+// exact per-particle routine (the body of pypic_picard_iter_k); deposits with global REDs
+template <bool FIRST>
+__device__ __noinline__ int py_particle_exact(const PYK& k, long long i, double X0, double V0, double pX1,
+                                              const double* sF, double* __restrict__ acc, double* x1, double* v1) {
+    const int Ng = k.Ng;
+    int bad = 0;
+    if (k.flags & 2) X0 = wrap_mod(X0, k.L);
+    const double dtdt = k.dt * k.dt;
+    const double xs = FIRST ? X0 : wrap_mod((X0 + pX1) * 0.5, k.L);
+    Cell c = cell_pypic<false>(xs, k.dx, k.idx, Ng);
+    pypic_fix(c, Ng, bad);
+    const double Ei = sF[c.iL] * c.wL + sF[c.iR] * c.wR;
+    const double X1 = X0 + k.dt * V0 + dtdt * k.qm * Ei * 0.5;
+    const double V1 = V0 + k.dt * k.qm * Ei;
+    const double XH = (X0 + X1) * 0.5, VH = (V0 + V1) * 0.5;
+    x1[i] = X1; v1[i] = V1;
+    const double xhw = wrap_mod(XH, k.L), x1w = wrap_mod(X1, k.L);
+    Cell ch = cell_pypic<false>(xhw, k.dx, k.idx, Ng);
+    pypic_fix(ch, Ng, bad);
+    const double jh_i = k.q * VH * k.p2c * k.idx;
+    atomicAdd(&acc[ch.iL], jh_i * ch.wL); atomicAdd(&acc[ch.iR], jh_i * ch.wR);
+    Cell cf = cell_pypic<false>(x1w, k.dx, k.idx, Ng);
+    pypic_fix(cf, Ng, bad);
+    const double j1_i = k.q * V1 * k.p2c * k.idx;
+    atomicAdd(&acc[Ng + cf.iL], j1_i * cf.wL); atomicAdd(&acc[Ng + cf.iR], j1_i * cf.wR);
+    return bad;
+}
+
+template <bool FIRST, int NST>
+__global__ void __launch_bounds__(S_T, 1) pypic_picard_iter_v2_k(const __grid_constant__ PYK k, int nchunks,
+                                                                  const double* __restrict__ x0,
+                                                                  const double* __restrict__ v0, double* x1, double* v1,
+                                                                  const double* __restrict__ Fs, double* __restrict__ acc,
+                                                                  int* __restrict__ range_err) {
+    extern __shared__ __align__(128) double sm[];
+    __shared__ int s_bad;
+    constexpr int NA = FIRST ? 2 : 3;
+    const int Ng = k.Ng;
+    const int NP = (Ng + 15) & ~15;
+    double* sF = sm;
+    double* win = sm + NP;                                   // [2*S_W][S_T]
+    double* ring = win + 2 * S_W * S_T;                      // [warp][stage][x0|v0|x1][64]
+    unsigned long long* bars = (unsigned long long*)(ring + (S_T / 32) * NST * 192);
+    for (int i = threadIdx.x; i < Ng; i += S_T) sF[i] = Fs[i];
+    double* myw = win + threadIdx.x;
+#pragma unroll
+    for (int n = 0; n < 2 * S_W; ++n) myw[n * S_T] = 0.0;
+    if (threadIdx.x == 0) s_bad = 0;
+    const unsigned full = 0xffffffffu;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wbase = threadIdx.x & ~31;
+    const int NOWIN = -0x40000000;
+    const double* wring = ring + warp * (NST * 192);
+    const uint32_t ring_s = smem_u32(wring);
+    const uint32_t bar_s = smem_u32(bars + warp * NST);
+    if (lane == 0) {
+#pragma unroll
+        for (int s = 0; s < NST; ++s) mbar_init(bar_s + 8 * s, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    PFastC fc;
+    fc.dx = k.dx; fc.idx = k.idx; fc.dt = k.dt; fc.L = k.L;
+    fc.c1 = k.dt * k.qm; fc.c2 = k.dt * k.dt * k.qm;
+    fc.qpi = k.q * k.p2c * k.idx;
+    // strictly inside (0, (Ng-1)*dx): no wrap and the right node is iL+1 (the last cell wraps to node 0)
+    fc.hi_lim = (unsigned)__double2hiint((double)(Ng - 1) * k.dx) - 1u;
+    const int my_chunks = (nchunks - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+    const long long woff = (long long)warp * (64 * S_ROWS);
+    const long long chunk_step = (long long)gridDim.x * S_CHUNK;
+    auto issue = [&](long long base, int st) {
+        if (elect_one()) {
+            const uint32_t dst = ring_s + st * 1536, bar = bar_s + 8 * st;
+            mbar_expect_tx(bar, NA * 512u);
+            bulk_g2s(dst, x0 + base, 512, bar);
+            bulk_g2s(dst + 512, v0 + base, 512, bar);
+            if (!FIRST) bulk_g2s(dst + 1024, x1 + base, 512, bar);
+        }
+    };
+    long long cbase = (long long)blockIdx.x * S_CHUNK + woff;
+    if (my_chunks > 0) {
+#pragma unroll
+        for (int s = 0; s < NST; ++s) issue(cbase + 64 * s, s);
+    }
+    int stage = 0, bad = 0;
+    uint32_t phase = 0;
+#pragma unroll 1
+    for (int c = 0; c < my_chunks; ++c, cbase += chunk_step) {
+        const bool more = c + 1 < my_chunks;
+        int wb = NOWIN;
+        long long ci = cbase + 2 * lane;
+#pragma unroll 1
+        for (int row = 0; row < S_ROWS; ++row, ci += 64) {
+            mbar_wait(bar_s + 8 * stage, phase);
+            const double* sb = wring + stage * 192 + 2 * lane;
+            const double2 X0 = *(const double2*)sb, V0 = *(const double2*)(sb + 64);
+            double2 pX1 = make_double2(0., 0.);
+            if (!FIRST) pX1 = *(const double2*)(sb + 128);
+            const int st_cur = stage;
+            if (++stage == NST) { stage = 0; phase ^= 1u; }
+            PFastO a, b;
+            py_fast<FIRST>(fc, sF, Ng, X0.x, V0.x, pX1.x, a);
+            py_fast<FIRST>(fc, sF, Ng, X0.y, V0.y, pX1.y, b);
+            const bool ra = (a.fr > PIC_HI_SPAN) | (a.ps >= fc.hi_lim);
+            const bool rb = (b.fr > PIC_HI_SPAN) | (b.ps >= fc.hi_lim);
+            if (row == 0) {
+                int nok = __reduce_add_sync(full, (ra ? 0 : 1) + (rb ? 0 : 1));
+                int sum = __reduce_add_sync(full, (ra ? 0 : a.cH) + (rb ? 0 : b.cH));
+                wb = nok ? sum / nok - (S_W - 2) / 2 : NOWIN;
+            }
+            if (!(ra | rb)) {
+                __stcs((double2*)(x1 + ci), make_double2(a.X1, b.X1));
+                __stcs((double2*)(v1 + ci), make_double2(a.V1, b.V1));
+                swin_add(myw, acc, wb, a.cH, a.hL, a.hR); swin_add(myw + S_W * S_T, acc + Ng, wb, a.cF, a.fL, a.fR);
+                swin_add(myw, acc, wb, b.cH, b.hL, b.hR); swin_add(myw + S_W * S_T, acc + Ng, wb, b.cF, b.fL, b.fR);
+            } else {
+                if (ra) bad += py_particle_exact<FIRST>(k, ci, X0.x, V0.x, pX1.x, sF, acc, x1, v1);
+                else {
+                    x1[ci] = a.X1; v1[ci] = a.V1;
+                    swin_add(myw, acc, wb, a.cH, a.hL, a.hR); swin_add(myw + S_W * S_T, acc + Ng, wb, a.cF, a.fL, a.fR);
+                }
+                if (rb) bad += py_particle_exact<FIRST>(k, ci + 1, X0.y, V0.y, pX1.y, sF, acc, x1, v1);
+                else {
+                    x1[ci + 1] = b.X1; v1[ci + 1] = b.V1;
+                    swin_add(myw, acc, wb, b.cH, b.hL, b.hR); swin_add(myw + S_W * S_T, acc + Ng, wb, b.cF, b.fL, b.fR);
+                }
+            }
+            __syncwarp();
+            if (row < S_ROWS - NST) issue(cbase + 64 * (row + NST), st_cur);
+            else if (more) issue(cbase + chunk_step + 64 * (row + NST - S_ROWS), st_cur);
+        }
+        __syncwarp();
+        if (wb != NOWIN) swin_flush<2>(win, myw, wbase, lane, wb, acc, Ng, Ng);
+    }
+    if (bad) atomicAdd(&s_bad, bad);
+    __syncthreads();
+    if (threadIdx.x == 0 && s_bad && range_err) atomicAdd(range_err, s_bad);
+}
+
 // field phase build: fold rho, rhs of the gauge-fixed periodic system over `nodes` unknowns
 __global__ void l_field_build_k(double* __restrict__ rho_acc, double* __restrict__ rho, double* __restrict__ a,
                                 double* __restrict__ b, double* __restrict__ c, double* __restrict__ d, int nodes,
@@ -380,16 +759,11 @@ int pic_dev_pypic_weight(const double* x, const double* q, const double* v, doub
     return PIC_OK;
 }
 
-int pic_dev_pypic_picard_iter(const pic_pypic_params* p, const double* x0, const double* v0, double* x1, double* v1,
-                              const double* Fs, double* acc, int first, int* range_err, void* stream) {
-    PIC_REQUIRE(p && x0 && v0 && x1 && v1 && Fs && acc, "pypic_picard_iter: null pointer");
-    PIC_REQUIRE(p->Ng >= 2 && p->dx > 0, "pypic_picard_iter: bad parameters");
-    if (p->N == 0) return PIC_OK;
-    PYK k = make_pyk(p);
+static int pypic_iter_v1(const PYK& k, int flags, const double* x0, const double* v0, double* x1, double* v1,
+                         const double* Fs, double* acc, int first, int* range_err, cudaStream_t st) {
     size_t smem = (size_t)3 * k.Ng * sizeof(double);
     PIC_REQUIRE(smem <= (size_t)max_optin_smem() - 1024, "pypic_picard_iter: Ng too large for the shared-memory tiles");
-    cudaStream_t st = (cudaStream_t)stream;
-    bool agg = !(p->flags & 1);
+    bool agg = !(flags & 1);
 #define PIC_PY_LAUNCH(F, A)                                                                                     \
     do {                                                                                                        \
         auto kern = pypic_picard_iter_k<F, A>;                                                                  \
@@ -403,6 +777,36 @@ int pic_dev_pypic_picard_iter(const pic_pypic_params* p, const double* x0, const
 #undef PIC_PY_LAUNCH
     PIC_CHECK_LAUNCH();
     return PIC_OK;
+}
+
+#define PY_NST 4
+int pic_dev_pypic_picard_iter(const pic_pypic_params* p, const double* x0, const double* v0, double* x1, double* v1,
+                              const double* Fs, double* acc, int first, int* range_err, void* stream) {
+    PIC_REQUIRE(p && x0 && v0 && x1 && v1 && Fs && acc, "pypic_picard_iter: null pointer");
+    PIC_REQUIRE(p->Ng >= 2 && p->dx > 0, "pypic_picard_iter: bad parameters");
+    if (p->N == 0) return PIC_OK;
+    PYK k = make_pyk(p);
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t smem2 = ((size_t)((k.Ng + 15) & ~15) + (size_t)2 * S_W * S_T + (size_t)(S_T / 32) * PY_NST * 192 +
+                          (size_t)(S_T / 32) * PY_NST) * sizeof(double);
+    const bool aligned16 = (((uintptr_t)x0 | (uintptr_t)v0 | (uintptr_t)x1 | (uintptr_t)v1) & 15) == 0;
+    long long done = 0;
+    if (!(p->flags & (1 | 4)) && aligned16 && k.Ng >= 8 && smem2 <= (size_t)max_optin_smem() - 512) {
+        // default: TMA-staged private-window kernel over whole chunks, v1 kernel on the tail
+        const long long nchunks = k.N / S_CHUNK;
+        if (nchunks > 0) {
+            auto kern = first ? pypic_picard_iter_v2_k<true, PY_NST> : pypic_picard_iter_v2_k<false, PY_NST>;
+            PIC_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
+            long long cap = device_sm_count();
+            kern<<<(int)(nchunks < cap ? nchunks : cap), S_T, smem2, st>>>(k, (int)nchunks, x0, v0, x1, v1, Fs, acc, range_err);
+            PIC_CHECK_LAUNCH();
+        }
+        done = nchunks * S_CHUNK;
+        if (done >= k.N) return PIC_OK;
+    }
+    PYK t = k;
+    t.N = k.N - done;
+    return pypic_iter_v1(t, p->flags, x0 + done, v0 + done, x1 + done, v1 + done, Fs, acc, first, range_err, st);
 }
 
 int pic_dev_pypic_field_update(const pic_pypic_params* p, double* acc, const double* E0, double* Es, double* Fs,
@@ -456,21 +860,42 @@ int pic_dev_l_weight(const double* x, const double* q, const double* v, double* 
     return PIC_OK;
 }
 
+#define L_NST 6
 int pic_dev_l_push_deposit(const pic_l_params* p, double* x, double* v, const double* E, double* rho_acc,
                            int* range_err, void* stream) {
     PIC_REQUIRE(p && x && v && E && rho_acc, "l_push_deposit: null pointer");
     PIC_REQUIRE(p->Ng >= 2 && p->dx > 0, "l_push_deposit: bad parameters");
     if (p->N == 0) return PIC_OK;
     LK k = make_lk(p);
+    cudaStream_t st = (cudaStream_t)stream;
+    const int nodes = k.Ng + 1;
+    const size_t smem2 = ((size_t)((nodes + 15) & ~15) + (size_t)S_W * S_T + (size_t)(S_T / 32) * L_NST * 128 +
+                          (size_t)(S_T / 32) * L_NST) * sizeof(double);
+    const bool aligned16 = (((uintptr_t)x | (uintptr_t)v) & 15) == 0;
+    long long done = 0;
+    if (!(p->flags & (1 | 2 | 4)) && aligned16 && k.Ng >= 8 && smem2 <= (size_t)max_optin_smem() - 512) {
+        const long long nchunks = k.N / S_CHUNK;
+        if (nchunks > 0) {
+            auto kern = l_push_deposit_v2_k<L_NST>;
+            PIC_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
+            long long cap = device_sm_count();
+            kern<<<(int)(nchunks < cap ? nchunks : cap), S_T, smem2, st>>>(k, (int)nchunks, x, v, E, rho_acc, range_err);
+            PIC_CHECK_LAUNCH();
+        }
+        done = nchunks * S_CHUNK;
+        if (done >= k.N) return PIC_OK;
+    }
+    LK t = k;
+    t.N = k.N - done;
+    t.n_split = k.n_split - done < 0 ? 0 : (k.n_split - done > t.N ? t.N : k.n_split - done);
     size_t smem = (size_t)2 * (k.Ng + 1) * sizeof(double);
     PIC_REQUIRE(smem <= (size_t)max_optin_smem() - 1024, "l_push_deposit: Ng too large for the shared-memory tiles");
-    cudaStream_t st = (cudaStream_t)stream;
     bool agg = !(p->flags & 1);
     auto kern = agg ? l_push_deposit_k<true> : l_push_deposit_k<false>;
     PIC_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int occ = 0;
     PIC_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, 256, smem));
-    kern<<<grid_for(k.N, 256, occ > 0 ? occ : 1), 256, smem, st>>>(k, x, v, E, rho_acc, range_err);
+    kern<<<grid_for(t.N, 256, occ > 0 ? occ : 1), 256, smem, st>>>(t, x + done, v + done, E, rho_acc, range_err);
     PIC_CHECK_LAUNCH();
     return PIC_OK;
 }

@@ -22,7 +22,7 @@ kb = 1.38E-23
 
 class PeriodicImplicitSim:
     def __init__(self, N, Ng, dx, dt, L, p2c, q=-e, m=me, tol=1e-3, maxiter=20, deposit="warp", comm=None,
-                 device=None):
+                 device=None, sort_every=0):
         self.dev = D.require_cuda(device)
         self.comm = comm if comm is not None else Comm()
         self.N_global = int(N)
@@ -32,7 +32,17 @@ class PeriodicImplicitSim:
         self.p2c = float(int(p2c))           # numba's int32 signature truncates p2c
         self.p2c_raw = float(p2c)            # the Python-level diagnostics use the untruncated value
         self.tol, self.maxiter = float(tol), int(maxiter)
-        flags = 1 if deposit == "atomic" else 0
+        # deposit: "window" = TMA-staged private-window kernel (needs a store sorted by cell: set
+        # sort_every), "warp" = grid-stride kernel with warp pre-reduced shared-memory atomics (any
+        # particle order; the default of the drop-in modules), "atomic" = one atomicAdd per contribution
+        if sort_every and deposit == "warp":
+            deposit = "window"
+        # bit1: the store keeps the UNWRAPPED x1 of the previous step and the kernels apply
+        # ``x % L`` (pypic.py:277) when they load it -- saves a 16 B/particle pass per step
+        flags = {"window": 0, "warp": 4, "atomic": 1 | 4}[deposit] | 2
+        self.sort_every = int(sort_every)
+        self.t = 0
+        self.perm = None                     # original index of the particle in each slot (after sorting)
         self.params = _lib.PypicParams(self.N, self.Ng, flags, self.dx, self.dt, self.L, self.p2c, float(q), float(m))
         dev, n, g = self.dev, max(self.N, 1), self.Ng
         self.x0 = D.f64(n, dev, True); self.v0 = D.f64(n, dev, True)
@@ -52,10 +62,32 @@ class PeriodicImplicitSim:
         if E0 is not None:
             self.E0.copy_(torch.as_tensor(np.ascontiguousarray(E0)))
 
+    def sort_by_cell(self):
+        """Counting sort of the store by cell (pic_dev_dd_sort_by_cell) into the Picard scratch
+        arrays; the original index of every particle rides along as a payload so that
+        download() can return the arrays in the caller's order."""
+        n = max(self.N, 1)
+        if self.perm is None:
+            self.perm = torch.arange(n, dtype=torch.float64, device=self.dev)
+            self._perm2 = torch.empty_like(self.perm)
+            self._sort_counts = torch.zeros(2 * self.Ng + 2, dtype=torch.int32, device=self.dev)
+            self._sort_params = _lib.DDParams(self.N, self.N, self.Ng, 0, self.dx, self.dt, self.L, self.p2c,
+                                              (C.c_double * 2)(0., 0.), (C.c_double * 2)(1., 1.))
+        _lib.call("pic_dev_dd_sort_by_cell", C.byref(self._sort_params), D.ptr(self.x0), D.ptr(self.v0),
+                  D.ptr(self.perm), None, D.ptr(self.x1), D.ptr(self.v1), D.ptr(self._perm2), None,
+                  D.ptr(self._sort_counts), D.stream())
+        self.kernel_launches += 3
+        self.x0, self.x1 = self.x1, self.x0
+        self.v0, self.v1 = self.v1, self.v0
+        self.perm, self._perm2 = self._perm2, self.perm
+
     def push(self):
         """particle_push_p: Picard loop + commit (x wrapped into [0,L)).  Returns (k, r)."""
         st = D.stream()
         P = C.byref(self.params)
+        if self.sort_every and self.t % self.sort_every == 0:
+            self.sort_by_cell()
+        self.t += 1
         self.Es.copy_(self.E0)
         _lib.call("pic_dev_smooth", D.ptr(self.Es), D.ptr(self.Fs), self.Ng, 0, st)
         self.stats.zero_()
@@ -73,8 +105,7 @@ class PeriodicImplicitSim:
             self.x0, self.x1 = self.x1, self.x0
             self.v0, self.v1 = self.v1, self.v0
             self.E0, self.E1 = self.E1, self.E0
-            _lib.call("pic_dev_wrap_periodic", D.ptr(self.x0), self.N, self.L, st)   # x1 = x1 % L (pypic.py:277)
-            self.kernel_launches += 2
+            # x1 = x1 % L (pypic.py:277) is applied lazily: on load by the next push, or by download()
         self.last_iters, self.last_resid = k, r
         return k, r
 
@@ -87,8 +118,13 @@ class PeriodicImplicitSim:
         return dict(EE=float(s[2]), KE=self.p2c_raw * float(sc.item()), jbias=float(s[1]))
 
     def download(self):
-        return dict(x0=self.x0.cpu().numpy(), v0=self.v0.cpu().numpy(), E0=self.E0.cpu().numpy(),
-                    j0=self.j0.cpu().numpy())
+        x, v = self.x0[:self.N].cpu().numpy() % self.L, self.v0[:self.N].cpu().numpy()
+        if self.perm is not None:            # undo the cell sort: slot s holds original particle perm[s]
+            idx = self.perm[:self.N].cpu().numpy().astype(np.int64)
+            xo, vo = np.empty_like(x), np.empty_like(v)
+            xo[idx] = x; vo[idx] = v
+            x, v = xo, vo
+        return dict(x0=x, v0=v, E0=self.E0.cpu().numpy(), j0=self.j0.cpu().numpy())
 
     def check(self):
         D.check_range(self.range_err, "pypic push")
@@ -99,7 +135,7 @@ class ExplicitSim:
     the NEXT step fused into the push kernel."""
 
     def __init__(self, N, Ng, dx, dt, p2c, q=(-e, -e), m=(me, me), n_split=None, deposit="warp", comm=None,
-                 device=None):
+                 device=None, sort_every=0):
         self.dev = D.require_cuda(device)
         self.comm = comm if comm is not None else Comm()
         self.N_global = int(N)
@@ -109,7 +145,12 @@ class ExplicitSim:
         self.n_split = local_split(ns, self.start, self.stop)
         self.Ng, self.dx, self.dt, self.p2c = int(Ng), float(dx), float(dt), float(p2c)
         self.L = dx * (Ng - 1)              # PIC_L.py:645; the wrap length is L+dx
-        flags = 1 if deposit == "atomic" else 0
+        if sort_every and deposit == "warp":
+            deposit = "window"               # see PeriodicImplicitSim
+        flags = {"window": 0, "warp": 4, "atomic": 1 | 4}[deposit]
+        self.sort_every = int(sort_every)
+        self.t = 0
+        self.perm = None
         self.params = _lib.LParams(self.N, self.n_split, self.Ng, flags, self.dx, self.dt, self.L, self.p2c,
                                    (C.c_double * 2)(*q), (C.c_double * 2)(*m))
         dev, n, g = self.dev, max(self.N, 1), self.Ng + 1
@@ -160,7 +201,28 @@ class ExplicitSim:
         self.kernel_launches += 1
         self._have_rho = True
 
+    def sort_by_cell(self):
+        """Counting sort by (species, cell) with the original index as a payload."""
+        n = max(self.N, 1)
+        if self.perm is None:
+            self.perm = torch.arange(n, dtype=torch.float64, device=self.dev)
+            self._perm2 = torch.empty_like(self.perm)
+            self._x2 = torch.empty_like(self.x); self._v2 = torch.empty_like(self.v)
+            self._sort_counts = torch.zeros(2 * self.Ng + 2, dtype=torch.int32, device=self.dev)
+            self._sort_params = _lib.DDParams(self.N, self.n_split, self.Ng, 0, self.dx, self.dt, self.L, self.p2c,
+                                              (C.c_double * 2)(0., 0.), (C.c_double * 2)(1., 1.))
+        _lib.call("pic_dev_dd_sort_by_cell", C.byref(self._sort_params), D.ptr(self.x), D.ptr(self.v),
+                  D.ptr(self.perm), None, D.ptr(self._x2), D.ptr(self._v2), D.ptr(self._perm2), None,
+                  D.ptr(self._sort_counts), D.stream())
+        self.kernel_launches += 3
+        self.x, self._x2 = self._x2, self.x
+        self.v, self._v2 = self._v2, self.v
+        self.perm, self._perm2 = self._perm2, self.perm
+
     def step(self):
+        if self.sort_every and self.t % self.sort_every == 0:
+            self.sort_by_cell()
+        self.t += 1
         self.field_solve()
         self.push()
 
@@ -176,8 +238,13 @@ class ExplicitSim:
         return float(D.read_f64(sc, 1)[0])
 
     def download(self):
-        return dict(x=self.x.cpu().numpy(), v=self.v.cpu().numpy(), rho=self.rho.cpu().numpy(),
-                    phi=self.phi.cpu().numpy(), E=self.E.cpu().numpy())
+        x, v = self.x[:self.N].cpu().numpy(), self.v[:self.N].cpu().numpy()
+        if self.perm is not None:
+            idx = self.perm[:self.N].cpu().numpy().astype(np.int64)
+            xo, vo = np.empty_like(x), np.empty_like(v)
+            xo[idx] = x; vo[idx] = v
+            x, v = xo, vo
+        return dict(x=x, v=v, rho=self.rho.cpu().numpy(), phi=self.phi.cpu().numpy(), E=self.E.cpu().numpy())
 
     def check(self):
         D.check_range(self.range_err, "PIC_L step")

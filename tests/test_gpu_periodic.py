@@ -31,12 +31,15 @@ def test_pypic_function_level(golden, tag):
     assert relmax(phi, g[f"{tag}_phi"]) < 1e-9
 
 
-def test_pypic_push_vs_reference_golden(golden):
+@pytest.mark.parametrize("sort_every", [0, 1, 2])
+def test_pypic_push_vs_reference_golden(golden, sort_every):
+    """sort_every > 0: the store is re-sorted by cell (window kernel on whole chunks) and
+    download() restores the caller's particle order."""
     from pypic_b200.periodic import PeriodicImplicitSim
     g = golden("pypic_push")
     N = int(g["N"]); Ng = int(g["Ng"])
     sim = PeriodicImplicitSim(N, Ng, float(g["dx"]), float(g["dt"]), float(g["L"]), float(g["p2c"]),
-                              tol=float(g["tol"]), maxiter=int(g["maxiter"]))
+                              tol=float(g["tol"]), maxiter=int(g["maxiter"]), sort_every=sort_every)
     sim.upload(g["x0"], g["v0"], g["E0"])
     for t in range(3):
         k, r = sim.push()
@@ -103,7 +106,8 @@ def test_pic_l_explicit_step_bit_exact_push(golden):
     assert int(err.item()) == 0
 
 
-def test_pic_l_main_loop_vs_reference_golden(golden):
+@pytest.mark.parametrize("sort_every", [0, 3])
+def test_pic_l_main_loop_vs_reference_golden(golden, sort_every):
     """PIC_L.main (explicit leapfrog, Poisson every step): the reference's EE series and
     per-step E arrays from the same initial particles."""
     from pypic_b200.periodic import ExplicitSim
@@ -114,7 +118,7 @@ def test_pic_l_main_loop_vs_reference_golden(golden):
     kBTe = O.kb * 10.0 * 11600.
     x = g["x_init"].copy()
     v = g["vn_init"] * np.sqrt(kBTe / O.me)
-    sim = ExplicitSim(N, Ng, dx, dt, p2c)
+    sim = ExplicitSim(N, Ng, dx, dt, p2c, sort_every=sort_every)
     sim.upload(x, v)
     EE = []
     sim.field_solve()                      # initial solve before the loop (PIC_L.py:688-691)
@@ -134,3 +138,85 @@ def test_tridiag_pcr_small_and_large():
         x = ops.tridiag(a, b, c, d)
         ref = O.solve_tridiagonal_fast(a, b, c, d)
         assert relmax(x, ref) < 1e-11, n
+
+
+# --------------------------------------------------------------------------------------
+# v2 streaming kernels (TMA ring + private windows) against the v1 grid-stride kernels and
+# the oracle on the same inputs: per-particle state bit-exact, deposited sums <=1e-13.
+def _adversarial_positions(rs, N, ncell, dx, Lw):
+    """cell-sorted positions with particles planted on / next to cell edges, at both domain
+    ends and in the last cell (periodic right node)."""
+    x = np.sort(rs.uniform(0, Lw, N))
+    j = rs.choice(N, 4000, replace=False)
+    cells = rs.randint(0, ncell, 4000)
+    x[j[:1000]] = cells[:1000] * dx                                     # exactly on a node
+    x[j[1000:2000]] = np.nextafter(cells[1000:2000] * dx, -1.0)         # one ulp below
+    x[j[2000:3000]] = cells[2000:3000] * dx * (1 + 1e-9)                # inside the guard band
+    x[j[3000:3500]] = rs.uniform(0, 1e-3 * dx, 500)                     # will leave on the left
+    x[j[3500:]] = Lw - rs.uniform(1e-6 * dx, 1e-3 * dx, 500)                    # will leave on the right
+    return np.clip(x, 0.0, Lw - 1e-7 * dx)
+
+
+def test_pic_l_v2_kernel_matches_v1_and_oracle():
+    import ctypes as C
+    import torch
+    from pypic_b200 import _lib, device as D
+    rs = np.random.RandomState(11)
+    Ng = 512; dx = 1e-5; dt = 2e-11; L = dx * (Ng - 1); Lw = L + dx
+    N = 3 * 16384 + 777                      # whole chunks + a tail for the v1 kernel
+    n_split = 16384 + 700                    # species boundary inside a slice, inside a 64-row
+    x = _adversarial_positions(rs, N, Ng, dx, Lw)
+    x[:n_split] = np.sort(x[:n_split]); x[n_split:] = np.sort(x[n_split:])
+    v = np.concatenate([rs.normal(0, 1.3e6, n_split), rs.normal(0, 3e4, N - n_split)])
+    E = rs.normal(0, 2e4, Ng + 1)
+    q = (-O.e, O.e); m = (O.me, O.mp)
+    dev = D.require_cuda()
+    res = {}
+    for flags in (0, 4):
+        P = _lib.LParams(N, n_split, Ng, flags, dx, dt, L, 1e9, (C.c_double * 2)(*q), (C.c_double * 2)(*m))
+        tx, tv, tE = D.to_dev(x, dev), D.to_dev(v, dev), D.to_dev(E, dev)
+        acc = D.f64(Ng + 1, dev, True); err = torch.zeros(1, dtype=torch.int32, device=dev)
+        _lib.call("pic_dev_l_push_deposit", C.byref(P), D.ptr(tx), D.ptr(tv), D.ptr(tE), D.ptr(acc), D.ptr(err), D.stream())
+        res[flags] = (tx.cpu().numpy(), tv.cpu().numpy(), acc.cpu().numpy(), int(err.item()))
+    assert np.array_equal(res[0][0], res[4][0]) and np.array_equal(res[0][1], res[4][1])
+    assert res[0][3] == res[4][3]
+    assert relmax(res[0][2], res[4][2]) < 1e-13
+    # oracle: PIC_L.pushParticlesExplicit + applyBoundaryConditionsPeriodic per particle
+    qa = np.where(np.arange(N) < n_split, q[0], q[1]); ma = np.where(np.arange(N) < n_split, m[0], m[1])
+    Ei = O.l_interpolateFieldPeriodic(E, x, Ng, dx)
+    vhalf = v + (qa / ma) * (dt * 0.5) * Ei
+    xo = (x + vhalf * dt) % (L + dx)
+    vo = vhalf + (qa / ma) * (dt * 0.5) * Ei
+    assert np.array_equal(res[0][0], xo) and np.array_equal(res[0][1], vo)
+    assert (np.abs(x + vhalf * dt - xo) > 0).sum() > 100        # the wrap path was exercised
+
+
+def test_pypic_v2_kernel_matches_v1_and_oracle():
+    from pypic_b200.periodic import PeriodicImplicitSim
+    rs = np.random.RandomState(12)
+    Ng = 512; dx = 1e-5; dt = 2e-11; L = dx * Ng
+    N = 3 * 16384 + 333
+    x0 = _adversarial_positions(rs, N, Ng, dx, L)
+    v0 = rs.normal(0, 1.3e6, N)
+    E0 = rs.normal(0, 2e4, Ng)
+    p2c = 1e9
+    outs = {}
+    for dep in ("window", "warp"):
+        sim = PeriodicImplicitSim(N, Ng, dx, dt, L, p2c, tol=1e-30, maxiter=3, deposit=dep)
+        sim.upload(x0, v0, E0)
+        k, r = sim.push(); sim.check()
+        outs[dep] = (sim.download(), k, r)
+    a, b = outs["window"][0], outs["warp"][0]
+    assert outs["window"][1] == outs["warp"][1] == 3
+    # iteration 1 is bit-exact; later iterations feed the (re-associated) field back
+    assert relmax(a["x0"], b["x0"]) < 1e-13 and relmax(a["v0"], b["v0"]) < 1e-12
+    assert relmax(a["E0"], b["E0"]) < 1e-11 and relmax(a["j0"], b["j0"]) < 1e-11
+    # one iteration against the oracle: bit-exact particle state
+    q = -np.ones(N) * O.e; m = np.ones(N) * O.me
+    x1, v1, E1, j1, k, r = O.pypic_particle_push_p(x0, v0, q, m, E0, np.zeros(Ng), N, Ng, p2c, dx, dt, L, 1e-30, 1)
+    sim = PeriodicImplicitSim(N, Ng, dx, dt, L, p2c, tol=1e-30, maxiter=1, deposit="window")
+    sim.upload(x0, v0, E0)
+    sim.push(); sim.check()
+    out = sim.download()
+    assert np.array_equal(out["x0"], x1) and np.array_equal(out["v0"], v1)
+    assert relmax(out["E0"], E1) < 1e-12 and relmax(out["j0"], j1) < 1e-12

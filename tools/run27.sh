@@ -1,0 +1,9 @@
+set -x
+timeout 900 python tools/bench_paths.py 1e8 explicit,pypic,gc 4 > gpurun_out/paths_base.json 2> gpurun_out/paths_base.err; tail -5 gpurun_out/paths_base.err
+python - <<'PY'
+import json
+d = json.load(open('gpurun_out/paths_base.json'))
+for r in d['results']:
+    if 'error' in r: print(r); continue
+    print("%-55s %9.3f ms  %.3e p-s/s  %7.1f GB/s  frac %.3f %s" % (r['path'], r['ms'], r['particle_steps_per_s'], r['achieved_gbs'], r['frac'], r.get('picard_iterations','')))
+PY
