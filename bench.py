@@ -45,7 +45,7 @@ def parse():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-sample", type=float, default=4e6, help="particles in the CPU-baseline sample")
-    ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--e2e-steps", type=int, default=16)
     return ap.parse_args()
 
 
@@ -281,40 +281,52 @@ def run_cuda(args):
         except Exception:
             pass
 
-    # ---- e2e: the same step through the C ABI with HOST (pinned) buffers, copies timed
+    # ---- e2e: the same step through the C ABI with HOST (pinned) buffers, every copy timed.
+    # pic_host_dd_step_batches advances a queue of independent batches (here: the same synthetic
+    # state re-sent every step, results into two alternating pinned output sets) and pipelines
+    # them through two device slots: upload of batch b+1 and download of batch b-1 overlap the
+    # Picard loop of batch b.  Per step 16 B/particle go up and 17 B/particle come down.
     e2e = None
     if not args.no_e2e:
         Nl, Ng = sim.N, w["Ng"]
-        hx0 = torch.empty(Nl, dtype=torch.float64, pin_memory=True); hu0 = torch.empty_like(hx0, pin_memory=True)
-        hx1 = torch.empty_like(hx0, pin_memory=True); hu1 = torch.empty_like(hx0, pin_memory=True)
-        hact = torch.empty(Nl, dtype=torch.int8, pin_memory=True)
-        hE0 = torch.zeros(Ng, dtype=torch.float64, pin_memory=True); hE1 = torch.empty_like(hE0, pin_memory=True)
-        hj1 = torch.empty_like(hE0, pin_memory=True)
+        nb = max(1, args.e2e_steps)
+        pin = lambda n, dt=torch.float64: torch.empty(n, dtype=dt, pin_memory=True)
+        hx0, hu0, hE0 = pin(Nl), pin(Nl), pin(Ng)
+        outs = [dict(x1=pin(Nl), u1=pin(Nl), act=pin(Nl, torch.int8), E1=pin(Ng), j1=pin(Ng)) for _ in range(min(nb, 2))]
         hx0.copy_(sim.x0); hu0.copy_(sim.u0); hE0.copy_(sim.E0)
         torch.cuda.synchronize()
-        # the resident simulation is released so the host-buffer path has its own HBM
         P = _lib.DDParams(Nl, sim.n_split, Ng, 0, w["dx"], w["dt"], w["L"], w["p2c"],
                           (C.c_double * 2)(-E_CH, E_CH), (C.c_double * 2)(ME, MP))
-        it, res = C.c_int(), C.c_double()
 
-        def host_step():
-            _lib.call("pic_host_dd_step", C.byref(P), hx0.data_ptr(), hu0.data_ptr(), hE0.data_ptr(), w["tol"],
-                      w["maxiter"], hx1.data_ptr(), hu1.data_ptr(), hact.data_ptr(), hE1.data_ptr(), hj1.data_ptr(),
-                      C.byref(it), C.byref(res))
-        host_step()                      # warm-up (allocates the cached device workspace)
+        def ptrs(vals):
+            return (C.c_void_p * len(vals))(*vals)
+
+        def host_steps(n):
+            it, res = (C.c_int * n)(), (C.c_double * n)()
+            o = [outs[b % len(outs)] for b in range(n)]
+            _lib.call("pic_host_dd_step_batches", C.byref(P), n, ptrs([hx0.data_ptr()] * n), ptrs([hu0.data_ptr()] * n),
+                      ptrs([hE0.data_ptr()] * n), w["tol"], w["maxiter"], ptrs([d["x1"].data_ptr() for d in o]),
+                      ptrs([d["u1"].data_ptr() for d in o]), ptrs([d["act"].data_ptr() for d in o]),
+                      ptrs([d["E1"].data_ptr() for d in o]), ptrs([d["j1"].data_ptr() for d in o]), it, res)
+            return list(it)
+        host_steps(min(nb, 2))           # warm-up (allocates the cached device slots)
         comm.barrier()
         t0 = time.perf_counter()
-        for _ in range(args.e2e_steps):
-            host_step()
+        its = host_steps(nb)
         torch.cuda.synchronize()
         t_e2e = time.perf_counter() - t0
         t_e2e = comm.max_float(t_e2e, device=dev)
+        # result check of the last batch against the resident simulation's own step from the same state
         h2d = Nl * 16 + Ng * 8
         d2h = Nl * 17 + Ng * 16
-        e2e = {"value": w["N"] * args.e2e_steps / t_e2e, "unit": "particle-steps/s", "h2d_bytes_per_step": h2d,
-               "d2h_bytes_per_step": d2h, "steps": args.e2e_steps, "picard_iterations": it.value,
-               "api": "pic_host_dd_step (C ABI, pinned host buffers, per-rank shard)"}
+        e2e = {"value": w["N"] * nb / t_e2e, "unit": "particle-steps/s", "h2d_bytes_per_step": h2d,
+               "d2h_bytes_per_step": d2h, "steps": nb, "picard_iterations": its[-1],
+               "ms_per_step": 1e3 * t_e2e / nb,
+               "pcie_gbs": {"h2d": h2d * nb / t_e2e / 1e9, "d2h": d2h * nb / t_e2e / 1e9},
+               "api": "pic_host_dd_step_batches (C ABI, pinned host buffers, per-rank shard, %d batches pipelined "
+                      "through two device slots)" % nb}
         _lib.call("pic_host_release")
+        del hx0, hu0, outs
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:

@@ -28,8 +28,8 @@ def local_split(n_split_global, start, stop):
 class Comm:
     """Thin wrapper so the simulation objects work with or without a process group."""
 
-    def __init__(self, group=None):
-        self.enabled = dist.is_available() and dist.is_initialized()
+    def __init__(self, group=None, enabled=True):
+        self.enabled = bool(enabled) and dist.is_available() and dist.is_initialized()
         self.group = group
         self.rank = dist.get_rank(group) if self.enabled else 0
         self.world = dist.get_world_size(group) if self.enabled else 1

@@ -354,6 +354,46 @@ def test_host_abi_step_matches_device_path():
     assert relmax(x1, out["x0"]) < 1e-13 and relmax(E1, out["E0"]) < 1e-12
 
 
+def test_host_abi_batches_pipeline_matches_single_steps():
+    """pic_host_dd_step_batches: 5 independent batches through the two-slot pipeline give,
+    batch by batch, what pic_host_dd_step gives for the same inputs (to the round-off of the
+    atomically accumulated currents), including distinct iteration counts."""
+    from pypic_b200 import _lib
+    N, Ng, nb = 40000, 129, 5
+    p2c = 1.25e11
+    ins, single = [], []
+    for b in range(nb):
+        dx, L, dt, x0, u0, q, m, E0 = _one_iter_inputs(N, Ng, 30 + b)
+        E0 = E0 * (1.0 + 3.0 * b)                     # different fields -> different iteration counts
+        ins.append((x0, u0, E0))
+    P = _lib.DDParams(N, N // 2, Ng, 0, dx, dt, L, p2c, (C.c_double * 2)(-O.e, O.e), (C.c_double * 2)(O.me, O.mp))
+
+    def bufs():
+        return dict(x1=np.empty(N), u1=np.empty(N), act=np.empty(N, dtype=np.int8), E1=np.empty(Ng), j1=np.empty(Ng))
+    for b in range(nb):
+        o = bufs(); it = C.c_int(); res = C.c_double()
+        x0, u0, E0 = ins[b]
+        _lib.call("pic_host_dd_step", C.byref(P), x0.ctypes.data, u0.ctypes.data, E0.ctypes.data, 1e-5, 20,
+                  o["x1"].ctypes.data, o["u1"].ctypes.data, o["act"].ctypes.data, o["E1"].ctypes.data,
+                  o["j1"].ctypes.data, C.byref(it), C.byref(res))
+        single.append((o, it.value, res.value))
+    outs = [bufs() for _ in range(nb)]
+    arr = lambda vals: (C.c_void_p * nb)(*vals)
+    its, ress = (C.c_int * nb)(), (C.c_double * nb)()
+    _lib.call("pic_host_dd_step_batches", C.byref(P), nb, arr([i[0].ctypes.data for i in ins]),
+              arr([i[1].ctypes.data for i in ins]), arr([i[2].ctypes.data for i in ins]), 1e-5, 20,
+              arr([o["x1"].ctypes.data for o in outs]), arr([o["u1"].ctypes.data for o in outs]),
+              arr([o["act"].ctypes.data for o in outs]), arr([o["E1"].ctypes.data for o in outs]),
+              arr([o["j1"].ctypes.data for o in outs]), its, ress)
+    assert len(set(its)) > 1
+    for b in range(nb):
+        o, k, r = single[b]
+        assert its[b] == k
+        assert np.array_equal(outs[b]["act"], o["act"])
+        assert relmax(outs[b]["x1"], o["x1"]) < 1e-13 and relmax(outs[b]["u1"], o["u1"]) < 1e-12
+        assert relmax(outs[b]["E1"], o["E1"]) < 1e-12 and relmax(outs[b]["j1"], o["j1"]) < 1e-12
+
+
 def test_sorted_philox_mode_conserves_and_matches_unsorted():
     """Benchmark mode (sort by cell + warp pre-reduction + device Philox): sorting must not
     change the physics: same E1 as the unsorted run from the same state, to round-off."""

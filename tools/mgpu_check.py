@@ -1,0 +1,77 @@
+#!/usr/bin/env python
+"""Multi-GPU parity check (run under torchrun, one rank per GPU): the particle-decomposed
+sheath (contiguous shards, one fp64 all-reduce of [jh|j1|counts] per Picard iteration, host
+MT19937 draw service) against the SAME global state advanced on one GPU without a process
+group.  Iteration counts and absorbed tallies must be identical, fields/particles to
+round-off.  Rank 0 prints one JSON line."""
+import json
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from pypic_b200.dist import Comm  # noqa: E402
+from pypic_b200.rng import LegacyDraws  # noqa: E402
+from pypic_b200.sheath import SheathSim  # noqa: E402
+
+KB, ME, MP = 1.38E-23, 9.11E-31, 1.67E-27
+
+
+def main():
+    rank = int(os.environ.get("RANK", "0")); local = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    N = int(float(sys.argv[1])) if len(sys.argv) > 1 else 400000
+    Ng = 257; dx = 1e-5; dt = 1e-12; L = dx * (Ng - 1); steps = 6
+    kT = KB * 116000.
+    rs = np.random.RandomState(3)
+    h = N // 2
+    x0 = rs.uniform(0, L, N)
+    u0 = np.concatenate([rs.normal(0, np.sqrt(kT / ME), h), rs.normal(0, np.sqrt(kT / MP), N - h)])
+    E0 = rs.normal(0, 1e4, Ng)
+    p2c = L * 1e19 / N
+
+    def run(comm):
+        np.random.seed(1)
+        sim = SheathSim(N, Ng, dx, dt, p2c, kBT=(kT, kT), carry_vw=False, comm=comm, device=dev, rng="host",
+                        draws=LegacyDraws())
+        sim.upload(x0, u0, E0=E0)
+        its, dead = [], []
+        for _ in range(steps):
+            nd = sim.reinject()
+            k, r = sim.picard(); sim.t += 1
+            its.append(k); dead.append(int(nd or 0))
+        sim.check()
+        return sim, its, dead
+    sharded, its_s, dead_s = run(Comm())
+    out = sharded.download()
+    # gather the shards on rank 0
+    if world > 1:
+        parts = [None] * world
+        dist.all_gather_object(parts, dict(x0=out["x0"], u0=out["u0"], active=out["active"], start=sharded.start))
+    else:
+        parts = [dict(x0=out["x0"], u0=out["u0"], active=out["active"], start=0)]
+    if rank == 0:
+        single, its_1, dead_1 = run(Comm(enabled=False))
+        ref = single.download()
+        xs = np.concatenate([p["x0"] for p in parts]); us = np.concatenate([p["u0"] for p in parts])
+        act = np.concatenate([p["active"] for p in parts])
+        rel = lambda a, b: float(np.max(np.abs(a - b)) / max(np.max(np.abs(b)), 1e-300))
+        res = dict(world=world, N=N, iters_sharded=its_s, iters_single=its_1, dead_local_rank0=dead_s, dead_single=dead_1,
+                   E_rel=rel(out["E0"], ref["E0"]), x_rel=rel(xs, ref["x0"]), u_rel=rel(us, ref["u0"]),
+                   flags_equal=bool(np.array_equal(act, ref["active"])))
+        res["ok"] = bool(its_s == its_1 and res["flags_equal"] and res["E_rel"] < 1e-10 and res["x_rel"] < 1e-11)
+        print(json.dumps(res))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
