@@ -868,11 +868,19 @@ __global__ void dd_sort_hist_k(DDK k, const double* __restrict__ x0, int32_t* __
     const int nk = 2 * k.Ng;
     for (int i = threadIdx.x; i < nk; i += blockDim.x) sh[i] = 0;
     __syncthreads();
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < k.N; i += (long long)gridDim.x * blockDim.x)
-        atomicAdd(&sh[dd_sort_key(k, x0[i], i)], 1);
+    // warp-aggregated: lanes holding the same key elect one leader that adds their count (a store
+    // that is already nearly sorted has one or two keys per warp, i.e. 32-way same-address conflicts)
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    const long long nIter = (k.N + stride - 1) / stride;
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    for (long long it = 0; it < nIter; ++it, i += stride) {
+        const int key = i < k.N ? dd_sort_key(k, x0[i], i) : -1;
+        const unsigned peers = __match_any_sync(0xffffffffu, key);
+        if (key >= 0 && (threadIdx.x & 31) == (unsigned)(__ffs(peers) - 1)) atomicAdd(&sh[key], __popc(peers));
+    }
     __syncthreads();
-    for (int i = threadIdx.x; i < nk; i += blockDim.x)
-        if (sh[i]) atomicAdd(&counts[i], sh[i]);
+    for (int i2 = threadIdx.x; i2 < nk; i2 += blockDim.x)
+        if (sh[i2]) atomicAdd(&counts[i2], sh[i2]);
 }
 // exclusive scan of counts (one CTA, sequential over chunks)
 __global__ void dd_sort_scan_k(int32_t* __restrict__ counts, int nk) {
@@ -928,7 +936,15 @@ __global__ void __launch_bounds__(SORT_T) dd_sort_scatter_k(DDK k, const double*
         for (int j = 0; j < SORT_PER; ++j) {
             const long long i = base + (long long)j * SORT_T + threadIdx.x;
             key[j] = -1; rank[j] = 0; X[j] = 0.;
-            if (i < k.N) { X[j] = x0[i]; key[j] = dd_sort_key(k, X[j], i); rank[j] = atomicAdd(&cnt[key[j]], 1); }
+            if (i < k.N) { X[j] = x0[i]; key[j] = dd_sort_key(k, X[j], i); }
+            // warp-aggregated rank: one shared-memory atomic per distinct key in the warp
+            const unsigned peers = __match_any_sync(0xffffffffu, key[j]);
+            const unsigned lane = threadIdx.x & 31;
+            const int leader = __ffs(peers) - 1;
+            int rbase = 0;
+            if (key[j] >= 0 && (int)lane == leader) rbase = atomicAdd(&cnt[key[j]], __popc(peers));
+            rbase = __shfl_sync(0xffffffffu, rbase, leader);
+            rank[j] = rbase + __popc(peers & ((1u << lane) - 1u));
         }
         __syncthreads();
 #pragma unroll
