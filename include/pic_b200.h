@@ -278,6 +278,22 @@ int pic_dev_gc_weight(const double* x, const double* charge_state, const double*
 int pic_dev_gc_push_boris(const pic_gc_params* p, double* const r[7], const double* charge_state,
                           const double* m, int8_t* active, int8_t* at_wall, int8_t* hit_flag,
                           const double* Egrid, long long* hit_count, int* range_err, void* stream);
+/* The same step for a SPECIES-UNIFORM store (every particle has this charge_state, m, p2c), on the
+ * TMA-ring / private-window design, optionally fused with the CIC deposit of the number density
+ * at the NEW positions of the particles still active (pygcpic.py:871-883, the next step's D5):
+ * n_acc fp64[ng] is accumulated (not zeroed) when non-NULL.  hit_flag is only written for
+ * particles that are inactive or absorbed by this call (it must start zeroed and be cleared
+ * when a slot is re-activated).  The arrays must be 16-byte aligned. */
+int pic_dev_gc_push_boris_uniform(const pic_gc_params* p, double* const r[7], double charge_state, double m,
+                                  double p2c, int8_t* active, int8_t* at_wall, int8_t* hit_flag,
+                                  const double* Egrid, double* n_acc, long long* hit_count, int* range_err,
+                                  void* stream);
+/* n = n_acc ; rho = charge_state*e*n_acc for a species-uniform store */
+int pic_dev_gc_uniform_finish(const double* n_acc, double* n, double* rho, int ng, double charge_state,
+                              void* stream);
+/* adds the CIC number density of the slots idx[0..M) (int64 indices; re-activated particles) */
+int pic_dev_gc_deposit_idx(const double* x, const int64_t* idx, int64_t M, double p2c, double dx, int ng,
+                           double* n_acc, int* range_err, void* stream);
 /* Particle.apply_BCs_dirichlet :668-689 alone */
 int pic_dev_gc_apply_bcs(const double* x, int8_t* active, int8_t* at_wall, int64_t N, double length,
                          void* stream);

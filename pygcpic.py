@@ -381,15 +381,21 @@ def run_sheath(grid, store, dt, steps, source_N, source, p2c, m, charge_state=1,
     out = dict(length=[], hits=[], deleted=[], reactivated=[], n0=[], ekin=[], angle=[])
     for _ in range(int(steps)):
         time += dt
-        store.apply_BCs_dirichlet(grid)
-        grid.weight_particles_to_grid_boltzmann(store, dt)
+        if grid.have_fused_n:
+            # a species-uniform store: the previous step's push kernel already deposited the
+            # survivors at their new positions (and flagged everything outside the walls), the
+            # re-activated slots were added by ParticleStore.reactivate
+            grid.finish_fused_deposit(charge_state, dt)
+        else:
+            store.apply_BCs_dirichlet(grid)
+            grid.weight_particles_to_grid_boltzmann(store, dt)
         grid.smooth_rho()
         grid.reset_added_particles()
         grid.solve_for_phi_dirichlet_boltzmann()
         grid.differentiate_phi_to_E_dirichlet()
         inactive_entry = (store.active != 1).to(torch.int8)
         contrib_entry = store.source_ion_flags(Z)
-        hits = store.push_6D(dt, grid)
+        hits = store.push_6D(dt, grid, deposit=True)
         ke, ang, _ = store.wall_hit_tallies()
         contrib_after = store.source_ion_flags(Z)
         dec, n_react, n_del = store.decide(inactive_entry, contrib_entry, contrib_after, source_N)

@@ -89,6 +89,9 @@ _SIGS = {
     "pic_dev_gc_interpolate": [P, P, P, I64, I32, F64, P, P],
     "pic_dev_gc_weight": [P, P, P, P, P, P, I64, I32, F64, P, P],
     "pic_dev_gc_push_boris": [C.POINTER(GCParams), C.POINTER(R7), P, P, P, P, P, P, P, P, P],
+    "pic_dev_gc_push_boris_uniform": [C.POINTER(GCParams), C.POINTER(R7), F64, F64, F64, P, P, P, P, P, P, P, P],
+    "pic_dev_gc_uniform_finish": [P, P, P, I32, F64, P],
+    "pic_dev_gc_deposit_idx": [P, P, I64, F64, F64, I32, P, P, P],
     "pic_dev_gc_apply_bcs": [P, P, P, I64, F64, P],
     "pic_dev_gc_to_gc": [C.POINTER(GCParams), C.POINTER(R7), P, P, P, P],
     "pic_dev_gc_to_6d": [C.POINTER(GCParams), C.POINTER(R7), P, P, P, P, P, P, P],

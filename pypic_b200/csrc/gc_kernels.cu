@@ -4,6 +4,7 @@
 // order-dependent reactivate-or-delete rule as a prefix scan, and warp-ballot stable
 // stream compaction.
 #include "common.cuh"
+#include "ring.cuh"
 #include "host_common.h"
 
 namespace pic {
@@ -49,17 +50,37 @@ __global__ void gc_weight_k(const double* __restrict__ x, const double* __restri
     for (int i = threadIdx.x; i < 2 * ng; i += blockDim.x) sm[i] = 0.0;
     __syncthreads();
     int bad = 0;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < N; i += (long long)gridDim.x * blockDim.x) {
-        if (active[i] != 1) continue;
-        Cell c = cell_dd(x[i], dx);
-        if (c.iL < 0 || c.iL > ng - 2) { ++bad; c.iL = clampi(c.iL, 0, ng - 2); }
-        double pc = p2c[i];
-        double qr = cs[i] * PIC_E * pc / dx;      // charge_state*e*p2c/dx
-        double nr = pc / dx;
-        atomicAdd(&sr[c.iL], qr * c.wL);
-        atomicAdd(&sr[c.iL + 1], qr * c.wR);
-        atomicAdd(&sn[c.iL], nr * c.wL);
-        atomicAdd(&sn[c.iL + 1], nr * c.wR);
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    const long long nIter = (N + stride - 1) / stride;
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    for (long long it = 0; it < nIter; ++it, i += stride) {
+        const bool valid = i < N && active[i] == 1;
+        int iL = -1;
+        double a0 = 0., a1 = 0., b0 = 0., b1 = 0.;
+        if (valid) {
+            Cell c = cell_dd(x[i], dx);
+            if (c.iL < 0 || c.iL > ng - 2) { ++bad; c.iL = clampi(c.iL, 0, ng - 2); }
+            double pc = p2c[i];
+            double qr = cs[i] * PIC_E * pc / dx;      // charge_state*e*p2c/dx
+            double nr = pc / dx;
+            iL = c.iL;
+            a0 = qr * c.wL; a1 = qr * c.wR; b0 = nr * c.wL; b1 = nr * c.wR;
+        }
+        // warp pre-reduction when the whole warp sits in one cell (store sorted by cell): fp64
+        // shared-memory atomics are CAS loops, 32-way same-address conflicts serialise badly
+        const int k0 = __shfl_sync(0xffffffffu, iL, 0);
+        if (__all_sync(0xffffffffu, iL == k0)) {
+            if (k0 < 0) continue;
+            a0 = warp_sum(a0); a1 = warp_sum(a1); b0 = warp_sum(b0); b1 = warp_sum(b1);
+            if ((threadIdx.x & 31) == 0) {
+                atomicAdd(&sr[k0], a0); atomicAdd(&sr[k0 + 1], a1); atomicAdd(&sn[k0], b0); atomicAdd(&sn[k0 + 1], b1);
+            }
+        } else if (valid) {
+            atomicAdd(&sr[iL], a0);
+            atomicAdd(&sr[iL + 1], a1);
+            atomicAdd(&sn[iL], b0);
+            atomicAdd(&sn[iL + 1], b1);
+        }
     }
     __syncthreads();
     for (int i = threadIdx.x; i < ng; i += blockDim.x) {
@@ -111,6 +132,280 @@ __global__ void __launch_bounds__(256) gc_push_boris_k(GCK k, R7 r, const double
         if (hit_flag) hit_flag[i] = hit ? 1 : 0;
     }
     if (hits && hit_count) atomicAdd((unsigned long long*)hit_count, (unsigned long long)hits);
+    if (bad && range_err) atomicAdd(range_err, bad);
+}
+
+// =====================================================================================
+// v2 fused kernel for a SPECIES-UNIFORM store (every particle has the same charge_state, m,
+// p2c -- the host checks): gather (mirrored weights) + Boris 1D3V + Dirichlet walls + optional
+// CIC deposit of the number density at the NEW position (the next step's D5 for the particles
+// still active; rho = charge_state*e*n for a uniform store), in one pass.  Same design as
+// dd_picard_iter_v6_k: persistent 512-thread CTA per SM, rows of 64 particles of all seven
+// components staged by 1-D TMA bulk copies into a per-warp ring, two particles per lane,
+// private shared-memory deposit windows.  Traffic: 7x8 B in + 7x8 B out + 1 B flag per particle.
+#define G_T 512
+#define G_W 7
+#define G_ROWS 16
+#define G_CHUNK (G_T * 2 * G_ROWS)
+
+struct GUni { double cs, m, p2c; };
+struct GFastC {
+    double dx, idx, dt, cE, tx, ty, tz, sx, sy, sz, nr;
+    unsigned hi_lim;
+};
+struct GFastO { double x, y, z, vx, vy, vz, t, fL, fR; int cF; unsigned fr, ps; };
+
+__device__ __forceinline__ void gc_fast(const GFastC& c, const double* __restrict__ sE, int ng, double x, double y,
+                                        double z, double vx, double vy, double vz, double t, GFastO& o) {
+    const double ts = x * c.idx, fs = floor(ts);
+    const unsigned f0 = (unsigned)__double2hiint(ts - fs) - PIC_HI_G;
+    const double rs = fma(-fs, c.dx, x);
+    const int is = min(max((int)fs, 0), ng - 2);
+    const double w_l = div_const(rs, c.dx, c.idx), w_r = 1.0 - w_l;       // pygcpic.py:344-346 (mirrored)
+    const double Ex = sE[is] * w_l + sE[is + 1] * w_r;
+    vx += c.cE * Ex;                                                      // :480
+    const double vfx = vx + vy * c.tz - vz * c.ty;                        // :492-494
+    const double vfy = vy + vz * c.tx - vx * c.tz;
+    const double vfz = vz + vx * c.ty - vy * c.tx;
+    vx += vfy * c.sz - vfz * c.sy;                                        // :496-498
+    vy += vfz * c.sx - vfx * c.sz;
+    vz += vfx * c.sy - vfy * c.sx;
+    vx += c.cE * Ex;                                                      // :500
+    o.x = x + vx * c.dt; o.y = y + vy * c.dt; o.z = z + vz * c.dt;        // :502-504
+    o.vx = vx; o.vy = vy; o.vz = vz;
+    o.t = t + c.dt;                                                       // :506
+    o.ps = max((unsigned)__double2hiint(x) - 1u, (unsigned)__double2hiint(o.x) - 1u);
+    const double tf = o.x * c.idx, ff = floor(tf);
+    const unsigned f1 = (unsigned)__double2hiint(tf - ff) - PIC_HI_G;
+    const double rf = fma(-ff, c.dx, o.x);
+    o.cF = (int)ff;
+    o.fr = max(f0, f1);
+    o.fR = c.nr * (rf * c.idx); o.fL = c.nr - o.fR;                       // :880-883 up to re-association
+}
+
+// exact per-particle routine (the body of gc_push_boris_k + gc_weight_k's n deposit)
+__device__ __noinline__ int gc_particle_exact(const GCK& k, const GUni& u, const R7& r, long long i, int act,
+                                              const double* sE, int8_t* __restrict__ active,
+                                              int8_t* __restrict__ at_wall, int8_t* __restrict__ hit_flag,
+                                              double* __restrict__ n_acc, int* hits) {
+    int bad = 0;
+    if (act != 1) { if (hit_flag) hit_flag[i] = 0; return 0; }
+    double x = r.r[0][i], y = r.r[1][i], z = r.r[2][i], vx = r.r[3][i], vy = r.r[4][i], vz = r.r[5][i];
+    const double Ex = gather_mirrored(sE, x, k.dx, k.ng, bad);
+    const double constant = 0.5 * k.dt * u.cs * 1.602e-19 / u.m;
+    vx += constant * Ex;
+    const double tx = constant * k.B[0], ty = constant * k.B[1], tz = constant * k.B[2];
+    const double t2 = tx * tx + ty * ty + tz * tz;
+    const double sx = 2. * tx / (1. + t2), sy = 2. * ty / (1. + t2), sz = 2. * tz / (1. + t2);
+    const double vfx = vx + vy * tz - vz * ty;
+    const double vfy = vy + vz * tx - vx * tz;
+    const double vfz = vz + vx * ty - vy * tx;
+    vx += vfy * sz - vfz * sy;
+    vy += vfz * sx - vfx * sz;
+    vz += vfx * sy - vfy * sx;
+    vx += constant * Ex;
+    x += vx * k.dt; y += vy * k.dt; z += vz * k.dt;
+    r.r[0][i] = x; r.r[1][i] = y; r.r[2][i] = z; r.r[3][i] = vx; r.r[4][i] = vy; r.r[5][i] = vz;
+    r.r[6][i] = r.r[6][i] + k.dt;
+    const bool hit = (x < 0.0) || (x > k.length);                         // :685
+    if (hit) { active[i] = 0; at_wall[i] = 1; ++*hits; }
+    if (hit_flag) hit_flag[i] = hit ? 1 : 0;
+    if (!hit && n_acc) {
+        Cell c = cell_dd(x, k.dx);
+        if (c.iL < 0 || c.iL > k.ng - 2) { ++bad; c.iL = clampi(c.iL, 0, k.ng - 2); }
+        const double nr = u.p2c / k.dx;
+        atomicAdd(&n_acc[c.iL], nr * c.wL);
+        atomicAdd(&n_acc[c.iL + 1], nr * c.wR);
+    }
+    return bad;
+}
+
+__device__ __forceinline__ void gwin_add(double* myw, double* __restrict__ acc, int wb, int c, double vL, double vR) {
+    const unsigned d = (unsigned)(c - wb);
+    if (d <= (unsigned)(G_W - 2)) { double* p = myw + d * G_T; p[0] += vL; p[G_T] += vR; }
+    else { atomicAdd(&acc[c], vL); atomicAdd(&acc[c + 1], vR); }
+}
+
+template <int NST, bool DEP>
+__global__ void __launch_bounds__(G_T, 1) gc_push_boris_v2_k(const __grid_constant__ GCK k, const GUni u, int nchunks,
+                                                              const R7 r, int8_t* __restrict__ active,
+                                                              int8_t* __restrict__ at_wall, int8_t* __restrict__ hit_flag,
+                                                              const double* __restrict__ Egrid,
+                                                              double* __restrict__ n_acc,
+                                                              long long* __restrict__ hit_count,
+                                                              int* __restrict__ range_err) {
+    extern __shared__ __align__(128) double sm[];
+    __shared__ int s_cnt[2];
+    const int ng = k.ng;
+    const int NP = (ng + 15) & ~15;
+    double* sE = sm;
+    double* win = sm + NP;                                   // [G_W][G_T]
+    double* ring = win + (DEP ? G_W * G_T : 0);              // [warp][stage][7][64]
+    unsigned long long* bars = (unsigned long long*)(ring + (G_T / 32) * NST * 448);
+    for (int i = threadIdx.x; i < ng; i += G_T) sE[i] = Egrid[i];
+    double* myw = win + threadIdx.x;
+    if (DEP) {
+#pragma unroll
+        for (int n = 0; n < G_W; ++n) myw[n * G_T] = 0.0;
+    }
+    if (threadIdx.x < 2) s_cnt[threadIdx.x] = 0;
+    const unsigned full = 0xffffffffu;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wbase = threadIdx.x & ~31;
+    const int NOWIN = -0x40000000;
+    const double* wring = ring + warp * (NST * 448);
+    const uint32_t ring_s = smem_u32(wring);
+    const uint32_t bar_s = smem_u32(bars + warp * NST);
+    if (lane == 0) {
+#pragma unroll
+        for (int s = 0; s < NST; ++s) mbar_init(bar_s + 8 * s, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    GFastC fc;
+    fc.dx = k.dx; fc.idx = 1.0 / k.dx; fc.dt = k.dt;
+    fc.cE = 0.5 * k.dt * u.cs * 1.602e-19 / u.m;                          // pygcpic.py:478
+    fc.tx = fc.cE * k.B[0]; fc.ty = fc.cE * k.B[1]; fc.tz = fc.cE * k.B[2];
+    {
+        const double t2 = fc.tx * fc.tx + fc.ty * fc.ty + fc.tz * fc.tz;
+        fc.sx = 2. * fc.tx / (1. + t2); fc.sy = 2. * fc.ty / (1. + t2); fc.sz = 2. * fc.tz / (1. + t2);
+    }
+    fc.nr = u.p2c / k.dx;
+    fc.hi_lim = (unsigned)__double2hiint(k.length) - 1u;
+    const int my_chunks = (nchunks - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+    const long long woff = (long long)warp * (64 * G_ROWS);
+    const long long chunk_step = (long long)gridDim.x * G_CHUNK;
+    auto issue = [&](long long base, int st) {
+        if (elect_one()) {
+            const uint32_t dst = ring_s + st * 3584, bar = bar_s + 8 * st;
+            mbar_expect_tx(bar, 3584u);
+#pragma unroll
+            for (int a = 0; a < 7; ++a) bulk_g2s(dst + 512 * a, r.r[a] + base, 512, bar);
+        }
+    };
+    long long cbase = (long long)blockIdx.x * G_CHUNK + woff;
+    if (my_chunks > 0) {
+#pragma unroll
+        for (int s = 0; s < NST; ++s) issue(cbase + 64 * s, s);
+    }
+    int stage = 0, bad = 0, hits = 0;
+    uint32_t phase = 0;
+#pragma unroll 1
+    for (int c = 0; c < my_chunks; ++c, cbase += chunk_step) {
+        const bool more = c + 1 < my_chunks;
+        int wb = NOWIN;
+        long long ci = cbase + 2 * lane;
+#pragma unroll 1
+        for (int row = 0; row < G_ROWS; ++row, ci += 64) {
+            // flags of the pair first (plain global load; overlaps the barrier wait)
+            const short fl = *(const short*)(active + ci);
+            const int acta = (int)(signed char)(fl & 0xff), actb = (int)(signed char)(fl >> 8);
+            mbar_wait(bar_s + 8 * stage, phase);
+            const double* sb = wring + stage * 448 + 2 * lane;
+            const double2 X = *(const double2*)sb, Y = *(const double2*)(sb + 64), Z = *(const double2*)(sb + 128);
+            const double2 VX = *(const double2*)(sb + 192), VY = *(const double2*)(sb + 256), VZ = *(const double2*)(sb + 320);
+            const double2 T = *(const double2*)(sb + 384);
+            const int st_cur = stage;
+            if (++stage == NST) { stage = 0; phase ^= 1u; }
+            GFastO a, b;
+            gc_fast(fc, sE, ng, X.x, Y.x, Z.x, VX.x, VY.x, VZ.x, T.x, a);
+            gc_fast(fc, sE, ng, X.y, Y.y, Z.y, VX.y, VY.y, VZ.y, T.y, b);
+            const bool ra = (a.fr > PIC_HI_SPAN) | (a.ps >= fc.hi_lim) | (acta != 1);
+            const bool rb = (b.fr > PIC_HI_SPAN) | (b.ps >= fc.hi_lim) | (actb != 1);
+            if (DEP && row == 0) {
+                int nok = __reduce_add_sync(full, (ra ? 0 : 1) + (rb ? 0 : 1));
+                int sum = __reduce_add_sync(full, (ra ? 0 : a.cF) + (rb ? 0 : b.cF));
+                wb = nok ? sum / nok - (G_W - 2) / 2 : NOWIN;
+            }
+            if (!(ra | rb)) {
+                __stcs((double2*)(r.r[0] + ci), make_double2(a.x, b.x));
+                __stcs((double2*)(r.r[1] + ci), make_double2(a.y, b.y));
+                __stcs((double2*)(r.r[2] + ci), make_double2(a.z, b.z));
+                __stcs((double2*)(r.r[3] + ci), make_double2(a.vx, b.vx));
+                __stcs((double2*)(r.r[4] + ci), make_double2(a.vy, b.vy));
+                __stcs((double2*)(r.r[5] + ci), make_double2(a.vz, b.vz));
+                __stcs((double2*)(r.r[6] + ci), make_double2(a.t, b.t));
+                if (DEP) { gwin_add(myw, n_acc, wb, a.cF, a.fL, a.fR); gwin_add(myw, n_acc, wb, b.cF, b.fL, b.fR); }
+            } else {
+                if (ra) bad += gc_particle_exact(k, u, r, ci, acta, sE, active, at_wall, hit_flag, DEP ? n_acc : nullptr, &hits);
+                else {
+                    r.r[0][ci] = a.x; r.r[1][ci] = a.y; r.r[2][ci] = a.z; r.r[3][ci] = a.vx; r.r[4][ci] = a.vy;
+                    r.r[5][ci] = a.vz; r.r[6][ci] = a.t;
+                    if (DEP) gwin_add(myw, n_acc, wb, a.cF, a.fL, a.fR);
+                }
+                if (rb) bad += gc_particle_exact(k, u, r, ci + 1, actb, sE, active, at_wall, hit_flag, DEP ? n_acc : nullptr, &hits);
+                else {
+                    r.r[0][ci + 1] = b.x; r.r[1][ci + 1] = b.y; r.r[2][ci + 1] = b.z; r.r[3][ci + 1] = b.vx;
+                    r.r[4][ci + 1] = b.vy; r.r[5][ci + 1] = b.vz; r.r[6][ci + 1] = b.t;
+                    if (DEP) gwin_add(myw, n_acc, wb, b.cF, b.fL, b.fR);
+                }
+            }
+            __syncwarp();
+            if (row < G_ROWS - NST) issue(cbase + 64 * (row + NST), st_cur);
+            else if (more) issue(cbase + chunk_step + 64 * (row + NST - G_ROWS), st_cur);
+        }
+        __syncwarp();
+        if (DEP && wb != NOWIN) {
+            double s = 0.0;
+            const int n = lane >> 1, half = lane & 1;
+            if (n < G_W) {
+                const double* col = win + n * G_T + wbase + half * 16;
+#pragma unroll
+                for (int j = 0; j < 16; ++j) s += col[(j + n) & 15];
+            }
+            s += __shfl_xor_sync(full, s, 1);
+            if (n < G_W && half == 0) {
+                const int node = wb + n;
+                if (node >= 0 && node < ng && s != 0.0) atomicAdd(&n_acc[node], s);
+            }
+            __syncwarp();
+#pragma unroll
+            for (int n2 = 0; n2 < G_W; ++n2) myw[n2 * G_T] = 0.0;
+            __syncwarp();
+        }
+    }
+    if (bad) atomicAdd(&s_cnt[0], bad);
+    if (hits) atomicAdd(&s_cnt[1], hits);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        if (s_cnt[0] && range_err) atomicAdd(range_err, s_cnt[0]);
+        if (s_cnt[1] && hit_count) atomicAdd((unsigned long long*)hit_count, (unsigned long long)s_cnt[1]);
+    }
+}
+
+// tail of the uniform fused step (N % G_CHUNK particles): the exact per-particle routine
+__global__ void gc_tail_uniform_k(GCK k, GUni u, R7 r, long long first, int8_t* __restrict__ active,
+                                  int8_t* __restrict__ at_wall, int8_t* __restrict__ hit_flag,
+                                  const double* __restrict__ Egrid, double* __restrict__ n_acc,
+                                  long long* __restrict__ hit_count, int* __restrict__ range_err) {
+    int bad = 0, hits = 0;
+    for (long long i = first + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < k.N; i += (long long)gridDim.x * blockDim.x)
+        bad += gc_particle_exact(k, u, r, i, active[i], Egrid, active, at_wall, hit_flag, n_acc, &hits);
+    if (hits && hit_count) atomicAdd((unsigned long long*)hit_count, (unsigned long long)hits);
+    if (bad && range_err) atomicAdd(range_err, bad);
+}
+
+// n_acc -> (n, rho) of a species-uniform store: n = n_acc, rho = (charge_state*e)*n  (pygcpic.py:880-883)
+__global__ void gc_uniform_finish_k(const double* __restrict__ n_acc, double* __restrict__ n, double* __restrict__ rho,
+                                    int ng, double cs) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < ng; i += gridDim.x * blockDim.x) {
+        const double v = n_acc[i];
+        n[i] = v;
+        rho[i] = cs * PIC_E * v;
+    }
+}
+
+// CIC deposit of the number density of the listed slots (the particles re-activated after a fused
+// push): n_acc[iL] += p2c/dx*wl, n_acc[iL+1] += p2c/dx*wr.
+__global__ void gc_deposit_idx_k(const double* __restrict__ x, const int64_t* __restrict__ idx, long long M, double p2c,
+                                 double dx, int ng, double* __restrict__ n_acc, int* __restrict__ range_err) {
+    int bad = 0;
+    for (long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x; j < M; j += (long long)gridDim.x * blockDim.x) {
+        Cell c = cell_dd(x[idx[j]], dx);
+        if (c.iL < 0 || c.iL > ng - 2) { ++bad; c.iL = clampi(c.iL, 0, ng - 2); }
+        const double nr = p2c / dx;
+        atomicAdd(&n_acc[c.iL], nr * c.wL);
+        atomicAdd(&n_acc[c.iL + 1], nr * c.wR);
+    }
     if (bad && range_err) atomicAdd(range_err, bad);
 }
 
@@ -474,6 +769,73 @@ int pic_dev_gc_push_boris(const pic_gc_params* p, double* const r[7], const doub
     PIC_CHECK_CUDA(cudaFuncSetAttribute(gc_push_boris_k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(smem ? smem : 1)));
     gc_push_boris_k<<<grid_for(k.N, 256, 6), 256, smem, (cudaStream_t)stream>>>(k, rr, charge_state, m, active, at_wall,
                                                                                  hit_flag, Egrid, hit_count, range_err);
+    PIC_CHECK_LAUNCH();
+    return PIC_OK;
+}
+
+// Species-uniform fused Boris step (see gc_push_boris_v2_k).  n_acc == NULL: no deposit.
+int pic_dev_gc_push_boris_uniform(const pic_gc_params* p, double* const r[7], double charge_state, double m, double p2c,
+                                  int8_t* active, int8_t* at_wall, int8_t* hit_flag, const double* Egrid,
+                                  double* n_acc, long long* hit_count, int* range_err, void* stream) {
+    PIC_REQUIRE(p && r && active && at_wall && Egrid, "gc_push_boris_uniform: null pointer");
+    PIC_REQUIRE(!(p->flags & 3), "gc_push_boris_uniform: pre-gathered E / no-BC modes are not supported");
+    PIC_REQUIRE(p->ng >= 8, "gc_push_boris_uniform: grid too small");
+    if (p->N == 0) return PIC_OK;
+    GCK k = make_gck(p);
+    GUni u{charge_state, m, p2c};
+    R7 rr;
+    bool aligned = true;
+    for (int i = 0; i < 7; ++i) {
+        PIC_REQUIRE(r[i], "gc_push_boris_uniform: null component array");
+        rr.r[i] = r[i];
+        aligned = aligned && (((uintptr_t)r[i]) & 15) == 0;
+    }
+    PIC_REQUIRE(aligned && (((uintptr_t)active) & 1) == 0, "gc_push_boris_uniform: arrays must be 16-byte aligned");
+    cudaStream_t st = (cudaStream_t)stream;
+    const bool dep = n_acc != nullptr;
+    auto smem_for = [&](int nst) {
+        return ((size_t)((k.ng + 15) & ~15) + (dep ? (size_t)G_W * G_T : 0) + (size_t)(G_T / 32) * nst * 448 +
+                (size_t)(G_T / 32) * nst) * sizeof(double);
+    };
+    const size_t cap = (size_t)max_optin_smem() - 512;
+    const int nst = smem_for(3) <= cap ? 3 : 2;
+    const size_t smem = smem_for(nst);
+    PIC_REQUIRE(smem <= cap, "gc_push_boris_uniform: ng too large for the shared-memory field tile");
+    const long long nchunks = k.N / G_CHUNK;
+    if (nchunks > 0) {
+        long long capc = device_sm_count();
+        const int grid = (int)(nchunks < capc ? nchunks : capc);
+#define PIC_GC_LAUNCH(NST, DEP)                                                                                  \
+        do {                                                                                                     \
+            auto kern = gc_push_boris_v2_k<NST, DEP>;                                                            \
+            PIC_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+            kern<<<grid, G_T, smem, st>>>(k, u, (int)nchunks, rr, active, at_wall, hit_flag, Egrid, n_acc,       \
+                                           hit_count, range_err);                                                \
+        } while (0)
+        if (nst == 3) { if (dep) PIC_GC_LAUNCH(3, true); else PIC_GC_LAUNCH(3, false); }
+        else { if (dep) PIC_GC_LAUNCH(2, true); else PIC_GC_LAUNCH(2, false); }
+#undef PIC_GC_LAUNCH
+        PIC_CHECK_LAUNCH();
+    }
+    const long long done = nchunks * G_CHUNK;
+    if (done < k.N) gc_tail_uniform_k<<<grid_for(k.N - done, 256, 4), 256, 0, st>>>(k, u, rr, done, active, at_wall, hit_flag, Egrid, n_acc, hit_count, range_err);
+    PIC_CHECK_LAUNCH();
+    return PIC_OK;
+}
+
+int pic_dev_gc_uniform_finish(const double* n_acc, double* n, double* rho, int ng, double charge_state, void* stream) {
+    PIC_REQUIRE(n_acc && n && rho && ng >= 2, "gc_uniform_finish: bad argument");
+    gc_uniform_finish_k<<<(ng + 255) / 256, 256, 0, (cudaStream_t)stream>>>(n_acc, n, rho, ng, charge_state);
+    PIC_CHECK_LAUNCH();
+    return PIC_OK;
+}
+
+int pic_dev_gc_deposit_idx(const double* x, const int64_t* idx, int64_t M, double p2c, double dx, int ng, double* n_acc,
+                           int* range_err, void* stream) {
+    PIC_REQUIRE(M >= 0, "gc_deposit_idx: M<0");
+    if (M == 0) return PIC_OK;
+    PIC_REQUIRE(x && idx && n_acc && ng >= 2, "gc_deposit_idx: bad argument");
+    gc_deposit_idx_k<<<grid_for(M, 256, 4), 256, 0, (cudaStream_t)stream>>>(x, idx, M, p2c, dx, ng, n_acc, range_err);
     PIC_CHECK_LAUNCH();
     return PIC_OK;
 }

@@ -43,6 +43,8 @@ class GridDev:
         self.range_err = torch.zeros(1, dtype=torch.int32, device=dev)
         self.added_particles = 0.0
         self.newton_iterations = 0
+        self.n_acc = D.f64(ng, dev, True)           # number density deposited by the fused push
+        self.have_fused_n = False
 
     # -- reference-density state ------------------------------------------------------
     @property
@@ -80,6 +82,28 @@ class GridDev:
                   D.ptr(self.range_err), st)
         _lib.call("pic_dev_gc_n0_update", D.ptr(self.phi), D.ptr(self.n), D.ptr(self.domain), self.ng, self.Te, self.ve,
                   float(self.added_particles), float(dt), D.ptr(self.state), st)
+
+    # -- fused deposit (species-uniform stores) -----------------------------------------------
+    def begin_fused_deposit(self):
+        self.n_acc.zero_()
+        self.have_fused_n = True
+
+    def deposit_slots(self, store, idx, p2c):
+        """Adds the number density of the slots idx (int64 device tensor) -- the particles
+        re-activated after the fused push -- to the pending deposit."""
+        if idx.numel():
+            _lib.call("pic_dev_gc_deposit_idx", D.ptr(store.r[0]), D.ptr(idx), idx.numel(), float(p2c), self.dx, self.ng,
+                      D.ptr(self.n_acc), D.ptr(self.range_err), D.stream())
+
+    def finish_fused_deposit(self, charge_state, dt):
+        """n, rho from the density the fused push deposited (+ re-activated slots), then the
+        Boltzmann reference-density update of pygcpic.py:889-904."""
+        st = D.stream()
+        _lib.call("pic_dev_gc_uniform_finish", D.ptr(self.n_acc), D.ptr(self.n), D.ptr(self.rho), self.ng,
+                  float(charge_state), st)
+        _lib.call("pic_dev_gc_n0_update", D.ptr(self.phi), D.ptr(self.n), D.ptr(self.domain), self.ng, self.Te, self.ve,
+                  float(self.added_particles), float(dt), D.ptr(self.state), st)
+        self.have_fused_n = False
 
     def smooth_rho(self):
         out = torch.empty_like(self.rho)
@@ -135,6 +159,7 @@ class ParticleStore:
         self.hit_count = torch.zeros(1, dtype=torch.int64, device=dev)
         self.range_err = torch.zeros(1, dtype=torch.int32, device=dev)
         self.mode = 0
+        self._uniform = False                       # False: unknown, None: not uniform, tuple: (cs, m, p2c)
 
     # -- construction / export -----------------------------------------------------------
     @classmethod
@@ -153,6 +178,28 @@ class ParticleStore:
             if val is not None:
                 getattr(s, name).copy_(torch.as_tensor(np.asarray(val).astype(np.int8)))
         return s
+
+    FUSED_MIN = 16384                               # one chunk of the v2 kernel
+
+    def uniform(self):
+        """(charge_state, m, p2c) if every slot holds the same values (then the push can take
+        them as scalars instead of streaming 24 B/particle), else None.  Cached; methods that
+        write these arrays invalidate or re-check it."""
+        if self._uniform is False:
+            n = self.N
+            if n == 0:
+                self._uniform = None
+            else:
+                vals = []
+                for a in (self.charge_state, self.m, self.p2c):
+                    lo, hi = torch.aminmax(a[:n])
+                    vals.append((float(lo), float(hi)))
+                self._uniform = tuple(v[0] for v in vals) if all(v[0] == v[1] for v in vals) else None
+        return self._uniform
+
+    def invalidate_uniform(self):
+        """Call after writing charge_state / m / p2c tensors directly."""
+        self._uniform = False
 
     def r_host(self):
         return np.stack([c[:self.N].cpu().numpy() for c in self.r], 1)
@@ -181,12 +228,24 @@ class ParticleStore:
                   D.ptr(self.range_err), D.stream())
         return out[:self.N].cpu().numpy()
 
-    def push_6D(self, dt, grid):
+    def push_6D(self, dt, grid, deposit=False):
         """Fused interpolate_electric_field_dirichlet + push_6D + apply_BCs_dirichlet for all
-        active particles (pygcpic.py:1500-1502).  Returns the number of wall hits."""
+        active particles (pygcpic.py:1500-1502).  Returns the number of wall hits.
+
+        A species-uniform store takes the TMA-ring kernel; with deposit=True that kernel also
+        deposits the number density of the survivors at their new positions into grid.n_acc
+        (the next step's weight_particles_to_grid_boltzmann, see GridDev.finish_fused_deposit)."""
         P = self._params(grid, dt)
         r7 = self._r7()
         self.hit_count.zero_()
+        u = self.uniform() if self.N >= self.FUSED_MIN and grid.ng >= 8 else None
+        if u is not None:
+            if deposit:
+                grid.begin_fused_deposit()
+            _lib.call("pic_dev_gc_push_boris_uniform", C.byref(P), C.byref(r7), u[0], u[1], u[2], D.ptr(self.active),
+                      D.ptr(self.at_wall), D.ptr(self.hit_flag), D.ptr(grid.E), D.ptr(grid.n_acc) if deposit else None,
+                      D.ptr(self.hit_count), D.ptr(self.range_err), D.stream())
+            return int(D.read_raw(self.hit_count, 1, np.int64)[0])
         _lib.call("pic_dev_gc_push_boris", C.byref(P), C.byref(r7), D.ptr(self.charge_state), D.ptr(self.m),
                   D.ptr(self.active), D.ptr(self.at_wall), D.ptr(self.hit_flag), D.ptr(grid.E), D.ptr(self.hit_count),
                   D.ptr(self.range_err), D.stream())
@@ -263,6 +322,11 @@ class ParticleStore:
         self.p2c[idx] = float(p2c); self.m[idx] = float(m); self.charge_state[idx] = float(charge_state)
         self.Z[idx] = int(Z)
         self.active[idx] = 1; self.at_wall[idx] = 0; self.from_wall[idx] = 0
+        self.hit_flag[idx] = 0
+        if self._uniform not in (False, None) and self._uniform != (float(charge_state), float(m), float(p2c)):
+            self._uniform = None
+        if grid.have_fused_n:                      # the fused push has already deposited the survivors
+            grid.deposit_slots(self, idx, p2c)
         for _ in range(len(where_idx)):
             grid.add_particles(p2c)
 
@@ -296,6 +360,43 @@ class ParticleStore:
         self.N = M
         return removed
 
+    def sort_by_cell(self, grid):
+        """Re-orders the store by grid cell (counting sort of x with the slot index as payload,
+        then gathers of every other array): keeps a warp's particles inside the deposit window of
+        the fused kernel.  The order inside a cell is unspecified; self.perm composes the
+        permutations so that slot s holds the particle that was at self.perm[s] when the store
+        was created (or last compacted)."""
+        N = self.N
+        if N < 2:
+            return
+        dev = self.dev
+        P = _lib.DDParams(N, N, grid.ng, 0, grid.dx, 1.0, grid.length, 1.0, (C.c_double * 2)(0., 0.),
+                          (C.c_double * 2)(1., 1.))
+        ident = torch.arange(N, dtype=torch.float64, device=dev)
+        xs = torch.empty(N, dtype=torch.float64, device=dev); ps = torch.empty_like(xs)
+        counts = torch.zeros(2 * grid.ng + 2, dtype=torch.int32, device=dev)
+        st = D.stream()
+        _lib.call("pic_dev_dd_sort_by_cell", C.byref(P), D.ptr(self.r[0]), D.ptr(ident), None, None, D.ptr(xs), D.ptr(ps),
+                  None, None, D.ptr(counts), st)
+        idx = ps.to(torch.int32)
+
+        def g64(src):
+            dst = torch.empty(N, dtype=torch.float64, device=dev)
+            _lib.call("pic_dev_gather_f64", D.ptr(src), D.ptr(idx), D.ptr(dst), N, st)
+            return dst
+
+        def g8(src):
+            dst = torch.empty(N, dtype=torch.int8, device=dev)
+            _lib.call("pic_dev_gather_i8", D.ptr(src), D.ptr(idx), D.ptr(dst), N, st)
+            return dst
+        self.r = [xs] + [g64(c) for c in self.r[1:]]
+        self.charge_state, self.m, self.p2c = g64(self.charge_state), g64(self.m), g64(self.p2c)
+        self.Z = self.Z[:N][idx.long()].contiguous()
+        self.active, self.at_wall, self.from_wall, self.hit_flag = (g8(self.active), g8(self.at_wall),
+                                                                    g8(self.from_wall), g8(self.hit_flag))
+        prev = getattr(self, "perm", None)
+        self.perm = idx.long() if prev is None else prev[idx.long()]
+
     def append(self, other):
         """particles += new_particles (pygcpic.py:1624)."""
         keep = self.N
@@ -304,6 +405,7 @@ class ParticleStore:
         for name in self.FIELDS_F64 + self.FLAGS + ("Z", "hit_flag"):
             setattr(self, name, cat(getattr(self, name), getattr(other, name), keep, other.N))
         self.N = keep + other.N
+        self._uniform = False
 
     def wall_hit_tallies(self):
         """kinetic_energy/e and angle w.r.t. the wall (pygcpic.py:262-275, 228-259) of the

@@ -194,3 +194,76 @@ def test_mini_driver_vs_reference_golden(golden):
     assert relmax(st.r_host(), g["drv_r_final"]) < 1e-6
     assert relmax(np.concatenate(ek), g["drv_ekin"]) < 1e-5
     assert relmax(np.concatenate(ang), g["drv_ang"]) < 1e-5
+
+
+def test_uniform_fused_boris_matches_v1_kernels():
+    """gc_push_boris_v2_k (species-uniform store, TMA ring, fused n deposit) against the v1
+    push + separate weight kernels on the same inputs: r, flags and hit counts bit-identical,
+    n and rho to 1e-13.  Inputs include inactive slots, wall hits on both sides, node-aligned
+    and guard-band positions, and a tail that is not a whole chunk."""
+    from pypic_b200.gcstore import GridDev, ParticleStore
+    rs = np.random.RandomState(5)
+    ng = 300; Lg = 3e-3; Te = 60 * 11600.; dt = 2e-9
+    N = 3 * 16384 + 517
+    dx = Lg / (ng - 1)
+    x = np.sort(rs.uniform(0, Lg, N))
+    j = rs.choice(N, 3000, replace=False)
+    cells = rs.randint(1, ng - 1, 3000)
+    x[j[:800]] = cells[:800] * dx
+    x[j[800:1600]] = np.nextafter(cells[800:1600] * dx, 0.0)
+    x[j[1600:2200]] = cells[1600:2200] * dx * (1 + 1e-9)
+    x[j[2200:2600]] = rs.uniform(0, 2e-2 * dx, 400)
+    x[j[2600:]] = Lg - rs.uniform(0, 2e-2 * dx, 400)
+    r = np.zeros((N, 7))
+    r[:, 0] = x; r[:, 1:3] = rs.normal(0, 1e-4, (N, 2)); r[:, 3:6] = rs.normal(0, 7e4, (N, 3)); r[:, 6] = rs.uniform(0, 1e-8, N)
+    active = np.ones(N, dtype=np.int8); active[rs.choice(N, 700, replace=False)] = 0
+    B = (2 * np.cos(1.5), 2 * np.sin(1.5), 0.)
+    E = rs.normal(0, 5e4, ng)
+    p2c = 3.1e9
+    res = {}
+    for fused in (False, True):
+        grid = GridDev(ng, Lg, Te)
+        grid.E.copy_(__import__("torch").as_tensor(E))
+        st = ParticleStore.from_arrays(r, 1.0, O.mp, p2c, Z=1, active=active, B=B)
+        st.FUSED_MIN = 0 if fused else 10 ** 12
+        hits = st.push_6D(dt, grid, deposit=fused)
+        if fused:
+            assert grid.have_fused_n
+            grid.finish_fused_deposit(1.0, dt)
+        else:
+            st.apply_BCs_dirichlet(grid)
+            grid.weight_particles_to_grid_boltzmann(st, dt)
+        st.check(); grid.check()
+        res[fused] = (st.r_host(), st.flags_host(), hits, st.hit_flag[:N].cpu().numpy(), grid.n.cpu().numpy(),
+                      grid.rho.cpu().numpy(), grid.n0)
+    a, b = res[False], res[True]
+    assert np.array_equal(a[0], b[0])
+    for kf in ("active", "at_wall", "from_wall"):
+        assert np.array_equal(a[1][kf], b[1][kf])
+    assert a[2] == b[2] and a[2] > 200
+    assert np.array_equal(a[3], b[3])
+    assert relmax(b[4], a[4]) < 1e-13 and relmax(b[5], a[5]) < 1e-13
+    assert abs(b[6] - a[6]) <= 1e-13 * abs(a[6])
+
+
+def test_mini_driver_fused_path_vs_reference_golden(golden):
+    """pygcpic.run_sheath with the fused push+deposit path forced on (uniform store): the same
+    integer outcomes per step as the reference's object loop."""
+    import pygcpic as G
+    g = golden("gc")
+    Ld = float(g["drv_L"]); ngd = int(g["drv_ng"]); Nd = int(g["drv_N"]); dt = float(g["drv_dt"])
+    p2c = float(g["drv_p2c"]); Ti = float(g["drv_Ti"]); Te = float(g["drv_Te"]); source_N = int(g["drv_source_N"])
+    np.random.seed(int(g["drv_seed"]))
+    host_grid = G.Grid(ngd, Ld, Te)
+    parts = [G.Particle(G.mp, 1, p2c, Ti, Z=1, B0=g["B"].copy(), E0=np.zeros(3), grid=host_grid) for _ in range(Nd)]
+    r = np.array([p.r for p in parts])
+    grid = G.GridDev(ngd, Ld, Te)
+    st = G.ParticleStore.from_arrays(r, 1.0, G.mp, p2c, Z=1, B=g["B"])
+    st.FUSED_MIN = 0
+    src = G.source_distribution_6D(host_grid, Ti, G.mp)
+    out = G.run_sheath(grid, st, dt, 25, source_N, src, p2c, G.mp)
+    assert np.array_equal(out["length"], g["drv_len"]) and np.array_equal(out["hits"], g["drv_hits"])
+    assert np.array_equal(out["deleted"], g["drv_ndel"]) and np.array_equal(out["reactivated"], g["drv_nreact"])
+    assert relmax(out["n0"], g["drv_n0"]) < 1e-9
+    assert np.array_equal(st.flags_host()["active"], g["drv_active_final"])
+    assert relmax(st.r_host(), g["drv_r_final"]) < 1e-6
