@@ -42,6 +42,9 @@ def parse():
     ap.add_argument("--cells", type=int, default=4096)
     ap.add_argument("--sort-every", type=int, default=8)
     ap.add_argument("--deposit", default="window", choices=["window", "window-ldg", "warp", "atomic"])
+    ap.add_argument("--workload", default="sheath", choices=["sheath", "explicit", "pypic", "boris"],
+                    help="sheath = BASELINE configs[1] (default, the driver's bench); explicit / pypic / boris = "
+                         "the other movers of SURVEY.md 8(d) at the same size (single GPU, device-resident)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-sample", type=float, default=4e6, help="particles in the CPU-baseline sample")
@@ -354,10 +357,134 @@ def run_cuda(args):
         dist.destroy_process_group()
 
 
+# ----------------------------------------------------------------------------- other movers
+def run_other(args):
+    """The other hot-path rows at benchmark size, one GPU, device-resident state:
+    explicit = PIC_L explicit leapfrog full step (push+gather+deposit fused, periodic Poisson by PCR);
+    pypic    = pypic.py periodic implicit CN/Picard full step;
+    boris    = pygcpic Boris 1D3V step (fused gather+push+walls+deposit, Newton-Boltzmann solve)."""
+    import torch
+    from pypic_b200.periodic import ExplicitSim, PeriodicImplicitSim
+    from pypic_b200.gcstore import GridDev, ParticleStore
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (there is no CPU fallback)")
+    dev = torch.device("cuda", 0)
+    torch.cuda.set_device(0)
+    N = int(args.particles_per_gpu); N -= N % 2
+    cells = args.cells
+    dx, dt = 1e-5, 1e-12
+    kT = KB * 116000.
+    gen = torch.Generator(device=dev); gen.manual_seed(1234)
+    kernel_events = []
+
+    def timed_call(fn):
+        def wrapped(*a, **k):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(); out = fn(*a, **k); e1.record()
+            kernel_events.append((e0, e1))
+            return out
+        return wrapped
+    iters = []
+    if args.workload == "explicit":
+        L = dx * (cells - 1)
+        sim = ExplicitSim(N, cells, dx, dt, (L + dx) * 1e19 / N, q=(-E_CH, E_CH), m=(ME, MP), n_split=N // 2, device=dev,
+                          sort_every=args.sort_every)
+        sim.x.uniform_(0., 1., generator=gen).mul_(L + dx).clamp_(1e-12, (L + dx) * (1 - 1e-12))
+        sim.v.normal_(0., 1., generator=gen)
+        sim.v[:N // 2].mul_(float(np.sqrt(kT / ME))); sim.v[N // 2:].mul_(float(np.sqrt(kT / MP)))
+        sim.push = timed_call(sim.push)
+        step, check, launches = sim.step, sim.check, (lambda: sim.kernel_launches)
+        alg, kname = (lambda k: 32.0), "l_push_deposit_v2_k"
+        desc = "PIC_L explicit leapfrog: %d particles (e-/p+ halves), %d-cell periodic grid, Poisson solve every step" % (N, cells)
+    elif args.workload == "pypic":
+        L = dx * cells
+        sim = PeriodicImplicitSim(N, cells, dx, dt, L, L * 1e19 / N, tol=1e-3, maxiter=20, device=dev,
+                                  sort_every=args.sort_every)
+        sim.x0.uniform_(0., 1., generator=gen).mul_(L).clamp_(1e-12, L * (1 - 1e-12))
+        sim.v0.normal_(0., 1., generator=gen).mul_(float(np.sqrt(kT / ME)))
+        sim.iter_events = kernel_events
+
+        def step():
+            k, r = sim.push(); iters.append(k)
+        check, launches = sim.check, (lambda: sim.kernel_launches)
+        alg, kname = (lambda k: 32.0 + 16.0 / k), "pypic_picard_iter_v2_k"
+        desc = "pypic periodic implicit CN/Picard (tol=1e-3): %d electrons, %d-cell grid" % (N, cells)
+    else:
+        ng = cells + 1
+        Te, Ti = 60. * 11600., 50. * 11600.
+        lamD = np.sqrt(8.854e-12 * KB * Te / (1e19 * E_CH ** 2))
+        Lg = 100. * lamD * (ng - 1) / 149.       # the reference's resolution (150 nodes per 100 Debye lengths)
+        alpha = 86. * np.pi / 180.
+        grid = GridDev(ng, Lg, Te, device=dev)
+        store = ParticleStore(N, B=(2. * np.cos(alpha), 2. * np.sin(alpha), 0.), device=dev)
+        store.r[0].uniform_(0., 1., generator=gen).mul_(Lg).clamp_(Lg * 1e-9, Lg * (1 - 1e-9))
+        vth = float(np.sqrt(KB * Ti / MP))
+        for c in (3, 4, 5):
+            store.r[c].normal_(0., vth, generator=gen)
+        p2c = Lg * 1e19 / N
+        store.charge_state.fill_(1.); store.m.fill_(MP); store.p2c.fill_(p2c); store.Z.fill_(1)
+        dtg = 1e-10
+        store.push_6D = timed_call(store.push_6D)
+        state = {"t": 0, "launches": 0}
+        grid.weight_particles_to_grid_boltzmann(store, dtg)
+
+        def step():
+            if state["t"] % max(1, args.sort_every // 2) == 0:
+                store.sort_by_cell(grid); state["launches"] += 16
+            if grid.have_fused_n:
+                grid.finish_fused_deposit(1.0, dtg)
+            grid.smooth_rho(); grid.reset_added_particles()
+            grid.solve_for_phi_dirichlet_boltzmann(); grid.differentiate_phi_to_E_dirichlet()
+            store.push_6D(dtg, grid, deposit=True)
+            state["t"] += 1; state["launches"] += 6
+
+        def check():
+            store.check(); grid.check()
+        launches = lambda: state["launches"]
+        alg, kname = (lambda k: 112.0), "gc_push_boris_v2_k"
+        desc = ("pygcpic Boris 1D3V (B=2 T at 86 deg, H+, Ti=50 eV, Te=60 eV): %d particles, %d-node grid, fused "
+                "gather+push+walls+deposit, Newton-Boltzmann field solve, store re-sorted every %d steps"
+                % (N, ng, max(1, args.sort_every // 2)))
+    for _ in range(args.warmup):
+        step()
+    check()
+    torch.cuda.synchronize()
+    kernel_events.clear(); iters.clear()
+    sampler = ClockSampler(0); sampler.start()
+    l0 = launches()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for _ in range(args.steps):
+        step()
+    ev1.record()
+    torch.cuda.synchronize()
+    sampler.stop_flag = True
+    check()
+    ms = ev0.elapsed_time(ev1)
+    kms = [a.elapsed_time(b) for a, b in kernel_events]
+    kbar = float(np.mean(iters)) if iters else 1.0
+    peak, peak_src = measured_peak()
+    per_launch = N * alg(kbar)
+    achieved = per_launch / (float(np.mean(kms)) * 1e-3) / 1e9
+    line = {"metric": METRIC, "value": N * args.steps / (ms * 1e-3), "unit": "particle-steps/s", "n_gpus": 1,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": desc, "parallelism": "single GPU", "sort_every": args.sort_every,
+                       "picard_iterations_per_step": kbar if iters else None,
+                       "l2_policy": "particle arrays (%.1f GB) are far larger than the 126 MB L2" % (N * alg(kbar) / 2 / 1e9)},
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": None, "kernel": kname, "peak_source": peak_src, "kernel_ms_mean": float(np.mean(kms)),
+                         "kernel_share_of_step": float(np.sum(kms) / ms), "algorithmic_bytes_per_launch": per_launch},
+            "cpu_baseline": None, "e2e": None, "gpu_launches": int(launches() - l0), "clocks": sampler.summary()}
+    print(json.dumps(line))
+
+
 def main():
     args = parse()
     if args.impl == "reference":
         run_reference(args)
+    elif args.workload != "sheath":
+        run_other(args)
     else:
         run_cuda(args)
 

@@ -181,6 +181,17 @@ int pic_dev_sum_sq(const double* u, int64_t N, double scale, double* out1, void*
 int pic_dev_dd_sort_by_cell(const pic_dd_params* p, const double* x0, const double* u0,
                             const double* v0, const double* w0, double* x0s, double* u0s,
                             double* v0s, double* w0s, int32_t* counts, void* stream);
+/* The same counting sort for any structure-of-arrays store: xs receives the sorted positions and
+ * perm (int32[N]) the source slot of every output slot; apply it to the other arrays with
+ * pic_dev_soa_permute.  Only p->N, n_split, Ng, dx are read. */
+int pic_dev_sort_perm_by_cell(const pic_dd_params* p, const double* x, double* xs, int32_t* perm,
+                              int32_t* counts, void* stream);
+/* dst[t] = src[perm[t]] for up to 12 fp64, 2 int32 and 6 int8 arrays in ONE pass (arrays of device
+ * pointers passed from the host). */
+int pic_dev_soa_permute(const int32_t* perm, int64_t n, const double* const* src_f64,
+                        double* const* dst_f64, int n_f64, const int32_t* const* src_i32,
+                        int32_t* const* dst_i32, int n_i32, const int8_t* const* src_i8,
+                        int8_t* const* dst_i8, int n_i8, void* stream);
 
 /* ------------------------------------------------------------------------- *
  * pypic.py -- periodic implicit PIC

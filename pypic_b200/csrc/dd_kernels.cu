@@ -916,6 +916,7 @@ __global__ void dd_sort_scan_k(int32_t* __restrict__ counts, int nk) {
 // per chunk is O(particles), not O(keys) (a nearly sorted store touches a handful of keys).
 #define SORT_T 1024
 #define SORT_PER 4
+template <bool PERM>   // PERM: `us` is an int32 array receiving the source index of every output slot
 __global__ void __launch_bounds__(SORT_T) dd_sort_scatter_k(DDK k, const double* __restrict__ x0,
                                                             const double* __restrict__ u0,
                                                             const double* __restrict__ v0,
@@ -956,7 +957,8 @@ __global__ void __launch_bounds__(SORT_T) dd_sort_scatter_k(DDK k, const double*
             const long long i = base + (long long)j * SORT_T + threadIdx.x;
             if (key[j] >= 0) {
                 const long long pos = (long long)gbase[key[j]] + rank[j];
-                xs[pos] = X[j]; us[pos] = u0[i];
+                xs[pos] = X[j];
+                if (PERM) ((int32_t*)us)[pos] = (int32_t)i; else us[pos] = u0[i];
                 if (vs) vs[pos] = v0[i];
                 if (ws) ws[pos] = w0[i];
             }
@@ -1222,12 +1224,36 @@ int pic_dev_dd_sort_by_cell(const pic_dd_params* p, const double* x0, const doub
     PIC_CHECK_CUDA(cudaMemsetAsync(counts, 0, (size_t)(nk + 2) * sizeof(int32_t), st));
     if (k.N == 0) return PIC_OK;
     PIC_CHECK_CUDA(cudaFuncSetAttribute(dd_sort_hist_k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    PIC_CHECK_CUDA(cudaFuncSetAttribute(dd_sort_scatter_k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_sc));
+    PIC_CHECK_CUDA(cudaFuncSetAttribute(dd_sort_scatter_k<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_sc));
     dd_sort_hist_k<<<grid_for(k.N, 1024, 2), 1024, smem, st>>>(k, x0, counts);
     PIC_CHECK_LAUNCH();
     dd_sort_scan_k<<<1, 1024, 0, st>>>(counts, nk);
     PIC_CHECK_LAUNCH();
-    dd_sort_scatter_k<<<grid_for((k.N + SORT_PER - 1) / SORT_PER, SORT_T, 2), SORT_T, smem_sc, st>>>(k, x0, u0, v0, w0, x0s, u0s, v0s, w0s, counts);
+    dd_sort_scatter_k<false><<<grid_for((k.N + SORT_PER - 1) / SORT_PER, SORT_T, 2), SORT_T, smem_sc, st>>>(k, x0, u0, v0, w0, x0s, u0s, v0s, w0s, counts);
+    PIC_CHECK_LAUNCH();
+    return PIC_OK;
+}
+
+int pic_dev_sort_perm_by_cell(const pic_dd_params* p, const double* x, double* xs, int32_t* perm, int32_t* counts,
+                              void* stream) {
+    PIC_REQUIRE(p && x && xs && perm && counts, "sort_perm_by_cell: null pointer");
+    PIC_REQUIRE(p->N < 2147483647LL, "sort_perm_by_cell: store too large for int32 indices");
+    DDK k = make_ddk(p);
+    cudaStream_t st = (cudaStream_t)stream;
+    const int nk = 2 * k.Ng;
+    size_t smem = (size_t)nk * sizeof(int);
+    const size_t smem_sc = 2 * smem;
+    PIC_REQUIRE(smem_sc <= (size_t)max_optin_smem() - 1024, "sort_perm_by_cell: grid too large for the shared-memory histogram");
+    PIC_CHECK_CUDA(cudaMemsetAsync(counts, 0, (size_t)(nk + 2) * sizeof(int32_t), st));
+    if (k.N == 0) return PIC_OK;
+    PIC_CHECK_CUDA(cudaFuncSetAttribute(dd_sort_hist_k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    PIC_CHECK_CUDA(cudaFuncSetAttribute(dd_sort_scatter_k<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_sc));
+    dd_sort_hist_k<<<grid_for(k.N, 1024, 2), 1024, smem, st>>>(k, x, counts);
+    PIC_CHECK_LAUNCH();
+    dd_sort_scan_k<<<1, 1024, 0, st>>>(counts, nk);
+    PIC_CHECK_LAUNCH();
+    dd_sort_scatter_k<true><<<grid_for((k.N + SORT_PER - 1) / SORT_PER, SORT_T, 2), SORT_T, smem_sc, st>>>(
+        k, x, nullptr, nullptr, nullptr, xs, (double*)perm, nullptr, nullptr, counts);
     PIC_CHECK_LAUNCH();
     return PIC_OK;
 }

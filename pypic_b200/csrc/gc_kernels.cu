@@ -709,6 +709,23 @@ __global__ void gather_f64_k(const double* __restrict__ src, const int32_t* __re
     for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < n; t += (long long)gridDim.x * blockDim.x)
         dst[t] = src[idx[t]];
 }
+// dst[t] = src[perm[t]] for a whole structure of arrays in one pass (the index is read once)
+struct SoAPerm {
+    const double* sf[12]; double* df[12];
+    const int32_t* si[2]; int32_t* di[2];
+    const int8_t* sb[6]; int8_t* db[6];
+    int nf, ni, nb;
+};
+__global__ void __launch_bounds__(256) soa_permute_k(const __grid_constant__ SoAPerm a, const int32_t* __restrict__ perm,
+                                                     long long n) {
+    for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < n; t += (long long)gridDim.x * blockDim.x) {
+        const int s = perm[t];
+#pragma unroll 4
+        for (int f = 0; f < a.nf; ++f) __stcs(a.df[f] + t, __ldg(a.sf[f] + s));
+        for (int f = 0; f < a.ni; ++f) a.di[f][t] = a.si[f][s];
+        for (int f = 0; f < a.nb; ++f) a.db[f][t] = a.sb[f][s];
+    }
+}
 __global__ void gather_i8_k(const int8_t* __restrict__ src, const int32_t* __restrict__ idx, int8_t* __restrict__ dst,
                             long long n) {
     for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < n; t += (long long)gridDim.x * blockDim.x)
@@ -927,6 +944,23 @@ int pic_dev_gather_f64(const double* src, const int32_t* idx, double* dst, int64
     if (n == 0) return PIC_OK;
     PIC_REQUIRE(src && idx && dst, "gather_f64: null pointer");
     gather_f64_k<<<grid_for(n, 256, 8), 256, 0, (cudaStream_t)stream>>>(src, idx, dst, n);
+    PIC_CHECK_LAUNCH();
+    return PIC_OK;
+}
+int pic_dev_soa_permute(const int32_t* perm, int64_t n, const double* const* src_f64, double* const* dst_f64, int n_f64,
+                        const int32_t* const* src_i32, int32_t* const* dst_i32, int n_i32, const int8_t* const* src_i8,
+                        int8_t* const* dst_i8, int n_i8, void* stream) {
+    PIC_REQUIRE(n >= 0 && n_f64 >= 0 && n_f64 <= 12 && n_i32 >= 0 && n_i32 <= 2 && n_i8 >= 0 && n_i8 <= 6,
+                "soa_permute: bad array counts");
+    if (n == 0) return PIC_OK;
+    PIC_REQUIRE(perm, "soa_permute: null permutation");
+    SoAPerm a;
+    memset(&a, 0, sizeof(a));
+    a.nf = n_f64; a.ni = n_i32; a.nb = n_i8;
+    for (int f = 0; f < n_f64; ++f) { PIC_REQUIRE(src_f64[f] && dst_f64[f], "soa_permute: null f64 array"); a.sf[f] = src_f64[f]; a.df[f] = dst_f64[f]; }
+    for (int f = 0; f < n_i32; ++f) { PIC_REQUIRE(src_i32[f] && dst_i32[f], "soa_permute: null i32 array"); a.si[f] = src_i32[f]; a.di[f] = dst_i32[f]; }
+    for (int f = 0; f < n_i8; ++f) { PIC_REQUIRE(src_i8[f] && dst_i8[f], "soa_permute: null i8 array"); a.sb[f] = src_i8[f]; a.db[f] = dst_i8[f]; }
+    soa_permute_k<<<grid_for(n, 256, 8), 256, 0, (cudaStream_t)stream>>>(a, perm, n);
     PIC_CHECK_LAUNCH();
     return PIC_OK;
 }

@@ -356,46 +356,44 @@ class ParticleStore:
         self.Z = self.Z[idx[:M].long()].contiguous() if M else self.Z[:1]
         self.active, self.at_wall, self.from_wall = g8(self.active), g8(self.at_wall), g8(self.from_wall)
         self.hit_flag = torch.zeros(max(M, 1), dtype=torch.int8, device=self.dev)
+        if getattr(self, "perm", None) is not None:
+            self.perm = self.perm[idx[:M].long()]
         removed = N - M
         self.N = M
         return removed
 
-    def sort_by_cell(self, grid):
+    def sort_by_cell(self, grid, track=False):
         """Re-orders the store by grid cell (counting sort of x with the slot index as payload,
         then gathers of every other array): keeps a warp's particles inside the deposit window of
-        the fused kernel.  The order inside a cell is unspecified; self.perm composes the
-        permutations so that slot s holds the particle that was at self.perm[s] when the store
-        was created (or last compacted)."""
+        the fused kernel.  The order inside a cell is unspecified; with track=True self.perm
+        composes the permutations so that slot s holds the particle that was at self.perm[s] when
+        the store was created."""
         N = self.N
         if N < 2:
             return
         dev = self.dev
         P = _lib.DDParams(N, N, grid.ng, 0, grid.dx, 1.0, grid.length, 1.0, (C.c_double * 2)(0., 0.),
                           (C.c_double * 2)(1., 1.))
-        ident = torch.arange(N, dtype=torch.float64, device=dev)
-        xs = torch.empty(N, dtype=torch.float64, device=dev); ps = torch.empty_like(xs)
+        xs = torch.empty(N, dtype=torch.float64, device=dev)
+        idx = torch.empty(N, dtype=torch.int32, device=dev)
         counts = torch.zeros(2 * grid.ng + 2, dtype=torch.int32, device=dev)
         st = D.stream()
-        _lib.call("pic_dev_dd_sort_by_cell", C.byref(P), D.ptr(self.r[0]), D.ptr(ident), None, None, D.ptr(xs), D.ptr(ps),
-                  None, None, D.ptr(counts), st)
-        idx = ps.to(torch.int32)
-
-        def g64(src):
-            dst = torch.empty(N, dtype=torch.float64, device=dev)
-            _lib.call("pic_dev_gather_f64", D.ptr(src), D.ptr(idx), D.ptr(dst), N, st)
-            return dst
-
-        def g8(src):
-            dst = torch.empty(N, dtype=torch.int8, device=dev)
-            _lib.call("pic_dev_gather_i8", D.ptr(src), D.ptr(idx), D.ptr(dst), N, st)
-            return dst
-        self.r = [xs] + [g64(c) for c in self.r[1:]]
-        self.charge_state, self.m, self.p2c = g64(self.charge_state), g64(self.m), g64(self.p2c)
-        self.Z = self.Z[:N][idx.long()].contiguous()
-        self.active, self.at_wall, self.from_wall, self.hit_flag = (g8(self.active), g8(self.at_wall),
-                                                                    g8(self.from_wall), g8(self.hit_flag))
-        prev = getattr(self, "perm", None)
-        self.perm = idx.long() if prev is None else prev[idx.long()]
+        _lib.call("pic_dev_sort_perm_by_cell", C.byref(P), D.ptr(self.r[0]), D.ptr(xs), D.ptr(idx), D.ptr(counts), st)
+        f_src = self.r[1:] + [self.charge_state, self.m, self.p2c]
+        f_dst = [torch.empty(N, dtype=torch.float64, device=dev) for _ in f_src]
+        b_src = [self.active, self.at_wall, self.from_wall, self.hit_flag]
+        b_dst = [torch.empty(N, dtype=torch.int8, device=dev) for _ in b_src]
+        z_dst = torch.empty(N, dtype=torch.int32, device=dev)
+        arr = lambda ts: (C.c_void_p * len(ts))(*[t.data_ptr() for t in ts])
+        _lib.call("pic_dev_soa_permute", D.ptr(idx), N, arr(f_src), arr(f_dst), len(f_src), arr([self.Z]), arr([z_dst]), 1,
+                  arr(b_src), arr(b_dst), len(b_src), st)
+        self.r = [xs] + f_dst[:6]
+        self.charge_state, self.m, self.p2c = f_dst[6:]
+        self.Z = z_dst
+        self.active, self.at_wall, self.from_wall, self.hit_flag = b_dst
+        if track:
+            prev = getattr(self, "perm", None)
+            self.perm = idx.long() if prev is None else prev[idx.long()]
 
     def append(self, other):
         """particles += new_particles (pygcpic.py:1624)."""

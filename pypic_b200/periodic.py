@@ -54,6 +54,7 @@ class PeriodicImplicitSim:
         self.range_err = torch.zeros(1, dtype=torch.int32, device=dev)
         self.last_iters, self.last_resid = 0, 1.0
         self.kernel_launches = 0
+        self.iter_events = None     # set to a list to record a CUDA-event pair per particle-kernel launch
 
     def upload(self, x0, v0, E0=None):
         s = slice(self.start, self.stop)
@@ -93,8 +94,15 @@ class PeriodicImplicitSim:
         self.stats.zero_()
         r, k = 1.0, 0
         while (r > self.tol) and (k < self.maxiter):
+            ev = None
+            if self.iter_events is not None:
+                ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+                ev[0].record()
             _lib.call("pic_dev_pypic_picard_iter", P, D.ptr(self.x0), D.ptr(self.v0), D.ptr(self.x1), D.ptr(self.v1),
                       D.ptr(self.Fs), D.ptr(self.acc), 1 if k == 0 else 0, D.ptr(self.range_err), st)
+            if ev is not None:
+                ev[1].record()
+                self.iter_events.append(ev)
             self.comm.allreduce_sum(self.acc)
             _lib.call("pic_dev_pypic_field_update", P, D.ptr(self.acc), D.ptr(self.E0), D.ptr(self.Es), D.ptr(self.Fs),
                       D.ptr(self.E1), D.ptr(self.j0), D.ptr(self.stats), st)

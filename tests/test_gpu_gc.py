@@ -267,3 +267,27 @@ def test_mini_driver_fused_path_vs_reference_golden(golden):
     assert relmax(out["n0"], g["drv_n0"]) < 1e-9
     assert np.array_equal(st.flags_host()["active"], g["drv_active_final"])
     assert relmax(st.r_host(), g["drv_r_final"]) < 1e-6
+
+
+def test_store_sort_by_cell_is_a_cell_ordered_permutation():
+    import torch
+    from pypic_b200.gcstore import GridDev, ParticleStore
+    rs = np.random.RandomState(8)
+    N, ng, Lg = 70001, 129, 2e-3
+    r = rs.normal(size=(N, 7)); r[:, 0] = rs.uniform(0, Lg, N)
+    cs = rs.randint(1, 3, N).astype(float); m = rs.uniform(1, 2, N) * O.mp; p2c = rs.uniform(1, 2, N) * 1e9
+    Z = rs.randint(1, 5, N); act = (rs.uniform(size=N) < 0.9).astype(np.int8); aw = 1 - act
+    grid = GridDev(ng, Lg, 6e5)
+    st = ParticleStore.from_arrays(r, cs, m, p2c, Z=Z, active=act, at_wall=aw, B=(0, 0, 1))
+    st.sort_by_cell(grid, track=True)
+    perm = st.perm.cpu().numpy()
+    assert np.array_equal(np.sort(perm), np.arange(N))
+    assert np.array_equal(st.r_host(), r[perm])
+    assert np.array_equal(st.charge_state.cpu().numpy(), cs[perm]) and np.array_equal(st.m.cpu().numpy(), m[perm])
+    assert np.array_equal(st.p2c.cpu().numpy(), p2c[perm]) and np.array_equal(st.Z.cpu().numpy(), Z[perm])
+    f = st.flags_host()
+    assert np.array_equal(f["active"], act[perm]) and np.array_equal(f["at_wall"], aw[perm])
+    cells = np.floor(st.r_host()[:, 0] / grid.dx)
+    assert np.all(np.diff(cells) >= 0)
+    st.sort_by_cell(grid, track=True)          # a second sort composes
+    assert np.array_equal(st.r_host(), r[st.perm.cpu().numpy()])
