@@ -124,6 +124,23 @@ class ClockSampler(threading.Thread):
                 "source": self.src}
 
 
+def bind_to_gpu_numa_node(index):
+    """Pins this rank's host threads to the CPUs next to its GPU (NVML's ideal affinity) so that the
+    pinned staging buffers of the e2e leg are first-touched on the GPU's own NUMA node; with 8
+    ranks on one socket's memory the host<->device copies are limited by the inter-socket link."""
+    try:
+        import pynvml as nv
+        nv.nvmlInit()
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES", "")
+        phys = index
+        if vis and all(t.strip().isdigit() for t in vis.split(",")):
+            phys = int(vis.split(",")[index])
+        nv.nvmlDeviceSetCpuAffinity(nv.nvmlDeviceGetHandleByIndex(phys))
+        return True
+    except Exception:
+        return False
+
+
 def measured_peak():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.isfile(p):
@@ -208,6 +225,7 @@ def run_cuda(args):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device (there is no CPU fallback; use --impl reference for the CPU port)")
     torch.cuda.set_device(local)
+    bind_to_gpu_numa_node(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     comm = Comm()
