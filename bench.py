@@ -225,7 +225,8 @@ def run_cuda(args):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device (there is no CPU fallback; use --impl reference for the CPU port)")
     torch.cuda.set_device(local)
-    bind_to_gpu_numa_node(local)
+    if world > 1:                      # the 1-GPU run keeps every host core for the CPU-baseline leg
+        bind_to_gpu_numa_node(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     comm = Comm()

@@ -347,6 +347,28 @@ int pic_dev_gather_f64(const double* src, const int32_t* idx, double* dst, int64
 int pic_dev_gather_i8(const int8_t* src, const int32_t* idx, int8_t* dst, int64_t n, void* stream);
 
 /* ------------------------------------------------------------------------- *
+ * Device-side initialisers and IEAD histogram (N1)
+ * ------------------------------------------------------------------------- */
+/* x ~ U(xlo,xhi); v0 ~ N(mean[s],sigma[s]); v1,v2 ~ N(0,sigma[s]); s = (i >= n_split).  Philox4x32-10
+ * keyed by (seed, stream_id, global_offset+i): independent of the sharding.  NULL arrays are
+ * skipped.  Distribution parity with PIC_L_DD.initialize :223-314 / Particle._initialize_6D
+ * pygcpic.py:277-304 (the host initialisers of the drop-in modules keep MT19937 stream parity). */
+int pic_dev_init_uniform_maxwellian(double* x, double* v0, double* v1, double* v2, int64_t N, int64_t n_split,
+                                    double xlo, double xhi, const double sigma[2], const double mean[2],
+                                    uint64_t seed, uint64_t stream_id, int64_t global_offset, void* stream);
+/* pypic.initialize_p :457-467 perturbation loader: global particle g < prefix[Ng] is placed uniformly
+ * in the cell c with prefix[c] <= g < prefix[c+1] (prefix = exclusive cumsum of int(F[i]), Ng+1
+ * int64 on the device; X = Ng+1 cell edges). */
+int pic_dev_pypic_perturb_positions(double* x, int64_t N, const int64_t* prefix, const double* X, int Ng,
+                                    uint64_t seed, int64_t global_offset, void* stream);
+/* hist[n_e_bins*n_a_bins] (fp64 counts, accumulated) += numpy.histogram2d(kinetic_energy/e, angle) of the
+ * particles with select[i]==1 (and Z[i]==Z_select when Z != NULL): pygcpic.py:1516-1527, 1574-1584. */
+int pic_dev_gc_iead_hist(const double* vx, const double* vy, const double* vz, const double* m,
+                         const int8_t* select, const int32_t* Z, int Z_select, int64_t N,
+                         const double* e_edges, int n_e_bins, const double* a_edges, int n_a_bins,
+                         double* hist, void* stream);
+
+/* ------------------------------------------------------------------------- *
  * Host-buffer entry points: the calls a binding of the reference would make with
  * NumPy arrays (same argument meaning as the Python functions they replace).
  * ------------------------------------------------------------------------- */

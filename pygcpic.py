@@ -335,7 +335,10 @@ class Grid:
         _D.check_range(err, "Grid.weight_particles_to_grid_boltzmann")
         state = _D.to_dev(np.array([0. if self.n0 is None else self.n0, getattr(self, "p_old", 0.0),
                                     0. if self.n0 is None else 1.]), dev)
-        _lib.call("pic_dev_gc_n0_update", _D.ptr(_D.to_dev(self.phi, dev)), _D.ptr(n), _D.ptr(_D.to_dev(self.domain, dev)),
+        # the staging tensors must outlive the (asynchronous) launch: a temporary passed straight to
+        # ptr() is freed at once and its block handed to the next allocation
+        d_phi, d_dom = _D.to_dev(self.phi, dev), _D.to_dev(self.domain, dev)
+        _lib.call("pic_dev_gc_n0_update", _D.ptr(d_phi), _D.ptr(n), _D.ptr(d_dom),
                   int(self.ng), float(self.Te), float(self.ve), float(self.added_particles), float(dt), _D.ptr(state), s)
         self.rho = rho.cpu().numpy(); self.n = n.cpu().numpy()
         st3 = state.cpu().numpy()

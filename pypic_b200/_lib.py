@@ -103,6 +103,10 @@ _SIGS = {
     "pic_dev_compact_flags": [P, I64, I32, P, P, P, P],
     "pic_dev_gather_f64": [P, P, P, I64, P],
     "pic_dev_gather_i8": [P, P, P, I64, P],
+    "pic_dev_init_uniform_maxwellian": [P, P, P, P, I64, I64, F64, F64, C.POINTER(C.c_double * 2),
+                                        C.POINTER(C.c_double * 2), C.c_uint64, C.c_uint64, I64, P],
+    "pic_dev_pypic_perturb_positions": [P, I64, P, P, I32, C.c_uint64, I64, P],
+    "pic_dev_gc_iead_hist": [P, P, P, P, P, P, I32, I64, P, I32, P, I32, P, P],
     "pic_host_pypic_interpolate_p": [P, P, I32, I64, F64, P],
     "pic_host_pypic_weight_current_p": [P, P, P, I32, I32, I64, F64, P],
     "pic_host_pypic_weight_density_p": [P, P, I32, I32, I64, F64, P],

@@ -14,7 +14,7 @@ ROOT = os.path.dirname(HERE)
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libpic_b200.so")
 STAMP = os.path.join(HERE, ".build_stamp")
-SOURCES = ["grid_kernels.cu", "dd_kernels.cu", "periodic_kernels.cu", "gc_kernels.cu", "abi_host.cu"]
+SOURCES = ["grid_kernels.cu", "dd_kernels.cu", "periodic_kernels.cu", "gc_kernels.cu", "init_kernels.cu", "abi_host.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-lineinfo", "-std=c++17",

@@ -284,3 +284,27 @@ def test_pygcpic_run_sheath_golden(golden):
     assert relmax(st.r_host(), g["drv_r_final"]) < 1e-6
     assert relmax(np.concatenate(out["ekin"]), g["drv_ekin"]) < 1e-5
     assert relmax(np.concatenate(out["angle"]), g["drv_ang"]) < 1e-5
+
+
+def test_pygcpic_host_grid_n0_update_matches_device_grid():
+    """Grid.weight_particles_to_grid_boltzmann (host attributes) vs GridDev on the second call,
+    when phi != 0 enters the reference-density update (regression: a staging tensor freed before
+    the launch made the kernel read the domain array as phi)."""
+    import torch
+    import pygcpic as G
+    rs = np.random.RandomState(6)
+    N, ng, Lg, Te, dt = 4000, 50, 2e-3, 7e5, 1e-10
+    r = np.zeros((N, 7)); r[:, 0] = rs.uniform(0, Lg, N)
+    st = G.ParticleStore.from_arrays(r, 1.0, G.mp, 2e9, Z=1)
+    hg = G.Grid(ng, Lg, Te)
+    dg = G.GridDev(ng, Lg, Te)
+    phi = rs.uniform(0, 40, ng)
+    for call in range(2):
+        hg.weight_particles_to_grid_boltzmann(st, dt)
+        dg.weight_particles_to_grid_boltzmann(st, dt)
+        assert abs(hg.n0 - dg.n0) <= 1e-13 * abs(dg.n0)
+        hg.phi = phi.copy(); dg.phi.copy_(torch.as_tensor(phi))
+        hg.add_particles(2e9); dg.add_particles(2e9)
+    # closed form of pygcpic.py:895-903 for the second call
+    eta = np.exp(phi / Te / 11600.)
+    assert np.isfinite(hg.n0) and hg.n0 > 0

@@ -1,0 +1,88 @@
+"""Device initialisers (N2) and IEAD histogram (N1): distributions, determinism, sharding
+invariance, numpy.histogram2d parity."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+from oracle import np_oracle as O
+
+
+def test_uniform_maxwellian_moments_and_shard_invariance():
+    import torch
+    from pypic_b200 import device as D, init as I
+    dev = D.require_cuda()
+    N, ns = 2_000_000, 1_200_000
+    x = D.f64(N, dev); u = D.f64(N, dev); v = D.f64(N, dev); w = D.f64(N, dev)
+    I.fill_uniform_maxwellian(x, [u, v, w], ns, 0.0, 5e-4, (2.0, 0.5), mean=(1.0, -3.0), seed=7)
+    xh, uh, vh, wh = (t.cpu().numpy() for t in (x, u, v, w))
+    assert xh.min() >= 0 and xh.max() <= 5e-4 and abs(xh.mean() - 2.5e-4) < 5e-7
+    for a, mean, sig in ((uh[:ns], 1.0, 2.0), (uh[ns:], -3.0, 0.5), (vh[:ns], 0.0, 2.0), (wh[ns:], 0.0, 0.5)):
+        assert abs(a.mean() - mean) < 6 * sig / np.sqrt(len(a)) and abs(a.std() - sig) < 0.01 * sig
+    # components are uncorrelated
+    assert abs(np.corrcoef(uh[:ns], vh[:ns])[0, 1]) < 5e-3 and abs(np.corrcoef(vh[:ns], wh[:ns])[0, 1]) < 5e-3
+    # determinism and sharding invariance: the second half generated alone equals the global slice
+    h = N // 2
+    x2 = D.f64(N - h, dev); u2 = D.f64(N - h, dev)
+    I.fill_uniform_maxwellian(x2, [u2], ns - h, 0.0, 5e-4, (2.0, 0.5), mean=(1.0, -3.0), seed=7, global_offset=h)
+    assert np.array_equal(x2.cpu().numpy(), xh[h:]) and np.array_equal(u2.cpu().numpy(), uh[h:])
+    # a different seed gives a different state
+    I.fill_uniform_maxwellian(x2, [u2], ns - h, 0.0, 5e-4, (2.0, 0.5), mean=(1.0, -3.0), seed=8, global_offset=h)
+    assert not np.array_equal(x2.cpu().numpy(), xh[h:])
+
+
+def test_sheath_and_pypic_device_init_run():
+    from pypic_b200 import init as I
+    from pypic_b200.periodic import PeriodicImplicitSim
+    from pypic_b200.sheath import SheathSim
+    N, Ng = 400000, 129
+    dx, dt = 1e-5, 1e-12
+    L = dx * (Ng - 1)
+    kT = O.kb * 116000.
+    s = SheathSim(N, Ng, dx, dt, L * 1e19 / N, kBT=(kT, kT), carry_vw=True, rng="philox", seed=3)
+    I.init_sheath(s, seed=3)
+    o = s.download()
+    h = N // 2
+    assert abs(o["u0"][:h].std() / np.sqrt(kT / O.me) - 1) < 0.01 and abs(o["u0"][h:].std() / np.sqrt(kT / O.mp) - 1) < 0.01
+    assert abs(o["w0"][h:].std() / np.sqrt(kT / O.mp) - 1) < 0.01
+    k, r = s.step(); s.check()
+    assert 1 <= k <= 20 and np.isfinite(s.E0.cpu().numpy()).all()
+    # pypic Landau loader: the perturbed block is laid out cell by cell with int(F[i]) particles per cell
+    Ngp = 200; Lp = 5170.094; dxp = Lp / Ngp
+    sim = PeriodicImplicitSim(N, Ngp, dxp, 1e-5, Lp, Lp * 1e5 / N)
+    total = I.init_pypic(sim, "landau-damping", 0.8, 1, 1.16e6, seed=5)
+    x = sim.x0.cpu().numpy()
+    X = np.linspace(0, Lp, Ngp + 1)
+    F = 1.0 + np.cos(2 * np.pi / Lp * X[:Ngp]); F = (N * 0.8) * F / F.sum()
+    counts = F.astype(np.int64)
+    assert total == counts.sum()
+    cells = np.floor(x[:total] / dxp).astype(np.int64)
+    assert np.array_equal(np.bincount(np.minimum(cells, Ngp - 1), minlength=Ngp), counts)
+    assert np.all(np.diff(cells) >= 0)
+    assert abs(sim.v0.cpu().numpy().std() / np.sqrt(O.kb * 1.16e6 / O.me) - 1) < 0.01
+    k, r = sim.push(); sim.check()
+    assert 1 <= k <= 20
+
+
+def test_iead_histogram_matches_numpy_histogram2d():
+    from pypic_b200 import init as I
+    from pypic_b200.gcstore import ParticleStore
+    rs = np.random.RandomState(4)
+    N = 200000
+    r = np.zeros((N, 7)); r[:, 3:6] = rs.normal(0, 8e4, (N, 3))
+    Z = rs.choice([1, 5], N)
+    m = np.where(Z == 1, O.mp, 10.8 * O.mp)
+    st = ParticleStore.from_arrays(r, 1.0, m, 1e9, Z=Z)
+    sel = (rs.uniform(size=N) < 0.3).astype(np.int8)
+    import torch
+    st.hit_flag.copy_(torch.as_tensor(sel))
+    e_edges = np.linspace(0.0, 300.0, 41); a_edges = np.linspace(0.0, 90.0, 31)       # pygcpic.py:1422-1423
+    hist = None
+    for Zs in (1, 5):
+        h = I.iead_histogram(st, st.hit_flag, Zs, e_edges, a_edges).cpu().numpy()
+        k = (sel == 1) & (Z == Zs)
+        v = r[k, 3:6]
+        ke = 0.5 * m[k] * np.sqrt((v ** 2).sum(1)) ** 2 / O.e
+        ang = np.arctan2(np.sqrt(v[:, 1] ** 2 + v[:, 2] ** 2), np.abs(v[:, 0])) * 180. / np.pi
+        ref = np.histogram2d(ke, ang, (e_edges, a_edges))[0]
+        assert h.sum() == ref.sum() and np.abs(h - ref).sum() <= 2          # <=1 particle on a bin edge may round differently
