@@ -102,7 +102,10 @@ typedef struct {
                          "fast atomicAdd" variant benchmarked alongside); bit2: grid-stride
                          kernel with warp-uniform pre-reduction; bit3: the register-prefetch
                          (non-TMA) build of the window kernel; bit1: keep the grid tiles in
-                         global memory (grids too large for shared memory)               */
+                         global memory (grids too large for shared memory); bit4: force the
+                         large-grid build of the window kernel (per-warp field windows of 32
+                         nodes instead of the whole-grid tile, deposit windows flushed every 4
+                         rows) -- taken automatically when the grid does not fit shared memory */
     double dx, dt, L, p2c;
     double q[2], m[2];
 } pic_dd_params;
@@ -156,8 +159,10 @@ int pic_dev_debug_cta_timer(uint64_t* buf);
 /* Field phase of the same iteration (PIC_L_DD.py:55-66,516-527), one CTA:
  *   wall_cum fp64[4] += acc[2Ng..2Ng+3]; jh,j1 get wall terms + edge fold;
  *   E1 = E0 + (dt/eps0)(mean(jh) - jh); Eh=(E1+E0)/2; r=|Es-Eh|_2; Es=Eh;
- *   acc is zeroed for the next iteration.  stats (device or mapped-host fp64[4]):
- *   [0]=r, [1]=mean(j1), [2]=sum(eps0*E1^2*dx/2), [3]=iteration counter (incremented). */
+ *   acc is zeroed for the next iteration.  stats (device fp64[8]):
+ *   [0]=r, [1]=mean(j1), [2]=sum(eps0*E1^2*dx/2), [3]=iteration counter (incremented);
+ *   [4..7] must be zero on entry: reduction scratch of the cooperative multi-CTA build used
+ *   for Ng > 32768 (its sums are re-associated relative to the one-CTA kernel). */
 int pic_dev_dd_field_update(const pic_dd_params* p, double* acc, double* wall_cum, const double* E0,
                             double* Es, double* E1, double* j1, double* stats, void* stream);
 /* Re-injection (PIC_L_DD.py:429-450).  Host-RNG parity mode: compact the indices of
@@ -177,7 +182,9 @@ int pic_dev_dd_reinject_philox(const pic_dd_params* p, double* x0, double* u0, d
 int pic_dev_sum_sq(const double* u, int64_t N, double scale, double* out1, void* stream);
 /* Counting sort by (species, cell) of the n-level state; out-of-place.  Keeps species
  * ranges contiguous; order inside a cell is unspecified (benchmark mode only).
- * counts: int32 scratch of 2*Ng+2 entries.  v0/w0 (and outputs) may be NULL. */
+ * counts: int32 scratch of 2*Ng+2 + ceil(2*Ng/1024)+2 entries (the tail is used by the
+ * global-memory histogram path taken when 2*Ng counters do not fit shared memory).
+ * v0/w0 (and outputs) may be NULL. */
 int pic_dev_dd_sort_by_cell(const pic_dd_params* p, const double* x0, const double* u0,
                             const double* v0, const double* w0, double* x0s, double* u0s,
                             double* v0s, double* w0s, int32_t* counts, void* stream);

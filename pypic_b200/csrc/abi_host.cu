@@ -246,7 +246,7 @@ int pic_host_dd_step_batches(const pic_dd_params* p, int nbatch, const double* c
         if ((rc = g_ws.get(base + 2, (size_t)N * 8, (void**)&dx1[s]))) return rc;
         if ((rc = g_ws.get(base + 3, (size_t)N * 8, (void**)&du1[s]))) return rc;
         if ((rc = g_ws.get(base + 4, (size_t)N, (void**)&dact[s]))) return rc;
-        if ((rc = g_ws.get(base + 5, (8 * (size_t)Ng + 16) * 8, (void**)&grid[s]))) return rc;
+        if ((rc = g_ws.get(base + 5, (8 * (size_t)Ng + 24) * 8, (void**)&grid[s]))) return rc;
         if ((rc = g_ws.get(base + 6, sizeof(int), (void**)&derr[s]))) return rc;
     }
     double* resid_dev = nullptr;
@@ -270,7 +270,7 @@ int pic_host_dd_step_batches(const pic_dd_params* p, int nbatch, const double* c
         PIC_CHECK_CUDA(cudaStreamWaitEvent(q.cmp, q.ev_in[s], 0));
         if (b >= 2) PIC_CHECK_CUDA(cudaStreamWaitEvent(q.cmp, q.ev_out[s], 0));   // results of b-2 have left the slot
         PIC_CHECK_CUDA(cudaMemsetAsync(derr[s], 0, sizeof(int), q.cmp));
-        PIC_CHECK_CUDA(cudaMemsetAsync(dacc, 0, (size_t)(2 * Ng + 4 + 4 + 4) * 8, q.cmp));   // acc, wall_cum, stats
+        PIC_CHECK_CUDA(cudaMemsetAsync(dacc, 0, (size_t)(2 * Ng + 4 + 4 + 8) * 8, q.cmp));   // acc, wall_cum, stats[8]
         PIC_CHECK_CUDA(cudaMemsetAsync(dact[s], 1, (size_t)N, q.cmp));
         PIC_CHECK_CUDA(cudaMemcpyAsync(dEs, dE0, (size_t)Ng * 8, cudaMemcpyDeviceToDevice, q.cmp));
         double r = 1.0;

@@ -2,9 +2,11 @@
 // The particle phase of one Picard iteration is ONE fused kernel: gather, push,
 // wall absorption and the deposition of BOTH currents (jh at the half step, j1 at the
 // full step) in a single pass over the structure-of-arrays particle store.
+#include <cooperative_groups.h>
 #include "common.cuh"
 #include "ring.cuh"
 #include "host_common.h"
+namespace cg = cooperative_groups;
 
 namespace pic {
 
@@ -424,16 +426,26 @@ __device__ __forceinline__ void win_add6(double* myw, double* acc, int wb, int t
 //        -- hence not absorbed, and every cell index inside the grid -- iff ps < hi32(L) - 1.
 __device__ __forceinline__ double floor_frac_hi(double xs, double idx) { const double t = xs * idx; return t - floor(t); }
 
-struct FastO6 { double X1, U1, hL, hR, fL, fR; int cH, cF; unsigned fr, ps; };
+struct FastO6 { double X1, U1, hL, hR, fL, fR; int cH, cF; unsigned fr, ps; bool emiss; };
 
-template <bool FIRST>
-__device__ __forceinline__ void dd_fast6(const FastC& c, const double* __restrict__ sF, int Ng, double X0, double U0,
-                                         double pX1, FastO6& o) {
+// BIG (large-grid build): sF is the warp's window of V6_EW field nodes starting at node eb instead
+// of the whole field tile; a gather cell outside it sets o.emiss and the particle is redone by the
+// exact routine with the field read from global memory.
+#define V6_EW 32
+template <bool FIRST, bool BIG>
+__device__ __forceinline__ void dd_fast6(const FastC& c, const double* __restrict__ sF, int Ng, int eb, double X0,
+                                         double U0, double pX1, FastO6& o) {
     const double xs = FIRST ? X0 : (X0 + pX1) * 0.5;
     const double ts = xs * c.idx, fs = floor(ts);
     const unsigned f0 = (unsigned)__double2hiint(ts - fs) - PIC_HI_G;
     const double rs = fma(-fs, c.dx, xs);
-    const int isc = min(max((int)fs, 0), Ng - 2);              // keeps the tile read in bounds for rare particles
+    int isc = min(max((int)fs, 0), Ng - 2);                    // keeps the tile read in bounds for rare particles
+    o.emiss = false;
+    if (BIG) {
+        isc -= eb;
+        o.emiss = (unsigned)isc > (unsigned)(V6_EW - 2);
+        isc = min(max(isc, 0), V6_EW - 2);
+    }
     const double wRs = div_const(rs, c.dx, c.idx), wLs = 1.0 - wRs;
     const double Ei = wLs * sF[isc] + wRs * sF[isc + 1];
     o.X1 = X0 + c.dt * U0 + c.c2 * Ei * 0.5;            // PIC_L_DD.py:479
@@ -469,7 +481,7 @@ __device__ __forceinline__ void dd_medium(const DDK& k, const FastC& fc, long lo
     const unsigned f0 = (unsigned)__double2hiint(floor_frac_hi(FIRST ? X0 : (X0 + pX1) * 0.5, fc.idx)) - PIC_HI_G;
     const unsigned p0 = (unsigned)__double2hiint(X0) - 1u;
     const unsigned pp = FIRST ? 0u : (unsigned)__double2hiint(pX1) - 1u;
-    if (!straddle && f0 <= PIC_HI_SPAN && p0 < fc.hi_Lm1 && pp < fc.hi_Lm1) {
+    if (!straddle && !o.emiss && f0 <= PIC_HI_SPAN && p0 < fc.hi_Lm1 && pp < fc.hi_Lm1) {
         const double XH = (X0 + o.X1) * 0.5;
         if (X0 >= k.L || XH >= k.L || o.X1 >= k.L) {                    // PIC_L_DD.py:495-499
             x1[i] = o.X1; if (u1) u1[i] = o.U1; active[i] = 0; atomicAdd(&s_cnt[sp ? 4 : 3], 1); return;
@@ -488,9 +500,9 @@ __device__ __forceinline__ void dd_medium(const DDK& k, const FastC& fc, long lo
     if (so.bad) atomicAdd(&s_cnt[0], so.bad);
 }
 
-template <bool FIRST, bool WU>
+template <bool FIRST, bool WU, bool BIG = false>
 __global__ void __launch_bounds__(V6_T, 1) dd_picard_iter_v6_k(
-    const __grid_constant__ DDK k, int nchunks, const double* __restrict__ x0, const double* __restrict__ u0,
+    const __grid_constant__ DDK k, int nchunks_fr, const double* __restrict__ x0, const double* __restrict__ u0,
     const double* x1i, double* x1, double* u1, int8_t* __restrict__ active, const double* __restrict__ Es,
     double* __restrict__ acc, int* __restrict__ range_err) {
     extern __shared__ __align__(128) double sm[];
@@ -498,12 +510,21 @@ __global__ void __launch_bounds__(V6_T, 1) dd_picard_iter_v6_k(
     unsigned long long* const tbuf = g_cta_timer;
     if (tbuf && threadIdx.x == 0) tbuf[2 * blockIdx.x] = gtimer();
     const int Ng = k.Ng;
-    const int NgP = (Ng + 15) & ~15;                 // keep everything behind the field tile 128-byte aligned
-    double* sF = sm;                                 // field tile
+    // field tile (whole grid) or, in the large-grid build, one V6_EW-node window per warp
+    const int NgP = BIG ? (V6_T / 32) * V6_EW : ((Ng + 15) & ~15);   // keeps what follows 128-byte aligned
+    double* sF = sm;
     double* win = sm + NgP;                          // private windows [2*V6_W][V6_T]
     double* ring = win + 2 * V6_W * V6_T;            // [warp][stage][x0|u0|x1][64]
     unsigned long long* bars = (unsigned long long*)(ring + (V6_T / 32) * V6_NST * 192);   // [warp][stage]
-    for (int i = threadIdx.x; i < Ng; i += V6_T) sF[i] = Es[i];
+    if (!BIG) for (int i = threadIdx.x; i < Ng; i += V6_T) sF[i] = Es[i];
+    double* const wE = sm + (threadIdx.x >> 5) * V6_EW;     // BIG: this warp's field window
+    const double* const fE = BIG ? wE : sF;                 // what the fast path gathers from
+    const double* const gE = BIG ? Es : sF;                 // what the exact routines gather from
+    // BIG: few particles per cell -> a 1024-particle slice spans many cells, so the deposit window
+    // (and the field window) is re-centred and flushed every V6_FR rows instead of once per slice
+    const int FRm = BIG ? (nchunks_fr >> 28) : (V6_ROWS - 1);     // rows per window - 1 (a power of two minus one)
+    const int nchunks = nchunks_fr & 0x0fffffff;
+    int eb = 0;
     double* myw = win + threadIdx.x;
 #pragma unroll
     for (int n = 0; n < 2 * V6_W; ++n) myw[n * V6_T] = 0.0;
@@ -547,6 +568,28 @@ __global__ void __launch_bounds__(V6_T, 1) dd_picard_iter_v6_k(
 #pragma unroll
         for (int s = 0; s < V6_NST; ++s) issue(cbase + 64 * s, s);
     }
+    // column sums of the warp's 32 private windows -> global accumulators, windows cleared
+    auto flush_windows = [&](int wbase_node) {
+        __syncwarp();
+        if (wbase_node != NOWIN) {
+            double s = 0.0;
+            const int n = lane >> 1, half = lane & 1;
+            if (lane < 4 * V6_W) {
+                const double* col = win + n * V6_T + wbase + half * 16;
+#pragma unroll
+                for (int j = 0; j < 16; ++j) s += col[(j + n) & 15];
+            }
+            s += __shfl_xor_sync(full, s, 1);
+            if (lane < 4 * V6_W && half == 0) {
+                int node = wbase_node + (n < V6_W ? n : n - V6_W);
+                if (node >= 0 && node < Ng && s != 0.0) atomicAdd(&acc[(n < V6_W ? 0 : Ng) + node], s);
+            }
+            __syncwarp();
+#pragma unroll
+            for (int n2 = 0; n2 < 2 * V6_W; ++n2) myw[n2 * V6_T] = 0.0;
+            __syncwarp();
+        }
+    };
     int stage = 0;
     uint32_t phase = 0;
 #pragma unroll 1
@@ -561,6 +604,7 @@ __global__ void __launch_bounds__(V6_T, 1) dd_picard_iter_v6_k(
         long long ci = cbase + 2 * lane;
 #pragma unroll 1
         for (int row = 0; row < V6_ROWS; ++row, ci += 64) {
+            if (BIG && row > 0 && (row & FRm) == 0) flush_windows(wb);
             mbar_wait(bar_s + 8 * stage, phase);
             const double* sb = wring + stage * 192 + 2 * lane;
             const double2 X0 = *(const double2*)sb, U0 = *(const double2*)(sb + 64);
@@ -576,12 +620,21 @@ __global__ void __launch_bounds__(V6_T, 1) dd_picard_iter_v6_k(
                 fc.c1 = sp ? k.c1[1] : k.c1[0]; fc.c2 = sp ? k.c2[1] : k.c2[0];
                 fc.qpi = (sp ? k.q[1] : k.q[0]) * k.p2c * k.idx;
             }
+            if (BIG && (row & FRm) == 0) {
+                // field window around the gather cell of the row's first particle
+                const double xf = __shfl_sync(full, FIRST ? X0.x : (X0.x + pX1.x) * 0.5, 0);
+                const int cb = (int)floor(xf * k.idx);
+                eb = min(max(cb - V6_EW / 4, 0), Ng - V6_EW);
+                __syncwarp();
+                wE[lane] = __ldg(Es + eb + lane);
+                __syncwarp();
+            }
             FastO6 a, b;
-            dd_fast6<FIRST>(fc, sF, Ng, X0.x, U0.x, pX1.x, a);
-            dd_fast6<FIRST>(fc, sF, Ng, X0.y, U0.y, pX1.y, b);
-            const bool ra = (a.fr > PIC_HI_SPAN) | (a.ps >= fc.hi_Lm1) | straddle;
-            const bool rb = (b.fr > PIC_HI_SPAN) | (b.ps >= fc.hi_Lm1) | straddle;
-            if (row == 0) {
+            dd_fast6<FIRST, BIG>(fc, fE, Ng, eb, X0.x, U0.x, pX1.x, a);
+            dd_fast6<FIRST, BIG>(fc, fE, Ng, eb, X0.y, U0.y, pX1.y, b);
+            const bool ra = (a.fr > PIC_HI_SPAN) | (a.ps >= fc.hi_Lm1) | straddle | a.emiss;
+            const bool rb = (b.fr > PIC_HI_SPAN) | (b.ps >= fc.hi_Lm1) | straddle | b.emiss;
+            if ((row & FRm) == 0) {
                 // window base: centre on the mean deposit cell of the warp's first row
                 int nok = __reduce_add_sync(full, (ra ? 0 : 1) + (rb ? 0 : 1));
                 int sum = __reduce_add_sync(full, (ra ? 0 : a.cH) + (rb ? 0 : b.cH));
@@ -613,8 +666,8 @@ __global__ void __launch_bounds__(V6_T, 1) dd_picard_iter_v6_k(
                     const short fl = *(const short*)(active + ci);
                     acta = (int)(signed char)(fl & 0xff); actb = (int)(signed char)(fl >> 8);
                 }
-                dd_medium<FIRST>(k, fc, ci, X0.x, U0.x, pX1.x, a, acta, straddle, sp, sF, myw, wb, acc, s_cnt, x1, WU ? u1 : nullptr, active);
-                dd_medium<FIRST>(k, fc, ci + 1, X0.y, U0.y, pX1.y, b, actb, straddle, sp, sF, myw, wb, acc, s_cnt, x1, WU ? u1 : nullptr, active);
+                dd_medium<FIRST>(k, fc, ci, X0.x, U0.x, pX1.x, a, acta, straddle, sp, gE, myw, wb, acc, s_cnt, x1, WU ? u1 : nullptr, active);
+                dd_medium<FIRST>(k, fc, ci + 1, X0.y, U0.y, pX1.y, b, actb, straddle, sp, gE, myw, wb, acc, s_cnt, x1, WU ? u1 : nullptr, active);
             }
             // Refill the stage this row drained with the row V6_NST ahead (possibly in the next chunk).
             // This must not happen before every lane's LDS of the stage has EXECUTED: an LDS can sit
@@ -626,26 +679,7 @@ __global__ void __launch_bounds__(V6_T, 1) dd_picard_iter_v6_k(
             if (row < V6_ROWS - V6_NST) issue(cbase + 64 * (row + V6_NST), st_cur);
             else if (more) issue(cbase + chunk_step + 64 * (row + V6_NST - V6_ROWS), st_cur);
         }
-        // column sums of the warp's 32 private windows -> global accumulators
-        __syncwarp();
-        if (wb != NOWIN) {
-            double s = 0.0;
-            const int n = lane >> 1, half = lane & 1;
-            if (lane < 4 * V6_W) {
-                const double* col = win + n * V6_T + wbase + half * 16;
-#pragma unroll
-                for (int j = 0; j < 16; ++j) s += col[(j + n) & 15];
-            }
-            s += __shfl_xor_sync(full, s, 1);
-            if (lane < 4 * V6_W && half == 0) {
-                int node = wb + (n < V6_W ? n : n - V6_W);
-                if (node >= 0 && node < Ng && s != 0.0) atomicAdd(&acc[(n < V6_W ? 0 : Ng) + node], s);
-            }
-            __syncwarp();
-#pragma unroll
-            for (int n2 = 0; n2 < 2 * V6_W; ++n2) myw[n2 * V6_T] = 0.0;
-            __syncwarp();
-        }
+        flush_windows(wb);
     }
     __syncthreads();
     if (threadIdx.x >= 1 && threadIdx.x <= 4 && s_cnt[threadIdx.x])
@@ -734,6 +768,67 @@ __global__ void __launch_bounds__(1024) dd_field_update_k(DDK k, double* __restr
 }
 
 // ---- function-level drop-ins ---------------------------------------------------------
+// The same field phase for grids too large for one CTA (Ng > 32768): cooperative launch, one
+// CTA per SM, grid-wide barriers between the phases; the four sums are accumulated with one
+// atomic per CTA in `red` (4 doubles, zero on entry, re-zeroed on exit), so they are re-associated
+// relative to the single-CTA kernel (round-off level differences in the residual).
+__global__ void __launch_bounds__(1024) dd_field_update_big_k(DDK k, double* __restrict__ acc,
+                                                              double* __restrict__ wall_cum,
+                                                              const double* __restrict__ E0, double* __restrict__ Es,
+                                                              double* __restrict__ E1, double* __restrict__ j1o,
+                                                              double* __restrict__ stats, double* __restrict__ red) {
+    cg::grid_group grid = cg::this_grid();
+    __shared__ double scratch[33];
+    const int Ng = k.Ng;
+    const double w0 = wall_cum[0] + acc[2 * Ng + 0], w1 = wall_cum[1] + acc[2 * Ng + 1];
+    const double w2 = wall_cum[2] + acc[2 * Ng + 2], w3 = wall_cum[3] + acc[2 * Ng + 3];
+    const double wallL = w0 * (k.dx * k.q[0] * k.p2c / k.dt) + w1 * (k.dx * k.q[1] * k.p2c / k.dt);
+    const double wallR = w2 * (-k.dx * k.q[0] * k.p2c / k.dt) + w3 * (-k.dx * k.q[1] * k.p2c / k.dt);
+    double* jh = acc;
+    double* j1 = acc + Ng;
+    const int gtid = blockIdx.x * blockDim.x + threadIdx.x, gsz = gridDim.x * blockDim.x;
+    double sh = 0.0, s1 = 0.0;
+    for (int i = gtid; i < Ng; i += gsz) {
+        double a = jh[i], b = j1[i];
+        if (i == 0) { a = (a + wallL) + jh[1]; b = (b + wallL) + j1[1]; }
+        if (i == Ng - 1) { a = (a + wallR) + jh[Ng - 2]; b = (b + wallR) + j1[Ng - 2]; }
+        sh += a; s1 += b;
+        E1[i] = a;
+        j1o[i] = b;
+    }
+    sh = block_reduce<0>(sh, scratch);
+    s1 = block_reduce<0>(s1, scratch);
+    if (threadIdx.x == 0) { atomicAdd(&red[0], sh); atomicAdd(&red[1], s1); }
+    grid.sync();
+    const double meanh = red[0] / (double)Ng;
+    const double coef = k.dt / PIC_EPS0;
+    double rr = 0.0, ee = 0.0;
+    for (int i = gtid; i < Ng; i += gsz) {
+        double e0 = E0[i];
+        double e1 = e0 + coef * (meanh - E1[i]);
+        double eh = (e1 + e0) * 0.5;
+        double d = Es[i] - eh;
+        rr += d * d;
+        ee += PIC_EPS0 * e1 * e1 * k.dx / 2.;
+        E1[i] = e1;
+        Es[i] = eh;
+    }
+    rr = block_reduce<0>(rr, scratch);
+    ee = block_reduce<0>(ee, scratch);
+    if (threadIdx.x == 0) { atomicAdd(&red[2], rr); atomicAdd(&red[3], ee); }
+    grid.sync();
+    for (int i = gtid; i < 2 * Ng + 4; i += gsz) acc[i] = 0.0;
+    if (gtid == 0) {
+        wall_cum[0] = w0; wall_cum[1] = w1; wall_cum[2] = w2; wall_cum[3] = w3;
+        stats[0] = sqrt(red[2]);
+        stats[1] = red[1] / (double)Ng;
+        stats[2] = red[3];
+        stats[3] = stats[3] + 1.0;
+    }
+    grid.sync();      // every CTA has read red[] and the wall counts before they are reset
+    if (gtid == 0) { red[0] = 0.0; red[1] = 0.0; red[2] = 0.0; red[3] = 0.0; }
+}
+
 __global__ void dd_interpolate_k(const double* __restrict__ F, const double* __restrict__ x,
                                  double* __restrict__ out, long long N, int Ng, double dx,
                                  int* __restrict__ range_err) {
@@ -971,9 +1066,115 @@ __global__ void __launch_bounds__(SORT_T) dd_sort_scatter_k(DDK k, const double*
     }
 }
 
+// ---- the same counting sort for grids whose histogram does not fit shared memory: counts and
+// cursors live in global memory (L2), one warp-aggregated atomic per distinct key per warp ----
+__global__ void dd_sort_hist_big_k(DDK k, const double* __restrict__ x0, int32_t* __restrict__ counts) {
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    const long long nIter = (k.N + stride - 1) / stride;
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    for (long long it = 0; it < nIter; ++it, i += stride) {
+        const int key = i < k.N ? dd_sort_key(k, x0[i], i) : -1;
+        const unsigned peers = __match_any_sync(0xffffffffu, key);
+        if (key >= 0 && (threadIdx.x & 31) == (unsigned)(__ffs(peers) - 1)) atomicAdd(&counts[key], __popc(peers));
+    }
+}
+// exclusive scan in three passes: per-1024-block local scan + block sums, scan of the sums (dd_sort_scan_k), add
+__global__ void __launch_bounds__(1024) scan_local_k(int32_t* __restrict__ v, int n, int32_t* __restrict__ sums) {
+    __shared__ int wsum[32];
+    const int i = blockIdx.x * 1024 + threadIdx.x, lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int x = i < n ? v[i] : 0;
+    int t = x;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { int y = __shfl_up_sync(0xffffffffu, t, o); if (lane >= o) t += y; }
+    if (lane == 31) wsum[w] = t;
+    __syncthreads();
+    if (w == 0) {
+        int s2 = wsum[lane];
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { int y = __shfl_up_sync(0xffffffffu, s2, o); if (lane >= o) s2 += y; }
+        wsum[lane] = s2;
+    }
+    __syncthreads();
+    const int pre = w > 0 ? wsum[w - 1] : 0;
+    if (i < n) v[i] = pre + t - x;
+    if (threadIdx.x == 1023) sums[blockIdx.x] = pre + t;
+}
+__global__ void scan_add_k(int32_t* __restrict__ v, int n, const int32_t* __restrict__ sums) {
+    const int i = blockIdx.x * 1024 + threadIdx.x;
+    if (i < n) v[i] += sums[blockIdx.x];
+}
+template <bool PERM>
+__global__ void __launch_bounds__(256) dd_sort_scatter_big_k(DDK k, const double* __restrict__ x0,
+                                                             const double* __restrict__ u0,
+                                                             const double* __restrict__ v0,
+                                                             const double* __restrict__ w0, double* __restrict__ xs,
+                                                             double* __restrict__ us, double* __restrict__ vs,
+                                                             double* __restrict__ ws, int32_t* __restrict__ cursor) {
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    const long long nIter = (k.N + stride - 1) / stride;
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const unsigned lane = threadIdx.x & 31;
+    for (long long it = 0; it < nIter; ++it, i += stride) {
+        double X = 0.;
+        int key = -1;
+        if (i < k.N) { X = x0[i]; key = dd_sort_key(k, X, i); }
+        const unsigned peers = __match_any_sync(0xffffffffu, key);
+        const int leader = __ffs(peers) - 1;
+        int base = 0;
+        if (key >= 0 && (int)lane == leader) base = atomicAdd(&cursor[key], __popc(peers));
+        base = __shfl_sync(0xffffffffu, base, leader);
+        if (key >= 0) {
+            const long long pos = (long long)base + __popc(peers & ((1u << lane) - 1u));
+            xs[pos] = X;
+            if (PERM) ((int32_t*)us)[pos] = (int32_t)i; else us[pos] = u0[i];
+            if (vs) vs[pos] = v0[i];
+            if (ws) ws[pos] = w0[i];
+        }
+    }
+}
+
 }  // namespace pic
 
 using namespace pic;
+
+// counting sort driver shared by pic_dev_dd_sort_by_cell / pic_dev_sort_perm_by_cell
+template <bool PERM>
+static int sort_by_cell_impl(const DDK& k, const double* x0, const double* u0, const double* v0, const double* w0,
+                             double* x0s, double* u0s, double* v0s, double* w0s, int32_t* counts, cudaStream_t st) {
+    const int nk = 2 * k.Ng;
+    const size_t smem = (size_t)nk * sizeof(int);
+    const size_t smem_sc = 2 * smem;
+    const bool big = smem_sc > (size_t)max_optin_smem() - 1024;
+    // big: counts needs nk + 2 + ceil(nk/1024) + 2 entries (block sums of the three-pass scan behind the keys)
+    const int nblk = (nk + 1023) / 1024;
+    PIC_CHECK_CUDA(cudaMemsetAsync(counts, 0, (size_t)(nk + 2 + (big ? nblk + 2 : 0)) * sizeof(int32_t), st));
+    if (k.N == 0) return PIC_OK;
+    if (big) {
+        PIC_REQUIRE(nblk <= 1024 * 1024, "sort_by_cell: grid too large");
+        int32_t* sums = counts + nk + 2;
+        dd_sort_hist_big_k<<<grid_for(k.N, 256, 8), 256, 0, st>>>(k, x0, counts);
+        PIC_CHECK_LAUNCH();
+        scan_local_k<<<nblk, 1024, 0, st>>>(counts, nk, sums);
+        PIC_CHECK_LAUNCH();
+        dd_sort_scan_k<<<1, 1024, 0, st>>>(sums, nblk);
+        PIC_CHECK_LAUNCH();
+        scan_add_k<<<nblk, 1024, 0, st>>>(counts, nk, sums);
+        PIC_CHECK_LAUNCH();
+        dd_sort_scatter_big_k<PERM><<<grid_for(k.N, 256, 8), 256, 0, st>>>(k, x0, u0, v0, w0, x0s, u0s, v0s, w0s, counts);
+        PIC_CHECK_LAUNCH();
+        return PIC_OK;
+    }
+    PIC_CHECK_CUDA(cudaFuncSetAttribute(dd_sort_hist_k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    PIC_CHECK_CUDA(cudaFuncSetAttribute(dd_sort_scatter_k<PERM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_sc));
+    dd_sort_hist_k<<<grid_for(k.N, 1024, 2), 1024, smem, st>>>(k, x0, counts);
+    PIC_CHECK_LAUNCH();
+    dd_sort_scan_k<<<1, 1024, 0, st>>>(counts, nk);
+    PIC_CHECK_LAUNCH();
+    dd_sort_scatter_k<PERM><<<grid_for((k.N + SORT_PER - 1) / SORT_PER, SORT_T, 2), SORT_T, smem_sc, st>>>(
+        k, x0, u0, v0, w0, x0s, u0s, v0s, w0s, counts);
+    PIC_CHECK_LAUNCH();
+    return PIC_OK;
+}
 
 template <bool FIRST, bool TILE, bool AGG>
 static int launch_iter(const DDK& k, const double* x0, const double* u0, const double* x1i, double* x1, double* u1,
@@ -1012,11 +1213,16 @@ static int launch_tail(const DDK& k, long long done, const double* x0, const dou
 __global__ void __launch_bounds__(256) dd_commit_u_k(DDK k, const double* __restrict__ x0, const double* __restrict__ u0,
                                                      const double* __restrict__ x1_prev, const double* __restrict__ x1_last,
                                                      const int8_t* __restrict__ active, const double* __restrict__ Es,
-                                                     double* __restrict__ u1, int first, int* __restrict__ range_err) {
-    extern __shared__ double sF[];
+                                                     double* __restrict__ u1, int first, int tile,
+                                                     int* __restrict__ range_err) {
+    extern __shared__ double sFt[];
     const int Ng = k.Ng;
-    for (int i = threadIdx.x; i < Ng; i += blockDim.x) sF[i] = Es[i];
-    __syncthreads();
+    const double* sF = Es;                       // large grids: gather from global memory / L2
+    if (tile) {
+        for (int i = threadIdx.x; i < Ng; i += blockDim.x) sFt[i] = Es[i];
+        __syncthreads();
+        sF = sFt;
+    }
     int bad = 0;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < k.N; i += (long long)gridDim.x * blockDim.x) {
         const double X0 = ld_stream(x0 + i), U0 = ld_stream(u0 + i);
@@ -1053,6 +1259,38 @@ int pic_dev_dd_picard_iter2(const pic_dd_params* p, const double* x0, const doub
     const size_t smem6 = ((size_t)((k.Ng + 15) & ~15) + (size_t)2 * V6_W * V6_T + (size_t)(V6_T / 32) * V6_NST * 192 +
                           (size_t)(V6_T / 32) * V6_NST) * sizeof(double);
     const bool aligned16 = (((uintptr_t)x0 | (uintptr_t)u0 | (uintptr_t)x1i | (uintptr_t)x1 | (uintptr_t)u1) & 15) == 0;
+    // large-grid build of the same kernel: per-warp field windows instead of the whole-grid tile, so
+    // the shared-memory footprint does not depend on Ng (flags bit4 forces it, for tests)
+    const size_t smem6b = ((size_t)(V6_T / 32) * V6_EW + (size_t)2 * V6_W * V6_T + (size_t)(V6_T / 32) * V6_NST * 192 +
+                           (size_t)(V6_T / 32) * V6_NST) * sizeof(double);
+    const bool big = ((p->flags & 16) || smem6 > (size_t)max_optin_smem() - 512) && k.Ng >= V6_EW;
+    if (big && aligned16 && !(p->flags & (1 | 4 | 8))) {
+        const long long nchunks = k.N / V6_CHUNK;
+        if (nchunks > 0) {
+            auto kern = first ? (u1 ? dd_picard_iter_v6_k<true, true, true> : dd_picard_iter_v6_k<true, false, true>)
+                              : (u1 ? dd_picard_iter_v6_k<false, true, true> : dd_picard_iter_v6_k<false, false, true>);
+            PIC_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem6b));
+            long long cap = device_sm_count();
+            int grid = (int)(nchunks < cap ? nchunks : cap);
+            // rows (of 64 particles) per deposit/field window: about three cells' worth of particles
+            const double ppc = (double)k.N / 2.0 / (double)k.Ng;
+            int fr = 16;
+            while (fr > 1 && 64.0 * fr > 3.0 * ppc) fr >>= 1;
+            PIC_REQUIRE(nchunks < (1 << 28), "dd_picard_iter: shard too large");
+            kern<<<grid, V6_T, smem6b, st>>>(k, (int)nchunks | ((fr - 1) << 28), x0, u0, x1i, x1, u1, active, Es, acc, range_err);
+            PIC_CHECK_LAUNCH();
+        }
+        const long long done = nchunks * V6_CHUNK;
+        if (done >= k.N) return PIC_OK;
+        DDK t = k;
+        t.N = k.N - done;
+        t.n_split = k.n_split - done < 0 ? 0 : (k.n_split - done > t.N ? t.N : k.n_split - done);
+        // tail: grid-stride kernel with the grids left in global memory
+        return first ? launch_iter<true, false, true>(t, x0 + done, u0 + done, x1i + done, x1 + done, u1 ? u1 + done : nullptr,
+                                                      active + done, Es, acc, range_err, st)
+                     : launch_iter<false, false, true>(t, x0 + done, u0 + done, x1i + done, x1 + done, u1 ? u1 + done : nullptr,
+                                                       active + done, Es, acc, range_err, st);
+    }
     if (!(p->flags & (1 | 2 | 4 | 8)) && aligned16 && smem6 <= (size_t)max_optin_smem() - 512) {
         // default: TMA-staged private-window kernel, one persistent CTA per SM
         const long long nchunks = k.N / V6_CHUNK;
@@ -1108,12 +1346,13 @@ int pic_dev_dd_commit_u(const pic_dd_params* p, const double* x0, const double* 
     if (p->N == 0) return PIC_OK;
     DDK k = make_ddk(p);
     size_t smem = (size_t)k.Ng * sizeof(double);
-    PIC_REQUIRE(smem <= (size_t)max_optin_smem() - 1024, "dd_commit_u: grid too large for the shared-memory tile");
-    PIC_CHECK_CUDA(cudaFuncSetAttribute(dd_commit_u_k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int tile = smem <= (size_t)max_optin_smem() - 1024;
+    if (!tile) smem = 0;
+    PIC_CHECK_CUDA(cudaFuncSetAttribute(dd_commit_u_k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(smem ? smem : 1)));
     int occ = 0;
     PIC_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, dd_commit_u_k, 256, smem));
     dd_commit_u_k<<<grid_for(k.N, 256, occ > 0 ? occ : 1), 256, smem, (cudaStream_t)stream>>>(
-        k, x0, u0, x1_prev, x1_last, active, Es, u1, first, range_err);
+        k, x0, u0, x1_prev, x1_last, active, Es, u1, first, tile, range_err);
     PIC_CHECK_LAUNCH();
     return PIC_OK;
 }
@@ -1136,6 +1375,16 @@ int pic_dev_dd_field_update(const pic_dd_params* p, double* acc, double* wall_cu
                             double* E1, double* j1, double* stats, void* stream) {
     PIC_REQUIRE(p && acc && wall_cum && E0 && Es && E1 && j1 && stats, "dd_field_update: null pointer");
     DDK k = make_ddk(p);
+    if (k.Ng > 32768) {
+        // stats[4..7] is the reduction scratch of the cooperative kernel (the caller provides 8 doubles)
+        double* red = stats + 4;
+        int grid = (k.Ng + 1023) / 1024;
+        if (grid > device_sm_count()) grid = device_sm_count();
+        void* args[] = {&k, &acc, &wall_cum, (void*)&E0, &Es, &E1, &j1, &stats, &red};
+        PIC_CHECK_CUDA(cudaLaunchCooperativeKernel((const void*)dd_field_update_big_k, dim3(grid), dim3(1024), args, 0,
+                                                   (cudaStream_t)stream));
+        return PIC_OK;
+    }
     dd_field_update_k<<<1, 1024, 0, (cudaStream_t)stream>>>(k, acc, wall_cum, E0, Es, E1, j1, stats);
     PIC_CHECK_LAUNCH();
     return PIC_OK;
@@ -1215,47 +1464,15 @@ int pic_dev_dd_sort_by_cell(const pic_dd_params* p, const double* x0, const doub
                             void* stream) {
     PIC_REQUIRE(p && x0 && u0 && x0s && u0s && counts, "dd_sort_by_cell: null pointer");
     PIC_REQUIRE(p->N < 2147483647LL, "dd_sort_by_cell: shard too large for int32 cursors");
-    DDK k = make_ddk(p);
-    cudaStream_t st = (cudaStream_t)stream;
-    const int nk = 2 * k.Ng;
-    size_t smem = (size_t)nk * sizeof(int);
-    const size_t smem_sc = 2 * smem;
-    PIC_REQUIRE(smem_sc <= (size_t)max_optin_smem() - 1024, "dd_sort_by_cell: grid too large for the shared-memory histogram");
-    PIC_CHECK_CUDA(cudaMemsetAsync(counts, 0, (size_t)(nk + 2) * sizeof(int32_t), st));
-    if (k.N == 0) return PIC_OK;
-    PIC_CHECK_CUDA(cudaFuncSetAttribute(dd_sort_hist_k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    PIC_CHECK_CUDA(cudaFuncSetAttribute(dd_sort_scatter_k<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_sc));
-    dd_sort_hist_k<<<grid_for(k.N, 1024, 2), 1024, smem, st>>>(k, x0, counts);
-    PIC_CHECK_LAUNCH();
-    dd_sort_scan_k<<<1, 1024, 0, st>>>(counts, nk);
-    PIC_CHECK_LAUNCH();
-    dd_sort_scatter_k<false><<<grid_for((k.N + SORT_PER - 1) / SORT_PER, SORT_T, 2), SORT_T, smem_sc, st>>>(k, x0, u0, v0, w0, x0s, u0s, v0s, w0s, counts);
-    PIC_CHECK_LAUNCH();
-    return PIC_OK;
+    return sort_by_cell_impl<false>(make_ddk(p), x0, u0, v0, w0, x0s, u0s, v0s, w0s, counts, (cudaStream_t)stream);
 }
 
 int pic_dev_sort_perm_by_cell(const pic_dd_params* p, const double* x, double* xs, int32_t* perm, int32_t* counts,
                               void* stream) {
     PIC_REQUIRE(p && x && xs && perm && counts, "sort_perm_by_cell: null pointer");
     PIC_REQUIRE(p->N < 2147483647LL, "sort_perm_by_cell: store too large for int32 indices");
-    DDK k = make_ddk(p);
-    cudaStream_t st = (cudaStream_t)stream;
-    const int nk = 2 * k.Ng;
-    size_t smem = (size_t)nk * sizeof(int);
-    const size_t smem_sc = 2 * smem;
-    PIC_REQUIRE(smem_sc <= (size_t)max_optin_smem() - 1024, "sort_perm_by_cell: grid too large for the shared-memory histogram");
-    PIC_CHECK_CUDA(cudaMemsetAsync(counts, 0, (size_t)(nk + 2) * sizeof(int32_t), st));
-    if (k.N == 0) return PIC_OK;
-    PIC_CHECK_CUDA(cudaFuncSetAttribute(dd_sort_hist_k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    PIC_CHECK_CUDA(cudaFuncSetAttribute(dd_sort_scatter_k<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_sc));
-    dd_sort_hist_k<<<grid_for(k.N, 1024, 2), 1024, smem, st>>>(k, x, counts);
-    PIC_CHECK_LAUNCH();
-    dd_sort_scan_k<<<1, 1024, 0, st>>>(counts, nk);
-    PIC_CHECK_LAUNCH();
-    dd_sort_scatter_k<true><<<grid_for((k.N + SORT_PER - 1) / SORT_PER, SORT_T, 2), SORT_T, smem_sc, st>>>(
-        k, x, nullptr, nullptr, nullptr, xs, (double*)perm, nullptr, nullptr, counts);
-    PIC_CHECK_LAUNCH();
-    return PIC_OK;
+    return sort_by_cell_impl<true>(make_ddk(p), x, nullptr, nullptr, nullptr, xs, (double*)perm, nullptr, nullptr, counts,
+                                   (cudaStream_t)stream);
 }
 
 }  // extern "C"

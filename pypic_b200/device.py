@@ -60,3 +60,10 @@ def check_range(err_t, what):
         err_t.zero_()
         raise _lib.PicError(_lib.PIC_ERR_RANGE, "%s: %d particle position(s) outside the grid "
                             "(undefined behaviour in the reference); indices were clamped" % (what, n))
+
+
+def sort_counts_size(Ng):
+    """int32 entries of the scratch pic_dev_dd_sort_by_cell / pic_dev_sort_perm_by_cell need:
+    2*Ng keys + 2, plus the block sums of the three-pass scan used for large grids."""
+    nk = 2 * int(Ng)
+    return nk + 2 + (nk + 1023) // 1024 + 2

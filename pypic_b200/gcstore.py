@@ -376,7 +376,7 @@ class ParticleStore:
                           (C.c_double * 2)(1., 1.))
         xs = torch.empty(N, dtype=torch.float64, device=dev)
         idx = torch.empty(N, dtype=torch.int32, device=dev)
-        counts = torch.zeros(2 * grid.ng + 2, dtype=torch.int32, device=dev)
+        counts = torch.zeros(D.sort_counts_size(grid.ng), dtype=torch.int32, device=dev)
         st = D.stream()
         _lib.call("pic_dev_sort_perm_by_cell", C.byref(P), D.ptr(self.r[0]), D.ptr(xs), D.ptr(idx), D.ptr(counts), st)
         f_src = self.r[1:] + [self.charge_state, self.m, self.p2c]

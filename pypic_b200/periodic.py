@@ -71,7 +71,7 @@ class PeriodicImplicitSim:
         if self.perm is None:
             self.perm = torch.arange(n, dtype=torch.float64, device=self.dev)
             self._perm2 = torch.empty_like(self.perm)
-            self._sort_counts = torch.zeros(2 * self.Ng + 2, dtype=torch.int32, device=self.dev)
+            self._sort_counts = torch.zeros(D.sort_counts_size(self.Ng), dtype=torch.int32, device=self.dev)
             self._sort_params = _lib.DDParams(self.N, self.N, self.Ng, 0, self.dx, self.dt, self.L, self.p2c,
                                               (C.c_double * 2)(0., 0.), (C.c_double * 2)(1., 1.))
         _lib.call("pic_dev_dd_sort_by_cell", C.byref(self._sort_params), D.ptr(self.x0), D.ptr(self.v0),
@@ -216,7 +216,7 @@ class ExplicitSim:
             self.perm = torch.arange(n, dtype=torch.float64, device=self.dev)
             self._perm2 = torch.empty_like(self.perm)
             self._x2 = torch.empty_like(self.x); self._v2 = torch.empty_like(self.v)
-            self._sort_counts = torch.zeros(2 * self.Ng + 2, dtype=torch.int32, device=self.dev)
+            self._sort_counts = torch.zeros(D.sort_counts_size(self.Ng), dtype=torch.int32, device=self.dev)
             self._sort_params = _lib.DDParams(self.N, self.n_split, self.Ng, 0, self.dx, self.dt, self.L, self.p2c,
                                               (C.c_double * 2)(0., 0.), (C.c_double * 2)(1., 1.))
         _lib.call("pic_dev_dd_sort_by_cell", C.byref(self._sort_params), D.ptr(self.x), D.ptr(self.v),

@@ -47,7 +47,9 @@ class SheathSim:
         # "window-ldg" = the same with register-prefetched loads instead of the TMA ring,
         # "atomic" = one shared-memory atomicAdd per contribution, "warp" = grid-stride kernel
         # with warp-uniform pre-reduction; tiles: "smem" or "global" (grid too large for smem)
-        flags = {"window": 0, "window-ldg": 8, "atomic": 1, "warp": 4}[deposit] | (2 if tiles == "global" else 0)
+        # "window-big" forces the large-grid build of the window kernel (per-warp field windows, no
+        # whole-grid tile; chosen automatically when the grid does not fit shared memory)
+        flags = {"window": 0, "window-big": 16, "window-ldg": 8, "atomic": 1, "warp": 4}[deposit] | (2 if tiles == "global" else 0)
         self.params = _lib.DDParams(self.N, self.n_split, self.Ng, flags, self.dx, self.dt, self.L, self.p2c,
                                     (C.c_double * 2)(*self.q), (C.c_double * 2)(*self.m))
         dev = self.dev
@@ -69,12 +71,12 @@ class SheathSim:
         self.j0 = D.f64(g, dev, True)
         self.acc = D.f64(2 * g + 4, dev, True)
         self.wall_cum = D.f64(4, dev, True)
-        self.stats = D.f64(4, dev, True)
+        self.stats = D.f64(8, dev, True)      # [r, mean j1, EE, iterations | 4 doubles of reduction scratch]
         self.range_err = torch.zeros(1, dtype=torch.int32, device=dev)
         self.dead_idx = torch.empty(n, dtype=torch.int32, device=dev)
         self.count = torch.zeros(1, dtype=torch.int64, device=dev)
         self.block_counts = torch.zeros(2 * (n // 2048 + 2), dtype=torch.int64, device=dev)
-        self.sort_counts = torch.zeros(2 * g + 2, dtype=torch.int32, device=dev) if self.sort_every else None
+        self.sort_counts = torch.zeros(D.sort_counts_size(g), dtype=torch.int32, device=dev) if self.sort_every else None
         self.scalar = D.f64(1, dev, True)
         self.t = 0
         self.last_iters = 0

@@ -423,3 +423,76 @@ def test_sorted_philox_mode_conserves_and_matches_unsorted():
     assert xa.min() > 0 and xa.max() < L
     a.step(); b.step(); a.check(); b.check()
     assert np.isfinite(a.E0.cpu().numpy()).all() and np.isfinite(b.E0.cpu().numpy()).all()
+
+
+def test_large_grid_build_matches_default_kernel():
+    """flags bit4: per-warp field windows + deposit windows flushed every 4 rows (the build taken
+    when the grid does not fit shared memory) against the default window kernel on the same
+    sorted state: x1,u1,flags bit-identical over 3 iterations, currents to 1e-13."""
+    from pypic_b200 import _lib, device as D
+    from pypic_b200.sheath import SheathSim
+    N, Ng = 6 * 16384 + 321, 1025
+    dx, L, dt, x0, u0, q, m, E0 = _one_iter_inputs(N, Ng, 17)
+    h = N // 2
+    x0[:h] = np.sort(x0[:h]); x0[h:] = np.sort(x0[h:])
+    p2c = 1e9
+    sims = {}
+    for dep in ("window", "window-big"):
+        s = SheathSim(N, Ng, dx, dt, p2c, kBT=(1.6e-18, 1.6e-18), carry_vw=False, deposit=dep, elide_u=False)
+        s.upload(x0, u0, E0=E0)
+        s.Es.copy_(s.E0)
+        outs = []
+        for it in range(3):
+            s.acc.zero_()
+            _lib.call("pic_dev_dd_picard_iter", C.byref(s.params), D.ptr(s.x0), D.ptr(s.u0), D.ptr(s.x1), D.ptr(s.u1),
+                      D.ptr(s.active), D.ptr(s.Es), D.ptr(s.acc), 1 if it == 0 else 0, D.ptr(s.range_err), D.stream())
+            outs.append((s.x1.cpu().numpy().copy(), s.u1.cpu().numpy().copy(), s.active.cpu().numpy().copy(),
+                         s.acc.cpu().numpy().copy()))
+        s.check()
+        sims[dep] = outs
+    for a, b in zip(sims["window"], sims["window-big"]):
+        assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1]) and np.array_equal(a[2], b[2])
+        assert np.array_equal(a[3][2 * Ng:], b[3][2 * Ng:])                       # absorbed counts
+        assert relmax(b[3][:2 * Ng], a[3][:2 * Ng]) < 1e-13
+
+
+def test_large_grid_step_one_million_cells():
+    """Ng = 1,000,001 nodes (BASELINE config 5's grid): global-memory histogram sort, large-grid
+    window kernel, cooperative field update.  One iteration against the grid-stride kernel with
+    the grids in global memory (same exact arithmetic per particle), then full steps."""
+    from pypic_b200 import _lib, device as D
+    from pypic_b200.sheath import SheathSim
+    N, Ng = 2_000_000, 1_000_001
+    dx, dt = 1e-8, 1e-12
+    L = dx * (Ng - 1)
+    kT = O.kb * 116000.
+    rs = np.random.RandomState(9)
+    h = N // 2
+    x0 = rs.uniform(0, L, N)
+    u0 = np.concatenate([rs.normal(0, np.sqrt(kT / O.me), h), rs.normal(0, np.sqrt(kT / O.mp), N - h)]) * 1e-3
+    E0 = rs.normal(0, 1e3, Ng)
+    p2c = L * 1e19 / N
+    a = SheathSim(N, Ng, dx, dt, p2c, kBT=(kT * 1e-6, kT * 1e-6), carry_vw=False, rng="philox", sort_every=1, elide_u=False)
+    a.upload(x0, u0, E0=E0)
+    a.sort_by_cell()
+    xs = a.x0.cpu().numpy()
+    cells = np.floor(xs / dx)
+    assert np.all(np.diff(cells[:h]) >= 0) and np.all(np.diff(cells[h:]) >= 0)
+    assert abs(xs.sum() - x0.sum()) < 1e-9 * x0.sum()
+    b = SheathSim(N, Ng, dx, dt, p2c, kBT=(kT * 1e-6, kT * 1e-6), carry_vw=False, deposit="warp", tiles="global", elide_u=False)
+    b.x0.copy_(a.x0); b.u0.copy_(a.u0); b.E0.copy_(a.E0)
+    res = []
+    for s in (a, b):
+        s.Es.copy_(s.E0); s.acc.zero_()
+        _lib.call("pic_dev_dd_picard_iter", C.byref(s.params), D.ptr(s.x0), D.ptr(s.u0), D.ptr(s.x1), D.ptr(s.u1),
+                  D.ptr(s.active), D.ptr(s.Es), D.ptr(s.acc), 1, D.ptr(s.range_err), D.stream())
+        s.check()
+        res.append((s.x1.cpu().numpy(), s.u1.cpu().numpy(), s.active.cpu().numpy(), s.acc.cpu().numpy()))
+    assert np.array_equal(res[0][0], res[1][0]) and np.array_equal(res[0][1], res[1][1])
+    assert np.array_equal(res[0][2], res[1][2])
+    assert relmax(res[0][3], res[1][3]) < 1e-12
+    a.active.fill_(1)
+    for _ in range(3):
+        k, r = a.step()
+        assert 1 <= k <= 20 and np.isfinite(r)
+    a.check()

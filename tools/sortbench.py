@@ -5,12 +5,12 @@ import numpy as np, torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from pypic_b200 import _lib, device as D
 N = int(float(sys.argv[1])) if len(sys.argv) > 1 else 200000000
-Ng = 4097; dx = 1e-5; L = dx * (Ng - 1)
+Ng = int(sys.argv[2]) if len(sys.argv) > 2 else 4097; dx = 1e-5; L = dx * (Ng - 1)
 dev = torch.device("cuda", 0)
 P = _lib.DDParams(N, N // 2, Ng, 0, dx, 1e-12, L, 1.0, (C.c_double * 2)(0, 0), (C.c_double * 2)(1, 1))
 x = torch.empty(N, dtype=torch.float64, device=dev).uniform_(0, L); u = torch.randn(N, dtype=torch.float64, device=dev)
 xs = torch.empty_like(x); us = torch.empty_like(u)
-cnt = torch.zeros(2 * Ng + 2, dtype=torch.int32, device=dev)
+cnt = torch.zeros(D.sort_counts_size(Ng), dtype=torch.int32, device=dev)
 def run(a, b, c, d):
     _lib.call("pic_dev_dd_sort_by_cell", C.byref(P), D.ptr(a), D.ptr(b), None, None, D.ptr(c), D.ptr(d), None, None, D.ptr(cnt), D.stream())
 def timed(a, b, c, d, reps=4):
