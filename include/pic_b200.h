@@ -306,6 +306,18 @@ int pic_dev_gc_push_boris_uniform(const pic_gc_params* p, double* const r[7], do
                                   double p2c, int8_t* active, int8_t* at_wall, int8_t* hit_flag,
                                   const double* Egrid, double* n_acc, long long* hit_count, int* range_err,
                                   void* stream);
+/* Post-push pass of pic_bca_aps' particle loop (pygcpic.py:1509-1541), N3: per particle the
+ * ionisation eligibility (Z==1 & charge 0: attempt_first_ionization :350-395; Z==5 & charge<3:
+ * attempt_nth_ionization :397-458) and probability density^2*rate*dx*dt/p2c (density = CIC gather
+ * of n_grid; rate[4] = np.interp'd coefficients for (Z,charge) = (1,0),(5,0),(5,1),(5,2)); the
+ * mid-domain exit of wall-born particles :1530-1541 (active <- 0, flag returned); and the
+ * particle's deterministic contribution to the running source-ion count of :1544.  The uniform
+ * draws and the decisions are made on the host in index order (legacy stream parity). */
+int pic_dev_gc_post_push(const double* x, const double* p2c, const double* charge_state, const int32_t* Z,
+                         const int8_t* from_wall, int8_t* active, const double* n_grid, int ng, double dx,
+                         double dt, double length, const double rate[4], int source_Z, double* prob,
+                         int8_t* eligible, int8_t* midexit, int8_t* contrib, int64_t N, int* range_err,
+                         void* stream);
 /* n = n_acc ; rho = charge_state*e*n_acc for a species-uniform store */
 int pic_dev_gc_uniform_finish(const double* n_acc, double* n, double* rho, int ng, double charge_state,
                               void* stream);

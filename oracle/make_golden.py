@@ -383,9 +383,109 @@ def gen_gc():
     print("pygcpic golden done; lens", n_hist[-5:], "hits", sum(hits), "del", sum(ndel), "react", sum(nreact))
 
 
+def gen_gc_ion():
+    """Monte-Carlo ionisation (pygcpic.py:350-458) inside the particle loop of pic_bca_aps
+    (pygcpic.py:1496-1549: push, walls, ionisation attempts, mid-domain exit of wall-born
+    particles, reactivate-or-delete) driven with the reference's own objects.  Neutral hydrogen
+    and boron in charge states 0..2 are mixed into the ion population; their p2c is scaled so
+    that the ionisation probabilities are O(0.1)."""
+    g = refshim.load("pygcpic")
+    e, mp = g.e, g.mp
+    out = {}
+    B = np.array([2 * np.cos(86 * np.pi / 180), 2 * np.sin(86 * np.pi / 180), 0.0])
+    np.random.seed(41)
+    density = 1e19
+    Ti = 10. * 11600; Te = 50. * 11600
+    LD = np.sqrt(g.kb * Te * g.epsilon0 / e / e / density)
+    Ld = 40 * LD; ngd = 121; dt = 8e-11
+    n_ion, n_h0, n_b = 1500, 300, 300
+    Nd = n_ion + n_h0 + n_b
+    p2c = density * Ld / n_ion
+    p2c_n = p2c * 2e-4                      # neutrals / boron: probabilities of order 0.1
+    source_N = n_ion - 30
+    grid = g.Grid(ngd, Ld, Te)
+    kinds = np.array([0] * n_ion + [1] * n_h0 + [2] * n_b)
+    np.random.shuffle(kinds)
+    parts = []
+    for kd in kinds:
+        if kd == 0:
+            p_ = g.Particle(mp, 1, p2c, Ti, Z=1, B0=B.copy(), E0=np.zeros(3), grid=grid)
+        elif kd == 1:
+            p_ = g.Particle(mp, 0, p2c_n, Ti, Z=1, B0=B.copy(), E0=np.zeros(3), grid=grid)
+            p_.from_wall = int(np.random.uniform() < 0.5)
+        else:
+            p_ = g.Particle(10.81 * mp, int(np.random.randint(0, 3)), p2c_n, Ti, Z=5, B0=B.copy(), E0=np.zeros(3), grid=grid)
+            p_.from_wall = int(np.random.uniform() < 0.5)
+        parts.append(p_)
+    out["r_init"] = np.array([p_.r.copy() for p_ in parts])
+    out["cs_init"] = np.array([float(p_.charge_state) for p_ in parts]); out["m_init"] = np.array([p_.m for p_ in parts])
+    out["p2c_init"] = np.array([p_.p2c for p_ in parts]); out["Z_init"] = np.array([p_.Z for p_ in parts])
+    out["from_wall_init"] = np.array([p_.from_wall for p_ in parts])
+    out.update(L=Ld, ng=ngd, N=Nd, dt=dt, p2c=p2c, Ti=Ti, Te=Te, source_N=source_N, B=B)
+    out["rng_state_keys"] = np.random.get_state()[1].copy(); out["rng_state_pos"] = np.random.get_state()[2]
+    src = g.source_distribution_6D(grid, Ti, mp)
+    time = 0.
+    deletion_flags = []
+    hist = dict(length=[], hits=[], ndel=[], nreact=[], nion_h=[], nion_b=[], nexit=[], n0=[], added=[])
+    sink = io.StringIO()
+    for step in range(20):
+        time += dt
+        for p_ in parts:
+            p_.apply_BCs_dirichlet(grid)
+        grid.weight_particles_to_grid_boltzmann(parts, dt)
+        grid.smooth_rho()
+        grid.reset_added_particles()
+        grid.solve_for_phi_dirichlet_boltzmann()
+        grid.differentiate_phi_to_E_dirichlet()
+        nh = nr = nih = nib = nex = 0
+        for pi, p_ in enumerate(parts):
+            if p_.is_active():
+                p_.interpolate_electric_field_dirichlet(grid)
+                p_.push_6D(dt)
+                p_.apply_BCs_dirichlet(grid)
+                cs_before = p_.charge_state
+                with contextlib.redirect_stdout(sink):
+                    if p_.Z == 1 and p_.charge_state == 0 and p_.is_active():
+                        p_.attempt_first_ionization(dt, Te, grid)
+                    if p_.Z == 5 and p_.charge_state < 3 and p_.is_active():
+                        p_.attempt_nth_ionization(dt, Te, grid)
+                if p_.charge_state != cs_before:
+                    if p_.Z == 1: nih += 1
+                    else: nib += 1
+                if not p_.is_active() and p_.at_wall:
+                    nh += 1
+                dxm = grid.length / 8
+                if p_.from_wall and (grid.length / 2 - dxm < p_.x < grid.length / 2 + dxm):
+                    p_.active = False
+                    nex += 1
+            else:
+                if sum(1 for q_ in parts if (q_.Z == 1 and q_.is_active() and q_.charge_state > 0)) < source_N:
+                    p_.reactivate(src, grid, time, p2c, mp, 1, 1)
+                    p_.from_wall = 0; p_.at_wall = 0
+                    nr += 1
+                else:
+                    deletion_flags.append(pi)
+        dset = set(deletion_flags)
+        parts = [p_ for pi, p_ in enumerate(parts) if pi not in dset]
+        hist["ndel"].append(len(deletion_flags)); deletion_flags = []
+        hist["length"].append(len(parts)); hist["hits"].append(nh); hist["nreact"].append(nr)
+        hist["nion_h"].append(nih); hist["nion_b"].append(nib); hist["nexit"].append(nex)
+        hist["n0"].append(grid.n0); hist["added"].append(grid.added_particles)
+    for k_, v_ in hist.items():
+        out["h_" + k_] = np.array(v_)
+    out["r_final"] = np.array([p_.r.copy() for p_ in parts])
+    out["cs_final"] = np.array([float(p_.charge_state) for p_ in parts]); out["Z_final"] = np.array([p_.Z for p_ in parts])
+    out["active_final"] = np.array([int(p_.active) for p_ in parts])
+    out["next_uniform"] = np.random.uniform()            # pins the number of draws consumed
+    np.savez_compressed(os.path.join(GOLD, "gc_ion.npz"), **out)
+    print("pygcpic ionisation golden done;", {k_: int(np.sum(v_)) for k_, v_ in hist.items() if k_ not in ("n0", "added")})
+
+
 def main():
     os.makedirs(GOLD, exist_ok=True)
-    which = sys.argv[1:] or ["pypic", "ddk", "ddm", "l", "gc"]
+    which = sys.argv[1:] or ["pypic", "ddk", "ddm", "l", "gc", "gcion"]
+    if "gcion" in which:
+        gen_gc_ion()
     if "pypic" in which:
         gen_pypic()
     if "ddk" in which:

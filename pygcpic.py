@@ -372,16 +372,56 @@ class Grid:
         self.added_particles += 2 * particles
 
 
-def run_sheath(grid, store, dt, steps, source_N, source, p2c, m, charge_state=1, Z=1, time=0.0, on_step=None):
+def _ionizing_decisions(grid, store, dt, ionize_Te, inactive_entry, contrib_entry, Z, source_N, source):
+    """One pass of pygcpic.py:1509-1549 after the push for a store that may hold neutrals:
+    device probabilities + mid-domain exits, then the sequential event loop on the host (see
+    pypic_b200/ionization.py).  Returns (decision tensor, idx_react, r_new, n_del, tallies)."""
+    from pypic_b200 import ionization as ION
+    N = store.N
+    prob, elig, mx, contrib = store.post_push(grid, dt, ION.rates(ionize_Te), Z)
+    ev_ion = torch.nonzero(elig[:N] == 1).flatten()
+    ev_in = torch.nonzero(inactive_entry[:N] == 1).flatten()
+    ev = torch.cat([ev_ion, ev_in])
+    kind = torch.cat([torch.zeros_like(ev_ion), torch.ones_like(ev_in)])
+    order = torch.argsort(ev)
+    ev, kind = ev[order], kind[order]
+    ca = contrib[:N].to(torch.int64); ce = contrib_entry[:N].to(torch.int64)
+    A = torch.cumsum(ca, 0) - ca                                  # slots before the event, updated state
+    Bs = torch.flip(torch.cumsum(torch.flip(ce, [0]), 0), [0])    # slots from the event on, entry state
+    h = lambda t: t[ev].cpu().numpy()
+    r_new = []
+    ionised, new_cs, added, react, deleted = ION.run_events(
+        ev.cpu().numpy(), kind.cpu().numpy(), h(prob), h(store.charge_state), h(store.Z), h(store.p2c), h(mx), h(A), h(Bs),
+        int(Z), int(source_N), lambda i: r_new.append(next(source)))
+    if ionised:
+        ii = torch.as_tensor(np.asarray(ionised, dtype=np.int64), device=store.dev)
+        store.charge_state[ii] = torch.as_tensor(np.asarray(new_cs), device=store.dev)
+        store.invalidate_uniform()
+        for a in added:
+            grid.add_particles(a)
+    dec = torch.zeros(max(N, 1), dtype=torch.int8, device=store.dev)
+    if react:
+        dec[torch.as_tensor(np.asarray(react, dtype=np.int64), device=store.dev)] = 1
+    if deleted:
+        dec[torch.as_tensor(np.asarray(deleted, dtype=np.int64), device=store.dev)] = 2
+    Zi = h(store.Z)[np.searchsorted(ev.cpu().numpy(), np.asarray(ionised, dtype=np.int64))] if ionised else np.zeros(0)
+    tall = dict(ionised_h=int((Zi == 1).sum()), ionised_b=int((Zi == 5).sum()), midexit=int(mx[:N].sum().item()))
+    return dec, np.asarray(react, dtype=np.int64), np.array(r_new).reshape(-1, 7), len(deleted), tall
+
+
+def run_sheath(grid, store, dt, steps, source_N, source, p2c, m, charge_state=1, Z=1, time=0.0, on_step=None,
+               ionize_Te=None):
     """Device-resident time loop with the structure of pic_bca_aps' particle phase
-    (pygcpic.py:1486-1563, without the BCA coupling and ionisation):
+    (pygcpic.py:1486-1563, without the BCA coupling; Monte-Carlo ionisation :350-458 and the
+    mid-domain exit of wall-born particles :1530-1541 when ionize_Te is given):
 
         apply_BCs -> deposit (+Boltzmann n0) -> smooth -> Newton-Boltzmann solve -> E ->
         [gather + Boris + BC fused] -> reactivate-or-delete decision (prefix scan) ->
         re-activation from `source` (host generator, legacy RNG order) -> stable compaction.
 
     grid: GridDev, store: ParticleStore.  Returns a dict of per-step tallies."""
-    out = dict(length=[], hits=[], deleted=[], reactivated=[], n0=[], ekin=[], angle=[])
+    out = dict(length=[], hits=[], deleted=[], reactivated=[], n0=[], ekin=[], angle=[], ionised_h=[], ionised_b=[],
+               midexit=[])
     for _ in range(int(steps)):
         time += dt
         if grid.have_fused_n:
@@ -400,12 +440,23 @@ def run_sheath(grid, store, dt, steps, source_N, source, p2c, m, charge_state=1,
         contrib_entry = store.source_ion_flags(Z)
         hits = store.push_6D(dt, grid, deposit=True)
         ke, ang, _ = store.wall_hit_tallies()
-        contrib_after = store.source_ion_flags(Z)
-        dec, n_react, n_del = store.decide(inactive_entry, contrib_entry, contrib_after, source_N)
-        if n_react:
-            idx = torch.nonzero(dec[:store.N] == 1).flatten().cpu().numpy()
-            r_new = np.array([next(source) for _ in idx])
-            store.reactivate(idx, r_new, p2c, m, charge_state, Z, time, grid)
+        if ionize_Te is None:
+            contrib_after = store.source_ion_flags(Z)
+            dec, n_react, n_del = store.decide(inactive_entry, contrib_entry, contrib_after, source_N)
+            if n_react:
+                idx = torch.nonzero(dec[:store.N] == 1).flatten().cpu().numpy()
+                r_new = np.array([next(source) for _ in idx])
+                store.reactivate(idx, r_new, p2c, m, charge_state, Z, time, grid)
+        else:
+            # Monte-Carlo ionisation + mid-domain exits (ionize_Te = electron temperature [K] of
+            # attempt_*_ionization's np.interp): decisions by the host event loop, index order
+            dec, idx, r_new, n_del, tall = _ionizing_decisions(grid, store, dt, ionize_Te, inactive_entry, contrib_entry,
+                                                               Z, source_N, source)
+            n_react = len(idx)
+            if n_react:
+                store.reactivate(idx, r_new, p2c, m, charge_state, Z, time, grid)
+            for k_, v_ in tall.items():
+                out[k_].append(v_)
         store.compact(dec)
         out["length"].append(store.N); out["hits"].append(hits); out["deleted"].append(n_del)
         out["reactivated"].append(n_react); out["n0"].append(grid.n0); out["ekin"].append(ke); out["angle"].append(ang)

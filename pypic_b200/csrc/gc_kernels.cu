@@ -384,6 +384,46 @@ __global__ void gc_tail_uniform_k(GCK k, GUni u, R7 r, long long first, int8_t* 
     if (bad && range_err) atomicAdd(range_err, bad);
 }
 
+// Post-push pass of pic_bca_aps' particle loop (pygcpic.py:1509-1541) for every particle:
+//  * Monte-Carlo ionisation attempts (attempt_first_ionization :350-395 for Z==1, charge 0;
+//    attempt_nth_ionization :397-458 for Z==5, charge < 3): eligibility flag and the probability
+//    density**2 * rate * dx * dt / p2c with the CIC-gathered number density; the uniform draw and
+//    the decision stay on the host (legacy stream, index order);
+//  * mid-domain exit of wall-born particles (:1530-1541): from_wall and L/2-L/8 < x < L/2+L/8 ->
+//    active = 0 (flag returned for the tallies);
+//  * the particle's deterministic contribution to the running source-ion count of :1544.
+// rate[0..3]: np.interp'd rate coefficients [m^3/s] for (Z,charge) = (1,0), (5,0), (5,1), (5,2).
+__global__ void gc_post_push_k(const double* __restrict__ x, const double* __restrict__ p2c, const double* __restrict__ cs,
+                               const int32_t* __restrict__ Z, const int8_t* __restrict__ from_wall,
+                               int8_t* __restrict__ active, const double* __restrict__ ngrid, int ng, double dx, double dt,
+                               double length, double r10, double r50, double r51, double r52, int src_Z,
+                               double* __restrict__ prob, int8_t* __restrict__ elig, int8_t* __restrict__ midexit,
+                               int8_t* __restrict__ contrib, long long N, int* __restrict__ range_err) {
+    int bad = 0;
+    const double lo = length / 2 - length / 8, hi = length / 2 + length / 8;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < N; i += (long long)gridDim.x * blockDim.x) {
+        const int act = active[i];
+        const int z = Z[i];
+        const double c = cs[i], X = x[i];
+        const bool el = act == 1 && ((z == 1 && c == 0.0) || (z == 5 && c < 3.0));
+        double pr = 0.0;
+        if (el) {
+            Cell cl = cell_dd(X, dx);
+            if (cl.iL < 0 || cl.iL > ng - 2) { ++bad; cl.iL = clampi(cl.iL, 0, ng - 2); }
+            const double dens = cl.wL * ngrid[cl.iL] + cl.wR * ngrid[cl.iL + 1];
+            const double rate = z == 1 ? r10 : (c == 0.0 ? r50 : (c == 1.0 ? r51 : r52));
+            pr = dens * dens * rate * dx * dt / p2c[i];
+        }
+        const bool mx = from_wall[i] != 0 && act == 1 && (lo < X && X < hi);
+        if (mx) active[i] = 0;
+        prob[i] = pr;
+        elig[i] = el ? 1 : 0;
+        midexit[i] = mx ? 1 : 0;
+        contrib[i] = (z == src_Z && act == 1 && c > 0.0 && !mx) ? 1 : 0;
+    }
+    if (bad && range_err) atomicAdd(range_err, bad);
+}
+
 // n_acc -> (n, rho) of a species-uniform store: n = n_acc, rho = (charge_state*e)*n  (pygcpic.py:880-883)
 __global__ void gc_uniform_finish_k(const double* __restrict__ n_acc, double* __restrict__ n, double* __restrict__ rho,
                                     int ng, double cs) {
@@ -836,6 +876,22 @@ int pic_dev_gc_push_boris_uniform(const pic_gc_params* p, double* const r[7], do
     }
     const long long done = nchunks * G_CHUNK;
     if (done < k.N) gc_tail_uniform_k<<<grid_for(k.N - done, 256, 4), 256, 0, st>>>(k, u, rr, done, active, at_wall, hit_flag, Egrid, n_acc, hit_count, range_err);
+    PIC_CHECK_LAUNCH();
+    return PIC_OK;
+}
+
+int pic_dev_gc_post_push(const double* x, const double* p2c, const double* charge_state, const int32_t* Z,
+                         const int8_t* from_wall, int8_t* active, const double* n_grid, int ng, double dx, double dt,
+                         double length, const double rate[4], int source_Z, double* prob, int8_t* eligible,
+                         int8_t* midexit, int8_t* contrib, int64_t N, int* range_err, void* stream) {
+    PIC_REQUIRE(N >= 0, "gc_post_push: N<0");
+    if (N == 0) return PIC_OK;
+    PIC_REQUIRE(x && p2c && charge_state && Z && from_wall && active && n_grid && rate && prob && eligible && midexit &&
+                    contrib && ng >= 2,
+                "gc_post_push: bad argument");
+    gc_post_push_k<<<grid_for(N, 256, 8), 256, 0, (cudaStream_t)stream>>>(x, p2c, charge_state, Z, from_wall, active, n_grid, ng,
+                                                                          dx, dt, length, rate[0], rate[1], rate[2], rate[3],
+                                                                          source_Z, prob, eligible, midexit, contrib, N, range_err);
     PIC_CHECK_LAUNCH();
     return PIC_OK;
 }

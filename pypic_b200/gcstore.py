@@ -290,6 +290,20 @@ class ParticleStore:
         _lib.call("pic_dev_gc_push_rk4", C.byref(P), C.byref(r7), D.ptr(self.charge_state), D.ptr(self.m),
                   D.ptr(self.active), D.ptr(grid.E) if grid is not None else None, D.ptr(self.range_err), D.stream())
 
+    def post_push(self, grid, dt, rate4, source_Z):
+        """pic_dev_gc_post_push: ionisation eligibility/probability, mid-domain exit of wall-born
+        particles (applied to `active`), deterministic source-ion contribution.  Returns device
+        tensors (prob f64, eligible i8, midexit i8, contrib i8)."""
+        n = max(self.N, 1)
+        prob = D.f64(n, self.dev)
+        elig = torch.empty(n, dtype=torch.int8, device=self.dev)
+        mx = torch.empty_like(elig); contrib = torch.empty_like(elig)
+        _lib.call("pic_dev_gc_post_push", D.ptr(self.r[0]), D.ptr(self.p2c), D.ptr(self.charge_state), D.ptr(self.Z),
+                  D.ptr(self.from_wall), D.ptr(self.active), D.ptr(grid.n), grid.ng, grid.dx, float(dt), grid.length,
+                  C.byref((C.c_double * 4)(*rate4)), int(source_Z), D.ptr(prob), D.ptr(elig), D.ptr(mx), D.ptr(contrib),
+                  self.N, D.ptr(self.range_err), D.stream())
+        return prob, elig, mx, contrib
+
     # -- reactivate-or-delete + compaction -------------------------------------------------
     def source_ion_flags(self, source_Z):
         """int8 flag: Z==source and active and charge_state>0 (pygcpic.py:1544)."""

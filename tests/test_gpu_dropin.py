@@ -308,3 +308,51 @@ def test_pygcpic_host_grid_n0_update_matches_device_grid():
     # closed form of pygcpic.py:895-903 for the second call
     eta = np.exp(phi / Te / 11600.)
     assert np.isfinite(hg.n0) and hg.n0 > 0
+
+
+def test_pygcpic_run_sheath_with_ionisation_golden(golden):
+    """N3: Monte-Carlo ionisation of neutral H and B(0..2), mid-domain exits of wall-born particles
+    and the reactivate-or-delete rule coupled through the running source-ion count, against the
+    reference's own objects driven through pic_bca_aps' particle loop (tests/golden/gc_ion.npz,
+    oracle/make_golden.py::gen_gc_ion): identical integer outcomes per step, identical number of
+    RNG draws consumed."""
+    import pygcpic as G
+    g = golden("gc_ion")
+    Ld = float(g["L"]); ngd = int(g["ng"]); Nd = int(g["N"]); dt = float(g["dt"]); p2c = float(g["p2c"])
+    Ti = float(g["Ti"]); Te = float(g["Te"]); source_N = int(g["source_N"]); B = g["B"]
+    n_ion, n_h0, n_b = 1500, 300, 300
+    p2c_n = p2c * 2e-4
+    np.random.seed(41)
+    host_grid = G.Grid(ngd, Ld, Te)
+    kinds = np.array([0] * n_ion + [1] * n_h0 + [2] * n_b)
+    np.random.shuffle(kinds)
+    parts = []
+    for kd in kinds:                       # same construction (and draw) order as the generator
+        if kd == 0:
+            p_ = G.Particle(G.mp, 1, p2c, Ti, Z=1, B0=B.copy(), E0=np.zeros(3), grid=host_grid)
+        elif kd == 1:
+            p_ = G.Particle(G.mp, 0, p2c_n, Ti, Z=1, B0=B.copy(), E0=np.zeros(3), grid=host_grid)
+            p_.from_wall = int(np.random.uniform() < 0.5)
+        else:
+            p_ = G.Particle(10.81 * G.mp, int(np.random.randint(0, 3)), p2c_n, Ti, Z=5, B0=B.copy(), E0=np.zeros(3), grid=host_grid)
+            p_.from_wall = int(np.random.uniform() < 0.5)
+        parts.append(p_)
+    r = np.array([p_.r for p_ in parts])
+    assert np.array_equal(r, g["r_init"])
+    assert np.array_equal([float(p_.charge_state) for p_ in parts], g["cs_init"])
+    assert np.array_equal([p_.from_wall for p_ in parts], g["from_wall_init"])
+    st = G.ParticleStore.from_arrays(r, g["cs_init"], g["m_init"], g["p2c_init"], Z=g["Z_init"],
+                                     from_wall=g["from_wall_init"], B=B)
+    grid = G.GridDev(ngd, Ld, Te)
+    src = G.source_distribution_6D(host_grid, Ti, G.mp)
+    out = G.run_sheath(grid, st, dt, 20, source_N, src, p2c, G.mp, ionize_Te=Te)
+    assert np.array_equal(out["length"], g["h_length"]) and np.array_equal(out["hits"], g["h_hits"])
+    assert np.array_equal(out["deleted"], g["h_ndel"]) and np.array_equal(out["reactivated"], g["h_nreact"])
+    assert np.array_equal(out["ionised_h"], g["h_nion_h"]) and np.array_equal(out["ionised_b"], g["h_nion_b"])
+    assert np.array_equal(out["midexit"], g["h_nexit"])
+    assert relmax(out["n0"], g["h_n0"]) < 1e-9
+    assert np.array_equal(st.charge_state[:st.N].cpu().numpy(), g["cs_final"])
+    assert np.array_equal(st.Z[:st.N].cpu().numpy(), g["Z_final"])
+    assert np.array_equal(st.flags_host()["active"], g["active_final"])
+    assert relmax(st.r_host(), g["r_final"]) < 1e-6
+    assert np.random.uniform() == float(g["next_uniform"])        # exactly as many draws as the reference
