@@ -207,7 +207,7 @@ def run_reference(args):
         "e2e": {"value": res["value"], "unit": "particle-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line))
+    return line
 
 
 # ----------------------------------------------------------------------------- GPU arm
@@ -371,9 +371,9 @@ def run_cuda(args):
                        "l2_policy": "inputs (%.1f GB of particle arrays per GPU) are far larger than the 126 MB L2" % (sim.N * 32 / 1e9)},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
         }
-        print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
+    return line if rank == 0 else None
 
 
 # ----------------------------------------------------------------------------- other movers
@@ -495,17 +495,37 @@ def run_other(args):
                          "traffic": None, "kernel": kname, "peak_source": peak_src, "kernel_ms_mean": float(np.mean(kms)),
                          "kernel_share_of_step": float(np.sum(kms) / ms), "algorithmic_bytes_per_launch": per_launch},
             "cpu_baseline": None, "e2e": None, "gpu_launches": int(launches() - l0), "clocks": sampler.summary()}
-    print(json.dumps(line))
+    return line
+
+
+class _StdoutGuard:
+    """Keeps the real stdout for the ONE JSON line: anything libraries print to fd 1 meanwhile
+    (e.g. NCCL's version banner) goes to stderr."""
+
+    def __enter__(self):
+        sys.stdout.flush()
+        self.real = os.dup(1)
+        os.dup2(2, 1)
+        return self
+
+    def __exit__(self, *exc):
+        sys.stdout.flush()
+        os.dup2(self.real, 1)
+        os.close(self.real)
+        return False
 
 
 def main():
     args = parse()
-    if args.impl == "reference":
-        run_reference(args)
-    elif args.workload != "sheath":
-        run_other(args)
-    else:
-        run_cuda(args)
+    with _StdoutGuard():
+        if args.impl == "reference":
+            line = run_reference(args)
+        elif args.workload != "sheath":
+            line = run_other(args)
+        else:
+            line = run_cuda(args)
+    if line is not None:
+        print(json.dumps(line), flush=True)
 
 
 if __name__ == "__main__":
