@@ -19,7 +19,9 @@ def test_two_rank_sheath_matches_single_gpu():
            "127.0.0.1", "--master-port", "29533", os.path.join(ROOT, "tools", "mgpu_check.py"), "200000"]
     res = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=ROOT)
     assert res.returncode == 0, res.stderr[-2000:]
-    line = [l for l in res.stdout.splitlines() if l.startswith("{")][-1]
-    out = json.loads(line)
+    lines = [json.loads(l) for l in res.stdout.splitlines() if l.startswith("{")]
+    out = [l for l in lines if "iters_sharded" in l][-1]
     assert out["ok"], out
     assert out["iters_sharded"] == out["iters_single"]
+    per = [l for l in lines if "periodic" in l][-1]["periodic"]
+    assert per["ok"], per

@@ -20,6 +20,9 @@ from pypic_b200.sheath import SheathSim  # noqa: E402
 KB, ME, MP = 1.38E-23, 9.11E-31, 1.67E-27
 
 
+rel = lambda a, b: float(np.max(np.abs(a - b)) / max(np.max(np.abs(b)), 1e-300))
+
+
 def main():
     rank = int(os.environ.get("RANK", "0")); local = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -62,12 +65,54 @@ def main():
         ref = single.download()
         xs = np.concatenate([p["x0"] for p in parts]); us = np.concatenate([p["u0"] for p in parts])
         act = np.concatenate([p["active"] for p in parts])
-        rel = lambda a, b: float(np.max(np.abs(a - b)) / max(np.max(np.abs(b)), 1e-300))
         res = dict(world=world, N=N, iters_sharded=its_s, iters_single=its_1, dead_local_rank0=dead_s, dead_single=dead_1,
                    E_rel=rel(out["E0"], ref["E0"]), x_rel=rel(xs, ref["x0"]), u_rel=rel(us, ref["u0"]),
                    flags_equal=bool(np.array_equal(act, ref["active"])))
         res["ok"] = bool(its_s == its_1 and res["flags_equal"] and res["E_rel"] < 1e-10 and res["x_rel"] < 1e-11)
         print(json.dumps(res))
+    # ---- the two periodic codes: rho / [jh|j1] all-reduced per deposit, field phase replicated
+    from pypic_b200.periodic import ExplicitSim, PeriodicImplicitSim
+    Np, Ngp = N, 256
+    Lp = dx * Ngp
+    xp = rs.uniform(0, Lp, Np); vp = rs.normal(0, np.sqrt(kT / ME), Np)
+    Ep = rs.normal(0, 1e4, Ngp)
+
+    def run_pypic(comm):
+        sim = PeriodicImplicitSim(Np, Ngp, dx, dt, Lp, Lp * 1e19 / Np, tol=1e-3, maxiter=20, comm=comm, device=dev)
+        sim.upload(xp, vp, Ep)
+        its = [sim.push()[0] for _ in range(4)]
+        sim.check()
+        return sim, its
+
+    def run_explicit(comm):
+        Le = dx * (Ngp - 1)
+        sim = ExplicitSim(Np, Ngp, dx, dt * 50, (Le + dx) * 1e16 / Np, q=(-1.602e-19, 1.602e-19), m=(ME, MP), n_split=Np // 2,
+                          comm=comm, device=dev)
+        sim.upload(xp, np.concatenate([vp[:Np // 2], vp[Np // 2:] * np.sqrt(ME / MP)]))
+        for _ in range(4):
+            sim.step()
+        sim.field_solve()
+        sim.check()
+        return sim
+    sp, its_p = run_pypic(Comm())
+    se = run_explicit(Comm())
+    op, oe = sp.download(), se.download()
+    if world > 1:
+        parts2 = [None] * world
+        dist.all_gather_object(parts2, dict(px=op["x0"], pv=op["v0"], ex=oe["x"], ev=oe["v"]))
+    else:
+        parts2 = [dict(px=op["x0"], pv=op["v0"], ex=oe["x"], ev=oe["v"])]
+    if rank == 0:
+        s1, its_1p = run_pypic(Comm(enabled=False)); e1 = run_explicit(Comm(enabled=False))
+        r1, r2 = s1.download(), e1.download()
+        cat = lambda k: np.concatenate([p[k] for p in parts2])
+        res2 = dict(pypic_iters_sharded=its_p, pypic_iters_single=its_1p, pypic_E_rel=rel(op["E0"], r1["E0"]),
+                    pypic_x_rel=rel(cat("px"), r1["x0"]), pypic_v_rel=rel(cat("pv"), r1["v0"]),
+                    explicit_E_rel=rel(oe["E"], r2["E"]), explicit_x_rel=rel(cat("ex"), r2["x"]),
+                    explicit_v_rel=rel(cat("ev"), r2["v"]))
+        res2["ok"] = bool(its_p == its_1p and res2["pypic_E_rel"] < 1e-10 and res2["pypic_x_rel"] < 1e-11 and
+                          res2["explicit_E_rel"] < 1e-9 and res2["explicit_x_rel"] < 1e-11)
+        print(json.dumps(dict(periodic=res2)))
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
