@@ -785,3 +785,89 @@ def gc_compact_stable(arrays, delete_mask):
     """pygcpic.py:1552-1563: order-preserving removal of flagged indices."""
     keep = ~delete_mask
     return [a[keep] for a in arrays]
+
+
+# --------------------------------------------------------------------------
+# Monte-Carlo ionisation inside the particle loop (pygcpic.py:350-458, 1496-1549)
+# --------------------------------------------------------------------------
+_ION_TABLES = {     # (Z, charge_state) -> (Te [eV], R [cm^3/s]); data of pygcpic.py:373-383, 409-438
+    (1, 0): ([8.626E-01, 1.011E+00, 2.178E+00, 3.539E+00, 5.146E+00, 7.069E+00, 9.410E+00, 1.231E+01, 1.598E+01,
+              2.076E+01, 2.720E+01, 3.625E+01, 4.973E+01, 7.133E+01, 1.099E+02, 1.904E+02, 4.079E+02, 1.355E+03,
+              1.390E+04, 8.595E+04],
+             [7.553E-16, 8.291E-15, 1.714E-11, 2.470E-10, 9.985E-10, 2.398E-09, 4.412E-09, 6.940E-09, 9.869E-09,
+              1.309E-08, 1.649E-08, 1.996E-08, 2.329E-08, 2.624E-08, 2.834E-08, 2.881E-08, 2.627E-08, 1.926E-08,
+              8.109E-09, 3.829E-09]),
+    (5, 0): ([8.626E-01, 1.329E+00, 2.160E+00, 3.140E+00, 4.314E+00, 5.741E+00, 7.508E+00, 9.746E+00, 1.267E+01,
+              1.660E+01, 2.212E+01, 3.034E+01, 4.353E+01, 6.704E+01, 1.162E+02, 2.490E+02, 8.265E+02, 8.481E+03,
+              8.669E+04],
+             [1.057E-12, 3.996E-11, 5.912E-10, 2.458E-09, 6.083E-09, 1.155E-08, 1.878E-08, 2.767E-08, 3.806E-08,
+              4.979E-08, 6.257E-08, 7.590E-08, 8.901E-08, 1.005E-07, 1.080E-07, 1.079E-07, 9.470E-08, 5.161E-08,
+              2.159E-08]),
+    (5, 1): ([8.612E-01, 1.869E+00, 4.028E+00, 6.547E+00, 9.522E+00, 1.308E+01, 1.741E+01, 2.276E+01, 2.956E+01,
+              3.840E+01, 5.031E+01, 6.707E+01, 9.203E+01, 1.319E+02, 2.033E+02, 3.522E+02, 7.547E+02, 2.505E+03,
+              2.571E+04, 8.582E+04],
+             [1.375E-21, 1.396E-14, 2.693E-11, 3.643E-10, 1.393E-09, 3.188E-09, 5.629E-09, 8.554E-09, 1.182E-08,
+              1.533E-08, 1.900E-08, 2.273E-08, 2.639E-08, 2.972E-08, 3.221E-08, 3.300E-08, 3.032E-08, 2.252E-08,
+              9.306E-09, 5.538E-09]),
+    (5, 2): ([1.366E+00, 2.819E+00, 6.073E+00, 9.875E+00, 1.436E+01, 1.972E+01, 2.624E+01, 3.432E+01, 4.456E+01,
+              5.790E+01, 7.587E+01, 1.012E+02, 1.387E+02, 1.990E+02, 3.064E+02, 5.311E+02, 1.138E+03, 3.778E+03,
+              3.877E+04, 8.602E+04],
+             [1.230E-21, 2.871E-15, 5.524E-12, 7.439E-11, 2.824E-10, 6.401E-10, 1.117E-09, 1.677E-09, 2.293E-09,
+              2.946E-09, 3.629E-09, 4.337E-09, 5.055E-09, 5.759E-09, 6.382E-09, 6.779E-09, 6.575E-09, 5.269E-09,
+              2.483E-09, 1.829E-09]),
+}
+
+
+def gc_ionization_probability(x, p2c, Z, charge_state, n, dx, dt, temperature):
+    """pygcpic.py:385-391 / 440-446 for ONE particle: np.interp'd rate, CIC-gathered density."""
+    Te, R = _ION_TABLES[(int(Z), int(charge_state))]
+    rate = np.interp(temperature, [T * 11600. for T in Te], [r_ / 1e6 for r_ in R])
+    il = int(np.floor(x / dx))
+    w_r = (x % dx) / dx
+    w_l = 1.0 - w_r
+    density = w_l * n[il] + w_r * n[il + 1]
+    return density ** 2 * rate * dx * dt / p2c
+
+
+def gc_ionizing_particle_loop(r, cs, m, p2c, Z, active, at_wall, from_wall, E, n, B, dt, dx, length, Te, source_Z,
+                              source_N, source, src_p2c, src_m, time, rng=np.random):
+    """One pass of the particle loop of pic_bca_aps (pygcpic.py:1496-1549) over SoA arrays,
+    sequential like the reference (test sizes only).  Mutates the arrays; returns
+    (hits, reactivated, deleted indices, ionised H, ionised B, mid exits, added p2c list)."""
+    N = len(cs)
+    nh = nr = nih = nib = nex = 0
+    deleted, added = [], []
+    for i in range(N):
+        if active[i] == 1:
+            Ex = gc_gather_mirrored(E, r[i:i + 1, 0], dx)
+            r[i] = gc_push_6D(r[i:i + 1], Ex, B, cs[i], m[i], dt)[0]
+            if r[i, 0] < 0.0 or r[i, 0] > length:
+                active[i] = 0; at_wall[i] = 1
+            tried = False
+            if Z[i] == 1 and cs[i] == 0 and active[i] == 1:
+                pr = gc_ionization_probability(r[i, 0], p2c[i], 1, 0, n, dx, dt, Te)
+                if rng.uniform(0., 1.) < pr and cs[i] == 0.:
+                    cs[i] = 1; added.append(p2c[i]); nih += 1
+                tried = True
+            if Z[i] == 5 and cs[i] < 3 and active[i] == 1:
+                pr = gc_ionization_probability(r[i, 0], p2c[i], 5, cs[i], n, dx, dt, Te)
+                if rng.uniform(0., 1.) < pr and cs[i] == 0.:
+                    cs[i] += 1; added.append(p2c[i]); nib += 1
+            if active[i] != 1 and at_wall[i]:
+                nh += 1
+            dxm = length / 8
+            if from_wall[i] and (length / 2 - dxm < r[i, 0] < length / 2 + dxm):
+                if active[i] == 1:
+                    nex += 1
+                active[i] = 0
+        else:
+            count = int(np.sum((Z == source_Z) & (active == 1) & (cs > 0)))
+            if count < source_N:
+                rn = next(source)
+                r[i] = rn; r[i, 6] = time
+                p2c[i] = src_p2c; m[i] = src_m; cs[i] = 1; Z[i] = source_Z
+                active[i] = 1; at_wall[i] = 0; from_wall[i] = 0
+                added.append(src_p2c); nr += 1
+            else:
+                deleted.append(i)
+    return nh, nr, deleted, nih, nib, nex, added

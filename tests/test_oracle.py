@@ -258,3 +258,75 @@ def test_c_oracle_matches_numpy_oracle(nthreads):
     assert ck == k and np.array_equal(a1, a2)
     assert relmax(cE1, E1) < 1e-12 and relmax(cj1, j1) < 1e-12
     assert relmax(cx1, x1) < 1e-13 and relmax(cu1, u1) < 1e-13
+
+
+def test_gc_ionising_loop_golden(golden):
+    """The oracle's restatement of pic_bca_aps' particle loop WITH Monte-Carlo ionisation
+    (pygcpic.py:350-458, 1496-1549) against the reference's own objects (gc_ion.npz): identical
+    integer outcomes per step, identical charge states and RNG draw count."""
+    g = golden("gc_ion")
+    Ld = float(g["L"]); ng = int(g["ng"]); dt = float(g["dt"]); p2c = float(g["p2c"]); Ti = float(g["Ti"]); Te = float(g["Te"])
+    source_N = int(g["source_N"]); B = g["B"]
+    # replay the construction of the generator (same seed, same draw order) to get the exact
+    # legacy-stream state, including a cached gaussian
+    np.random.seed(41)
+    n_ion, n_h0, n_b = 1500, 300, 300
+    kinds = np.array([0] * n_ion + [1] * n_h0 + [2] * n_b)
+    np.random.shuffle(kinds)
+    vth = {0: np.sqrt(O.kb * Ti / O.mp), 1: np.sqrt(O.kb * Ti / O.mp), 2: np.sqrt(O.kb * Ti / (10.81 * O.mp))}
+    N = len(kinds)
+    r = np.zeros((N, 7))
+    for i, kd in enumerate(kinds):                 # Particle._initialize_6D draw order, pygcpic.py:299-301
+        if kd == 2:
+            np.random.randint(0, 3)                # the boron charge state is drawn as a constructor ARGUMENT
+        r[i, 0] = np.random.uniform(0.0, Ld)
+        r[i, 3:6] = np.random.normal(0.0, vth[int(kd)], 3) + 0.
+        if kd != 0:
+            np.random.uniform()                    # from_wall flag
+    assert np.array_equal(r, g["r_init"])
+    cs = g["cs_init"].copy(); m = g["m_init"].copy(); pc = g["p2c_init"].copy(); Z = g["Z_init"].copy()
+    fw = g["from_wall_init"].copy()
+    active = np.ones(N, dtype=np.int64); at_wall = np.zeros(N, dtype=np.int64)
+    dx = Ld / (ng - 1)
+    domain = np.linspace(0.0, Ld, ng)
+    dx = domain[1] - domain[0]
+    ve = np.sqrt(8. / np.pi * O.kb * Te / O.me)
+
+    def source():
+        while True:                                 # source_distribution_6D, pygcpic.py:745-753
+            v = np.sqrt(O.kb * Ti / O.mp)
+            rn = np.empty(7)
+            rn[0] = np.random.normal(Ld / 2, Ld / 12.0)
+            rn[0] %= Ld
+            rn[1:3] = 0.
+            rn[3:6] = np.random.normal(0.0, v, 3) + 0.
+            yield rn
+    src = source()
+    n0 = None; p_old = None; added_particles = 0.0; phi = np.zeros(ng)
+    time = 0.
+    H = dict(length=[], hits=[], ndel=[], nreact=[], nion_h=[], nion_b=[], nexit=[], n0=[])
+    for step in range(20):
+        time += dt
+        active, at_wall = O.gc_apply_BCs_dirichlet(r[:, 0], active, at_wall, Ld)
+        rho, n = O.gc_weight_particles(r[:, 0], cs, pc, active, ng, dx)
+        n0, rho0, p_old = O.gc_boltzmann_n0_update(phi, domain, Te, n, n0, p_old, added_particles, dt, ve)
+        rho = O.gc_smooth_rho(rho)
+        added_particles = 0.0
+        phi, _ = O.gc_solve_for_phi_dirichlet_boltzmann(rho, n0, Te, dx)
+        E = O.gc_differentiate_phi_to_E(phi, dx)
+        nh, nr, deleted, nih, nib, nex, added = O.gc_ionizing_particle_loop(
+            r, cs, m, pc, Z, active, at_wall, fw, E, n, B, dt, dx, Ld, Te, 1, source_N, src, p2c, O.mp, time)
+        for a in added:
+            added_particles += 2 * a
+        keep = np.ones(len(cs), dtype=bool); keep[deleted] = False
+        r, cs, m, pc, Z, active, at_wall, fw = (a[keep] for a in (r, cs, m, pc, Z, active, at_wall, fw))
+        for k_, v_ in (("length", len(cs)), ("hits", nh), ("ndel", len(deleted)), ("nreact", nr), ("nion_h", nih),
+                       ("nion_b", nib), ("nexit", nex), ("n0", n0)):
+            H[k_].append(v_)
+    for k_ in ("length", "hits", "ndel", "nreact", "nion_h", "nion_b", "nexit"):
+        assert np.array_equal(H[k_], g["h_" + k_]), k_
+    assert relmax(H["n0"], g["h_n0"]) < 1e-9
+    assert np.array_equal(cs, g["cs_final"]) and np.array_equal(Z, g["Z_final"])
+    assert np.array_equal(active, g["active_final"])
+    assert relmax(r, g["r_final"]) < 1e-6
+    assert np.random.uniform() == float(g["next_uniform"])
