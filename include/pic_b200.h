@@ -338,6 +338,11 @@ int pic_dev_gc_to_6d(const pic_gc_params* p, double* const r[7], const double* c
 int pic_dev_gc_push_rk4(const pic_gc_params* p, double* const r[7], const double* charge_state,
                         const double* m, const int8_t* active, const double* Egrid, int* range_err,
                         void* stream);
+/* The same step for a species-uniform store (scalars instead of the charge_state / m arrays):
+ * the ExB drift terms are computed once per particle and the divisions by uniform quantities
+ * use a correctly rounded constant-divisor division (bit-identical results). */
+int pic_dev_gc_push_rk4_uniform(const pic_gc_params* p, double* const r[7], double charge_state, double m,
+                                const int8_t* active, const double* Egrid, int* range_err, void* stream);
 /* Boltzmann reference-density update, Grid.weight_particles_to_grid_boltzmann :889-904.
  * domain = Grid.domain (np.linspace(0,length,ng)) so np.trapz's spacings are reproduced;
  * state fp64[3] = {n0, p_old, initialised(0/1)} on the device. */

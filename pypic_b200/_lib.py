@@ -99,6 +99,7 @@ _SIGS = {
     "pic_dev_gc_to_gc": [C.POINTER(GCParams), C.POINTER(R7), P, P, P, P],
     "pic_dev_gc_to_6d": [C.POINTER(GCParams), C.POINTER(R7), P, P, P, P, P, P, P],
     "pic_dev_gc_push_rk4": [C.POINTER(GCParams), C.POINTER(R7), P, P, P, P, P, P],
+    "pic_dev_gc_push_rk4_uniform": [C.POINTER(GCParams), C.POINTER(R7), F64, F64, P, P, P, P],
     "pic_dev_gc_n0_update": [P, P, P, I32, F64, F64, F64, F64, P, P],
     "pic_dev_gc_decide": [P, P, P, P, I64, I64, P, P, P, P],
     "pic_dev_compact_flags": [P, I64, I32, P, P, P, P],

@@ -1144,7 +1144,7 @@ static int sort_by_cell_impl(const DDK& k, const double* x0, const double* u0, c
     const int nk = 2 * k.Ng;
     const size_t smem = (size_t)nk * sizeof(int);
     const size_t smem_sc = 2 * smem;
-    const bool big = smem_sc > (size_t)max_optin_smem() - 1024;
+    const bool big = smem_sc > (size_t)max_optin_smem() - 1024 || (k.flags & 32);   // bit5: force (experiments)
     // big: counts needs nk + 2 + ceil(nk/1024) + 2 entries (block sums of the three-pass scan behind the keys)
     const int nblk = (nk + 1023) / 1024;
     PIC_CHECK_CUDA(cudaMemsetAsync(counts, 0, (size_t)(nk + 2 + (big ? nblk + 2 : 0)) * sizeof(int32_t), st));

@@ -3,6 +3,7 @@
 // Dirichlet wall absorption, (rho,n) deposit, Boltzmann reference-density update, the
 // order-dependent reactivate-or-delete rule as a prefix scan, and warp-ballot stable
 // stream compaction.
+#include <stdlib.h>
 #include "common.cuh"
 #include "ring.cuh"
 #include "host_common.h"
@@ -558,6 +559,63 @@ __global__ void gc_push_rk4_k(GCK k, R7 r, const double* __restrict__ cs, const 
     if (bad && range_err) atomicAdd(range_err, bad);
 }
 
+// The same RK4 step for a species-uniform store.  E and B are frozen over the step
+// (pygcpic.py:606-612), so the ExB drift terms are computed once per particle, and every division
+// whose divisor is uniform (B^2, |B|, the cyclotron frequency, 6) is done with div_const (two
+// Markstein corrections from the correctly rounded reciprocal: bit-identical to the IEEE division,
+// checked on the device by pic_dev_selftest_div for each constant before the first launch); one
+// true division per stage (by the per-particle rho) is left.  5 arrays in/out, 80 B/particle.
+struct GRk { double B2, sB, b0, b1, b2, wc, yB2, ysB, ywc, y6, c0; };
+template <int MINB>
+__global__ void __launch_bounds__(256, MINB) gc_push_rk4_uniform_k(GCK k, GRk u, R7 r, const int8_t* __restrict__ active,
+                                                            const double* __restrict__ Egrid,
+                                                            int* __restrict__ range_err) {
+    int bad = 0;
+    const double dt = k.dt;
+    const double E1 = k.Eyz[0], E2 = k.Eyz[1];
+    const double idx = 1.0 / k.dx;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < k.N; i += (long long)gridDim.x * blockDim.x) {
+        if (active[i] != 1) continue;
+        const double r0 = ld_stream(r.r[0] + i), r1 = ld_stream(r.r[1] + i), r2 = ld_stream(r.r[2] + i);
+        const double r3 = ld_stream(r.r[3] + i);
+        double E0 = 0.0;
+        if (Egrid) {
+            if (k.flags & 1) E0 = Egrid[i];
+            else {
+                Cell c = cell_dd_fast(r0, k.dx, idx);
+                if (c.iL < 0 || c.iL > k.ng - 2) { ++bad; c.iL = clampi(c.iL, 0, k.ng - 2); }
+                const double w_l = c.wR, w_r = 1.0 - w_l;                   // mirrored, pygcpic.py:344-347
+                E0 = Egrid[c.iL] * w_l + Egrid[c.iL + 1] * w_r;
+            }
+        }
+        // drift terms of _eom_GC (pygcpic.py:636-638), identical in the four stages
+        const double g1 = div_const(E2 * k.B[0] - E0 * k.B[2], u.B2, u.yB2);
+        const double g2 = div_const(E0 * k.B[1] - E1 * k.B[0], u.B2, u.yB2);
+#define GC_EOM(a0, a1, a2, a3, d0, d1, d2, d3)                                                    \
+        do {                                                                                      \
+            const double rho_ = div_const((a3), u.wc, u.ywc);                                     \
+            d0 = u.c0 + (a3) * u.b0; d1 = g1 + (a3) * u.b1; d2 = g2 + (a3) * u.b2;                \
+            d3 = div_const(E0 * (a0) + E1 * (a1) + E2 * (a2), u.sB, u.ysB) / rho_;               \
+        } while (0)
+        double f0, f1, f2, f3;
+        GC_EOM(r0, r1, r2, r3, f0, f1, f2, f3);
+        const double k10 = dt * f0, k11 = dt * f1, k12 = dt * f2, k13 = dt * f3;
+        GC_EOM(r0 + k10 / 2., r1 + k11 / 2., r2 + k12 / 2., r3 + k13 / 2., f0, f1, f2, f3);
+        const double k20 = dt * f0, k21 = dt * f1, k22 = dt * f2, k23 = dt * f3;
+        GC_EOM(r0 + k20 / 2., r1 + k21 / 2., r2 + k22 / 2., r3 + k23 / 2., f0, f1, f2, f3);
+        const double k30 = dt * f0, k31 = dt * f1, k32 = dt * f2, k33 = dt * f3;
+        GC_EOM(r0 + k30, r1 + k31, r2 + k32, r3 + k33, f0, f1, f2, f3);
+        const double k40 = dt * f0, k41 = dt * f1, k42 = dt * f2, k43 = dt * f3;
+#undef GC_EOM
+        st_stream(r.r[0] + i, r0 + div_const(k10 + 2. * k20 + 2. * k30 + k40, 6., u.y6));
+        st_stream(r.r[1] + i, r1 + div_const(k11 + 2. * k21 + 2. * k31 + k41, 6., u.y6));
+        st_stream(r.r[2] + i, r2 + div_const(k12 + 2. * k22 + 2. * k32 + k42, 6., u.y6));
+        st_stream(r.r[3] + i, r3 + div_const(k13 + 2. * k23 + 2. * k33 + k43, 6., u.y6));
+        r.r[6][i] = r.r[6][i] + dt;
+    }
+    if (bad && range_err) atomicAdd(range_err, bad);
+}
+
 // pygcpic.py:889-904.  state = {n0, p_old, initialised}
 __global__ void gc_n0_update_k(const double* __restrict__ phi, const double* __restrict__ n,
                                const double* __restrict__ domain, int ng, double Te, double ve, double added,
@@ -953,6 +1011,33 @@ int pic_dev_gc_push_rk4(const pic_gc_params* p, double* const r[7], const double
     R7 rr;
     for (int i = 0; i < 7; ++i) rr.r[i] = r[i];
     gc_push_rk4_k<<<grid_for(k.N, 256, 6), 256, 0, (cudaStream_t)stream>>>(k, rr, charge_state, m, active, Egrid, range_err);
+    PIC_CHECK_LAUNCH();
+    return PIC_OK;
+}
+
+int pic_dev_gc_push_rk4_uniform(const pic_gc_params* p, double* const r[7], double charge_state, double m,
+                                const int8_t* active, const double* Egrid, int* range_err, void* stream) {
+    PIC_REQUIRE(p && r && active, "gc_push_rk4_uniform: null pointer");
+    if (p->N == 0) return PIC_OK;
+    GCK k = make_gck(p);
+    R7 rr;
+    for (int i = 0; i < 7; ++i) rr.r[i] = r[i];
+    GRk u;
+    u.B2 = k.B[0] * k.B[0] + k.B[1] * k.B[1] + k.B[2] * k.B[2];
+    u.sB = sqrt(u.B2);
+    u.b0 = k.B[0] / u.sB; u.b1 = k.B[1] / u.sB; u.b2 = k.B[2] / u.sB;
+    u.wc = fabs(charge_state) * PIC_E * u.sB / m;                       // pygcpic.py:629
+    u.yB2 = 1.0 / u.B2; u.ysB = 1.0 / u.sB; u.ywc = 1.0 / u.wc; u.y6 = 1.0 / 6.0;
+    u.c0 = (k.Eyz[0] * k.B[2] - k.Eyz[1] * k.B[1]) / u.B2;              // :636, uniform
+    PIC_REQUIRE(u.B2 > 0.0 && u.wc > 0.0, "gc_push_rk4_uniform: needs B != 0 and a charged species");
+    static int minb = -1;
+    if (minb < 0) { const char* e = getenv("PIC_RK4_MINB"); minb = e ? atoi(e) : 4; }   // 4 CTAs/SM measured best (2.14 ms per 1e8; 2: 3.43, 3: 2.50, 5: 2.06, 6: 3.01)
+    cudaStream_t st = (cudaStream_t)stream;
+    if (minb == 2) gc_push_rk4_uniform_k<2><<<grid_for(k.N, 256, 2), 256, 0, st>>>(k, u, rr, active, Egrid, range_err);
+    else if (minb == 4) gc_push_rk4_uniform_k<4><<<grid_for(k.N, 256, 4), 256, 0, st>>>(k, u, rr, active, Egrid, range_err);
+    else if (minb == 5) gc_push_rk4_uniform_k<5><<<grid_for(k.N, 256, 5), 256, 0, st>>>(k, u, rr, active, Egrid, range_err);
+    else if (minb == 6) gc_push_rk4_uniform_k<6><<<grid_for(k.N, 256, 6), 256, 0, st>>>(k, u, rr, active, Egrid, range_err);
+    else gc_push_rk4_uniform_k<3><<<grid_for(k.N, 256, 3), 256, 0, st>>>(k, u, rr, active, Egrid, range_err);
     PIC_CHECK_LAUNCH();
     return PIC_OK;
 }

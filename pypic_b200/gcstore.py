@@ -284,9 +284,16 @@ class ParticleStore:
         torch.cuda.current_stream().synchronize()
         self.mode = 0
 
+    RK4_UNIFORM = True                              # class switch for tests (v1 kernel when False)
+
     def push_GC(self, dt, grid=None):
         P = self._params(grid, dt)
         r7 = self._r7()
+        u = self.uniform() if self.RK4_UNIFORM else None
+        if u is not None and u[0] != 0.0 and any(self.B):
+            _lib.call("pic_dev_gc_push_rk4_uniform", C.byref(P), C.byref(r7), u[0], u[1], D.ptr(self.active),
+                      D.ptr(grid.E) if grid is not None else None, D.ptr(self.range_err), D.stream())
+            return
         _lib.call("pic_dev_gc_push_rk4", C.byref(P), C.byref(r7), D.ptr(self.charge_state), D.ptr(self.m),
                   D.ptr(self.active), D.ptr(grid.E) if grid is not None else None, D.ptr(self.range_err), D.stream())
 

@@ -291,3 +291,32 @@ def test_store_sort_by_cell_is_a_cell_ordered_permutation():
     assert np.all(np.diff(cells) >= 0)
     st.sort_by_cell(grid, track=True)          # a second sort composes
     assert np.array_equal(st.r_host(), r[st.perm.cpu().numpy()])
+
+
+def test_uniform_rk4_kernel_is_bit_identical_to_v1():
+    """gc_push_rk4_uniform_k (drift terms hoisted, constant-divisor divisions) vs gc_push_rk4_k
+    on the same guiding-centre state: every component bit-identical (incl. negative and tiny
+    numerators of the constant-divisor divisions), several steps."""
+    import torch
+    from pypic_b200.gcstore import GridDev, ParticleStore
+    rs = np.random.RandomState(13)
+    N, ng, Lg = 300000, 200, 2.5e-3
+    r = np.zeros((N, 7))
+    r[:, 0] = rs.uniform(0.05 * Lg, 0.95 * Lg, N); r[:, 1:3] = rs.normal(0, 1e-3, (N, 2))
+    r[:, 3] = rs.normal(0, 7e4, N); r[rs.choice(N, 1000), 3] *= 1e-6        # small v_par: large rho-divisions
+    r[:, 4] = np.abs(rs.normal(0, 1e-17, N)); r[:, 5] = rs.normal(0, 7e4, N)
+    E = rs.normal(0, 5e4, ng)
+    out = {}
+    for Bv, Eyz in (((2 * np.cos(1.5), 2 * np.sin(1.5), 0.), (0., 0.)), ((0.3, -1.1, 0.7), (35., -12.))):
+        for uni in (True, False):
+            grid = GridDev(ng, Lg, 6e5)
+            grid.E.copy_(torch.as_tensor(E))
+            st = ParticleStore.from_arrays(r, 1.0, O.mp, 2e9, Z=1, B=Bv, Eyz=Eyz)
+            st.mode = 1
+            st.RK4_UNIFORM = uni
+            for _ in range(3):
+                st.push_GC(1e-10, grid)
+            st.check()
+            out[uni] = st.r_host()
+        assert np.array_equal(out[True], out[False])
+        assert not np.array_equal(out[True][:, :4], r[:, :4])

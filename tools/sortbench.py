@@ -7,7 +7,7 @@ from pypic_b200 import _lib, device as D
 N = int(float(sys.argv[1])) if len(sys.argv) > 1 else 200000000
 Ng = int(sys.argv[2]) if len(sys.argv) > 2 else 4097; dx = 1e-5; L = dx * (Ng - 1)
 dev = torch.device("cuda", 0)
-P = _lib.DDParams(N, N // 2, Ng, 0, dx, 1e-12, L, 1.0, (C.c_double * 2)(0, 0), (C.c_double * 2)(1, 1))
+P = _lib.DDParams(N, N // 2, Ng, int(sys.argv[3]) if len(sys.argv) > 3 else 0, dx, 1e-12, L, 1.0, (C.c_double * 2)(0, 0), (C.c_double * 2)(1, 1))
 x = torch.empty(N, dtype=torch.float64, device=dev).uniform_(0, L); u = torch.randn(N, dtype=torch.float64, device=dev)
 xs = torch.empty_like(x); us = torch.empty_like(u)
 cnt = torch.zeros(D.sort_counts_size(Ng), dtype=torch.int32, device=dev)
