@@ -1,0 +1,375 @@
+"""Spatial (slab) domain decomposition of the bounded two-species sheath (BASELINE config 5;
+a capability the reference does not have -- SURVEY.md 8e).
+
+Rank r owns the cells [c_r, c_{r+1}) of the global grid and the particles inside them, one
+structure-of-arrays block per species.  The particle kernels are the ones of the
+particle-decomposed path (pypic_b200/sheath.py: fused gather + CN push + walls + jh/j1 deposit
+on the global node numbering), so what changes is the communication:
+
+* **halo exchange** instead of an all-reduce of the whole grid: a rank's particles deposit only
+  on its own nodes and on `guard` nodes either side, so per Picard iteration the two strips of
+  guard nodes go to the two neighbours (point-to-point) and are added there; the completed
+  owned segments (plus the four absorbed-particle counts) are then all-gathered so that the
+  (cheap, replicated) field update sees the whole grid;
+* **particle migration**: every `sort_every` steps each species block is counting-sorted by cell
+  (pic_dev_dd_sort_by_cell).  In a sorted block the particles that left the slab are contiguous
+  runs at its two ends, ordered by destination rank, so the send buffers are views of the sorted
+  array (no packing pass) and one all-to-all moves them; arrivals are placed in the headroom
+  directly before / after the stayers (no copy of the bulk).  `guard` must cover the drift of
+  `sort_every` steps;
+* **re-injection** (PIC_L_DD.py:429-450) draws x uniformly over the WHOLE domain, so a revived
+  particle usually belongs to another rank: the draws of a step are keyed by the global ordinal of
+  the dead particle within its species (Philox; the particle set is therefore identical for any
+  number of ranks), the ones that land elsewhere are shipped immediately (all-to-all) and their
+  slots are closed by swap-removal.
+"""
+import ctypes as C
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+from . import _lib, device as D
+from .dist import Comm
+
+epsilon0 = 8.854E-12
+e = 1.602E-19
+mp = 1.67E-27
+me = 9.11E-31
+
+
+def slab_bounds(Ng, world):
+    """First cell of every rank's slab (world+1 entries; cells = Ng-1)."""
+    cells = int(Ng) - 1
+    return [r * cells // int(world) for r in range(int(world))] + [cells]
+
+
+def swap_remove_plan(n, holes, n_arrivals):
+    """Index plan that closes `holes` (ascending slot indices < n) of a block of n slots and adds
+    n_arrivals new particles, moving as little as possible: arrivals fill holes first; left-over
+    holes are filled from the block's tail (slots that are not holes themselves); left-over
+    arrivals are appended.  Returns (arrival_dst, move_src, move_dst, new_n)."""
+    holes = np.asarray(holes, dtype=np.int64)
+    k = min(len(holes), int(n_arrivals))
+    arrival_dst = list(holes[:k])
+    rest = holes[k:]
+    if len(rest) == 0:
+        extra = int(n_arrivals) - k
+        arrival_dst += list(range(n, n + extra))
+        return np.asarray(arrival_dst, dtype=np.int64), np.zeros(0, np.int64), np.zeros(0, np.int64), n + extra
+    new_n = n - len(rest)
+    hole_set = set(int(h) for h in rest)
+    src = [s for s in range(new_n, n) if s not in hole_set]
+    dst = [int(h) for h in rest if h < new_n]
+    assert len(src) == len(dst)
+    return (np.asarray(arrival_dst, dtype=np.int64), np.asarray(src, dtype=np.int64), np.asarray(dst, dtype=np.int64), new_n)
+
+
+class _Block:
+    """One species on one rank: current state (x0,u0) as views into one of two allocations,
+    the other allocation is the Picard / sort scratch."""
+
+    def __init__(self, cap, dev, species):
+        self.cap, self.dev, self.species = int(cap), dev, species
+        self.X = [D.f64(self.cap, dev, True), D.f64(self.cap, dev, True)]
+        self.U = [D.f64(self.cap, dev, True), D.f64(self.cap, dev, True)]
+        self.cur, self.off, self.n = 0, 0, 0
+        self.active = torch.ones(self.cap, dtype=torch.int8, device=dev)
+        self.dead_idx = torch.empty(self.cap, dtype=torch.int32, device=dev)
+        self.count = torch.zeros(1, dtype=torch.int64, device=dev)
+        self.block_counts = torch.zeros(2 * (self.cap // 2048 + 2), dtype=torch.int64, device=dev)
+
+    # current / scratch views (the scratch always starts at slot 0 of the other allocation)
+    @property
+    def x0(self): return self.X[self.cur][self.off:]
+    @property
+    def u0(self): return self.U[self.cur][self.off:]
+    @property
+    def x1(self): return self.X[1 - self.cur]
+    @property
+    def u1(self): return self.U[1 - self.cur]
+
+    def commit(self):
+        self.cur, self.off = 1 - self.cur, 0
+
+
+class SlabSheathSim:
+    def __init__(self, N, Ng, dx, dt, p2c, q=(-e, e), m=(me, mp), kBT=(None, None), tol=1e-5, maxiter=20, seed=1,
+                 comm=None, device=None, sort_every=8, guard=16, capacity=1.3, headroom=None):
+        self.dev = D.require_cuda(device)
+        self.comm = comm if comm is not None else Comm()
+        self.rank, self.world = self.comm.rank, self.comm.world
+        self.N_global, self.Ng, self.dx, self.dt, self.p2c = int(N), int(Ng), float(dx), float(dt), float(p2c)
+        self.L = dx * (Ng - 1)
+        self.q, self.m, self.kBT = tuple(q), tuple(m), tuple(kBT)
+        self.tol, self.maxiter, self.seed = float(tol), int(maxiter), int(seed)
+        self.sort_every, self.G = int(sort_every), int(guard)
+        self.cb = slab_bounds(Ng, self.world)
+        self.c0, self.c1 = self.cb[self.rank], self.cb[self.rank + 1]
+        if self.world > 1 and min(b - a for a, b in zip(self.cb, self.cb[1:])) <= 2 * self.G + 2:
+            raise ValueError("slabs must be wider than 2*guard+2 cells")
+        per = self.N_global // 2 // self.world + 1
+        self.H = int(headroom) if headroom is not None else max(4096, per // 50)
+        self.H += self.H % 2
+        cap = int(per * capacity) + 2 * self.H + 1024
+        self.blocks = [_Block(cap, self.dev, 0), _Block(cap, self.dev, 1)]
+        g, dev = self.Ng, self.dev
+        self.E0 = D.f64(g, dev, True); self.Es = D.f64(g, dev, True); self.E1 = D.f64(g, dev, True)
+        self.j0 = D.f64(g, dev, True)
+        self.acc = D.f64(2 * g + 4, dev, True)
+        self.wall_cum = D.f64(4, dev, True)
+        self.stats = D.f64(8, dev, True)
+        self.range_err = torch.zeros(1, dtype=torch.int32, device=dev)
+        self.sort_counts = torch.zeros(D.sort_counts_size(g), dtype=torch.int32, device=dev)
+        self.cb_dev = torch.as_tensor(np.asarray(self.cb[1:-1], dtype=np.int64), device=dev)
+        self.t = 0
+        self.kernel_launches = 0
+        self.stat = dict(migrated=0, exported=0, imported=0)
+        # segment bookkeeping of the all-gather (owned nodes; the last rank also owns node Ng-1)
+        self.seg = [(self.cb[r], self.cb[r + 1] + (1 if r == self.world - 1 else 0)) for r in range(self.world)]
+        self.seglen = max(b - a for a, b in self.seg)
+        self.sendbuf = D.f64(2 * self.seglen + 4, dev, True)
+        self.gathbuf = D.f64(self.world * (2 * self.seglen + 4), dev, True)
+
+    # ------------------------------------------------------------------ helpers
+    def _params(self, blk, n=None, sort=False):
+        n = blk.n if n is None else n
+        ns = n if (blk.species == 0 or sort) else 0          # sort keys: one species per block
+        return _lib.DDParams(n, ns, self.Ng, 0, self.dx, self.dt, self.L, self.p2c, (C.c_double * 2)(*self.q),
+                             (C.c_double * 2)(*self.m))
+
+    def _sigma(self, sp):
+        return float(np.sqrt(self.kBT[sp] / self.m[sp]))
+
+    def _dest(self, x):
+        """Owner rank of positions x (device tensor)."""
+        cell = torch.clamp(torch.floor(x / self.dx).to(torch.int64), 0, self.Ng - 2)
+        return torch.searchsorted(self.cb_dev, cell, right=True)
+
+    def _all_to_all(self, send_list):
+        """Variable-size all-to-all of fp64 vectors: exchanges the sizes, then the payloads."""
+        W = self.world
+        sizes = torch.tensor([t.numel() for t in send_list], dtype=torch.int64, device=self.dev)
+        rsizes = torch.empty_like(sizes)
+        dist.all_to_all_single(rsizes, sizes, group=self.comm.group)
+        rs = [int(v) for v in rsizes.cpu().numpy()]
+        recv = [torch.empty(n, dtype=torch.float64, device=self.dev) for n in rs]
+        dist.all_to_all(recv, [t.contiguous() for t in send_list], group=self.comm.group)
+        return recv
+
+    # ------------------------------------------------------------------ state I/O
+    def upload(self, x0, u0, E0=None):
+        """GLOBAL host arrays (first half electrons, second half ions): every rank keeps the
+        particles inside its slab."""
+        h = self.N_global // 2
+        lo, hi = self.c0 * self.dx, self.c1 * self.dx
+        for sp, sl in ((0, slice(0, h)), (1, slice(h, self.N_global))):
+            xs, us = np.asarray(x0[sl]), np.asarray(u0[sl])
+            cell = np.clip(np.floor(xs / self.dx).astype(np.int64), 0, self.Ng - 2)
+            keep = (cell >= self.c0) & (cell < self.c1)
+            blk = self.blocks[sp]
+            blk.n = int(keep.sum())
+            assert blk.n + 2 * self.H < blk.cap, "slab block capacity too small"
+            blk.cur, blk.off = 0, 0
+            blk.X[0][:blk.n].copy_(torch.as_tensor(np.ascontiguousarray(xs[keep])))
+            blk.U[0][:blk.n].copy_(torch.as_tensor(np.ascontiguousarray(us[keep])))
+            blk.active.fill_(1)
+        if E0 is not None:
+            self.E0.copy_(torch.as_tensor(np.ascontiguousarray(E0)))
+
+    def init_device(self, seed=None):
+        """Uniform density, Maxwellian velocities, generated in place (Philox keyed by rank)."""
+        seed = self.seed if seed is None else seed
+        h = self.N_global // 2
+        lo, hi = self.c0 * self.dx, self.c1 * self.dx
+        for sp, blk in enumerate(self.blocks):
+            blk.n = h * (self.c1 - self.c0) // (self.Ng - 1)
+            blk.cur, blk.off = 0, 0
+            sig = (self._sigma(sp), self._sigma(sp))
+            _lib.call("pic_dev_init_uniform_maxwellian", D.ptr(blk.X[0]), D.ptr(blk.U[0]), None, None, blk.n, blk.n,
+                      max(lo, 1e-12 * self.L), min(hi, self.L * (1 - 1e-12)), C.byref((C.c_double * 2)(*sig)),
+                      C.byref((C.c_double * 2)(0., 0.)), seed, 100 + sp, self.rank * (1 << 40), D.stream())
+            blk.active.fill_(1)
+
+    def gather_particles(self):
+        """All particles of both species on every rank (tests): lists of numpy arrays [x_e, u_e, x_i, u_i]."""
+        out = []
+        for blk in self.blocks:
+            x = blk.x0[:blk.n].cpu().numpy(); u = blk.u0[:blk.n].cpu().numpy(); a = blk.active[:blk.n].cpu().numpy()
+            if self.world > 1:
+                parts = [None] * self.world
+                dist.all_gather_object(parts, (x, u, a), group=self.comm.group)
+                x = np.concatenate([p[0] for p in parts]); u = np.concatenate([p[1] for p in parts])
+                a = np.concatenate([p[2] for p in parts])
+            out += [x, u, a]
+        return out
+
+    # ------------------------------------------------------------------ re-injection
+    def reinject(self):
+        st = D.stream()
+        dead = []
+        for blk in self.blocks:
+            _lib.call("pic_dev_compact_flags", D.ptr(blk.active), blk.n, 0, D.ptr(blk.dead_idx), D.ptr(blk.count),
+                      D.ptr(blk.block_counts), st)
+            dead.append(int(D.read_raw(blk.count, 1, np.int64)[0]))
+        self.kernel_launches += 6
+        if self.world > 1:
+            t = torch.tensor(dead, dtype=torch.int64, device=self.dev)
+            allc = [torch.empty_like(t) for _ in range(self.world)]
+            dist.all_gather(allc, t, group=self.comm.group)
+            allc = np.stack([a.cpu().numpy() for a in allc])            # [rank, species]
+        else:
+            allc = np.asarray([dead])
+        for sp, blk in enumerate(self.blocks):
+            nd = dead[sp]
+            if int(allc[:, sp].sum()) == 0:
+                continue
+            ordinal = int(allc[:self.rank, sp].sum())
+            xd = D.f64(max(nd, 1), self.dev); ud = D.f64(max(nd, 1), self.dev)
+            if nd:
+                sig = (self._sigma(sp), self._sigma(sp))
+                _lib.call("pic_dev_init_uniform_maxwellian", D.ptr(xd), D.ptr(ud), None, None, nd, nd, 0.0, self.L,
+                          C.byref((C.c_double * 2)(*sig)), C.byref((C.c_double * 2)(0., 0.)), self.seed,
+                          1000 + 2 * self.t + sp, ordinal, st)
+            xd, ud = xd[:nd], ud[:nd]
+            idx = blk.dead_idx[:nd].to(torch.int64)
+            if self.world == 1:
+                if nd:
+                    blk.x0[idx] = xd; blk.u0[idx] = ud; blk.active[idx] = 1
+                continue
+            dest = self._dest(xd)
+            mine = dest == self.rank
+            li = idx[mine]
+            if li.numel():
+                blk.x0[li] = xd[mine]; blk.u0[li] = ud[mine]; blk.active[li] = 1
+            order = torch.argsort(dest[~mine], stable=True)
+            xs_, us_, ds_ = xd[~mine][order], ud[~mine][order], dest[~mine][order]
+            cnt = torch.bincount(ds_, minlength=self.world).cpu().numpy() if ds_.numel() else np.zeros(self.world, np.int64)
+            offs = np.concatenate([[0], np.cumsum(cnt)])
+            rx = self._all_to_all([xs_[offs[r]:offs[r + 1]] for r in range(self.world)])
+            ru = self._all_to_all([us_[offs[r]:offs[r + 1]] for r in range(self.world)])
+            ax, au = torch.cat(rx), torch.cat(ru)
+            holes = np.sort(idx[~mine].cpu().numpy())
+            adst, msrc, mdst, new_n = swap_remove_plan(blk.n, holes, ax.numel())
+            assert blk.off + new_n + 16 < blk.cap, "slab block capacity exhausted"
+            if len(msrc):
+                ms = torch.as_tensor(msrc, device=self.dev); md = torch.as_tensor(mdst, device=self.dev)
+                blk.x0[md] = blk.x0[ms]; blk.u0[md] = blk.u0[ms]; blk.active[md] = blk.active[ms]
+            if len(adst):
+                ad = torch.as_tensor(adst, device=self.dev)
+                blk.x0[ad] = ax; blk.u0[ad] = au; blk.active[ad] = 1
+            blk.n = new_n
+            self.stat["exported"] += len(holes); self.stat["imported"] += int(ax.numel())
+
+    # ------------------------------------------------------------------ sort + migration
+    def migrate_sort(self):
+        st = D.stream()
+        W, me_ = self.world, self.rank
+        for blk in self.blocks:
+            n, H = blk.n, self.H
+            xs, us = blk.x1[H:], blk.u1[H:]
+            P = self._params(blk, n, sort=True)
+            _lib.call("pic_dev_dd_sort_by_cell", C.byref(P), D.ptr(blk.x0), D.ptr(blk.u0), None, None, D.ptr(xs), D.ptr(us),
+                      None, None, D.ptr(self.sort_counts), st)
+            self.kernel_launches += 3
+            # after the scatter cursor[key] = end of key's run = start of the next key's run
+            if W > 1:
+                ends = self.sort_counts[torch.as_tensor([c - 1 for c in self.cb[1:-1]], device=self.dev)].cpu().numpy()
+                offs = np.concatenate([[0], ends.astype(np.int64), [n]])
+            else:
+                offs = np.asarray([0, n], dtype=np.int64)
+            start, stay = H + int(offs[me_]), int(offs[me_ + 1] - offs[me_])
+            if W > 1:
+                send_x = [xs[offs[r]:offs[r + 1]] if r != me_ else xs[:0] for r in range(W)]
+                send_u = [us[offs[r]:offs[r + 1]] if r != me_ else us[:0] for r in range(W)]
+                rx, ru = self._all_to_all(send_x), self._all_to_all(send_u)
+                lo_x, hi_x = torch.cat(rx[:me_] + [xs[:0]]), torch.cat(rx[me_ + 1:] + [xs[:0]])
+                lo_u, hi_u = torch.cat(ru[:me_] + [us[:0]]), torch.cat(ru[me_ + 1:] + [us[:0]])
+                nlo, nhi = lo_x.numel(), hi_x.numel()
+                assert nlo <= start, "headroom too small for the arrivals from lower ranks"
+                Xs, Us = blk.x1, blk.u1
+                if nlo:
+                    Xs[start - nlo:start] = lo_x; Us[start - nlo:start] = lo_u
+                if nhi:
+                    Xs[start + stay:start + stay + nhi] = hi_x; Us[start + stay:start + stay + nhi] = hi_u
+                self.stat["migrated"] += int(n - stay)
+                start, n = start - nlo, nlo + stay + nhi
+            if start % 2:                       # keep the block 16-byte aligned for the TMA / 128-bit paths
+                Xs, Us = blk.x1, blk.u1
+                Xs[start - 1] = Xs[start + n - 1]; Us[start - 1] = Us[start + n - 1]
+                start -= 1
+            assert start + n + 16 < blk.cap, "slab block capacity exhausted"
+            blk.cur, blk.off, blk.n = 1 - blk.cur, start, n
+            blk.active[:n] = 1
+
+    # ------------------------------------------------------------------ halo exchange
+    def exchange_acc(self):
+        W = self.world
+        if W == 1:
+            return
+        Ng, G, r = self.Ng, self.G, self.rank
+        jh, j1 = self.acc[:Ng], self.acc[Ng:2 * Ng]
+        ops, recv = [], {}
+        if r > 0:        # my deposits on the left neighbour's nodes [c0-G, c0)
+            s = torch.cat([jh[self.c0 - G:self.c0], j1[self.c0 - G:self.c0]])
+            recv["L"] = torch.empty(2 * (G + 1), dtype=torch.float64, device=self.dev)
+            ops += [dist.P2POp(dist.isend, s, r - 1, group=self.comm.group), dist.P2POp(dist.irecv, recv["L"], r - 1, group=self.comm.group)]
+        if r < W - 1:    # my deposits on the right neighbour's nodes [c1, c1+G]
+            s2 = torch.cat([jh[self.c1:self.c1 + G + 1], j1[self.c1:self.c1 + G + 1]])
+            recv["R"] = torch.empty(2 * G, dtype=torch.float64, device=self.dev)
+            ops += [dist.P2POp(dist.isend, s2, r + 1, group=self.comm.group), dist.P2POp(dist.irecv, recv["R"], r + 1, group=self.comm.group)]
+        for w in dist.batch_isend_irecv(ops):
+            w.wait()
+        if "L" in recv:  # the left neighbour's deposits on my first G+1 nodes
+            jh[self.c0:self.c0 + G + 1] += recv["L"][:G + 1]; j1[self.c0:self.c0 + G + 1] += recv["L"][G + 1:]
+        if "R" in recv:  # the right neighbour's deposits on my last G nodes
+            jh[self.c1 - G:self.c1] += recv["R"][:G]; j1[self.c1 - G:self.c1] += recv["R"][G:]
+        a, b = self.seg[r]
+        sl = self.seglen
+        self.sendbuf.zero_()
+        self.sendbuf[:b - a] = jh[a:b]; self.sendbuf[sl:sl + b - a] = j1[a:b]; self.sendbuf[2 * sl:] = self.acc[2 * Ng:]
+        dist.all_gather_into_tensor(self.gathbuf, self.sendbuf, group=self.comm.group)
+        gb = self.gathbuf.view(W, 2 * sl + 4)
+        for rr, (a2, b2) in enumerate(self.seg):
+            jh[a2:b2] = gb[rr, :b2 - a2]; j1[a2:b2] = gb[rr, sl:sl + b2 - a2]
+        self.acc[2 * Ng:] = gb[:, 2 * sl:].sum(0)
+
+    # ------------------------------------------------------------------ one timestep
+    def picard(self):
+        st = D.stream()
+        self.Es.copy_(self.E0)
+        self.wall_cum.zero_(); self.stats.zero_()
+        r, k = 1.0, 0
+        Pg = self._params(self.blocks[0])
+        while (r > self.tol) and (k < self.maxiter):
+            for blk in self.blocks:
+                if blk.n:
+                    _lib.call("pic_dev_dd_picard_iter", C.byref(self._params(blk)), D.ptr(blk.x0), D.ptr(blk.u0), D.ptr(blk.x1),
+                              D.ptr(blk.u1), D.ptr(blk.active), D.ptr(self.Es), D.ptr(self.acc), 1 if k == 0 else 0,
+                              D.ptr(self.range_err), st)
+                    self.kernel_launches += 1
+            self.exchange_acc()
+            _lib.call("pic_dev_dd_field_update", C.byref(Pg), D.ptr(self.acc), D.ptr(self.wall_cum), D.ptr(self.E0),
+                      D.ptr(self.Es), D.ptr(self.E1), D.ptr(self.j0), D.ptr(self.stats), st)
+            self.kernel_launches += 1
+            r = float(D.read_f64(self.stats, 1)[0])
+            k += 1
+        if k > 0:
+            for blk in self.blocks:
+                blk.commit()
+            self.E0, self.E1 = self.E1, self.E0
+        return k, r
+
+    def step(self):
+        self.reinject()
+        if self.sort_every and self.t % self.sort_every == 0:
+            self.migrate_sort()
+        out = self.picard()
+        self.t += 1
+        return out
+
+    def check(self):
+        D.check_range(self.range_err, "slab sheath step")
+
+    def local_particles(self):
+        return sum(b.n for b in self.blocks)
