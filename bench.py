@@ -45,6 +45,9 @@ def parse():
     ap.add_argument("--workload", default="sheath", choices=["sheath", "explicit", "pypic", "boris"],
                     help="sheath = BASELINE configs[1] (default, the driver's bench); explicit / pypic / boris = "
                          "the other movers of SURVEY.md 8(d) at the same size (single GPU, device-resident)")
+    ap.add_argument("--decomposition", default="particle", choices=["particle", "slab"],
+                    help="sheath workload only: particle decomposition (default, all-reduce of the grid) or spatial "
+                         "slabs (halo exchange + particle migration, BASELINE config 5)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-sample", type=float, default=4e6, help="particles in the CPU-baseline sample")
@@ -376,6 +379,76 @@ def run_cuda(args):
     return line if rank == 0 else None
 
 
+# ----------------------------------------------------------------------------- slab decomposition
+def run_slab(args):
+    """BASELINE config 5: the sheath on spatial slabs (pypic_b200/spatial.py), device-resident."""
+    import torch
+    import torch.distributed as dist
+    from pypic_b200.dist import Comm
+    from pypic_b200.spatial import SlabSheathSim
+    world = int(os.environ.get("WORLD_SIZE", "1")); rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (there is no CPU fallback)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    comm = Comm()
+    w = workload(args, world)
+    sim = SlabSheathSim(w["N"], w["Ng"], w["dx"], w["dt"], w["p2c"], kBT=(w["kBTe"], w["kBTi"]), tol=w["tol"],
+                        maxiter=w["maxiter"], seed=1, comm=comm, device=dev, sort_every=args.sort_every, guard=16)
+    sim.init_device(seed=1234)
+    for _ in range(args.warmup):
+        sim.step()
+    sim.check()
+    torch.cuda.synchronize(); comm.barrier()
+    sampler = ClockSampler(local) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    sim.iter_events = []
+    l0 = sim.kernel_launches
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    iters = []
+    ev0.record()
+    for _ in range(args.steps):
+        k, r = sim.step(); iters.append(k)
+    ev1.record()
+    torch.cuda.synchronize(); comm.barrier()
+    if sampler:
+        sampler.stop_flag = True
+    ms = comm.max_float(ev0.elapsed_time(ev1), device=dev)
+    sim.check()
+    kms = [a.elapsed_time(b) for a, b in sim.iter_events]
+    kbar = float(np.mean(iters))
+    nloc = sim.local_particles()
+    peak, peak_src = measured_peak()
+    per_launch = nloc * 40.0                       # x0,u0,x1 in; x1,u1 out (u1 is always stored on this path)
+    achieved = per_launch / (float(np.mean(kms)) * 1e-3) / 1e9
+    line = None
+    if rank == 0:
+        line = {"metric": METRIC, "value": w["N"] * args.steps / (ms * 1e-3), "unit": "particle-steps/s", "n_gpus": world,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
+                "scaling": w["scaling"], "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": {"workload": "1D sheath (PIC_L_DD physics) on %d spatial slabs: %d particles, %d-node grid, implicit "
+                                       "CN/Picard tol=1e-5" % (world, w["N"], w["Ng"]),
+                           "parallelism": "slab decomposition x%d: halo exchange of 16 guard nodes + all-gather of owned "
+                                          "segments per Picard iteration, migration with the sort every %d steps, routed "
+                                          "re-injection" % (world, args.sort_every),
+                           "picard_iterations_per_step": kbar, "sort_every": args.sort_every,
+                           "migration": sim.stat, "local_particles_rank0": nloc,
+                           "l2_policy": "particle arrays (%.1f GB per GPU) are far larger than the 126 MB L2" % (nloc * 32 / 1e9)},
+                "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                             "traffic": None, "kernel": "dd_picard_iter_v6_k (one launch per species block)",
+                             "peak_source": peak_src, "kernel_ms_mean": float(np.mean(kms)),
+                             "kernel_share_of_step": float(np.sum(kms) / ms), "algorithmic_bytes_per_launch": per_launch},
+                "cpu_baseline": None, "e2e": None, "gpu_launches": int(sim.kernel_launches - l0),
+                "clocks": sampler.summary() if sampler else {}}
+    if world > 1:
+        dist.destroy_process_group()
+    return line
+
+
 # ----------------------------------------------------------------------------- other movers
 def run_other(args):
     """The other hot-path rows at benchmark size, one GPU, device-resident state:
@@ -522,6 +595,8 @@ def main():
             line = run_reference(args)
         elif args.workload != "sheath":
             line = run_other(args)
+        elif args.decomposition == "slab":
+            line = run_slab(args)
         else:
             line = run_cuda(args)
     if line is not None:

@@ -116,7 +116,7 @@ class SlabSheathSim:
         g, dev = self.Ng, self.dev
         self.E0 = D.f64(g, dev, True); self.Es = D.f64(g, dev, True); self.E1 = D.f64(g, dev, True)
         self.j0 = D.f64(g, dev, True)
-        self.acc = D.f64(2 * g + 4, dev, True)
+        self.acc = D.f64(2 * g + 5, dev, True)       # [jh | j1 | 4 absorbed counts | one always-zero slot]
         self.wall_cum = D.f64(4, dev, True)
         self.stats = D.f64(8, dev, True)
         self.range_err = torch.zeros(1, dtype=torch.int32, device=dev)
@@ -125,11 +125,13 @@ class SlabSheathSim:
         self.t = 0
         self.kernel_launches = 0
         self.stat = dict(migrated=0, exported=0, imported=0)
+        self._plan = None
+        self.local_dead = [0, 0]     # absorbed particles of each species on this rank in the last step
+        self.profile = None          # set to a dict to accumulate wall-clock seconds per section of step()
+        self.iter_events = None      # set to a list to record a CUDA-event pair per Picard iteration (both blocks)
         # segment bookkeeping of the all-gather (owned nodes; the last rank also owns node Ng-1)
         self.seg = [(self.cb[r], self.cb[r + 1] + (1 if r == self.world - 1 else 0)) for r in range(self.world)]
         self.seglen = max(b - a for a, b in self.seg)
-        self.sendbuf = D.f64(2 * self.seglen + 4, dev, True)
-        self.gathbuf = D.f64(self.world * (2 * self.seglen + 4), dev, True)
 
     # ------------------------------------------------------------------ helpers
     def _params(self, blk, n=None, sort=False):
@@ -206,51 +208,89 @@ class SlabSheathSim:
 
     # ------------------------------------------------------------------ re-injection
     def reinject(self):
+        """PIC_L_DD.py:429-450 on slabs: every dead slot gets (x ~ U(0,L), u ~ N(0, sigma_s)) drawn for the
+        GLOBAL ordinal of that dead particle within its species; draws that land in another slab are
+        shipped there (one size exchange + one payload all-to-all per step for both species) and the
+        slots they leave are closed by swap-removal."""
         st = D.stream()
+        W, me_ = self.world, self.rank
         dead = []
-        for blk in self.blocks:
+        for sp, blk in enumerate(self.blocks):
+            # the kernels count what they absorb (acc[2Ng..], saved per rank by picard()): a species that
+            # lost nothing here needs no scan of its flags (always the case on interior ranks)
+            if self.local_dead[sp] == 0 and self.t > 0:
+                dead.append(0)
+                continue
             _lib.call("pic_dev_compact_flags", D.ptr(blk.active), blk.n, 0, D.ptr(blk.dead_idx), D.ptr(blk.count),
                       D.ptr(blk.block_counts), st)
             dead.append(int(D.read_raw(blk.count, 1, np.int64)[0]))
-        self.kernel_launches += 6
-        if self.world > 1:
+            self.kernel_launches += 3
+        if W > 1:
             t = torch.tensor(dead, dtype=torch.int64, device=self.dev)
-            allc = [torch.empty_like(t) for _ in range(self.world)]
-            dist.all_gather(allc, t, group=self.comm.group)
-            allc = np.stack([a.cpu().numpy() for a in allc])            # [rank, species]
+            allc = torch.empty(W * 2, dtype=torch.int64, device=self.dev)
+            dist.all_gather_into_tensor(allc, t, group=self.comm.group)
+            allc = allc.cpu().numpy().reshape(W, 2)                       # [rank, species]
         else:
             allc = np.asarray([dead])
+        if int(allc.sum()) == 0:
+            return
+        send = [[None, None] for _ in range(2)]      # per species: (x, u) sorted by destination, counts per destination
+        cnts = np.zeros((W, 2), dtype=np.int64)
+        holes = [np.zeros(0, np.int64), np.zeros(0, np.int64)]
         for sp, blk in enumerate(self.blocks):
             nd = dead[sp]
-            if int(allc[:, sp].sum()) == 0:
+            if nd == 0:
                 continue
-            ordinal = int(allc[:self.rank, sp].sum())
-            xd = D.f64(max(nd, 1), self.dev); ud = D.f64(max(nd, 1), self.dev)
-            if nd:
-                sig = (self._sigma(sp), self._sigma(sp))
-                _lib.call("pic_dev_init_uniform_maxwellian", D.ptr(xd), D.ptr(ud), None, None, nd, nd, 0.0, self.L,
-                          C.byref((C.c_double * 2)(*sig)), C.byref((C.c_double * 2)(0., 0.)), self.seed,
-                          1000 + 2 * self.t + sp, ordinal, st)
-            xd, ud = xd[:nd], ud[:nd]
+            ordinal = int(allc[:me_, sp].sum())
+            xd = D.f64(nd, self.dev); ud = D.f64(nd, self.dev)
+            sig = (self._sigma(sp), self._sigma(sp))
+            _lib.call("pic_dev_init_uniform_maxwellian", D.ptr(xd), D.ptr(ud), None, None, nd, nd, 0.0, self.L,
+                      C.byref((C.c_double * 2)(*sig)), C.byref((C.c_double * 2)(0., 0.)), self.seed,
+                      1000 + 2 * self.t + sp, ordinal, st)
             idx = blk.dead_idx[:nd].to(torch.int64)
-            if self.world == 1:
-                if nd:
-                    blk.x0[idx] = xd; blk.u0[idx] = ud; blk.active[idx] = 1
+            if W == 1:
+                blk.x0[idx] = xd; blk.u0[idx] = ud; blk.active[idx] = 1
                 continue
             dest = self._dest(xd)
-            mine = dest == self.rank
+            mine = dest == me_
             li = idx[mine]
-            if li.numel():
-                blk.x0[li] = xd[mine]; blk.u0[li] = ud[mine]; blk.active[li] = 1
-            order = torch.argsort(dest[~mine], stable=True)
-            xs_, us_, ds_ = xd[~mine][order], ud[~mine][order], dest[~mine][order]
-            cnt = torch.bincount(ds_, minlength=self.world).cpu().numpy() if ds_.numel() else np.zeros(self.world, np.int64)
-            offs = np.concatenate([[0], np.cumsum(cnt)])
-            rx = self._all_to_all([xs_[offs[r]:offs[r + 1]] for r in range(self.world)])
-            ru = self._all_to_all([us_[offs[r]:offs[r + 1]] for r in range(self.world)])
-            ax, au = torch.cat(rx), torch.cat(ru)
-            holes = np.sort(idx[~mine].cpu().numpy())
-            adst, msrc, mdst, new_n = swap_remove_plan(blk.n, holes, ax.numel())
+            blk.x0[li] = xd[mine]; blk.u0[li] = ud[mine]; blk.active[li] = 1
+            out = ~mine
+            order = torch.argsort(dest[out], stable=True)
+            send[sp] = [xd[out][order], ud[out][order]]
+            cnts[:, sp] = torch.bincount(dest[out], minlength=W).cpu().numpy()
+            holes[sp] = np.sort(idx[out].cpu().numpy())
+        if W == 1:
+            return
+        # ---- one size exchange, one payload exchange: to rank r goes [x_e | u_e | x_i | u_i] of its arrivals
+        sizes = torch.as_tensor(cnts.reshape(-1), device=self.dev)
+        rsizes = torch.empty_like(sizes)
+        dist.all_to_all_single(rsizes, sizes, group=self.comm.group)
+        rc = rsizes.cpu().numpy().reshape(W, 2)                           # arrivals from rank r, per species
+        offs = np.concatenate([np.zeros((1, 2), np.int64), np.cumsum(cnts, 0)])
+        empty = torch.empty(0, dtype=torch.float64, device=self.dev)
+        pieces = []
+        for r in range(W):
+            for sp in range(2):
+                for comp in range(2):
+                    pieces.append(send[sp][comp][offs[r, sp]:offs[r + 1, sp]] if send[sp][0] is not None else empty)
+        payload = torch.cat(pieces) if pieces else empty
+        in_splits = [int(2 * (cnts[r, 0] + cnts[r, 1])) for r in range(W)]
+        out_splits = [int(2 * (rc[r, 0] + rc[r, 1])) for r in range(W)]
+        recv = torch.empty(sum(out_splits), dtype=torch.float64, device=self.dev)
+        dist.all_to_all_single(recv, payload, out_splits, in_splits, group=self.comm.group)
+        arr = [[[], []], [[], []]]
+        o = 0
+        for r in range(W):
+            for sp in range(2):
+                n_ = int(rc[r, sp])
+                arr[sp][0].append(recv[o:o + n_]); arr[sp][1].append(recv[o + n_:o + 2 * n_])
+                o += 2 * n_
+        for sp, blk in enumerate(self.blocks):
+            ax, au = torch.cat(arr[sp][0]), torch.cat(arr[sp][1])
+            if ax.numel() == 0 and len(holes[sp]) == 0:
+                continue
+            adst, msrc, mdst, new_n = swap_remove_plan(blk.n, holes[sp], ax.numel())
             assert blk.off + new_n + 16 < blk.cap, "slab block capacity exhausted"
             if len(msrc):
                 ms = torch.as_tensor(msrc, device=self.dev); md = torch.as_tensor(mdst, device=self.dev)
@@ -259,7 +299,7 @@ class SlabSheathSim:
                 ad = torch.as_tensor(adst, device=self.dev)
                 blk.x0[ad] = ax; blk.u0[ad] = au; blk.active[ad] = 1
             blk.n = new_n
-            self.stat["exported"] += len(holes); self.stat["imported"] += int(ax.numel())
+            self.stat["exported"] += len(holes[sp]); self.stat["imported"] += int(ax.numel())
 
     # ------------------------------------------------------------------ sort + migration
     def migrate_sort(self):
@@ -303,52 +343,89 @@ class SlabSheathSim:
             blk.active[:n] = 1
 
     # ------------------------------------------------------------------ halo exchange
+    def _build_exchange_plan(self):
+        """Index tensors of the exchange (built once).  Every rank contributes one message
+        [left guard strip | right guard strip | owned segment (jh, j1) | 4 absorbed counts]; the strips
+        of a rank are ITS deposits on its neighbours' nodes.  One all-gather moves all messages;
+        unpacking places the owned segments and adds every strip at its global position."""
+        Ng, G, W, dev = self.Ng, self.G, self.world, self.dev
+        ar = lambda a, b: np.arange(a, b, dtype=np.int64)
+        both = lambda a, b: np.concatenate([ar(a, b), Ng + ar(a, b)])          # the same nodes of jh and of j1
+        t = lambda v: torch.as_tensor(v, device=dev)
+        sl = self.seglen
+        nL, nR = 2 * G, 2 * (G + 1)
+        M = nL + nR + 2 * sl + 4                                          # message length
+        PAD = 2 * Ng + 4                                                  # index of the always-zero slot of acc
+        pack = np.full(M, PAD, dtype=np.int64)
+        r = self.rank
+        if r > 0:
+            pack[:nL] = both(self.c0 - G, self.c0)
+        if r < W - 1:
+            pack[nL:nL + nR] = both(self.c1, self.c1 + G + 1)
+        a, b = self.seg[r]
+        o = nL + nR
+        pack[o:o + b - a] = ar(a, b); pack[o + sl:o + sl + b - a] = Ng + ar(a, b); pack[o + 2 * sl:] = 2 * Ng + ar(0, 4)
+        src = np.zeros(2 * Ng, dtype=np.int64)
+        add_dst, add_src = [], []
+        for rr, (a2, b2) in enumerate(self.seg):
+            base = rr * M
+            src[a2:b2] = base + o + ar(0, b2 - a2); src[Ng + a2:Ng + b2] = base + o + sl + ar(0, b2 - a2)
+            c0r, c1r = self.cb[rr], self.cb[rr + 1]
+            if rr > 0:
+                add_dst.append(both(c0r - G, c0r)); add_src.append(base + ar(0, nL))
+            if rr < W - 1:
+                add_dst.append(both(c1r, c1r + G + 1)); add_src.append(base + nL + ar(0, nR))
+        self.sendbuf = D.f64(M, dev, True)
+        self.gathbuf = D.f64(W * M, dev, True)
+        return dict(pack=t(pack), unpack=t(src), add_dst=t(np.concatenate(add_dst)), add_src=t(np.concatenate(add_src)),
+                    counts=t(np.concatenate([rr * M + o + 2 * sl + ar(0, 4) for rr in range(W)])))
+
     def exchange_acc(self):
+        """Halo exchange of the guard strips + completion of the grid, one collective per Picard
+        iteration (see _build_exchange_plan).  self.acc has one extra, always-zero slot."""
         W = self.world
         if W == 1:
             return
-        Ng, G, r = self.Ng, self.G, self.rank
-        jh, j1 = self.acc[:Ng], self.acc[Ng:2 * Ng]
-        ops, recv = [], {}
-        if r > 0:        # my deposits on the left neighbour's nodes [c0-G, c0)
-            s = torch.cat([jh[self.c0 - G:self.c0], j1[self.c0 - G:self.c0]])
-            recv["L"] = torch.empty(2 * (G + 1), dtype=torch.float64, device=self.dev)
-            ops += [dist.P2POp(dist.isend, s, r - 1, group=self.comm.group), dist.P2POp(dist.irecv, recv["L"], r - 1, group=self.comm.group)]
-        if r < W - 1:    # my deposits on the right neighbour's nodes [c1, c1+G]
-            s2 = torch.cat([jh[self.c1:self.c1 + G + 1], j1[self.c1:self.c1 + G + 1]])
-            recv["R"] = torch.empty(2 * G, dtype=torch.float64, device=self.dev)
-            ops += [dist.P2POp(dist.isend, s2, r + 1, group=self.comm.group), dist.P2POp(dist.irecv, recv["R"], r + 1, group=self.comm.group)]
-        for w in dist.batch_isend_irecv(ops):
-            w.wait()
-        if "L" in recv:  # the left neighbour's deposits on my first G+1 nodes
-            jh[self.c0:self.c0 + G + 1] += recv["L"][:G + 1]; j1[self.c0:self.c0 + G + 1] += recv["L"][G + 1:]
-        if "R" in recv:  # the right neighbour's deposits on my last G nodes
-            jh[self.c1 - G:self.c1] += recv["R"][:G]; j1[self.c1 - G:self.c1] += recv["R"][G:]
-        a, b = self.seg[r]
-        sl = self.seglen
-        self.sendbuf.zero_()
-        self.sendbuf[:b - a] = jh[a:b]; self.sendbuf[sl:sl + b - a] = j1[a:b]; self.sendbuf[2 * sl:] = self.acc[2 * Ng:]
+        if self._plan is None:
+            self._plan = self._build_exchange_plan()
+        pl, Ng = self._plan, self.Ng
+        acc = self.acc
+        torch.index_select(acc, 0, pl["pack"], out=self.sendbuf)
         dist.all_gather_into_tensor(self.gathbuf, self.sendbuf, group=self.comm.group)
-        gb = self.gathbuf.view(W, 2 * sl + 4)
-        for rr, (a2, b2) in enumerate(self.seg):
-            jh[a2:b2] = gb[rr, :b2 - a2]; j1[a2:b2] = gb[rr, sl:sl + b2 - a2]
-        self.acc[2 * Ng:] = gb[:, 2 * sl:].sum(0)
+        torch.index_select(self.gathbuf, 0, pl["unpack"], out=acc[:2 * Ng])
+        acc.index_add_(0, pl["add_dst"], self.gathbuf[pl["add_src"]])
+        acc[2 * Ng:2 * Ng + 4] = self.gathbuf[pl["counts"]].view(W, 4).sum(0)
 
     # ------------------------------------------------------------------ one timestep
     def picard(self):
         st = D.stream()
         self.Es.copy_(self.E0)
         self.wall_cum.zero_(); self.stats.zero_()
+        self._absorbed_local = torch.zeros(4, dtype=torch.float64, device=self.dev)
         r, k = 1.0, 0
         Pg = self._params(self.blocks[0])
         while (r > self.tol) and (k < self.maxiter):
+            ev = None
+            if self.iter_events is not None:
+                ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+                ev[0].record()
             for blk in self.blocks:
                 if blk.n:
                     _lib.call("pic_dev_dd_picard_iter", C.byref(self._params(blk)), D.ptr(blk.x0), D.ptr(blk.u0), D.ptr(blk.x1),
                               D.ptr(blk.u1), D.ptr(blk.active), D.ptr(self.Es), D.ptr(self.acc), 1 if k == 0 else 0,
                               D.ptr(self.range_err), st)
                     self.kernel_launches += 1
-            self.exchange_acc()
+            if ev is not None:
+                ev[1].record()
+                self.iter_events.append(ev)
+            self._absorbed_local += self.acc[2 * self.Ng:2 * self.Ng + 4]   # this rank's own absorptions (before the exchange)
+            if self.profile is not None:
+                import time
+                torch.cuda.synchronize(); t0 = time.perf_counter()
+                self.exchange_acc()
+                torch.cuda.synchronize(); self.profile["exchange"] = self.profile.get("exchange", 0.0) + time.perf_counter() - t0
+            else:
+                self.exchange_acc()
             _lib.call("pic_dev_dd_field_update", C.byref(Pg), D.ptr(self.acc), D.ptr(self.wall_cum), D.ptr(self.E0),
                       D.ptr(self.Es), D.ptr(self.E1), D.ptr(self.j0), D.ptr(self.stats), st)
             self.kernel_launches += 1
@@ -358,13 +435,34 @@ class SlabSheathSim:
             for blk in self.blocks:
                 blk.commit()
             self.E0, self.E1 = self.E1, self.E0
+        a = self._absorbed_local.cpu().numpy()                      # [left e, left i, right e, right i]
+        self.local_dead = [int(round(a[0] + a[2])), int(round(a[1] + a[3]))]
         return k, r
 
     def step(self):
+        if self.profile is not None:
+            return self._step_profiled()
         self.reinject()
         if self.sort_every and self.t % self.sort_every == 0:
             self.migrate_sort()
         out = self.picard()
+        self.t += 1
+        return out
+
+    def _step_profiled(self):
+        """step() with host-side wall-clock sections (synchronising; diagnostics only)."""
+        import time
+        pr = self.profile
+
+        def section(name, fn):
+            torch.cuda.synchronize(); t0 = time.perf_counter()
+            out = fn()
+            torch.cuda.synchronize(); pr[name] = pr.get(name, 0.0) + time.perf_counter() - t0
+            return out
+        section("reinject", self.reinject)
+        if self.sort_every and self.t % self.sort_every == 0:
+            section("migrate_sort", self.migrate_sort)
+        out = section("picard", self.picard)
         self.t += 1
         return out
 
