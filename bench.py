@@ -41,7 +41,7 @@ def parse():
     ap.add_argument("--total-particles", type=float, default=0, help="strong scaling: fixed total (e.g. 1e9)")
     ap.add_argument("--cells", type=int, default=4096)
     ap.add_argument("--sort-every", type=int, default=8)
-    ap.add_argument("--deposit", default="window", choices=["window", "window-big", "window-ldg", "warp", "atomic"])
+    ap.add_argument("--deposit", default="window", choices=["window", "window-blocked", "window-big", "window-ldg", "warp", "atomic"])
     ap.add_argument("--workload", default="sheath", choices=["sheath", "explicit", "pypic", "boris"],
                     help="sheath = BASELINE configs[1] (default, the driver's bench); explicit / pypic / boris = "
                          "the other movers of SURVEY.md 8(d) at the same size (single GPU, device-resident)")

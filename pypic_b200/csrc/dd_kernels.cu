@@ -547,9 +547,16 @@ __global__ void __launch_bounds__(V6_T, 1) dd_picard_iter_v6_k(
     fc.dx = k.dx; fc.idx = k.idx; fc.dt = k.dt;
     fc.hi_dx = 0; fc.ngm2 = 0;
     fc.hi_Lm1 = (unsigned)__double2hiint(k.L) - 1u;
-    const int my_chunks = (nchunks - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+    // chunk -> CTA mapping: round-robin (CTA b takes chunks b, b+grid, ...: all CTAs sweep the same
+    // region of the sorted store together) or, flags bit6, blocked (CTA b owns a contiguous range of
+    // chunks: CTAs sit in different cells, so their window flushes do not meet on the same nodes)
+    const bool blocked = (k.flags & 64) != 0;
+    const int q_ = nchunks / (int)gridDim.x, rem_ = nchunks % (int)gridDim.x;
+    const int my_chunks = blocked ? q_ + ((int)blockIdx.x < rem_ ? 1 : 0)
+                                  : (nchunks - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+    const long long first_chunk = blocked ? (long long)blockIdx.x * q_ + min((int)blockIdx.x, rem_) : (long long)blockIdx.x;
     const long long woff = (long long)warp * (64 * V6_ROWS);
-    const long long chunk_step = (long long)gridDim.x * V6_CHUNK;
+    const long long chunk_step = blocked ? (long long)V6_CHUNK : (long long)gridDim.x * V6_CHUNK;
     const uint32_t row_bytes = FIRST ? 1024u : 1536u;
     // ---- producer: stateless -- the row requested is always the one V6_NST rows ahead of the row
     // being consumed and goes into the stage that row just drained, so every quantity is derived
@@ -563,7 +570,7 @@ __global__ void __launch_bounds__(V6_T, 1) dd_picard_iter_v6_k(
             if (!FIRST) bulk_g2s(dst + 1024, x1i + base, 512, bar);
         }
     };
-    long long cbase = (long long)blockIdx.x * V6_CHUNK + woff;     // first particle of this warp's slice
+    long long cbase = first_chunk * V6_CHUNK + woff;               // first particle of this warp's slice
     if (my_chunks > 0) {
 #pragma unroll
         for (int s = 0; s < V6_NST; ++s) issue(cbase + 64 * s, s);
