@@ -167,16 +167,16 @@ class ParticleStore:
                     Eyz=(0, 0), device=None):
         r = np.asarray(r, dtype=np.float64)
         s = cls(r.shape[0], B, Eyz, device)
+        N = s.N                     # the arrays hold max(N, 1) slots so that an empty store still has pointers
         for c in range(7):
-            s.r[c].copy_(torch.as_tensor(np.ascontiguousarray(r[:, c])))
-        N = s.N
+            s.r[c][:N].copy_(torch.as_tensor(np.ascontiguousarray(r[:, c])))
         for name, val in (("charge_state", charge_state), ("m", m), ("p2c", p2c)):
-            getattr(s, name).copy_(torch.as_tensor(np.broadcast_to(np.asarray(val, dtype=np.float64), (N,)).copy()))
+            getattr(s, name)[:N].copy_(torch.as_tensor(np.broadcast_to(np.asarray(val, dtype=np.float64), (N,)).copy()))
         if Z is not None:
-            s.Z.copy_(torch.as_tensor(np.broadcast_to(np.asarray(Z, dtype=np.int32), (N,)).copy()))
+            s.Z[:N].copy_(torch.as_tensor(np.broadcast_to(np.asarray(Z, dtype=np.int32), (N,)).copy()))
         for name, val in (("active", active), ("at_wall", at_wall), ("from_wall", from_wall)):
             if val is not None:
-                getattr(s, name).copy_(torch.as_tensor(np.asarray(val).astype(np.int8)))
+                getattr(s, name)[:N].copy_(torch.as_tensor(np.asarray(val).astype(np.int8)))
         return s
 
     FUSED_MIN = 16384                               # one chunk of the v2 kernel

@@ -58,8 +58,8 @@ class PeriodicImplicitSim:
 
     def upload(self, x0, v0, E0=None):
         s = slice(self.start, self.stop)
-        self.x0.copy_(torch.as_tensor(np.ascontiguousarray(x0[s])))
-        self.v0.copy_(torch.as_tensor(np.ascontiguousarray(v0[s])))
+        self.x0[:self.N].copy_(torch.as_tensor(np.ascontiguousarray(x0[s])))
+        self.v0[:self.N].copy_(torch.as_tensor(np.ascontiguousarray(v0[s])))
         if E0 is not None:
             self.E0.copy_(torch.as_tensor(np.ascontiguousarray(E0)))
 
@@ -175,8 +175,8 @@ class ExplicitSim:
 
     def upload(self, x, v):
         s = slice(self.start, self.stop)
-        self.x.copy_(torch.as_tensor(np.ascontiguousarray(x[s])))
-        self.v.copy_(torch.as_tensor(np.ascontiguousarray(v[s])))
+        self.x[:self.N].copy_(torch.as_tensor(np.ascontiguousarray(x[s])))
+        self.v[:self.N].copy_(torch.as_tensor(np.ascontiguousarray(v[s])))
         self._have_rho = False
 
     def _deposit_initial(self):

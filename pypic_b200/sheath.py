@@ -92,24 +92,26 @@ class SheathSim:
     def upload(self, x0, u0, v0=None, w0=None, E0=None, active=None):
         """Global (unsharded) host arrays in; each rank keeps its slice."""
         s = slice(self.start, self.stop)
-        self.x0.copy_(torch.as_tensor(np.ascontiguousarray(x0[s])))
-        self.u0.copy_(torch.as_tensor(np.ascontiguousarray(u0[s])))
+        n = self.N                      # the arrays hold max(N, 1) slots so that an empty shard still has pointers
+        self.x0[:n].copy_(torch.as_tensor(np.ascontiguousarray(x0[s])))
+        self.u0[:n].copy_(torch.as_tensor(np.ascontiguousarray(u0[s])))
         if self.carry_vw:
             if v0 is not None:
-                self.v0.copy_(torch.as_tensor(np.ascontiguousarray(v0[s])))
+                self.v0[:n].copy_(torch.as_tensor(np.ascontiguousarray(v0[s])))
             if w0 is not None:
-                self.w0.copy_(torch.as_tensor(np.ascontiguousarray(w0[s])))
+                self.w0[:n].copy_(torch.as_tensor(np.ascontiguousarray(w0[s])))
         if E0 is not None:
             self.E0.copy_(torch.as_tensor(np.ascontiguousarray(E0)))
         if active is not None:
-            self.active.copy_(torch.as_tensor(np.ascontiguousarray(active[s]).astype(np.int8)))
+            self.active[:n].copy_(torch.as_tensor(np.ascontiguousarray(active[s]).astype(np.int8)))
 
     def download(self):
-        out = dict(x0=self.x0.cpu().numpy(), u0=self.u0.cpu().numpy(),
-                   active=self.active.cpu().numpy().astype(np.float64),
+        n = self.N
+        out = dict(x0=self.x0[:n].cpu().numpy(), u0=self.u0[:n].cpu().numpy(),
+                   active=self.active[:n].cpu().numpy().astype(np.float64),
                    E0=self.E0.cpu().numpy(), j0=self.j0.cpu().numpy())
         if self.carry_vw:
-            out["v0"] = self.v0.cpu().numpy(); out["w0"] = self.w0.cpu().numpy()
+            out["v0"] = self.v0[:n].cpu().numpy(); out["w0"] = self.w0[:n].cpu().numpy()
         return out
 
     # ------------------------------------------------------------------ re-injection
