@@ -422,6 +422,10 @@ def run_slab(args):
     kms = [a.elapsed_time(b) for a, b in sim.iter_events]
     kbar = float(np.mean(iters))
     nloc = sim.local_particles()
+    by_rank = [float(np.mean(kms))]
+    if world > 1:
+        by_rank = [None] * world
+        dist.all_gather_object(by_rank, (float(np.mean(kms)), nloc))
     peak, peak_src = measured_peak()
     per_launch = nloc * 40.0                       # x0,u0,x1 in; x1,u1 out (u1 is always stored on this path)
     achieved = per_launch / (float(np.mean(kms)) * 1e-3) / 1e9
@@ -436,7 +440,7 @@ def run_slab(args):
                                           "segments per Picard iteration, migration with the sort every %d steps, routed "
                                           "re-injection" % (world, args.sort_every),
                            "picard_iterations_per_step": kbar, "sort_every": args.sort_every,
-                           "migration": sim.stat, "local_particles_rank0": nloc,
+                           "migration": sim.stat, "local_particles_rank0": nloc, "kernel_ms_and_particles_by_rank": by_rank,
                            "l2_policy": "particle arrays (%.1f GB per GPU) are far larger than the 126 MB L2" % (nloc * 32 / 1e9)},
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                              "traffic": None, "kernel": "dd_picard_iter_v6_k (one launch per species block)",

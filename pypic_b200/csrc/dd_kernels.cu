@@ -10,6 +10,11 @@ namespace cg = cooperative_groups;
 
 namespace pic {
 
+// slice counters of the dynamically scheduled window kernels: one int per launch, taken round-robin
+// from this pool and zeroed on the launch's stream right before it
+#define PIC_SCHED_SLOTS 256
+__device__ int g_sched_pool[PIC_SCHED_SLOTS];
+
 // optional per-CTA (start,end) %globaltimer pairs for load-balance studies (tools/kbench.py)
 __device__ unsigned long long* g_cta_timer = nullptr;
 __device__ __forceinline__ unsigned long long gtimer() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
@@ -504,7 +509,7 @@ template <bool FIRST, bool WU, bool BIG = false>
 __global__ void __launch_bounds__(V6_T, 1) dd_picard_iter_v6_k(
     const __grid_constant__ DDK k, int nchunks_fr, const double* __restrict__ x0, const double* __restrict__ u0,
     const double* x1i, double* x1, double* u1, int8_t* __restrict__ active, const double* __restrict__ Es,
-    double* __restrict__ acc, int* __restrict__ range_err) {
+    double* __restrict__ acc, int* __restrict__ range_err, int* __restrict__ sched) {
     extern __shared__ __align__(128) double sm[];
     __shared__ int s_cnt[8];
     unsigned long long* const tbuf = g_cta_timer;
@@ -547,16 +552,21 @@ __global__ void __launch_bounds__(V6_T, 1) dd_picard_iter_v6_k(
     fc.dx = k.dx; fc.idx = k.idx; fc.dt = k.dt;
     fc.hi_dx = 0; fc.ngm2 = 0;
     fc.hi_Lm1 = (unsigned)__double2hiint(k.L) - 1u;
-    // chunk -> CTA mapping: round-robin (CTA b takes chunks b, b+grid, ...: all CTAs sweep the same
-    // region of the sorted store together) or, flags bit6, blocked (CTA b owns a contiguous range of
-    // chunks: CTAs sit in different cells, so their window flushes do not meet on the same nodes)
-    const bool blocked = (k.flags & 64) != 0;
-    const int q_ = nchunks / (int)gridDim.x, rem_ = nchunks % (int)gridDim.x;
-    const int my_chunks = blocked ? q_ + ((int)blockIdx.x < rem_ ? 1 : 0)
-                                  : (nchunks - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
-    const long long first_chunk = blocked ? (long long)blockIdx.x * q_ + min((int)blockIdx.x, rem_) : (long long)blockIdx.x;
-    const long long woff = (long long)warp * (64 * V6_ROWS);
-    const long long chunk_step = blocked ? (long long)V6_CHUNK : (long long)gridDim.x * V6_CHUNK;
+    // Work units are 1024-particle SLICES, one warp each.  A warp's first slice is static
+    // (warp id), every further one is taken from a global counter (sched, zero at launch): a
+    // slice that is slow -- e.g. the re-injected, hence unsorted, slots that cluster where the
+    // wall-absorbed particles sat -- then delays one warp, not the CTA and not the kernel.  The
+    // next slice is acquired when the current one starts, so the TMA ring can run NST rows ahead
+    // across the slice boundary.  flags bit6 keeps the static round-robin of whole chunks.
+    const bool dynamic = !(k.flags & 64) && sched != nullptr;
+    const int nslices = nchunks * (V6_T / 32);
+    const int nwarps_total = (int)gridDim.x * (V6_T / 32);
+    auto next_slice = [&](int cur) -> int {
+        if (!dynamic) return cur + nwarps_total;       // == the same slice position of the CTA's next chunk
+        int v = 0;
+        if (lane == 0) v = atomicAdd(sched, 1);
+        return __shfl_sync(full, v, 0) + nwarps_total;
+    };
     const uint32_t row_bytes = FIRST ? 1024u : 1536u;
     // ---- producer: stateless -- the row requested is always the one V6_NST rows ahead of the row
     // being consumed and goes into the stage that row just drained, so every quantity is derived
@@ -570,10 +580,10 @@ __global__ void __launch_bounds__(V6_T, 1) dd_picard_iter_v6_k(
             if (!FIRST) bulk_g2s(dst + 1024, x1i + base, 512, bar);
         }
     };
-    long long cbase = first_chunk * V6_CHUNK + woff;               // first particle of this warp's slice
-    if (my_chunks > 0) {
+    int cur_slice = (int)blockIdx.x * (V6_T / 32) + warp;
+    if (cur_slice < nslices) {
 #pragma unroll
-        for (int s = 0; s < V6_NST; ++s) issue(cbase + 64 * s, s);
+        for (int s = 0; s < V6_NST; ++s) issue((long long)cur_slice * (64 * V6_ROWS) + 64 * s, s);
     }
     // column sums of the warp's 32 private windows -> global accumulators, windows cleared
     auto flush_windows = [&](int wbase_node) {
@@ -600,13 +610,16 @@ __global__ void __launch_bounds__(V6_T, 1) dd_picard_iter_v6_k(
     int stage = 0;
     uint32_t phase = 0;
 #pragma unroll 1
-    for (int c = 0; c < my_chunks; ++c, cbase += chunk_step) {
+    while (cur_slice < nslices) {
+        const int nxt_slice = next_slice(cur_slice);
+        const long long cbase = (long long)cur_slice * (64 * V6_ROWS);      // first particle of this slice
+        const long long nbase = (long long)nxt_slice * (64 * V6_ROWS);
         // species of the slice; a slice holding the species boundary re-selects per row
         const bool mixed = cbase < k.n_split && cbase + 64 * V6_ROWS > k.n_split;
         const bool sp_slice = cbase >= k.n_split;
         fc.c1 = sp_slice ? k.c1[1] : k.c1[0]; fc.c2 = sp_slice ? k.c2[1] : k.c2[0];
         fc.qpi = (sp_slice ? k.q[1] : k.q[0]) * k.p2c * k.idx;
-        const bool more = c + 1 < my_chunks;
+        const bool more = nxt_slice < nslices;
         int wb = NOWIN;
         long long ci = cbase + 2 * lane;
 #pragma unroll 1
@@ -684,9 +697,10 @@ __global__ void __launch_bounds__(V6_T, 1) dd_picard_iter_v6_k(
             // the barrier orders those uses before the elected lane's copy.
             __syncwarp();
             if (row < V6_ROWS - V6_NST) issue(cbase + 64 * (row + V6_NST), st_cur);
-            else if (more) issue(cbase + chunk_step + 64 * (row + V6_NST - V6_ROWS), st_cur);
+            else if (more) issue(nbase + 64 * (row + V6_NST - V6_ROWS), st_cur);
         }
         flush_windows(wb);
+        cur_slice = nxt_slice;
     }
     __syncthreads();
     if (threadIdx.x >= 1 && threadIdx.x <= 4 && s_cnt[threadIdx.x])
@@ -1144,6 +1158,17 @@ __global__ void __launch_bounds__(256) dd_sort_scatter_big_k(DDK k, const double
 
 using namespace pic;
 
+// a zeroed slice counter for one launch on stream st (see g_sched_pool)
+static int next_sched_slot(cudaStream_t st, int** out) {
+    static int* base = nullptr;
+    static unsigned next = 0;
+    if (!base) PIC_CHECK_CUDA(cudaGetSymbolAddress((void**)&base, g_sched_pool));
+    int* p = base + (next++ % PIC_SCHED_SLOTS);
+    PIC_CHECK_CUDA(cudaMemsetAsync(p, 0, sizeof(int), st));
+    *out = p;
+    return PIC_OK;
+}
+
 // counting sort driver shared by pic_dev_dd_sort_by_cell / pic_dev_sort_perm_by_cell
 template <bool PERM>
 static int sort_by_cell_impl(const DDK& k, const double* x0, const double* u0, const double* v0, const double* w0,
@@ -1284,7 +1309,10 @@ int pic_dev_dd_picard_iter2(const pic_dd_params* p, const double* x0, const doub
             int fr = 16;
             while (fr > 1 && 64.0 * fr > 3.0 * ppc) fr >>= 1;
             PIC_REQUIRE(nchunks < (1 << 28), "dd_picard_iter: shard too large");
-            kern<<<grid, V6_T, smem6b, st>>>(k, (int)nchunks | ((fr - 1) << 28), x0, u0, x1i, x1, u1, active, Es, acc, range_err);
+            int* sched = nullptr;
+            int rcs = next_sched_slot(st, &sched);
+            if (rcs) return rcs;
+            kern<<<grid, V6_T, smem6b, st>>>(k, (int)nchunks | ((fr - 1) << 28), x0, u0, x1i, x1, u1, active, Es, acc, range_err, sched);
             PIC_CHECK_LAUNCH();
         }
         const long long done = nchunks * V6_CHUNK;
@@ -1307,7 +1335,10 @@ int pic_dev_dd_picard_iter2(const pic_dd_params* p, const double* x0, const doub
             PIC_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem6));
             long long cap = device_sm_count();
             int grid = (int)(nchunks < cap ? nchunks : cap);
-            kern<<<grid, V6_T, smem6, st>>>(k, (int)nchunks, x0, u0, x1i, x1, u1, active, Es, acc, range_err);
+            int* sched = nullptr;
+            int rcs = next_sched_slot(st, &sched);
+            if (rcs) return rcs;
+            kern<<<grid, V6_T, smem6, st>>>(k, (int)nchunks, x0, u0, x1i, x1, u1, active, Es, acc, range_err, sched);
             PIC_CHECK_LAUNCH();
         }
         const long long done = nchunks * V6_CHUNK;

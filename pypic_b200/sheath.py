@@ -49,7 +49,7 @@ class SheathSim:
         # with warp-uniform pre-reduction; tiles: "smem" or "global" (grid too large for smem)
         # "window-big" forces the large-grid build of the window kernel (per-warp field windows, no
         # whole-grid tile; chosen automatically when the grid does not fit shared memory)
-        # "window-blocked": contiguous chunk ranges per CTA instead of the round-robin sweep (bit6)
+        # "window-blocked": static round-robin of whole chunks instead of dynamically scheduled slices (bit6)
         flags = {"window": 0, "window-blocked": 64, "window-big": 16, "window-ldg": 8, "atomic": 1,
                  "warp": 4}[deposit] | (2 if tiles == "global" else 0)
         self.params = _lib.DDParams(self.N, self.n_split, self.Ng, flags, self.dx, self.dt, self.L, self.p2c,
