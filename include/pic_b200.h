@@ -104,8 +104,11 @@ typedef struct {
                          (non-TMA) build of the window kernel; bit1: keep the grid tiles in
                          global memory (grids too large for shared memory); bit4: force the
                          large-grid build of the window kernel (per-warp field windows of 32
-                         nodes instead of the whole-grid tile, deposit windows flushed every 4
-                         rows) -- taken automatically when the grid does not fit shared memory */
+                         nodes instead of the whole-grid tile, deposit windows flushed every 1-16
+                         rows) -- taken automatically when the grid does not fit shared memory;
+                         bit5: pic_dev_dd_sort_by_cell takes its global-memory cursor path (faster
+                         on a nearly sorted store); bit6: static round-robin of whole chunks over
+                         the CTAs instead of dynamically scheduled 1024-particle slices */
     double dx, dt, L, p2c;
     double q[2], m[2];
 } pic_dd_params;
