@@ -292,6 +292,7 @@ def run_cuda(args):
     achieved = alg_bytes_launch / (mean_iter_ms * 1e-3) / 1e9
     peak, peak_src = measured_peak()
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "frac_of_nominal_8TBs": achieved / 8000.0,
                 "traffic": None, "kernel": "dd_picard_iter_v6_k", "peak_source": peak_src,
                 "kernel_ms_mean": mean_iter_ms, "kernel_share_of_step": float(np.sum(kernel_ms) / ms),
                 "algorithmic_bytes_per_launch": alg_bytes_launch, "mean_picard_iterations": kbar,
