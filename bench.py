@@ -485,7 +485,7 @@ def run_other(args):
     if args.workload == "explicit":
         L = dx * (cells - 1)
         sim = ExplicitSim(N, cells, dx, dt, (L + dx) * 1e19 / N, q=(-E_CH, E_CH), m=(ME, MP), n_split=N // 2, device=dev,
-                          sort_every=args.sort_every)
+                          sort_every=args.sort_every, track_order=False)
         sim.x.uniform_(0., 1., generator=gen).mul_(L + dx).clamp_(1e-12, (L + dx) * (1 - 1e-12))
         sim.v.normal_(0., 1., generator=gen)
         sim.v[:N // 2].mul_(float(np.sqrt(kT / ME))); sim.v[N // 2:].mul_(float(np.sqrt(kT / MP)))
@@ -496,7 +496,7 @@ def run_other(args):
     elif args.workload == "pypic":
         L = dx * cells
         sim = PeriodicImplicitSim(N, cells, dx, dt, L, L * 1e19 / N, tol=1e-3, maxiter=20, device=dev,
-                                  sort_every=args.sort_every)
+                                  sort_every=args.sort_every, track_order=False)
         sim.x0.uniform_(0., 1., generator=gen).mul_(L).clamp_(1e-12, L * (1 - 1e-12))
         sim.v0.normal_(0., 1., generator=gen).mul_(float(np.sqrt(kT / ME)))
         sim.iter_events = kernel_events

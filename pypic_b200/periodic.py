@@ -22,7 +22,7 @@ kb = 1.38E-23
 
 class PeriodicImplicitSim:
     def __init__(self, N, Ng, dx, dt, L, p2c, q=-e, m=me, tol=1e-3, maxiter=20, deposit="warp", comm=None,
-                 device=None, sort_every=0):
+                 device=None, sort_every=0, track_order=True):
         self.dev = D.require_cuda(device)
         self.comm = comm if comm is not None else Comm()
         self.N_global = int(N)
@@ -43,6 +43,8 @@ class PeriodicImplicitSim:
         self.sort_every = int(sort_every)
         self.t = 0
         self.perm = None                     # original index of the particle in each slot (after sorting)
+        self.track_order = bool(track_order)  # False: do not carry the original index through the sorts (download()
+                                              # then returns the particles in store order)
         self.params = _lib.PypicParams(self.N, self.Ng, flags, self.dx, self.dt, self.L, self.p2c, float(q), float(m))
         dev, n, g = self.dev, max(self.N, 1), self.Ng
         self.x0 = D.f64(n, dev, True); self.v0 = D.f64(n, dev, True)
@@ -55,6 +57,8 @@ class PeriodicImplicitSim:
         self.last_iters, self.last_resid = 0, 1.0
         self.kernel_launches = 0
         self.iter_events = None     # set to a list to record a CUDA-event pair per particle-kernel launch
+        self._sort_params = None
+        self._perm2 = None
 
     def upload(self, x0, v0, E0=None):
         s = slice(self.start, self.stop)
@@ -68,19 +72,22 @@ class PeriodicImplicitSim:
         arrays; the original index of every particle rides along as a payload so that
         download() can return the arrays in the caller's order."""
         n = max(self.N, 1)
-        if self.perm is None:
-            self.perm = torch.arange(n, dtype=torch.float64, device=self.dev)
-            self._perm2 = torch.empty_like(self.perm)
+        if self._sort_params is None:
+            if self.track_order:
+                self.perm = torch.arange(n, dtype=torch.float64, device=self.dev)
+                self._perm2 = torch.empty_like(self.perm)
             self._sort_counts = torch.zeros(D.sort_counts_size(self.Ng), dtype=torch.int32, device=self.dev)
             self._sort_params = _lib.DDParams(self.N, self.N, self.Ng, 0, self.dx, self.dt, self.L, self.p2c,
                                               (C.c_double * 2)(0., 0.), (C.c_double * 2)(1., 1.))
         _lib.call("pic_dev_dd_sort_by_cell", C.byref(self._sort_params), D.ptr(self.x0), D.ptr(self.v0),
-                  D.ptr(self.perm), None, D.ptr(self.x1), D.ptr(self.v1), D.ptr(self._perm2), None,
+                  D.ptr(self.perm), None, D.ptr(self.x1), D.ptr(self.v1), D.ptr(self._perm2) if self.track_order else None, None,
                   D.ptr(self._sort_counts), D.stream())
+        self._sort_params.flags = 32          # later sorts see a nearly sorted store: global-cursor path
         self.kernel_launches += 3
         self.x0, self.x1 = self.x1, self.x0
         self.v0, self.v1 = self.v1, self.v0
-        self.perm, self._perm2 = self._perm2, self.perm
+        if self.track_order:
+            self.perm, self._perm2 = self._perm2, self.perm
 
     def push(self):
         """particle_push_p: Picard loop + commit (x wrapped into [0,L)).  Returns (k, r)."""
@@ -143,7 +150,7 @@ class ExplicitSim:
     the NEXT step fused into the push kernel."""
 
     def __init__(self, N, Ng, dx, dt, p2c, q=(-e, -e), m=(me, me), n_split=None, deposit="warp", comm=None,
-                 device=None, sort_every=0):
+                 device=None, sort_every=0, track_order=True):
         self.dev = D.require_cuda(device)
         self.comm = comm if comm is not None else Comm()
         self.N_global = int(N)
@@ -159,6 +166,9 @@ class ExplicitSim:
         self.sort_every = int(sort_every)
         self.t = 0
         self.perm = None
+        self.track_order = bool(track_order)
+        self._sort_params = None
+        self._perm2 = None
         self.params = _lib.LParams(self.N, self.n_split, self.Ng, flags, self.dx, self.dt, self.L, self.p2c,
                                    (C.c_double * 2)(*q), (C.c_double * 2)(*m))
         dev, n, g = self.dev, max(self.N, 1), self.Ng + 1
@@ -212,20 +222,23 @@ class ExplicitSim:
     def sort_by_cell(self):
         """Counting sort by (species, cell) with the original index as a payload."""
         n = max(self.N, 1)
-        if self.perm is None:
-            self.perm = torch.arange(n, dtype=torch.float64, device=self.dev)
-            self._perm2 = torch.empty_like(self.perm)
+        if self._sort_params is None:
+            if self.track_order:
+                self.perm = torch.arange(n, dtype=torch.float64, device=self.dev)
+                self._perm2 = torch.empty_like(self.perm)
             self._x2 = torch.empty_like(self.x); self._v2 = torch.empty_like(self.v)
             self._sort_counts = torch.zeros(D.sort_counts_size(self.Ng), dtype=torch.int32, device=self.dev)
             self._sort_params = _lib.DDParams(self.N, self.n_split, self.Ng, 0, self.dx, self.dt, self.L, self.p2c,
                                               (C.c_double * 2)(0., 0.), (C.c_double * 2)(1., 1.))
         _lib.call("pic_dev_dd_sort_by_cell", C.byref(self._sort_params), D.ptr(self.x), D.ptr(self.v),
-                  D.ptr(self.perm), None, D.ptr(self._x2), D.ptr(self._v2), D.ptr(self._perm2), None,
+                  D.ptr(self.perm), None, D.ptr(self._x2), D.ptr(self._v2), D.ptr(self._perm2) if self.track_order else None, None,
                   D.ptr(self._sort_counts), D.stream())
+        self._sort_params.flags = 32          # later sorts see a nearly sorted store: global-cursor path
         self.kernel_launches += 3
         self.x, self._x2 = self._x2, self.x
         self.v, self._v2 = self._v2, self.v
-        self.perm, self._perm2 = self._perm2, self.perm
+        if self.track_order:
+            self.perm, self._perm2 = self._perm2, self.perm
 
     def step(self):
         if self.sort_every and self.t % self.sort_every == 0:
