@@ -41,6 +41,7 @@ def parse():
     ap.add_argument("--total-particles", type=float, default=0, help="strong scaling: fixed total (e.g. 1e9)")
     ap.add_argument("--cells", type=int, default=4096)
     ap.add_argument("--sort-every", type=int, default=8)
+    ap.add_argument("--heavy-sort-every", type=int, default=1, help="every n-th sort also re-sorts the ions (1 = always)")
     ap.add_argument("--deposit", default="window", choices=["window", "window-blocked", "window-big", "window-ldg", "warp", "atomic"])
     ap.add_argument("--workload", default="sheath", choices=["sheath", "explicit", "pypic", "boris"],
                     help="sheath = BASELINE configs[1] (default, the driver's bench); explicit / pypic / boris = "
@@ -239,6 +240,7 @@ def run_cuda(args):
     sim = SheathSim(w["N"], w["Ng"], w["dx"], w["dt"], w["p2c"], tol=w["tol"], maxiter=w["maxiter"],
                     kBT=(w["kBTe"], w["kBTi"]), carry_vw=False, deposit=args.deposit, rng="philox", seed=1,
                     comm=comm, device=dev, sort_every=args.sort_every)
+    sim.heavy_sort_every = max(1, args.heavy_sort_every)
     # synthetic initial state, generated on the device (x~U(0,L), u~N(0,sqrt(kT/m)))
     gen = torch.Generator(device=dev); gen.manual_seed(1234 + rank)
     n, ns = sim.N, sim.n_split
@@ -371,6 +373,8 @@ def run_cuda(args):
                        "parallelism": "particle decomposition x%d, fp64 all-reduce of [jh|j1|counts] per Picard iteration" % world
                        if world > 1 else "single GPU",
                        "picard_iterations_per_step": kbar, "deposit": args.deposit, "sort_every": args.sort_every,
+                       "sort": "electrons every %d steps, ions with them every %d steps" % (args.sort_every,
+                                                                                             args.sort_every * sim.heavy_sort_every),
                        "reinjection": "device Philox4x32-10 (statistical parity)",
                        "l2_policy": "inputs (%.1f GB of particle arrays per GPU) are far larger than the 126 MB L2" % (sim.N * 32 / 1e9)},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,

@@ -82,6 +82,9 @@ class SheathSim:
         self.scalar = D.f64(1, dev, True)
         self.t = 0
         self._sorted_once = False
+        self._sorts = 0
+        self.heavy_sort_every = 1     # n > 1: only every n-th sort also re-sorts the heavy species (measured: no gain,
+                                      # the kernel loses more on the ageing ion block than the sort saves)
         self.last_iters = 0
         self.last_resid = 1.0
         self.kernel_launches = 0
@@ -159,6 +162,22 @@ class SheathSim:
         # the sort (flags bit5) is then faster than the shared-memory one (2.5 vs 3.0 ms at 2e8
         # particles); the first sort of a random store takes the shared-memory path
         P = self.params
+        ns = self.n_split
+        light_only = (self._sorted_once and self._sorts % self.heavy_sort_every != 0 and 0 < ns < self.N
+                      and ns % 2 == 0 and self.m[0] < self.m[1])
+        self._sorts += 1
+        if light_only:
+            # the heavy species (ions) crosses a cell ~40x more slowly than the light one: between
+            # its own (rarer) sorts only the light block [0, n_split) is sorted, into the scratch
+            # arrays, and copied back -- 2.1 ms instead of 3.1 ms at 2e8 particles
+            P = _lib.DDParams(ns, ns, self.Ng, self.params.flags | 32, self.dx, self.dt, self.L, self.p2c,
+                              (C.c_double * 2)(*self.q), (C.c_double * 2)(*self.m))
+            _lib.call("pic_dev_dd_sort_by_cell", C.byref(P), D.ptr(self.x0), D.ptr(self.u0), None, None,
+                      D.ptr(self.x1), D.ptr(self.u1), None, None, D.ptr(self.sort_counts), st)
+            _lib.call("pic_dev_copy", D.ptr(self.x0), D.ptr(self.x1), ns * 8, st)
+            _lib.call("pic_dev_copy", D.ptr(self.u0), D.ptr(self.u1), ns * 8, st)
+            self.kernel_launches += 5
+            return
         if self._sorted_once:
             P = _lib.DDParams(self.N, self.n_split, self.Ng, self.params.flags | 32, self.dx, self.dt, self.L, self.p2c,
                               (C.c_double * 2)(*self.q), (C.c_double * 2)(*self.m))
