@@ -400,7 +400,10 @@ class ParticleStore:
         counts = torch.zeros(D.sort_counts_size(grid.ng), dtype=torch.int32, device=dev)
         st = D.stream()
         _lib.call("pic_dev_sort_perm_by_cell", C.byref(P), D.ptr(self.r[0]), D.ptr(xs), D.ptr(idx), D.ptr(counts), st)
-        f_src = self.r[1:] + [self.charge_state, self.m, self.p2c]
+        # a species-uniform store holds the same charge_state / m / p2c in every slot: permuting
+        # those three arrays would be the identity (saves 48 of ~180 B/particle of the permutation)
+        uni = self.uniform() is not None
+        f_src = self.r[1:] + ([] if uni else [self.charge_state, self.m, self.p2c])
         f_dst = [torch.empty(N, dtype=torch.float64, device=dev) for _ in f_src]
         b_src = [self.active, self.at_wall, self.from_wall, self.hit_flag]
         b_dst = [torch.empty(N, dtype=torch.int8, device=dev) for _ in b_src]
@@ -409,7 +412,8 @@ class ParticleStore:
         _lib.call("pic_dev_soa_permute", D.ptr(idx), N, arr(f_src), arr(f_dst), len(f_src), arr([self.Z]), arr([z_dst]), 1,
                   arr(b_src), arr(b_dst), len(b_src), st)
         self.r = [xs] + f_dst[:6]
-        self.charge_state, self.m, self.p2c = f_dst[6:]
+        if not uni:
+            self.charge_state, self.m, self.p2c = f_dst[6:]
         self.Z = z_dst
         self.active, self.at_wall, self.from_wall, self.hit_flag = b_dst
         if track:
