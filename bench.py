@@ -465,17 +465,27 @@ def run_other(args):
     pypic    = pypic.py periodic implicit CN/Picard full step;
     boris    = pygcpic Boris 1D3V step (fused gather+push+walls+deposit, Newton-Boltzmann solve)."""
     import torch
+    import torch.distributed as dist
+    from pypic_b200.dist import Comm
     from pypic_b200.periodic import ExplicitSim, PeriodicImplicitSim
     from pypic_b200.gcstore import GridDev, ParticleStore
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device (there is no CPU fallback)")
-    dev = torch.device("cuda", 0)
-    torch.cuda.set_device(0)
+    world = int(os.environ.get("WORLD_SIZE", "1")); rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    dev = torch.device("cuda", local)
+    torch.cuda.set_device(local)
+    if world > 1:
+        if args.workload != "boris":
+            raise SystemExit("bench.py: multi-GPU runs of --workload %s are not wired into bench.py "
+                             "(tools/mgpu_check.py covers their sharded parity)" % args.workload)
+        dist.init_process_group("nccl", device_id=dev)
+    comm = Comm()
     N = int(args.particles_per_gpu); N -= N % 2
     cells = args.cells
     dx, dt = 1e-5, 1e-12
     kT = KB * 116000.
-    gen = torch.Generator(device=dev); gen.manual_seed(1234)
+    gen = torch.Generator(device=dev); gen.manual_seed(1234 + rank)
     kernel_events = []
 
     def timed_call(fn):
@@ -516,13 +526,13 @@ def run_other(args):
         lamD = np.sqrt(8.854e-12 * KB * Te / (1e19 * E_CH ** 2))
         Lg = 100. * lamD * (ng - 1) / 149.       # the reference's resolution (150 nodes per 100 Debye lengths)
         alpha = 86. * np.pi / 180.
-        grid = GridDev(ng, Lg, Te, device=dev)
+        grid = GridDev(ng, Lg, Te, device=dev, comm=comm if world > 1 else None)
         store = ParticleStore(N, B=(2. * np.cos(alpha), 2. * np.sin(alpha), 0.), device=dev)
         store.r[0].uniform_(0., 1., generator=gen).mul_(Lg).clamp_(Lg * 1e-9, Lg * (1 - 1e-9))
         vth = float(np.sqrt(KB * Ti / MP))
         for c in (3, 4, 5):
             store.r[c].normal_(0., vth, generator=gen)
-        p2c = Lg * 1e19 / N
+        p2c = Lg * 1e19 / (N * world)
         store.charge_state.fill_(1.); store.m.fill_(MP); store.p2c.fill_(p2c); store.Z.fill_(1)
         dtg = 1e-10
         store.push_6D = timed_call(store.push_6D)
@@ -549,35 +559,39 @@ def run_other(args):
     for _ in range(args.warmup):
         step()
     check()
-    torch.cuda.synchronize()
+    torch.cuda.synchronize(); comm.barrier()
     kernel_events.clear(); iters.clear()
-    sampler = ClockSampler(0); sampler.start()
+    sampler = ClockSampler(local); sampler.start()
     l0 = launches()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record()
     for _ in range(args.steps):
         step()
     ev1.record()
-    torch.cuda.synchronize()
+    torch.cuda.synchronize(); comm.barrier()
     sampler.stop_flag = True
     check()
-    ms = ev0.elapsed_time(ev1)
+    ms = comm.max_float(ev0.elapsed_time(ev1), device=dev)
     kms = [a.elapsed_time(b) for a, b in kernel_events]
     kbar = float(np.mean(iters)) if iters else 1.0
     peak, peak_src = measured_peak()
     per_launch = N * alg(kbar)
     achieved = per_launch / (float(np.mean(kms)) * 1e-3) / 1e9
-    line = {"metric": METRIC, "value": N * args.steps / (ms * 1e-3), "unit": "particle-steps/s", "n_gpus": 1,
+    line = {"metric": METRIC, "value": N * world * args.steps / (ms * 1e-3), "unit": "particle-steps/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": desc, "parallelism": "single GPU", "sort_every": args.sort_every,
+            "config": {"workload": desc, "parallelism": "single GPU" if world == 1 else
+                       "particle decomposition x%d (%d particles per GPU), all-reduce of the deposited density per step" % (world, N),
+                       "sort_every": args.sort_every,
                        "picard_iterations_per_step": kbar if iters else None,
                        "l2_policy": "particle arrays (%.1f GB) are far larger than the 126 MB L2" % (N * alg(kbar) / 2 / 1e9)},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": None, "kernel": kname, "peak_source": peak_src, "kernel_ms_mean": float(np.mean(kms)),
                          "kernel_share_of_step": float(np.sum(kms) / ms), "algorithmic_bytes_per_launch": per_launch},
             "cpu_baseline": None, "e2e": None, "gpu_launches": int(launches() - l0), "clocks": sampler.summary()}
-    return line
+    if world > 1:
+        dist.destroy_process_group()
+    return line if rank == 0 else None
 
 
 class _StdoutGuard:

@@ -21,7 +21,10 @@ kb = 1.38e-23
 
 
 class GridDev:
-    def __init__(self, ng, length, Te, bc="dirichlet-dirichlet", device=None):
+    def __init__(self, ng, length, Te, bc="dirichlet-dirichlet", device=None, comm=None):
+        """comm (pypic_b200.dist.Comm): particle decomposition over ranks -- every rank deposits its
+        own particles and the grid moments [rho | n] are all-reduced; the field
+        solve is replicated."""
         assert ng > 1, "Number of grid points must be greater than 1"
         assert length > 0.0, "Length must be greater than 0"
         if not isinstance(bc, str):
@@ -29,6 +32,7 @@ class GridDev:
         if bc not in ("dirichlet-dirichlet", "dirichlet-neumann"):
             raise ValueError("Unimplemented boundary condition. Choose dirichlet_dirichlet or dirichlet_neumann")
         self.dev = D.require_cuda(device)
+        self.comm = comm
         self.ng, self.length, self.Te, self.bc = int(ng), float(length), float(Te), bc
         self.domain_h = np.linspace(0.0, length, ng)
         self.dx = float(self.domain_h[1] - self.domain_h[0])
@@ -80,6 +84,8 @@ class GridDev:
         _lib.call("pic_dev_gc_weight", D.ptr(store.r[0]), D.ptr(store.charge_state), D.ptr(store.p2c),
                   D.ptr(store.active), D.ptr(self.rho), D.ptr(self.n), store.N, self.ng, self.dx,
                   D.ptr(self.range_err), st)
+        if self.comm is not None:
+            self.comm.allreduce_sum(self.rho); self.comm.allreduce_sum(self.n)
         _lib.call("pic_dev_gc_n0_update", D.ptr(self.phi), D.ptr(self.n), D.ptr(self.domain), self.ng, self.Te, self.ve,
                   float(self.added_particles), float(dt), D.ptr(self.state), st)
 
@@ -99,6 +105,8 @@ class GridDev:
         """n, rho from the density the fused push deposited (+ re-activated slots), then the
         Boltzmann reference-density update of pygcpic.py:889-904."""
         st = D.stream()
+        if self.comm is not None:
+            self.comm.allreduce_sum(self.n_acc)
         _lib.call("pic_dev_gc_uniform_finish", D.ptr(self.n_acc), D.ptr(self.n), D.ptr(self.rho), self.ng,
                   float(charge_state), st)
         _lib.call("pic_dev_gc_n0_update", D.ptr(self.phi), D.ptr(self.n), D.ptr(self.domain), self.ng, self.Te, self.ve,

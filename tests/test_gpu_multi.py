@@ -25,6 +25,8 @@ def test_two_rank_sheath_matches_single_gpu():
     assert out["iters_sharded"] == out["iters_single"]
     per = [l for l in lines if "periodic" in l][-1]["periodic"]
     assert per["ok"], per
+    bor = [l for l in lines if "boris" in l][-1]["boris"]
+    assert bor["ok"], bor
 
 
 def test_two_rank_slab_decomposition_matches_single_rank():
