@@ -152,6 +152,17 @@ int pic_dev_dd_picard_iter2(const pic_dd_params* p, const double* x0, const doub
 int pic_dev_dd_commit_u(const pic_dd_params* p, const double* x0, const double* u0, const double* x1_prev,
                         const double* x1_last, const int8_t* active, const double* Es, double* u1, int first,
                         int* range_err, void* stream);
+/* Light iterations: pic_dev_dd_picard_iter2 called with u1 == NULL neither stores the velocities nor
+ * deposits j1 (the current at n+1, PIC_L_DD.py:513, is only used after the Picard loop).  If the loop
+ * ends on such an iteration, pic_dev_dd_commit_u2 recomputes u1 AND deposits the survivors' j1 into
+ * acc[Ng..2Ng) (acc != NULL), and -- after the caller's all-reduce of acc when sharded --
+ * pic_dev_dd_j1_finish applies the wall terms from the cumulative counts and the edge fold
+ * (PIC_L_DD.py:55-66), writes j1[Ng] and stats[1] = mean(j1), and zeroes the accumulator. */
+int pic_dev_dd_commit_u2(const pic_dd_params* p, const double* x0, const double* u0, const double* x1_prev,
+                         const double* x1_last, const int8_t* active, const double* Es, double* u1,
+                         int first, double* acc, int* range_err, void* stream);
+int pic_dev_dd_j1_finish(const pic_dd_params* p, double* acc, const double* wall_cum, double* j1,
+                         double* stats, void* stream);
 /* Device self test: compares the constant-divisor division and the fast cell lookup used
  * on the hot path against the IEEE operations for n pseudo-random / adversarial operands;
  * *mismatches_dev (device uint64, zeroed by the caller) must stay 0. */

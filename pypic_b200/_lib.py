@@ -69,6 +69,8 @@ _SIGS = {
     "pic_dev_dd_picard_iter": [C.POINTER(DDParams), P, P, P, P, P, P, P, I32, P, P],
     "pic_dev_dd_picard_iter2": [C.POINTER(DDParams), P, P, P, P, P, P, P, P, I32, P, P],
     "pic_dev_dd_commit_u": [C.POINTER(DDParams), P, P, P, P, P, P, P, I32, P, P],
+    "pic_dev_dd_commit_u2": [C.POINTER(DDParams), P, P, P, P, P, P, P, I32, P, P, P],
+    "pic_dev_dd_j1_finish": [C.POINTER(DDParams), P, P, P, P, P],
     "pic_dev_debug_cta_timer": [P],
     "pic_dev_selftest_div": [F64, C.c_uint64, C.c_uint64, P, P],
     "pic_dev_dd_field_update": [C.POINTER(DDParams), P, P, P, P, P, P, P, P],

@@ -131,13 +131,15 @@ __global__ void __launch_bounds__(256) dd_picard_iter_k(DDK k, const double* __r
             const double qs = sp ? k.q[1] : k.q[0];
             double qv = qs * UH * k.p2c;
             hL = qv * ch.wL * k.idx; hR = qv * ch.wR * k.idx;
-            cf = cell_dd(X1, k.dx);
-            if (cf.iL < 0 || cf.iL > Ng - 2) { ++bad; cf.iL = clampi(cf.iL, 0, Ng - 2); }
-            double qf = qs * U1 * k.p2c;
-            fL = qf * cf.wL * k.idx; fR = qf * cf.wR * k.idx;
+            if (u1) {                 // a light iteration (no velocity store) deposits only jh
+                cf = cell_dd(X1, k.dx);
+                if (cf.iL < 0 || cf.iL > Ng - 2) { ++bad; cf.iL = clampi(cf.iL, 0, Ng - 2); }
+                double qf = qs * U1 * k.p2c;
+                fL = qf * cf.wL * k.idx; fR = qf * cf.wR * k.idx;
+            }
         }
         deposit_pair<AGG>(jh, ch.iL, hL, hR, alive);
-        deposit_pair<AGG>(j1, cf.iL, fL, fR, alive);
+        if (u1) deposit_pair<AGG>(j1, cf.iL, fL, fR, alive);
     }
     if (TILE) {
         __syncthreads();
@@ -189,7 +191,7 @@ struct SlowOut { int code; int bad; };   // code: 0 deposited, 1..4 absorbed (L 
 // atomics into the CTA's fallback tiles tj = [jh | j1].
 __device__ __noinline__ SlowOut dd_particle_slow(const DDK& k, long long i, double X0, double U0, double pX1, int act,
                                                  bool first, const double* sF, double* tj, double* x1,
-                                                 double* u1, int8_t* __restrict__ active) {
+                                                 double* u1, int8_t* __restrict__ active, bool j1 = true) {
     SlowOut o{0, 0};
     const int Ng = k.Ng;
     if (!first && act != 1) { x1[i] = 0.0; if (u1) u1[i] = 0.0; o.code = 5; return o; }   // reference leaves zeros
@@ -205,13 +207,17 @@ __device__ __noinline__ SlowOut dd_particle_slow(const DDK& k, long long i, doub
     x1[i] = X1; if (u1) u1[i] = U1;
     if (X0 >= k.L || XH >= k.L || X1 >= k.L) { active[i] = 0; o.code = sp ? 4 : 3; return o; }
     if (X0 <= 0.0 || XH <= 0.0 || X1 <= 0.0) { active[i] = -1; o.code = sp ? 2 : 1; return o; }
-    Cell a = cell_dd(XH, k.dx), b = cell_dd(X1, k.dx);
+    Cell a = cell_dd(XH, k.dx);
     if (a.iL < 0 || a.iL > Ng - 2) { ++o.bad; a.iL = clampi(a.iL, 0, Ng - 2); }
-    if (b.iL < 0 || b.iL > Ng - 2) { ++o.bad; b.iL = clampi(b.iL, 0, Ng - 2); }
     const double qs = sp ? k.q[1] : k.q[0];
-    double qv = qs * UH * k.p2c, qf = qs * U1 * k.p2c;
+    double qv = qs * UH * k.p2c;
     atomicAdd(&tj[a.iL], qv * a.wL * k.idx); atomicAdd(&tj[a.iL + 1], qv * a.wR * k.idx);
-    atomicAdd(&tj[Ng + b.iL], qf * b.wL * k.idx); atomicAdd(&tj[Ng + b.iL + 1], qf * b.wR * k.idx);
+    if (j1) {
+        Cell b = cell_dd(X1, k.dx);
+        if (b.iL < 0 || b.iL > Ng - 2) { ++o.bad; b.iL = clampi(b.iL, 0, Ng - 2); }
+        double qf = qs * U1 * k.p2c;
+        atomicAdd(&tj[Ng + b.iL], qf * b.wL * k.idx); atomicAdd(&tj[Ng + b.iL + 1], qf * b.wR * k.idx);
+    }
     return o;
 }
 
@@ -437,7 +443,9 @@ struct FastO6 { double X1, U1, hL, hR, fL, fR; int cH, cF; unsigned fr, ps; bool
 // of the whole field tile; a gather cell outside it sets o.emiss and the particle is redone by the
 // exact routine with the field read from global memory.
 #define V6_EW 32
-template <bool FIRST, bool BIG>
+// J1 = false: a "light" iteration that deposits only jh -- j1 (the current at n+1, PIC_L_DD.py:513) is
+// only used after the Picard loop, so only the LAST iteration needs it (see SheathSim.picard).
+template <bool FIRST, bool BIG, bool J1>
 __device__ __forceinline__ void dd_fast6(const FastC& c, const double* __restrict__ sF, int Ng, int eb, double X0,
                                          double U0, double pX1, FastO6& o) {
     const double xs = FIRST ? X0 : (X0 + pX1) * 0.5;
@@ -462,14 +470,19 @@ __device__ __forceinline__ void dd_fast6(const FastC& c, const double* __restric
     const unsigned f1 = (unsigned)__double2hiint(th - fh) - PIC_HI_G;
     const double rh = fma(-fh, c.dx, XH);
     o.cH = (int)fh;
-    const double tf = o.X1 * c.idx, ff = floor(tf);
-    const unsigned f2 = (unsigned)__double2hiint(tf - ff) - PIC_HI_G;
-    const double rf = fma(-ff, c.dx, o.X1);
-    o.cF = (int)ff;
-    o.fr = __vimax3_u32(f0, f1, f2);
-    const double ah = c.qpi * UH, af = c.qpi * o.U1;
+    const double ah = c.qpi * UH;
     o.hR = ah * (rh * c.idx); o.hL = ah - o.hR;
-    o.fR = af * (rf * c.idx); o.fL = af - o.fR;
+    if (J1) {
+        const double tf = o.X1 * c.idx, ff = floor(tf);
+        const unsigned f2 = (unsigned)__double2hiint(tf - ff) - PIC_HI_G;
+        const double rf = fma(-ff, c.dx, o.X1);
+        o.cF = (int)ff;
+        o.fr = __vimax3_u32(f0, f1, f2);
+        const double af = c.qpi * o.U1;
+        o.fR = af * (rf * c.idx); o.fL = af - o.fR;
+    } else {
+        o.cF = o.cH; o.fr = max(f0, f1); o.fR = 0.0; o.fL = 0.0;
+    }
 }
 
 // Non-common cases of one particle, cheapest first: (1) absorbed in an earlier iteration of this
@@ -477,7 +490,7 @@ __device__ __forceinline__ void dd_fast6(const FastC& c, const double* __restric
 // inside the domain at entry -> the fast-path X1,U1 are the exact values, the walls are tested
 // with the reference's comparisons and a survivor deposits into the window (or the global
 // accumulators); (3) everything else -> dd_particle_slow (IEEE divisions).
-template <bool FIRST>
+template <bool FIRST, bool J1>
 __device__ __forceinline__ void dd_medium(const DDK& k, const FastC& fc, long long i, double X0, double U0, double pX1,
                                           const FastO6& o, int act, bool straddle, bool sp, const double* sF, double* myw,
                                           int wb, double* __restrict__ acc, int* s_cnt, double* x1,
@@ -496,11 +509,12 @@ __device__ __forceinline__ void dd_medium(const DDK& k, const FastC& fc, long lo
         }
         if (o.fr <= PIC_HI_SPAN && o.ps < fc.hi_Lm1) {
             x1[i] = o.X1; if (u1) u1[i] = o.U1;
-            win_add6(myw, acc, wb, 0, k.Ng, o.cH, o.hL, o.hR); win_add6(myw, acc, wb, 1, k.Ng, o.cF, o.fL, o.fR);
+            win_add6(myw, acc, wb, 0, k.Ng, o.cH, o.hL, o.hR);
+            if (J1) win_add6(myw, acc, wb, 1, k.Ng, o.cF, o.fL, o.fR);
             return;
         }
     }
-    SlowOut so = dd_particle_slow(k, i, X0, U0, pX1, act, FIRST, sF, acc, x1, u1, active);
+    SlowOut so = dd_particle_slow(k, i, X0, U0, pX1, act, FIRST, sF, acc, x1, u1, active, J1);
     if (so.code >= 1 && so.code <= 4) atomicAdd(&s_cnt[so.code], 1);
     if (so.bad) atomicAdd(&s_cnt[0], so.bad);
 }
@@ -650,8 +664,8 @@ __global__ void __launch_bounds__(V6_T, 1) dd_picard_iter_v6_k(
                 __syncwarp();
             }
             FastO6 a, b;
-            dd_fast6<FIRST, BIG>(fc, fE, Ng, eb, X0.x, U0.x, pX1.x, a);
-            dd_fast6<FIRST, BIG>(fc, fE, Ng, eb, X0.y, U0.y, pX1.y, b);
+            dd_fast6<FIRST, BIG, WU>(fc, fE, Ng, eb, X0.x, U0.x, pX1.x, a);
+            dd_fast6<FIRST, BIG, WU>(fc, fE, Ng, eb, X0.y, U0.y, pX1.y, b);
             const bool ra = (a.fr > PIC_HI_SPAN) | (a.ps >= fc.hi_Lm1) | straddle | a.emiss;
             const bool rb = (b.fr > PIC_HI_SPAN) | (b.ps >= fc.hi_Lm1) | straddle | b.emiss;
             if ((row & FRm) == 0) {
@@ -662,7 +676,7 @@ __global__ void __launch_bounds__(V6_T, 1) dd_picard_iter_v6_k(
             }
             const unsigned dah = (unsigned)(a.cH - wb), daf = (unsigned)(a.cF - wb);
             const unsigned dbh = (unsigned)(b.cH - wb), dbf = (unsigned)(b.cF - wb);
-            const bool inwin = max(__vimax3_u32(dah, daf, dbh), dbf) <= (unsigned)(V6_W - 2);
+            const bool inwin = (WU ? max(__vimax3_u32(dah, daf, dbh), dbf) : max(dah, dbh)) <= (unsigned)(V6_W - 2);
             if (!(ra | rb)) {
                 // the common case: two 128-bit streaming stores and eight conflict-free private RMWs;
                 // a lane whose particles drifted out of the warp's window since the last sort falls
@@ -671,12 +685,14 @@ __global__ void __launch_bounds__(V6_T, 1) dd_picard_iter_v6_k(
                 if (WU) __stcs((double2*)(u1 + ci), make_double2(a.U1, b.U1));
                 if (inwin) {
                     double* p = myw + dah * V6_T; p[0] += a.hL; p[V6_T] += a.hR;
-                    p = myw + (V6_W + daf) * V6_T; p[0] += a.fL; p[V6_T] += a.fR;
+                    if (WU) { p = myw + (V6_W + daf) * V6_T; p[0] += a.fL; p[V6_T] += a.fR; }
                     p = myw + dbh * V6_T; p[0] += b.hL; p[V6_T] += b.hR;
-                    p = myw + (V6_W + dbf) * V6_T; p[0] += b.fL; p[V6_T] += b.fR;
+                    if (WU) { p = myw + (V6_W + dbf) * V6_T; p[0] += b.fL; p[V6_T] += b.fR; }
                 } else {
-                    win_add6(myw, acc, wb, 0, Ng, a.cH, a.hL, a.hR); win_add6(myw, acc, wb, 1, Ng, a.cF, a.fL, a.fR);
-                    win_add6(myw, acc, wb, 0, Ng, b.cH, b.hL, b.hR); win_add6(myw, acc, wb, 1, Ng, b.cF, b.fL, b.fR);
+                    win_add6(myw, acc, wb, 0, Ng, a.cH, a.hL, a.hR);
+                    if (WU) win_add6(myw, acc, wb, 1, Ng, a.cF, a.fL, a.fR);
+                    win_add6(myw, acc, wb, 0, Ng, b.cH, b.hL, b.hR);
+                    if (WU) win_add6(myw, acc, wb, 1, Ng, b.cF, b.fL, b.fR);
                 }
             } else {
                 // one flag load for the pair (ci is even); dead and freshly absorbed particles are
@@ -686,8 +702,8 @@ __global__ void __launch_bounds__(V6_T, 1) dd_picard_iter_v6_k(
                     const short fl = *(const short*)(active + ci);
                     acta = (int)(signed char)(fl & 0xff); actb = (int)(signed char)(fl >> 8);
                 }
-                dd_medium<FIRST>(k, fc, ci, X0.x, U0.x, pX1.x, a, acta, straddle, sp, gE, myw, wb, acc, s_cnt, x1, WU ? u1 : nullptr, active);
-                dd_medium<FIRST>(k, fc, ci + 1, X0.y, U0.y, pX1.y, b, actb, straddle, sp, gE, myw, wb, acc, s_cnt, x1, WU ? u1 : nullptr, active);
+                dd_medium<FIRST, WU>(k, fc, ci, X0.x, U0.x, pX1.x, a, acta, straddle, sp, gE, myw, wb, acc, s_cnt, x1, WU ? u1 : nullptr, active);
+                dd_medium<FIRST, WU>(k, fc, ci + 1, X0.y, U0.y, pX1.y, b, actb, straddle, sp, gE, myw, wb, acc, s_cnt, x1, WU ? u1 : nullptr, active);
             }
             // Refill the stage this row drained with the row V6_NST ahead (possibly in the next chunk).
             // This must not happen before every lane's LDS of the stage has EXECUTED: an LDS can sit
@@ -1246,7 +1262,7 @@ __global__ void __launch_bounds__(256) dd_commit_u_k(DDK k, const double* __rest
                                                      const double* __restrict__ x1_prev, const double* __restrict__ x1_last,
                                                      const int8_t* __restrict__ active, const double* __restrict__ Es,
                                                      double* __restrict__ u1, int first, int tile,
-                                                     int* __restrict__ range_err) {
+                                                     double* __restrict__ j1_acc, int* __restrict__ range_err) {
     extern __shared__ double sFt[];
     const int Ng = k.Ng;
     const double* sF = Es;                       // large grids: gather from global memory / L2
@@ -1268,9 +1284,41 @@ __global__ void __launch_bounds__(256) dd_commit_u_k(DDK k, const double* __rest
         Cell c = cell_dd_fast(xs, k.dx, k.idx);
         if (c.iL < 0 || c.iL > Ng - 2) { ++bad; c.iL = clampi(c.iL, 0, Ng - 2); }
         const double Ei = c.wL * sF[c.iL] + c.wR * sF[c.iL + 1];
-        st_stream(u1 + i, U0 + ((i >= k.n_split) ? k.c1[1] : k.c1[0]) * Ei);
+        const bool sp = i >= k.n_split;
+        const double U1 = U0 + (sp ? k.c1[1] : k.c1[0]) * Ei;
+        st_stream(u1 + i, U1);
+        // j1 of a light last iteration: the survivors' current at n+1 (PIC_L_DD.py:513)
+        if (j1_acc && active[i] == 1) {
+            Cell b = cell_dd(x1_last[i], k.dx);
+            if (b.iL < 0 || b.iL > Ng - 2) { ++bad; b.iL = clampi(b.iL, 0, Ng - 2); }
+            const double qf = (sp ? k.q[1] : k.q[0]) * U1 * k.p2c;
+            atomicAdd(&j1_acc[b.iL], qf * b.wL * k.idx); atomicAdd(&j1_acc[b.iL + 1], qf * b.wR * k.idx);
+        }
     }
     if (bad && range_err) atomicAdd(range_err, bad);
+}
+
+// j1 part of the field phase alone (PIC_L_DD.py:55-66 applied to j1, :551): wall terms from the
+// cumulative counts, edge fold, mean; the j1 accumulator is zeroed.  One CTA.
+__global__ void __launch_bounds__(1024) dd_j1_finish_k(DDK k, double* __restrict__ acc, const double* __restrict__ wall_cum,
+                                                       double* __restrict__ j1o, double* __restrict__ stats) {
+    __shared__ double scratch[33];
+    const int Ng = k.Ng;
+    const double wallL = wall_cum[0] * (k.dx * k.q[0] * k.p2c / k.dt) + wall_cum[1] * (k.dx * k.q[1] * k.p2c / k.dt);
+    const double wallR = wall_cum[2] * (-k.dx * k.q[0] * k.p2c / k.dt) + wall_cum[3] * (-k.dx * k.q[1] * k.p2c / k.dt);
+    double* j1 = acc + Ng;
+    double s1 = 0.0;
+    for (int i = threadIdx.x; i < Ng; i += blockDim.x) {
+        double b = j1[i];
+        if (i == 0) b = (b + wallL) + j1[1];
+        if (i == Ng - 1) b = (b + wallR) + j1[Ng - 2];
+        s1 += b;
+        j1o[i] = b;
+    }
+    s1 = block_reduce<0>(s1, scratch);
+    __syncthreads();
+    for (int i = threadIdx.x; i < Ng; i += blockDim.x) j1[i] = 0.0;
+    if (threadIdx.x == 0) stats[1] = s1 / (double)Ng;
 }
 
 extern "C" {
@@ -1380,6 +1428,21 @@ int pic_dev_dd_picard_iter(const pic_dd_params* p, const double* x0, const doubl
 int pic_dev_dd_commit_u(const pic_dd_params* p, const double* x0, const double* u0, const double* x1_prev,
                         const double* x1_last, const int8_t* active, const double* Es, double* u1, int first,
                         int* range_err, void* stream) {
+    return pic_dev_dd_commit_u2(p, x0, u0, x1_prev, x1_last, active, Es, u1, first, nullptr, range_err, stream);
+}
+
+int pic_dev_dd_j1_finish(const pic_dd_params* p, double* acc, const double* wall_cum, double* j1, double* stats,
+                         void* stream) {
+    PIC_REQUIRE(p && acc && wall_cum && j1 && stats, "dd_j1_finish: null pointer");
+    DDK k = make_ddk(p);
+    dd_j1_finish_k<<<1, 1024, 0, (cudaStream_t)stream>>>(k, acc, wall_cum, j1, stats);
+    PIC_CHECK_LAUNCH();
+    return PIC_OK;
+}
+
+int pic_dev_dd_commit_u2(const pic_dd_params* p, const double* x0, const double* u0, const double* x1_prev,
+                         const double* x1_last, const int8_t* active, const double* Es, double* u1, int first,
+                         double* acc, int* range_err, void* stream) {
     PIC_REQUIRE(p && x0 && u0 && x1_prev && x1_last && active && Es && u1, "dd_commit_u: null pointer");
     if (p->N == 0) return PIC_OK;
     DDK k = make_ddk(p);
@@ -1390,7 +1453,7 @@ int pic_dev_dd_commit_u(const pic_dd_params* p, const double* x0, const double* 
     int occ = 0;
     PIC_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, dd_commit_u_k, 256, smem));
     dd_commit_u_k<<<grid_for(k.N, 256, occ > 0 ? occ : 1), 256, smem, (cudaStream_t)stream>>>(
-        k, x0, u0, x1_prev, x1_last, active, Es, u1, first, tile, range_err);
+        k, x0, u0, x1_prev, x1_last, active, Es, u1, first, tile, acc ? acc + k.Ng : nullptr, range_err);
     PIC_CHECK_LAUNCH();
     return PIC_OK;
 }

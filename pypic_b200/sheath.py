@@ -201,10 +201,11 @@ class SheathSim:
     def picard(self):
         """PIC_L_DD.py:452-545: Picard loop + commit.  Returns (iterations, residual).
 
-        The velocities u1 are only needed by the commit, so an iteration streams them (8 of its
-        40 bytes per particle) only when it is expected to be the last one; if the loop ends on an
-        iteration that skipped them, pic_dev_dd_commit_u recomputes them from that iteration's
-        inputs (kept intact by ping-ponging the position buffers)."""
+        The velocities u1 and the current j1 at n+1 are only needed after the loop, so an iteration
+        stores / deposits them only when it is expected to be the last one ("light" iterations
+        stream 32 instead of 40 bytes per particle and skip a third of the deposit work); if the
+        loop ends on a light iteration, pic_dev_dd_commit_u2 + pic_dev_dd_j1_finish recompute both
+        from that iteration's inputs (kept intact by ping-ponging the position buffers)."""
         st = D.stream()
         P = C.byref(self.params)
         self.Es.copy_(self.E0)
@@ -241,10 +242,13 @@ class SheathSim:
             if self.elide_u:
                 xin, xout = xout, xin
         if k > 0 and not wrote_u:
-            _lib.call("pic_dev_dd_commit_u", P, D.ptr(self.x0), D.ptr(self.u0), D.ptr(last_in), D.ptr(last_out),
-                      D.ptr(self.active), D.ptr(self.Es_prev), D.ptr(self.u1), 1 if k == 1 else 0,
+            # the loop ended on a light iteration: recompute its velocities and its j1
+            _lib.call("pic_dev_dd_commit_u2", P, D.ptr(self.x0), D.ptr(self.u0), D.ptr(last_in), D.ptr(last_out),
+                      D.ptr(self.active), D.ptr(self.Es_prev), D.ptr(self.u1), 1 if k == 1 else 0, D.ptr(self.acc),
                       D.ptr(self.range_err), st)
-            self.kernel_launches += 1
+            self.comm.allreduce_sum(self.acc)
+            _lib.call("pic_dev_dd_j1_finish", P, D.ptr(self.acc), D.ptr(self.wall_cum), D.ptr(self.j0), D.ptr(self.stats), st)
+            self.kernel_launches += 2
             self.u_repairs += 1
         if hist:
             ratios = [b / a for a, b in zip(hist, hist[1:]) if a > 0.0]

@@ -253,12 +253,20 @@ def test_velocity_store_elision_and_repair_bit_exact(deposit):
                   D.ptr(tEs), D.ptr(acc), first, D.ptr(err), D.stream())
         assert torch.equal(xout, rx1) and torch.equal(eact, ract), it
         assert torch.equal(acc[2 * Ng:], acc_ref[2 * Ng:])
-        assert relmax(acc.cpu().numpy()[:2 * Ng], acc_ref.cpu().numpy()[:2 * Ng]) < 1e-13
+        # a light iteration deposits jh only; j1 stays zero until the repair pass
+        assert relmax(acc.cpu().numpy()[:Ng], acc_ref.cpu().numpy()[:Ng]) < 1e-13
+        assert float(acc[Ng:2 * Ng].abs().max()) == 0.0
         assert float(eu1.min()) == 7.0 and float(eu1.max()) == 7.0            # the iteration did not touch u1
         rep = torch.full((N,), -3.0, dtype=torch.float64, device=dev)
         _lib.call("pic_dev_dd_commit_u", C.byref(P), D.ptr(tx0), D.ptr(tu0), D.ptr(xin), D.ptr(xout), D.ptr(eact), D.ptr(tEs),
                   D.ptr(rep), first, D.ptr(err), D.stream())
         assert torch.equal(rep, ru1), it
+        # the repair pass with an accumulator also deposits the survivors' j1 (raw CIC sums)
+        rep2 = torch.full((N,), -3.0, dtype=torch.float64, device=dev)
+        _lib.call("pic_dev_dd_commit_u2", C.byref(P), D.ptr(tx0), D.ptr(tu0), D.ptr(xin), D.ptr(xout), D.ptr(eact), D.ptr(tEs),
+                  D.ptr(rep2), first, D.ptr(acc), D.ptr(err), D.stream())
+        assert torch.equal(rep2, ru1), it
+        assert relmax(acc.cpu().numpy()[Ng:2 * Ng], acc_ref.cpu().numpy()[Ng:2 * Ng]) < 1e-13
         dead = int((ract != 1).sum())
         assert dead > 20
         if it >= 2:
@@ -269,9 +277,10 @@ def test_velocity_store_elision_and_repair_bit_exact(deposit):
 
 
 def test_sheath_sim_elision_modes_agree():
-    """SheathSim with the velocity-store elision (default), with every prediction forced wrong
-    (repair pass after every step) and without elision: same iteration counts, same fields and
-    particles to round-off over several steps."""
+    """SheathSim with light iterations (no velocity store, no j1 deposit unless the iteration is
+    expected to be the last; default), with every prediction forced wrong (repair pass after every
+    step) and without them: same iteration counts, same fields, currents and particles to
+    round-off over several steps."""
     from pypic_b200.sheath import SheathSim
     N, Ng = 200000, 257
     dx, L, dt, x0, u0, q, m, E0 = _one_iter_inputs(N, Ng, 5)
@@ -292,6 +301,9 @@ def test_sheath_sim_elision_modes_agree():
             assert np.array_equal(o["active"], ref["active"])
             assert relmax(o["E0"], ref["E0"]) < 1e-12
             assert relmax(o["x0"], ref["x0"]) < 1e-13 and relmax(o["u0"], ref["u0"]) < 1e-12
+            # j1 (the current at n+1) is deposited only by the last iteration, or by the repair pass
+            assert relmax(o["j0"], ref["j0"]) < 1e-12
+            assert abs(s.diagnostics()["jbias"] - sims[0].diagnostics()["jbias"]) <= 1e-12 * np.max(np.abs(ref["j0"]))
     assert sims[0].u_repairs == 0 and sims[2].u_repairs == 5
     assert sims[1].u_repairs <= 1            # only the very first step has no contraction history
     for s in sims:
