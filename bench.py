@@ -301,7 +301,11 @@ def run_cuda(args):
                 "kernel_ms_by_kind": {"first_iteration": float(np.mean(ms_first)) if ms_first else None,
                                       "later_without_u1_store": float(np.mean(ms_without_u)) if ms_without_u else None,
                                       "later_with_u1_store": float(np.mean(ms_with_u)) if ms_with_u else None},
-                "u1_repair_passes": int(sim.u_repairs)}
+                "u1_repair_passes": int(sim.u_repairs),
+                "note": "achieved = ALGORITHMIC bytes (SURVEY 8d: 32 B per Picard iteration + 16 B commit per particle-step) / "
+                        "measured launch time; the kernel moves fewer DRAM bytes than that (traffic: first iteration 24 B, "
+                        "light iterations 32 B, last iteration 40 B per particle -> 160 B instead of 176 B per 5-iteration "
+                        "particle-step), so frac can approach 1 while the actual DRAM rate is ~0.88 of the copy peak"}
     tf = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.isfile(tf):
         try:
