@@ -508,3 +508,53 @@ def test_large_grid_step_one_million_cells():
         k, r = a.step()
         assert 1 <= k <= 20 and np.isfinite(r)
     a.check()
+
+
+def test_full_size_properties_partition_of_unity_and_counts():
+    """BASELINE config 2 size (2e8 particles, 4097 nodes): size-independent properties of one fused
+    Picard iteration on the sorted store -- CIC partition of unity (sum_nodes j*dx == p2c * sum_p q*v
+    over the surviving particles, for jh and j1), absorbed tallies == flags changed, survivors inside
+    the domain, and the light iteration reproducing x1/flags/jh of the full one bit for bit."""
+    import torch
+    from pypic_b200 import _lib, device as D
+    from pypic_b200.sheath import SheathSim
+    N, Ng = 200_000_000, 4097
+    dx, dt = 1e-5, 1e-12
+    L = dx * (Ng - 1)
+    kT = O.kb * 116000.
+    p2c = L * 1e19 / N
+    s = SheathSim(N, Ng, dx, dt, p2c, kBT=(kT, kT), carry_vw=False, rng="philox", sort_every=1, seed=2)
+    gen = torch.Generator(device=s.dev); gen.manual_seed(77)
+    s.x0.uniform_(0.0, 1.0, generator=gen).mul_(L).clamp_(1e-12, L * (1 - 1e-12))
+    s.u0.normal_(0.0, 1.0, generator=gen)
+    h = s.n_split
+    s.u0[:h].mul_(float(np.sqrt(kT / O.me))); s.u0[h:].mul_(float(np.sqrt(kT / O.mp)))
+    s.sort_by_cell()
+    s.E0.normal_(0.0, 2e4, generator=gen); s.Es.copy_(s.E0)
+    P = C.byref(s.params)
+    s.acc.zero_()
+    _lib.call("pic_dev_dd_picard_iter2", P, D.ptr(s.x0), D.ptr(s.u0), D.ptr(s.x1), D.ptr(s.x1), D.ptr(s.u1), D.ptr(s.active),
+              D.ptr(s.Es), D.ptr(s.acc), 1, D.ptr(s.range_err), D.stream())
+    s.check()
+    acc = s.acc.cpu().numpy()
+    alive = s.active == 1
+    n_abs = int((~alive).sum().item())
+    assert n_abs > 1000 and n_abs == int(round(acc[2 * Ng:2 * Ng + 4].sum()))
+    xs = s.x1[alive]
+    assert float(xs.min()) > 0.0 and float(xs.max()) < L
+    uh = (s.u0 + s.u1) * 0.5
+    qv_h = -O.e * float(uh[:h][alive[:h]].sum()) + O.e * float(uh[h:][alive[h:]].sum())
+    qv_1 = -O.e * float(s.u1[:h][alive[:h]].sum()) + O.e * float(s.u1[h:][alive[h:]].sum())
+    scale = O.e * float(uh[:h].abs().sum()) * p2c
+    assert abs(acc[:Ng].sum() * dx - p2c * qv_h) < 1e-9 * scale
+    assert abs(acc[Ng:2 * Ng].sum() * dx - p2c * qv_1) < 1e-9 * scale
+    # light iteration from the same inputs: same x1 and flags, same jh, no j1, u1 untouched
+    x1_full = s.x1.clone(); act_full = s.active.clone(); jh_full = acc[:Ng].copy()
+    s.active.fill_(1); s.acc.zero_(); s.u1.fill_(7.0)
+    _lib.call("pic_dev_dd_picard_iter2", P, D.ptr(s.x0), D.ptr(s.u0), D.ptr(s.x1b), D.ptr(s.x1b), None, D.ptr(s.active),
+              D.ptr(s.Es), D.ptr(s.acc), 1, D.ptr(s.range_err), D.stream())
+    assert torch.equal(s.x1b, x1_full) and torch.equal(s.active, act_full)
+    acc2 = s.acc.cpu().numpy()
+    assert relmax(acc2[:Ng], jh_full) < 1e-12 and np.all(acc2[Ng:2 * Ng] == 0.0)
+    assert float(s.u1.min()) == 7.0 and float(s.u1.max()) == 7.0
+    assert np.array_equal(acc2[2 * Ng:2 * Ng + 4], acc[2 * Ng:2 * Ng + 4])
