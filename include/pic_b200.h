@@ -231,7 +231,8 @@ typedef struct {
                               chunks (fast on a store sorted by cell), grid-stride kernel on the tail;
                               bit0: plain shared-memory atomics per contribution; bit2: grid-stride kernel
                               with warp-uniform pre-reduction for every particle (any particle order);
-                              bit1: x0 holds UNWRAPPED positions, ``x % L`` (pypic.py:277) is applied on load */
+                              bit1: x0 holds UNWRAPPED positions, ``x % L`` (pypic.py:277) is applied on load;
+                              bit3: light iteration (no v1 store, no j1 deposit, see pic_dev_pypic_j1_repair) */
     double dx, dt, L, p2c; /* p2c already truncated */
     double q, m;           /* single species (electrons)            */
 } pic_pypic_params;
@@ -247,6 +248,21 @@ int pic_dev_pypic_picard_iter(const pic_pypic_params* p, const double* x0, const
  * stats fp64[4]: r, mean(j1), sum(eps0 E1^2 dx/2), iteration counter. */
 int pic_dev_pypic_field_update(const pic_pypic_params* p, double* acc, const double* E0, double* Es,
                                double* Fs, double* E1, double* j1, double* stats, void* stream);
+/* The same iteration with separate input / output buffers for the n+1 positions (ping-pong), so that
+ * the inputs of the last iteration survive it. */
+int pic_dev_pypic_picard_iter2(const pic_pypic_params* p, const double* x0, const double* v0,
+                               const double* x1_in, double* x1_out, double* v1, const double* Fs,
+                               double* acc, int first, int* range_err, void* stream);
+/* Light iterations (flags bit3 of pic_pypic_params): the iteration neither stores v1 nor deposits j1 --
+ * both are only used after the Picard loop.  If the loop ends on one, pic_dev_pypic_j1_repair recomputes
+ * v1 = v0 + dt*(q/m)*E(xs) from that iteration's inputs (x1_prev, the smoothed field Fs_prev it
+ * gathered from) and deposits weight_current_p(x1 % L, q, v1) (pypic.py:277-279) into acc[Ng..2Ng);
+ * after the caller's all-reduce when sharded, pic_dev_pypic_j1_finish writes j1[Ng], stats[1] =
+ * mean(j1) and zeroes the accumulator. */
+int pic_dev_pypic_j1_repair(const pic_pypic_params* p, const double* x0, const double* v0,
+                            const double* x1_prev, const double* x1_last, const double* Fs_prev, double* v1,
+                            int first, double* acc, int* range_err, void* stream);
+int pic_dev_pypic_j1_finish(const pic_pypic_params* p, double* acc, double* j1, double* stats, void* stream);
 /* x[i] = x[i] % L in place (pypic.py:277 applied to the committed positions) */
 int pic_dev_wrap_periodic(double* x, int64_t N, double L, void* stream);
 

@@ -85,6 +85,9 @@ _SIGS = {
     "pic_dev_pypic_weight": [P, P, P, P, I64, I32, F64, F64, P, P],
     "pic_dev_pypic_picard_iter": [C.POINTER(PypicParams), P, P, P, P, P, P, I32, P, P],
     "pic_dev_pypic_field_update": [C.POINTER(PypicParams), P, P, P, P, P, P, P, P],
+    "pic_dev_pypic_picard_iter2": [C.POINTER(PypicParams), P, P, P, P, P, P, P, I32, P, P],
+    "pic_dev_pypic_j1_repair": [C.POINTER(PypicParams), P, P, P, P, P, P, I32, P, P, P],
+    "pic_dev_pypic_j1_finish": [C.POINTER(PypicParams), P, P, P, P],
     "pic_dev_wrap_periodic": [P, I64, F64, P],
     "pic_dev_l_interpolate": [P, P, P, I64, I32, F64, P, P],
     "pic_dev_l_weight": [P, P, P, P, I64, I32, F64, F64, P, P],

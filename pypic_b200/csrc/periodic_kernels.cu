@@ -85,7 +85,7 @@ __global__ void pypic_weight_k(const double* __restrict__ x, const double* __res
 // x1 holds the UNWRAPPED n+1 position of the previous iteration.
 template <bool FIRST, bool AGG>
 __global__ void __launch_bounds__(256) pypic_picard_iter_k(PYK k, const double* __restrict__ x0,
-                                                           const double* __restrict__ v0, double* __restrict__ x1,
+                                                           const double* __restrict__ v0, const double* x1i, double* x1,
                                                            double* __restrict__ v1, const double* __restrict__ Fs,
                                                            double* __restrict__ acc, int* __restrict__ range_err) {
     extern __shared__ double sm[];
@@ -106,7 +106,7 @@ __global__ void __launch_bounds__(256) pypic_picard_iter_k(PYK k, const double* 
         if (valid) {
             double X0 = ld_stream(x0 + i), V0 = ld_stream(v0 + i);
             if (k.flags & 2) X0 = wrap_mod(X0, k.L);                 // store keeps the unwrapped x1 of the last step
-            double xs = FIRST ? X0 : wrap_mod((X0 + ld_stream(x1 + i)) * 0.5, k.L);
+            double xs = FIRST ? X0 : wrap_mod((X0 + ld_stream(x1i + i)) * 0.5, k.L);
             Cell c = cell_pypic<false>(xs, k.dx, k.idx, Ng);
             pypic_fix(c, Ng, bad);
             double Ei = sF[c.iL] * c.wL + sF[c.iR] * c.wR;
@@ -114,20 +114,22 @@ __global__ void __launch_bounds__(256) pypic_picard_iter_k(PYK k, const double* 
             double V1 = V0 + k.dt * k.qm * Ei;                       // :265
             double XH = (X0 + X1) * 0.5, VH = (V0 + V1) * 0.5;      // :268-269
             st_stream(x1 + i, X1);
-            st_stream(v1 + i, V1);
+            if (!(k.flags & 8)) st_stream(v1 + i, V1);               // bit3: light iteration (no v1 store, no j1 deposit)
             double xhw = wrap_mod(XH, k.L);                          // :272
             double x1w = wrap_mod(X1, k.L);                          // :277
             ch = cell_pypic<false>(xhw, k.dx, k.idx, Ng);
             pypic_fix(ch, Ng, bad);
             double jh_i = k.q * VH * k.p2c * k.idx;                  // :121
             hL = jh_i * ch.wL; hR = jh_i * ch.wR;
-            cf = cell_pypic<false>(x1w, k.dx, k.idx, Ng);
-            pypic_fix(cf, Ng, bad);
-            double j1_i = k.q * V1 * k.p2c * k.idx;
-            fL = j1_i * cf.wL; fR = j1_i * cf.wR;
+            if (!(k.flags & 8)) {       // bit3: light iteration, j1 (only used after the loop) is not deposited
+                cf = cell_pypic<false>(x1w, k.dx, k.idx, Ng);
+                pypic_fix(cf, Ng, bad);
+                double j1_i = k.q * V1 * k.p2c * k.idx;
+                fL = j1_i * cf.wL; fR = j1_i * cf.wR;
+            }
         }
         deposit2<AGG>(jh, ch.iL, ch.iR, hL, hR, valid);
-        deposit2<AGG>(j1, cf.iL, cf.iR, fL, fR, valid);
+        if (!(k.flags & 8)) deposit2<AGG>(j1, cf.iL, cf.iR, fL, fR, valid);
     }
     __syncthreads();
     for (int n = threadIdx.x; n < 2 * Ng; n += blockDim.x) {
@@ -181,6 +183,45 @@ __global__ void __launch_bounds__(1024) pypic_field_update_k(PYK k, double* __re
         stats[2] = ee;
         stats[3] = stats[3] + 1.0;
     }
+}
+
+// Repair of a Picard loop that ended on a light iteration: deposit j1 = weight_current_p(x1 % L, q, v1)
+// (pypic.py:277-279) from the committed x1, v1 into acc[Ng..2Ng) with the exact lookup.
+__global__ void pypic_j1_repair_k(PYK k, const double* __restrict__ x0, const double* __restrict__ v0,
+                                  const double* __restrict__ x1_prev, const double* __restrict__ x1,
+                                  const double* __restrict__ Fs_prev, double* __restrict__ v1, int first,
+                                  double* __restrict__ acc, int* __restrict__ range_err) {
+    int bad = 0;
+    const int Ng = k.Ng;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < k.N; i += (long long)gridDim.x * blockDim.x) {
+        // v1 of the last (light) iteration: v0 + dt*(q/m)*E(xs) with the field and xs that iteration used (:261-265)
+        double X0 = x0[i];
+        if (k.flags & 2) X0 = wrap_mod(X0, k.L);
+        const double xs = first ? X0 : wrap_mod((X0 + x1_prev[i]) * 0.5, k.L);
+        Cell c = cell_pypic<false>(xs, k.dx, k.idx, Ng);
+        pypic_fix(c, Ng, bad);
+        const double Ei = Fs_prev[c.iL] * c.wL + Fs_prev[c.iR] * c.wR;
+        const double V1 = v0[i] + k.dt * k.qm * Ei;
+        v1[i] = V1;
+        const double x1w = wrap_mod(x1[i], k.L);
+        Cell cf = cell_pypic<false>(x1w, k.dx, k.idx, Ng);
+        pypic_fix(cf, Ng, bad);
+        const double j1_i = k.q * V1 * k.p2c * k.idx;
+        atomicAdd(&acc[Ng + cf.iL], j1_i * cf.wL); atomicAdd(&acc[Ng + cf.iR], j1_i * cf.wR);
+    }
+    if (bad && range_err) atomicAdd(range_err, bad);
+}
+// j1 part of pypic_field_update_k alone: j1 copied out, stats[1] = mean(j1), accumulator zeroed
+__global__ void __launch_bounds__(1024) pypic_j1_finish_k(int Ng, double* __restrict__ acc, double* __restrict__ j1o,
+                                                          double* __restrict__ stats) {
+    __shared__ double scratch[33];
+    double* j1 = acc + Ng;
+    double s1 = 0.0;
+    for (int i = threadIdx.x; i < Ng; i += blockDim.x) { s1 += j1[i]; j1o[i] = j1[i]; }
+    s1 = block_reduce<0>(s1, scratch);
+    __syncthreads();
+    for (int i = threadIdx.x; i < Ng; i += blockDim.x) j1[i] = 0.0;
+    if (threadIdx.x == 0) stats[1] = s1 / (double)Ng;
 }
 
 __global__ void wrap_periodic_k(double* __restrict__ x, long long N, double L) {
@@ -512,7 +553,7 @@ __global__ void __launch_bounds__(S_T, 1) l_push_deposit_v2_k(const __grid_const
 struct PFastC { double dx, idx, dt, c1, c2, qpi, L; unsigned hi_lim; };
 struct PFastO { double X1, V1, hL, hR, fL, fR; int cH, cF; unsigned fr, ps; };
 
-template <bool FIRST>
+template <bool FIRST, bool J1>
 __device__ __forceinline__ void py_fast(const PFastC& c, const double* __restrict__ sF, int Ng, double X0, double V0,
                                         double pX1, PFastO& o) {
     const double xs = FIRST ? X0 : (X0 + pX1) * 0.5;                  // wrapped xh of the previous iteration
@@ -531,14 +572,19 @@ __device__ __forceinline__ void py_fast(const PFastC& c, const double* __restric
     const unsigned f1 = (unsigned)__double2hiint(th - fh) - PIC_HI_G;
     const double rh = fma(-fh, c.dx, XH);
     o.cH = (int)fh;
-    const double tf = o.X1 * c.idx, ff = floor(tf);
-    const unsigned f2 = (unsigned)__double2hiint(tf - ff) - PIC_HI_G;
-    const double rf = fma(-ff, c.dx, o.X1);
-    o.cF = (int)ff;
-    o.fr = __vimax3_u32(f0, f1, f2);
-    const double ah = c.qpi * VH, af = c.qpi * o.V1;                  // :121 up to re-association
+    const double ah = c.qpi * VH;                                     // :121 up to re-association
     o.hR = ah * (rh * c.idx); o.hL = ah - o.hR;
-    o.fR = af * (rf * c.idx); o.fL = af - o.fR;
+    if (J1) {
+        const double tf = o.X1 * c.idx, ff = floor(tf);
+        const unsigned f2 = (unsigned)__double2hiint(tf - ff) - PIC_HI_G;
+        const double rf = fma(-ff, c.dx, o.X1);
+        o.cF = (int)ff;
+        o.fr = __vimax3_u32(f0, f1, f2);
+        const double af = c.qpi * o.V1;
+        o.fR = af * (rf * c.idx); o.fL = af - o.fR;
+    } else {
+        o.cF = o.cH; o.fr = max(f0, f1); o.fR = 0.0; o.fL = 0.0;
+    }
 }
 
 // exact per-particle routine (the body of pypic_picard_iter_k); deposits with global REDs
@@ -556,25 +602,28 @@ __device__ __noinline__ int py_particle_exact(const PYK& k, long long i, double 
     const double X1 = X0 + k.dt * V0 + dtdt * k.qm * Ei * 0.5;
     const double V1 = V0 + k.dt * k.qm * Ei;
     const double XH = (X0 + X1) * 0.5, VH = (V0 + V1) * 0.5;
-    x1[i] = X1; v1[i] = V1;
+    x1[i] = X1;
+    if (!(k.flags & 8)) v1[i] = V1;
     const double xhw = wrap_mod(XH, k.L), x1w = wrap_mod(X1, k.L);
     Cell ch = cell_pypic<false>(xhw, k.dx, k.idx, Ng);
     pypic_fix(ch, Ng, bad);
     const double jh_i = k.q * VH * k.p2c * k.idx;
     atomicAdd(&acc[ch.iL], jh_i * ch.wL); atomicAdd(&acc[ch.iR], jh_i * ch.wR);
-    Cell cf = cell_pypic<false>(x1w, k.dx, k.idx, Ng);
-    pypic_fix(cf, Ng, bad);
-    const double j1_i = k.q * V1 * k.p2c * k.idx;
-    atomicAdd(&acc[Ng + cf.iL], j1_i * cf.wL); atomicAdd(&acc[Ng + cf.iR], j1_i * cf.wR);
+    if (!(k.flags & 8)) {
+        Cell cf = cell_pypic<false>(x1w, k.dx, k.idx, Ng);
+        pypic_fix(cf, Ng, bad);
+        const double j1_i = k.q * V1 * k.p2c * k.idx;
+        atomicAdd(&acc[Ng + cf.iL], j1_i * cf.wL); atomicAdd(&acc[Ng + cf.iR], j1_i * cf.wR);
+    }
     return bad;
 }
 
-template <bool FIRST, int NST>
+template <bool FIRST, int NST, bool J1>
 __global__ void __launch_bounds__(S_T, 1) pypic_picard_iter_v2_k(const __grid_constant__ PYK k, int nchunks,
                                                                   const double* __restrict__ x0,
-                                                                  const double* __restrict__ v0, double* x1, double* v1,
-                                                                  const double* __restrict__ Fs, double* __restrict__ acc,
-                                                                  int* __restrict__ range_err) {
+                                                                  const double* __restrict__ v0, const double* x1i, double* x1,
+                                                                  double* v1, const double* __restrict__ Fs,
+                                                                  double* __restrict__ acc, int* __restrict__ range_err) {
     extern __shared__ __align__(128) double sm[];
     __shared__ int s_bad;
     constexpr int NA = FIRST ? 2 : 3;
@@ -616,7 +665,7 @@ __global__ void __launch_bounds__(S_T, 1) pypic_picard_iter_v2_k(const __grid_co
             mbar_expect_tx(bar, NA * 512u);
             bulk_g2s(dst, x0 + base, 512, bar);
             bulk_g2s(dst + 512, v0 + base, 512, bar);
-            if (!FIRST) bulk_g2s(dst + 1024, x1 + base, 512, bar);
+            if (!FIRST) bulk_g2s(dst + 1024, x1i + base, 512, bar);
         }
     };
     long long cbase = (long long)blockIdx.x * S_CHUNK + woff;
@@ -641,8 +690,8 @@ __global__ void __launch_bounds__(S_T, 1) pypic_picard_iter_v2_k(const __grid_co
             const int st_cur = stage;
             if (++stage == NST) { stage = 0; phase ^= 1u; }
             PFastO a, b;
-            py_fast<FIRST>(fc, sF, Ng, X0.x, V0.x, pX1.x, a);
-            py_fast<FIRST>(fc, sF, Ng, X0.y, V0.y, pX1.y, b);
+            py_fast<FIRST, J1>(fc, sF, Ng, X0.x, V0.x, pX1.x, a);
+            py_fast<FIRST, J1>(fc, sF, Ng, X0.y, V0.y, pX1.y, b);
             const bool ra = (a.fr > PIC_HI_SPAN) | (a.ps >= fc.hi_lim);
             const bool rb = (b.fr > PIC_HI_SPAN) | (b.ps >= fc.hi_lim);
             if (row == 0) {
@@ -652,19 +701,23 @@ __global__ void __launch_bounds__(S_T, 1) pypic_picard_iter_v2_k(const __grid_co
             }
             if (!(ra | rb)) {
                 __stcs((double2*)(x1 + ci), make_double2(a.X1, b.X1));
-                __stcs((double2*)(v1 + ci), make_double2(a.V1, b.V1));
-                swin_add(myw, acc, wb, a.cH, a.hL, a.hR); swin_add(myw + S_W * S_T, acc + Ng, wb, a.cF, a.fL, a.fR);
-                swin_add(myw, acc, wb, b.cH, b.hL, b.hR); swin_add(myw + S_W * S_T, acc + Ng, wb, b.cF, b.fL, b.fR);
+                if (J1) __stcs((double2*)(v1 + ci), make_double2(a.V1, b.V1));
+                swin_add(myw, acc, wb, a.cH, a.hL, a.hR);
+                if (J1) swin_add(myw + S_W * S_T, acc + Ng, wb, a.cF, a.fL, a.fR);
+                swin_add(myw, acc, wb, b.cH, b.hL, b.hR);
+                if (J1) swin_add(myw + S_W * S_T, acc + Ng, wb, b.cF, b.fL, b.fR);
             } else {
                 if (ra) bad += py_particle_exact<FIRST>(k, ci, X0.x, V0.x, pX1.x, sF, acc, x1, v1);
                 else {
-                    x1[ci] = a.X1; v1[ci] = a.V1;
-                    swin_add(myw, acc, wb, a.cH, a.hL, a.hR); swin_add(myw + S_W * S_T, acc + Ng, wb, a.cF, a.fL, a.fR);
+                    x1[ci] = a.X1; if (J1) v1[ci] = a.V1;
+                    swin_add(myw, acc, wb, a.cH, a.hL, a.hR);
+                    if (J1) swin_add(myw + S_W * S_T, acc + Ng, wb, a.cF, a.fL, a.fR);
                 }
                 if (rb) bad += py_particle_exact<FIRST>(k, ci + 1, X0.y, V0.y, pX1.y, sF, acc, x1, v1);
                 else {
-                    x1[ci + 1] = b.X1; v1[ci + 1] = b.V1;
-                    swin_add(myw, acc, wb, b.cH, b.hL, b.hR); swin_add(myw + S_W * S_T, acc + Ng, wb, b.cF, b.fL, b.fR);
+                    x1[ci + 1] = b.X1; if (J1) v1[ci + 1] = b.V1;
+                    swin_add(myw, acc, wb, b.cH, b.hL, b.hR);
+                    if (J1) swin_add(myw + S_W * S_T, acc + Ng, wb, b.cF, b.fL, b.fR);
                 }
             }
             __syncwarp();
@@ -759,8 +812,8 @@ int pic_dev_pypic_weight(const double* x, const double* q, const double* v, doub
     return PIC_OK;
 }
 
-static int pypic_iter_v1(const PYK& k, int flags, const double* x0, const double* v0, double* x1, double* v1,
-                         const double* Fs, double* acc, int first, int* range_err, cudaStream_t st) {
+static int pypic_iter_v1(const PYK& k, int flags, const double* x0, const double* v0, const double* x1i, double* x1,
+                         double* v1, const double* Fs, double* acc, int first, int* range_err, cudaStream_t st) {
     size_t smem = (size_t)3 * k.Ng * sizeof(double);
     PIC_REQUIRE(smem <= (size_t)max_optin_smem() - 1024, "pypic_picard_iter: Ng too large for the shared-memory tiles");
     bool agg = !(flags & 1);
@@ -770,7 +823,7 @@ static int pypic_iter_v1(const PYK& k, int flags, const double* x0, const double
         PIC_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));     \
         int occ = 0;                                                                                            \
         PIC_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, 256, smem));                   \
-        kern<<<grid_for(k.N, 256, occ > 0 ? occ : 1), 256, smem, st>>>(k, x0, v0, x1, v1, Fs, acc, range_err);  \
+        kern<<<grid_for(k.N, 256, occ > 0 ? occ : 1), 256, smem, st>>>(k, x0, v0, x1i, x1, v1, Fs, acc, range_err); \
     } while (0)
     if (first) { if (agg) PIC_PY_LAUNCH(true, true); else PIC_PY_LAUNCH(true, false); }
     else { if (agg) PIC_PY_LAUNCH(false, true); else PIC_PY_LAUNCH(false, false); }
@@ -782,23 +835,30 @@ static int pypic_iter_v1(const PYK& k, int flags, const double* x0, const double
 #define PY_NST 4
 int pic_dev_pypic_picard_iter(const pic_pypic_params* p, const double* x0, const double* v0, double* x1, double* v1,
                               const double* Fs, double* acc, int first, int* range_err, void* stream) {
-    PIC_REQUIRE(p && x0 && v0 && x1 && v1 && Fs && acc, "pypic_picard_iter: null pointer");
+    return pic_dev_pypic_picard_iter2(p, x0, v0, x1, x1, v1, Fs, acc, first, range_err, stream);
+}
+
+int pic_dev_pypic_picard_iter2(const pic_pypic_params* p, const double* x0, const double* v0, const double* x1i, double* x1,
+                               double* v1, const double* Fs, double* acc, int first, int* range_err, void* stream) {
+    PIC_REQUIRE(p && x0 && v0 && x1i && x1 && v1 && Fs && acc, "pypic_picard_iter: null pointer");
     PIC_REQUIRE(p->Ng >= 2 && p->dx > 0, "pypic_picard_iter: bad parameters");
     if (p->N == 0) return PIC_OK;
     PYK k = make_pyk(p);
     cudaStream_t st = (cudaStream_t)stream;
     const size_t smem2 = ((size_t)((k.Ng + 15) & ~15) + (size_t)2 * S_W * S_T + (size_t)(S_T / 32) * PY_NST * 192 +
                           (size_t)(S_T / 32) * PY_NST) * sizeof(double);
-    const bool aligned16 = (((uintptr_t)x0 | (uintptr_t)v0 | (uintptr_t)x1 | (uintptr_t)v1) & 15) == 0;
+    const bool aligned16 = (((uintptr_t)x0 | (uintptr_t)v0 | (uintptr_t)x1i | (uintptr_t)x1 | (uintptr_t)v1) & 15) == 0;
     long long done = 0;
     if (!(p->flags & (1 | 4)) && aligned16 && k.Ng >= 8 && smem2 <= (size_t)max_optin_smem() - 512) {
         // default: TMA-staged private-window kernel over whole chunks, v1 kernel on the tail
         const long long nchunks = k.N / S_CHUNK;
         if (nchunks > 0) {
-            auto kern = first ? pypic_picard_iter_v2_k<true, PY_NST> : pypic_picard_iter_v2_k<false, PY_NST>;
+            const bool light = (p->flags & 8) != 0;
+            auto kern = first ? (light ? pypic_picard_iter_v2_k<true, PY_NST, false> : pypic_picard_iter_v2_k<true, PY_NST, true>)
+                              : (light ? pypic_picard_iter_v2_k<false, PY_NST, false> : pypic_picard_iter_v2_k<false, PY_NST, true>);
             PIC_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
             long long cap = device_sm_count();
-            kern<<<(int)(nchunks < cap ? nchunks : cap), S_T, smem2, st>>>(k, (int)nchunks, x0, v0, x1, v1, Fs, acc, range_err);
+            kern<<<(int)(nchunks < cap ? nchunks : cap), S_T, smem2, st>>>(k, (int)nchunks, x0, v0, x1i, x1, v1, Fs, acc, range_err);
             PIC_CHECK_LAUNCH();
         }
         done = nchunks * S_CHUNK;
@@ -806,7 +866,7 @@ int pic_dev_pypic_picard_iter(const pic_pypic_params* p, const double* x0, const
     }
     PYK t = k;
     t.N = k.N - done;
-    return pypic_iter_v1(t, p->flags, x0 + done, v0 + done, x1 + done, v1 + done, Fs, acc, first, range_err, st);
+    return pypic_iter_v1(t, p->flags, x0 + done, v0 + done, x1i + done, x1 + done, v1 + done, Fs, acc, first, range_err, st);
 }
 
 int pic_dev_pypic_field_update(const pic_pypic_params* p, double* acc, const double* E0, double* Es, double* Fs,
@@ -814,6 +874,24 @@ int pic_dev_pypic_field_update(const pic_pypic_params* p, double* acc, const dou
     PIC_REQUIRE(p && acc && E0 && Es && Fs && E1 && j1 && stats, "pypic_field_update: null pointer");
     PYK k = make_pyk(p);
     pypic_field_update_k<<<1, 1024, 0, (cudaStream_t)stream>>>(k, acc, E0, Es, Fs, E1, j1, stats);
+    PIC_CHECK_LAUNCH();
+    return PIC_OK;
+}
+
+int pic_dev_pypic_j1_repair(const pic_pypic_params* p, const double* x0, const double* v0, const double* x1_prev,
+                            const double* x1_last, const double* Fs_prev, double* v1, int first, double* acc,
+                            int* range_err, void* stream) {
+    PIC_REQUIRE(p && x0 && v0 && x1_prev && x1_last && Fs_prev && v1 && acc, "pypic_j1_repair: null pointer");
+    if (p->N == 0) return PIC_OK;
+    PYK k = make_pyk(p);
+    pypic_j1_repair_k<<<grid_for(k.N, 256, 8), 256, 0, (cudaStream_t)stream>>>(k, x0, v0, x1_prev, x1_last, Fs_prev, v1, first,
+                                                                             acc, range_err);
+    PIC_CHECK_LAUNCH();
+    return PIC_OK;
+}
+int pic_dev_pypic_j1_finish(const pic_pypic_params* p, double* acc, double* j1, double* stats, void* stream) {
+    PIC_REQUIRE(p && acc && j1 && stats, "pypic_j1_finish: null pointer");
+    pypic_j1_finish_k<<<1, 1024, 0, (cudaStream_t)stream>>>(p->Ng, acc, j1, stats);
     PIC_CHECK_LAUNCH();
     return PIC_OK;
 }

@@ -57,6 +57,11 @@ class PeriodicImplicitSim:
         self.last_iters, self.last_resid = 0, 1.0
         self.kernel_launches = 0
         self.iter_events = None     # set to a list to record a CUDA-event pair per particle-kernel launch
+        self.light_iterations = True
+        self.x1b = None              # second n+1 position buffer (allocated with the first light push)
+        self.Fs_prev = None
+        self._ratio, self._r1 = None, None
+        self.j1_repairs = 0
         self._sort_params = None
         self._perm2 = None
 
@@ -66,6 +71,13 @@ class PeriodicImplicitSim:
         self.v0[:self.N].copy_(torch.as_tensor(np.ascontiguousarray(v0[s])))
         if E0 is not None:
             self.E0.copy_(torch.as_tensor(np.ascontiguousarray(E0)))
+
+    def _expect_last(self, k, hist):
+        """Will iteration k (1-based) be the last one?  (Same predictor as SheathSim.)"""
+        if k >= self.maxiter or self._ratio is None:
+            return True
+        pred = self._r1 if k == 1 else hist[-1] * self._ratio
+        return pred is None or pred <= 100.0 * self.tol
 
     def sort_by_cell(self):
         """Counting sort of the store by cell (pic_dev_dd_sort_by_cell) into the Picard scratch
@@ -100,12 +112,31 @@ class PeriodicImplicitSim:
         _lib.call("pic_dev_smooth", D.ptr(self.Es), D.ptr(self.Fs), self.Ng, 0, st)
         self.stats.zero_()
         r, k = 1.0, 0
+        hist = []
+        full = True
+        base_flags = self.params.flags & ~8
+        light_ok = self.light_iterations
+        if light_ok and self.x1b is None:
+            self.x1b = D.f64(max(self.N, 1), self.dev, True)
+            self.Fs_prev = D.f64(self.Ng, self.dev, True)
+        # the n+1 positions ping-pong between two buffers so that the inputs of the last iteration
+        # survive it (needed by the repair pass when that iteration turns out to have been light)
+        xin, xout = (self.x1, self.x1b) if light_ok else (self.x1, self.x1)
+        last_in = last_out = xout
         while (r > self.tol) and (k < self.maxiter):
+            # v1 and j1 (the current at n+1) are only used after the loop: iterations that are not expected
+            # to be the last one run "light" (flags bit3: no v1 store, no j1 lookup / deposit: 32 instead of
+            # 40 B/particle); the prediction comes from the regular contraction of the residual, a wrong one
+            # costs the repair pass below
+            full = (not light_ok) or self._expect_last(k + 1, hist)
+            self.params.flags = base_flags | (0 if full else 8)
+            if light_ok:
+                self.Fs_prev.copy_(self.Fs)
             ev = None
             if self.iter_events is not None:
                 ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
                 ev[0].record()
-            _lib.call("pic_dev_pypic_picard_iter", P, D.ptr(self.x0), D.ptr(self.v0), D.ptr(self.x1), D.ptr(self.v1),
+            _lib.call("pic_dev_pypic_picard_iter2", P, D.ptr(self.x0), D.ptr(self.v0), D.ptr(xin), D.ptr(xout), D.ptr(self.v1),
                       D.ptr(self.Fs), D.ptr(self.acc), 1 if k == 0 else 0, D.ptr(self.range_err), st)
             if ev is not None:
                 ev[1].record()
@@ -116,8 +147,30 @@ class PeriodicImplicitSim:
             self.kernel_launches += 2
             r = float(D.read_f64(self.stats, 1)[0])
             k += 1
+            hist.append(r)
+            last_in, last_out = xin, xout
+            if light_ok:
+                xin, xout = xout, xin
+        self.params.flags = base_flags
+        if k > 0 and not full:
+            _lib.call("pic_dev_pypic_j1_repair", P, D.ptr(self.x0), D.ptr(self.v0), D.ptr(last_in), D.ptr(last_out),
+                      D.ptr(self.Fs_prev), D.ptr(self.v1), 1 if k == 1 else 0, D.ptr(self.acc), D.ptr(self.range_err), st)
+            self.comm.allreduce_sum(self.acc)
+            _lib.call("pic_dev_pypic_j1_finish", P, D.ptr(self.acc), D.ptr(self.j0), D.ptr(self.stats), st)
+            self.kernel_launches += 2
+            self.j1_repairs += 1
+        if hist:
+            ratios = [b_ / a_ for a_, b_ in zip(hist, hist[1:]) if a_ > 0.0]
+            self._r1 = hist[0]
+            if ratios:
+                self._ratio = max(ratios)
         if k > 0:
-            self.x0, self.x1 = self.x1, self.x0
+            if light_ok:
+                spare = self.x0
+                self.x0 = last_out
+                self.x1, self.x1b = (last_in, spare) if last_in is not last_out else (spare, self.x1b)
+            else:
+                self.x0, self.x1 = self.x1, self.x0
             self.v0, self.v1 = self.v1, self.v0
             self.E0, self.E1 = self.E1, self.E0
             # x1 = x1 % L (pypic.py:277) is applied lazily: on load by the next push, or by download()

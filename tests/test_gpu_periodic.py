@@ -220,3 +220,34 @@ def test_pypic_v2_kernel_matches_v1_and_oracle():
     out = sim.download()
     assert np.array_equal(out["x0"], x1) and np.array_equal(out["v0"], v1)
     assert relmax(out["E0"], E1) < 1e-12 and relmax(out["j0"], j1) < 1e-12
+
+
+def test_pypic_light_iterations_and_repair_agree_with_full_iterations():
+    """PeriodicImplicitSim with light iterations (default), with every prediction forced wrong
+    (j1 repair pass after every push) and with full iterations only: same iteration counts, same
+    fields, currents and particles over several steps."""
+    from pypic_b200.periodic import PeriodicImplicitSim
+    rs = np.random.RandomState(21)
+    Ng = 256; dx = 1e-5; dt = 2e-12; L = dx * Ng
+    N = 5 * 16384 + 99
+    x0 = np.sort(rs.uniform(0, L, N)); v0 = rs.normal(0, 1.3e6, N); E0 = rs.normal(0, 2e4, Ng)
+    sims = []
+    for mode in ("full", "light", "always-repair"):
+        s = PeriodicImplicitSim(N, Ng, dx, dt, L, 1e9, tol=1e-3, maxiter=20, deposit="window")
+        s.light_iterations = mode != "full"
+        if mode == "always-repair":
+            s._expect_last = lambda k, hist: False
+        s.upload(x0, v0, E0)
+        sims.append(s)
+    for step in range(4):
+        ks = [s.push()[0] for s in sims]
+        assert ks[0] == ks[1] == ks[2] and ks[0] >= 2, ks
+        ref = sims[0].download()
+        for s in sims[1:]:
+            o = s.download()
+            assert relmax(o["x0"], ref["x0"]) < 1e-13 and relmax(o["v0"], ref["v0"]) < 1e-12
+            assert relmax(o["E0"], ref["E0"]) < 1e-12 and relmax(o["j0"], ref["j0"]) < 1e-12
+            assert abs(s.diagnostics()["jbias"] - sims[0].diagnostics()["jbias"]) <= 1e-12 * np.max(np.abs(ref["j0"]))
+    assert sims[0].j1_repairs == 0 and sims[2].j1_repairs == 4
+    for s in sims:
+        s.check()
