@@ -196,14 +196,15 @@ def test_mini_driver_vs_reference_golden(golden):
     assert relmax(np.concatenate(ang), g["drv_ang"]) < 1e-5
 
 
-def test_uniform_fused_boris_matches_v1_kernels():
+@pytest.mark.parametrize("ng", [300, 6000])       # 6000 nodes: the field tile leaves room for a 2-stage ring only
+def test_uniform_fused_boris_matches_v1_kernels(ng):
     """gc_push_boris_v2_k (species-uniform store, TMA ring, fused n deposit) against the v1
     push + separate weight kernels on the same inputs: r, flags and hit counts bit-identical,
     n and rho to 1e-13.  Inputs include inactive slots, wall hits on both sides, node-aligned
     and guard-band positions, and a tail that is not a whole chunk."""
     from pypic_b200.gcstore import GridDev, ParticleStore
     rs = np.random.RandomState(5)
-    ng = 300; Lg = 3e-3; Te = 60 * 11600.; dt = 2e-9
+    Lg = 3e-3; Te = 60 * 11600.; dt = 2e-9 * 300 / ng
     N = 3 * 16384 + 517
     dx = Lg / (ng - 1)
     x = np.sort(rs.uniform(0, Lg, N))
