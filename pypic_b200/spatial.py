@@ -44,6 +44,46 @@ def slab_bounds(Ng, world):
     return [r * cells // int(world) for r in range(int(world))] + [cells]
 
 
+def exchange_plan(Ng, G, cb, rank):
+    """Index plan of the per-iteration exchange of the accumulator [jh(Ng) | j1(Ng) | 4 counts | zero].
+
+    Every rank contributes one message [left guard strip | right guard strip | owned segment (jh,
+    j1) | 4 absorbed counts]; the strips of a rank are ITS deposits on its neighbours' nodes (G nodes
+    below its first cell, G+1 nodes from its last cell boundary on).  One all-gather moves all
+    messages; unpacking places the owned segments (`unpack`: where node i of jh / j1 sits in the
+    gathered buffer) and adds every strip at its global position (`add_src` -> `add_dst`).
+    Pure index arithmetic (NumPy), tested on the CPU by emulating the ranks."""
+    W = len(cb) - 1
+    ar = lambda a, b: np.arange(a, b, dtype=np.int64)
+    both = lambda a, b: np.concatenate([ar(a, b), Ng + ar(a, b)])          # the same nodes of jh and of j1
+    seg = [(cb[r], cb[r + 1] + (1 if r == W - 1 else 0)) for r in range(W)]   # the last rank also owns node Ng-1
+    sl = max(b - a for a, b in seg)
+    nL, nR = 2 * G, 2 * (G + 1)
+    M = nL + nR + 2 * sl + 4                                          # message length
+    PAD = 2 * Ng + 4                                                  # index of the always-zero slot of acc
+    pack = np.full(M, PAD, dtype=np.int64)
+    c0, c1 = cb[rank], cb[rank + 1]
+    if rank > 0:
+        pack[:nL] = both(c0 - G, c0)
+    if rank < W - 1:
+        pack[nL:nL + nR] = both(c1, c1 + G + 1)
+    a, b = seg[rank]
+    o = nL + nR
+    pack[o:o + b - a] = ar(a, b); pack[o + sl:o + sl + b - a] = Ng + ar(a, b); pack[o + 2 * sl:] = 2 * Ng + ar(0, 4)
+    src = np.zeros(2 * Ng, dtype=np.int64)
+    add_dst, add_src = [np.zeros(0, np.int64)], [np.zeros(0, np.int64)]
+    for rr, (a2, b2) in enumerate(seg):
+        base = rr * M
+        src[a2:b2] = base + o + ar(0, b2 - a2); src[Ng + a2:Ng + b2] = base + o + sl + ar(0, b2 - a2)
+        c0r, c1r = cb[rr], cb[rr + 1]
+        if rr > 0:
+            add_dst.append(both(c0r - G, c0r)); add_src.append(base + ar(0, nL))
+        if rr < W - 1:
+            add_dst.append(both(c1r, c1r + G + 1)); add_src.append(base + nL + ar(0, nR))
+    return dict(M=M, pack=pack, unpack=src, add_dst=np.concatenate(add_dst), add_src=np.concatenate(add_src),
+                counts=np.concatenate([rr * M + o + 2 * sl + ar(0, 4) for rr in range(W)]))
+
+
 def swap_remove_plan(n, holes, n_arrivals):
     """Index plan that closes `holes` (ascending slot indices < n) of a block of n slots and adds
     n_arrivals new particles, moving as little as possible: arrivals fill holes first; left-over
@@ -344,41 +384,12 @@ class SlabSheathSim:
 
     # ------------------------------------------------------------------ halo exchange
     def _build_exchange_plan(self):
-        """Index tensors of the exchange (built once).  Every rank contributes one message
-        [left guard strip | right guard strip | owned segment (jh, j1) | 4 absorbed counts]; the strips
-        of a rank are ITS deposits on its neighbours' nodes.  One all-gather moves all messages;
-        unpacking places the owned segments and adds every strip at its global position."""
-        Ng, G, W, dev = self.Ng, self.G, self.world, self.dev
-        ar = lambda a, b: np.arange(a, b, dtype=np.int64)
-        both = lambda a, b: np.concatenate([ar(a, b), Ng + ar(a, b)])          # the same nodes of jh and of j1
-        t = lambda v: torch.as_tensor(v, device=dev)
-        sl = self.seglen
-        nL, nR = 2 * G, 2 * (G + 1)
-        M = nL + nR + 2 * sl + 4                                          # message length
-        PAD = 2 * Ng + 4                                                  # index of the always-zero slot of acc
-        pack = np.full(M, PAD, dtype=np.int64)
-        r = self.rank
-        if r > 0:
-            pack[:nL] = both(self.c0 - G, self.c0)
-        if r < W - 1:
-            pack[nL:nL + nR] = both(self.c1, self.c1 + G + 1)
-        a, b = self.seg[r]
-        o = nL + nR
-        pack[o:o + b - a] = ar(a, b); pack[o + sl:o + sl + b - a] = Ng + ar(a, b); pack[o + 2 * sl:] = 2 * Ng + ar(0, 4)
-        src = np.zeros(2 * Ng, dtype=np.int64)
-        add_dst, add_src = [], []
-        for rr, (a2, b2) in enumerate(self.seg):
-            base = rr * M
-            src[a2:b2] = base + o + ar(0, b2 - a2); src[Ng + a2:Ng + b2] = base + o + sl + ar(0, b2 - a2)
-            c0r, c1r = self.cb[rr], self.cb[rr + 1]
-            if rr > 0:
-                add_dst.append(both(c0r - G, c0r)); add_src.append(base + ar(0, nL))
-            if rr < W - 1:
-                add_dst.append(both(c1r, c1r + G + 1)); add_src.append(base + nL + ar(0, nR))
-        self.sendbuf = D.f64(M, dev, True)
-        self.gathbuf = D.f64(W * M, dev, True)
-        return dict(pack=t(pack), unpack=t(src), add_dst=t(np.concatenate(add_dst)), add_src=t(np.concatenate(add_src)),
-                    counts=t(np.concatenate([rr * M + o + 2 * sl + ar(0, 4) for rr in range(W)])))
+        """Device copies of the index plan of exchange_plan(); allocates the message buffers."""
+        pl = exchange_plan(self.Ng, self.G, self.cb, self.rank)
+        t = lambda v: torch.as_tensor(v, device=self.dev)
+        self.sendbuf = D.f64(pl["M"], self.dev, True)
+        self.gathbuf = D.f64(self.world * pl["M"], self.dev, True)
+        return {k: t(v) for k, v in pl.items() if k != "M"}
 
     def exchange_acc(self):
         """Halo exchange of the guard strips + completion of the grid, one collective per Picard

@@ -36,3 +36,31 @@ def test_swap_remove_plan_keeps_every_survivor_once():
             survivors = sorted(i for i in range(n) if i not in set(holes.tolist()))
             assert sorted(v for k, v in out if k == "p") == survivors
             assert sorted(v for k, v in out if k == "a") == arrivals
+
+
+def test_exchange_plan_reproduces_the_global_sum():
+    """Emulates W ranks on the CPU: every rank deposits only on its own nodes and on `G` guard nodes
+    either side; pack -> all-gather -> unpack must give, on EVERY rank, the sum over ranks of the
+    accumulators (jh, j1) and of the 4 absorbed counts."""
+    from pypic_b200.spatial import exchange_plan
+    rs = np.random.RandomState(1)
+    for Ng, W, G in ((257, 2, 16), (513, 3, 8), (4097, 8, 16), (1000, 5, 3)):
+        cb = slab_bounds(Ng, W)
+        accs = []
+        for r in range(W):
+            acc = np.zeros(2 * Ng + 5)
+            lo, hi = max(cb[r] - G, 0), min(cb[r + 1] + G + 1, Ng)          # nodes this rank can touch
+            acc[lo:hi] = rs.normal(size=hi - lo); acc[Ng + lo:Ng + hi] = rs.normal(size=hi - lo)
+            acc[2 * Ng:2 * Ng + 4] = rs.randint(0, 50, 4)
+            accs.append(acc)
+        want = np.sum(accs, 0)
+        plans = [exchange_plan(Ng, G, cb, r) for r in range(W)]
+        gathered = np.concatenate([accs[r][plans[r]["pack"]] for r in range(W)])     # what all_gather_into_tensor delivers
+        for r in range(W):
+            pl = plans[r]
+            out = accs[r].copy()
+            out[:2 * Ng] = gathered[pl["unpack"]]
+            np.add.at(out, pl["add_dst"], gathered[pl["add_src"]])
+            out[2 * Ng:2 * Ng + 4] = gathered[pl["counts"]].reshape(W, 4).sum(0)
+            assert np.allclose(out[:2 * Ng + 4], want[:2 * Ng + 4], rtol=0, atol=1e-12), (Ng, W, G, r)
+            assert out[2 * Ng + 4] == 0.0
