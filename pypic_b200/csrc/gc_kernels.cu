@@ -26,8 +26,9 @@ static GCK make_gck(const pic_gc_params* p) {
 struct R7 { double* r[7]; };
 
 // pygcpic.py:344-347: the LEFT node is weighted with the fractional distance (mirrored)
-__device__ __forceinline__ double gather_mirrored(const double* E, double x, double dx, int ng, int& bad) {
-    Cell c = cell_dd(x, dx);
+// idx = RN(1/dx): the division-free lookup (cell_dd_fast) is bit-identical to cell_dd
+__device__ __forceinline__ double gather_mirrored(const double* E, double x, double dx, double idx, int ng, int& bad) {
+    Cell c = cell_dd_fast(x, dx, idx);
     if (c.iL < 0 || c.iL > ng - 2) { ++bad; c.iL = clampi(c.iL, 0, ng - 2); }
     double w_l = c.wR;            // (x%dx)/dx
     double w_r = 1.0 - w_l;
@@ -37,8 +38,9 @@ __device__ __forceinline__ double gather_mirrored(const double* E, double x, dou
 __global__ void gc_interpolate_k(const double* __restrict__ E, const double* __restrict__ x, double* __restrict__ out,
                                  long long N, int ng, double dx, int* __restrict__ range_err) {
     int bad = 0;
+    const double idx = 1.0 / dx;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < N; i += (long long)gridDim.x * blockDim.x)
-        out[i] = gather_mirrored(E, x[i], dx, ng, bad);
+        out[i] = gather_mirrored(E, x[i], dx, idx, ng, bad);
     if (bad && range_err) atomicAdd(range_err, bad);
 }
 
@@ -51,6 +53,7 @@ __global__ void gc_weight_k(const double* __restrict__ x, const double* __restri
     for (int i = threadIdx.x; i < 2 * ng; i += blockDim.x) sm[i] = 0.0;
     __syncthreads();
     int bad = 0;
+    const double idx = 1.0 / dx;
     const long long stride = (long long)gridDim.x * blockDim.x;
     const long long nIter = (N + stride - 1) / stride;
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -59,11 +62,11 @@ __global__ void gc_weight_k(const double* __restrict__ x, const double* __restri
         int iL = -1;
         double a0 = 0., a1 = 0., b0 = 0., b1 = 0.;
         if (valid) {
-            Cell c = cell_dd(x[i], dx);
+            Cell c = cell_dd_fast(x[i], dx, idx);      // bit-identical to cell_dd, no IEEE division
             if (c.iL < 0 || c.iL > ng - 2) { ++bad; c.iL = clampi(c.iL, 0, ng - 2); }
             double pc = p2c[i];
-            double qr = cs[i] * PIC_E * pc / dx;      // charge_state*e*p2c/dx
-            double nr = pc / dx;
+            double qr = div_const(cs[i] * PIC_E * pc, dx, idx);      // charge_state*e*p2c/dx
+            double nr = div_const(pc, dx, idx);
             iL = c.iL;
             a0 = qr * c.wL; a1 = qr * c.wR; b0 = nr * c.wL; b1 = nr * c.wR;
         }
@@ -107,11 +110,12 @@ __global__ void __launch_bounds__(256) gc_push_boris_k(GCK k, R7 r, const double
         E = sE;
     }
     int bad = 0, hits = 0;
+    const double idx = 1.0 / k.dx;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < k.N; i += (long long)gridDim.x * blockDim.x) {
         if (active[i] != 1) { if (hit_flag) hit_flag[i] = 0; continue; }
         double x = ld_stream(r.r[0] + i), y = ld_stream(r.r[1] + i), z = ld_stream(r.r[2] + i);
         double vx = ld_stream(r.r[3] + i), vy = ld_stream(r.r[4] + i), vz = ld_stream(r.r[5] + i);
-        double Ex = pre ? Egrid[i] : gather_mirrored(E, x, k.dx, k.ng, bad);
+        double Ex = pre ? Egrid[i] : gather_mirrored(E, x, k.dx, idx, k.ng, bad);
         double constant = 0.5 * k.dt * cs[i] * 1.602e-19 / m[i];
         vx += constant * Ex;
         double tx = constant * k.B[0], ty = constant * k.B[1], tz = constant * k.B[2];
@@ -192,7 +196,7 @@ __device__ __noinline__ int gc_particle_exact(const GCK& k, const GUni& u, const
     int bad = 0;
     if (act != 1) { if (hit_flag) hit_flag[i] = 0; return 0; }
     double x = r.r[0][i], y = r.r[1][i], z = r.r[2][i], vx = r.r[3][i], vy = r.r[4][i], vz = r.r[5][i];
-    const double Ex = gather_mirrored(sE, x, k.dx, k.ng, bad);
+    const double Ex = gather_mirrored(sE, x, k.dx, 1.0 / k.dx, k.ng, bad);
     const double constant = 0.5 * k.dt * u.cs * 1.602e-19 / u.m;
     vx += constant * Ex;
     const double tx = constant * k.B[0], ty = constant * k.B[1], tz = constant * k.B[2];
@@ -535,10 +539,11 @@ __global__ void gc_push_rk4_k(GCK k, R7 r, const double* __restrict__ cs, const 
     const double sB = sqrt(B2);
     const double b0 = k.B[0] / sB, b1 = k.B[1] / sB, b2 = k.B[2] / sB;
     int bad = 0;
+    const double idx_ = 1.0 / k.dx;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < k.N; i += (long long)gridDim.x * blockDim.x) {
         if (active[i] != 1) continue;
         double r0 = r.r[0][i], r1 = r.r[1][i], r2 = r.r[2][i], r3 = r.r[3][i];
-        double E0 = Egrid ? ((k.flags & 1) ? Egrid[i] : gather_mirrored(Egrid, r0, k.dx, k.ng, bad)) : 0.0;
+        double E0 = Egrid ? ((k.flags & 1) ? Egrid[i] : gather_mirrored(Egrid, r0, k.dx, idx_, k.ng, bad)) : 0.0;
         double E1 = k.Eyz[0], E2 = k.Eyz[1];
         double wc = fabs(cs[i]) * PIC_E * sB / m[i];
         const double dt = k.dt;
