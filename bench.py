@@ -42,7 +42,7 @@ def parse():
     ap.add_argument("--cells", type=int, default=4096)
     ap.add_argument("--sort-every", type=int, default=8)
     ap.add_argument("--heavy-sort-every", type=int, default=1, help="every n-th sort also re-sorts the ions (1 = always)")
-    ap.add_argument("--deposit", default="window", choices=["window", "window-blocked", "window-big", "window-ldg", "warp", "atomic"])
+    ap.add_argument("--deposit", default="window", choices=["window", "window-det", "window-blocked", "window-big", "window-ldg", "warp", "atomic"])
     ap.add_argument("--workload", default="sheath", choices=["sheath", "explicit", "pypic", "boris"],
                     help="sheath = BASELINE configs[1] (default, the driver's bench); explicit / pypic / boris = "
                          "the other movers of SURVEY.md 8(d) at the same size (single GPU, device-resident)")

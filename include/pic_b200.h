@@ -108,7 +108,17 @@ typedef struct {
                          rows) -- taken automatically when the grid does not fit shared memory;
                          bit5: pic_dev_dd_sort_by_cell takes its global-memory cursor path (faster
                          on a nearly sorted store); bit6: static round-robin of whole chunks over
-                         the CTAs instead of dynamically scheduled 1024-particle slices */
+                         the CTAs instead of dynamically scheduled 1024-particle slices;
+                         bit7: REPRODUCIBLE build of the default window kernel -- every addition to
+                         the global accumulators is made on a pair of 64-bit fixed-point words
+                         (integer atomics: the sum does not depend on the order of the additions,
+                         i.e. not on scheduling, grid size or the number of ranks).  `acc` then has
+                         2*Ng+4 doubles FOLLOWED by 4*Ng int64 words [hi(2Ng) | lo(2Ng)], all zero
+                         on entry; pic_dev_dd_field_update / pic_dev_dd_j1_finish convert the words
+                         (one rounding per node) and clear them.  A sharded run all-reduces the
+                         words as int64 and the four counts as fp64.  One hi unit is 2^-s with
+                         2^(31-s) > max|q|*p2c/dx*c (c = speed of light), lo adds 32 bits; a
+                         contribution 2048 times beyond that bound is counted in range_err. */
     double dx, dt, L, p2c;
     double q[2], m[2];
 } pic_dd_params;
@@ -202,6 +212,16 @@ int pic_dev_sum_sq(const double* u, int64_t N, double scale, double* out1, void*
 int pic_dev_dd_sort_by_cell(const pic_dd_params* p, const double* x0, const double* u0,
                             const double* v0, const double* w0, double* x0s, double* u0s,
                             double* v0s, double* w0s, int32_t* counts, void* stream);
+/* STABLE sort by (species, cell): LSD radix sort of each species block with 8-bit digits of the
+ * cell index (per-tile digit histograms, exclusive scan, scatter with index-order ranks).  Equal
+ * cells keep their previous order, so the result is independent of scheduling -- the sort of
+ * the reproducible build (flags bit7).  The passes ping-pong between (x0,u0) and (xs,us):
+ * *result_in_scratch (host int) = 1 when the sorted state ends in (xs,us), 0 when it is back in
+ * (x0,u0).  scratch: int32[scratch_entries], at least 256*T + ceil(256*T/1024) + 2 entries with
+ * T = ceil(max species block / 4096). */
+int pic_dev_dd_sort_by_cell_stable(const pic_dd_params* p, double* x0, double* u0, double* xs, double* us,
+                                   int32_t* scratch, int64_t scratch_entries, int32_t* result_in_scratch,
+                                   void* stream);
 /* The same counting sort for any structure-of-arrays store: xs receives the sorted positions and
  * perm (int32[N]) the source slot of every output slot; apply it to the other arrays with
  * pic_dev_soa_permute.  Only p->N, n_split, Ng, dx are read. */

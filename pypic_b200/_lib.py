@@ -79,6 +79,7 @@ _SIGS = {
                                    C.c_uint64, I64, P],
     "pic_dev_sum_sq": [P, I64, F64, P, P],
     "pic_dev_dd_sort_by_cell": [C.POINTER(DDParams), P, P, P, P, P, P, P, P, P, P],
+    "pic_dev_dd_sort_by_cell_stable": [C.POINTER(DDParams), P, P, P, P, P, I64, C.POINTER(C.c_int), P],
     "pic_dev_sort_perm_by_cell": [C.POINTER(DDParams), P, P, P, P, P],
     "pic_dev_soa_permute": [P, I64, P, P, I32, P, P, I32, P, P, I32, P],
     "pic_dev_pypic_interpolate": [P, P, P, I64, I32, F64, P, P],

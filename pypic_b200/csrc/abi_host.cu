@@ -227,6 +227,7 @@ int pic_host_dd_step_batches(const pic_dd_params* p, int nbatch, const double* c
                              int8_t* const* active, double* const* E1, double* const* j1, int* iters, double* resid) {
     PIC_REQUIRE(p && x0 && u0 && E0 && x1 && u1 && active && E1 && j1 && iters && resid, "dd_step_batches: null pointer");
     PIC_REQUIRE(nbatch >= 1 && p->N >= 1 && p->Ng >= 3, "dd_step_batches: bad sizes");
+    PIC_REQUIRE(!(p->flags & 128), "dd_step_batches: the reproducible build (flags bit7) is served by the device-resident driver");
     for (int b = 0; b < nbatch; ++b)
         PIC_REQUIRE(x0[b] && u0[b] && E0[b] && x1[b] && u1[b] && active[b] && E1[b] && j1[b], "dd_step_batches: null batch pointer");
     std::lock_guard<std::mutex> lk(g_ws.mu);

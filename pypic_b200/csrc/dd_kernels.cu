@@ -24,6 +24,12 @@ struct DDK {
     int Ng, flags;
     double dx, idx, dt, L, p2c;
     double q[2], c1[2], c2[2];   // c1 = dt*(q/m), c2 = (dt*dt)*(q/m)  (Python evaluation order)
+    // reproducible build (flags bit7): every addition to the global accumulators goes to a pair of
+    // 64-bit FIXED-POINT words instead (integer addition is associative, so the sums do not depend
+    // on which warp, CTA or rank adds first); fix = [hi(2Ng) | lo(2Ng)] behind the fp64 accumulators
+    long long* fix;
+    int* ferr;                   // device error counter for contributions beyond the fixed-point range
+    double fs1, fi1;             // 2^s and 2^-s: one hi unit = 2^-s, one lo unit = 2^-(s+32)
 };
 
 static DDK make_ddk(const pic_dd_params* p) {
@@ -36,14 +42,50 @@ static DDK make_ddk(const pic_dd_params* p) {
         k.c1[s] = p->dt * qm;
         k.c2[s] = p->dt * p->dt * qm;
     }
+    k.fix = nullptr; k.ferr = nullptr; k.fs1 = 1.0; k.fi1 = 1.0;
+    if (p->flags & 128) {
+        // one contribution is q*p2c*u*w/dx with |u| < c: |v| < amax < 2^e, so |v|*2^(31-e) < 2^31 and a
+        // node can take 2^31 contributions before the hi word overflows; the lo word carries 32 more bits
+        const double qa = fabs(p->q[0]) > fabs(p->q[1]) ? fabs(p->q[0]) : fabs(p->q[1]);
+        int e = 0;
+        frexp(qa * p->p2c * k.idx * 2.99792458e8, &e);
+        k.fs1 = ldexp(1.0, 31 - e); k.fi1 = ldexp(1.0, e - 31);
+    }
     return k;
+}
+// binds the fixed-point words that follow the fp64 accumulators acc[2*Ng+4] (flags bit7)
+static void ddk_bind_fix(DDK& k, double* acc, int* range_err) {
+    if ((k.flags & 128) && acc) { k.fix = (long long*)(acc + 2 * k.Ng + 4); k.ferr = range_err; }
+}
+
+// acc[n] += v on the global accumulators.  Reproducible build: v is split exactly into
+// hi = rint(v*2^s) and the remainder, which is rounded to a multiple of 2^-(s+32); both words are
+// added with integer atomics, so the result is independent of the order of the additions.
+__device__ __forceinline__ void acc_add(const DDK& k, double* __restrict__ acc, int n, double v) {
+    if (k.fix) {
+        const double t = v * k.fs1, h = rint(t);
+        if (!(fabs(h) < 4398046511104.0)) { if (k.ferr) atomicAdd(k.ferr, 1); return; }   // 2^42: 2048 c
+        const long long lo = __double2ll_rn((t - h) * 4294967296.0);
+        atomicAdd((unsigned long long*)k.fix + n, (unsigned long long)(long long)h);
+        atomicAdd((unsigned long long*)k.fix + 2 * k.Ng + n, (unsigned long long)lo);
+    } else {
+        atomicAdd(&acc[n], v);
+    }
+}
+// fixed-point words of node n -> fp64 (one rounding), words cleared
+__device__ __forceinline__ double fix_take(const DDK& k, int n) {
+    const long long hi = k.fix[n], lo = k.fix[2 * k.Ng + n];
+    k.fix[n] = 0; k.fix[2 * k.Ng + n] = 0;
+    return ((double)hi + (double)lo * (1.0 / 4294967296.0)) * k.fi1;
 }
 
 // Warp-aggregated deposit of (vL -> node i, vR -> node i+1).  When every lane of the warp
 // targets the same cell (the common case once particles are sorted by cell) the warp
 // reduces with shuffles and issues ONE pair of atomics; otherwise each lane adds its own.
-template <bool AGG>
-__device__ __forceinline__ void deposit_pair(double* tile, int i, double vL, double vR, bool valid) {
+// GLOB: `tile` is the global accumulator array and off+i the accumulator index (acc_add)
+template <bool AGG, bool GLOB = false>
+__device__ __forceinline__ void deposit_pair(double* tile, int i, double vL, double vR, bool valid,
+                                             const DDK* k = nullptr, int off = 0) {
     if (AGG) {
         unsigned full = 0xffffffffu;
         int key = valid ? i : -1;
@@ -53,11 +95,17 @@ __device__ __forceinline__ void deposit_pair(double* tile, int i, double vL, dou
             if (k0 < 0) return;
             vL = warp_sum(vL);
             vR = warp_sum(vR);
-            if ((threadIdx.x & 31) == 0) { atomicAdd(&tile[i], vL); atomicAdd(&tile[i + 1], vR); }
+            if ((threadIdx.x & 31) == 0) {
+                if (GLOB) { acc_add(*k, tile, off + i, vL); acc_add(*k, tile, off + i + 1, vR); }
+                else { atomicAdd(&tile[i], vL); atomicAdd(&tile[i + 1], vR); }
+            }
             return;
         }
     }
-    if (valid) { atomicAdd(&tile[i], vL); atomicAdd(&tile[i + 1], vR); }
+    if (valid) {
+        if (GLOB) { acc_add(*k, tile, off + i, vL); acc_add(*k, tile, off + i + 1, vR); }
+        else { atomicAdd(&tile[i], vL); atomicAdd(&tile[i + 1], vR); }
+    }
 }
 
 // One Picard iteration, particle phase.  TILE: field + both current tiles live in shared
@@ -138,8 +186,13 @@ __global__ void __launch_bounds__(256) dd_picard_iter_k(DDK k, const double* __r
                 fL = qf * cf.wL * k.idx; fR = qf * cf.wR * k.idx;
             }
         }
-        deposit_pair<AGG>(jh, ch.iL, hL, hR, alive);
-        if (u1) deposit_pair<AGG>(j1, cf.iL, fL, fR, alive);
+        if (TILE) {
+            deposit_pair<AGG>(jh, ch.iL, hL, hR, alive);
+            if (u1) deposit_pair<AGG>(j1, cf.iL, fL, fR, alive);
+        } else {
+            deposit_pair<AGG, true>(acc, ch.iL, hL, hR, alive, &k, 0);
+            if (u1) deposit_pair<AGG, true>(acc, cf.iL, fL, fR, alive, &k, Ng);
+        }
     }
     if (TILE) {
         __syncthreads();
@@ -191,7 +244,8 @@ struct SlowOut { int code; int bad; };   // code: 0 deposited, 1..4 absorbed (L 
 // atomics into the CTA's fallback tiles tj = [jh | j1].
 __device__ __noinline__ SlowOut dd_particle_slow(const DDK& k, long long i, double X0, double U0, double pX1, int act,
                                                  bool first, const double* sF, double* tj, double* x1,
-                                                 double* u1, int8_t* __restrict__ active, bool j1 = true) {
+                                                 double* u1, int8_t* __restrict__ active, bool j1 = true,
+                                                 bool glob = false) {      // glob: tj is the global accumulator array
     SlowOut o{0, 0};
     const int Ng = k.Ng;
     if (!first && act != 1) { x1[i] = 0.0; if (u1) u1[i] = 0.0; o.code = 5; return o; }   // reference leaves zeros
@@ -211,12 +265,14 @@ __device__ __noinline__ SlowOut dd_particle_slow(const DDK& k, long long i, doub
     if (a.iL < 0 || a.iL > Ng - 2) { ++o.bad; a.iL = clampi(a.iL, 0, Ng - 2); }
     const double qs = sp ? k.q[1] : k.q[0];
     double qv = qs * UH * k.p2c;
-    atomicAdd(&tj[a.iL], qv * a.wL * k.idx); atomicAdd(&tj[a.iL + 1], qv * a.wR * k.idx);
+    if (glob) { acc_add(k, tj, a.iL, qv * a.wL * k.idx); acc_add(k, tj, a.iL + 1, qv * a.wR * k.idx); }
+    else { atomicAdd(&tj[a.iL], qv * a.wL * k.idx); atomicAdd(&tj[a.iL + 1], qv * a.wR * k.idx); }
     if (j1) {
         Cell b = cell_dd(X1, k.dx);
         if (b.iL < 0 || b.iL > Ng - 2) { ++o.bad; b.iL = clampi(b.iL, 0, Ng - 2); }
         double qf = qs * U1 * k.p2c;
-        atomicAdd(&tj[Ng + b.iL], qf * b.wL * k.idx); atomicAdd(&tj[Ng + b.iL + 1], qf * b.wR * k.idx);
+        if (glob) { acc_add(k, tj, Ng + b.iL, qf * b.wL * k.idx); acc_add(k, tj, Ng + b.iL + 1, qf * b.wR * k.idx); }
+        else { atomicAdd(&tj[Ng + b.iL], qf * b.wL * k.idx); atomicAdd(&tj[Ng + b.iL + 1], qf * b.wR * k.idx); }
     }
     return o;
 }
@@ -420,12 +476,12 @@ __global__ void __launch_bounds__(V5_T, 1) dd_picard_iter_v5_k(
 #endif
 #define V6_CHUNK (V6_T * 2 * V6_ROWS)
 
-__device__ __forceinline__ void win_add6(double* myw, double* acc, int wb, int tile, int Ng, int c, double vL, double vR) {
+__device__ __forceinline__ void win_add6(const DDK& k, double* myw, double* acc, int wb, int tile, int Ng, int c, double vL, double vR) {
     const unsigned d = (unsigned)(c - wb);
     if (d <= (unsigned)(V6_W - 2)) {
         double* p = myw + (tile * V6_W + d) * V6_T;
         p[0] += vL; p[V6_T] += vR;
-    } else { atomicAdd(&acc[tile * Ng + c], vL); atomicAdd(&acc[tile * Ng + c + 1], vR); }
+    } else { acc_add(k, acc, tile * Ng + c, vL); acc_add(k, acc, tile * Ng + c + 1, vR); }
 }
 
 // Fast path of one particle, v6 flavour.  Instead of a predicate per rare condition it returns
@@ -509,12 +565,12 @@ __device__ __forceinline__ void dd_medium(const DDK& k, const FastC& fc, long lo
         }
         if (o.fr <= PIC_HI_SPAN && o.ps < fc.hi_Lm1) {
             x1[i] = o.X1; if (u1) u1[i] = o.U1;
-            win_add6(myw, acc, wb, 0, k.Ng, o.cH, o.hL, o.hR);
-            if (J1) win_add6(myw, acc, wb, 1, k.Ng, o.cF, o.fL, o.fR);
+            win_add6(k, myw, acc, wb, 0, k.Ng, o.cH, o.hL, o.hR);
+            if (J1) win_add6(k, myw, acc, wb, 1, k.Ng, o.cF, o.fL, o.fR);
             return;
         }
     }
-    SlowOut so = dd_particle_slow(k, i, X0, U0, pX1, act, FIRST, sF, acc, x1, u1, active, J1);
+    SlowOut so = dd_particle_slow(k, i, X0, U0, pX1, act, FIRST, sF, acc, x1, u1, active, J1, true);
     if (so.code >= 1 && so.code <= 4) atomicAdd(&s_cnt[so.code], 1);
     if (so.bad) atomicAdd(&s_cnt[0], so.bad);
 }
@@ -613,7 +669,7 @@ __global__ void __launch_bounds__(V6_T, 1) dd_picard_iter_v6_k(
             s += __shfl_xor_sync(full, s, 1);
             if (lane < 4 * V6_W && half == 0) {
                 int node = wbase_node + (n < V6_W ? n : n - V6_W);
-                if (node >= 0 && node < Ng && s != 0.0) atomicAdd(&acc[(n < V6_W ? 0 : Ng) + node], s);
+                if (node >= 0 && node < Ng && s != 0.0) acc_add(k, acc, (n < V6_W ? 0 : Ng) + node, s);
             }
             __syncwarp();
 #pragma unroll
@@ -689,10 +745,10 @@ __global__ void __launch_bounds__(V6_T, 1) dd_picard_iter_v6_k(
                     p = myw + dbh * V6_T; p[0] += b.hL; p[V6_T] += b.hR;
                     if (WU) { p = myw + (V6_W + dbf) * V6_T; p[0] += b.fL; p[V6_T] += b.fR; }
                 } else {
-                    win_add6(myw, acc, wb, 0, Ng, a.cH, a.hL, a.hR);
-                    if (WU) win_add6(myw, acc, wb, 1, Ng, a.cF, a.fL, a.fR);
-                    win_add6(myw, acc, wb, 0, Ng, b.cH, b.hL, b.hR);
-                    if (WU) win_add6(myw, acc, wb, 1, Ng, b.cF, b.fL, b.fR);
+                    win_add6(k, myw, acc, wb, 0, Ng, a.cH, a.hL, a.hR);
+                    if (WU) win_add6(k, myw, acc, wb, 1, Ng, a.cF, a.fL, a.fR);
+                    win_add6(k, myw, acc, wb, 0, Ng, b.cH, b.hL, b.hR);
+                    if (WU) win_add6(k, myw, acc, wb, 1, Ng, b.cF, b.fL, b.fR);
                 }
             } else {
                 // one flag load for the pair (ci is even); dead and freshly absorbed particles are
@@ -756,6 +812,8 @@ __global__ void __launch_bounds__(1024) dd_field_update_k(DDK k, double* __restr
     __shared__ double scratch[33];
     __shared__ double wl[2], wr[2];
     const int Ng = k.Ng;
+    if (k.fix)      // reproducible build: the currents arrive as fixed-point words
+        for (int i = threadIdx.x; i < 2 * Ng; i += blockDim.x) acc[i] += fix_take(k, i);
     if (threadIdx.x < 4) {
         double v = wall_cum[threadIdx.x] + acc[2 * Ng + threadIdx.x];
         wall_cum[threadIdx.x] = v;
@@ -817,6 +875,10 @@ __global__ void __launch_bounds__(1024) dd_field_update_big_k(DDK k, double* __r
     cg::grid_group grid = cg::this_grid();
     __shared__ double scratch[33];
     const int Ng = k.Ng;
+    if (k.fix) {
+        for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < 2 * Ng; i += gridDim.x * blockDim.x) acc[i] += fix_take(k, i);
+        grid.sync();
+    }
     const double w0 = wall_cum[0] + acc[2 * Ng + 0], w1 = wall_cum[1] + acc[2 * Ng + 1];
     const double w2 = wall_cum[2] + acc[2 * Ng + 2], w3 = wall_cum[3] + acc[2 * Ng + 3];
     const double wallL = w0 * (k.dx * k.q[0] * k.p2c / k.dt) + w1 * (k.dx * k.q[1] * k.p2c / k.dt);
@@ -1140,6 +1202,84 @@ __global__ void scan_add_k(int32_t* __restrict__ v, int n, const int32_t* __rest
     const int i = blockIdx.x * 1024 + threadIdx.x;
     if (i < n) v[i] += sums[blockIdx.x];
 }
+// ---- STABLE sort by cell (reproducible build): least-significant-digit radix sort of one species
+// block, 8-bit digits of the cell index, three launches per pass (per-tile digit histogram laid out
+// [digit][tile], exclusive scan of that table, scatter).  The rank of an element inside its tile is
+// its position in index order among the tile's elements with the same digit (warp ballot ranks +
+// a per-digit prefix over the tile's warps), so equal cells keep their previous order and the
+// result does not depend on scheduling -- unlike the counting sort above, whose order inside a cell
+// follows the arrival order of atomic reservations.
+#define RS_T 1024
+#define RS_PER 4
+#define RS_TILE (RS_T * RS_PER)
+__device__ __forceinline__ int rs_digit(double x, double dx, int Ng, int shift) {
+    int c = (int)floor(x / dx);
+    c = clampi(c, 0, Ng - 1);
+    return (c >> shift) & 255;
+}
+__global__ void __launch_bounds__(RS_T) rsort_hist_k(const double* __restrict__ x, long long n, double dx, int Ng,
+                                                     int shift, int ntiles, int32_t* __restrict__ H) {
+    __shared__ int hist[256];
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        if (threadIdx.x < 256) hist[threadIdx.x] = 0;
+        __syncthreads();
+        const long long base = (long long)tile * RS_TILE;
+#pragma unroll
+        for (int j = 0; j < RS_PER; ++j) {
+            const long long i = base + (long long)j * RS_T + threadIdx.x;
+            const int d = i < n ? rs_digit(x[i], dx, Ng, shift) : -1;
+            const unsigned peers = __match_any_sync(0xffffffffu, d);
+            if (d >= 0 && (threadIdx.x & 31) == (unsigned)(__ffs(peers) - 1)) atomicAdd(&hist[d], __popc(peers));
+        }
+        __syncthreads();
+        if (threadIdx.x < 256) H[(long long)threadIdx.x * ntiles + tile] = hist[threadIdx.x];
+        __syncthreads();
+    }
+}
+__global__ void __launch_bounds__(RS_T) rsort_scatter_k(const double* __restrict__ x, const double* __restrict__ u,
+                                                        long long n, double dx, int Ng, int shift, int ntiles,
+                                                        const int32_t* __restrict__ H, double* __restrict__ xo,
+                                                        double* __restrict__ uo) {
+    extern __shared__ int rs_sm[];
+    int (*wcnt)[256] = (int (*)[256])rs_sm;                // elements of warp w with digit d in the current round (kept zero between rounds)
+    int (*wpre)[256] = (int (*)[256])(rs_sm + 32 * 256);   // output position of the first of them
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    for (int i = threadIdx.x; i < 32 * 256; i += RS_T) rs_sm[i] = 0;
+    __syncthreads();
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        // thread d < 256 owns digit d: where the tile's run of that digit starts in the output
+        int run = threadIdx.x < 256 ? H[(long long)threadIdx.x * ntiles + tile] : 0;
+        const long long base = (long long)tile * RS_TILE;
+#pragma unroll 1
+        for (int j = 0; j < RS_PER; ++j) {
+            const long long i = base + (long long)j * RS_T + threadIdx.x;
+            double X = 0.;
+            int d = -1;
+            if (i < n) { X = x[i]; d = rs_digit(X, dx, Ng, shift); }
+            const unsigned peers = __match_any_sync(0xffffffffu, d);
+            const int below = __popc(peers & ((1u << lane) - 1u));
+            if (d >= 0 && below == 0) wcnt[w][d] = __popc(peers);
+            __syncthreads();
+            if (threadIdx.x < 256) {
+#pragma unroll 8
+                for (int ww = 0; ww < 32; ++ww) {
+                    const int c = wcnt[ww][threadIdx.x];
+                    wcnt[ww][threadIdx.x] = 0;
+                    wpre[ww][threadIdx.x] = run;
+                    run += c;
+                }
+            }
+            __syncthreads();
+            if (d >= 0) {
+                const long long pos = (long long)wpre[w][d] + below;
+                xo[pos] = X;
+                uo[pos] = u[i];
+            }
+            // the next round rewrites wpre only after its own first barrier, which every thread
+            // reaches after the reads above
+        }
+    }
+}
 template <bool PERM>
 __global__ void __launch_bounds__(256) dd_sort_scatter_big_k(DDK k, const double* __restrict__ x0,
                                                              const double* __restrict__ u0,
@@ -1228,7 +1368,7 @@ template <bool FIRST, bool TILE, bool AGG>
 static int launch_iter(const DDK& k, const double* x0, const double* u0, const double* x1i, double* x1, double* u1,
                        int8_t* active, const double* Es, double* acc, int* range_err, cudaStream_t st) {
     // a short tail is cheaper with the grids left in L2 than with 3*Ng doubles staged per CTA
-    if (TILE && k.N < 16 * (long long)k.Ng)
+    if (TILE && (k.N < 16 * (long long)k.Ng || k.fix))      // reproducible build: no shared-memory fp64 atomics
         return launch_iter<FIRST, false, AGG>(k, x0, u0, x1i, x1, u1, active, Es, acc, range_err, st);
     size_t smem = TILE ? (size_t)3 * k.Ng * sizeof(double) : 0;
     auto kern = dd_picard_iter_k<FIRST, TILE, AGG>;
@@ -1292,7 +1432,7 @@ __global__ void __launch_bounds__(256) dd_commit_u_k(DDK k, const double* __rest
             Cell b = cell_dd(x1_last[i], k.dx);
             if (b.iL < 0 || b.iL > Ng - 2) { ++bad; b.iL = clampi(b.iL, 0, Ng - 2); }
             const double qf = (sp ? k.q[1] : k.q[0]) * U1 * k.p2c;
-            atomicAdd(&j1_acc[b.iL], qf * b.wL * k.idx); atomicAdd(&j1_acc[b.iL + 1], qf * b.wR * k.idx);
+            acc_add(k, j1_acc - Ng, Ng + b.iL, qf * b.wL * k.idx); acc_add(k, j1_acc - Ng, Ng + b.iL + 1, qf * b.wR * k.idx);
         }
     }
     if (bad && range_err) atomicAdd(range_err, bad);
@@ -1307,6 +1447,10 @@ __global__ void __launch_bounds__(1024) dd_j1_finish_k(DDK k, double* __restrict
     const double wallL = wall_cum[0] * (k.dx * k.q[0] * k.p2c / k.dt) + wall_cum[1] * (k.dx * k.q[1] * k.p2c / k.dt);
     const double wallR = wall_cum[2] * (-k.dx * k.q[0] * k.p2c / k.dt) + wall_cum[3] * (-k.dx * k.q[1] * k.p2c / k.dt);
     double* j1 = acc + Ng;
+    if (k.fix) {
+        for (int i = threadIdx.x; i < Ng; i += blockDim.x) j1[i] += fix_take(k, Ng + i);
+        __syncthreads();
+    }
     double s1 = 0.0;
     for (int i = threadIdx.x; i < Ng; i += blockDim.x) {
         double b = j1[i];
@@ -1330,6 +1474,9 @@ int pic_dev_dd_picard_iter2(const pic_dd_params* p, const double* x0, const doub
     PIC_REQUIRE(p->N >= 0 && p->Ng >= 3 && p->dx > 0 && p->dt > 0, "dd_picard_iter: bad parameters");
     if (p->N == 0) return PIC_OK;
     DDK k = make_ddk(p);
+    PIC_REQUIRE(!(p->flags & 128) || !(p->flags & (1 | 2 | 4 | 8)),
+                "dd_picard_iter: the reproducible build (flags bit7) exists for the default window kernel only");
+    ddk_bind_fix(k, acc, range_err);
     cudaStream_t st = (cudaStream_t)stream;
     const double* x1i = x1_in;
     double* x1 = x1_out;
@@ -1435,6 +1582,7 @@ int pic_dev_dd_j1_finish(const pic_dd_params* p, double* acc, const double* wall
                          void* stream) {
     PIC_REQUIRE(p && acc && wall_cum && j1 && stats, "dd_j1_finish: null pointer");
     DDK k = make_ddk(p);
+    ddk_bind_fix(k, acc, nullptr);
     dd_j1_finish_k<<<1, 1024, 0, (cudaStream_t)stream>>>(k, acc, wall_cum, j1, stats);
     PIC_CHECK_LAUNCH();
     return PIC_OK;
@@ -1446,6 +1594,7 @@ int pic_dev_dd_commit_u2(const pic_dd_params* p, const double* x0, const double*
     PIC_REQUIRE(p && x0 && u0 && x1_prev && x1_last && active && Es && u1, "dd_commit_u: null pointer");
     if (p->N == 0) return PIC_OK;
     DDK k = make_ddk(p);
+    ddk_bind_fix(k, acc, range_err);
     size_t smem = (size_t)k.Ng * sizeof(double);
     const int tile = smem <= (size_t)max_optin_smem() - 1024;
     if (!tile) smem = 0;
@@ -1476,6 +1625,7 @@ int pic_dev_dd_field_update(const pic_dd_params* p, double* acc, double* wall_cu
                             double* E1, double* j1, double* stats, void* stream) {
     PIC_REQUIRE(p && acc && wall_cum && E0 && Es && E1 && j1 && stats, "dd_field_update: null pointer");
     DDK k = make_ddk(p);
+    ddk_bind_fix(k, acc, nullptr);
     if (k.Ng > 32768) {
         // stats[4..7] is the reduction scratch of the cooperative kernel (the caller provides 8 doubles)
         double* red = stats + 4;
@@ -1557,6 +1707,49 @@ int pic_dev_sum_sq(const double* u, int64_t N, double scale, double* out1, void*
     if (N == 0) return PIC_OK;
     sum_sq_k<<<grid_for(N, 256, 8), 256, 0, st>>>(u, N, scale, out1);
     PIC_CHECK_LAUNCH();
+    return PIC_OK;
+}
+
+int pic_dev_dd_sort_by_cell_stable(const pic_dd_params* p, double* x0, double* u0, double* xs, double* us,
+                                   int32_t* scratch, int64_t scratch_entries, int32_t* result_in_scratch,
+                                   void* stream) {
+    PIC_REQUIRE(p && x0 && u0 && xs && us && scratch && result_in_scratch, "dd_sort_by_cell_stable: null pointer");
+    PIC_REQUIRE(p->N >= 0 && p->N < 2147483647LL && p->Ng >= 2 && p->dx > 0, "dd_sort_by_cell_stable: bad parameters");
+    cudaStream_t st = (cudaStream_t)stream;
+    int bits = 0;
+    while ((1 << bits) < p->Ng) ++bits;           // cells 0 .. Ng-1
+    const int passes = (bits + 7) / 8;
+    *result_in_scratch = passes & 1;
+    const long long blk[3] = {0, p->n_split < 0 ? 0 : (p->n_split > p->N ? p->N : p->n_split), p->N};
+    for (int sp = 0; sp < 2; ++sp) {
+        const long long off = blk[sp], n = blk[sp + 1] - blk[sp];
+        if (n <= 0) continue;
+        const long long ntl = (n + RS_TILE - 1) / RS_TILE;
+        const long long nH = 256 * ntl, nblk = (nH + 1023) / 1024;
+        PIC_REQUIRE(nH + nblk + 2 <= scratch_entries && nH < 2147483647LL && nblk <= 1024 * 1024,
+                    "dd_sort_by_cell_stable: scratch too small");
+        int32_t* H = scratch;
+        int32_t* sums = scratch + nH;
+        const int ntiles = (int)ntl;
+        const int grid = (int)(ntl < (long long)device_sm_count() * 2 ? ntl : (long long)device_sm_count() * 2);
+        double *sx = x0 + off, *su = u0 + off, *dx_ = xs + off, *du = us + off;
+        const size_t smem = (size_t)2 * 32 * 256 * sizeof(int);
+        PIC_CHECK_CUDA(cudaFuncSetAttribute(rsort_scatter_k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        for (int ps = 0; ps < passes; ++ps) {
+            rsort_hist_k<<<grid, RS_T, 0, st>>>(sx, n, p->dx, p->Ng, 8 * ps, ntiles, H);
+            PIC_CHECK_LAUNCH();
+            scan_local_k<<<(int)nblk, 1024, 0, st>>>(H, (int)nH, sums);
+            PIC_CHECK_LAUNCH();
+            dd_sort_scan_k<<<1, 1024, 0, st>>>(sums, (int)nblk);
+            PIC_CHECK_LAUNCH();
+            scan_add_k<<<(int)nblk, 1024, 0, st>>>(H, (int)nH, sums);
+            PIC_CHECK_LAUNCH();
+            rsort_scatter_k<<<grid, RS_T, smem, st>>>(sx, su, n, p->dx, p->Ng, 8 * ps, ntiles, H, dx_, du);
+            PIC_CHECK_LAUNCH();
+            double* t = sx; sx = dx_; dx_ = t;
+            t = su; su = du; du = t;
+        }
+    }
     return PIC_OK;
 }
 

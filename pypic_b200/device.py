@@ -67,3 +67,10 @@ def sort_counts_size(Ng):
     2*Ng keys + 2, plus the block sums of the three-pass scan used for large grids."""
     nk = 2 * int(Ng)
     return nk + 2 + (nk + 1023) // 1024 + 2
+
+
+def sort_stable_scratch_size(N):
+    """int32 entries of the scratch pic_dev_dd_sort_by_cell_stable needs for species blocks of at
+    most N particles: the [digit][tile] histogram of one radix pass plus the block sums of its scan."""
+    nh = 256 * ((int(N) + 4095) // 4096)
+    return nh + (nh + 1023) // 1024 + 2

@@ -50,8 +50,13 @@ class SheathSim:
         # "window-big" forces the large-grid build of the window kernel (per-warp field windows, no
         # whole-grid tile; chosen automatically when the grid does not fit shared memory)
         # "window-blocked": static round-robin of whole chunks instead of dynamically scheduled slices (bit6)
+        # "window-det": the REPRODUCIBLE build of the default kernel (bit7): every addition to the global
+        # accumulators is an integer addition on 2x64-bit fixed-point words (order-independent, also
+        # across ranks: the all-reduce is an int64 sum) and the cell sort is the stable radix sort, so
+        # two runs -- and runs on different numbers of CTAs -- give bit-identical states
         flags = {"window": 0, "window-blocked": 64, "window-big": 16, "window-ldg": 8, "atomic": 1,
-                 "warp": 4}[deposit] | (2 if tiles == "global" else 0)
+                 "warp": 4, "window-det": 128}[deposit] | (2 if tiles == "global" else 0)
+        self.det = deposit == "window-det"
         self.params = _lib.DDParams(self.N, self.n_split, self.Ng, flags, self.dx, self.dt, self.L, self.p2c,
                                     (C.c_double * 2)(*self.q), (C.c_double * 2)(*self.m))
         dev = self.dev
@@ -71,7 +76,8 @@ class SheathSim:
         self.E0 = D.f64(g, dev, True); self.Es = D.f64(g, dev, True); self.E1 = D.f64(g, dev, True)
         self.Es_prev = D.f64(g, dev, True)
         self.j0 = D.f64(g, dev, True)
-        self.acc = D.f64(2 * g + 4, dev, True)
+        # reproducible build: [jh | j1 | 4 counts] as fp64 followed by the int64 words [hi(2g) | lo(2g)]
+        self.acc = D.f64(2 * g + 4 + (4 * g if self.det else 0), dev, True)
         self.wall_cum = D.f64(4, dev, True)
         self.stats = D.f64(8, dev, True)      # [r, mean j1, EE, iterations | 4 doubles of reduction scratch]
         self.range_err = torch.zeros(1, dtype=torch.int32, device=dev)
@@ -79,6 +85,8 @@ class SheathSim:
         self.count = torch.zeros(1, dtype=torch.int64, device=dev)
         self.block_counts = torch.zeros(2 * (n // 2048 + 2), dtype=torch.int64, device=dev)
         self.sort_counts = torch.zeros(D.sort_counts_size(g), dtype=torch.int32, device=dev) if self.sort_every else None
+        self.sort_scratch = (torch.zeros(D.sort_stable_scratch_size(n), dtype=torch.int32, device=dev)
+                             if self.sort_every and self.det else None)
         self.scalar = D.f64(1, dev, True)
         self.t = 0
         self._sorted_once = False
@@ -158,6 +166,20 @@ class SheathSim:
     def sort_by_cell(self):
         """Benchmark mode: counting sort by (species, cell) into the scratch arrays."""
         st = D.stream()
+        if self.det:
+            # reproducible build: stable radix sort (the order inside a cell is the previous order)
+            where = C.c_int(0)
+            _lib.call("pic_dev_dd_sort_by_cell_stable", C.byref(self.params), D.ptr(self.x0), D.ptr(self.u0),
+                      D.ptr(self.x1), D.ptr(self.u1), D.ptr(self.sort_scratch), self.sort_scratch.numel(),
+                      C.byref(where), st)
+            passes = (max(1, (self.Ng - 1).bit_length()) + 7) // 8
+            self.kernel_launches += 5 * passes * ((self.n_split > 0) + (self.n_split < self.N))
+            self._sorted_once = True
+            self._sorts += 1
+            if where.value:
+                self.x0, self.x1 = self.x1, self.x0
+                self.u0, self.u1 = self.u1, self.u0
+            return
         # a store that was sorted a few steps ago is NEARLY sorted: the global-memory cursor path of
         # the sort (flags bit5) is then faster than the shared-memory one (2.5 vs 3.0 ms at 2e8
         # particles); the first sort of a random store takes the shared-memory path
@@ -198,6 +220,18 @@ class SheathSim:
         pred = self._r1 if k == 1 else hist[-1] * self._ratio
         return pred is None or pred <= 100.0 * self.tol
 
+    def _allreduce_acc(self):
+        """One sum over ranks per deposit.  Reproducible build: the currents travel as int64
+        fixed-point words (an integer all-reduce is exact in any order), the four absorbed counts
+        as exact fp64 integers."""
+        if not self.det:
+            return self.comm.allreduce_sum(self.acc)
+        if self.comm.world > 1:
+            g = self.Ng
+            self.comm.allreduce_sum(self.acc[2 * g:2 * g + 4])
+            self.comm.allreduce_sum(self.acc[2 * g + 4:].view(torch.int64))
+        return self.acc
+
     def picard(self):
         """PIC_L_DD.py:452-545: Picard loop + commit.  Returns (iterations, residual).
 
@@ -229,7 +263,7 @@ class SheathSim:
             if self.iter_events is not None:
                 ev[1].record()
                 self.iter_events.append(ev + (want_u, k == 0))
-            self.comm.allreduce_sum(self.acc)
+            self._allreduce_acc()
             _lib.call("pic_dev_dd_field_update", P, D.ptr(self.acc), D.ptr(self.wall_cum), D.ptr(self.E0),
                       D.ptr(self.Es), D.ptr(self.E1), D.ptr(self.j0), D.ptr(self.stats), st)
             self.kernel_launches += 2
@@ -246,7 +280,7 @@ class SheathSim:
             _lib.call("pic_dev_dd_commit_u2", P, D.ptr(self.x0), D.ptr(self.u0), D.ptr(last_in), D.ptr(last_out),
                       D.ptr(self.active), D.ptr(self.Es_prev), D.ptr(self.u1), 1 if k == 1 else 0, D.ptr(self.acc),
                       D.ptr(self.range_err), st)
-            self.comm.allreduce_sum(self.acc)
+            self._allreduce_acc()
             _lib.call("pic_dev_dd_j1_finish", P, D.ptr(self.acc), D.ptr(self.wall_cum), D.ptr(self.j0), D.ptr(self.stats), st)
             self.kernel_launches += 2
             self.u_repairs += 1
