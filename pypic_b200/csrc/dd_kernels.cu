@@ -1167,14 +1167,35 @@ __global__ void __launch_bounds__(SORT_T) dd_sort_scatter_k(DDK k, const double*
 
 // ---- the same counting sort for grids whose histogram does not fit shared memory: counts and
 // cursors live in global memory (L2), one warp-aggregated atomic per distinct key per warp ----
-__global__ void dd_sort_hist_big_k(DDK k, const double* __restrict__ x0, int32_t* __restrict__ counts) {
-    const long long stride = (long long)gridDim.x * blockDim.x;
-    const long long nIter = (k.N + stride - 1) / stride;
-    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    for (long long it = 0; it < nIter; ++it, i += stride) {
-        const int key = i < k.N ? dd_sort_key(k, x0[i], i) : -1;
-        const unsigned peers = __match_any_sync(0xffffffffu, key);
-        if (key >= 0 && (threadIdx.x & 31) == (unsigned)(__ffs(peers) - 1)) atomicAdd(&counts[key], __popc(peers));
+// Every CTA walks a CONTIGUOUS range of the store (on a nearly sorted store the CTAs then work on
+// different cells, so their atomics go to different addresses instead of all hammering the few
+// counters of the cells a grid-stride sweep is crossing), four elements per thread in flight.
+#define SORTB_T 256
+#define SORTB_PER 4
+__device__ __forceinline__ long long sortb_range(long long N, long long* end) {
+    long long per = (N + gridDim.x - 1) / gridDim.x;
+    per = (per + SORTB_T * SORTB_PER - 1) / (SORTB_T * SORTB_PER) * (SORTB_T * SORTB_PER);
+    const long long beg = (long long)blockIdx.x * per;
+    *end = beg + per < N ? beg + per : N;
+    return beg;
+}
+__global__ void __launch_bounds__(SORTB_T) dd_sort_hist_big_k(DDK k, const double* __restrict__ x0, int32_t* __restrict__ counts) {
+    long long end;
+    const long long beg = sortb_range(k.N, &end);
+    for (long long base = beg; base < end; base += SORTB_T * SORTB_PER) {
+        double X[SORTB_PER];
+#pragma unroll
+        for (int j = 0; j < SORTB_PER; ++j) {
+            const long long i = base + j * SORTB_T + threadIdx.x;
+            X[j] = i < end ? x0[i] : 0.0;
+        }
+#pragma unroll
+        for (int j = 0; j < SORTB_PER; ++j) {
+            const long long i = base + j * SORTB_T + threadIdx.x;
+            const int key = i < end ? dd_sort_key(k, X[j], i) : -1;
+            const unsigned peers = __match_any_sync(0xffffffffu, key);
+            if (key >= 0 && (threadIdx.x & 31) == (unsigned)(__ffs(peers) - 1)) atomicAdd(&counts[key], __popc(peers));
+        }
     }
 }
 // exclusive scan in three passes: per-1024-block local scan + block sums, scan of the sums (dd_sort_scan_k), add
@@ -1281,31 +1302,45 @@ __global__ void __launch_bounds__(RS_T) rsort_scatter_k(const double* __restrict
     }
 }
 template <bool PERM>
-__global__ void __launch_bounds__(256) dd_sort_scatter_big_k(DDK k, const double* __restrict__ x0,
-                                                             const double* __restrict__ u0,
-                                                             const double* __restrict__ v0,
-                                                             const double* __restrict__ w0, double* __restrict__ xs,
-                                                             double* __restrict__ us, double* __restrict__ vs,
-                                                             double* __restrict__ ws, int32_t* __restrict__ cursor) {
-    const long long stride = (long long)gridDim.x * blockDim.x;
-    const long long nIter = (k.N + stride - 1) / stride;
-    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+__global__ void __launch_bounds__(SORTB_T) dd_sort_scatter_big_k(DDK k, const double* __restrict__ x0,
+                                                                 const double* __restrict__ u0,
+                                                                 const double* __restrict__ v0,
+                                                                 const double* __restrict__ w0, double* __restrict__ xs,
+                                                                 double* __restrict__ us, double* __restrict__ vs,
+                                                                 double* __restrict__ ws, int32_t* __restrict__ cursor) {
+    long long end;
+    const long long beg = sortb_range(k.N, &end);
     const unsigned lane = threadIdx.x & 31;
-    for (long long it = 0; it < nIter; ++it, i += stride) {
-        double X = 0.;
-        int key = -1;
-        if (i < k.N) { X = x0[i]; key = dd_sort_key(k, X, i); }
-        const unsigned peers = __match_any_sync(0xffffffffu, key);
-        const int leader = __ffs(peers) - 1;
-        int base = 0;
-        if (key >= 0 && (int)lane == leader) base = atomicAdd(&cursor[key], __popc(peers));
-        base = __shfl_sync(0xffffffffu, base, leader);
-        if (key >= 0) {
-            const long long pos = (long long)base + __popc(peers & ((1u << lane) - 1u));
-            xs[pos] = X;
-            if (PERM) ((int32_t*)us)[pos] = (int32_t)i; else us[pos] = u0[i];
-            if (vs) vs[pos] = v0[i];
-            if (ws) ws[pos] = w0[i];
+    for (long long base = beg; base < end; base += SORTB_T * SORTB_PER) {
+        double X[SORTB_PER], U[SORTB_PER];
+        int key[SORTB_PER], res[SORTB_PER];
+        unsigned peers[SORTB_PER];
+#pragma unroll
+        for (int j = 0; j < SORTB_PER; ++j) {
+            const long long i = base + j * SORTB_T + threadIdx.x;
+            X[j] = 0.; U[j] = 0.;
+            if (i < end) { X[j] = x0[i]; if (!PERM) U[j] = u0[i]; }
+        }
+        // one reservation per distinct key per warp; the four atomics of a thread are independent
+#pragma unroll
+        for (int j = 0; j < SORTB_PER; ++j) {
+            const long long i = base + j * SORTB_T + threadIdx.x;
+            key[j] = i < end ? dd_sort_key(k, X[j], i) : -1;
+            peers[j] = __match_any_sync(0xffffffffu, key[j]);
+            res[j] = 0;
+            if (key[j] >= 0 && (int)lane == __ffs(peers[j]) - 1) res[j] = atomicAdd(&cursor[key[j]], __popc(peers[j]));
+        }
+#pragma unroll
+        for (int j = 0; j < SORTB_PER; ++j) {
+            const long long i = base + j * SORTB_T + threadIdx.x;
+            const int b = __shfl_sync(0xffffffffu, res[j], __ffs(peers[j]) - 1);
+            if (key[j] >= 0) {
+                const long long pos = (long long)b + __popc(peers[j] & ((1u << lane) - 1u));
+                xs[pos] = X[j];
+                if (PERM) ((int32_t*)us)[pos] = (int32_t)i; else us[pos] = U[j];
+                if (vs) vs[pos] = v0[i];
+                if (ws) ws[pos] = w0[i];
+            }
         }
     }
 }
@@ -1340,7 +1375,7 @@ static int sort_by_cell_impl(const DDK& k, const double* x0, const double* u0, c
     if (big) {
         PIC_REQUIRE(nblk <= 1024 * 1024, "sort_by_cell: grid too large");
         int32_t* sums = counts + nk + 2;
-        dd_sort_hist_big_k<<<grid_for(k.N, 256, 8), 256, 0, st>>>(k, x0, counts);
+        dd_sort_hist_big_k<<<grid_for(k.N, SORTB_T * SORTB_PER, 4), SORTB_T, 0, st>>>(k, x0, counts);
         PIC_CHECK_LAUNCH();
         scan_local_k<<<nblk, 1024, 0, st>>>(counts, nk, sums);
         PIC_CHECK_LAUNCH();
@@ -1348,7 +1383,7 @@ static int sort_by_cell_impl(const DDK& k, const double* x0, const double* u0, c
         PIC_CHECK_LAUNCH();
         scan_add_k<<<nblk, 1024, 0, st>>>(counts, nk, sums);
         PIC_CHECK_LAUNCH();
-        dd_sort_scatter_big_k<PERM><<<grid_for(k.N, 256, 8), 256, 0, st>>>(k, x0, u0, v0, w0, x0s, u0s, v0s, w0s, counts);
+        dd_sort_scatter_big_k<PERM><<<grid_for(k.N, SORTB_T * SORTB_PER, 4), SORTB_T, 0, st>>>(k, x0, u0, v0, w0, x0s, u0s, v0s, w0s, counts);
         PIC_CHECK_LAUNCH();
         return PIC_OK;
     }

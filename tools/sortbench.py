@@ -31,4 +31,17 @@ x.add_(torch.randn(N, dtype=torch.float64, device=dev) * (0.5 * dx)).clamp_(1e-1
 out["nearly_sorted"] = timed(x, u, xs, us)
 k0 = torch.floor(xs[:h] / dx); k1 = torch.floor(xs[h:] / dx)
 out["sorted_ok2"] = bool((k0[1:] >= k0[:-1]).all().item() and (k1[1:] >= k1[:-1]).all().item())
+# the stable radix sort of the reproducible build on the same nearly sorted store
+scr = torch.zeros(D.sort_stable_scratch_size(N), dtype=torch.int32, device=dev)
+where = C.c_int(0)
+xa, ua = x.clone(), u.clone()
+ts = []
+for _ in range(3):
+    xa.copy_(x); ua.copy_(u)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    _lib.call("pic_dev_dd_sort_by_cell_stable", C.byref(P), D.ptr(xa), D.ptr(ua), D.ptr(xs), D.ptr(us), D.ptr(scr),
+              scr.numel(), C.byref(where), D.stream())
+    e1.record(); torch.cuda.synchronize(); ts.append(e0.elapsed_time(e1))
+out["stable_nearly_sorted"] = ts
 print(json.dumps(out))
