@@ -156,6 +156,14 @@ int pic_dev_dd_picard_iter(const pic_dd_params* p, const double* x0, const doubl
 int pic_dev_dd_picard_iter2(const pic_dd_params* p, const double* x0, const double* u0, const double* x1_in,
                             double* x1_out, double* u1, int8_t* active, const double* Es, double* acc, int first,
                             int* range_err, void* stream);
+/* Enqueue-ahead variant: `done` (device int32, may be NULL) is read at kernel entry and a non-zero
+ * value makes the launch a no-op.  Together with pic_dev_dd_field_update2, which raises the flag
+ * when the loop condition `r > tol and k < maxiter` (PIC_L_DD.py:452) fails, the host can queue
+ * the iterations it expects back to back and read the outcome once per step instead of once per
+ * iteration. */
+int pic_dev_dd_picard_iter3(const pic_dd_params* p, const double* x0, const double* u0, const double* x1_in,
+                            double* x1_out, double* u1, int8_t* active, const double* Es, double* acc, int first,
+                            int* range_err, const int32_t* done, void* stream);
 /* u1 of the last iteration after the fact: x1_prev/x1_last are that iteration's input and output
  * positions, Es the field it gathered with, `first` whether it was the first iteration of the
  * step.  Particles absorbed before it get the reference's 0.0 (PIC_L_DD.py:459-462). */
@@ -189,6 +197,15 @@ int pic_dev_debug_cta_timer(uint64_t* buf);
  *   for Ng > 32768 (its sums are re-associated relative to the one-CTA kernel). */
 int pic_dev_dd_field_update(const pic_dd_params* p, double* acc, double* wall_cum, const double* E0,
                             double* Es, double* E1, double* j1, double* stats, void* stream);
+/* The same field phase for the enqueue-ahead loop.  All extra arguments may be NULL / 0:
+ *   Es_prev fp64[Ng] receives the field the iteration gathered with (Es on entry) -- what
+ *           pic_dev_dd_commit_u2 needs if the loop ends on a light iteration;
+ *   rhist   fp64[maxiter]: rhist[k-1] = residual of the k-th iteration of the step (k = stats[3]);
+ *   ctl     device int32: a non-zero value on entry makes the launch a no-op; set to 1 on exit
+ *           when not (r > tol) or k >= maxiter, i.e. when PIC_L_DD.py:452 leaves the loop. */
+int pic_dev_dd_field_update2(const pic_dd_params* p, double* acc, double* wall_cum, const double* E0,
+                             double* Es, double* E1, double* j1, double* stats, double* Es_prev,
+                             double* rhist, int32_t* ctl, double tol, int maxiter, void* stream);
 /* Re-injection (PIC_L_DD.py:429-450).  Host-RNG parity mode: compact the indices of
  * inactive slots in index order (pic_dev_compact_flags), draw on the host with the
  * legacy MT19937 stream, then scatter: */

@@ -68,12 +68,14 @@ _SIGS = {
     "pic_dev_dd_weight": [P, P, P, P, P, I64, I32, F64, F64, F64, P, P],
     "pic_dev_dd_picard_iter": [C.POINTER(DDParams), P, P, P, P, P, P, P, I32, P, P],
     "pic_dev_dd_picard_iter2": [C.POINTER(DDParams), P, P, P, P, P, P, P, P, I32, P, P],
+    "pic_dev_dd_picard_iter3": [C.POINTER(DDParams), P, P, P, P, P, P, P, P, I32, P, P, P],
     "pic_dev_dd_commit_u": [C.POINTER(DDParams), P, P, P, P, P, P, P, I32, P, P],
     "pic_dev_dd_commit_u2": [C.POINTER(DDParams), P, P, P, P, P, P, P, I32, P, P, P],
     "pic_dev_dd_j1_finish": [C.POINTER(DDParams), P, P, P, P, P],
     "pic_dev_debug_cta_timer": [P],
     "pic_dev_selftest_div": [F64, C.c_uint64, C.c_uint64, P, P],
     "pic_dev_dd_field_update": [C.POINTER(DDParams), P, P, P, P, P, P, P, P],
+    "pic_dev_dd_field_update2": [C.POINTER(DDParams), P, P, P, P, P, P, P, P, P, P, F64, I32, P],
     "pic_dev_dd_apply_draws": [P, P, P, P, P, I64, P, P, P, P, P, P],
     "pic_dev_dd_reinject_philox": [C.POINTER(DDParams), P, P, P, P, P, C.POINTER(C.c_double * 2), C.c_uint64,
                                    C.c_uint64, I64, P],

@@ -29,6 +29,10 @@ struct DDK {
     // on which warp, CTA or rank adds first); fix = [hi(2Ng) | lo(2Ng)] behind the fp64 accumulators
     long long* fix;
     int* ferr;                   // device error counter for contributions beyond the fixed-point range
+    // enqueue-ahead Picard loop: when non-null and *done != 0 the particle kernels return at once
+    // (the field kernel sets it when the residual meets the tolerance), so the host can queue the
+    // iterations it expects without a round trip per iteration
+    const int* done;
     double fs1, fi1;             // 2^s and 2^-s: one hi unit = 2^-s, one lo unit = 2^-(s+32)
 };
 
@@ -42,7 +46,7 @@ static DDK make_ddk(const pic_dd_params* p) {
         k.c1[s] = p->dt * qm;
         k.c2[s] = p->dt * p->dt * qm;
     }
-    k.fix = nullptr; k.ferr = nullptr; k.fs1 = 1.0; k.fi1 = 1.0;
+    k.fix = nullptr; k.ferr = nullptr; k.fs1 = 1.0; k.fi1 = 1.0; k.done = nullptr;
     if (p->flags & 128) {
         // one contribution is q*p2c*u*w/dx with |u| < c: |v| < amax < 2^e, so |v|*2^(31-e) < 2^31 and a
         // node can take 2^31 contributions before the hi word overflows; the lo word carries 32 more bits
@@ -117,6 +121,7 @@ __global__ void __launch_bounds__(256) dd_picard_iter_k(DDK k, const double* __r
                                                         const double* __restrict__ Es, double* __restrict__ acc,
                                                         int* __restrict__ range_err) {
     extern __shared__ double sm[];
+    if (k.done && *(const volatile int*)k.done) return;
     const int Ng = k.Ng;
     const double* F = Es;
     double* jh = acc;
@@ -582,6 +587,7 @@ __global__ void __launch_bounds__(V6_T, 1) dd_picard_iter_v6_k(
     double* __restrict__ acc, int* __restrict__ range_err, int* __restrict__ sched) {
     extern __shared__ __align__(128) double sm[];
     __shared__ int s_cnt[8];
+    if (k.done && *(const volatile int*)k.done) return;
     unsigned long long* const tbuf = g_cta_timer;
     if (tbuf && threadIdx.x == 0) tbuf[2 * blockIdx.x] = gtimer();
     const int Ng = k.Ng;
@@ -808,10 +814,13 @@ __global__ void __launch_bounds__(1024) dd_field_update_k(DDK k, double* __restr
                                                           double* __restrict__ wall_cum,
                                                           const double* __restrict__ E0, double* __restrict__ Es,
                                                           double* __restrict__ E1, double* __restrict__ j1o,
-                                                          double* __restrict__ stats) {
+                                                          double* __restrict__ stats, double* __restrict__ Es_prev,
+                                                          double* __restrict__ rhist, int* __restrict__ ctl,
+                                                          double tol, int maxiter) {
     __shared__ double scratch[33];
     __shared__ double wl[2], wr[2];
     const int Ng = k.Ng;
+    if (ctl && *(volatile int*)ctl) return;       // the loop already ended (enqueue-ahead mode)
     if (k.fix)      // reproducible build: the currents arrive as fixed-point words
         for (int i = threadIdx.x; i < 2 * Ng; i += blockDim.x) acc[i] += fix_take(k, i);
     if (threadIdx.x < 4) {
@@ -844,10 +853,12 @@ __global__ void __launch_bounds__(1024) dd_field_update_k(DDK k, double* __restr
         double e0 = E0[i];
         double e1 = e0 + coef * (meanh - E1[i]);      // :516
         double eh = (e1 + e0) * 0.5;                   // :521
-        double d = Es[i] - eh;
+        const double es = Es[i];
+        double d = es - eh;
         rr += d * d;
         ee += PIC_EPS0 * e1 * e1 * k.dx / 2.;
         E1[i] = e1;
+        if (Es_prev) Es_prev[i] = es;                  // the field this iteration gathered with
         Es[i] = eh;
     }
     rr = block_reduce<0>(rr, scratch);
@@ -855,10 +866,14 @@ __global__ void __launch_bounds__(1024) dd_field_update_k(DDK k, double* __restr
     __syncthreads();
     for (int i = threadIdx.x; i < 2 * Ng + 4; i += blockDim.x) acc[i] = 0.0;
     if (threadIdx.x == 0) {
-        stats[0] = sqrt(rr);               // np.linalg.norm(Es-Eh), :525
+        const double r = sqrt(rr);         // np.linalg.norm(Es-Eh), :525
+        const double it = stats[3] + 1.0;
+        stats[0] = r;
         stats[1] = s1 / (double)Ng;        // np.average(j1) -> jbias, :551
         stats[2] = ee;                     // sum(eps0*E*E*dx/2), :548
-        stats[3] = stats[3] + 1.0;
+        stats[3] = it;
+        if (rhist && it <= (double)maxiter) rhist[(int)it - 1] = r;
+        if (ctl && (!(r > tol) || it >= (double)maxiter)) *ctl = 1;      // `while r > tol and k < maxiter`, :452
     }
 }
 
@@ -871,10 +886,13 @@ __global__ void __launch_bounds__(1024) dd_field_update_big_k(DDK k, double* __r
                                                               double* __restrict__ wall_cum,
                                                               const double* __restrict__ E0, double* __restrict__ Es,
                                                               double* __restrict__ E1, double* __restrict__ j1o,
-                                                              double* __restrict__ stats, double* __restrict__ red) {
+                                                              double* __restrict__ stats, double* __restrict__ red,
+                                                              double* __restrict__ Es_prev, double* __restrict__ rhist,
+                                                              int* __restrict__ ctl, double tol, int maxiter) {
     cg::grid_group grid = cg::this_grid();
     __shared__ double scratch[33];
     const int Ng = k.Ng;
+    if (ctl && *(volatile int*)ctl) return;       // read by every CTA before the first grid barrier; set after the last
     if (k.fix) {
         for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < 2 * Ng; i += gridDim.x * blockDim.x) acc[i] += fix_take(k, i);
         grid.sync();
@@ -906,10 +924,12 @@ __global__ void __launch_bounds__(1024) dd_field_update_big_k(DDK k, double* __r
         double e0 = E0[i];
         double e1 = e0 + coef * (meanh - E1[i]);
         double eh = (e1 + e0) * 0.5;
-        double d = Es[i] - eh;
+        const double es = Es[i];
+        double d = es - eh;
         rr += d * d;
         ee += PIC_EPS0 * e1 * e1 * k.dx / 2.;
         E1[i] = e1;
+        if (Es_prev) Es_prev[i] = es;
         Es[i] = eh;
     }
     rr = block_reduce<0>(rr, scratch);
@@ -919,13 +939,19 @@ __global__ void __launch_bounds__(1024) dd_field_update_big_k(DDK k, double* __r
     for (int i = gtid; i < 2 * Ng + 4; i += gsz) acc[i] = 0.0;
     if (gtid == 0) {
         wall_cum[0] = w0; wall_cum[1] = w1; wall_cum[2] = w2; wall_cum[3] = w3;
-        stats[0] = sqrt(red[2]);
+        const double r = sqrt(red[2]);
+        const double it = stats[3] + 1.0;
+        stats[0] = r;
         stats[1] = red[1] / (double)Ng;
         stats[2] = red[3];
-        stats[3] = stats[3] + 1.0;
+        stats[3] = it;
+        if (rhist && it <= (double)maxiter) rhist[(int)it - 1] = r;
     }
     grid.sync();      // every CTA has read red[] and the wall counts before they are reset
-    if (gtid == 0) { red[0] = 0.0; red[1] = 0.0; red[2] = 0.0; red[3] = 0.0; }
+    if (gtid == 0) {
+        if (ctl && (!(stats[0] > tol) || stats[3] >= (double)maxiter)) *ctl = 1;
+        red[0] = 0.0; red[1] = 0.0; red[2] = 0.0; red[3] = 0.0;
+    }
 }
 
 __global__ void dd_interpolate_k(const double* __restrict__ F, const double* __restrict__ x,
@@ -1505,6 +1531,12 @@ extern "C" {
 int pic_dev_dd_picard_iter2(const pic_dd_params* p, const double* x0, const double* u0, const double* x1_in,
                             double* x1_out, double* u1, int8_t* active, const double* Es, double* acc, int first,
                             int* range_err, void* stream) {
+    return pic_dev_dd_picard_iter3(p, x0, u0, x1_in, x1_out, u1, active, Es, acc, first, range_err, nullptr, stream);
+}
+
+int pic_dev_dd_picard_iter3(const pic_dd_params* p, const double* x0, const double* u0, const double* x1_in,
+                            double* x1_out, double* u1, int8_t* active, const double* Es, double* acc, int first,
+                            int* range_err, const int32_t* done, void* stream) {
     PIC_REQUIRE(p && x0 && u0 && x1_in && x1_out && active && Es && acc, "dd_picard_iter: null pointer");
     PIC_REQUIRE(p->N >= 0 && p->Ng >= 3 && p->dx > 0 && p->dt > 0, "dd_picard_iter: bad parameters");
     if (p->N == 0) return PIC_OK;
@@ -1512,6 +1544,7 @@ int pic_dev_dd_picard_iter2(const pic_dd_params* p, const double* x0, const doub
     PIC_REQUIRE(!(p->flags & 128) || !(p->flags & (1 | 2 | 4 | 8)),
                 "dd_picard_iter: the reproducible build (flags bit7) exists for the default window kernel only");
     ddk_bind_fix(k, acc, range_err);
+    k.done = done;
     cudaStream_t st = (cudaStream_t)stream;
     const double* x1i = x1_in;
     double* x1 = x1_out;
@@ -1658,7 +1691,14 @@ int pic_dev_selftest_div(double b, uint64_t n, uint64_t seed, uint64_t* mismatch
 
 int pic_dev_dd_field_update(const pic_dd_params* p, double* acc, double* wall_cum, const double* E0, double* Es,
                             double* E1, double* j1, double* stats, void* stream) {
+    return pic_dev_dd_field_update2(p, acc, wall_cum, E0, Es, E1, j1, stats, nullptr, nullptr, nullptr, 0.0, 0, stream);
+}
+
+int pic_dev_dd_field_update2(const pic_dd_params* p, double* acc, double* wall_cum, const double* E0, double* Es,
+                             double* E1, double* j1, double* stats, double* Es_prev, double* rhist, int32_t* ctl,
+                             double tol, int maxiter, void* stream) {
     PIC_REQUIRE(p && acc && wall_cum && E0 && Es && E1 && j1 && stats, "dd_field_update: null pointer");
+    PIC_REQUIRE(!(ctl || rhist) || maxiter >= 1, "dd_field_update: maxiter must be >= 1 with ctl / rhist");
     DDK k = make_ddk(p);
     ddk_bind_fix(k, acc, nullptr);
     if (k.Ng > 32768) {
@@ -1666,12 +1706,13 @@ int pic_dev_dd_field_update(const pic_dd_params* p, double* acc, double* wall_cu
         double* red = stats + 4;
         int grid = (k.Ng + 1023) / 1024;
         if (grid > device_sm_count()) grid = device_sm_count();
-        void* args[] = {&k, &acc, &wall_cum, (void*)&E0, &Es, &E1, &j1, &stats, &red};
+        void* args[] = {&k, &acc, &wall_cum, (void*)&E0, &Es, &E1, &j1, &stats, &red, &Es_prev, &rhist, &ctl, &tol, &maxiter};
         PIC_CHECK_CUDA(cudaLaunchCooperativeKernel((const void*)dd_field_update_big_k, dim3(grid), dim3(1024), args, 0,
                                                    (cudaStream_t)stream));
         return PIC_OK;
     }
-    dd_field_update_k<<<1, 1024, 0, (cudaStream_t)stream>>>(k, acc, wall_cum, E0, Es, E1, j1, stats);
+    dd_field_update_k<<<1, 1024, 0, (cudaStream_t)stream>>>(k, acc, wall_cum, E0, Es, E1, j1, stats, Es_prev, rhist, ctl, tol,
+                                                            maxiter);
     PIC_CHECK_LAUNCH();
     return PIC_OK;
 }

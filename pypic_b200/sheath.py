@@ -25,7 +25,8 @@ kb = 1.38E-23
 class SheathSim:
     def __init__(self, N, Ng, dx, dt, p2c, q=(-e, e), m=(me, mp), n_split=None, tol=1e-5, maxiter=20,
                  kBT=(None, None), gamma=0.0, carry_vw=True, deposit="window", tiles="smem",
-                 rng="host", seed=1, draws=None, comm=None, device=None, sort_every=0, elide_u=True):
+                 rng="host", seed=1, draws=None, comm=None, device=None, sort_every=0, elide_u=True,
+                 enqueue_ahead=True):
         self.dev = D.require_cuda(device)
         self.comm = comm if comm is not None else Comm()
         self.N_global = int(N)
@@ -79,7 +80,14 @@ class SheathSim:
         # reproducible build: [jh | j1 | 4 counts] as fp64 followed by the int64 words [hi(2g) | lo(2g)]
         self.acc = D.f64(2 * g + 4 + (4 * g if self.det else 0), dev, True)
         self.wall_cum = D.f64(4, dev, True)
-        self.stats = D.f64(8, dev, True)      # [r, mean j1, EE, iterations | 4 doubles of reduction scratch]
+        # [r, mean j1, EE, iterations | 4 doubles of reduction scratch | residual of every iteration of the step]
+        self.stats = D.f64(8 + self.maxiter, dev, True)
+        # enqueue-ahead Picard loop: the iterations the previous step needed are queued back to back,
+        # guarded by a device flag that the field kernel raises when the loop condition fails; the
+        # host reads the outcome once per step instead of once per iteration
+        self.enqueue_ahead = bool(enqueue_ahead)
+        self.ctl = torch.zeros(1, dtype=torch.int32, device=dev)
+        self._prev_hist = None
         self.range_err = torch.zeros(1, dtype=torch.int32, device=dev)
         self.dead_idx = torch.empty(n, dtype=torch.int32, device=dev)
         self.count = torch.zeros(1, dtype=torch.int64, device=dev)
@@ -239,42 +247,66 @@ class SheathSim:
         stores / deposits them only when it is expected to be the last one ("light" iterations
         stream 32 instead of 40 bytes per particle and skip a third of the deposit work); if the
         loop ends on a light iteration, pic_dev_dd_commit_u2 + pic_dev_dd_j1_finish recompute both
-        from that iteration's inputs (kept intact by ping-ponging the position buffers)."""
+        from that iteration's inputs (kept intact by ping-ponging the position buffers).
+
+        Enqueue-ahead: the residuals of consecutive steps differ by a few per cent, so the
+        iterations the previous step needed are queued without waiting for their residuals; every
+        launch is guarded by the device flag `ctl`, which the field kernel raises as soon as
+        `r > tol and k < maxiter` fails, so a loop that ends earlier turns the rest of the queue into
+        no-ops and one that needs more continues one iteration at a time."""
         st = D.stream()
         P = C.byref(self.params)
         self.Es.copy_(self.E0)
         self.wall_cum.zero_()
         self.stats.zero_()
-        r, k = 1.0, 0
+        self.ctl.zero_()
+        rhist = D.ptr(self.stats) + 8 * 8
+        pairs = [(self.x1, self.x1b), (self.x1b, self.x1)] if self.elide_u else [(self.x1, self.x1)]
+        queued = []                      # per iteration launched: (want_u, events or None)
         hist = []
-        xin, xout = (self.x1, self.x1b) if self.elide_u else (self.x1, self.x1)
-        last_in = last_out = xout
-        wrote_u = True
-        while (r > self.tol) and (k < self.maxiter):
-            want_u = (not self.elide_u) or self._expect_last(k + 1, hist)
-            if self.elide_u:
-                self.Es_prev.copy_(self.Es)
+
+        def launch(j, want_u):           # j: 0-based iteration
+            xin, xout = pairs[j % len(pairs)]
+            ev = None
             if self.iter_events is not None:
                 ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
                 ev[0].record()
-            _lib.call("pic_dev_dd_picard_iter2", P, D.ptr(self.x0), D.ptr(self.u0), D.ptr(xin), D.ptr(xout),
+            _lib.call("pic_dev_dd_picard_iter3", P, D.ptr(self.x0), D.ptr(self.u0), D.ptr(xin), D.ptr(xout),
                       D.ptr(self.u1) if want_u else None, D.ptr(self.active), D.ptr(self.Es), D.ptr(self.acc),
-                      1 if k == 0 else 0, D.ptr(self.range_err), st)
-            if self.iter_events is not None:
+                      1 if j == 0 else 0, D.ptr(self.range_err), D.ptr(self.ctl), st)
+            if ev is not None:
                 ev[1].record()
-                self.iter_events.append(ev + (want_u, k == 0))
             self._allreduce_acc()
-            _lib.call("pic_dev_dd_field_update", P, D.ptr(self.acc), D.ptr(self.wall_cum), D.ptr(self.E0),
-                      D.ptr(self.Es), D.ptr(self.E1), D.ptr(self.j0), D.ptr(self.stats), st)
-            self.kernel_launches += 2
-            r = float(D.read_f64(self.stats, 1)[0])
-            k += 1
-            hist.append(r)
-            if self.resid_trace is not None:
-                self.resid_trace.append(r)
-            wrote_u, last_in, last_out = want_u, xin, xout
-            if self.elide_u:
-                xin, xout = xout, xin
+            _lib.call("pic_dev_dd_field_update2", P, D.ptr(self.acc), D.ptr(self.wall_cum), D.ptr(self.E0),
+                      D.ptr(self.Es), D.ptr(self.E1), D.ptr(self.j0), D.ptr(self.stats),
+                      D.ptr(self.Es_prev) if self.elide_u else None, rhist, D.ptr(self.ctl), self.tol, self.maxiter, st)
+            queued.append((want_u, ev))
+
+        def outcome():
+            s = D.read_f64(self.stats, 8 + self.maxiter)
+            k = int(s[3])
+            return k, [float(v) for v in s[8:8 + k]]
+
+        k = 0
+        ahead = self._prev_hist if (self.enqueue_ahead and self.maxiter >= 1) else None
+        if ahead:
+            # the previous step's residuals stand in for this step's in the last-iteration predictor
+            for j in range(min(len(ahead), self.maxiter)):
+                launch(j, (not self.elide_u) or self._expect_last(j + 1, ahead[:j]))
+            k, hist = outcome()
+        r = hist[-1] if hist else 1.0
+        while (r > self.tol) and (k < self.maxiter) and k == len(queued):
+            launch(k, (not self.elide_u) or self._expect_last(k + 1, hist))
+            k, hist = outcome()
+            r = hist[-1]
+        # launches behind the end of the loop were no-ops
+        if self.iter_events is not None:
+            self.iter_events.extend(ev + (wu, j == 0) for j, (wu, ev) in enumerate(queued[:k]))
+        self.kernel_launches += 2 * k
+        if self.resid_trace is not None:
+            self.resid_trace.extend(hist)
+        wrote_u = queued[k - 1][0] if k > 0 else True
+        last_in, last_out = pairs[(k - 1) % len(pairs)] if k > 0 else pairs[0]
         if k > 0 and not wrote_u:
             # the loop ended on a light iteration: recompute its velocities and its j1
             _lib.call("pic_dev_dd_commit_u2", P, D.ptr(self.x0), D.ptr(self.u0), D.ptr(last_in), D.ptr(last_out),
@@ -289,6 +321,7 @@ class SheathSim:
             self._r1 = hist[0]
             if ratios:
                 self._ratio = max(ratios)
+            self._prev_hist = list(hist)
         # commit (PIC_L_DD.py:538-545): pointer swaps
         if k > 0:
             if self.elide_u:

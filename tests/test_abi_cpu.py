@@ -31,6 +31,21 @@ def test_exports_every_declared_symbol(lib):
     assert set(syms) == set(lib.EXPORTS)
 
 
+def test_binding_table_matches_the_prototypes(lib):
+    """Every ctypes signature in pypic_b200/_lib.py has as many arguments as the prototype in
+    include/pic_b200.h (a wrong count only shows up as a TypeError on the GPU box otherwise)."""
+    src = open(os.path.join(ROOT, "include", "pic_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    protos = re.findall(r"\b(?:int|const char\*|void)\s+(pic_[a-zA-Z0-9_]+)\s*\(([^;{]*?)\)\s*;", src, flags=re.S)
+    assert len(protos) > 40
+    for name, args in protos:
+        if name in ("pic_last_error", "pic_version"):
+            continue
+        args = args.strip()
+        n = 0 if args in ("", "void") else len(args.split(","))
+        assert len(lib._SIGS[name]) == n, "%s: header has %d arguments, binding table %d" % (name, n, len(lib._SIGS[name]))
+
+
 def test_version_and_error_string(lib):
     l = lib.load()
     assert l.pic_version() >= 100

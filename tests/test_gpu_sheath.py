@@ -310,6 +310,51 @@ def test_sheath_sim_elision_modes_agree():
         s.check()
 
 
+def test_enqueue_ahead_loop_matches_the_synchronous_loop():
+    """The Picard loop queued ahead of its residuals (device flag raised by the field kernel, the
+    rest of the queue turned into no-ops) against the loop that reads the residual after every
+    iteration: same iteration counts and residual histories, same state to round-off -- also when
+    the queue is SHORTER than the step needs (the loop continues one iteration at a time), LONGER
+    (no-op launches), and longer with every iteration predicted "not the last" (no-ops + repair
+    pass)."""
+    from pypic_b200.sheath import SheathSim
+    N, Ng = 200000, 257
+    dx, L, dt, x0, u0, q, m, E0 = _one_iter_inputs(N, Ng, 5)
+    sims = []
+    for ahead in (False, True):
+        s = SheathSim(N, Ng, dx, dt, 1e9, kBT=(1.6e-18, 1.6e-18), carry_vw=False, rng="philox", sort_every=0,
+                      enqueue_ahead=ahead)
+        s.upload(x0, u0, E0=E0)
+        s.resid_trace = []
+        sims.append(s)
+    sync, ahead = sims
+    counts = []
+    for step, mode in enumerate(["first", "same", "short", "long", "long-light", "same"]):
+        h = ahead._prev_hist
+        if mode == "short":
+            ahead._prev_hist = h[:1]
+        elif mode == "long":
+            ahead._prev_hist = h + [h[-1] * 1e-3] * 3
+        elif mode == "long-light":
+            ahead._prev_hist = [1e30] * (len(h) + 2)
+        repairs = ahead.u_repairs
+        ks = [s.step() for s in sims]
+        assert ks[0][0] == ks[1][0] >= 2, (step, ks)
+        if mode == "long-light":
+            assert ahead.u_repairs == repairs + 1
+        counts.append(ks[0][0])
+        a, b = sync.download(), ahead.download()
+        assert np.array_equal(a["active"], b["active"])
+        assert relmax(b["E0"], a["E0"]) < 1e-12 and relmax(b["j0"], a["j0"]) < 1e-12
+        assert relmax(b["x0"], a["x0"]) < 1e-13 and relmax(b["u0"], a["u0"]) < 1e-12
+        assert int(ahead.ctl.item()) == 1
+    assert len(sync.resid_trace) == len(ahead.resid_trace) == sum(counts)
+    ra, rb = np.array(sync.resid_trace), np.array(ahead.resid_trace)
+    assert np.all(np.abs(ra - rb) <= 1e-6 * ra + 1e-9)
+    for s in sims:
+        s.check()
+
+
 @pytest.mark.parametrize("tag", ["small", "default"])
 def test_whole_loop_vs_reference_golden(golden, tag):
     """PIC_L_DD.main_i itself (golden from the reference run): same seed, the host draw
