@@ -23,6 +23,8 @@ def test_two_rank_sheath_matches_single_gpu():
     out = [l for l in lines if "iters_sharded" in l][-1]
     assert out["ok"], out
     assert out["iters_sharded"] == out["iters_single"]
+    det = [l for l in lines if "det" in l][-1]["det"]
+    assert det["ok"], det
     per = [l for l in lines if "periodic" in l][-1]["periodic"]
     assert per["ok"], per
     bor = [l for l in lines if "boris" in l][-1]["boris"]
