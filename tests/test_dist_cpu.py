@@ -111,3 +111,70 @@ def test_world2_gloo_allreduce_and_draw_service():
     assert np.array_equal(got, ref)
     nxt = rs.uniform()
     assert res[0][8] == nxt and res[1][8] == nxt
+
+
+def _worker_det(rank, world, port, q):
+    """Reproducible build, sharded: SheathSim._allreduce_acc on the layout
+    [jh | j1 | 4 counts] fp64 + [hi(2Ng) | lo(2Ng)] int64 (gloo stands in for NCCL)."""
+    import types
+    from pypic_b200 import fixedpoint as FP
+    from pypic_b200.sheath import SheathSim
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        comm = Comm()
+        Ng, n = 17, 6000
+        e, p2c, dx = 1.602e-19, 2.048e9, 1e-5
+        s = FP.scale_exponent((-e, e), p2c, dx)
+        rs = np.random.RandomState(11)                     # the same global deposits on every rank
+        node = rs.randint(0, 2 * Ng, n)
+        v = rs.normal(0, 20.0, n)
+        out = []
+        for part in ("interleaved", "halves"):
+            mine = (np.arange(n) % world == rank) if part == "interleaved" else (np.arange(n) * world // n == rank)
+            hi, lo = FP.split(v[mine], s)
+            H = np.zeros(2 * Ng, dtype=np.int64); Lo = np.zeros(2 * Ng, dtype=np.int64)
+            np.add.at(H, node[mine], hi); np.add.at(Lo, node[mine], lo)
+            acc = torch.zeros(2 * Ng + 4 + 4 * Ng, dtype=torch.float64)
+            acc[2 * Ng:2 * Ng + 4] = torch.tensor([1.0 + rank, 2.0, 0.0, 5.0 * rank])
+            acc[2 * Ng + 4:].view(torch.int64).copy_(torch.as_tensor(np.concatenate([H, Lo])))
+            sim = types.SimpleNamespace(det=True, comm=comm, Ng=Ng, acc=acc)
+            SheathSim._allreduce_acc(sim)
+            out.append(acc.numpy().copy())
+        q.put((rank, out, s))
+        comm.barrier()
+    finally:
+        dist.destroy_process_group()
+
+
+def test_world2_gloo_reproducible_build_allreduce_is_partition_independent():
+    from pypic_b200 import fixedpoint as FP
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker_det, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = sorted([q.get(timeout=120) for _ in range(world)], key=lambda t: t[0])
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    Ng, n = 17, 6000
+    s = res[0][2]
+    # both ranks and both partitions of the deposits end with the same bits
+    ref = res[0][1][0]
+    for r in res:
+        for acc in r[1]:
+            assert acc.tobytes() == ref.tobytes()
+    assert np.array_equal(ref[:2 * Ng], np.zeros(2 * Ng))                       # the fp64 current slots are not used
+    assert np.array_equal(ref[2 * Ng:2 * Ng + 4], [3.0, 4.0, 0.0, 5.0])         # counts: exact fp64 integers
+    words = ref[2 * Ng + 4:].view(np.int64)
+    rs = np.random.RandomState(11)
+    node = rs.randint(0, 2 * Ng, n); v = rs.normal(0, 20.0, n)
+    import math
+    for g in range(2 * Ng):
+        exact = math.fsum(v[node == g].tolist())
+        got = FP.merge(int(words[g]), int(words[2 * Ng + g]), s)
+        assert abs(got - exact) <= 1e-15 * max(abs(exact), 1.0)
