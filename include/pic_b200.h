@@ -290,6 +290,17 @@ int pic_dev_pypic_field_update(const pic_pypic_params* p, double* acc, const dou
 int pic_dev_pypic_picard_iter2(const pic_pypic_params* p, const double* x0, const double* v0,
                                const double* x1_in, double* x1_out, double* v1, const double* Fs,
                                double* acc, int first, int* range_err, void* stream);
+/* Enqueue-ahead variants (see pic_dev_dd_picard_iter3 / pic_dev_dd_field_update2): `done` / `ctl`
+ * is a device int32 read at kernel entry, a non-zero value makes the launch a no-op; the field kernel
+ * sets it when `r > tol and k < maxiter` (pypic.py:259) fails, writes the smoothed field the
+ * iteration gathered with to Fs_prev (what pic_dev_pypic_j1_repair needs) and the residual of the
+ * k-th iteration to rhist[k-1].  Fs_prev, rhist, ctl may be NULL. */
+int pic_dev_pypic_picard_iter3(const pic_pypic_params* p, const double* x0, const double* v0,
+                               const double* x1_in, double* x1_out, double* v1, const double* Fs,
+                               double* acc, int first, int* range_err, const int32_t* done, void* stream);
+int pic_dev_pypic_field_update2(const pic_pypic_params* p, double* acc, const double* E0, double* Es,
+                                double* Fs, double* E1, double* j1, double* stats, double* Fs_prev,
+                                double* rhist, int32_t* ctl, double tol, int maxiter, void* stream);
 /* Light iterations (flags bit3 of pic_pypic_params): the iteration neither stores v1 nor deposits j1 --
  * both are only used after the Picard loop.  If the loop ends on one, pic_dev_pypic_j1_repair recomputes
  * v1 = v0 + dt*(q/m)*E(xs) from that iteration's inputs (x1_prev, the smoothed field Fs_prev it

@@ -89,6 +89,8 @@ _SIGS = {
     "pic_dev_pypic_picard_iter": [C.POINTER(PypicParams), P, P, P, P, P, P, I32, P, P],
     "pic_dev_pypic_field_update": [C.POINTER(PypicParams), P, P, P, P, P, P, P, P],
     "pic_dev_pypic_picard_iter2": [C.POINTER(PypicParams), P, P, P, P, P, P, P, I32, P, P],
+    "pic_dev_pypic_picard_iter3": [C.POINTER(PypicParams), P, P, P, P, P, P, P, I32, P, P, P],
+    "pic_dev_pypic_field_update2": [C.POINTER(PypicParams), P, P, P, P, P, P, P, P, P, P, F64, I32, P],
     "pic_dev_pypic_j1_repair": [C.POINTER(PypicParams), P, P, P, P, P, P, I32, P, P, P],
     "pic_dev_pypic_j1_finish": [C.POINTER(PypicParams), P, P, P, P],
     "pic_dev_wrap_periodic": [P, I64, F64, P],

@@ -30,9 +30,11 @@ struct PYK {
     long long N;
     int Ng, flags;
     double dx, idx, dt, L, p2c, q, qm;
+    const int* done;      // enqueue-ahead Picard loop: non-null and *done != 0 -> the particle kernels return at once
 };
 static PYK make_pyk(const pic_pypic_params* p) {
     PYK k;
+    k.done = nullptr;
     k.N = p->N; k.Ng = p->Ng; k.flags = p->flags; k.dx = p->dx; k.idx = 1. / p->dx; k.dt = p->dt;
     k.L = p->L; k.p2c = p->p2c; k.q = p->q; k.qm = p->q / p->m;
     return k;
@@ -89,6 +91,7 @@ __global__ void __launch_bounds__(256) pypic_picard_iter_k(PYK k, const double* 
                                                            double* __restrict__ v1, const double* __restrict__ Fs,
                                                            double* __restrict__ acc, int* __restrict__ range_err) {
     extern __shared__ double sm[];
+    if (k.done && *(const volatile int*)k.done) return;
     const int Ng = k.Ng;
     double *sF = sm, *jh = sm + Ng, *j1 = sm + 2 * Ng;
     for (int i = threadIdx.x; i < Ng; i += blockDim.x) { sF[i] = Fs[i]; jh[i] = 0.0; j1[i] = 0.0; }
@@ -143,9 +146,12 @@ __global__ void __launch_bounds__(256) pypic_picard_iter_k(PYK k, const double* 
 __global__ void __launch_bounds__(1024) pypic_field_update_k(PYK k, double* __restrict__ acc,
                                                              const double* __restrict__ E0, double* __restrict__ Es,
                                                              double* __restrict__ Fs, double* __restrict__ E1,
-                                                             double* __restrict__ j1o, double* __restrict__ stats) {
+                                                             double* __restrict__ j1o, double* __restrict__ stats,
+                                                             double* __restrict__ Fs_prev, double* __restrict__ rhist,
+                                                             int* __restrict__ ctl, double tol, int maxiter) {
     __shared__ double scratch[33];
     const int Ng = k.Ng;
+    if (ctl && *(volatile int*)ctl) return;       // the loop already ended (enqueue-ahead mode)
     double* jh = acc;
     double* j1 = acc + Ng;
     double sh = 0.0, s1 = 0.0;
@@ -165,6 +171,7 @@ __global__ void __launch_bounds__(1024) pypic_field_update_k(PYK k, double* __re
         rr += d * d;                                                   // :289 (squared, no sqrt)
         ee += PIC_EPS0 * e1 * e1 * k.dx / 2.;
         E1[i] = e1;
+        if (Fs_prev) Fs_prev[i] = Fs[i];   // the smoothed field this iteration gathered with
         Fs[i] = eh;        // staged: Eh, smoothed below
     }
     rr = block_reduce<0>(rr, scratch);
@@ -178,10 +185,13 @@ __global__ void __launch_bounds__(1024) pypic_field_update_k(PYK k, double* __re
     }
     for (int i = threadIdx.x; i < 2 * Ng; i += blockDim.x) acc[i] = 0.0;
     if (threadIdx.x == 0) {
+        const double it = stats[3] + 1.0;
         stats[0] = rr;
         stats[1] = s1 / (double)Ng;
         stats[2] = ee;
-        stats[3] = stats[3] + 1.0;
+        stats[3] = it;
+        if (rhist && it <= (double)maxiter) rhist[(int)it - 1] = rr;
+        if (ctl && (!(rr > tol) || it >= (double)maxiter)) *ctl = 1;     // `while r > tol and k < maxiter`, pypic.py:259
     }
 }
 
@@ -626,6 +636,7 @@ __global__ void __launch_bounds__(S_T, 1) pypic_picard_iter_v2_k(const __grid_co
                                                                   double* __restrict__ acc, int* __restrict__ range_err) {
     extern __shared__ __align__(128) double sm[];
     __shared__ int s_bad;
+    if (k.done && *(const volatile int*)k.done) return;
     constexpr int NA = FIRST ? 2 : 3;
     const int Ng = k.Ng;
     const int NP = (Ng + 15) & ~15;
@@ -840,10 +851,17 @@ int pic_dev_pypic_picard_iter(const pic_pypic_params* p, const double* x0, const
 
 int pic_dev_pypic_picard_iter2(const pic_pypic_params* p, const double* x0, const double* v0, const double* x1i, double* x1,
                                double* v1, const double* Fs, double* acc, int first, int* range_err, void* stream) {
+    return pic_dev_pypic_picard_iter3(p, x0, v0, x1i, x1, v1, Fs, acc, first, range_err, nullptr, stream);
+}
+
+int pic_dev_pypic_picard_iter3(const pic_pypic_params* p, const double* x0, const double* v0, const double* x1i, double* x1,
+                               double* v1, const double* Fs, double* acc, int first, int* range_err, const int32_t* done_flag,
+                               void* stream) {
     PIC_REQUIRE(p && x0 && v0 && x1i && x1 && v1 && Fs && acc, "pypic_picard_iter: null pointer");
     PIC_REQUIRE(p->Ng >= 2 && p->dx > 0, "pypic_picard_iter: bad parameters");
     if (p->N == 0) return PIC_OK;
     PYK k = make_pyk(p);
+    k.done = done_flag;
     cudaStream_t st = (cudaStream_t)stream;
     const size_t smem2 = ((size_t)((k.Ng + 15) & ~15) + (size_t)2 * S_W * S_T + (size_t)(S_T / 32) * PY_NST * 192 +
                           (size_t)(S_T / 32) * PY_NST) * sizeof(double);
@@ -871,9 +889,17 @@ int pic_dev_pypic_picard_iter2(const pic_pypic_params* p, const double* x0, cons
 
 int pic_dev_pypic_field_update(const pic_pypic_params* p, double* acc, const double* E0, double* Es, double* Fs,
                                double* E1, double* j1, double* stats, void* stream) {
+    return pic_dev_pypic_field_update2(p, acc, E0, Es, Fs, E1, j1, stats, nullptr, nullptr, nullptr, 0.0, 0, stream);
+}
+
+int pic_dev_pypic_field_update2(const pic_pypic_params* p, double* acc, const double* E0, double* Es, double* Fs,
+                                double* E1, double* j1, double* stats, double* Fs_prev, double* rhist, int32_t* ctl,
+                                double tol, int maxiter, void* stream) {
     PIC_REQUIRE(p && acc && E0 && Es && Fs && E1 && j1 && stats, "pypic_field_update: null pointer");
+    PIC_REQUIRE(!(ctl || rhist) || maxiter >= 1, "pypic_field_update: maxiter must be >= 1 with ctl / rhist");
     PYK k = make_pyk(p);
-    pypic_field_update_k<<<1, 1024, 0, (cudaStream_t)stream>>>(k, acc, E0, Es, Fs, E1, j1, stats);
+    pypic_field_update_k<<<1, 1024, 0, (cudaStream_t)stream>>>(k, acc, E0, Es, Fs, E1, j1, stats, Fs_prev, rhist, ctl, tol,
+                                                               maxiter);
     PIC_CHECK_LAUNCH();
     return PIC_OK;
 }

@@ -6,6 +6,7 @@
   (PIC_L.main, PIC_L.py:762-768).
 """
 import ctypes as C
+import os
 
 import numpy as np
 import torch
@@ -52,7 +53,13 @@ class PeriodicImplicitSim:
         self.E0 = D.f64(g, dev, True); self.Es = D.f64(g, dev, True); self.Fs = D.f64(g, dev, True)
         self.E1 = D.f64(g, dev, True); self.j0 = D.f64(g, dev, True)
         self.acc = D.f64(2 * g, dev, True)
-        self.stats = D.f64(4, dev, True)
+        # [r, mean j1, EE, iterations | residual of every iteration of the step]
+        self.stats = D.f64(4 + self.maxiter, dev, True)
+        # enqueue-ahead Picard loop (see SheathSim.picard): the iterations the previous step needed are
+        # queued without a host round trip each, guarded by a device flag the field kernel raises
+        self.enqueue_ahead = os.environ.get("PIC_ENQUEUE_AHEAD", "1") != "0"   # env: A/B runs
+        self.ctl = torch.zeros(1, dtype=torch.int32, device=dev)
+        self._prev_hist = None
         self.range_err = torch.zeros(1, dtype=torch.int32, device=dev)
         self.last_iters, self.last_resid = 0, 1.0
         self.kernel_launches = 0
@@ -111,9 +118,7 @@ class PeriodicImplicitSim:
         self.Es.copy_(self.E0)
         _lib.call("pic_dev_smooth", D.ptr(self.Es), D.ptr(self.Fs), self.Ng, 0, st)
         self.stats.zero_()
-        r, k = 1.0, 0
-        hist = []
-        full = True
+        self.ctl.zero_()
         base_flags = self.params.flags & ~8
         light_ok = self.light_iterations
         if light_ok and self.x1b is None:
@@ -121,36 +126,54 @@ class PeriodicImplicitSim:
             self.Fs_prev = D.f64(self.Ng, self.dev, True)
         # the n+1 positions ping-pong between two buffers so that the inputs of the last iteration
         # survive it (needed by the repair pass when that iteration turns out to have been light)
-        xin, xout = (self.x1, self.x1b) if light_ok else (self.x1, self.x1)
-        last_in = last_out = xout
-        while (r > self.tol) and (k < self.maxiter):
+        pairs = [(self.x1, self.x1b), (self.x1b, self.x1)] if light_ok else [(self.x1, self.x1)]
+        rhist = D.ptr(self.stats) + 4 * 8
+        queued = []                      # per iteration launched: (full, events or None)
+        hist = []
+
+        def launch(j, full):
             # v1 and j1 (the current at n+1) are only used after the loop: iterations that are not expected
             # to be the last one run "light" (flags bit3: no v1 store, no j1 lookup / deposit: 32 instead of
             # 40 B/particle); the prediction comes from the regular contraction of the residual, a wrong one
             # costs the repair pass below
-            full = (not light_ok) or self._expect_last(k + 1, hist)
+            xin, xout = pairs[j % len(pairs)]
             self.params.flags = base_flags | (0 if full else 8)
-            if light_ok:
-                self.Fs_prev.copy_(self.Fs)
             ev = None
             if self.iter_events is not None:
                 ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
                 ev[0].record()
-            _lib.call("pic_dev_pypic_picard_iter2", P, D.ptr(self.x0), D.ptr(self.v0), D.ptr(xin), D.ptr(xout), D.ptr(self.v1),
-                      D.ptr(self.Fs), D.ptr(self.acc), 1 if k == 0 else 0, D.ptr(self.range_err), st)
+            _lib.call("pic_dev_pypic_picard_iter3", P, D.ptr(self.x0), D.ptr(self.v0), D.ptr(xin), D.ptr(xout), D.ptr(self.v1),
+                      D.ptr(self.Fs), D.ptr(self.acc), 1 if j == 0 else 0, D.ptr(self.range_err), D.ptr(self.ctl), st)
             if ev is not None:
                 ev[1].record()
-                self.iter_events.append(ev)
             self.comm.allreduce_sum(self.acc)
-            _lib.call("pic_dev_pypic_field_update", P, D.ptr(self.acc), D.ptr(self.E0), D.ptr(self.Es), D.ptr(self.Fs),
-                      D.ptr(self.E1), D.ptr(self.j0), D.ptr(self.stats), st)
-            self.kernel_launches += 2
-            r = float(D.read_f64(self.stats, 1)[0])
-            k += 1
-            hist.append(r)
-            last_in, last_out = xin, xout
-            if light_ok:
-                xin, xout = xout, xin
+            _lib.call("pic_dev_pypic_field_update2", P, D.ptr(self.acc), D.ptr(self.E0), D.ptr(self.Es), D.ptr(self.Fs),
+                      D.ptr(self.E1), D.ptr(self.j0), D.ptr(self.stats), D.ptr(self.Fs_prev) if light_ok else None,
+                      rhist, D.ptr(self.ctl), self.tol, self.maxiter, st)
+            queued.append((full, ev))
+
+        def outcome():
+            sv = D.read_f64(self.stats, 4 + self.maxiter)
+            kk = int(sv[3])
+            return kk, [float(v) for v in sv[4:4 + kk]]
+
+        k = 0
+        ahead = self._prev_hist if (self.enqueue_ahead and self.maxiter >= 1) else None
+        if ahead:
+            for j in range(min(len(ahead), self.maxiter)):
+                launch(j, (not light_ok) or self._expect_last(j + 1, ahead[:j]))
+            k, hist = outcome()
+        r = hist[-1] if hist else 1.0
+        while (r > self.tol) and (k < self.maxiter) and k == len(queued):
+            launch(k, (not light_ok) or self._expect_last(k + 1, hist))
+            k, hist = outcome()
+            r = hist[-1]
+        if self.iter_events is not None:
+            self.iter_events.extend(ev for _, ev in queued[:k])       # launches behind the end of the loop were no-ops
+        self.kernel_launches += 2 * k
+        full = queued[k - 1][0] if k > 0 else True
+        last_in, last_out = pairs[(k - 1) % len(pairs)] if k > 0 else pairs[0]
+        self._prev_hist = list(hist) if hist else self._prev_hist
         self.params.flags = base_flags
         if k > 0 and not full:
             _lib.call("pic_dev_pypic_j1_repair", P, D.ptr(self.x0), D.ptr(self.v0), D.ptr(last_in), D.ptr(last_out),

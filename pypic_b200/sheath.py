@@ -7,6 +7,7 @@ and the small grid arrays.  One Picard iteration = one fused particle kernel
 (gather+push+absorb+deposit jh,j1) + [one all-reduce if sharded] + one field kernel.
 """
 import ctypes as C
+import os
 
 import numpy as np
 import torch
@@ -85,7 +86,7 @@ class SheathSim:
         # enqueue-ahead Picard loop: the iterations the previous step needed are queued back to back,
         # guarded by a device flag that the field kernel raises when the loop condition fails; the
         # host reads the outcome once per step instead of once per iteration
-        self.enqueue_ahead = bool(enqueue_ahead)
+        self.enqueue_ahead = bool(enqueue_ahead) and os.environ.get("PIC_ENQUEUE_AHEAD", "1") != "0"   # env: A/B runs
         self.ctl = torch.zeros(1, dtype=torch.int32, device=dev)
         self._prev_hist = None
         self.range_err = torch.zeros(1, dtype=torch.int32, device=dev)

@@ -251,3 +251,42 @@ def test_pypic_light_iterations_and_repair_agree_with_full_iterations():
     assert sims[0].j1_repairs == 0 and sims[2].j1_repairs == 4
     for s in sims:
         s.check()
+
+
+def test_pypic_enqueue_ahead_loop_matches_the_synchronous_loop():
+    """PeriodicImplicitSim's Picard loop queued ahead of its residuals (device flag raised by the
+    field kernel; later launches are no-ops) against the loop that reads the residual after every
+    iteration -- with a queue that is too short, too long, and too long with every iteration
+    predicted "not the last" (no-ops + j1 repair)."""
+    from pypic_b200.periodic import PeriodicImplicitSim
+    rs = np.random.RandomState(22)
+    Ng = 256; dx = 1e-5; dt = 2e-12; L = dx * Ng
+    N = 5 * 16384 + 99
+    x0 = np.sort(rs.uniform(0, L, N)); v0 = rs.normal(0, 1.3e6, N); E0 = rs.normal(0, 2e4, Ng)
+    sims = []
+    for ahead in (False, True):
+        s = PeriodicImplicitSim(N, Ng, dx, dt, L, 1e9, tol=1e-3, maxiter=20, deposit="window")
+        s.enqueue_ahead = ahead
+        s.upload(x0, v0, E0)
+        sims.append(s)
+    sync, ahead = sims
+    for step, mode in enumerate(["first", "same", "short", "long", "long-light", "same"]):
+        h = ahead._prev_hist
+        if mode == "short":
+            ahead._prev_hist = h[:1]
+        elif mode == "long":
+            ahead._prev_hist = h + [h[-1] * 1e-3] * 3
+        elif mode == "long-light":
+            ahead._prev_hist = [1e30] * (len(h) + 2)
+        repairs = ahead.j1_repairs
+        ks = [s.push() for s in sims]
+        assert ks[0][0] == ks[1][0] >= 2, (step, ks)
+        assert abs(ks[0][1] - ks[1][1]) <= 1e-6 * ks[0][1] + 1e-12
+        if mode == "long-light":
+            assert ahead.j1_repairs == repairs + 1
+        a, b = sync.download(), ahead.download()
+        assert relmax(b["x0"], a["x0"]) < 1e-13 and relmax(b["v0"], a["v0"]) < 1e-12
+        assert relmax(b["E0"], a["E0"]) < 1e-12 and relmax(b["j0"], a["j0"]) < 1e-12
+        assert int(ahead.ctl.item()) == 1
+    for s in sims:
+        s.check()
