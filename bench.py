@@ -380,6 +380,8 @@ def run_cuda(args):
                        "sort": "electrons every %d steps, ions with them every %d steps" % (args.sort_every,
                                                                                              args.sort_every * sim.heavy_sort_every),
                        "reinjection": "device Philox4x32-10 (statistical parity)",
+                       "picard_loop": ("enqueue-ahead: the iterations the previous step needed are queued behind a device flag, "
+                                       "one host round trip per step") if sim.enqueue_ahead else "one host round trip per iteration",
                        "l2_policy": "inputs (%.1f GB of particle arrays per GPU) are far larger than the 126 MB L2" % (sim.N * 32 / 1e9)},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
         }
