@@ -117,6 +117,8 @@ class PeriodicImplicitSim:
         self.t += 1
         self.Es.copy_(self.E0)
         _lib.call("pic_dev_smooth", D.ptr(self.Es), D.ptr(self.Fs), self.Ng, 0, st)
+        if self.stats.numel() < 4 + self.maxiter:          # maxiter was raised after construction
+            self.stats = D.f64(4 + self.maxiter, self.dev, True)
         self.stats.zero_()
         self.ctl.zero_()
         base_flags = self.params.flags & ~8

@@ -259,6 +259,8 @@ class SheathSim:
         P = C.byref(self.params)
         self.Es.copy_(self.E0)
         self.wall_cum.zero_()
+        if self.stats.numel() < 8 + self.maxiter:          # maxiter was raised after construction
+            self.stats = D.f64(8 + self.maxiter, self.dev, True)
         self.stats.zero_()
         self.ctl.zero_()
         rhist = D.ptr(self.stats) + 8 * 8

@@ -59,6 +59,7 @@ def make_sim(maxiter=6, tol=1e-5, enqueue_ahead=True):
     sim = object.__new__(S.SheathSim)
     f = lambda n: torch.zeros(n, dtype=torch.float64)
     sim.maxiter, sim.tol, sim.elide_u, sim.enqueue_ahead, sim.det = maxiter, tol, True, enqueue_ahead, False
+    sim.dev = torch.device("cpu")
     sim.params = S._lib.DDParams()
     for nm in ("x0", "u0", "x1", "x1b", "u1", "E0", "Es", "E1", "Es_prev", "j0", "acc", "wall_cum"):
         setattr(sim, nm, f(4))
@@ -143,3 +144,13 @@ def test_synchronous_loop_gives_the_same_counts(fake):
         assert k == len(script) and r == script[-1]
         assert not [e for e in log if e[0] == "noop"]
         assert int(sim.x0[0]) == 100 * step + k
+
+
+def test_raising_maxiter_after_construction_grows_the_residual_history(fake):
+    sim = make_sim(maxiter=3)
+    dev = fake(sim, [[1e3, 9e2, 8e2], [1e3, 5e2, 1e2, 50.0, 20.0, 10.0, 5.0, 1.0]])
+    k, r, _, _ = run_step(sim, dev)
+    assert k == 3
+    sim.maxiter = 8
+    k, r, log, _ = run_step(sim, dev)
+    assert k == 8 and r == 1.0 and sim.stats.numel() >= 16 and sim._prev_hist[-1] == 1.0
