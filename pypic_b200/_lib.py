@@ -76,6 +76,12 @@ _SIGS = {
     "pic_dev_selftest_div": [F64, C.c_uint64, C.c_uint64, P, P],
     "pic_dev_dd_field_update": [C.POINTER(DDParams), P, P, P, P, P, P, P, P],
     "pic_dev_dd_field_update2": [C.POINTER(DDParams), P, P, P, P, P, P, P, P, P, P, F64, I32, P],
+    "pic_p2p_alloc": [I64, I32, C.POINTER(C.c_void_p), P],
+    "pic_p2p_open": [P, C.POINTER(C.c_void_p)],
+    "pic_p2p_close": [P],
+    "pic_p2p_free": [P],
+    "pic_dev_p2p_reduce": [P, I32, I32, C.c_uint32, I64, P, P, P],
+    "pic_dev_dd_field_update_p2p": [C.POINTER(DDParams), P, I32, I32, C.c_uint32, P, P, P, P, P, P, P, P, P, P, F64, I32, P, P],
     "pic_dev_dd_apply_draws": [P, P, P, P, P, I64, P, P, P, P, P, P],
     "pic_dev_dd_reinject_philox": [C.POINTER(DDParams), P, P, P, P, P, C.POINTER(C.c_double * 2), C.c_uint64,
                                    C.c_uint64, I64, P],

@@ -877,6 +877,162 @@ __global__ void __launch_bounds__(1024) dd_field_update_k(DDK k, double* __restr
     }
 }
 
+// The same field phase as a device function for the kernel fused with the peer-memory reduction
+// below (kept textually separate from dd_field_update_k, the validated default, until the fused
+// kernel has been through the same GPU parity suite; to be merged then).
+__device__ __forceinline__ void dd_field_update_body(const DDK& k, double* __restrict__ acc,
+                                                     double* __restrict__ wall_cum,
+                                                     const double* __restrict__ E0, double* __restrict__ Es,
+                                                     double* __restrict__ E1, double* __restrict__ j1o,
+                                                     double* __restrict__ stats, double* __restrict__ Es_prev,
+                                                     double* __restrict__ rhist, int* __restrict__ ctl,
+                                                     double tol, int maxiter, double* scratch, double* wl, double* wr) {
+    const int Ng = k.Ng;
+    if (k.fix)      // reproducible build: the currents arrive as fixed-point words
+        for (int i = threadIdx.x; i < 2 * Ng; i += blockDim.x) acc[i] += fix_take(k, i);
+    if (threadIdx.x < 4) {
+        double v = wall_cum[threadIdx.x] + acc[2 * Ng + threadIdx.x];
+        wall_cum[threadIdx.x] = v;
+        if (threadIdx.x < 2) wl[threadIdx.x] = v; else wr[threadIdx.x - 2] = v;
+    }
+    __syncthreads();
+    // wall-charge current of every absorbed particle (PIC_L_DD.py:58,62): count * value
+    double wallL = wl[0] * (k.dx * k.q[0] * k.p2c / k.dt) + wl[1] * (k.dx * k.q[1] * k.p2c / k.dt);
+    double wallR = wr[0] * (-k.dx * k.q[0] * k.p2c / k.dt) + wr[1] * (-k.dx * k.q[1] * k.p2c / k.dt);
+    double* jh = acc;
+    double* j1 = acc + Ng;
+    double sh = 0.0, s1 = 0.0;
+    // edge fold j[0]+=j[1]; j[-1]+=j[-2] uses the unfolded neighbours (:65-66)
+    for (int i = threadIdx.x; i < Ng; i += blockDim.x) {
+        double a = jh[i], b = j1[i];
+        if (i == 0) { a = (a + wallL) + jh[1]; b = (b + wallL) + j1[1]; }
+        if (i == Ng - 1) { a = (a + wallR) + jh[Ng - 2]; b = (b + wallR) + j1[Ng - 2]; }
+        sh += a; s1 += b;
+        E1[i] = a;      // staged: folded jh
+        j1o[i] = b;
+    }
+    sh = block_reduce<0>(sh, scratch);
+    s1 = block_reduce<0>(s1, scratch);
+    const double meanh = sh / (double)Ng;
+    const double coef = k.dt / PIC_EPS0;
+    double rr = 0.0, ee = 0.0;
+    for (int i = threadIdx.x; i < Ng; i += blockDim.x) {
+        double e0 = E0[i];
+        double e1 = e0 + coef * (meanh - E1[i]);      // :516
+        double eh = (e1 + e0) * 0.5;                   // :521
+        const double es = Es[i];
+        double d = es - eh;
+        rr += d * d;
+        ee += PIC_EPS0 * e1 * e1 * k.dx / 2.;
+        E1[i] = e1;
+        if (Es_prev) Es_prev[i] = es;                  // the field this iteration gathered with
+        Es[i] = eh;
+    }
+    rr = block_reduce<0>(rr, scratch);
+    ee = block_reduce<0>(ee, scratch);
+    __syncthreads();
+    for (int i = threadIdx.x; i < 2 * Ng + 4; i += blockDim.x) acc[i] = 0.0;
+    if (threadIdx.x == 0) {
+        const double r = sqrt(rr);         // np.linalg.norm(Es-Eh), :525
+        const double it = stats[3] + 1.0;
+        stats[0] = r;
+        stats[1] = s1 / (double)Ng;        // np.average(j1) -> jbias, :551
+        stats[2] = ee;                     // sum(eps0*E*E*dx/2), :548
+        stats[3] = it;
+        if (rhist && it <= (double)maxiter) rhist[(int)it - 1] = r;
+        if (ctl && (!(r > tol) || it >= (double)maxiter)) *ctl = 1;      // `while r > tol and k < maxiter`, :452
+    }
+}
+
+
+// ---------------------------------------------------------------------------------------
+// Particle decomposition WITHOUT a library collective: the sum over ranks of the grid
+// accumulators is done by the field kernel itself over NVLink peer memory.  Every rank's
+// accumulators live in a buffer that all ranks have mapped (CUDA IPC): nacc doubles followed by
+// 2*world 32-bit flags (ready[world], done[world]).  Per iteration (sequence number seq, the
+// same on every rank):
+//   1. rank r stores seq into ready[r] of EVERY rank's buffer (release, system scope): "my
+//      accumulators of iteration seq are complete" (the particle kernel ran before on the stream);
+//   2. it waits until ready[*] of its OWN buffer have reached seq, then loads every rank's
+//      accumulators and adds them in rank order -- every rank computes the same bits, so all ranks
+//      take the same Picard exit, exactly as with an all-reduce;
+//   3. it stores seq into done[r] of every rank ("I have read your accumulators"), runs the field
+//      phase on the sum, waits for done[*] in its own buffer and zeroes its accumulators for the
+//      next particle kernel.
+// Waits are bounded (a few seconds): on time-out *err is set and the kernel proceeds, so a peer
+// that died cannot hang the GPU.
+struct P2P {
+    double* const* peers;      // device array [world] of the ranks' buffers (own entry = local pointer)
+    int rank, world, nacc;
+    unsigned seq;
+    int* err;
+};
+__device__ __forceinline__ unsigned ld_acquire_sys_u32(const unsigned* p) {
+    unsigned v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_sys_u32(unsigned* p, unsigned v) {
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ double ld_relaxed_sys_f64(const double* p) {
+    double v;
+    asm volatile("ld.relaxed.sys.global.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ unsigned* p2p_flags(double* buf, int nacc) { return (unsigned*)(buf + nacc); }
+__device__ __noinline__ bool p2p_wait(const unsigned* flag, unsigned seq) {
+    for (int spin = 0; spin < (1 << 22); ++spin) {
+        if ((int)(ld_acquire_sys_u32(flag) - seq) >= 0) return true;      // wrap-safe "flag >= seq"
+        __nanosleep(200);
+    }
+    return false;
+}
+__device__ __forceinline__ void p2p_reduce(const P2P& P, double* __restrict__ sum) {
+    const int t = threadIdx.x;
+    unsigned* myf = p2p_flags(P.peers[P.rank], P.nacc);
+    __threadfence_system();
+    if (t < P.world) {
+        st_release_sys_u32(p2p_flags(P.peers[t], P.nacc) + P.rank, P.seq);
+        if (!p2p_wait(myf + t, P.seq)) atomicExch(P.err, 1);
+    }
+    __syncthreads();
+    for (int i = t; i < P.nacc; i += blockDim.x) {
+        double s = 0.0;
+        for (int r = 0; r < P.world; ++r) s += ld_relaxed_sys_f64(P.peers[r] + i);
+        sum[i] = s;
+    }
+    __syncthreads();
+    __threadfence_system();
+    if (t < P.world) st_release_sys_u32(p2p_flags(P.peers[t], P.nacc) + P.world + P.rank, P.seq);
+}
+__device__ __forceinline__ void p2p_finish(const P2P& P) {
+    const int t = threadIdx.x;
+    double* mine = P.peers[P.rank];
+    if (t < P.world && !p2p_wait(p2p_flags(mine, P.nacc) + P.world + t, P.seq)) atomicExch(P.err, 1);
+    __syncthreads();
+    for (int i = t; i < P.nacc; i += blockDim.x) mine[i] = 0.0;
+}
+__global__ void __launch_bounds__(1024) dd_field_update_p2p_k(DDK k, P2P P, double* __restrict__ acc_sum,
+                                                              double* __restrict__ wall_cum,
+                                                              const double* __restrict__ E0, double* __restrict__ Es,
+                                                              double* __restrict__ E1, double* __restrict__ j1o,
+                                                              double* __restrict__ stats, double* __restrict__ Es_prev,
+                                                              double* __restrict__ rhist, int* __restrict__ ctl,
+                                                              double tol, int maxiter) {
+    __shared__ double scratch[33];
+    __shared__ double wl[2], wr[2];
+    if (ctl && *(volatile int*)ctl) return;       // the same decision on every rank: nobody waits for a rank that left
+    p2p_reduce(P, acc_sum);
+    dd_field_update_body(k, acc_sum, wall_cum, E0, Es, E1, j1o, stats, Es_prev, rhist, ctl, tol, maxiter, scratch, wl, wr);
+    p2p_finish(P);
+}
+// the reduction alone (the j1 repair pass): sum[nacc] = sum over ranks, own accumulators zeroed
+__global__ void __launch_bounds__(1024) p2p_reduce_k(P2P P, double* __restrict__ sum) {
+    p2p_reduce(P, sum);
+    p2p_finish(P);
+}
+
 // ---- function-level drop-ins ---------------------------------------------------------
 // The same field phase for grids too large for one CTA (Ng > 32768): cooperative launch, one
 // CTA per SM, grid-wide barriers between the phases; the four sums are accumulated with one
@@ -1713,6 +1869,68 @@ int pic_dev_dd_field_update2(const pic_dd_params* p, double* acc, double* wall_c
     }
     dd_field_update_k<<<1, 1024, 0, (cudaStream_t)stream>>>(k, acc, wall_cum, E0, Es, E1, j1, stats, Es_prev, rhist, ctl, tol,
                                                             maxiter);
+    PIC_CHECK_LAUNCH();
+    return PIC_OK;
+}
+
+// ---- peer-memory reduction (see dd_field_update_p2p_k) ----
+int pic_p2p_alloc(int64_t nacc, int world, void** dev_ptr, void* handle64) {
+    PIC_REQUIRE(nacc > 0 && world >= 1 && world <= 64 && dev_ptr && handle64, "p2p_alloc: bad argument");
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is expected to be 64 bytes");
+    const size_t bytes = (size_t)nacc * sizeof(double) + (size_t)2 * world * sizeof(unsigned);
+    void* p = nullptr;
+    PIC_CHECK_CUDA(cudaMalloc(&p, bytes));
+    PIC_CHECK_CUDA(cudaMemset(p, 0, bytes));
+    cudaIpcMemHandle_t h;
+    PIC_CHECK_CUDA(cudaIpcGetMemHandle(&h, p));
+    memcpy(handle64, &h, sizeof(h));
+    PIC_CHECK_CUDA(cudaDeviceSynchronize());
+    *dev_ptr = p;
+    return PIC_OK;
+}
+
+int pic_p2p_open(const void* handle64, void** peer_ptr) {
+    PIC_REQUIRE(handle64 && peer_ptr, "p2p_open: null pointer");
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle64, sizeof(h));
+    void* p = nullptr;
+    PIC_CHECK_CUDA(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+    *peer_ptr = p;
+    return PIC_OK;
+}
+
+int pic_p2p_close(void* peer_ptr) {
+    if (peer_ptr) PIC_CHECK_CUDA(cudaIpcCloseMemHandle(peer_ptr));
+    return PIC_OK;
+}
+
+int pic_p2p_free(void* dev_ptr) {
+    if (dev_ptr) PIC_CHECK_CUDA(cudaFree(dev_ptr));
+    return PIC_OK;
+}
+
+int pic_dev_p2p_reduce(const double* const* peers_dev, int rank, int world, uint32_t seq, int64_t nacc, double* sum,
+                       int* err, void* stream) {
+    PIC_REQUIRE(peers_dev && sum && err && world >= 1 && world <= 64 && rank >= 0 && rank < world && nacc > 0,
+                "p2p_reduce: bad argument");
+    P2P P{(double* const*)peers_dev, rank, world, (int)nacc, seq, err};
+    p2p_reduce_k<<<1, 1024, 0, (cudaStream_t)stream>>>(P, sum);
+    PIC_CHECK_LAUNCH();
+    return PIC_OK;
+}
+
+int pic_dev_dd_field_update_p2p(const pic_dd_params* p, const double* const* peers_dev, int rank, int world, uint32_t seq,
+                                double* acc_sum, double* wall_cum, const double* E0, double* Es, double* E1, double* j1,
+                                double* stats, double* Es_prev, double* rhist, int32_t* ctl, double tol, int maxiter,
+                                int* err, void* stream) {
+    PIC_REQUIRE(p && peers_dev && acc_sum && wall_cum && E0 && Es && E1 && j1 && stats && err, "dd_field_update_p2p: null pointer");
+    PIC_REQUIRE(world >= 1 && world <= 64 && rank >= 0 && rank < world, "dd_field_update_p2p: bad rank / world");
+    PIC_REQUIRE(!(ctl || rhist) || maxiter >= 1, "dd_field_update_p2p: maxiter must be >= 1 with ctl / rhist");
+    PIC_REQUIRE(p->Ng <= 32768 && !(p->flags & 128), "dd_field_update_p2p: one-CTA field phase of the default build only");
+    DDK k = make_ddk(p);
+    P2P P{(double* const*)peers_dev, rank, world, 2 * k.Ng + 4, seq, err};
+    dd_field_update_p2p_k<<<1, 1024, 0, (cudaStream_t)stream>>>(k, P, acc_sum, wall_cum, E0, Es, E1, j1, stats, Es_prev, rhist,
+                                                                ctl, tol, maxiter);
     PIC_CHECK_LAUNCH();
     return PIC_OK;
 }

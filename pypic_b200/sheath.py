@@ -27,7 +27,7 @@ class SheathSim:
     def __init__(self, N, Ng, dx, dt, p2c, q=(-e, e), m=(me, mp), n_split=None, tol=1e-5, maxiter=20,
                  kBT=(None, None), gamma=0.0, carry_vw=True, deposit="window", tiles="smem",
                  rng="host", seed=1, draws=None, comm=None, device=None, sort_every=0, elide_u=True,
-                 enqueue_ahead=True):
+                 enqueue_ahead=True, reduce="nccl"):
         self.dev = D.require_cuda(device)
         self.comm = comm if comm is not None else Comm()
         self.N_global = int(N)
@@ -80,6 +80,18 @@ class SheathSim:
         self.j0 = D.f64(g, dev, True)
         # reproducible build: [jh | j1 | 4 counts] as fp64 followed by the int64 words [hi(2g) | lo(2g)]
         self.acc = D.f64(2 * g + 4 + (4 * g if self.det else 0), dev, True)
+        # reduce: how a sharded run sums the accumulators over ranks -- "nccl": one all-reduce per deposit
+        # (default); "p2p": the field kernel reads every rank's accumulators over NVLink peer memory
+        # itself (pypic_b200/p2p.py; the particle kernels then add to the shared buffer and self.acc
+        # receives the sum)
+        self.p2p = None
+        if reduce == "p2p" and self.comm.world > 1:
+            if self.det or g > 32768:
+                raise ValueError("reduce='p2p' serves the default build with Ng <= 32768")
+            from .p2p import PeerAccumulators
+            self.p2p = PeerAccumulators(self.comm, 2 * g + 4, dev)
+        elif reduce not in ("nccl", "p2p"):
+            raise ValueError("reduce must be 'nccl' or 'p2p'")
         self.wall_cum = D.f64(4, dev, True)
         # [r, mean j1, EE, iterations | 4 doubles of reduction scratch | residual of every iteration of the step]
         self.stats = D.f64(8 + self.maxiter, dev, True)
@@ -229,10 +241,16 @@ class SheathSim:
         pred = self._r1 if k == 1 else hist[-1] * self._ratio
         return pred is None or pred <= 100.0 * self.tol
 
+    def _acc_ptr(self):
+        """Where the particle kernels deposit."""
+        return self.p2p.mine if self.p2p is not None else D.ptr(self.acc)
+
     def _allreduce_acc(self):
         """One sum over ranks per deposit.  Reproducible build: the currents travel as int64
         fixed-point words (an integer all-reduce is exact in any order), the four absorbed counts
         as exact fp64 integers."""
+        if self.p2p is not None:
+            return self.acc                      # summed by the field kernel over peer memory
         if not self.det:
             return self.comm.allreduce_sum(self.acc)
         if self.comm.world > 1:
@@ -275,14 +293,21 @@ class SheathSim:
                 ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
                 ev[0].record()
             _lib.call("pic_dev_dd_picard_iter3", P, D.ptr(self.x0), D.ptr(self.u0), D.ptr(xin), D.ptr(xout),
-                      D.ptr(self.u1) if want_u else None, D.ptr(self.active), D.ptr(self.Es), D.ptr(self.acc),
+                      D.ptr(self.u1) if want_u else None, D.ptr(self.active), D.ptr(self.Es), self._acc_ptr(),
                       1 if j == 0 else 0, D.ptr(self.range_err), D.ptr(self.ctl), st)
             if ev is not None:
                 ev[1].record()
-            self._allreduce_acc()
-            _lib.call("pic_dev_dd_field_update2", P, D.ptr(self.acc), D.ptr(self.wall_cum), D.ptr(self.E0),
-                      D.ptr(self.Es), D.ptr(self.E1), D.ptr(self.j0), D.ptr(self.stats),
-                      D.ptr(self.Es_prev) if self.elide_u else None, rhist, D.ptr(self.ctl), self.tol, self.maxiter, st)
+            if self.p2p is not None:
+                pp = self.p2p
+                _lib.call("pic_dev_dd_field_update_p2p", P, D.ptr(pp.peers_dev), pp.rank, pp.world, pp.next_seq(),
+                          D.ptr(self.acc), D.ptr(self.wall_cum), D.ptr(self.E0), D.ptr(self.Es), D.ptr(self.E1),
+                          D.ptr(self.j0), D.ptr(self.stats), D.ptr(self.Es_prev) if self.elide_u else None, rhist,
+                          D.ptr(self.ctl), self.tol, self.maxiter, D.ptr(pp.err), st)
+            else:
+                self._allreduce_acc()
+                _lib.call("pic_dev_dd_field_update2", P, D.ptr(self.acc), D.ptr(self.wall_cum), D.ptr(self.E0),
+                          D.ptr(self.Es), D.ptr(self.E1), D.ptr(self.j0), D.ptr(self.stats),
+                          D.ptr(self.Es_prev) if self.elide_u else None, rhist, D.ptr(self.ctl), self.tol, self.maxiter, st)
             queued.append((want_u, ev))
 
         def outcome():
@@ -313,8 +338,12 @@ class SheathSim:
         if k > 0 and not wrote_u:
             # the loop ended on a light iteration: recompute its velocities and its j1
             _lib.call("pic_dev_dd_commit_u2", P, D.ptr(self.x0), D.ptr(self.u0), D.ptr(last_in), D.ptr(last_out),
-                      D.ptr(self.active), D.ptr(self.Es_prev), D.ptr(self.u1), 1 if k == 1 else 0, D.ptr(self.acc),
+                      D.ptr(self.active), D.ptr(self.Es_prev), D.ptr(self.u1), 1 if k == 1 else 0, self._acc_ptr(),
                       D.ptr(self.range_err), st)
+            if self.p2p is not None:
+                pp = self.p2p
+                _lib.call("pic_dev_p2p_reduce", D.ptr(pp.peers_dev), pp.rank, pp.world, pp.next_seq(), pp.nacc,
+                          D.ptr(self.acc), D.ptr(pp.err), st)
             self._allreduce_acc()
             _lib.call("pic_dev_dd_j1_finish", P, D.ptr(self.acc), D.ptr(self.wall_cum), D.ptr(self.j0), D.ptr(self.stats), st)
             self.kernel_launches += 2
@@ -368,3 +397,5 @@ class SheathSim:
 
     def check(self):
         D.check_range(self.range_err, "sheath step")
+        if self.p2p is not None:
+            self.p2p.check()

@@ -139,7 +139,7 @@ def _worker_det(rank, world, port, q):
             acc = torch.zeros(2 * Ng + 4 + 4 * Ng, dtype=torch.float64)
             acc[2 * Ng:2 * Ng + 4] = torch.tensor([1.0 + rank, 2.0, 0.0, 5.0 * rank])
             acc[2 * Ng + 4:].view(torch.int64).copy_(torch.as_tensor(np.concatenate([H, Lo])))
-            sim = types.SimpleNamespace(det=True, comm=comm, Ng=Ng, acc=acc)
+            sim = types.SimpleNamespace(det=True, comm=comm, Ng=Ng, acc=acc, p2p=None)
             SheathSim._allreduce_acc(sim)
             out.append(acc.numpy().copy())
         q.put((rank, out, s))

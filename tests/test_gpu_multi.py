@@ -31,6 +31,20 @@ def test_two_rank_sheath_matches_single_gpu():
     assert bor["ok"], bor
 
 
+def test_two_rank_peer_memory_reduction_matches_nccl():
+    """SheathSim(reduce="p2p"): the field kernel sums the ranks' accumulators over NVLink peer
+    memory (CUDA IPC buffers, flag handshake) instead of an NCCL all-reduce (tools/p2p_check.py)."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
+           "127.0.0.1", "--master-port", "29535", os.path.join(ROOT, "tools", "p2p_check.py"), "400000", "5"]
+    res = subprocess.run(cmd, capture_output=True, text=True, timeout=300, cwd=ROOT)
+    assert res.returncode == 0, res.stderr[-2000:]
+    out = json.loads([l for l in res.stdout.splitlines() if l.startswith("{")][-1])
+    assert out["ok"], out
+
+
 def test_two_rank_slab_decomposition_matches_single_rank():
     """Spatial (slab) decomposition: halo exchange + particle migration + routed re-injection on 2
     ranks vs the same global particles on one rank (tools/slab_check.py)."""

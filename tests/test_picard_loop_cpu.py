@@ -60,6 +60,7 @@ def make_sim(maxiter=6, tol=1e-5, enqueue_ahead=True):
     f = lambda n: torch.zeros(n, dtype=torch.float64)
     sim.maxiter, sim.tol, sim.elide_u, sim.enqueue_ahead, sim.det = maxiter, tol, True, enqueue_ahead, False
     sim.dev = torch.device("cpu")
+    sim.p2p = None
     sim.params = S._lib.DDParams()
     for nm in ("x0", "u0", "x1", "x1b", "u1", "E0", "Es", "E1", "Es_prev", "j0", "acc", "wall_cum"):
         setattr(sim, nm, f(4))
