@@ -49,6 +49,9 @@ def parse():
     ap.add_argument("--decomposition", default="particle", choices=["particle", "slab"],
                     help="sheath workload only: particle decomposition (default, all-reduce of the grid) or spatial "
                          "slabs (halo exchange + particle migration, BASELINE config 5)")
+    ap.add_argument("--reduce", default="nccl", choices=["nccl", "p2p"],
+                    help="N > 1: sum of the grid accumulators over ranks by NCCL all-reduce (default) or inside the field "
+                         "kernel over NVLink peer memory (off by default: parity run pending, DESIGN.md 6)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-sample", type=float, default=4e6, help="particles in the CPU-baseline sample")
@@ -239,7 +242,7 @@ def run_cuda(args):
 
     sim = SheathSim(w["N"], w["Ng"], w["dx"], w["dt"], w["p2c"], tol=w["tol"], maxiter=w["maxiter"],
                     kBT=(w["kBTe"], w["kBTi"]), carry_vw=False, deposit=args.deposit, rng="philox", seed=1,
-                    comm=comm, device=dev, sort_every=args.sort_every)
+                    comm=comm, device=dev, sort_every=args.sort_every, reduce=args.reduce)
     sim.heavy_sort_every = max(1, args.heavy_sort_every)
     # synthetic initial state, generated on the device (x~U(0,L), u~N(0,sqrt(kT/m)))
     gen = torch.Generator(device=dev); gen.manual_seed(1234 + rank)
@@ -374,7 +377,9 @@ def run_cuda(args):
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": "1D sheath (PIC_L_DD physics): %d particles (%d per GPU, e-/p+ halves), %d-node grid, "
                                    "implicit CN/Picard tol=1e-5" % (w["N"], sim.N, w["Ng"]),
-                       "parallelism": "particle decomposition x%d, fp64 all-reduce of [jh|j1|counts] per Picard iteration" % world
+                       "parallelism": ("particle decomposition x%d, %s of [jh|j1|counts] per Picard iteration"
+                                       % (world, "fp64 all-reduce" if sim.p2p is None else
+                                          "sum over NVLink peer memory inside the field kernel (rank order)"))
                        if world > 1 else "single GPU",
                        "picard_iterations_per_step": kbar, "deposit": args.deposit, "sort_every": args.sort_every,
                        "sort": "electrons every %d steps, ions with them every %d steps" % (args.sort_every,
