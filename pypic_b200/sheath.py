@@ -59,6 +59,9 @@ class SheathSim:
         flags = {"window": 0, "window-blocked": 64, "window-big": 16, "window-ldg": 8, "atomic": 1,
                  "warp": 4, "window-det": 128}[deposit] | (2 if tiles == "global" else 0)
         self.det = deposit == "window-det"
+        if self.det and int(Ng) > 32768:
+            raise ValueError("deposit='window-det': the cooperative field kernel used for Ng > 32768 adds its per-CTA "
+                             "partial sums with fp64 atomics, so the run would not be bit-reproducible")
         self.params = _lib.DDParams(self.N, self.n_split, self.Ng, flags, self.dx, self.dt, self.L, self.p2c,
                                     (C.c_double * 2)(*self.q), (C.c_double * 2)(*self.m))
         dev = self.dev
