@@ -600,6 +600,11 @@ def run_other(args):
                          "traffic": None, "kernel": kname, "peak_source": peak_src, "kernel_ms_mean": float(np.mean(kms)),
                          "kernel_share_of_step": float(np.sum(kms) / ms), "algorithmic_bytes_per_launch": per_launch},
             "cpu_baseline": None, "e2e": None, "gpu_launches": int(launches() - l0), "clocks": sampler.summary()}
+    try:        # DRAM bytes per launch of this workload's kernel from its ncu --set full capture (profiles/traffic.json)
+        tk = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))["other_kernels"][args.workload]
+        line["roofline"]["traffic"] = (tk["dram_bytes_read"] + tk["dram_bytes_write"]) / tk["particles"] * N
+    except Exception:
+        pass
     if world > 1:
         dist.destroy_process_group()
     return line if rank == 0 else None
