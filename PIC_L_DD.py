@@ -6,6 +6,10 @@ on the GPU; only configuration, the legacy-RNG draw service and I/O stay on the 
 """
 from __future__ import print_function
 
+import os
+import sys
+import time
+
 import numpy as np
 
 from pypic_b200 import ops
@@ -121,10 +125,16 @@ def initialize(system, N, density, Kp, perturbation, dx, Ng, Te, Ti, L, X):
 
 
 def main_i(T, nplot, N=40000, Ng=51, dt=1E-12, dx=0.00001, Ti=10.0 * 11600., Te=10.0 * 11600., density=1E19,
-           gamma=0.0, tol=1E-5, maxiter=20, outdir='.', rng='host', result=None):
+           gamma=0.0, tol=1E-5, maxiter=20, outdir='.', rng='host', result=None, sort_every=8, vion_after=2000):
     """PIC_L_DD.main_i (PIC_L_DD.py:316-644).  The positional signature is the reference's;
     the keyword arguments default to its hard-coded literals.  `result` (a dict) receives
-    the time series and the final state."""
+    the time series and the final state.
+
+    The particle store is re-sorted by cell every `sort_every` steps so that the loop runs on the
+    fused TMA kernel; the sort carries every particle's original index, so the legacy-RNG
+    re-injection draws (made in index order, :429-450), vionout (:497-503) and every array handed
+    back are in the reference's particle numbering.  The thermostat's uniforms of a gamma == 0 run
+    are skipped by an MT19937 jump-ahead instead of being generated (pypic_b200/rng.py)."""
     perturbation = 0.0
     Kp = 1.0
     L = dx * (Ng - 1)
@@ -143,17 +153,20 @@ def main_i(T, nplot, N=40000, Ng=51, dt=1E-12, dx=0.00001, Ti=10.0 * 11600., Te=
     print("floating potential: ", (kb * Te / e) * (0.5) * np.log(mp / 2.0 / np.pi / me))
 
     sim = SheathSim(N, Ng, dx, dt, p2c, q=(-e, e), m=(me, mp), tol=tol, maxiter=maxiter, kBT=(kBTe, kBTi),
-                    gamma=gamma, carry_vw=True, rng=rng)
+                    gamma=gamma, carry_vw=True, rng=rng, sort_every=sort_every, vion_after=vion_after)
     sim.upload(x0, u0, v0, w0)          # E0 = -d(phi0)/dx with phi0 == 0 (PIC_L_DD.py:386-388)
     mpl, plt = get_plt()
     KE, EE, TT, jbias = [], [], [], []
+    kBTe_now = sim.kBTe_from(*sim.moments())       # np.std(u0)**2*me/e; afterwards it comes with the step's diagnostics
+    t_loop = time.perf_counter()
     for t in range(T + 1):
         print('t: ', t)
-        print('kBTe: ', float(sim.u0[:sim.N].std(unbiased=False).item())**2 * me / e)   # np.std(u0)**2*me/e
+        print('kBTe: ', kBTe_now)
         k, r = sim.step()
         print("Iterations: ", k)
         print("r: ", r)
         d = sim.diagnostics()
+        kBTe_now = d["kBTe"]
         EE.append(d["EE"]); KE.append(d["KE"]); TT.append(t * dt); jbias.append(d["jbias"])
         if plt is not None and (t % nplot == 0):
             st = sim.download()
@@ -168,13 +181,19 @@ def main_i(T, nplot, N=40000, Ng=51, dt=1E-12, dx=0.00001, Ti=10.0 * 11600., Te=
             plt.plot(X, st["E0"], linewidth=lw)
             plt.savefig('plots/e_' + str(t))
     sim.check()
+    t_loop = time.perf_counter() - t_loop
+    if os.environ.get("PIC_TIMING"):
+        sys.stderr.write("PIC_L_DD.main_i: time loop %d steps, %d particles: %.4f s = %.4e particle-steps/s (%.3f ms/step, "
+                         "%d sorts, MT jumps %d, prefetched %d)\n" % (T + 1, N, t_loop, N * (T + 1) / t_loop,
+                                                                      1e3 * t_loop / (T + 1), sim._sorts, sim.draws.jumps,
+                                                                      sim.draws.prefetch_hits))
     st = sim.download()
-    np.savetxt(outdir + '/vionout.txt', sim.vionout)
+    np.savetxt(outdir + '/vionout.txt', sim.collect_vionout())
     np.savetxt(outdir + '/E0.txt', st["E0"])
     np.savetxt(outdir + '/jb.txt', jbias)
     if result is not None:
         result.update(st, EE=np.array(EE), KE=np.array(KE), TT=np.array(TT), jbias=np.array(jbias),
-                      phih=sim.phi(), p2c=p2c)
+                      phih=sim.phi(), p2c=p2c, loop_seconds=t_loop)
 # end main_i
 
 

@@ -52,6 +52,10 @@ def parse():
     ap.add_argument("--reduce", default="nccl", choices=["nccl", "p2p"],
                     help="N > 1: sum of the grid accumulators over ranks by NCCL all-reduce (default) or inside the field "
                          "kernel over NVLink peer memory (off by default: parity run pending, DESIGN.md 6)")
+    ap.add_argument("--strong-total", type=float, default=1e9,
+                    help="second timed region: the north-star strong-scaling case, this many particles in TOTAL over the "
+                         "N GPUs (BASELINE config 4), reported as the sub-record `strong_scaling`; 0 disables it")
+    ap.add_argument("--strong-steps", type=int, default=12)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-sample", type=float, default=4e6, help="particles in the CPU-baseline sample")
@@ -148,6 +152,16 @@ def bind_to_gpu_numa_node(index):
         return False
 
 
+def host_threads():
+    """Host cores this process may use.  torchrun exports OMP_NUM_THREADS=1 to every rank, which would
+    make the CPU arm a one-thread run: the thread count is taken from the affinity mask instead and
+    passed to the port explicitly (its OpenMP regions carry a num_threads clause)."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return max(1, os.cpu_count() or 1)
+
+
 def measured_peak():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.isfile(p):
@@ -164,7 +178,7 @@ def cpu_port_run(w, n_sample, steps, warmup, threads=None):
     host cores.  Bounded sample of the same workload: same grid, same physics, n_sample
     particles (p2c rescaled so the plasma density is unchanged)."""
     from oracle import c_oracle
-    threads = threads or c_oracle.max_threads()
+    threads = threads or host_threads()
     n = int(n_sample); n -= n % 2
     rs = np.random.RandomState(1)
     h = n // 2
@@ -198,8 +212,7 @@ def run_reference(args):
     if rank != 0:
         return
     w = workload(args, max(1, args.gpus))
-    from oracle import c_oracle
-    threads = c_oracle.max_threads()
+    threads = host_threads()
     # size the sample so the whole run ends within a few minutes
     res = cpu_port_run(w, args.cpu_sample, max(1, min(args.steps, 10)), max(1, min(args.warmup, 2)), threads)
     line = {
@@ -240,49 +253,54 @@ def run_cuda(args):
     w = workload(args, world)
     dev = torch.device("cuda", local)
 
-    sim = SheathSim(w["N"], w["Ng"], w["dx"], w["dt"], w["p2c"], tol=w["tol"], maxiter=w["maxiter"],
-                    kBT=(w["kBTe"], w["kBTi"]), carry_vw=False, deposit=args.deposit, rng="philox", seed=1,
-                    comm=comm, device=dev, sort_every=args.sort_every, reduce=args.reduce)
-    sim.heavy_sort_every = max(1, args.heavy_sort_every)
-    # synthetic initial state, generated on the device (x~U(0,L), u~N(0,sqrt(kT/m)))
-    gen = torch.Generator(device=dev); gen.manual_seed(1234 + rank)
-    n, ns = sim.N, sim.n_split
-    sim.x0.uniform_(0.0, 1.0, generator=gen).mul_(w["L"]).clamp_(1e-12, w["L"] * (1 - 1e-12))
-    sim.u0.normal_(0.0, 1.0, generator=gen)
-    sim.u0[:ns].mul_(float(np.sqrt(w["kBTe"] / ME)))
-    sim.u0[ns:].mul_(float(np.sqrt(w["kBTi"] / MP)))
-    torch.cuda.synchronize()
+    def make_sim(wl):
+        sm = SheathSim(wl["N"], wl["Ng"], wl["dx"], wl["dt"], wl["p2c"], tol=wl["tol"], maxiter=wl["maxiter"],
+                       kBT=(wl["kBTe"], wl["kBTi"]), carry_vw=False, deposit=args.deposit, rng="philox", seed=1,
+                       comm=comm, device=dev, sort_every=args.sort_every, reduce=args.reduce)
+        sm.heavy_sort_every = max(1, args.heavy_sort_every)
+        # synthetic initial state, generated on the device (x~U(0,L), u~N(0,sqrt(kT/m)))
+        gen = torch.Generator(device=dev); gen.manual_seed(1234 + rank)
+        ns = sm.n_split
+        sm.x0.uniform_(0.0, 1.0, generator=gen).mul_(wl["L"]).clamp_(1e-12, wl["L"] * (1 - 1e-12))
+        sm.u0.normal_(0.0, 1.0, generator=gen)
+        sm.u0[:ns].mul_(float(np.sqrt(wl["kBTe"] / ME)))
+        sm.u0[ns:].mul_(float(np.sqrt(wl["kBTi"] / MP)))
+        torch.cuda.synchronize()
+        return sm
 
-    for _ in range(args.warmup):
-        sim.step()
-    sim.check()
-    torch.cuda.synchronize()
-    comm.barrier()
+    def timed_steps(sm, steps, warmup, sampler=None):
+        """W untimed steps, then exactly K steps between barrier + synchronize, CUDA events, max over ranks."""
+        for _ in range(warmup):
+            sm.step()
+        sm.check()
+        torch.cuda.synchronize()
+        comm.barrier()
+        if sampler:
+            sampler.start()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        events = sm.iter_events = []
+        l0 = sm.kernel_launches
+        its = []
+        torch.cuda.synchronize()
+        comm.barrier()
+        ev0.record()
+        for _ in range(steps):
+            k, r = sm.step()
+            its.append(k)
+        ev1.record()
+        torch.cuda.synchronize()
+        comm.barrier()
+        sm.iter_events = None
+        if sampler:
+            sampler.stop_flag = True
+        t_ms = comm.max_float(ev0.elapsed_time(ev1), device=dev)
+        sm.check()
+        return dict(ms=t_ms, iters=its, events=events, launches=sm.kernel_launches - l0)
 
-    # ---- timed region: K full steps, CUDA events, per-launch events on the dominant kernel
+    sim = make_sim(w)
     sampler = ClockSampler(local) if rank == 0 else None
-    if sampler:
-        sampler.start()
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    iter_events = sim.iter_events = []
-    launches0 = sim.kernel_launches
-    iters = []
-    torch.cuda.synchronize()
-    comm.barrier()
-    ev0.record()
-    for _ in range(args.steps):
-        k, r = sim.step()
-        iters.append(k)
-    ev1.record()
-    torch.cuda.synchronize()
-    comm.barrier()
-    sim.iter_events = None
-    if sampler:
-        sampler.stop_flag = True
-    ms = ev0.elapsed_time(ev1)
-    ms = comm.max_float(ms, device=dev)
-    launches = sim.kernel_launches - launches0
-    sim.check()
+    tr = timed_steps(sim, args.steps, args.warmup, sampler)
+    ms, iters, iter_events, launches = tr["ms"], tr["iters"], tr["events"], tr["launches"]
     kernel_ms = [e[0].elapsed_time(e[1]) for e in iter_events]
     ms_with_u = [e[0].elapsed_time(e[1]) for e in iter_events if e[2] and not e[3]]
     ms_without_u = [e[0].elapsed_time(e[1]) for e in iter_events if not e[2] and not e[3]]
@@ -330,44 +348,109 @@ def run_cuda(args):
         outs = [dict(x1=pin(Nl), u1=pin(Nl), act=pin(Nl, torch.int8), E1=pin(Ng), j1=pin(Ng)) for _ in range(min(nb, 2))]
         hx0.copy_(sim.x0); hu0.copy_(sim.u0); hE0.copy_(sim.E0)
         torch.cuda.synchronize()
-        P = _lib.DDParams(Nl, sim.n_split, Ng, 0, w["dx"], w["dt"], w["L"], w["p2c"],
-                          (C.c_double * 2)(-E_CH, E_CH), (C.c_double * 2)(ME, MP))
+        h2d = Nl * 16 + Ng * 8
+        d2h = Nl * 17 + Ng * 16
+        if world == 1:
+            P = _lib.DDParams(Nl, sim.n_split, Ng, 0, w["dx"], w["dt"], w["L"], w["p2c"],
+                              (C.c_double * 2)(-E_CH, E_CH), (C.c_double * 2)(ME, MP))
 
-        def ptrs(vals):
-            return (C.c_void_p * len(vals))(*vals)
+            def ptrs(vals):
+                return (C.c_void_p * len(vals))(*vals)
 
-        def host_steps(n):
-            it, res = (C.c_int * n)(), (C.c_double * n)()
-            o = [outs[b % len(outs)] for b in range(n)]
-            _lib.call("pic_host_dd_step_batches", C.byref(P), n, ptrs([hx0.data_ptr()] * n), ptrs([hu0.data_ptr()] * n),
-                      ptrs([hE0.data_ptr()] * n), w["tol"], w["maxiter"], ptrs([d["x1"].data_ptr() for d in o]),
-                      ptrs([d["u1"].data_ptr() for d in o]), ptrs([d["act"].data_ptr() for d in o]),
-                      ptrs([d["E1"].data_ptr() for d in o]), ptrs([d["j1"].data_ptr() for d in o]), it, res)
-            return list(it)
-        host_steps(min(nb, 2))           # warm-up (allocates the cached device slots)
+            def host_steps(n):
+                it, res = (C.c_int * n)(), (C.c_double * n)()
+                o = [outs[b % len(outs)] for b in range(n)]
+                _lib.call("pic_host_dd_step_batches", C.byref(P), n, ptrs([hx0.data_ptr()] * n), ptrs([hu0.data_ptr()] * n),
+                          ptrs([hE0.data_ptr()] * n), w["tol"], w["maxiter"], ptrs([d["x1"].data_ptr() for d in o]),
+                          ptrs([d["u1"].data_ptr() for d in o]), ptrs([d["act"].data_ptr() for d in o]),
+                          ptrs([d["E1"].data_ptr() for d in o]), ptrs([d["j1"].data_ptr() for d in o]), it, res)
+                return list(it)
+            api = ("pic_host_dd_step_batches (C ABI, pinned host buffers, %d batches pipelined through two device slots)" % nb)
+        else:
+            # N > 1 is ONE coupled system (every Picard iteration sums the ranks' accumulators), so the host-buffer
+            # path goes through the resident driver, whose Picard loop holds the reduction: per step every rank
+            # copies its shard in from pinned memory, all ranks take the coupled step, results are copied back out
+            from pypic_b200.hostpipe import HostPipelinedSheath
+            pipe = HostPipelinedSheath(sim)
+
+            def host_steps(n):
+                return pipe.run([dict(x0=hx0, u0=hu0, E0=hE0)] * n, outs)
+            api = ("HostPipelinedSheath over SheathSim (pinned host buffers per rank; COUPLED: %s per Picard iteration; "
+                   "copies of step b+1 / b-1 overlap the Picard loop of step b)"
+                   % ("all-reduce of [jh|j1|counts]" if sim.p2p is None else "peer-memory sum inside the field kernel"))
+        host_steps(min(nb, 2))           # warm-up (allocates the device slots)
+        torch.cuda.synchronize()
         comm.barrier()
         t0 = time.perf_counter()
         its = host_steps(nb)
         torch.cuda.synchronize()
         t_e2e = time.perf_counter() - t0
         t_e2e = comm.max_float(t_e2e, device=dev)
-        # result check of the last batch against the resident simulation's own step from the same state
-        h2d = Nl * 16 + Ng * 8
-        d2h = Nl * 17 + Ng * 16
+        # ---- what the host<->device link allows: the same bytes per step in both directions at once, all ranks
+        # concurrently, nothing else running -- the ceiling of any host-buffer path on this box
+        cs_up, cs_dn = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+        dbuf_in = torch.empty(2 * Nl, dtype=torch.float64, device=dev)
+        dbuf_out = torch.empty(2 * Nl + Nl // 8 + 1, dtype=torch.float64, device=dev)
+        hin = torch.empty(2 * Nl, dtype=torch.float64, pin_memory=True)
+        hout = torch.empty(2 * Nl + Nl // 8 + 1, dtype=torch.float64, pin_memory=True)
+        reps = 3
+        torch.cuda.synchronize(); comm.barrier()
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            with torch.cuda.stream(cs_up):
+                dbuf_in.copy_(hin, non_blocking=True)
+            with torch.cuda.stream(cs_dn):
+                hout.copy_(dbuf_out, non_blocking=True)
+        torch.cuda.synchronize()
+        t_copy = comm.max_float(time.perf_counter() - t0, device=dev) / reps
+        del dbuf_in, dbuf_out, hin, hout
         e2e = {"value": w["N"] * nb / t_e2e, "unit": "particle-steps/s", "h2d_bytes_per_step": h2d,
                "d2h_bytes_per_step": d2h, "steps": nb, "picard_iterations": its[-1],
-               "ms_per_step": 1e3 * t_e2e / nb,
+               "ms_per_step": 1e3 * t_e2e / nb, "coupled_over_ranks": bool(world > 1),
                "pcie_gbs": {"h2d": h2d * nb / t_e2e / 1e9, "d2h": d2h * nb / t_e2e / 1e9},
-               "api": "pic_host_dd_step_batches (C ABI, pinned host buffers, per-rank shard, %d batches pipelined "
-                      "through two device slots)" % nb}
-        _lib.call("pic_host_release")
+               "pcie_ceiling": {"ms_per_step": 1e3 * t_copy, "h2d_gbs": Nl * 16 / t_copy / 1e9, "d2h_gbs": Nl * 17 / t_copy / 1e9,
+                                "particle_steps_per_s": w["N"] / t_copy,
+                                "note": "this step's bytes copied both ways concurrently from/to pinned memory on every rank at once, "
+                                        "no compute: the bound of any host-buffer path on this box (per rank)"},
+               "api": api}
+        if world == 1:
+            _lib.call("pic_host_release")
+        else:
+            del pipe
         del hx0, hu0, outs
 
+    enq = sim.enqueue_ahead
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         res = cpu_port_run(w, args.cpu_sample, 3, 1)
         cpu = {"value": res["value"], "unit": "particle-steps/s", "cores": res["cores"], "kind": "port",
                "sample": res["sample"]}
+
+    # ---- the north-star strong-scaling case (BASELINE config 4): a fixed TOTAL of particles over the N GPUs, same
+    # code, same run -- the driver's 1/2/4/8 sweep then holds the whole curve (sub-record `strong_scaling`)
+    strong = None
+    if args.strong_total and not args.total_particles and args.strong_total != w["N"]:
+        n_main, p2p_main = sim.N, sim.p2p is not None
+        sim.close()
+        del sim
+        torch.cuda.empty_cache()
+        a2 = argparse.Namespace(**vars(args)); a2.total_particles = args.strong_total
+        w2 = workload(a2, world)
+        sim = make_sim(w2)
+        tr2 = timed_steps(sim, max(1, args.strong_steps), max(3, min(args.warmup, 3)))
+        kms2 = [e[0].elapsed_time(e[1]) for e in tr2["events"]]
+        kbar2 = float(np.mean(tr2["iters"]))
+        ach2 = sim.N * (32.0 + 16.0 / kbar2) / (float(np.mean(kms2)) * 1e-3) / 1e9
+        strong = {"particles_total": w2["N"], "particles_per_gpu": sim.N, "n_gpus": world, "scaling": "strong",
+                  "value": w2["N"] * len(tr2["iters"]) / (tr2["ms"] * 1e-3), "unit": "particle-steps/s",
+                  "ms_per_step": tr2["ms"] / len(tr2["iters"]), "steps": len(tr2["iters"]), "picard_iterations_per_step": kbar2,
+                  "kernel_ms_mean": float(np.mean(kms2)), "kernel_share_of_step": float(np.sum(kms2) / tr2["ms"]),
+                  "roofline_frac": ach2 / peak, "gpu_launches": int(tr2["launches"]),
+                  "note": "speed-up at N GPUs = this value / the same sub-record of the --gpus 1 run (one code version)"}
+        n_local = n_main
+    else:
+        n_local, p2p_main = sim.N, sim.p2p is not None
+        sim.close()
 
     if rank == 0:
         clocks = sampler.summary() if sampler else {}
@@ -376,19 +459,24 @@ def run_cuda(args):
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": w["scaling"],
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": "1D sheath (PIC_L_DD physics): %d particles (%d per GPU, e-/p+ halves), %d-node grid, "
-                                   "implicit CN/Picard tol=1e-5" % (w["N"], sim.N, w["Ng"]),
+                                   "implicit CN/Picard tol=1e-5" % (w["N"], n_local, w["Ng"]),
                        "parallelism": ("particle decomposition x%d, %s of [jh|j1|counts] per Picard iteration"
-                                       % (world, "fp64 all-reduce" if sim.p2p is None else
+                                       % (world, "fp64 all-reduce" if not p2p_main else
                                           "sum over NVLink peer memory inside the field kernel (rank order)"))
                        if world > 1 else "single GPU",
                        "picard_iterations_per_step": kbar, "deposit": args.deposit, "sort_every": args.sort_every,
                        "sort": "electrons every %d steps, ions with them every %d steps" % (args.sort_every,
-                                                                                             args.sort_every * sim.heavy_sort_every),
+                                                                                             args.sort_every * max(1, args.heavy_sort_every)),
                        "reinjection": "device Philox4x32-10 (statistical parity)",
                        "picard_loop": ("enqueue-ahead: the iterations the previous step needed are queued behind a device flag, "
-                                       "one host round trip per step") if sim.enqueue_ahead else "one host round trip per iteration",
-                       "l2_policy": "inputs (%.1f GB of particle arrays per GPU) are far larger than the 126 MB L2" % (sim.N * 32 / 1e9)},
-            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
+                                       "one host round trip per step") if enq else "one host round trip per iteration",
+                       "parity_tolerance": "bit-exact cell indices, flags, counts, iteration counts; fields and particles after N steps "
+                                           "within 1e-11 relative of the reference (fp64; north_star asks 1e-12 -- the order of the "
+                                           "parallel deposit re-associates sums at 1e-13 per step and that round-off feeds back, "
+                                           "DESIGN.md section 4)",
+                       "l2_policy": "inputs (%.1f GB of particle arrays per GPU) are far larger than the 126 MB L2" % (n_local * 32 / 1e9)},
+            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "strong_scaling": strong, "gpu_launches": int(launches),
+            "clocks": clocks,
         }
     if world > 1:
         dist.destroy_process_group()

@@ -91,6 +91,33 @@ int pic_dev_newton_boltzmann(const double* src, double* phi, int n, double dx, d
                              int bc, double tol, int iter_max, int* iters_out, void* stream);
 
 /* ------------------------------------------------------------------------- *
+ * Host draw service of the RNG-parity mode (no GPU involved): NumPy's legacy MT19937 stream
+ * (np.random.get_state(): key uint32[624], pos in [0,624], has_gauss, cached_gaussian), which
+ * PIC_L_DD.py:419-450 consumes in particle index order.
+ *   pic_mt_jump_poly   g(t) = t^nwords mod phi(t) (phi: characteristic polynomial of MT19937,
+ *                      found once by Berlekamp-Massey), 19937 coefficients packed in uint32[624];
+ *   pic_mt_jump        advances (key,pos) by the number of 32-bit outputs g encodes (~1 ms however
+ *                      large the jump): the thermostat's one uniform per ACTIVE particle
+ *                      (PIC_L_DD.py:421; two words each) is skipped without generating it;
+ *   pic_mt_skip        the same by plain generation (small remainders);
+ *   pic_mt_sheath_draws  per dead slot x = uniform(0,L), u,v,w = normal(0,sigma[k]) exactly as
+ *                      np.random.uniform / np.random.normal would return them (:433-436, :443-446);
+ *                      xd == NULL only advances the stream (slots owned by other ranks);
+ *   pic_mt_sheath_thermostat  gamma != 0 (:419-427): n_active uniforms in index order, every
+ *                      u < gamma followed by three normals of sigma0 (ordinal < k_split) / sigma1;
+ *                      the hits' ordinals and draws are returned (capacity cap; on overflow the state
+ *                      is left untouched, *nhits holds the count and PIC_ERR_ARG is returned).
+ * ------------------------------------------------------------------------- */
+int pic_mt_jump_poly(uint64_t nwords, uint32_t* g624);
+int pic_mt_jump(uint32_t* key624, int32_t* pos, const uint32_t* g624);
+int pic_mt_skip(uint32_t* key624, int32_t* pos, uint64_t nwords);
+int pic_mt_sheath_draws(uint32_t* key624, int32_t* pos, int32_t* has_gauss, double* gauss, int64_t n,
+                        const double* sigma, double L, double* xd, double* ud, double* vd, double* wd);
+int pic_mt_sheath_thermostat(uint32_t* key624, int32_t* pos, int32_t* has_gauss, double* gauss, int64_t n_active,
+                             int64_t k_split, double gamma, double sigma0, double sigma1, int64_t cap,
+                             int64_t* hit_k, double* hu, double* hv, double* hw, int64_t* nhits);
+
+/* ------------------------------------------------------------------------- *
  * PIC_L_DD.py -- bounded two-species implicit sheath (the benchmark path)
  * ------------------------------------------------------------------------- */
 typedef struct {
@@ -167,6 +194,15 @@ int pic_dev_dd_picard_iter3(const pic_dd_params* p, const double* x0, const doub
 /* u1 of the last iteration after the fact: x1_prev/x1_last are that iteration's input and output
  * positions, Es the field it gathered with, `first` whether it was the first iteration of the
  * step.  Particles absorbed before it get the reference's 0.0 (PIC_L_DD.py:459-462). */
+/* pic_dev_dd_picard_iter3 with the ABSORPTION LOG: every particle this launch absorbs appends
+ * (iteration << 32 | slot) to dead_log[dead_cap] through the device counter *dead_count (which may
+ * exceed dead_cap: entries beyond the capacity are dropped and the caller falls back to scanning
+ * the flags).  The re-injection visits the logged slots instead of scanning N flags, and the
+ * iteration number orders the vionout tally (PIC_L_DD.py:497-503). */
+int pic_dev_dd_picard_iter4(const pic_dd_params* p, const double* x0, const double* u0, const double* x1_in,
+                            double* x1_out, double* u1, int8_t* active, const double* Es, double* acc, int first,
+                            int* range_err, const int32_t* done, int64_t* dead_log, int32_t* dead_count,
+                            int32_t dead_cap, int32_t iteration, void* stream);
 int pic_dev_dd_commit_u(const pic_dd_params* p, const double* x0, const double* u0, const double* x1_prev,
                         const double* x1_last, const int8_t* active, const double* Es, double* u1, int first,
                         int* range_err, void* stream);
@@ -222,6 +258,8 @@ int pic_dev_dd_field_update2(const pic_dd_params* p, double* acc, double* wall_c
  *   pic_dev_p2p_reduce  the reduction alone (sum[nacc] local), e.g. for the j1 repair pass. */
 int pic_p2p_alloc(int64_t nacc, int world, void** dev_ptr, void* handle64);
 int pic_p2p_open(const void* handle64, void** peer_ptr);
+/* bound of the flag waits: 2^log2_spins polls of >= 200 ns (default 25, i.e. 7 s or more) */
+int pic_p2p_set_timeout(int log2_spins);
 int pic_p2p_close(void* peer_ptr);
 int pic_p2p_free(void* dev_ptr);
 int pic_dev_p2p_reduce(const double* const* peers_dev, int rank, int world, uint32_t seq, int64_t nacc,
@@ -236,6 +274,33 @@ int pic_dev_dd_field_update_p2p(const pic_dd_params* p, const double* const* pee
 int pic_dev_dd_apply_draws(const int32_t* idx, const double* xd, const double* ud, const double* vd,
                            const double* wd, int64_t n, double* x0, double* u0, double* v0, double* w0,
                            int8_t* active, void* stream);
+/* The same for a cell-sorted store that keeps the reference's particle numbering: slot[t] is where
+ * the particle sits now, orig[t] its original index (NULL: = slot).  x0,u0,active are written at
+ * the slot, the passive v0,w0 -- kept in ORIGINAL order, they are never streamed by the Picard
+ * kernels -- at the original index.  xd == NULL / active == NULL leave x0 / the flags alone (the
+ * thermostat, PIC_L_DD.py:419-427, redraws only the velocities). */
+int pic_dev_dd_apply_draws2(const int32_t* slot, const int32_t* orig, const double* xd, const double* ud,
+                            const double* vd, const double* wd, int64_t n, double* x0, double* u0, double* v0,
+                            double* w0, int8_t* active, void* stream);
+/* Device-mode re-injection of the slots named in the absorption log (no flag scan), and the
+ * device-mode thermostat (every active particle redraws u,v,w from sigma[species] with probability
+ * gamma).  Philox is keyed by the ORIGINAL global index orig[i] + global_offset (orig == NULL: the
+ * slot), and v0/w0 are addressed by it. */
+int pic_dev_dd_reinject_philox_log(const pic_dd_params* p, const int64_t* dead_log, const int32_t* dead_count,
+                                   int32_t dead_cap, double* x0, double* u0, double* v0, double* w0, int8_t* active,
+                                   const int32_t* orig, const double sigma[2], uint64_t seed, uint64_t step,
+                                   int64_t global_offset, void* stream);
+/* pic_dev_dd_reinject_philox with the original-index payload (draws keyed by orig[i] + global_offset,
+ * v0/w0 written at orig[i]) and a guard: when dead_count != NULL and *dead_count <= dead_cap the
+ * kernel returns at entry, because pic_dev_dd_reinject_philox_log has visited every dead slot (and
+ * vice versa: on overflow the log kernel does nothing and this scan re-injects). */
+int pic_dev_dd_reinject_philox2(const pic_dd_params* p, double* x0, double* u0, double* v0, double* w0,
+                                int8_t* active, const int32_t* orig, const double sigma[2], uint64_t seed,
+                                uint64_t step, int64_t global_offset, const int32_t* dead_count, int32_t dead_cap,
+                                void* stream);
+int pic_dev_dd_thermostat_philox(const pic_dd_params* p, double* u0, double* v0, double* w0, const int8_t* active,
+                                 const int32_t* orig, double gamma, const double sigma[2], uint64_t seed, uint64_t step,
+                                 int64_t global_offset, void* stream);
 /* Device mode (benchmark sizes, statistical parity only): Philox4x32-10 keyed by
  * (seed, step, global particle id); x~U(0,L), u,v,w~N(0,sqrt(kT/m)). v0/w0 may be NULL. */
 int pic_dev_dd_reinject_philox(const pic_dd_params* p, double* x0, double* u0, double* v0, double* w0,
@@ -245,6 +310,8 @@ int pic_dev_dd_reinject_philox(const pic_dd_params* p, double* x0, double* u0, d
  * started hold x1=u1=0 like the reference (PIC_L_DD.py:459-462); the commit itself is a
  * pointer swap on the host.  KE diagnostic sum(me*u^2/2) (PIC_L_DD.py:549): */
 int pic_dev_sum_sq(const double* u, int64_t N, double scale, double* out1, void* stream);
+/* out2 = {sum u, sum u*u} in one pass: np.std(u0) (PIC_L_DD.py:417) and KE (:549) together */
+int pic_dev_moments(const double* u, int64_t N, double* out2, void* stream);
 /* Counting sort by (species, cell) of the n-level state; out-of-place.  Keeps species
  * ranges contiguous; order inside a cell is unspecified (benchmark mode only).
  * counts: int32 scratch of 2*Ng+2 + ceil(2*Ng/1024)+2 entries (the tail is used by the
@@ -253,6 +320,11 @@ int pic_dev_sum_sq(const double* u, int64_t N, double scale, double* out1, void*
 int pic_dev_dd_sort_by_cell(const pic_dd_params* p, const double* x0, const double* u0,
                             const double* v0, const double* w0, double* x0s, double* u0s,
                             double* v0s, double* w0s, int32_t* counts, void* stream);
+/* The same sort carrying the ORIGINAL INDEX of every particle as an int32 payload (orig == NULL on
+ * the first sort: the identity), so that a sorted store still knows the reference's particle
+ * numbering: re-injection draws in index order (PIC_L_DD.py:429-450), vionout, downloads. */
+int pic_dev_dd_sort_by_cell2(const pic_dd_params* p, const double* x0, const double* u0, const int32_t* orig,
+                             double* x0s, double* u0s, int32_t* origs, int32_t* counts, void* stream);
 /* STABLE sort by (species, cell): LSD radix sort of each species block with 8-bit digits of the
  * cell index (per-tile digit histograms, exclusive scan, scatter with index-order ranks).  Equal
  * cells keep their previous order, so the result is independent of scheduling -- the sort of
@@ -471,6 +543,11 @@ int pic_dev_compact_flags(const int8_t* flags, int64_t N, int mode, int32_t* idx
 /* dst[k] = src[idx[k]] for k<n (fp64 / int8 payloads) */
 int pic_dev_gather_f64(const double* src, const int32_t* idx, double* dst, int64_t n, void* stream);
 int pic_dev_gather_i8(const int8_t* src, const int32_t* idx, int8_t* dst, int64_t n, void* stream);
+int pic_dev_gather_i32(const int32_t* src, const int32_t* idx, int32_t* dst, int64_t n, void* stream);
+/* dst[idx[t]] = src[t] (a sorted store back to the original order; idx == NULL: copy); inv[perm[t]] = t */
+int pic_dev_scatter_f64(const double* src, const int32_t* idx, double* dst, int64_t n, void* stream);
+int pic_dev_scatter_i8(const int8_t* src, const int32_t* idx, int8_t* dst, int64_t n, void* stream);
+int pic_dev_invert_perm(const int32_t* perm, int32_t* inv, int64_t n, void* stream);
 
 /* ------------------------------------------------------------------------- *
  * Device-side initialisers and IEAD histogram (N1)

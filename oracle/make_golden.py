@@ -98,6 +98,46 @@ def gen_pypic():
     print("pypic golden done, iters", ks)
 
 
+def gen_pypic_full():
+    """BASELINE config 1(a): pypic.main's own literals (pypic.py:846-860: landau-damping, N = 1 000 000,
+    Ng = 200) -- initialize_p from seed 1, then three steps of the reference's particle_push_p.  The
+    particle arrays are 8 MB each, so the file keeps every STRIDE-th particle (plus the fields, which
+    are complete); tests rebuild the full initial state with the drop-in's initialize_p from the same
+    seed and are pinned to it by the subsample."""
+    p = refshim.load("pypic")
+    np.random.seed(1)
+    STRIDE = 997
+    N, Ng = 1000000, 200
+    density, Kp, pert = 1e5, 1, 0.8
+    Te, Ti = 100.0 * 11600., 0.1 * 11600.
+    L = 22.0 * np.sqrt(p.kb * Te * p.epsilon0 / p.e / p.e / density)
+    dx = L / float(Ng)
+    X = np.linspace(0.0, L, Ng + 1)
+    dt, tol, maxiter = 1e-5, 1e-3, 20
+    m, q, x0, v0, kBTe, kBTi, growth, K, p2c, wp, invwp, LD = p.initialize_p(
+        'landau-damping', N, density, Kp, pert, dx, Ng, Te, Ti, L, X)
+    rho0 = p.weight_density_p(x0, q, p2c, Ng, N, dx)
+    j0 = p.weight_current_p(x0, q, v0, p2c, Ng, N, dx)
+    phi0 = p.solve_poisson_p(dx, Ng, rho0, np.zeros(Ng))
+    phi0 = phi0 - np.max(phi0)
+    E0 = -p.differentiate_p(phi0, dx, Ng)
+    o = dict(N=N, Ng=Ng, L=L, dx=dx, dt=dt, tol=tol, maxiter=maxiter, p2c=p2c, stride=STRIDE, seed=1,
+             x0_sub=x0[::STRIDE].copy(), v0_sub=v0[::STRIDE].copy(), E0=E0.copy(), j0=j0.copy(), rho0=rho0, phi0=phi0,
+             x0_sum=np.sum(x0), v0_sumsq=np.sum(v0 * v0))
+    ks = []
+    for t in range(3):
+        buf = io.StringIO()
+        with contextlib.redirect_stdout(buf):
+            x1, v1, E1, j1 = p.particle_push_p(x0, v0, q, m, E0, j0, N, Ng, p2c, dx, dt, L, tol, maxiter)
+        ks.append(int(re.search(r"Iterations:\s+(\d+)", buf.getvalue()).group(1)))
+        E0, x0, v0, j0 = E1, x1, v1, j1
+        o[f"x_{t}"] = x1[::STRIDE].copy(); o[f"v_{t}"] = v1[::STRIDE].copy(); o[f"E_{t}"] = E1.copy(); o[f"j_{t}"] = j1.copy()
+        o[f"xsum_{t}"] = np.sum(x1); o[f"vsumsq_{t}"] = np.sum(v1 * v1)
+    o["iters"] = np.array(ks)
+    np.savez_compressed(os.path.join(GOLD, "pypic_push_1e6.npz"), **o)
+    print("pypic 1e6 golden done, iters", ks)
+
+
 def gen_dd_kernels():
     d = refshim.load("PIC_L_DD")
     rng = np.random.RandomState(5)
@@ -164,11 +204,16 @@ def _run_main_with_literals(modname, func, args, literals):
     return mod, tmp, buf.getvalue(), plt
 
 
-def gen_dd_main(tag, N, Ng, T, seed=1):
+def gen_dd_main(tag, N, Ng, T, seed=1, gamma=None, vion_after=None):
+    """gamma: literal override of the thermostat probability (PIC_L_DD.py:331, shipped as 0.0);
+    vion_after: literal override of the `t > 2000` threshold of the vionout tally (:497,:502)."""
     np.random.seed(seed)
-    mod, tmp, out, plt = _run_main_with_literals(
-        "PIC_L_DD", "main_i", (T, 1),
-        [(r"\n\tN = 40000\n", f"\n\tN = {N}\n"), (r"\n\tNg = 51\n", f"\n\tNg = {Ng}\n")])
+    lits = [(r"\n\tN = 40000\n", f"\n\tN = {N}\n"), (r"\n\tNg = 51\n", f"\n\tNg = {Ng}\n")]
+    if gamma is not None:
+        lits.append((r"\n\tgamma = 0\.0\n", f"\n\tgamma = {gamma!r}\n"))
+    if vion_after is not None:
+        lits.append((r"t > 2000", f"t > {int(vion_after)}"))
+    mod, tmp, out, plt = _run_main_with_literals("PIC_L_DD", "main_i", (T, 1), lits)
     iters = np.array([int(s) for s in re.findall(r"Iterations:\s+(\d+)", out)])
     resid = np.array([float(s) for s in re.findall(r"\nr:\s+(\S+)", out)])
     E0 = np.loadtxt(os.path.join(tmp, "E0.txt"))
@@ -183,6 +228,12 @@ def gen_dd_main(tag, N, Ng, T, seed=1):
     ee_series = np.array([c.args[1] for c in sc[1::2]])
     o = dict(N=N, Ng=Ng, T=T, seed=seed, iters=iters, resid=resid, E0_final=E0, jbias=jb,
              j_series=j_series, phi_series=phi_series, E_series=E_series)
+    if gamma is not None:
+        o["gamma"] = gamma
+    if vion_after is not None:
+        o["vion_after"] = vion_after
+        o["vionout"] = np.atleast_1d(np.loadtxt(os.path.join(tmp, "vionout.txt")))
+    o["next_uniform"] = np.random.uniform()          # pins the number of legacy-stream words the run consumed
     if N <= 4000:
         o.update(xi_series=xi_series, xe_series=xe_series, ei_series=ei_series, ee_series=ee_series)
     else:
@@ -483,16 +534,21 @@ def gen_gc_ion():
 
 def main():
     os.makedirs(GOLD, exist_ok=True)
-    which = sys.argv[1:] or ["pypic", "ddk", "ddm", "l", "gc", "gcion"]
+    which = sys.argv[1:] or ["pypic", "pypicfull", "ddk", "ddm", "ddx", "l", "gc", "gcion"]
     if "gcion" in which:
         gen_gc_ion()
     if "pypic" in which:
         gen_pypic()
+    if "pypicfull" in which:
+        gen_pypic_full()
     if "ddk" in which:
         gen_dd_kernels()
     if "ddm" in which:
         gen_dd_main("small", 2000, 51, 40)
         gen_dd_main("default", 40000, 51, 2)
+    if "ddx" in which:
+        gen_dd_main("gamma", 2000, 51, 12, gamma=0.02)
+        gen_dd_main("vion", 2000, 51, 40, vion_after=5)
     if "l" in which:
         gen_pic_l()
     if "gc" in which:

@@ -69,6 +69,20 @@ _SIGS = {
     "pic_dev_dd_picard_iter": [C.POINTER(DDParams), P, P, P, P, P, P, P, I32, P, P],
     "pic_dev_dd_picard_iter2": [C.POINTER(DDParams), P, P, P, P, P, P, P, P, I32, P, P],
     "pic_dev_dd_picard_iter3": [C.POINTER(DDParams), P, P, P, P, P, P, P, P, I32, P, P, P],
+    "pic_dev_dd_picard_iter4": [C.POINTER(DDParams), P, P, P, P, P, P, P, P, I32, P, P, P, P, I32, I32, P],
+    "pic_dev_dd_sort_by_cell2": [C.POINTER(DDParams), P, P, P, P, P, P, P, P],
+    "pic_dev_dd_apply_draws2": [P, P, P, P, P, P, I64, P, P, P, P, P, P],
+    "pic_dev_dd_reinject_philox_log": [C.POINTER(DDParams), P, P, I32, P, P, P, P, P, P, C.POINTER(C.c_double * 2),
+                                       C.c_uint64, C.c_uint64, I64, P],
+    "pic_dev_dd_reinject_philox2": [C.POINTER(DDParams), P, P, P, P, P, P, C.POINTER(C.c_double * 2), C.c_uint64,
+                                    C.c_uint64, I64, P, I32, P],
+    "pic_dev_dd_thermostat_philox": [C.POINTER(DDParams), P, P, P, P, P, F64, C.POINTER(C.c_double * 2), C.c_uint64,
+                                     C.c_uint64, I64, P],
+    "pic_dev_gather_i32": [P, P, P, I64, P],
+    "pic_dev_scatter_f64": [P, P, P, I64, P],
+    "pic_dev_scatter_i8": [P, P, P, I64, P],
+    "pic_dev_invert_perm": [P, P, I64, P],
+    "pic_dev_moments": [P, I64, P, P],
     "pic_dev_dd_commit_u": [C.POINTER(DDParams), P, P, P, P, P, P, P, I32, P, P],
     "pic_dev_dd_commit_u2": [C.POINTER(DDParams), P, P, P, P, P, P, P, I32, P, P, P],
     "pic_dev_dd_j1_finish": [C.POINTER(DDParams), P, P, P, P, P],
@@ -78,6 +92,7 @@ _SIGS = {
     "pic_dev_dd_field_update2": [C.POINTER(DDParams), P, P, P, P, P, P, P, P, P, P, F64, I32, P],
     "pic_p2p_alloc": [I64, I32, C.POINTER(C.c_void_p), P],
     "pic_p2p_open": [P, C.POINTER(C.c_void_p)],
+    "pic_p2p_set_timeout": [I32],
     "pic_p2p_close": [P],
     "pic_p2p_free": [P],
     "pic_dev_p2p_reduce": [P, I32, I32, C.c_uint32, I64, P, P, P],
@@ -125,6 +140,12 @@ _SIGS = {
                                         C.POINTER(C.c_double * 2), C.c_uint64, C.c_uint64, I64, P],
     "pic_dev_pypic_perturb_positions": [P, I64, P, P, I32, C.c_uint64, I64, P],
     "pic_dev_gc_iead_hist": [P, P, P, P, P, P, I32, I64, P, I32, P, I32, P, P],
+    "pic_mt_jump_poly": [C.c_uint64, P],
+    "pic_mt_jump": [P, C.POINTER(C.c_int32), P],
+    "pic_mt_skip": [P, C.POINTER(C.c_int32), C.c_uint64],
+    "pic_mt_sheath_draws": [P, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_double), I64, P, F64, P, P, P, P],
+    "pic_mt_sheath_thermostat": [P, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_double), I64, I64, F64, F64,
+                                 F64, I64, P, P, P, P, C.POINTER(C.c_int64)],
     "pic_host_pypic_interpolate_p": [P, P, I32, I64, F64, P],
     "pic_host_pypic_weight_current_p": [P, P, P, I32, I32, I64, F64, P],
     "pic_host_pypic_weight_density_p": [P, P, I32, I32, I64, F64, P],

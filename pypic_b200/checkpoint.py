@@ -36,13 +36,13 @@ def _host(t, n=None):
 def sheath_state(sim):
     """Host copy of everything SheathSim needs to continue: particle arrays of this rank's
     shard, flags, fields, counters."""
-    n = sim.N
+    st = sim.download()                      # the reference's particle order, whatever the cell sort did
     d = dict(format=np.int64(FORMAT_VERSION), kind="sheath", N_global=np.int64(sim.N_global), start=np.int64(sim.start),
              stop=np.int64(sim.stop), n_split=np.int64(sim.n_split), Ng=np.int64(sim.Ng), dx=np.float64(sim.dx),
-             dt=np.float64(sim.dt), p2c=np.float64(sim.p2c), t=np.int64(sim.t),
-             x0=_host(sim.x0, n), u0=_host(sim.u0, n), active=_host(sim.active, n), E0=_host(sim.E0), j0=_host(sim.j0))
+             dt=np.float64(sim.dt), p2c=np.float64(sim.p2c), t=np.int64(sim.t), carry_vw=np.int64(sim.carry_vw),
+             x0=st["x0"], u0=st["u0"], active=st["active"].astype(np.int8), E0=st["E0"], j0=st["j0"])
     if sim.carry_vw:
-        d["v0"] = _host(sim.v0, n); d["w0"] = _host(sim.w0, n)
+        d["v0"] = st["v0"]; d["w0"] = st["w0"]
     d.update(_rng_state())
     return d
 
@@ -58,14 +58,28 @@ def load_sheath(sim, path, restore_rng=True):
     z = np.load(path, allow_pickle=False)
     if str(z["kind"]) != "sheath" or int(z["format"]) != FORMAT_VERSION:
         raise ValueError("not a sheath checkpoint of format %d: %s" % (FORMAT_VERSION, path))
-    for k, want in (("N_global", sim.N_global), ("start", sim.start), ("stop", sim.stop), ("Ng", sim.Ng)):
+    for k, want in (("N_global", sim.N_global), ("start", sim.start), ("stop", sim.stop), ("Ng", sim.Ng),
+                    ("n_split", sim.n_split)):
         if int(z[k]) != int(want):
             raise ValueError("checkpoint %s=%d does not match the simulation (%d)" % (k, int(z[k]), int(want)))
+    for k, want in (("dx", sim.dx), ("dt", sim.dt), ("p2c", sim.p2c)):
+        if float(z[k]) != float(want):
+            raise ValueError("checkpoint %s=%r does not match the simulation (%r)" % (k, float(z[k]), float(want)))
+    if sim.carry_vw and "v0" not in z:
+        raise ValueError("the simulation carries v,w but the checkpoint was written without them")
     n = sim.N
-    for name in ("x0", "u0") + (("v0", "w0") if sim.carry_vw else ()):
-        getattr(sim, name)[:n].copy_(torch.as_tensor(z[name]))
-    sim.active[:n].copy_(torch.as_tensor(z["active"]))
-    sim.E0.copy_(torch.as_tensor(z["E0"])); sim.j0.copy_(torch.as_tensor(z["j0"]))
+    # the shard's arrays are stored in the reference's particle order: SheathSim.upload slices global
+    # arrays, so place them at the shard's offset of an (otherwise unread) global-length view
+    class _Shard:
+        def __init__(self, a, start):
+            self.a, self.start = a, start
+
+        def __getitem__(self, s):
+            return self.a[s.start - self.start:s.stop - self.start]
+    sh = lambda name: _Shard(z[name], sim.start)
+    sim.upload(sh("x0"), sh("u0"), sh("v0") if sim.carry_vw else None, sh("w0") if sim.carry_vw else None,
+               E0=z["E0"], active=sh("active"))
+    sim.j0.copy_(torch.as_tensor(z["j0"]))
     sim.t = int(z["t"])
     if restore_rng:
         _set_rng_state(z)

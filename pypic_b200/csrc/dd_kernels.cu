@@ -34,7 +34,20 @@ struct DDK {
     // iterations it expects without a round trip per iteration
     const int* done;
     double fs1, fi1;             // 2^s and 2^-s: one hi unit = 2^-s, one lo unit = 2^-(s+32)
+    // absorption log: every particle absorbed by this launch appends (iteration << 32 | slot) -- the
+    // re-injection then visits the few dead slots instead of scanning N flags, and the iteration
+    // orders the vionout tally (PIC_L_DD.py:497-503).  Absorption is on the rare path only.
+    long long* dead_log;
+    int* dead_cnt;
+    int dead_cap, iter;
+    long long slot0;             // slot of particle 0 of this launch (tail launches run on offset pointers)
 };
+__device__ __forceinline__ void dead_note(const DDK& k, long long i) {
+    if (k.dead_cnt) {
+        const int at = atomicAdd(k.dead_cnt, 1);
+        if (at < k.dead_cap) k.dead_log[at] = ((long long)k.iter << 32) | (k.slot0 + i);
+    }
+}
 
 static DDK make_ddk(const pic_dd_params* p) {
     DDK k;
@@ -47,6 +60,7 @@ static DDK make_ddk(const pic_dd_params* p) {
         k.c2[s] = p->dt * p->dt * qm;
     }
     k.fix = nullptr; k.ferr = nullptr; k.fs1 = 1.0; k.fi1 = 1.0; k.done = nullptr;
+    k.dead_log = nullptr; k.dead_cnt = nullptr; k.dead_cap = 0; k.iter = 0; k.slot0 = 0;
     if (p->flags & 128) {
         // one contribution is q*p2c*u*w/dx with |u| < c: |v| < amax < 2^e, so |v|*2^(31-e) < 2^31 and a
         // node can take 2^31 contributions before the hi word overflows; the lo word carries 32 more bits
@@ -167,10 +181,10 @@ __global__ void __launch_bounds__(256) dd_picard_iter_k(DDK k, const double* __r
             if (u1) st_stream(u1 + i, U1);
             // absorption, right wall first (PIC_L_DD.py:495-504)
             if (X0 >= k.L || XH >= k.L || X1 >= k.L) {
-                active[i] = 0; alive = false;
+                active[i] = 0; alive = false; dead_note(k, i);
                 if (sp) ++nR1; else ++nR0;
             } else if (X0 <= 0.0 || XH <= 0.0 || X1 <= 0.0) {
-                active[i] = -1; alive = false;
+                active[i] = -1; alive = false; dead_note(k, i);
                 if (sp) ++nL1; else ++nL0;
             }
         }
@@ -264,8 +278,8 @@ __device__ __noinline__ SlowOut dd_particle_slow(const DDK& k, long long i, doub
     double XH = (X0 + X1) * 0.5;
     double UH = (U0 + U1) * 0.5;
     x1[i] = X1; if (u1) u1[i] = U1;
-    if (X0 >= k.L || XH >= k.L || X1 >= k.L) { active[i] = 0; o.code = sp ? 4 : 3; return o; }
-    if (X0 <= 0.0 || XH <= 0.0 || X1 <= 0.0) { active[i] = -1; o.code = sp ? 2 : 1; return o; }
+    if (X0 >= k.L || XH >= k.L || X1 >= k.L) { active[i] = 0; dead_note(k, i); o.code = sp ? 4 : 3; return o; }
+    if (X0 <= 0.0 || XH <= 0.0 || X1 <= 0.0) { active[i] = -1; dead_note(k, i); o.code = sp ? 2 : 1; return o; }
     Cell a = cell_dd(XH, k.dx);
     if (a.iL < 0 || a.iL > Ng - 2) { ++o.bad; a.iL = clampi(a.iL, 0, Ng - 2); }
     const double qs = sp ? k.q[1] : k.q[0];
@@ -563,10 +577,10 @@ __device__ __forceinline__ void dd_medium(const DDK& k, const FastC& fc, long lo
     if (!straddle && !o.emiss && f0 <= PIC_HI_SPAN && p0 < fc.hi_Lm1 && pp < fc.hi_Lm1) {
         const double XH = (X0 + o.X1) * 0.5;
         if (X0 >= k.L || XH >= k.L || o.X1 >= k.L) {                    // PIC_L_DD.py:495-499
-            x1[i] = o.X1; if (u1) u1[i] = o.U1; active[i] = 0; atomicAdd(&s_cnt[sp ? 4 : 3], 1); return;
+            x1[i] = o.X1; if (u1) u1[i] = o.U1; active[i] = 0; dead_note(k, i); atomicAdd(&s_cnt[sp ? 4 : 3], 1); return;
         }
         if (X0 <= 0.0 || XH <= 0.0 || o.X1 <= 0.0) {                     // :500-504
-            x1[i] = o.X1; if (u1) u1[i] = o.U1; active[i] = -1; atomicAdd(&s_cnt[sp ? 2 : 1], 1); return;
+            x1[i] = o.X1; if (u1) u1[i] = o.U1; active[i] = -1; dead_note(k, i); atomicAdd(&s_cnt[sp ? 2 : 1], 1); return;
         }
         if (o.fr <= PIC_HI_SPAN && o.ps < fc.hi_Lm1) {
             x1[i] = o.X1; if (u1) u1[i] = o.U1;
@@ -981,8 +995,13 @@ __device__ __forceinline__ double ld_relaxed_sys_f64(const double* p) {
     return v;
 }
 __device__ __forceinline__ unsigned* p2p_flags(double* buf, int nacc) { return (unsigned*)(buf + nacc); }
+// bounded wait: 2^g_p2p_spin_log2 polls of >= 200 ns each (default 2^25: 7 s or more, far beyond any
+// start-up skew between ranks -- first-call module loads, host-RNG re-injection, a checkpoint write);
+// pic_p2p_set_timeout changes it
+__device__ int g_p2p_spin_log2 = 25;
 __device__ __noinline__ bool p2p_wait(const unsigned* flag, unsigned seq) {
-    for (int spin = 0; spin < (1 << 22); ++spin) {
+    const long long nspin = 1ll << g_p2p_spin_log2;
+    for (long long spin = 0; spin < nspin; ++spin) {
         if ((int)(ld_acquire_sys_u32(flag) - seq) >= 0) return true;      // wrap-safe "flag >= seq"
         __nanosleep(200);
     }
@@ -1179,11 +1198,15 @@ __device__ __forceinline__ double u52(uint32_t a, uint32_t b) {
     return ((double)v + 0.5) * (1.0 / 4503599627370496.0);
 }
 
+// i: slot; o: index the draws are keyed by and where the passive v,w live (the slot itself, or the
+// particle's ORIGINAL index when the store tracks it)
 __device__ __forceinline__ void dd_reinject_one(const DDK& k, long long i, double* __restrict__ x0,
                                                 double* __restrict__ u0, double* __restrict__ v0,
                                                 double* __restrict__ w0, int8_t* __restrict__ active, double s0,
-                                                double s1, uint64_t seed, uint64_t step, long long goff) {
-    uint64_t gid = (uint64_t)(goff + i);
+                                                double s1, uint64_t seed, uint64_t step, long long goff,
+                                                const int32_t* __restrict__ oid = nullptr) {
+    const long long o = oid ? (long long)oid[i] : i;
+    uint64_t gid = (uint64_t)(goff + o);
     uint32_t c[4] = {(uint32_t)gid, (uint32_t)(gid >> 32), (uint32_t)step, (uint32_t)(step >> 32)};
     uint32_t d[4] = {c[0], c[1], c[2], c[3] ^ 0x80000000u};
     uint32_t g[4] = {c[0], c[1], c[2], c[3] ^ 0x40000000u};
@@ -1197,8 +1220,8 @@ __device__ __forceinline__ void dd_reinject_one(const DDK& k, long long i, doubl
     double sg = (i >= k.n_split) ? s1 : s0;
     x0[i] = ux * k.L;
     u0[i] = sg * r1 * cos(t1);
-    if (v0) v0[i] = sg * r1 * sin(t1);
-    if (w0) w0[i] = sg * r2 * cos(t2);
+    if (v0) v0[o] = sg * r1 * sin(t1);
+    if (w0) w0[o] = sg * r2 * cos(t2);
     active[i] = 1;
 }
 
@@ -1206,7 +1229,10 @@ __device__ __forceinline__ void dd_reinject_one(const DDK& k, long long i, doubl
 __global__ void dd_reinject_philox_k(DDK k, double* __restrict__ x0, double* __restrict__ u0,
                                      double* __restrict__ v0, double* __restrict__ w0,
                                      int8_t* __restrict__ active, double s0, double s1, uint64_t seed,
-                                     uint64_t step, long long goff) {
+                                     uint64_t step, long long goff, const int32_t* __restrict__ oid,
+                                     const int* __restrict__ log_cnt) {
+    // the absorption log named every dead slot and the log kernel handled them: nothing to scan
+    if (log_cnt && *log_cnt <= k.dead_cap) return;
     const long long nvec = ((uintptr_t)active & 15) == 0 ? k.N / 16 : 0;
     const long long stride = (long long)gridDim.x * blockDim.x;
     for (long long v = (long long)blockIdx.x * blockDim.x + threadIdx.x; v < nvec; v += stride) {
@@ -1216,10 +1242,10 @@ __global__ void dd_reinject_philox_k(DDK k, double* __restrict__ x0, double* __r
 #pragma unroll
         for (int j = 0; j < 16; ++j)
             if ((signed char)(w[j >> 2] >> (8 * (j & 3))) != 1)
-                dd_reinject_one(k, v * 16 + j, x0, u0, v0, w0, active, s0, s1, seed, step, goff);
+                dd_reinject_one(k, v * 16 + j, x0, u0, v0, w0, active, s0, s1, seed, step, goff, oid);
     }
     for (long long i = nvec * 16 + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < k.N; i += stride)
-        if (active[i] != 1) dd_reinject_one(k, i, x0, u0, v0, w0, active, s0, s1, seed, step, goff);
+        if (active[i] != 1) dd_reinject_one(k, i, x0, u0, v0, w0, active, s0, s1, seed, step, goff, oid);
 }
 
 __global__ void sum_sq_k(const double* __restrict__ u, long long N, double scale, double* __restrict__ out) {
@@ -1298,7 +1324,8 @@ __global__ void __launch_bounds__(SORT_T) dd_sort_scatter_k(DDK k, const double*
                                                             const double* __restrict__ v0,
                                                             const double* __restrict__ w0, double* __restrict__ xs,
                                                             double* __restrict__ us, double* __restrict__ vs,
-                                                            double* __restrict__ ws, int32_t* __restrict__ cursor) {
+                                                            double* __restrict__ ws, int32_t* __restrict__ cursor,
+                                                            const int32_t* __restrict__ oid, int32_t* __restrict__ oids) {
     extern __shared__ int sh[];   // [0,nk) count of the chunk, [nk,2nk) global base of the chunk's run
     const int nk = 2 * k.Ng;
     int* cnt = sh;
@@ -1337,6 +1364,7 @@ __global__ void __launch_bounds__(SORT_T) dd_sort_scatter_k(DDK k, const double*
                 if (PERM) ((int32_t*)us)[pos] = (int32_t)i; else us[pos] = u0[i];
                 if (vs) vs[pos] = v0[i];
                 if (ws) ws[pos] = w0[i];
+                if (oids) oids[pos] = oid ? oid[i] : (int32_t)i;     // original-index payload (identity on the first sort)
             }
         }
         __syncthreads();
@@ -1489,7 +1517,8 @@ __global__ void __launch_bounds__(SORTB_T) dd_sort_scatter_big_k(DDK k, const do
                                                                  const double* __restrict__ v0,
                                                                  const double* __restrict__ w0, double* __restrict__ xs,
                                                                  double* __restrict__ us, double* __restrict__ vs,
-                                                                 double* __restrict__ ws, int32_t* __restrict__ cursor) {
+                                                                 double* __restrict__ ws, int32_t* __restrict__ cursor,
+                                                                 const int32_t* __restrict__ oid, int32_t* __restrict__ oids) {
     long long end;
     const long long beg = sortb_range(k.N, &end);
     const unsigned lane = threadIdx.x & 31;
@@ -1522,8 +1551,90 @@ __global__ void __launch_bounds__(SORTB_T) dd_sort_scatter_big_k(DDK k, const do
                 if (PERM) ((int32_t*)us)[pos] = (int32_t)i; else us[pos] = U[j];
                 if (vs) vs[pos] = v0[i];
                 if (ws) ws[pos] = w0[i];
+                if (oids) oids[pos] = oid ? oid[i] : (int32_t)i;
             }
         }
+    }
+}
+
+
+// ---- re-injection / bookkeeping of a cell-sorted store that keeps the reference's particle
+// numbering: `orig` is the original index of the particle in each slot (the sort's payload); the
+// passive velocities v,w are never streamed, so they stay in ORIGINAL order (PIC_L_DD.py:482-483
+// copies them unchanged; only re-injection and the thermostat write them) ----
+__global__ void dd_apply_draws2_k(const int32_t* __restrict__ slot, const int32_t* __restrict__ orig,
+                                  const double* __restrict__ xd, const double* __restrict__ ud,
+                                  const double* __restrict__ vd, const double* __restrict__ wd, long long n,
+                                  double* __restrict__ x0, double* __restrict__ u0, double* __restrict__ v0,
+                                  double* __restrict__ w0, int8_t* __restrict__ active) {
+    for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < n; t += (long long)gridDim.x * blockDim.x) {
+        const int s = slot[t], o = orig ? orig[t] : s;
+        if (xd) x0[s] = xd[t];
+        u0[s] = ud[t];
+        if (v0) v0[o] = vd[t];
+        if (w0) w0[o] = wd[t];
+        if (active) active[s] = 1;
+    }
+}
+__global__ void gather_i32_k(const int32_t* __restrict__ src, const int32_t* __restrict__ idx, int32_t* __restrict__ dst, long long n) {
+    for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < n; t += (long long)gridDim.x * blockDim.x) dst[t] = src[idx[t]];
+}
+// dst[idx[t]] = src[t]  (back to the original order); idx == NULL: plain copy
+template <typename T>
+__global__ void scatter_k(const T* __restrict__ src, const int32_t* __restrict__ idx, T* __restrict__ dst, long long n) {
+    for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < n; t += (long long)gridDim.x * blockDim.x)
+        dst[idx ? idx[t] : t] = src[t];
+}
+__global__ void invert_perm_k(const int32_t* __restrict__ perm, int32_t* __restrict__ inv, long long n) {
+    for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < n; t += (long long)gridDim.x * blockDim.x) inv[perm[t]] = (int32_t)t;
+}
+// out[0] += sum u, out[1] += sum u*u  (np.std(u0) and the kinetic-energy diagnostic from ONE pass)
+__global__ void moments_k(const double* __restrict__ u, long long N, double* __restrict__ out) {
+    __shared__ double scratch[33];
+    double s1 = 0.0, s2 = 0.0;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < N; i += (long long)gridDim.x * blockDim.x) {
+        const double v = ld_stream(u + i);
+        s1 += v; s2 += v * v;
+    }
+    s1 = block_reduce<0>(s1, scratch);
+    s2 = block_reduce<0>(s2, scratch);
+    if (threadIdx.x == 0) { atomicAdd(out, s1); atomicAdd(out + 1, s2); }
+}
+// slots named in the absorption log -> re-injected with Philox draws (no flag scan)
+__global__ void dd_reinject_philox_log_k(DDK k, const long long* __restrict__ log, const int* __restrict__ cnt,
+                                         double* __restrict__ x0, double* __restrict__ u0, double* __restrict__ v0,
+                                         double* __restrict__ w0, int8_t* __restrict__ active, double s0, double s1,
+                                         uint64_t seed, uint64_t step, long long goff, const int32_t* __restrict__ oid) {
+    const int n = *cnt;
+    if (n > k.dead_cap) return;          // overflow: the flag scan (dd_reinject_philox_k) takes over
+    for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < n; t += gridDim.x * blockDim.x)
+        dd_reinject_one(k, (long long)(log[t] & 0xffffffffll), x0, u0, v0, w0, active, s0, s1, seed, step, goff, oid);
+}
+// Thermostat, device mode (PIC_L_DD.py:419-427): every ACTIVE particle redraws u,v,w from the ION
+// temperature (as written: sqrt(kBTi/m[i]) for both species) with probability gamma.  Philox keyed
+// by (seed, step, global original index), so the outcome does not depend on the sort or the sharding.
+__global__ void dd_thermostat_philox_k(DDK k, double* __restrict__ u0, double* __restrict__ v0, double* __restrict__ w0,
+                                       const int8_t* __restrict__ active, const int32_t* __restrict__ orig, double gamma,
+                                       double s0, double s1, uint64_t seed, uint64_t step, long long goff) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < k.N; i += (long long)gridDim.x * blockDim.x) {
+        if (active[i] != 1) continue;
+        const long long o = orig ? orig[i] : i;
+        const uint64_t gid = (uint64_t)(goff + o);
+        uint32_t c[4] = {(uint32_t)gid, (uint32_t)(gid >> 32), (uint32_t)step, (uint32_t)(step >> 32) ^ 0x20000000u};
+        philox4x32(c, (uint32_t)seed, (uint32_t)(seed >> 32));
+        if (!(u52(c[0], c[1]) < gamma)) continue;
+        uint32_t d[4] = {(uint32_t)gid, (uint32_t)(gid >> 32), (uint32_t)step, (uint32_t)(step >> 32) ^ 0x10000000u};
+        philox4x32(d, (uint32_t)seed, (uint32_t)(seed >> 32));
+        const double twopi = 6.283185307179586;
+        const double r1 = sqrt(-2.0 * log(u52(c[2], c[3]))), t1 = twopi * u52(d[0], d[1]);
+        const double r2 = sqrt(-2.0 * log(u52(d[2], d[3])));
+        uint32_t g[4] = {(uint32_t)gid, (uint32_t)(gid >> 32), (uint32_t)step, (uint32_t)(step >> 32) ^ 0x08000000u};
+        philox4x32(g, (uint32_t)seed, (uint32_t)(seed >> 32));
+        const double t2 = twopi * u52(g[0], g[1]);
+        const double sg = (i >= k.n_split) ? s1 : s0;
+        u0[i] = sg * r1 * cos(t1);
+        if (v0) v0[o] = sg * r1 * sin(t1);
+        if (w0) w0[o] = sg * r2 * cos(t2);
     }
 }
 
@@ -1545,7 +1656,8 @@ static int next_sched_slot(cudaStream_t st, int** out) {
 // counting sort driver shared by pic_dev_dd_sort_by_cell / pic_dev_sort_perm_by_cell
 template <bool PERM>
 static int sort_by_cell_impl(const DDK& k, const double* x0, const double* u0, const double* v0, const double* w0,
-                             double* x0s, double* u0s, double* v0s, double* w0s, int32_t* counts, cudaStream_t st) {
+                             double* x0s, double* u0s, double* v0s, double* w0s, int32_t* counts, cudaStream_t st,
+                             const int32_t* oid = nullptr, int32_t* oids = nullptr) {
     const int nk = 2 * k.Ng;
     const size_t smem = (size_t)nk * sizeof(int);
     const size_t smem_sc = 2 * smem;
@@ -1565,7 +1677,7 @@ static int sort_by_cell_impl(const DDK& k, const double* x0, const double* u0, c
         PIC_CHECK_LAUNCH();
         scan_add_k<<<nblk, 1024, 0, st>>>(counts, nk, sums);
         PIC_CHECK_LAUNCH();
-        dd_sort_scatter_big_k<PERM><<<grid_for(k.N, SORTB_T * SORTB_PER, 4), SORTB_T, 0, st>>>(k, x0, u0, v0, w0, x0s, u0s, v0s, w0s, counts);
+        dd_sort_scatter_big_k<PERM><<<grid_for(k.N, SORTB_T * SORTB_PER, 4), SORTB_T, 0, st>>>(k, x0, u0, v0, w0, x0s, u0s, v0s, w0s, counts, oid, oids);
         PIC_CHECK_LAUNCH();
         return PIC_OK;
     }
@@ -1576,7 +1688,7 @@ static int sort_by_cell_impl(const DDK& k, const double* x0, const double* u0, c
     dd_sort_scan_k<<<1, 1024, 0, st>>>(counts, nk);
     PIC_CHECK_LAUNCH();
     dd_sort_scatter_k<PERM><<<grid_for((k.N + SORT_PER - 1) / SORT_PER, SORT_T, 2), SORT_T, smem_sc, st>>>(
-        k, x0, u0, v0, w0, x0s, u0s, v0s, w0s, counts);
+        k, x0, u0, v0, w0, x0s, u0s, v0s, w0s, counts, oid, oids);
     PIC_CHECK_LAUNCH();
     return PIC_OK;
 }
@@ -1608,6 +1720,7 @@ static int launch_tail(const DDK& k, long long done, const double* x0, const dou
     DDK t = k;
     t.N = k.N - done;
     t.n_split = k.n_split - done < 0 ? 0 : (k.n_split - done > t.N ? t.N : k.n_split - done);
+    t.slot0 = k.slot0 + done;
     return launch_iter<FIRST, true, true>(t, x0 + done, u0 + done, x1i + done, x1 + done, u1 ? u1 + done : nullptr,
                                           active + done, Es, acc, range_err, st);
 }
@@ -1693,10 +1806,20 @@ int pic_dev_dd_picard_iter2(const pic_dd_params* p, const double* x0, const doub
 int pic_dev_dd_picard_iter3(const pic_dd_params* p, const double* x0, const double* u0, const double* x1_in,
                             double* x1_out, double* u1, int8_t* active, const double* Es, double* acc, int first,
                             int* range_err, const int32_t* done, void* stream) {
+    return pic_dev_dd_picard_iter4(p, x0, u0, x1_in, x1_out, u1, active, Es, acc, first, range_err, done, nullptr, nullptr, 0,
+                                   0, stream);
+}
+
+int pic_dev_dd_picard_iter4(const pic_dd_params* p, const double* x0, const double* u0, const double* x1_in,
+                            double* x1_out, double* u1, int8_t* active, const double* Es, double* acc, int first,
+                            int* range_err, const int32_t* done, int64_t* dead_log, int32_t* dead_count,
+                            int32_t dead_cap, int32_t iteration, void* stream) {
     PIC_REQUIRE(p && x0 && u0 && x1_in && x1_out && active && Es && acc, "dd_picard_iter: null pointer");
     PIC_REQUIRE(p->N >= 0 && p->Ng >= 3 && p->dx > 0 && p->dt > 0, "dd_picard_iter: bad parameters");
+    PIC_REQUIRE(!dead_count || (dead_log && dead_cap > 0), "dd_picard_iter: absorption log without storage");
     if (p->N == 0) return PIC_OK;
     DDK k = make_ddk(p);
+    k.dead_log = (long long*)dead_log; k.dead_cnt = dead_count; k.dead_cap = dead_cap; k.iter = iteration;
     PIC_REQUIRE(!(p->flags & 128) || !(p->flags & (1 | 2 | 4 | 8)),
                 "dd_picard_iter: the reproducible build (flags bit7) exists for the default window kernel only");
     ddk_bind_fix(k, acc, range_err);
@@ -1739,6 +1862,7 @@ int pic_dev_dd_picard_iter3(const pic_dd_params* p, const double* x0, const doub
         DDK t = k;
         t.N = k.N - done;
         t.n_split = k.n_split - done < 0 ? 0 : (k.n_split - done > t.N ? t.N : k.n_split - done);
+        t.slot0 = k.slot0 + done;
         // tail: grid-stride kernel with the grids left in global memory
         return first ? launch_iter<true, false, true>(t, x0 + done, u0 + done, x1i + done, x1 + done, u1 ? u1 + done : nullptr,
                                                       active + done, Es, acc, range_err, st)
@@ -1889,6 +2013,12 @@ int pic_p2p_alloc(int64_t nacc, int world, void** dev_ptr, void* handle64) {
     return PIC_OK;
 }
 
+int pic_p2p_set_timeout(int log2_spins) {
+    PIC_REQUIRE(log2_spins >= 10 && log2_spins <= 34, "p2p_set_timeout: log2_spins must be in [10, 34]");
+    PIC_CHECK_CUDA(cudaMemcpyToSymbol(g_p2p_spin_log2, &log2_spins, sizeof(int)));
+    return PIC_OK;
+}
+
 int pic_p2p_open(const void* handle64, void** peer_ptr) {
     PIC_REQUIRE(handle64 && peer_ptr, "p2p_open: null pointer");
     cudaIpcMemHandle_t h;
@@ -1985,11 +2115,19 @@ int pic_dev_dd_apply_draws(const int32_t* idx, const double* xd, const double* u
 int pic_dev_dd_reinject_philox(const pic_dd_params* p, double* x0, double* u0, double* v0, double* w0,
                                int8_t* active, const double sigma[2], uint64_t seed, uint64_t step,
                                int64_t global_offset, void* stream) {
+    return pic_dev_dd_reinject_philox2(p, x0, u0, v0, w0, active, nullptr, sigma, seed, step, global_offset, nullptr, 0, stream);
+}
+
+int pic_dev_dd_reinject_philox2(const pic_dd_params* p, double* x0, double* u0, double* v0, double* w0,
+                                int8_t* active, const int32_t* orig, const double sigma[2], uint64_t seed,
+                                uint64_t step, int64_t global_offset, const int32_t* dead_count, int32_t dead_cap,
+                                void* stream) {
     PIC_REQUIRE(p && x0 && u0 && active && sigma, "dd_reinject_philox: null pointer");
     if (p->N == 0) return PIC_OK;
     DDK k = make_ddk(p);
-    dd_reinject_philox_k<<<grid_for((k.N + 15) / 16, 256, 8), 256, 0, (cudaStream_t)stream>>>(k, x0, u0, v0, w0, active, sigma[0],
-                                                                                sigma[1], seed, step, global_offset);
+    k.dead_cap = dead_cap;
+    dd_reinject_philox_k<<<grid_for((k.N + 15) / 16, 256, 8), 256, 0, (cudaStream_t)stream>>>(
+        k, x0, u0, v0, w0, active, sigma[0], sigma[1], seed, step, global_offset, orig, dead_count);
     PIC_CHECK_LAUNCH();
     return PIC_OK;
 }
@@ -2061,6 +2199,97 @@ int pic_dev_sort_perm_by_cell(const pic_dd_params* p, const double* x, double* x
     PIC_REQUIRE(p->N < 2147483647LL, "sort_perm_by_cell: store too large for int32 indices");
     return sort_by_cell_impl<true>(make_ddk(p), x, nullptr, nullptr, nullptr, xs, (double*)perm, nullptr, nullptr, counts,
                                    (cudaStream_t)stream);
+}
+
+int pic_dev_dd_sort_by_cell2(const pic_dd_params* p, const double* x0, const double* u0, const int32_t* orig,
+                             double* x0s, double* u0s, int32_t* origs, int32_t* counts, void* stream) {
+    PIC_REQUIRE(p && x0 && u0 && x0s && u0s && origs && counts, "dd_sort_by_cell2: null pointer");
+    PIC_REQUIRE(p->N < 2147483647LL, "dd_sort_by_cell2: shard too large for int32 cursors");
+    return sort_by_cell_impl<false>(make_ddk(p), x0, u0, nullptr, nullptr, x0s, u0s, nullptr, nullptr, counts,
+                                    (cudaStream_t)stream, orig, origs);
+}
+
+int pic_dev_dd_apply_draws2(const int32_t* slot, const int32_t* orig, const double* xd, const double* ud,
+                            const double* vd, const double* wd, int64_t n, double* x0, double* u0, double* v0,
+                            double* w0, int8_t* active, void* stream) {
+    PIC_REQUIRE(n >= 0, "dd_apply_draws2: n<0");
+    if (n == 0) return PIC_OK;
+    PIC_REQUIRE(slot && ud && u0, "dd_apply_draws2: null pointer");
+    PIC_REQUIRE((!xd || x0) && (!v0 || vd) && (!w0 || wd), "dd_apply_draws2: draws / targets missing");
+    dd_apply_draws2_k<<<grid_for(n, 256, 4), 256, 0, (cudaStream_t)stream>>>(slot, orig, xd, ud, vd, wd, n, x0, u0, v0, w0, active);
+    PIC_CHECK_LAUNCH();
+    return PIC_OK;
+}
+
+int pic_dev_dd_reinject_philox_log(const pic_dd_params* p, const int64_t* dead_log, const int32_t* dead_count,
+                                   int32_t dead_cap, double* x0, double* u0, double* v0, double* w0, int8_t* active,
+                                   const int32_t* orig, const double sigma[2], uint64_t seed, uint64_t step,
+                                   int64_t global_offset, void* stream) {
+    PIC_REQUIRE(p && dead_log && dead_count && dead_cap > 0 && x0 && u0 && active && sigma, "dd_reinject_philox_log: null pointer");
+    if (p->N == 0) return PIC_OK;
+    DDK k = make_ddk(p);
+    k.dead_cap = dead_cap;
+    dd_reinject_philox_log_k<<<64, 256, 0, (cudaStream_t)stream>>>(k, (const long long*)dead_log, dead_count, x0, u0, v0, w0,
+                                                                  active, sigma[0], sigma[1], seed, step, global_offset, orig);
+    PIC_CHECK_LAUNCH();
+    return PIC_OK;
+}
+
+int pic_dev_dd_thermostat_philox(const pic_dd_params* p, double* u0, double* v0, double* w0, const int8_t* active,
+                                 const int32_t* orig, double gamma, const double sigma[2], uint64_t seed, uint64_t step,
+                                 int64_t global_offset, void* stream) {
+    PIC_REQUIRE(p && u0 && active && sigma, "dd_thermostat_philox: null pointer");
+    if (p->N == 0 || !(gamma > 0.0)) return PIC_OK;
+    dd_thermostat_philox_k<<<grid_for(p->N, 256, 8), 256, 0, (cudaStream_t)stream>>>(make_ddk(p), u0, v0, w0, active, orig, gamma,
+                                                                                    sigma[0], sigma[1], seed, step, global_offset);
+    PIC_CHECK_LAUNCH();
+    return PIC_OK;
+}
+
+int pic_dev_gather_i32(const int32_t* src, const int32_t* idx, int32_t* dst, int64_t n, void* stream) {
+    PIC_REQUIRE(n >= 0, "gather_i32: n<0");
+    if (n == 0) return PIC_OK;
+    PIC_REQUIRE(src && idx && dst, "gather_i32: null pointer");
+    gather_i32_k<<<grid_for(n, 256, 8), 256, 0, (cudaStream_t)stream>>>(src, idx, dst, n);
+    PIC_CHECK_LAUNCH();
+    return PIC_OK;
+}
+
+int pic_dev_scatter_f64(const double* src, const int32_t* idx, double* dst, int64_t n, void* stream) {
+    PIC_REQUIRE(n >= 0, "scatter_f64: n<0");
+    if (n == 0) return PIC_OK;
+    PIC_REQUIRE(src && dst, "scatter_f64: null pointer");
+    scatter_k<double><<<grid_for(n, 256, 8), 256, 0, (cudaStream_t)stream>>>(src, idx, dst, n);
+    PIC_CHECK_LAUNCH();
+    return PIC_OK;
+}
+
+int pic_dev_scatter_i8(const int8_t* src, const int32_t* idx, int8_t* dst, int64_t n, void* stream) {
+    PIC_REQUIRE(n >= 0, "scatter_i8: n<0");
+    if (n == 0) return PIC_OK;
+    PIC_REQUIRE(src && dst, "scatter_i8: null pointer");
+    scatter_k<int8_t><<<grid_for(n, 256, 8), 256, 0, (cudaStream_t)stream>>>(src, idx, dst, n);
+    PIC_CHECK_LAUNCH();
+    return PIC_OK;
+}
+
+int pic_dev_invert_perm(const int32_t* perm, int32_t* inv, int64_t n, void* stream) {
+    PIC_REQUIRE(n >= 0, "invert_perm: n<0");
+    if (n == 0) return PIC_OK;
+    PIC_REQUIRE(perm && inv, "invert_perm: null pointer");
+    invert_perm_k<<<grid_for(n, 256, 8), 256, 0, (cudaStream_t)stream>>>(perm, inv, n);
+    PIC_CHECK_LAUNCH();
+    return PIC_OK;
+}
+
+int pic_dev_moments(const double* u, int64_t N, double* out2, void* stream) {
+    PIC_REQUIRE(u && out2 && N >= 0, "moments: bad argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    PIC_CHECK_CUDA(cudaMemsetAsync(out2, 0, 2 * sizeof(double), st));
+    if (N == 0) return PIC_OK;
+    moments_k<<<grid_for(N, 256, 8), 256, 0, st>>>(u, N, out2);
+    PIC_CHECK_LAUNCH();
+    return PIC_OK;
 }
 
 }  // extern "C"

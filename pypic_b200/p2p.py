@@ -14,6 +14,7 @@ class PeerAccumulators:
     def __init__(self, comm, nacc, device):
         self.comm, self.nacc = comm, int(nacc)
         self.rank, self.world = comm.rank, comm.world
+        torch.cuda.set_device(device)        # pic_p2p_alloc allocates on the current device
         mine, handle = C.c_void_p(), (C.c_char * 64)()
         _lib.call("pic_p2p_alloc", self.nacc, self.world, C.byref(mine), handle)
         self.mine = mine.value

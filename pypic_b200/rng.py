@@ -1,56 +1,165 @@
 """Host draw service: reproduces the reference's NumPy legacy MT19937 draw order
 so that a seeded run re-injects exactly the particles the reference would.
 
-The legacy stream is inherently sequential (polar legacy_gauss with a cached second
-variate, data-dependent rejection), so for parity-sized runs the draws are made on
-the host with ``np.random`` (global state by default -- exactly what the reference
-uses) in the reference's call order and shipped to the device.  Benchmark-sized runs
-use the device Philox generator instead (statistical parity only).
+The reference (PIC_L_DD.py:419-450) consumes the global legacy stream in particle index
+order: one uniform per ACTIVE particle for the thermostat -- even at gamma == 0, Python
+still evaluates the right operand of ``active[i]==1 and np.random.uniform(0,1) < gamma`` --
+then x = uniform(0,L) and u,v,w = normal(0,sigma) per dead slot.  The draws that matter
+(a few hundred per step) are made by pypic_b200/csrc/mt_host.cpp bit-identically to
+np.random; the thermostat uniforms of a large run are SKIPPED by an MT19937 jump-ahead
+(polynomial t^J mod the characteristic polynomial applied to the state, ~1 ms whatever J)
+instead of being generated, and the jump for the next step is started in a background
+thread as soon as this step's draws are done, so it overlaps the GPU's Picard loop.
+Benchmark-sized runs that do not need stream parity use the device Philox generator.
 """
+import ctypes as C
+import threading
+
 import numpy as np
+
+from . import _lib
 
 
 class LegacyDraws:
+    JUMP_MIN = 200000        # uniforms; below this plain generation is cheaper than the jump
+    CHUNK = 16384            # jump polynomials are cached per multiple of CHUNK uniforms; the rest is generated
+    MARGIN = 4096            # the prefetched jump stops this many uniforms short of the expected skip
+
     def __init__(self, rng=None):
         self.rng = np.random if rng is None else rng
+        self._polys = {}
+        self._pref = None
+        self.jumps = 0           # statistics: jumps applied / prefetched jumps used
+        self.prefetch_hits = 0
+
+    # ------------------------------------------------------------------ legacy state <-> C
+    def _get(self):
+        s = self.rng.get_state()
+        if s[0] != "MT19937":
+            raise ValueError("the legacy draw service needs an MT19937 stream, got %r" % (s[0],))
+        return [np.array(s[1], dtype=np.uint32), C.c_int32(int(s[2])), C.c_int32(int(s[3])), C.c_double(float(s[4]))]
+
+    def _put(self, st):
+        self.rng.set_state(("MT19937", st[0], int(st[1].value), int(st[2].value), float(st[3].value)))
+
+    def _poly(self, nwords):
+        g = self._polys.get(nwords)
+        if g is None:
+            g = np.zeros(624, dtype=np.uint32)
+            _lib.call("pic_mt_jump_poly", C.c_uint64(nwords), g.ctypes.data)
+            if len(self._polys) > 64:
+                self._polys.clear()
+            self._polys[nwords] = g
+        return g
+
+    def skip_uniforms(self, n):
+        """Advance the stream past n np.random.uniform() draws (two 32-bit words each)."""
+        n = int(n)
+        if n <= 0:
+            return
+        pref, self._pref = self._pref, None
+        if pref is not None:
+            pref["thread"].join()
+        if n < self.JUMP_MIN:
+            self.rng.uniform(0.0, 1.0, n)
+            return
+        st = self._get()
+        if (pref is not None and pref["n"] <= n and pref["pos"] == st[1].value and np.array_equal(pref["key0"], st[0])):
+            st[0], st[1] = pref["key1"], C.c_int32(pref["pos1"])
+            done = pref["n"]
+            self.prefetch_hits += 1
+        else:
+            done = (n // self.CHUNK) * self.CHUNK
+            _lib.call("pic_mt_jump", st[0].ctypes.data, C.byref(st[1]), self._poly(2 * done).ctypes.data)
+        self.jumps += 1
+        self._put(st)
+        if n > done:
+            self.rng.uniform(0.0, 1.0, n - done)
+
+    def prefetch_skip(self, n_expected):
+        """Start the jump for the NEXT skip_uniforms() now, from the current state, in a thread (the C
+        call releases the GIL).  It stops MARGIN uniforms short of the expectation; skip_uniforms
+        generates the remainder, or discards the result if the stream moved or the skip is shorter."""
+        n = ((int(n_expected) - self.MARGIN) // self.CHUNK) * self.CHUNK
+        if n < self.JUMP_MIN:
+            return
+        st = self._get()
+        poly = self._poly(2 * n)
+        job = dict(n=n, key0=st[0].copy(), pos=st[1].value, key1=st[0], pos1=0)
+
+        def run():
+            p = C.c_int32(job["pos"])
+            _lib.call("pic_mt_jump", job["key1"].ctypes.data, C.byref(p), poly.ctypes.data)
+            job["pos1"] = p.value
+        job["thread"] = threading.Thread(target=run, daemon=True)
+        job["thread"].start()
+        self._pref = job
 
     # PIC_L_DD.py:419-450 -------------------------------------------------------------
     def sheath_thermostat_skip(self, n_active):
-        """gamma == 0: the short-circuit ``and`` still draws one uniform per ACTIVE
-        particle (PIC_L_DD.py:421); vectorised draws consume the same stream."""
-        if n_active:
-            self.rng.uniform(0.0, 1.0, int(n_active))
+        """gamma == 0: the short-circuit ``and`` still draws one uniform per ACTIVE particle
+        (PIC_L_DD.py:421)."""
+        self.skip_uniforms(n_active)
+
+    def sheath_thermostat(self, n_active, k_split, gamma, sigma0, sigma1):
+        """gamma != 0 (PIC_L_DD.py:419-427): uniforms in index order over the active particles, every
+        u < gamma followed by three normals.  Returns (ordinals of the hits among the active
+        particles, u, v, w draws); sigma0 applies to ordinals < k_split."""
+        cap = max(1024, int(1.5 * gamma * n_active) + 1024)
+        while True:
+            st = self._get()
+            hk = np.empty(cap, dtype=np.int64)
+            hu, hv, hw = np.empty(cap), np.empty(cap), np.empty(cap)
+            nh = C.c_int64(0)
+            lib = _lib.load()
+            rc = lib.pic_mt_sheath_thermostat(st[0].ctypes.data, C.byref(st[1]), C.byref(st[2]), C.byref(st[3]), int(n_active),
+                                              int(k_split), float(gamma), float(sigma0), float(sigma1), cap, hk.ctypes.data,
+                                              hu.ctypes.data, hv.ctypes.data, hw.ctypes.data, C.byref(nh))
+            if rc == 0:
+                self._put(st)
+                n = int(nh.value)
+                return hk[:n], hu[:n], hv[:n], hw[:n]
+            if nh.value <= cap:
+                raise _lib.PicError(rc, lib.pic_last_error().decode())
+            cap = int(nh.value) + 1024            # the state was left untouched: retry with room for every hit
 
     def sheath_reinject(self, n_dead, sigma, L):
         """Per dead slot, in index order: x=uniform(0,L) then u,v,w=normal(0,sigma_i)
         (PIC_L_DD.py:433-436 / 443-446).  sigma: array of per-slot thermal speeds."""
+        n_dead = int(n_dead)
         xd = np.empty(n_dead); ud = np.empty(n_dead); vd = np.empty(n_dead); wd = np.empty(n_dead)
-        rng = self.rng
-        for k in range(n_dead):
-            s = sigma[k]
-            xd[k] = rng.uniform(0.0, L)
-            ud[k] = rng.normal(0.0, s)
-            vd[k] = rng.normal(0.0, s)
-            wd[k] = rng.normal(0.0, s)
+        if n_dead:
+            sg = np.ascontiguousarray(np.broadcast_to(np.asarray(sigma, dtype=np.float64), (n_dead,)))
+            st = self._get()
+            _lib.call("pic_mt_sheath_draws", st[0].ctypes.data, C.byref(st[1]), C.byref(st[2]), C.byref(st[3]), n_dead,
+                      sg.ctypes.data, float(L), xd.ctypes.data, ud.ctypes.data, vd.ctypes.data, wd.ctypes.data)
+            self._put(st)
         return xd, ud, vd, wd
 
     def sheath_skip_foreign(self, n_dead):
-        """Advance the stream past the draws of dead slots owned by lower ranks."""
-        rng = self.rng
-        for _ in range(int(n_dead)):
-            rng.uniform(0.0, 1.0)
-            rng.normal(0.0, 1.0); rng.normal(0.0, 1.0); rng.normal(0.0, 1.0)
+        """Advance the stream past the draws of dead slots owned by other ranks."""
+        if int(n_dead) > 0:
+            st = self._get()
+            _lib.call("pic_mt_sheath_draws", st[0].ctypes.data, C.byref(st[1]), C.byref(st[2]), C.byref(st[3]), int(n_dead),
+                      None, 1.0, None, None, None, None)
+            self._put(st)
 
 
 def sheath_step_draws(draws, counts, rank, N_global, sigma_local, L):
-    """Sharded re-injection with stream parity: advances `draws` exactly as the reference's
-    single process would for the GLOBAL particle list (PIC_L_DD.py:419-450: one thermostat
-    uniform per active particle, then x,u,v,w per dead slot in index order) and returns only the
-    draws of this rank's dead slots.  counts[r] = number of dead slots on rank r (rank order =
-    index order because shards are contiguous index ranges); sigma_local = thermal speed of each
-    of this rank's dead slots."""
+    """Sharded re-injection with stream parity (gamma == 0): advances `draws` exactly as the
+    reference's single process would for the GLOBAL particle list (PIC_L_DD.py:419-450: one
+    thermostat uniform per active particle, then x,u,v,w per dead slot in index order) and returns
+    only the draws of this rank's dead slots.  counts[r] = number of dead slots on rank r (rank order
+    = index order because shards are contiguous index ranges); sigma_local = thermal speed of each of
+    this rank's dead slots, in index order."""
     counts = [int(c) for c in counts]
     draws.sheath_thermostat_skip(int(N_global) - sum(counts))
+    return sheath_reinject_draws(draws, counts, rank, sigma_local, L)
+
+
+def sheath_reinject_draws(draws, counts, rank, sigma_local, L):
+    """The re-injection part alone (after the thermostat consumed its share of the stream)."""
+    counts = [int(c) for c in counts]
     draws.sheath_skip_foreign(sum(counts[:rank]))
     out = draws.sheath_reinject(counts[rank], sigma_local, L)
     draws.sheath_skip_foreign(sum(counts[rank + 1:]))

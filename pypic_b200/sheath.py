@@ -14,7 +14,7 @@ import torch
 
 from . import _lib, device as D
 from .dist import Comm, local_split, shard_range
-from .rng import LegacyDraws, sheath_step_draws
+from .rng import LegacyDraws, sheath_reinject_draws
 
 epsilon0 = 8.854E-12
 e = 1.602E-19
@@ -27,7 +27,7 @@ class SheathSim:
     def __init__(self, N, Ng, dx, dt, p2c, q=(-e, e), m=(me, mp), n_split=None, tol=1e-5, maxiter=20,
                  kBT=(None, None), gamma=0.0, carry_vw=True, deposit="window", tiles="smem",
                  rng="host", seed=1, draws=None, comm=None, device=None, sort_every=0, elide_u=True,
-                 enqueue_ahead=True, reduce="nccl"):
+                 enqueue_ahead=True, reduce="nccl", track_order=None, vion_after=None):
         self.dev = D.require_cuda(device)
         self.comm = comm if comm is not None else Comm()
         self.N_global = int(N)
@@ -35,6 +35,7 @@ class SheathSim:
         self.start, self.stop = shard_range(N, self.comm.rank, self.comm.world)
         self.N = self.stop - self.start
         self.n_split = local_split(n_split_g, self.start, self.stop)
+        self._n_split_g = n_split_g
         self.Ng, self.dx, self.dt, self.p2c = int(Ng), float(dx), float(dt), float(p2c)
         self.L = dx * (Ng - 1)
         self.tol, self.maxiter, self.gamma = float(tol), int(maxiter), float(gamma)
@@ -45,6 +46,16 @@ class SheathSim:
         self.seed = int(seed)
         self.draws = draws if draws is not None else LegacyDraws()
         self.sort_every = int(sort_every)
+        # track_order: a cell-sorted store that keeps the reference's particle NUMBERING -- the sort
+        # carries the original index of every particle as a payload (self.oid), the passive v0,w0 stay
+        # in original order (they are never streamed), re-injection draws are made in original-index
+        # order (PIC_L_DD.py:429-450) and download() returns the caller's order.  Default: on whenever a
+        # sorted run needs it (host RNG parity or carried v,w); bench mode (Philox, no v,w) runs without.
+        self.track = (bool(track_order) if track_order is not None
+                      else (self.sort_every > 0 and (rng == "host" or self.carry_vw)))
+        # vionout (PIC_L_DD.py:497-503): +/-u0 of electrons absorbed in steps t > vion_after
+        self.vion_after = None if vion_after is None else int(vion_after)
+        self._vion = []                 # (step, iteration, global index, value)
         # deposit: "window" = TMA-staged private-window kernel over contiguous chunks (default),
         # "window-ldg" = the same with register-prefetched loads instead of the TMA ring,
         # "atomic" = one shared-memory atomicAdd per contribution, "warp" = grid-stride kernel
@@ -59,6 +70,9 @@ class SheathSim:
         flags = {"window": 0, "window-blocked": 64, "window-big": 16, "window-ldg": 8, "atomic": 1,
                  "warp": 4, "window-det": 128}[deposit] | (2 if tiles == "global" else 0)
         self.det = deposit == "window-det"
+        if self.det and self.track and self.sort_every:
+            raise ValueError("deposit='window-det' sorts with the stable radix sort, which does not carry the original-index "
+                             "payload yet: use sort_every=0 or track_order=False")
         if self.det and int(Ng) > 32768:
             raise ValueError("deposit='window-det': the cooperative field kernel used for Ng > 32768 adds its per-CTA "
                              "partial sums with fp64 atomics, so the run would not be bit-reproducible")
@@ -111,7 +125,16 @@ class SheathSim:
         self.sort_counts = torch.zeros(D.sort_counts_size(g), dtype=torch.int32, device=dev) if self.sort_every else None
         self.sort_scratch = (torch.zeros(D.sort_stable_scratch_size(n), dtype=torch.int32, device=dev)
                              if self.sort_every and self.det else None)
-        self.scalar = D.f64(1, dev, True)
+        self.scalar = D.f64(2, dev, True)
+        # absorption log (pic_dev_dd_picard_iter4): slots absorbed during the step, (iteration << 32 | slot)
+        self.dead_cap = int(min(max(n, 1), max(1 << 16, n // 64)))
+        self.dead_log = torch.zeros(self.dead_cap, dtype=torch.int64, device=dev)
+        self.dead_cnt = torch.zeros(1, dtype=torch.int32, device=dev)
+        self._log_valid = False         # the log describes the flags only after a step that started all-active
+        self._harvested = None
+        self.oid = None                 # int32 original index per slot; None = identity (never sorted)
+        self.oid_alt = None
+        self._inv = None                # inverse of oid (built on demand for the host-draw thermostat)
         self.t = 0
         self._sorted_once = False
         self._sorts = 0
@@ -126,7 +149,7 @@ class SheathSim:
 
     # ------------------------------------------------------------------ state I/O
     def upload(self, x0, u0, v0=None, w0=None, E0=None, active=None):
-        """Global (unsharded) host arrays in; each rank keeps its slice."""
+        """Global (unsharded) host arrays in, in the reference's particle order; each rank keeps its slice."""
         s = slice(self.start, self.stop)
         n = self.N                      # the arrays hold max(N, 1) slots so that an empty shard still has pointers
         self.x0[:n].copy_(torch.as_tensor(np.ascontiguousarray(x0[s])))
@@ -140,14 +163,37 @@ class SheathSim:
             self.E0.copy_(torch.as_tensor(np.ascontiguousarray(E0)))
         if active is not None:
             self.active[:n].copy_(torch.as_tensor(np.ascontiguousarray(active[s]).astype(np.int8)))
+        else:
+            self.active.fill_(1)
+        # the store is in the caller's order again: identity numbering, nothing logged, nothing sorted
+        self.oid = self._inv = None
+        self._log_valid = False
+        self._harvested = None
+        self._sorted_once = False
+
+    def _to_original_order(self, t, kind):
+        """A per-slot array of this shard in the reference's particle order (host copy)."""
+        n = self.N
+        if self.oid is None:
+            return t[:n].cpu().numpy()
+        out = torch.empty(max(n, 1), dtype=t.dtype, device=self.dev)
+        _lib.call("pic_dev_scatter_" + kind, D.ptr(t), D.ptr(self.oid), D.ptr(out), n, D.stream())
+        self.kernel_launches += 1
+        return out[:n].cpu().numpy()
 
     def download(self):
+        """The state of this shard in the reference's particle order (whatever the sort did)."""
         n = self.N
-        out = dict(x0=self.x0[:n].cpu().numpy(), u0=self.u0[:n].cpu().numpy(),
-                   active=self.active[:n].cpu().numpy().astype(np.float64),
-                   E0=self.E0.cpu().numpy(), j0=self.j0.cpu().numpy())
+        act = self._to_original_order(self.active, "i8")
+        out = dict(x0=self._to_original_order(self.x0, "f64"), u0=self._to_original_order(self.u0, "f64"),
+                   active=act.astype(np.float64), E0=self.E0.cpu().numpy(), j0=self.j0.cpu().numpy())
         if self.carry_vw:
-            out["v0"] = self.v0[:n].cpu().numpy(); out["w0"] = self.w0[:n].cpu().numpy()
+            # v,w are passive and live in original order.  A particle absorbed BEFORE the last Picard
+            # iteration of the step holds the reference's zeros (PIC_L_DD.py:459-462 zero x1,u1,v1,w1 and
+            # only active particles are pushed); one absorbed IN the last iteration keeps its values
+            early = (act != 1) & (out["x0"] == 0.0)
+            out["v0"] = np.where(early, 0.0, self.v0[:n].cpu().numpy())
+            out["w0"] = np.where(early, 0.0, self.w0[:n].cpu().numpy())
         return out
 
     # ------------------------------------------------------------------ re-injection
@@ -155,41 +201,192 @@ class SheathSim:
         kT = self.kBT[sp]
         return float(np.sqrt(kT / self.m[sp]))
 
+    def _harvest_dead(self):
+        """The slots absorbed during the last step, in ORIGINAL-index order: (slots, original local
+        indices, Picard iteration each one died in or None).  From the absorption log when it is
+        valid (a few hundred entries), otherwise by compacting the flag array.  Also tallies vionout
+        (PIC_L_DD.py:497-503).  Cached until the next step."""
+        if self._harvested is not None and self._harvested[0] == self.t:
+            return self._harvested[1:]
+        st = D.stream()
+        slots = iters = None
+        if self._log_valid:
+            cnt = int(D.read_raw(self.dead_cnt, 1, np.int32)[0])
+            if cnt <= self.dead_cap:
+                log = D.read_raw(self.dead_log, cnt, np.int64) if cnt else np.zeros(0, dtype=np.int64)
+                slots = (log & 0xffffffff).astype(np.int32)
+                iters = (log >> 32).astype(np.int32)
+        if slots is None:
+            _lib.call("pic_dev_compact_flags", D.ptr(self.active), self.N, 0, D.ptr(self.dead_idx), D.ptr(self.count),
+                      D.ptr(self.block_counts), st)
+            self.kernel_launches += 3
+            cnt = int(D.read_raw(self.count, 1, np.int64)[0])
+            slots = D.read_raw(self.dead_idx, cnt, np.int32) if cnt else np.zeros(0, dtype=np.int32)
+        orig = slots
+        if self.oid is not None and len(slots):
+            dslots = D.to_dev(slots, self.dev, torch.int32)
+            dorig = torch.empty(len(slots), dtype=torch.int32, device=self.dev)
+            _lib.call("pic_dev_gather_i32", D.ptr(self.oid), D.ptr(dslots), D.ptr(dorig), len(slots), st)
+            self.kernel_launches += 1
+            orig = D.read_raw(dorig, len(slots), np.int32)
+        order = np.argsort(orig, kind="stable")
+        slots, orig = np.ascontiguousarray(slots[order]), np.ascontiguousarray(orig[order])
+        iters = None if iters is None else iters[order]
+        self._tally_vionout(slots, orig, iters)
+        self._harvested = (self.t, slots, orig, iters)
+        return slots, orig, iters
+
+    def _tally_vionout(self, slots, orig, iters):
+        """PIC_L_DD.py:497-503: for steps t > 2000 every absorbed electron (i < N/2) appends u0[i]
+        (right wall) or -u0[i] (left wall), in (Picard iteration, index) order.  The deaths harvested at
+        the start of step t happened in step t-1; u0 of that step is what the commit left in self.u1."""
+        step = self.t - 1
+        if self.vion_after is None or step <= self.vion_after or not len(slots):
+            return
+        sel = np.nonzero((orig.astype(np.int64) + self.start) < self.N_global // 2)[0]
+        if not len(sel):
+            return
+        if iters is None:
+            raise _lib.PicError(_lib.PIC_ERR_ARG, "vionout needs the absorption log of the step (the state was uploaded or "
+                                "restored with absorbed particles, or the log overflowed)")
+        ds = D.to_dev(slots[sel], self.dev, torch.int32)
+        du = torch.empty(len(sel), dtype=torch.float64, device=self.dev)
+        df = torch.empty(len(sel), dtype=torch.int8, device=self.dev)
+        _lib.call("pic_dev_gather_f64", D.ptr(self.u1), D.ptr(ds), D.ptr(du), len(sel), D.stream())
+        _lib.call("pic_dev_gather_i8", D.ptr(self.active), D.ptr(ds), D.ptr(df), len(sel), D.stream())
+        self.kernel_launches += 2
+        u = D.read_f64(du, len(sel)); f = D.read_raw(df, len(sel), np.int8)
+        for k, j in enumerate(sel):
+            self._vion.append((step, int(iters[j]), int(orig[j]) + self.start, float(u[k]) if f[k] == 0 else -float(u[k])))
+
+    def collect_vionout(self):
+        """The vionout list of the whole run (all ranks), in the reference's append order."""
+        if self.vion_after is not None:
+            self._harvest_dead()                  # the deaths of the last step have not been visited by a re-injection
+        rows = list(self._vion)
+        if self.comm.enabled and self.comm.world > 1:
+            import torch.distributed as dist
+            parts = [None] * self.comm.world
+            dist.all_gather_object(parts, rows, group=self.comm.group)
+            rows = [r for p in parts for r in p]
+        rows.sort(key=lambda r: r[:3])
+        self.vionout = [r[3] for r in rows]
+        return self.vionout
+
+    def _thermostat_host(self, dead_orig_global):
+        """PIC_L_DD.py:419-427 with the legacy stream: one uniform per ACTIVE particle in index order;
+        u < gamma redraws u,v,w from the ION temperature (kBTi for both species, as written).  Every
+        rank runs the whole stream and applies the hits inside its own index range."""
+        nd = len(dead_orig_global)
+        n_active = self.N_global - nd
+        hs = self.N_global // 2 if self._n_split_g is None else self._n_split_g
+        k_split = hs - int(np.searchsorted(dead_orig_global, hs, side="left"))
+        sig = [float(np.sqrt(self.kBT[1] / self.m[0])), float(np.sqrt(self.kBT[1] / self.m[1]))]
+        hk, hu, hv, hw = self.draws.sheath_thermostat(n_active, k_split, self.gamma, sig[0], sig[1])
+        if not len(hk):
+            return 0
+        # ordinal among the active particles -> global index: skip the dead slots below it
+        gi = hk + np.searchsorted(dead_orig_global - np.arange(nd), hk, side="right")
+        mine = (gi >= self.start) & (gi < self.stop)
+        if not mine.any():
+            return 0
+        orig = (gi[mine] - self.start).astype(np.int32)
+        if self.oid is not None:
+            if self._inv is None:
+                self._inv = torch.empty(max(self.N, 1), dtype=torch.int32, device=self.dev)
+                _lib.call("pic_dev_invert_perm", D.ptr(self.oid), D.ptr(self._inv), self.N, D.stream())
+            dorig = D.to_dev(orig, self.dev, torch.int32)
+            dslot = torch.empty(len(orig), dtype=torch.int32, device=self.dev)
+            _lib.call("pic_dev_gather_i32", D.ptr(self._inv), D.ptr(dorig), D.ptr(dslot), len(orig), D.stream())
+        else:
+            dorig = dslot = D.to_dev(orig, self.dev, torch.int32)
+        dd = D.to_dev(np.stack([hu[mine], hv[mine], hw[mine]]), self.dev)
+        _lib.call("pic_dev_dd_apply_draws2", D.ptr(dslot), D.ptr(dorig), None, D.ptr(dd[0]), D.ptr(dd[1]), D.ptr(dd[2]),
+                  len(orig), None, D.ptr(self.u0), D.ptr(self.v0), D.ptr(self.w0), None, D.stream())
+        self.kernel_launches += 3
+        return int(mine.sum())
+
     def reinject(self):
-        """PIC_L_DD.py:419-450."""
+        """PIC_L_DD.py:419-450: thermostat, then re-injection of the absorbed slots."""
         st = D.stream()
         if self.rng_mode == "philox":
             sig = (C.c_double * 2)(self._sigma(0), self._sigma(1))
-            _lib.call("pic_dev_dd_reinject_philox", C.byref(self.params), D.ptr(self.x0), D.ptr(self.u0),
-                      D.ptr(self.v0), D.ptr(self.w0), D.ptr(self.active), C.byref(sig), self.seed, self.t,
-                      self.start, st)
+            if self.gamma != 0.0:
+                sgi = (C.c_double * 2)(float(np.sqrt(self.kBT[1] / self.m[0])), float(np.sqrt(self.kBT[1] / self.m[1])))
+                _lib.call("pic_dev_dd_thermostat_philox", C.byref(self.params), D.ptr(self.u0), D.ptr(self.v0), D.ptr(self.w0),
+                          D.ptr(self.active), D.ptr(self.oid), self.gamma, C.byref(sgi), self.seed, self.t, self.start, st)
+                self.kernel_launches += 1
+            if self.vion_after is not None:
+                self._harvest_dead()
+            # the slots named in the absorption log (a few hundred) are re-injected without touching the
+            # flag array; the flag scan only runs when there is no valid log (first step, overflow).
+            # With a tracked order the draws are keyed by the ORIGINAL index and v,w written there.
+            if self._log_valid:
+                _lib.call("pic_dev_dd_reinject_philox_log", C.byref(self.params), D.ptr(self.dead_log), D.ptr(self.dead_cnt),
+                          self.dead_cap, D.ptr(self.x0), D.ptr(self.u0), D.ptr(self.v0), D.ptr(self.w0), D.ptr(self.active),
+                          D.ptr(self.oid), C.byref(sig), self.seed, self.t, self.start, st)
+            _lib.call("pic_dev_dd_reinject_philox2", C.byref(self.params), D.ptr(self.x0), D.ptr(self.u0),
+                      D.ptr(self.v0), D.ptr(self.w0), D.ptr(self.active), D.ptr(self.oid), C.byref(sig), self.seed, self.t,
+                      self.start, D.ptr(self.dead_cnt) if self._log_valid else None, self.dead_cap, st)
             self.kernel_launches += 1
+            self._reset_log()
             return None
-        if self.gamma != 0.0:
-            raise NotImplementedError("thermostat with gamma != 0 (PIC_L_DD.py:421-426) is not on the device path; "
-                                      "the reference's only driven configuration uses gamma = 0")
-        _lib.call("pic_dev_compact_flags", D.ptr(self.active), self.N, 0, D.ptr(self.dead_idx), D.ptr(self.count),
-                  D.ptr(self.block_counts), st)
-        self.kernel_launches += 3
-        n_dead = int(D.read_raw(self.count, 1, np.int64)[0])
+        slots, orig, _ = self._harvest_dead()
+        n_dead = len(slots)
         counts = self.comm.allgather_int(n_dead, device=self.dev)
-        idx = D.read_raw(self.dead_idx, n_dead, np.int32) if n_dead else np.zeros(0, dtype=np.int32)
-        sigma = np.where(idx >= self.n_split, self._sigma(1), self._sigma(0))
-        xd, ud, vd, wd = sheath_step_draws(self.draws, counts, self.comm.rank, self.N_global, sigma, self.L)
+        if self.gamma != 0.0:
+            g_orig = orig.astype(np.int64) + self.start
+            if self.comm.enabled and self.comm.world > 1:
+                import torch.distributed as dist
+                parts = [None] * self.comm.world
+                dist.all_gather_object(parts, g_orig, group=self.comm.group)
+                g_orig = np.concatenate(parts)
+            self._thermostat_host(np.sort(g_orig))
+        else:
+            self.draws.sheath_thermostat_skip(self.N_global - sum(counts))
+        sigma = np.where(orig >= self.n_split, self._sigma(1), self._sigma(0))
+        xd, ud, vd, wd = sheath_reinject_draws(self.draws, counts, self.comm.rank, sigma, self.L)
+        if self.gamma == 0.0:
+            # the next step skips about as many thermostat uniforms: jump ahead while the GPU works
+            self.draws.prefetch_skip(self.N_global - sum(counts))
         if n_dead:
-            dxd, dud = D.to_dev(xd, self.dev), D.to_dev(ud, self.dev)
-            dvd = D.to_dev(vd, self.dev) if self.carry_vw else None
-            dwd = D.to_dev(wd, self.dev) if self.carry_vw else None
-            _lib.call("pic_dev_dd_apply_draws", D.ptr(self.dead_idx), D.ptr(dxd), D.ptr(dud), D.ptr(dvd),
-                      D.ptr(dwd), n_dead, D.ptr(self.x0), D.ptr(self.u0), D.ptr(self.v0), D.ptr(self.w0),
-                      D.ptr(self.active), st)
+            dd = D.to_dev(np.stack([xd, ud, vd, wd]), self.dev)
+            di = D.to_dev(np.stack([slots, orig]), self.dev, torch.int32)
+            _lib.call("pic_dev_dd_apply_draws2", D.ptr(di[0]), D.ptr(di[1]), D.ptr(dd[0]), D.ptr(dd[1]),
+                      D.ptr(dd[2]) if self.carry_vw else None, D.ptr(dd[3]) if self.carry_vw else None, n_dead,
+                      D.ptr(self.x0), D.ptr(self.u0), D.ptr(self.v0), D.ptr(self.w0), D.ptr(self.active), st)
             self.kernel_launches += 1
-            torch.cuda.current_stream().synchronize()   # keep the staging tensors alive until consumed
+        self._reset_log()
         return n_dead
 
+    def _reset_log(self):
+        """Every slot is alive now: the absorption log of the coming step starts empty."""
+        self.dead_cnt.zero_()
+        self._log_valid = True
+
     def sort_by_cell(self):
-        """Benchmark mode: counting sort by (species, cell) into the scratch arrays."""
+        """Counting sort by (species, cell) into the scratch arrays."""
         st = D.stream()
+        if self.track:
+            # the sort carries the original index of every particle (identity on the first sort); all
+            # slots are alive here (re-injection ran before), so the flags need no permutation, and the
+            # passive v,w are not moved at all
+            P = self.params
+            if self._sorted_once:
+                P = _lib.DDParams(self.N, self.n_split, self.Ng, self.params.flags | 32, self.dx, self.dt, self.L, self.p2c,
+                                  (C.c_double * 2)(*self.q), (C.c_double * 2)(*self.m))
+            if self.oid_alt is None:
+                self.oid_alt = torch.empty(max(self.N, 1), dtype=torch.int32, device=self.dev)
+            _lib.call("pic_dev_dd_sort_by_cell2", C.byref(P), D.ptr(self.x0), D.ptr(self.u0), D.ptr(self.oid),
+                      D.ptr(self.x1), D.ptr(self.u1), D.ptr(self.oid_alt), D.ptr(self.sort_counts), st)
+            self.kernel_launches += 3
+            self.oid, self.oid_alt = self.oid_alt, (self.oid if self.oid is not None else None)
+            self._inv = None
+            self._sorted_once = True
+            self._sorts += 1
+            self.x0, self.x1 = self.x1, self.x0
+            self.u0, self.u1 = self.u1, self.u0
+            return
         if self.det:
             # reproducible build: stable radix sort (the order inside a cell is the previous order)
             where = C.c_int(0)
@@ -295,9 +492,10 @@ class SheathSim:
             if self.iter_events is not None:
                 ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
                 ev[0].record()
-            _lib.call("pic_dev_dd_picard_iter3", P, D.ptr(self.x0), D.ptr(self.u0), D.ptr(xin), D.ptr(xout),
+            _lib.call("pic_dev_dd_picard_iter4", P, D.ptr(self.x0), D.ptr(self.u0), D.ptr(xin), D.ptr(xout),
                       D.ptr(self.u1) if want_u else None, D.ptr(self.active), D.ptr(self.Es), self._acc_ptr(),
-                      1 if j == 0 else 0, D.ptr(self.range_err), D.ptr(self.ctl), st)
+                      1 if j == 0 else 0, D.ptr(self.range_err), D.ptr(self.ctl), D.ptr(self.dead_log),
+                      D.ptr(self.dead_cnt), self.dead_cap, j, st)
             if ev is not None:
                 ev[1].record()
             if self.p2p is not None:
@@ -315,6 +513,8 @@ class SheathSim:
 
         def outcome():
             s = D.read_f64(self.stats, 8 + self.maxiter)
+            if self.p2p is not None:
+                self.p2p.check()         # a timed-out wait summed incomplete accumulators: stop at once
             k = int(s[3])
             return k, [float(v) for v in s[8:8 + k]]
 
@@ -371,11 +571,9 @@ class SheathSim:
         return k, r
 
     def step(self):
-        if self.sort_every and self.t % self.sort_every == 0 and self.rng_mode == "philox" and not self.carry_vw:
-            self.reinject()
+        self.reinject()
+        if self.sort_every and self.t % self.sort_every == 0 and (self.track or (self.rng_mode == "philox" and not self.carry_vw)):
             self.sort_by_cell()
-        else:
-            self.reinject()
         out = self.picard()
         self.t += 1
         return out
@@ -384,11 +582,21 @@ class SheathSim:
     def diagnostics(self):
         """EE, KE, jbias of PIC_L_DD.py:548-551 (KE uses me for every particle, as written)."""
         s = D.read_f64(self.stats, 4)
-        _lib.call("pic_dev_sum_sq", D.ptr(self.u0), self.N, me / 2., D.ptr(self.scalar), D.stream())
+        m1, m2 = self.moments()
+        return dict(EE=float(s[2]), KE=me / 2. * m2, jbias=float(s[1]), kBTe=self.kBTe_from(m1, m2))
+
+    def moments(self):
+        """(sum u0, sum u0^2) over all ranks from one pass over the velocities."""
+        _lib.call("pic_dev_moments", D.ptr(self.u0), self.N, D.ptr(self.scalar), D.stream())
         self.kernel_launches += 1
         self.comm.allreduce_sum(self.scalar)
-        ke = float(D.read_f64(self.scalar, 1)[0])
-        return dict(EE=float(s[2]), KE=ke, jbias=float(s[1]))
+        m = D.read_f64(self.scalar, 2)
+        return float(m[0]), float(m[1])
+
+    def kBTe_from(self, m1, m2):
+        """np.std(u0)**2 * me / e (PIC_L_DD.py:417; dead slots count with their zeros, as there)."""
+        n = float(self.N_global)
+        return max(m2 / n - (m1 / n) ** 2, 0.0) * me / e
 
     def phi(self):
         """phih of the last Picard iteration: -cumtrapz(Eh) - max (PIC_L_DD.py:522-523);
@@ -402,3 +610,9 @@ class SheathSim:
         D.check_range(self.range_err, "sheath step")
         if self.p2p is not None:
             self.p2p.check()
+
+    def close(self):
+        """Releases the peer-memory buffers (collective over the ranks); a no-op otherwise."""
+        if self.p2p is not None:
+            self.p2p.close()
+            self.p2p = None

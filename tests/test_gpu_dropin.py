@@ -35,6 +35,49 @@ def scratch_cwd(tmp_path):
 
 
 # ------------------------------------------------------------------------------- PIC_L_DD
+@pytest.mark.parametrize("sort_every", [0, 2])
+def test_pic_l_dd_main_i_thermostat_golden(golden, tmp_path, sort_every):
+    """gamma != 0 (the reference ships gamma = 0.0; golden made with the literal overridden): the
+    thermostat's uniforms and the normals of its hits interleave in the legacy stream exactly as in
+    PIC_L_DD.py:419-427, the hits land on the same particles (also in a cell-sorted store) and the
+    stream ends at the same word."""
+    import re
+    import PIC_L_DD
+    g = golden("dd_main_gamma")
+    N = int(g["N"]); Ng = int(g["Ng"]); T = int(g["T"])
+    res = {}
+    np.random.seed(int(g["seed"]))
+    with scratch_cwd(str(tmp_path)) as buf:
+        PIC_L_DD.main_i(T, 10, N=N, Ng=Ng, gamma=float(g["gamma"]), result=res, sort_every=sort_every)
+        E0 = np.loadtxt("E0.txt"); jb = np.loadtxt("jb.txt")
+    assert np.random.uniform() == float(g["next_uniform"])
+    iters = np.array([int(s) for s in re.findall(r"Iterations:\s+(\d+)", buf.getvalue())])
+    assert np.array_equal(iters, g["iters"])
+    assert relmax(E0, g["E0_final"]) < 1e-11 and relmax(jb, g["jbias"]) < 1e-8
+    h = N // 2
+    assert relmax(res["x0"][:h], g["xe_series"][-1]) < 1e-11 and relmax(res["x0"][h:], g["xi_series"][-1]) < 1e-11
+    ee = np.sign(res["u0"]) * res["u0"] ** 2 * 0.5 * np.where(np.arange(N) < h, O.me, O.mp) / O.e
+    assert relmax(ee[:h], g["ee_series"][-1]) < 1e-10 and relmax(ee[h:], g["ei_series"][-1]) < 1e-10
+
+
+@pytest.mark.parametrize("sort_every", [0, 3])
+def test_pic_l_dd_main_i_vionout_golden(golden, tmp_path, sort_every):
+    """vionout.txt (PIC_L_DD.py:497-503; golden made with the `t > 2000` literal lowered to 5): the
+    velocities of the absorbed electrons, signed by wall, in (step, Picard iteration, index) order."""
+    import PIC_L_DD
+    g = golden("dd_main_vion")
+    N = int(g["N"]); Ng = int(g["Ng"]); T = int(g["T"])
+    np.random.seed(int(g["seed"]))
+    with scratch_cwd(str(tmp_path)):
+        PIC_L_DD.main_i(T, 10, N=N, Ng=Ng, vion_after=int(g["vion_after"]), sort_every=sort_every)
+        vion = np.atleast_1d(np.loadtxt("vionout.txt")); E0 = np.loadtxt("E0.txt")
+    assert np.random.uniform() == float(g["next_uniform"])
+    assert vion.shape == g["vionout"].shape and len(vion) > 10
+    assert np.array_equal(np.sign(vion), np.sign(g["vionout"]))
+    assert relmax(vion, g["vionout"]) < 1e-11
+    assert relmax(E0, g["E0_final"]) < 1e-11
+
+
 @pytest.mark.parametrize("tag", ["small", "default"])
 def test_pic_l_dd_main_i_module(golden, tag, tmp_path):
     """`import PIC_L_DD; PIC_L_DD.main_i(T, nplot)` (what run_pypic_dd.py does) with the seed the

@@ -37,8 +37,6 @@ def test_two_rank_peer_memory_reduction_matches_nccl():
     import torch
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
-    if os.environ.get("PIC_TEST_P2P", "0") != "1":
-        pytest.skip("reduce='p2p' is off by default and its parity run is pending (DESIGN.md 6): set PIC_TEST_P2P=1")
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
            "127.0.0.1", "--master-port", "29535", os.path.join(ROOT, "tools", "p2p_check.py"), "400000", "5"]
     res = subprocess.run(cmd, capture_output=True, text=True, timeout=300, cwd=ROOT)

@@ -52,6 +52,30 @@ def test_pypic_push_vs_reference_golden(golden, sort_every):
         assert relmax(out["j0"], g[f"j_{t}"]) < 1e-10
 
 
+@pytest.mark.parametrize("sort_every", [0, 1])
+def test_pypic_push_at_the_reference_default_size(golden, sort_every):
+    """BASELINE config 1(a): pypic.main's own literals (N = 1e6, Ng = 200, pypic.py:846-860) -- three
+    steps from the reference's initial state against the golden produced by the reference's
+    particle_push_p at that size: iteration counts, fields, every 997th particle and the global sums."""
+    from pypic_b200.periodic import PeriodicImplicitSim
+    from test_oracle import pypic_full_initial_state
+    g = golden("pypic_push_1e6")
+    m, q, x0, v0 = pypic_full_initial_state(g)
+    N = int(g["N"]); Ng = int(g["Ng"]); st = int(g["stride"])
+    sim = PeriodicImplicitSim(N, Ng, float(g["dx"]), float(g["dt"]), float(g["L"]), float(g["p2c"]),
+                              tol=float(g["tol"]), maxiter=int(g["maxiter"]), sort_every=sort_every)
+    sim.upload(x0, v0, g["E0"])
+    for t in range(3):
+        k, r = sim.push()
+        sim.check()
+        out = sim.download()
+        assert k == g["iters"][t]
+        assert relmax(out["x0"][::st], g[f"x_{t}"]) < 1e-12 and relmax(out["v0"][::st], g[f"v_{t}"]) < 1e-12
+        assert relmax(out["E0"], g[f"E_{t}"]) < 1e-10 and relmax(out["j0"], g[f"j_{t}"]) < 1e-10
+        assert abs(np.sum(out["x0"]) - float(g[f"xsum_{t}"])) <= 1e-12 * abs(float(g[f"xsum_{t}"]))
+        assert abs(np.sum(out["v0"] ** 2) - float(g[f"vsumsq_{t}"])) <= 1e-12 * float(g[f"vsumsq_{t}"])
+
+
 def test_pypic_push_bit_exact_first_iteration():
     """maxiter=1: one fused iteration from identical inputs -> x1,v1 bit-identical to the
     oracle's unfused NumPy arithmetic (incl. the floored-modulo wrap)."""

@@ -3,6 +3,7 @@ golden vectors produced by the reference.  Bit-exact for indices, flags, counts 
 per-particle arithmetic given identical inputs; stated tolerances for reduced
 quantities (summation order differs from the reference's serial loop)."""
 import ctypes as C
+import os
 
 import numpy as np
 import pytest
@@ -355,10 +356,15 @@ def test_enqueue_ahead_loop_matches_the_synchronous_loop():
         s.check()
 
 
-@pytest.mark.parametrize("tag", ["small", "default"])
-def test_whole_loop_vs_reference_golden(golden, tag):
+@pytest.mark.parametrize("tag,sort_every,jump", [("small", 0, False), ("small", 1, False), ("small", 3, True),
+                                                  ("default", 0, False), ("default", 2, True)])
+def test_whole_loop_vs_reference_golden(golden, tag, sort_every, jump):
     """PIC_L_DD.main_i itself (golden from the reference run): same seed, the host draw
-    service reproduces the legacy MT19937 stream, the device runs the loop."""
+    service reproduces the legacy MT19937 stream, the device runs the loop.  sort_every > 0: the
+    store is re-sorted by cell (the fused TMA kernel's layout) and keeps the reference's particle
+    numbering through the original-index payload, so the draws still go to the same particles;
+    jump: the thermostat uniforms are skipped by MT19937 jump-ahead (prefetched) instead of drawn."""
+    from pypic_b200.rng import LegacyDraws
     from pypic_b200.sheath import SheathSim
     g = golden("dd_main_" + tag)
     N = int(g["N"]); Ng = int(g["Ng"]); T = int(g["T"])
@@ -366,7 +372,12 @@ def test_whole_loop_vs_reference_golden(golden, tag):
     np.random.seed(int(g["seed"]))
     m, q, x0, u0, v0, w0, species, kBTe, kBTi = O.dd_initialize_beam(N, 1e19, dx, Ng, Te, Ti, L, np.random)
     p2c = L * 1e19 / N
-    sim = SheathSim(N, Ng, dx, dt, p2c, tol=1e-5, maxiter=20, kBT=(kBTe, kBTi), carry_vw=True, rng="host")
+    draws = LegacyDraws()
+    if jump:
+        draws.JUMP_MIN, draws.CHUNK, draws.MARGIN = 256, 128, 64
+    sim = SheathSim(N, Ng, dx, dt, p2c, tol=1e-5, maxiter=20, kBT=(kBTe, kBTi), carry_vw=True, rng="host",
+                    sort_every=sort_every, draws=draws)
+    assert sim.track == (sort_every > 0)
     sim.upload(x0, u0, v0, w0)
     iters, jb, Es, js = [], [], [], []
     for t in range(T + 1):
@@ -374,7 +385,24 @@ def test_whole_loop_vs_reference_golden(golden, tag):
         d = sim.diagnostics()
         iters.append(k); jb.append(d["jbias"])
         Es.append(sim.E0.cpu().numpy()); js.append(sim.j0.cpu().numpy())
+        if "xe_series" in g.files and sort_every and t % 7 == 3:
+            # every particle is where the reference has it, in the reference's numbering, mid-run.  (The
+            # arrays the reference handed to plt.scatter at step t are views that the re-injection of step
+            # t+1 then wrote into, so only the slots that are alive here can be compared at this point;
+            # the re-injected ones are covered by everything that follows from them.)
+            o = sim.download(); h = N // 2
+            alive = o["active"] == 1
+            xs = np.concatenate([g["xe_series"][t], g["xi_series"][t]])
+            es = np.concatenate([g["ee_series"][t], g["ei_series"][t]])
+            assert alive.sum() > 0.98 * N
+            assert relmax(o["x0"][alive], xs[alive]) < 1e-11
+            ee = np.sign(o["u0"]) * o["u0"] * o["u0"] * 0.5 * m / O.e
+            assert relmax(ee[alive], es[alive]) < 1e-10
     sim.check()
+    if jump:
+        assert draws.jumps >= T and draws.prefetch_hits >= T - 2
+    if sort_every:
+        assert sim._sorts >= 1 and sim.oid is not None
     assert np.array_equal(np.array(iters), g["iters"])
     assert relmax(np.array(Es), g["E_series"]) < 1e-11
     assert relmax(np.array(js), g["j_series"]) < 1e-11
@@ -388,6 +416,57 @@ def test_whole_loop_vs_reference_golden(golden, tag):
     else:
         assert relmax(out["x0"][:h][::20], g["xe_last"]) < 1e-11
         assert relmax(out["x0"][h:][::20], g["xi_last"]) < 1e-11
+
+
+def test_baseline_grid_multi_step_vs_c_oracle():
+    """BASELINE config 2's grid (4097 nodes) with 1e7 particles, four whole timesteps of the product
+    path -- cell-sorted store, fused TMA kernel with light iterations, absorption log, MT19937
+    jump-ahead, host draws in original-index order -- against the C restatement of the reference loop
+    (oracle/c/dd_oracle.c, OpenMP) fed the same legacy stream: Picard iteration counts, absorb flags
+    (hence the wall tallies per species and side) exact, E, j and the particles within 1e-11."""
+    from oracle import c_oracle
+    from pypic_b200.rng import LegacyDraws
+    from pypic_b200.sheath import SheathSim
+    N, Ng, steps = 10_000_000, 4097, 4
+    dx, dt = 1e-5, 1e-12
+    L = dx * (Ng - 1)
+    kT = O.kb * 116000.
+    h = N // 2
+    rs = np.random.RandomState(11)
+    x0 = rs.uniform(0, L, N)
+    sig = np.concatenate([np.full(h, np.sqrt(kT / O.me)), np.full(N - h, np.sqrt(kT / O.mp))])
+    u0 = rs.normal(0, 1, N) * sig
+    E0 = np.zeros(Ng)
+    p2c = L * 1e19 / N
+    threads = max(1, len(os.sched_getaffinity(0)))
+    sim = SheathSim(N, Ng, dx, dt, p2c, kBT=(kT, kT), carry_vw=False, rng="host", sort_every=2,
+                    draws=LegacyDraws(np.random.RandomState(77)))
+    assert sim.track
+    sim.upload(x0, u0, E0=E0)
+    cpu_rng = np.random.RandomState(77)
+    dead_total = 0
+    for step in range(steps):
+        act = np.ones(N)
+        x1, u1, E1, j1, k_cpu, r_cpu = c_oracle.dd_picard_step(x0, u0, [-O.e, O.e], [O.me, O.mp], h, act, E0, p2c, Ng, dx, dt, L,
+                                                               1e-5, 20, threads)
+        k_gpu, r_gpu = sim.step()
+        out = sim.download()
+        assert k_gpu == k_cpu, (step, k_gpu, k_cpu)
+        assert np.array_equal(out["active"], act), step
+        assert relmax(out["E0"], E1) < 1e-11 and relmax(out["j0"], j1) < 1e-11
+        assert np.max(np.abs(out["x0"] - x1)) < 1e-11 * L
+        assert relmax(out["u0"], u1) < 1e-11
+        assert abs(r_gpu - r_cpu) <= 1e-6 * r_cpu + 1e-12
+        # the reference's re-injection (PIC_L_DD.py:419-450) on the CPU side, from the same stream
+        dead = np.nonzero(act != 1)[0]
+        dead_total += len(dead)
+        cpu_rng.uniform(0.0, 1.0, N - len(dead))
+        x0, u0, E0 = x1, u1, E1
+        for i in dead:
+            x0[i] = cpu_rng.uniform(0.0, L)
+            u0[i] = cpu_rng.normal(0.0, sig[i]); cpu_rng.normal(0.0, sig[i]); cpu_rng.normal(0.0, sig[i])
+    sim.check()
+    assert dead_total > 100 and sim._sorts == 2 and sim.draws.jumps == steps
 
 
 def test_host_abi_step_matches_device_path():

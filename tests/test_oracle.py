@@ -48,6 +48,38 @@ def test_pypic_push(golden):
         x0, v0, E0, j0 = x1, v1, E1, j1
 
 
+def pypic_full_initial_state(g):
+    """BASELINE config 1(a) (pypic.main's literals, 1e6 particles): the drop-in's host initialiser from
+    the golden's seed; the golden pins it through every 997th particle and two global sums."""
+    import pypic
+    N = int(g["N"]); Ng = int(g["Ng"]); L = float(g["L"]); dx = float(g["dx"])
+    np.random.seed(int(g["seed"]))
+    X = np.linspace(0.0, L, Ng + 1)
+    m, q, x0, v0 = pypic.initialize_p('landau-damping', N, 1e5, 1, 0.8, dx, Ng, 100.0 * 11600., 0.1 * 11600., L, X)[:4]
+    st = int(g["stride"])
+    assert np.array_equal(x0[::st], g["x0_sub"]) and np.array_equal(v0[::st], g["v0_sub"])
+    assert np.sum(x0) == float(g["x0_sum"]) and np.sum(v0 * v0) == float(g["v0_sumsq"])
+    return m, q, x0, v0
+
+
+def test_pypic_push_at_the_reference_default_size(golden):
+    """pypic.main's own size (N = 1e6, Ng = 200; pypic.py:846-860): initialiser bit-identical to the
+    reference's, oracle push equal to the reference's three steps (subsampled particles, complete
+    fields, iteration counts)."""
+    g = golden("pypic_push_1e6")
+    m, q, x0, v0 = pypic_full_initial_state(g)
+    N = int(g["N"]); Ng = int(g["Ng"]); st = int(g["stride"])
+    E0, j0 = g["E0"], g["j0"]
+    args = (float(g["p2c"]), float(g["dx"]), float(g["dt"]), float(g["L"]), float(g["tol"]), int(g["maxiter"]))
+    for t in range(3):
+        x1, v1, E1, j1, k, r = O.pypic_particle_push_p(x0, v0, q, m, E0, j0, N, Ng, *args)
+        assert k == g["iters"][t]
+        assert relmax(x1[::st], g[f"x_{t}"]) < 1e-12 and relmax(v1[::st], g[f"v_{t}"]) < 1e-12
+        assert relmax(E1, g[f"E_{t}"]) < 1e-10 and relmax(j1, g[f"j_{t}"]) < 1e-10
+        assert abs(np.sum(x1) - float(g[f"xsum_{t}"])) <= 1e-12 * abs(float(g[f"xsum_{t}"]))
+        x0, v0, E0, j0 = x1, v1, E1, j1
+
+
 # ---------------------------------------------------------------- PIC_L_DD
 @pytest.mark.parametrize("tag", ["a", "b"])
 def test_dd_kernels(golden, tag):

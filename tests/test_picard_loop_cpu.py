@@ -1,5 +1,5 @@
 """CPU test of the host logic of SheathSim.picard (enqueue-ahead Picard loop): the C ABI is replaced
-by a fake device that implements only the CONTROL contract of pic_dev_dd_picard_iter3 /
+by a fake device that implements only the CONTROL contract of pic_dev_dd_picard_iter4 /
 pic_dev_dd_field_update2 (include/pic_b200.h: launches are no-ops once the flag is up; the field
 kernel counts iterations, records residuals and raises the flag when `r > tol and k < maxiter`
 fails) with scripted residuals.  Checked: iteration counts, which launches ran as light / full
@@ -27,7 +27,8 @@ class FakeDevice:
 
     def call(self, name, *a):
         sim = self.sim
-        if name == "pic_dev_dd_picard_iter3":
+        if name == "pic_dev_dd_picard_iter4":
+            assert a[15] == len([e for e in self.log if e[0] in ("iter", "noop")])      # 0-based iteration number of the launch
             ctl = self.tensor_at(a[11])[1]
             if int(ctl[0]):
                 self.log.append(("noop",))
@@ -67,6 +68,7 @@ def make_sim(maxiter=6, tol=1e-5, enqueue_ahead=True):
     sim.active = torch.ones(4, dtype=torch.int8)
     sim.stats = f(8 + maxiter)
     sim.ctl = torch.zeros(1, dtype=torch.int32)
+    sim.dead_log = torch.zeros(16, dtype=torch.int64); sim.dead_cnt = torch.zeros(1, dtype=torch.int32); sim.dead_cap = 16
     sim.range_err = torch.zeros(1, dtype=torch.int32)
     sim.comm = types.SimpleNamespace(world=1, allreduce_sum=lambda t: t)
     sim._ratio = sim._r1 = sim._prev_hist = None

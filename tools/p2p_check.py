@@ -1,7 +1,9 @@
 #!/usr/bin/env python
 """Peer-memory reduction (SheathSim(reduce="p2p")) against the NCCL all-reduce path on the same
-shards: iteration counts and flags identical, fields bit-identical at 2 ranks (a+b is the same in
-either order) and to round-off beyond.
+shards: iteration counts and absorb flags identical, fields and particles equal to round-off.  (Not
+bit-identical even at 2 ranks: the default build merges its deposit windows with fp64 REDs whose
+order follows scheduling, so two NCCL runs differ from each other by the same few 1e-16 -- the
+check runs the NCCL path twice and reports that noise floor next to the p2p difference.)
     torchrun --nproc-per-node 2 tools/p2p_check.py [N] [steps]"""
 import json, os, sys, time
 import numpy as np, torch
@@ -43,19 +45,22 @@ def main():
         torch.cuda.synchronize(); t1 = time.perf_counter()
         sim.check()
         return sim, its, t1 - t0
+    def rel(p, q):
+        p, q = p.cpu().numpy(), q.cpu().numpy()
+        return float(np.max(np.abs(p - q)) / max(np.max(np.abs(p)), 1e-300))
     a, its_a, ta = run("nccl")
+    a2, its_a2, _ = run("nccl")
     out = dict(world=world, N=N, steps=steps)
     try:
         b, its_b, tb = run("p2p")
-        Ea, Eb = a.E0.cpu().numpy(), b.E0.cpu().numpy()
         out.update(iters_nccl=its_a, iters_p2p=its_b, repairs=(a.u_repairs, b.u_repairs),
-                   E_bit_identical=bool(np.array_equal(Ea, Eb)), E_rel=float(np.max(np.abs(Ea - Eb)) / np.max(np.abs(Ea))),
-                   j_rel=float(np.max(np.abs(a.j0.cpu().numpy() - b.j0.cpu().numpy())) / np.max(np.abs(a.j0.cpu().numpy()))),
-                   particles_equal=bool(torch.equal(a.x0, b.x0) and torch.equal(a.u0, b.u0) and torch.equal(a.active, b.active)),
+                   E_rel=rel(a.E0, b.E0), j_rel=rel(a.j0, b.j0), x_rel=rel(a.x0, b.x0), u_rel=rel(a.u0, b.u0),
+                   flags_equal=bool(torch.equal(a.active, b.active)),
+                   nccl_vs_nccl=dict(E_rel=rel(a.E0, a2.E0), j_rel=rel(a.j0, a2.j0), x_rel=rel(a.x0, a2.x0)),
                    seconds=(ta, tb), seq=b.p2p.seq)
-        out["ok"] = bool(its_a == its_b and out["particles_equal"] and out["E_rel"] < 1e-12 and out["j_rel"] < 1e-12
-                         and (world != 2 or out["E_bit_identical"]))
-        b.p2p.close()
+        out["ok"] = bool(its_a == its_b == its_a2 and out["flags_equal"] and out["E_rel"] < 1e-13 and out["j_rel"] < 1e-13
+                         and out["x_rel"] < 1e-13 and out["u_rel"] < 1e-12)
+        b.close()
     except Exception as e:                       # report instead of hanging the other rank's collectives
         out.update(ok=False, error=repr(e))
     allout = [None] * world
