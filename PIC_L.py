@@ -5,8 +5,8 @@ through pypic_b200.  No CPU fallback: every numerical function runs on the GPU; 
 configuration, the legacy-RNG initialiser and I/O stay on the host.
 
 The reference file is Python 2 (``N/2`` used as an index); the integer divisions are
-written ``//`` here.  Functions the reference's drivers never call are kept where they map to
-a device kernel and raise NotImplementedError (with the reason) where they do not.
+written ``//`` here.  Functions the reference's drivers never call are served by device kernels too; only main_i
+(a duplicate of pypic.implicit_pic with a stale-variable bug) is not rebuilt.
 """
 from __future__ import print_function
 
@@ -46,9 +46,8 @@ def interpolateFieldPeriodic(F, x, Ng, dx):
 
 
 def weightCurrents(x, q, v, p2c, Ng, N, dx):
-    """PIC_L.py:48-60: bounded CIC current without wall terms or edge fold."""
-    raise NotImplementedError("PIC_L.weightCurrents (PIC_L.py:48-60) is never called by the reference's drivers; "
-                              "the bounded current deposit on the GPU is PIC_L_DD.weightCurrents")
+    """PIC_L.py:48-60: bounded CIC current on Ng nodes, without wall terms or edge fold."""
+    return ops.l_weight_bounded(np.asarray(x)[:N], np.asarray(q)[:N], np.asarray(v)[:N], p2c, Ng, dx)
 
 
 def weightCurrentsPeriodic(x, q, v, p2c, Ng, N, dx):
@@ -57,8 +56,8 @@ def weightCurrentsPeriodic(x, q, v, p2c, Ng, N, dx):
 
 
 def weightDensities(x, q, p2c, Ng, N, dx):
-    raise NotImplementedError("PIC_L.weightDensities (PIC_L.py:83-98) is never called by the reference's drivers; "
-                              "the bounded density deposit on the GPU is PIC_L_DD.weightDensities")
+    """PIC_L.py:83-98: bounded CIC density on Ng nodes."""
+    return ops.l_weight_bounded(np.asarray(x)[:N], np.asarray(q)[:N], None, p2c, Ng, dx)
 
 
 def weightDensitiesPeriodic(x, q, p2c, Ng, N, dx):
@@ -87,12 +86,16 @@ def laplacian1D(Ng):
 
 
 def solvePoisson(dx, Ng, rho, kBT, tol, maxiter, phi0):
-    raise NotImplementedError("PIC_L.solvePoisson (Boltzmann-Newton, PIC_L.py:146-177) is never called by the reference's "
-                              "drivers; the Newton-Boltzmann solve on the GPU is pygcpic.Grid.solve_for_phi_dirichlet_boltzmann")
+    """PIC_L.py:146-177: Boltzmann-Newton solve on Ng nodes as written (reference node Ng/2, the
+    three-entry last row of laplacian1D, `while resid > tol and k <= maxiter`), whole loop in one
+    kernel launch with a PCR solve per iteration in place of scipy.sparse.linalg.inv."""
+    return ops.newton_boltzmann_l(np.asarray(rho)[:Ng], phi0, dx, kBT, tol, maxiter, periodic=False)
 
 
 def solvePoissonPeriodic(dx, Ng, rho, kBT, tol, maxiter, phi0):
-    raise NotImplementedError("PIC_L.solvePoissonPeriodic (PIC_L.py:179-206) is never called by the reference's drivers")
+    """PIC_L.py:179-206: the periodic Boltzmann-Newton solve on the Ng+1 nodes (cyclic tridiagonal
+    system by Sherman-Morrison over PCR)."""
+    return ops.newton_boltzmann_l(np.asarray(rho)[:Ng + 1], phi0, dx, kBT, tol, maxiter, periodic=True)
 
 
 def solvePoissonPeriodicElectronsNeutralized(dx, Ng, rho, kBT, tol, maxiter, phi0):
@@ -143,14 +146,22 @@ def pushParticlesExplicit(x, v, q, m, N, Ng, dt, dx, E):
 
 
 def pushParticlesImplicit(x0, xh, v, q, m, N, Ng, dt, dx, Eh):
-    raise NotImplementedError("PIC_L.pushParticlesImplicit (PIC_L.py:261-270) is the function form of the Crank-Nicolson "
-                              "push; the fused implicit path on the GPU is pypic.particle_push_p (SURVEY.md C2: main_i "
-                              "duplicates pypic.py with a stale-variable bug, so pypic.py is the implicit spec)")
+    """PIC_L.py:261-270: function form of the Crank-Nicolson push (periodic gather of Eh at xh)."""
+    f = lambda a: np.asarray(a, dtype=np.float64)[:N]
+    return ops.l_push_implicit(f(x0), f(xh), f(v), f(q), f(m), Ng, dt, dx, Eh)
 
 
 def applyBoundaryConditions(x, v, m, N, L, dx, kBT):
-    raise NotImplementedError("PIC_L.applyBoundaryConditions (PIC_L.py:272-282) is never called by the reference's drivers; "
-                              "wall absorption + re-injection on the GPU is PIC_L_DD.main_i")
+    """PIC_L.py:272-282: particles with x > L or x <= 0 are redrawn -- x = uniform(dx, L-dx),
+    v = normal(0, sqrt(kBT/mp)) -- in index order from the global legacy stream.  The device finds
+    them (flag + stable compaction); the draws are the reference's; x and v are modified in place
+    and returned, like there."""
+    idx = ops.l_outside(np.asarray(x, dtype=np.float64)[:N], L)
+    s = np.sqrt(kBT / mp)
+    for i in idx:
+        x[i] = np.random.uniform(1. * dx, L - 1. * dx)
+        v[i] = np.random.normal(0.0, s, 1)[0]
+    return x, v
 
 
 def applyBoundaryConditionsPeriodic(x, v, m, N, L, dx, kBT):

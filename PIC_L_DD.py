@@ -63,12 +63,15 @@ def laplacian1D(Ng):
 
 
 def solvePoisson(dx, Ng, rho, kBT, tol, maxiter, phi0):
-    raise NotImplementedError("PIC_L_DD.solvePoisson (Boltzmann-Newton, PIC_L_DD.py:116-147) is never called by the "
-                              "reference's drivers; the Newton-Boltzmann solve on the GPU is pygcpic.Grid.solve_for_phi_*")
+    """PIC_L_DD.py:116-147: Boltzmann-Newton solve on Ng nodes as written (reference node Ng/2, the
+    three-entry last row of laplacian1D, `while resid > tol and k <= maxiter`); the whole Newton
+    loop is one kernel launch, a PCR solve per iteration in place of scipy.sparse.linalg.inv."""
+    return ops.newton_boltzmann_l(np.asarray(rho)[:Ng], phi0, dx, kBT, tol, maxiter, periodic=False)
 
 
 def solvePoissonPeriodic(dx, Ng, rho, kBT, tol, maxiter, phi0):
-    raise NotImplementedError("PIC_L_DD.solvePoissonPeriodic (PIC_L_DD.py:149-176) is never called by the reference's drivers")
+    """PIC_L_DD.py:149-176: the periodic variant on Ng nodes (cyclic system by Sherman-Morrison)."""
+    return ops.newton_boltzmann_l(np.asarray(rho)[:Ng], phi0, dx, kBT, tol, maxiter, periodic=True)
 
 
 def solvePoissonPeriodicElectronsNeutralized(dx, Ng, rho, kBT, tol, maxiter, phi0):
@@ -159,27 +162,40 @@ def main_i(T, nplot, N=40000, Ng=51, dt=1E-12, dx=0.00001, Ti=10.0 * 11600., Te=
     KE, EE, TT, jbias = [], [], [], []
     kBTe_now = sim.kBTe_from(*sim.moments())       # np.std(u0)**2*me/e; afterwards it comes with the step's diagnostics
     t_loop = time.perf_counter()
-    for t in range(T + 1):
-        print('t: ', t)
-        print('kBTe: ', kBTe_now)
-        k, r = sim.step()
-        print("Iterations: ", k)
-        print("r: ", r)
-        d = sim.diagnostics()
-        kBTe_now = d["kBTe"]
-        EE.append(d["EE"]); KE.append(d["KE"]); TT.append(t * dt); jbias.append(d["jbias"])
-        if plt is not None and (t % nplot == 0):
-            st = sim.download()
-            h = N // 2
-            for fig, sl, name, size in ((1, slice(h, N), 'ps_i_', 2.0), (4, slice(0, h), 'ps_e_', 0.5)):
-                plt.figure(fig); plt.clf()
-                uu = st["u0"][sl]
-                plt.scatter(st["x0"][sl], np.sign(uu) * uu * uu * 0.5 * m[sl] / e, s=size)
-                plt.axis([0.0, L, -100.0, 100.0])
-                plt.savefig('plots/' + name + str(t))
-            plt.figure(3); plt.clf()
-            plt.plot(X, st["E0"], linewidth=lw)
-            plt.savefig('plots/e_' + str(t))
+    pending = False
+
+    def finish_step():
+        """EE, KE, jbias of the step that just ran (PIC_L_DD.py:548-551).  Their device pass was launched
+        right after the step; the numbers are read when the host next has to wait for the device."""
+        d = sim.diagnostics_end()
+        EE.append(d["EE"]); KE.append(d["KE"]); jbias.append(d["jbias"])
+        return d["kBTe"]
+    with sim.draws.hold():                           # the legacy stream's state stays in C for the duration of the loop
+        for t in range(T + 1):
+            if pending:
+                kBTe_now = finish_step()
+            print('t: ', t)
+            print('kBTe: ', kBTe_now)
+            k, r = sim.step()
+            print("Iterations: ", k)
+            print("r: ", r)
+            sim.diagnostics_begin()
+            pending = True
+            TT.append(t * dt)
+            if plt is not None and (t % nplot == 0):
+                st = sim.download()
+                h = N // 2
+                for fig, sl, name, size in ((1, slice(h, N), 'ps_i_', 2.0), (4, slice(0, h), 'ps_e_', 0.5)):
+                    plt.figure(fig); plt.clf()
+                    uu = st["u0"][sl]
+                    plt.scatter(st["x0"][sl], np.sign(uu) * uu * uu * 0.5 * m[sl] / e, s=size)
+                    plt.axis([0.0, L, -100.0, 100.0])
+                    plt.savefig('plots/' + name + str(t))
+                plt.figure(3); plt.clf()
+                plt.plot(X, st["E0"], linewidth=lw)
+                plt.savefig('plots/e_' + str(t))
+        if pending:
+            finish_step()
     sim.check()
     t_loop = time.perf_counter() - t_loop
     if os.environ.get("PIC_TIMING"):

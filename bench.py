@@ -178,7 +178,7 @@ def cpu_port_run(w, n_sample, steps, warmup, threads=None):
     host cores.  Bounded sample of the same workload: same grid, same physics, n_sample
     particles (p2c rescaled so the plasma density is unchanged)."""
     from oracle import c_oracle
-    threads = threads or host_threads()
+    threads = c_oracle.team_size(threads or host_threads())      # what OpenMP grants, not what was asked for
     n = int(n_sample); n -= n % 2
     rs = np.random.RandomState(1)
     h = n // 2

@@ -89,6 +89,15 @@ int pic_dev_poisson_dirichlet(const double* rho, double* phi, int n, double dx, 
  * iters_out: device int[1] receiving the Newton iteration count. */
 int pic_dev_newton_boltzmann(const double* src, double* phi, int n, double dx, double n0, double Te,
                              int bc, double tol, int iter_max, int* iters_out, void* stream);
+/* The Boltzmann-Newton solves of the other two codes, as written there (reference node n/2,
+ * `while resid > tol and k <= maxiter`, resid = |dphi|_2, start from the phi passed in):
+ * periodic 0: PIC_L.solvePoisson :146-177 == PIC_L_DD.solvePoisson :116-147 (laplacian1D with its
+ *             three-entry last row [1,1,-2], F[0]=phi[0], F[-1]=phi[-1]);
+ * periodic 1: PIC_L.solvePoissonPeriodic :179-206 (n = Ng+1) == PIC_L_DD.solvePoissonPeriodic
+ *             :149-176 (n = Ng): cyclic system by Sherman-Morrison, work = n doubles of scratch.
+ * The reference inverts J with scipy.sparse.linalg.inv; here PCR.  n <= PIC_PCR_SMEM_MAX. */
+int pic_dev_newton_boltzmann_l(const double* rho, double* phi, int n, double dx, double kBT, double tol, int maxiter,
+                               int periodic, double* work, int* iters_out, void* stream);
 
 /* ------------------------------------------------------------------------- *
  * Host draw service of the RNG-parity mode (no GPU involved): NumPy's legacy MT19937 stream
@@ -194,15 +203,16 @@ int pic_dev_dd_picard_iter3(const pic_dd_params* p, const double* x0, const doub
 /* u1 of the last iteration after the fact: x1_prev/x1_last are that iteration's input and output
  * positions, Es the field it gathered with, `first` whether it was the first iteration of the
  * step.  Particles absorbed before it get the reference's 0.0 (PIC_L_DD.py:459-462). */
-/* pic_dev_dd_picard_iter3 with the ABSORPTION LOG: every particle this launch absorbs appends
- * (iteration << 32 | slot) to dead_log[dead_cap] through the device counter *dead_count (which may
+/* pic_dev_dd_picard_iter3 with the ABSORPTION LOG: every particle this launch absorbs appends the
+ * int32 quadruple {slot, original index (orig[slot], or the slot when orig == NULL), iteration, 0}
+ * to dead_buf = int32[4 + 4*dead_cap] (16-byte aligned), whose word 0 is the device counter (it may
  * exceed dead_cap: entries beyond the capacity are dropped and the caller falls back to scanning
- * the flags).  The re-injection visits the logged slots instead of scanning N flags, and the
- * iteration number orders the vionout tally (PIC_L_DD.py:497-503). */
+ * the flags).  The re-injection visits the logged slots instead of scanning N flags, in the
+ * reference's index order, and the iteration number orders the vionout tally (PIC_L_DD.py:497-503). */
 int pic_dev_dd_picard_iter4(const pic_dd_params* p, const double* x0, const double* u0, const double* x1_in,
                             double* x1_out, double* u1, int8_t* active, const double* Es, double* acc, int first,
-                            int* range_err, const int32_t* done, int64_t* dead_log, int32_t* dead_count,
-                            int32_t dead_cap, int32_t iteration, void* stream);
+                            int* range_err, const int32_t* done, int32_t* dead_buf, int32_t dead_cap,
+                            const int32_t* orig, int32_t iteration, void* stream);
 int pic_dev_dd_commit_u(const pic_dd_params* p, const double* x0, const double* u0, const double* x1_prev,
                         const double* x1_last, const int8_t* active, const double* Es, double* u1, int first,
                         int* range_err, void* stream);
@@ -286,10 +296,10 @@ int pic_dev_dd_apply_draws2(const int32_t* slot, const int32_t* orig, const doub
  * device-mode thermostat (every active particle redraws u,v,w from sigma[species] with probability
  * gamma).  Philox is keyed by the ORIGINAL global index orig[i] + global_offset (orig == NULL: the
  * slot), and v0/w0 are addressed by it. */
-int pic_dev_dd_reinject_philox_log(const pic_dd_params* p, const int64_t* dead_log, const int32_t* dead_count,
-                                   int32_t dead_cap, double* x0, double* u0, double* v0, double* w0, int8_t* active,
-                                   const int32_t* orig, const double sigma[2], uint64_t seed, uint64_t step,
-                                   int64_t global_offset, void* stream);
+int pic_dev_dd_reinject_philox_log(const pic_dd_params* p, const int32_t* dead_buf, int32_t dead_cap, double* x0,
+                                   double* u0, double* v0, double* w0, int8_t* active, const int32_t* orig,
+                                   const double sigma[2], uint64_t seed, uint64_t step, int64_t global_offset,
+                                   void* stream);
 /* pic_dev_dd_reinject_philox with the original-index payload (draws keyed by orig[i] + global_offset,
  * v0/w0 written at orig[i]) and a guard: when dead_count != NULL and *dead_count <= dead_cap the
  * kernel returns at entry, because pic_dev_dd_reinject_philox_log has visited every dead slot (and
@@ -427,6 +437,16 @@ int pic_dev_l_interpolate(const double* F, const double* x, double* out, int64_t
 /* PIC_L.weightDensitiesPeriodic :100-118 (v==NULL) / weightCurrentsPeriodic :62-80; folds included */
 int pic_dev_l_weight(const double* x, const double* q, const double* v, double* out, int64_t N, int Ng,
                      double dx, double p2c, int* range_err, void* stream);
+/* PIC_L.weightDensities :83-98 (v==NULL) / weightCurrents :48-60: bounded CIC on Ng nodes, no folds */
+int pic_dev_l_weight_bounded(const double* x, const double* q, const double* v, double* out, int64_t N, int Ng,
+                             double dx, double p2c, int* range_err, void* stream);
+/* PIC_L.pushParticlesImplicit :261-270 (function form of the Crank-Nicolson push; per-particle q, m) */
+int pic_dev_l_push_implicit(const double* x0, const double* xh, const double* v, const double* q, const double* m,
+                            const double* Eh, double* xout, double* vout, int64_t N, int Ng, double dx, double dt,
+                            int* range_err, void* stream);
+/* PIC_L.applyBoundaryConditions :272-282, device half: flags[i] = 0 where x > L or x <= 0, else 1 (the host
+ * then redraws those particles from the legacy stream in index order and scatters them back) */
+int pic_dev_l_outside_flags(const double* x, int8_t* flags, int64_t N, double L, void* stream);
 /* Fused explicit step, particle phase (PIC_L.py:767-768 + next step's :763):
  * gather E at x, kick-drift-kick, wrap x%(L+dx), and deposit rho of the NEW positions
  * into rho_acc fp64[Ng+1] (zero on entry, raw CIC; fold applied by pic_dev_l_field_solve).

@@ -102,8 +102,9 @@ int dd_picard_step_c(long N, long n_split, int Ng, double dx, double dt, double 
             memset(priv, 0, sizeof(double) * 2 * Ng * (size_t)nthreads);
 #pragma omp parallel num_threads(nthreads)
             {
-                int t = omp_get_thread_num();
-                long lo = N * t / nthreads, hi = N * (t + 1) / nthreads;
+                /* the runtime may grant fewer threads than requested: partition by what it granted */
+                int t = omp_get_thread_num(), nt = omp_get_num_threads();
+                long lo = (long)((double)N * t / nt), hi = t + 1 == nt ? N : (long)((double)N * (t + 1) / nt);
                 iter_range(lo, hi, n_split, Ng, dx, dt, L, p2c, q, m, x0, u0, x1, u1, xs, active, Es,
                            priv + 2 * (size_t)Ng * t, priv + 2 * (size_t)Ng * t + Ng, k == 0);
             }
@@ -141,4 +142,18 @@ int dd_oracle_max_threads(void) {
 #else
     return 1;
 #endif
+}
+
+/* threads the runtime actually grants to a team of the requested size */
+int dd_oracle_team_size(int nthreads) {
+    int got = 1;
+#ifdef _OPENMP
+    if (nthreads < 1) nthreads = 1;
+#pragma omp parallel num_threads(nthreads)
+    {
+#pragma omp single
+        got = omp_get_num_threads();
+    }
+#endif
+    return got;
 }

@@ -34,11 +34,18 @@ def load():
                                           dp, dp, dp, dp, dp, dp, C.c_double, C.c_int, dp, dp, dp, dp,
                                           C.POINTER(C.c_double), C.c_int]
         _lib.dd_oracle_max_threads.restype = C.c_int
+        _lib.dd_oracle_team_size.restype = C.c_int
+        _lib.dd_oracle_team_size.argtypes = [C.c_int]
     return _lib
 
 
 def max_threads():
     return int(load().dd_oracle_max_threads())
+
+
+def team_size(nthreads):
+    """Threads OpenMP actually grants when `nthreads` are requested (what a timing should report)."""
+    return int(load().dd_oracle_team_size(int(nthreads)))
 
 
 def dd_picard_step(x0, u0, q2, m2, n_split, active, E0, p2c, Ng, dx, dt, L, tol, maxiter, nthreads=1):

@@ -532,9 +532,82 @@ def gen_gc_ion():
     print("pygcpic ionisation golden done;", {k_: int(np.sum(v_)) for k_, v_ in hist.items() if k_ not in ("n0", "added")})
 
 
+def gen_stub_functions():
+    """The module functions no reference driver calls (PIC_L.py:48-60,83-98,146-206,261-282;
+    PIC_L_DD.py:116-176; pygcpic.py:350-458), executed as they are on seeded inputs."""
+    l = refshim.load("PIC_L"); d = refshim.load("PIC_L_DD"); g = refshim.load("pygcpic")
+    rng = np.random.RandomState(21)
+    out = {}
+    Ng, dx = 64, 1e-5
+    L = dx * (Ng - 1)
+    N = 3000
+    x = adversarial_positions(Ng, dx, L, rng); x = x[(x > 0) & (x < L)][:N]; N = len(x)
+    q = np.where(rng.uniform(size=N) < 0.5, -l.e, l.e); m = np.where(q < 0, l.me, l.mp)
+    v = rng.normal(0, 1e5, N)
+    p2c = 3.0e9
+    out.update(Ng=Ng, dx=dx, x=x, q=q, m=m, v=v, p2c=p2c)
+    out["l_j"] = l.weightCurrents(x, q, v, p2c, Ng, N, dx)
+    out["l_rho"] = l.weightDensities(x, q, p2c, Ng, N, dx)
+    # Boltzmann-Newton solves: smooth positive charge density; the bounded variant does not converge as
+    # written (its last Jacobian row does not belong to F[-1] = phi[-1]), so it is pinned after a FIXED
+    # number of iterations (tol = 0 -> maxiter + 1 iterations)
+    kBT = l.kb * 116000.
+    X = np.arange(Ng) * dx
+    rho = l.e * 1e17 * (1 + 0.05 * np.cos(2 * np.pi * X / (Ng * dx)) + 0.02 * np.sin(6 * np.pi * X / (Ng * dx)))
+    phi0 = 0.3 * np.sin(np.pi * X / L)
+    out.update(kBT=kBT, rho_b=rho, phi0_b=phi0)
+    import warnings
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        out["l_phi_b1"] = l.solvePoisson(dx, Ng, rho.copy(), kBT, 0.0, 1, phi0.copy())
+        out["l_phi_b3"] = l.solvePoisson(dx, Ng, rho.copy(), kBT, 0.0, 3, phi0.copy())
+        out["dd_phi_b3"] = d.solvePoisson(dx, Ng, rho.copy(), kBT, 0.0, 3, phi0.copy())
+    rho1 = l.e * 1e17 * (1 + 0.05 * np.cos(2 * np.pi * np.arange(Ng + 1) / (Ng + 1)))
+    out["rho_p"] = rho1
+    out["l_phi_p"] = l.solvePoissonPeriodic(dx, Ng, rho1.copy(), kBT, 1e-8, 20, np.zeros(Ng + 1))
+    out["dd_phi_p"] = d.solvePoissonPeriodic(dx, Ng, rho1[:Ng].copy(), kBT, 1e-8, 20, np.zeros(Ng))
+    # implicit push, function form (periodic gather on Ng+1 nodes)
+    Eh = rng.normal(0, 1e4, Ng + 1)
+    xh = rng.uniform(0, (L + dx) * (1 - 1e-9), N)
+    out.update(Eh=Eh, xh=xh)
+    xo, vo = l.pushParticlesImplicit(x, xh, v, q, m, N, Ng, 1e-10, dx, Eh)
+    out["l_xi"] = xo; out["l_vi"] = vo
+    # applyBoundaryConditions: redraws x > L or x <= 0 from the global legacy stream
+    xb = x.copy(); vb = v.copy()
+    k = rng.choice(N, 40, replace=False)
+    xb[k[:20]] = L * (1 + rng.uniform(0, 0.1, 20)); xb[k[20:30]] = -rng.uniform(0, 1e-5, 10); xb[k[30:]] = 0.0
+    out["bc_x_in"] = xb.copy(); out["bc_v_in"] = vb.copy()
+    np.random.seed(5)
+    xb2, vb2 = l.applyBoundaryConditions(xb, vb, m, N, L, dx, kBT)
+    out["bc_x"] = xb2.copy(); out["bc_v"] = vb2.copy(); out["bc_next_uniform"] = np.random.uniform()
+    # pygcpic object-level ionisation attempts on a handful of particles
+    ng, Lg = 50, 5e-3
+    grid = g.Grid(ng, Lg, 60. * 11600.)
+    grid.n[:] = 2e15 * (1 + 0.3 * np.sin(np.arange(ng)))
+    np.random.seed(9)
+    rows = []
+    for t in range(60):
+        Z = 5 if t % 2 else 1
+        cs = [0, 0, 1, 2][t % 4] if Z == 5 else 0
+        pt = g.Particle(g.mp * (10.81 if Z == 5 else 1.0), cs, 2.0e6 * (1 + t % 3), 1.0, Z, grid=grid)
+        pt.r[0] = (0.03 + 0.9 * ((t * 0.6180339887) % 1.0)) * Lg
+        before = grid.added_particles
+        which = "first" if (t % 3 or Z == 1) else "nth"
+        import contextlib as _cl, io as _io
+        with _cl.redirect_stdout(_io.StringIO()):
+            if which == "first":
+                pt.attempt_first_ionization(2e-7, 60. * 11600., grid)
+            else:
+                pt.attempt_nth_ionization(2e-7, 60. * 11600., grid)
+        rows.append([Z, cs, pt.p2c, pt.r[0], 1.0 if which == "nth" else 0.0, float(pt.charge_state), grid.added_particles - before])
+    out.update(ion_rows=np.array(rows), ion_ng=ng, ion_L=Lg, ion_n=grid.n.copy(), ion_next_uniform=np.random.uniform())
+    np.savez_compressed(os.path.join(GOLD, "stub_functions.npz"), **out)
+    print("stub-function golden done; ionised:", int(sum(r[5] != r[1] for r in rows)), "of", len(rows))
+
+
 def main():
     os.makedirs(GOLD, exist_ok=True)
-    which = sys.argv[1:] or ["pypic", "pypicfull", "ddk", "ddm", "ddx", "l", "gc", "gcion"]
+    which = sys.argv[1:] or ["pypic", "pypicfull", "ddk", "ddm", "ddx", "l", "stubs", "gc", "gcion"]
     if "gcion" in which:
         gen_gc_ion()
     if "pypic" in which:
@@ -551,6 +624,8 @@ def main():
         gen_dd_main("vion", 2000, 51, 40, vion_after=5)
     if "l" in which:
         gen_pic_l()
+    if "stubs" in which:
+        gen_stub_functions()
     if "gc" in which:
         gen_gc()
 

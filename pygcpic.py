@@ -218,10 +218,36 @@ class Particle:
         self.from_wall = 0
         grid.add_particles(p2c)
 
-    def attempt_first_ionization(self, *a, **k):
-        raise NotImplementedError("Monte-Carlo ionisation (pygcpic.py:350-458) is a 'next' row (SURVEY.md 8f N3), not built yet")
+    def _ionization_attempt(self, table_state, dt, temperature, grid):
+        """Common body of pygcpic.py:385-399 / 440-458: rate from the tabulated coefficients, plasma
+        density gathered at the particle (plain CIC weights, on the device), probability
+        density^2 * rate * dx * dt / p2c, ONE uniform from the global legacy stream, and -- in both
+        routines -- the ionisation only if charge_state == 0 (tested after the draw)."""
+        from pypic_b200 import ionization, ops
+        if (int(self.Z), int(table_state)) not in ionization._TABLES:
+            raise UnboundLocalError("no rate table for Z=%r, charge_state=%r (the reference's tables cover H and B 0..2+)"
+                                    % (self.Z, table_state))
+        ionization_rate = ionization.rate(self.Z, table_state, temperature)
+        density = float(ops.dd_interpolate(grid.n, self.x, grid.ng, grid.dx)[0])
+        probability = density**2 * ionization_rate * grid.dx * dt / self.p2c
+        if np.random.uniform(0., 1.) < probability and self.charge_state == 0.:
+            return True
+        return False
 
-    attempt_nth_ionization = attempt_first_ionization
+    def attempt_first_ionization(self, dt, temperature, grid):
+        """pygcpic.py:350-399 (the table is chosen by Z alone)."""
+        if self._ionization_attempt(0, dt, temperature, grid):
+            self.charge_state = 1
+            grid.add_particles(self.p2c)
+
+    def attempt_nth_ionization(self, dt, temperature, grid):
+        """pygcpic.py:401-458 (boron only; the table follows the charge state)."""
+        if int(self.Z) != 5:
+            raise UnboundLocalError("attempt_nth_ionization has tables for boron (Z = 5) only, as in the reference")
+        if self._ionization_attempt(self.charge_state, dt, temperature, grid):
+            print(f'Ionized boron from {self.charge_state} to {self.charge_state+1}!')
+            self.charge_state += 1
+            grid.add_particles(self.p2c)
 
 
 def source_distribution_6D(grid, Ti, mass, vx=0.):
@@ -438,7 +464,11 @@ def run_sheath(grid, store, dt, steps, source_N, source, p2c, m, charge_state=1,
         grid.differentiate_phi_to_E_dirichlet()
         inactive_entry = (store.active != 1).to(torch.int8)
         contrib_entry = store.source_ion_flags(Z)
-        hits = store.push_6D(dt, grid, deposit=True)
+        # The fused kernel may deposit the survivors for the NEXT step only if nothing changes them in
+        # between: with Monte-Carlo ionisation the charge states change, wall-born particles leave
+        # mid-domain (pygcpic.py:1530-1541) and the deposit needs every particle's own charge state
+        # (:871-883), so that case deposits in its own pass at the top of the next step.
+        hits = store.push_6D(dt, grid, deposit=ionize_Te is None)
         ke, ang, _ = store.wall_hit_tallies()
         if ionize_Te is None:
             contrib_after = store.source_ion_flags(Z)
@@ -461,6 +491,9 @@ def run_sheath(grid, store, dt, steps, source_N, source, p2c, m, charge_state=1,
         out["length"].append(store.N); out["hits"].append(hits); out["deleted"].append(n_del)
         out["reactivated"].append(n_react); out["n0"].append(grid.n0); out["ekin"].append(ke); out["angle"].append(ang)
         if on_step is not None:
+            n_before = store.N
             on_step(grid, store)
+            if store.N != n_before or store._uniform is False:
+                grid.have_fused_n = False          # the callback changed the store: deposit it afresh next step
     store.check(); grid.check()
     return out

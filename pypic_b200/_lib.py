@@ -64,15 +64,16 @@ _SIGS = {
     "pic_dev_poisson_periodic": [P, P, I32, F64, I32, P, P],
     "pic_dev_poisson_dirichlet": [P, P, I32, F64, P, P],
     "pic_dev_newton_boltzmann": [P, P, I32, F64, F64, F64, I32, F64, I32, P, P],
+    "pic_dev_newton_boltzmann_l": [P, P, I32, F64, F64, F64, I32, I32, P, P, P],
     "pic_dev_dd_interpolate": [P, P, P, I64, I32, F64, P, P],
     "pic_dev_dd_weight": [P, P, P, P, P, I64, I32, F64, F64, F64, P, P],
     "pic_dev_dd_picard_iter": [C.POINTER(DDParams), P, P, P, P, P, P, P, I32, P, P],
     "pic_dev_dd_picard_iter2": [C.POINTER(DDParams), P, P, P, P, P, P, P, P, I32, P, P],
     "pic_dev_dd_picard_iter3": [C.POINTER(DDParams), P, P, P, P, P, P, P, P, I32, P, P, P],
-    "pic_dev_dd_picard_iter4": [C.POINTER(DDParams), P, P, P, P, P, P, P, P, I32, P, P, P, P, I32, I32, P],
+    "pic_dev_dd_picard_iter4": [C.POINTER(DDParams), P, P, P, P, P, P, P, P, I32, P, P, P, I32, P, I32, P],
     "pic_dev_dd_sort_by_cell2": [C.POINTER(DDParams), P, P, P, P, P, P, P, P],
     "pic_dev_dd_apply_draws2": [P, P, P, P, P, P, I64, P, P, P, P, P, P],
-    "pic_dev_dd_reinject_philox_log": [C.POINTER(DDParams), P, P, I32, P, P, P, P, P, P, C.POINTER(C.c_double * 2),
+    "pic_dev_dd_reinject_philox_log": [C.POINTER(DDParams), P, I32, P, P, P, P, P, P, C.POINTER(C.c_double * 2),
                                        C.c_uint64, C.c_uint64, I64, P],
     "pic_dev_dd_reinject_philox2": [C.POINTER(DDParams), P, P, P, P, P, P, C.POINTER(C.c_double * 2), C.c_uint64,
                                     C.c_uint64, I64, P, I32, P],
@@ -117,6 +118,9 @@ _SIGS = {
     "pic_dev_wrap_periodic": [P, I64, F64, P],
     "pic_dev_l_interpolate": [P, P, P, I64, I32, F64, P, P],
     "pic_dev_l_weight": [P, P, P, P, I64, I32, F64, F64, P, P],
+    "pic_dev_l_weight_bounded": [P, P, P, P, I64, I32, F64, F64, P, P],
+    "pic_dev_l_push_implicit": [P, P, P, P, P, P, P, P, I64, I32, F64, F64, P, P],
+    "pic_dev_l_outside_flags": [P, P, I64, F64, P],
     "pic_dev_l_push_deposit": [C.POINTER(LParams), P, P, P, P, P, P],
     "pic_dev_l_field_solve": [C.POINTER(LParams), P, P, P, P, P, P, P],
     "pic_dev_gc_interpolate": [P, P, P, I64, I32, F64, P, P],

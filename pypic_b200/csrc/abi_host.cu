@@ -262,6 +262,7 @@ int pic_host_dd_step_batches(const pic_dd_params* p, int nbatch, const double* c
         return PIC_OK;
     };
     q.err_host[0] = q.err_host[1] = 0;
+    long long bad_total = 0;        // range errors of every batch (the two pinned words are reused per slot)
     if ((rc = upload(0))) return rc;
     for (int b = 0; b < nbatch; ++b) {
         const int s = b & (nslot - 1);
@@ -298,14 +299,19 @@ int pic_host_dd_step_batches(const pic_dd_params* p, int nbatch, const double* c
         PIC_CHECK_CUDA(cudaMemcpyAsync(j1[b], dj1, (size_t)Ng * 8, cudaMemcpyDeviceToHost, q.d2h));
         PIC_CHECK_CUDA(cudaMemcpyAsync(&q.err_host[s], derr[s], sizeof(int), cudaMemcpyDeviceToHost, q.d2h));
         PIC_CHECK_CUDA(cudaEventRecord(q.ev_out[s], q.d2h));
-        if (b >= 1) {   // the previous batch's results (other slot) must be complete before its error word is read
-            PIC_CHECK_CUDA(cudaEventSynchronize(q.ev_out[(b - 1) & (nslot - 1)]));
+        if (b >= 1) {   // the previous batch's results (other slot) are complete: take its error word before the
+                        // slot's next batch (b+1) overwrites it
+            const int sp = (b - 1) & (nslot - 1);
+            PIC_CHECK_CUDA(cudaEventSynchronize(q.ev_out[sp]));
+            bad_total += q.err_host[sp];
+            q.err_host[sp] = 0;
         }
     }
     PIC_CHECK_CUDA(cudaStreamSynchronize(q.d2h));
-    const int bad = q.err_host[0] + q.err_host[1];
+    bad_total += q.err_host[(nbatch - 1) & (nslot - 1)];
+    const long long bad = bad_total;
     if (bad) {
-        pic::set_error("dd_step: %d particle position(s) outside the grid (reference behaviour undefined); indices were clamped", bad);
+        pic::set_error("dd_step: %lld particle position(s) outside the grid (reference behaviour undefined); indices were clamped", bad);
         return PIC_ERR_RANGE;
     }
     return PIC_OK;

@@ -34,18 +34,20 @@ struct DDK {
     // iterations it expects without a round trip per iteration
     const int* done;
     double fs1, fi1;             // 2^s and 2^-s: one hi unit = 2^-s, one lo unit = 2^-(s+32)
-    // absorption log: every particle absorbed by this launch appends (iteration << 32 | slot) -- the
-    // re-injection then visits the few dead slots instead of scanning N flags, and the iteration
-    // orders the vionout tally (PIC_L_DD.py:497-503).  Absorption is on the rare path only.
-    long long* dead_log;
-    int* dead_cnt;
+    // absorption log: every particle absorbed by this launch appends {slot, original index, Picard
+    // iteration} -- the re-injection then visits the few dead slots instead of scanning N flags, in
+    // the reference's index order (PIC_L_DD.py:429-450), and the iteration orders the vionout tally
+    // (:497-503).  Absorption is on the rare path only.  dead_buf: int32 [count, 0, 0, 0 | cap x int4]
+    int* dead_buf;
+    const int* oid;              // original index of the particle in each slot (nullptr: the slot itself)
     int dead_cap, iter;
     long long slot0;             // slot of particle 0 of this launch (tail launches run on offset pointers)
 };
 __device__ __forceinline__ void dead_note(const DDK& k, long long i) {
-    if (k.dead_cnt) {
-        const int at = atomicAdd(k.dead_cnt, 1);
-        if (at < k.dead_cap) k.dead_log[at] = ((long long)k.iter << 32) | (k.slot0 + i);
+    if (k.dead_buf) {
+        const int at = atomicAdd(k.dead_buf, 1);
+        const int slot = (int)(k.slot0 + i);
+        if (at < k.dead_cap) ((int4*)(k.dead_buf + 4))[at] = make_int4(slot, k.oid ? k.oid[slot] : slot, k.iter, 0);
     }
 }
 
@@ -60,7 +62,7 @@ static DDK make_ddk(const pic_dd_params* p) {
         k.c2[s] = p->dt * p->dt * qm;
     }
     k.fix = nullptr; k.ferr = nullptr; k.fs1 = 1.0; k.fi1 = 1.0; k.done = nullptr;
-    k.dead_log = nullptr; k.dead_cnt = nullptr; k.dead_cap = 0; k.iter = 0; k.slot0 = 0;
+    k.dead_buf = nullptr; k.oid = nullptr; k.dead_cap = 0; k.iter = 0; k.slot0 = 0;
     if (p->flags & 128) {
         // one contribution is q*p2c*u*w/dx with |u| < c: |v| < amax < 2^e, so |v|*2^(31-e) < 2^31 and a
         // node can take 2^31 contributions before the hi word overflows; the lo word carries 32 more bits
@@ -1524,13 +1526,13 @@ __global__ void __launch_bounds__(SORTB_T) dd_sort_scatter_big_k(DDK k, const do
     const unsigned lane = threadIdx.x & 31;
     for (long long base = beg; base < end; base += SORTB_T * SORTB_PER) {
         double X[SORTB_PER], U[SORTB_PER];
-        int key[SORTB_PER], res[SORTB_PER];
+        int key[SORTB_PER], res[SORTB_PER], O[SORTB_PER];
         unsigned peers[SORTB_PER];
 #pragma unroll
         for (int j = 0; j < SORTB_PER; ++j) {
             const long long i = base + j * SORTB_T + threadIdx.x;
-            X[j] = 0.; U[j] = 0.;
-            if (i < end) { X[j] = x0[i]; if (!PERM) U[j] = u0[i]; }
+            X[j] = 0.; U[j] = 0.; O[j] = (int)i;
+            if (i < end) { X[j] = x0[i]; if (!PERM) U[j] = u0[i]; if (oid) O[j] = oid[i]; }
         }
         // one reservation per distinct key per warp; the four atomics of a thread are independent
 #pragma unroll
@@ -1551,7 +1553,7 @@ __global__ void __launch_bounds__(SORTB_T) dd_sort_scatter_big_k(DDK k, const do
                 if (PERM) ((int32_t*)us)[pos] = (int32_t)i; else us[pos] = U[j];
                 if (vs) vs[pos] = v0[i];
                 if (ws) ws[pos] = w0[i];
-                if (oids) oids[pos] = oid ? oid[i] : (int32_t)i;
+                if (oids) oids[pos] = O[j];
             }
         }
     }
@@ -1601,14 +1603,14 @@ __global__ void moments_k(const double* __restrict__ u, long long N, double* __r
     if (threadIdx.x == 0) { atomicAdd(out, s1); atomicAdd(out + 1, s2); }
 }
 // slots named in the absorption log -> re-injected with Philox draws (no flag scan)
-__global__ void dd_reinject_philox_log_k(DDK k, const long long* __restrict__ log, const int* __restrict__ cnt,
-                                         double* __restrict__ x0, double* __restrict__ u0, double* __restrict__ v0,
-                                         double* __restrict__ w0, int8_t* __restrict__ active, double s0, double s1,
-                                         uint64_t seed, uint64_t step, long long goff, const int32_t* __restrict__ oid) {
-    const int n = *cnt;
+__global__ void dd_reinject_philox_log_k(DDK k, const int* __restrict__ buf, double* __restrict__ x0,
+                                         double* __restrict__ u0, double* __restrict__ v0, double* __restrict__ w0,
+                                         int8_t* __restrict__ active, double s0, double s1, uint64_t seed, uint64_t step,
+                                         long long goff, const int32_t* __restrict__ oid) {
+    const int n = buf[0];
     if (n > k.dead_cap) return;          // overflow: the flag scan (dd_reinject_philox_k) takes over
     for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < n; t += gridDim.x * blockDim.x)
-        dd_reinject_one(k, (long long)(log[t] & 0xffffffffll), x0, u0, v0, w0, active, s0, s1, seed, step, goff, oid);
+        dd_reinject_one(k, (long long)buf[4 + 4 * t], x0, u0, v0, w0, active, s0, s1, seed, step, goff, oid);
 }
 // Thermostat, device mode (PIC_L_DD.py:419-427): every ACTIVE particle redraws u,v,w from the ION
 // temperature (as written: sqrt(kBTi/m[i]) for both species) with probability gamma.  Philox keyed
@@ -1806,20 +1808,20 @@ int pic_dev_dd_picard_iter2(const pic_dd_params* p, const double* x0, const doub
 int pic_dev_dd_picard_iter3(const pic_dd_params* p, const double* x0, const double* u0, const double* x1_in,
                             double* x1_out, double* u1, int8_t* active, const double* Es, double* acc, int first,
                             int* range_err, const int32_t* done, void* stream) {
-    return pic_dev_dd_picard_iter4(p, x0, u0, x1_in, x1_out, u1, active, Es, acc, first, range_err, done, nullptr, nullptr, 0,
+    return pic_dev_dd_picard_iter4(p, x0, u0, x1_in, x1_out, u1, active, Es, acc, first, range_err, done, nullptr, 0, nullptr,
                                    0, stream);
 }
 
 int pic_dev_dd_picard_iter4(const pic_dd_params* p, const double* x0, const double* u0, const double* x1_in,
                             double* x1_out, double* u1, int8_t* active, const double* Es, double* acc, int first,
-                            int* range_err, const int32_t* done, int64_t* dead_log, int32_t* dead_count,
-                            int32_t dead_cap, int32_t iteration, void* stream) {
+                            int* range_err, const int32_t* done, int32_t* dead_buf, int32_t dead_cap,
+                            const int32_t* orig, int32_t iteration, void* stream) {
     PIC_REQUIRE(p && x0 && u0 && x1_in && x1_out && active && Es && acc, "dd_picard_iter: null pointer");
     PIC_REQUIRE(p->N >= 0 && p->Ng >= 3 && p->dx > 0 && p->dt > 0, "dd_picard_iter: bad parameters");
-    PIC_REQUIRE(!dead_count || (dead_log && dead_cap > 0), "dd_picard_iter: absorption log without storage");
+    PIC_REQUIRE(!dead_buf || (dead_cap > 0 && ((uintptr_t)dead_buf & 15) == 0), "dd_picard_iter: absorption log without storage / unaligned");
     if (p->N == 0) return PIC_OK;
     DDK k = make_ddk(p);
-    k.dead_log = (long long*)dead_log; k.dead_cnt = dead_count; k.dead_cap = dead_cap; k.iter = iteration;
+    k.dead_buf = dead_buf; k.oid = orig; k.dead_cap = dead_cap; k.iter = iteration;
     PIC_REQUIRE(!(p->flags & 128) || !(p->flags & (1 | 2 | 4 | 8)),
                 "dd_picard_iter: the reproducible build (flags bit7) exists for the default window kernel only");
     ddk_bind_fix(k, acc, range_err);
@@ -2221,16 +2223,16 @@ int pic_dev_dd_apply_draws2(const int32_t* slot, const int32_t* orig, const doub
     return PIC_OK;
 }
 
-int pic_dev_dd_reinject_philox_log(const pic_dd_params* p, const int64_t* dead_log, const int32_t* dead_count,
-                                   int32_t dead_cap, double* x0, double* u0, double* v0, double* w0, int8_t* active,
-                                   const int32_t* orig, const double sigma[2], uint64_t seed, uint64_t step,
-                                   int64_t global_offset, void* stream) {
-    PIC_REQUIRE(p && dead_log && dead_count && dead_cap > 0 && x0 && u0 && active && sigma, "dd_reinject_philox_log: null pointer");
+int pic_dev_dd_reinject_philox_log(const pic_dd_params* p, const int32_t* dead_buf, int32_t dead_cap, double* x0,
+                                   double* u0, double* v0, double* w0, int8_t* active, const int32_t* orig,
+                                   const double sigma[2], uint64_t seed, uint64_t step, int64_t global_offset,
+                                   void* stream) {
+    PIC_REQUIRE(p && dead_buf && dead_cap > 0 && x0 && u0 && active && sigma, "dd_reinject_philox_log: null pointer");
     if (p->N == 0) return PIC_OK;
     DDK k = make_ddk(p);
     k.dead_cap = dead_cap;
-    dd_reinject_philox_log_k<<<64, 256, 0, (cudaStream_t)stream>>>(k, (const long long*)dead_log, dead_count, x0, u0, v0, w0,
-                                                                  active, sigma[0], sigma[1], seed, step, global_offset, orig);
+    dd_reinject_philox_log_k<<<64, 256, 0, (cudaStream_t)stream>>>(k, dead_buf, x0, u0, v0, w0, active, sigma[0], sigma[1], seed,
+                                                                  step, global_offset, orig);
     PIC_CHECK_LAUNCH();
     return PIC_OK;
 }

@@ -354,6 +354,96 @@ __global__ void __launch_bounds__(PCR_THREADS) newton_boltzmann_k(const double* 
     if (threadIdx.x == 0 && iters_out) *iters_out = it;
 }
 
+
+// ------------------------------------------------------------------ PIC_L / PIC_L_DD Boltzmann-Newton solves
+// PIC_L.solvePoisson :146-177 = PIC_L_DD.solvePoisson :116-147 (periodic == 0) and
+// PIC_L.solvePoissonPeriodic :179-206 = PIC_L_DD.solvePoissonPeriodic :149-176 (periodic == 1), whole
+// Newton loop in one launch.  As written there: c0 = rho[mid]/eps0 (mid = n/2), c1 = e/kBT,
+// F = A phi - dx^2 c0 exp(c1 (phi - phi[mid])) + dx^2 rho/eps0, J = A + diag(-dx^2 c0 c1 exp(..)),
+// dphi = inv(J) F, loop `while resid > tol and k <= maxiter` with resid = |dphi|_2.
+//  bounded: A = laplacian1D (first row e_0, LAST ROW [.., 1, 1, -2]); F[0] = phi[0], F[-1] = phi[-1];
+//           J[0,0] = 1 - dx^2 c0 c1, J[-1,-1] = -2 - dx^2 c0 c1.  The three-entry last row is reduced with
+//           row n-2 before the tridiagonal (PCR) solve.
+//  periodic: A cyclic [1,-2,1]; the cyclic system is solved by Sherman-Morrison (two PCR solves).
+__global__ void __launch_bounds__(PCR_THREADS) newton_boltzmann_l_k(const double* __restrict__ rho,
+                                                                    double* __restrict__ phi, int n, double dx,
+                                                                    double kBT, double tol, int maxiter, int periodic,
+                                                                    double* __restrict__ work,
+                                                                    int* __restrict__ iters_out) {
+    extern __shared__ double sm[];
+    __shared__ double scratch[33];
+    __shared__ double s_bc[4];
+    double *sa = sm, *sb = sm + n, *sc = sm + 2 * n, *sd = sm + 3 * n;
+    const int mid = n / 2;
+    const double dx2 = dx * dx;
+    const double c0 = rho[mid] / PIC_EPS0;
+    const double c1 = PIC_E / kBT;
+    double resid = 1.0;
+    int k = 0;
+    while (resid > tol && k <= maxiter) {
+        const double pm = phi[mid];
+        // pass 0: the Newton system; periodic pass 1: the same matrix with the Sherman-Morrison vector u as rhs
+        for (int pass = 0; pass < (periodic ? 2 : 1); ++pass) {
+            for (int i = threadIdx.x; i < n; i += blockDim.x) {
+                const double p = phi[i];
+                const double ex = exp(c1 * (p - pm));
+                const double D = -dx2 * c0 * c1 * ex;
+                double av = 1.0, bv = -2.0 + D, cv = 1.0, F;
+                if (periodic) {
+                    const double pl = phi[i == 0 ? n - 1 : i - 1], pr = phi[i == n - 1 ? 0 : i + 1];
+                    F = (pl - 2.0 * p + pr) - dx2 * c0 * ex + dx2 * (rho[i] / PIC_EPS0);
+                    // J = T + u v^T, gamma = -b0: T has b0 - gamma and b_{n-1} - 1/gamma on the corners' diagonal
+                    const double gamma = -(-2.0 + (-dx2 * c0 * c1 * exp(c1 * (phi[0] - pm))));
+                    if (i == 0) { bv = bv - gamma; av = 0.0; }
+                    if (i == n - 1) { bv = bv - 1.0 / gamma; cv = 0.0; }
+                    if (pass == 1) F = (i == 0) ? gamma : (i == n - 1 ? 1.0 : 0.0);
+                    if (i == 0 && pass == 0) s_bc[0] = gamma;
+                } else {
+                    F = (i == 0 || i == n - 1) ? p : (phi[i - 1] - 2.0 * p + phi[i + 1]) - dx2 * c0 * ex + dx2 * (rho[i] / PIC_EPS0);
+                    if (i == 0) { bv = 1.0 + (-dx2 * c0 * c1); av = 0.0; cv = 0.0; }
+                    if (i == n - 1) { bv = -2.0 + (-dx2 * c0 * c1); av = 1.0; cv = 0.0; }     // + the entry at n-3, folded below
+                }
+                sa[i] = av; sb[i] = bv; sc[i] = cv; sd[i] = F;
+            }
+            __syncthreads();
+            if (!periodic && threadIdx.x == 0) {
+                // last row [1, 1, b] minus row n-2 ([1, b', 1]) -> [0, 1 - b', b - 1], rhs F[n-1] - F[n-2]
+                sa[n - 1] = 1.0 - sb[n - 2];
+                sb[n - 1] = sb[n - 1] - 1.0;
+                sd[n - 1] = sd[n - 1] - sd[n - 2];
+            }
+            __syncthreads();
+            pcr_smem(sa, sb, sc, sd, n);
+            if (periodic && pass == 0) {
+                for (int i = threadIdx.x; i < n; i += blockDim.x) work[i] = sd[i];      // y
+                __syncthreads();
+            }
+        }
+        double fac = 0.0;
+        if (periodic) {
+            // x = y - z (v.y)/(1 + v.z), v = [1, 0, ..., 0, 1/gamma]
+            if (threadIdx.x == 0) {
+                const double g = s_bc[0];
+                const double vy = work[0] + work[n - 1] / g, vz = sd[0] + sd[n - 1] / g;
+                s_bc[1] = vy / (1.0 + vz);
+            }
+            __syncthreads();
+            fac = s_bc[1];
+        }
+        double s = 0.0;
+        for (int i = threadIdx.x; i < n; i += blockDim.x) {
+            const double dp = periodic ? work[i] - fac * sd[i] : sd[i];
+            phi[i] = phi[i] - dp;
+            s += dp * dp;
+        }
+        s = block_reduce<0>(s, scratch);
+        resid = sqrt(s);
+        ++k;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0 && iters_out) *iters_out = k;
+}
+
 }  // namespace pic
 
 using namespace pic;
@@ -451,6 +541,19 @@ int pic_dev_newton_boltzmann(const double* src, double* phi, int n, double dx, d
     PIC_CHECK_CUDA(cudaFuncSetAttribute(newton_boltzmann_k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     newton_boltzmann_k<<<1, PCR_THREADS, smem, (cudaStream_t)stream>>>(src, phi, n, dx, n0, Te, bc, tol, iter_max,
                                                                        iters_out);
+    PIC_CHECK_LAUNCH();
+    return PIC_OK;
+}
+
+int pic_dev_newton_boltzmann_l(const double* rho, double* phi, int n, double dx, double kBT, double tol, int maxiter,
+                               int periodic, double* work, int* iters_out, void* stream) {
+    PIC_REQUIRE(rho && phi && n >= 4 && kBT > 0 && (periodic == 0 || periodic == 1), "newton_boltzmann_l: bad argument");
+    PIC_REQUIRE(n <= PIC_PCR_SMEM_MAX, "newton_boltzmann_l: n exceeds PIC_PCR_SMEM_MAX");
+    PIC_REQUIRE(!periodic || work, "newton_boltzmann_l: the periodic solve needs a work buffer of n doubles");
+    size_t smem = (size_t)4 * n * sizeof(double);
+    PIC_CHECK_CUDA(cudaFuncSetAttribute(newton_boltzmann_l_k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    newton_boltzmann_l_k<<<1, PCR_THREADS, smem, (cudaStream_t)stream>>>(rho, phi, n, dx, kBT, tol, maxiter, periodic, work,
+                                                                        iters_out);
     PIC_CHECK_LAUNCH();
     return PIC_OK;
 }

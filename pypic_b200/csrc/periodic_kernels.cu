@@ -300,6 +300,58 @@ __global__ void l_fold_k(const double* __restrict__ acc, double* __restrict__ ou
     }
 }
 
+// PIC_L.weightCurrents :48-60 / weightDensities :83-98: BOUNDED CIC on Ng nodes, no wall terms, no fold
+template <bool CURRENT>
+__global__ void l_weight_bounded_k(const double* __restrict__ x, const double* __restrict__ q, const double* __restrict__ v,
+                                   double* __restrict__ acc, long long N, int Ng, double dx, double p2c,
+                                   int* __restrict__ range_err) {
+    extern __shared__ double sm[];
+    for (int i = threadIdx.x; i < Ng; i += blockDim.x) sm[i] = 0.0;
+    __syncthreads();
+    const double idx = 1. / dx;
+    int bad = 0;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < N; i += (long long)gridDim.x * blockDim.x) {
+        Cell c = cell_dd(x[i], dx);
+        if (c.iL < 0 || c.iL > Ng - 2) { ++bad; c.iL = clampi(c.iL, 0, Ng - 2); }
+        if (CURRENT) {          // (1./dx) * q[i] * p2c * v[i] * w   (:57-58)
+            const double pre = idx * q[i] * p2c * v[i];
+            atomicAdd(&sm[c.iL], pre * c.wL); atomicAdd(&sm[c.iL + 1], pre * c.wR);
+        } else {                // q[i] * p2c * w * idx               (:93-94)
+            const double pre = q[i] * p2c;
+            atomicAdd(&sm[c.iL], pre * c.wL * idx); atomicAdd(&sm[c.iL + 1], pre * c.wR * idx);
+        }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < Ng; i += blockDim.x)
+        if (sm[i] != 0.0) atomicAdd(&acc[i], sm[i]);
+    if (bad && range_err) atomicAdd(range_err, bad);
+}
+// PIC_L.pushParticlesImplicit :261-270: gather Eh at xh (periodic), xout = x0 + dt*v + dt*dt*(q/m)*E*0.5,
+// vout = v + dt*(q/m)*E, per-particle q and m
+__global__ void l_push_implicit_k(const double* __restrict__ x0, const double* __restrict__ xh, const double* __restrict__ v,
+                                  const double* __restrict__ q, const double* __restrict__ m, const double* __restrict__ Eh,
+                                  double* __restrict__ xout, double* __restrict__ vout, long long N, int Ng, double dx,
+                                  double dt, int* __restrict__ range_err) {
+    const int nodes = Ng + 1;
+    int bad = 0;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < N; i += (long long)gridDim.x * blockDim.x) {
+        Cell c = cell_lper(xh[i], dx, nodes);
+        l_fix(c, nodes, bad);
+        const double Ei = c.wL * Eh[c.iL] + c.wR * Eh[c.iR];
+        const double qm = q[i] / m[i];
+        xout[i] = x0[i] + dt * v[i] + dt * dt * qm * Ei * 0.5;
+        vout[i] = v[i] + dt * qm * Ei;
+    }
+    if (bad && range_err) atomicAdd(range_err, bad);
+}
+// PIC_L.applyBoundaryConditions :272-282: flag = 0 where x > L or x <= 0, 1 elsewhere (pic_dev_compact_flags mode 1)
+__global__ void l_outside_flags_k(const double* __restrict__ x, int8_t* __restrict__ flags, long long N, double L) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < N; i += (long long)gridDim.x * blockDim.x) {
+        const double X = x[i];
+        flags[i] = (X > L || X <= 0.) ? 0 : 1;
+    }
+}
+
 // fused explicit particle phase: gather, kick-drift-kick, wrap, deposit rho(x_new)
 template <bool AGG>
 __global__ void __launch_bounds__(256) l_push_deposit_k(LK k, double* __restrict__ x, double* __restrict__ v,
@@ -1016,6 +1068,43 @@ int pic_dev_l_field_solve(const pic_l_params* p, double* rho_acc, double* rho, d
     int rc = pic_dev_tridiag_pcr(a, b, c, d, x, nodes - 1, work + 5 * (size_t)nodes, stream);
     if (rc) return rc;
     l_field_finish_k<<<1, 1024, 0, st>>>(x, phi, E, nodes, p->dx, stats);
+    PIC_CHECK_LAUNCH();
+    return PIC_OK;
+}
+
+int pic_dev_l_weight_bounded(const double* x, const double* q, const double* v, double* out, int64_t N, int Ng, double dx,
+                             double p2c, int* range_err, void* stream) {
+    PIC_REQUIRE(x && q && out && N >= 0 && Ng >= 2, "l_weight_bounded: bad argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    PIC_CHECK_CUDA(cudaMemsetAsync(out, 0, (size_t)Ng * sizeof(double), st));
+    if (N == 0) return PIC_OK;
+    const size_t smem = (size_t)Ng * sizeof(double);
+    PIC_REQUIRE(smem <= (size_t)max_optin_smem() - 1024, "l_weight_bounded: grid too large for the shared-memory tile");
+    if (v) {
+        PIC_CHECK_CUDA(cudaFuncSetAttribute(l_weight_bounded_k<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        l_weight_bounded_k<true><<<grid_for(N, 256, 4), 256, smem, st>>>(x, q, v, out, N, Ng, dx, p2c, range_err);
+    } else {
+        PIC_CHECK_CUDA(cudaFuncSetAttribute(l_weight_bounded_k<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        l_weight_bounded_k<false><<<grid_for(N, 256, 4), 256, smem, st>>>(x, q, v, out, N, Ng, dx, p2c, range_err);
+    }
+    PIC_CHECK_LAUNCH();
+    return PIC_OK;
+}
+
+int pic_dev_l_push_implicit(const double* x0, const double* xh, const double* v, const double* q, const double* m,
+                            const double* Eh, double* xout, double* vout, int64_t N, int Ng, double dx, double dt,
+                            int* range_err, void* stream) {
+    PIC_REQUIRE(x0 && xh && v && q && m && Eh && xout && vout && N >= 0 && Ng >= 2, "l_push_implicit: bad argument");
+    if (N == 0) return PIC_OK;
+    l_push_implicit_k<<<grid_for(N, 256, 8), 256, 0, (cudaStream_t)stream>>>(x0, xh, v, q, m, Eh, xout, vout, N, Ng, dx, dt, range_err);
+    PIC_CHECK_LAUNCH();
+    return PIC_OK;
+}
+
+int pic_dev_l_outside_flags(const double* x, int8_t* flags, int64_t N, double L, void* stream) {
+    PIC_REQUIRE(x && flags && N >= 0, "l_outside_flags: bad argument");
+    if (N == 0) return PIC_OK;
+    l_outside_flags_k<<<grid_for(N, 256, 8), 256, 0, (cudaStream_t)stream>>>(x, flags, N, L);
     PIC_CHECK_LAUNCH();
     return PIC_OK;
 }

@@ -78,6 +78,18 @@ def newton_boltzmann(src, phi_start, dx, n0, Te, bc, tol, iter_max):
     return phi.cpu().numpy(), int(it.item())
 
 
+def newton_boltzmann_l(rho, phi0, dx, kBT, tol, maxiter, periodic):
+    """PIC_L / PIC_L_DD solvePoisson (periodic False) and solvePoissonPeriodic (True)."""
+    dev = D.require_cuda()
+    dr = _up(rho, dev); n = dr.numel()
+    phi = _up(np.array(phi0, dtype=np.float64), dev)
+    work = D.f64(n, dev, True)
+    it = torch.zeros(1, dtype=torch.int32, device=dev)
+    _lib.call("pic_dev_newton_boltzmann_l", D.ptr(dr), D.ptr(phi), n, float(dx), float(kBT), float(tol), int(maxiter),
+              int(bool(periodic)), D.ptr(work), D.ptr(it), D.stream())
+    return phi.cpu().numpy()
+
+
 # ------------------------------------------------------------------ gathers
 def _interp(name, F, x, Ng, dx):
     dev = D.require_cuda()
@@ -134,6 +146,40 @@ def l_weight(x, q, v, p2c, Ng, dx):
               float(p2c), D.ptr(err), D.stream())
     D.check_range(err, "PIC_L weight")
     return out.cpu().numpy()
+
+
+def l_weight_bounded(x, q, v, p2c, Ng, dx):
+    """PIC_L.weightCurrents (v given) / weightDensities (v None): bounded CIC on Ng nodes."""
+    dev = D.require_cuda()
+    dx_ = _up(x, dev); dq = _up(q, dev); dv = _up(v, dev) if v is not None else None
+    out = D.f64(Ng, dev, True); err = _err(dev)
+    _lib.call("pic_dev_l_weight_bounded", D.ptr(dx_), D.ptr(dq), D.ptr(dv), D.ptr(out), dx_.numel(), int(Ng), float(dx),
+              float(p2c), D.ptr(err), D.stream())
+    D.check_range(err, "PIC_L bounded weight")
+    return out.cpu().numpy()
+
+
+def l_push_implicit(x0, xh, v, q, m, Ng, dt, dx, Eh):
+    dev = D.require_cuda()
+    a = [_up(t, dev) for t in (x0, xh, v, q, m, Eh)]
+    xout = torch.empty_like(a[0]); vout = torch.empty_like(a[0]); err = _err(dev)
+    _lib.call("pic_dev_l_push_implicit", *[D.ptr(t) for t in a], D.ptr(xout), D.ptr(vout), a[0].numel(), int(Ng), float(dx),
+              float(dt), D.ptr(err), D.stream())
+    D.check_range(err, "PIC_L.pushParticlesImplicit")
+    return xout.cpu().numpy(), vout.cpu().numpy()
+
+
+def l_outside(x, L):
+    """Indices (ascending) of the particles with x > L or x <= 0 (PIC_L.applyBoundaryConditions)."""
+    dev = D.require_cuda()
+    dx_ = _up(x, dev); N = dx_.numel()
+    flags = torch.empty(max(N, 1), dtype=torch.int8, device=dev)
+    _lib.call("pic_dev_l_outside_flags", D.ptr(dx_), D.ptr(flags), N, float(L), D.stream())
+    idx = torch.empty(max(N, 1), dtype=torch.int32, device=dev)
+    cnt = torch.zeros(1, dtype=torch.int64, device=dev)
+    bc = torch.zeros(2 * (N // 2048 + 2), dtype=torch.int64, device=dev)
+    _lib.call("pic_dev_compact_flags", D.ptr(flags), N, 1, D.ptr(idx), D.ptr(cnt), D.ptr(bc), D.stream())
+    return idx[:int(cnt.item())].cpu().numpy()
 
 
 def gc_weight(x, charge_state, p2c, active, ng, dx):

@@ -13,6 +13,7 @@ thread as soon as this step's draws are done, so it overlaps the GPU's Picard lo
 Benchmark-sized runs that do not need stream parity use the device Philox generator.
 """
 import ctypes as C
+import queue
 import threading
 
 import numpy as np
@@ -20,27 +21,95 @@ import numpy as np
 from . import _lib
 
 
+class _Done(threading.Event):
+    """What skip_uniforms waits on (the interface of Thread.join)."""
+
+    def join(self):
+        self.wait()
+
+
+_jobs = None
+
+
+def _worker():
+    """One persistent daemon thread runs the prefetched jumps (starting a thread per step costs more
+    than the jump); the C call releases the GIL, so the jump overlaps the host's kernel launches."""
+    global _jobs
+    if _jobs is None:
+        _jobs = queue.SimpleQueue()
+
+        def loop():
+            while True:
+                job = _jobs.get()
+                try:
+                    p = C.c_int32(job["pos"])
+                    _lib.call("pic_mt_jump", job["key1"].ctypes.data, C.byref(p), job["poly"].ctypes.data)
+                    job["pos1"] = p.value
+                except Exception:                       # leaves pos1 = 0 with an unchanged key: detected below
+                    job["n"] = -1
+                finally:
+                    job["thread"].set()
+        threading.Thread(target=loop, daemon=True).start()
+    return _jobs
+
+
 class LegacyDraws:
     JUMP_MIN = 200000        # uniforms; below this plain generation is cheaper than the jump
-    CHUNK = 16384            # jump polynomials are cached per multiple of CHUNK uniforms; the rest is generated
-    MARGIN = 4096            # the prefetched jump stops this many uniforms short of the expected skip
+    CHUNK = 2048             # jump polynomials are cached per multiple of CHUNK uniforms; the rest is generated
+    MARGIN = 1024            # the prefetched jump stops this many uniforms short of the expected skip
 
     def __init__(self, rng=None):
         self.rng = np.random if rng is None else rng
         self._polys = {}
         self._pref = None
+        self._held = None        # the stream's state while hold() owns it
         self.jumps = 0           # statistics: jumps applied / prefetched jumps used
         self.prefetch_hits = 0
 
     # ------------------------------------------------------------------ legacy state <-> C
     def _get(self):
+        if self._held is not None:
+            return self._held
         s = self.rng.get_state()
         if s[0] != "MT19937":
             raise ValueError("the legacy draw service needs an MT19937 stream, got %r" % (s[0],))
         return [np.array(s[1], dtype=np.uint32), C.c_int32(int(s[2])), C.c_int32(int(s[3])), C.c_double(float(s[4]))]
 
     def _put(self, st):
+        if self._held is not None:
+            self._held = st
+            return
         self.rng.set_state(("MT19937", st[0], int(st[1].value), int(st[2].value), float(st[3].value)))
+
+    def _uniforms(self, n):
+        """n plain np.random.uniform() draws, discarded."""
+        if self._held is not None:
+            st = self._held
+            _lib.call("pic_mt_skip", st[0].ctypes.data, C.byref(st[1]), C.c_uint64(2 * int(n)))
+        else:
+            self.rng.uniform(0.0, 1.0, int(n))
+
+    def hold(self):
+        """Context manager: for the duration of a time loop the stream's state lives in this object
+        (C arrays) instead of being fetched from / stored to np.random around every call -- the state is
+        written back on exit.  Nothing else may draw from the stream meanwhile."""
+        import contextlib
+
+        @contextlib.contextmanager
+        def cm():
+            if self._held is not None:
+                yield self
+                return
+            self._held = self._get()
+            try:
+                yield self
+            finally:
+                st, self._held = self._held, None
+                if self._pref is not None:
+                    self._pref["thread"].join()
+                    self._pref = None
+                self._put(st)
+        return cm()
 
     def _poly(self, nwords):
         g = self._polys.get(nwords)
@@ -61,11 +130,11 @@ class LegacyDraws:
         if pref is not None:
             pref["thread"].join()
         if n < self.JUMP_MIN:
-            self.rng.uniform(0.0, 1.0, n)
+            self._uniforms(n)
             return
         st = self._get()
-        if (pref is not None and pref["n"] <= n and pref["pos"] == st[1].value and np.array_equal(pref["key0"], st[0])):
-            st[0], st[1] = pref["key1"], C.c_int32(pref["pos1"])
+        if (pref is not None and 0 < pref["n"] <= n and pref["pos"] == st[1].value and np.array_equal(pref["key0"], st[0])):
+            st = [pref["key1"], C.c_int32(pref["pos1"]), st[2], st[3]]
             done = pref["n"]
             self.prefetch_hits += 1
         else:
@@ -74,7 +143,7 @@ class LegacyDraws:
         self.jumps += 1
         self._put(st)
         if n > done:
-            self.rng.uniform(0.0, 1.0, n - done)
+            self._uniforms(n - done)
 
     def prefetch_skip(self, n_expected):
         """Start the jump for the NEXT skip_uniforms() now, from the current state, in a thread (the C
@@ -85,14 +154,8 @@ class LegacyDraws:
             return
         st = self._get()
         poly = self._poly(2 * n)
-        job = dict(n=n, key0=st[0].copy(), pos=st[1].value, key1=st[0], pos1=0)
-
-        def run():
-            p = C.c_int32(job["pos"])
-            _lib.call("pic_mt_jump", job["key1"].ctypes.data, C.byref(p), poly.ctypes.data)
-            job["pos1"] = p.value
-        job["thread"] = threading.Thread(target=run, daemon=True)
-        job["thread"].start()
+        job = dict(n=n, key0=st[0].copy(), pos=st[1].value, key1=st[0].copy(), pos1=0, poly=poly, thread=_Done())
+        _worker().put(job)
         self._pref = job
 
     # PIC_L_DD.py:419-450 -------------------------------------------------------------

@@ -111,7 +111,7 @@ class SheathSim:
             raise ValueError("reduce must be 'nccl' or 'p2p'")
         self.wall_cum = D.f64(4, dev, True)
         # [r, mean j1, EE, iterations | 4 doubles of reduction scratch | residual of every iteration of the step]
-        self.stats = D.f64(8 + self.maxiter, dev, True)
+        self.stats = D.f64(8 + self.maxiter + 2, dev, True)     # + [sum u0, sum u0^2] of the diagnostics
         # enqueue-ahead Picard loop: the iterations the previous step needed are queued back to back,
         # guarded by a device flag that the field kernel raises when the loop condition fails; the
         # host reads the outcome once per step instead of once per iteration
@@ -126,11 +126,11 @@ class SheathSim:
         self.sort_scratch = (torch.zeros(D.sort_stable_scratch_size(n), dtype=torch.int32, device=dev)
                              if self.sort_every and self.det else None)
         self.scalar = D.f64(2, dev, True)
-        # absorption log (pic_dev_dd_picard_iter4): slots absorbed during the step, (iteration << 32 | slot)
+        # absorption log (pic_dev_dd_picard_iter4): int32 [count,0,0,0 | {slot, original index, iteration, 0} x cap]
         self.dead_cap = int(min(max(n, 1), max(1 << 16, n // 64)))
-        self.dead_log = torch.zeros(self.dead_cap, dtype=torch.int64, device=dev)
-        self.dead_cnt = torch.zeros(1, dtype=torch.int32, device=dev)
+        self.dead_buf = torch.zeros(4 + 4 * self.dead_cap, dtype=torch.int32, device=dev)
         self._log_valid = False         # the log describes the flags only after a step that started all-active
+        self._log_guess = 256           # entries fetched with the counter in ONE read (grows with the counts seen)
         self._harvested = None
         self.oid = None                 # int32 original index per slot; None = identity (never sorted)
         self.oid_alt = None
@@ -209,26 +209,31 @@ class SheathSim:
         if self._harvested is not None and self._harvested[0] == self.t:
             return self._harvested[1:]
         st = D.stream()
-        slots = iters = None
+        slots = orig = iters = None
         if self._log_valid:
-            cnt = int(D.read_raw(self.dead_cnt, 1, np.int32)[0])
+            # counter and (normally) all entries in ONE device->host read
+            g = min(self._log_guess, self.dead_cap)
+            buf = D.read_raw(self.dead_buf, 4 + 4 * g, np.int32)
+            cnt = int(buf[0])
             if cnt <= self.dead_cap:
-                log = D.read_raw(self.dead_log, cnt, np.int64) if cnt else np.zeros(0, dtype=np.int64)
-                slots = (log & 0xffffffff).astype(np.int32)
-                iters = (log >> 32).astype(np.int32)
+                if cnt > g:
+                    buf = D.read_raw(self.dead_buf, 4 + 4 * cnt, np.int32)
+                self._log_guess = max(256, 2 * cnt)
+                ent = buf[4:4 + 4 * cnt].reshape(cnt, 4)
+                slots, orig, iters = ent[:, 0].copy(), ent[:, 1].copy(), ent[:, 2].copy()
         if slots is None:
             _lib.call("pic_dev_compact_flags", D.ptr(self.active), self.N, 0, D.ptr(self.dead_idx), D.ptr(self.count),
                       D.ptr(self.block_counts), st)
             self.kernel_launches += 3
             cnt = int(D.read_raw(self.count, 1, np.int64)[0])
             slots = D.read_raw(self.dead_idx, cnt, np.int32) if cnt else np.zeros(0, dtype=np.int32)
-        orig = slots
-        if self.oid is not None and len(slots):
-            dslots = D.to_dev(slots, self.dev, torch.int32)
-            dorig = torch.empty(len(slots), dtype=torch.int32, device=self.dev)
-            _lib.call("pic_dev_gather_i32", D.ptr(self.oid), D.ptr(dslots), D.ptr(dorig), len(slots), st)
-            self.kernel_launches += 1
-            orig = D.read_raw(dorig, len(slots), np.int32)
+            orig = slots
+            if self.oid is not None and len(slots):
+                dslots = D.to_dev(slots, self.dev, torch.int32)
+                dorig = torch.empty(len(slots), dtype=torch.int32, device=self.dev)
+                _lib.call("pic_dev_gather_i32", D.ptr(self.oid), D.ptr(dslots), D.ptr(dorig), len(slots), st)
+                self.kernel_launches += 1
+                orig = D.read_raw(dorig, len(slots), np.int32)
         order = np.argsort(orig, kind="stable")
         slots, orig = np.ascontiguousarray(slots[order]), np.ascontiguousarray(orig[order])
         iters = None if iters is None else iters[order]
@@ -322,12 +327,12 @@ class SheathSim:
             # flag array; the flag scan only runs when there is no valid log (first step, overflow).
             # With a tracked order the draws are keyed by the ORIGINAL index and v,w written there.
             if self._log_valid:
-                _lib.call("pic_dev_dd_reinject_philox_log", C.byref(self.params), D.ptr(self.dead_log), D.ptr(self.dead_cnt),
-                          self.dead_cap, D.ptr(self.x0), D.ptr(self.u0), D.ptr(self.v0), D.ptr(self.w0), D.ptr(self.active),
+                _lib.call("pic_dev_dd_reinject_philox_log", C.byref(self.params), D.ptr(self.dead_buf), self.dead_cap,
+                          D.ptr(self.x0), D.ptr(self.u0), D.ptr(self.v0), D.ptr(self.w0), D.ptr(self.active),
                           D.ptr(self.oid), C.byref(sig), self.seed, self.t, self.start, st)
             _lib.call("pic_dev_dd_reinject_philox2", C.byref(self.params), D.ptr(self.x0), D.ptr(self.u0),
                       D.ptr(self.v0), D.ptr(self.w0), D.ptr(self.active), D.ptr(self.oid), C.byref(sig), self.seed, self.t,
-                      self.start, D.ptr(self.dead_cnt) if self._log_valid else None, self.dead_cap, st)
+                      self.start, D.ptr(self.dead_buf) if self._log_valid else None, self.dead_cap, st)
             self.kernel_launches += 1
             self._reset_log()
             return None
@@ -350,18 +355,33 @@ class SheathSim:
             # the next step skips about as many thermostat uniforms: jump ahead while the GPU works
             self.draws.prefetch_skip(self.N_global - sum(counts))
         if n_dead:
-            dd = D.to_dev(np.stack([xd, ud, vd, wd]), self.dev)
-            di = D.to_dev(np.stack([slots, orig]), self.dev, torch.int32)
-            _lib.call("pic_dev_dd_apply_draws2", D.ptr(di[0]), D.ptr(di[1]), D.ptr(dd[0]), D.ptr(dd[1]),
-                      D.ptr(dd[2]) if self.carry_vw else None, D.ptr(dd[3]) if self.carry_vw else None, n_dead,
+            # one asynchronous copy from a pinned staging buffer: [x | u | v | w | (slot, orig) as int32]
+            hs, ds = self._staging(n_dead)
+            hv = hs.numpy()
+            hv[0:n_dead] = xd; hv[n_dead:2 * n_dead] = ud; hv[2 * n_dead:3 * n_dead] = vd; hv[3 * n_dead:4 * n_dead] = wd
+            iv = hv[4 * n_dead:5 * n_dead + 1].view(np.int32)
+            iv[0:n_dead] = slots; iv[n_dead:2 * n_dead] = orig
+            _lib.call("pic_dev_write", D.ptr(ds), D.ptr(hs), (5 * n_dead + 1) * 8, st)
+            base = D.ptr(ds)
+            _lib.call("pic_dev_dd_apply_draws2", base + 32 * n_dead, base + 36 * n_dead, base, base + 8 * n_dead,
+                      base + 16 * n_dead if self.carry_vw else None, base + 24 * n_dead if self.carry_vw else None, n_dead,
                       D.ptr(self.x0), D.ptr(self.u0), D.ptr(self.v0), D.ptr(self.w0), D.ptr(self.active), st)
             self.kernel_launches += 1
         self._reset_log()
         return n_dead
 
+    def _staging(self, n):
+        """(pinned host, device) staging pair for this step's draws.  Two pairs alternate: the copy of
+        step t is long complete (the Picard loop of step t synchronises) when step t+2 refills its pair."""
+        if not hasattr(self, "_stage") or self._stage[0][0].numel() < 5 * n + 2:
+            cap = max(4096, 2 * (5 * n + 2))
+            self._stage = [(torch.empty(cap, dtype=torch.float64, pin_memory=True),
+                            torch.empty(cap, dtype=torch.float64, device=self.dev)) for _ in range(2)]
+        return self._stage[self.t & 1]
+
     def _reset_log(self):
         """Every slot is alive now: the absorption log of the coming step starts empty."""
-        self.dead_cnt.zero_()
+        _lib.call("pic_dev_zero", D.ptr(self.dead_buf), 16, D.stream())
         self._log_valid = True
 
     def sort_by_cell(self):
@@ -477,8 +497,8 @@ class SheathSim:
         P = C.byref(self.params)
         self.Es.copy_(self.E0)
         self.wall_cum.zero_()
-        if self.stats.numel() < 8 + self.maxiter:          # maxiter was raised after construction
-            self.stats = D.f64(8 + self.maxiter, self.dev, True)
+        if self.stats.numel() < 8 + self.maxiter + 2:      # maxiter was raised after construction
+            self.stats = D.f64(8 + self.maxiter + 2, self.dev, True)
         self.stats.zero_()
         self.ctl.zero_()
         rhist = D.ptr(self.stats) + 8 * 8
@@ -494,8 +514,8 @@ class SheathSim:
                 ev[0].record()
             _lib.call("pic_dev_dd_picard_iter4", P, D.ptr(self.x0), D.ptr(self.u0), D.ptr(xin), D.ptr(xout),
                       D.ptr(self.u1) if want_u else None, D.ptr(self.active), D.ptr(self.Es), self._acc_ptr(),
-                      1 if j == 0 else 0, D.ptr(self.range_err), D.ptr(self.ctl), D.ptr(self.dead_log),
-                      D.ptr(self.dead_cnt), self.dead_cap, j, st)
+                      1 if j == 0 else 0, D.ptr(self.range_err), D.ptr(self.ctl), D.ptr(self.dead_buf), self.dead_cap,
+                      D.ptr(self.oid), j, st)
             if ev is not None:
                 ev[1].record()
             if self.p2p is not None:
@@ -581,17 +601,37 @@ class SheathSim:
     # ------------------------------------------------------------------ diagnostics
     def diagnostics(self):
         """EE, KE, jbias of PIC_L_DD.py:548-551 (KE uses me for every particle, as written)."""
-        s = D.read_f64(self.stats, 4)
-        m1, m2 = self.moments()
+        s = self._moments_and_stats()
+        m1, m2 = float(s[-2]), float(s[-1])
         return dict(EE=float(s[2]), KE=me / 2. * m2, jbias=float(s[1]), kBTe=self.kBTe_from(m1, m2))
 
-    def moments(self):
-        """(sum u0, sum u0^2) over all ranks from one pass over the velocities."""
-        _lib.call("pic_dev_moments", D.ptr(self.u0), self.N, D.ptr(self.scalar), D.stream())
+    def diagnostics_begin(self):
+        """Launch the pass for the step's diagnostics without waiting for it; diagnostics_end() reads
+        the numbers -- e.g. at the top of the next step, where the host has to wait for the device
+        anyway (the values do not change in between: nothing touches u0 or the statistics)."""
+        tail = self.stats[8 + self.maxiter:8 + self.maxiter + 2]
+        _lib.call("pic_dev_moments", D.ptr(self.u0), self.N, D.ptr(tail), D.stream())
         self.kernel_launches += 1
-        self.comm.allreduce_sum(self.scalar)
-        m = D.read_f64(self.scalar, 2)
-        return float(m[0]), float(m[1])
+        self.comm.allreduce_sum(tail)
+
+    def diagnostics_end(self):
+        s = D.read_f64(self.stats, 8 + self.maxiter + 2)
+        m1, m2 = float(s[-2]), float(s[-1])
+        return dict(EE=float(s[2]), KE=me / 2. * m2, jbias=float(s[1]), kBTe=self.kBTe_from(m1, m2))
+
+    def _moments_and_stats(self):
+        """One pass over the velocities for (sum u0, sum u0^2), summed over the ranks into the tail of
+        the step's statistics, and ONE read of the whole block."""
+        tail = self.stats[8 + self.maxiter:8 + self.maxiter + 2]
+        _lib.call("pic_dev_moments", D.ptr(self.u0), self.N, D.ptr(tail), D.stream())
+        self.kernel_launches += 1
+        self.comm.allreduce_sum(tail)
+        return D.read_f64(self.stats, 8 + self.maxiter + 2)
+
+    def moments(self):
+        """(sum u0, sum u0^2) over all ranks."""
+        s = self._moments_and_stats()
+        return float(s[-2]), float(s[-1])
 
     def kBTe_from(self, m1, m2):
         """np.std(u0)**2 * me / e (PIC_L_DD.py:417; dead slots count with their zeros, as there)."""

@@ -148,6 +148,17 @@ class SlabSheathSim:
         self.c0, self.c1 = self.cb[self.rank], self.cb[self.rank + 1]
         if self.world > 1 and min(b - a for a, b in zip(self.cb, self.cb[1:])) <= 2 * self.G + 2:
             raise ValueError("slabs must be wider than 2*guard+2 cells")
+        # Between two sorts a particle may deposit at most `guard` cells outside its slab: beyond that the halo
+        # exchange does not carry its contribution.  Refuse configurations whose thermal drift (6 sigma of the
+        # fastest species over sort_every steps) already exceeds the guard, and detect any leak at run time
+        # (exchange_acc sums what lies outside the band; check() raises).
+        if self.world > 1 and self.sort_every and all(k is not None for k in self.kBT):
+            vmax = 6.0 * max(float(np.sqrt(self.kBT[s] / self.m[s])) for s in range(2))
+            drift = vmax * self.dt * self.sort_every / self.dx
+            if drift > self.G:
+                raise ValueError("guard=%d cells cannot hold the drift of %d steps between sorts (6 sigma = %.1f cells): raise "
+                                 "guard or lower sort_every" % (self.G, self.sort_every, drift))
+        self.guard_leak = D.f64(1, self.dev, True)
         per = self.N_global // 2 // self.world + 1
         self.H = int(headroom) if headroom is not None else max(4096, per // 50)
         self.H += self.H % 2
@@ -389,6 +400,9 @@ class SlabSheathSim:
         t = lambda v: torch.as_tensor(v, device=self.dev)
         self.sendbuf = D.f64(pl["M"], self.dev, True)
         self.gathbuf = D.f64(self.world * pl["M"], self.dev, True)
+        lo, hi = max(self.c0 - self.G, 0), min(self.c1 + self.G + 1, self.Ng)
+        out = np.concatenate([np.arange(0, lo), np.arange(hi, self.Ng)]).astype(np.int64)
+        pl["outside"] = np.concatenate([out, self.Ng + out])
         return {k: t(v) for k, v in pl.items() if k != "M"}
 
     def exchange_acc(self):
@@ -401,6 +415,8 @@ class SlabSheathSim:
             self._plan = self._build_exchange_plan()
         pl, Ng = self._plan, self.Ng
         acc = self.acc
+        # anything this rank deposited OUTSIDE its slab + guard band would be dropped by the unpack below
+        self.guard_leak += acc[pl["outside"]].abs().sum()
         torch.index_select(acc, 0, pl["pack"], out=self.sendbuf)
         dist.all_gather_into_tensor(self.gathbuf, self.sendbuf, group=self.comm.group)
         torch.index_select(self.gathbuf, 0, pl["unpack"], out=acc[:2 * Ng])
@@ -479,6 +495,11 @@ class SlabSheathSim:
 
     def check(self):
         D.check_range(self.range_err, "slab sheath step")
+        leak = float(self.guard_leak.item())
+        if leak != 0.0:
+            self.guard_leak.zero_()
+            raise _lib.PicError(_lib.PIC_ERR_RANGE, "slab decomposition: particles deposited beyond the %d guard cells of their "
+                                "slab (the halo exchange dropped that current): raise guard or lower sort_every" % self.G)
 
     def local_particles(self):
         return sum(b.n for b in self.blocks)

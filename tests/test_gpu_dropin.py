@@ -138,6 +138,52 @@ def test_pic_l_functions_module(golden):
     assert np.array_equal(xb, g["xbc"])
 
 
+def test_pic_l_and_pic_l_dd_undriven_functions_golden(golden):
+    """The module functions no reference driver calls (PIC_L.py:48-60, 83-98, 146-206, 261-282 and
+    PIC_L_DD.py:116-176), against the reference's own output on the same inputs."""
+    import PIC_L
+    import PIC_L_DD
+    g = golden("stub_functions")
+    Ng = int(g["Ng"]); dx = float(g["dx"]); L = dx * (Ng - 1)
+    x, q, m, v, p2c = g["x"], g["q"], g["m"], g["v"], float(g["p2c"]); N = len(x)
+    assert relmax(PIC_L.weightCurrents(x, q, v, p2c, Ng, N, dx), g["l_j"]) < 1e-13
+    assert relmax(PIC_L.weightDensities(x, q, p2c, Ng, N, dx), g["l_rho"]) < 1e-13
+    kBT = float(g["kBT"])
+    # bounded Boltzmann-Newton: pinned after a fixed number of iterations (tol = 0), see the generator
+    assert relmax(PIC_L.solvePoisson(dx, Ng, g["rho_b"], kBT, 0.0, 1, g["phi0_b"].copy()), g["l_phi_b1"]) < 1e-9
+    assert relmax(PIC_L.solvePoisson(dx, Ng, g["rho_b"], kBT, 0.0, 3, g["phi0_b"].copy()), g["l_phi_b3"]) < 1e-8
+    assert relmax(PIC_L_DD.solvePoisson(dx, Ng, g["rho_b"], kBT, 0.0, 3, g["phi0_b"].copy()), g["dd_phi_b3"]) < 1e-8
+    assert relmax(PIC_L.solvePoissonPeriodic(dx, Ng, g["rho_p"], kBT, 1e-8, 20, np.zeros(Ng + 1)), g["l_phi_p"]) < 1e-9
+    assert relmax(PIC_L_DD.solvePoissonPeriodic(dx, Ng, g["rho_p"][:Ng], kBT, 1e-8, 20, np.zeros(Ng)), g["dd_phi_p"]) < 1e-9
+    xo, vo = PIC_L.pushParticlesImplicit(x, g["xh"], v, q, m, N, Ng, 1e-10, dx, g["Eh"])
+    assert np.array_equal(xo, g["l_xi"]) and np.array_equal(vo, g["l_vi"])
+    xb, vb = g["bc_x_in"].copy(), g["bc_v_in"].copy()
+    np.random.seed(5)
+    xb2, vb2 = PIC_L.applyBoundaryConditions(xb, vb, m, N, L, dx, kBT)
+    assert xb2 is xb and np.array_equal(xb2, g["bc_x"]) and np.array_equal(vb2, g["bc_v"])
+    assert np.random.uniform() == float(g["bc_next_uniform"])
+
+
+def test_pygcpic_particle_ionisation_attempts_golden(golden):
+    """Particle.attempt_first_ionization / attempt_nth_ionization (pygcpic.py:350-458) object by object:
+    same charge states, same added_particles, same number of legacy-stream draws as the reference."""
+    import pygcpic as G
+    g = golden("stub_functions")
+    grid = G.Grid(int(g["ion_ng"]), float(g["ion_L"]), 60. * 11600.)
+    grid.n[:] = g["ion_n"]
+    np.random.seed(9)
+    for Z, cs, p2c, x, nth, cs_after, added in g["ion_rows"]:
+        pt = G.Particle(G.mp * (10.81 if Z == 5 else 1.0), cs, p2c, 1.0, int(Z), grid=grid)
+        pt.r[0] = x
+        before = grid.added_particles
+        with contextlib.redirect_stdout(io.StringIO()):
+            (pt.attempt_nth_ionization if nth else pt.attempt_first_ionization)(2e-7, 60. * 11600., grid)
+        assert float(pt.charge_state) == cs_after and grid.added_particles - before == added
+    assert np.random.uniform() == float(g["ion_next_uniform"])
+    with pytest.raises(UnboundLocalError):
+        G.Particle(G.mp, 0, 1.0, 1.0, 1, grid=grid).attempt_nth_ionization(1e-7, 1e5, grid)
+
+
 def test_pic_l_main_module(golden, tmp_path):
     """PIC_L.main(T, nplot) from the same seed as the golden reference run (N literal 6000)."""
     import PIC_L
@@ -399,3 +445,41 @@ def test_pygcpic_run_sheath_with_ionisation_golden(golden):
     assert np.array_equal(st.flags_host()["active"], g["active_final"])
     assert relmax(st.r_host(), g["r_final"]) < 1e-6
     assert np.random.uniform() == float(g["next_uniform"])        # exactly as many draws as the reference
+
+
+def test_pygcpic_run_sheath_ionisation_on_a_fused_eligible_store():
+    """A species-uniform store large enough for the fused push kernel, WITH Monte-Carlo ionisation and
+    wall-born particles: the fused kernel must not pre-deposit for the next step (charge states change,
+    mid-domain exits deactivate particles after the push), so the run has to equal the same run on the
+    per-particle kernels -- integer tallies exactly, n0 to round-off, same number of RNG draws."""
+    import pygcpic as G
+    N, ng, Lg = 3 * 16384 + 123, 150, 6e-3
+    Te, Ti = 60. * 11600., 50. * 11600.
+    B = np.array([2 * np.cos(86 * np.pi / 180), 2 * np.sin(86 * np.pi / 180), 0.0])
+    rs = np.random.RandomState(8)
+    r = np.zeros((N, 7)); r[:, 0] = rs.uniform(0.02 * Lg, 0.98 * Lg, N)
+    r[:, 3:6] = rs.normal(0, np.sqrt(G.kb * Ti / G.mp), (N, 3))
+    fw = (rs.uniform(size=N) < 0.5).astype(np.int8)
+    p2c = 4e15 * Lg / N
+    host_grid = G.Grid(ng, Lg, Te)
+
+    def run(fused):
+        np.random.seed(3)
+        st = G.ParticleStore.from_arrays(r.copy(), np.zeros(N), np.full(N, G.mp), np.full(N, p2c), Z=np.ones(N, dtype=np.int32),
+                                         from_wall=fw, B=B)
+        if not fused:
+            st.FUSED_MIN = 10**12
+        assert (st.uniform() is not None) and (st.N >= G.ParticleStore.FUSED_MIN)
+        grid = G.GridDev(ng, Lg, Te)
+        src = G.source_distribution_6D(host_grid, Ti, G.mp)
+        out = G.run_sheath(grid, st, 2e-9, 6, N // 2, src, p2c, G.mp, charge_state=1, Z=1, ionize_Te=Te)
+        return out, st, np.random.uniform()
+    a, sa, ua = run(True)
+    b, sb, ub = run(False)
+    assert ua == ub
+    for k in ("length", "hits", "deleted", "reactivated", "ionised_h", "midexit"):
+        assert np.array_equal(a[k], b[k]), k
+    assert sum(a["ionised_h"]) > 0 and sum(a["midexit"]) > 0
+    assert relmax(a["n0"], b["n0"]) < 1e-10
+    assert np.array_equal(sa.charge_state[:sa.N].cpu().numpy(), sb.charge_state[:sb.N].cpu().numpy())
+    assert relmax(sa.r_host(), sb.r_host()) < 1e-9

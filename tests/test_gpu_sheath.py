@@ -438,14 +438,21 @@ def test_baseline_grid_multi_step_vs_c_oracle():
     u0 = rs.normal(0, 1, N) * sig
     E0 = np.zeros(Ng)
     p2c = L * 1e19 / N
-    threads = max(1, len(os.sched_getaffinity(0)))
+    threads = max(1, min(32, len(os.sched_getaffinity(0))))
     sim = SheathSim(N, Ng, dx, dt, p2c, kBT=(kT, kT), carry_vw=False, rng="host", sort_every=2,
                     draws=LegacyDraws(np.random.RandomState(77)))
     assert sim.track
     sim.upload(x0, u0, E0=E0)
     cpu_rng = np.random.RandomState(77)
     dead_total = 0
+    dead = np.zeros(0, dtype=np.int64)
     for step in range(steps):
+        # the reference's thermostat + re-injection at the top of the step (PIC_L_DD.py:419-450), CPU side,
+        # from the same legacy stream: one uniform per active particle, then x,u,v,w per dead slot in index order
+        cpu_rng.uniform(0.0, 1.0, N - len(dead))
+        for i in dead:
+            x0[i] = cpu_rng.uniform(0.0, L)
+            u0[i] = cpu_rng.normal(0.0, sig[i]); cpu_rng.normal(0.0, sig[i]); cpu_rng.normal(0.0, sig[i])
         act = np.ones(N)
         x1, u1, E1, j1, k_cpu, r_cpu = c_oracle.dd_picard_step(x0, u0, [-O.e, O.e], [O.me, O.mp], h, act, E0, p2c, Ng, dx, dt, L,
                                                                1e-5, 20, threads)
@@ -453,18 +460,13 @@ def test_baseline_grid_multi_step_vs_c_oracle():
         out = sim.download()
         assert k_gpu == k_cpu, (step, k_gpu, k_cpu)
         assert np.array_equal(out["active"], act), step
-        assert relmax(out["E0"], E1) < 1e-11 and relmax(out["j0"], j1) < 1e-11
-        assert np.max(np.abs(out["x0"] - x1)) < 1e-11 * L
-        assert relmax(out["u0"], u1) < 1e-11
-        assert abs(r_gpu - r_cpu) <= 1e-6 * r_cpu + 1e-12
-        # the reference's re-injection (PIC_L_DD.py:419-450) on the CPU side, from the same stream
+        assert relmax(out["E0"], E1) < 1e-11 and relmax(out["j0"], j1) < 1e-11, step
+        assert np.max(np.abs(out["x0"] - x1)) < 1e-11 * L, step
+        assert relmax(out["u0"], u1) < 1e-11, step
+        assert abs(r_gpu - r_cpu) <= 1e-6 * r_cpu + 1e-9          # a norm of differences of fields of size 1e4
         dead = np.nonzero(act != 1)[0]
         dead_total += len(dead)
-        cpu_rng.uniform(0.0, 1.0, N - len(dead))
         x0, u0, E0 = x1, u1, E1
-        for i in dead:
-            x0[i] = cpu_rng.uniform(0.0, L)
-            u0[i] = cpu_rng.normal(0.0, sig[i]); cpu_rng.normal(0.0, sig[i]); cpu_rng.normal(0.0, sig[i])
     sim.check()
     assert dead_total > 100 and sim._sorts == 2 and sim.draws.jumps == steps
 

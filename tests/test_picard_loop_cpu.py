@@ -68,7 +68,7 @@ def make_sim(maxiter=6, tol=1e-5, enqueue_ahead=True):
     sim.active = torch.ones(4, dtype=torch.int8)
     sim.stats = f(8 + maxiter)
     sim.ctl = torch.zeros(1, dtype=torch.int32)
-    sim.dead_log = torch.zeros(16, dtype=torch.int64); sim.dead_cnt = torch.zeros(1, dtype=torch.int32); sim.dead_cap = 16
+    sim.dead_buf = torch.zeros(4 + 4 * 16, dtype=torch.int32); sim.dead_cap = 16; sim.oid = None
     sim.range_err = torch.zeros(1, dtype=torch.int32)
     sim.comm = types.SimpleNamespace(world=1, allreduce_sum=lambda t: t)
     sim._ratio = sim._r1 = sim._prev_hist = None

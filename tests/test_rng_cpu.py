@@ -103,3 +103,27 @@ def _advance(r):
     c = np.random.RandomState(0)
     c.set_state(r.get_state())
     return c
+
+
+def test_held_stream_gives_the_same_draws_and_is_written_back():
+    """hold(): the state lives in the draw service during a time loop and returns to np.random at the end."""
+    a, b = np.random.RandomState(21), np.random.RandomState(21)
+    d = LegacyDraws(b)
+    d.JUMP_MIN, d.CHUNK, d.MARGIN = 1000, 256, 100
+    L = 2e-3
+    with d.hold():
+        for step in range(6):
+            n_act, n_dead = 40000 - step, 3 + step
+            a.uniform(0, 1, n_act)
+            d.sheath_thermostat_skip(n_act)
+            sig = np.full(n_dead, 7.0 + step)
+            xd, ud, vd, wd = d.sheath_reinject(n_dead, sig, L)
+            for k in range(n_dead):
+                assert (xd[k], ud[k], vd[k], wd[k]) == (a.uniform(0.0, L), a.normal(0.0, sig[k]), a.normal(0.0, sig[k]),
+                                                         a.normal(0.0, sig[k]))
+            d.prefetch_skip(n_act)
+        d.sheath_skip_foreign(2)
+        for _ in range(2):
+            a.uniform(0.0, 1.0); a.normal(); a.normal(); a.normal()
+    assert d.prefetch_hits >= 4
+    assert _same_stream(a, b)
