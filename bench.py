@@ -56,6 +56,9 @@ def parse():
                     help="second timed region: the north-star strong-scaling case, this many particles in TOTAL over the "
                          "N GPUs (BASELINE config 4), reported as the sub-record `strong_scaling`; 0 disables it")
     ap.add_argument("--strong-steps", type=int, default=12)
+    ap.add_argument("--boris-full-store", action="store_true",
+                    help="--workload boris: carry y, z and the per-particle clock through the push (112 B per particle-step) "
+                         "instead of the lean store (x, vx, vy, vz: the 64 B row of SURVEY.md 8d)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-sample", type=float, default=4e6, help="particles in the CPU-baseline sample")
@@ -633,6 +636,7 @@ def run_other(args):
             store.r[c].normal_(0., vth, generator=gen)
         p2c = Lg * 1e19 / (N * world)
         store.charge_state.fill_(1.); store.m.fill_(MP); store.p2c.fill_(p2c); store.Z.fill_(1)
+        store.carry_yzt = bool(args.boris_full_store)
         dtg = 1e-10
         store.push_6D = timed_call(store.push_6D)
         state = {"t": 0, "launches": 0}
@@ -651,10 +655,12 @@ def run_other(args):
         def check():
             store.check(); grid.check()
         launches = lambda: state["launches"]
-        alg, kname = (lambda k: 112.0), "gc_push_boris_v2_k"
+        alg, kname = (lambda k: 112.0 if args.boris_full_store else 64.0), "gc_push_boris_v2_k"
         desc = ("pygcpic Boris 1D3V (B=2 T at 86 deg, H+, Ti=50 eV, Te=60 eV): %d particles, %d-node grid, fused "
-                "gather+push+walls+deposit, Newton-Boltzmann field solve, store re-sorted every %d steps"
-                % (N, ng, max(1, args.sort_every // 2)))
+                "gather+push+walls+deposit, Newton-Boltzmann field solve, store re-sorted every %d steps; %s"
+                % (N, ng, max(1, args.sort_every // 2),
+                   "full store (x,y,z,v,t streamed: 112 B per particle-step)" if args.boris_full_store else
+                   "lean store (x,vx,vy,vz streamed: 64 B per particle-step; y,z not tracked, clocks implicit)"))
     for _ in range(args.warmup):
         step()
     check()

@@ -404,6 +404,12 @@ int pic_dev_pypic_picard_iter2(const pic_pypic_params* p, const double* x0, cons
 int pic_dev_pypic_picard_iter3(const pic_pypic_params* p, const double* x0, const double* v0,
                                const double* x1_in, double* x1_out, double* v1, const double* Fs,
                                double* acc, int first, int* range_err, const int32_t* done, void* stream);
+/* One Picard iteration with PER-PARTICLE charge and mass (particle_push_p takes q, m as arrays,
+ * pypic.py:248: q_m = q / m; the deposit uses q[i]): grid-stride kernel, any particle order, every
+ * iteration stores v1 and deposits j1.  p->q, p->m are ignored. */
+int pic_dev_pypic_picard_iter_qm(const pic_pypic_params* p, const double* x0, const double* v0, const double* x1i,
+                                 double* x1, double* v1, const double* q, const double* m, const double* Fs, double* acc,
+                                 int first, int* range_err, const int32_t* done_flag, void* stream);
 int pic_dev_pypic_field_update2(const pic_pypic_params* p, double* acc, const double* E0, double* Es,
                                 double* Fs, double* E1, double* j1, double* stats, double* Fs_prev,
                                 double* rhist, int32_t* ctl, double tol, int maxiter, void* stream);
@@ -500,6 +506,14 @@ int pic_dev_gc_push_boris_uniform(const pic_gc_params* p, double* const r[7], do
                                   double p2c, int8_t* active, int8_t* at_wall, int8_t* hit_flag,
                                   const double* Egrid, double* n_acc, long long* hit_count, int* range_err,
                                   void* stream);
+/* The same with the LEAN store mode: lean != 0 streams x, vx, vy, vz only (64 B per particle-step, the
+ * Boris row of SURVEY.md 8(d)); y, z and the per-particle clock r[6] are not advanced (nothing on the
+ * path reads them; r[1], r[2] may be NULL) and a particle absorbed by this push gets r[6] = t_now, so
+ * the clock of every particle is still known: t_now for the active ones, the time of death otherwise. */
+int pic_dev_gc_push_boris_uniform2(const pic_gc_params* p, double* const r[7], double charge_state, double m, double p2c,
+                                   int lean, double t_now, int8_t* active, int8_t* at_wall, int8_t* hit_flag,
+                                   const double* Egrid, double* n_acc, long long* hit_count, int* range_err,
+                                   void* stream);
 /* Post-push pass of pic_bca_aps' particle loop (pygcpic.py:1509-1541), N3: per particle the
  * ionisation eligibility (Z==1 & charge 0: attempt_first_ionization :350-395; Z==5 & charge<3:
  * attempt_nth_ionization :397-458) and probability density^2*rate*dx*dt/p2c (density = CIC gather

@@ -55,17 +55,18 @@ def differentiate_p(F, dx, Ng):
     return ops.differentiate(F, dx, 0)
 
 
-def _uniform(a, name):
+def _scalar_or_array(a):
+    """One species (every entry equal: the reference's only use) -> scalar, which takes the fused TMA
+    kernel; genuinely per-particle values -> the array, served by the grid-stride kernel."""
     a = np.asarray(a, dtype=np.float64)
-    if a.size and np.any(a != a.flat[0]):
-        raise NotImplementedError("per-particle %s arrays with different values are not supported on the device path "
-                                  "(the reference only ever uses one species)" % name)
-    return float(a.flat[0])
+    if a.size == 0 or not np.any(a != a.flat[0]):
+        return float(a.flat[0]) if a.size else 0.0
+    return a
 
 
 def particle_push_p(x0, v0, q, m, E0, j0, N, Ng, p2c, dx, dt, L, tol, maxiter):
     """pypic.py:216-300: implicit particle push + field advance.  Returns x1, v1, E1, j1."""
-    sim = PeriodicImplicitSim(N, Ng, dx, dt, L, p2c, q=_uniform(q, "q"), m=_uniform(m, "m"), tol=tol, maxiter=maxiter)
+    sim = PeriodicImplicitSim(N, Ng, dx, dt, L, p2c, q=_scalar_or_array(q), m=_scalar_or_array(m), tol=tol, maxiter=maxiter)
     sim.upload(np.asarray(x0, dtype=np.float64), np.asarray(v0, dtype=np.float64), np.asarray(E0, dtype=np.float64))
     k, r = sim.push()
     sim.check()

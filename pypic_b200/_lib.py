@@ -112,6 +112,7 @@ _SIGS = {
     "pic_dev_pypic_field_update": [C.POINTER(PypicParams), P, P, P, P, P, P, P, P],
     "pic_dev_pypic_picard_iter2": [C.POINTER(PypicParams), P, P, P, P, P, P, P, I32, P, P],
     "pic_dev_pypic_picard_iter3": [C.POINTER(PypicParams), P, P, P, P, P, P, P, I32, P, P, P],
+    "pic_dev_pypic_picard_iter_qm": [C.POINTER(PypicParams), P, P, P, P, P, P, P, P, P, I32, P, P, P],
     "pic_dev_pypic_field_update2": [C.POINTER(PypicParams), P, P, P, P, P, P, P, P, P, P, F64, I32, P],
     "pic_dev_pypic_j1_repair": [C.POINTER(PypicParams), P, P, P, P, P, P, I32, P, P, P],
     "pic_dev_pypic_j1_finish": [C.POINTER(PypicParams), P, P, P, P],
@@ -127,6 +128,7 @@ _SIGS = {
     "pic_dev_gc_weight": [P, P, P, P, P, P, I64, I32, F64, P, P],
     "pic_dev_gc_push_boris": [C.POINTER(GCParams), C.POINTER(R7), P, P, P, P, P, P, P, P, P],
     "pic_dev_gc_push_boris_uniform": [C.POINTER(GCParams), C.POINTER(R7), F64, F64, F64, P, P, P, P, P, P, P, P],
+    "pic_dev_gc_push_boris_uniform2": [C.POINTER(GCParams), C.POINTER(R7), F64, F64, F64, I32, F64, P, P, P, P, P, P, P, P],
     "pic_dev_gc_post_push": [P, P, P, P, P, P, P, I32, F64, F64, F64, C.POINTER(C.c_double * 4), I32, P, P, P, P, I64, P, P],
     "pic_dev_gc_uniform_finish": [P, P, P, I32, F64, P],
     "pic_dev_gc_deposit_idx": [P, P, I64, F64, F64, I32, P, P, P],

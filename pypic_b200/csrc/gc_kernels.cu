@@ -153,7 +153,10 @@ __global__ void __launch_bounds__(256) gc_push_boris_k(GCK k, R7 r, const double
 #define G_ROWS 16
 #define G_CHUNK (G_T * 2 * G_ROWS)
 
-struct GUni { double cs, m, p2c; };
+// lean: the store does not track y, z and the per-particle clock (nothing on the path reads them: E
+// depends on x only); the kernel then streams x,vx,vy,vz alone -- 64 B per particle-step, the row of
+// SURVEY.md 8(d) -- and a particle that hits a wall gets its clock r[6] = tnow (the time of this push)
+struct GUni { double cs, m, p2c; int lean; double tnow; };
 struct GFastC {
     double dx, idx, dt, cE, tx, ty, tz, sx, sy, sz, nr;
     unsigned hi_lim;
@@ -195,7 +198,7 @@ __device__ __noinline__ int gc_particle_exact(const GCK& k, const GUni& u, const
                                               double* __restrict__ n_acc, int* hits) {
     int bad = 0;
     if (act != 1) { if (hit_flag) hit_flag[i] = 0; return 0; }
-    double x = r.r[0][i], y = r.r[1][i], z = r.r[2][i], vx = r.r[3][i], vy = r.r[4][i], vz = r.r[5][i];
+    double x = r.r[0][i], y = u.lean ? 0.0 : r.r[1][i], z = u.lean ? 0.0 : r.r[2][i], vx = r.r[3][i], vy = r.r[4][i], vz = r.r[5][i];
     const double Ex = gather_mirrored(sE, x, k.dx, 1.0 / k.dx, k.ng, bad);
     const double constant = 0.5 * k.dt * u.cs * 1.602e-19 / u.m;
     vx += constant * Ex;
@@ -210,9 +213,10 @@ __device__ __noinline__ int gc_particle_exact(const GCK& k, const GUni& u, const
     vz += vfx * sy - vfy * sx;
     vx += constant * Ex;
     x += vx * k.dt; y += vy * k.dt; z += vz * k.dt;
-    r.r[0][i] = x; r.r[1][i] = y; r.r[2][i] = z; r.r[3][i] = vx; r.r[4][i] = vy; r.r[5][i] = vz;
-    r.r[6][i] = r.r[6][i] + k.dt;
+    r.r[0][i] = x; r.r[3][i] = vx; r.r[4][i] = vy; r.r[5][i] = vz;
     const bool hit = (x < 0.0) || (x > k.length);                         // :685
+    if (!u.lean) { r.r[1][i] = y; r.r[2][i] = z; r.r[6][i] = r.r[6][i] + k.dt; }
+    else if (hit) r.r[6][i] = u.tnow;
     if (hit) { active[i] = 0; at_wall[i] = 1; ++*hits; }
     if (hit_flag) hit_flag[i] = hit ? 1 : 0;
     if (!hit && n_acc) {
@@ -231,7 +235,7 @@ __device__ __forceinline__ void gwin_add(double* myw, double* __restrict__ acc, 
     else { atomicAdd(&acc[c], vL); atomicAdd(&acc[c + 1], vR); }
 }
 
-template <int NST, bool DEP>
+template <int NST, bool DEP, bool LEAN = false>
 __global__ void __launch_bounds__(G_T, 1) gc_push_boris_v2_k(const __grid_constant__ GCK k, const GUni u, int nchunks,
                                                               const R7 r, int8_t* __restrict__ active,
                                                               int8_t* __restrict__ at_wall, int8_t* __restrict__ hit_flag,
@@ -245,8 +249,9 @@ __global__ void __launch_bounds__(G_T, 1) gc_push_boris_v2_k(const __grid_consta
     const int NP = (ng + 15) & ~15;
     double* sE = sm;
     double* win = sm + NP;                                   // [G_W][G_T]
-    double* ring = win + (DEP ? G_W * G_T : 0);              // [warp][stage][7][64]
-    unsigned long long* bars = (unsigned long long*)(ring + (G_T / 32) * NST * 448);
+    constexpr int SD = LEAN ? 256 : 448;                     // doubles per stage: 4 or 7 arrays x 64 particles
+    double* ring = win + (DEP ? G_W * G_T : 0);              // [warp][stage][7 or 4][64]
+    unsigned long long* bars = (unsigned long long*)(ring + (G_T / 32) * NST * SD);
     for (int i = threadIdx.x; i < ng; i += G_T) sE[i] = Egrid[i];
     double* myw = win + threadIdx.x;
     if (DEP) {
@@ -257,7 +262,7 @@ __global__ void __launch_bounds__(G_T, 1) gc_push_boris_v2_k(const __grid_consta
     const unsigned full = 0xffffffffu;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wbase = threadIdx.x & ~31;
     const int NOWIN = -0x40000000;
-    const double* wring = ring + warp * (NST * 448);
+    const double* wring = ring + warp * (NST * SD);
     const uint32_t ring_s = smem_u32(wring);
     const uint32_t bar_s = smem_u32(bars + warp * NST);
     if (lane == 0) {
@@ -281,10 +286,16 @@ __global__ void __launch_bounds__(G_T, 1) gc_push_boris_v2_k(const __grid_consta
     const long long chunk_step = (long long)gridDim.x * G_CHUNK;
     auto issue = [&](long long base, int st) {
         if (elect_one()) {
-            const uint32_t dst = ring_s + st * 3584, bar = bar_s + 8 * st;
-            mbar_expect_tx(bar, 3584u);
+            const uint32_t dst = ring_s + st * (SD * 8), bar = bar_s + 8 * st;
+            mbar_expect_tx(bar, (uint32_t)(SD * 8));
+            if (LEAN) {
+                bulk_g2s(dst, r.r[0] + base, 512, bar);
 #pragma unroll
-            for (int a = 0; a < 7; ++a) bulk_g2s(dst + 512 * a, r.r[a] + base, 512, bar);
+                for (int a = 3; a < 6; ++a) bulk_g2s(dst + 512 * (a - 2), r.r[a] + base, 512, bar);
+            } else {
+#pragma unroll
+                for (int a = 0; a < 7; ++a) bulk_g2s(dst + 512 * a, r.r[a] + base, 512, bar);
+            }
         }
     };
     long long cbase = (long long)blockIdx.x * G_CHUNK + woff;
@@ -305,10 +316,13 @@ __global__ void __launch_bounds__(G_T, 1) gc_push_boris_v2_k(const __grid_consta
             const short fl = *(const short*)(active + ci);
             const int acta = (int)(signed char)(fl & 0xff), actb = (int)(signed char)(fl >> 8);
             mbar_wait(bar_s + 8 * stage, phase);
-            const double* sb = wring + stage * 448 + 2 * lane;
-            const double2 X = *(const double2*)sb, Y = *(const double2*)(sb + 64), Z = *(const double2*)(sb + 128);
-            const double2 VX = *(const double2*)(sb + 192), VY = *(const double2*)(sb + 256), VZ = *(const double2*)(sb + 320);
-            const double2 T = *(const double2*)(sb + 384);
+            const double* sb = wring + stage * SD + 2 * lane;
+            const double2 X = *(const double2*)sb;
+            const double2 zero2 = make_double2(0., 0.);
+            const double2 Y = LEAN ? zero2 : *(const double2*)(sb + 64), Z = LEAN ? zero2 : *(const double2*)(sb + 128);
+            const double2 VX = *(const double2*)(sb + (LEAN ? 64 : 192)), VY = *(const double2*)(sb + (LEAN ? 128 : 256));
+            const double2 VZ = *(const double2*)(sb + (LEAN ? 192 : 320));
+            const double2 T = LEAN ? zero2 : *(const double2*)(sb + 384);
             const int st_cur = stage;
             if (++stage == NST) { stage = 0; phase ^= 1u; }
             GFastO a, b;
@@ -323,24 +337,26 @@ __global__ void __launch_bounds__(G_T, 1) gc_push_boris_v2_k(const __grid_consta
             }
             if (!(ra | rb)) {
                 __stcs((double2*)(r.r[0] + ci), make_double2(a.x, b.x));
-                __stcs((double2*)(r.r[1] + ci), make_double2(a.y, b.y));
-                __stcs((double2*)(r.r[2] + ci), make_double2(a.z, b.z));
+                if (!LEAN) {
+                    __stcs((double2*)(r.r[1] + ci), make_double2(a.y, b.y));
+                    __stcs((double2*)(r.r[2] + ci), make_double2(a.z, b.z));
+                }
                 __stcs((double2*)(r.r[3] + ci), make_double2(a.vx, b.vx));
                 __stcs((double2*)(r.r[4] + ci), make_double2(a.vy, b.vy));
                 __stcs((double2*)(r.r[5] + ci), make_double2(a.vz, b.vz));
-                __stcs((double2*)(r.r[6] + ci), make_double2(a.t, b.t));
+                if (!LEAN) __stcs((double2*)(r.r[6] + ci), make_double2(a.t, b.t));
                 if (DEP) { gwin_add(myw, n_acc, wb, a.cF, a.fL, a.fR); gwin_add(myw, n_acc, wb, b.cF, b.fL, b.fR); }
             } else {
                 if (ra) bad += gc_particle_exact(k, u, r, ci, acta, sE, active, at_wall, hit_flag, DEP ? n_acc : nullptr, &hits);
                 else {
-                    r.r[0][ci] = a.x; r.r[1][ci] = a.y; r.r[2][ci] = a.z; r.r[3][ci] = a.vx; r.r[4][ci] = a.vy;
-                    r.r[5][ci] = a.vz; r.r[6][ci] = a.t;
+                    r.r[0][ci] = a.x; r.r[3][ci] = a.vx; r.r[4][ci] = a.vy; r.r[5][ci] = a.vz;
+                    if (!LEAN) { r.r[1][ci] = a.y; r.r[2][ci] = a.z; r.r[6][ci] = a.t; }
                     if (DEP) gwin_add(myw, n_acc, wb, a.cF, a.fL, a.fR);
                 }
                 if (rb) bad += gc_particle_exact(k, u, r, ci + 1, actb, sE, active, at_wall, hit_flag, DEP ? n_acc : nullptr, &hits);
                 else {
-                    r.r[0][ci + 1] = b.x; r.r[1][ci + 1] = b.y; r.r[2][ci + 1] = b.z; r.r[3][ci + 1] = b.vx;
-                    r.r[4][ci + 1] = b.vy; r.r[5][ci + 1] = b.vz; r.r[6][ci + 1] = b.t;
+                    r.r[0][ci + 1] = b.x; r.r[3][ci + 1] = b.vx; r.r[4][ci + 1] = b.vy; r.r[5][ci + 1] = b.vz;
+                    if (!LEAN) { r.r[1][ci + 1] = b.y; r.r[2][ci + 1] = b.z; r.r[6][ci + 1] = b.t; }
                     if (DEP) gwin_add(myw, n_acc, wb, b.cF, b.fL, b.fR);
                 }
             }
@@ -897,16 +913,24 @@ int pic_dev_gc_push_boris(const pic_gc_params* p, double* const r[7], const doub
 int pic_dev_gc_push_boris_uniform(const pic_gc_params* p, double* const r[7], double charge_state, double m, double p2c,
                                   int8_t* active, int8_t* at_wall, int8_t* hit_flag, const double* Egrid,
                                   double* n_acc, long long* hit_count, int* range_err, void* stream) {
+    return pic_dev_gc_push_boris_uniform2(p, r, charge_state, m, p2c, 0, 0.0, active, at_wall, hit_flag, Egrid, n_acc,
+                                          hit_count, range_err, stream);
+}
+
+int pic_dev_gc_push_boris_uniform2(const pic_gc_params* p, double* const r[7], double charge_state, double m, double p2c,
+                                   int lean, double t_now, int8_t* active, int8_t* at_wall, int8_t* hit_flag,
+                                   const double* Egrid, double* n_acc, long long* hit_count, int* range_err,
+                                   void* stream) {
     PIC_REQUIRE(p && r && active && at_wall && Egrid, "gc_push_boris_uniform: null pointer");
     PIC_REQUIRE(!(p->flags & 3), "gc_push_boris_uniform: pre-gathered E / no-BC modes are not supported");
     PIC_REQUIRE(p->ng >= 8, "gc_push_boris_uniform: grid too small");
     if (p->N == 0) return PIC_OK;
     GCK k = make_gck(p);
-    GUni u{charge_state, m, p2c};
+    GUni u{charge_state, m, p2c, lean ? 1 : 0, t_now};
     R7 rr;
     bool aligned = true;
     for (int i = 0; i < 7; ++i) {
-        PIC_REQUIRE(r[i], "gc_push_boris_uniform: null component array");
+        PIC_REQUIRE(r[i] || (lean && (i == 1 || i == 2)), "gc_push_boris_uniform: null component array");
         rr.r[i] = r[i];
         aligned = aligned && (((uintptr_t)r[i]) & 15) == 0;
     }
@@ -914,25 +938,28 @@ int pic_dev_gc_push_boris_uniform(const pic_gc_params* p, double* const r[7], do
     cudaStream_t st = (cudaStream_t)stream;
     const bool dep = n_acc != nullptr;
     auto smem_for = [&](int nst) {
-        return ((size_t)((k.ng + 15) & ~15) + (dep ? (size_t)G_W * G_T : 0) + (size_t)(G_T / 32) * nst * 448 +
+        return ((size_t)((k.ng + 15) & ~15) + (dep ? (size_t)G_W * G_T : 0) + (size_t)(G_T / 32) * nst * (lean ? 256 : 448) +
                 (size_t)(G_T / 32) * nst) * sizeof(double);
     };
     const size_t cap = (size_t)max_optin_smem() - 512;
-    const int nst = smem_for(3) <= cap ? 3 : 2;
+    const int nst = lean ? (smem_for(4) <= cap ? 4 : 3) : (smem_for(3) <= cap ? 3 : 2);
     const size_t smem = smem_for(nst);
     PIC_REQUIRE(smem <= cap, "gc_push_boris_uniform: ng too large for the shared-memory field tile");
     const long long nchunks = k.N / G_CHUNK;
     if (nchunks > 0) {
         long long capc = device_sm_count();
         const int grid = (int)(nchunks < capc ? nchunks : capc);
-#define PIC_GC_LAUNCH(NST, DEP)                                                                                  \
+#define PIC_GC_LAUNCH(NST, DEP, ...)                                                                             \
         do {                                                                                                     \
-            auto kern = gc_push_boris_v2_k<NST, DEP>;                                                            \
+            auto kern = gc_push_boris_v2_k<NST, DEP, ##__VA_ARGS__>;                                             \
             PIC_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
             kern<<<grid, G_T, smem, st>>>(k, u, (int)nchunks, rr, active, at_wall, hit_flag, Egrid, n_acc,       \
                                            hit_count, range_err);                                                \
         } while (0)
-        if (nst == 3) { if (dep) PIC_GC_LAUNCH(3, true); else PIC_GC_LAUNCH(3, false); }
+        if (lean) {
+            if (nst == 4) { if (dep) PIC_GC_LAUNCH(4, true, true); else PIC_GC_LAUNCH(4, false, true); }
+            else { if (dep) PIC_GC_LAUNCH(3, true, true); else PIC_GC_LAUNCH(3, false, true); }
+        } else if (nst == 3) { if (dep) PIC_GC_LAUNCH(3, true); else PIC_GC_LAUNCH(3, false); }
         else { if (dep) PIC_GC_LAUNCH(2, true); else PIC_GC_LAUNCH(2, false); }
 #undef PIC_GC_LAUNCH
         PIC_CHECK_LAUNCH();

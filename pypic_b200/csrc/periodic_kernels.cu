@@ -31,10 +31,14 @@ struct PYK {
     int Ng, flags;
     double dx, idx, dt, L, p2c, q, qm;
     const int* done;      // enqueue-ahead Picard loop: non-null and *done != 0 -> the particle kernels return at once
+    // per-particle charge and mass (pypic.py:248 takes q, m as arrays: q_m = q / m): served by the
+    // grid-stride kernel, which then reads them instead of the scalars above
+    const double* qa;
+    const double* ma;
 };
 static PYK make_pyk(const pic_pypic_params* p) {
     PYK k;
-    k.done = nullptr;
+    k.done = nullptr; k.qa = nullptr; k.ma = nullptr;
     k.N = p->N; k.Ng = p->Ng; k.flags = p->flags; k.dx = p->dx; k.idx = 1. / p->dx; k.dt = p->dt;
     k.L = p->L; k.p2c = p->p2c; k.q = p->q; k.qm = p->q / p->m;
     return k;
@@ -113,8 +117,10 @@ __global__ void __launch_bounds__(256) pypic_picard_iter_k(PYK k, const double* 
             Cell c = cell_pypic<false>(xs, k.dx, k.idx, Ng);
             pypic_fix(c, Ng, bad);
             double Ei = sF[c.iL] * c.wL + sF[c.iR] * c.wR;
-            double X1 = X0 + k.dt * V0 + dtdt * k.qm * Ei * 0.5;   // pypic.py:264
-            double V1 = V0 + k.dt * k.qm * Ei;                       // :265
+            const double qi = k.qa ? k.qa[i] : k.q;
+            const double qmi = k.qa ? qi / k.ma[i] : k.qm;           // q_m = q/m, pypic.py:248
+            double X1 = X0 + k.dt * V0 + dtdt * qmi * Ei * 0.5;    // pypic.py:264
+            double V1 = V0 + k.dt * qmi * Ei;                        // :265
             double XH = (X0 + X1) * 0.5, VH = (V0 + V1) * 0.5;      // :268-269
             st_stream(x1 + i, X1);
             if (!(k.flags & 8)) st_stream(v1 + i, V1);               // bit3: light iteration (no v1 store, no j1 deposit)
@@ -122,12 +128,12 @@ __global__ void __launch_bounds__(256) pypic_picard_iter_k(PYK k, const double* 
             double x1w = wrap_mod(X1, k.L);                          // :277
             ch = cell_pypic<false>(xhw, k.dx, k.idx, Ng);
             pypic_fix(ch, Ng, bad);
-            double jh_i = k.q * VH * k.p2c * k.idx;                  // :121
+            double jh_i = qi * VH * k.p2c * k.idx;                   // :121
             hL = jh_i * ch.wL; hR = jh_i * ch.wR;
             if (!(k.flags & 8)) {       // bit3: light iteration, j1 (only used after the loop) is not deposited
                 cf = cell_pypic<false>(x1w, k.dx, k.idx, Ng);
                 pypic_fix(cf, Ng, bad);
-                double j1_i = k.q * V1 * k.p2c * k.idx;
+                double j1_i = qi * V1 * k.p2c * k.idx;
                 fL = j1_i * cf.wL; fR = j1_i * cf.wR;
             }
         }
@@ -937,6 +943,18 @@ int pic_dev_pypic_picard_iter3(const pic_pypic_params* p, const double* x0, cons
     PYK t = k;
     t.N = k.N - done;
     return pypic_iter_v1(t, p->flags, x0 + done, v0 + done, x1i + done, x1 + done, v1 + done, Fs, acc, first, range_err, st);
+}
+
+int pic_dev_pypic_picard_iter_qm(const pic_pypic_params* p, const double* x0, const double* v0, const double* x1i,
+                                 double* x1, double* v1, const double* q, const double* m, const double* Fs, double* acc,
+                                 int first, int* range_err, const int32_t* done_flag, void* stream) {
+    PIC_REQUIRE(p && x0 && v0 && x1i && x1 && v1 && q && m && Fs && acc, "pypic_picard_iter_qm: null pointer");
+    PIC_REQUIRE(p->Ng >= 2 && p->dx > 0, "pypic_picard_iter_qm: bad parameters");
+    PIC_REQUIRE(!(p->flags & 8), "pypic_picard_iter_qm: light iterations are not offered with per-particle q, m");
+    if (p->N == 0) return PIC_OK;
+    PYK k = make_pyk(p);
+    k.done = done_flag; k.qa = q; k.ma = m;
+    return pypic_iter_v1(k, p->flags | 4, x0, v0, x1i, x1, v1, Fs, acc, first, range_err, (cudaStream_t)stream);
 }
 
 int pic_dev_pypic_field_update(const pic_pypic_params* p, double* acc, const double* E0, double* Es, double* Fs,

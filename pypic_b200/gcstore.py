@@ -168,6 +168,12 @@ class ParticleStore:
         self.range_err = torch.zeros(1, dtype=torch.int32, device=dev)
         self.mode = 0
         self._uniform = False                       # False: unknown, None: not uniform, tuple: (cs, m, p2c)
+        # carry_yzt = False ("lean" store): the fused Boris kernel streams x, vx, vy, vz only (64 B per
+        # particle-step instead of 112 B): y and z are not advanced (nothing on the path reads them: the
+        # field depends on x alone) and the per-particle clock r[6] is kept implicitly -- it equals the
+        # time of the last push for every active particle and is written at the moment a particle dies
+        self.carry_yzt = True
+        self.time = 0.0                             # time of the last push_6D (lean stores: the active particles' clock)
 
     # -- construction / export -----------------------------------------------------------
     @classmethod
@@ -210,7 +216,12 @@ class ParticleStore:
         self._uniform = False
 
     def r_host(self):
-        return np.stack([c[:self.N].cpu().numpy() for c in self.r], 1)
+        r = np.stack([c[:self.N].cpu().numpy() for c in self.r], 1)
+        if not self.carry_yzt:
+            act = self.active[:self.N].cpu().numpy() == 1
+            r[:, 1:3] = np.nan                      # not tracked by a lean store
+            r[act, 6] = self.time                   # the clock of the active particles is the time of the last push
+        return r
 
     def flags_host(self):
         return {k: getattr(self, k)[:self.N].cpu().numpy() for k in self.FLAGS}
@@ -236,23 +247,29 @@ class ParticleStore:
                   D.ptr(self.range_err), D.stream())
         return out[:self.N].cpu().numpy()
 
-    def push_6D(self, dt, grid, deposit=False):
+    def push_6D(self, dt, grid, deposit=False, time=None):
         """Fused interpolate_electric_field_dirichlet + push_6D + apply_BCs_dirichlet for all
         active particles (pygcpic.py:1500-1502).  Returns the number of wall hits.
 
         A species-uniform store takes the TMA-ring kernel; with deposit=True that kernel also
         deposits the number density of the survivors at their new positions into grid.n_acc
-        (the next step's weight_particles_to_grid_boltzmann, see GridDev.finish_fused_deposit)."""
+        (the next step's weight_particles_to_grid_boltzmann, see GridDev.finish_fused_deposit).
+        time: the simulation time after this push (default: the store's own clock + dt)."""
         P = self._params(grid, dt)
         r7 = self._r7()
         self.hit_count.zero_()
+        self.time = float(time) if time is not None else self.time + float(dt)
         u = self.uniform() if self.N >= self.FUSED_MIN and grid.ng >= 8 else None
+        if u is None and not self.carry_yzt:
+            raise _lib.PicError(_lib.PIC_ERR_ARG, "a lean store (carry_yzt=False) is served by the species-uniform fused kernel only "
+                                "(all particles share charge_state, m, p2c; N >= %d)" % self.FUSED_MIN)
         if u is not None:
             if deposit:
                 grid.begin_fused_deposit()
-            _lib.call("pic_dev_gc_push_boris_uniform", C.byref(P), C.byref(r7), u[0], u[1], u[2], D.ptr(self.active),
-                      D.ptr(self.at_wall), D.ptr(self.hit_flag), D.ptr(grid.E), D.ptr(grid.n_acc) if deposit else None,
-                      D.ptr(self.hit_count), D.ptr(self.range_err), D.stream())
+            _lib.call("pic_dev_gc_push_boris_uniform2", C.byref(P), C.byref(r7), u[0], u[1], u[2],
+                      0 if self.carry_yzt else 1, self.time, D.ptr(self.active), D.ptr(self.at_wall), D.ptr(self.hit_flag),
+                      D.ptr(grid.E), D.ptr(grid.n_acc) if deposit else None, D.ptr(self.hit_count), D.ptr(self.range_err),
+                      D.stream())
             return int(D.read_raw(self.hit_count, 1, np.int64)[0])
         _lib.call("pic_dev_gc_push_boris", C.byref(P), C.byref(r7), D.ptr(self.charge_state), D.ptr(self.m),
                   D.ptr(self.active), D.ptr(self.at_wall), D.ptr(self.hit_flag), D.ptr(grid.E), D.ptr(self.hit_count),
@@ -411,7 +428,8 @@ class ParticleStore:
         # a species-uniform store holds the same charge_state / m / p2c in every slot: permuting
         # those three arrays would be the identity (saves 48 of ~180 B/particle of the permutation)
         uni = self.uniform() is not None
-        f_src = self.r[1:] + ([] if uni else [self.charge_state, self.m, self.p2c])
+        comps = list(range(1, 7)) if self.carry_yzt else [3, 4, 5, 6]      # a lean store does not track y, z
+        f_src = [self.r[c] for c in comps] + ([] if uni else [self.charge_state, self.m, self.p2c])
         f_dst = [torch.empty(N, dtype=torch.float64, device=dev) for _ in f_src]
         b_src = [self.active, self.at_wall, self.from_wall, self.hit_flag]
         b_dst = [torch.empty(N, dtype=torch.int8, device=dev) for _ in b_src]
@@ -419,9 +437,13 @@ class ParticleStore:
         arr = lambda ts: (C.c_void_p * len(ts))(*[t.data_ptr() for t in ts])
         _lib.call("pic_dev_soa_permute", D.ptr(idx), N, arr(f_src), arr(f_dst), len(f_src), arr([self.Z]), arr([z_dst]), 1,
                   arr(b_src), arr(b_dst), len(b_src), st)
-        self.r = [xs] + f_dst[:6]
+        newr = list(self.r)
+        newr[0] = xs
+        for c, t in zip(comps, f_dst):
+            newr[c] = t
+        self.r = newr
         if not uni:
-            self.charge_state, self.m, self.p2c = f_dst[6:]
+            self.charge_state, self.m, self.p2c = f_dst[len(comps):]
         self.Z = z_dst
         self.active, self.at_wall, self.from_wall, self.hit_flag = b_dst
         if track:

@@ -46,6 +46,16 @@ class PeriodicImplicitSim:
         self.perm = None                     # original index of the particle in each slot (after sorting)
         self.track_order = bool(track_order)  # False: do not carry the original index through the sorts (download()
                                               # then returns the particles in store order)
+        # q, m: scalars (one species, the reference's only use) or per-particle arrays (the signature of
+        # particle_push_p, pypic.py:248): arrays take the grid-stride kernel, unsorted, full iterations
+        self.qm_arrays = None
+        if np.ndim(q) or np.ndim(m):
+            qa = np.broadcast_to(np.asarray(q, dtype=np.float64), (self.N_global,))[self.start:self.stop]
+            ma = np.broadcast_to(np.asarray(m, dtype=np.float64), (self.N_global,))[self.start:self.stop]
+            self.qm_arrays = (D.to_dev(qa, self.dev), D.to_dev(ma, self.dev))
+            self.sort_every = 0
+            flags = (flags | 4) & ~1
+            q, m = float(qa[0]) if len(qa) else -e, float(ma[0]) if len(ma) else me
         self.params = _lib.PypicParams(self.N, self.Ng, flags, self.dx, self.dt, self.L, self.p2c, float(q), float(m))
         dev, n, g = self.dev, max(self.N, 1), self.Ng
         self.x0 = D.f64(n, dev, True); self.v0 = D.f64(n, dev, True)
@@ -64,7 +74,7 @@ class PeriodicImplicitSim:
         self.last_iters, self.last_resid = 0, 1.0
         self.kernel_launches = 0
         self.iter_events = None     # set to a list to record a CUDA-event pair per particle-kernel launch
-        self.light_iterations = True
+        self.light_iterations = self.qm_arrays is None
         self.x1b = None              # second n+1 position buffer (allocated with the first light push)
         self.Fs_prev = None
         self._ratio, self._r1 = None, None
@@ -144,8 +154,14 @@ class PeriodicImplicitSim:
             if self.iter_events is not None:
                 ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
                 ev[0].record()
-            _lib.call("pic_dev_pypic_picard_iter3", P, D.ptr(self.x0), D.ptr(self.v0), D.ptr(xin), D.ptr(xout), D.ptr(self.v1),
-                      D.ptr(self.Fs), D.ptr(self.acc), 1 if j == 0 else 0, D.ptr(self.range_err), D.ptr(self.ctl), st)
+            if self.qm_arrays is not None:
+                _lib.call("pic_dev_pypic_picard_iter_qm", P, D.ptr(self.x0), D.ptr(self.v0), D.ptr(xin), D.ptr(xout),
+                          D.ptr(self.v1), D.ptr(self.qm_arrays[0]), D.ptr(self.qm_arrays[1]), D.ptr(self.Fs), D.ptr(self.acc),
+                          1 if j == 0 else 0, D.ptr(self.range_err), D.ptr(self.ctl), st)
+            else:
+                _lib.call("pic_dev_pypic_picard_iter3", P, D.ptr(self.x0), D.ptr(self.v0), D.ptr(xin), D.ptr(xout),
+                          D.ptr(self.v1), D.ptr(self.Fs), D.ptr(self.acc), 1 if j == 0 else 0, D.ptr(self.range_err),
+                          D.ptr(self.ctl), st)
             if ev is not None:
                 ev[1].record()
             self.comm.allreduce_sum(self.acc)

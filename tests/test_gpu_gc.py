@@ -247,6 +247,42 @@ def test_uniform_fused_boris_matches_v1_kernels(ng):
     assert abs(b[6] - a[6]) <= 1e-13 * abs(a[6])
 
 
+def test_lean_store_boris_is_bit_identical_in_x_and_v():
+    """ParticleStore.carry_yzt = False: the fused kernel streams x, vx, vy, vz only (64 B per
+    particle-step).  Over several steps with wall hits: x, v, flags, hit counts and the deposited
+    density bit-identical to the full store; the clock of every particle is still known (time of the
+    last push for the active ones, time of death for the absorbed ones); y, z are reported as NaN."""
+    import torch
+    from pypic_b200.gcstore import GridDev, ParticleStore
+    rs = np.random.RandomState(6)
+    ng = 301; Lg = 3e-3; Te = 60 * 11600.; dt = 2e-9
+    N = 4 * 16384 + 77
+    r = np.zeros((N, 7))
+    r[:, 0] = np.sort(rs.uniform(0, Lg, N)); r[:, 3:6] = rs.normal(0, 7e4, (N, 3))
+    B = (2 * np.cos(1.5), 2 * np.sin(1.5), 0.)
+    E = rs.normal(0, 5e4, ng)
+    out = {}
+    for lean in (False, True):
+        grid = GridDev(ng, Lg, Te); grid.E.copy_(torch.as_tensor(E))
+        st = ParticleStore.from_arrays(r, 1.0, O.mp, 3.1e9, Z=1, B=B)
+        st.carry_yzt = not lean
+        hits = []
+        for s_ in range(5):
+            hits.append(st.push_6D(dt, grid, deposit=True))
+            grid.finish_fused_deposit(1.0, dt)
+        st.check(); grid.check()
+        out[lean] = (st.r_host(), st.flags_host(), hits, grid.n.cpu().numpy())
+    a, b = out[False], out[True]
+    assert a[2] == b[2] and sum(a[2]) > 100
+    for c in (0, 3, 4, 5):
+        assert np.array_equal(a[0][:, c], b[0][:, c])
+    assert np.array_equal(a[1]["active"], b[1]["active"]) and np.array_equal(a[1]["at_wall"], b[1]["at_wall"])
+    assert np.array_equal(a[3], b[3])
+    assert np.all(np.isnan(b[0][:, 1:3]))
+    # clocks: the full store accumulates t += dt per push; the lean one reports the same numbers
+    assert np.array_equal(a[0][:, 6], b[0][:, 6])
+
+
 def test_mini_driver_fused_path_vs_reference_golden(golden):
     """pygcpic.run_sheath with the fused push+deposit path forced on (uniform store): the same
     integer outcomes per step as the reference's object loop."""

@@ -76,6 +76,27 @@ def test_pypic_push_at_the_reference_default_size(golden, sort_every):
         assert abs(np.sum(out["v0"] ** 2) - float(g[f"vsumsq_{t}"])) <= 1e-12 * float(g[f"vsumsq_{t}"])
 
 
+def test_pypic_push_with_per_particle_charge_and_mass():
+    """particle_push_p takes q and m as ARRAYS (pypic.py:248: q_m = q/m): a mixed electron / heavy-ion
+    store through the drop-in function against the oracle's restatement of the same loop."""
+    import contextlib, io
+    import pypic
+    rs = np.random.RandomState(12)
+    N, Ng = 30000, 64
+    L = 5170.094; dx = L / Ng; dt = 1e-5
+    x0 = rs.uniform(0, L * (1 - 1e-12), N)
+    ion = rs.uniform(size=N) < 0.4
+    q = np.where(ion, O.e, -O.e); m = np.where(ion, 50 * O.me, O.me)
+    v0 = rs.normal(0, 4e6, N) / np.sqrt(m / O.me)
+    E0 = rs.normal(0, 1e-3, Ng); j0 = np.zeros(Ng)
+    p2c = 5170.09
+    x1, v1, E1, j1, k, r = O.pypic_particle_push_p(x0, v0, q, m, E0, j0, N, Ng, p2c, dx, dt, L, 1e-3, 20)
+    with contextlib.redirect_stdout(io.StringIO()):
+        xg, vg, Eg, jg = pypic.particle_push_p(x0, v0, q, m, E0, j0, N, Ng, p2c, dx, dt, L, 1e-3, 20)
+    assert relmax(xg, x1) < 1e-12 and relmax(vg, v1) < 1e-12
+    assert relmax(Eg, E1) < 1e-10 and relmax(jg, j1) < 1e-10
+
+
 def test_pypic_push_bit_exact_first_iteration():
     """maxiter=1: one fused iteration from identical inputs -> x1,v1 bit-identical to the
     oracle's unfused NumPy arithmetic (incl. the floored-modulo wrap)."""
