@@ -871,3 +871,73 @@ def gc_ionizing_particle_loop(r, cs, m, p2c, Z, active, at_wall, from_wall, E, n
             else:
                 deleted.append(i)
     return nh, nr, deleted, nih, nib, nex, added
+
+
+# --------------------------------------------------------------------------
+# Device-mode random draws: the counter-based Philox4x32-10 generator (Salmon et
+# al., "Parallel random numbers: as easy as 1, 2, 3", SC'11; Random123 -- a published algorithm, not
+# reference code: the reference only has the MT19937 host draws) and the mappings the kernels of
+# pypic_b200/csrc/init_kernels.cu and dd_kernels.cu apply to its output.  Pinned by Random123's
+# known-answer vectors in tests/test_oracle.py.
+# --------------------------------------------------------------------------
+def philox4x32_10(c, k0, k1):
+    """c: (n,4) uint32 counters; k0, k1: uint32 key words (scalars).  Returns the (n,4) uint32 output."""
+    c = np.array(c, dtype=np.uint64).reshape(-1, 4)
+    c0, c1, c2, c3 = (c[:, j].copy() for j in range(4))
+    k0 = np.uint64(int(k0) & 0xffffffff); k1 = np.uint64(int(k1) & 0xffffffff)
+    M0, M1, mask = np.uint64(0xD2511F53), np.uint64(0xCD9E8D57), np.uint64(0xffffffff)
+    for _ in range(10):
+        p0 = M0 * c0; p1 = M1 * c2
+        hi0, lo0, hi1, lo1 = p0 >> np.uint64(32), p0 & mask, p1 >> np.uint64(32), p1 & mask
+        c0, c1, c2, c3 = hi1 ^ c1 ^ k0, lo1, hi0 ^ c3 ^ k1, lo0
+        k0 = (k0 + np.uint64(0x9E3779B9)) & mask; k1 = (k1 + np.uint64(0xBB67AE85)) & mask
+    return np.stack([c0, c1, c2, c3], 1).astype(np.uint32)
+
+
+def u53(a, b):
+    """uniform in (0,1) from two uint32 words (53 random bits), common.cuh:u53"""
+    v = (a.astype(np.uint64) << np.uint64(21)) ^ (b.astype(np.uint64) >> np.uint64(11))
+    return (v.astype(np.float64) + 0.5) * (1.0 / 9007199254740992.0)
+
+
+def u52(a, b):
+    """dd_kernels.cu:u52 (the re-injection draws)"""
+    v = (a.astype(np.uint64) << np.uint64(20)) ^ (b.astype(np.uint64) >> np.uint64(12))
+    return (v.astype(np.float64) + 0.5) * (1.0 / 4503599627370496.0)
+
+
+def dev_init_uniform_maxwellian(N, n_split, xlo, xhi, sigma, mean, seed, stream_id, goff=0):
+    """pic_dev_init_uniform_maxwellian: x ~ U(xlo,xhi), v0 ~ N(mean_s, sigma_s), v1, v2 ~ N(0, sigma_s),
+    Philox keyed by (seed, stream_id, global index).  Returns x, v0, v1, v2."""
+    g = np.arange(N, dtype=np.uint64) + np.uint64(goff)
+    lo, hi = (g & np.uint64(0xffffffff)), (g >> np.uint64(32))
+    sid = int(stream_id)
+    k0, k1 = int(seed) & 0xffffffff, ((int(seed) >> 32) & 0xffffffff) ^ 0x5bd1e995
+    c = philox4x32_10(np.stack([lo, hi, np.full(N, sid & 0xffffffff, np.uint64), np.full(N, sid >> 32, np.uint64)], 1), k0, k1)
+    d = philox4x32_10(np.stack([lo, hi, np.full(N, (sid & 0xffffffff) ^ 0x9e3779b9, np.uint64), np.full(N, sid >> 32, np.uint64)], 1),
+                      k0, k1)
+    sp = np.arange(N) >= n_split
+    sig = np.where(sp, sigma[1], sigma[0]); mu = np.where(sp, mean[1], mean[0])
+    x = xlo + u53(c[:, 0], c[:, 1]) * (xhi - xlo)
+
+    def bm(u1, u2):
+        r = np.sqrt(-2.0 * np.log(u1))
+        return r * np.cos(np.pi * (2.0 * u2)), r * np.sin(np.pi * (2.0 * u2))
+    z0, z1 = bm(u53(c[:, 2], c[:, 3]), u53(d[:, 0], d[:, 1]))
+    z2, _ = bm(u53(d[:, 2], d[:, 3]), u53(c[:, 1], d[:, 2]))
+    return x, mu + sig * z0, sig * z1, sig * z2
+
+
+def dev_reinject_philox(gid, step, seed, L, sig):
+    """dd_reinject_one (dd_kernels.cu): the device-mode re-injection draws of PIC_L_DD.py:429-450 for
+    the particles with global keys gid at time step `step`.  Returns x, u, v, w."""
+    g = np.asarray(gid, dtype=np.uint64); n = len(g)
+    lo, hi = (g & np.uint64(0xffffffff)), (g >> np.uint64(32))
+    s_lo, s_hi = int(step) & 0xffffffff, (int(step) >> 32) & 0xffffffff
+    k0, k1 = int(seed) & 0xffffffff, (int(seed) >> 32) & 0xffffffff
+    mk = lambda x3: philox4x32_10(np.stack([lo, hi, np.full(n, s_lo, np.uint64), np.full(n, s_hi ^ x3, np.uint64)], 1), k0, k1)
+    c, d, gg = mk(0), mk(0x80000000), mk(0x40000000)
+    twopi = 6.283185307179586
+    r1 = np.sqrt(-2.0 * np.log(u52(c[:, 2], c[:, 3]))); t1 = twopi * u52(d[:, 0], d[:, 1])
+    r2 = np.sqrt(-2.0 * np.log(u52(d[:, 2], d[:, 3]))); t2 = twopi * u52(gg[:, 0], gg[:, 1])
+    return u52(c[:, 0], c[:, 1]) * L, sig * r1 * np.cos(t1), sig * r1 * np.sin(t1), sig * r2 * np.cos(t2)

@@ -1056,9 +1056,12 @@ __global__ void __launch_bounds__(1024) p2p_reduce_k(P2P P, double* __restrict__
 
 // ---- function-level drop-ins ---------------------------------------------------------
 // The same field phase for grids too large for one CTA (Ng > 32768): cooperative launch, one
-// CTA per SM, grid-wide barriers between the phases; the four sums are accumulated with one
-// atomic per CTA in `red` (4 doubles, zero on entry, re-zeroed on exit), so they are re-associated
-// relative to the single-CTA kernel (round-off level differences in the residual).
+// CTA per SM, grid-wide barriers between the phases.  The four sums are formed from per-CTA partial
+// sums (g_field_part, written without atomics) that every CTA adds IN CTA ORDER after the barrier,
+// so the result does not depend on scheduling (the reproducible build stays bit-reproducible at
+// any grid size); relative to the single-CTA kernel the sums are re-associated (round-off level
+// differences in the residual).
+__device__ double g_field_part[4 * 1024];
 __global__ void __launch_bounds__(1024) dd_field_update_big_k(DDK k, double* __restrict__ acc,
                                                               double* __restrict__ wall_cum,
                                                               const double* __restrict__ E0, double* __restrict__ Es,
@@ -1068,6 +1071,7 @@ __global__ void __launch_bounds__(1024) dd_field_update_big_k(DDK k, double* __r
                                                               int* __restrict__ ctl, double tol, int maxiter) {
     cg::grid_group grid = cg::this_grid();
     __shared__ double scratch[33];
+    __shared__ double s_tot[2];
     const int Ng = k.Ng;
     if (ctl && *(volatile int*)ctl) return;       // read by every CTA before the first grid barrier; set after the last
     if (k.fix) {
@@ -1092,9 +1096,16 @@ __global__ void __launch_bounds__(1024) dd_field_update_big_k(DDK k, double* __r
     }
     sh = block_reduce<0>(sh, scratch);
     s1 = block_reduce<0>(s1, scratch);
-    if (threadIdx.x == 0) { atomicAdd(&red[0], sh); atomicAdd(&red[1], s1); }
+    if (threadIdx.x == 0) { g_field_part[4 * blockIdx.x + 0] = sh; g_field_part[4 * blockIdx.x + 1] = s1; }
     grid.sync();
-    const double meanh = red[0] / (double)Ng;
+    if (threadIdx.x == 0) {
+        double a = 0.0, b = 0.0;
+        for (int c = 0; c < (int)gridDim.x; ++c) { a += g_field_part[4 * c + 0]; b += g_field_part[4 * c + 1]; }
+        s_tot[0] = a; s_tot[1] = b;
+    }
+    __syncthreads();
+    const double meanh = s_tot[0] / (double)Ng;
+    const double sum_j1 = s_tot[1];
     const double coef = k.dt / PIC_EPS0;
     double rr = 0.0, ee = 0.0;
     for (int i = gtid; i < Ng; i += gsz) {
@@ -1111,24 +1122,23 @@ __global__ void __launch_bounds__(1024) dd_field_update_big_k(DDK k, double* __r
     }
     rr = block_reduce<0>(rr, scratch);
     ee = block_reduce<0>(ee, scratch);
-    if (threadIdx.x == 0) { atomicAdd(&red[2], rr); atomicAdd(&red[3], ee); }
+    if (threadIdx.x == 0) { g_field_part[4 * blockIdx.x + 2] = rr; g_field_part[4 * blockIdx.x + 3] = ee; }
     grid.sync();
     for (int i = gtid; i < 2 * Ng + 4; i += gsz) acc[i] = 0.0;
     if (gtid == 0) {
+        double a = 0.0, b = 0.0;
+        for (int c = 0; c < (int)gridDim.x; ++c) { a += g_field_part[4 * c + 2]; b += g_field_part[4 * c + 3]; }
         wall_cum[0] = w0; wall_cum[1] = w1; wall_cum[2] = w2; wall_cum[3] = w3;
-        const double r = sqrt(red[2]);
+        const double r = sqrt(a);
         const double it = stats[3] + 1.0;
         stats[0] = r;
-        stats[1] = red[1] / (double)Ng;
-        stats[2] = red[3];
+        stats[1] = sum_j1 / (double)Ng;
+        stats[2] = b;
         stats[3] = it;
         if (rhist && it <= (double)maxiter) rhist[(int)it - 1] = r;
+        if (ctl && (!(r > tol) || it >= (double)maxiter)) *ctl = 1;
     }
-    grid.sync();      // every CTA has read red[] and the wall counts before they are reset
-    if (gtid == 0) {
-        if (ctl && (!(stats[0] > tol) || stats[3] >= (double)maxiter)) *ctl = 1;
-        red[0] = 0.0; red[1] = 0.0; red[2] = 0.0; red[3] = 0.0;
-    }
+    (void)red;
 }
 
 __global__ void dd_interpolate_k(const double* __restrict__ F, const double* __restrict__ x,

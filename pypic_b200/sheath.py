@@ -73,9 +73,6 @@ class SheathSim:
         if self.det and self.track and self.sort_every:
             raise ValueError("deposit='window-det' sorts with the stable radix sort, which does not carry the original-index "
                              "payload yet: use sort_every=0 or track_order=False")
-        if self.det and int(Ng) > 32768:
-            raise ValueError("deposit='window-det': the cooperative field kernel used for Ng > 32768 adds its per-CTA "
-                             "partial sums with fp64 atomics, so the run would not be bit-reproducible")
         self.params = _lib.DDParams(self.N, self.n_split, self.Ng, flags, self.dx, self.dt, self.L, self.p2c,
                                     (C.c_double * 2)(*self.q), (C.c_double * 2)(*self.m))
         dev = self.dev

@@ -362,3 +362,17 @@ def test_gc_ionising_loop_golden(golden):
     assert np.array_equal(active, g["active_final"])
     assert relmax(r, g["r_final"]) < 1e-6
     assert np.random.uniform() == float(g["next_uniform"])
+
+
+def test_philox4x32_10_known_answers():
+    """The counter-based generator of the device-mode draws against Random123's published known-answer
+    vectors (kat_vectors: philox4x32 10 rounds)."""
+    kats = [([0, 0, 0, 0], (0, 0), "6627e8d5 e169c58d bc57ac4c 9b00dbd8"),
+            ([0xffffffff] * 4, (0xffffffff, 0xffffffff), "408f276d 41c83b0e a20bc7c6 6d5451fd"),
+            ([0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344], (0xa4093822, 0x299f31d0), "d16cfe09 94fdcceb 5001e420 24126ea1")]
+    for ctr, key, want in kats:
+        got = O.philox4x32_10([ctr], *key)[0]
+        assert " ".join("%08x" % v for v in got) == want
+    x, v0, v1, v2 = O.dev_init_uniform_maxwellian(200000, 100000, 0.0, 2.0, (1.0, 3.0), (0.5, 0.0), 7, 3)
+    assert 0.0 < x.min() and x.max() < 2.0 and abs(x.mean() - 1.0) < 0.01
+    assert abs(v0[:100000].mean() - 0.5) < 0.02 and abs(v1[100000:].std() - 3.0) < 0.03 and abs(v2[:100000].std() - 1.0) < 0.01
