@@ -60,6 +60,9 @@ def parse():
                     help="--workload boris: carry y, z and the per-particle clock through the push (112 B per particle-step) "
                          "instead of the lean store (x, vx, vy, vz: the 64 B row of SURVEY.md 8d)")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-api-leg", action="store_true",
+                    help="skip the `reference_api` record (the step as PIC_L_DD.main_i drives it: host MT19937 draws, carried v,w)")
+    ap.add_argument("--api-steps", type=int, default=40)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-sample", type=float, default=4e6, help="particles in the CPU-baseline sample")
     ap.add_argument("--e2e-steps", type=int, default=16)
@@ -429,6 +432,49 @@ def run_cuda(args):
         cpu = {"value": res["value"], "unit": "particle-steps/s", "cores": res["cores"], "kind": "port",
                "sample": res["sample"]}
 
+    # ---- the same workload the way the REFERENCE'S OWN API drives it (PIC_L_DD.main_i -> SheathSim(rng="host",
+    # carry_vw=True, sort_every=8)): per step the host draws the re-injected particles from the legacy MT19937 stream
+    # in the reference's index order (the thermostat's uniforms are jumped over), copies them in, and reads the
+    # step's diagnostics (iteration count, residuals, EE, KE, jbias, kBTe) and the absorption log back
+    api = None
+    if not args.no_api_leg and world == 1:
+        from pypic_b200.rng import LegacyDraws
+        sim.close(); del sim
+        torch.cuda.empty_cache()
+        sm = SheathSim(w["N"], w["Ng"], w["dx"], w["dt"], w["p2c"], tol=w["tol"], maxiter=w["maxiter"],
+                       kBT=(w["kBTe"], w["kBTi"]), carry_vw=True, rng="host", comm=comm, device=dev, sort_every=args.sort_every,
+                       draws=LegacyDraws(np.random.RandomState(1)), vion_after=2000)
+        gen = torch.Generator(device=dev); gen.manual_seed(4321)
+        sm.x0.uniform_(0.0, 1.0, generator=gen).mul_(w["L"]).clamp_(1e-12, w["L"] * (1 - 1e-12))
+        sm.u0.normal_(0.0, 1.0, generator=gen)
+        sm.u0[:sm.n_split].mul_(float(np.sqrt(w["kBTe"] / ME))); sm.u0[sm.n_split:].mul_(float(np.sqrt(w["kBTi"] / MP)))
+        torch.cuda.synchronize()
+        na = max(1, args.api_steps)
+        with sm.draws.hold():
+            for _ in range(max(3, args.warmup)):
+                sm.step(); sm.diagnostics_begin(); sm.diagnostics_end()
+            torch.cuda.synchronize()
+            l0, dead0 = sm.kernel_launches, 0
+            t0 = time.perf_counter()
+            its_api = []
+            for s_ in range(na):
+                if s_:
+                    sm.diagnostics_end()
+                its_api.append(sm.step()[0])
+                sm.diagnostics_begin()
+            d_last = sm.diagnostics_end()
+            torch.cuda.synchronize()
+            t_api = time.perf_counter() - t0
+        sm.check()
+        api = {"value": w["N"] * na / t_api, "unit": "particle-steps/s", "ms_per_step": 1e3 * t_api / na, "steps": na,
+               "picard_iterations_per_step": float(np.mean(its_api)), "gpu_launches": int(sm.kernel_launches - l0),
+               "mt_jumps": int(sm.draws.jumps), "mt_jumps_prefetched": int(sm.draws.prefetch_hits), "sorts": int(sm._sorts),
+               "timing": "host wall clock around the loop (every step ends in a device->host read)",
+               "api": "SheathSim as PIC_L_DD.main_i builds it (rng='host': legacy MT19937 draws in original-index order; "
+                      "carry_vw=True; cell sort every %d steps with the original-index payload)" % args.sort_every,
+               "last_step": {k_: float(v_) for k_, v_ in d_last.items()}}
+        sim = sm
+
     # ---- the north-star strong-scaling case (BASELINE config 4): a fixed TOTAL of particles over the N GPUs, same
     # code, same run -- the driver's 1/2/4/8 sweep then holds the whole curve (sub-record `strong_scaling`)
     strong = None
@@ -478,7 +524,8 @@ def run_cuda(args):
                                            "parallel deposit re-associates sums at 1e-13 per step and that round-off feeds back, "
                                            "DESIGN.md section 4)",
                        "l2_policy": "inputs (%.1f GB of particle arrays per GPU) are far larger than the 126 MB L2" % (n_local * 32 / 1e9)},
-            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "strong_scaling": strong, "gpu_launches": int(launches),
+            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "reference_api": api, "strong_scaling": strong,
+            "gpu_launches": int(launches),
             "clocks": clocks,
         }
     if world > 1:

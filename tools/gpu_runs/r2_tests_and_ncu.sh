@@ -13,11 +13,11 @@ done
 timeout 600 python bench.py --workload boris --boris-full-store --steps 40 --warmup 3 > gpurun_out/bench_r2_boris_full.json 2>/dev/null
 python -c "
 import json; d=json.load(open('gpurun_out/bench_r2_boris_full.json')); print('boris full store', '%.3e'%d['value'], 'frac(112B) %.3f'%d['roofline']['frac'], 'kernel ms %.3f'%d['roofline']['kernel_ms_mean'])"
-CMD="python bench.py --steps 8 --warmup 3 --no-e2e --no-cpu-baseline --strong-total 0"
+CMD="python bench.py --steps 8 --warmup 3 --no-e2e --no-cpu-baseline --no-api-leg --strong-total 0"
 $CMD > gpurun_out/plain.log 2>&1 && \
 ncu --metrics gpu__time_duration.sum --clock-control none -c 700 --csv --log-file gpurun_out/launches_r2.csv $CMD > gpurun_out/ncu_l.log 2>&1
 tail -2 gpurun_out/ncu_l.log
-CMD2="python bench.py --steps 2 --warmup 3 --no-e2e --no-cpu-baseline --strong-total 0"
+CMD2="python bench.py --steps 2 --warmup 3 --no-e2e --no-cpu-baseline --no-api-leg --strong-total 0"
 $CMD2 > gpurun_out/plain2.log 2>&1 && \
 ncu --set full --clock-control none --import-source on -k regex:dd_picard_iter_v6 -s 14 -c 6 -o gpurun_out/prof_r2_v6 $CMD2 > gpurun_out/ncu.log 2>&1
 tail -2 gpurun_out/ncu.log
