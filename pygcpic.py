@@ -16,8 +16,10 @@ Two ways to use it:
   resident in HBM as structure-of-arrays; ``run_sheath`` is the per-timestep loop of
   pic_bca_aps (pygcpic.py:1486-1563) on that store.
 
-Out of scope: the F-TRIDYN (BCA) coupling, IEAD histograms,
-Monte-Carlo ionisation and the plotting drivers ``pic_iead`` / ``pic_bca_aps`` / ``pic_bca``.
+Monte-Carlo ionisation (``Particle.attempt_first_ionization`` / ``attempt_nth_ionization`` and
+``run_sheath(..., ionize_Te=)``) and the IEAD wall-hit histograms (``pypic_b200.ops`` /
+``pic_dev_gc_iead_hist``) are built.  Out of scope: the F-TRIDYN (BCA)
+binary itself and the plotting drivers ``pic_iead`` / ``pic_bca_aps`` / ``pic_bca`` that wrap it.
 """
 import numpy as np
 import torch

@@ -249,8 +249,9 @@ __global__ void __launch_bounds__(G_T, 1) gc_push_boris_v2_k(const __grid_consta
     const int NP = (ng + 15) & ~15;
     double* sE = sm;
     double* win = sm + NP;                                   // [G_W][G_T]
-    constexpr int SD = LEAN ? 256 : 448;                     // doubles per stage: 4 or 7 arrays x 64 particles
-    double* ring = win + (DEP ? G_W * G_T : 0);              // [warp][stage][7 or 4][64]
+    constexpr int SDP = LEAN ? 256 : 448;                    // doubles of particle data per stage: 4 or 7 arrays x 64 particles
+    constexpr int SD = SDP + 16;                             // + the 64 activity flags of the row (padded to 128 B)
+    double* ring = win + (DEP ? G_W * G_T : 0);              // [warp][stage][7 or 4 arrays][64] + flags
     unsigned long long* bars = (unsigned long long*)(ring + (G_T / 32) * NST * SD);
     for (int i = threadIdx.x; i < ng; i += G_T) sE[i] = Egrid[i];
     double* myw = win + threadIdx.x;
@@ -287,7 +288,10 @@ __global__ void __launch_bounds__(G_T, 1) gc_push_boris_v2_k(const __grid_consta
     auto issue = [&](long long base, int st) {
         if (elect_one()) {
             const uint32_t dst = ring_s + st * (SD * 8), bar = bar_s + 8 * st;
-            mbar_expect_tx(bar, (uint32_t)(SD * 8));
+            mbar_expect_tx(bar, (uint32_t)(SDP * 8 + 64));
+            // the row's activity flags ride in the same stage: a plain global load of them at the top of
+            // every row would expose a full memory latency per row (they gate the fast path)
+            bulk_g2s(dst + SDP * 8, active + base, 64, bar);
             if (LEAN) {
                 bulk_g2s(dst, r.r[0] + base, 512, bar);
 #pragma unroll
@@ -312,10 +316,9 @@ __global__ void __launch_bounds__(G_T, 1) gc_push_boris_v2_k(const __grid_consta
         long long ci = cbase + 2 * lane;
 #pragma unroll 1
         for (int row = 0; row < G_ROWS; ++row, ci += 64) {
-            // flags of the pair first (plain global load; overlaps the barrier wait)
-            const short fl = *(const short*)(active + ci);
-            const int acta = (int)(signed char)(fl & 0xff), actb = (int)(signed char)(fl >> 8);
             mbar_wait(bar_s + 8 * stage, phase);
+            const short fl = *(const short*)((const char*)(wring + stage * SD + SDP) + 2 * lane);
+            const int acta = (int)(signed char)(fl & 0xff), actb = (int)(signed char)(fl >> 8);
             const double* sb = wring + stage * SD + 2 * lane;
             const double2 X = *(const double2*)sb;
             const double2 zero2 = make_double2(0., 0.);
@@ -934,11 +937,11 @@ int pic_dev_gc_push_boris_uniform2(const pic_gc_params* p, double* const r[7], d
         rr.r[i] = r[i];
         aligned = aligned && (((uintptr_t)r[i]) & 15) == 0;
     }
-    PIC_REQUIRE(aligned && (((uintptr_t)active) & 1) == 0, "gc_push_boris_uniform: arrays must be 16-byte aligned");
+    PIC_REQUIRE(aligned && (((uintptr_t)active) & 15) == 0, "gc_push_boris_uniform: arrays must be 16-byte aligned");
     cudaStream_t st = (cudaStream_t)stream;
     const bool dep = n_acc != nullptr;
     auto smem_for = [&](int nst) {
-        return ((size_t)((k.ng + 15) & ~15) + (dep ? (size_t)G_W * G_T : 0) + (size_t)(G_T / 32) * nst * (lean ? 256 : 448) +
+        return ((size_t)((k.ng + 15) & ~15) + (dep ? (size_t)G_W * G_T : 0) + (size_t)(G_T / 32) * nst * ((lean ? 256 : 448) + 16) +
                 (size_t)(G_T / 32) * nst) * sizeof(double);
     };
     const size_t cap = (size_t)max_optin_smem() - 512;

@@ -277,7 +277,7 @@ def test_lean_store_boris_is_bit_identical_in_x_and_v():
     for c in (0, 3, 4, 5):
         assert np.array_equal(a[0][:, c], b[0][:, c])
     assert np.array_equal(a[1]["active"], b[1]["active"]) and np.array_equal(a[1]["at_wall"], b[1]["at_wall"])
-    assert np.array_equal(a[3], b[3])
+    assert relmax(b[3], a[3]) < 1e-13                 # same contributions, merged in a different order
     assert np.all(np.isnan(b[0][:, 1:3]))
     # clocks: the full store accumulates t += dt per push; the lean one reports the same numbers
     assert np.array_equal(a[0][:, 6], b[0][:, 6])
