@@ -690,7 +690,7 @@ def run_other(args):
         grid.weight_particles_to_grid_boltzmann(store, dtg)
 
         def step():
-            if state["t"] % max(1, args.sort_every // 2) == 0:
+            if state["t"] % max(1, args.sort_every) == 0:
                 store.sort_by_cell(grid); state["launches"] += 16
             if grid.have_fused_n:
                 grid.finish_fused_deposit(1.0, dtg)
@@ -705,7 +705,7 @@ def run_other(args):
         alg, kname = (lambda k: 112.0 if args.boris_full_store else 64.0), "gc_push_boris_v2_k"
         desc = ("pygcpic Boris 1D3V (B=2 T at 86 deg, H+, Ti=50 eV, Te=60 eV): %d particles, %d-node grid, fused "
                 "gather+push+walls+deposit, Newton-Boltzmann field solve, store re-sorted every %d steps; %s"
-                % (N, ng, max(1, args.sort_every // 2),
+                % (N, ng, max(1, args.sort_every),
                    "full store (x,y,z,v,t streamed: 112 B per particle-step)" if args.boris_full_store else
                    "lean store (x,vx,vy,vz streamed: 64 B per particle-step; y,z not tracked, clocks implicit)"))
     for _ in range(args.warmup):

@@ -149,7 +149,13 @@ __global__ void __launch_bounds__(256) gc_push_boris_k(GCK k, R7 r, const double
 // components staged by 1-D TMA bulk copies into a per-warp ring, two particles per lane,
 // private shared-memory deposit windows.  Traffic: 7x8 B in + 7x8 B out + 1 B flag per particle.
 #define G_T 512
-#define G_W 7
+// deposit window of G_W nodes per thread.  Hydrogen ions at the reference's resolution cross ~0.6 cells per
+// step, so a 7-node window (the sheath kernel's) is left after 2-3 steps; 15 nodes hold 8 steps of drift:
+// measured at 2e8 particles (profiles/r2_boris_window_width.txt) 5.1e10 particle-steps/s with a sort every
+// 8 steps against 4.2e10 with 7 nodes and a sort every 4
+#ifndef G_W
+#define G_W 15
+#endif
 #define G_ROWS 16
 #define G_CHUNK (G_T * 2 * G_ROWS)
 
