@@ -646,6 +646,76 @@ __global__ void __launch_bounds__(256, MINB) gc_push_rk4_uniform_k(GCK k, GRk u,
     if (bad && range_err) atomicAdd(range_err, bad);
 }
 
+// Two particles per thread (128-bit loads and stores, two independent RK4 dependency chains in
+// flight per thread): the step is bound by fp64 issue and by the latency of its four dependent
+// divisions per particle, so instruction-level parallelism is what the grid-stride kernel above lacks.
+struct Rk4Out { double x0, x1, x2, x3; };
+__device__ __forceinline__ Rk4Out rk4_uniform_one(const GCK& k, const GRk& u, double r0, double r1, double r2, double r3,
+                                                  double E0, double E1, double E2, double dt) {
+    const double g1 = div_const(E2 * k.B[0] - E0 * k.B[2], u.B2, u.yB2);
+    const double g2 = div_const(E0 * k.B[1] - E1 * k.B[0], u.B2, u.yB2);
+#define GC_EOM(a0, a1, a2, a3, d0, d1, d2, d3)                                                    \
+    do {                                                                                          \
+        const double rho_ = div_const((a3), u.wc, u.ywc);                                         \
+        d0 = u.c0 + (a3) * u.b0; d1 = g1 + (a3) * u.b1; d2 = g2 + (a3) * u.b2;                    \
+        d3 = div_const(E0 * (a0) + E1 * (a1) + E2 * (a2), u.sB, u.ysB) / rho_;                   \
+    } while (0)
+    double f0, f1, f2, f3;
+    GC_EOM(r0, r1, r2, r3, f0, f1, f2, f3);
+    const double k10 = dt * f0, k11 = dt * f1, k12 = dt * f2, k13 = dt * f3;
+    GC_EOM(r0 + k10 / 2., r1 + k11 / 2., r2 + k12 / 2., r3 + k13 / 2., f0, f1, f2, f3);
+    const double k20 = dt * f0, k21 = dt * f1, k22 = dt * f2, k23 = dt * f3;
+    GC_EOM(r0 + k20 / 2., r1 + k21 / 2., r2 + k22 / 2., r3 + k23 / 2., f0, f1, f2, f3);
+    const double k30 = dt * f0, k31 = dt * f1, k32 = dt * f2, k33 = dt * f3;
+    GC_EOM(r0 + k30, r1 + k31, r2 + k32, r3 + k33, f0, f1, f2, f3);
+    const double k40 = dt * f0, k41 = dt * f1, k42 = dt * f2, k43 = dt * f3;
+#undef GC_EOM
+    Rk4Out o;
+    o.x0 = r0 + div_const(k10 + 2. * k20 + 2. * k30 + k40, 6., u.y6);
+    o.x1 = r1 + div_const(k11 + 2. * k21 + 2. * k31 + k41, 6., u.y6);
+    o.x2 = r2 + div_const(k12 + 2. * k22 + 2. * k32 + k42, 6., u.y6);
+    o.x3 = r3 + div_const(k13 + 2. * k23 + 2. * k33 + k43, 6., u.y6);
+    return o;
+}
+__device__ __forceinline__ double rk4_gather(const GCK& k, const double* __restrict__ Egrid, double r0, long long i,
+                                             double idx, int& bad) {
+    if (!Egrid) return 0.0;
+    if (k.flags & 1) return Egrid[i];
+    Cell c = cell_dd_fast(r0, k.dx, idx);
+    if (c.iL < 0 || c.iL > k.ng - 2) { ++bad; c.iL = clampi(c.iL, 0, k.ng - 2); }
+    const double w_l = c.wR, w_r = 1.0 - w_l;                   // mirrored, pygcpic.py:344-347
+    return Egrid[c.iL] * w_l + Egrid[c.iL + 1] * w_r;
+}
+template <int MINB>
+__global__ void __launch_bounds__(256, MINB) gc_push_rk4_uniform_pair_k(GCK k, GRk u, R7 r, const int8_t* __restrict__ active,
+                                                                        const double* __restrict__ Egrid, long long npairs,
+                                                                        int* __restrict__ range_err) {
+    int bad = 0;
+    const double dt = k.dt;
+    const double E1 = k.Eyz[0], E2 = k.Eyz[1];
+    const double idx = 1.0 / k.dx;
+    for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; p < npairs; p += (long long)gridDim.x * blockDim.x) {
+        const long long i = 2 * p;
+        const short fl = *(const short*)(active + i);
+        const bool aa = (signed char)(fl & 0xff) == 1, ab = (signed char)(fl >> 8) == 1;
+        if (!(aa | ab)) continue;
+        const double2 R0 = __ldcs((const double2*)(r.r[0] + i)), R1 = __ldcs((const double2*)(r.r[1] + i));
+        const double2 R2 = __ldcs((const double2*)(r.r[2] + i)), R3 = __ldcs((const double2*)(r.r[3] + i));
+        const double2 T = __ldcs((const double2*)(r.r[6] + i));
+        const double Ea = aa ? rk4_gather(k, Egrid, R0.x, i, idx, bad) : 0.0;
+        const double Eb = ab ? rk4_gather(k, Egrid, R0.y, i + 1, idx, bad) : 0.0;
+        Rk4Out a = rk4_uniform_one(k, u, R0.x, R1.x, R2.x, R3.x, Ea, E1, E2, dt);
+        Rk4Out b = rk4_uniform_one(k, u, R0.y, R1.y, R2.y, R3.y, Eb, E1, E2, dt);
+        // an inactive particle of the pair keeps its state
+        __stcs((double2*)(r.r[0] + i), make_double2(aa ? a.x0 : R0.x, ab ? b.x0 : R0.y));
+        __stcs((double2*)(r.r[1] + i), make_double2(aa ? a.x1 : R1.x, ab ? b.x1 : R1.y));
+        __stcs((double2*)(r.r[2] + i), make_double2(aa ? a.x2 : R2.x, ab ? b.x2 : R2.y));
+        __stcs((double2*)(r.r[3] + i), make_double2(aa ? a.x3 : R3.x, ab ? b.x3 : R3.y));
+        __stcs((double2*)(r.r[6] + i), make_double2(aa ? T.x + dt : T.x, ab ? T.y + dt : T.y));
+    }
+    if (bad && range_err) atomicAdd(range_err, bad);
+}
+
 // pygcpic.py:889-904.  state = {n0, p_old, initialised}
 __global__ void gc_n0_update_k(const double* __restrict__ phi, const double* __restrict__ n,
                                const double* __restrict__ domain, int ng, double Te, double ve, double added,
@@ -1074,6 +1144,25 @@ int pic_dev_gc_push_rk4_uniform(const pic_gc_params* p, double* const r[7], doub
     static int minb = -1;
     if (minb < 0) { const char* e = getenv("PIC_RK4_MINB"); minb = e ? atoi(e) : 4; }   // 4 CTAs/SM measured best (2.14 ms per 1e8; 2: 3.43, 3: 2.50, 5: 2.06, 6: 3.01)
     cudaStream_t st = (cudaStream_t)stream;
+    static int pair = -1;
+    if (pair < 0) { const char* e = getenv("PIC_RK4_PAIR"); pair = e ? atoi(e) : 3; }   // CTAs/SM of the pair kernel; 0: off
+    bool al = (((uintptr_t)active) & 1) == 0;
+    for (int i = 0; i < 7; ++i) al = al && (((uintptr_t)r[i]) & 15) == 0;
+    if (pair > 0 && al && k.N >= 2) {
+        const long long npairs = k.N / 2;
+        if (pair == 2) gc_push_rk4_uniform_pair_k<2><<<grid_for(npairs, 256, 2), 256, 0, st>>>(k, u, rr, active, Egrid, npairs, range_err);
+        else if (pair == 4) gc_push_rk4_uniform_pair_k<4><<<grid_for(npairs, 256, 4), 256, 0, st>>>(k, u, rr, active, Egrid, npairs, range_err);
+        else gc_push_rk4_uniform_pair_k<3><<<grid_for(npairs, 256, 3), 256, 0, st>>>(k, u, rr, active, Egrid, npairs, range_err);
+        PIC_CHECK_LAUNCH();
+        if (k.N % 2 == 0) return PIC_OK;
+        // the odd last particle: the one-per-thread kernel on a one-element view
+        GCK t = k; t.N = 1;
+        R7 r1;
+        for (int i = 0; i < 7; ++i) r1.r[i] = rr.r[i] + (k.N - 1);
+        gc_push_rk4_uniform_k<4><<<1, 32, 0, st>>>(t, u, r1, active + (k.N - 1), (Egrid && (k.flags & 1)) ? Egrid + (k.N - 1) : Egrid, range_err);
+        PIC_CHECK_LAUNCH();
+        return PIC_OK;
+    }
     if (minb == 2) gc_push_rk4_uniform_k<2><<<grid_for(k.N, 256, 2), 256, 0, st>>>(k, u, rr, active, Egrid, range_err);
     else if (minb == 4) gc_push_rk4_uniform_k<4><<<grid_for(k.N, 256, 4), 256, 0, st>>>(k, u, rr, active, Egrid, range_err);
     else if (minb == 5) gc_push_rk4_uniform_k<5><<<grid_for(k.N, 256, 5), 256, 0, st>>>(k, u, rr, active, Egrid, range_err);
