@@ -23,6 +23,8 @@ def test_two_rank_sheath_matches_single_gpu():
     out = [l for l in lines if "iters_sharded" in l][-1]
     assert out["ok"], out
     assert out["iters_sharded"] == out["iters_single"]
+    tracked = [l["tracked"] for l in lines if "tracked" in l]
+    assert len(tracked) == 2 and all(t["ok"] for t in tracked), tracked
     det = [l for l in lines if "det" in l][-1]["det"]
     assert det["ok"], det
     per = [l for l in lines if "periodic" in l][-1]["periodic"]

@@ -70,6 +70,42 @@ def main():
                    flags_equal=bool(np.array_equal(act, ref["active"])))
         res["ok"] = bool(its_s == its_1 and res["flags_equal"] and res["E_rel"] < 1e-10 and res["x_rel"] < 1e-11)
         print(json.dumps(res))
+    # ---- tracked order, sharded (the path PIC_L_DD.main_i takes): every rank sorts its shard by cell with the
+    # original-index payload, the host draws follow the GLOBAL original-index order (thermostat with gamma != 0
+    # included: every rank walks the whole legacy stream and applies the hits inside its range), carried v,w
+    v0 = rs.normal(0, 1e5, N); w0 = rs.normal(0, 1e5, N)
+
+    def run_tracked(comm, gamma):
+        np.random.seed(5)
+        sim = SheathSim(N, Ng, dx, dt, p2c, kBT=(kT, kT), carry_vw=True, comm=comm, device=dev, rng="host",
+                        draws=LegacyDraws(), sort_every=2, gamma=gamma, vion_after=1)
+        sim.upload(x0, u0, v0, w0, E0=E0)
+        its = [sim.step()[0] for _ in range(steps)]
+        sim.check()
+        vion = sim.collect_vionout()
+        return sim, its, vion, np.random.uniform()
+    for gamma in (0.0, 0.01):
+        ts, its_t, vion_t, nxt_t = run_tracked(Comm(), gamma)
+        ot = ts.download()
+        keys = ("x0", "u0", "v0", "w0", "active")
+        if world > 1:
+            pt = [None] * world
+            dist.all_gather_object(pt, {k_: ot[k_] for k_ in keys})
+        else:
+            pt = [{k_: ot[k_] for k_ in keys}]
+        if rank == 0:
+            t1, its_t1, vion_1, nxt_1 = run_tracked(Comm(enabled=False), gamma)
+            o1 = t1.download()
+            cat = lambda k_: np.concatenate([p_[k_] for p_ in pt])
+            rt = dict(gamma=gamma, iters_sharded=its_t, iters_single=its_t1, sorts=ts._sorts, E_rel=rel(ot["E0"], o1["E0"]),
+                      x_rel=rel(cat("x0"), o1["x0"]), u_rel=rel(cat("u0"), o1["u0"]), v_rel=rel(cat("v0"), o1["v0"]),
+                      w_rel=rel(cat("w0"), o1["w0"]), flags_equal=bool(np.array_equal(cat("active"), o1["active"])),
+                      stream_position_equal=bool(nxt_t == nxt_1), vionout_len=[len(vion_t), len(vion_1)],
+                      vionout_rel=(rel(np.array(vion_t), np.array(vion_1)) if len(vion_t) == len(vion_1) and len(vion_1) else None))
+            rt["ok"] = bool(its_t == its_t1 and rt["flags_equal"] and rt["stream_position_equal"] and rt["E_rel"] < 1e-10
+                            and rt["x_rel"] < 1e-11 and rt["u_rel"] < 1e-10 and rt["v_rel"] < 1e-12 and rt["w_rel"] < 1e-12
+                            and len(vion_t) == len(vion_1) and (rt["vionout_rel"] is None or rt["vionout_rel"] < 1e-10))
+            print(json.dumps({"tracked": rt}))
     # ---- reproducible build, sharded: the currents are all-reduced as int64 fixed-point words, so two
     # runs give bit-identical fields, every rank holds the same bits, and the result matches the
     # single-GPU reproducible run to round-off (the window partial sums differ with the sharding)
