@@ -46,6 +46,10 @@ int pic_dev_read(const void* dev, void* host, int64_t bytes, void* stream);
 int pic_dev_write(void* dev, const void* host, int64_t bytes, void* stream);
 int pic_dev_zero(void* dev, int64_t bytes, void* stream);
 int pic_dev_copy(void* dst, const void* src, int64_t bytes, void* stream);
+/* Start of a sheath timestep (PIC_L_DD.py:452-456: Es = E0, k = 0, r = 1): Es <- E0 and the cumulative
+ * wall counts (4 doubles), the step statistics (nstats doubles) and the loop flag cleared, in one call */
+int pic_dev_dd_step_begin(double* Es, const double* E0, int Ng, double* wall_cum, double* stats, int64_t nstats,
+                          int32_t* ctl, void* stream);
 int pic_stream_sync(void* stream);
 /* frees the device workspaces cached by the pic_host_* entry points */
 int pic_host_release(void);
@@ -350,6 +354,13 @@ int pic_dev_dd_sort_by_cell_stable(const pic_dd_params* p, double* x0, double* u
  * pic_dev_soa_permute.  Only p->N, n_split, Ng, dx are read. */
 int pic_dev_sort_perm_by_cell(const pic_dd_params* p, const double* x, double* xs, int32_t* perm,
                               int32_t* counts, void* stream);
+/* The counting sort carrying up to three fp64 payload arrays THROUGH the scatter (a; b, c may be NULL)
+ * and, when perm != NULL, the source slot of every output slot for the remaining arrays
+ * (pic_dev_soa_permute).  The pygcpic store sorts x with vx, vy, vz this way: the scatter writes runs,
+ * where a gather by permutation reads 8 bytes per 32-byte sector. */
+int pic_dev_sort_by_cell_payload(const pic_dd_params* p, const double* x, const double* a, const double* b, const double* c,
+                                 double* xs, double* as, double* bs, double* cs, int32_t* perm, int32_t* counts,
+                                 void* stream);
 /* dst[t] = src[perm[t]] for up to 12 fp64, 2 int32 and 6 int8 arrays in ONE pass (arrays of device
  * pointers passed from the host). */
 int pic_dev_soa_permute(const int32_t* perm, int64_t n, const double* const* src_f64,

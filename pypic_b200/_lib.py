@@ -55,6 +55,7 @@ _SIGS = {
     "pic_dev_zero": [P, I64, P],
     "pic_dev_copy": [P, P, I64, P],
     "pic_stream_sync": [P],
+    "pic_dev_dd_step_begin": [P, P, I32, P, P, I64, P, P],
     "pic_host_release": [],
     "pic_dev_smooth": [P, P, I32, I32, P],
     "pic_dev_differentiate": [P, P, I32, F64, I32, P],
@@ -105,6 +106,7 @@ _SIGS = {
     "pic_dev_dd_sort_by_cell": [C.POINTER(DDParams), P, P, P, P, P, P, P, P, P, P],
     "pic_dev_dd_sort_by_cell_stable": [C.POINTER(DDParams), P, P, P, P, P, I64, C.POINTER(C.c_int), P],
     "pic_dev_sort_perm_by_cell": [C.POINTER(DDParams), P, P, P, P, P],
+    "pic_dev_sort_by_cell_payload": [C.POINTER(DDParams), P, P, P, P, P, P, P, P, P, P, P],
     "pic_dev_soa_permute": [P, I64, P, P, I32, P, P, I32, P, P, I32, P],
     "pic_dev_pypic_interpolate": [P, P, P, I64, I32, F64, P, P],
     "pic_dev_pypic_weight": [P, P, P, P, I64, I32, F64, F64, P, P],

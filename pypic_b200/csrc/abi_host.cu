@@ -73,6 +73,17 @@ int pic_dev_zero(void* dev, int64_t bytes, void* stream) {
     PIC_CHECK_CUDA(cudaMemsetAsync(dev, 0, (size_t)bytes, (cudaStream_t)stream));
     return PIC_OK;
 }
+// start of a sheath timestep: Es = E0 and the per-step accumulators / statistics / loop flag cleared, one call
+int pic_dev_dd_step_begin(double* Es, const double* E0, int Ng, double* wall_cum, double* stats, int64_t nstats,
+                          int32_t* ctl, void* stream) {
+    PIC_REQUIRE(Es && E0 && Ng > 0 && wall_cum && stats && nstats > 0 && ctl, "dd_step_begin: bad argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    PIC_CHECK_CUDA(cudaMemcpyAsync(Es, E0, (size_t)Ng * sizeof(double), cudaMemcpyDeviceToDevice, st));
+    PIC_CHECK_CUDA(cudaMemsetAsync(wall_cum, 0, 4 * sizeof(double), st));
+    PIC_CHECK_CUDA(cudaMemsetAsync(stats, 0, (size_t)nstats * sizeof(double), st));
+    PIC_CHECK_CUDA(cudaMemsetAsync(ctl, 0, sizeof(int32_t), st));
+    return PIC_OK;
+}
 int pic_dev_copy(void* dst, const void* src, int64_t bytes, void* stream) {
     PIC_REQUIRE(dst && src && bytes >= 0, "dev_copy: bad argument");
     PIC_CHECK_CUDA(cudaMemcpyAsync(dst, src, (size_t)bytes, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));

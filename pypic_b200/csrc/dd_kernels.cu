@@ -1535,14 +1535,18 @@ __global__ void __launch_bounds__(SORTB_T) dd_sort_scatter_big_k(DDK k, const do
     const long long beg = sortb_range(k.N, &end);
     const unsigned lane = threadIdx.x & 31;
     for (long long base = beg; base < end; base += SORTB_T * SORTB_PER) {
-        double X[SORTB_PER], U[SORTB_PER];
+        double X[SORTB_PER], U[SORTB_PER], V[SORTB_PER], W[SORTB_PER];
         int key[SORTB_PER], res[SORTB_PER], O[SORTB_PER];
         unsigned peers[SORTB_PER];
 #pragma unroll
         for (int j = 0; j < SORTB_PER; ++j) {
             const long long i = base + j * SORTB_T + threadIdx.x;
-            X[j] = 0.; U[j] = 0.; O[j] = (int)i;
-            if (i < end) { X[j] = x0[i]; if (!PERM) U[j] = u0[i]; if (oid) O[j] = oid[i]; }
+            X[j] = 0.; U[j] = 0.; V[j] = 0.; W[j] = 0.; O[j] = (int)i;
+            if (i < end) {          // every payload is loaded up front: a load behind the reservation atomics would serialise
+                X[j] = x0[i]; if (!PERM) U[j] = u0[i]; if (oid) O[j] = oid[i];
+                if (vs) V[j] = v0[i];
+                if (ws) W[j] = w0[i];
+            }
         }
         // one reservation per distinct key per warp; the four atomics of a thread are independent
 #pragma unroll
@@ -1561,8 +1565,8 @@ __global__ void __launch_bounds__(SORTB_T) dd_sort_scatter_big_k(DDK k, const do
                 const long long pos = (long long)b + __popc(peers[j] & ((1u << lane) - 1u));
                 xs[pos] = X[j];
                 if (PERM) ((int32_t*)us)[pos] = (int32_t)i; else us[pos] = U[j];
-                if (vs) vs[pos] = v0[i];
-                if (ws) ws[pos] = w0[i];
+                if (vs) vs[pos] = V[j];
+                if (ws) ws[pos] = W[j];
                 if (oids) oids[pos] = O[j];
             }
         }
@@ -2219,6 +2223,16 @@ int pic_dev_dd_sort_by_cell2(const pic_dd_params* p, const double* x0, const dou
     PIC_REQUIRE(p->N < 2147483647LL, "dd_sort_by_cell2: shard too large for int32 cursors");
     return sort_by_cell_impl<false>(make_ddk(p), x0, u0, nullptr, nullptr, x0s, u0s, nullptr, nullptr, counts,
                                     (cudaStream_t)stream, orig, origs);
+}
+
+int pic_dev_sort_by_cell_payload(const pic_dd_params* p, const double* x, const double* a, const double* b, const double* c,
+                                 double* xs, double* as, double* bs, double* cs, int32_t* perm, int32_t* counts,
+                                 void* stream) {
+    PIC_REQUIRE(p && x && a && xs && as && counts, "sort_by_cell_payload: null pointer");
+    PIC_REQUIRE((!b || bs) && (!c || cs), "sort_by_cell_payload: payload output missing");
+    PIC_REQUIRE(p->N < 2147483647LL, "sort_by_cell_payload: store too large for int32 indices");
+    return sort_by_cell_impl<false>(make_ddk(p), x, a, b, c, xs, as, b ? bs : nullptr, c ? cs : nullptr, counts,
+                                    (cudaStream_t)stream, nullptr, perm);
 }
 
 int pic_dev_dd_apply_draws2(const int32_t* slot, const int32_t* orig, const double* xd, const double* ud,

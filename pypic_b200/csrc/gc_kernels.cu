@@ -916,12 +916,34 @@ struct SoAPerm {
 };
 __global__ void __launch_bounds__(256) soa_permute_k(const __grid_constant__ SoAPerm a, const int32_t* __restrict__ perm,
                                                      long long n) {
-    for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < n; t += (long long)gridDim.x * blockDim.x) {
-        const int s = perm[t];
-#pragma unroll 4
-        for (int f = 0; f < a.nf; ++f) __stcs(a.df[f] + t, __ldg(a.sf[f] + s));
-        for (int f = 0; f < a.ni; ++f) a.di[f][t] = a.si[f][s];
-        for (int f = 0; f < a.nb; ++f) a.db[f][t] = a.sb[f][s];
+    // four output slots per thread, every load of an array issued before its stores: the gathers are latency
+    // bound (a dependent load behind the permutation word), so memory-level parallelism is what counts
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long t0 = (long long)blockIdx.x * blockDim.x + threadIdx.x; t0 < n; t0 += 4 * stride) {
+        long long t[4]; int s[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { t[j] = t0 + j * stride; s[j] = t[j] < n ? __ldg(perm + t[j]) : 0; }
+        for (int f = 0; f < a.nf; ++f) {
+            double v[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) v[j] = t[j] < n ? __ldg(a.sf[f] + s[j]) : 0.0;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) if (t[j] < n) __stcs(a.df[f] + t[j], v[j]);
+        }
+        for (int f = 0; f < a.ni; ++f) {
+            int v[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) v[j] = t[j] < n ? __ldg(a.si[f] + s[j]) : 0;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) if (t[j] < n) a.di[f][t[j]] = v[j];
+        }
+        for (int f = 0; f < a.nb; ++f) {
+            int8_t v[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) v[j] = t[j] < n ? __ldg(a.sb[f] + s[j]) : (int8_t)0;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) if (t[j] < n) a.db[f][t[j]] = v[j];
+        }
     }
 }
 __global__ void gather_i8_k(const int8_t* __restrict__ src, const int32_t* __restrict__ idx, int8_t* __restrict__ dst,

@@ -418,27 +418,34 @@ class ParticleStore:
         if N < 2:
             return
         dev = self.dev
-        P = _lib.DDParams(N, N, grid.ng, 0, grid.dx, 1.0, grid.length, 1.0, (C.c_double * 2)(0., 0.),
-                          (C.c_double * 2)(1., 1.))
-        xs = torch.empty(N, dtype=torch.float64, device=dev)
-        idx = torch.empty(N, dtype=torch.int32, device=dev)
+        # a store sorted a few steps ago is NEARLY sorted: the global-cursor path of the counting sort (flags
+        # bit5) is then the faster one
+        P = _lib.DDParams(N, N, grid.ng, 32 if getattr(self, "_sorted_once", False) else 0, grid.dx, 1.0, grid.length, 1.0,
+                          (C.c_double * 2)(0., 0.), (C.c_double * 2)(1., 1.))
+        self._sorted_once = True
+        new = lambda dt=torch.float64: torch.empty(N, dtype=dt, device=dev)
+        xs, vxs, vys, vzs = new(), new(), new(), new()
+        idx = new(torch.int32)
         counts = torch.zeros(D.sort_counts_size(grid.ng), dtype=torch.int32, device=dev)
         st = D.stream()
-        _lib.call("pic_dev_sort_perm_by_cell", C.byref(P), D.ptr(self.r[0]), D.ptr(xs), D.ptr(idx), D.ptr(counts), st)
+        # x and the three velocity components travel THROUGH the scatter of the counting sort (runs of
+        # coalesced writes); only the remaining, smaller arrays are gathered through the permutation
+        _lib.call("pic_dev_sort_by_cell_payload", C.byref(P), D.ptr(self.r[0]), D.ptr(self.r[3]), D.ptr(self.r[4]),
+                  D.ptr(self.r[5]), D.ptr(xs), D.ptr(vxs), D.ptr(vys), D.ptr(vzs), D.ptr(idx), D.ptr(counts), st)
         # a species-uniform store holds the same charge_state / m / p2c in every slot: permuting
         # those three arrays would be the identity (saves 48 of ~180 B/particle of the permutation)
         uni = self.uniform() is not None
-        comps = list(range(1, 7)) if self.carry_yzt else [3, 4, 5, 6]      # a lean store does not track y, z
+        comps = [1, 2, 6] if self.carry_yzt else [6]                       # a lean store does not track y, z
         f_src = [self.r[c] for c in comps] + ([] if uni else [self.charge_state, self.m, self.p2c])
-        f_dst = [torch.empty(N, dtype=torch.float64, device=dev) for _ in f_src]
+        f_dst = [new() for _ in f_src]
         b_src = [self.active, self.at_wall, self.from_wall, self.hit_flag]
-        b_dst = [torch.empty(N, dtype=torch.int8, device=dev) for _ in b_src]
-        z_dst = torch.empty(N, dtype=torch.int32, device=dev)
+        b_dst = [new(torch.int8) for _ in b_src]
+        z_dst = new(torch.int32)
         arr = lambda ts: (C.c_void_p * len(ts))(*[t.data_ptr() for t in ts])
         _lib.call("pic_dev_soa_permute", D.ptr(idx), N, arr(f_src), arr(f_dst), len(f_src), arr([self.Z]), arr([z_dst]), 1,
                   arr(b_src), arr(b_dst), len(b_src), st)
         newr = list(self.r)
-        newr[0] = xs
+        newr[0], newr[3], newr[4], newr[5] = xs, vxs, vys, vzs
         for c, t in zip(comps, f_dst):
             newr[c] = t
         self.r = newr

@@ -492,12 +492,10 @@ class SheathSim:
         no-ops and one that needs more continues one iteration at a time."""
         st = D.stream()
         P = C.byref(self.params)
-        self.Es.copy_(self.E0)
-        self.wall_cum.zero_()
         if self.stats.numel() < 8 + self.maxiter + 2:      # maxiter was raised after construction
             self.stats = D.f64(8 + self.maxiter + 2, self.dev, True)
-        self.stats.zero_()
-        self.ctl.zero_()
+        _lib.call("pic_dev_dd_step_begin", D.ptr(self.Es), D.ptr(self.E0), self.Ng, D.ptr(self.wall_cum), D.ptr(self.stats),
+                  self.stats.numel(), D.ptr(self.ctl), st)
         rhist = D.ptr(self.stats) + 8 * 8
         pairs = [(self.x1, self.x1b), (self.x1b, self.x1)] if self.elide_u else [(self.x1, self.x1)]
         queued = []                      # per iteration launched: (want_u, events or None)

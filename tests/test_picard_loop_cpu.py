@@ -49,6 +49,8 @@ class FakeDevice:
             sim.stats[0] = r; sim.stats[3] = it; st[off + it - 1] = r
             if not (r > tol) or it >= maxiter:
                 ctl[0] = 1
+        elif name == "pic_dev_dd_step_begin":
+            sim.Es.copy_(sim.E0); sim.wall_cum.zero_(); sim.stats.zero_(); sim.ctl.zero_()
         elif name in ("pic_dev_dd_commit_u2", "pic_dev_dd_j1_finish"):
             if name == "pic_dev_dd_commit_u2":
                 self.log.append(("repair", self.tensor_at(a[3])[0], self.tensor_at(a[4])[0], a[8]))
@@ -61,6 +63,7 @@ def make_sim(maxiter=6, tol=1e-5, enqueue_ahead=True):
     f = lambda n: torch.zeros(n, dtype=torch.float64)
     sim.maxiter, sim.tol, sim.elide_u, sim.enqueue_ahead, sim.det = maxiter, tol, True, enqueue_ahead, False
     sim.dev = torch.device("cpu")
+    sim.Ng = 4
     sim.p2p = None
     sim.params = S._lib.DDParams()
     for nm in ("x0", "u0", "x1", "x1b", "u1", "E0", "Es", "E1", "Es_prev", "j0", "acc", "wall_cum"):
