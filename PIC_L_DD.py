@@ -160,28 +160,25 @@ def main_i(T, nplot, N=40000, Ng=51, dt=1E-12, dx=0.00001, Ti=10.0 * 11600., Te=
     sim.upload(x0, u0, v0, w0)          # E0 = -d(phi0)/dx with phi0 == 0 (PIC_L_DD.py:386-388)
     mpl, plt = get_plt()
     KE, EE, TT, jbias = [], [], [], []
-    kBTe_now = sim.kBTe_from(*sim.moments())       # np.std(u0)**2*me/e; afterwards it comes with the step's diagnostics
+    # np.std(u0) printed at the top of a step (:417) and KE summed at the end of the previous one (:549) are
+    # moments of the same velocities: the first Picard iteration of the step accumulates them while it streams
+    # u0 (SheathSim.fused_moments), so they arrive with the step's one device->host read and 'kBTe' is printed
+    # right after the step has run -- in the reference's output order (nothing else prints in between)
+    sim.fused_moments = (rng == 'host')              # device-mode re-injection: a pass of their own before the step
     t_loop = time.perf_counter()
-    pending = False
-
-    def finish_step():
-        """EE, KE, jbias of the step that just ran (PIC_L_DD.py:548-551).  Their device pass was launched
-        right after the step; the numbers are read when the host next has to wait for the device."""
-        d = sim.diagnostics_end()
-        EE.append(d["EE"]); KE.append(d["KE"]); jbias.append(d["jbias"])
-        return d["kBTe"]
     with sim.draws.hold():                           # the legacy stream's state stays in C for the duration of the loop
         for t in range(T + 1):
-            if pending:
-                kBTe_now = finish_step()
             print('t: ', t)
-            print('kBTe: ', kBTe_now)
+            pre = None if sim.fused_moments else sim.moments()
             k, r = sim.step()
+            m1, m2 = sim.pre_step_moments() if pre is None else pre
+            print('kBTe: ', sim.kBTe_from(m1, m2))
             print("Iterations: ", k)
             print("r: ", r)
-            sim.diagnostics_begin()
-            pending = True
-            TT.append(t * dt)
+            if t > 0:
+                KE.append(me / 2. * m2)              # KE of step t-1 (:549)
+            d = sim.step_stats()
+            EE.append(d["EE"]); jbias.append(d["jbias"]); TT.append(t * dt)
             if plt is not None and (t % nplot == 0):
                 st = sim.download()
                 h = N // 2
@@ -194,8 +191,7 @@ def main_i(T, nplot, N=40000, Ng=51, dt=1E-12, dx=0.00001, Ti=10.0 * 11600., Te=
                 plt.figure(3); plt.clf()
                 plt.plot(X, st["E0"], linewidth=lw)
                 plt.savefig('plots/e_' + str(t))
-        if pending:
-            finish_step()
+    KE.append(me / 2. * sim.moments()[1])            # KE of the last step
     sim.check()
     t_loop = time.perf_counter() - t_loop
     if os.environ.get("PIC_TIMING"):

@@ -450,19 +450,18 @@ def run_cuda(args):
         sm.u0[:sm.n_split].mul_(float(np.sqrt(w["kBTe"] / ME))); sm.u0[sm.n_split:].mul_(float(np.sqrt(w["kBTi"] / MP)))
         torch.cuda.synchronize()
         na = max(1, args.api_steps)
+        sm.fused_moments = True                  # as main_i: np.std(u0) / KE ride the first Picard iteration
         with sm.draws.hold():
             for _ in range(max(3, args.warmup)):
-                sm.step(); sm.diagnostics_begin(); sm.diagnostics_end()
+                sm.step()
             torch.cuda.synchronize()
             l0, dead0 = sm.kernel_launches, 0
             t0 = time.perf_counter()
             its_api = []
             for s_ in range(na):
-                if s_:
-                    sm.diagnostics_end()
                 its_api.append(sm.step()[0])
-                sm.diagnostics_begin()
-            d_last = sm.diagnostics_end()
+                m1_, m2_ = sm.pre_step_moments()
+                d_last = dict(sm.step_stats(), KE_previous_step=ME / 2. * m2_, kBTe=sm.kBTe_from(m1_, m2_))
             torch.cuda.synchronize()
             t_api = time.perf_counter() - t0
         sm.check()

@@ -217,6 +217,15 @@ int pic_dev_dd_picard_iter4(const pic_dd_params* p, const double* x0, const doub
                             double* x1_out, double* u1, int8_t* active, const double* Es, double* acc, int first,
                             int* range_err, const int32_t* done, int32_t* dead_buf, int32_t dead_cap,
                             const int32_t* orig, int32_t iteration, void* stream);
+/* ... and with the velocity moments of the step's INITIAL state for free: the first iteration (first != 0)
+ * streams u0 anyway, so with moments != NULL it adds sum(u0) and sum(u0*u0) over its particles to
+ * moments[0..1] (zero on entry) -- np.std(u0) of PIC_L_DD.py:417 and the kinetic energy of :549 without a
+ * pass of their own.  The sums describe the state AFTER re-injection; pic_dev_dd_apply_draws3 accumulates
+ * the correction back to the state before it. */
+int pic_dev_dd_picard_iter5(const pic_dd_params* p, const double* x0, const double* u0, const double* x1_in,
+                            double* x1_out, double* u1, int8_t* active, const double* Es, double* acc, int first,
+                            int* range_err, const int32_t* done, int32_t* dead_buf, int32_t dead_cap,
+                            const int32_t* orig, int32_t iteration, double* moments, void* stream);
 int pic_dev_dd_commit_u(const pic_dd_params* p, const double* x0, const double* u0, const double* x1_prev,
                         const double* x1_last, const int8_t* active, const double* Es, double* u1, int first,
                         int* range_err, void* stream);
@@ -296,6 +305,11 @@ int pic_dev_dd_apply_draws(const int32_t* idx, const double* xd, const double* u
 int pic_dev_dd_apply_draws2(const int32_t* slot, const int32_t* orig, const double* xd, const double* ud,
                             const double* vd, const double* wd, int64_t n, double* x0, double* u0, double* v0,
                             double* w0, int8_t* active, void* stream);
+/* pic_dev_dd_apply_draws2 that also accumulates corr[0] += sum(u_new - u_old), corr[1] += sum(u_new^2 -
+ * u_old^2) over the slots it rewrites (corr may be NULL) */
+int pic_dev_dd_apply_draws3(const int32_t* slot, const int32_t* orig, const double* xd, const double* ud,
+                            const double* vd, const double* wd, int64_t n, double* x0, double* u0, double* v0,
+                            double* w0, int8_t* active, double* corr, void* stream);
 /* Device-mode re-injection of the slots named in the absorption log (no flag scan), and the
  * device-mode thermostat (every active particle redraws u,v,w from sigma[species] with probability
  * gamma).  Philox is keyed by the ORIGINAL global index orig[i] + global_offset (orig == NULL: the

@@ -72,6 +72,8 @@ _SIGS = {
     "pic_dev_dd_picard_iter2": [C.POINTER(DDParams), P, P, P, P, P, P, P, P, I32, P, P],
     "pic_dev_dd_picard_iter3": [C.POINTER(DDParams), P, P, P, P, P, P, P, P, I32, P, P, P],
     "pic_dev_dd_picard_iter4": [C.POINTER(DDParams), P, P, P, P, P, P, P, P, I32, P, P, P, I32, P, I32, P],
+    "pic_dev_dd_picard_iter5": [C.POINTER(DDParams), P, P, P, P, P, P, P, P, I32, P, P, P, I32, P, I32, P, P],
+    "pic_dev_dd_apply_draws3": [P, P, P, P, P, P, I64, P, P, P, P, P, P, P],
     "pic_dev_dd_sort_by_cell2": [C.POINTER(DDParams), P, P, P, P, P, P, P, P],
     "pic_dev_dd_apply_draws2": [P, P, P, P, P, P, I64, P, P, P, P, P, P],
     "pic_dev_dd_reinject_philox_log": [C.POINTER(DDParams), P, I32, P, P, P, P, P, P, C.POINTER(C.c_double * 2),

@@ -42,6 +42,10 @@ struct DDK {
     const int* oid;              // original index of the particle in each slot (nullptr: the slot itself)
     int dead_cap, iter;
     long long slot0;             // slot of particle 0 of this launch (tail launches run on offset pointers)
+    // FIRST iteration only, optional: mom[0] += sum u0, mom[1] += sum u0*u0 over every particle of the launch --
+    // the first iteration streams u0 anyway, so np.std(u0) (PIC_L_DD.py:417) and the kinetic-energy diagnostic
+    // (:549) cost no extra pass (the host corrects for the slots re-injected in between, see pic_dev_dd_apply_draws3)
+    double* mom;
 };
 __device__ __forceinline__ void dead_note(const DDK& k, long long i) {
     if (k.dead_buf) {
@@ -62,7 +66,7 @@ static DDK make_ddk(const pic_dd_params* p) {
         k.c2[s] = p->dt * p->dt * qm;
     }
     k.fix = nullptr; k.ferr = nullptr; k.fs1 = 1.0; k.fi1 = 1.0; k.done = nullptr;
-    k.dead_buf = nullptr; k.oid = nullptr; k.dead_cap = 0; k.iter = 0; k.slot0 = 0;
+    k.dead_buf = nullptr; k.oid = nullptr; k.dead_cap = 0; k.iter = 0; k.slot0 = 0; k.mom = nullptr;
     if (p->flags & 128) {
         // one contribution is q*p2c*u*w/dx with |u| < c: |v| < amax < 2^e, so |v|*2^(31-e) < 2^31 and a
         // node can take 2^31 contributions before the hi word overflows; the lo word carries 32 more bits
@@ -149,6 +153,7 @@ __global__ void __launch_bounds__(256) dd_picard_iter_k(DDK k, const double* __r
         F = sF; jh = sm + Ng; j1 = sm + 2 * Ng;
     }
     int nL0 = 0, nL1 = 0, nR0 = 0, nR1 = 0, bad = 0;
+    double ms1 = 0.0, ms2 = 0.0;
     const long long stride = (long long)gridDim.x * blockDim.x;
     // the trip count is uniform across the warp so the shuffles in deposit_pair are safe
     const long long nIter = (k.N + stride - 1) / stride;
@@ -171,6 +176,7 @@ __global__ void __launch_bounds__(256) dd_picard_iter_k(DDK k, const double* __r
         if (alive) {
             X0 = ld_stream(x0 + i);
             U0 = ld_stream(u0 + i);
+            if (FIRST) { ms1 += U0; ms2 += U0 * U0; }
             double xs = FIRST ? X0 : (X0 + ld_stream(x1i + i)) * 0.5;   // xs = xh of the previous iteration
             Cell c = cell_dd(xs, k.dx);
             if (c.iL < 0 || c.iL > Ng - 2) { ++bad; c.iL = clampi(c.iL, 0, Ng - 2); c.iR = c.iL + 1; }
@@ -229,6 +235,10 @@ __global__ void __launch_bounds__(256) dd_picard_iter_k(DDK k, const double* __r
         nL0 += __shfl_xor_sync(full, nL0, o); nL1 += __shfl_xor_sync(full, nL1, o);
         nR0 += __shfl_xor_sync(full, nR0, o); nR1 += __shfl_xor_sync(full, nR1, o);
         bad += __shfl_xor_sync(full, bad, o);
+    }
+    if (FIRST && k.mom) {
+        ms1 = warp_sum(ms1); ms2 = warp_sum(ms2);
+        if ((threadIdx.x & 31) == 0) { atomicAdd(k.mom, ms1); atomicAdd(k.mom + 1, ms2); }
     }
     if ((threadIdx.x & 31) == 0) {
         if (nL0) atomicAdd(&acc[2 * Ng + 0], (double)nL0);
@@ -701,6 +711,7 @@ __global__ void __launch_bounds__(V6_T, 1) dd_picard_iter_v6_k(
     };
     int stage = 0;
     uint32_t phase = 0;
+    double ms1 = 0.0, ms2 = 0.0;          // FIRST && k.mom: sum u0, sum u0^2 of this thread's particles
 #pragma unroll 1
     while (cur_slice < nslices) {
         const int nxt_slice = next_slice(cur_slice);
@@ -722,6 +733,7 @@ __global__ void __launch_bounds__(V6_T, 1) dd_picard_iter_v6_k(
             const double2 X0 = *(const double2*)sb, U0 = *(const double2*)(sb + 64);
             double2 pX1 = make_double2(0., 0.);
             if (!FIRST) pX1 = *(const double2*)(sb + 128);
+            if (FIRST && k.mom) { ms1 += U0.x + U0.y; ms2 += U0.x * U0.x + U0.y * U0.y; }
             const int st_cur = stage;
             if (++stage == V6_NST) { stage = 0; phase ^= 1u; }
             bool straddle = false, sp = sp_slice;
@@ -795,6 +807,10 @@ __global__ void __launch_bounds__(V6_T, 1) dd_picard_iter_v6_k(
         }
         flush_windows(wb);
         cur_slice = nxt_slice;
+    }
+    if (FIRST && k.mom) {
+        ms1 = warp_sum(ms1); ms2 = warp_sum(ms2);
+        if (lane == 0) { atomicAdd(k.mom, ms1); atomicAdd(k.mom + 1, ms2); }
     }
     __syncthreads();
     if (threadIdx.x >= 1 && threadIdx.x <= 4 && s_cnt[threadIdx.x])
@@ -1582,14 +1598,22 @@ __global__ void dd_apply_draws2_k(const int32_t* __restrict__ slot, const int32_
                                   const double* __restrict__ xd, const double* __restrict__ ud,
                                   const double* __restrict__ vd, const double* __restrict__ wd, long long n,
                                   double* __restrict__ x0, double* __restrict__ u0, double* __restrict__ v0,
-                                  double* __restrict__ w0, int8_t* __restrict__ active) {
+                                  double* __restrict__ w0, int8_t* __restrict__ active, double* __restrict__ corr) {
+    double c1 = 0.0, c2 = 0.0;
     for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < n; t += (long long)gridDim.x * blockDim.x) {
         const int s = slot[t], o = orig ? orig[t] : s;
         if (xd) x0[s] = xd[t];
-        u0[s] = ud[t];
+        const double un = ud[t];
+        if (corr) { const double uo = u0[s]; c1 += un - uo; c2 += un * un - uo * uo; }
+        u0[s] = un;
         if (v0) v0[o] = vd[t];
         if (w0) w0[o] = wd[t];
         if (active) active[s] = 1;
+    }
+    if (corr) {          // corr[0] += sum(u_new - u_old), corr[1] += sum(u_new^2 - u_old^2): turns the moments of the
+                         // re-injected state (first Picard iteration) back into those of the state before re-injection
+        c1 = warp_sum(c1); c2 = warp_sum(c2);
+        if ((threadIdx.x & 31) == 0 && (c1 != 0.0 || c2 != 0.0)) { atomicAdd(corr, c1); atomicAdd(corr + 1, c2); }
     }
 }
 __global__ void gather_i32_k(const int32_t* __restrict__ src, const int32_t* __restrict__ idx, int32_t* __restrict__ dst, long long n) {
@@ -1830,12 +1854,21 @@ int pic_dev_dd_picard_iter4(const pic_dd_params* p, const double* x0, const doub
                             double* x1_out, double* u1, int8_t* active, const double* Es, double* acc, int first,
                             int* range_err, const int32_t* done, int32_t* dead_buf, int32_t dead_cap,
                             const int32_t* orig, int32_t iteration, void* stream) {
+    return pic_dev_dd_picard_iter5(p, x0, u0, x1_in, x1_out, u1, active, Es, acc, first, range_err, done, dead_buf, dead_cap, orig,
+                                   iteration, nullptr, stream);
+}
+
+int pic_dev_dd_picard_iter5(const pic_dd_params* p, const double* x0, const double* u0, const double* x1_in,
+                            double* x1_out, double* u1, int8_t* active, const double* Es, double* acc, int first,
+                            int* range_err, const int32_t* done, int32_t* dead_buf, int32_t dead_cap,
+                            const int32_t* orig, int32_t iteration, double* moments, void* stream) {
     PIC_REQUIRE(p && x0 && u0 && x1_in && x1_out && active && Es && acc, "dd_picard_iter: null pointer");
+    PIC_REQUIRE(!moments || first, "dd_picard_iter: the velocity moments are accumulated by the FIRST iteration only");
     PIC_REQUIRE(p->N >= 0 && p->Ng >= 3 && p->dx > 0 && p->dt > 0, "dd_picard_iter: bad parameters");
     PIC_REQUIRE(!dead_buf || (dead_cap > 0 && ((uintptr_t)dead_buf & 15) == 0), "dd_picard_iter: absorption log without storage / unaligned");
     if (p->N == 0) return PIC_OK;
     DDK k = make_ddk(p);
-    k.dead_buf = dead_buf; k.oid = orig; k.dead_cap = dead_cap; k.iter = iteration;
+    k.dead_buf = dead_buf; k.oid = orig; k.dead_cap = dead_cap; k.iter = iteration; k.mom = moments;
     PIC_REQUIRE(!(p->flags & 128) || !(p->flags & (1 | 2 | 4 | 8)),
                 "dd_picard_iter: the reproducible build (flags bit7) exists for the default window kernel only");
     ddk_bind_fix(k, acc, range_err);
@@ -2242,7 +2275,17 @@ int pic_dev_dd_apply_draws2(const int32_t* slot, const int32_t* orig, const doub
     if (n == 0) return PIC_OK;
     PIC_REQUIRE(slot && ud && u0, "dd_apply_draws2: null pointer");
     PIC_REQUIRE((!xd || x0) && (!v0 || vd) && (!w0 || wd), "dd_apply_draws2: draws / targets missing");
-    dd_apply_draws2_k<<<grid_for(n, 256, 4), 256, 0, (cudaStream_t)stream>>>(slot, orig, xd, ud, vd, wd, n, x0, u0, v0, w0, active);
+    return pic_dev_dd_apply_draws3(slot, orig, xd, ud, vd, wd, n, x0, u0, v0, w0, active, nullptr, stream);
+}
+
+int pic_dev_dd_apply_draws3(const int32_t* slot, const int32_t* orig, const double* xd, const double* ud,
+                            const double* vd, const double* wd, int64_t n, double* x0, double* u0, double* v0,
+                            double* w0, int8_t* active, double* corr, void* stream) {
+    PIC_REQUIRE(n >= 0, "dd_apply_draws3: n<0");
+    if (n == 0) return PIC_OK;
+    PIC_REQUIRE(slot && ud && u0, "dd_apply_draws3: null pointer");
+    PIC_REQUIRE((!xd || x0) && (!v0 || vd) && (!w0 || wd), "dd_apply_draws3: draws / targets missing");
+    dd_apply_draws2_k<<<grid_for(n, 256, 4), 256, 0, (cudaStream_t)stream>>>(slot, orig, xd, ud, vd, wd, n, x0, u0, v0, w0, active, corr);
     PIC_CHECK_LAUNCH();
     return PIC_OK;
 }

@@ -108,7 +108,15 @@ class SheathSim:
             raise ValueError("reduce must be 'nccl' or 'p2p'")
         self.wall_cum = D.f64(4, dev, True)
         # [r, mean j1, EE, iterations | 4 doubles of reduction scratch | residual of every iteration of the step]
-        self.stats = D.f64(8 + self.maxiter + 2, dev, True)     # + [sum u0, sum u0^2] of the diagnostics
+        # ... | sum u0, sum u0^2 (diagnostics pass, or the step's first iteration when fused_moments is on) |
+        # correction of the re-injection: sum(u_new - u_old), sum(u_new^2 - u_old^2)]
+        self.stats = D.f64(8 + self.maxiter + 4, dev, True)
+        # fused_moments: the first Picard iteration of every step also sums u0 and u0^2 (it streams u0 anyway) and
+        # the re-injection kernel records what it changed, so np.std(u0) / KE of the state BEFORE the step
+        # (PIC_L_DD.py:417, :549 of the previous step) come with the step's outcome read instead of a pass of
+        # their own (pre_step_moments)
+        self.fused_moments = False
+        self._pre_mom = None
         # enqueue-ahead Picard loop: the iterations the previous step needed are queued back to back,
         # guarded by a device flag that the field kernel raises when the loop condition fails; the
         # host reads the outcome once per step instead of once per iteration
@@ -303,8 +311,9 @@ class SheathSim:
         else:
             dorig = dslot = D.to_dev(orig, self.dev, torch.int32)
         dd = D.to_dev(np.stack([hu[mine], hv[mine], hw[mine]]), self.dev)
-        _lib.call("pic_dev_dd_apply_draws2", D.ptr(dslot), D.ptr(dorig), None, D.ptr(dd[0]), D.ptr(dd[1]), D.ptr(dd[2]),
-                  len(orig), None, D.ptr(self.u0), D.ptr(self.v0), D.ptr(self.w0), None, D.stream())
+        _lib.call("pic_dev_dd_apply_draws3", D.ptr(dslot), D.ptr(dorig), None, D.ptr(dd[0]), D.ptr(dd[1]), D.ptr(dd[2]),
+                  len(orig), None, D.ptr(self.u0), D.ptr(self.v0), D.ptr(self.w0), None, getattr(self, "_corr_ptr", None),
+                  D.stream())
         self.kernel_launches += 3
         return int(mine.sum())
 
@@ -336,6 +345,10 @@ class SheathSim:
         slots, orig, _ = self._harvest_dead()
         n_dead = len(slots)
         counts = self.comm.allgather_int(n_dead, device=self.dev)
+        self._corr_ptr = None
+        if self.fused_moments:
+            self._corr_ptr = D.ptr(self.stats) + 8 * (8 + self.maxiter + 2)
+            _lib.call("pic_dev_zero", self._corr_ptr, 16, st)
         if self.gamma != 0.0:
             g_orig = orig.astype(np.int64) + self.start
             if self.comm.enabled and self.comm.world > 1:
@@ -360,9 +373,9 @@ class SheathSim:
             iv[0:n_dead] = slots; iv[n_dead:2 * n_dead] = orig
             _lib.call("pic_dev_write", D.ptr(ds), D.ptr(hs), (5 * n_dead + 1) * 8, st)
             base = D.ptr(ds)
-            _lib.call("pic_dev_dd_apply_draws2", base + 32 * n_dead, base + 36 * n_dead, base, base + 8 * n_dead,
+            _lib.call("pic_dev_dd_apply_draws3", base + 32 * n_dead, base + 36 * n_dead, base, base + 8 * n_dead,
                       base + 16 * n_dead if self.carry_vw else None, base + 24 * n_dead if self.carry_vw else None, n_dead,
-                      D.ptr(self.x0), D.ptr(self.u0), D.ptr(self.v0), D.ptr(self.w0), D.ptr(self.active), st)
+                      D.ptr(self.x0), D.ptr(self.u0), D.ptr(self.v0), D.ptr(self.w0), D.ptr(self.active), self._corr_ptr, st)
             self.kernel_launches += 1
         self._reset_log()
         return n_dead
@@ -492,10 +505,14 @@ class SheathSim:
         no-ops and one that needs more continues one iteration at a time."""
         st = D.stream()
         P = C.byref(self.params)
-        if self.stats.numel() < 8 + self.maxiter + 2:      # maxiter was raised after construction
-            self.stats = D.f64(8 + self.maxiter + 2, self.dev, True)
+        if self.stats.numel() < 8 + self.maxiter + 4:      # maxiter was raised after construction
+            self.stats = D.f64(8 + self.maxiter + 4, self.dev, True)
+        nst = 8 + self.maxiter
+        # clears the statistics and the moments; the re-injection correction behind them was written by this
+        # step's reinject() and is cleared by the next one
         _lib.call("pic_dev_dd_step_begin", D.ptr(self.Es), D.ptr(self.E0), self.Ng, D.ptr(self.wall_cum), D.ptr(self.stats),
-                  self.stats.numel(), D.ptr(self.ctl), st)
+                  nst + 2, D.ptr(self.ctl), st)
+        mom_ptr = D.ptr(self.stats) + 8 * nst if self.fused_moments else None
         rhist = D.ptr(self.stats) + 8 * 8
         pairs = [(self.x1, self.x1b), (self.x1b, self.x1)] if self.elide_u else [(self.x1, self.x1)]
         queued = []                      # per iteration launched: (want_u, events or None)
@@ -507,10 +524,12 @@ class SheathSim:
             if self.iter_events is not None:
                 ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
                 ev[0].record()
-            _lib.call("pic_dev_dd_picard_iter4", P, D.ptr(self.x0), D.ptr(self.u0), D.ptr(xin), D.ptr(xout),
+            _lib.call("pic_dev_dd_picard_iter5", P, D.ptr(self.x0), D.ptr(self.u0), D.ptr(xin), D.ptr(xout),
                       D.ptr(self.u1) if want_u else None, D.ptr(self.active), D.ptr(self.Es), self._acc_ptr(),
                       1 if j == 0 else 0, D.ptr(self.range_err), D.ptr(self.ctl), D.ptr(self.dead_buf), self.dead_cap,
-                      D.ptr(self.oid), j, st)
+                      D.ptr(self.oid), j, mom_ptr if j == 0 else None, st)
+            if j == 0 and mom_ptr is not None and self.comm.enabled and self.comm.world > 1:
+                self.comm.allreduce_sum(self.stats[nst:nst + 4])        # one small collective per step (the diagnostics)
             if ev is not None:
                 ev[1].record()
             if self.p2p is not None:
@@ -527,10 +546,14 @@ class SheathSim:
             queued.append((want_u, ev))
 
         def outcome():
-            s = D.read_f64(self.stats, 8 + self.maxiter)
+            s = D.read_f64(self.stats, 8 + self.maxiter + 4)
+            if self.fused_moments:
+                # moments of the state BEFORE this step's re-injection / thermostat = after the previous step
+                self._pre_mom = (float(s[nst] - s[nst + 2]), float(s[nst + 1] - s[nst + 3]))
             if self.p2p is not None:
                 self.p2p.check()         # a timed-out wait summed incomplete accumulators: stop at once
             k = int(s[3])
+            self._last_stats = [float(v) for v in s[:4]]
             return k, [float(v) for v in s[8:8 + k]]
 
         k = 0
@@ -608,6 +631,17 @@ class SheathSim:
         _lib.call("pic_dev_moments", D.ptr(self.u0), self.N, D.ptr(tail), D.stream())
         self.kernel_launches += 1
         self.comm.allreduce_sum(tail)
+
+    def pre_step_moments(self):
+        """fused_moments: (sum u0, sum u0^2) over all ranks of the state BEFORE the step that just ran (i.e. after
+        the step before it, re-injection and thermostat not yet applied) -- what the reference prints as
+        np.std(u0) at the top of the step (PIC_L_DD.py:417) and sums into KE at the end of the previous one (:549)."""
+        return self._pre_mom
+
+    def step_stats(self):
+        """EE and jbias of the step that just ran (PIC_L_DD.py:548,551) from the statistics the Picard loop's
+        outcome read already fetched (no device access)."""
+        return dict(EE=self._last_stats[2], jbias=self._last_stats[1])
 
     def diagnostics_end(self):
         s = D.read_f64(self.stats, 8 + self.maxiter + 2)

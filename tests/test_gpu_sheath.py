@@ -471,6 +471,39 @@ def test_baseline_grid_multi_step_vs_c_oracle():
     assert dead_total > 100 and sim._sorts == 2 and sim.draws.jumps == steps
 
 
+@pytest.mark.parametrize("gamma,sort_every", [(0.0, 2), (0.02, 3), (0.0, 0)])
+def test_fused_velocity_moments_equal_a_pass_over_the_pre_step_state(gamma, sort_every):
+    """SheathSim.fused_moments: sum u0 and sum u0^2 accumulated by the step's first Picard iteration, corrected
+    on the device for what re-injection / thermostat rewrote, equal the sums over the state before the step
+    (what the reference prints as np.std(u0) at the top of the step and sums into KE at the end of the
+    previous one) -- at the TMA-kernel size, tail included."""
+    from pypic_b200.rng import LegacyDraws
+    from pypic_b200.sheath import SheathSim
+    N, Ng = 5 * 16384 + 999, 257
+    dx, dt = 1e-5, 1e-12
+    L = dx * (Ng - 1); kT = O.kb * 116000.
+    rs = np.random.RandomState(9)
+    h = N // 2
+    x0 = rs.uniform(0, L, N)
+    u0 = np.concatenate([rs.normal(0, np.sqrt(kT / O.me), h), rs.normal(0, np.sqrt(kT / O.mp), N - h)])
+    sim = SheathSim(N, Ng, dx, dt, L * 1e19 / N, kBT=(kT, kT), carry_vw=True, rng="host", gamma=gamma, sort_every=sort_every,
+                    draws=LegacyDraws(np.random.RandomState(4)))
+    sim.upload(x0, u0, np.zeros(N), np.zeros(N), E0=rs.normal(0, 1e4, Ng))
+    sim.fused_moments = True
+    dead_seen = 0
+    for t in range(6):
+        o = sim.download()
+        dead_seen += int((o["active"] != 1).sum())
+        want = (float(np.sum(o["u0"])), float(np.sum(o["u0"] ** 2)))
+        sim.step()
+        m1, m2 = sim.pre_step_moments()
+        assert abs(m2 - want[1]) <= 1e-12 * want[1], (t, m2, want[1])
+        assert abs(m1 - want[0]) <= 1e-9 * np.sqrt(N * want[1]), (t, m1, want[0])
+        assert abs(sim.kBTe_from(m1, m2) - np.std(o["u0"]) ** 2 * O.me / O.e) <= 1e-11 * (np.std(o["u0"]) ** 2 * O.me / O.e)
+    sim.check()
+    assert dead_seen > 0
+
+
 def test_host_abi_step_matches_device_path():
     """pic_host_dd_step (host buffers through the C ABI) == the resident path."""
     from pypic_b200 import _lib

@@ -1,5 +1,5 @@
 """CPU test of the host logic of SheathSim.picard (enqueue-ahead Picard loop): the C ABI is replaced
-by a fake device that implements only the CONTROL contract of pic_dev_dd_picard_iter4 /
+by a fake device that implements only the CONTROL contract of pic_dev_dd_picard_iter5 /
 pic_dev_dd_field_update2 (include/pic_b200.h: launches are no-ops once the flag is up; the field
 kernel counts iterations, records residuals and raises the flag when `r > tol and k < maxiter`
 fails) with scripted residuals.  Checked: iteration counts, which launches ran as light / full
@@ -27,7 +27,7 @@ class FakeDevice:
 
     def call(self, name, *a):
         sim = self.sim
-        if name == "pic_dev_dd_picard_iter4":
+        if name == "pic_dev_dd_picard_iter5":
             assert a[15] == len([e for e in self.log if e[0] in ("iter", "noop")])      # 0-based iteration number of the launch
             ctl = self.tensor_at(a[11])[1]
             if int(ctl[0]):
@@ -64,12 +64,13 @@ def make_sim(maxiter=6, tol=1e-5, enqueue_ahead=True):
     sim.maxiter, sim.tol, sim.elide_u, sim.enqueue_ahead, sim.det = maxiter, tol, True, enqueue_ahead, False
     sim.dev = torch.device("cpu")
     sim.Ng = 4
+    sim.fused_moments = False
     sim.p2p = None
     sim.params = S._lib.DDParams()
     for nm in ("x0", "u0", "x1", "x1b", "u1", "E0", "Es", "E1", "Es_prev", "j0", "acc", "wall_cum"):
         setattr(sim, nm, f(4))
     sim.active = torch.ones(4, dtype=torch.int8)
-    sim.stats = f(8 + maxiter)
+    sim.stats = f(8 + maxiter + 4)
     sim.ctl = torch.zeros(1, dtype=torch.int32)
     sim.dead_buf = torch.zeros(4 + 4 * 16, dtype=torch.int32); sim.dead_cap = 16; sim.oid = None
     sim.range_err = torch.zeros(1, dtype=torch.int32)

@@ -22,18 +22,17 @@ def sec(name, fn):
     T[name] = T.get(name, 0.0) + time.perf_counter() - t0
     return out
 for _ in range(5):
-    sim.step(); sim.diagnostics()
+    sim.step()
 T.clear()
 torch.cuda.synchronize(); t_all = time.perf_counter()
+sim.fused_moments = True
 with sim.draws.hold():
     for s in range(steps):
-        if s:
-            sec("diag_end", sim.diagnostics_end)
         sec("reinject", sim.reinject)
         if sim.t % sim.sort_every == 0:
             sec("sort", sim.sort_by_cell)
         sec("picard", sim.picard); sim.t += 1
-        sec("diag_begin", sim.diagnostics_begin)
+        sim.pre_step_moments(); sim.step_stats()
 torch.cuda.synchronize(); t_all = time.perf_counter() - t_all
 print("N=%g sync=%s: %.3f ms/step;" % (N, sync, 1e3 * t_all / steps), {k: "%.3f" % (1e3 * v / steps) for k, v in T.items()},
       "jumps", sim.draws.jumps, "prefetched", sim.draws.prefetch_hits, "k", sim.last_iters)
@@ -42,6 +41,6 @@ import cProfile, pstats, io
 pr = cProfile.Profile(); pr.enable()
 with sim.draws.hold():
     for s in range(50):
-        sim.step(); sim.diagnostics_begin(); sim.diagnostics_end()
+        sim.step(); sim.pre_step_moments()
 pr.disable()
 st = io.StringIO(); pstats.Stats(pr, stream=st).sort_stats("cumulative").print_stats(28); print(st.getvalue()[:5000])
