@@ -55,8 +55,8 @@ def _worker():
 
 class LegacyDraws:
     JUMP_MIN = 200000        # uniforms; below this plain generation is cheaper than the jump
-    CHUNK = 2048             # jump polynomials are cached per multiple of CHUNK uniforms; the rest is generated
-    MARGIN = 1024            # the prefetched jump stops this many uniforms short of the expected skip
+    CHUNK = 512              # jump polynomials are cached per multiple of CHUNK uniforms; the rest is generated
+    MARGIN = 512             # the prefetched jump stops this many uniforms short of the expected skip
 
     def __init__(self, rng=None):
         self.rng = np.random if rng is None else rng
@@ -85,7 +85,7 @@ class LegacyDraws:
         """n plain np.random.uniform() draws, discarded."""
         if self._held is not None:
             st = self._held
-            _lib.call("pic_mt_skip", st[0].ctypes.data, C.byref(st[1]), C.c_uint64(2 * int(n)))
+            _lib.load().pic_mt_skip(st[0].ctypes.data, C.byref(st[1]), 2 * int(n))
         else:
             self.rng.uniform(0.0, 1.0, int(n))
 
@@ -133,7 +133,10 @@ class LegacyDraws:
             self._uniforms(n)
             return
         st = self._get()
-        if (pref is not None and 0 < pref["n"] <= n and pref["pos"] == st[1].value and np.array_equal(pref["key0"], st[0])):
+        # the prefetched jump started from the stream's state at that time: usable if the stream has not moved
+        # (guaranteed while hold() owns it: nothing else can draw; otherwise compare the snapshot)
+        if (pref is not None and 0 < pref["n"] <= n and pref["pos"] == st[1].value and
+                (pref["held"] and self._held is not None or np.array_equal(pref["key0"], st[0]))):
             st = [pref["key1"], C.c_int32(pref["pos1"]), st[2], st[3]]
             done = pref["n"]
             self.prefetch_hits += 1
@@ -154,7 +157,9 @@ class LegacyDraws:
             return
         st = self._get()
         poly = self._poly(2 * n)
-        job = dict(n=n, key0=st[0].copy(), pos=st[1].value, key1=st[0].copy(), pos1=0, poly=poly, thread=_Done())
+        held = self._held is not None
+        job = dict(n=n, key0=None if held else st[0].copy(), pos=st[1].value, key1=st[0].copy(), pos1=0, poly=poly,
+                   thread=_Done(), held=held)
         _worker().put(job)
         self._pref = job
 
@@ -190,14 +195,17 @@ class LegacyDraws:
         """Per dead slot, in index order: x=uniform(0,L) then u,v,w=normal(0,sigma_i)
         (PIC_L_DD.py:433-436 / 443-446).  sigma: array of per-slot thermal speeds."""
         n_dead = int(n_dead)
-        xd = np.empty(n_dead); ud = np.empty(n_dead); vd = np.empty(n_dead); wd = np.empty(n_dead)
+        out = np.empty((4, n_dead))              # one allocation: rows x, u, v, w
         if n_dead:
-            sg = np.ascontiguousarray(np.broadcast_to(np.asarray(sigma, dtype=np.float64), (n_dead,)))
+            sg = sigma if (isinstance(sigma, np.ndarray) and sigma.dtype == np.float64 and sigma.shape == (n_dead,)
+                           and sigma.flags.c_contiguous) else \
+                np.ascontiguousarray(np.broadcast_to(np.asarray(sigma, dtype=np.float64), (n_dead,)))
             st = self._get()
+            p0 = out.ctypes.data
             _lib.call("pic_mt_sheath_draws", st[0].ctypes.data, C.byref(st[1]), C.byref(st[2]), C.byref(st[3]), n_dead,
-                      sg.ctypes.data, float(L), xd.ctypes.data, ud.ctypes.data, vd.ctypes.data, wd.ctypes.data)
+                      sg.ctypes.data, float(L), p0, p0 + 8 * n_dead, p0 + 16 * n_dead, p0 + 24 * n_dead)
             self._put(st)
-        return xd, ud, vd, wd
+        return out[0], out[1], out[2], out[3]
 
     def sheath_skip_foreign(self, n_dead):
         """Advance the stream past the draws of dead slots owned by other ranks."""
