@@ -60,6 +60,10 @@ def parse():
                     help="--workload boris: carry y, z and the per-particle clock through the push (112 B per particle-step) "
                          "instead of the lean store (x, vx, vy, vz: the 64 B row of SURVEY.md 8d)")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-slab-leg", action="store_true",
+                    help="N > 1: skip the `slab_decomposition` sub-record (the same workload on spatial slabs: halo exchange + "
+                         "particle migration, BASELINE config 5's decomposition)")
+    ap.add_argument("--slab-steps", type=int, default=16)
     ap.add_argument("--no-api-leg", action="store_true",
                     help="skip the `reference_api` record (the step as PIC_L_DD.main_i drives it: host MT19937 draws, carried v,w)")
     ap.add_argument("--api-steps", type=int, default=40)
@@ -474,13 +478,52 @@ def run_cuda(args):
                "last_step": {k_: float(v_) for k_, v_ in d_last.items()}}
         sim = sm
 
+    # ---- N > 1: the same workload on SPATIAL SLABS (pypic_b200/spatial.py: every rank owns a cell range and the
+    # particles inside it; halo exchange of the guard strips per Picard iteration, particle migration with the sort,
+    # routed re-injection) as a sub-record, so that the driver's scaling sweep holds a number for that decomposition too
+    slab = None
+    if world > 1 and not args.no_slab_leg and args.decomposition == "particle":
+        try:
+            from pypic_b200.spatial import SlabSheathSim
+            n_keep, p2p_keep, enq_keep = sim.N, sim.p2p is not None, sim.enqueue_ahead
+            sim.close(); del sim
+            torch.cuda.empty_cache()
+            ss = SlabSheathSim(w["N"], w["Ng"], w["dx"], w["dt"], w["p2c"], kBT=(w["kBTe"], w["kBTi"]), tol=w["tol"],
+                               maxiter=w["maxiter"], seed=1, comm=comm, device=dev, sort_every=args.sort_every, guard=16)
+            ss.init_device(seed=1234)
+            for _ in range(3):
+                ss.step()
+            ss.check()
+            torch.cuda.synchronize(); comm.barrier()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            its_sl = []
+            e0.record()
+            for _ in range(max(1, args.slab_steps)):
+                its_sl.append(ss.step()[0])
+            e1.record()
+            torch.cuda.synchronize(); comm.barrier()
+            ms_sl = comm.max_float(e0.elapsed_time(e1), device=dev)
+            ss.check()
+            slab = {"value": w["N"] * len(its_sl) / (ms_sl * 1e-3), "unit": "particle-steps/s", "ms_per_step": ms_sl / len(its_sl),
+                    "steps": len(its_sl), "picard_iterations_per_step": float(np.mean(its_sl)), "n_gpus": world,
+                    "migration": dict(ss.stat), "guard_cells": 16,
+                    "note": "spatial slab decomposition of the same workload; the particle decomposition above is the default"}
+            del ss
+            torch.cuda.empty_cache()
+        except Exception as ex:                      # the sub-record must never take the main line down
+            slab = {"error": repr(ex)[:300]}
+        sim = None
+
     # ---- the north-star strong-scaling case (BASELINE config 4): a fixed TOTAL of particles over the N GPUs, same
     # code, same run -- the driver's 1/2/4/8 sweep then holds the whole curve (sub-record `strong_scaling`)
     strong = None
     if args.strong_total and not args.total_particles and args.strong_total != w["N"]:
-        n_main, p2p_main = sim.N, sim.p2p is not None
-        sim.close()
-        del sim
+        if sim is not None:
+            n_main, p2p_main = sim.N, sim.p2p is not None
+            sim.close()
+            del sim
+        else:
+            n_main, p2p_main = n_keep, p2p_keep
         torch.cuda.empty_cache()
         a2 = argparse.Namespace(**vars(args)); a2.total_particles = args.strong_total
         w2 = workload(a2, world)
@@ -496,9 +539,11 @@ def run_cuda(args):
                   "roofline_frac": ach2 / peak, "gpu_launches": int(tr2["launches"]),
                   "note": "speed-up at N GPUs = this value / the same sub-record of the --gpus 1 run (one code version)"}
         n_local = n_main
-    else:
+    elif sim is not None:
         n_local, p2p_main = sim.N, sim.p2p is not None
         sim.close()
+    else:
+        n_local, p2p_main = n_keep, p2p_keep
 
     if rank == 0:
         clocks = sampler.summary() if sampler else {}
@@ -524,6 +569,7 @@ def run_cuda(args):
                                            "DESIGN.md section 4)",
                        "l2_policy": "inputs (%.1f GB of particle arrays per GPU) are far larger than the 126 MB L2" % (n_local * 32 / 1e9)},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "reference_api": api, "strong_scaling": strong,
+            "slab_decomposition": slab,
             "gpu_launches": int(launches),
             "clocks": clocks,
         }
