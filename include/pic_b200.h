@@ -546,6 +546,15 @@ int pic_dev_gc_push_boris_uniform2(const pic_gc_params* p, double* const r[7], d
  * mid-domain exit of wall-born particles :1530-1541 (active <- 0, flag returned); and the
  * particle's deterministic contribution to the running source-ion count of :1544.  The uniform
  * draws and the decisions are made on the host in index order (legacy stream parity). */
+/* The fused step for a MIXED store (ions, neutrals, several charge states in one list, as in the
+ * reference's loop pygcpic.py:1498-1549): per-particle charge_state, m, p2c; results bit-identical to
+ * pic_dev_gc_push_boris; with n_acc != NULL both deposits of Grid.weight_particles_to_grid_boltzmann
+ * :871-883 are fused (n_acc += p2c/dx*w, rho_acc += charge_state*e*p2c/dx*w at the new positions of the
+ * particles still active).  lean as in pic_dev_gc_push_boris_uniform2. */
+int pic_dev_gc_push_boris_mixed(const pic_gc_params* p, double* const r[7], const double* charge_state, const double* m,
+                                const double* p2c, int lean, double t_now, int8_t* active, int8_t* at_wall,
+                                int8_t* hit_flag, const double* Egrid, double* n_acc, double* rho_acc,
+                                long long* hit_count, int* range_err, void* stream);
 int pic_dev_gc_post_push(const double* x, const double* p2c, const double* charge_state, const int32_t* Z,
                          const int8_t* from_wall, int8_t* active, const double* n_grid, int ng, double dx,
                          double dt, double length, const double rate[4], int source_Z, double* prob,

@@ -133,6 +133,7 @@ _SIGS = {
     "pic_dev_gc_push_boris": [C.POINTER(GCParams), C.POINTER(R7), P, P, P, P, P, P, P, P, P],
     "pic_dev_gc_push_boris_uniform": [C.POINTER(GCParams), C.POINTER(R7), F64, F64, F64, P, P, P, P, P, P, P, P],
     "pic_dev_gc_push_boris_uniform2": [C.POINTER(GCParams), C.POINTER(R7), F64, F64, F64, I32, F64, P, P, P, P, P, P, P, P],
+    "pic_dev_gc_push_boris_mixed": [C.POINTER(GCParams), C.POINTER(R7), P, P, P, I32, F64, P, P, P, P, P, P, P, P, P],
     "pic_dev_gc_post_push": [P, P, P, P, P, P, P, I32, F64, F64, F64, C.POINTER(C.c_double * 4), I32, P, P, P, P, I64, P, P],
     "pic_dev_gc_uniform_finish": [P, P, P, I32, F64, P],
     "pic_dev_gc_deposit_idx": [P, P, I64, F64, F64, I32, P, P, P],

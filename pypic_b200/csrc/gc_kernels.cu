@@ -402,6 +402,239 @@ __global__ void __launch_bounds__(G_T, 1) gc_push_boris_v2_k(const __grid_consta
     }
 }
 
+// =====================================================================================
+// The same fused step for a MIXED store (ions, neutrals, boron in several charge states in one
+// list, as in the reference's particle loop pygcpic.py:1498-1549): charge_state, m and p2c are
+// per-particle arrays and ride the TMA ring next to x, vx, vy, vz and the activity flags; the Boris
+// constants are formed per particle with the IEEE operations of gc_push_boris_k (bit-identical
+// results), and BOTH deposits of D5 are fused: n (p2c/dx) and rho (charge_state*e*p2c/dx) in two
+// private 7-node windows per thread.  y, z and the clock (a full store) are only accumulated, so they
+// bypass the ring: loaded at the top of a row, stored at its end.  Two ring stages.
+#define GM_W 7
+#define GM_NST 2
+#define GM_SDP (7 * 64)
+#define GM_SD (GM_SDP + 16)
+struct GMix { const double* cs; const double* m; const double* p2c; int lean; double tnow; };
+struct GMixO { double x, vx, vy, vz, nL, nR, qL, qR; int cF; unsigned fr, ps; };
+
+__device__ __forceinline__ void gm_fast(const GCK& k, double idx, const double* __restrict__ sE, int ng, double x, double vx,
+                                        double vy, double vz, double cs, double m, double pc, GMixO& o) {
+    const double ts = x * idx, fs = floor(ts);
+    const unsigned f0 = (unsigned)__double2hiint(ts - fs) - PIC_HI_G;
+    const double rs = fma(-fs, k.dx, x);
+    const int is = min(max((int)fs, 0), ng - 2);
+    const double w_l = div_const(rs, k.dx, idx), w_r = 1.0 - w_l;         // pygcpic.py:344-346 (mirrored)
+    const double Ex = sE[is] * w_l + sE[is + 1] * w_r;
+    const double constant = 0.5 * k.dt * cs * 1.602e-19 / m;              // :478
+    vx += constant * Ex;
+    const double tx = constant * k.B[0], ty = constant * k.B[1], tz = constant * k.B[2];
+    const double t2 = tx * tx + ty * ty + tz * tz;
+    const double sx = 2. * tx / (1. + t2), sy = 2. * ty / (1. + t2), sz = 2. * tz / (1. + t2);
+    const double vfx = vx + vy * tz - vz * ty;
+    const double vfy = vy + vz * tx - vx * tz;
+    const double vfz = vz + vx * ty - vy * tx;
+    vx += vfy * sz - vfz * sy;
+    vy += vfz * sx - vfx * sz;
+    vz += vfx * sy - vfy * sx;
+    vx += constant * Ex;
+    o.x = x + vx * k.dt; o.vx = vx; o.vy = vy; o.vz = vz;
+    o.ps = max((unsigned)__double2hiint(x) - 1u, (unsigned)__double2hiint(o.x) - 1u);
+    const double tf = o.x * idx, ff = floor(tf);
+    const unsigned f1 = (unsigned)__double2hiint(tf - ff) - PIC_HI_G;
+    const double rf = fma(-ff, k.dx, o.x);
+    o.cF = (int)ff;
+    o.fr = max(f0, f1);
+    const double nr = div_const(pc, k.dx, idx), qr = div_const(cs * PIC_E * pc, k.dx, idx);   // gc_weight_k
+    const double wR = rf * idx;
+    o.nR = nr * wR; o.nL = nr - o.nR; o.qR = qr * wR; o.qL = qr - o.qR;
+}
+
+// exact per-particle routine of the mixed kernel (the body of gc_push_boris_k + gc_weight_k)
+__device__ __noinline__ int gm_particle_exact(const GCK& k, const GMix& u, const R7& r, long long i, int act,
+                                              const double* sE, int8_t* __restrict__ active, int8_t* __restrict__ at_wall,
+                                              int8_t* __restrict__ hit_flag, double* __restrict__ n_acc,
+                                              double* __restrict__ rho_acc, int* hits) {
+    int bad = 0;
+    if (act != 1) { if (hit_flag) hit_flag[i] = 0; return 0; }
+    GUni one{u.cs[i], u.m[i], u.p2c[i], u.lean, u.tnow};
+    bad = gc_particle_exact(k, one, r, i, act, sE, active, at_wall, hit_flag, nullptr, hits);
+    if (active[i] == 1 && n_acc) {
+        Cell c = cell_dd_fast(r.r[0][i], k.dx, 1.0 / k.dx);
+        if (c.iL < 0 || c.iL > k.ng - 2) { ++bad; c.iL = clampi(c.iL, 0, k.ng - 2); }
+        const double nr = div_const(one.p2c, k.dx, 1.0 / k.dx), qr = div_const(one.cs * PIC_E * one.p2c, k.dx, 1.0 / k.dx);
+        atomicAdd(&n_acc[c.iL], nr * c.wL); atomicAdd(&n_acc[c.iL + 1], nr * c.wR);
+        atomicAdd(&rho_acc[c.iL], qr * c.wL); atomicAdd(&rho_acc[c.iL + 1], qr * c.wR);
+    }
+    return bad;
+}
+
+__device__ __forceinline__ void gmwin_add(double* myw, double* __restrict__ nacc, double* __restrict__ racc, int wb, int c,
+                                          const GMixO& o) {
+    const unsigned d = (unsigned)(c - wb);
+    if (d <= (unsigned)(GM_W - 2)) {
+        double* p = myw + d * G_T; p[0] += o.nL; p[G_T] += o.nR;
+        p += GM_W * G_T; p[0] += o.qL; p[G_T] += o.qR;
+    } else {
+        atomicAdd(&nacc[c], o.nL); atomicAdd(&nacc[c + 1], o.nR); atomicAdd(&racc[c], o.qL); atomicAdd(&racc[c + 1], o.qR);
+    }
+}
+
+template <bool DEP>
+__global__ void __launch_bounds__(G_T, 1) gc_push_boris_mix_k(const __grid_constant__ GCK k, const GMix u, int nchunks, const R7 r,
+                                                               int8_t* __restrict__ active, int8_t* __restrict__ at_wall,
+                                                               int8_t* __restrict__ hit_flag, const double* __restrict__ Egrid,
+                                                               double* __restrict__ n_acc, double* __restrict__ rho_acc,
+                                                               long long* __restrict__ hit_count, int* __restrict__ range_err) {
+    extern __shared__ __align__(128) double sm[];
+    __shared__ int s_cnt[2];
+    const int ng = k.ng;
+    const int NP = (ng + 15) & ~15;
+    double* sE = sm;
+    double* win = sm + NP;                                   // [2 (n, rho)][GM_W][G_T]
+    double* ring = win + (DEP ? 2 * GM_W * G_T : 0);         // [warp][stage][x,vx,vy,vz,cs,m,p2c][64] + flags
+    unsigned long long* bars = (unsigned long long*)(ring + (G_T / 32) * GM_NST * GM_SD);
+    for (int i = threadIdx.x; i < ng; i += G_T) sE[i] = Egrid[i];
+    double* myw = win + threadIdx.x;
+    if (DEP) {
+#pragma unroll
+        for (int n = 0; n < 2 * GM_W; ++n) myw[n * G_T] = 0.0;
+    }
+    if (threadIdx.x < 2) s_cnt[threadIdx.x] = 0;
+    const unsigned full = 0xffffffffu;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wbase = threadIdx.x & ~31;
+    const int NOWIN = -0x40000000;
+    const double* wring = ring + warp * (GM_NST * GM_SD);
+    const uint32_t ring_s = smem_u32(wring);
+    const uint32_t bar_s = smem_u32(bars + warp * GM_NST);
+    if (lane == 0) {
+#pragma unroll
+        for (int s = 0; s < GM_NST; ++s) mbar_init(bar_s + 8 * s, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    const double idx = 1.0 / k.dx;
+    const unsigned hi_lim = (unsigned)__double2hiint(k.length) - 1u;
+    const int my_chunks = (nchunks - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+    const long long woff = (long long)warp * (64 * G_ROWS);
+    const long long chunk_step = (long long)gridDim.x * G_CHUNK;
+    auto issue = [&](long long base, int st) {
+        if (elect_one()) {
+            const uint32_t dst = ring_s + st * (GM_SD * 8), bar = bar_s + 8 * st;
+            mbar_expect_tx(bar, (uint32_t)(GM_SDP * 8 + 64));
+            bulk_g2s(dst, r.r[0] + base, 512, bar);
+            bulk_g2s(dst + 512, r.r[3] + base, 512, bar);
+            bulk_g2s(dst + 1024, r.r[4] + base, 512, bar);
+            bulk_g2s(dst + 1536, r.r[5] + base, 512, bar);
+            bulk_g2s(dst + 2048, u.cs + base, 512, bar);
+            bulk_g2s(dst + 2560, u.m + base, 512, bar);
+            bulk_g2s(dst + 3072, u.p2c + base, 512, bar);
+            bulk_g2s(dst + GM_SDP * 8, active + base, 64, bar);
+        }
+    };
+    long long cbase = (long long)blockIdx.x * G_CHUNK + woff;
+    if (my_chunks > 0) {
+#pragma unroll
+        for (int s = 0; s < GM_NST; ++s) issue(cbase + 64 * s, s);
+    }
+    int stage = 0, bad = 0, hits = 0;
+    uint32_t phase = 0;
+#pragma unroll 1
+    for (int c = 0; c < my_chunks; ++c, cbase += chunk_step) {
+        const bool more = c + 1 < my_chunks;
+        int wb = NOWIN;
+        long long ci = cbase + 2 * lane;
+#pragma unroll 1
+        for (int row = 0; row < G_ROWS; ++row, ci += 64) {
+            // y, z and the clock are only accumulated: plain loads now, used at the end of the row
+            double2 Y = make_double2(0., 0.), Z = Y, T = Y;
+            if (!u.lean) { Y = __ldcs((const double2*)(r.r[1] + ci)); Z = __ldcs((const double2*)(r.r[2] + ci)); T = __ldcs((const double2*)(r.r[6] + ci)); }
+            mbar_wait(bar_s + 8 * stage, phase);
+            const double* sb = wring + stage * GM_SD + 2 * lane;
+            const short fl = *(const short*)((const char*)(wring + stage * GM_SD + GM_SDP) + 2 * lane);
+            const int acta = (int)(signed char)(fl & 0xff), actb = (int)(signed char)(fl >> 8);
+            const double2 X = *(const double2*)sb, VX = *(const double2*)(sb + 64), VY = *(const double2*)(sb + 128);
+            const double2 VZ = *(const double2*)(sb + 192), CS = *(const double2*)(sb + 256), MM = *(const double2*)(sb + 320);
+            const double2 PC = *(const double2*)(sb + 384);
+            const int st_cur = stage;
+            if (++stage == GM_NST) { stage = 0; phase ^= 1u; }
+            GMixO a, b;
+            gm_fast(k, idx, sE, ng, X.x, VX.x, VY.x, VZ.x, CS.x, MM.x, PC.x, a);
+            gm_fast(k, idx, sE, ng, X.y, VX.y, VY.y, VZ.y, CS.y, MM.y, PC.y, b);
+            const bool ra = (a.fr > PIC_HI_SPAN) | (a.ps >= hi_lim) | (acta != 1);
+            const bool rb = (b.fr > PIC_HI_SPAN) | (b.ps >= hi_lim) | (actb != 1);
+            if (DEP && row == 0) {
+                int nok = __reduce_add_sync(full, (ra ? 0 : 1) + (rb ? 0 : 1));
+                int sum = __reduce_add_sync(full, (ra ? 0 : a.cF) + (rb ? 0 : b.cF));
+                wb = nok ? sum / nok - (GM_W - 2) / 2 : NOWIN;
+            }
+            if (!(ra | rb)) {
+                __stcs((double2*)(r.r[0] + ci), make_double2(a.x, b.x));
+                __stcs((double2*)(r.r[3] + ci), make_double2(a.vx, b.vx));
+                __stcs((double2*)(r.r[4] + ci), make_double2(a.vy, b.vy));
+                __stcs((double2*)(r.r[5] + ci), make_double2(a.vz, b.vz));
+                if (!u.lean) {
+                    __stcs((double2*)(r.r[1] + ci), make_double2(Y.x + a.vy * k.dt, Y.y + b.vy * k.dt));
+                    __stcs((double2*)(r.r[2] + ci), make_double2(Z.x + a.vz * k.dt, Z.y + b.vz * k.dt));
+                    __stcs((double2*)(r.r[6] + ci), make_double2(T.x + k.dt, T.y + k.dt));
+                }
+                if (DEP) { gmwin_add(myw, n_acc, rho_acc, wb, a.cF, a); gmwin_add(myw, n_acc, rho_acc, wb, b.cF, b); }
+            } else {
+                if (ra) bad += gm_particle_exact(k, u, r, ci, acta, sE, active, at_wall, hit_flag, DEP ? n_acc : nullptr, rho_acc, &hits);
+                else {
+                    r.r[0][ci] = a.x; r.r[3][ci] = a.vx; r.r[4][ci] = a.vy; r.r[5][ci] = a.vz;
+                    if (!u.lean) { r.r[1][ci] = Y.x + a.vy * k.dt; r.r[2][ci] = Z.x + a.vz * k.dt; r.r[6][ci] = T.x + k.dt; }
+                    if (DEP) gmwin_add(myw, n_acc, rho_acc, wb, a.cF, a);
+                }
+                if (rb) bad += gm_particle_exact(k, u, r, ci + 1, actb, sE, active, at_wall, hit_flag, DEP ? n_acc : nullptr, rho_acc, &hits);
+                else {
+                    r.r[0][ci + 1] = b.x; r.r[3][ci + 1] = b.vx; r.r[4][ci + 1] = b.vy; r.r[5][ci + 1] = b.vz;
+                    if (!u.lean) { r.r[1][ci + 1] = Y.y + b.vy * k.dt; r.r[2][ci + 1] = Z.y + b.vz * k.dt; r.r[6][ci + 1] = T.y + k.dt; }
+                    if (DEP) gmwin_add(myw, n_acc, rho_acc, wb, b.cF, b);
+                }
+            }
+            __syncwarp();
+            if (row < G_ROWS - GM_NST) issue(cbase + 64 * (row + GM_NST), st_cur);
+            else if (more) issue(cbase + chunk_step + 64 * (row + GM_NST - G_ROWS), st_cur);
+        }
+        __syncwarp();
+        if (DEP && wb != NOWIN) {
+            // column sums of the warp's 32 private windows of both quantities -> global accumulators
+            double s = 0.0;
+            const int n = lane >> 1, half = lane & 1;
+            if (n < 2 * GM_W) {
+                const double* col = win + n * G_T + wbase + half * 16;
+#pragma unroll
+                for (int j = 0; j < 16; ++j) s += col[(j + n) & 15];
+            }
+            s += __shfl_xor_sync(full, s, 1);
+            if (n < 2 * GM_W && half == 0) {
+                const int node = wb + (n < GM_W ? n : n - GM_W);
+                if (node >= 0 && node < ng && s != 0.0) atomicAdd((n < GM_W ? n_acc : rho_acc) + node, s);
+            }
+            __syncwarp();
+#pragma unroll
+            for (int n2 = 0; n2 < 2 * GM_W; ++n2) myw[n2 * G_T] = 0.0;
+            __syncwarp();
+        }
+    }
+    if (bad) atomicAdd(&s_cnt[0], bad);
+    if (hits) atomicAdd(&s_cnt[1], hits);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        if (s_cnt[0] && range_err) atomicAdd(range_err, s_cnt[0]);
+        if (s_cnt[1] && hit_count) atomicAdd((unsigned long long*)hit_count, (unsigned long long)s_cnt[1]);
+    }
+}
+__global__ void gc_tail_mix_k(GCK k, GMix u, R7 r, long long first, int8_t* __restrict__ active, int8_t* __restrict__ at_wall,
+                              int8_t* __restrict__ hit_flag, const double* __restrict__ Egrid, double* __restrict__ n_acc,
+                              double* __restrict__ rho_acc, long long* __restrict__ hit_count, int* __restrict__ range_err) {
+    int bad = 0, hits = 0;
+    for (long long i = first + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < k.N; i += (long long)gridDim.x * blockDim.x)
+        bad += gm_particle_exact(k, u, r, i, active[i], Egrid, active, at_wall, hit_flag, n_acc, rho_acc, &hits);
+    if (hits && hit_count) atomicAdd((unsigned long long*)hit_count, (unsigned long long)hits);
+    if (bad && range_err) atomicAdd(range_err, bad);
+}
+
 // tail of the uniform fused step (N % G_CHUNK particles): the exact per-particle routine
 __global__ void gc_tail_uniform_k(GCK k, GUni u, R7 r, long long first, int8_t* __restrict__ active,
                                   int8_t* __restrict__ at_wall, int8_t* __restrict__ hit_flag,
@@ -1067,6 +1300,52 @@ int pic_dev_gc_push_boris_uniform2(const pic_gc_params* p, double* const r[7], d
     }
     const long long done = nchunks * G_CHUNK;
     if (done < k.N) gc_tail_uniform_k<<<grid_for(k.N - done, 256, 4), 256, 0, st>>>(k, u, rr, done, active, at_wall, hit_flag, Egrid, n_acc, hit_count, range_err);
+    PIC_CHECK_LAUNCH();
+    return PIC_OK;
+}
+
+// Mixed-store fused Boris step (see gc_push_boris_mix_k).  n_acc == NULL: no deposit (then rho_acc is ignored).
+int pic_dev_gc_push_boris_mixed(const pic_gc_params* p, double* const r[7], const double* charge_state, const double* m,
+                                const double* p2c, int lean, double t_now, int8_t* active, int8_t* at_wall,
+                                int8_t* hit_flag, const double* Egrid, double* n_acc, double* rho_acc,
+                                long long* hit_count, int* range_err, void* stream) {
+    PIC_REQUIRE(p && r && charge_state && m && p2c && active && at_wall && Egrid, "gc_push_boris_mixed: null pointer");
+    PIC_REQUIRE(!(p->flags & 3), "gc_push_boris_mixed: pre-gathered E / no-BC modes are not supported");
+    PIC_REQUIRE(p->ng >= 8, "gc_push_boris_mixed: grid too small");
+    PIC_REQUIRE(!n_acc || rho_acc, "gc_push_boris_mixed: the fused deposit needs both accumulators");
+    if (p->N == 0) return PIC_OK;
+    GCK k = make_gck(p);
+    GMix u{charge_state, m, p2c, lean ? 1 : 0, t_now};
+    R7 rr;
+    bool aligned = (((uintptr_t)charge_state | (uintptr_t)m | (uintptr_t)p2c | (uintptr_t)active) & 15) == 0;
+    for (int i = 0; i < 7; ++i) {
+        PIC_REQUIRE(r[i] || (lean && (i == 1 || i == 2)), "gc_push_boris_mixed: null component array");
+        rr.r[i] = r[i];
+        aligned = aligned && (((uintptr_t)r[i]) & 15) == 0;
+    }
+    PIC_REQUIRE(aligned, "gc_push_boris_mixed: arrays must be 16-byte aligned");
+    cudaStream_t st = (cudaStream_t)stream;
+    const bool dep = n_acc != nullptr;
+    const size_t smem = ((size_t)((k.ng + 15) & ~15) + (dep ? (size_t)2 * GM_W * G_T : 0) + (size_t)(G_T / 32) * GM_NST * GM_SD +
+                         (size_t)(G_T / 32) * GM_NST) * sizeof(double);
+    PIC_REQUIRE(smem <= (size_t)max_optin_smem() - 512, "gc_push_boris_mixed: ng too large for the shared-memory field tile");
+    const long long nchunks = k.N / G_CHUNK;
+    if (nchunks > 0) {
+        long long capc = device_sm_count();
+        const int grid = (int)(nchunks < capc ? nchunks : capc);
+        if (dep) {
+            PIC_CHECK_CUDA(cudaFuncSetAttribute(gc_push_boris_mix_k<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            gc_push_boris_mix_k<true><<<grid, G_T, smem, st>>>(k, u, (int)nchunks, rr, active, at_wall, hit_flag, Egrid, n_acc, rho_acc,
+                                                               hit_count, range_err);
+        } else {
+            PIC_CHECK_CUDA(cudaFuncSetAttribute(gc_push_boris_mix_k<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            gc_push_boris_mix_k<false><<<grid, G_T, smem, st>>>(k, u, (int)nchunks, rr, active, at_wall, hit_flag, Egrid, n_acc, rho_acc,
+                                                                hit_count, range_err);
+        }
+        PIC_CHECK_LAUNCH();
+    }
+    const long long done = nchunks * G_CHUNK;
+    if (done < k.N) gc_tail_mix_k<<<grid_for(k.N - done, 256, 4), 256, 0, st>>>(k, u, rr, done, active, at_wall, hit_flag, Egrid, n_acc, rho_acc, hit_count, range_err);
     PIC_CHECK_LAUNCH();
     return PIC_OK;
 }

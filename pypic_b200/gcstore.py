@@ -48,7 +48,9 @@ class GridDev:
         self.added_particles = 0.0
         self.newton_iterations = 0
         self.n_acc = D.f64(ng, dev, True)           # number density deposited by the fused push
+        self.rho_acc = D.f64(ng, dev, True)         # charge density, the same (mixed-species stores only)
         self.have_fused_n = False
+        self._fused_mixed = False
 
     # -- reference-density state ------------------------------------------------------
     @property
@@ -89,17 +91,37 @@ class GridDev:
         _lib.call("pic_dev_gc_n0_update", D.ptr(self.phi), D.ptr(self.n), D.ptr(self.domain), self.ng, self.Te, self.ve,
                   float(self.added_particles), float(dt), D.ptr(self.state), st)
 
-    # -- fused deposit (species-uniform stores) -----------------------------------------------
-    def begin_fused_deposit(self):
+    # -- fused deposit ----------------------------------------------------------------------
+    def begin_fused_deposit(self, mixed=False):
+        """mixed: the push kernel deposits rho per particle as well (a store with several species);
+        otherwise rho = charge_state*e*n at finish_fused_deposit."""
         self.n_acc.zero_()
+        if mixed:
+            self.rho_acc.zero_()
         self.have_fused_n = True
+        self._fused_mixed = bool(mixed)
 
-    def deposit_slots(self, store, idx, p2c):
-        """Adds the number density of the slots idx (int64 device tensor) -- the particles
+    def promote_fused_to_mixed(self, charge_state):
+        """A pending species-uniform deposit (rho implied by n) becomes a two-accumulator one: a particle
+        of another species is about to be added to it."""
+        if self.have_fused_n and not self._fused_mixed:
+            _lib.call("pic_dev_gc_uniform_finish", D.ptr(self.n_acc), D.ptr(self.n), D.ptr(self.rho_acc), self.ng,
+                      float(charge_state), D.stream())
+            self._fused_mixed = True
+
+    def deposit_slots(self, store, idx, p2c, charge_state=None):
+        """Adds the density of the slots idx (int64 device tensor) -- the particles
         re-activated after the fused push -- to the pending deposit."""
         if idx.numel():
             _lib.call("pic_dev_gc_deposit_idx", D.ptr(store.r[0]), D.ptr(idx), idx.numel(), float(p2c), self.dx, self.ng,
                       D.ptr(self.n_acc), D.ptr(self.range_err), D.stream())
+            if self._fused_mixed:
+                if charge_state is None:
+                    raise _lib.PicError(_lib.PIC_ERR_ARG, "deposit_slots: a mixed-species pending deposit needs the charge state")
+                # charge_state*e*p2c in the reference's product order (pygcpic.py:871-873)
+                _lib.call("pic_dev_gc_deposit_idx", D.ptr(store.r[0]), D.ptr(idx), idx.numel(),
+                          float(charge_state) * 1.602e-19 * float(p2c), self.dx, self.ng, D.ptr(self.rho_acc),
+                          D.ptr(self.range_err), D.stream())
 
     def finish_fused_deposit(self, charge_state, dt):
         """n, rho from the density the fused push deposited (+ re-activated slots), then the
@@ -107,8 +129,13 @@ class GridDev:
         st = D.stream()
         if self.comm is not None:
             self.comm.allreduce_sum(self.n_acc)
-        _lib.call("pic_dev_gc_uniform_finish", D.ptr(self.n_acc), D.ptr(self.n), D.ptr(self.rho), self.ng,
-                  float(charge_state), st)
+            if self._fused_mixed:
+                self.comm.allreduce_sum(self.rho_acc)
+        if self._fused_mixed:
+            self.n.copy_(self.n_acc); self.rho.copy_(self.rho_acc)
+        else:
+            _lib.call("pic_dev_gc_uniform_finish", D.ptr(self.n_acc), D.ptr(self.n), D.ptr(self.rho), self.ng,
+                      float(charge_state), st)
         _lib.call("pic_dev_gc_n0_update", D.ptr(self.phi), D.ptr(self.n), D.ptr(self.domain), self.ng, self.Te, self.ve,
                   float(self.added_particles), float(dt), D.ptr(self.state), st)
         self.have_fused_n = False
@@ -194,6 +221,7 @@ class ParticleStore:
         return s
 
     FUSED_MIN = 16384                               # one chunk of the v2 kernel
+    MIXED_MAX_NG = 6900                             # field tile + two deposit windows + ring of the mixed kernel in 227 KB
 
     def uniform(self):
         """(charge_state, m, p2c) if every slot holds the same values (then the push can take
@@ -259,10 +287,11 @@ class ParticleStore:
         r7 = self._r7()
         self.hit_count.zero_()
         self.time = float(time) if time is not None else self.time + float(dt)
-        u = self.uniform() if self.N >= self.FUSED_MIN and grid.ng >= 8 else None
-        if u is None and not self.carry_yzt:
-            raise _lib.PicError(_lib.PIC_ERR_ARG, "a lean store (carry_yzt=False) is served by the species-uniform fused kernel only "
-                                "(all particles share charge_state, m, p2c; N >= %d)" % self.FUSED_MIN)
+        fused = self.N >= self.FUSED_MIN and grid.ng >= 8
+        u = self.uniform() if fused else None
+        if not fused and not self.carry_yzt:
+            raise _lib.PicError(_lib.PIC_ERR_ARG, "a lean store (carry_yzt=False) is served by the fused kernels only "
+                                "(N >= %d)" % self.FUSED_MIN)
         if u is not None:
             if deposit:
                 grid.begin_fused_deposit()
@@ -270,6 +299,15 @@ class ParticleStore:
                       0 if self.carry_yzt else 1, self.time, D.ptr(self.active), D.ptr(self.at_wall), D.ptr(self.hit_flag),
                       D.ptr(grid.E), D.ptr(grid.n_acc) if deposit else None, D.ptr(self.hit_count), D.ptr(self.range_err),
                       D.stream())
+            return int(D.read_raw(self.hit_count, 1, np.int64)[0])
+        if fused and (grid.ng <= self.MIXED_MAX_NG or not self.carry_yzt):
+            # several species in one list: per-particle charge_state, m, p2c ride the ring; n AND rho deposited
+            if deposit:
+                grid.begin_fused_deposit(mixed=True)
+            _lib.call("pic_dev_gc_push_boris_mixed", C.byref(P), C.byref(r7), D.ptr(self.charge_state), D.ptr(self.m),
+                      D.ptr(self.p2c), 0 if self.carry_yzt else 1, self.time, D.ptr(self.active), D.ptr(self.at_wall),
+                      D.ptr(self.hit_flag), D.ptr(grid.E), D.ptr(grid.n_acc) if deposit else None,
+                      D.ptr(grid.rho_acc) if deposit else None, D.ptr(self.hit_count), D.ptr(self.range_err), D.stream())
             return int(D.read_raw(self.hit_count, 1, np.int64)[0])
         _lib.call("pic_dev_gc_push_boris", C.byref(P), C.byref(r7), D.ptr(self.charge_state), D.ptr(self.m),
                   D.ptr(self.active), D.ptr(self.at_wall), D.ptr(self.hit_flag), D.ptr(grid.E), D.ptr(self.hit_count),
@@ -370,9 +408,10 @@ class ParticleStore:
         self.active[idx] = 1; self.at_wall[idx] = 0; self.from_wall[idx] = 0
         self.hit_flag[idx] = 0
         if self._uniform not in (False, None) and self._uniform != (float(charge_state), float(m), float(p2c)):
+            grid.promote_fused_to_mixed(self._uniform[0])
             self._uniform = None
         if grid.have_fused_n:                      # the fused push has already deposited the survivors
-            grid.deposit_slots(self, idx, p2c)
+            grid.deposit_slots(self, idx, p2c, charge_state)
         for _ in range(len(where_idx)):
             grid.add_particles(p2c)
 

@@ -247,6 +247,103 @@ def test_uniform_fused_boris_matches_v1_kernels(ng):
     assert abs(b[6] - a[6]) <= 1e-13 * abs(a[6])
 
 
+@pytest.mark.parametrize("ng,lean", [(300, False), (4097, False), (300, True)])
+def test_mixed_species_fused_boris_matches_v1_kernels(ng, lean):
+    """gc_push_boris_mix_k (several species in one list: per-particle charge_state, m, p2c in the TMA
+    ring, n and rho deposits fused) against the v1 push + separate weight kernels: r, flags, hit counts
+    bit-identical; n, rho and the Boltzmann n0 to 1e-13.  Hydrogen ions, neutrals (charge 0), B+, B2+
+    with different weights; inactive slots, wall hits, node-aligned positions, a ragged tail; several
+    steps so that particles leave their deposit windows."""
+    import torch
+    from pypic_b200.gcstore import GridDev, ParticleStore
+    rs = np.random.RandomState(15)
+    Lg = 3e-3; Te = 60 * 11600.; dt = 2e-9 * 300 / ng
+    N = 3 * 16384 + 517
+    dx = Lg / (ng - 1)
+    x = np.sort(rs.uniform(0, Lg, N))
+    j = rs.choice(N, 2400, replace=False)
+    cells = rs.randint(1, ng - 1, 2400)
+    x[j[:800]] = cells[:800] * dx
+    x[j[800:1600]] = np.nextafter(cells[800:1600] * dx, 0.0)
+    x[j[1600:2000]] = rs.uniform(0, 2e-2 * dx, 400)
+    x[j[2000:]] = Lg - rs.uniform(0, 2e-2 * dx, 400)
+    r = np.zeros((N, 7))
+    r[:, 0] = x; r[:, 1:3] = rs.normal(0, 1e-4, (N, 2)); r[:, 3:6] = rs.normal(0, 7e4, (N, 3)); r[:, 6] = rs.uniform(0, 1e-8, N)
+    sp = rs.choice(4, N, p=[0.6, 0.15, 0.15, 0.1])
+    cs = np.array([1., 0., 1., 2.])[sp]; m = np.array([O.mp, O.mp, 10.81 * O.mp, 10.81 * O.mp])[sp]
+    p2c = np.array([3.1e9, 1.0e9, 2.0e8, 2.0e8])[sp]; Zs = np.array([1, 1, 5, 5])[sp]
+    active = np.ones(N, dtype=np.int8); active[rs.choice(N, 700, replace=False)] = 0
+    B = (2 * np.cos(1.5), 2 * np.sin(1.5), 0.)
+    E = rs.normal(0, 5e4, ng)
+    res = {}
+    for fused in (False, True):
+        grid = GridDev(ng, Lg, Te)
+        grid.E.copy_(torch.as_tensor(E))
+        st = ParticleStore.from_arrays(r, cs, m, p2c, Z=Zs, active=active, B=B)
+        assert st.uniform() is None
+        st.FUSED_MIN = 0 if fused else 10 ** 12
+        if lean and fused:
+            st.carry_yzt = False
+        hits = []
+        for _ in range(3):
+            hits.append(st.push_6D(dt, grid, deposit=fused))
+            if fused:
+                assert grid.have_fused_n and grid._fused_mixed
+                grid.finish_fused_deposit(1.0, dt)
+            else:
+                st.apply_BCs_dirichlet(grid)
+                grid.weight_particles_to_grid_boltzmann(st, dt)
+        st.check(); grid.check()
+        res[fused] = (st.r_host(), st.flags_host(), hits, st.hit_flag[:N].cpu().numpy(), grid.n.cpu().numpy(),
+                      grid.rho.cpu().numpy(), grid.n0)
+    a, b = res[False], res[True]
+    cols = (0, 3, 4, 5) if lean else range(7)
+    for c in cols:
+        assert np.array_equal(a[0][:, c], b[0][:, c]), c
+    for kf in ("active", "at_wall", "from_wall"):
+        assert np.array_equal(a[1][kf], b[1][kf])
+    assert a[2] == b[2] and sum(a[2]) > 200
+    assert np.array_equal(a[3], b[3])
+    assert relmax(b[4], a[4]) < 1e-13 and relmax(b[5], a[5]) < 1e-13
+    assert abs(b[6] - a[6]) <= 1e-13 * abs(a[6])
+
+
+def test_species_change_promotes_the_pending_fused_deposit():
+    """A species-uniform store whose fused push has deposited n (rho implied) receives re-activated
+    particles of ANOTHER species: the pending deposit becomes a two-accumulator one
+    (GridDev.promote_fused_to_mixed), the next push takes the mixed kernel, and n, rho equal the
+    separate weight pass over the final store (pygcpic.py:871-883)."""
+    import torch
+    from pypic_b200.gcstore import GridDev, ParticleStore
+    rs = np.random.RandomState(16)
+    ng = 301; Lg = 3e-3; Te = 60 * 11600.; dt = 2e-9
+    N = 2 * 16384 + 31
+    r = np.zeros((N, 7)); r[:, 0] = rs.uniform(0, Lg, N); r[:, 3:6] = rs.normal(0, 7e4, (N, 3))
+    active = np.ones(N, dtype=np.int8); dead = rs.choice(N, 400, replace=False); active[dead] = 0
+    grid = GridDev(ng, Lg, Te); grid.E.copy_(torch.as_tensor(rs.normal(0, 5e4, ng)))
+    st = ParticleStore.from_arrays(r, 1.0, O.mp, 3.1e9, Z=1, active=active, B=(0.3, 1.9, 0.))
+    st.push_6D(dt, grid, deposit=True)
+    assert grid.have_fused_n and not grid._fused_mixed
+    idx = np.sort(dead[:150])
+    r_new = np.zeros((150, 7)); r_new[:, 0] = rs.uniform(0, Lg, 150); r_new[:, 3:6] = rs.normal(0, 2e4, (150, 3))
+    st.reactivate(idx, r_new, 2.0e8, 10.81 * O.mp, 2.0, 5, dt, grid)
+    assert grid._fused_mixed and st.uniform() is None
+    grid.finish_fused_deposit(1.0, dt)
+    n1, rho1 = grid.n.cpu().numpy(), grid.rho.cpu().numpy()
+    ref = GridDev(ng, Lg, Te)
+    ref.weight_particles_to_grid_boltzmann(st, dt)
+    assert relmax(n1, ref.n.cpu().numpy()) < 1e-13 and relmax(rho1, ref.rho.cpu().numpy()) < 1e-13
+    # and the next push of the (now mixed) store deposits both accumulators itself
+    st.push_6D(dt, grid, deposit=True)
+    assert grid._fused_mixed
+    grid.finish_fused_deposit(1.0, dt)
+    st.apply_BCs_dirichlet(ref)
+    ref.weight_particles_to_grid_boltzmann(st, dt)
+    assert relmax(grid.n.cpu().numpy(), ref.n.cpu().numpy()) < 1e-13
+    assert relmax(grid.rho.cpu().numpy(), ref.rho.cpu().numpy()) < 1e-13
+    st.check(); grid.check()
+
+
 def test_lean_store_boris_is_bit_identical_in_x_and_v():
     """ParticleStore.carry_yzt = False: the fused kernel streams x, vx, vy, vz only (64 B per
     particle-step).  Over several steps with wall hits: x, v, flags, hit counts and the deposited
