@@ -310,6 +310,21 @@ int pic_dev_dd_apply_draws2(const int32_t* slot, const int32_t* orig, const doub
 int pic_dev_dd_apply_draws3(const int32_t* slot, const int32_t* orig, const double* xd, const double* ud,
                             const double* vd, const double* wd, int64_t n, double* x0, double* u0, double* v0,
                             double* w0, int8_t* active, double* corr, void* stream);
+/* Start of a sheath timestep in one launch: re-injection of the slots the previous step absorbed
+ * (PIC_L_DD.py:429-450) and the per-step clears of pic_dev_dd_step_begin.
+ *   philox != 0: device draws for the slots named in `log` (the absorption log the previous step's
+ *     iterations wrote; flag scan when it overflowed), as pic_dev_dd_reinject_philox_log / _philox2;
+ *   n_draws > 0: host draws (legacy MT19937 order) applied as pic_dev_dd_apply_draws3 does;
+ *   next_log: header of the log the coming step writes (a different buffer than `log`), cleared. */
+typedef struct {
+    const int32_t* log; int32_t* next_log; int32_t log_cap; int32_t philox;
+    double sigma[2]; uint64_t seed, step; int64_t global_offset;
+    const int32_t* slot; const int32_t* orig_of_draw; const double* xd; const double* ud; const double* vd; const double* wd;
+    int64_t n_draws; double* corr;
+    double* x0; double* u0; double* v0; double* w0; int8_t* active; const int32_t* orig;
+    double* Es; const double* E0; double* wall_cum; double* stats; int64_t nstats; int32_t* ctl;
+} pic_dd_prologue;
+int pic_dev_dd_step_prologue(const pic_dd_params* p, const pic_dd_prologue* a, void* stream);
 /* Device-mode re-injection of the slots named in the absorption log (no flag scan), and the
  * device-mode thermostat (every active particle redraws u,v,w from sigma[species] with probability
  * gamma).  Philox is keyed by the ORIGINAL global index orig[i] + global_offset (orig == NULL: the

@@ -25,6 +25,18 @@ class DDParams(C.Structure):
                 ("q", C.c_double * 2), ("m", C.c_double * 2)]
 
 
+class DDPrologue(C.Structure):
+    """pic_dd_prologue (include/pic_b200.h)."""
+    _fields_ = [("log", C.c_void_p), ("next_log", C.c_void_p), ("log_cap", C.c_int32), ("philox", C.c_int32),
+                ("sigma", C.c_double * 2), ("seed", C.c_uint64), ("step", C.c_uint64), ("global_offset", C.c_int64),
+                ("slot", C.c_void_p), ("orig_of_draw", C.c_void_p), ("xd", C.c_void_p), ("ud", C.c_void_p),
+                ("vd", C.c_void_p), ("wd", C.c_void_p), ("n_draws", C.c_int64), ("corr", C.c_void_p),
+                ("x0", C.c_void_p), ("u0", C.c_void_p), ("v0", C.c_void_p), ("w0", C.c_void_p), ("active", C.c_void_p),
+                ("orig", C.c_void_p),
+                ("Es", C.c_void_p), ("E0", C.c_void_p), ("wall_cum", C.c_void_p), ("stats", C.c_void_p),
+                ("nstats", C.c_int64), ("ctl", C.c_void_p)]
+
+
 class PypicParams(C.Structure):
     _fields_ = [("N", C.c_int64), ("Ng", C.c_int32), ("flags", C.c_int32),
                 ("dx", C.c_double), ("dt", C.c_double), ("L", C.c_double), ("p2c", C.c_double),
@@ -56,6 +68,7 @@ _SIGS = {
     "pic_dev_copy": [P, P, I64, P],
     "pic_stream_sync": [P],
     "pic_dev_dd_step_begin": [P, P, I32, P, P, I64, P, P],
+    "pic_dev_dd_step_prologue": [C.POINTER(DDParams), C.POINTER(DDPrologue), P],
     "pic_host_release": [],
     "pic_dev_smooth": [P, P, I32, I32, P],
     "pic_dev_differentiate": [P, P, I32, F64, I32, P],

@@ -808,6 +808,17 @@ __global__ void __launch_bounds__(V6_T, 1) dd_picard_iter_v6_k(
         flush_windows(wb);
         cur_slice = nxt_slice;
     }
+    // the N % V6_CHUNK particles behind the last whole chunk: at most one per thread of the grid, by the exact
+    // per-particle routine (deposits straight to the global accumulators) -- a second launch for them cost
+    // more than the work (profiles/r2_step_gaps.txt)
+    for (long long i = (long long)nchunks * V6_CHUNK + (long long)blockIdx.x * V6_T + threadIdx.x; i < k.N;
+         i += (long long)gridDim.x * V6_T) {
+        const double X0 = x0[i], U0 = u0[i], pX1 = FIRST ? 0.0 : x1i[i];
+        if (FIRST && k.mom) { ms1 += U0; ms2 += U0 * U0; }
+        SlowOut so = dd_particle_slow(k, i, X0, U0, pX1, FIRST ? 1 : (int)active[i], FIRST, gE, acc, x1, WU ? u1 : nullptr, active, WU, true);
+        if (so.code >= 1 && so.code <= 4) atomicAdd(&s_cnt[so.code], 1);
+        if (so.bad) atomicAdd(&s_cnt[0], so.bad);
+    }
     if (FIRST && k.mom) {
         ms1 = warp_sum(ms1); ms2 = warp_sum(ms2);
         if (lane == 0) { atomicAdd(k.mom, ms1); atomicAdd(k.mom + 1, ms2); }
@@ -1650,6 +1661,59 @@ __global__ void dd_reinject_philox_log_k(DDK k, const int* __restrict__ buf, dou
     for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < n; t += gridDim.x * blockDim.x)
         dd_reinject_one(k, (long long)buf[4 + 4 * t], x0, u0, v0, w0, active, s0, s1, seed, step, goff, oid);
 }
+// Start of a sheath timestep in ONE launch (PIC_L_DD.py:429-450 + the per-step clears): the re-injection of
+// the slots the previous step absorbed -- device Philox draws for the slots named in the absorption log (flag
+// scan if the log overflowed), or host draws applied by block 0, which also accumulates the moments'
+// correction -- then Es = E0 and the per-step accumulators / statistics / loop flag cleared, and the header
+// of the log the coming step writes (another buffer than the one read here) reset.  The host used to
+// issue 4-7 tiny operations here with the GPU idle in between (profiles/r2_step_gaps.txt).
+struct DDPro {
+    const int* log; int* next_log; int philox;
+    double s0, s1; uint64_t seed, step; long long goff;
+    const int32_t* slot; const int32_t* dorig; const double* xd; const double* ud; const double* vd; const double* wd;
+    long long n_draws; double* corr;
+    double* x0; double* u0; double* v0; double* w0; int8_t* active; const int32_t* oid;
+    double* Es; const double* E0; double* wall_cum; double* stats; long long nstats; int* ctl;
+};
+__global__ void __launch_bounds__(256) dd_step_prologue_k(DDK k, const DDPro a) {
+    const int tid = blockIdx.x * blockDim.x + threadIdx.x, nth = gridDim.x * blockDim.x;
+    for (int i = tid; i < k.Ng; i += nth) a.Es[i] = a.E0[i];
+    if (blockIdx.x == 0) {
+        for (long long i = threadIdx.x; i < a.nstats; i += blockDim.x) a.stats[i] = 0.0;
+        if (threadIdx.x < 4) { a.wall_cum[threadIdx.x] = 0.0; if (a.next_log) a.next_log[threadIdx.x] = 0; }
+        if (threadIdx.x == 0) *a.ctl = 0;
+        if (a.corr && threadIdx.x < 2) a.corr[threadIdx.x] = 0.0;
+        if (a.n_draws > 0) {
+            __syncthreads();
+            double c1 = 0.0, c2 = 0.0;
+            for (long long t = threadIdx.x; t < a.n_draws; t += blockDim.x) {
+                const int s = a.slot[t], o = a.dorig ? a.dorig[t] : s;
+                if (a.xd) a.x0[s] = a.xd[t];
+                const double un = a.ud[t];
+                if (a.corr) { const double uo = a.u0[s]; c1 += un - uo; c2 += un * un - uo * uo; }
+                a.u0[s] = un;
+                if (a.v0) a.v0[o] = a.vd[t];
+                if (a.w0) a.w0[o] = a.wd[t];
+                a.active[s] = 1;
+            }
+            if (a.corr) {
+                c1 = warp_sum(c1); c2 = warp_sum(c2);
+                if ((threadIdx.x & 31) == 0 && (c1 != 0.0 || c2 != 0.0)) { atomicAdd(a.corr, c1); atomicAdd(a.corr + 1, c2); }
+            }
+        }
+    }
+    if (a.philox) {
+        const int n = a.log[0];
+        if (n <= k.dead_cap) {
+            for (int t = tid; t < n; t += nth)
+                dd_reinject_one(k, (long long)a.log[4 + 4 * t], a.x0, a.u0, a.v0, a.w0, a.active, a.s0, a.s1, a.seed, a.step, a.goff, a.oid);
+        } else {
+            // the log overflowed (a step that absorbed more than dead_cap particles): scan the flags
+            for (long long i = tid; i < k.N; i += nth)
+                if (a.active[i] != 1) dd_reinject_one(k, i, a.x0, a.u0, a.v0, a.w0, a.active, a.s0, a.s1, a.seed, a.step, a.goff, a.oid);
+        }
+    }
+}
 // Thermostat, device mode (PIC_L_DD.py:419-427): every ACTIVE particle redraws u,v,w from the ION
 // temperature (as written: sqrt(kBTi/m[i]) for both species) with probability gamma.  Philox keyed
 // by (seed, step, global original index), so the outcome does not depend on the sort or the sharding.
@@ -1907,7 +1971,7 @@ int pic_dev_dd_picard_iter5(const pic_dd_params* p, const double* x0, const doub
             PIC_CHECK_LAUNCH();
         }
         const long long done = nchunks * V6_CHUNK;
-        if (done >= k.N) return PIC_OK;
+        if (done >= k.N || nchunks > 0) return PIC_OK;      // the kernel finishes the ragged tail itself
         DDK t = k;
         t.N = k.N - done;
         t.n_split = k.n_split - done < 0 ? 0 : (k.n_split - done > t.N ? t.N : k.n_split - done);
@@ -1932,6 +1996,7 @@ int pic_dev_dd_picard_iter5(const pic_dd_params* p, const double* x0, const doub
             if (rcs) return rcs;
             kern<<<grid, V6_T, smem6, st>>>(k, (int)nchunks, x0, u0, x1i, x1, u1, active, Es, acc, range_err, sched);
             PIC_CHECK_LAUNCH();
+            return PIC_OK;                                   // the kernel finishes the ragged tail itself
         }
         const long long done = nchunks * V6_CHUNK;
         return first ? launch_tail<true>(k, done, x0, u0, x1i, x1, u1, active, Es, acc, range_err, st)
@@ -2300,6 +2365,33 @@ int pic_dev_dd_reinject_philox_log(const pic_dd_params* p, const int32_t* dead_b
     k.dead_cap = dead_cap;
     dd_reinject_philox_log_k<<<64, 256, 0, (cudaStream_t)stream>>>(k, dead_buf, x0, u0, v0, w0, active, sigma[0], sigma[1], seed,
                                                                   step, global_offset, orig);
+    PIC_CHECK_LAUNCH();
+    return PIC_OK;
+}
+
+int pic_dev_dd_step_prologue(const pic_dd_params* p, const pic_dd_prologue* a, void* stream) {
+    PIC_REQUIRE(p && a, "dd_step_prologue: null pointer");
+    PIC_REQUIRE(a->Es && a->E0 && a->wall_cum && a->stats && a->nstats > 0 && a->ctl, "dd_step_prologue: step state missing");
+    PIC_REQUIRE(a->n_draws >= 0, "dd_step_prologue: n_draws<0");
+    PIC_REQUIRE(!(a->philox && a->n_draws), "dd_step_prologue: device and host draws are exclusive");
+    PIC_REQUIRE(a->next_log != a->log || !a->philox, "dd_step_prologue: the log read and the log reset must differ");
+    if (a->philox) PIC_REQUIRE(a->log && a->log_cap > 0 && a->x0 && a->u0 && a->active, "dd_step_prologue: philox re-injection arguments");
+    if (a->n_draws) {
+        PIC_REQUIRE(a->slot && a->ud && a->u0 && a->active, "dd_step_prologue: host draws missing");
+        PIC_REQUIRE((!a->xd || a->x0) && (!a->v0 || a->vd) && (!a->w0 || a->wd), "dd_step_prologue: draws / targets missing");
+    }
+    DDK k = make_ddk(p);
+    k.dead_cap = a->log_cap;
+    DDPro d;
+    d.log = a->log; d.next_log = a->next_log; d.philox = a->philox ? 1 : 0;
+    d.s0 = a->sigma[0]; d.s1 = a->sigma[1]; d.seed = a->seed; d.step = a->step; d.goff = a->global_offset;
+    d.slot = a->slot; d.dorig = a->orig_of_draw; d.xd = a->xd; d.ud = a->ud; d.vd = a->vd; d.wd = a->wd;
+    d.n_draws = a->n_draws; d.corr = a->corr;
+    d.x0 = a->x0; d.u0 = a->u0; d.v0 = a->v0; d.w0 = a->w0; d.active = a->active; d.oid = a->orig;
+    d.Es = a->Es; d.E0 = a->E0; d.wall_cum = a->wall_cum; d.stats = a->stats; d.nstats = a->nstats; d.ctl = a->ctl;
+    int blocks = (k.Ng + 255) / 256;
+    blocks = blocks < 16 ? 16 : (blocks > 592 ? 592 : blocks);
+    dd_step_prologue_k<<<blocks, 256, 0, (cudaStream_t)stream>>>(k, d);
     PIC_CHECK_LAUNCH();
     return PIC_OK;
 }

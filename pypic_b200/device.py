@@ -1,5 +1,6 @@
 """Thin helpers between torch device tensors and the raw pointers the C ABI takes."""
 import ctypes as C
+import threading
 
 import numpy as np
 import torch
@@ -39,18 +40,35 @@ def to_dev(a, device, dtype=torch.float64):
     return torch.as_tensor(np.ascontiguousarray(a)).to(device=device, dtype=dtype)
 
 
-def read_f64(t, n=None):
-    """Synchronous device->host read of a small fp64 tensor through the C ABI."""
-    n = t.numel() if n is None else n
-    out = np.empty(n, dtype=np.float64)
-    _lib.call("pic_dev_read", ptr(t), out.ctypes.data, n * 8, stream())
-    return out
+_pin = threading.local()
+PIN_MAX = 1 << 20
+
+
+def _pinned(nbytes):
+    """Per-thread page-locked landing buffer for the small per-step reads (loop statistics, absorption
+    log): a copy into pageable memory is staged by the driver and costs ~3x as long (the device idles
+    meanwhile: every step ends in one of these reads)."""
+    b = getattr(_pin, "buf", None)
+    if b is None:
+        b = _pin.buf = torch.empty(PIN_MAX, dtype=torch.uint8, pin_memory=True).numpy()
+    return b[:nbytes]
 
 
 def read_raw(t, n, dtype):
+    """Synchronous device->host read of n elements through the C ABI."""
+    nbytes = int(n) * np.dtype(dtype).itemsize
+    if 0 < nbytes <= PIN_MAX:
+        land = _pinned(nbytes)
+        _lib.call("pic_dev_read", ptr(t), land.ctypes.data, nbytes, stream())
+        return land.view(dtype).copy()
     out = np.empty(n, dtype=dtype)
     _lib.call("pic_dev_read", ptr(t), out.ctypes.data, out.nbytes, stream())
     return out
+
+
+def read_f64(t, n=None):
+    """Synchronous device->host read of a small fp64 tensor through the C ABI."""
+    return read_raw(t, t.numel() if n is None else n, np.float64)
 
 
 def check_range(err_t, what):

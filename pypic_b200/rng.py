@@ -43,7 +43,8 @@ def _worker():
                 job = _jobs.get()
                 try:
                     p = C.c_int32(job["pos"])
-                    _lib.call("pic_mt_jump", job["key1"].ctypes.data, C.byref(p), job["poly"].ctypes.data)
+                    poly = job["owner"]._poly(2 * job["n"])          # a cache miss costs 0.5 ms: paid here, not by the time loop
+                    _lib.call("pic_mt_jump", job["key1"].ctypes.data, C.byref(p), poly.ctypes.data)
                     job["pos1"] = p.value
                 except Exception:                       # leaves pos1 = 0 with an unchanged key: detected below
                     job["n"] = -1
@@ -55,8 +56,9 @@ def _worker():
 
 class LegacyDraws:
     JUMP_MIN = 200000        # uniforms; below this plain generation is cheaper than the jump
-    CHUNK = 512              # jump polynomials are cached per multiple of CHUNK uniforms; the rest is generated
-    MARGIN = 512             # the prefetched jump stops this many uniforms short of the expected skip
+    CHUNK = 4096             # jump polynomials are cached per multiple of CHUNK uniforms; the rest is generated
+                             # (~3 ns per uniform; a polynomial that is not cached costs 0.5 ms)
+    MARGIN = 1024            # the prefetched jump stops this many uniforms short of the expected skip
 
     def __init__(self, rng=None):
         self.rng = np.random if rng is None else rng
@@ -156,9 +158,8 @@ class LegacyDraws:
         if n < self.JUMP_MIN:
             return
         st = self._get()
-        poly = self._poly(2 * n)
         held = self._held is not None
-        job = dict(n=n, key0=None if held else st[0].copy(), pos=st[1].value, key1=st[0].copy(), pos1=0, poly=poly,
+        job = dict(n=n, key0=None if held else st[0].copy(), pos=st[1].value, key1=st[0].copy(), pos1=0, owner=self,
                    thread=_Done(), held=held)
         _worker().put(job)
         self._pref = job

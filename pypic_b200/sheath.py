@@ -135,6 +135,9 @@ class SheathSim:
         self.dead_cap = int(min(max(n, 1), max(1 << 16, n // 64)))
         self.dead_buf = torch.zeros(4 + 4 * self.dead_cap, dtype=torch.int32, device=dev)
         self._log_valid = False         # the log describes the flags only after a step that started all-active
+        self.dead_alt = torch.zeros_like(self.dead_buf)      # step() alternates the two logs (see _prologue)
+        self.merge_prologue = True      # step(): re-injection + start-of-step clears in one launch
+        self._begun = False
         self._log_guess = 256           # entries fetched with the counter in ONE read (grows with the counts seen)
         self._harvested = None
         self.oid = None                 # int32 original index per slot; None = identity (never sorted)
@@ -317,8 +320,43 @@ class SheathSim:
         self.kernel_launches += 3
         return int(mine.sum())
 
-    def reinject(self):
-        """PIC_L_DD.py:419-450: thermostat, then re-injection of the absorbed slots."""
+    def _prologue(self, philox, n_draws=0, base=0):
+        """One launch for the re-injection and the start-of-step clears (pic_dev_dd_step_prologue).  It reads
+        the log the previous step wrote and resets the OTHER log buffer, which the coming step then writes."""
+        nst = 8 + self.maxiter
+        if self.stats.numel() < nst + 4:
+            self.stats = D.f64(nst + 4, self.dev, True)
+        a = getattr(self, "_pro", None)
+        if a is None:
+            a = self._pro = _lib.DDPrologue()        # filled once; only what changes from step to step below
+            a.log_cap = self.dead_cap
+            a.sigma[0], a.sigma[1] = self._sigma(0), self._sigma(1)
+            a.seed, a.global_offset = self.seed, self.start
+            a.v0, a.w0 = D.ptr(self.v0), D.ptr(self.w0)
+            a.wall_cum, a.ctl = D.ptr(self.wall_cum), D.ptr(self.ctl)
+        a.log, a.next_log = self.dead_buf.data_ptr(), self.dead_alt.data_ptr()
+        a.philox = 1 if philox else 0
+        a.step = self.t
+        a.x0, a.u0, a.active = self.x0.data_ptr(), self.u0.data_ptr(), self.active.data_ptr()
+        a.orig = D.ptr(self.oid)
+        a.n_draws = int(n_draws)
+        if n_draws:
+            a.slot, a.orig_of_draw = base + 32 * n_draws, base + 36 * n_draws
+            a.xd, a.ud = base, base + 8 * n_draws
+            a.vd, a.wd = (base + 16 * n_draws, base + 24 * n_draws) if self.carry_vw else (None, None)
+        self._corr_ptr = self.stats.data_ptr() + 8 * (nst + 2) if (self.fused_moments and not philox) else None
+        a.corr = self._corr_ptr
+        a.Es, a.E0, a.stats = self.Es.data_ptr(), self.E0.data_ptr(), self.stats.data_ptr()
+        a.nstats = nst + 2
+        _lib.call("pic_dev_dd_step_prologue", C.byref(self.params), C.byref(a), D.stream())
+        self.kernel_launches += 1
+        self.dead_buf, self.dead_alt = self.dead_alt, self.dead_buf
+        self._log_valid = True
+        self._begun = True
+
+    def reinject(self, merge=False):
+        """PIC_L_DD.py:419-450: thermostat, then re-injection of the absorbed slots.  merge: the start-of-step
+        clears of picard() ride in the same launch (step() asks for that)."""
         st = D.stream()
         if self.rng_mode == "philox":
             sig = (C.c_double * 2)(self._sigma(0), self._sigma(1))
@@ -332,6 +370,9 @@ class SheathSim:
             # the slots named in the absorption log (a few hundred) are re-injected without touching the
             # flag array; the flag scan only runs when there is no valid log (first step, overflow).
             # With a tracked order the draws are keyed by the ORIGINAL index and v,w written there.
+            if merge and self._log_valid:
+                self._prologue(True)
+                return None
             if self._log_valid:
                 _lib.call("pic_dev_dd_reinject_philox_log", C.byref(self.params), D.ptr(self.dead_buf), self.dead_cap,
                           D.ptr(self.x0), D.ptr(self.u0), D.ptr(self.v0), D.ptr(self.w0), D.ptr(self.active),
@@ -342,13 +383,15 @@ class SheathSim:
             self.kernel_launches += 1
             self._reset_log()
             return None
+        merge = merge and self.gamma == 0.0      # the host thermostat adds its own share of the moments' correction first
         slots, orig, _ = self._harvest_dead()
         n_dead = len(slots)
         counts = self.comm.allgather_int(n_dead, device=self.dev)
         self._corr_ptr = None
         if self.fused_moments:
             self._corr_ptr = D.ptr(self.stats) + 8 * (8 + self.maxiter + 2)
-            _lib.call("pic_dev_zero", self._corr_ptr, 16, st)
+            if not merge:
+                _lib.call("pic_dev_zero", self._corr_ptr, 16, st)
         if self.gamma != 0.0:
             g_orig = orig.astype(np.int64) + self.start
             if self.comm.enabled and self.comm.world > 1:
@@ -373,10 +416,16 @@ class SheathSim:
             iv[0:n_dead] = slots; iv[n_dead:2 * n_dead] = orig
             _lib.call("pic_dev_write", D.ptr(ds), D.ptr(hs), (5 * n_dead + 1) * 8, st)
             base = D.ptr(ds)
+            if merge:
+                self._prologue(False, n_dead, base)
+                return n_dead
             _lib.call("pic_dev_dd_apply_draws3", base + 32 * n_dead, base + 36 * n_dead, base, base + 8 * n_dead,
                       base + 16 * n_dead if self.carry_vw else None, base + 24 * n_dead if self.carry_vw else None, n_dead,
                       D.ptr(self.x0), D.ptr(self.u0), D.ptr(self.v0), D.ptr(self.w0), D.ptr(self.active), self._corr_ptr, st)
             self.kernel_launches += 1
+        elif merge:
+            self._prologue(False)
+            return 0
         self._reset_log()
         return n_dead
 
@@ -510,8 +559,11 @@ class SheathSim:
         nst = 8 + self.maxiter
         # clears the statistics and the moments; the re-injection correction behind them was written by this
         # step's reinject() and is cleared by the next one
-        _lib.call("pic_dev_dd_step_begin", D.ptr(self.Es), D.ptr(self.E0), self.Ng, D.ptr(self.wall_cum), D.ptr(self.stats),
-                  nst + 2, D.ptr(self.ctl), st)
+        if self._begun:
+            self._begun = False          # step()'s merged prologue did it
+        else:
+            _lib.call("pic_dev_dd_step_begin", D.ptr(self.Es), D.ptr(self.E0), self.Ng, D.ptr(self.wall_cum), D.ptr(self.stats),
+                      nst + 2, D.ptr(self.ctl), st)
         mom_ptr = D.ptr(self.stats) + 8 * nst if self.fused_moments else None
         rhist = D.ptr(self.stats) + 8 * 8
         pairs = [(self.x1, self.x1b), (self.x1b, self.x1)] if self.elide_u else [(self.x1, self.x1)]
@@ -609,7 +661,7 @@ class SheathSim:
         return k, r
 
     def step(self):
-        self.reinject()
+        self.reinject(merge=self.merge_prologue)
         if self.sort_every and self.t % self.sort_every == 0 and (self.track or (self.rng_mode == "philox" and not self.carry_vw)):
             self.sort_by_cell()
         out = self.picard()

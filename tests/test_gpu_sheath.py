@@ -506,6 +506,54 @@ def test_fused_velocity_moments_equal_a_pass_over_the_pre_step_state(gamma, sort
     assert dead_seen > 0
 
 
+@pytest.mark.parametrize("rng,track", [("host", True), ("philox", True), ("philox", False)])
+def test_merged_step_prologue_equals_the_separate_launches(rng, track):
+    """SheathSim.step() with the one-launch prologue (pic_dev_dd_step_prologue: re-injection + start-of-step
+    clears, alternating absorption logs) against the separate launches it replaces: particles, flags and
+    iteration counts identical, fields to round-off, over steps with sorts, absorptions and a ragged tail."""
+    from pypic_b200.rng import LegacyDraws
+    from pypic_b200.sheath import SheathSim
+    N, Ng = 4 * 16384 + 777, 257
+    dx, dt = 1e-5, 1e-12
+    L = dx * (Ng - 1); kT = O.kb * 116000.
+    rs = np.random.RandomState(19)
+    h = N // 2
+    x0 = rs.uniform(0, L, N)
+    u0 = np.concatenate([rs.normal(0, np.sqrt(kT / O.me), h), rs.normal(0, np.sqrt(kT / O.mp), N - h)])
+    E0 = rs.normal(0, 1e4, Ng)
+    res = {}
+    for merge in (False, True):
+        sim = SheathSim(N, Ng, dx, dt, L * 1e19 / N, kBT=(kT, kT), carry_vw=(rng == "host"), rng=rng, seed=3,
+                        sort_every=3 if track else 0,     # untracked Philox draws are keyed by the slot: keep the slots fixed
+                        track_order=track, draws=LegacyDraws(np.random.RandomState(4)))
+        sim.merge_prologue = merge
+        sim.fused_moments = rng == "host"
+        if rng == "host":
+            sim.upload(x0, u0, np.zeros(N), np.zeros(N), E0=E0)
+        else:
+            sim.upload(x0, u0, E0=E0)
+        ks, moms = [], []
+        for t in range(7):
+            ks.append(sim.step()[0])
+            moms.append(sim.pre_step_moments() if rng == "host" else None)
+        sim.check()
+        o = sim.download()
+        res[merge] = (ks, moms, o, sim.kernel_launches)
+    a, b = res[False], res[True]
+    assert a[0] == b[0]
+    assert np.array_equal(a[2]["active"], b[2]["active"]) and int((a[2]["active"] != 1).sum()) > 0
+    if track:
+        # the download is in the original order: comparable slot by slot
+        assert relmax(b[2]["x0"], a[2]["x0"]) < 1e-10 and relmax(b[2]["u0"], a[2]["u0"]) < 1e-10
+    else:
+        assert relmax(np.sort(b[2]["x0"]), np.sort(a[2]["x0"])) < 1e-10
+    assert relmax(b[2]["E0"], a[2]["E0"]) < 1e-10          # the deposit's summation order differs from run to run
+    if rng == "host":
+        for ma, mb in zip(a[1], b[1]):
+            assert abs(ma[1] - mb[1]) <= 1e-12 * ma[1]
+    assert b[3] < a[3]                                   # fewer launches
+
+
 def test_host_abi_step_matches_device_path():
     """pic_host_dd_step (host buffers through the C ABI) == the resident path."""
     from pypic_b200 import _lib

@@ -65,6 +65,7 @@ def make_sim(maxiter=6, tol=1e-5, enqueue_ahead=True):
     sim.dev = torch.device("cpu")
     sim.Ng = 4
     sim.fused_moments = False
+    sim._begun = False
     sim.p2p = None
     sim.params = S._lib.DDParams()
     for nm in ("x0", "u0", "x1", "x1b", "u1", "E0", "Es", "E1", "Es_prev", "j0", "acc", "wall_cum"):
