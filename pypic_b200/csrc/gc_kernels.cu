@@ -393,6 +393,9 @@ __global__ void __launch_bounds__(G_T, 1) gc_push_boris_v2_k(const __grid_consta
             __syncwarp();
         }
     }
+    // the N % G_CHUNK particles behind the last whole chunk: at most one per thread, exact routine
+    for (long long i = (long long)nchunks * G_CHUNK + (long long)blockIdx.x * G_T + threadIdx.x; i < k.N; i += (long long)gridDim.x * G_T)
+        bad += gc_particle_exact(k, u, r, i, active[i], sE, active, at_wall, hit_flag, DEP ? n_acc : nullptr, &hits);
     if (bad) atomicAdd(&s_cnt[0], bad);
     if (hits) atomicAdd(&s_cnt[1], hits);
     __syncthreads();
@@ -617,6 +620,9 @@ __global__ void __launch_bounds__(G_T, 1) gc_push_boris_mix_k(const __grid_const
             __syncwarp();
         }
     }
+    // the N % G_CHUNK particles behind the last whole chunk: at most one per thread, exact routine
+    for (long long i = (long long)nchunks * G_CHUNK + (long long)blockIdx.x * G_T + threadIdx.x; i < k.N; i += (long long)gridDim.x * G_T)
+        bad += gm_particle_exact(k, u, r, i, active[i], sE, active, at_wall, hit_flag, DEP ? n_acc : nullptr, rho_acc, &hits);
     if (bad) atomicAdd(&s_cnt[0], bad);
     if (hits) atomicAdd(&s_cnt[1], hits);
     __syncthreads();
@@ -1299,7 +1305,7 @@ int pic_dev_gc_push_boris_uniform2(const pic_gc_params* p, double* const r[7], d
         PIC_CHECK_LAUNCH();
     }
     const long long done = nchunks * G_CHUNK;
-    if (done < k.N) gc_tail_uniform_k<<<grid_for(k.N - done, 256, 4), 256, 0, st>>>(k, u, rr, done, active, at_wall, hit_flag, Egrid, n_acc, hit_count, range_err);
+    if (done < k.N && nchunks == 0) gc_tail_uniform_k<<<grid_for(k.N - done, 256, 4), 256, 0, st>>>(k, u, rr, done, active, at_wall, hit_flag, Egrid, n_acc, hit_count, range_err);
     PIC_CHECK_LAUNCH();
     return PIC_OK;
 }
@@ -1345,7 +1351,7 @@ int pic_dev_gc_push_boris_mixed(const pic_gc_params* p, double* const r[7], cons
         PIC_CHECK_LAUNCH();
     }
     const long long done = nchunks * G_CHUNK;
-    if (done < k.N) gc_tail_mix_k<<<grid_for(k.N - done, 256, 4), 256, 0, st>>>(k, u, rr, done, active, at_wall, hit_flag, Egrid, n_acc, rho_acc, hit_count, range_err);
+    if (done < k.N && nchunks == 0) gc_tail_mix_k<<<grid_for(k.N - done, 256, 4), 256, 0, st>>>(k, u, rr, done, active, at_wall, hit_flag, Egrid, n_acc, rho_acc, hit_count, range_err);
     PIC_CHECK_LAUNCH();
     return PIC_OK;
 }

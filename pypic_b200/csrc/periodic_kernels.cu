@@ -612,6 +612,9 @@ __global__ void __launch_bounds__(S_T, 1) l_push_deposit_v2_k(const __grid_const
         __syncwarp();
         if (wb != NOWIN) swin_flush<1>(win, myw, wbase, lane, wb, rho_acc, 0, nodes);
     }
+    // the N % S_CHUNK particles behind the last whole chunk: at most one per thread, exact routine, global REDs
+    for (long long i = (long long)nchunks * S_CHUNK + (long long)blockIdx.x * S_T + threadIdx.x; i < k.N; i += (long long)gridDim.x * S_T)
+        bad += l_particle_exact(k, i, x[i], v[i], sE, rho_acc, x, v);
     if (bad) atomicAdd(&s_bad, bad);
     __syncthreads();
     if (threadIdx.x == 0 && s_bad && range_err) atomicAdd(range_err, s_bad);
@@ -796,6 +799,9 @@ __global__ void __launch_bounds__(S_T, 1) pypic_picard_iter_v2_k(const __grid_co
         __syncwarp();
         if (wb != NOWIN) swin_flush<2>(win, myw, wbase, lane, wb, acc, Ng, Ng);
     }
+    // the N % S_CHUNK particles behind the last whole chunk: at most one per thread, exact routine, global REDs
+    for (long long i = (long long)nchunks * S_CHUNK + (long long)blockIdx.x * S_T + threadIdx.x; i < k.N; i += (long long)gridDim.x * S_T)
+        bad += py_particle_exact<FIRST>(k, i, x0[i], v0[i], FIRST ? 0.0 : x1i[i], sF, acc, x1, v1);
     if (bad) atomicAdd(&s_bad, bad);
     __syncthreads();
     if (threadIdx.x == 0 && s_bad && range_err) atomicAdd(range_err, s_bad);
@@ -936,6 +942,7 @@ int pic_dev_pypic_picard_iter3(const pic_pypic_params* p, const double* x0, cons
             long long cap = device_sm_count();
             kern<<<(int)(nchunks < cap ? nchunks : cap), S_T, smem2, st>>>(k, (int)nchunks, x0, v0, x1i, x1, v1, Fs, acc, range_err);
             PIC_CHECK_LAUNCH();
+            return PIC_OK;                       // the kernel finishes the ragged tail itself
         }
         done = nchunks * S_CHUNK;
         if (done >= k.N) return PIC_OK;
@@ -1055,6 +1062,7 @@ int pic_dev_l_push_deposit(const pic_l_params* p, double* x, double* v, const do
             long long cap = device_sm_count();
             kern<<<(int)(nchunks < cap ? nchunks : cap), S_T, smem2, st>>>(k, (int)nchunks, x, v, E, rho_acc, range_err);
             PIC_CHECK_LAUNCH();
+            return PIC_OK;                       // the kernel finishes the ragged tail itself
         }
         done = nchunks * S_CHUNK;
         if (done >= k.N) return PIC_OK;
