@@ -622,16 +622,26 @@ __global__ void __launch_bounds__(S_T, 1) l_push_deposit_v2_k(const __grid_const
 
 // ---------------------------------------------------------------- pypic Picard iteration
 struct PFastC { double dx, idx, dt, c1, c2, qpi, L; unsigned hi_lim; };
-struct PFastO { double X1, V1, hL, hR, fL, fR; int cH, cF; unsigned fr, ps; };
+struct PFastO { double X1, V1, hL, hR, fL, fR; int cH, cF; unsigned fr, ps; bool emiss; };
 
-template <bool FIRST, bool J1>
-__device__ __forceinline__ void py_fast(const PFastC& c, const double* __restrict__ sF, int Ng, double X0, double V0,
+// BIG (large-grid build, as dd_picard_iter_v6_k's): sF is the warp's window of PY_EW field nodes starting at node
+// eb instead of the whole smoothed field; a gather cell outside it sets o.emiss and the particle is redone by the
+// exact routine with the field read from global memory.
+#define PY_EW 32
+template <bool FIRST, bool J1, bool BIG>
+__device__ __forceinline__ void py_fast(const PFastC& c, const double* __restrict__ sF, int Ng, int eb, double X0, double V0,
                                         double pX1, PFastO& o) {
     const double xs = FIRST ? X0 : (X0 + pX1) * 0.5;                  // wrapped xh of the previous iteration
     const double ts = xs * c.idx, fs = floor(ts);
     const unsigned f0 = (unsigned)__double2hiint(ts - fs) - PIC_HI_G;
     const double rs = fma(-fs, c.dx, xs);
-    const int is = min(max((int)fs, 0), Ng - 2);
+    int is = min(max((int)fs, 0), Ng - 2);
+    o.emiss = false;
+    if (BIG) {
+        is -= eb;
+        o.emiss = (unsigned)is > (unsigned)(PY_EW - 2);
+        is = min(max(is, 0), PY_EW - 2);
+    }
     const double wR = rs * c.idx, wL = 1.0 - wR;                      // pypic.py:52-53
     const double Ei = sF[is] * wL + sF[is + 1] * wR;                  // :57
     o.X1 = X0 + c.dt * V0 + c.c2 * Ei * 0.5;                          // :264
@@ -689,8 +699,8 @@ __device__ __noinline__ int py_particle_exact(const PYK& k, long long i, double 
     return bad;
 }
 
-template <bool FIRST, int NST, bool J1>
-__global__ void __launch_bounds__(S_T, 1) pypic_picard_iter_v2_k(const __grid_constant__ PYK k, int nchunks,
+template <bool FIRST, int NST, bool J1, bool BIG = false>
+__global__ void __launch_bounds__(S_T, 1) pypic_picard_iter_v2_k(const __grid_constant__ PYK k, int nchunks_fr,
                                                                   const double* __restrict__ x0,
                                                                   const double* __restrict__ v0, const double* x1i, double* x1,
                                                                   double* v1, const double* __restrict__ Fs,
@@ -700,12 +710,19 @@ __global__ void __launch_bounds__(S_T, 1) pypic_picard_iter_v2_k(const __grid_co
     if (k.done && *(const volatile int*)k.done) return;
     constexpr int NA = FIRST ? 2 : 3;
     const int Ng = k.Ng;
-    const int NP = (Ng + 15) & ~15;
+    // smoothed field: the whole grid or, in the large-grid build, one PY_EW-node window per warp
+    const int NP = BIG ? (S_T / 32) * PY_EW : ((Ng + 15) & ~15);
+    const int nchunks = nchunks_fr & 0x0fffffff;
+    const int FRm = BIG ? (nchunks_fr >> 28) : (S_ROWS - 1);      // rows per deposit / field window - 1
     double* sF = sm;
     double* win = sm + NP;                                   // [2*S_W][S_T]
     double* ring = win + 2 * S_W * S_T;                      // [warp][stage][x0|v0|x1][64]
     unsigned long long* bars = (unsigned long long*)(ring + (S_T / 32) * NST * 192);
-    for (int i = threadIdx.x; i < Ng; i += S_T) sF[i] = Fs[i];
+    if (!BIG) for (int i = threadIdx.x; i < Ng; i += S_T) sF[i] = Fs[i];
+    double* const wE = sm + (threadIdx.x >> 5) * PY_EW;      // BIG: this warp's field window
+    const double* const fE = BIG ? wE : sF;                  // what the fast path gathers from
+    const double* const gE = BIG ? Fs : sF;                  // what the exact routine gathers from
+    int eb = 0;
     double* myw = win + threadIdx.x;
 #pragma unroll
     for (int n = 0; n < 2 * S_W; ++n) myw[n * S_T] = 0.0;
@@ -761,12 +778,23 @@ __global__ void __launch_bounds__(S_T, 1) pypic_picard_iter_v2_k(const __grid_co
             if (!FIRST) pX1 = *(const double2*)(sb + 128);
             const int st_cur = stage;
             if (++stage == NST) { stage = 0; phase ^= 1u; }
+            if (BIG && (row & FRm) == 0) {
+                // few particles per cell: the windows are flushed and re-centred every FRm+1 rows, and the
+                // field window is loaded around the gather cell of the row's first particle
+                if (row > 0 && wb != NOWIN) { __syncwarp(); swin_flush<2>(win, myw, wbase, lane, wb, acc, Ng, Ng); }
+                const double xf = __shfl_sync(full, FIRST ? X0.x : (X0.x + pX1.x) * 0.5, 0);
+                const int cb = (int)floor(xf * k.idx);
+                eb = min(max(cb - PY_EW / 4, 0), Ng - PY_EW);
+                __syncwarp();
+                wE[lane] = __ldg(Fs + eb + lane);
+                __syncwarp();
+            }
             PFastO a, b;
-            py_fast<FIRST, J1>(fc, sF, Ng, X0.x, V0.x, pX1.x, a);
-            py_fast<FIRST, J1>(fc, sF, Ng, X0.y, V0.y, pX1.y, b);
-            const bool ra = (a.fr > PIC_HI_SPAN) | (a.ps >= fc.hi_lim);
-            const bool rb = (b.fr > PIC_HI_SPAN) | (b.ps >= fc.hi_lim);
-            if (row == 0) {
+            py_fast<FIRST, J1, BIG>(fc, fE, Ng, eb, X0.x, V0.x, pX1.x, a);
+            py_fast<FIRST, J1, BIG>(fc, fE, Ng, eb, X0.y, V0.y, pX1.y, b);
+            const bool ra = (a.fr > PIC_HI_SPAN) | (a.ps >= fc.hi_lim) | a.emiss;
+            const bool rb = (b.fr > PIC_HI_SPAN) | (b.ps >= fc.hi_lim) | b.emiss;
+            if ((row & FRm) == 0) {
                 int nok = __reduce_add_sync(full, (ra ? 0 : 1) + (rb ? 0 : 1));
                 int sum = __reduce_add_sync(full, (ra ? 0 : a.cH) + (rb ? 0 : b.cH));
                 wb = nok ? sum / nok - (S_W - 2) / 2 : NOWIN;
@@ -779,13 +807,13 @@ __global__ void __launch_bounds__(S_T, 1) pypic_picard_iter_v2_k(const __grid_co
                 swin_add(myw, acc, wb, b.cH, b.hL, b.hR);
                 if (J1) swin_add(myw + S_W * S_T, acc + Ng, wb, b.cF, b.fL, b.fR);
             } else {
-                if (ra) bad += py_particle_exact<FIRST>(k, ci, X0.x, V0.x, pX1.x, sF, acc, x1, v1);
+                if (ra) bad += py_particle_exact<FIRST>(k, ci, X0.x, V0.x, pX1.x, gE, acc, x1, v1);
                 else {
                     x1[ci] = a.X1; if (J1) v1[ci] = a.V1;
                     swin_add(myw, acc, wb, a.cH, a.hL, a.hR);
                     if (J1) swin_add(myw + S_W * S_T, acc + Ng, wb, a.cF, a.fL, a.fR);
                 }
-                if (rb) bad += py_particle_exact<FIRST>(k, ci + 1, X0.y, V0.y, pX1.y, sF, acc, x1, v1);
+                if (rb) bad += py_particle_exact<FIRST>(k, ci + 1, X0.y, V0.y, pX1.y, gE, acc, x1, v1);
                 else {
                     x1[ci + 1] = b.X1; if (J1) v1[ci + 1] = b.V1;
                     swin_add(myw, acc, wb, b.cH, b.hL, b.hR);
@@ -801,7 +829,7 @@ __global__ void __launch_bounds__(S_T, 1) pypic_picard_iter_v2_k(const __grid_co
     }
     // the N % S_CHUNK particles behind the last whole chunk: at most one per thread, exact routine, global REDs
     for (long long i = (long long)nchunks * S_CHUNK + (long long)blockIdx.x * S_T + threadIdx.x; i < k.N; i += (long long)gridDim.x * S_T)
-        bad += py_particle_exact<FIRST>(k, i, x0[i], v0[i], FIRST ? 0.0 : x1i[i], sF, acc, x1, v1);
+        bad += py_particle_exact<FIRST>(k, i, x0[i], v0[i], FIRST ? 0.0 : x1i[i], gE, acc, x1, v1);
     if (bad) atomicAdd(&s_bad, bad);
     __syncthreads();
     if (threadIdx.x == 0 && s_bad && range_err) atomicAdd(range_err, s_bad);
@@ -931,6 +959,28 @@ int pic_dev_pypic_picard_iter3(const pic_pypic_params* p, const double* x0, cons
                           (size_t)(S_T / 32) * PY_NST) * sizeof(double);
     const bool aligned16 = (((uintptr_t)x0 | (uintptr_t)v0 | (uintptr_t)x1i | (uintptr_t)x1 | (uintptr_t)v1) & 15) == 0;
     long long done = 0;
+    // large-grid build of the same kernel (flags bit4 forces it, for tests): per-warp field windows, so the
+    // shared-memory footprint does not depend on Ng
+    const size_t smem2b = ((size_t)(S_T / 32) * PY_EW + (size_t)2 * S_W * S_T + (size_t)(S_T / 32) * PY_NST * 192 +
+                           (size_t)(S_T / 32) * PY_NST) * sizeof(double);
+    const bool big = ((p->flags & 16) || smem2 > (size_t)max_optin_smem() - 512) && k.Ng >= PY_EW;
+    if (big && !(p->flags & (1 | 4)) && aligned16 && k.N >= S_CHUNK) {
+        const long long nchunks = k.N / S_CHUNK;
+        PIC_REQUIRE(nchunks < (1 << 28), "pypic_picard_iter: shard too large");
+        const bool light = (p->flags & 8) != 0;
+        auto kern = first ? (light ? pypic_picard_iter_v2_k<true, PY_NST, false, true> : pypic_picard_iter_v2_k<true, PY_NST, true, true>)
+                          : (light ? pypic_picard_iter_v2_k<false, PY_NST, false, true> : pypic_picard_iter_v2_k<false, PY_NST, true, true>);
+        PIC_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2b));
+        // rows (of 64 particles) per deposit / field window: about three cells' worth of particles
+        const double ppc = (double)k.N / (double)k.Ng;
+        int fr = 16;
+        while (fr > 1 && 64.0 * fr > 3.0 * ppc) fr >>= 1;
+        long long cap = device_sm_count();
+        kern<<<(int)(nchunks < cap ? nchunks : cap), S_T, smem2b, st>>>(k, (int)nchunks | ((fr - 1) << 28), x0, v0, x1i, x1, v1, Fs,
+                                                                          acc, range_err);
+        PIC_CHECK_LAUNCH();
+        return PIC_OK;
+    }
     if (!(p->flags & (1 | 4)) && aligned16 && k.Ng >= 8 && smem2 <= (size_t)max_optin_smem() - 512) {
         // default: TMA-staged private-window kernel over whole chunks, v1 kernel on the tail
         const long long nchunks = k.N / S_CHUNK;

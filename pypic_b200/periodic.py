@@ -40,7 +40,9 @@ class PeriodicImplicitSim:
             deposit = "window"
         # bit1: the store keeps the UNWRAPPED x1 of the previous step and the kernels apply
         # ``x % L`` (pypic.py:277) when they load it -- saves a 16 B/particle pass per step
-        flags = {"window": 0, "warp": 4, "atomic": 1 | 4}[deposit] | 2
+        # "window-big" forces the large-grid build of the window kernel (per-warp field windows instead of the
+        # whole-grid tile; taken automatically when the grid does not fit shared memory, Ng >~ 9000)
+        flags = {"window": 0, "window-big": 16, "warp": 4, "atomic": 1 | 4}[deposit] | 2
         self.sort_every = int(sort_every)
         self.t = 0
         self.perm = None                     # original index of the particle in each slot (after sorting)
@@ -50,8 +52,8 @@ class PeriodicImplicitSim:
         # particle_push_p, pypic.py:248): arrays take the grid-stride kernel, unsorted, full iterations
         self.qm_arrays = None
         if np.ndim(q) or np.ndim(m):
-            qa = np.broadcast_to(np.asarray(q, dtype=np.float64), (self.N_global,))[self.start:self.stop]
-            ma = np.broadcast_to(np.asarray(m, dtype=np.float64), (self.N_global,))[self.start:self.stop]
+            qa = np.broadcast_to(np.asarray(q, dtype=np.float64), (self.N_global,))[self.start:self.stop].copy()
+            ma = np.broadcast_to(np.asarray(m, dtype=np.float64), (self.N_global,))[self.start:self.stop].copy()
             self.qm_arrays = (D.to_dev(qa, self.dev), D.to_dev(ma, self.dev))
             self.sort_every = 0
             flags = (flags | 4) & ~1

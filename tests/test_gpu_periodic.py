@@ -267,6 +267,62 @@ def test_pypic_v2_kernel_matches_v1_and_oracle():
     assert relmax(out["E0"], E1) < 1e-12 and relmax(out["j0"], j1) < 1e-12
 
 
+def test_pypic_large_grid_build_matches_the_default_and_the_oracle():
+    """Large-grid build of pypic_picard_iter_v2_k (per-warp field windows, windows re-centred every few rows):
+    forced at a grid the default build also takes -> particles bit-identical after one iteration, fields to
+    round-off after three; and at 20001 nodes (no shared-memory tile possible) against the numpy oracle."""
+    from pypic_b200.periodic import PeriodicImplicitSim
+    rs = np.random.RandomState(31)
+    Ng = 512; dx = 1e-5; dt = 2e-11; L = dx * Ng
+    N = 3 * 16384 + 333
+    x0 = _adversarial_positions(rs, N, Ng, dx, L)
+    v0 = rs.normal(0, 1.3e6, N)
+    E0 = rs.normal(0, 2e4, Ng)
+    outs = {}
+    for dep in ("window", "window-big"):
+        for it in (1, 3):
+            sim = PeriodicImplicitSim(N, Ng, dx, dt, L, 1e9, tol=1e-30, maxiter=it, deposit=dep)
+            sim.upload(x0, v0, E0)
+            k, r = sim.push(); sim.check()
+            assert k == it
+            outs[dep, it] = sim.download()
+    a, b = outs["window", 1], outs["window-big", 1]
+    assert np.array_equal(a["x0"], b["x0"]) and np.array_equal(a["v0"], b["v0"])
+    a, b = outs["window", 3], outs["window-big", 3]
+    assert relmax(a["x0"], b["x0"]) < 1e-13 and relmax(a["v0"], b["v0"]) < 1e-12
+    assert relmax(a["E0"], b["E0"]) < 1e-11 and relmax(a["j0"], b["j0"]) < 1e-11
+    # a grid that does not fit shared memory: sorted and unsorted stores, few particles per cell
+    Ng = 20001; L = dx * Ng
+    N = 6 * 16384 + 41
+    for sort in (True, False):
+        x0 = rs.uniform(0, L, N)
+        if sort:
+            x0 = np.sort(x0)
+        x0[:50] = np.arange(50) * 400 * dx                  # node-aligned
+        x0[50:60] = L - rs.uniform(0, 0.5 * dx, 10)         # last cell: the right node wraps to node 0
+        v0 = rs.normal(0, 1.3e6, N); E0 = rs.normal(0, 2e4, Ng)
+        q = -np.ones(N) * O.e; m = np.ones(N) * O.me
+        x1, v1, E1, j1, k, r = O.pypic_particle_push_p(x0, v0, q, m, E0, np.zeros(Ng), N, Ng, 1e9, dx, dt, L, 1e-30, 1)
+        sim = PeriodicImplicitSim(N, Ng, dx, dt, L, 1e9, tol=1e-30, maxiter=1, deposit="window", sort_every=0)
+        sim.upload(x0, v0, E0)
+        sim.push(); sim.check()
+        out = sim.download()
+        assert np.array_equal(out["x0"], x1) and np.array_equal(out["v0"], v1)
+        assert relmax(out["E0"], E1) < 1e-12 and relmax(out["j0"], j1) < 1e-12
+    # several steps with light iterations, sorts and the j1 repair on the large grid: runs and stays in range
+    sim = PeriodicImplicitSim(N, Ng, dx, 2e-12, L, 1e9, tol=1e-3, maxiter=20, deposit="window", sort_every=2)
+    sim.upload(np.sort(rs.uniform(0, L, N)), rs.normal(0, 1.3e6, N), rs.normal(0, 2e4, Ng))
+    full = PeriodicImplicitSim(N, Ng, dx, 2e-12, L, 1e9, tol=1e-3, maxiter=20, deposit="window", sort_every=2)
+    full.light_iterations = False
+    o = sim.download(); full.upload(o["x0"], o["v0"], o["E0"])
+    for _ in range(4):
+        ka, kb = sim.push()[0], full.push()[0]
+        assert ka == kb
+    sim.check(); full.check()
+    a, b = sim.download(), full.download()
+    assert relmax(a["x0"], b["x0"]) < 1e-12 and relmax(a["E0"], b["E0"]) < 1e-11 and relmax(a["j0"], b["j0"]) < 1e-11
+
+
 def test_pypic_light_iterations_and_repair_agree_with_full_iterations():
     """PeriodicImplicitSim with light iterations (default), with every prediction forced wrong
     (j1 repair pass after every push) and with full iterations only: same iteration counts, same
