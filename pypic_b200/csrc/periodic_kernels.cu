@@ -277,11 +277,15 @@ __global__ void l_interpolate_k(const double* __restrict__ F, const double* __re
 template <bool CURRENT>
 __global__ void l_weight_k(const double* __restrict__ x, const double* __restrict__ q, const double* __restrict__ v,
                            double* __restrict__ acc, long long N, int Ng, double dx, double p2c,
-                           int* __restrict__ range_err) {
+                           int* __restrict__ range_err, int tile) {
     extern __shared__ double sm[];
     const int nodes = Ng + 1;
-    for (int i = threadIdx.x; i < nodes; i += blockDim.x) sm[i] = 0.0;
-    __syncthreads();
+    double* dst = acc;                         // grids too large for a shared-memory tile: global REDs
+    if (tile) {
+        for (int i = threadIdx.x; i < nodes; i += blockDim.x) sm[i] = 0.0;
+        __syncthreads();
+        dst = sm;
+    }
     const double idx = 1. / dx;
     int bad = 0;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < N; i += (long long)gridDim.x * blockDim.x) {
@@ -289,12 +293,14 @@ __global__ void l_weight_k(const double* __restrict__ x, const double* __restric
         l_fix(c, nodes, bad);
         // PIC_L.py:73-74 / 112-113: q*v*p2c*w*idx  |  q*p2c*w*idx
         double pre = CURRENT ? q[i] * v[i] * p2c : q[i] * p2c;
-        atomicAdd(&sm[c.iL], pre * c.wL * idx);
-        atomicAdd(&sm[c.iR], pre * c.wR * idx);
+        atomicAdd(&dst[c.iL], pre * c.wL * idx);
+        atomicAdd(&dst[c.iR], pre * c.wR * idx);
     }
-    __syncthreads();
-    for (int i = threadIdx.x; i < nodes; i += blockDim.x)
-        if (sm[i] != 0.0) atomicAdd(&acc[i], sm[i]);
+    if (tile) {
+        __syncthreads();
+        for (int i = threadIdx.x; i < nodes; i += blockDim.x)
+            if (sm[i] != 0.0) atomicAdd(&acc[i], sm[i]);
+    }
     if (bad && range_err) atomicAdd(range_err, bad);
 }
 // folds: rho[-1]=rho[0]+rho[-1]; rho[0]=rho[-1]  |  j[0]=j[-1]+j[0]; j[-1]=j[0]
@@ -462,14 +468,24 @@ __device__ __forceinline__ void swin_flush(double* win, double* myw, int wbase, 
 
 // ---------------------------------------------------------------- PIC_L explicit step
 struct LFastC { double dx, idx, dt, qmh, qpi; unsigned hi_lim; };
-struct LFastO { double X, V, fL, fR; int cF; unsigned fr, ps; };
+struct LFastO { double X, V, fL, fR; int cF; unsigned fr, ps; bool emiss; };
 
-__device__ __forceinline__ void l_fast(const LFastC& c, const double* __restrict__ sE, int nodes, double X, double V,
+// BIG (large-grid build): sE is the warp's window of L_EW field nodes starting at node eb; a gather cell outside
+// it sets o.emiss and the particle is redone by the exact routine with the field read from global memory.
+#define L_EW 32
+template <bool BIG>
+__device__ __forceinline__ void l_fast(const LFastC& c, const double* __restrict__ sE, int nodes, int eb, double X, double V,
                                        LFastO& o) {
     const double ts = X * c.idx, fs = floor(ts);
     const unsigned f0 = (unsigned)__double2hiint(ts - fs) - PIC_HI_G;
     const double rs = fma(-fs, c.dx, X);
-    const int is = min(max((int)fs, 0), nodes - 2);
+    int is = min(max((int)fs, 0), nodes - 2);
+    o.emiss = false;
+    if (BIG) {
+        is -= eb;
+        o.emiss = (unsigned)is > (unsigned)(L_EW - 2);
+        is = min(max(is, 0), L_EW - 2);
+    }
     const double wR = div_const(rs, c.dx, c.idx), wL = 1.0 - wR;
     const double Ei = wL * sE[is] + wR * sE[is + 1];                 // PIC_L.py:45
     const double vh = V + c.qmh * Ei;                                 // :255
@@ -508,19 +524,25 @@ __device__ __noinline__ int l_particle_exact(const LK& k, long long i, double X,
     return bad;
 }
 
-template <int NST>
-__global__ void __launch_bounds__(S_T, 1) l_push_deposit_v2_k(const __grid_constant__ LK k, int nchunks, double* x,
+template <int NST, bool BIG = false>
+__global__ void __launch_bounds__(S_T, 1) l_push_deposit_v2_k(const __grid_constant__ LK k, int nchunks_fr, double* x,
                                                                double* v, const double* __restrict__ E,
                                                                double* __restrict__ rho_acc, int* __restrict__ range_err) {
     extern __shared__ __align__(128) double sm[];
     __shared__ int s_bad;
     const int nodes = k.Ng + 1;
-    const int NP = (nodes + 15) & ~15;
+    const int NP = BIG ? (S_T / 32) * L_EW : ((nodes + 15) & ~15);
+    const int nchunks = nchunks_fr & 0x0fffffff;
+    const int FRm = BIG ? (nchunks_fr >> 28) : (S_ROWS - 1);      // rows per deposit / field window - 1
     double* sE = sm;
     double* win = sm + NP;                                   // [S_W][S_T]
     double* ring = win + S_W * S_T;                          // [warp][stage][x|v][64]
     unsigned long long* bars = (unsigned long long*)(ring + (S_T / 32) * NST * 128);
-    for (int i = threadIdx.x; i < nodes; i += S_T) sE[i] = E[i];
+    if (!BIG) for (int i = threadIdx.x; i < nodes; i += S_T) sE[i] = E[i];
+    double* const wE = sm + (threadIdx.x >> 5) * L_EW;       // BIG: this warp's field window
+    const double* const fE = BIG ? wE : sE;                  // what the fast path gathers from
+    const double* const gE = BIG ? E : sE;                   // what the exact routine gathers from
+    int eb = 0;
     double* myw = win + threadIdx.x;
 #pragma unroll
     for (int n = 0; n < S_W; ++n) myw[n * S_T] = 0.0;
@@ -583,12 +605,20 @@ __global__ void __launch_bounds__(S_T, 1) l_push_deposit_v2_k(const __grid_const
                 fc.qmh = (sp ? k.qm[1] : k.qm[0]) * hdt;
                 fc.qpi = (sp ? k.q[1] : k.q[0]) * k.p2c * k.idx;
             }
+            if (BIG && (row & FRm) == 0) {
+                if (row > 0 && wb != NOWIN) { __syncwarp(); swin_flush<1>(win, myw, wbase, lane, wb, rho_acc, 0, nodes); }
+                const int cb = (int)floor(__shfl_sync(full, X.x, 0) * k.idx);
+                eb = min(max(cb - L_EW / 4, 0), nodes - L_EW);
+                __syncwarp();
+                wE[lane] = __ldg(E + eb + lane);
+                __syncwarp();
+            }
             LFastO a, b;
-            l_fast(fc, sE, nodes, X.x, V.x, a);
-            l_fast(fc, sE, nodes, X.y, V.y, b);
-            const bool ra = (a.fr > PIC_HI_SPAN) | (a.ps >= fc.hi_lim) | straddle;
-            const bool rb = (b.fr > PIC_HI_SPAN) | (b.ps >= fc.hi_lim) | straddle;
-            if (row == 0) {
+            l_fast<BIG>(fc, fE, nodes, eb, X.x, V.x, a);
+            l_fast<BIG>(fc, fE, nodes, eb, X.y, V.y, b);
+            const bool ra = (a.fr > PIC_HI_SPAN) | (a.ps >= fc.hi_lim) | straddle | a.emiss;
+            const bool rb = (b.fr > PIC_HI_SPAN) | (b.ps >= fc.hi_lim) | straddle | b.emiss;
+            if ((row & FRm) == 0) {
                 int nok = __reduce_add_sync(full, (ra ? 0 : 1) + (rb ? 0 : 1));
                 int sum = __reduce_add_sync(full, (ra ? 0 : a.cF) + (rb ? 0 : b.cF));
                 wb = nok ? sum / nok - (S_W - 2) / 2 : NOWIN;
@@ -599,9 +629,9 @@ __global__ void __launch_bounds__(S_T, 1) l_push_deposit_v2_k(const __grid_const
                 swin_add(myw, rho_acc, wb, a.cF, a.fL, a.fR);
                 swin_add(myw, rho_acc, wb, b.cF, b.fL, b.fR);
             } else {
-                if (ra) bad += l_particle_exact(k, ci, X.x, V.x, sE, rho_acc, x, v);
+                if (ra) bad += l_particle_exact(k, ci, X.x, V.x, gE, rho_acc, x, v);
                 else { x[ci] = a.X; v[ci] = a.V; swin_add(myw, rho_acc, wb, a.cF, a.fL, a.fR); }
-                if (rb) bad += l_particle_exact(k, ci + 1, X.y, V.y, sE, rho_acc, x, v);
+                if (rb) bad += l_particle_exact(k, ci + 1, X.y, V.y, gE, rho_acc, x, v);
                 else { x[ci + 1] = b.X; v[ci + 1] = b.V; swin_add(myw, rho_acc, wb, b.cF, b.fL, b.fR); }
             }
             // refill the drained stage only after every lane's LDS of it has executed (see v6)
@@ -614,7 +644,7 @@ __global__ void __launch_bounds__(S_T, 1) l_push_deposit_v2_k(const __grid_const
     }
     // the N % S_CHUNK particles behind the last whole chunk: at most one per thread, exact routine, global REDs
     for (long long i = (long long)nchunks * S_CHUNK + (long long)blockIdx.x * S_T + threadIdx.x; i < k.N; i += (long long)gridDim.x * S_T)
-        bad += l_particle_exact(k, i, x[i], v[i], sE, rho_acc, x, v);
+        bad += l_particle_exact(k, i, x[i], v[i], gE, rho_acc, x, v);
     if (bad) atomicAdd(&s_bad, bad);
     __syncthreads();
     if (threadIdx.x == 0 && s_bad && range_err) atomicAdd(range_err, s_bad);
@@ -1076,12 +1106,14 @@ int pic_dev_l_weight(const double* x, const double* q, const double* v, double* 
     PIC_CHECK_CUDA(cudaMemsetAsync(acc, 0, (size_t)nodes * sizeof(double), st));
     if (N > 0) {
         size_t smem = (size_t)nodes * sizeof(double);
+        const int tile = smem <= (size_t)max_optin_smem() - 1024;
+        if (!tile) smem = 0;
         if (v) {
-            PIC_CHECK_CUDA(cudaFuncSetAttribute(l_weight_k<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            l_weight_k<true><<<grid_for(N, 256, 4), 256, smem, st>>>(x, q, v, acc, N, Ng, dx, p2c, range_err);
+            PIC_CHECK_CUDA(cudaFuncSetAttribute(l_weight_k<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(smem ? smem : 1)));
+            l_weight_k<true><<<grid_for(N, 256, 4), 256, smem, st>>>(x, q, v, acc, N, Ng, dx, p2c, range_err, tile);
         } else {
-            PIC_CHECK_CUDA(cudaFuncSetAttribute(l_weight_k<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            l_weight_k<false><<<grid_for(N, 256, 4), 256, smem, st>>>(x, q, v, acc, N, Ng, dx, p2c, range_err);
+            PIC_CHECK_CUDA(cudaFuncSetAttribute(l_weight_k<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(smem ? smem : 1)));
+            l_weight_k<false><<<grid_for(N, 256, 4), 256, smem, st>>>(x, q, v, acc, N, Ng, dx, p2c, range_err, tile);
         }
         PIC_CHECK_LAUNCH();
     }
@@ -1104,6 +1136,23 @@ int pic_dev_l_push_deposit(const pic_l_params* p, double* x, double* v, const do
                           (size_t)(S_T / 32) * L_NST) * sizeof(double);
     const bool aligned16 = (((uintptr_t)x | (uintptr_t)v) & 15) == 0;
     long long done = 0;
+    // large-grid build of the same kernel (flags bit4 forces it, for tests): per-warp field windows
+    const size_t smem2b = ((size_t)(S_T / 32) * L_EW + (size_t)S_W * S_T + (size_t)(S_T / 32) * L_NST * 128 +
+                           (size_t)(S_T / 32) * L_NST) * sizeof(double);
+    const bool big = ((p->flags & 16) || smem2 > (size_t)max_optin_smem() - 512) && nodes >= L_EW;
+    if (big && !(p->flags & (1 | 2 | 4)) && aligned16 && k.N >= S_CHUNK) {
+        const long long nchunks = k.N / S_CHUNK;
+        PIC_REQUIRE(nchunks < (1 << 28), "l_push_deposit: shard too large");
+        auto kern = l_push_deposit_v2_k<L_NST, true>;
+        PIC_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2b));
+        const double ppc = (double)k.N / 2.0 / (double)nodes;       // two species interleave over the same cells
+        int fr = 16;
+        while (fr > 1 && 64.0 * fr > 3.0 * ppc) fr >>= 1;
+        long long cap = device_sm_count();
+        kern<<<(int)(nchunks < cap ? nchunks : cap), S_T, smem2b, st>>>(k, (int)nchunks | ((fr - 1) << 28), x, v, E, rho_acc, range_err);
+        PIC_CHECK_LAUNCH();
+        return PIC_OK;
+    }
     if (!(p->flags & (1 | 2 | 4)) && aligned16 && k.Ng >= 8 && smem2 <= (size_t)max_optin_smem() - 512) {
         const long long nchunks = k.N / S_CHUNK;
         if (nchunks > 0) {

@@ -258,7 +258,7 @@ class ExplicitSim:
         self.L = dx * (Ng - 1)              # PIC_L.py:645; the wrap length is L+dx
         if sort_every and deposit == "warp":
             deposit = "window"               # see PeriodicImplicitSim
-        flags = {"window": 0, "warp": 4, "atomic": 1 | 4}[deposit]
+        flags = {"window": 0, "window-big": 16, "warp": 4, "atomic": 1 | 4}[deposit]     # window-big: see PeriodicImplicitSim
         self.sort_every = int(sort_every)
         self.t = 0
         self.perm = None

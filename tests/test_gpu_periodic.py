@@ -217,15 +217,16 @@ def test_pic_l_v2_kernel_matches_v1_and_oracle():
     q = (-O.e, O.e); m = (O.me, O.mp)
     dev = D.require_cuda()
     res = {}
-    for flags in (0, 4):
+    for flags in (0, 4, 16):                 # 16: the large-grid build of the window kernel, forced
         P = _lib.LParams(N, n_split, Ng, flags, dx, dt, L, 1e9, (C.c_double * 2)(*q), (C.c_double * 2)(*m))
         tx, tv, tE = D.to_dev(x, dev), D.to_dev(v, dev), D.to_dev(E, dev)
         acc = D.f64(Ng + 1, dev, True); err = torch.zeros(1, dtype=torch.int32, device=dev)
         _lib.call("pic_dev_l_push_deposit", C.byref(P), D.ptr(tx), D.ptr(tv), D.ptr(tE), D.ptr(acc), D.ptr(err), D.stream())
         res[flags] = (tx.cpu().numpy(), tv.cpu().numpy(), acc.cpu().numpy(), int(err.item()))
-    assert np.array_equal(res[0][0], res[4][0]) and np.array_equal(res[0][1], res[4][1])
-    assert res[0][3] == res[4][3]
-    assert relmax(res[0][2], res[4][2]) < 1e-13
+    for f in (4, 16):
+        assert np.array_equal(res[0][0], res[f][0]) and np.array_equal(res[0][1], res[f][1])
+        assert res[0][3] == res[f][3]
+        assert relmax(res[0][2], res[f][2]) < 1e-13
     # oracle: PIC_L.pushParticlesExplicit + applyBoundaryConditionsPeriodic per particle
     qa = np.where(np.arange(N) < n_split, q[0], q[1]); ma = np.where(np.arange(N) < n_split, m[0], m[1])
     Ei = O.l_interpolateFieldPeriodic(E, x, Ng, dx)
@@ -234,6 +235,49 @@ def test_pic_l_v2_kernel_matches_v1_and_oracle():
     vo = vhalf + (qa / ma) * (dt * 0.5) * Ei
     assert np.array_equal(res[0][0], xo) and np.array_equal(res[0][1], vo)
     assert (np.abs(x + vhalf * dt - xo) > 0).sum() > 100        # the wrap path was exercised
+
+
+def test_pic_l_large_grid_step_matches_the_oracle_formulas():
+    """PIC_L explicit step on a 30000-cell grid (no shared-memory field tile possible: large-grid build of the
+    window kernel, global-memory deposit and PCR solve): particles bit-identical to the reference formulas,
+    rho of the next step to round-off; the whole step (field solve included) runs through ExplicitSim."""
+    import ctypes as C
+    import torch
+    from pypic_b200 import _lib, device as D
+    from pypic_b200.periodic import ExplicitSim
+    rs = np.random.RandomState(41)
+    Ng = 30000; dx = 1e-5; dt = 2e-11; L = dx * (Ng - 1); Lw = L + dx
+    N = 6 * 16384 + 123; n_split = N // 2
+    x = rs.uniform(0, Lw, N)
+    x[:n_split] = np.sort(x[:n_split]); x[n_split:] = np.sort(x[n_split:])
+    x[:40] = np.arange(40) * 700 * dx
+    v = np.concatenate([rs.normal(0, 1.3e6, n_split), rs.normal(0, 3e4, N - n_split)])
+    E = rs.normal(0, 2e4, Ng + 1)
+    q = (-O.e, O.e); m = (O.me, O.mp)
+    dev = D.require_cuda()
+    P = _lib.LParams(N, n_split, Ng, 0, dx, dt, L, 1e9, (C.c_double * 2)(*q), (C.c_double * 2)(*m))
+    tx, tv, tE = D.to_dev(x, dev), D.to_dev(v, dev), D.to_dev(E, dev)
+    acc = D.f64(Ng + 1, dev, True); err = torch.zeros(1, dtype=torch.int32, device=dev)
+    _lib.call("pic_dev_l_push_deposit", C.byref(P), D.ptr(tx), D.ptr(tv), D.ptr(tE), D.ptr(acc), D.ptr(err), D.stream())
+    qa = np.where(np.arange(N) < n_split, q[0], q[1]); ma = np.where(np.arange(N) < n_split, m[0], m[1])
+    Ei = O.l_interpolateFieldPeriodic(E, x, Ng, dx)
+    vhalf = v + (qa / ma) * (dt * 0.5) * Ei
+    xo = (x + vhalf * dt) % Lw
+    vo = vhalf + (qa / ma) * (dt * 0.5) * Ei
+    assert int(err.item()) == 0
+    assert np.array_equal(tx.cpu().numpy(), xo) and np.array_equal(tv.cpu().numpy(), vo)
+    # the deposit of the pushed positions, before the fold (PIC_L.py:100-118 without :115-116; weights (x % dx)/dx)
+    iL = np.floor(xo / dx).astype(int); wR = (xo % dx) / dx
+    rho = np.zeros(Ng + 1)
+    np.add.at(rho, iL, qa * 1e9 * (1 - wR) / dx); np.add.at(rho, np.minimum(iL + 1, Ng), qa * 1e9 * wR / dx)
+    assert relmax(acc.cpu().numpy(), rho) < 1e-12
+    sim = ExplicitSim(N, Ng, dx, dt, 1e9, q=q, m=m, n_split=n_split, deposit="window", sort_every=2)
+    sim.upload(x, v)
+    for _ in range(3):
+        sim.step()
+    sim.check()
+    o = sim.download()
+    assert np.all(np.isfinite(o["E"])) and np.all((o["x"] >= 0) & (o["x"] < Lw))
 
 
 def test_pypic_v2_kernel_matches_v1_and_oracle():
