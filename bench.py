@@ -337,6 +337,16 @@ def run_cuda(args):
                         "measured launch time; the kernel moves fewer DRAM bytes than that (traffic: first iteration 24 B, "
                         "light iterations 32 B, last iteration 40 B per particle -> 160 B instead of 176 B per 5-iteration "
                         "particle-step), so frac can approach 1 while the actual DRAM rate is ~0.88 of the copy peak"}
+    if world > 1:
+        # the coupled step runs at the pace of the slowest rank in every Picard iteration: the spread of the
+        # per-rank kernel times (clocks differ from GPU to GPU under the power cap) is what the weak-scaling
+        # efficiency loses, whatever the reduction costs
+        t = torch.tensor([mean_iter_ms], dtype=torch.float64, device=dev)
+        allk = [torch.zeros_like(t) for _ in range(world)]
+        dist.all_gather(allk, t)
+        per_rank = [float(v.item()) for v in allk]
+        roofline["kernel_ms_mean_per_rank"] = per_rank
+        roofline["step_ms_if_every_iteration_waits_for_the_slowest_rank"] = float(kbar * max(per_rank) + (ms - kbar * mean_iter_ms))
     tf = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.isfile(tf):
         try:

@@ -265,19 +265,22 @@ int pic_dev_dd_field_update(const pic_dd_params* p, double* acc, double* wall_cu
 int pic_dev_dd_field_update2(const pic_dd_params* p, double* acc, double* wall_cum, const double* E0,
                              double* Es, double* E1, double* j1, double* stats, double* Es_prev,
                              double* rhist, int32_t* ctl, double tol, int maxiter, void* stream);
-/* Particle decomposition without a library collective: the field kernel itself sums the ranks'
- * accumulators over NVLink peer memory (one process per GPU; buffers shared through CUDA IPC).
- *   pic_p2p_alloc   allocates this rank's buffer: nacc doubles (the accumulators the particle
- *                   kernels add to, zero) + 2*world uint32 flags, and writes its 64-byte IPC handle;
+/* Particle decomposition without a library collective: the field kernel itself exchanges and sums the
+ * ranks' accumulators over NVLink peer memory (one process per GPU; buffers shared through CUDA IPC).
+ *   pic_p2p_alloc   allocates this rank's buffer -- nacc doubles (the accumulators the particle
+ *                   kernels add to, zero; nacc even), an inbox of 2 x world x nacc doubles the PEERS
+ *                   write to, 2*world + 2 uint32 of flags / counters -- and writes its 64-byte IPC handle;
  *   pic_p2p_open    maps another rank's buffer from its handle (exchange the handles with any host
  *                   collective); pic_p2p_close / pic_p2p_free undo the two.
  *   pic_dev_dd_field_update_p2p = pic_dev_dd_field_update2 with the all-reduce inside: peers_dev is
  *                   a DEVICE array of the world buffer pointers in rank order (own entry = the local
- *                   pointer); seq is a counter the caller increments for every launch, identical on
- *                   every rank; acc_sum (fp64[2*Ng+4], local) receives the sum in rank order -- the
- *                   same bits on every rank -- and is consumed by the field phase; the rank's own
- *                   accumulators are zeroed once every peer has read them.  Waits are bounded
- *                   (seconds); *err (device int) is set to 1 on a time-out.  Ng <= 32768.
+ *                   pointer).  Every rank pushes its accumulators into its slot of every rank's
+ *                   inbox (posted NVLink stores, double-buffered by the parity of a reduction counter
+ *                   kept on the device), zeroes them, raises a flag in every rank's buffer, waits for
+ *                   the world flags in its OWN buffer and sums the slots in rank order from local
+ *                   memory into acc_sum (fp64[2*Ng+4], local) -- the same bits on every rank -- which
+ *                   the field phase consumes.  seq is ignored (kept for ABI stability).  Waits are
+ *                   bounded (seconds); *err (device int) is set to 1 on a time-out.  Ng <= 32768.
  *   pic_dev_p2p_reduce  the reduction alone (sum[nacc] local), e.g. for the j1 repair pass. */
 int pic_p2p_alloc(int64_t nacc, int world, void** dev_ptr, void* handle64);
 int pic_p2p_open(const void* handle64, void** peer_ptr);

@@ -989,25 +989,33 @@ __device__ __forceinline__ void dd_field_update_body(const DDK& k, double* __res
 
 
 // ---------------------------------------------------------------------------------------
-// Particle decomposition WITHOUT a library collective: the sum over ranks of the grid
-// accumulators is done by the field kernel itself over NVLink peer memory.  Every rank's
-// accumulators live in a buffer that all ranks have mapped (CUDA IPC): nacc doubles followed by
-// 2*world 32-bit flags (ready[world], done[world]).  Per iteration (sequence number seq, the
-// same on every rank):
-//   1. rank r stores seq into ready[r] of EVERY rank's buffer (release, system scope): "my
-//      accumulators of iteration seq are complete" (the particle kernel ran before on the stream);
-//   2. it waits until ready[*] of its OWN buffer have reached seq, then loads every rank's
-//      accumulators and adds them in rank order -- every rank computes the same bits, so all ranks
-//      take the same Picard exit, exactly as with an all-reduce;
-//   3. it stores seq into done[r] of every rank ("I have read your accumulators"), runs the field
-//      phase on the sum, waits for done[*] in its own buffer and zeroes its accumulators for the
-//      next particle kernel.
+// Particle decomposition WITHOUT a library collective: the field kernel itself exchanges and sums
+// the ranks' grid accumulators over NVLink peer memory.  Every rank owns a buffer that all ranks
+// have mapped (CUDA IPC):
+//     acc  [nacc]                  what this rank's particle kernels add to
+//     inbox[2][world][nacc]        inbox[parity][source rank]: the accumulators every rank PUSHED here
+//     ready[2][world]   (uint32)   ready[parity][source] = number of the reduction whose data is complete
+//     nreal, cnt        (uint32)   local: reductions done so far; CTA arrival counter
+// Reduction number n (counted on the device: launches the Picard loop's flag turned into no-ops are
+// not counted, identically on every rank), parity b = n & 1, P2P_NB CTAs:
+//   1. push: all CTAs copy acc (128-bit loads) into inbox[b][me] of EVERY rank -- posted stores, no
+//      round trip over NVLink -- and zero acc; each CTA fences (system scope) and counts in; the last
+//      one stores n into ready[b][me] of every rank (release);
+//   2. CTA 0 waits until ready[b][*] of its OWN buffer have reached n (local polls), sums the world
+//      inbox slots in rank order from LOCAL memory -- the same bits on every rank, so all ranks take
+//      the same Picard exit, exactly as with an all-reduce -- runs the field phase and publishes
+//      nreal = n.
+// No acknowledgement is needed: a rank can push reduction n+2 (the next use of buffer b) only after
+// its own reduction n+1 completed, which needed every peer's push of n+1, which every peer issued
+// after it had finished reading reduction n.
+// (Round 1's protocol PULLED the peers' accumulators with serialized system-scope loads from one CTA
+// and acknowledged every read: slower than NCCL.)
 // Waits are bounded (a few seconds): on time-out *err is set and the kernel proceeds, so a peer
 // that died cannot hang the GPU.
+#define P2P_NB 8
 struct P2P {
     double* const* peers;      // device array [world] of the ranks' buffers (own entry = local pointer)
     int rank, world, nacc;
-    unsigned seq;
     int* err;
 };
 __device__ __forceinline__ unsigned ld_acquire_sys_u32(const unsigned* p) {
@@ -1018,48 +1026,70 @@ __device__ __forceinline__ unsigned ld_acquire_sys_u32(const unsigned* p) {
 __device__ __forceinline__ void st_release_sys_u32(unsigned* p, unsigned v) {
     asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
-__device__ __forceinline__ double ld_relaxed_sys_f64(const double* p) {
-    double v;
-    asm volatile("ld.relaxed.sys.global.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory");
-    return v;
+__device__ __forceinline__ double* p2p_inbox(double* buf, int nacc, int world, int par, int src) {
+    return buf + (size_t)nacc * (1 + (size_t)par * world + src);
 }
-__device__ __forceinline__ unsigned* p2p_flags(double* buf, int nacc) { return (unsigned*)(buf + nacc); }
-// bounded wait: 2^g_p2p_spin_log2 polls of >= 200 ns each (default 2^25: 7 s or more, far beyond any
+__device__ __forceinline__ unsigned* p2p_ready(double* buf, int nacc, int world) {
+    return (unsigned*)(buf + (size_t)nacc * (1 + 2 * (size_t)world));
+}
+__device__ __forceinline__ unsigned* p2p_state(double* buf, int nacc, int world) { return p2p_ready(buf, nacc, world) + 2 * world; }
+// bounded wait: 2^g_p2p_spin_log2 polls of >= 100 ns each (default 2^25: seconds, far beyond any
 // start-up skew between ranks -- first-call module loads, host-RNG re-injection, a checkpoint write);
 // pic_p2p_set_timeout changes it
 __device__ int g_p2p_spin_log2 = 25;
-__device__ __noinline__ bool p2p_wait(const unsigned* flag, unsigned seq) {
+__device__ __noinline__ bool p2p_wait(const unsigned* flag, unsigned n) {
     const long long nspin = 1ll << g_p2p_spin_log2;
     for (long long spin = 0; spin < nspin; ++spin) {
-        if ((int)(ld_acquire_sys_u32(flag) - seq) >= 0) return true;      // wrap-safe "flag >= seq"
-        __nanosleep(200);
+        if ((int)(ld_acquire_sys_u32(flag) - n) >= 0) return true;      // wrap-safe "flag >= n"
+        __nanosleep(100);
     }
     return false;
 }
-__device__ __forceinline__ void p2p_reduce(const P2P& P, double* __restrict__ sum) {
-    const int t = threadIdx.x;
-    unsigned* myf = p2p_flags(P.peers[P.rank], P.nacc);
-    __threadfence_system();
-    if (t < P.world) {
-        st_release_sys_u32(p2p_flags(P.peers[t], P.nacc) + P.rank, P.seq);
-        if (!p2p_wait(myf + t, P.seq)) atomicExch(P.err, 1);
-    }
-    __syncthreads();
-    for (int i = t; i < P.nacc; i += blockDim.x) {
-        double s = 0.0;
-        for (int r = 0; r < P.world; ++r) s += ld_relaxed_sys_f64(P.peers[r] + i);
-        sum[i] = s;
-    }
-    __syncthreads();
-    __threadfence_system();
-    if (t < P.world) st_release_sys_u32(p2p_flags(P.peers[t], P.nacc) + P.world + P.rank, P.seq);
-}
-__device__ __forceinline__ void p2p_finish(const P2P& P) {
-    const int t = threadIdx.x;
+// step 1 (every CTA of the grid); returns the reduction number
+__device__ __forceinline__ unsigned p2p_push(const P2P& P) {
     double* mine = P.peers[P.rank];
-    if (t < P.world && !p2p_wait(p2p_flags(mine, P.nacc) + P.world + t, P.seq)) atomicExch(P.err, 1);
+    unsigned* st = p2p_state(mine, P.nacc, P.world);
+    const unsigned n = *(volatile unsigned*)st + 1u;
+    const int par = (int)(n & 1u);
+    const int nv = P.nacc >> 1;                                   // nacc is even (2*Ng + 4)
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nv; i += gridDim.x * blockDim.x) {
+        const double2 v = ((const double2*)mine)[i];
+        ((double2*)mine)[i] = make_double2(0.0, 0.0);
+        for (int r = 0; r < P.world; ++r) ((double2*)p2p_inbox(P.peers[r], P.nacc, P.world, par, P.rank))[i] = v;
+    }
+    __threadfence_system();
     __syncthreads();
-    for (int i = t; i < P.nacc; i += blockDim.x) mine[i] = 0.0;
+    if (threadIdx.x == 0) {
+        const unsigned old = atomicAdd(st + 1, 1u);
+        if (old == gridDim.x - 1) {
+            st[1] = 0u;
+            __threadfence_system();
+            for (int r = 0; r < P.world; ++r)
+                st_release_sys_u32(p2p_ready(P.peers[r], P.nacc, P.world) + par * P.world + P.rank, n);
+        }
+    }
+    return n;
+}
+// step 2 (CTA 0): sum[nacc] = sum over ranks in rank order
+__device__ __forceinline__ void p2p_collect(const P2P& P, unsigned n, double* __restrict__ sum) {
+    double* mine = P.peers[P.rank];
+    const int par = (int)(n & 1u), t = threadIdx.x;
+    if (t < P.world && !p2p_wait(p2p_ready(mine, P.nacc, P.world) + par * P.world + t, n)) atomicExch(P.err, 1);
+    __syncthreads();
+    const int nv = P.nacc >> 1;
+    for (int i = t; i < nv; i += blockDim.x) {
+        double2 s = make_double2(0.0, 0.0);
+        for (int r = 0; r < P.world; ++r) {
+            const double2 v = __ldcg((const double2*)p2p_inbox(mine, P.nacc, P.world, par, r) + i);    // L2: written by the peers
+            s.x += v.x; s.y += v.y;
+        }
+        ((double2*)sum)[i] = s;
+    }
+    __syncthreads();
+}
+__device__ __forceinline__ void p2p_publish(const P2P& P, unsigned n) {
+    __syncthreads();
+    if (threadIdx.x == 0) *(volatile unsigned*)p2p_state(P.peers[P.rank], P.nacc, P.world) = n;
 }
 __global__ void __launch_bounds__(1024) dd_field_update_p2p_k(DDK k, P2P P, double* __restrict__ acc_sum,
                                                               double* __restrict__ wall_cum,
@@ -1070,15 +1100,21 @@ __global__ void __launch_bounds__(1024) dd_field_update_p2p_k(DDK k, P2P P, doub
                                                               double tol, int maxiter) {
     __shared__ double scratch[33];
     __shared__ double wl[2], wr[2];
-    if (ctl && *(volatile int*)ctl) return;       // the same decision on every rank: nobody waits for a rank that left
-    p2p_reduce(P, acc_sum);
+    // the same decision in every CTA and on every rank (ctl is only written at the end of an earlier launch):
+    // nobody waits for a rank that left
+    if (ctl && *(volatile int*)ctl) return;
+    const unsigned n = p2p_push(P);
+    if (blockIdx.x != 0) return;
+    p2p_collect(P, n, acc_sum);
     dd_field_update_body(k, acc_sum, wall_cum, E0, Es, E1, j1o, stats, Es_prev, rhist, ctl, tol, maxiter, scratch, wl, wr);
-    p2p_finish(P);
+    p2p_publish(P, n);
 }
 // the reduction alone (the j1 repair pass): sum[nacc] = sum over ranks, own accumulators zeroed
 __global__ void __launch_bounds__(1024) p2p_reduce_k(P2P P, double* __restrict__ sum) {
-    p2p_reduce(P, sum);
-    p2p_finish(P);
+    const unsigned n = p2p_push(P);
+    if (blockIdx.x != 0) return;
+    p2p_collect(P, n, sum);
+    p2p_publish(P, n);
 }
 
 // ---- function-level drop-ins ---------------------------------------------------------
@@ -2115,7 +2151,9 @@ int pic_dev_dd_field_update2(const pic_dd_params* p, double* acc, double* wall_c
 int pic_p2p_alloc(int64_t nacc, int world, void** dev_ptr, void* handle64) {
     PIC_REQUIRE(nacc > 0 && world >= 1 && world <= 64 && dev_ptr && handle64, "p2p_alloc: bad argument");
     static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is expected to be 64 bytes");
-    const size_t bytes = (size_t)nacc * sizeof(double) + (size_t)2 * world * sizeof(unsigned);
+    PIC_REQUIRE(nacc % 2 == 0, "p2p_alloc: nacc must be even (128-bit copies)");
+    // acc[nacc] | inbox[2][world][nacc] | ready[2][world] | nreal, cnt  (see dd_field_update_p2p_k)
+    const size_t bytes = (size_t)nacc * (1 + 2 * (size_t)world) * sizeof(double) + ((size_t)2 * world + 2) * sizeof(unsigned);
     void* p = nullptr;
     PIC_CHECK_CUDA(cudaMalloc(&p, bytes));
     PIC_CHECK_CUDA(cudaMemset(p, 0, bytes));
@@ -2157,8 +2195,10 @@ int pic_dev_p2p_reduce(const double* const* peers_dev, int rank, int world, uint
                        int* err, void* stream) {
     PIC_REQUIRE(peers_dev && sum && err && world >= 1 && world <= 64 && rank >= 0 && rank < world && nacc > 0,
                 "p2p_reduce: bad argument");
-    P2P P{(double* const*)peers_dev, rank, world, (int)nacc, seq, err};
-    p2p_reduce_k<<<1, 1024, 0, (cudaStream_t)stream>>>(P, sum);
+    (void)seq;                   // the kernels count the reductions themselves
+    PIC_REQUIRE(nacc % 2 == 0, "p2p_reduce: nacc must be even");
+    P2P P{(double* const*)peers_dev, rank, world, (int)nacc, err};
+    p2p_reduce_k<<<P2P_NB, 1024, 0, (cudaStream_t)stream>>>(P, sum);
     PIC_CHECK_LAUNCH();
     return PIC_OK;
 }
@@ -2172,8 +2212,9 @@ int pic_dev_dd_field_update_p2p(const pic_dd_params* p, const double* const* pee
     PIC_REQUIRE(!(ctl || rhist) || maxiter >= 1, "dd_field_update_p2p: maxiter must be >= 1 with ctl / rhist");
     PIC_REQUIRE(p->Ng <= 32768 && !(p->flags & 128), "dd_field_update_p2p: one-CTA field phase of the default build only");
     DDK k = make_ddk(p);
-    P2P P{(double* const*)peers_dev, rank, world, 2 * k.Ng + 4, seq, err};
-    dd_field_update_p2p_k<<<1, 1024, 0, (cudaStream_t)stream>>>(k, P, acc_sum, wall_cum, E0, Es, E1, j1, stats, Es_prev, rhist,
+    (void)seq;                   // the kernels count the reductions themselves
+    P2P P{(double* const*)peers_dev, rank, world, 2 * k.Ng + 4, err};
+    dd_field_update_p2p_k<<<P2P_NB, 1024, 0, (cudaStream_t)stream>>>(k, P, acc_sum, wall_cum, E0, Es, E1, j1, stats, Es_prev, rhist,
                                                                 ctl, tol, maxiter);
     PIC_CHECK_LAUNCH();
     return PIC_OK;

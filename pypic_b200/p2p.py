@@ -1,7 +1,8 @@
-"""Peer-memory accumulators for the particle decomposition (one process per GPU): every rank's
-grid accumulators live in a buffer that all ranks map through CUDA IPC, and the field kernel sums
-them over NVLink itself (pic_dev_dd_field_update_p2p) instead of calling a library all-reduce.
-torch.distributed is only used to exchange the 64-byte IPC handles at start-up."""
+"""Peer-memory accumulators for the particle decomposition (one process per GPU): every rank owns a
+buffer (its grid accumulators + an inbox with one slot per rank) that all ranks map through CUDA IPC;
+the field kernel pushes the accumulators into every rank's inbox over NVLink and sums its own inbox
+(pic_dev_dd_field_update_p2p) instead of calling a library all-reduce.  torch.distributed is only used
+to exchange the 64-byte IPC handles at start-up."""
 import ctypes as C
 
 import torch
