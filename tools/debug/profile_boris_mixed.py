@@ -51,7 +51,18 @@ for name, fused, lean in (("v1 kernels (push, BC, weight)", False, False), ("fus
         step()
     e1.record(); torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / steps
+    # the push (+ fused deposit) launch alone, right after a sort
+    st.sort_by_cell(grid)
+    k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    kms = []
+    for _ in range(4):
+        k0.record(); st.push_6D(dt, grid, deposit=fused); k1.record(); torch.cuda.synchronize()
+        kms.append(k0.elapsed_time(k1))
+        if fused:
+            grid.finish_fused_deposit(1.0, dt)
     st.check(); grid.check()
-    print("%-32s %8.3f ms/step  %.3e particle-steps/s" % (name, ms, N / ms * 1e3))
+    bpp = (7 * 16 + 3 * 8 + 1) if not lean else (4 * 16 + 3 * 8 + 1)
+    print("%-32s %8.3f ms/step  %.3e particle-steps/s   push launch %.3f ms (%d B/particle -> %.0f GB/s)"
+          % (name, ms, N / ms * 1e3, min(kms), bpp, N * bpp / min(kms) / 1e6))
     del st, grid
     torch.cuda.empty_cache()
