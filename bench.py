@@ -95,6 +95,7 @@ class ClockSampler(threading.Thread):
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
     NAMES = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+    PERIOD = float(os.environ.get("PIC_CLOCK_PERIOD_MS", "5")) * 1e-3     # seconds between NVML samples
 
     def __init__(self, index):
         super().__init__(daemon=True)
@@ -133,7 +134,7 @@ class ClockSampler(threading.Thread):
                 self.rows.append(self.sample())
             except Exception:
                 pass
-            time.sleep(0.005 if self.h is not None else 0.2)
+            time.sleep(self.PERIOD if self.h is not None else 0.2)
 
     def summary(self):
         if not self.rows:

@@ -118,6 +118,10 @@ class _Block:
         self.dead_idx = torch.empty(self.cap, dtype=torch.int32, device=dev)
         self.count = torch.zeros(1, dtype=torch.int64, device=dev)
         self.block_counts = torch.zeros(2 * (self.cap // 2048 + 2), dtype=torch.int64, device=dev)
+        # absorption log of the particle kernels (pic_dev_dd_picard_iter4): int32 [count,0,0,0 | {slot,orig,iteration,0} x cap]
+        self.dead_cap = int(max(1 << 16, self.cap // 64))
+        self.dead_buf = torch.zeros(4 + 4 * self.dead_cap, dtype=torch.int32, device=dev)
+        self.log_valid = False           # the log names every dead slot only after a step that started all-active
 
     # current / scratch views (the scratch always starts at slot 0 of the other allocation)
     @property
@@ -169,7 +173,14 @@ class SlabSheathSim:
         self.j0 = D.f64(g, dev, True)
         self.acc = D.f64(2 * g + 5, dev, True)       # [jh | j1 | 4 absorbed counts | one always-zero slot]
         self.wall_cum = D.f64(4, dev, True)
-        self.stats = D.f64(8, dev, True)
+        # [r, mean j1, EE, iterations | 4 words of reduction scratch | residual of every iteration of the step]
+        self.stats = D.f64(8 + self.maxiter, dev, True)
+        # enqueue-ahead Picard loop (see SheathSim.picard): the iterations the previous step needed are queued
+        # without a host round trip each, behind a device flag the field kernel raises when the loop ends
+        self.ctl = torch.zeros(1, dtype=torch.int32, device=dev)
+        self.enqueue_ahead = True
+        self._prev_k = 0
+        self._absorbed_local = torch.zeros(4, dtype=torch.float64, device=dev)
         self.range_err = torch.zeros(1, dtype=torch.int32, device=dev)
         self.sort_counts = torch.zeros(D.sort_counts_size(g), dtype=torch.int32, device=dev)
         self.cb_dev = torch.as_tensor(np.asarray(self.cb[1:-1], dtype=np.int64), device=dev)
@@ -226,7 +237,7 @@ class SlabSheathSim:
             blk.cur, blk.off = 0, 0
             blk.X[0][:blk.n].copy_(torch.as_tensor(np.ascontiguousarray(xs[keep])))
             blk.U[0][:blk.n].copy_(torch.as_tensor(np.ascontiguousarray(us[keep])))
-            blk.active.fill_(1)
+            blk.active.fill_(1); blk.log_valid = False
         if E0 is not None:
             self.E0.copy_(torch.as_tensor(np.ascontiguousarray(E0)))
 
@@ -242,7 +253,7 @@ class SlabSheathSim:
             _lib.call("pic_dev_init_uniform_maxwellian", D.ptr(blk.X[0]), D.ptr(blk.U[0]), None, None, blk.n, blk.n,
                       max(lo, 1e-12 * self.L), min(hi, self.L * (1 - 1e-12)), C.byref((C.c_double * 2)(*sig)),
                       C.byref((C.c_double * 2)(0., 0.)), seed, 100 + sp, self.rank * (1 << 40), D.stream())
-            blk.active.fill_(1)
+            blk.active.fill_(1); blk.log_valid = False
 
     def gather_particles(self):
         """All particles of both species on every rank (tests): lists of numpy arrays [x_e, u_e, x_i, u_i]."""
@@ -272,10 +283,21 @@ class SlabSheathSim:
             if self.local_dead[sp] == 0 and self.t > 0:
                 dead.append(0)
                 continue
-            _lib.call("pic_dev_compact_flags", D.ptr(blk.active), blk.n, 0, D.ptr(blk.dead_idx), D.ptr(blk.count),
-                      D.ptr(blk.block_counts), st)
-            dead.append(int(D.read_raw(blk.count, 1, np.int64)[0]))
-            self.kernel_launches += 3
+            # the slots the particle kernels logged while absorbing (a few hundred), sorted into index order;
+            # the flag scan only runs without a valid log (first step, overflow)
+            nd = -1
+            if blk.log_valid:
+                nd = int(D.read_raw(blk.dead_buf, 1, np.int32)[0])
+                if nd > blk.dead_cap:
+                    nd = -1
+                elif nd:
+                    blk.dead_idx[:nd] = torch.sort(blk.dead_buf[4:4 + 4 * nd].view(nd, 4)[:, 0]).values
+            if nd < 0:
+                _lib.call("pic_dev_compact_flags", D.ptr(blk.active), blk.n, 0, D.ptr(blk.dead_idx), D.ptr(blk.count),
+                          D.ptr(blk.block_counts), st)
+                nd = int(D.read_raw(blk.count, 1, np.int64)[0])
+                self.kernel_launches += 3
+            dead.append(nd)
         if W > 1:
             t = torch.tensor(dead, dtype=torch.int64, device=self.dev)
             allc = torch.empty(W * 2, dtype=torch.int64, device=self.dev)
@@ -425,27 +447,35 @@ class SlabSheathSim:
 
     # ------------------------------------------------------------------ one timestep
     def picard(self):
+        """PIC_L_DD.py:452-545 on slabs.  Every launch of an iteration (particle kernels, field kernel) is
+        guarded by the device flag `ctl`; the exchange between them is made of unguarded library calls, which
+        move zeros once the loop has ended (the accumulators are cleared by the last field update), so queued
+        iterations behind the end of the loop are harmless no-ops."""
         st = D.stream()
+        if self.stats.numel() < 8 + self.maxiter:
+            self.stats = D.f64(8 + self.maxiter, self.dev, True)
         self.Es.copy_(self.E0)
-        self.wall_cum.zero_(); self.stats.zero_()
-        self._absorbed_local = torch.zeros(4, dtype=torch.float64, device=self.dev)
-        r, k = 1.0, 0
+        self.wall_cum.zero_(); self.stats.zero_(); self.ctl.zero_()
+        self._absorbed_local.zero_()
         Pg = self._params(self.blocks[0])
-        while (r > self.tol) and (k < self.maxiter):
+        rhist = D.ptr(self.stats) + 8 * 8
+        Ng = self.Ng
+
+        def launch(j):
             ev = None
             if self.iter_events is not None:
                 ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
                 ev[0].record()
             for blk in self.blocks:
                 if blk.n:
-                    _lib.call("pic_dev_dd_picard_iter", C.byref(self._params(blk)), D.ptr(blk.x0), D.ptr(blk.u0), D.ptr(blk.x1),
-                              D.ptr(blk.u1), D.ptr(blk.active), D.ptr(self.Es), D.ptr(self.acc), 1 if k == 0 else 0,
-                              D.ptr(self.range_err), st)
+                    _lib.call("pic_dev_dd_picard_iter4", C.byref(self._params(blk)), D.ptr(blk.x0), D.ptr(blk.u0), D.ptr(blk.x1),
+                              D.ptr(blk.x1), D.ptr(blk.u1), D.ptr(blk.active), D.ptr(self.Es), D.ptr(self.acc), 1 if j == 0 else 0,
+                              D.ptr(self.range_err), D.ptr(self.ctl), D.ptr(blk.dead_buf), blk.dead_cap, None, j, st)
                     self.kernel_launches += 1
             if ev is not None:
                 ev[1].record()
                 self.iter_events.append(ev)
-            self._absorbed_local += self.acc[2 * self.Ng:2 * self.Ng + 4]   # this rank's own absorptions (before the exchange)
+            self._absorbed_local += self.acc[2 * Ng:2 * Ng + 4]   # this rank's own absorptions (before the exchange)
             if self.profile is not None:
                 import time
                 torch.cuda.synchronize(); t0 = time.perf_counter()
@@ -453,11 +483,27 @@ class SlabSheathSim:
                 torch.cuda.synchronize(); self.profile["exchange"] = self.profile.get("exchange", 0.0) + time.perf_counter() - t0
             else:
                 self.exchange_acc()
-            _lib.call("pic_dev_dd_field_update", C.byref(Pg), D.ptr(self.acc), D.ptr(self.wall_cum), D.ptr(self.E0),
-                      D.ptr(self.Es), D.ptr(self.E1), D.ptr(self.j0), D.ptr(self.stats), st)
+            _lib.call("pic_dev_dd_field_update2", C.byref(Pg), D.ptr(self.acc), D.ptr(self.wall_cum), D.ptr(self.E0),
+                      D.ptr(self.Es), D.ptr(self.E1), D.ptr(self.j0), D.ptr(self.stats), None, rhist, D.ptr(self.ctl),
+                      self.tol, self.maxiter, st)
             self.kernel_launches += 1
-            r = float(D.read_f64(self.stats, 1)[0])
-            k += 1
+
+        def outcome():
+            s_ = D.read_f64(self.stats, 8 + self.maxiter)
+            k_ = int(s_[3])
+            return k_, [float(v) for v in s_[8:8 + k_]]
+
+        k, hist, queued = 0, [], 0
+        if self.enqueue_ahead and self._prev_k and self.profile is None:
+            for j in range(min(self._prev_k, self.maxiter)):
+                launch(j); queued += 1
+            k, hist = outcome()
+        r = hist[-1] if hist else 1.0
+        while (r > self.tol) and (k < self.maxiter) and k == queued:
+            launch(k); queued += 1
+            k, hist = outcome()
+            r = hist[-1]
+        self._prev_k = k
         if k > 0:
             for blk in self.blocks:
                 blk.commit()
@@ -470,11 +516,18 @@ class SlabSheathSim:
         if self.profile is not None:
             return self._step_profiled()
         self.reinject()
+        self._reset_logs()
         if self.sort_every and self.t % self.sort_every == 0:
             self.migrate_sort()
         out = self.picard()
         self.t += 1
         return out
+
+    def _reset_logs(self):
+        """Every slot is alive after the re-injection: the absorption logs of the coming step start empty."""
+        for blk in self.blocks:
+            blk.dead_buf[:4].zero_()
+            blk.log_valid = True
 
     def _step_profiled(self):
         """step() with host-side wall-clock sections (synchronising; diagnostics only)."""
@@ -487,6 +540,7 @@ class SlabSheathSim:
             torch.cuda.synchronize(); pr[name] = pr.get(name, 0.0) + time.perf_counter() - t0
             return out
         section("reinject", self.reinject)
+        self._reset_logs()
         if self.sort_every and self.t % self.sort_every == 0:
             section("migrate_sort", self.migrate_sort)
         out = section("picard", self.picard)
