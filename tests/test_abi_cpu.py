@@ -46,6 +46,31 @@ def test_binding_table_matches_the_prototypes(lib):
         assert len(lib._SIGS[name]) == n, "%s: header has %d arguments, binding table %d" % (name, n, len(lib._SIGS[name]))
 
 
+def test_struct_layouts_match_the_header(lib, tmp_path):
+    """The ctypes mirrors of the parameter structs (pypic_b200/_lib.py) against the C compiler's view of
+    include/pic_b200.h: same size, same offset for every field (a mismatch would silently shift every
+    argument behind it)."""
+    import ctypes as C
+    import subprocess
+    pairs = [("pic_dd_params", lib.DDParams), ("pic_dd_prologue", lib.DDPrologue), ("pic_pypic_params", lib.PypicParams),
+             ("pic_l_params", lib.LParams), ("pic_gc_params", lib.GCParams)]
+    lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "pic_b200.h"', 'int main(void) {']
+    for cname, cls in pairs:
+        lines.append('printf("%s %%zu\\n", sizeof(%s));' % (cname, cname))
+        for fname, _ in cls._fields_:
+            lines.append('printf("%s.%s %%zu\\n", offsetof(%s, %s));' % (cname, fname, cname, fname))
+    lines += ['return 0;', '}']
+    src = tmp_path / "layout.c"
+    src.write_text("\n".join(lines))
+    exe = tmp_path / "layout"
+    subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)], check=True)
+    out = dict(l.split() for l in subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.splitlines())
+    for cname, cls in pairs:
+        assert int(out[cname]) == C.sizeof(cls), cname
+        for fname, _ in cls._fields_:
+            assert int(out["%s.%s" % (cname, fname)]) == getattr(cls, fname).offset, (cname, fname)
+
+
 def test_version_and_error_string(lib):
     l = lib.load()
     assert l.pic_version() >= 100

@@ -399,7 +399,8 @@ def test_pygcpic_host_grid_n0_update_matches_device_grid():
     assert np.isfinite(hg.n0) and hg.n0 > 0
 
 
-def test_pygcpic_run_sheath_with_ionisation_golden(golden):
+@pytest.mark.parametrize("fused_min", [None, 0])          # 0: the mixed-species fused kernel's ABI (its per-particle routine at this size)
+def test_pygcpic_run_sheath_with_ionisation_golden(golden, fused_min):
     """N3: Monte-Carlo ionisation of neutral H and B(0..2), mid-domain exits of wall-born particles
     and the reactivate-or-delete rule coupled through the running source-ion count, against the
     reference's own objects driven through pic_bca_aps' particle loop (tests/golden/gc_ion.npz,
@@ -432,6 +433,8 @@ def test_pygcpic_run_sheath_with_ionisation_golden(golden):
     assert np.array_equal([p_.from_wall for p_ in parts], g["from_wall_init"])
     st = G.ParticleStore.from_arrays(r, g["cs_init"], g["m_init"], g["p2c_init"], Z=g["Z_init"],
                                      from_wall=g["from_wall_init"], B=B)
+    if fused_min is not None:
+        st.FUSED_MIN = fused_min
     grid = G.GridDev(ngd, Ld, Te)
     src = G.source_distribution_6D(host_grid, Ti, G.mp)
     out = G.run_sheath(grid, st, dt, 20, source_N, src, p2c, G.mp, ionize_Te=Te)
