@@ -437,8 +437,80 @@ def _ionizing_decisions(grid, store, dt, ionize_Te, inactive_entry, contrib_entr
     return dec, np.asarray(react, dtype=np.int64), np.array(r_new).reshape(-1, 7), len(deleted), tall
 
 
+def _global_decisions(grid, store, dt, ionize_Te, inactive_entry, contrib_entry, Z, source_N, source):
+    """The decisions of one pass of pygcpic.py:1509-1549 with the particle list SHARDED over the ranks of
+    grid.comm (contiguous index ranges in rank order, as every sharded path of this package): every rank
+    gathers every rank's event slots (slots inactive at loop entry; ionisation attempts when ionize_Te is
+    given), runs the ONE sequential pass of the reference over the global list -- consuming np.random and the
+    source generator exactly as a single process would, so all ranks must hold the same stream -- and keeps
+    its own share.  Also serves a single rank (event-loop formulation of ParticleStore.decide).
+    Returns (decision tensor, own re-activated slots, their 7-vectors, global number deleted, global number
+    re-activated, global tallies)."""
+    from pypic_b200 import ionization as ION
+    comm = grid.comm
+    world = comm.world if (comm is not None and comm.enabled) else 1
+    rank = comm.rank if world > 1 else 0
+    N, dev = store.N, store.dev
+    if ionize_Te is not None:
+        prob, elig, mx, contrib = store.post_push(grid, dt, ION.rates(ionize_Te), Z)
+        ev_ion = torch.nonzero(elig[:N] == 1).flatten()
+    else:
+        contrib = store.source_ion_flags(Z)
+        mx = torch.zeros(max(N, 1), dtype=torch.int8, device=dev)
+        prob = torch.zeros(max(N, 1), dtype=torch.float64, device=dev)
+        ev_ion = torch.zeros(0, dtype=torch.int64, device=dev)
+    ev_in = torch.nonzero(inactive_entry[:N] == 1).flatten()
+    ev = torch.cat([ev_ion, ev_in])
+    kind = torch.cat([torch.zeros_like(ev_ion), torch.ones_like(ev_in)])
+    order = torch.argsort(ev)
+    ev, kind = ev[order], kind[order]
+    ca = contrib[:N].to(torch.int64); ce = contrib_entry[:N].to(torch.int64)
+    A = torch.cumsum(ca, 0) - ca                                  # slots before the event, updated state
+    Bs = torch.flip(torch.cumsum(torch.flip(ce, [0]), 0), [0])    # slots from the event on, entry state
+    h = lambda t: t[ev].cpu().numpy()
+    mine = dict(N=N, ev=ev.cpu().numpy(), kind=kind.cpu().numpy(), prob=h(prob), cs=h(store.charge_state), Z=h(store.Z),
+                p2c=h(store.p2c), mx=h(mx), A=h(A), Bs=h(Bs), ca=int(ca.sum().item()) if N else 0,
+                ce=int(ce.sum().item()) if N else 0, mxn=int(mx[:N].sum().item()) if N else 0)
+    parts = [mine]
+    if world > 1:
+        import torch.distributed as dist
+        parts = [None] * world
+        dist.all_gather_object(parts, mine, group=comm.group)
+    lo = [0]; Aoff = [0]
+    for q in parts:
+        lo.append(lo[-1] + q["N"]); Aoff.append(Aoff[-1] + q["ca"])
+    Boff = [sum(q["ce"] for q in parts[r + 1:]) for r in range(world)]
+    cat = lambda key, add=None: np.concatenate([np.asarray(q[key]) + (0 if add is None else add[r]) for r, q in enumerate(parts)])
+    ev_g = cat("ev", lo)
+    r_all = []
+    ionised, new_cs, added, react, deleted = ION.run_events(
+        ev_g, cat("kind"), cat("prob"), cat("cs"), cat("Z"), cat("p2c"), cat("mx"), cat("A", Aoff), cat("Bs", Boff),
+        int(Z), int(source_N), lambda i: r_all.append(next(source)))
+    a, b = lo[rank], lo[rank + 1]
+    own = lambda lst: np.asarray([i - a for i in lst if a <= i < b], dtype=np.int64)
+    if ionised:
+        sel = [j for j, i in enumerate(ionised) if a <= i < b]
+        if sel:
+            ii = torch.as_tensor(own(ionised), device=dev)
+            store.charge_state[ii] = torch.as_tensor(np.asarray([new_cs[j] for j in sel]), device=dev)
+            store.invalidate_uniform()
+        for p_ in added:                       # the Boltzmann reference density counts every rank's additions
+            grid.add_particles(p_)
+    dec = torch.zeros(max(N, 1), dtype=torch.int8, device=dev)
+    idx = own(react)
+    if len(idx):
+        dec[torch.as_tensor(idx, device=dev)] = 1
+    dl = own(deleted)
+    if len(dl):
+        dec[torch.as_tensor(dl, device=dev)] = 2
+    r_new = np.array([r_all[j] for j, i in enumerate(react) if a <= i < b]).reshape(-1, 7)
+    Zi = cat("Z")[np.searchsorted(ev_g, np.asarray(ionised, dtype=np.int64))] if ionised else np.zeros(0)
+    tall = dict(ionised_h=int((Zi == 1).sum()), ionised_b=int((Zi == 5).sum()), midexit=sum(q["mxn"] for q in parts))
+    return dec, idx, r_new, len(deleted), len(react), tall
+
+
 def run_sheath(grid, store, dt, steps, source_N, source, p2c, m, charge_state=1, Z=1, time=0.0, on_step=None,
-               ionize_Te=None):
+               ionize_Te=None, event_loop=False):
     """Device-resident time loop with the structure of pic_bca_aps' particle phase
     (pygcpic.py:1486-1563, without the BCA coupling; Monte-Carlo ionisation :350-458 and the
     mid-domain exit of wall-born particles :1530-1541 when ionize_Te is given):
@@ -447,9 +519,17 @@ def run_sheath(grid, store, dt, steps, source_N, source, p2c, m, charge_state=1,
         [gather + Boris + BC fused] -> reactivate-or-delete decision (prefix scan) ->
         re-activation from `source` (host generator, legacy RNG order) -> stable compaction.
 
-    grid: GridDev, store: ParticleStore.  Returns a dict of per-step tallies."""
+    grid: GridDev, store: ParticleStore.  Returns a dict of per-step tallies.
+
+    Sharded runs (GridDev(comm=) over more than one rank, every rank holding a contiguous index range of the
+    reference's particle list, rank order = index order, and the SAME np.random / source-generator state): the
+    deposits are all-reduced by GridDev, the order-dependent decisions are taken over the global event list on
+    every rank (_global_decisions), and the per-step tallies are global.  event_loop=True forces that
+    formulation on a single rank (tests)."""
     out = dict(length=[], hits=[], deleted=[], reactivated=[], n0=[], ekin=[], angle=[], ionised_h=[], ionised_b=[],
                midexit=[])
+    comm = getattr(grid, "comm", None)
+    sharded = comm is not None and comm.enabled and comm.world > 1
     for _ in range(int(steps)):
         time += dt
         if grid.have_fused_n:
@@ -472,7 +552,24 @@ def run_sheath(grid, store, dt, steps, source_N, source, p2c, m, charge_state=1,
         # (:871-883), so that case deposits in its own pass at the top of the next step.
         hits = store.push_6D(dt, grid, deposit=ionize_Te is None)
         ke, ang, _ = store.wall_hit_tallies()
-        if ionize_Te is None:
+        if sharded or event_loop:
+            dec, idx, r_new, n_del, n_react, tall = _global_decisions(grid, store, dt, ionize_Te, inactive_entry, contrib_entry,
+                                                                      Z, source_N, source)
+            if len(idx):
+                store.reactivate(idx, r_new, p2c, m, charge_state, Z, time, grid)
+            for _k in range(n_react - len(idx)):       # the other ranks' re-activations count in the reference density
+                grid.add_particles(p2c)
+            if ionize_Te is not None:
+                for k_, v_ in tall.items():
+                    out[k_].append(v_)
+            if sharded:
+                import torch.distributed as dist
+                got = [None] * comm.world
+                dist.all_gather_object(got, (hits, ke, ang, store.N - int((dec[:store.N] == 2).sum().item())), group=comm.group)
+                hits = sum(g_[0] for g_ in got)
+                ke = np.concatenate([np.asarray(g_[1]) for g_ in got]); ang = np.concatenate([np.asarray(g_[2]) for g_ in got])
+                n_global_after = sum(g_[3] for g_ in got)
+        elif ionize_Te is None:
             contrib_after = store.source_ion_flags(Z)
             dec, n_react, n_del = store.decide(inactive_entry, contrib_entry, contrib_after, source_N)
             if n_react:
@@ -490,7 +587,7 @@ def run_sheath(grid, store, dt, steps, source_N, source, p2c, m, charge_state=1,
             for k_, v_ in tall.items():
                 out[k_].append(v_)
         store.compact(dec)
-        out["length"].append(store.N); out["hits"].append(hits); out["deleted"].append(n_del)
+        out["length"].append(n_global_after if sharded else store.N); out["hits"].append(hits); out["deleted"].append(n_del)
         out["reactivated"].append(n_react); out["n0"].append(grid.n0); out["ekin"].append(ke); out["angle"].append(ang)
         if on_step is not None:
             n_before = store.N

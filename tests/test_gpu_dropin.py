@@ -399,8 +399,8 @@ def test_pygcpic_host_grid_n0_update_matches_device_grid():
     assert np.isfinite(hg.n0) and hg.n0 > 0
 
 
-@pytest.mark.parametrize("fused_min", [None, 0])          # 0: the mixed-species fused kernel's ABI (its per-particle routine at this size)
-def test_pygcpic_run_sheath_with_ionisation_golden(golden, fused_min):
+@pytest.mark.parametrize("fused_min,event_loop", [(None, False), (0, False), (None, True)])
+def test_pygcpic_run_sheath_with_ionisation_golden(golden, fused_min, event_loop):
     """N3: Monte-Carlo ionisation of neutral H and B(0..2), mid-domain exits of wall-born particles
     and the reactivate-or-delete rule coupled through the running source-ion count, against the
     reference's own objects driven through pic_bca_aps' particle loop (tests/golden/gc_ion.npz,
@@ -437,7 +437,9 @@ def test_pygcpic_run_sheath_with_ionisation_golden(golden, fused_min):
         st.FUSED_MIN = fused_min
     grid = G.GridDev(ngd, Ld, Te)
     src = G.source_distribution_6D(host_grid, Ti, G.mp)
-    out = G.run_sheath(grid, st, dt, 20, source_N, src, p2c, G.mp, ionize_Te=Te)
+    # fused_min=0: the mixed-species fused kernel's ABI (its per-particle routine at this size); event_loop: the
+    # global-event-list formulation of the decisions that sharded runs use
+    out = G.run_sheath(grid, st, dt, 20, source_N, src, p2c, G.mp, ionize_Te=Te, event_loop=event_loop)
     assert np.array_equal(out["length"], g["h_length"]) and np.array_equal(out["hits"], g["h_hits"])
     assert np.array_equal(out["deleted"], g["h_ndel"]) and np.array_equal(out["reactivated"], g["h_nreact"])
     assert np.array_equal(out["ionised_h"], g["h_nion_h"]) and np.array_equal(out["ionised_b"], g["h_nion_b"])

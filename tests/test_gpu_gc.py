@@ -380,7 +380,8 @@ def test_lean_store_boris_is_bit_identical_in_x_and_v():
     assert np.array_equal(a[0][:, 6], b[0][:, 6])
 
 
-def test_mini_driver_fused_path_vs_reference_golden(golden):
+@pytest.mark.parametrize("event_loop", [False, True])     # True: the global-event-list formulation the sharded runs use
+def test_mini_driver_fused_path_vs_reference_golden(golden, event_loop):
     """pygcpic.run_sheath with the fused push+deposit path forced on (uniform store): the same
     integer outcomes per step as the reference's object loop."""
     import pygcpic as G
@@ -395,7 +396,7 @@ def test_mini_driver_fused_path_vs_reference_golden(golden):
     st = G.ParticleStore.from_arrays(r, 1.0, G.mp, p2c, Z=1, B=g["B"])
     st.FUSED_MIN = 0
     src = G.source_distribution_6D(host_grid, Ti, G.mp)
-    out = G.run_sheath(grid, st, dt, 25, source_N, src, p2c, G.mp)
+    out = G.run_sheath(grid, st, dt, 25, source_N, src, p2c, G.mp, event_loop=event_loop)
     assert np.array_equal(out["length"], g["drv_len"]) and np.array_equal(out["hits"], g["drv_hits"])
     assert np.array_equal(out["deleted"], g["drv_ndel"]) and np.array_equal(out["reactivated"], g["drv_nreact"])
     assert relmax(out["n0"], g["drv_n0"]) < 1e-9

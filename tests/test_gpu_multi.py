@@ -47,6 +47,21 @@ def test_two_rank_peer_memory_reduction_matches_nccl():
     assert out["ok"], out
 
 
+def test_two_rank_pygcpic_run_sheath_matches_single_rank():
+    """pygcpic.run_sheath with the particle list sharded over 2 ranks (all-reduced deposits, decisions over the
+    global event list, RNG / source generator consumed as by one process) vs one rank: tools/gc_sharded_check.py."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
+           "127.0.0.1", "--master-port", "29536", os.path.join(ROOT, "tools", "gc_sharded_check.py"), "60000"]
+    res = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=ROOT)
+    assert res.returncode == 0, res.stderr[-2000:]
+    out = json.loads([l for l in res.stdout.splitlines() if l.startswith("{")][-1])
+    assert out["ok"], out
+    assert sum(out["uniform_fused"]["reactivated"]) > 0 and sum(out["mixed_ionising"]["ionised_h"]) > 0
+
+
 def test_two_rank_slab_decomposition_matches_single_rank():
     """Spatial (slab) decomposition: halo exchange + particle migration + routed re-injection on 2
     ranks vs the same global particles on one rank (tools/slab_check.py)."""
