@@ -128,7 +128,7 @@ def initialize(system, N, density, Kp, perturbation, dx, Ng, Te, Ti, L, X):
 
 
 def main_i(T, nplot, N=40000, Ng=51, dt=1E-12, dx=0.00001, Ti=10.0 * 11600., Te=10.0 * 11600., density=1E19,
-           gamma=0.0, tol=1E-5, maxiter=20, outdir='.', rng='host', result=None, sort_every=8, vion_after=2000):
+           gamma=0.0, tol=1E-5, maxiter=20, outdir='.', rng='host', result=None, sort_every=None, vion_after=2000):
     """PIC_L_DD.main_i (PIC_L_DD.py:316-644).  The positional signature is the reference's;
     the keyword arguments default to its hard-coded literals.  `result` (a dict) receives
     the time series and the final state.

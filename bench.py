@@ -40,7 +40,9 @@ def parse():
     ap.add_argument("--particles-per-gpu", type=float, default=2e8)
     ap.add_argument("--total-particles", type=float, default=0, help="strong scaling: fixed total (e.g. 1e9)")
     ap.add_argument("--cells", type=int, default=4096)
-    ap.add_argument("--sort-every", type=int, default=8)
+    ap.add_argument("--sort-every", type=int, default=None,
+                    help="steps between cell sorts (default: 12 for the sheath on grids the wide-window kernel serves, "
+                         "<= 4352 nodes, with the particle decomposition and the default deposit; 8 otherwise)")
     ap.add_argument("--heavy-sort-every", type=int, default=1, help="every n-th sort also re-sorts the ions (1 = always)")
     ap.add_argument("--deposit", default="window", choices=["window", "window-det", "window-blocked", "window-big", "window-ldg", "warp", "atomic"])
     ap.add_argument("--workload", default="sheath", choices=["sheath", "explicit", "pypic", "boris"],
@@ -70,7 +72,12 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-sample", type=float, default=4e6, help="particles in the CPU-baseline sample")
     ap.add_argument("--e2e-steps", type=int, default=16)
-    return ap.parse_args()
+    args = ap.parse_args()
+    if args.sort_every is None:
+        wide = (args.workload == "sheath" and args.decomposition == "particle" and args.cells + 1 <= 4352
+                and args.deposit in ("window", "window-det", "window-blocked") and os.environ.get("PIC_V6_NARROW") != "1")
+        args.sort_every = 12 if wide else 8
+    return args
 
 
 def workload(args, world):

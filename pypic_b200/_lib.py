@@ -187,9 +187,11 @@ _lib = None
 
 def load():
     """Loads the shared library (once).  Raises PicError if it is missing."""
-    global _lib
+    global _lib, LIB_PATH
     if _lib is not None:
         return _lib
+    if os.environ.get("PIC_LIB_PATH"):             # A/B runs of differently built libraries (tools/gpu_runs)
+        LIB_PATH = os.environ["PIC_LIB_PATH"]
     if not os.path.isfile(LIB_PATH):
         raise PicError(PIC_ERR_NODEVICE,
                        "%s not found -- run `python -m pypic_b200.build` (or __graft_entry__.build()); "

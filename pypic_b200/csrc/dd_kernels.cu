@@ -501,17 +501,28 @@ __global__ void __launch_bounds__(V5_T, 1) dd_picard_iter_v5_k(
 // deposits go straight to the global accumulators (fire-and-forget RED), which frees the
 // shared memory the fallback tiles of v5 used for the ring.
 #define V6_T 512
+// nodes per private deposit window (per tile, per thread) and ring stages.  The window is centred on the slice's
+// mean cell after a sort and the electrons then drift ballistically (~0.13 cell per step at 1 sigma): a
+// contribution that has left the window is a global RED.  7 nodes lose ~3 sigma after 8 steps.  Two builds of the
+// kernel: WIDE (15 nodes, 3 stages: 2-2.5 % faster over a sort interval and good for 12 steps between sorts,
+// profiles/r2_window_width_sheath.txt) when the field tile leaves room for it (Ng <= 4352), else 7 nodes / 4 stages
+// (Ng <= ~9000, and the large-grid build).
+#ifndef V6_W
 #define V6_W 7
-#define V6_ROWS 16
+#endif
 #ifndef V6_NST
 #define V6_NST 4
 #endif
+#define V6_W_WIDE 15
+#define V6_NST_WIDE 3
+#define V6_ROWS 16
 #define V6_CHUNK (V6_T * 2 * V6_ROWS)
 
+template <int W>
 __device__ __forceinline__ void win_add6(const DDK& k, double* myw, double* acc, int wb, int tile, int Ng, int c, double vL, double vR) {
     const unsigned d = (unsigned)(c - wb);
-    if (d <= (unsigned)(V6_W - 2)) {
-        double* p = myw + (tile * V6_W + d) * V6_T;
+    if (d <= (unsigned)(W - 2)) {
+        double* p = myw + (tile * W + d) * V6_T;
         p[0] += vL; p[V6_T] += vR;
     } else { acc_add(k, acc, tile * Ng + c, vL); acc_add(k, acc, tile * Ng + c + 1, vR); }
 }
@@ -582,7 +593,7 @@ __device__ __forceinline__ void dd_fast6(const FastC& c, const double* __restric
 // inside the domain at entry -> the fast-path X1,U1 are the exact values, the walls are tested
 // with the reference's comparisons and a survivor deposits into the window (or the global
 // accumulators); (3) everything else -> dd_particle_slow (IEEE divisions).
-template <bool FIRST, bool J1>
+template <bool FIRST, bool J1, int W>
 __device__ __forceinline__ void dd_medium(const DDK& k, const FastC& fc, long long i, double X0, double U0, double pX1,
                                           const FastO6& o, int act, bool straddle, bool sp, const double* sF, double* myw,
                                           int wb, double* __restrict__ acc, int* s_cnt, double* x1,
@@ -601,8 +612,8 @@ __device__ __forceinline__ void dd_medium(const DDK& k, const FastC& fc, long lo
         }
         if (o.fr <= PIC_HI_SPAN && o.ps < fc.hi_Lm1) {
             x1[i] = o.X1; if (u1) u1[i] = o.U1;
-            win_add6(k, myw, acc, wb, 0, k.Ng, o.cH, o.hL, o.hR);
-            if (J1) win_add6(k, myw, acc, wb, 1, k.Ng, o.cF, o.fL, o.fR);
+            win_add6<W>(k, myw, acc, wb, 0, k.Ng, o.cH, o.hL, o.hR);
+            if (J1) win_add6<W>(k, myw, acc, wb, 1, k.Ng, o.cF, o.fL, o.fR);
             return;
         }
     }
@@ -611,13 +622,15 @@ __device__ __forceinline__ void dd_medium(const DDK& k, const FastC& fc, long lo
     if (so.bad) atomicAdd(&s_cnt[0], so.bad);
 }
 
-template <bool FIRST, bool WU, bool BIG = false>
+template <bool FIRST, bool WU, bool BIG = false, bool WIDE = false>
 __global__ void __launch_bounds__(V6_T, 1) dd_picard_iter_v6_k(
     const __grid_constant__ DDK k, int nchunks_fr, const double* __restrict__ x0, const double* __restrict__ u0,
     const double* x1i, double* x1, double* u1, int8_t* __restrict__ active, const double* __restrict__ Es,
     double* __restrict__ acc, int* __restrict__ range_err, int* __restrict__ sched) {
     extern __shared__ __align__(128) double sm[];
     __shared__ int s_cnt[8];
+    constexpr int W = WIDE ? V6_W_WIDE : V6_W, NST = WIDE ? V6_NST_WIDE : V6_NST;
+    static_assert(W >= 5 && W <= 16, "one lane per (column, half-warp) in the window flush");
     if (k.done && *(const volatile int*)k.done) return;
     unsigned long long* const tbuf = g_cta_timer;
     if (tbuf && threadIdx.x == 0) tbuf[2 * blockIdx.x] = gtimer();
@@ -625,9 +638,9 @@ __global__ void __launch_bounds__(V6_T, 1) dd_picard_iter_v6_k(
     // field tile (whole grid) or, in the large-grid build, one V6_EW-node window per warp
     const int NgP = BIG ? (V6_T / 32) * V6_EW : ((Ng + 15) & ~15);   // keeps what follows 128-byte aligned
     double* sF = sm;
-    double* win = sm + NgP;                          // private windows [2*V6_W][V6_T]
-    double* ring = win + 2 * V6_W * V6_T;            // [warp][stage][x0|u0|x1][64]
-    unsigned long long* bars = (unsigned long long*)(ring + (V6_T / 32) * V6_NST * 192);   // [warp][stage]
+    double* win = sm + NgP;                          // private windows [2*W][V6_T]
+    double* ring = win + 2 * W * V6_T;            // [warp][stage][x0|u0|x1][64]
+    unsigned long long* bars = (unsigned long long*)(ring + (V6_T / 32) * NST * 192);   // [warp][stage]
     if (!BIG) for (int i = threadIdx.x; i < Ng; i += V6_T) sF[i] = Es[i];
     double* const wE = sm + (threadIdx.x >> 5) * V6_EW;     // BIG: this warp's field window
     const double* const fE = BIG ? wE : sF;                 // what the fast path gathers from
@@ -639,19 +652,19 @@ __global__ void __launch_bounds__(V6_T, 1) dd_picard_iter_v6_k(
     int eb = 0;
     double* myw = win + threadIdx.x;
 #pragma unroll
-    for (int n = 0; n < 2 * V6_W; ++n) myw[n * V6_T] = 0.0;
+    for (int n = 0; n < 2 * W; ++n) myw[n * V6_T] = 0.0;
     if (threadIdx.x < 8) s_cnt[threadIdx.x] = 0;
     const unsigned full = 0xffffffffu;
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
     const int wbase = threadIdx.x & ~31;
     const int NOWIN = -0x40000000;
-    const double* wring = ring + warp * (V6_NST * 192);
+    const double* wring = ring + warp * (NST * 192);
     const uint32_t ring_s = smem_u32(wring);
-    const uint32_t bar_s = smem_u32(bars + warp * V6_NST);
+    const uint32_t bar_s = smem_u32(bars + warp * NST);
     if (lane == 0) {
 #pragma unroll
-        for (int s = 0; s < V6_NST; ++s) mbar_init(bar_s + 8 * s, 1);
+        for (int s = 0; s < NST; ++s) mbar_init(bar_s + 8 * s, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
@@ -676,7 +689,7 @@ __global__ void __launch_bounds__(V6_T, 1) dd_picard_iter_v6_k(
         return __shfl_sync(full, v, 0) + nwarps_total;
     };
     const uint32_t row_bytes = FIRST ? 1024u : 1536u;
-    // ---- producer: stateless -- the row requested is always the one V6_NST rows ahead of the row
+    // ---- producer: stateless -- the row requested is always the one NST rows ahead of the row
     // being consumed and goes into the stage that row just drained, so every quantity is derived
     // from the consumer's own loop variables (nothing accumulates across iterations) ----
     auto issue = [&](long long base, int st) {
@@ -691,27 +704,32 @@ __global__ void __launch_bounds__(V6_T, 1) dd_picard_iter_v6_k(
     int cur_slice = (int)blockIdx.x * (V6_T / 32) + warp;
     if (cur_slice < nslices) {
 #pragma unroll
-        for (int s = 0; s < V6_NST; ++s) issue((long long)cur_slice * (64 * V6_ROWS) + 64 * s, s);
+        for (int s = 0; s < NST; ++s) issue((long long)cur_slice * (64 * V6_ROWS) + 64 * s, s);
     }
     // column sums of the warp's 32 private windows -> global accumulators, windows cleared
     auto flush_windows = [&](int wbase_node) {
         __syncwarp();
         if (wbase_node != NOWIN) {
-            double s = 0.0;
+            // one lane per (column, half of the warp's 32 windows); the jh tile, then -- only an iteration that
+            // deposits j1 ever writes it -- the j1 tile
             const int n = lane >> 1, half = lane & 1;
-            if (lane < 4 * V6_W) {
-                const double* col = win + n * V6_T + wbase + half * 16;
 #pragma unroll
-                for (int j = 0; j < 16; ++j) s += col[(j + n) & 15];
-            }
-            s += __shfl_xor_sync(full, s, 1);
-            if (lane < 4 * V6_W && half == 0) {
-                int node = wbase_node + (n < V6_W ? n : n - V6_W);
-                if (node >= 0 && node < Ng && s != 0.0) acc_add(k, acc, (n < V6_W ? 0 : Ng) + node, s);
+            for (int tile = 0; tile < (WU ? 2 : 1); ++tile) {
+                double s = 0.0;
+                if (n < W) {
+                    const double* col = win + (tile * W + n) * V6_T + wbase + half * 16;
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) s += col[(j + n) & 15];
+                }
+                s += __shfl_xor_sync(full, s, 1);
+                if (n < W && half == 0) {
+                    const int node = wbase_node + n;
+                    if (node >= 0 && node < Ng && s != 0.0) acc_add(k, acc, tile * Ng + node, s);
+                }
             }
             __syncwarp();
 #pragma unroll
-            for (int n2 = 0; n2 < 2 * V6_W; ++n2) myw[n2 * V6_T] = 0.0;
+            for (int n2 = 0; n2 < (WU ? 2 : 1) * W; ++n2) myw[n2 * V6_T] = 0.0;
             __syncwarp();
         }
     };
@@ -742,7 +760,7 @@ __global__ void __launch_bounds__(V6_T, 1) dd_picard_iter_v6_k(
             if (!FIRST) pX1 = *(const double2*)(sb + 128);
             if (FIRST && k.mom) { ms1 += U0.x + U0.y; ms2 += U0.x * U0.x + U0.y * U0.y; }
             const int st_cur = stage;
-            if (++stage == V6_NST) { stage = 0; phase ^= 1u; }
+            if (++stage == NST) { stage = 0; phase ^= 1u; }
             bool straddle = false, sp = sp_slice;
             if (mixed) {
                 const long long rstart = cbase + 64 * row;
@@ -770,11 +788,11 @@ __global__ void __launch_bounds__(V6_T, 1) dd_picard_iter_v6_k(
                 // window base: centre on the mean deposit cell of the warp's first row
                 int nok = __reduce_add_sync(full, (ra ? 0 : 1) + (rb ? 0 : 1));
                 int sum = __reduce_add_sync(full, (ra ? 0 : a.cH) + (rb ? 0 : b.cH));
-                wb = nok ? sum / nok - (V6_W - 2) / 2 : NOWIN;
+                wb = nok ? sum / nok - (W - 2) / 2 : NOWIN;
             }
             const unsigned dah = (unsigned)(a.cH - wb), daf = (unsigned)(a.cF - wb);
             const unsigned dbh = (unsigned)(b.cH - wb), dbf = (unsigned)(b.cF - wb);
-            const bool inwin = (WU ? max(__vimax3_u32(dah, daf, dbh), dbf) : max(dah, dbh)) <= (unsigned)(V6_W - 2);
+            const bool inwin = (WU ? max(__vimax3_u32(dah, daf, dbh), dbf) : max(dah, dbh)) <= (unsigned)(W - 2);
             if (!(ra | rb)) {
                 // the common case: two 128-bit streaming stores and eight conflict-free private RMWs;
                 // a lane whose particles drifted out of the warp's window since the last sort falls
@@ -783,14 +801,14 @@ __global__ void __launch_bounds__(V6_T, 1) dd_picard_iter_v6_k(
                 if (WU) __stcs((double2*)(u1 + ci), make_double2(a.U1, b.U1));
                 if (inwin) {
                     double* p = myw + dah * V6_T; p[0] += a.hL; p[V6_T] += a.hR;
-                    if (WU) { p = myw + (V6_W + daf) * V6_T; p[0] += a.fL; p[V6_T] += a.fR; }
+                    if (WU) { p = myw + (W + daf) * V6_T; p[0] += a.fL; p[V6_T] += a.fR; }
                     p = myw + dbh * V6_T; p[0] += b.hL; p[V6_T] += b.hR;
-                    if (WU) { p = myw + (V6_W + dbf) * V6_T; p[0] += b.fL; p[V6_T] += b.fR; }
+                    if (WU) { p = myw + (W + dbf) * V6_T; p[0] += b.fL; p[V6_T] += b.fR; }
                 } else {
-                    win_add6(k, myw, acc, wb, 0, Ng, a.cH, a.hL, a.hR);
-                    if (WU) win_add6(k, myw, acc, wb, 1, Ng, a.cF, a.fL, a.fR);
-                    win_add6(k, myw, acc, wb, 0, Ng, b.cH, b.hL, b.hR);
-                    if (WU) win_add6(k, myw, acc, wb, 1, Ng, b.cF, b.fL, b.fR);
+                    win_add6<W>(k, myw, acc, wb, 0, Ng, a.cH, a.hL, a.hR);
+                    if (WU) win_add6<W>(k, myw, acc, wb, 1, Ng, a.cF, a.fL, a.fR);
+                    win_add6<W>(k, myw, acc, wb, 0, Ng, b.cH, b.hL, b.hR);
+                    if (WU) win_add6<W>(k, myw, acc, wb, 1, Ng, b.cF, b.fL, b.fR);
                 }
             } else {
                 // one flag load for the pair (ci is even); dead and freshly absorbed particles are
@@ -800,18 +818,18 @@ __global__ void __launch_bounds__(V6_T, 1) dd_picard_iter_v6_k(
                     const short fl = *(const short*)(active + ci);
                     acta = (int)(signed char)(fl & 0xff); actb = (int)(signed char)(fl >> 8);
                 }
-                dd_medium<FIRST, WU>(k, fc, ci, X0.x, U0.x, pX1.x, a, acta, straddle, sp, gE, myw, wb, acc, s_cnt, x1, WU ? u1 : nullptr, active);
-                dd_medium<FIRST, WU>(k, fc, ci + 1, X0.y, U0.y, pX1.y, b, actb, straddle, sp, gE, myw, wb, acc, s_cnt, x1, WU ? u1 : nullptr, active);
+                dd_medium<FIRST, WU, W>(k, fc, ci, X0.x, U0.x, pX1.x, a, acta, straddle, sp, gE, myw, wb, acc, s_cnt, x1, WU ? u1 : nullptr, active);
+                dd_medium<FIRST, WU, W>(k, fc, ci + 1, X0.y, U0.y, pX1.y, b, actb, straddle, sp, gE, myw, wb, acc, s_cnt, x1, WU ? u1 : nullptr, active);
             }
-            // Refill the stage this row drained with the row V6_NST ahead (possibly in the next chunk).
+            // Refill the stage this row drained with the row NST ahead (possibly in the next chunk).
             // This must not happen before every lane's LDS of the stage has EXECUTED: an LDS can sit
             // in the load/store queue behind a burst of global atomics for longer than a bulk copy
             // takes, and the copy (async proxy) would then overwrite the slot under it.  Every lane
             // has consumed all three loaded vectors by now (the branch above depends on them), and
             // the barrier orders those uses before the elected lane's copy.
             __syncwarp();
-            if (row < V6_ROWS - V6_NST) issue(cbase + 64 * (row + V6_NST), st_cur);
-            else if (more) issue(nbase + 64 * (row + V6_NST - V6_ROWS), st_cur);
+            if (row < V6_ROWS - NST) issue(cbase + 64 * (row + NST), st_cur);
+            else if (more) issue(nbase + 64 * (row + NST - V6_ROWS), st_cur);
         }
         flush_windows(wb);
         cur_slice = nxt_slice;
@@ -2027,18 +2045,26 @@ int pic_dev_dd_picard_iter5(const pic_dd_params* p, const double* x0, const doub
                                                        active + done, Es, acc, range_err, st);
     }
     if (!(p->flags & (1 | 2 | 4 | 8)) && aligned16 && smem6 <= (size_t)max_optin_smem() - 512) {
-        // default: TMA-staged private-window kernel, one persistent CTA per SM
+        // default: TMA-staged private-window kernel, one persistent CTA per SM; the wide-window build when the
+        // field tile leaves room for it (env PIC_V6_NARROW=1 keeps the 7-node build, for A/B runs)
         const long long nchunks = k.N / V6_CHUNK;
         if (nchunks > 0) {
-            auto kern = first ? (u1 ? dd_picard_iter_v6_k<true, true> : dd_picard_iter_v6_k<true, false>)
-                              : (u1 ? dd_picard_iter_v6_k<false, true> : dd_picard_iter_v6_k<false, false>);
-            PIC_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem6));
+            const size_t smem6w = ((size_t)((k.Ng + 15) & ~15) + (size_t)2 * V6_W_WIDE * V6_T + (size_t)(V6_T / 32) * V6_NST_WIDE * 192 +
+                                   (size_t)(V6_T / 32) * V6_NST_WIDE) * sizeof(double);
+            static const bool narrow = [] { const char* e = getenv("PIC_V6_NARROW"); return e && e[0] == '1'; }();
+            const bool wide = !narrow && smem6w <= (size_t)max_optin_smem() - 512;
+            auto kern = wide ? (first ? (u1 ? dd_picard_iter_v6_k<true, true, false, true> : dd_picard_iter_v6_k<true, false, false, true>)
+                                      : (u1 ? dd_picard_iter_v6_k<false, true, false, true> : dd_picard_iter_v6_k<false, false, false, true>))
+                             : (first ? (u1 ? dd_picard_iter_v6_k<true, true> : dd_picard_iter_v6_k<true, false>)
+                                      : (u1 ? dd_picard_iter_v6_k<false, true> : dd_picard_iter_v6_k<false, false>));
+            const size_t smem = wide ? smem6w : smem6;
+            PIC_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             long long cap = device_sm_count();
             int grid = (int)(nchunks < cap ? nchunks : cap);
             int* sched = nullptr;
             int rcs = next_sched_slot(st, &sched);
             if (rcs) return rcs;
-            kern<<<grid, V6_T, smem6, st>>>(k, (int)nchunks, x0, u0, x1i, x1, u1, active, Es, acc, range_err, sched);
+            kern<<<grid, V6_T, smem, st>>>(k, (int)nchunks, x0, u0, x1i, x1, u1, active, Es, acc, range_err, sched);
             PIC_CHECK_LAUNCH();
             return PIC_OK;                                   // the kernel finishes the ragged tail itself
         }

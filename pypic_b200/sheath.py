@@ -45,6 +45,10 @@ class SheathSim:
         self.rng_mode = rng
         self.seed = int(seed)
         self.draws = draws if draws is not None else LegacyDraws()
+        # sort_every=None: the interval the window kernel is tuned for -- 12 steps with the 15-node deposit windows
+        # (grids up to 4352 nodes), 8 with the 7-node ones (profiles/r2_window_width_sheath.txt)
+        if sort_every is None:
+            sort_every = 12 if int(Ng) <= 4352 else 8
         self.sort_every = int(sort_every)
         # track_order: a cell-sorted store that keeps the reference's particle NUMBERING -- the sort
         # carries the original index of every particle as a payload (self.oid), the passive v0,w0 stay
