@@ -647,7 +647,7 @@ __global__ void __launch_bounds__(V6_T, 1) dd_picard_iter_v6_k(
     const double* const gE = BIG ? Es : sF;                 // what the exact routines gather from
     // BIG: few particles per cell -> a 1024-particle slice spans many cells, so the deposit window
     // (and the field window) is re-centred and flushed every V6_FR rows instead of once per slice
-    const int FRm = BIG ? (nchunks_fr >> 28) : (V6_ROWS - 1);     // rows per window - 1 (a power of two minus one)
+    const int FRm = BIG ? (int)((unsigned)nchunks_fr >> 28) : (V6_ROWS - 1);     // rows per window - 1 (a power of two minus one)
     const int nchunks = nchunks_fr & 0x0fffffff;
     int eb = 0;
     double* myw = win + threadIdx.x;
@@ -2016,20 +2016,30 @@ int pic_dev_dd_picard_iter5(const pic_dd_params* p, const double* x0, const doub
     if (big && aligned16 && !(p->flags & (1 | 4 | 8))) {
         const long long nchunks = k.N / V6_CHUNK;
         if (nchunks > 0) {
-            auto kern = first ? (u1 ? dd_picard_iter_v6_k<true, true, true> : dd_picard_iter_v6_k<true, false, true>)
-                              : (u1 ? dd_picard_iter_v6_k<false, true, true> : dd_picard_iter_v6_k<false, false, true>);
-            PIC_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem6b));
+            // the wide-window build (15-node deposit windows) holds more cells per window, so the windows are
+            // flushed and re-centred less often (env PIC_V6_NARROW=1 keeps the 7-node build, for A/B runs)
+            static const bool narrow_b = [] { const char* e = getenv("PIC_V6_NARROW"); return e && e[0] == '1'; }();
+            const bool wide = !narrow_b;
+            const size_t smem6bw = ((size_t)(V6_T / 32) * V6_EW + (size_t)2 * V6_W_WIDE * V6_T + (size_t)(V6_T / 32) * V6_NST_WIDE * 192 +
+                                    (size_t)(V6_T / 32) * V6_NST_WIDE) * sizeof(double);
+            auto kern = wide ? (first ? (u1 ? dd_picard_iter_v6_k<true, true, true, true> : dd_picard_iter_v6_k<true, false, true, true>)
+                                      : (u1 ? dd_picard_iter_v6_k<false, true, true, true> : dd_picard_iter_v6_k<false, false, true, true>))
+                             : (first ? (u1 ? dd_picard_iter_v6_k<true, true, true> : dd_picard_iter_v6_k<true, false, true>)
+                                      : (u1 ? dd_picard_iter_v6_k<false, true, true> : dd_picard_iter_v6_k<false, false, true>));
+            const size_t smemb = wide ? smem6bw : smem6b;
+            PIC_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemb));
             long long cap = device_sm_count();
             int grid = (int)(nchunks < cap ? nchunks : cap);
-            // rows (of 64 particles) per deposit/field window: about three cells' worth of particles
+            // rows (of 64 particles) per deposit/field window: about three cells' worth of particles with 7-node
+            // windows, eight with 15-node ones (the rest of the window is for the drift between sorts)
             const double ppc = (double)k.N / 2.0 / (double)k.Ng;
             int fr = 16;
-            while (fr > 1 && 64.0 * fr > 3.0 * ppc) fr >>= 1;
+            while (fr > 1 && 64.0 * fr > (wide ? 8.0 : 3.0) * ppc) fr >>= 1;
             PIC_REQUIRE(nchunks < (1 << 28), "dd_picard_iter: shard too large");
             int* sched = nullptr;
             int rcs = next_sched_slot(st, &sched);
             if (rcs) return rcs;
-            kern<<<grid, V6_T, smem6b, st>>>(k, (int)nchunks | ((fr - 1) << 28), x0, u0, x1i, x1, u1, active, Es, acc, range_err, sched);
+            kern<<<grid, V6_T, smemb, st>>>(k, (int)((unsigned)nchunks | ((unsigned)(fr - 1) << 28)), x0, u0, x1i, x1, u1, active, Es, acc, range_err, sched);
             PIC_CHECK_LAUNCH();
         }
         const long long done = nchunks * V6_CHUNK;

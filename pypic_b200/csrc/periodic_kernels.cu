@@ -533,7 +533,7 @@ __global__ void __launch_bounds__(S_T, 1) l_push_deposit_v2_k(const __grid_const
     const int nodes = k.Ng + 1;
     const int NP = BIG ? (S_T / 32) * L_EW : ((nodes + 15) & ~15);
     const int nchunks = nchunks_fr & 0x0fffffff;
-    const int FRm = BIG ? (nchunks_fr >> 28) : (S_ROWS - 1);      // rows per deposit / field window - 1
+    const int FRm = BIG ? (int)((unsigned)nchunks_fr >> 28) : (S_ROWS - 1);      // rows per deposit / field window - 1
     double* sE = sm;
     double* win = sm + NP;                                   // [S_W][S_T]
     double* ring = win + S_W * S_T;                          // [warp][stage][x|v][64]
@@ -743,7 +743,7 @@ __global__ void __launch_bounds__(S_T, 1) pypic_picard_iter_v2_k(const __grid_co
     // smoothed field: the whole grid or, in the large-grid build, one PY_EW-node window per warp
     const int NP = BIG ? (S_T / 32) * PY_EW : ((Ng + 15) & ~15);
     const int nchunks = nchunks_fr & 0x0fffffff;
-    const int FRm = BIG ? (nchunks_fr >> 28) : (S_ROWS - 1);      // rows per deposit / field window - 1
+    const int FRm = BIG ? (int)((unsigned)nchunks_fr >> 28) : (S_ROWS - 1);      // rows per deposit / field window - 1
     double* sF = sm;
     double* win = sm + NP;                                   // [2*S_W][S_T]
     double* ring = win + 2 * S_W * S_T;                      // [warp][stage][x0|v0|x1][64]
@@ -1006,7 +1006,7 @@ int pic_dev_pypic_picard_iter3(const pic_pypic_params* p, const double* x0, cons
         int fr = 16;
         while (fr > 1 && 64.0 * fr > 3.0 * ppc) fr >>= 1;
         long long cap = device_sm_count();
-        kern<<<(int)(nchunks < cap ? nchunks : cap), S_T, smem2b, st>>>(k, (int)nchunks | ((fr - 1) << 28), x0, v0, x1i, x1, v1, Fs,
+        kern<<<(int)(nchunks < cap ? nchunks : cap), S_T, smem2b, st>>>(k, (int)((unsigned)nchunks | ((unsigned)(fr - 1) << 28)), x0, v0, x1i, x1, v1, Fs,
                                                                           acc, range_err);
         PIC_CHECK_LAUNCH();
         return PIC_OK;
@@ -1149,7 +1149,7 @@ int pic_dev_l_push_deposit(const pic_l_params* p, double* x, double* v, const do
         int fr = 16;
         while (fr > 1 && 64.0 * fr > 3.0 * ppc) fr >>= 1;
         long long cap = device_sm_count();
-        kern<<<(int)(nchunks < cap ? nchunks : cap), S_T, smem2b, st>>>(k, (int)nchunks | ((fr - 1) << 28), x, v, E, rho_acc, range_err);
+        kern<<<(int)(nchunks < cap ? nchunks : cap), S_T, smem2b, st>>>(k, (int)((unsigned)nchunks | ((unsigned)(fr - 1) << 28)), x, v, E, rho_acc, range_err);
         PIC_CHECK_LAUNCH();
         return PIC_OK;
     }
