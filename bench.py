@@ -77,6 +77,8 @@ def parse():
         wide = (args.workload == "sheath" and args.decomposition == "particle" and args.cells + 1 <= 4352
                 and args.deposit in ("window", "window-det", "window-blocked") and os.environ.get("PIC_V6_NARROW") != "1")
         args.sort_every = 12 if wide else 8
+        if args.workload == "explicit" and os.environ.get("PIC_S_NARROW") != "1" and args.cells + 1 <= 8192:
+            args.sort_every = 16          # 15-node windows of l_push_deposit_v2_k (profiles/r2_periodic_wide.txt)
     return args
 
 

@@ -433,36 +433,42 @@ __global__ void __launch_bounds__(256) l_push_deposit_k(LK k, double* __restrict
 // the exact routine of the v1 kernels with global REDs.
 #define S_T 512
 #define S_W 7
+// wide build: 15-node windows (see V6_W_WIDE in dd_kernels.cu), chosen by the host when shared memory allows
+#define S_W_WIDE 15
 #define S_ROWS 16
 #define S_CHUNK (S_T * 2 * S_ROWS)
 
+template <int W>
 __device__ __forceinline__ void swin_add(double* myw, double* __restrict__ acc, int wb, int c, double vL, double vR) {
     const unsigned d = (unsigned)(c - wb);
-    if (d <= (unsigned)(S_W - 2)) { double* p = myw + d * S_T; p[0] += vL; p[S_T] += vR; }
+    if (d <= (unsigned)(W - 2)) { double* p = myw + d * S_T; p[0] += vL; p[S_T] += vR; }
     else { atomicAdd(&acc[c], vL); atomicAdd(&acc[c + 1], vR); }
 }
 
-// column sums of the warp's 32 private windows (NC = tiles * S_W columns <= 16) -> global REDs
-template <int TILES>
+// column sums of the warp's 32 private windows -> global REDs, one tile of W <= 16 columns per pass (one lane
+// per column and half of the warp's windows); the windows are cleared
+template <int TILES, int W>
 __device__ __forceinline__ void swin_flush(double* win, double* myw, int wbase, int lane, int wb, double* __restrict__ acc,
                                            int tile_stride, int nodes) {
-    constexpr int NC = TILES * S_W;
-    double s = 0.0;
+    static_assert(W >= 5 && W <= 16, "one lane per (column, half-warp)");
     const int n = lane >> 1, half = lane & 1;
-    if (n < NC) {
-        const double* col = win + n * S_T + wbase + half * 16;
 #pragma unroll
-        for (int j = 0; j < 16; ++j) s += col[(j + n) & 15];
-    }
-    s += __shfl_xor_sync(0xffffffffu, s, 1);
-    if (n < NC && half == 0) {
-        const int t = n / S_W;
-        const int node = wb + (n - t * S_W);
-        if (node >= 0 && node < nodes && s != 0.0) atomicAdd(&acc[t * tile_stride + node], s);
+    for (int t = 0; t < TILES; ++t) {
+        double s = 0.0;
+        if (n < W) {
+            const double* col = win + (t * W + n) * S_T + wbase + half * 16;
+#pragma unroll
+            for (int j = 0; j < 16; ++j) s += col[(j + n) & 15];
+        }
+        s += __shfl_xor_sync(0xffffffffu, s, 1);
+        if (n < W && half == 0) {
+            const int node = wb + n;
+            if (node >= 0 && node < nodes && s != 0.0) atomicAdd(&acc[t * tile_stride + node], s);
+        }
     }
     __syncwarp();
 #pragma unroll
-    for (int n2 = 0; n2 < NC; ++n2) myw[n2 * S_T] = 0.0;
+    for (int n2 = 0; n2 < TILES * W; ++n2) myw[n2 * S_T] = 0.0;
     __syncwarp();
 }
 
@@ -524,7 +530,7 @@ __device__ __noinline__ int l_particle_exact(const LK& k, long long i, double X,
     return bad;
 }
 
-template <int NST, bool BIG = false>
+template <int NST, bool BIG = false, int W = S_W>
 __global__ void __launch_bounds__(S_T, 1) l_push_deposit_v2_k(const __grid_constant__ LK k, int nchunks_fr, double* x,
                                                                double* v, const double* __restrict__ E,
                                                                double* __restrict__ rho_acc, int* __restrict__ range_err) {
@@ -535,8 +541,8 @@ __global__ void __launch_bounds__(S_T, 1) l_push_deposit_v2_k(const __grid_const
     const int nchunks = nchunks_fr & 0x0fffffff;
     const int FRm = BIG ? (int)((unsigned)nchunks_fr >> 28) : (S_ROWS - 1);      // rows per deposit / field window - 1
     double* sE = sm;
-    double* win = sm + NP;                                   // [S_W][S_T]
-    double* ring = win + S_W * S_T;                          // [warp][stage][x|v][64]
+    double* win = sm + NP;                                   // [W][S_T]
+    double* ring = win + W * S_T;                          // [warp][stage][x|v][64]
     unsigned long long* bars = (unsigned long long*)(ring + (S_T / 32) * NST * 128);
     if (!BIG) for (int i = threadIdx.x; i < nodes; i += S_T) sE[i] = E[i];
     double* const wE = sm + (threadIdx.x >> 5) * L_EW;       // BIG: this warp's field window
@@ -545,7 +551,7 @@ __global__ void __launch_bounds__(S_T, 1) l_push_deposit_v2_k(const __grid_const
     int eb = 0;
     double* myw = win + threadIdx.x;
 #pragma unroll
-    for (int n = 0; n < S_W; ++n) myw[n * S_T] = 0.0;
+    for (int n = 0; n < W; ++n) myw[n * S_T] = 0.0;
     if (threadIdx.x == 0) s_bad = 0;
     const unsigned full = 0xffffffffu;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wbase = threadIdx.x & ~31;
@@ -606,7 +612,7 @@ __global__ void __launch_bounds__(S_T, 1) l_push_deposit_v2_k(const __grid_const
                 fc.qpi = (sp ? k.q[1] : k.q[0]) * k.p2c * k.idx;
             }
             if (BIG && (row & FRm) == 0) {
-                if (row > 0 && wb != NOWIN) { __syncwarp(); swin_flush<1>(win, myw, wbase, lane, wb, rho_acc, 0, nodes); }
+                if (row > 0 && wb != NOWIN) { __syncwarp(); swin_flush<1, W>(win, myw, wbase, lane, wb, rho_acc, 0, nodes); }
                 const int cb = (int)floor(__shfl_sync(full, X.x, 0) * k.idx);
                 eb = min(max(cb - L_EW / 4, 0), nodes - L_EW);
                 __syncwarp();
@@ -621,18 +627,18 @@ __global__ void __launch_bounds__(S_T, 1) l_push_deposit_v2_k(const __grid_const
             if ((row & FRm) == 0) {
                 int nok = __reduce_add_sync(full, (ra ? 0 : 1) + (rb ? 0 : 1));
                 int sum = __reduce_add_sync(full, (ra ? 0 : a.cF) + (rb ? 0 : b.cF));
-                wb = nok ? sum / nok - (S_W - 2) / 2 : NOWIN;
+                wb = nok ? sum / nok - (W - 2) / 2 : NOWIN;
             }
             if (!(ra | rb)) {
                 __stcs((double2*)(x + ci), make_double2(a.X, b.X));
                 __stcs((double2*)(v + ci), make_double2(a.V, b.V));
-                swin_add(myw, rho_acc, wb, a.cF, a.fL, a.fR);
-                swin_add(myw, rho_acc, wb, b.cF, b.fL, b.fR);
+                swin_add<W>(myw, rho_acc, wb, a.cF, a.fL, a.fR);
+                swin_add<W>(myw, rho_acc, wb, b.cF, b.fL, b.fR);
             } else {
                 if (ra) bad += l_particle_exact(k, ci, X.x, V.x, gE, rho_acc, x, v);
-                else { x[ci] = a.X; v[ci] = a.V; swin_add(myw, rho_acc, wb, a.cF, a.fL, a.fR); }
+                else { x[ci] = a.X; v[ci] = a.V; swin_add<W>(myw, rho_acc, wb, a.cF, a.fL, a.fR); }
                 if (rb) bad += l_particle_exact(k, ci + 1, X.y, V.y, gE, rho_acc, x, v);
-                else { x[ci + 1] = b.X; v[ci + 1] = b.V; swin_add(myw, rho_acc, wb, b.cF, b.fL, b.fR); }
+                else { x[ci + 1] = b.X; v[ci + 1] = b.V; swin_add<W>(myw, rho_acc, wb, b.cF, b.fL, b.fR); }
             }
             // refill the drained stage only after every lane's LDS of it has executed (see v6)
             __syncwarp();
@@ -640,7 +646,7 @@ __global__ void __launch_bounds__(S_T, 1) l_push_deposit_v2_k(const __grid_const
             else if (more) issue(cbase + chunk_step + 64 * (row + NST - S_ROWS), st_cur);
         }
         __syncwarp();
-        if (wb != NOWIN) swin_flush<1>(win, myw, wbase, lane, wb, rho_acc, 0, nodes);
+        if (wb != NOWIN) swin_flush<1, W>(win, myw, wbase, lane, wb, rho_acc, 0, nodes);
     }
     // the N % S_CHUNK particles behind the last whole chunk: at most one per thread, exact routine, global REDs
     for (long long i = (long long)nchunks * S_CHUNK + (long long)blockIdx.x * S_T + threadIdx.x; i < k.N; i += (long long)gridDim.x * S_T)
@@ -729,7 +735,7 @@ __device__ __noinline__ int py_particle_exact(const PYK& k, long long i, double 
     return bad;
 }
 
-template <bool FIRST, int NST, bool J1, bool BIG = false>
+template <bool FIRST, int NST, bool J1, bool BIG = false, int W = S_W>
 __global__ void __launch_bounds__(S_T, 1) pypic_picard_iter_v2_k(const __grid_constant__ PYK k, int nchunks_fr,
                                                                   const double* __restrict__ x0,
                                                                   const double* __restrict__ v0, const double* x1i, double* x1,
@@ -745,8 +751,8 @@ __global__ void __launch_bounds__(S_T, 1) pypic_picard_iter_v2_k(const __grid_co
     const int nchunks = nchunks_fr & 0x0fffffff;
     const int FRm = BIG ? (int)((unsigned)nchunks_fr >> 28) : (S_ROWS - 1);      // rows per deposit / field window - 1
     double* sF = sm;
-    double* win = sm + NP;                                   // [2*S_W][S_T]
-    double* ring = win + 2 * S_W * S_T;                      // [warp][stage][x0|v0|x1][64]
+    double* win = sm + NP;                                   // [2*W][S_T]
+    double* ring = win + 2 * W * S_T;                      // [warp][stage][x0|v0|x1][64]
     unsigned long long* bars = (unsigned long long*)(ring + (S_T / 32) * NST * 192);
     if (!BIG) for (int i = threadIdx.x; i < Ng; i += S_T) sF[i] = Fs[i];
     double* const wE = sm + (threadIdx.x >> 5) * PY_EW;      // BIG: this warp's field window
@@ -755,7 +761,7 @@ __global__ void __launch_bounds__(S_T, 1) pypic_picard_iter_v2_k(const __grid_co
     int eb = 0;
     double* myw = win + threadIdx.x;
 #pragma unroll
-    for (int n = 0; n < 2 * S_W; ++n) myw[n * S_T] = 0.0;
+    for (int n = 0; n < 2 * W; ++n) myw[n * S_T] = 0.0;
     if (threadIdx.x == 0) s_bad = 0;
     const unsigned full = 0xffffffffu;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wbase = threadIdx.x & ~31;
@@ -811,7 +817,7 @@ __global__ void __launch_bounds__(S_T, 1) pypic_picard_iter_v2_k(const __grid_co
             if (BIG && (row & FRm) == 0) {
                 // few particles per cell: the windows are flushed and re-centred every FRm+1 rows, and the
                 // field window is loaded around the gather cell of the row's first particle
-                if (row > 0 && wb != NOWIN) { __syncwarp(); swin_flush<2>(win, myw, wbase, lane, wb, acc, Ng, Ng); }
+                if (row > 0 && wb != NOWIN) { __syncwarp(); swin_flush<J1 ? 2 : 1, W>(win, myw, wbase, lane, wb, acc, Ng, Ng); }
                 const double xf = __shfl_sync(full, FIRST ? X0.x : (X0.x + pX1.x) * 0.5, 0);
                 const int cb = (int)floor(xf * k.idx);
                 eb = min(max(cb - PY_EW / 4, 0), Ng - PY_EW);
@@ -827,27 +833,27 @@ __global__ void __launch_bounds__(S_T, 1) pypic_picard_iter_v2_k(const __grid_co
             if ((row & FRm) == 0) {
                 int nok = __reduce_add_sync(full, (ra ? 0 : 1) + (rb ? 0 : 1));
                 int sum = __reduce_add_sync(full, (ra ? 0 : a.cH) + (rb ? 0 : b.cH));
-                wb = nok ? sum / nok - (S_W - 2) / 2 : NOWIN;
+                wb = nok ? sum / nok - (W - 2) / 2 : NOWIN;
             }
             if (!(ra | rb)) {
                 __stcs((double2*)(x1 + ci), make_double2(a.X1, b.X1));
                 if (J1) __stcs((double2*)(v1 + ci), make_double2(a.V1, b.V1));
-                swin_add(myw, acc, wb, a.cH, a.hL, a.hR);
-                if (J1) swin_add(myw + S_W * S_T, acc + Ng, wb, a.cF, a.fL, a.fR);
-                swin_add(myw, acc, wb, b.cH, b.hL, b.hR);
-                if (J1) swin_add(myw + S_W * S_T, acc + Ng, wb, b.cF, b.fL, b.fR);
+                swin_add<W>(myw, acc, wb, a.cH, a.hL, a.hR);
+                if (J1) swin_add<W>(myw + W * S_T, acc + Ng, wb, a.cF, a.fL, a.fR);
+                swin_add<W>(myw, acc, wb, b.cH, b.hL, b.hR);
+                if (J1) swin_add<W>(myw + W * S_T, acc + Ng, wb, b.cF, b.fL, b.fR);
             } else {
                 if (ra) bad += py_particle_exact<FIRST>(k, ci, X0.x, V0.x, pX1.x, gE, acc, x1, v1);
                 else {
                     x1[ci] = a.X1; if (J1) v1[ci] = a.V1;
-                    swin_add(myw, acc, wb, a.cH, a.hL, a.hR);
-                    if (J1) swin_add(myw + S_W * S_T, acc + Ng, wb, a.cF, a.fL, a.fR);
+                    swin_add<W>(myw, acc, wb, a.cH, a.hL, a.hR);
+                    if (J1) swin_add<W>(myw + W * S_T, acc + Ng, wb, a.cF, a.fL, a.fR);
                 }
                 if (rb) bad += py_particle_exact<FIRST>(k, ci + 1, X0.y, V0.y, pX1.y, gE, acc, x1, v1);
                 else {
                     x1[ci + 1] = b.X1; if (J1) v1[ci + 1] = b.V1;
-                    swin_add(myw, acc, wb, b.cH, b.hL, b.hR);
-                    if (J1) swin_add(myw + S_W * S_T, acc + Ng, wb, b.cF, b.fL, b.fR);
+                    swin_add<W>(myw, acc, wb, b.cH, b.hL, b.hR);
+                    if (J1) swin_add<W>(myw + W * S_T, acc + Ng, wb, b.cF, b.fL, b.fR);
                 }
             }
             __syncwarp();
@@ -855,7 +861,7 @@ __global__ void __launch_bounds__(S_T, 1) pypic_picard_iter_v2_k(const __grid_co
             else if (more) issue(cbase + chunk_step + 64 * (row + NST - S_ROWS), st_cur);
         }
         __syncwarp();
-        if (wb != NOWIN) swin_flush<2>(win, myw, wbase, lane, wb, acc, Ng, Ng);
+        if (wb != NOWIN) swin_flush<J1 ? 2 : 1, W>(win, myw, wbase, lane, wb, acc, Ng, Ng);
     }
     // the N % S_CHUNK particles behind the last whole chunk: at most one per thread, exact routine, global REDs
     for (long long i = (long long)nchunks * S_CHUNK + (long long)blockIdx.x * S_T + threadIdx.x; i < k.N; i += (long long)gridDim.x * S_T)
@@ -966,6 +972,17 @@ static int pypic_iter_v1(const PYK& k, int flags, const double* x0, const double
 }
 
 #define PY_NST 4
+#define PY_NST_WIDE 3
+// 15-node windows: default in the explicit kernel (+8 % per step with a sort every 16 steps instead of 8); in the
+// Picard kernel they cost a ring stage and measure no gain (profiles/r2_periodic_wide.txt), so they are opt-in there
+static bool s_narrow() {
+    static const bool narrow = [] { const char* e = getenv("PIC_S_NARROW"); return e && e[0] == '1'; }();
+    return narrow;
+}
+static bool s_wide_picard() {
+    static const bool wide = [] { const char* e = getenv("PIC_S_WIDE_PICARD"); return e && e[0] == '1'; }();
+    return wide;
+}
 int pic_dev_pypic_picard_iter(const pic_pypic_params* p, const double* x0, const double* v0, double* x1, double* v1,
                               const double* Fs, double* acc, int first, int* range_err, void* stream) {
     return pic_dev_pypic_picard_iter2(p, x0, v0, x1, x1, v1, Fs, acc, first, range_err, stream);
@@ -1016,11 +1033,20 @@ int pic_dev_pypic_picard_iter3(const pic_pypic_params* p, const double* x0, cons
         const long long nchunks = k.N / S_CHUNK;
         if (nchunks > 0) {
             const bool light = (p->flags & 8) != 0;
-            auto kern = first ? (light ? pypic_picard_iter_v2_k<true, PY_NST, false> : pypic_picard_iter_v2_k<true, PY_NST, true>)
-                              : (light ? pypic_picard_iter_v2_k<false, PY_NST, false> : pypic_picard_iter_v2_k<false, PY_NST, true>);
-            PIC_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
+            // 15-node deposit windows (3 ring stages): env PIC_S_WIDE_PICARD=1, for A/B runs
+            const size_t smem2w = ((size_t)((k.Ng + 15) & ~15) + (size_t)2 * S_W_WIDE * S_T + (size_t)(S_T / 32) * PY_NST_WIDE * 192 +
+                                   (size_t)(S_T / 32) * PY_NST_WIDE) * sizeof(double);
+            const bool wide = s_wide_picard() && smem2w <= (size_t)max_optin_smem() - 512;
+            auto kern = wide ? (first ? (light ? pypic_picard_iter_v2_k<true, PY_NST_WIDE, false, false, S_W_WIDE>
+                                               : pypic_picard_iter_v2_k<true, PY_NST_WIDE, true, false, S_W_WIDE>)
+                                      : (light ? pypic_picard_iter_v2_k<false, PY_NST_WIDE, false, false, S_W_WIDE>
+                                               : pypic_picard_iter_v2_k<false, PY_NST_WIDE, true, false, S_W_WIDE>))
+                             : (first ? (light ? pypic_picard_iter_v2_k<true, PY_NST, false> : pypic_picard_iter_v2_k<true, PY_NST, true>)
+                                      : (light ? pypic_picard_iter_v2_k<false, PY_NST, false> : pypic_picard_iter_v2_k<false, PY_NST, true>));
+            const size_t smem = wide ? smem2w : smem2;
+            PIC_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             long long cap = device_sm_count();
-            kern<<<(int)(nchunks < cap ? nchunks : cap), S_T, smem2, st>>>(k, (int)nchunks, x0, v0, x1i, x1, v1, Fs, acc, range_err);
+            kern<<<(int)(nchunks < cap ? nchunks : cap), S_T, smem, st>>>(k, (int)nchunks, x0, v0, x1i, x1, v1, Fs, acc, range_err);
             PIC_CHECK_LAUNCH();
             return PIC_OK;                       // the kernel finishes the ragged tail itself
         }
@@ -1156,10 +1182,13 @@ int pic_dev_l_push_deposit(const pic_l_params* p, double* x, double* v, const do
     if (!(p->flags & (1 | 2 | 4)) && aligned16 && k.Ng >= 8 && smem2 <= (size_t)max_optin_smem() - 512) {
         const long long nchunks = k.N / S_CHUNK;
         if (nchunks > 0) {
-            auto kern = l_push_deposit_v2_k<L_NST>;
-            PIC_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
+            const size_t smem2w = smem2 + (size_t)(S_W_WIDE - S_W) * S_T * sizeof(double);      // 15-node windows
+            const bool wide = !s_narrow() && smem2w <= (size_t)max_optin_smem() - 512;
+            auto kern = wide ? l_push_deposit_v2_k<L_NST, false, S_W_WIDE> : l_push_deposit_v2_k<L_NST>;
+            const size_t smem = wide ? smem2w : smem2;
+            PIC_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             long long cap = device_sm_count();
-            kern<<<(int)(nchunks < cap ? nchunks : cap), S_T, smem2, st>>>(k, (int)nchunks, x, v, E, rho_acc, range_err);
+            kern<<<(int)(nchunks < cap ? nchunks : cap), S_T, smem, st>>>(k, (int)nchunks, x, v, E, rho_acc, range_err);
             PIC_CHECK_LAUNCH();
             return PIC_OK;                       // the kernel finishes the ragged tail itself
         }
