@@ -66,6 +66,9 @@ def parse():
                     help="N > 1: skip the `slab_decomposition` sub-record (the same workload on spatial slabs: halo exchange + "
                          "particle migration, BASELINE config 5's decomposition)")
     ap.add_argument("--slab-steps", type=int, default=16)
+    ap.add_argument("--slab-field", default="distributed", choices=["distributed", "replicated"],
+                    help="slab decomposition: field update on every rank's own nodes + guard nodes with two small all-gathers "
+                         "per Picard iteration (default), or the whole grid gathered and updated on every rank (A/B)")
     ap.add_argument("--no-api-leg", action="store_true",
                     help="skip the `reference_api` record (the step as PIC_L_DD.main_i drives it: host MT19937 draws, carried v,w)")
     ap.add_argument("--api-steps", type=int, default=40)
@@ -509,7 +512,8 @@ def run_cuda(args):
             sim.close(); del sim
             torch.cuda.empty_cache()
             ss = SlabSheathSim(w["N"], w["Ng"], w["dx"], w["dt"], w["p2c"], kBT=(w["kBTe"], w["kBTi"]), tol=w["tol"],
-                               maxiter=w["maxiter"], seed=1, comm=comm, device=dev, sort_every=args.sort_every, guard=16)
+                               maxiter=w["maxiter"], seed=1, comm=comm, device=dev, sort_every=args.sort_every, guard=16,
+                               field=args.slab_field)
             ss.init_device(seed=1234)
             for _ in range(3):
                 ss.step()
@@ -526,7 +530,7 @@ def run_cuda(args):
             ss.check()
             slab = {"value": w["N"] * len(its_sl) / (ms_sl * 1e-3), "unit": "particle-steps/s", "ms_per_step": ms_sl / len(its_sl),
                     "steps": len(its_sl), "picard_iterations_per_step": float(np.mean(its_sl)), "n_gpus": world,
-                    "migration": dict(ss.stat), "guard_cells": 16,
+                    "migration": dict(ss.stat), "guard_cells": 16, "field_update": args.slab_field,
                     "note": "spatial slab decomposition of the same workload; the particle decomposition above is the default"}
             del ss
             torch.cuda.empty_cache()
@@ -616,7 +620,8 @@ def run_slab(args):
     comm = Comm()
     w = workload(args, world)
     sim = SlabSheathSim(w["N"], w["Ng"], w["dx"], w["dt"], w["p2c"], kBT=(w["kBTe"], w["kBTi"]), tol=w["tol"],
-                        maxiter=w["maxiter"], seed=1, comm=comm, device=dev, sort_every=args.sort_every, guard=16)
+                        maxiter=w["maxiter"], seed=1, comm=comm, device=dev, sort_every=args.sort_every, guard=16,
+                        field=args.slab_field)
     sim.init_device(seed=1234)
     for _ in range(args.warmup):
         sim.step()
@@ -655,9 +660,12 @@ def run_slab(args):
                 "scaling": w["scaling"], "vs_baseline": None, "dtype": "f64", "data": "synthetic",
                 "config": {"workload": "1D sheath (PIC_L_DD physics) on %d spatial slabs: %d particles, %d-node grid, implicit "
                                        "CN/Picard tol=1e-5" % (world, w["N"], w["Ng"]),
-                           "parallelism": "slab decomposition x%d: halo exchange of 16 guard nodes + all-gather of owned "
-                                          "segments per Picard iteration, migration with the sort every %d steps, routed "
-                                          "re-injection" % (world, args.sort_every),
+                           "parallelism": ("slab decomposition x%d: %s, migration with the sort every %d steps, routed re-injection"
+                                           % (world, "field update distributed over the slabs (own nodes + 16 guard nodes); per "
+                                              "Picard iteration one all-gather of the boundary bands and partial sums and one of "
+                                              "the residual partials" if args.slab_field == "distributed" else
+                                              "halo exchange of 16 guard nodes + all-gather of owned segments per Picard "
+                                              "iteration, field update replicated", args.sort_every)),
                            "picard_iterations_per_step": kbar, "sort_every": args.sort_every,
                            "migration": sim.stat, "local_particles_rank0": nloc, "kernel_ms_and_particles_by_rank": by_rank,
                            "l2_policy": "particle arrays (%.1f GB per GPU) are far larger than the 126 MB L2" % (nloc * 32 / 1e9)},

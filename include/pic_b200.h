@@ -294,6 +294,34 @@ int pic_dev_dd_field_update_p2p(const pic_dd_params* p, const double* const* pee
                                 uint32_t seq, double* acc_sum, double* wall_cum, const double* E0, double* Es,
                                 double* E1, double* j1, double* stats, double* Es_prev, double* rhist,
                                 int32_t* ctl, double tol, int maxiter, int* err, void* stream);
+/* Field phase of the same iteration on SPATIAL SLABS (pypic_b200/spatial.py, BASELINE config 5; formulas of
+ * pic_dev_dd_field_update2 = PIC_L_DD.py:55-66,516-527, evaluated by every rank on its own nodes and `guard`
+ * nodes either side).  Rank r owns the cells [c0, c1); its particles deposit on the nodes [c0-guard, c1+guard].
+ * Per iteration: pic_dev_slab_pack -> all-gather of the messages -> pic_dev_slab_field_update -> all-gather of the
+ * two partial sums -> pic_dev_slab_finish.  The collectives are the caller's (NCCL); every kernel is a no-op when
+ * *ctl != 0 (enqueue-ahead loop).
+ *   pic_slab_message_len(guard)  doubles per rank message: the raw jh, j1 of the 2*guard+1 nodes around each
+ *                       slab boundary, the sums of all raw deposits of the rank (+ its fold nodes), the four
+ *                       absorbed counts of the iteration and the fold nodes j[1], j[Ng-2];
+ *   pic_slab_work_len()  doubles of device scratch (zero-initialised once by the caller);
+ *   pic_dev_slab_pack    acc fp64[2Ng+4] (raw accumulators of the particle kernels) -> msg; adds the four counts to
+ *                       absorbed_local (fp64[4], may be NULL: this rank's own absorptions of the step) and clears them;
+ *   pic_dev_slab_field_update  gathered = the messages of all ranks in rank order; completes jh, j1 on the band,
+ *                       applies wall terms and fold, E1 = E0 + (dt/eps0)(mean(jh) - jh), Eh, Es := Eh and j1 on the
+ *                       band; clears the band of acc; partial[2] = (sum over OWNED nodes of (Es-Eh)^2, field energy);
+ *                       neighbours compute identical bits on the nodes they share;
+ *   pic_dev_slab_finish partials = partial[2] of all ranks in rank order: wall_cum += counts, stats[0..3] and rhist
+ *                       as pic_dev_dd_field_update2, raises *ctl when the loop ends (same value on every rank). */
+int pic_slab_message_len(int guard);
+int pic_slab_work_len(void);
+int pic_dev_slab_pack(const pic_dd_params* p, int c0, int c1, int guard, int rank, int world, double* acc, double* msg,
+                      double* work, double* absorbed_local, const int32_t* ctl, void* stream);
+int pic_dev_slab_field_update(const pic_dd_params* p, int c0, int c1, int guard, int rank, int world, double* acc,
+                              const double* gathered, const double* wall_cum, const double* E0, double* Es, double* E1,
+                              double* j1, double* partial, double* work, const int32_t* ctl, void* stream);
+int pic_dev_slab_finish(const pic_dd_params* p, int c0, int c1, int guard, int rank, int world, const double* gathered,
+                        const double* partials, double* wall_cum, double* stats, double* rhist, int32_t* ctl, double tol,
+                        int maxiter, void* stream);
 /* Re-injection (PIC_L_DD.py:429-450).  Host-RNG parity mode: compact the indices of
  * inactive slots in index order (pic_dev_compact_flags), draw on the host with the
  * legacy MT19937 stream, then scatter: */

@@ -146,8 +146,12 @@ def initialize_p(system, N, density, Kp, perturbation, dx, Ng, Te, Ti, L, X):
 
 
 def implicit_pic(T, nplot, system, density, perturbation, Kp, N, Ng, Nv, Vmax, dt, Ti, Te, L, tol, maxiter,
-                 outdir='plots', result=None):
-    """pypic.py:472-651: main implicit PIC routine (particles stay resident on the GPU)."""
+                 outdir='plots', result=None, sort_every=None):
+    """pypic.py:472-651: main implicit PIC routine (particles stay resident on the GPU).
+
+    The store is re-sorted by cell every `sort_every` steps (default: 8 from 2^17 particles on, never below) so that
+    the loop runs on the TMA-staged window kernel; the original index of every particle rides along, so the
+    tracer, the plots and `result` see the reference's particle order."""
     tracer = 9999
     Nv = int(Nv)
     X = np.linspace(0.0, L, Ng + 1)
@@ -166,7 +170,9 @@ def implicit_pic(T, nplot, system, density, perturbation, Kp, N, Ng, Nv, Vmax, d
     phi0 = solve_poisson_p(dx, Ng, rho0, np.zeros(Ng))
     phi0 = phi0 - np.max(phi0)
     E0 = -differentiate_p(phi0, dx, Ng)
-    sim = PeriodicImplicitSim(N, Ng, dx, dt, L, p2c, q=-e, m=me, tol=tol, maxiter=maxiter)
+    if sort_every is None:
+        sort_every = 8 if N >= (1 << 17) else 0
+    sim = PeriodicImplicitSim(N, Ng, dx, dt, L, p2c, q=-e, m=me, tol=tol, maxiter=maxiter, sort_every=sort_every)
     sim.upload(x0, v0, E0)
     mpl, plt = get_plt()
     for t in range(T):
@@ -181,8 +187,9 @@ def implicit_pic(T, nplot, system, density, perturbation, Kp, N, Ng, Nv, Vmax, d
         print("Total Energy: ", d["EE"] + d["KE"])
         j_bias.append(d["jbias"])
         if tracer < N:
-            trajectory_x.append(float(sim.x0[tracer].item()) % L)      # the store wraps lazily
-            trajectory_v.append(float(sim.v0[tracer].item()) / np.sqrt(kBTe / me))
+            slot = sim.slot_of(tracer)
+            trajectory_x.append(float(sim.x0[slot].item()) % L)        # the store wraps lazily
+            trajectory_v.append(float(sim.v0[slot].item()) / np.sqrt(kBTe / me))
         if plt is not None and (t % nplot == 0):
             st = sim.download()
             fig = plt.figure(1); plt.clf()
@@ -211,7 +218,7 @@ def explicit_pic(T, nplot):
 
 
 def main(T, nplot, N=1000000, Ng=200, dt=1e-5, density=1e5, perturbation=0.8, Kp=1, system='landau-damping',
-         tol=1e-3, maxiter=20, outdir='plots', result=None):
+         tol=1e-3, maxiter=20, outdir='plots', result=None, sort_every=None):
     """pypic.main (pypic.py:814-863); keyword arguments default to its hard-coded literals."""
     Ti = 0.1 * 11600.
     Te = 100.0 * 11600.
@@ -219,7 +226,7 @@ def main(T, nplot, N=1000000, Ng=200, dt=1e-5, density=1e5, perturbation=0.8, Kp
     Vmax = 8.0
     Nv = Ng // 2
     implicit_pic(T, nplot, system, density, perturbation, Kp, N, Ng, Nv, Vmax, dt, Ti, Te, L, tol, maxiter,
-                 outdir=outdir, result=result)
+                 outdir=outdir, result=result, sort_every=sort_every)
 
 
 if __name__ == '__main__':

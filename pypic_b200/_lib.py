@@ -107,6 +107,11 @@ _SIGS = {
     "pic_dev_selftest_div": [F64, C.c_uint64, C.c_uint64, P, P],
     "pic_dev_dd_field_update": [C.POINTER(DDParams), P, P, P, P, P, P, P, P],
     "pic_dev_dd_field_update2": [C.POINTER(DDParams), P, P, P, P, P, P, P, P, P, P, F64, I32, P],
+    "pic_slab_message_len": [I32],
+    "pic_slab_work_len": [],
+    "pic_dev_slab_pack": [C.POINTER(DDParams), I32, I32, I32, I32, I32, P, P, P, P, P, P],
+    "pic_dev_slab_field_update": [C.POINTER(DDParams), I32, I32, I32, I32, I32, P, P, P, P, P, P, P, P, P, P, P],
+    "pic_dev_slab_finish": [C.POINTER(DDParams), I32, I32, I32, I32, I32, P, P, P, P, P, P, F64, I32, P],
     "pic_p2p_alloc": [I64, I32, C.POINTER(C.c_void_p), P],
     "pic_p2p_open": [P, C.POINTER(C.c_void_p)],
     "pic_p2p_set_timeout": [I32],

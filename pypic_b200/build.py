@@ -15,7 +15,7 @@ CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libpic_b200.so")
 STAMP = os.path.join(HERE, ".build_stamp")
 OBJ = os.path.join(HERE, "_obj")
-SOURCES = ["grid_kernels.cu", "dd_kernels.cu", "periodic_kernels.cu", "gc_kernels.cu", "init_kernels.cu", "abi_host.cu", "mt_host.cpp"]
+SOURCES = ["grid_kernels.cu", "dd_kernels.cu", "slab_kernels.cu", "periodic_kernels.cu", "gc_kernels.cu", "init_kernels.cu", "abi_host.cu", "mt_host.cpp"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-lineinfo", "-std=c++17",

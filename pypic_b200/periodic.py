@@ -220,6 +220,12 @@ class PeriodicImplicitSim:
         self.last_iters, self.last_resid = k, r
         return k, r
 
+    def slot_of(self, i):
+        """Store slot of the particle the caller uploaded as number i (local index)."""
+        if self.perm is None:
+            return int(i)
+        return int(torch.nonzero(self.perm[:self.N] == float(i))[0, 0].item())
+
     def diagnostics(self, m=me):
         s = D.read_f64(self.stats, 4)
         sc = D.f64(1, self.dev, True)

@@ -139,8 +139,15 @@ class _Block:
 
 class SlabSheathSim:
     def __init__(self, N, Ng, dx, dt, p2c, q=(-e, e), m=(me, mp), kBT=(None, None), tol=1e-5, maxiter=20, seed=1,
-                 comm=None, device=None, sort_every=8, guard=16, capacity=1.3, headroom=None):
+                 comm=None, device=None, sort_every=8, guard=16, capacity=1.3, headroom=None, field="distributed"):
         self.dev = D.require_cuda(device)
+        # field="distributed" (default): every rank updates E on its own nodes + guard nodes; per Picard iteration two
+        # small all-gathers (boundary bands + partial sums, then the residual partials; csrc/slab_kernels.cu).
+        # field="replicated": the round-1 scheme -- all-gather of the owned segments, every rank updates the whole
+        # grid (kept for A/B runs and as a cross-check)
+        if field not in ("distributed", "replicated"):
+            raise ValueError("field must be 'distributed' or 'replicated'")
+        self.field = field
         self.comm = comm if comm is not None else Comm()
         self.rank, self.world = self.comm.rank, self.comm.world
         self.N_global, self.Ng, self.dx, self.dt, self.p2c = int(N), int(Ng), float(dx), float(dt), float(p2c)
@@ -191,9 +198,37 @@ class SlabSheathSim:
         self.local_dead = [0, 0]     # absorbed particles of each species on this rank in the last step
         self.profile = None          # set to a dict to accumulate wall-clock seconds per section of step()
         self.iter_events = None      # set to a list to record a CUDA-event pair per Picard iteration (both blocks)
+        self.rprof = None            # set to a dict: synchronising wall-clock sections of reinject() (diagnostics)
+        self.phase_events = None     # set to a list: CUDA events at the phase boundaries of every iteration (distributed field)
         # segment bookkeeping of the all-gather (owned nodes; the last rank also owns node Ng-1)
         self.seg = [(self.cb[r], self.cb[r + 1] + (1 if r == self.world - 1 else 0)) for r in range(self.world)]
         self.seglen = max(b - a for a, b in self.seg)
+        # distributed field update: message / gather buffers (layout in csrc/slab_kernels.cu)
+        lib = _lib.load()
+        self.M = int(lib.pic_slab_message_len(self.G))
+        self.msg = D.f64(self.M, dev, True); self.gath = D.f64(self.world * self.M, dev, True)
+        self.part = D.f64(2, dev, True); self.gath2 = D.f64(2 * self.world, dev, True)
+        self.work = D.f64(int(lib.pic_slab_work_len()), dev, True)
+        self.b0, self.b1 = max(self.c0 - self.G, 0), min(self.c1 + self.G + 1, self.Ng)     # the band this rank computes
+        self._leak_idx = None
+        if self.world > 1:
+            self._warm_collectives()
+
+    def _warm_collectives(self):
+        """One call of every collective the step uses, with non-empty messages: NCCL sets up its point-to-point
+        connections on first use (100-400 ms per kind, measured), which would otherwise land in whichever step first
+        ships a re-injected particle or migrates one."""
+        W, g = self.world, self.comm.group
+        z = torch.zeros(2 * W, dtype=torch.float64, device=self.dev); o = torch.empty_like(z)
+        dist.all_to_all_single(o, z, [2] * W, [2] * W, group=g)
+        zi = torch.zeros(2 * W, dtype=torch.int64, device=self.dev); oi = torch.empty_like(zi)
+        dist.all_to_all_single(oi, zi, group=g)
+        dist.all_to_all([torch.empty(1, dtype=torch.float64, device=self.dev) for _ in range(W)],
+                        [torch.zeros(1, dtype=torch.float64, device=self.dev) for _ in range(W)], group=g)
+        dist.all_gather_into_tensor(oi, zi[:2], group=g)
+        dist.all_gather_into_tensor(self.gath, self.msg, group=g)
+        dist.all_gather_into_tensor(self.gath2, self.part, group=g)
+        torch.cuda.synchronize()
 
     # ------------------------------------------------------------------ helpers
     def _params(self, blk, n=None, sort=False):
@@ -277,6 +312,13 @@ class SlabSheathSim:
         st = D.stream()
         W, me_ = self.world, self.rank
         dead = []
+        import time
+        t_last = [time.perf_counter()]
+
+        def tick(name):
+            if self.rprof is not None:
+                torch.cuda.synchronize(); t = time.perf_counter()
+                self.rprof[name] = self.rprof.get(name, 0.0) + t - t_last[0]; t_last[0] = t
         for sp, blk in enumerate(self.blocks):
             # the kernels count what they absorb (acc[2Ng..], saved per rank by picard()): a species that
             # lost nothing here needs no scan of its flags (always the case on interior ranks)
@@ -298,6 +340,7 @@ class SlabSheathSim:
                 nd = int(D.read_raw(blk.count, 1, np.int64)[0])
                 self.kernel_launches += 3
             dead.append(nd)
+        tick("dead_slots")
         if W > 1:
             t = torch.tensor(dead, dtype=torch.int64, device=self.dev)
             allc = torch.empty(W * 2, dtype=torch.int64, device=self.dev)
@@ -305,6 +348,7 @@ class SlabSheathSim:
             allc = allc.cpu().numpy().reshape(W, 2)                       # [rank, species]
         else:
             allc = np.asarray([dead])
+        tick("count_exchange")
         if int(allc.sum()) == 0:
             return
         send = [[None, None] for _ in range(2)]      # per species: (x, u) sorted by destination, counts per destination
@@ -333,6 +377,7 @@ class SlabSheathSim:
             send[sp] = [xd[out][order], ud[out][order]]
             cnts[:, sp] = torch.bincount(dest[out], minlength=W).cpu().numpy()
             holes[sp] = np.sort(idx[out].cpu().numpy())
+        tick("draw_and_route")
         if W == 1:
             return
         # ---- one size exchange, one payload exchange: to rank r goes [x_e | u_e | x_i | u_i] of its arrivals
@@ -352,6 +397,7 @@ class SlabSheathSim:
         out_splits = [int(2 * (rc[r, 0] + rc[r, 1])) for r in range(W)]
         recv = torch.empty(sum(out_splits), dtype=torch.float64, device=self.dev)
         dist.all_to_all_single(recv, payload, out_splits, in_splits, group=self.comm.group)
+        tick("payload_exchange")
         arr = [[[], []], [[], []]]
         o = 0
         for r in range(W):
@@ -373,6 +419,7 @@ class SlabSheathSim:
                 blk.x0[ad] = ax; blk.u0[ad] = au; blk.active[ad] = 1
             blk.n = new_n
             self.stat["exported"] += len(holes[sp]); self.stat["imported"] += int(ax.numel())
+        tick("swap_remove")
 
     # ------------------------------------------------------------------ sort + migration
     def migrate_sort(self):
@@ -428,8 +475,8 @@ class SlabSheathSim:
         return {k: t(v) for k, v in pl.items() if k != "M"}
 
     def exchange_acc(self):
-        """Halo exchange of the guard strips + completion of the grid, one collective per Picard
-        iteration (see _build_exchange_plan).  self.acc has one extra, always-zero slot."""
+        """field="replicated": halo exchange of the guard strips + completion of the grid, one collective per
+        Picard iteration (see _build_exchange_plan).  self.acc has one extra, always-zero slot."""
         W = self.world
         if W == 1:
             return
@@ -445,37 +492,123 @@ class SlabSheathSim:
         acc.index_add_(0, pl["add_dst"], self.gathbuf[pl["add_src"]])
         acc[2 * Ng:2 * Ng + 4] = self.gathbuf[pl["counts"]].view(W, 4).sum(0)
 
-    # ------------------------------------------------------------------ one timestep
-    def picard(self):
-        """PIC_L_DD.py:452-545 on slabs.  Every launch of an iteration (particle kernels, field kernel) is
-        guarded by the device flag `ctl`; the exchange between them is made of unguarded library calls, which
-        move zeros once the loop has ended (the accumulators are cleared by the last field update), so queued
-        iterations behind the end of the loop are harmless no-ops."""
+    def _all_gather(self, out, src):
+        if self.world == 1:
+            out.copy_(src)
+        else:
+            dist.all_gather_into_tensor(out, src, group=self.comm.group)
+
+    def _slab_args(self):
+        return (C.byref(self._params(self.blocks[0])), self.c0, self.c1, self.G, self.rank, self.world)
+
+    # The three device phases of one Picard iteration with field="distributed" (the collectives between them are
+    # picard()'s; tests drive several emulated ranks on one GPU through these phases)
+    def iter_particles(self, j):
+        """Particle kernels of both species blocks, then the boundary bands / partial sums -> self.msg."""
         st = D.stream()
+        ev = None
+        if self.iter_events is not None:
+            ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+            ev[0].record()
+        for blk in self.blocks:
+            if blk.n:
+                _lib.call("pic_dev_dd_picard_iter4", C.byref(self._params(blk)), D.ptr(blk.x0), D.ptr(blk.u0), D.ptr(blk.x1),
+                          D.ptr(blk.x1), D.ptr(blk.u1), D.ptr(blk.active), D.ptr(self.Es), D.ptr(self.acc), 1 if j == 0 else 0,
+                          D.ptr(self.range_err), D.ptr(self.ctl), D.ptr(blk.dead_buf), blk.dead_cap, None, j, st)
+                self.kernel_launches += 1
+        if ev is not None:
+            ev[1].record()
+            self.iter_events.append(ev)
+        Ng = self.Ng
+        if self.field == "distributed":
+            # (also adds this rank's own absorptions of the iteration to _absorbed_local)
+            _lib.call("pic_dev_slab_pack", *self._slab_args(), D.ptr(self.acc), D.ptr(self.msg), D.ptr(self.work),
+                      D.ptr(self._absorbed_local), D.ptr(self.ctl), st)
+            self.kernel_launches += 1
+        else:
+            self._absorbed_local += self.acc[2 * Ng:2 * Ng + 4]   # this rank's own absorptions (before the exchange)
+
+    def iter_field(self):
+        """self.gath (all ranks' messages) -> E1, Es, j0 on the band; residual / energy partials -> self.part."""
+        _lib.call("pic_dev_slab_field_update", *self._slab_args(), D.ptr(self.acc), D.ptr(self.gath), D.ptr(self.wall_cum),
+                  D.ptr(self.E0), D.ptr(self.Es), D.ptr(self.E1), D.ptr(self.j0), D.ptr(self.part), D.ptr(self.work),
+                  D.ptr(self.ctl), D.stream())
+        self.kernel_launches += 1
+
+    def iter_finish(self):
+        """self.gath2 (all ranks' partials) -> counts, statistics, loop flag."""
+        _lib.call("pic_dev_slab_finish", *self._slab_args(), D.ptr(self.gath), D.ptr(self.gath2), D.ptr(self.wall_cum),
+                  D.ptr(self.stats), D.ptr(self.stats) + 8 * 8, D.ptr(self.ctl), self.tol, self.maxiter, D.stream())
+        self.kernel_launches += 1
+
+    def begin_step(self):
         if self.stats.numel() < 8 + self.maxiter:
             self.stats = D.f64(8 + self.maxiter, self.dev, True)
         self.Es.copy_(self.E0)
         self.wall_cum.zero_(); self.stats.zero_(); self.ctl.zero_()
         self._absorbed_local.zero_()
+
+    def outcome(self):
+        s_ = D.read_f64(self.stats, 8 + self.maxiter)
+        k_ = int(s_[3])
+        return k_, [float(v) for v in s_[8:8 + k_]]
+
+    def end_step(self, k):
+        self._prev_k = k
+        if k > 0:
+            for blk in self.blocks:
+                blk.commit()
+            self.E0, self.E1 = self.E1, self.E0
+        a = self._absorbed_local.cpu().numpy()                      # [left e, left i, right e, right i]
+        self.local_dead = [int(round(a[0] + a[2])), int(round(a[1] + a[3]))]
+        if self.field == "distributed" and self.world > 1:
+            # deposits outside the band are never exchanged (nor cleared): one look per step
+            if self._leak_idx is None:
+                out = np.concatenate([np.arange(0, self.b0), np.arange(self.b1, self.Ng)]).astype(np.int64)
+                self._leak_idx = torch.as_tensor(np.concatenate([out, self.Ng + out]), device=self.dev)
+            self.guard_leak += self.acc[self._leak_idx].abs().sum()
+
+    def gather_field(self, which="E0"):
+        """The complete grid array (E0 or j0) on every rank, assembled from the owned segments (diagnostics / tests;
+        with field="replicated" every rank already holds it)."""
+        a = getattr(self, which)
+        if self.field == "replicated" or self.world == 1:
+            return a.clone()
+        buf = D.f64(self.seglen, self.dev, True)
+        o0, o1 = self.seg[self.rank]
+        buf[:o1 - o0] = a[o0:o1]
+        allb = D.f64(self.world * self.seglen, self.dev, True)
+        dist.all_gather_into_tensor(allb, buf, group=self.comm.group)
+        out = D.f64(self.Ng, self.dev, True)
+        for r, (s0, s1) in enumerate(self.seg):
+            out[s0:s1] = allb[r * self.seglen:r * self.seglen + s1 - s0]
+        return out
+
+    # ------------------------------------------------------------------ one timestep
+    def picard(self):
+        """PIC_L_DD.py:452-545 on slabs.  Every launch of an iteration (particle kernels, field kernels) is
+        guarded by the device flag `ctl`; the exchanges between them are unguarded library calls, which move
+        stale messages once the loop has ended (nobody reads them), so queued iterations behind the end of the
+        loop are harmless no-ops."""
+        st = D.stream()
+        self.begin_step()
         Pg = self._params(self.blocks[0])
         rhist = D.ptr(self.stats) + 8 * 8
-        Ng = self.Ng
+
+        def mark():
+            if self.phase_events is not None:      # diagnostics: 6 marks per iteration (tools/slab_phases.py)
+                e = torch.cuda.Event(enable_timing=True); e.record(); self.phase_events.append(e)
 
         def launch(j):
-            ev = None
-            if self.iter_events is not None:
-                ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
-                ev[0].record()
-            for blk in self.blocks:
-                if blk.n:
-                    _lib.call("pic_dev_dd_picard_iter4", C.byref(self._params(blk)), D.ptr(blk.x0), D.ptr(blk.u0), D.ptr(blk.x1),
-                              D.ptr(blk.x1), D.ptr(blk.u1), D.ptr(blk.active), D.ptr(self.Es), D.ptr(self.acc), 1 if j == 0 else 0,
-                              D.ptr(self.range_err), D.ptr(self.ctl), D.ptr(blk.dead_buf), blk.dead_cap, None, j, st)
-                    self.kernel_launches += 1
-            if ev is not None:
-                ev[1].record()
-                self.iter_events.append(ev)
-            self._absorbed_local += self.acc[2 * Ng:2 * Ng + 4]   # this rank's own absorptions (before the exchange)
+            mark()
+            self.iter_particles(j)
+            if self.field == "distributed":
+                mark(); self._all_gather(self.gath, self.msg)
+                mark(); self.iter_field()
+                mark(); self._all_gather(self.gath2, self.part)
+                mark(); self.iter_finish()
+                mark()
+                return
             if self.profile is not None:
                 import time
                 torch.cuda.synchronize(); t0 = time.perf_counter()
@@ -488,11 +621,7 @@ class SlabSheathSim:
                       self.tol, self.maxiter, st)
             self.kernel_launches += 1
 
-        def outcome():
-            s_ = D.read_f64(self.stats, 8 + self.maxiter)
-            k_ = int(s_[3])
-            return k_, [float(v) for v in s_[8:8 + k_]]
-
+        outcome = self.outcome
         k, hist, queued = 0, [], 0
         if self.enqueue_ahead and self._prev_k and self.profile is None:
             for j in range(min(self._prev_k, self.maxiter)):
@@ -503,13 +632,7 @@ class SlabSheathSim:
             launch(k); queued += 1
             k, hist = outcome()
             r = hist[-1]
-        self._prev_k = k
-        if k > 0:
-            for blk in self.blocks:
-                blk.commit()
-            self.E0, self.E1 = self.E1, self.E0
-        a = self._absorbed_local.cpu().numpy()                      # [left e, left i, right e, right i]
-        self.local_dead = [int(round(a[0] + a[2])), int(round(a[1] + a[3]))]
+        self.end_step(k)
         return k, r
 
     def step(self):

@@ -184,19 +184,28 @@ def test_pygcpic_particle_ionisation_attempts_golden(golden):
         G.Particle(G.mp, 0, 1.0, 1.0, 1, grid=grid).attempt_nth_ionization(1e-7, 1e5, grid)
 
 
-def test_pic_l_main_module(golden, tmp_path):
-    """PIC_L.main(T, nplot) from the same seed as the golden reference run (N literal 6000)."""
+@pytest.mark.parametrize("sort_every", [None, 3])
+def test_pic_l_main_module(golden, tmp_path, sort_every):
+    """PIC_L.main(T, nplot) from the same seed as the golden reference run (N literal 6000); with the cell sort
+    (what main does by itself from 2^17 particles on) the window kernel runs and the particles come back in
+    the reference's order."""
     import PIC_L
     g = golden("l_main")
     N = int(g["N"]); T = int(g["T"])
     res = {}
     np.random.seed(1)
     with scratch_cwd(str(tmp_path)):
-        EE = PIC_L.main(T, 1, N=N, result=res)
+        EE = PIC_L.main(T, 1, N=N, result=res, sort_every=sort_every)
         EE_file = np.loadtxt("plots/E2.txt")
     assert relmax(EE, g["EE"]) < 1e-9
     assert np.array_equal(EE_file, np.array(EE))
     assert relmax(res["E_series"], g["E_series"]) < 1e-9
+    if sort_every:
+        ref = {}
+        np.random.seed(1)
+        with scratch_cwd(str(tmp_path)):
+            PIC_L.main(T, 1, N=N, result=ref, sort_every=0)
+        assert relmax(res["x"], ref["x"]) < 1e-12 and relmax(res["v"], ref["v"]) < 1e-10
 
 
 # ------------------------------------------------------------------------------- pypic
@@ -228,6 +237,15 @@ def test_pypic_main_module_runs(tmp_path):
     assert len(EE) == 6 and np.all(np.isfinite(EE)) and np.all(EE > 0)
     tot = res["EE"] + res["KE"]
     assert abs(tot[-1] - tot[0]) < 0.05 * abs(tot[0])
+    # the same run on the sorted store (implicit_pic's own choice from 2^17 particles on): the window kernel runs,
+    # particles and series come back in the reference's order
+    srt = {}
+    np.random.seed(1)
+    with scratch_cwd(str(tmp_path)):
+        pypic.main(6, 10, N=40000, Ng=64, result=srt, sort_every=2)
+    assert relmax(srt["EE"], res["EE"]) < 1e-10 and relmax(srt["KE"], res["KE"]) < 1e-12
+    assert relmax(srt["x0"], res["x0"]) < 1e-12 and relmax(srt["v0"], res["v0"]) < 1e-10
+    assert relmax(srt["E0"], res["E0"]) < 1e-10
     assert res["x0"].min() >= 0.0 and res["x0"].max() <= 22.0 * np.sqrt(pypic.kb * 100.0 * 11600. * pypic.epsilon0 / pypic.e**2 / 1e5)
 
 

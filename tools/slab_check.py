@@ -40,8 +40,11 @@ def main():
     E0 = rs.normal(0, 1e4, Ng)
     p2c = L * 1e19 / N
 
+    field = os.environ.get("PIC_SLAB_FIELD", "distributed")
+
     def run(comm):
-        sim = SlabSheathSim(N, Ng, dx, dt, p2c, kBT=(kT, kT), comm=comm, device=dev, sort_every=2, guard=16, seed=5)
+        sim = SlabSheathSim(N, Ng, dx, dt, p2c, kBT=(kT, kT), comm=comm, device=dev, sort_every=2, guard=16, seed=5,
+                            field=field)
         sim.upload(x0, u0, E0)
         its, counts = [], []
         for _ in range(steps):
@@ -52,6 +55,7 @@ def main():
         return sim, its, counts
     slab, its_s, cnt_s = run(Comm())
     parts = slab.gather_particles()
+    E_slab = slab.gather_field("E0").cpu().numpy()        # every rank holds its own nodes + guard nodes only
     tot = torch.tensor([slab.local_particles()], dtype=torch.int64, device=dev)
     if world > 1:
         dist.all_reduce(tot)
@@ -65,9 +69,9 @@ def main():
     if rank == 0:
         one, its_1, cnt_1 = run(Comm(enabled=False))
         ref = one.gather_particles()
-        res = dict(world=world, N=N, Ng=Ng, iters_slab=its_s, iters_single=its_1, total_particles=int(tot.item()),
+        res = dict(world=world, N=N, Ng=Ng, field=field, iters_slab=its_s, iters_single=its_1, total_particles=int(tot.item()),
                    local_counts_rank0=cnt_s, stat=slab.stat, inside_guard=inside,
-                   E_rel=rel(slab.E0.cpu().numpy(), one.E0.cpu().numpy()))
+                   E_rel=rel(E_slab, one.E0.cpu().numpy()))
         ok = its_s == its_1 and int(tot.item()) == N and inside and res["E_rel"] < 1e-9
         for name, i in (("electrons", 0), ("ions", 3)):
             xa, xb = np.sort(parts[i]), np.sort(ref[i])
