@@ -211,8 +211,8 @@ class SlabSheathSim:
         self.work = D.f64(int(lib.pic_slab_work_len()), dev, True)
         self.b0, self.b1 = max(self.c0 - self.G, 0), min(self.c1 + self.G + 1, self.Ng)     # the band this rank computes
         self._leak_idx = None
-        if self.world > 1:
-            self._warm_collectives()
+        if self.world > 1 and getattr(self.comm, "enabled", False) and dist.is_initialized():
+            self._warm_collectives()          # (emulated ranks -- tests -- have no process group)
 
     def _warm_collectives(self):
         """One call of every collective the step uses, with non-empty messages: NCCL sets up its point-to-point
