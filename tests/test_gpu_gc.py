@@ -455,3 +455,68 @@ def test_uniform_rk4_kernel_is_bit_identical_to_v1():
             out[uni] = st.r_host()
         assert np.array_equal(out[True], out[False])
         assert not np.array_equal(out[True][:, :4], r[:, :4])
+
+
+def test_boris_at_baseline_config_3_size_against_the_oracle_on_a_sample():
+    """BASELINE config 3 at its full size: 2e8 H+ in a field at 86 degrees to the wall normal, 4097 nodes, the fused
+    lean kernel (gather + Boris + walls + density deposit) on a cell-sorted store, three steps.  A random sample of
+    2e5 particles is checked BIT FOR BIT against the NumPy restatement of pygcpic.py:344-347 (mirrored gather),
+    :460-507 (Boris) and :668-689 (walls) every step; over ALL particles: the wall hits the kernel counts equal the
+    flags it cleared, and the deposited density integrates to the number of survivors (every particle puts
+    p2c/dx * (w_l + w_r) on the grid, pygcpic.py:873-883)."""
+    import torch
+    from pypic_b200.gcstore import GridDev, ParticleStore
+    free, _ = torch.cuda.mem_get_info()
+    N = 200_000_000 if free > 60e9 else 20_000_000
+    ng = 4097
+    Te, Ti = 60. * 11600., 50. * 11600.
+    lamD = np.sqrt(8.854e-12 * O.kb * Te / (1e19 * O.e ** 2))
+    Lg = 100. * lamD * (ng - 1) / 149.
+    alpha = 86. * np.pi / 180.
+    B = (2. * np.cos(alpha), 2. * np.sin(alpha), 0.)
+    dt = 1e-10
+    dev = torch.device("cuda", torch.cuda.current_device())
+    gen = torch.Generator(device=dev); gen.manual_seed(77)
+    grid = GridDev(ng, Lg, Te)
+    rs = np.random.RandomState(8)
+    E = rs.normal(0, 5e4, ng)
+    grid.E.copy_(torch.as_tensor(E))
+    dx = grid.dx
+    store = ParticleStore(N, B=B)
+    store.r[0].uniform_(0., 1., generator=gen).mul_(Lg).clamp_(Lg * 1e-9, Lg * (1 - 1e-9))
+    # a thin layer next to each wall so that every step absorbs particles there
+    edge = N // 2000
+    store.r[0][:edge].mul_(2e-3); store.r[0][edge:2 * edge].mul_(2e-3).neg_().add_(Lg)
+    vth = float(np.sqrt(O.kb * Ti / O.mp))
+    for c in (3, 4, 5):
+        store.r[c].normal_(0., vth, generator=gen)
+    p2c = Lg * 1e19 / N
+    store.charge_state.fill_(1.); store.m.fill_(O.mp); store.p2c.fill_(p2c); store.Z.fill_(1)
+    store.carry_yzt = False
+    store.sort_by_cell(grid)
+    idx = torch.randint(0, N, (200000,), generator=gen, device=dev)
+    total_hits = 0
+    for step in range(3):
+        xb = store.r[0][idx].cpu().numpy()
+        vb = np.stack([store.r[c][idx].cpu().numpy() for c in (3, 4, 5)], 1)
+        ab = store.active[idx].cpu().numpy()
+        hits = store.push_6D(dt, grid, deposit=True)
+        grid.finish_fused_deposit(1.0, dt)
+        store.check(); grid.check()
+        total_hits += hits
+        xa = store.r[0][idx].cpu().numpy()
+        va = np.stack([store.r[c][idx].cpu().numpy() for c in (3, 4, 5)], 1)
+        aa = store.active[idx].cpu().numpy()
+        r = np.zeros((len(xb), 7)); r[:, 0] = xb; r[:, 3:6] = vb
+        live = ab == 1
+        Ex = np.zeros(len(xb)); Ex[live] = O.gc_gather_mirrored(E, xb[live], dx)
+        r2 = O.gc_push_6D(r, Ex, B, 1.0, O.mp, dt)
+        act2, _ = O.gc_apply_BCs_dirichlet(r2[:, 0], ab.astype(np.int64), np.zeros(len(xb), np.int64), Lg)
+        assert np.array_equal(aa[live], act2[live])
+        assert np.array_equal(xa[live], r2[live, 0]) and np.array_equal(va[live], r2[live, 3:6])
+        assert np.array_equal(xa[~live], xb[~live]) and np.array_equal(va[~live], vb[~live])       # dead slots are not touched
+        dead_all = int((store.active[:N] != 1).sum().item())
+        assert dead_all == total_hits and hits > 0
+        n = grid.n.cpu().numpy()
+        assert abs(n.sum() * dx / p2c - (N - dead_all)) <= 1e-9 * N
+    assert total_hits > 100
