@@ -128,7 +128,8 @@ def initialize(system, N, density, Kp, perturbation, dx, Ng, Te, Ti, L, X):
 
 
 def main_i(T, nplot, N=40000, Ng=51, dt=1E-12, dx=0.00001, Ti=10.0 * 11600., Te=10.0 * 11600., density=1E19,
-           gamma=0.0, tol=1E-5, maxiter=20, outdir='.', rng='host', result=None, sort_every=None, vion_after=2000):
+           gamma=0.0, tol=1E-5, maxiter=20, outdir='.', rng='host', result=None, sort_every=None, vion_after=2000,
+           deposit='window'):
     """PIC_L_DD.main_i (PIC_L_DD.py:316-644).  The positional signature is the reference's;
     the keyword arguments default to its hard-coded literals.  `result` (a dict) receives
     the time series and the final state.
@@ -137,7 +138,9 @@ def main_i(T, nplot, N=40000, Ng=51, dt=1E-12, dx=0.00001, Ti=10.0 * 11600., Te=
     fused TMA kernel; the sort carries every particle's original index, so the legacy-RNG
     re-injection draws (made in index order, :429-450), vionout (:497-503) and every array handed
     back are in the reference's particle numbering.  The thermostat's uniforms of a gamma == 0 run
-    are skipped by an MT19937 jump-ahead instead of being generated (pypic_b200/rng.py)."""
+    are skipped by an MT19937 jump-ahead instead of being generated (pypic_b200/rng.py).
+    deposit='window-det' runs the REPRODUCIBLE build: fixed-point accumulation of the currents, stable radix sort
+    with the original-index payload and fixed-order diagnostics sums -- two runs give bit-identical output."""
     perturbation = 0.0
     Kp = 1.0
     L = dx * (Ng - 1)
@@ -156,7 +159,7 @@ def main_i(T, nplot, N=40000, Ng=51, dt=1E-12, dx=0.00001, Ti=10.0 * 11600., Te=
     print("floating potential: ", (kb * Te / e) * (0.5) * np.log(mp / 2.0 / np.pi / me))
 
     sim = SheathSim(N, Ng, dx, dt, p2c, q=(-e, e), m=(me, mp), tol=tol, maxiter=maxiter, kBT=(kBTe, kBTi),
-                    gamma=gamma, carry_vw=True, rng=rng, sort_every=sort_every, vion_after=vion_after)
+                    gamma=gamma, carry_vw=True, rng=rng, sort_every=sort_every, vion_after=vion_after, deposit=deposit)
     sim.upload(x0, u0, v0, w0)          # E0 = -d(phi0)/dx with phi0 == 0 (PIC_L_DD.py:386-388)
     mpl, plt = get_plt()
     KE, EE, TT, jbias = [], [], [], []
@@ -164,7 +167,8 @@ def main_i(T, nplot, N=40000, Ng=51, dt=1E-12, dx=0.00001, Ti=10.0 * 11600., Te=
     # moments of the same velocities: the first Picard iteration of the step accumulates them while it streams
     # u0 (SheathSim.fused_moments), so they arrive with the step's one device->host read and 'kBTe' is printed
     # right after the step has run -- in the reference's output order (nothing else prints in between)
-    sim.fused_moments = (rng == 'host')              # device-mode re-injection: a pass of their own before the step
+    # (device-mode re-injection and the reproducible build: a pass of their own before the step)
+    sim.fused_moments = (rng == 'host')
     t_loop = time.perf_counter()
     with sim.draws.hold():                           # the legacy stream's state stays in C for the duration of the loop
         for t in range(T + 1):

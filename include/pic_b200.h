@@ -384,7 +384,8 @@ int pic_dev_dd_reinject_philox(const pic_dd_params* p, double* x0, double* u0, d
  * started hold x1=u1=0 like the reference (PIC_L_DD.py:459-462); the commit itself is a
  * pointer swap on the host.  KE diagnostic sum(me*u^2/2) (PIC_L_DD.py:549): */
 int pic_dev_sum_sq(const double* u, int64_t N, double scale, double* out1, void* stream);
-/* out2 = {sum u, sum u*u} in one pass: np.std(u0) (PIC_L_DD.py:417) and KE (:549) together */
+/* out2 = {sum u, sum u*u} in one pass: np.std(u0) (PIC_L_DD.py:417) and KE (:549) together; per-CTA partial sums added
+ * in CTA order (for a given particle order the result does not depend on scheduling) */
 int pic_dev_moments(const double* u, int64_t N, double* out2, void* stream);
 /* Counting sort by (species, cell) of the n-level state; out-of-place.  Keeps species
  * ranges contiguous; order inside a cell is unspecified (benchmark mode only).
@@ -409,6 +410,13 @@ int pic_dev_dd_sort_by_cell2(const pic_dd_params* p, const double* x0, const dou
 int pic_dev_dd_sort_by_cell_stable(const pic_dd_params* p, double* x0, double* u0, double* xs, double* us,
                                    int32_t* scratch, int64_t scratch_entries, int32_t* result_in_scratch,
                                    void* stream);
+/* The stable sort carrying the ORIGINAL INDEX of every particle (int32) through its passes, for a reproducible
+ * run that keeps the reference's particle numbering (pic_dev_dd_sort_by_cell2's role in the reproducible build).
+ * orig / origs ping-pong like (x0,u0) / (xs,us); identity != 0: orig's content is ignored and the numbering
+ * starts as the slot index (first sort). */
+int pic_dev_dd_sort_by_cell_stable2(const pic_dd_params* p, double* x0, double* u0, double* xs, double* us, int32_t* orig,
+                                    int32_t* origs, int identity, int32_t* scratch, int64_t scratch_entries,
+                                    int32_t* result_in_scratch, void* stream);
 /* The same counting sort for any structure-of-arrays store: xs receives the sorted positions and
  * perm (int32[N]) the source slot of every output slot; apply it to the other arrays with
  * pic_dev_soa_permute.  Only p->N, n_split, Ng, dx are read. */

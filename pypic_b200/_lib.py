@@ -125,6 +125,7 @@ _SIGS = {
     "pic_dev_sum_sq": [P, I64, F64, P, P],
     "pic_dev_dd_sort_by_cell": [C.POINTER(DDParams), P, P, P, P, P, P, P, P, P, P],
     "pic_dev_dd_sort_by_cell_stable": [C.POINTER(DDParams), P, P, P, P, P, I64, C.POINTER(C.c_int), P],
+    "pic_dev_dd_sort_by_cell_stable2": [C.POINTER(DDParams), P, P, P, P, P, P, I32, P, I64, C.POINTER(C.c_int), P],
     "pic_dev_sort_perm_by_cell": [C.POINTER(DDParams), P, P, P, P, P],
     "pic_dev_sort_by_cell_payload": [C.POINTER(DDParams), P, P, P, P, P, P, P, P, P, P, P],
     "pic_dev_soa_permute": [P, I64, P, P, I32, P, P, I32, P, P, I32, P],

@@ -1571,7 +1571,8 @@ __global__ void __launch_bounds__(RS_T) rsort_hist_k(const double* __restrict__ 
 __global__ void __launch_bounds__(RS_T) rsort_scatter_k(const double* __restrict__ x, const double* __restrict__ u,
                                                         long long n, double dx, int Ng, int shift, int ntiles,
                                                         const int32_t* __restrict__ H, double* __restrict__ xo,
-                                                        double* __restrict__ uo) {
+                                                        double* __restrict__ uo, const int32_t* __restrict__ oid,
+                                                        int32_t* __restrict__ oido, long long oid_base) {
     extern __shared__ int rs_sm[];
     int (*wcnt)[256] = (int (*)[256])rs_sm;                // elements of warp w with digit d in the current round (kept zero between rounds)
     int (*wpre)[256] = (int (*)[256])(rs_sm + 32 * 256);   // output position of the first of them
@@ -1606,6 +1607,8 @@ __global__ void __launch_bounds__(RS_T) rsort_scatter_k(const double* __restrict
                 const long long pos = (long long)wpre[w][d] + below;
                 xo[pos] = X;
                 uo[pos] = u[i];
+                // original-index payload (oid == nullptr: this pass starts from the identity numbering)
+                if (oido) oido[pos] = oid ? oid[i] : (int32_t)(oid_base + i);
             }
             // the next round rewrites wpre only after its own first barrier, which every thread
             // reaches after the reads above
@@ -1702,6 +1705,9 @@ __global__ void invert_perm_k(const int32_t* __restrict__ perm, int32_t* __restr
     for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < n; t += (long long)gridDim.x * blockDim.x) inv[perm[t]] = (int32_t)t;
 }
 // out[0] += sum u, out[1] += sum u*u  (np.std(u0) and the kinetic-energy diagnostic from ONE pass)
+#define MOM_MAX_CTAS 2048
+__device__ double g_mom_part[2 * MOM_MAX_CTAS];
+__device__ unsigned g_mom_ticket;
 __global__ void moments_k(const double* __restrict__ u, long long N, double* __restrict__ out) {
     __shared__ double scratch[33];
     double s1 = 0.0, s2 = 0.0;
@@ -1711,7 +1717,23 @@ __global__ void moments_k(const double* __restrict__ u, long long N, double* __r
     }
     s1 = block_reduce<0>(s1, scratch);
     s2 = block_reduce<0>(s2, scratch);
-    if (threadIdx.x == 0) { atomicAdd(out, s1); atomicAdd(out + 1, s2); }
+    // per-CTA partial sums, added by the CTA that finishes last IN CTA ORDER: for a given particle order the two
+    // sums do not depend on scheduling (the reproducible build's diagnostics are bit-reproducible too)
+    __shared__ int s_last;
+    if (threadIdx.x == 0) {
+        g_mom_part[2 * blockIdx.x] = s1; g_mom_part[2 * blockIdx.x + 1] = s2;
+        __threadfence();
+        const unsigned t = atomicAdd(&g_mom_ticket, 1u);
+        s_last = (t == gridDim.x - 1);
+        if (s_last) g_mom_ticket = 0;
+        __threadfence();
+    }
+    __syncthreads();
+    if (s_last && threadIdx.x < 2) {
+        double a = 0.0;
+        for (int c = 0; c < (int)gridDim.x; ++c) a += __ldcg(&g_mom_part[2 * c + threadIdx.x]);
+        out[threadIdx.x] += a;
+    }
 }
 // slots named in the absorption log -> re-injected with Philox draws (no flag scan)
 __global__ void dd_reinject_philox_log_k(DDK k, const int* __restrict__ buf, double* __restrict__ x0,
@@ -2341,11 +2363,12 @@ int pic_dev_sum_sq(const double* u, int64_t N, double scale, double* out1, void*
     return PIC_OK;
 }
 
-int pic_dev_dd_sort_by_cell_stable(const pic_dd_params* p, double* x0, double* u0, double* xs, double* us,
-                                   int32_t* scratch, int64_t scratch_entries, int32_t* result_in_scratch,
-                                   void* stream) {
+static int sort_by_cell_stable_impl(const pic_dd_params* p, double* x0, double* u0, double* xs, double* us, int32_t* o0,
+                                    int32_t* o1, int identity, int32_t* scratch, int64_t scratch_entries,
+                                    int32_t* result_in_scratch, void* stream) {
     PIC_REQUIRE(p && x0 && u0 && xs && us && scratch && result_in_scratch, "dd_sort_by_cell_stable: null pointer");
     PIC_REQUIRE(p->N >= 0 && p->N < 2147483647LL && p->Ng >= 2 && p->dx > 0, "dd_sort_by_cell_stable: bad parameters");
+    PIC_REQUIRE((o0 == nullptr) == (o1 == nullptr), "dd_sort_by_cell_stable: both payload buffers or none");
     cudaStream_t st = (cudaStream_t)stream;
     int bits = 0;
     while ((1 << bits) < p->Ng) ++bits;           // cells 0 .. Ng-1
@@ -2364,6 +2387,7 @@ int pic_dev_dd_sort_by_cell_stable(const pic_dd_params* p, double* x0, double* u
         const int ntiles = (int)ntl;
         const int grid = (int)(ntl < (long long)device_sm_count() * 2 ? ntl : (long long)device_sm_count() * 2);
         double *sx = x0 + off, *su = u0 + off, *dx_ = xs + off, *du = us + off;
+        int32_t *so = o0 ? o0 + off : nullptr, *dso = o1 ? o1 + off : nullptr;
         const size_t smem = (size_t)2 * 32 * 256 * sizeof(int);
         PIC_CHECK_CUDA(cudaFuncSetAttribute(rsort_scatter_k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         for (int ps = 0; ps < passes; ++ps) {
@@ -2375,13 +2399,28 @@ int pic_dev_dd_sort_by_cell_stable(const pic_dd_params* p, double* x0, double* u
             PIC_CHECK_LAUNCH();
             scan_add_k<<<(int)nblk, 1024, 0, st>>>(H, (int)nH, sums);
             PIC_CHECK_LAUNCH();
-            rsort_scatter_k<<<grid, RS_T, smem, st>>>(sx, su, n, p->dx, p->Ng, 8 * ps, ntiles, H, dx_, du);
+            rsort_scatter_k<<<grid, RS_T, smem, st>>>(sx, su, n, p->dx, p->Ng, 8 * ps, ntiles, H, dx_, du,
+                                                      (ps == 0 && identity) ? nullptr : so, dso, off);
             PIC_CHECK_LAUNCH();
             double* t = sx; sx = dx_; dx_ = t;
             t = su; su = du; du = t;
+            int32_t* ti = so; so = dso; dso = ti;
         }
     }
     return PIC_OK;
+}
+
+int pic_dev_dd_sort_by_cell_stable(const pic_dd_params* p, double* x0, double* u0, double* xs, double* us,
+                                   int32_t* scratch, int64_t scratch_entries, int32_t* result_in_scratch,
+                                   void* stream) {
+    return sort_by_cell_stable_impl(p, x0, u0, xs, us, nullptr, nullptr, 0, scratch, scratch_entries, result_in_scratch, stream);
+}
+
+int pic_dev_dd_sort_by_cell_stable2(const pic_dd_params* p, double* x0, double* u0, double* xs, double* us, int32_t* orig,
+                                    int32_t* origs, int identity, int32_t* scratch, int64_t scratch_entries,
+                                    int32_t* result_in_scratch, void* stream) {
+    PIC_REQUIRE(orig && origs, "dd_sort_by_cell_stable2: null payload buffer");
+    return sort_by_cell_stable_impl(p, x0, u0, xs, us, orig, origs, identity, scratch, scratch_entries, result_in_scratch, stream);
 }
 
 int pic_dev_dd_sort_by_cell(const pic_dd_params* p, const double* x0, const double* u0, const double* v0,
@@ -2533,7 +2572,9 @@ int pic_dev_moments(const double* u, int64_t N, double* out2, void* stream) {
     cudaStream_t st = (cudaStream_t)stream;
     PIC_CHECK_CUDA(cudaMemsetAsync(out2, 0, 2 * sizeof(double), st));
     if (N == 0) return PIC_OK;
-    moments_k<<<grid_for(N, 256, 8), 256, 0, st>>>(u, N, out2);
+    int grid = grid_for(N, 256, 8);
+    if (grid > MOM_MAX_CTAS) grid = MOM_MAX_CTAS;
+    moments_k<<<grid, 256, 0, st>>>(u, N, out2);
     PIC_CHECK_LAUNCH();
     return PIC_OK;
 }

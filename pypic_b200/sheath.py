@@ -74,9 +74,7 @@ class SheathSim:
         flags = {"window": 0, "window-blocked": 64, "window-big": 16, "window-ldg": 8, "atomic": 1,
                  "warp": 4, "window-det": 128}[deposit] | (2 if tiles == "global" else 0)
         self.det = deposit == "window-det"
-        if self.det and self.track and self.sort_every:
-            raise ValueError("deposit='window-det' sorts with the stable radix sort, which does not carry the original-index "
-                             "payload yet: use sort_every=0 or track_order=False")
+        # (with the tracked order the stable sort carries the original-index payload: pic_dev_dd_sort_by_cell_stable2)
         self.params = _lib.DDParams(self.N, self.n_split, self.Ng, flags, self.dx, self.dt, self.L, self.p2c,
                                     (C.c_double * 2)(*self.q), (C.c_double * 2)(*self.m))
         dev = self.dev
@@ -119,7 +117,7 @@ class SheathSim:
         # the re-injection kernel records what it changed, so np.std(u0) / KE of the state BEFORE the step
         # (PIC_L_DD.py:417, :549 of the previous step) come with the step's outcome read instead of a pass of
         # their own (pre_step_moments)
-        self.fused_moments = False
+        self._fused_moments = False
         self._pre_mom = None
         # enqueue-ahead Picard loop: the iterations the previous step needed are queued back to back,
         # guarded by a device flag that the field kernel raises when the loop condition fails; the
@@ -447,6 +445,16 @@ class SheathSim:
         _lib.call("pic_dev_zero", D.ptr(self.dead_buf), 16, D.stream())
         self._log_valid = True
 
+    @property
+    def fused_moments(self):
+        return self._fused_moments
+
+    @fused_moments.setter
+    def fused_moments(self, on):
+        # the fused sums are merged with fp64 atomics in scheduling order: not with the reproducible build, whose
+        # diagnostics come from the fixed-order reduction of pic_dev_moments
+        self._fused_moments = bool(on) and not self.det
+
     def sort_by_cell(self):
         """Counting sort by (species, cell) into the scratch arrays."""
         st = D.stream()
@@ -455,6 +463,28 @@ class SheathSim:
             # slots are alive here (re-injection ran before), so the flags need no permutation, and the
             # passive v,w are not moved at all
             P = self.params
+            if self.det:
+                # reproducible build: the STABLE radix sort with the payload -- the order inside a cell is the previous
+                # order, so the private-window sums (and with them every bit of the run) do not depend on scheduling
+                identity = self.oid is None
+                if identity:
+                    self.oid = torch.empty(max(self.N, 1), dtype=torch.int32, device=self.dev)
+                if self.oid_alt is None:
+                    self.oid_alt = torch.empty(max(self.N, 1), dtype=torch.int32, device=self.dev)
+                where = C.c_int(0)
+                _lib.call("pic_dev_dd_sort_by_cell_stable2", C.byref(P), D.ptr(self.x0), D.ptr(self.u0), D.ptr(self.x1),
+                          D.ptr(self.u1), D.ptr(self.oid), D.ptr(self.oid_alt), 1 if identity else 0, D.ptr(self.sort_scratch),
+                          self.sort_scratch.numel(), C.byref(where), st)
+                passes = (max(1, (self.Ng - 1).bit_length()) + 7) // 8
+                self.kernel_launches += 5 * passes * ((self.n_split > 0) + (self.n_split < self.N))
+                if where.value:
+                    self.x0, self.x1 = self.x1, self.x0
+                    self.u0, self.u1 = self.u1, self.u0
+                    self.oid, self.oid_alt = self.oid_alt, self.oid
+                self._inv = None
+                self._sorted_once = True
+                self._sorts += 1
+                return
             if self._sorted_once:
                 P = _lib.DDParams(self.N, self.n_split, self.Ng, self.params.flags | 32, self.dx, self.dt, self.L, self.p2c,
                                   (C.c_double * 2)(*self.q), (C.c_double * 2)(*self.m))
@@ -568,7 +598,7 @@ class SheathSim:
         else:
             _lib.call("pic_dev_dd_step_begin", D.ptr(self.Es), D.ptr(self.E0), self.Ng, D.ptr(self.wall_cum), D.ptr(self.stats),
                       nst + 2, D.ptr(self.ctl), st)
-        mom_ptr = D.ptr(self.stats) + 8 * nst if self.fused_moments else None
+        mom_ptr = D.ptr(self.stats) + 8 * nst if self.fused_moments else None      # (never with the reproducible build)
         rhist = D.ptr(self.stats) + 8 * 8
         pairs = [(self.x1, self.x1b), (self.x1b, self.x1)] if self.elide_u else [(self.x1, self.x1)]
         queued = []                      # per iteration launched: (want_u, events or None)

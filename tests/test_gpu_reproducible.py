@@ -157,3 +157,64 @@ def test_reproducible_run_on_a_grid_beyond_one_cta():
         assert d.step()[0] == r.step()[0]
     Ed, Er = d.E0.cpu().numpy(), r.E0.cpu().numpy()
     assert np.abs(Ed - Er).max() < 1e-10 * np.abs(Ed).max()
+
+
+@pytest.mark.parametrize("N,Ng,n_split", [(300001, 4097, None), (70000, 51, 1234), (123457, 70001, 60000), (4096, 300, 4096)])
+def test_stable_sort_carries_the_original_index(N, Ng, n_split):
+    """pic_dev_dd_sort_by_cell_stable2: the int32 payload travels with (x, u) through every radix pass -- first sort
+    from the identity numbering, second sort (after the particles moved) from the carried one: the payload is
+    np.argsort(cell, kind='stable') composed with the previous permutation."""
+    import torch
+    from pypic_b200 import _lib, device as D
+    dev = D.require_cuda()
+    rs = np.random.RandomState(N % 997)
+    dx = 1e-5; L = dx * (Ng - 1)
+    x = rs.uniform(0, L, N); u = rs.normal(0, 1, N)
+    ns = N // 2 if n_split is None else n_split
+    P = _lib.DDParams(N, ns, Ng, 128, dx, 1e-12, L, 1.0, (C.c_double * 2)(-O.e, O.e), (C.c_double * 2)(O.me, O.mp))
+    bufs = [D.to_dev(x, dev), D.to_dev(u, dev), torch.empty(N, dtype=torch.float64, device=dev),
+            torch.empty(N, dtype=torch.float64, device=dev)]
+    oid = [torch.full((N,), -7, dtype=torch.int32, device=dev), torch.full((N,), -7, dtype=torch.int32, device=dev)]
+    scratch = torch.zeros(D.sort_stable_scratch_size(N), dtype=torch.int32, device=dev)
+    cur_x, cur_u, cur_o = x.copy(), u.copy(), np.arange(N)
+    for rnd in range(2):
+        where = C.c_int(-1)
+        _lib.call("pic_dev_dd_sort_by_cell_stable2", C.byref(P), D.ptr(bufs[0]), D.ptr(bufs[1]), D.ptr(bufs[2]), D.ptr(bufs[3]),
+                  D.ptr(oid[0]), D.ptr(oid[1]), 1 if rnd == 0 else 0, D.ptr(scratch), scratch.numel(), C.byref(where), D.stream())
+        if where.value:
+            bufs = [bufs[2], bufs[3], bufs[0], bufs[1]]; oid = [oid[1], oid[0]]
+        cell = np.clip(np.floor(cur_x / dx).astype(np.int64), 0, Ng - 1)
+        o = np.concatenate([lo + np.argsort(cell[lo:hi], kind="stable") for lo, hi in ((0, ns), (ns, N))]).astype(np.int64)
+        cur_x, cur_u, cur_o = cur_x[o], cur_u[o], cur_o[o]
+        assert np.array_equal(bufs[0].cpu().numpy(), cur_x) and np.array_equal(bufs[1].cpu().numpy(), cur_u)
+        assert np.array_equal(oid[0].cpu().numpy().astype(np.int64), cur_o)
+        # the particles move before the next sort
+        cur_x = np.clip(cur_x + rs.normal(0, 3 * dx, N), 0, L * (1 - 1e-12))
+        bufs[0].copy_(torch.as_tensor(cur_x))
+
+
+def test_reproducible_run_through_the_reference_api_keeps_the_particle_numbering(tmp_path):
+    """PIC_L_DD.main_i(deposit='window-det'): the reference's own loop (legacy MT19937 re-injection in index order,
+    carried v,w) on the reproducible build WITH the cell sort -- the stable radix sort carries the original index.
+    Two runs give bit-identical series and particles (in the reference's numbering); against the default build
+    the run agrees to round-off."""
+    import contextlib, io, os
+    import PIC_L_DD
+    outs = []
+    for dep in ("window-det", "window-det", "window"):
+        res = {}
+        np.random.seed(3)
+        cwd = os.getcwd(); os.chdir(str(tmp_path))
+        try:
+            with contextlib.redirect_stdout(io.StringIO()):
+                PIC_L_DD.main_i(9, 10 ** 9, N=120000, Ng=257, result=res, sort_every=2, deposit=dep)
+        finally:
+            os.chdir(cwd)
+        outs.append(res)
+    a, b, d = outs
+    keys = [k for k in a if isinstance(a[k], np.ndarray)]
+    assert {"x0", "u0", "E0"} <= set(keys)
+    for k in keys:
+        assert np.array_equal(a[k], b[k]), k                      # bit for bit, diagnostics included
+    for k in ("x0", "u0", "E0"):
+        assert np.max(np.abs(a[k] - d[k])) <= 1e-9 * np.max(np.abs(d[k])), k
