@@ -306,9 +306,11 @@ class SlabSheathSim:
     # ------------------------------------------------------------------ re-injection
     def reinject(self):
         """PIC_L_DD.py:429-450 on slabs: every dead slot gets (x ~ U(0,L), u ~ N(0, sigma_s)) drawn for the
-        GLOBAL ordinal of that dead particle within its species; draws that land in another slab are
-        shipped there (one size exchange + one payload all-to-all per step for both species) and the
-        slots they leave are closed by swap-removal."""
+        GLOBAL ordinal of that dead particle within its species (Philox keyed by the ordinal, so the particle set
+        does not depend on the number of ranks).  The draws are REPLICATED: after one all-gather of the per-rank
+        dead counts every rank generates all draws of the step (a few thousand) and keeps the ones that land in
+        its slab -- no size exchange, no payload exchange.  Arrivals fill the rank's dead slots first; left-over
+        slots are closed by swap-removal, left-over arrivals appended."""
         st = D.stream()
         W, me_ = self.world, self.rank
         dead = []
@@ -320,8 +322,8 @@ class SlabSheathSim:
                 torch.cuda.synchronize(); t = time.perf_counter()
                 self.rprof[name] = self.rprof.get(name, 0.0) + t - t_last[0]; t_last[0] = t
         for sp, blk in enumerate(self.blocks):
-            # the kernels count what they absorb (acc[2Ng..], saved per rank by picard()): a species that
-            # lost nothing here needs no scan of its flags (always the case on interior ranks)
+            # the kernels count what they absorb (saved per rank by picard()): a species that lost nothing here
+            # needs no look at its flags (always the case on interior ranks)
             if self.local_dead[sp] == 0 and self.t > 0:
                 dead.append(0)
                 continue
@@ -349,67 +351,30 @@ class SlabSheathSim:
         else:
             allc = np.asarray([dead])
         tick("count_exchange")
-        if int(allc.sum()) == 0:
-            return
-        send = [[None, None] for _ in range(2)]      # per species: (x, u) sorted by destination, counts per destination
-        cnts = np.zeros((W, 2), dtype=np.int64)
-        holes = [np.zeros(0, np.int64), np.zeros(0, np.int64)]
         for sp, blk in enumerate(self.blocks):
-            nd = dead[sp]
-            if nd == 0:
+            total = int(allc[:, sp].sum())
+            if total == 0:
                 continue
-            ordinal = int(allc[:me_, sp].sum())
-            xd = D.f64(nd, self.dev); ud = D.f64(nd, self.dev)
+            nd = dead[sp]
+            first = int(allc[:me_, sp].sum())                # global ordinal of this rank's first dead particle
+            xd = D.f64(total, self.dev); ud = D.f64(total, self.dev)
             sig = (self._sigma(sp), self._sigma(sp))
-            _lib.call("pic_dev_init_uniform_maxwellian", D.ptr(xd), D.ptr(ud), None, None, nd, nd, 0.0, self.L,
+            _lib.call("pic_dev_init_uniform_maxwellian", D.ptr(xd), D.ptr(ud), None, None, total, total, 0.0, self.L,
                       C.byref((C.c_double * 2)(*sig)), C.byref((C.c_double * 2)(0., 0.)), self.seed,
-                      1000 + 2 * self.t + sp, ordinal, st)
-            idx = blk.dead_idx[:nd].to(torch.int64)
+                      1000 + 2 * self.t + sp, 0, st)
+            self.kernel_launches += 1
             if W == 1:
+                idx = blk.dead_idx[:nd].to(torch.int64)
                 blk.x0[idx] = xd; blk.u0[idx] = ud; blk.active[idx] = 1
                 continue
-            dest = self._dest(xd)
-            mine = dest == me_
-            li = idx[mine]
-            blk.x0[li] = xd[mine]; blk.u0[li] = ud[mine]; blk.active[li] = 1
-            out = ~mine
-            order = torch.argsort(dest[out], stable=True)
-            send[sp] = [xd[out][order], ud[out][order]]
-            cnts[:, sp] = torch.bincount(dest[out], minlength=W).cpu().numpy()
-            holes[sp] = np.sort(idx[out].cpu().numpy())
-        tick("draw_and_route")
-        if W == 1:
-            return
-        # ---- one size exchange, one payload exchange: to rank r goes [x_e | u_e | x_i | u_i] of its arrivals
-        sizes = torch.as_tensor(cnts.reshape(-1), device=self.dev)
-        rsizes = torch.empty_like(sizes)
-        dist.all_to_all_single(rsizes, sizes, group=self.comm.group)
-        rc = rsizes.cpu().numpy().reshape(W, 2)                           # arrivals from rank r, per species
-        offs = np.concatenate([np.zeros((1, 2), np.int64), np.cumsum(cnts, 0)])
-        empty = torch.empty(0, dtype=torch.float64, device=self.dev)
-        pieces = []
-        for r in range(W):
-            for sp in range(2):
-                for comp in range(2):
-                    pieces.append(send[sp][comp][offs[r, sp]:offs[r + 1, sp]] if send[sp][0] is not None else empty)
-        payload = torch.cat(pieces) if pieces else empty
-        in_splits = [int(2 * (cnts[r, 0] + cnts[r, 1])) for r in range(W)]
-        out_splits = [int(2 * (rc[r, 0] + rc[r, 1])) for r in range(W)]
-        recv = torch.empty(sum(out_splits), dtype=torch.float64, device=self.dev)
-        dist.all_to_all_single(recv, payload, out_splits, in_splits, group=self.comm.group)
-        tick("payload_exchange")
-        arr = [[[], []], [[], []]]
-        o = 0
-        for r in range(W):
-            for sp in range(2):
-                n_ = int(rc[r, sp])
-                arr[sp][0].append(recv[o:o + n_]); arr[sp][1].append(recv[o + n_:o + 2 * n_])
-                o += 2 * n_
-        for sp, blk in enumerate(self.blocks):
-            ax, au = torch.cat(arr[sp][0]), torch.cat(arr[sp][1])
-            if ax.numel() == 0 and len(holes[sp]) == 0:
-                continue
-            adst, msrc, mdst, new_n = swap_remove_plan(blk.n, holes[sp], ax.numel())
+            mine = self._dest(xd) == me_
+            # ONE device->host read per species: [arrivals, own draws that stay | the rank's dead slots]
+            head = torch.stack([mine.sum(), mine[first:first + nd].sum()]).to(torch.int64)
+            info = torch.cat([head, blk.dead_idx[:nd].to(torch.int64)]).cpu().numpy()
+            n_arr, n_stay = int(info[0]), int(info[1])
+            holes = info[2:]
+            ax, au = xd[mine], ud[mine]
+            adst, msrc, mdst, new_n = swap_remove_plan(blk.n, holes, n_arr)
             assert blk.off + new_n + 16 < blk.cap, "slab block capacity exhausted"
             if len(msrc):
                 ms = torch.as_tensor(msrc, device=self.dev); md = torch.as_tensor(mdst, device=self.dev)
@@ -418,8 +383,8 @@ class SlabSheathSim:
                 ad = torch.as_tensor(adst, device=self.dev)
                 blk.x0[ad] = ax; blk.u0[ad] = au; blk.active[ad] = 1
             blk.n = new_n
-            self.stat["exported"] += len(holes[sp]); self.stat["imported"] += int(ax.numel())
-        tick("swap_remove")
+            self.stat["exported"] += nd - n_stay; self.stat["imported"] += n_arr - n_stay
+        tick("draw_and_place")
 
     # ------------------------------------------------------------------ sort + migration
     def migrate_sort(self):
