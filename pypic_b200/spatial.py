@@ -6,11 +6,13 @@ structure-of-arrays block per species.  The particle kernels are the ones of the
 particle-decomposed path (pypic_b200/sheath.py: fused gather + CN push + walls + jh/j1 deposit
 on the global node numbering), so what changes is the communication:
 
-* **halo exchange** instead of an all-reduce of the whole grid: a rank's particles deposit only
-  on its own nodes and on `guard` nodes either side, so per Picard iteration the two strips of
-  guard nodes go to the two neighbours (point-to-point) and are added there; the completed
-  owned segments (plus the four absorbed-particle counts) are then all-gathered so that the
-  (cheap, replicated) field update sees the whole grid;
+* **halo exchange + distributed field update** instead of an all-reduce of the whole grid: a rank's
+  particles deposit only on its own nodes and on `guard` nodes either side, and every rank updates the
+  field on that band only (csrc/slab_kernels.cu).  Per Picard iteration one all-gather carries each
+  rank's message (the raw currents of the 2*guard+1 nodes around its two boundaries, the sum of all its
+  raw deposits, four absorbed counts) and a second one the partial sums of the residual; neighbours
+  compute identical bits on the nodes they share.  field="replicated" keeps round 1's scheme (guard strips
+  + owned segments all-gathered, the whole grid updated on every rank);
 * **particle migration**: every `sort_every` steps each species block is counting-sorted by cell
   (pic_dev_dd_sort_by_cell).  In a sorted block the particles that left the slab are contiguous
   runs at its two ends, ordered by destination rank, so the send buffers are views of the sorted
@@ -20,8 +22,9 @@ on the global node numbering), so what changes is the communication:
 * **re-injection** (PIC_L_DD.py:429-450) draws x uniformly over the WHOLE domain, so a revived
   particle usually belongs to another rank: the draws of a step are keyed by the global ordinal of
   the dead particle within its species (Philox; the particle set is therefore identical for any
-  number of ranks), the ones that land elsewhere are shipped immediately (all-to-all) and their
-  slots are closed by swap-removal.
+  number of ranks) and REPLICATED -- after one all-gather of the dead counts every rank generates all
+  draws of the step and keeps the ones that land in its slab; arrivals fill the rank's dead slots,
+  left-over slots are closed by swap-removal.
 """
 import ctypes as C
 
