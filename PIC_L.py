@@ -223,12 +223,13 @@ def main_i(T, nplot):
 
 
 def main(T, nplot, system='landau damping', density=1e10, perturbation=0.05, Kp=2, N=100000, Ng=200, dt=1E-9, dx=0.02,
-         Te=10.0 * 11600., outdir='plots', result=None, sort_every=None):
+         Te=10.0 * 11600., outdir='plots', result=None, sort_every=None, deposit='warp'):
     """PIC_L.main (PIC_L.py:604-786): explicit leapfrog loop, Poisson solve every step.  The
     positional signature is the reference's; the keyword arguments default to its hard-coded
     literals.  Particles stay resident on the GPU; `result` (a dict) receives the series.
     The store is re-sorted by (species, cell) every `sort_every` steps (default: 16 from 2^17 particles
-    on, never below) for the window kernel; downloads return the reference's particle order."""
+    on, never below) for the window kernel; downloads return the reference's particle order.
+    deposit='window-det': the reproducible build (ExplicitSim) -- two runs give bit-identical output."""
     L = dx * (Ng - 1)
     X = np.linspace(0.0, L + dx, Ng + 1)
     wp = np.sqrt(e**2 * density / epsilon0 / me)
@@ -246,7 +247,7 @@ def main(T, nplot, system='landau damping', density=1e10, perturbation=0.05, Kp=
     if sort_every is None:
         sort_every = 16 if N >= (1 << 17) else 0
     sim = ExplicitSim(N, Ng, dx, dt, p2c, q=(float(q[0]), float(q[-1])), m=(float(m[0]), float(m[-1])), n_split=ns,
-                      sort_every=sort_every)
+                      sort_every=sort_every, deposit=deposit)
     sim.upload(x0, v0)
     mpl, plt = get_plt()
     EE, KE, TT, E_series = [], [], [], []

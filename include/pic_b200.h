@@ -539,7 +539,13 @@ int pic_dev_l_outside_flags(const double* x, int8_t* flags, int64_t N, double L,
  * a store sorted by (species, cell)), grid-stride kernel on the tail; bit0: plain shared-memory
  * atomics; bit2: grid-stride kernel with warp-uniform pre-reduction for every particle (any
  * order); bit1: function-level PIC_L.pushParticlesExplicit :248-259 -- x,v receive the UNWRAPPED
- * xout,vout and nothing is deposited. */
+ * xout,vout and nothing is deposited.
+ * bit7: REPRODUCIBLE build (as pic_dd_params'): rho_acc is fp64[Ng+1] followed by int64[2*(Ng+1)] fixed-point words
+ * [hi | lo]; every global addition of the window kernel is an integer addition on the words (order-independent),
+ * which pic_dev_l_field_solve folds back into rho_acc.  Together with the stable sort
+ * (pic_dev_dd_sort_by_cell_stable[2]) two runs are bit-identical.  pic_dev_l_deposit_fixed: the initial rho of
+ * the current positions (PIC_L.py:763 before the first step) on the words. */
+int pic_dev_l_deposit_fixed(const pic_l_params* p, const double* x, double* rho_acc, int* range_err, void* stream);
 int pic_dev_l_push_deposit(const pic_l_params* p, double* x, double* v, const double* E,
                            double* rho_acc, int* range_err, void* stream);
 /* PIC_L.py:763-766 field phase: fold rho_acc -> rho; periodic Poisson; -max; E=-dphi/dx.

@@ -146,6 +146,7 @@ _SIGS = {
     "pic_dev_l_push_implicit": [P, P, P, P, P, P, P, P, I64, I32, F64, F64, P, P],
     "pic_dev_l_outside_flags": [P, P, I64, F64, P],
     "pic_dev_l_push_deposit": [C.POINTER(LParams), P, P, P, P, P, P],
+    "pic_dev_l_deposit_fixed": [C.POINTER(LParams), P, P, P, P],
     "pic_dev_l_field_solve": [C.POINTER(LParams), P, P, P, P, P, P, P],
     "pic_dev_gc_interpolate": [P, P, P, I64, I32, F64, P, P],
     "pic_dev_gc_weight": [P, P, P, P, P, P, I64, I32, F64, P, P],

@@ -251,14 +251,46 @@ struct LK {
     int Ng, flags;
     double dx, idx, dt, L, p2c;
     double q[2], qm[2];
+    // reproducible build (flags bit7, as pic_dd_params'): the global additions go to 2 x 64-bit fixed-point words
+    // [hi(Ng+1) | lo(Ng+1)] behind the fp64 accumulator; one hi unit = 1/fs1
+    long long* fix;
+    double fs1, fi1;
 };
 static LK make_lk(const pic_l_params* p) {
     LK k;
     k.N = p->N; k.n_split = p->n_split; k.Ng = p->Ng; k.flags = p->flags; k.dx = p->dx; k.idx = 1. / p->dx;
     k.dt = p->dt; k.L = p->L; k.p2c = p->p2c;
     for (int s = 0; s < 2; ++s) { k.q[s] = p->q[s]; k.qm[s] = p->q[s] / p->m[s]; }
+    k.fix = nullptr; k.fs1 = 1.0; k.fi1 = 1.0;
+    if (p->flags & 128) {
+        // one contribution is q*p2c*w/dx with w <= 1: |v| < 2^e; a window column sums at most 2^10 of them per flush
+        const double qa = fabs(p->q[0]) > fabs(p->q[1]) ? fabs(p->q[0]) : fabs(p->q[1]);
+        int e = 0;
+        frexp(qa * p->p2c * k.idx, &e);
+        k.fs1 = ldexp(1.0, 31 - e); k.fi1 = ldexp(1.0, e - 31);
+    }
     return k;
 }
+// Where a kernel's global additions go: fp64 REDs (fix == nullptr) or, in the reproducible build, integer atomics
+// on fixed-point words (the sum is then independent of the order of the additions; see acc_add in dd_kernels.cu)
+struct GAcc {
+    double* acc;
+    long long* fix;
+    int nfix;
+    double fs1;
+    int* ferr;
+    __device__ __forceinline__ void add(int n, double v) const {
+        if (fix) {
+            const double t = v * fs1, h = rint(t);
+            if (!(fabs(h) < 4398046511104.0)) { if (ferr) atomicAdd(ferr, 1); return; }      // 2^42
+            const long long lo = __double2ll_rn((t - h) * 4294967296.0);
+            atomicAdd((unsigned long long*)fix + n, (unsigned long long)(long long)h);
+            atomicAdd((unsigned long long*)fix + nfix + n, (unsigned long long)lo);
+        } else {
+            atomicAdd(&acc[n], v);
+        }
+    }
+};
 __device__ __forceinline__ void l_fix(Cell& c, int nodes, int& bad) {
     if (c.iL < 0 || c.iL > nodes - 2) { ++bad; c.iL = clampi(c.iL, 0, nodes - 2); c.iR = c.iL + 1; }
 }
@@ -444,6 +476,12 @@ __device__ __forceinline__ void swin_add(double* myw, double* __restrict__ acc, 
     if (d <= (unsigned)(W - 2)) { double* p = myw + d * S_T; p[0] += vL; p[S_T] += vR; }
     else { atomicAdd(&acc[c], vL); atomicAdd(&acc[c + 1], vR); }
 }
+template <int W>
+__device__ __forceinline__ void swin_add(double* myw, const GAcc& ga, int wb, int c, double vL, double vR) {
+    const unsigned d = (unsigned)(c - wb);
+    if (d <= (unsigned)(W - 2)) { double* p = myw + d * S_T; p[0] += vL; p[S_T] += vR; }
+    else { ga.add(c, vL); ga.add(c + 1, vR); }
+}
 
 // column sums of the warp's 32 private windows -> global REDs, one tile of W <= 16 columns per pass (one lane
 // per column and half of the warp's windows); the windows are cleared
@@ -469,6 +507,28 @@ __device__ __forceinline__ void swin_flush(double* win, double* myw, int wbase, 
     __syncwarp();
 #pragma unroll
     for (int n2 = 0; n2 < TILES * W; ++n2) myw[n2 * S_T] = 0.0;
+    __syncwarp();
+}
+// one tile, additions through GAcc (the column sums are fp64 sums in a fixed order: lanes, then rows -- for a given
+// particle order they are reproducible; the merge into the global accumulator is what depends on scheduling)
+template <int W>
+__device__ __forceinline__ void swin_flush(double* win, double* myw, int wbase, int lane, int wb, const GAcc& ga, int nodes) {
+    static_assert(W >= 5 && W <= 16, "one lane per (column, half-warp)");
+    const int n = lane >> 1, half = lane & 1;
+    double s = 0.0;
+    if (n < W) {
+        const double* col = win + n * S_T + wbase + half * 16;
+#pragma unroll
+        for (int j = 0; j < 16; ++j) s += col[(j + n) & 15];
+    }
+    s += __shfl_xor_sync(0xffffffffu, s, 1);
+    if (n < W && half == 0) {
+        const int node = wb + n;
+        if (node >= 0 && node < nodes && s != 0.0) ga.add(node, s);
+    }
+    __syncwarp();
+#pragma unroll
+    for (int n2 = 0; n2 < W; ++n2) myw[n2 * S_T] = 0.0;
     __syncwarp();
 }
 
@@ -508,7 +568,7 @@ __device__ __forceinline__ void l_fast(const LFastC& c, const double* __restrict
 
 // exact per-particle routine (the body of l_push_deposit_k); deposits with global REDs
 __device__ __noinline__ int l_particle_exact(const LK& k, long long i, double X, double V, const double* sE,
-                                             double* __restrict__ rho_acc, double* x, double* v) {
+                                             const GAcc& ga, double* x, double* v) {
     const int nodes = k.Ng + 1;
     int bad = 0;
     const int sp = i >= k.n_split;
@@ -525,18 +585,20 @@ __device__ __noinline__ int l_particle_exact(const LK& k, long long i, double X,
     Cell cn = cell_lper(xw, k.dx, nodes);
     l_fix(cn, nodes, bad);
     const double pre = (sp ? k.q[1] : k.q[0]) * k.p2c;
-    atomicAdd(&rho_acc[cn.iL], pre * cn.wL * k.idx);
-    atomicAdd(&rho_acc[cn.iR], pre * cn.wR * k.idx);
+    ga.add(cn.iL, pre * cn.wL * k.idx);
+    ga.add(cn.iR, pre * cn.wR * k.idx);
     return bad;
 }
 
-template <int NST, bool BIG = false, int W = S_W>
+template <int NST, bool BIG = false, int W = S_W, bool DET = false>
 __global__ void __launch_bounds__(S_T, 1) l_push_deposit_v2_k(const __grid_constant__ LK k, int nchunks_fr, double* x,
                                                                double* v, const double* __restrict__ E,
                                                                double* __restrict__ rho_acc, int* __restrict__ range_err) {
     extern __shared__ __align__(128) double sm[];
     __shared__ int s_bad;
     const int nodes = k.Ng + 1;
+    // reproducible build: integer merges into the fixed-point words behind rho_acc (constant-folded away otherwise)
+    const GAcc ga = {rho_acc, DET ? k.fix : nullptr, nodes, k.fs1, range_err};
     const int NP = BIG ? (S_T / 32) * L_EW : ((nodes + 15) & ~15);
     const int nchunks = nchunks_fr & 0x0fffffff;
     const int FRm = BIG ? (int)((unsigned)nchunks_fr >> 28) : (S_ROWS - 1);      // rows per deposit / field window - 1
@@ -612,7 +674,7 @@ __global__ void __launch_bounds__(S_T, 1) l_push_deposit_v2_k(const __grid_const
                 fc.qpi = (sp ? k.q[1] : k.q[0]) * k.p2c * k.idx;
             }
             if (BIG && (row & FRm) == 0) {
-                if (row > 0 && wb != NOWIN) { __syncwarp(); swin_flush<1, W>(win, myw, wbase, lane, wb, rho_acc, 0, nodes); }
+                if (row > 0 && wb != NOWIN) { __syncwarp(); swin_flush<W>(win, myw, wbase, lane, wb, ga, nodes); }
                 const int cb = (int)floor(__shfl_sync(full, X.x, 0) * k.idx);
                 eb = min(max(cb - L_EW / 4, 0), nodes - L_EW);
                 __syncwarp();
@@ -632,13 +694,13 @@ __global__ void __launch_bounds__(S_T, 1) l_push_deposit_v2_k(const __grid_const
             if (!(ra | rb)) {
                 __stcs((double2*)(x + ci), make_double2(a.X, b.X));
                 __stcs((double2*)(v + ci), make_double2(a.V, b.V));
-                swin_add<W>(myw, rho_acc, wb, a.cF, a.fL, a.fR);
-                swin_add<W>(myw, rho_acc, wb, b.cF, b.fL, b.fR);
+                swin_add<W>(myw, ga, wb, a.cF, a.fL, a.fR);
+                swin_add<W>(myw, ga, wb, b.cF, b.fL, b.fR);
             } else {
-                if (ra) bad += l_particle_exact(k, ci, X.x, V.x, gE, rho_acc, x, v);
-                else { x[ci] = a.X; v[ci] = a.V; swin_add<W>(myw, rho_acc, wb, a.cF, a.fL, a.fR); }
-                if (rb) bad += l_particle_exact(k, ci + 1, X.y, V.y, gE, rho_acc, x, v);
-                else { x[ci + 1] = b.X; v[ci + 1] = b.V; swin_add<W>(myw, rho_acc, wb, b.cF, b.fL, b.fR); }
+                if (ra) bad += l_particle_exact(k, ci, X.x, V.x, gE, ga, x, v);
+                else { x[ci] = a.X; v[ci] = a.V; swin_add<W>(myw, ga, wb, a.cF, a.fL, a.fR); }
+                if (rb) bad += l_particle_exact(k, ci + 1, X.y, V.y, gE, ga, x, v);
+                else { x[ci + 1] = b.X; v[ci + 1] = b.V; swin_add<W>(myw, ga, wb, b.cF, b.fL, b.fR); }
             }
             // refill the drained stage only after every lane's LDS of it has executed (see v6)
             __syncwarp();
@@ -646,11 +708,11 @@ __global__ void __launch_bounds__(S_T, 1) l_push_deposit_v2_k(const __grid_const
             else if (more) issue(cbase + chunk_step + 64 * (row + NST - S_ROWS), st_cur);
         }
         __syncwarp();
-        if (wb != NOWIN) swin_flush<1, W>(win, myw, wbase, lane, wb, rho_acc, 0, nodes);
+        if (wb != NOWIN) swin_flush<W>(win, myw, wbase, lane, wb, ga, nodes);
     }
     // the N % S_CHUNK particles behind the last whole chunk: at most one per thread, exact routine, global REDs
     for (long long i = (long long)nchunks * S_CHUNK + (long long)blockIdx.x * S_T + threadIdx.x; i < k.N; i += (long long)gridDim.x * S_T)
-        bad += l_particle_exact(k, i, x[i], v[i], gE, rho_acc, x, v);
+        bad += l_particle_exact(k, i, x[i], v[i], gE, ga, x, v);
     if (bad) atomicAdd(&s_bad, bad);
     __syncthreads();
     if (threadIdx.x == 0 && s_bad && range_err) atomicAdd(range_err, s_bad);
@@ -872,6 +934,28 @@ __global__ void __launch_bounds__(S_T, 1) pypic_picard_iter_v2_k(const __grid_co
 }
 
 // field phase build: fold rho, rhs of the gauge-fixed periodic system over `nodes` unknowns
+// reproducible build: fixed-point words -> fp64 accumulator (one rounding per node), words cleared
+__global__ void l_fix_take_k(double* __restrict__ rho_acc, long long* __restrict__ fix, int nodes, double fi1) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nodes; i += gridDim.x * blockDim.x) {
+        const long long hi = fix[i], lo = fix[nodes + i];
+        fix[i] = 0; fix[nodes + i] = 0;
+        rho_acc[i] += ((double)hi + (double)lo * (1.0 / 4294967296.0)) * fi1;
+    }
+}
+// initial deposit of the reproducible build: rho of the current positions, one pair of fixed-point additions per particle
+__global__ void l_weight_fix_k(LK k, const double* __restrict__ x, int* __restrict__ range_err) {
+    const int nodes = k.Ng + 1;
+    const GAcc ga = {nullptr, k.fix, nodes, k.fs1, range_err};
+    int bad = 0;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < k.N; i += (long long)gridDim.x * blockDim.x) {
+        Cell c = cell_lper(x[i], k.dx, nodes);
+        l_fix(c, nodes, bad);
+        const double pre = (i >= k.n_split ? k.q[1] : k.q[0]) * k.p2c;
+        ga.add(c.iL, pre * c.wL * k.idx);
+        ga.add(c.iR, pre * c.wR * k.idx);
+    }
+    if (bad && range_err) atomicAdd(range_err, bad);
+}
 __global__ void l_field_build_k(double* __restrict__ rho_acc, double* __restrict__ rho, double* __restrict__ a,
                                 double* __restrict__ b, double* __restrict__ c, double* __restrict__ d, int nodes,
                                 double dx) {
@@ -1162,39 +1246,50 @@ int pic_dev_l_push_deposit(const pic_l_params* p, double* x, double* v, const do
                           (size_t)(S_T / 32) * L_NST) * sizeof(double);
     const bool aligned16 = (((uintptr_t)x | (uintptr_t)v) & 15) == 0;
     long long done = 0;
+    // reproducible build (flags bit7): rho_acc is fp64[nodes] followed by the fixed-point words int64[2*nodes]; only the
+    // window kernels are built for it (their exact routine serves ragged tails and stores shorter than a chunk)
+    const bool det = (p->flags & 128) != 0;
+    if (det) {
+        PIC_REQUIRE(!(p->flags & (1 | 2 | 4)) && aligned16, "l_push_deposit: the reproducible build needs the window kernel (16-byte aligned x, v)");
+        k.fix = (long long*)(rho_acc + nodes);
+    }
     // large-grid build of the same kernel (flags bit4 forces it, for tests): per-warp field windows
     const size_t smem2b = ((size_t)(S_T / 32) * L_EW + (size_t)S_W * S_T + (size_t)(S_T / 32) * L_NST * 128 +
                            (size_t)(S_T / 32) * L_NST) * sizeof(double);
     const bool big = ((p->flags & 16) || smem2 > (size_t)max_optin_smem() - 512) && nodes >= L_EW;
-    if (big && !(p->flags & (1 | 2 | 4)) && aligned16 && k.N >= S_CHUNK) {
+    if (big && !(p->flags & (1 | 2 | 4)) && aligned16 && (k.N >= S_CHUNK || det)) {
         const long long nchunks = k.N / S_CHUNK;
         PIC_REQUIRE(nchunks < (1 << 28), "l_push_deposit: shard too large");
-        auto kern = l_push_deposit_v2_k<L_NST, true>;
+        auto kern = det ? l_push_deposit_v2_k<L_NST, true, S_W, true> : l_push_deposit_v2_k<L_NST, true>;
         PIC_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2b));
         const double ppc = (double)k.N / 2.0 / (double)nodes;       // two species interleave over the same cells
         int fr = 16;
         while (fr > 1 && 64.0 * fr > 3.0 * ppc) fr >>= 1;
         long long cap = device_sm_count();
-        kern<<<(int)(nchunks < cap ? nchunks : cap), S_T, smem2b, st>>>(k, (int)((unsigned)nchunks | ((unsigned)(fr - 1) << 28)), x, v, E, rho_acc, range_err);
+        const long long gridb = nchunks < cap ? (nchunks > 0 ? nchunks : 1) : cap;
+        kern<<<(int)gridb, S_T, smem2b, st>>>(k, (int)((unsigned)nchunks | ((unsigned)(fr - 1) << 28)), x, v, E, rho_acc, range_err);
         PIC_CHECK_LAUNCH();
         return PIC_OK;
     }
     if (!(p->flags & (1 | 2 | 4)) && aligned16 && k.Ng >= 8 && smem2 <= (size_t)max_optin_smem() - 512) {
         const long long nchunks = k.N / S_CHUNK;
-        if (nchunks > 0) {
+        if (nchunks > 0 || det) {
             const size_t smem2w = smem2 + (size_t)(S_W_WIDE - S_W) * S_T * sizeof(double);      // 15-node windows
             const bool wide = !s_narrow() && smem2w <= (size_t)max_optin_smem() - 512;
-            auto kern = wide ? l_push_deposit_v2_k<L_NST, false, S_W_WIDE> : l_push_deposit_v2_k<L_NST>;
+            auto kern = det ? (wide ? l_push_deposit_v2_k<L_NST, false, S_W_WIDE, true> : l_push_deposit_v2_k<L_NST, false, S_W, true>)
+                            : (wide ? l_push_deposit_v2_k<L_NST, false, S_W_WIDE> : l_push_deposit_v2_k<L_NST>);
             const size_t smem = wide ? smem2w : smem2;
             PIC_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             long long cap = device_sm_count();
-            kern<<<(int)(nchunks < cap ? nchunks : cap), S_T, smem, st>>>(k, (int)nchunks, x, v, E, rho_acc, range_err);
+            const long long grid = nchunks < cap ? (nchunks > 0 ? nchunks : 1) : cap;
+            kern<<<(int)grid, S_T, smem, st>>>(k, (int)nchunks, x, v, E, rho_acc, range_err);
             PIC_CHECK_LAUNCH();
             return PIC_OK;                       // the kernel finishes the ragged tail itself
         }
         done = nchunks * S_CHUNK;
         if (done >= k.N) return PIC_OK;
     }
+    PIC_REQUIRE(!det, "l_push_deposit: the reproducible build needs a grid of at least 8 cells");
     LK t = k;
     t.N = k.N - done;
     t.n_split = k.n_split - done < 0 ? 0 : (k.n_split - done > t.N ? t.N : k.n_split - done);
@@ -1210,6 +1305,17 @@ int pic_dev_l_push_deposit(const pic_l_params* p, double* x, double* v, const do
     return PIC_OK;
 }
 
+int pic_dev_l_deposit_fixed(const pic_l_params* p, const double* x, double* rho_acc, int* range_err, void* stream) {
+    PIC_REQUIRE(p && x && rho_acc, "l_deposit_fixed: null pointer");
+    PIC_REQUIRE((p->flags & 128) && p->Ng >= 2 && p->dx > 0, "l_deposit_fixed: needs the parameters of the reproducible build (flags bit7)");
+    if (p->N == 0) return PIC_OK;
+    LK k = make_lk(p);
+    k.fix = (long long*)(rho_acc + k.Ng + 1);
+    l_weight_fix_k<<<grid_for(k.N, 256, 8), 256, 0, (cudaStream_t)stream>>>(k, x, range_err);
+    PIC_CHECK_LAUNCH();
+    return PIC_OK;
+}
+
 int pic_dev_l_field_solve(const pic_l_params* p, double* rho_acc, double* rho, double* phi, double* E, double* work,
                           double* stats, void* stream) {
     PIC_REQUIRE(p && rho_acc && rho && phi && E && work, "l_field_solve: null pointer");
@@ -1217,6 +1323,11 @@ int pic_dev_l_field_solve(const pic_l_params* p, double* rho_acc, double* rho, d
     const int nodes = p->Ng + 1;
     double *a = work, *b = work + nodes, *c = work + 2 * (size_t)nodes, *d = work + 3 * (size_t)nodes,
            *x = work + 4 * (size_t)nodes;
+    if (p->flags & 128) {          // reproducible build: the deposits arrive as fixed-point words behind rho_acc
+        LK k = make_lk(p);
+        l_fix_take_k<<<(nodes + 1023) / 1024 < 148 ? (nodes + 1023) / 1024 : 148, 1024, 0, st>>>(rho_acc, (long long*)(rho_acc + nodes), nodes, k.fi1);
+        PIC_CHECK_LAUNCH();
+    }
     l_field_build_k<<<1, 1024, 0, st>>>(rho_acc, rho, a, b, c, d, nodes, p->dx);
     PIC_CHECK_LAUNCH();
     int rc = pic_dev_tridiag_pcr(a, b, c, d, x, nodes - 1, work + 5 * (size_t)nodes, stream);

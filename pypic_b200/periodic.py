@@ -264,7 +264,12 @@ class ExplicitSim:
         self.L = dx * (Ng - 1)              # PIC_L.py:645; the wrap length is L+dx
         if sort_every and deposit == "warp":
             deposit = "window"               # see PeriodicImplicitSim
-        flags = {"window": 0, "window-big": 16, "warp": 4, "atomic": 1 | 4}[deposit]     # window-big: see PeriodicImplicitSim
+        # "window-det": the REPRODUCIBLE build of the window kernel (flags bit7, as SheathSim's): every addition to the
+        # global accumulator is an integer addition on fixed-point words, the cell sort is the stable radix sort
+        # (with the original index as its payload when track_order), the kinetic energy is summed in a fixed
+        # order -- two runs give bit-identical output
+        flags = {"window": 0, "window-big": 16, "warp": 4, "atomic": 1 | 4, "window-det": 128}[deposit]
+        self.det = deposit == "window-det"
         self.sort_every = int(sort_every)
         self.t = 0
         self.perm = None
@@ -276,7 +281,7 @@ class ExplicitSim:
         dev, n, g = self.dev, max(self.N, 1), self.Ng + 1
         self.x = D.f64(n, dev, True); self.v = D.f64(n, dev, True)
         self.q_arr = None
-        self.rho_acc = D.f64(g, dev, True)
+        self.rho_acc = D.f64(3 * g if self.det else g, dev, True)       # det: + int64[2g] fixed-point words
         self.rho = D.f64(g, dev, True); self.phi = D.f64(g, dev, True); self.E = D.f64(g, dev, True)
         self.work = D.f64(13 * g, dev, True)
         self.stats = D.f64(4, dev, True)
@@ -293,6 +298,12 @@ class ExplicitSim:
 
     def _deposit_initial(self):
         """rho of the current positions (PIC_L.py:763) -- only needed before the first step."""
+        if self.det:
+            self.rho_acc.zero_()
+            _lib.call("pic_dev_l_deposit_fixed", C.byref(self.params), D.ptr(self.x), D.ptr(self.rho_acc), D.ptr(self.range_err),
+                      D.stream())
+            self.kernel_launches += 1
+            return
         qarr = torch.empty(max(self.N, 1), dtype=torch.float64, device=self.dev)
         qarr[:self.n_split] = self.q[0]
         qarr[self.n_split:] = self.q[1]
@@ -309,7 +320,10 @@ class ExplicitSim:
         """PIC_L.py:763-766: (folded) rho -> phi (periodic Poisson, -max) -> E."""
         if not self._have_rho:
             self._deposit_initial()
-        self.comm.allreduce_sum(self.rho_acc)
+        if self.det and self.comm.enabled and self.comm.world > 1:
+            self.comm.allreduce_sum(self.rho_acc[self.Ng + 1:].view(torch.int64))      # exact in any order
+        else:
+            self.comm.allreduce_sum(self.rho_acc)
         _lib.call("pic_dev_l_field_solve", C.byref(self.params), D.ptr(self.rho_acc), D.ptr(self.rho), D.ptr(self.phi),
                   D.ptr(self.E), D.ptr(self.work), D.ptr(self.stats), D.stream())
         self.kernel_launches += 3
@@ -321,8 +335,38 @@ class ExplicitSim:
         self.kernel_launches += 1
         self._have_rho = True
 
+    def _sort_stable(self):
+        """Reproducible build: LSD radix sort by (species, cell); equal cells keep their previous order."""
+        n = max(self.N, 1)
+        first = self._sort_params is None
+        if first:
+            self._x2 = torch.empty_like(self.x); self._v2 = torch.empty_like(self.v)
+            self._sort_scratch = torch.zeros(D.sort_stable_scratch_size(n), dtype=torch.int32, device=self.dev)
+            self._sort_params = _lib.DDParams(self.N, self.n_split, self.Ng, 128, self.dx, self.dt, self.L, self.p2c,
+                                              (C.c_double * 2)(0., 0.), (C.c_double * 2)(1., 1.))
+            if self.track_order:
+                self.perm = torch.empty(n, dtype=torch.int32, device=self.dev)
+                self._perm2 = torch.empty(n, dtype=torch.int32, device=self.dev)
+        where = C.c_int(0)
+        if self.track_order:
+            _lib.call("pic_dev_dd_sort_by_cell_stable2", C.byref(self._sort_params), D.ptr(self.x), D.ptr(self.v), D.ptr(self._x2),
+                      D.ptr(self._v2), D.ptr(self.perm), D.ptr(self._perm2), 1 if first else 0, D.ptr(self._sort_scratch),
+                      self._sort_scratch.numel(), C.byref(where), D.stream())
+        else:
+            _lib.call("pic_dev_dd_sort_by_cell_stable", C.byref(self._sort_params), D.ptr(self.x), D.ptr(self.v), D.ptr(self._x2),
+                      D.ptr(self._v2), D.ptr(self._sort_scratch), self._sort_scratch.numel(), C.byref(where), D.stream())
+        passes = (max(1, (self.Ng - 1).bit_length()) + 7) // 8
+        self.kernel_launches += 5 * passes * ((self.n_split > 0) + (self.n_split < self.N))
+        if where.value:
+            self.x, self._x2 = self._x2, self.x
+            self.v, self._v2 = self._v2, self.v
+            if self.track_order:
+                self.perm, self._perm2 = self._perm2, self.perm
+
     def sort_by_cell(self):
         """Counting sort by (species, cell) with the original index as a payload."""
+        if self.det:
+            return self._sort_stable()
         n = max(self.N, 1)
         if self._sort_params is None:
             if self.track_order:
@@ -354,6 +398,12 @@ class ExplicitSim:
 
     def kinetic_energy(self, m=me):
         """sum(m v^2 / 2) over all particles (PIC_L.py:698 uses me for every particle)."""
+        if self.det:          # fixed-order reduction
+            sc2 = D.f64(2, self.dev, True)
+            _lib.call("pic_dev_moments", D.ptr(self.v), self.N, D.ptr(sc2), D.stream())
+            self.kernel_launches += 1
+            self.comm.allreduce_sum(sc2)
+            return m / 2. * float(D.read_f64(sc2, 2)[1])
         sc = D.f64(1, self.dev, True)
         _lib.call("pic_dev_sum_sq", D.ptr(self.v), self.N, m / 2., D.ptr(sc), D.stream())
         self.kernel_launches += 1

@@ -218,3 +218,33 @@ def test_reproducible_run_through_the_reference_api_keeps_the_particle_numbering
         assert np.array_equal(a[k], b[k]), k                      # bit for bit, diagnostics included
     for k in ("x0", "u0", "E0"):
         assert np.max(np.abs(a[k] - d[k])) <= 1e-9 * np.max(np.abs(d[k])), k
+
+
+@pytest.mark.parametrize("N", [200000, 6000])       # 6000: shorter than one chunk, every particle through the exact routine
+def test_explicit_loop_reproducible_build_through_the_reference_api(tmp_path, N):
+    """PIC_L.main(deposit='window-det'): the explicit leapfrog loop on the reproducible build of its window kernel
+    (fixed-point merges into rho, stable radix sort with the original-index payload, fixed-order kinetic-energy sum).
+    Two runs give bit-identical series, fields and particles (in the reference's numbering); against the default
+    build the run agrees to round-off."""
+    import contextlib, io, os
+    import PIC_L
+    outs = []
+    os.makedirs(os.path.join(str(tmp_path), "plots"), exist_ok=True)
+    for dep, se in (("window-det", 3), ("window-det", 3), ("warp", 0)):
+        res = {}
+        np.random.seed(5)
+        cwd = os.getcwd(); os.chdir(str(tmp_path))
+        try:
+            with contextlib.redirect_stdout(io.StringIO()):
+                PIC_L.main(8, 10 ** 9, N=N, result=res, sort_every=se, deposit=dep)
+        finally:
+            os.chdir(cwd)
+        outs.append(res)
+    a, b, d = outs
+    keys = [k for k in a if isinstance(a[k], np.ndarray)]
+    assert {"x", "v", "E", "EE", "KE", "E_series"} <= set(keys)
+    for k in keys:
+        assert np.array_equal(a[k], b[k]), k
+    for k in ("x", "v", "E", "EE", "E_series"):
+        assert np.max(np.abs(a[k] - d[k])) <= 1e-9 * np.max(np.abs(d[k])), k
+    assert np.max(np.abs(a["KE"] - d["KE"])) <= 1e-12 * np.max(np.abs(d["KE"]))
