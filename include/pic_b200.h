@@ -446,6 +446,10 @@ int pic_dev_pypic_interpolate(const double* F, const double* x, double* out, int
  * (v == NULL, wR=(x%dx)/dx).  p2c is the value AFTER int32 truncation. out zeroed by caller. */
 int pic_dev_pypic_weight(const double* x, const double* q, const double* v, double* out, int64_t N,
                          int Ng, double dx, double p2c, int* range_err, void* stream);
+/* The same deposit with ORDER-INDEPENDENT accumulation (fixed-point words, integer atomics; the initial rho of a
+ * reproducible implicit_pic run): out += the deposit, one rounding per node.  qmax = max |q[i]| (sets the scale). */
+int pic_dev_pypic_weight_fixed(const double* x, const double* q, const double* v, double* out, int64_t N, int Ng,
+                               double dx, double p2c, double qmax, int* range_err, void* stream);
 typedef struct {
     int64_t N;
     int32_t Ng;
@@ -454,7 +458,12 @@ typedef struct {
                               bit0: plain shared-memory atomics per contribution; bit2: grid-stride kernel
                               with warp-uniform pre-reduction for every particle (any particle order);
                               bit1: x0 holds UNWRAPPED positions, ``x % L`` (pypic.py:277) is applied on load;
-                              bit3: light iteration (no v1 store, no j1 deposit, see pic_dev_pypic_j1_repair) */
+                              bit3: light iteration (no v1 store, no j1 deposit, see pic_dev_pypic_j1_repair);
+                              bit4: large-grid build of the window kernel (per-warp field windows);
+                              bit7: REPRODUCIBLE build (as pic_dd_params'): acc is fp64[2Ng] followed by the
+                              fixed-point words int64[4Ng] = [hi(2Ng) | lo(2Ng)]; the window kernel and the j1
+                              repair add to the words with integer atomics (order-independent),
+                              pic_dev_pypic_field_update2 / pic_dev_pypic_j1_finish fold them back into acc */
     double dx, dt, L, p2c; /* p2c already truncated */
     double q, m;           /* single species (electrons)            */
 } pic_pypic_params;

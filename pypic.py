@@ -146,8 +146,9 @@ def initialize_p(system, N, density, Kp, perturbation, dx, Ng, Te, Ti, L, X):
 
 
 def implicit_pic(T, nplot, system, density, perturbation, Kp, N, Ng, Nv, Vmax, dt, Ti, Te, L, tol, maxiter,
-                 outdir='plots', result=None, sort_every=None):
+                 outdir='plots', result=None, sort_every=None, deposit='warp'):
     """pypic.py:472-651: main implicit PIC routine (particles stay resident on the GPU).
+    deposit='window-det': the reproducible build (PeriodicImplicitSim) -- two runs give bit-identical output.
 
     The store is re-sorted by cell every `sort_every` steps (default: 8 from 2^17 particles on, never below) so that
     the loop runs on the TMA-staged window kernel; the original index of every particle rides along, so the
@@ -166,13 +167,15 @@ def implicit_pic(T, nplot, system, density, perturbation, Kp, N, Ng, Nv, Vmax, d
     print("gamma: ", growth_rate)
     KE, EE, TT, j_bias, trajectory_x, trajectory_v = [], [], [], [], [], []
     # initial field from one Poisson solve (pypic.py:550-554)
-    rho0 = weight_density_p(x0, q, p2c, Ng, N, dx)
+    rho0 = (weight_density_p(x0, q, p2c, Ng, N, dx) if deposit != 'window-det' else
+            ops.pypic_weight(np.asarray(x0)[:N], np.asarray(q)[:N], None, p2c, Ng, dx, reproducible=True))
     phi0 = solve_poisson_p(dx, Ng, rho0, np.zeros(Ng))
     phi0 = phi0 - np.max(phi0)
     E0 = -differentiate_p(phi0, dx, Ng)
     if sort_every is None:
         sort_every = 8 if N >= (1 << 17) else 0
-    sim = PeriodicImplicitSim(N, Ng, dx, dt, L, p2c, q=-e, m=me, tol=tol, maxiter=maxiter, sort_every=sort_every)
+    sim = PeriodicImplicitSim(N, Ng, dx, dt, L, p2c, q=-e, m=me, tol=tol, maxiter=maxiter, sort_every=sort_every,
+                              deposit=deposit)
     sim.upload(x0, v0, E0)
     mpl, plt = get_plt()
     for t in range(T):
@@ -218,7 +221,7 @@ def explicit_pic(T, nplot):
 
 
 def main(T, nplot, N=1000000, Ng=200, dt=1e-5, density=1e5, perturbation=0.8, Kp=1, system='landau-damping',
-         tol=1e-3, maxiter=20, outdir='plots', result=None, sort_every=None):
+         tol=1e-3, maxiter=20, outdir='plots', result=None, sort_every=None, deposit='warp'):
     """pypic.main (pypic.py:814-863); keyword arguments default to its hard-coded literals."""
     Ti = 0.1 * 11600.
     Te = 100.0 * 11600.
@@ -226,7 +229,7 @@ def main(T, nplot, N=1000000, Ng=200, dt=1e-5, density=1e5, perturbation=0.8, Kp
     Vmax = 8.0
     Nv = Ng // 2
     implicit_pic(T, nplot, system, density, perturbation, Kp, N, Ng, Nv, Vmax, dt, Ti, Te, L, tol, maxiter,
-                 outdir=outdir, result=result, sort_every=sort_every)
+                 outdir=outdir, result=result, sort_every=sort_every, deposit=deposit)
 
 
 if __name__ == '__main__':

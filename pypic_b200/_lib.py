@@ -131,6 +131,7 @@ _SIGS = {
     "pic_dev_soa_permute": [P, I64, P, P, I32, P, P, I32, P, P, I32, P],
     "pic_dev_pypic_interpolate": [P, P, P, I64, I32, F64, P, P],
     "pic_dev_pypic_weight": [P, P, P, P, I64, I32, F64, F64, P, P],
+    "pic_dev_pypic_weight_fixed": [P, P, P, P, I64, I32, F64, F64, F64, P, P],
     "pic_dev_pypic_picard_iter": [C.POINTER(PypicParams), P, P, P, P, P, P, I32, P, P],
     "pic_dev_pypic_field_update": [C.POINTER(PypicParams), P, P, P, P, P, P, P, P],
     "pic_dev_pypic_picard_iter2": [C.POINTER(PypicParams), P, P, P, P, P, P, P, I32, P, P],

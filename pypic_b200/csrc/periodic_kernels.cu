@@ -26,6 +26,36 @@ __device__ __forceinline__ void deposit2(double* tile, int iL, int iR, double vL
 }
 
 // ============================================================ pypic.py
+// Where a kernel's global additions go: fp64 REDs (fix == nullptr) or, in the reproducible build, integer atomics
+// on fixed-point words (the sum is then independent of the order of the additions; see acc_add in dd_kernels.cu)
+struct GAcc {
+    double* acc;
+    long long* fix;
+    int nfix;
+    double fs1;
+    int* ferr;
+    __device__ __forceinline__ void add(int n, double v) const {
+        if (fix) {
+            const double t = v * fs1, h = rint(t);
+            if (!(fabs(h) < 4398046511104.0)) { if (ferr) atomicAdd(ferr, 1); return; }      // 2^42
+            const long long lo = __double2ll_rn((t - h) * 4294967296.0);
+            atomicAdd((unsigned long long*)fix + n, (unsigned long long)(long long)h);
+            atomicAdd((unsigned long long*)fix + nfix + n, (unsigned long long)lo);
+        } else {
+            atomicAdd(&acc[n], v);
+        }
+    }
+};
+// reproducible build: fixed-point words [hi(n) | lo(n)] -> fp64 accumulator (one rounding per node), words cleared
+__global__ void fix_take_k(double* __restrict__ acc, long long* __restrict__ fix, int n, double fi1) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const long long hi = fix[i], lo = fix[n + i];
+        fix[i] = 0; fix[n + i] = 0;
+        acc[i] += ((double)hi + (double)lo * (1.0 / 4294967296.0)) * fi1;
+    }
+}
+static inline int fix_take_grid(int n) { int g = (n + 1023) / 1024; return g < 1 ? 1 : (g > 148 ? 148 : g); }
+
 struct PYK {
     long long N;
     int Ng, flags;
@@ -35,12 +65,22 @@ struct PYK {
     // grid-stride kernel, which then reads them instead of the scalars above
     const double* qa;
     const double* ma;
+    // reproducible build (flags bit7): fixed-point words [hi(2Ng) | lo(2Ng)] behind the fp64 accumulators [jh | j1]
+    long long* fix;
+    double fs1, fi1;
 };
 static PYK make_pyk(const pic_pypic_params* p) {
     PYK k;
     k.done = nullptr; k.qa = nullptr; k.ma = nullptr;
     k.N = p->N; k.Ng = p->Ng; k.flags = p->flags; k.dx = p->dx; k.idx = 1. / p->dx; k.dt = p->dt;
     k.L = p->L; k.p2c = p->p2c; k.q = p->q; k.qm = p->q / p->m;
+    k.fix = nullptr; k.fs1 = 1.0; k.fi1 = 1.0;
+    if (p->flags & 128) {
+        // one contribution is q*v*p2c*w/dx with |v| below the speed of light (see make_ddk in dd_kernels.cu)
+        int e = 0;
+        frexp(fabs(p->q) * p->p2c * k.idx * 2.99792458e8, &e);
+        k.fs1 = ldexp(1.0, 31 - e); k.fi1 = ldexp(1.0, e - 31);
+    }
     return k;
 }
 
@@ -84,6 +124,25 @@ __global__ void pypic_weight_k(const double* __restrict__ x, const double* __res
     __syncthreads();
     for (int i = threadIdx.x; i < Ng; i += blockDim.x)
         if (sm[i] != 0.0) atomicAdd(&acc[i], sm[i]);
+    if (bad && range_err) atomicAdd(range_err, bad);
+}
+
+// weight_density_p / weight_current_p with order-independent accumulation (reproducible build: the initial rho of
+// implicit_pic): one pair of fixed-point additions per particle on words [hi(Ng) | lo(Ng)]
+template <bool CURRENT>
+__global__ void pypic_weight_fix_k(const double* __restrict__ x, const double* __restrict__ q, const double* __restrict__ v,
+                                   long long* __restrict__ fix, long long N, int Ng, double dx, double p2c, double fs1,
+                                   int* __restrict__ range_err) {
+    const double idx = 1. / dx;
+    const GAcc ga = {nullptr, fix, Ng, fs1, range_err};
+    int bad = 0;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < N; i += (long long)gridDim.x * blockDim.x) {
+        Cell c = cell_pypic<!CURRENT>(x[i], dx, idx, Ng);
+        pypic_fix(c, Ng, bad);
+        const double pre = CURRENT ? q[i] * v[i] * p2c * idx : q[i] * p2c * idx;   // pypic.py:121 / 168
+        ga.add(c.iL, pre * c.wL);
+        ga.add(c.iR, pre * c.wR);
+    }
     if (bad && range_err) atomicAdd(range_err, bad);
 }
 
@@ -209,6 +268,7 @@ __global__ void pypic_j1_repair_k(PYK k, const double* __restrict__ x0, const do
                                   double* __restrict__ acc, int* __restrict__ range_err) {
     int bad = 0;
     const int Ng = k.Ng;
+    const GAcc ga = {acc, k.fix, 2 * Ng, k.fs1, range_err};
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < k.N; i += (long long)gridDim.x * blockDim.x) {
         // v1 of the last (light) iteration: v0 + dt*(q/m)*E(xs) with the field and xs that iteration used (:261-265)
         double X0 = x0[i];
@@ -223,7 +283,7 @@ __global__ void pypic_j1_repair_k(PYK k, const double* __restrict__ x0, const do
         Cell cf = cell_pypic<false>(x1w, k.dx, k.idx, Ng);
         pypic_fix(cf, Ng, bad);
         const double j1_i = k.q * V1 * k.p2c * k.idx;
-        atomicAdd(&acc[Ng + cf.iL], j1_i * cf.wL); atomicAdd(&acc[Ng + cf.iR], j1_i * cf.wR);
+        ga.add(Ng + cf.iL, j1_i * cf.wL); ga.add(Ng + cf.iR, j1_i * cf.wR);
     }
     if (bad && range_err) atomicAdd(range_err, bad);
 }
@@ -271,26 +331,6 @@ static LK make_lk(const pic_l_params* p) {
     }
     return k;
 }
-// Where a kernel's global additions go: fp64 REDs (fix == nullptr) or, in the reproducible build, integer atomics
-// on fixed-point words (the sum is then independent of the order of the additions; see acc_add in dd_kernels.cu)
-struct GAcc {
-    double* acc;
-    long long* fix;
-    int nfix;
-    double fs1;
-    int* ferr;
-    __device__ __forceinline__ void add(int n, double v) const {
-        if (fix) {
-            const double t = v * fs1, h = rint(t);
-            if (!(fabs(h) < 4398046511104.0)) { if (ferr) atomicAdd(ferr, 1); return; }      // 2^42
-            const long long lo = __double2ll_rn((t - h) * 4294967296.0);
-            atomicAdd((unsigned long long*)fix + n, (unsigned long long)(long long)h);
-            atomicAdd((unsigned long long*)fix + nfix + n, (unsigned long long)lo);
-        } else {
-            atomicAdd(&acc[n], v);
-        }
-    }
-};
 __device__ __forceinline__ void l_fix(Cell& c, int nodes, int& bad) {
     if (c.iL < 0 || c.iL > nodes - 2) { ++bad; c.iL = clampi(c.iL, 0, nodes - 2); c.iR = c.iL + 1; }
 }
@@ -477,10 +517,10 @@ __device__ __forceinline__ void swin_add(double* myw, double* __restrict__ acc, 
     else { atomicAdd(&acc[c], vL); atomicAdd(&acc[c + 1], vR); }
 }
 template <int W>
-__device__ __forceinline__ void swin_add(double* myw, const GAcc& ga, int wb, int c, double vL, double vR) {
+__device__ __forceinline__ void swin_add(double* myw, const GAcc& ga, int wb, int c, double vL, double vR, int off = 0) {
     const unsigned d = (unsigned)(c - wb);
     if (d <= (unsigned)(W - 2)) { double* p = myw + d * S_T; p[0] += vL; p[S_T] += vR; }
-    else { ga.add(c, vL); ga.add(c + 1, vR); }
+    else { ga.add(off + c, vL); ga.add(off + c + 1, vR); }
 }
 
 // column sums of the warp's 32 private windows -> global REDs, one tile of W <= 16 columns per pass (one lane
@@ -509,26 +549,30 @@ __device__ __forceinline__ void swin_flush(double* win, double* myw, int wbase, 
     for (int n2 = 0; n2 < TILES * W; ++n2) myw[n2 * S_T] = 0.0;
     __syncwarp();
 }
-// one tile, additions through GAcc (the column sums are fp64 sums in a fixed order: lanes, then rows -- for a given
-// particle order they are reproducible; the merge into the global accumulator is what depends on scheduling)
-template <int W>
-__device__ __forceinline__ void swin_flush(double* win, double* myw, int wbase, int lane, int wb, const GAcc& ga, int nodes) {
+// the same with the additions through GAcc (the column sums are fp64 sums in a fixed order: lanes, then rows -- for
+// a given particle order they are reproducible; the merge into the global accumulator is what depends on scheduling)
+template <int TILES, int W>
+__device__ __forceinline__ void swin_flush(double* win, double* myw, int wbase, int lane, int wb, const GAcc& ga,
+                                           int tile_stride, int nodes) {
     static_assert(W >= 5 && W <= 16, "one lane per (column, half-warp)");
     const int n = lane >> 1, half = lane & 1;
-    double s = 0.0;
-    if (n < W) {
-        const double* col = win + n * S_T + wbase + half * 16;
 #pragma unroll
-        for (int j = 0; j < 16; ++j) s += col[(j + n) & 15];
-    }
-    s += __shfl_xor_sync(0xffffffffu, s, 1);
-    if (n < W && half == 0) {
-        const int node = wb + n;
-        if (node >= 0 && node < nodes && s != 0.0) ga.add(node, s);
+    for (int t = 0; t < TILES; ++t) {
+        double s = 0.0;
+        if (n < W) {
+            const double* col = win + (t * W + n) * S_T + wbase + half * 16;
+#pragma unroll
+            for (int j = 0; j < 16; ++j) s += col[(j + n) & 15];
+        }
+        s += __shfl_xor_sync(0xffffffffu, s, 1);
+        if (n < W && half == 0) {
+            const int node = wb + n;
+            if (node >= 0 && node < nodes && s != 0.0) ga.add(t * tile_stride + node, s);
+        }
     }
     __syncwarp();
 #pragma unroll
-    for (int n2 = 0; n2 < W; ++n2) myw[n2 * S_T] = 0.0;
+    for (int n2 = 0; n2 < TILES * W; ++n2) myw[n2 * S_T] = 0.0;
     __syncwarp();
 }
 
@@ -674,7 +718,7 @@ __global__ void __launch_bounds__(S_T, 1) l_push_deposit_v2_k(const __grid_const
                 fc.qpi = (sp ? k.q[1] : k.q[0]) * k.p2c * k.idx;
             }
             if (BIG && (row & FRm) == 0) {
-                if (row > 0 && wb != NOWIN) { __syncwarp(); swin_flush<W>(win, myw, wbase, lane, wb, ga, nodes); }
+                if (row > 0 && wb != NOWIN) { __syncwarp(); swin_flush<1, W>(win, myw, wbase, lane, wb, ga, 0, nodes); }
                 const int cb = (int)floor(__shfl_sync(full, X.x, 0) * k.idx);
                 eb = min(max(cb - L_EW / 4, 0), nodes - L_EW);
                 __syncwarp();
@@ -708,7 +752,7 @@ __global__ void __launch_bounds__(S_T, 1) l_push_deposit_v2_k(const __grid_const
             else if (more) issue(cbase + chunk_step + 64 * (row + NST - S_ROWS), st_cur);
         }
         __syncwarp();
-        if (wb != NOWIN) swin_flush<W>(win, myw, wbase, lane, wb, ga, nodes);
+        if (wb != NOWIN) swin_flush<1, W>(win, myw, wbase, lane, wb, ga, 0, nodes);
     }
     // the N % S_CHUNK particles behind the last whole chunk: at most one per thread, exact routine, global REDs
     for (long long i = (long long)nchunks * S_CHUNK + (long long)blockIdx.x * S_T + threadIdx.x; i < k.N; i += (long long)gridDim.x * S_T)
@@ -769,7 +813,7 @@ __device__ __forceinline__ void py_fast(const PFastC& c, const double* __restric
 // exact per-particle routine (the body of pypic_picard_iter_k); deposits with global REDs
 template <bool FIRST>
 __device__ __noinline__ int py_particle_exact(const PYK& k, long long i, double X0, double V0, double pX1,
-                                              const double* sF, double* __restrict__ acc, double* x1, double* v1) {
+                                              const double* sF, const GAcc& ga, double* x1, double* v1) {
     const int Ng = k.Ng;
     int bad = 0;
     if (k.flags & 2) X0 = wrap_mod(X0, k.L);
@@ -787,17 +831,17 @@ __device__ __noinline__ int py_particle_exact(const PYK& k, long long i, double 
     Cell ch = cell_pypic<false>(xhw, k.dx, k.idx, Ng);
     pypic_fix(ch, Ng, bad);
     const double jh_i = k.q * VH * k.p2c * k.idx;
-    atomicAdd(&acc[ch.iL], jh_i * ch.wL); atomicAdd(&acc[ch.iR], jh_i * ch.wR);
+    ga.add(ch.iL, jh_i * ch.wL); ga.add(ch.iR, jh_i * ch.wR);
     if (!(k.flags & 8)) {
         Cell cf = cell_pypic<false>(x1w, k.dx, k.idx, Ng);
         pypic_fix(cf, Ng, bad);
         const double j1_i = k.q * V1 * k.p2c * k.idx;
-        atomicAdd(&acc[Ng + cf.iL], j1_i * cf.wL); atomicAdd(&acc[Ng + cf.iR], j1_i * cf.wR);
+        ga.add(Ng + cf.iL, j1_i * cf.wL); ga.add(Ng + cf.iR, j1_i * cf.wR);
     }
     return bad;
 }
 
-template <bool FIRST, int NST, bool J1, bool BIG = false, int W = S_W>
+template <bool FIRST, int NST, bool J1, bool BIG = false, int W = S_W, bool DET = false>
 __global__ void __launch_bounds__(S_T, 1) pypic_picard_iter_v2_k(const __grid_constant__ PYK k, int nchunks_fr,
                                                                   const double* __restrict__ x0,
                                                                   const double* __restrict__ v0, const double* x1i, double* x1,
@@ -808,6 +852,7 @@ __global__ void __launch_bounds__(S_T, 1) pypic_picard_iter_v2_k(const __grid_co
     if (k.done && *(const volatile int*)k.done) return;
     constexpr int NA = FIRST ? 2 : 3;
     const int Ng = k.Ng;
+    const GAcc ga = {acc, DET ? k.fix : nullptr, 2 * Ng, k.fs1, range_err};      // reproducible build: integer merges
     // smoothed field: the whole grid or, in the large-grid build, one PY_EW-node window per warp
     const int NP = BIG ? (S_T / 32) * PY_EW : ((Ng + 15) & ~15);
     const int nchunks = nchunks_fr & 0x0fffffff;
@@ -879,7 +924,7 @@ __global__ void __launch_bounds__(S_T, 1) pypic_picard_iter_v2_k(const __grid_co
             if (BIG && (row & FRm) == 0) {
                 // few particles per cell: the windows are flushed and re-centred every FRm+1 rows, and the
                 // field window is loaded around the gather cell of the row's first particle
-                if (row > 0 && wb != NOWIN) { __syncwarp(); swin_flush<J1 ? 2 : 1, W>(win, myw, wbase, lane, wb, acc, Ng, Ng); }
+                if (row > 0 && wb != NOWIN) { __syncwarp(); swin_flush<J1 ? 2 : 1, W>(win, myw, wbase, lane, wb, ga, Ng, Ng); }
                 const double xf = __shfl_sync(full, FIRST ? X0.x : (X0.x + pX1.x) * 0.5, 0);
                 const int cb = (int)floor(xf * k.idx);
                 eb = min(max(cb - PY_EW / 4, 0), Ng - PY_EW);
@@ -900,22 +945,22 @@ __global__ void __launch_bounds__(S_T, 1) pypic_picard_iter_v2_k(const __grid_co
             if (!(ra | rb)) {
                 __stcs((double2*)(x1 + ci), make_double2(a.X1, b.X1));
                 if (J1) __stcs((double2*)(v1 + ci), make_double2(a.V1, b.V1));
-                swin_add<W>(myw, acc, wb, a.cH, a.hL, a.hR);
-                if (J1) swin_add<W>(myw + W * S_T, acc + Ng, wb, a.cF, a.fL, a.fR);
-                swin_add<W>(myw, acc, wb, b.cH, b.hL, b.hR);
-                if (J1) swin_add<W>(myw + W * S_T, acc + Ng, wb, b.cF, b.fL, b.fR);
+                swin_add<W>(myw, ga, wb, a.cH, a.hL, a.hR);
+                if (J1) swin_add<W>(myw + W * S_T, ga, wb, a.cF, a.fL, a.fR, Ng);
+                swin_add<W>(myw, ga, wb, b.cH, b.hL, b.hR);
+                if (J1) swin_add<W>(myw + W * S_T, ga, wb, b.cF, b.fL, b.fR, Ng);
             } else {
-                if (ra) bad += py_particle_exact<FIRST>(k, ci, X0.x, V0.x, pX1.x, gE, acc, x1, v1);
+                if (ra) bad += py_particle_exact<FIRST>(k, ci, X0.x, V0.x, pX1.x, gE, ga, x1, v1);
                 else {
                     x1[ci] = a.X1; if (J1) v1[ci] = a.V1;
-                    swin_add<W>(myw, acc, wb, a.cH, a.hL, a.hR);
-                    if (J1) swin_add<W>(myw + W * S_T, acc + Ng, wb, a.cF, a.fL, a.fR);
+                    swin_add<W>(myw, ga, wb, a.cH, a.hL, a.hR);
+                    if (J1) swin_add<W>(myw + W * S_T, ga, wb, a.cF, a.fL, a.fR, Ng);
                 }
-                if (rb) bad += py_particle_exact<FIRST>(k, ci + 1, X0.y, V0.y, pX1.y, gE, acc, x1, v1);
+                if (rb) bad += py_particle_exact<FIRST>(k, ci + 1, X0.y, V0.y, pX1.y, gE, ga, x1, v1);
                 else {
                     x1[ci + 1] = b.X1; if (J1) v1[ci + 1] = b.V1;
-                    swin_add<W>(myw, acc, wb, b.cH, b.hL, b.hR);
-                    if (J1) swin_add<W>(myw + W * S_T, acc + Ng, wb, b.cF, b.fL, b.fR);
+                    swin_add<W>(myw, ga, wb, b.cH, b.hL, b.hR);
+                    if (J1) swin_add<W>(myw + W * S_T, ga, wb, b.cF, b.fL, b.fR, Ng);
                 }
             }
             __syncwarp();
@@ -923,25 +968,17 @@ __global__ void __launch_bounds__(S_T, 1) pypic_picard_iter_v2_k(const __grid_co
             else if (more) issue(cbase + chunk_step + 64 * (row + NST - S_ROWS), st_cur);
         }
         __syncwarp();
-        if (wb != NOWIN) swin_flush<J1 ? 2 : 1, W>(win, myw, wbase, lane, wb, acc, Ng, Ng);
+        if (wb != NOWIN) swin_flush<J1 ? 2 : 1, W>(win, myw, wbase, lane, wb, ga, Ng, Ng);
     }
     // the N % S_CHUNK particles behind the last whole chunk: at most one per thread, exact routine, global REDs
     for (long long i = (long long)nchunks * S_CHUNK + (long long)blockIdx.x * S_T + threadIdx.x; i < k.N; i += (long long)gridDim.x * S_T)
-        bad += py_particle_exact<FIRST>(k, i, x0[i], v0[i], FIRST ? 0.0 : x1i[i], gE, acc, x1, v1);
+        bad += py_particle_exact<FIRST>(k, i, x0[i], v0[i], FIRST ? 0.0 : x1i[i], gE, ga, x1, v1);
     if (bad) atomicAdd(&s_bad, bad);
     __syncthreads();
     if (threadIdx.x == 0 && s_bad && range_err) atomicAdd(range_err, s_bad);
 }
 
 // field phase build: fold rho, rhs of the gauge-fixed periodic system over `nodes` unknowns
-// reproducible build: fixed-point words -> fp64 accumulator (one rounding per node), words cleared
-__global__ void l_fix_take_k(double* __restrict__ rho_acc, long long* __restrict__ fix, int nodes, double fi1) {
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nodes; i += gridDim.x * blockDim.x) {
-        const long long hi = fix[i], lo = fix[nodes + i];
-        fix[i] = 0; fix[nodes + i] = 0;
-        rho_acc[i] += ((double)hi + (double)lo * (1.0 / 4294967296.0)) * fi1;
-    }
-}
 // initial deposit of the reproducible build: rho of the current positions, one pair of fixed-point additions per particle
 __global__ void l_weight_fix_k(LK k, const double* __restrict__ x, int* __restrict__ range_err) {
     const int nodes = k.Ng + 1;
@@ -1035,6 +1072,26 @@ int pic_dev_pypic_weight(const double* x, const double* q, const double* v, doub
     return PIC_OK;
 }
 
+int pic_dev_pypic_weight_fixed(const double* x, const double* q, const double* v, double* out, int64_t N, int Ng, double dx,
+                               double p2c, double qmax, int* range_err, void* stream) {
+    PIC_REQUIRE(x && q && out && N >= 0 && Ng >= 2 && qmax > 0, "pypic_weight_fixed: bad argument");
+    if (N == 0) return PIC_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    int e = 0;
+    frexp(qmax * p2c / dx * (v ? 2.99792458e8 : 1.0), &e);
+    const double fs1 = ldexp(1.0, 31 - e), fi1 = ldexp(1.0, e - 31);
+    long long* fix = nullptr;
+    PIC_CHECK_CUDA(cudaMallocAsync((void**)&fix, (size_t)2 * Ng * sizeof(long long), st));
+    PIC_CHECK_CUDA(cudaMemsetAsync(fix, 0, (size_t)2 * Ng * sizeof(long long), st));
+    if (v) pypic_weight_fix_k<true><<<grid_for(N, 256, 8), 256, 0, st>>>(x, q, v, fix, N, Ng, dx, p2c, fs1, range_err);
+    else pypic_weight_fix_k<false><<<grid_for(N, 256, 8), 256, 0, st>>>(x, q, v, fix, N, Ng, dx, p2c, fs1, range_err);
+    PIC_CHECK_LAUNCH();
+    fix_take_k<<<fix_take_grid(Ng), 1024, 0, st>>>(out, fix, Ng, fi1);
+    PIC_CHECK_LAUNCH();
+    PIC_CHECK_CUDA(cudaFreeAsync(fix, st));
+    return PIC_OK;
+}
+
 static int pypic_iter_v1(const PYK& k, int flags, const double* x0, const double* v0, const double* x1i, double* x1,
                          double* v1, const double* Fs, double* acc, int first, int* range_err, cudaStream_t st) {
     size_t smem = (size_t)3 * k.Ng * sizeof(double);
@@ -1090,31 +1147,53 @@ int pic_dev_pypic_picard_iter3(const pic_pypic_params* p, const double* x0, cons
                           (size_t)(S_T / 32) * PY_NST) * sizeof(double);
     const bool aligned16 = (((uintptr_t)x0 | (uintptr_t)v0 | (uintptr_t)x1i | (uintptr_t)x1 | (uintptr_t)v1) & 15) == 0;
     long long done = 0;
+    // reproducible build (flags bit7): acc is fp64[2Ng] followed by the fixed-point words int64[4Ng]; window kernels only
+    const bool det = (p->flags & 128) != 0;
+    if (det) {
+        PIC_REQUIRE(!(p->flags & (1 | 4)) && aligned16 && k.Ng >= 8,
+                    "pypic_picard_iter: the reproducible build needs the window kernel (16-byte aligned arrays, Ng >= 8)");
+        k.fix = (long long*)(acc + 2 * k.Ng);
+    }
     // large-grid build of the same kernel (flags bit4 forces it, for tests): per-warp field windows, so the
     // shared-memory footprint does not depend on Ng
     const size_t smem2b = ((size_t)(S_T / 32) * PY_EW + (size_t)2 * S_W * S_T + (size_t)(S_T / 32) * PY_NST * 192 +
                            (size_t)(S_T / 32) * PY_NST) * sizeof(double);
     const bool big = ((p->flags & 16) || smem2 > (size_t)max_optin_smem() - 512) && k.Ng >= PY_EW;
-    if (big && !(p->flags & (1 | 4)) && aligned16 && k.N >= S_CHUNK) {
+    if (big && !(p->flags & (1 | 4)) && aligned16 && (k.N >= S_CHUNK || det)) {
         const long long nchunks = k.N / S_CHUNK;
         PIC_REQUIRE(nchunks < (1 << 28), "pypic_picard_iter: shard too large");
         const bool light = (p->flags & 8) != 0;
         auto kern = first ? (light ? pypic_picard_iter_v2_k<true, PY_NST, false, true> : pypic_picard_iter_v2_k<true, PY_NST, true, true>)
                           : (light ? pypic_picard_iter_v2_k<false, PY_NST, false, true> : pypic_picard_iter_v2_k<false, PY_NST, true, true>);
+        if (det)
+            kern = first ? (light ? pypic_picard_iter_v2_k<true, PY_NST, false, true, S_W, true> : pypic_picard_iter_v2_k<true, PY_NST, true, true, S_W, true>)
+                         : (light ? pypic_picard_iter_v2_k<false, PY_NST, false, true, S_W, true> : pypic_picard_iter_v2_k<false, PY_NST, true, true, S_W, true>);
         PIC_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2b));
         // rows (of 64 particles) per deposit / field window: about three cells' worth of particles
         const double ppc = (double)k.N / (double)k.Ng;
         int fr = 16;
         while (fr > 1 && 64.0 * fr > 3.0 * ppc) fr >>= 1;
         long long cap = device_sm_count();
-        kern<<<(int)(nchunks < cap ? nchunks : cap), S_T, smem2b, st>>>(k, (int)((unsigned)nchunks | ((unsigned)(fr - 1) << 28)), x0, v0, x1i, x1, v1, Fs,
-                                                                          acc, range_err);
+        const long long gridb = nchunks < cap ? (nchunks > 0 ? nchunks : 1) : cap;
+        kern<<<(int)gridb, S_T, smem2b, st>>>(k, (int)((unsigned)nchunks | ((unsigned)(fr - 1) << 28)), x0, v0, x1i, x1, v1, Fs,
+                                              acc, range_err);
         PIC_CHECK_LAUNCH();
         return PIC_OK;
     }
     if (!(p->flags & (1 | 4)) && aligned16 && k.Ng >= 8 && smem2 <= (size_t)max_optin_smem() - 512) {
         // default: TMA-staged private-window kernel over whole chunks, v1 kernel on the tail
         const long long nchunks = k.N / S_CHUNK;
+        if (det) {
+            const bool light = (p->flags & 8) != 0;
+            auto kern = first ? (light ? pypic_picard_iter_v2_k<true, PY_NST, false, false, S_W, true> : pypic_picard_iter_v2_k<true, PY_NST, true, false, S_W, true>)
+                              : (light ? pypic_picard_iter_v2_k<false, PY_NST, false, false, S_W, true> : pypic_picard_iter_v2_k<false, PY_NST, true, false, S_W, true>);
+            PIC_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
+            long long cap = device_sm_count();
+            const long long grid = nchunks < cap ? (nchunks > 0 ? nchunks : 1) : cap;
+            kern<<<(int)grid, S_T, smem2, st>>>(k, (int)nchunks, x0, v0, x1i, x1, v1, Fs, acc, range_err);
+            PIC_CHECK_LAUNCH();
+            return PIC_OK;
+        }
         if (nchunks > 0) {
             const bool light = (p->flags & 8) != 0;
             // 15-node deposit windows (3 ring stages): env PIC_S_WIDE_PICARD=1, for A/B runs
@@ -1137,6 +1216,7 @@ int pic_dev_pypic_picard_iter3(const pic_pypic_params* p, const double* x0, cons
         done = nchunks * S_CHUNK;
         if (done >= k.N) return PIC_OK;
     }
+    PIC_REQUIRE(!det, "pypic_picard_iter: grid too large for the reproducible build's field tile and too small for the large-grid kernel");
     PYK t = k;
     t.N = k.N - done;
     return pypic_iter_v1(t, p->flags, x0 + done, v0 + done, x1i + done, x1 + done, v1 + done, Fs, acc, first, range_err, st);
@@ -1146,6 +1226,7 @@ int pic_dev_pypic_picard_iter_qm(const pic_pypic_params* p, const double* x0, co
                                  double* x1, double* v1, const double* q, const double* m, const double* Fs, double* acc,
                                  int first, int* range_err, const int32_t* done_flag, void* stream) {
     PIC_REQUIRE(p && x0 && v0 && x1i && x1 && v1 && q && m && Fs && acc, "pypic_picard_iter_qm: null pointer");
+    PIC_REQUIRE(!(p->flags & 128), "pypic_picard_iter_qm: no reproducible build of the per-particle q, m kernel");
     PIC_REQUIRE(p->Ng >= 2 && p->dx > 0, "pypic_picard_iter_qm: bad parameters");
     PIC_REQUIRE(!(p->flags & 8), "pypic_picard_iter_qm: light iterations are not offered with per-particle q, m");
     if (p->N == 0) return PIC_OK;
@@ -1165,6 +1246,11 @@ int pic_dev_pypic_field_update2(const pic_pypic_params* p, double* acc, const do
     PIC_REQUIRE(p && acc && E0 && Es && Fs && E1 && j1 && stats, "pypic_field_update: null pointer");
     PIC_REQUIRE(!(ctl || rhist) || maxiter >= 1, "pypic_field_update: maxiter must be >= 1 with ctl / rhist");
     PYK k = make_pyk(p);
+    if (p->flags & 128) {          // reproducible build: the currents arrive as fixed-point words behind acc
+        // (a no-op launch of an ended loop finds zero words: the last real field update took them)
+        fix_take_k<<<fix_take_grid(2 * k.Ng), 1024, 0, (cudaStream_t)stream>>>(acc, (long long*)(acc + 2 * k.Ng), 2 * k.Ng, k.fi1);
+        PIC_CHECK_LAUNCH();
+    }
     pypic_field_update_k<<<1, 1024, 0, (cudaStream_t)stream>>>(k, acc, E0, Es, Fs, E1, j1, stats, Fs_prev, rhist, ctl, tol,
                                                                maxiter);
     PIC_CHECK_LAUNCH();
@@ -1177,6 +1263,7 @@ int pic_dev_pypic_j1_repair(const pic_pypic_params* p, const double* x0, const d
     PIC_REQUIRE(p && x0 && v0 && x1_prev && x1_last && Fs_prev && v1 && acc, "pypic_j1_repair: null pointer");
     if (p->N == 0) return PIC_OK;
     PYK k = make_pyk(p);
+    if (p->flags & 128) k.fix = (long long*)(acc + 2 * k.Ng);
     pypic_j1_repair_k<<<grid_for(k.N, 256, 8), 256, 0, (cudaStream_t)stream>>>(k, x0, v0, x1_prev, x1_last, Fs_prev, v1, first,
                                                                              acc, range_err);
     PIC_CHECK_LAUNCH();
@@ -1184,6 +1271,11 @@ int pic_dev_pypic_j1_repair(const pic_pypic_params* p, const double* x0, const d
 }
 int pic_dev_pypic_j1_finish(const pic_pypic_params* p, double* acc, double* j1, double* stats, void* stream) {
     PIC_REQUIRE(p && acc && j1 && stats, "pypic_j1_finish: null pointer");
+    if (p->flags & 128) {
+        PYK k = make_pyk(p);
+        fix_take_k<<<fix_take_grid(2 * k.Ng), 1024, 0, (cudaStream_t)stream>>>(acc, (long long*)(acc + 2 * k.Ng), 2 * k.Ng, k.fi1);
+        PIC_CHECK_LAUNCH();
+    }
     pypic_j1_finish_k<<<1, 1024, 0, (cudaStream_t)stream>>>(p->Ng, acc, j1, stats);
     PIC_CHECK_LAUNCH();
     return PIC_OK;
@@ -1325,7 +1417,7 @@ int pic_dev_l_field_solve(const pic_l_params* p, double* rho_acc, double* rho, d
            *x = work + 4 * (size_t)nodes;
     if (p->flags & 128) {          // reproducible build: the deposits arrive as fixed-point words behind rho_acc
         LK k = make_lk(p);
-        l_fix_take_k<<<(nodes + 1023) / 1024 < 148 ? (nodes + 1023) / 1024 : 148, 1024, 0, st>>>(rho_acc, (long long*)(rho_acc + nodes), nodes, k.fi1);
+        fix_take_k<<<fix_take_grid(nodes), 1024, 0, st>>>(rho_acc, (long long*)(rho_acc + nodes), nodes, k.fi1);
         PIC_CHECK_LAUNCH();
     }
     l_field_build_k<<<1, 1024, 0, st>>>(rho_acc, rho, a, b, c, d, nodes, p->dx);

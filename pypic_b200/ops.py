@@ -117,13 +117,19 @@ def gc_interpolate(E, x, ng, dx):
 
 
 # ------------------------------------------------------------------ deposits
-def pypic_weight(x, q, v, p2c, Ng, dx):
-    """v=None -> weight_density_p, else weight_current_p; p2c truncated like numba's int32."""
+def pypic_weight(x, q, v, p2c, Ng, dx, reproducible=False):
+    """v=None -> weight_density_p, else weight_current_p; p2c truncated like numba's int32.
+    reproducible: order-independent fixed-point accumulation (the same bits on every run)."""
     dev = D.require_cuda()
     dx_ = _up(x, dev); dq = _up(q, dev); dv = _up(v, dev) if v is not None else None
     out = D.f64(Ng, dev, True); err = _err(dev)
-    _lib.call("pic_dev_pypic_weight", D.ptr(dx_), D.ptr(dq), D.ptr(dv), D.ptr(out), dx_.numel(), int(Ng), float(dx),
-              float(int(p2c)), D.ptr(err), D.stream())
+    if reproducible:
+        qmax = float(np.max(np.abs(np.asarray(q)))) if np.size(q) else 1.0
+        _lib.call("pic_dev_pypic_weight_fixed", D.ptr(dx_), D.ptr(dq), D.ptr(dv), D.ptr(out), dx_.numel(), int(Ng), float(dx),
+                  float(int(p2c)), qmax if qmax > 0 else 1.0, D.ptr(err), D.stream())
+    else:
+        _lib.call("pic_dev_pypic_weight", D.ptr(dx_), D.ptr(dq), D.ptr(dv), D.ptr(out), dx_.numel(), int(Ng), float(dx),
+                  float(int(p2c)), D.ptr(err), D.stream())
     D.check_range(err, "pypic weight")
     return out.cpu().numpy()
 

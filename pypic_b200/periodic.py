@@ -42,7 +42,11 @@ class PeriodicImplicitSim:
         # ``x % L`` (pypic.py:277) when they load it -- saves a 16 B/particle pass per step
         # "window-big" forces the large-grid build of the window kernel (per-warp field windows instead of the
         # whole-grid tile; taken automatically when the grid does not fit shared memory, Ng >~ 9000)
-        flags = {"window": 0, "window-big": 16, "warp": 4, "atomic": 1 | 4}[deposit] | 2
+        # "window-det": the REPRODUCIBLE build (flags bit7, as SheathSim's): integer merges of the currents on fixed-point
+        # words, stable radix sort (with the original index as its payload when track_order), fixed-order kinetic
+        # energy -- two runs give bit-identical output
+        flags = {"window": 0, "window-big": 16, "warp": 4, "atomic": 1 | 4, "window-det": 128}[deposit] | 2
+        self.det = deposit == "window-det"
         self.sort_every = int(sort_every)
         self.t = 0
         self.perm = None                     # original index of the particle in each slot (after sorting)
@@ -51,6 +55,8 @@ class PeriodicImplicitSim:
         # q, m: scalars (one species, the reference's only use) or per-particle arrays (the signature of
         # particle_push_p, pypic.py:248): arrays take the grid-stride kernel, unsorted, full iterations
         self.qm_arrays = None
+        if (np.ndim(q) or np.ndim(m)) and self.det:
+            raise ValueError("deposit='window-det' is built for one species (scalar q, m)")
         if np.ndim(q) or np.ndim(m):
             qa = np.broadcast_to(np.asarray(q, dtype=np.float64), (self.N_global,))[self.start:self.stop].copy()
             ma = np.broadcast_to(np.asarray(m, dtype=np.float64), (self.N_global,))[self.start:self.stop].copy()
@@ -64,7 +70,7 @@ class PeriodicImplicitSim:
         self.x1 = D.f64(n, dev, True); self.v1 = D.f64(n, dev, True)
         self.E0 = D.f64(g, dev, True); self.Es = D.f64(g, dev, True); self.Fs = D.f64(g, dev, True)
         self.E1 = D.f64(g, dev, True); self.j0 = D.f64(g, dev, True)
-        self.acc = D.f64(2 * g, dev, True)
+        self.acc = D.f64(2 * g + (4 * g if self.det else 0), dev, True)     # det: + int64[4g] fixed-point words
         # [r, mean j1, EE, iterations | residual of every iteration of the step]
         self.stats = D.f64(4 + self.maxiter, dev, True)
         # enqueue-ahead Picard loop (see SheathSim.picard): the iterations the previous step needed are
@@ -103,6 +109,32 @@ class PeriodicImplicitSim:
         arrays; the original index of every particle rides along as a payload so that
         download() can return the arrays in the caller's order."""
         n = max(self.N, 1)
+        if self.det:
+            # reproducible build: stable LSD radix sort (equal cells keep their previous order), int32 payload
+            first = self._sort_params is None
+            if first:
+                self._sort_scratch = torch.zeros(D.sort_stable_scratch_size(n), dtype=torch.int32, device=self.dev)
+                self._sort_params = _lib.DDParams(self.N, self.N, self.Ng, 128, self.dx, self.dt, self.L, self.p2c,
+                                                  (C.c_double * 2)(0., 0.), (C.c_double * 2)(1., 1.))
+                if self.track_order:
+                    self.perm = torch.empty(n, dtype=torch.int32, device=self.dev)
+                    self._perm2 = torch.empty(n, dtype=torch.int32, device=self.dev)
+            where = C.c_int(0)
+            if self.track_order:
+                _lib.call("pic_dev_dd_sort_by_cell_stable2", C.byref(self._sort_params), D.ptr(self.x0), D.ptr(self.v0),
+                          D.ptr(self.x1), D.ptr(self.v1), D.ptr(self.perm), D.ptr(self._perm2), 1 if first else 0,
+                          D.ptr(self._sort_scratch), self._sort_scratch.numel(), C.byref(where), D.stream())
+            else:
+                _lib.call("pic_dev_dd_sort_by_cell_stable", C.byref(self._sort_params), D.ptr(self.x0), D.ptr(self.v0),
+                          D.ptr(self.x1), D.ptr(self.v1), D.ptr(self._sort_scratch), self._sort_scratch.numel(),
+                          C.byref(where), D.stream())
+            self.kernel_launches += 5 * ((max(1, (self.Ng - 1).bit_length()) + 7) // 8)
+            if where.value:
+                self.x0, self.x1 = self.x1, self.x0
+                self.v0, self.v1 = self.v1, self.v0
+                if self.track_order:
+                    self.perm, self._perm2 = self._perm2, self.perm
+            return
         if self._sort_params is None:
             if self.track_order:
                 self.perm = torch.arange(n, dtype=torch.float64, device=self.dev)
@@ -119,6 +151,14 @@ class PeriodicImplicitSim:
         self.v0, self.v1 = self.v1, self.v0
         if self.track_order:
             self.perm, self._perm2 = self._perm2, self.perm
+
+    def _allreduce_acc(self):
+        """Sum over ranks of the deposits; reproducible build: of the fixed-point words (exact in any order)."""
+        if self.det:
+            if self.comm.enabled and self.comm.world > 1:
+                self.comm.allreduce_sum(self.acc[2 * self.Ng:].view(torch.int64))
+        else:
+            self.comm.allreduce_sum(self.acc)
 
     def push(self):
         """particle_push_p: Picard loop + commit (x wrapped into [0,L)).  Returns (k, r)."""
@@ -166,7 +206,7 @@ class PeriodicImplicitSim:
                           D.ptr(self.ctl), st)
             if ev is not None:
                 ev[1].record()
-            self.comm.allreduce_sum(self.acc)
+            self._allreduce_acc()
             _lib.call("pic_dev_pypic_field_update2", P, D.ptr(self.acc), D.ptr(self.E0), D.ptr(self.Es), D.ptr(self.Fs),
                       D.ptr(self.E1), D.ptr(self.j0), D.ptr(self.stats), D.ptr(self.Fs_prev) if light_ok else None,
                       rhist, D.ptr(self.ctl), self.tol, self.maxiter, st)
@@ -198,7 +238,7 @@ class PeriodicImplicitSim:
         if k > 0 and not full:
             _lib.call("pic_dev_pypic_j1_repair", P, D.ptr(self.x0), D.ptr(self.v0), D.ptr(last_in), D.ptr(last_out),
                       D.ptr(self.Fs_prev), D.ptr(self.v1), 1 if k == 1 else 0, D.ptr(self.acc), D.ptr(self.range_err), st)
-            self.comm.allreduce_sum(self.acc)
+            self._allreduce_acc()
             _lib.call("pic_dev_pypic_j1_finish", P, D.ptr(self.acc), D.ptr(self.j0), D.ptr(self.stats), st)
             self.kernel_launches += 2
             self.j1_repairs += 1
@@ -228,6 +268,11 @@ class PeriodicImplicitSim:
 
     def diagnostics(self, m=me):
         s = D.read_f64(self.stats, 4)
+        if self.det:              # fixed-order reduction
+            sc2 = D.f64(2, self.dev, True)
+            _lib.call("pic_dev_moments", D.ptr(self.v0), self.N, D.ptr(sc2), D.stream())
+            self.comm.allreduce_sum(sc2)
+            return dict(EE=float(s[2]), KE=self.p2c_raw * (m / 2. * float(D.read_f64(sc2, 2)[1])), jbias=float(s[1]))
         sc = D.f64(1, self.dev, True)
         _lib.call("pic_dev_sum_sq", D.ptr(self.v0), self.N, m / 2., D.ptr(sc), D.stream())
         self.comm.allreduce_sum(sc)

@@ -248,3 +248,34 @@ def test_explicit_loop_reproducible_build_through_the_reference_api(tmp_path, N)
     for k in ("x", "v", "E", "EE", "E_series"):
         assert np.max(np.abs(a[k] - d[k])) <= 1e-9 * np.max(np.abs(d[k])), k
     assert np.max(np.abs(a["KE"] - d["KE"])) <= 1e-12 * np.max(np.abs(d["KE"]))
+
+
+@pytest.mark.parametrize("N", [200000, 9000])       # 9000: shorter than one chunk, every particle through the exact routine
+def test_periodic_implicit_loop_reproducible_build_through_the_reference_api(tmp_path, N):
+    """pypic.main(deposit='window-det'): the periodic Crank-Nicolson / Picard loop on the reproducible build of its
+    window kernel (fixed-point merges of jh and j1, also in the repair pass of a loop that ended on a light iteration;
+    order-independent initial density; stable radix sort with the original-index payload; fixed-order kinetic
+    energy).  Two runs give bit-identical series, fields and particles (in the reference's numbering); against
+    the default build the run agrees to round-off."""
+    import contextlib, io, os
+    import pypic
+    outs = []
+    os.makedirs(os.path.join(str(tmp_path), "plots"), exist_ok=True)
+    for dep, se in (("window-det", 2), ("window-det", 2), ("warp", 0)):
+        res = {}
+        np.random.seed(6)
+        cwd = os.getcwd(); os.chdir(str(tmp_path))
+        try:
+            with contextlib.redirect_stdout(io.StringIO()):
+                pypic.main(7, 10 ** 9, N=N, Ng=64, result=res, sort_every=se, deposit=dep)
+        finally:
+            os.chdir(cwd)
+        outs.append(res)
+    a, b, d = outs
+    keys = [k for k in a if isinstance(a[k], np.ndarray)]
+    assert {"x0", "v0", "E0", "j0", "EE", "KE", "j_bias"} <= set(keys)
+    for k in keys:
+        assert np.array_equal(a[k], b[k]), k
+    for k in ("x0", "v0", "E0", "EE"):
+        assert np.max(np.abs(a[k] - d[k])) <= 1e-9 * np.max(np.abs(d[k])), k
+    assert np.max(np.abs(a["KE"] - d["KE"])) <= 1e-12 * np.max(np.abs(d["KE"]))
