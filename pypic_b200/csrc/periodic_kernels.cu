@@ -68,13 +68,14 @@ struct PYK {
     // reproducible build (flags bit7): fixed-point words [hi(2Ng) | lo(2Ng)] behind the fp64 accumulators [jh | j1]
     long long* fix;
     double fs1, fi1;
+    int* ferr;            // error counter for contributions beyond the fixed-point range
 };
 static PYK make_pyk(const pic_pypic_params* p) {
     PYK k;
     k.done = nullptr; k.qa = nullptr; k.ma = nullptr;
     k.N = p->N; k.Ng = p->Ng; k.flags = p->flags; k.dx = p->dx; k.idx = 1. / p->dx; k.dt = p->dt;
     k.L = p->L; k.p2c = p->p2c; k.q = p->q; k.qm = p->q / p->m;
-    k.fix = nullptr; k.fs1 = 1.0; k.fi1 = 1.0;
+    k.fix = nullptr; k.fs1 = 1.0; k.fi1 = 1.0; k.ferr = nullptr;
     if (p->flags & 128) {
         // one contribution is q*v*p2c*w/dx with |v| below the speed of light (see make_ddk in dd_kernels.cu)
         int e = 0;
@@ -315,13 +316,14 @@ struct LK {
     // [hi(Ng+1) | lo(Ng+1)] behind the fp64 accumulator; one hi unit = 1/fs1
     long long* fix;
     double fs1, fi1;
+    int* ferr;
 };
 static LK make_lk(const pic_l_params* p) {
     LK k;
     k.N = p->N; k.n_split = p->n_split; k.Ng = p->Ng; k.flags = p->flags; k.dx = p->dx; k.idx = 1. / p->dx;
     k.dt = p->dt; k.L = p->L; k.p2c = p->p2c;
     for (int s = 0; s < 2; ++s) { k.q[s] = p->q[s]; k.qm[s] = p->q[s] / p->m[s]; }
-    k.fix = nullptr; k.fs1 = 1.0; k.fi1 = 1.0;
+    k.fix = nullptr; k.fs1 = 1.0; k.fi1 = 1.0; k.ferr = nullptr;
     if (p->flags & 128) {
         // one contribution is q*p2c*w/dx with w <= 1: |v| < 2^e; a window column sums at most 2^10 of them per flush
         const double qa = fabs(p->q[0]) > fabs(p->q[1]) ? fabs(p->q[0]) : fabs(p->q[1]);
@@ -611,9 +613,11 @@ __device__ __forceinline__ void l_fast(const LFastC& c, const double* __restrict
 }
 
 // exact per-particle routine (the body of l_push_deposit_k); deposits with global REDs
+template <bool DET = false>
 __device__ __noinline__ int l_particle_exact(const LK& k, long long i, double X, double V, const double* sE,
-                                             const GAcc& ga, double* x, double* v) {
+                                             double* __restrict__ rho_acc, double* x, double* v) {
     const int nodes = k.Ng + 1;
+    const GAcc ga = {rho_acc, DET ? k.fix : nullptr, nodes, k.fs1, DET ? k.ferr : nullptr};
     int bad = 0;
     const int sp = i >= k.n_split;
     Cell c = cell_lper(X, k.dx, nodes);
@@ -642,7 +646,7 @@ __global__ void __launch_bounds__(S_T, 1) l_push_deposit_v2_k(const __grid_const
     __shared__ int s_bad;
     const int nodes = k.Ng + 1;
     // reproducible build: integer merges into the fixed-point words behind rho_acc (constant-folded away otherwise)
-    const GAcc ga = {rho_acc, DET ? k.fix : nullptr, nodes, k.fs1, range_err};
+    const GAcc ga = {rho_acc, DET ? k.fix : nullptr, nodes, k.fs1, DET ? k.ferr : nullptr};
     const int NP = BIG ? (S_T / 32) * L_EW : ((nodes + 15) & ~15);
     const int nchunks = nchunks_fr & 0x0fffffff;
     const int FRm = BIG ? (int)((unsigned)nchunks_fr >> 28) : (S_ROWS - 1);      // rows per deposit / field window - 1
@@ -741,9 +745,9 @@ __global__ void __launch_bounds__(S_T, 1) l_push_deposit_v2_k(const __grid_const
                 swin_add<W>(myw, ga, wb, a.cF, a.fL, a.fR);
                 swin_add<W>(myw, ga, wb, b.cF, b.fL, b.fR);
             } else {
-                if (ra) bad += l_particle_exact(k, ci, X.x, V.x, gE, ga, x, v);
+                if (ra) bad += l_particle_exact<DET>(k, ci, X.x, V.x, gE, rho_acc, x, v);
                 else { x[ci] = a.X; v[ci] = a.V; swin_add<W>(myw, ga, wb, a.cF, a.fL, a.fR); }
-                if (rb) bad += l_particle_exact(k, ci + 1, X.y, V.y, gE, ga, x, v);
+                if (rb) bad += l_particle_exact<DET>(k, ci + 1, X.y, V.y, gE, rho_acc, x, v);
                 else { x[ci + 1] = b.X; v[ci + 1] = b.V; swin_add<W>(myw, ga, wb, b.cF, b.fL, b.fR); }
             }
             // refill the drained stage only after every lane's LDS of it has executed (see v6)
@@ -756,7 +760,7 @@ __global__ void __launch_bounds__(S_T, 1) l_push_deposit_v2_k(const __grid_const
     }
     // the N % S_CHUNK particles behind the last whole chunk: at most one per thread, exact routine, global REDs
     for (long long i = (long long)nchunks * S_CHUNK + (long long)blockIdx.x * S_T + threadIdx.x; i < k.N; i += (long long)gridDim.x * S_T)
-        bad += l_particle_exact(k, i, x[i], v[i], gE, ga, x, v);
+        bad += l_particle_exact<DET>(k, i, x[i], v[i], gE, rho_acc, x, v);
     if (bad) atomicAdd(&s_bad, bad);
     __syncthreads();
     if (threadIdx.x == 0 && s_bad && range_err) atomicAdd(range_err, s_bad);
@@ -811,10 +815,11 @@ __device__ __forceinline__ void py_fast(const PFastC& c, const double* __restric
 }
 
 // exact per-particle routine (the body of pypic_picard_iter_k); deposits with global REDs
-template <bool FIRST>
+template <bool FIRST, bool DET = false>
 __device__ __noinline__ int py_particle_exact(const PYK& k, long long i, double X0, double V0, double pX1,
-                                              const double* sF, const GAcc& ga, double* x1, double* v1) {
+                                              const double* sF, double* __restrict__ acc, double* x1, double* v1) {
     const int Ng = k.Ng;
+    const GAcc ga = {acc, DET ? k.fix : nullptr, 2 * Ng, k.fs1, DET ? k.ferr : nullptr};
     int bad = 0;
     if (k.flags & 2) X0 = wrap_mod(X0, k.L);
     const double dtdt = k.dt * k.dt;
@@ -852,7 +857,7 @@ __global__ void __launch_bounds__(S_T, 1) pypic_picard_iter_v2_k(const __grid_co
     if (k.done && *(const volatile int*)k.done) return;
     constexpr int NA = FIRST ? 2 : 3;
     const int Ng = k.Ng;
-    const GAcc ga = {acc, DET ? k.fix : nullptr, 2 * Ng, k.fs1, range_err};      // reproducible build: integer merges
+    const GAcc ga = {acc, DET ? k.fix : nullptr, 2 * Ng, k.fs1, DET ? k.ferr : nullptr};      // reproducible build: integer merges
     // smoothed field: the whole grid or, in the large-grid build, one PY_EW-node window per warp
     const int NP = BIG ? (S_T / 32) * PY_EW : ((Ng + 15) & ~15);
     const int nchunks = nchunks_fr & 0x0fffffff;
@@ -950,13 +955,13 @@ __global__ void __launch_bounds__(S_T, 1) pypic_picard_iter_v2_k(const __grid_co
                 swin_add<W>(myw, ga, wb, b.cH, b.hL, b.hR);
                 if (J1) swin_add<W>(myw + W * S_T, ga, wb, b.cF, b.fL, b.fR, Ng);
             } else {
-                if (ra) bad += py_particle_exact<FIRST>(k, ci, X0.x, V0.x, pX1.x, gE, ga, x1, v1);
+                if (ra) bad += py_particle_exact<FIRST, DET>(k, ci, X0.x, V0.x, pX1.x, gE, acc, x1, v1);
                 else {
                     x1[ci] = a.X1; if (J1) v1[ci] = a.V1;
                     swin_add<W>(myw, ga, wb, a.cH, a.hL, a.hR);
                     if (J1) swin_add<W>(myw + W * S_T, ga, wb, a.cF, a.fL, a.fR, Ng);
                 }
-                if (rb) bad += py_particle_exact<FIRST>(k, ci + 1, X0.y, V0.y, pX1.y, gE, ga, x1, v1);
+                if (rb) bad += py_particle_exact<FIRST, DET>(k, ci + 1, X0.y, V0.y, pX1.y, gE, acc, x1, v1);
                 else {
                     x1[ci + 1] = b.X1; if (J1) v1[ci + 1] = b.V1;
                     swin_add<W>(myw, ga, wb, b.cH, b.hL, b.hR);
@@ -972,7 +977,7 @@ __global__ void __launch_bounds__(S_T, 1) pypic_picard_iter_v2_k(const __grid_co
     }
     // the N % S_CHUNK particles behind the last whole chunk: at most one per thread, exact routine, global REDs
     for (long long i = (long long)nchunks * S_CHUNK + (long long)blockIdx.x * S_T + threadIdx.x; i < k.N; i += (long long)gridDim.x * S_T)
-        bad += py_particle_exact<FIRST>(k, i, x0[i], v0[i], FIRST ? 0.0 : x1i[i], gE, ga, x1, v1);
+        bad += py_particle_exact<FIRST, DET>(k, i, x0[i], v0[i], FIRST ? 0.0 : x1i[i], gE, acc, x1, v1);
     if (bad) atomicAdd(&s_bad, bad);
     __syncthreads();
     if (threadIdx.x == 0 && s_bad && range_err) atomicAdd(range_err, s_bad);
@@ -1152,7 +1157,7 @@ int pic_dev_pypic_picard_iter3(const pic_pypic_params* p, const double* x0, cons
     if (det) {
         PIC_REQUIRE(!(p->flags & (1 | 4)) && aligned16 && k.Ng >= 8,
                     "pypic_picard_iter: the reproducible build needs the window kernel (16-byte aligned arrays, Ng >= 8)");
-        k.fix = (long long*)(acc + 2 * k.Ng);
+        k.fix = (long long*)(acc + 2 * k.Ng); k.ferr = range_err;
     }
     // large-grid build of the same kernel (flags bit4 forces it, for tests): per-warp field windows, so the
     // shared-memory footprint does not depend on Ng
@@ -1343,7 +1348,7 @@ int pic_dev_l_push_deposit(const pic_l_params* p, double* x, double* v, const do
     const bool det = (p->flags & 128) != 0;
     if (det) {
         PIC_REQUIRE(!(p->flags & (1 | 2 | 4)) && aligned16, "l_push_deposit: the reproducible build needs the window kernel (16-byte aligned x, v)");
-        k.fix = (long long*)(rho_acc + nodes);
+        k.fix = (long long*)(rho_acc + nodes); k.ferr = range_err;
     }
     // large-grid build of the same kernel (flags bit4 forces it, for tests): per-warp field windows
     const size_t smem2b = ((size_t)(S_T / 32) * L_EW + (size_t)S_W * S_T + (size_t)(S_T / 32) * L_NST * 128 +
