@@ -26,6 +26,22 @@ def scale_exponent(q, p2c, dx):
     return 31 - e
 
 
+def scale_exponent_density(q, p2c, dx):
+    """The explicit loop's scale (make_lk in csrc/periodic_kernels.cu, pic_l_params.flags bit7): one deposit is
+    q*p2c*w/dx with w <= 1; a window column sums at most 2^10 of them per flush, which the 2^42 guard of the hi
+    word leaves room for."""
+    qa = max(abs(float(q[0])), abs(float(q[1])))
+    _, e = math.frexp(qa * float(p2c) * (1.0 / float(dx)))
+    return 31 - e
+
+
+def scale_exponent_current1(q, p2c, dx):
+    """The periodic Picard loop's scale (make_pyk, pic_pypic_params.flags bit7): one species, deposits
+    q*v*p2c*w/dx with |v| below the speed of light."""
+    _, e = math.frexp(abs(float(q)) * float(p2c) * (1.0 / float(dx)) * C_LIGHT)
+    return 31 - e
+
+
 def split(v, s):
     """(hi, lo) integer words of the deposits v (acc_add)."""
     v = np.asarray(v, dtype=np.float64)

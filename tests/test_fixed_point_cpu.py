@@ -53,3 +53,28 @@ def test_scale_leaves_headroom_for_two_billion_deposits_per_node():
         hi, lo = FP.split(np.array([vmax, -vmax]), s)
         assert 2 ** 30 <= abs(int(hi[0])) < 2 ** 31 and int(hi[1]) == -int(hi[0])
         assert abs(int(hi[0])) * 2 ** 31 < 2 ** 63
+
+
+def test_scales_of_the_periodic_loops():
+    """make_lk / make_pyk (csrc/periodic_kernels.cu): a single deposit stays below 2^31 hi units, the largest window
+    column sum (2^10 deposits) below the 2^42 guard, and the split is exact to the lo quantum."""
+    rs = np.random.RandomState(4)
+    # PIC_L.main's literals (density 1e10, N 1e5, Ng 200, dx 0.02) and the bench workload
+    for dx, p2c in ((0.02, 4e5), (1e-5, 2.048e9)):
+        s = FP.scale_exponent_density((-e, e), p2c, dx)
+        vmax = e * p2c / dx
+        hi, _ = FP.split(np.array([vmax]), s)
+        assert 2 ** 30 <= abs(int(hi[0])) < 2 ** 31 and abs(int(hi[0])) * 2 ** 10 < 2 ** 42
+        v = -e * p2c / dx * rs.uniform(0, 1, 100000)
+        h, lo = FP.split(v, s)
+        back = np.ldexp(h.astype(np.float64), -s) + np.ldexp(lo.astype(np.float64), -s - 32)
+        assert np.abs(back - v).max() <= math.ldexp(1.0, -s - 33) * (1 + 1e-12)
+        perm = rs.permutation(v.size)
+        assert int(h[perm].sum()) == int(h.sum()) and int(lo[perm].sum()) == int(lo.sum())
+    # pypic.main's literals (density 1e5, N 1e6, Ng 200): p2c truncated to an integer like numba's int32 argument
+    L = 22.0 * math.sqrt(kb * 100.0 * 11600. * 8.854E-12 / e / e / 1e5)
+    dx = L / 200.
+    p2c = float(int(L * 1e5 / 1e6))
+    s = FP.scale_exponent_current1(-e, max(p2c, 1.0), dx)
+    hi, _ = FP.split(np.array([e * max(p2c, 1.0) / dx * FP.C_LIGHT]), s)
+    assert 2 ** 30 <= abs(int(hi[0])) < 2 ** 31
