@@ -515,9 +515,20 @@ def run_cuda(args):
                                maxiter=w["maxiter"], seed=1, comm=comm, device=dev, sort_every=min(args.sort_every, 8), guard=16,
                                field=args.slab_field)     # 8 steps between migrations: the setting the 16 guard cells were validated with
             ss.init_device(seed=1234)
+
+            def agreed_check():
+                """check() on every rank, then ONE collective so that all ranks leave the leg together when any of them
+                failed (a rank that raised alone would meet the others in different collectives afterwards)."""
+                msg = ""
+                try:
+                    ss.check()
+                except Exception as ex_:
+                    msg = repr(ex_)[:300]
+                if comm.max_float(1.0 if msg else 0.0, device=dev) > 0.0:
+                    raise RuntimeError(msg or "slab check failed on another rank")
             for _ in range(3):
                 ss.step()
-            ss.check()
+            agreed_check()
             torch.cuda.synchronize(); comm.barrier()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             its_sl = []
@@ -527,7 +538,7 @@ def run_cuda(args):
             e1.record()
             torch.cuda.synchronize(); comm.barrier()
             ms_sl = comm.max_float(e0.elapsed_time(e1), device=dev)
-            ss.check()
+            agreed_check()
             slab = {"value": w["N"] * len(its_sl) / (ms_sl * 1e-3), "unit": "particle-steps/s", "ms_per_step": ms_sl / len(its_sl),
                     "steps": len(its_sl), "picard_iterations_per_step": float(np.mean(its_sl)), "n_gpus": world,
                     "migration": dict(ss.stat), "guard_cells": 16, "field_update": args.slab_field,
