@@ -385,7 +385,9 @@ int pic_dev_dd_reinject_philox(const pic_dd_params* p, double* x0, double* u0, d
  * pointer swap on the host.  KE diagnostic sum(me*u^2/2) (PIC_L_DD.py:549): */
 int pic_dev_sum_sq(const double* u, int64_t N, double scale, double* out1, void* stream);
 /* out2 = {sum u, sum u*u} in one pass: np.std(u0) (PIC_L_DD.py:417) and KE (:549) together; per-CTA partial sums added
- * in CTA order (for a given particle order the result does not depend on scheduling) */
+ * in CTA order (for a given particle order the result does not depend on scheduling).  The partial sums live in
+ * one static device buffer: calls must be stream-ordered with respect to each other (one stream per process, as
+ * all drivers of this library do). */
 int pic_dev_moments(const double* u, int64_t N, double* out2, void* stream);
 /* Counting sort by (species, cell) of the n-level state; out-of-place.  Keeps species
  * ranges contiguous; order inside a cell is unspecified (benchmark mode only).
