@@ -178,3 +178,67 @@ def test_world2_gloo_reproducible_build_allreduce_is_partition_independent():
         exact = math.fsum(v[node == g].tolist())
         got = FP.merge(int(words[g]), int(words[2 * Ng + g]), s)
         assert abs(got - exact) <= 1e-15 * max(abs(exact), 1.0)
+
+
+def _worker_det_periodic(rank, world, port, q):
+    """Reproducible builds of the periodic loops, sharded: PeriodicImplicitSim._allreduce_acc on [jh | j1] fp64 +
+    [hi(2Ng) | lo(2Ng)] int64 and ExplicitSim.field_solve's all-reduce of the words behind rho_acc."""
+    import types
+    from pypic_b200 import fixedpoint as FP
+    from pypic_b200.periodic import PeriodicImplicitSim
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        comm = Comm()
+        Ng, n = 16, 5000
+        s = FP.scale_exponent_current1(-1.602e-19, 517.0, 25.85)
+        rs = np.random.RandomState(12)
+        node = rs.randint(0, 2 * Ng, n)
+        v = rs.normal(0, 1e-9, n)
+        mine = np.arange(n) % world == rank
+        hi, lo = FP.split(v[mine], s)
+        H = np.zeros(2 * Ng, dtype=np.int64); Lo = np.zeros(2 * Ng, dtype=np.int64)
+        np.add.at(H, node[mine], hi); np.add.at(Lo, node[mine], lo)
+        acc = torch.zeros(2 * Ng + 4 * Ng, dtype=torch.float64)
+        acc[2 * Ng:].view(torch.int64).copy_(torch.as_tensor(np.concatenate([H, Lo])))
+        PeriodicImplicitSim._allreduce_acc(types.SimpleNamespace(det=True, comm=comm, Ng=Ng, acc=acc))
+        # the explicit loop's layout: fp64[g] + int64[2g] with g = Ng + 1 (the slice ExplicitSim.field_solve reduces)
+        g = Ng + 1
+        rho = torch.zeros(3 * g, dtype=torch.float64)
+        rho[g:].view(torch.int64).copy_(torch.as_tensor(np.arange(2 * g, dtype=np.int64) * (rank + 1)))
+        comm.allreduce_sum(rho[g:].view(torch.int64))
+        q.put((rank, acc.numpy().copy(), rho.numpy().copy(), s))
+        comm.barrier()
+    finally:
+        dist.destroy_process_group()
+
+
+def test_world2_gloo_reproducible_periodic_builds_allreduce_the_words():
+    import math
+    from pypic_b200 import fixedpoint as FP
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker_det_periodic, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = sorted([q.get(timeout=120) for _ in range(world)], key=lambda t: t[0])
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    Ng, n = 16, 5000
+    s = res[0][3]
+    assert res[0][1].tobytes() == res[1][1].tobytes() and res[0][2].tobytes() == res[1][2].tobytes()
+    acc = res[0][1]
+    assert np.array_equal(acc[:2 * Ng], np.zeros(2 * Ng))                  # the fp64 slots are filled by the field kernel's take
+    words = acc[2 * Ng:].view(np.int64)
+    rs = np.random.RandomState(12)
+    node = rs.randint(0, 2 * Ng, n); v = rs.normal(0, 1e-9, n)
+    for gi in range(2 * Ng):
+        exact = math.fsum(v[node == gi].tolist())
+        got = FP.merge(int(words[gi]), int(words[2 * Ng + gi]), s)
+        assert abs(got - exact) <= 1e-15 * max(abs(exact), 1e-12)
+    g = Ng + 1
+    assert np.array_equal(res[0][2][g:].view(np.int64), np.arange(2 * g, dtype=np.int64) * 3)
